@@ -1,0 +1,320 @@
+/* ugf.h — C ABI of libugf, the B200 (sm_100a) implementation of uniGasFoam's
+ * per-timestep particle loop (uniGasCloud::evolve()).
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, returns an
+ * int status (0 = ok, non-zero = error; ugf_last_error() gives the message) and
+ * never throws.  One handle = one GPU = one decomposePar subdomain (rank).
+ * Calls are stream-ordered on the handle's stream; entry points that hand data
+ * back to the host synchronise that stream.
+ *
+ * Each declaration cites the reference interface it replaces; paths are relative
+ * to the uniGasFoam repository root, with
+ *   U/   = src/lagrangian/uniGas/
+ *   CWM/ = src/lagrangian/CloudWithModels/
+ *
+ * The reference has no C ABI or FFI of its own: its plugin API is OpenFOAM's
+ * run-time selection tables (declareRunTimeSelectionTable).  The enums below are
+ * the TypeName strings of those tables, one enumerator per selectable model.
+ * INTEGRATION.md shows the shim classes a uniGasFoam maintainer would register
+ * under the same dictionary keys to forward into these calls.
+ */
+#ifndef UGF_H
+#define UGF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGF_ABI_VERSION 1
+#define UGF_MAX_SPECIES 8
+#define UGF_MAX_VIB_MODES 4
+#define UGF_MAX_ELEC_LEVELS 16
+
+/* ---- run-time selection tables as enums ---------------------------------- */
+
+/* constant/uniGasProperties: collisionModel  (U/clouds/uniGasCloud.C:236-248,656,708) */
+enum { UGF_COLL_DSMC = 1, UGF_COLL_BGK = 2, UGF_COLL_HYBRID = 3 };
+
+/* dsmcCollisionPartnerModel  (U/dsmcCollisionPartner/basic/dsmcCollisionPartner.H:78-89) */
+enum { UGF_PARTNER_NTC = 1, UGF_PARTNER_NTC_SUBCYCLED = 2 };
+
+/* dsmcCollisionModel  (U/dsmcCollisions/basic/dsmcCollisionModel/dsmcCollisionModel.H:76-86) */
+enum {
+    UGF_BINARY_NONE = 0,   /* noDSMCCollision */
+    UGF_BINARY_VHS = 1,    /* variableHardSphere */
+    UGF_BINARY_VSS = 2,    /* variableSoftSphere */
+    UGF_BINARY_LB_VHS = 3, /* LarsenBorgnakkeVariableHardSphere */
+    UGF_BINARY_LB_VSS = 4  /* LarsenBorgnakkeVariableSoftSphere */
+};
+
+/* bgkCollisionModel  (U/bgkCollisions/basic/bgkCollisionModel/bgkCollisionModel.H:82-93) */
+enum {
+    UGF_BGK_NONE = 0,     /* noBGKCollision */
+    UGF_BGK_BGK = 1,      /* stochasticParticleBGK */
+    UGF_BGK_ESBGK = 2,    /* stochasticParticleESBGK */
+    UGF_BGK_SBGK = 3,     /* stochasticParticleSBGK */
+    UGF_BGK_USP_SBGK = 4  /* unifiedStochasticParticleSBGK */
+};
+
+/* polyPatch types as seen by particle::trackToAndHitFace (OpenFOAM; call site
+ * U/parcels/uniGasParcel.C:74) */
+enum {
+    UGF_PATCH_WALL = 1,      /* -> hitWallPatch -> patch boundary model (U/parcels/uniGasParcel.C:131-145) */
+    UGF_PATCH_SYMMETRY = 2,  /* symmetry / symmetryPlane: reflect (U/parcels/uniGasParcel.C:148-155) */
+    UGF_PATCH_CYCLIC = 3,    /* jump to partner patch face (same local index) + separation */
+    UGF_PATCH_EMPTY = 4,     /* never hit: tracking velocity is constrained (U/parcels/uniGasParcel.C:64-71) */
+    UGF_PATCH_PROCESSOR = 5, /* hitProcessorPatch: migrate (U/parcels/uniGasParcel.C:121-128) */
+    UGF_PATCH_GENERIC = 6    /* "type patch": OpenFOAM default, td.keepParticle = false */
+};
+
+/* uniGasPatchBoundary models  (U/boundaries/basic/uniGasPatchBoundary/uniGasPatchBoundary.H:90-101) */
+enum {
+    UGF_WALL_UNSET = 0,
+    UGF_WALL_DIFFUSE = 1,  /* uniGasDiffuseWallPatch   params: T, Ux, Uy, Uz */
+    UGF_WALL_SPECULAR = 2, /* uniGasSpecularWallPatch  params: none */
+    UGF_WALL_MIXED = 3,    /* uniGasMixedDiffuseSpecularWallPatch params: T, Ux, Uy, Uz, diffuseFraction */
+    UGF_WALL_DELETION = 4  /* uniGasDeletionPatch      params: none */
+};
+
+/* ---- plain-old-data inputs ------------------------------------------------ */
+
+/* constant/uniGasProperties + system/controlDict subset. */
+typedef struct ugf_config {
+    int32_t abiVersion;        /* must be UGF_ABI_VERSION */
+    int32_t device;            /* CUDA device ordinal */
+    uint64_t seed;             /* counter-based Philox key; reference seeds from the wall clock
+                                  (U/clouds/uniGasCloud.C:490) */
+    double nParticle;          /* nEquivalentParticles, F_N  (U/clouds/uniGasCloud.C:414) */
+    double deltaT;             /* controlDict deltaT */
+    int32_t solutionD[3];      /* 1 = solved direction, 0 = empty  (U/clouds/uniGasCloud.C:513-532) */
+    int32_t collisionModel;    /* UGF_COLL_* */
+    int32_t partnerModel;      /* UGF_PARTNER_* */
+    int32_t binaryModel;       /* UGF_BINARY_* */
+    int32_t bgkModel;          /* UGF_BGK_* */
+    int32_t nSubCycles;        /* noTimeCounterSubCycled only */
+    int32_t macroInterpolation;/* collisionProperties.macroInterpolation; must be 0 (cell values) */
+    double Tref;               /* collisionProperties.Tref */
+    double theta;              /* collisionProperties.theta (default 1) */
+    double rotationalRelaxationCollisionNumber; /* LB: Z_rot  (…LBVHS.C:60-63) */
+    double electronicRelaxationCollisionNumber; /* LB: Z_elec (…LBVHS.C:64-67) */
+    int64_t parcelCapacity;    /* SoA capacity in parcels (resident state is 2 buffers of this size) */
+    int32_t sampleInterval;    /* fieldPropertiesDict timeProperties.sampleInterval (default 1) */
+    int32_t measureWalls;      /* 1 = accumulate boundaryMeasurements on wall faces */
+    int32_t rank;              /* subdomain index (Pstream::myProcNo) */
+    int32_t nRanks;
+} ugf_config;
+
+/* moleculeProperties.<species>  (U/parcels/uniGasParcel.H:68-120, uniGasParcelI.H:40-141) */
+typedef struct ugf_species {
+    double mass;
+    double d;              /* diameter */
+    double omega;
+    double alpha;
+    int32_t rotationalDoF;
+    int32_t vibrationalDoF;            /* number of vibrational modes */
+    double thetaV[UGF_MAX_VIB_MODES];
+    double thetaD[UGF_MAX_VIB_MODES];
+    double Zref[UGF_MAX_VIB_MODES];
+    double TrefZv[UGF_MAX_VIB_MODES];
+    int32_t charge;
+    int32_t nElectronicLevels;
+    double electronicEnergy[UGF_MAX_ELEC_LEVELS];
+    int32_t degeneracy[UGF_MAX_ELEC_LEVELS];
+} ugf_species;
+
+/* polyMesh flattened (constant/polyMesh/{points,faces,owner,neighbour,boundary} plus
+ * the derived geometry OpenFOAM computes: faceAreas, faceCentres, cellVolumes,
+ * cellCentres, cellPoints bounding box).  All vectors are AoS xyz, fp64; all
+ * labels int32 (WM_LABEL_SIZE=32).  Boundary faces of patch p are the contiguous
+ * range [patchStart[p], patchStart[p]+patchSize[p]).  Face area vectors point
+ * from owner to neighbour (out of the domain on boundary faces).
+ * points/facePointOffsets/facePoints are only needed for inflow patches
+ * (triangle fan for insertion, U/boundaries/basic/uniGasGeneralBoundary/uniGasGeneralBoundary.C:558-578)
+ * and may be NULL otherwise. */
+typedef struct ugf_mesh {
+    int32_t nCells, nFaces, nInternalFaces, nPatches, nPoints;
+    const int32_t* owner;           /* [nFaces] */
+    const int32_t* neighbour;       /* [nInternalFaces] */
+    const double* faceAreas;        /* [nFaces*3]  Sf */
+    const double* faceCentres;      /* [nFaces*3]  Cf */
+    const int32_t* cellFaceOffsets; /* [nCells+1]  CSR cell -> faces */
+    const int32_t* cellFaces;       /* [cellFaceOffsets[nCells]] */
+    const double* cellVolumes;      /* [nCells] */
+    const double* cellCentres;      /* [nCells*3] */
+    const double* cellBbMin;        /* [nCells*3] min over cellPoints (noTimeCounter.C:112-127) */
+    const double* cellBbMax;        /* [nCells*3] */
+    const int32_t* patchStart;      /* [nPatches] */
+    const int32_t* patchSize;       /* [nPatches] */
+    const int32_t* patchKind;       /* [nPatches] UGF_PATCH_* */
+    const int32_t* patchPartner;    /* [nPatches] cyclic: partner patch; processor: peer rank; else -1 */
+    const double* patchSeparation;  /* [nPatches*3] added to the position when crossing (cyclic, processorCyclic) */
+    const double* points;           /* [nPoints*3] or NULL */
+    const int32_t* facePointOffsets;/* [nFaces+1] or NULL */
+    const int32_t* facePoints;      /* CSR or NULL */
+} ugf_mesh;
+
+/* boundariesDict: uniGasFreeStreamInflowPatchProperties
+ * (U/boundaries/derived/generalBoundaries/uniGasFreeStreamInflowPatch/uniGasFreeStreamInflowPatch.C:61-96) */
+typedef struct ugf_inflow {
+    int32_t nTypeIds;
+    int32_t typeIds[UGF_MAX_SPECIES];
+    double numberDensities[UGF_MAX_SPECIES];
+    double translationalTemperature;
+    double rotationalTemperature;
+    double vibrationalTemperature;
+    double electronicTemperature;
+    double velocity[3];
+} ugf_inflow;
+
+/* Parcels as host SoA.  Mandatory: x,y,z,Ux,Uy,Uz,cell.  Optional (NULL = default):
+ * typeId (0), ERot (0), stepFraction/newParcel (0).  (U/parcels/uniGasParcel.H:217-239) */
+typedef struct ugf_parcels {
+    int64_t n;
+    double* x; double* y; double* z;
+    double* Ux; double* Uy; double* Uz;
+    int32_t* cell;
+    int32_t* typeId;
+    double* ERot;
+    int32_t* newParcel;
+} ugf_parcels;
+
+/* Per-step log quantities (noTimeCounter.C:318-342, …USP.C:976-992, uniGasCloud.C:878-920). */
+typedef struct ugf_counters {
+    int64_t step;                /* steps taken so far */
+    int64_t nParcels;            /* live parcels after the last phase */
+    int64_t collisionCandidates; /* NTC candidates, last step */
+    int64_t collisions;          /* accepted DSMC collisions, last step */
+    int64_t bgkRelaxations;      /* parcels relaxed by the BGK model, last step */
+    int64_t inserted;            /* parcels inserted by inflow patches, last step */
+    int64_t deleted;             /* parcels deleted at patches, last step */
+    int64_t migrated;            /* parcels sent to other ranks, last step */
+    int64_t wallHits;            /* wall-patch interactions, last step */
+    int64_t stuck;               /* parcels dropped by the tracking iteration guard (must stay 0) */
+    double linearKineticEnergy;  /* sum 0.5 m |U|^2 over parcels (x F_N = info()) */
+    double rotationalEnergy;     /* sum ERot */
+    double momentum[3];          /* sum m U */
+} ugf_counters;
+
+/* Number of fp64 values per (cell, species) in the cell-moment block; see DESIGN.md
+ * for the slot list.  (U/cellMeasurements/cellMeasurements.H:73-145) */
+#define UGF_NMOM 32
+
+/* Number of fp64 values per wall face in the boundary-measurement block
+ * (U/boundaryMeasurements/boundaryMeasurements.C:70-121). */
+#define UGF_NBM 16
+
+/* Number of fp64 output fields per cell from ugf_download_fields
+ * (U/macroscopicProperties/derived/volumetric/uniGasVolFields/uniGasVolFields.C:839-1254):
+ * 0 uniGasRhoNMean, 1 rhoN, 2 rhoM, 3-5 UMean, 6 translationalT, 7 rotationalT,
+ * 8 overallT, 9 p, 10 Ma, 11 densityError (0 if undefined). */
+#define UGF_NFIELD 12
+/* per wall face: 0 rhoN, 1 rhoM, 2-4 UMean, 5 translationalT, 6 q (surfaceHeatTransfer),
+ * 7-9 fD, 10 p, 11 tau. */
+#define UGF_NWALLFIELD 12
+
+typedef struct ugf_handle ugf_handle;
+
+/* ---- lifetime -------------------------------------------------------------- */
+
+/* uniGasCloud constructor (U/clouds/uniGasCloud.C:400-780). */
+int ugf_create(const ugf_config* cfg, ugf_handle** out);
+int ugf_destroy(ugf_handle* h);
+/* Message for the last non-zero status on this handle (h may be NULL for create errors).
+ * Replaces FatalErrorInFunction ... exit(FatalError). */
+const char* ugf_last_error(const ugf_handle* h);
+int ugf_abi_version(void);
+
+/* ---- case set-up (construction-time in the reference) ---------------------- */
+
+/* buildConstProps (U/clouds/uniGasCloud.C:42-62). */
+int ugf_set_species(ugf_handle* h, int32_t n, const ugf_species* sp);
+/* polyMesh reference held by the cloud; flattened to CSR + face planes on the device. */
+int ugf_set_mesh(ugf_handle* h, const ugf_mesh* mesh);
+/* uniGasBoundaries: patchToModelId_ (U/boundaries/basic/uniGasBoundaries/uniGasBoundaries.C:420-490).
+ * params: see UGF_WALL_*.  Only wall-kind patches take a model. */
+int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t wallModel, const double* params, int32_t nParams);
+/* uniGasFreeStreamInflowPatch on a patch (any kind). */
+int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* inflow);
+/* addNewParcel over a whole initial configuration (U/clouds/uniGasCloud.C:260-290). Replaces the cloud. */
+int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p);
+/* Cell state carried between steps (U/clouds/uniGasCloud.H:189-201): sigmaTcRMax [nCells],
+ * collModelId [nCells] (0 = bgk, 1 = dsmc), subCellLevels [nCells*3], cellWeightFactor [nCells] (must be 1).
+ * NULL keeps the current value. */
+int ugf_upload_cell_state(ugf_handle* h, const double* sigmaTcRMax, const int32_t* collModelId,
+                          const int32_t* subCellLevels, const double* cellWeightFactor);
+int ugf_set_deltaT(ugf_handle* h, double deltaT);
+
+/* ---- the hot path ----------------------------------------------------------- */
+
+/* uniGasCloud::evolve() nSteps times (U/clouds/uniGasCloud.C:821-869):
+ * inflow -> move(+patches) -> occupancy -> sample -> collide/relax -> field accumulation.
+ * Single-rank only; multi-rank callers drive the phases below with the migrate calls. */
+int ugf_step(ugf_handle* h, int32_t nSteps);
+
+/* Phase-wise entry points, for parity tests, profiling and multi-rank drivers. */
+/* boundaries_.controlBeforeMove(): free-stream insertion (uniGasGeneralBoundary.C:115-169,537-761). */
+int ugf_control_before_move(ugf_handle* h);
+/* Cloud<uniGasParcel>::move (U/clouds/uniGasCloud.C:836, U/parcels/uniGasParcel.C:35-108). Tracks every
+ * parcel to the end of the step or to a processor face; also counts parcels per destination cell. */
+int ugf_move(ugf_handle* h);
+/* buildCellOccupancy (CWM/CloudWithModels/CloudWithModels.C:110-138): CSR offsets + parcel ids, stable. */
+int ugf_sort(ugf_handle* h);
+/* Physically reorder the SoA into cell-major order (no reference analogue: the reference keeps pointers). */
+int ugf_reorder(ugf_handle* h);
+/* cellMeasurements::calculateFields (U/cellMeasurements/cellMeasurements.C:408-513). */
+int ugf_sample(ugf_handle* h);
+/* dsmcCollisionPartner::collide (…/noTimeCounter/noTimeCounter.C:66-343) with the selected binary model. */
+int ugf_collide(ugf_handle* h);
+/* bgkCollisionModel::collide (e.g. …/unifiedStochasticParticleSBGK.C:871-994). */
+int ugf_relax(ugf_handle* h);
+/* uniGasVolFields::calculateField accumulation part (uniGasVolFields.C:723-837) +
+ * cellMeas_/boundaryMeas_ clean (U/clouds/uniGasCloud.C:864-866). */
+int ugf_accumulate_fields(ugf_handle* h);
+/* End-of-step bookkeeping when phases are driven one by one: step counter ++. */
+int ugf_end_step(ugf_handle* h);
+
+/* ---- multi-rank parcel migration (Cloud::move transfer loop, OpenFOAM; §2.1 of SURVEY) ---- */
+
+/* After ugf_move: number of parcels waiting on each processor patch [nPatches] (0 for other kinds). */
+int ugf_migrate_counts(ugf_handle* h, int64_t* sendCounts);
+/* Pack the parcels waiting on `patch` into a device buffer of UGF_MIGRATE_STRIDE doubles per parcel
+ * (x,y,z,Ux,Uy,Uz,ERot,stepFraction,localFace,typeId as doubles) and remove them from the cloud.
+ * *devBuf is owned by the handle and valid until the next pack on the same patch. */
+#define UGF_MIGRATE_STRIDE 10
+int ugf_migrate_pack(ugf_handle* h, int32_t patch, double** devBuf, int64_t* nPacked);
+/* Append n received parcels (same record layout, device pointer) arriving through `patch`; they are
+ * placed in the owner cell of the matching local face.  Follow with ugf_move_received. */
+int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64_t n);
+/* Continue tracking the parcels appended since the last ugf_move / ugf_move_received. */
+int ugf_move_received(ugf_handle* h);
+/* Raw stream (cudaStream_t) the handle launches on, for interop with NCCL / torch. */
+int ugf_stream(ugf_handle* h, void** stream);
+
+/* ---- results ----------------------------------------------------------------- */
+
+int ugf_counters_get(ugf_handle* h, ugf_counters* out);
+int ugf_num_parcels(ugf_handle* h, int64_t* n);
+/* Download parcels in current device order; any pointer in p may be NULL. p->n in: capacity, out: count. */
+int ugf_download_parcels(ugf_handle* h, ugf_parcels* p);
+/* cellOccupancy() (CWM/CloudWithModels/CloudWithModelsI.H:65-75) as CSR: offsets [nCells+1], ids [n]. */
+int ugf_download_cell_occupancy(ugf_handle* h, int32_t* offsets, int32_t* ids);
+/* Moments of the last ugf_sample/ugf_collide: [nCells][nSpecies][UGF_NMOM]. */
+int ugf_download_cell_moments(ugf_handle* h, double* moments);
+/* sigmaTcRMax [nCells]; BGK persistent state maxProb [nCells], qPrev [nCells*3], sPrev [nCells*6] (NULL skips). */
+int ugf_download_cell_state(ugf_handle* h, double* sigmaTcRMax, double* maxProb, double* qPrev, double* sPrev);
+/* Time-averaged fields, derived as at write time: cells [nCells][UGF_NFIELD]; wall faces
+ * [nBoundaryFaces][UGF_NWALLFIELD] (zero on non-wall faces). resetAtOutput clears the accumulators. */
+int ugf_download_fields(ugf_handle* h, double* cellFields, double* wallFields, int32_t resetAtOutput);
+/* Raw per-step boundary measurements of the last move: [nBoundaryFaces][UGF_NBM]. */
+int ugf_download_boundary_meas(ugf_handle* h, double* bm);
+/* Per-phase device time of the last ugf_step in ms: inflow, move, sort, cell(sample+collide), relax, fields. */
+int ugf_phase_times(ugf_handle* h, double* ms6);
+/* Number of kernel launches issued by this handle so far. */
+int ugf_launch_count(ugf_handle* h, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGF_H */

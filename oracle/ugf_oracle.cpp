@@ -1,0 +1,1442 @@
+// ugf_oracle.cpp — CPU restatement of uniGasFoam's per-timestep particle loop.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product path (unigasfoam_b200/, libugf.so)
+// may include, link or call this file.  It is used by tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs, as the checker and as the timed
+// CPU baseline.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this
+// path, and cannot be built here (needs OpenFOAM >= v2212 + MPI).  The
+// restatement is pinned instead by closed-form kinetic-theory answers (tests/) and by
+// Philox known-answer vectors for the RNG.
+//
+// What is restated (paths relative to the uniGasFoam root; U/ = src/lagrangian/uniGas/,
+// CWM/ = src/lagrangian/CloudWithModels/):
+//   evolve() phase order                U/clouds/uniGasCloud.C:821-869
+//   parcel move loop                    U/parcels/uniGasParcel.C:35-108
+//   wall models / measurements          U/boundaries/basic/uniGasPatchBoundary/uniGasPatchBoundary.C:130-403
+//   free-stream inflow                  U/boundaries/basic/uniGasGeneralBoundary/uniGasGeneralBoundary.C:115-169,537-761
+//   cell occupancy ("the sort")         CWM/CloudWithModels/CloudWithModels.C:110-138
+//   cell moments                        U/cellMeasurements/cellMeasurements.C:408-513
+//   NTC partner selection               U/dsmcCollisionPartner/derived/noTimeCounter/noTimeCounter.C:66-343
+//   VHS / VSS / Larsen-Borgnakke        U/dsmcCollisions/derived/*/ *.C
+//   kinetic samplers                    U/clouds/uniGasCloud.C:927-1326
+//   BGK / ES-BGK / S-BGK / USP-SBGK     U/bgkCollisions/derived/*/ *.C
+//   volume + wall fields                U/macroscopicProperties/derived/volumetric/uniGasVolFields/uniGasVolFields.C:723-1352
+//
+// What is NOT in the reference tree and is restated from OpenFOAM's documented
+// behaviour: Cloud::move / particle::trackToAndHitFace are
+// replaced by a face-plane walker (identical on planar-faced convex cells), and
+// Foam::Random by counter-based Philox4x32-10 streams (the reference seeds from the wall
+// clock, so no stream is reproducible upstream anyway).  The stream layout is part of
+// the contract with the CUDA path and is documented in DESIGN.md §RNG.
+//
+// Layout follows the reference's style on purpose (array-of-structs parcels, one pass
+// per phase, per-cell index lists): this is also the timed CPU baseline.
+
+#include "../include/ugf.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// OpenFOAM DimensionedConstants defaults (SURVEY §8c "constants").
+constexpr double kB = 1.38065e-23;         // physicoChemical::k
+constexpr double NA = 6.02214e+23;         // physicoChemical::NA
+constexpr double PI = 3.14159265358979323846;
+constexpr double TWO_PI = 6.28318530717958647692;
+constexpr double VSMALL = 1e-300;
+constexpr double SMALL = 1e-15;
+
+// ---------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), restated from the published algorithm.
+// ---------------------------------------------------------------------------------
+inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+enum { KIND_MOVE = 1, KIND_NTC = 2, KIND_BGK = 3, KIND_INFLOW = 4 };
+
+// One stream = (seed, kind, aux) key + (a, b, c) counter prefix; the 4th counter word
+// counts Philox blocks.  Each block yields two uniforms in [0,1) with 53 random bits.
+struct Stream {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t out[4];
+    int have;
+    Stream(uint64_t seed, uint32_t kind, uint32_t aux, uint32_t a, uint32_t b, uint32_t c) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32) ^ (kind << 24) ^ aux;
+        ctr[0] = a; ctr[1] = b; ctr[2] = c; ctr[3] = 0;
+        have = 0;
+    }
+    inline double u01() {  // Random::sample01<scalar>()
+        if (!have) { philox4x32_10(ctr, key, out); ctr[3]++; have = 2; }
+        const uint32_t hi = out[(2 - have) * 2], lo = out[(2 - have) * 2 + 1];
+        have--;
+        return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+    }
+    // Two independent N(0,1) from two uniforms (Box-Muller).  Foam::Random::GaussNormal is
+    // a cached polar method; the distribution is the same, the draw count is fixed here.
+    inline void gauss2(double& g1, double& g2) {
+        const double u1 = u01(), u2 = u01();
+        const double r = std::sqrt(-2.0 * std::log(1.0 - u1));
+        const double th = TWO_PI * u2;
+        g1 = r * std::cos(th);
+        g2 = r * std::sin(th);
+    }
+    inline void gauss3(double g[3]) {
+        double d;
+        gauss2(g[0], g[1]);
+        gauss2(g[2], d);
+    }
+    // Random::position<label>(0, n-1)
+    inline int position(int n) {
+        int i = (int)(u01() * n);
+        return i < n - 1 ? i : n - 1;
+    }
+};
+
+struct Parcel {  // uniGasParcel (U/parcels/uniGasParcel.H:217-239) + particle position/cell
+    double x[3];
+    double U[3];
+    double ERot;
+    double sf;       // stepFraction
+    int32_t cell;    // >=0 live; -1 deleted; <= -2 waiting on a processor face (-2 - boundaryFaceIndex)
+    int32_t typeId;
+    int32_t newParcel;
+};
+
+struct WallModel { int model = UGF_WALL_UNSET; double T = 0, Uw[3] = {0, 0, 0}, diffuseFraction = 1; };
+
+struct InflowPatch { int patch; ugf_inflow in; };
+
+constexpr int NACC = 16;
+
+}  // namespace
+
+struct ugfo_handle {
+    ugf_config cfg;
+    std::string err;
+    int nSpecies = 0;
+    ugf_species sp[UGF_MAX_SPECIES];
+
+    // mesh
+    int nCells = 0, nFaces = 0, nInternal = 0, nPatches = 0, nBFaces = 0;
+    std::vector<int32_t> owner, neighbour, cfOff, cf, pStart, pSize, pKind, pPartner;
+    std::vector<double> Sf, Cf, vol, cc, bbMin, bbMax, pSep, points;
+    std::vector<int32_t> fpOff, fp;
+    std::vector<int32_t> facePatch;  // [nBFaces]
+    std::vector<WallModel> wall;     // [nPatches]
+    std::vector<InflowPatch> inflows;
+
+    // cloud
+    std::vector<Parcel> P;
+    int64_t nBeforeInsert = 0;
+    int64_t receivedStart = -1;
+    std::vector<int32_t> occOff, occIds;  // cell occupancy CSR
+    bool occValid = false, occIdentity = false;
+
+    // cell state (U/clouds/uniGasCloud.H:189-201)
+    std::vector<double> sigmaTcRMax;
+    std::vector<int32_t> collModelId, subLevels;
+    // BGK persistent state
+    std::vector<double> maxProb, qPrev, sPrev;
+    // per-step measurements
+    std::vector<double> mom;   // [nCells][nSpecies][UGF_NMOM]
+    bool momValid = false;
+    std::vector<double> bm;    // [nBFaces][UGF_NBM]
+    // time-averaged accumulators (uniGasVolFields)
+    std::vector<double> acc;   // [nCells][NACC]
+    std::vector<double> bacc;  // [nBFaces][UGF_NBM]
+    double timeAvCounter = 0;
+    int64_t nAvTimeSteps = 0;
+    int sampleCounter = 0;
+
+    int64_t step = 0;
+    bool stepOpen = false;
+    ugf_counters cnt;
+    std::vector<std::vector<double>> packBuf;
+};
+
+namespace {
+
+inline int fail(ugfo_handle* h, const std::string& m) { if (h) h->err = m; return 1; }
+
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// ---------------------------------------------------------------------------------
+// kinetic samplers  (U/clouds/uniGasCloud.C:975-1017, 1129-1189, 1267-1326)
+// ---------------------------------------------------------------------------------
+double equipartitionRotationalEnergy(Stream& r, double T, int rotDoF) {
+    if (rotDoF < 1) return 0.0;
+    if (rotDoF == 2) {
+        // reference: -log(sample01)*k*T; 1-u is used so that u = 0 cannot give inf.
+        return -std::log(1.0 - r.u01()) * kB * T;
+    }
+    const double a = 0.5 * rotDoF - 1;
+    double energyRatio, Pp;
+    const double eps = r.u01();
+    do {
+        energyRatio = 10 * r.u01();
+        Pp = std::pow(energyRatio / a, a) * std::exp(a - energyRatio);
+    } while (Pp < eps);
+    return energyRatio * kB * T;
+}
+
+double postCollisionRotationalEnergy(Stream& r, int rotDoF, double ChiB) {
+    double energyRatio = 0.0;
+    if (rotDoF == 2) {
+        energyRatio = 1.0 - std::pow(r.u01(), 1.0 / ChiB);
+    } else {
+        const double ChiA = 0.5 * rotDoF;
+        const double A1 = ChiA - 1, B1 = ChiB - 1;
+        if (A1 < SMALL && B1 < SMALL) return r.u01();
+        double Pp;
+        const double eps = r.u01();
+        do {
+            energyRatio = r.u01();
+            if (A1 < SMALL) Pp = std::pow(1.0 - energyRatio, B1);
+            else if (B1 < SMALL) Pp = std::pow(1.0 - energyRatio, A1);
+            else Pp = std::pow((A1 + B1) * energyRatio / A1, A1) * std::pow((A1 + B1) * (1 - energyRatio) / B1, B1);
+        } while (Pp < eps);
+    }
+    return energyRatio;
+}
+
+int postCollisionElectronicEnergyLevel(Stream& r, double Ec, int jMax, double omega, const double* EE, const int32_t* g) {
+    int nPossStates = 0;
+    if (jMax == 1) nPossStates = g[0];
+    else for (int n = 0; n < jMax; ++n) if (Ec > EE[n]) nPossStates += g[n];
+    int ELevel = -1;
+    for (;;) {
+        const int nState = (int)std::ceil(r.u01() * nPossStates);
+        int nAvail = 0, nLevel = -1;
+        for (int n = 0; n < jMax; ++n) {
+            nAvail += g[n];
+            if (nState <= nAvail && nLevel < 0) nLevel = n;
+        }
+        if (nLevel < 0) nLevel = 0;
+        if (Ec > EE[nLevel]) {
+            const double prob = std::pow(1.0 - EE[nLevel] / Ec, 1.5 - omega);
+            if (prob > r.u01()) { ELevel = nLevel; break; }
+        }
+    }
+    return ELevel;
+}
+
+// ---------------------------------------------------------------------------------
+// binary collision models
+// ---------------------------------------------------------------------------------
+// variableHardSphere::sigmaTcR (…/variableHardSphere/variableHardSphere.C:72-115); the VSS and
+// both LB models code the same expression.
+double sigmaTcR(const ugfo_handle& h, const Parcel& p, const Parcel& q) {
+    const double d0 = p.U[0] - q.U[0], d1 = p.U[1] - q.U[1], d2 = p.U[2] - q.U[2];
+    const double cR2 = d0 * d0 + d1 * d1 + d2 * d2;
+    if (cR2 < VSMALL) return 0;
+    const ugf_species& a = h.sp[p.typeId];
+    const ugf_species& b = h.sp[q.typeId];
+    const double dPQ = 0.5 * (a.d + b.d);
+    const double omegaPQ = 0.5 * (a.omega + b.omega);
+    const double mR = a.mass * b.mass / (a.mass + b.mass);
+    const double sigmaTPQ = PI * dPQ * dPQ * std::pow(2.0 * kB * h.cfg.Tref / (mR * cR2), omegaPQ - 0.5)
+                            / std::exp(std::lgamma(2.5 - omegaPQ));
+    return sigmaTPQ * std::sqrt(cR2);
+}
+
+// isotropic (VHS) scattering of a relative velocity of magnitude cR (variableHardSphere.C:137-160)
+inline void scatterVHS(Stream& r, double cR, double out[3]) {
+    const double cosTheta = 2.0 * r.u01() - 1.0;
+    const double sinTheta = std::sqrt(1.0 - cosTheta * cosTheta);
+    const double phi = TWO_PI * r.u01();
+    out[0] = cR * cosTheta;
+    out[1] = cR * (sinTheta * std::cos(phi));
+    out[2] = cR * (sinTheta * std::sin(phi));
+}
+
+// VSS scattering, Bird eq 2.22 (variableSoftSphere.C:147-170).  cRc = pre-collision relative
+// velocity components; scale = |c_r'|/|c_r| (1 for plain VSS, sqrt(Etr'/Etr) after LB exchange).
+inline void scatterVSS(Stream& r, const double cRc[3], double alphaPQ, double scale, double out[3]) {
+    const double cR = std::sqrt(cRc[0] * cRc[0] + cRc[1] * cRc[1] + cRc[2] * cRc[2]);
+    const double cosTheta = 2.0 * std::pow(r.u01(), 1.0 / alphaPQ) - 1.0;
+    const double sinTheta = std::sqrt(1.0 - cosTheta * cosTheta);
+    const double phi = TWO_PI * r.u01();
+    const double D = std::sqrt(cRc[1] * cRc[1] + cRc[2] * cRc[2]);
+    const double sp = std::sin(phi), cp = std::cos(phi);
+    out[0] = scale * (cosTheta * cRc[0] + sinTheta * sp * D);
+    out[1] = scale * (cosTheta * cRc[1] + sinTheta * (cR * cRc[2] * cp - cRc[0] * cRc[1] * sp) / D);
+    out[2] = scale * (cosTheta * cRc[2] - sinTheta * (cR * cRc[1] * cp + cRc[0] * cRc[2] * sp) / D);
+}
+
+void collidePair(const ugfo_handle& h, Stream& r, Parcel& p, Parcel& q) {
+    const ugf_species& a = h.sp[p.typeId];
+    const ugf_species& b = h.sp[q.typeId];
+    const double mP = a.mass, mQ = b.mass, mS = mP + mQ;
+    double Ucm[3], cRc[3];
+    for (int k = 0; k < 3; ++k) {
+        Ucm[k] = (mP * p.U[k] + mQ * q.U[k]) / mS;
+        cRc[k] = p.U[k] - q.U[k];
+    }
+    const double cRsqr = cRc[0] * cRc[0] + cRc[1] * cRc[1] + cRc[2] * cRc[2];
+    double rel[3];
+    const int model = h.cfg.binaryModel;
+    if (model == UGF_BINARY_VHS) {
+        scatterVHS(r, std::sqrt(cRsqr), rel);
+    } else if (model == UGF_BINARY_VSS) {
+        scatterVSS(r, cRc, 0.5 * (a.alpha + b.alpha), 1.0, rel);
+    } else {
+        // Larsen-Borgnakke, serial application, P then Q
+        // (…/LarsenBorgnakkeVariableHardSphere.C:125-416; vibration not supported: modes must be 0)
+        const double omegaPQ = 0.5 * (a.omega + b.omega);
+        const double mR = mP * mQ / mS;
+        double Etr = 0.5 * mR * cRsqr;
+        const double ChiB = 2.5 - omegaPQ;
+        const double invZrot = 1.0 / h.cfg.rotationalRelaxationCollisionNumber;
+        const double invZel = 1.0 / h.cfg.electronicRelaxationCollisionNumber;
+        const double preERotP = p.ERot, preERotQ = q.ERot;
+        // P: electronic, (vibrational), rotational
+        if (invZel > r.u01()) {
+            const double Ec = Etr + a.electronicEnergy[0];
+            const int lev = postCollisionElectronicEnergyLevel(r, Ec, a.nElectronicLevels, omegaPQ, a.electronicEnergy, a.degeneracy);
+            Etr = Ec - a.electronicEnergy[lev];
+        }
+        if (a.rotationalDoF > 0) {
+            if (invZrot > r.u01()) {
+                const double Ec = Etr + preERotP;
+                const double ratio = postCollisionRotationalEnergy(r, a.rotationalDoF, ChiB);
+                p.ERot = ratio * Ec;
+                Etr = Ec - p.ERot;
+            }
+        }
+        if (invZel > r.u01()) {
+            const double Ec = Etr + b.electronicEnergy[0];
+            const int lev = postCollisionElectronicEnergyLevel(r, Ec, b.nElectronicLevels, omegaPQ, b.electronicEnergy, b.degeneracy);
+            Etr = Ec - b.electronicEnergy[lev];
+        }
+        if (b.rotationalDoF > 0) {
+            if (invZrot > r.u01()) {
+                const double Ec = Etr + preERotQ;
+                const double ratio = postCollisionRotationalEnergy(r, b.rotationalDoF, ChiB);
+                q.ERot = ratio * Ec;
+                Etr = Ec - q.ERot;
+            }
+        }
+        const double cRnew = std::sqrt((2.0 * Etr) / mR);
+        if (model == UGF_BINARY_LB_VHS) scatterVHS(r, cRnew, rel);
+        else scatterVSS(r, cRc, 0.5 * (a.alpha + b.alpha), cRnew / std::sqrt(cRsqr), rel);
+    }
+    for (int k = 0; k < 3; ++k) {
+        p.U[k] = Ucm[k] + rel[k] * mQ / mS;
+        q.U[k] = Ucm[k] - rel[k] * mP / mS;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// wall interaction  (uniGasPatchBoundary.C:130-403)
+// ---------------------------------------------------------------------------------
+inline void unitNormal(const double* S, double nw[3], double& fA) {
+    fA = std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+    nw[0] = S[0] / fA; nw[1] = S[1] / fA; nw[2] = S[2] / fA;
+}
+
+void measureWall(ugfo_handle& h, const Parcel& p, int bfi, const double nw[3], double fA, double* preIE, double* preIMom, bool after) {
+    const ugf_species& s = h.sp[p.typeId];
+    const double m = s.mass;
+    const double Un = dot3(p.U, nw);
+    const double inv = 1.0 / std::max(std::fabs(Un) * fA, VSMALL);
+    const double UU = dot3(p.U, p.U);
+    double* b = &h.bm[(size_t)bfi * UGF_NBM];
+    const double add[UGF_NBM] = {
+        inv, m * inv, 0.5 * m * UU * inv, m * p.U[0] * inv, m * p.U[1] * inv, m * p.U[2] * inv,
+        p.ERot * inv, s.rotationalDoF * inv, 0, 0, 0, 0, (s.rotationalDoF > 0 ? inv : 0.0), 0, s.electronicEnergy[0] * inv,
+        after ? 0.0 : 1.0};
+    const double IE = 0.5 * m * UU + p.ERot + s.electronicEnergy[0];
+    double dq = 0, dfd[3] = {0, 0, 0};
+    if (!after) {
+        *preIE = IE;
+        for (int k = 0; k < 3; ++k) preIMom[k] = m * p.U[k];
+    } else {
+        const double nPart = h.cfg.nParticle;
+        dq = nPart * (*preIE - IE) / (h.cfg.deltaT * fA);
+        for (int k = 0; k < 3; ++k) dfd[k] = nPart * (preIMom[k] - m * p.U[k]) / (h.cfg.deltaT * fA);
+    }
+    for (int k = 0; k < UGF_NBM; ++k) {
+        double v = add[k];
+        if (k == 8) v = dq;
+        if (k >= 9 && k <= 11) v = dfd[k - 9];
+        if (v != 0.0) {
+#pragma omp atomic
+            b[k] += v;
+        }
+    }
+}
+
+void diffuseReflection(const ugfo_handle& h, Stream& r, Parcel& p, const double nw[3], double T, const double* Uw) {
+    double Un = dot3(p.U, nw);
+    double Ut[3] = {p.U[0] - Un * nw[0], p.U[1] - Un * nw[1], p.U[2] - Un * nw[2]};
+    double magUt = std::sqrt(dot3(Ut, Ut));
+    while (magUt < SMALL) {
+        p.U[0] = p.U[0] * (0.8 + 0.2 * r.u01());
+        p.U[1] = p.U[1] * (0.8 + 0.2 * r.u01());
+        p.U[2] = p.U[2] * (0.8 + 0.2 * r.u01());
+        Un = dot3(p.U, nw);
+        for (int k = 0; k < 3; ++k) Ut[k] = p.U[k] - Un * nw[k];
+        magUt = std::sqrt(dot3(Ut, Ut));
+        if (dot3(p.U, p.U) == 0.0) {  // reference would spin forever on U == 0; pick a tangent
+            const int kmin = std::fabs(nw[0]) <= std::fabs(nw[1]) ? (std::fabs(nw[0]) <= std::fabs(nw[2]) ? 0 : 2)
+                                                                 : (std::fabs(nw[1]) <= std::fabs(nw[2]) ? 1 : 2);
+            double e[3] = {0, 0, 0};
+            e[kmin] = 1.0;
+            const double en = dot3(e, nw);
+            for (int k = 0; k < 3; ++k) Ut[k] = e[k] - en * nw[k];
+            magUt = std::sqrt(dot3(Ut, Ut));
+        }
+    }
+    const double tw1[3] = {Ut[0] / magUt, Ut[1] / magUt, Ut[2] / magUt};
+    const double tw2[3] = {nw[1] * tw1[2] - nw[2] * tw1[1], nw[2] * tw1[0] - nw[0] * tw1[2], nw[0] * tw1[1] - nw[1] * tw1[0]};
+    const ugf_species& s = h.sp[p.typeId];
+    double g1, g2;
+    r.gauss2(g1, g2);
+    const double gn = std::sqrt(-2.0 * std::log(std::max(1 - r.u01(), VSMALL)));
+    const double c = std::sqrt(kB * T / s.mass);
+    for (int k = 0; k < 3; ++k) p.U[k] = c * (g1 * tw1[k] + g2 * tw2[k] - gn * nw[k]);
+    p.ERot = equipartitionRotationalEnergy(r, T, s.rotationalDoF);
+    for (int k = 0; k < 3; ++k) p.U[k] += Uw[k];
+}
+
+// ---------------------------------------------------------------------------------
+// move: face-plane walker standing in for particle::trackToAndHitFace
+// ---------------------------------------------------------------------------------
+constexpr int MAX_TRACK_ITERS = 4096;
+
+struct MoveTally { int64_t deleted = 0, wallHits = 0, stuck = 0, migrated = 0; };
+
+void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool freshStream) {
+    Stream r(h.cfg.seed, KIND_MOVE, freshStream ? 0u : 1u, (uint32_t)h.step, (uint32_t)idx, 0);
+    const double dt = h.cfg.deltaT;
+    if (p.newParcel == 1) {  // U/parcels/uniGasParcel.C:47-53
+        p.sf = r.u01();
+        p.newParcel = 0;
+    }
+    int iters = 0;
+    while (p.cell >= 0 && p.sf < 1) {
+        const double rem = 1 - p.sf;
+        const double s = rem * dt;
+        double disp[3];
+        for (int k = 0; k < 3; ++k) disp[k] = h.cfg.solutionD[k] ? s * p.U[k] : 0.0;  // constrainDirection
+        double lamMin = 1.0;
+        int hit = -1;
+        bool hitFlip = false;
+        const int c = p.cell;
+        for (int j = h.cfOff[c]; j < h.cfOff[c + 1]; ++j) {
+            const int f = h.cf[j];
+            const bool own = (h.owner[f] == c);
+            const double* S = &h.Sf[3 * (size_t)f];
+            const double* C = &h.Cf[3 * (size_t)f];
+            double nd = S[0] * disp[0] + S[1] * disp[1] + S[2] * disp[2];
+            double num = (S[0] * C[0] + S[1] * C[1] + S[2] * C[2]) - (S[0] * p.x[0] + S[1] * p.x[1] + S[2] * p.x[2]);
+            if (!own) { nd = -nd; num = -num; }
+            if (nd > 0) {
+                double lam = num / nd;
+                if (lam < 0) lam = 0;
+                if (lam < lamMin) { lamMin = lam; hit = f; hitFlip = !own; }
+            }
+        }
+        if (hit < 0) {
+            for (int k = 0; k < 3; ++k) p.x[k] = p.x[k] + disp[k];
+            p.sf = 1;
+            break;
+        }
+        for (int k = 0; k < 3; ++k) p.x[k] = p.x[k] + lamMin * disp[k];
+        p.sf = p.sf + rem * lamMin;
+        if (hit < h.nInternal) {
+            p.cell = hitFlip ? h.owner[hit] : h.neighbour[hit];
+        } else {
+            const int bfi = hit - h.nInternal;
+            const int patch = h.facePatch[bfi];
+            const int kind = h.pKind[patch];
+            const double* S = &h.Sf[3 * (size_t)hit];
+            if (kind == UGF_PATCH_WALL) {
+                const WallModel& w = h.wall[patch];
+                t.wallHits++;
+                if (w.model == UGF_WALL_DELETION) {
+                    p.cell = -1; t.deleted++;
+                } else {
+                    double nw[3], fA, preIE = 0, preIMom[3] = {0, 0, 0};
+                    unitNormal(S, nw, fA);
+                    if (h.cfg.measureWalls) measureWall(h, p, bfi, nw, fA, &preIE, preIMom, false);
+                    bool diffuse = (w.model == UGF_WALL_DIFFUSE);
+                    if (w.model == UGF_WALL_MIXED) diffuse = (w.diffuseFraction > r.u01());
+                    if (diffuse) {
+                        diffuseReflection(h, r, p, nw, w.T, w.Uw);
+                    } else {
+                        const double Un = dot3(p.U, nw);
+                        if (Un > 0.0) for (int k = 0; k < 3; ++k) p.U[k] = p.U[k] - 2.0 * Un * nw[k];
+                    }
+                    if (h.cfg.measureWalls) measureWall(h, p, bfi, nw, fA, &preIE, preIMom, true);
+                }
+            } else if (kind == UGF_PATCH_SYMMETRY) {
+                double nw[3], fA;
+                unitNormal(S, nw, fA);
+                const double Un = dot3(p.U, nw);
+                for (int k = 0; k < 3; ++k) p.U[k] = p.U[k] - 2.0 * Un * nw[k];
+            } else if (kind == UGF_PATCH_CYCLIC) {
+                const int q = h.pPartner[patch];
+                const int nf = h.pStart[q] + (hit - h.pStart[patch]);
+                p.cell = h.owner[nf];
+                for (int k = 0; k < 3; ++k) p.x[k] = p.x[k] + h.pSep[3 * patch + k];
+            } else if (kind == UGF_PATCH_PROCESSOR) {
+                for (int k = 0; k < 3; ++k) p.x[k] = p.x[k] + h.pSep[3 * patch + k];
+                p.cell = -2 - bfi;
+                t.migrated++;
+            } else if (kind == UGF_PATCH_GENERIC) {
+                p.cell = -1; t.deleted++;
+            } else {  // empty patch hit: mesh/solutionD mismatch
+                p.cell = -1; t.stuck++;
+            }
+        }
+        if (++iters > MAX_TRACK_ITERS) { p.cell = -1; t.stuck++; break; }
+    }
+}
+
+void moveRange(ugfo_handle& h, int64_t begin, int64_t end, bool fresh) {
+    int64_t deleted = 0, wallHits = 0, stuck = 0, migrated = 0;
+#pragma omp parallel for schedule(static) reduction(+ : deleted, wallHits, stuck, migrated)
+    for (int64_t i = begin; i < end; ++i) {
+        MoveTally t;
+        moveParcel(h, h.P[i], i, t, fresh);
+        deleted += t.deleted; wallHits += t.wallHits; stuck += t.stuck; migrated += t.migrated;
+    }
+    h.cnt.deleted += deleted; h.cnt.wallHits += wallHits; h.cnt.stuck += stuck; h.cnt.migrated += migrated;
+    h.occValid = false;
+    h.momValid = false;
+}
+
+// ---------------------------------------------------------------------------------
+// inflow  (uniGasGeneralBoundary.C:115-169, 537-761)
+// ---------------------------------------------------------------------------------
+void doInflow(ugfo_handle& h) {
+    h.nBeforeInsert = (int64_t)h.P.size();
+    const double dt = h.cfg.deltaT;
+    const double sqrtPi = std::sqrt(PI);
+    int64_t inserted = 0;
+    for (const InflowPatch& ip : h.inflows) {
+        const int patch = ip.patch;
+        for (int lf = 0; lf < h.pSize[patch]; ++lf) {
+            const int f = h.pStart[patch] + lf;
+            const int bfi = f - h.nInternal;
+            const int cellI = h.owner[f];
+            const double* S = &h.Sf[3 * (size_t)f];
+            const double* fC = &h.Cf[3 * (size_t)f];
+            const double fA = std::sqrt(dot3(S, S));
+            // triangle fan about the face's first point
+            const int np = h.fpOff[f + 1] - h.fpOff[f];
+            const int32_t* fpts = &h.fp[h.fpOff[f]];
+            const double* p0 = &h.points[3 * (size_t)fpts[0]];
+            std::vector<double> cTri(np - 2);
+            double cum = 0;
+            for (int t = 0; t < np - 2; ++t) {
+                const double* a = &h.points[3 * (size_t)fpts[t + 1]];
+                const double* b = &h.points[3 * (size_t)fpts[t + 2]];
+                const double e1[3] = {a[0] - p0[0], a[1] - p0[1], a[2] - p0[2]};
+                const double e2[3] = {b[0] - p0[0], b[1] - p0[1], b[2] - p0[2]};
+                const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+                cum += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz) / fA;
+                cTri[t] = cum;
+            }
+            cTri[np - 3] = 1.0;
+            const double n[3] = {S[0] / -fA, S[1] / -fA, S[2] / -fA};  // into the domain
+            double t1[3] = {fC[0] - p0[0], fC[1] - p0[1], fC[2] - p0[2]};
+            const double m1 = std::sqrt(dot3(t1, t1));
+            for (int k = 0; k < 3; ++k) t1[k] /= m1;
+            double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+            const double m2 = std::sqrt(dot3(t2, t2));
+            for (int k = 0; k < 3; ++k) t2[k] /= m2;
+            for (int iD = 0; iD < ip.in.nTypeIds; ++iD) {
+                const int typeId = ip.in.typeIds[iD];
+                const ugf_species& s = h.sp[typeId];
+                const double cmp = std::sqrt(2.0 * kB * ip.in.translationalTemperature / s.mass);
+                const double sCos = dot3(ip.in.velocity, n) / cmp;
+                // Bird eq 4.22 (uniGasGeneralBoundary.C:157-165); CWF = RWF = 1
+                const double accum = (fA * ip.in.numberDensities[iD] * dt * cmp
+                                      * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
+                                     / (2.0 * sqrtPi * h.cfg.nParticle);
+                Stream rc(h.cfg.seed, KIND_INFLOW, (uint32_t)iD, (uint32_t)h.step, (uint32_t)bfi, 0);
+                int nIns = std::max((int)accum, 0);
+                if ((accum - nIns) > rc.u01()) ++nIns;
+                for (int i = 0; i < nIns; ++i) {
+                    Stream r(h.cfg.seed, KIND_INFLOW, (uint32_t)iD, (uint32_t)h.step, (uint32_t)bfi, (uint32_t)(i + 1));
+                    const double triSel = r.u01();
+                    int sel = 0;
+                    for (int t = 0; t < np - 2; ++t) { sel = t; if (cTri[t] >= triSel) break; }
+                    const double* a = &h.points[3 * (size_t)fpts[sel + 1]];
+                    const double* b = &h.points[3 * (size_t)fpts[sel + 2]];
+                    double bs = r.u01(), bt = r.u01();
+                    if (bs + bt > 1) { bs = 1 - bs; bt = 1 - bt; }
+                    Parcel np_;
+                    for (int k = 0; k < 3; ++k) np_.x[k] = (1 - bs - bt) * p0[k] + bs * a[k] + bt * b[k];
+                    const double A = sCos + std::sqrt(sCos * sCos + 2.0);
+                    const double B = 0.5 * (1.0 + sCos * (sCos - std::sqrt(sCos * sCos + 2.0)));
+                    double scaling = 3.0;
+                    if (sCos < -3) scaling = std::fabs(sCos) + 1;
+                    double Pp = -1, uNormal, uNormalThermal;
+                    if (std::fabs(dot3(ip.in.velocity, n)) > VSMALL) {
+                        do {  // Bird eq 12.5
+                            uNormalThermal = scaling * (2.0 * r.u01() - 1);
+                            uNormal = uNormalThermal + sCos;
+                            if (uNormal < 0.0) Pp = -1;
+                            else Pp = 2.0 * uNormal / A * std::exp(B - uNormalThermal * uNormalThermal);
+                        } while (Pp < r.u01());
+                    } else {
+                        uNormal = std::sqrt(-std::log(1.0 - r.u01()));
+                    }
+                    double g1, g2;
+                    r.gauss2(g1, g2);
+                    const double cth = std::sqrt(kB * ip.in.translationalTemperature / s.mass);
+                    const double vt1 = dot3(t1, ip.in.velocity), vt2 = dot3(t2, ip.in.velocity);
+                    for (int k = 0; k < 3; ++k)
+                        np_.U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
+                    np_.ERot = equipartitionRotationalEnergy(r, ip.in.rotationalTemperature, s.rotationalDoF);
+                    np_.sf = 0;
+                    np_.cell = cellI;
+                    np_.typeId = typeId;
+                    np_.newParcel = 1;
+                    h.P.push_back(np_);
+                    ++inserted;
+                }
+            }
+        }
+    }
+    h.cnt.inserted += inserted;
+    h.occValid = false;
+    h.momValid = false;
+}
+
+// ---------------------------------------------------------------------------------
+// cell occupancy: stable counting sort w.r.t. current array order; deleted parcels and
+// parcels waiting on a processor patch are dropped.  (CloudWithModels.C:110-138)
+// ---------------------------------------------------------------------------------
+void buildOccupancy(ugfo_handle& h) {
+    const int nC = h.nCells;
+    h.occOff.assign(nC + 1, 0);
+    const int64_t n = (int64_t)h.P.size();
+    for (int64_t i = 0; i < n; ++i) if (h.P[i].cell >= 0) h.occOff[h.P[i].cell + 1]++;
+    for (int c = 0; c < nC; ++c) h.occOff[c + 1] += h.occOff[c];
+    h.occIds.resize(h.occOff[nC]);
+    std::vector<int32_t> cur(h.occOff.begin(), h.occOff.end() - 1);
+    for (int64_t i = 0; i < n; ++i) if (h.P[i].cell >= 0) h.occIds[cur[h.P[i].cell]++] = (int32_t)i;
+    h.occValid = true;
+    h.occIdentity = false;
+    h.cnt.nParcels = h.occOff[nC];
+}
+
+void reorder(ugfo_handle& h) {
+    if (!h.occValid) buildOccupancy(h);
+    if (h.occIdentity) return;
+    const int64_t n = (int64_t)h.occIds.size();
+    std::vector<Parcel> Q(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < n; ++j) { Q[j] = h.P[h.occIds[j]]; h.occIds[j] = (int32_t)j; }
+    h.P.swap(Q);
+    h.occIdentity = true;
+}
+
+// ---------------------------------------------------------------------------------
+// cell moments  (cellMeasurements.C:408-513); slot list in DESIGN.md
+// ---------------------------------------------------------------------------------
+void sampleCell(ugfo_handle& h, int c) {
+    const int nS = h.nSpecies;
+    double* M = &h.mom[(size_t)c * nS * UGF_NMOM];
+    std::fill(M, M + (size_t)nS * UGF_NMOM, 0.0);
+    for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
+        const Parcel& p = h.P[h.occIds[j]];
+        double* m = M + (size_t)p.typeId * UGF_NMOM;
+        const double u = p.U[0], v = p.U[1], w = p.U[2];
+        const double cc = u * u + v * v + w * w;
+        m[0] += 1.0; m[1] += 1.0;
+        m[2] += u; m[3] += v; m[4] += w;
+        m[5] += u; m[6] += v; m[7] += w;
+        m[8] += u * u; m[9] += u * v; m[10] += u * w; m[11] += v * v; m[12] += v * w; m[13] += w * w;
+        m[14] += cc;
+        m[15] += cc * u; m[16] += cc * v; m[17] += cc * w;
+        m[18] += p.ERot;
+        m[19] += p.ERot * u; m[20] += p.ERot * v; m[21] += p.ERot * w;
+        m[26] += h.sp[p.typeId].electronicEnergy[0];
+    }
+}
+
+void sampleAll(ugfo_handle& h) {
+    if (!h.occValid) buildOccupancy(h);
+    h.mom.resize((size_t)h.nCells * h.nSpecies * UGF_NMOM);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int c = 0; c < h.nCells; ++c) sampleCell(h, c);
+    h.momValid = true;
+}
+
+// ---------------------------------------------------------------------------------
+// NTC  (noTimeCounter.C:66-343)
+// ---------------------------------------------------------------------------------
+void collideCell(ugfo_handle& h, int c, int64_t& cand, int64_t& coll) {
+    if (h.collModelId[c] != 1) return;
+    const int beg = h.occOff[c];
+    const int nC = h.occOff[c + 1] - beg;
+    if (nC <= 1) return;
+    const int32_t* ids = &h.occIds[beg];
+    // sub-cells (:96-161)
+    const int32_t* L = &h.subLevels[3 * (size_t)c];
+    int dimW[3] = {0, 0, 0};
+    int prod = 1;
+    for (int d = 0; d < 3; ++d) if (h.cfg.solutionD[d]) { dimW[d] = prod; prod *= L[d]; }
+    const int nSub = L[0] * L[1] * L[2];
+    std::vector<int> which;
+    std::vector<std::vector<int>> sub;
+    if (nSub > 1) {
+        which.resize(nC);
+        sub.resize(nSub);
+        const double* mn = &h.bbMin[3 * (size_t)c];
+        const double* mx = &h.bbMax[3 * (size_t)c];
+        for (int i = 0; i < nC; ++i) {
+            const Parcel& p = h.P[ids[i]];
+            int sc = 0;
+            for (int d = 0; d < 3; ++d) if (h.cfg.solutionD[d]) {
+                int k = (int)(L[d] * (p.x[d] - mn[d]) / (mx[d] - mn[d]));
+                k = k < 0 ? 0 : (k > L[d] - 1 ? L[d] - 1 : k);  // reference overflows on the max face (Appendix D.8)
+                sc += k * dimW[d];
+            }
+            which[i] = sc;
+            sub[sc].push_back(i);
+        }
+    }
+    const double sMaxOld = h.sigmaTcRMax[c];
+    // :184  CWF = RWF = 1
+    const double selectedPairs = 0.5 * nC * (nC - 1) * h.cfg.nParticle * sMaxOld * h.cfg.deltaT / h.vol[c];
+    int nCand = (int)selectedPairs;
+    {
+        Stream rc(h.cfg.seed, KIND_NTC, 0, (uint32_t)h.step, (uint32_t)c, 0xFFFFFFFFu);
+        if (rc.u01() < (selectedPairs - nCand)) nCand++;
+    }
+    cand += nCand;
+    double sMax = sMaxOld;
+    for (int k = 0; k < nCand; ++k) {
+        Stream r(h.cfg.seed, KIND_NTC, 0, (uint32_t)h.step, (uint32_t)c, (uint32_t)k);
+        const int cP = r.position(nC);
+        int cQ = -1;
+        if (nSub > 1 && (int)sub[which[cP]].size() > 1) {
+            const std::vector<int>& s = sub[which[cP]];
+            do { cQ = s[r.position((int)s.size())]; } while (cP == cQ);
+        } else {
+            do { cQ = r.position(nC); } while (cP == cQ);
+        }
+        Parcel& pP = h.P[ids[cP]];
+        Parcel& pQ = h.P[ids[cQ]];
+        if (h.sp[pP.typeId].charge == -1 && h.sp[pQ.typeId].charge == -1) continue;
+        const double s = sigmaTcR(h, pP, pQ);
+        if (s > sMax) sMax = s;
+        if ((s / sMaxOld) > r.u01()) {
+            collidePair(h, r, pP, pQ);
+            coll++;
+        }
+    }
+    h.sigmaTcRMax[c] = sMax;
+}
+
+void collideAll(ugfo_handle& h) {
+    if (h.cfg.binaryModel == UGF_BINARY_NONE) return;
+    if (!(h.cfg.collisionModel == UGF_COLL_DSMC || h.cfg.collisionModel == UGF_COLL_HYBRID)) return;
+    int64_t cand = 0, coll = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : cand, coll)
+    for (int c = 0; c < h.nCells; ++c) collideCell(h, c, cand, coll);
+    h.cnt.collisionCandidates += cand;
+    h.cnt.collisions += coll;
+}
+
+// ---------------------------------------------------------------------------------
+// BGK family  (stochasticParticleBGK.C, …ESBGK.C, …SBGK.C, unifiedStochasticParticleSBGK.C)
+// ---------------------------------------------------------------------------------
+struct Macro {
+    bool perform;
+    double N, rhoN, p, T, U[3], q[3], s[6] /* shear stress xx,xy,xz,yy,yz,zz */, P[6] /* pressure tensor */, Pr, nu;
+    double rhoNX, rhoMX;  // weighted sums (x F_N)
+};
+
+// calculateProperties for one cell (…USP.C:379-800).  Blends q/sigma with the previous step and
+// stores them (…USP.C:777-783).
+void bgkMacro(ugfo_handle& h, int c, Macro& m) {
+    const int nS = h.nSpecies;
+    const int model = h.cfg.bgkModel;
+    const double* M = &h.mom[(size_t)c * nS * UGF_NMOM];
+    const double FN = h.cfg.nParticle;
+    double N = 0, rhoM = 0, rhoNX = 0, rhoMX = 0, momX[3] = {0, 0, 0}, keX = 0;
+    double muu[6] = {0, 0, 0, 0, 0, 0}, mcc = 0, mccu[3] = {0, 0, 0}, eInt = 0, eIntU[3] = {0, 0, 0};
+    for (int s = 0; s < nS; ++s) {
+        const double* a = M + (size_t)s * UGF_NMOM;
+        const double ms = h.sp[s].mass;
+        N += a[0]; rhoM += ms * a[0];
+        rhoNX += a[1] * FN; rhoMX += ms * a[1] * FN;
+        for (int k = 0; k < 3; ++k) momX[k] += ms * a[5 + k] * FN;
+        keX += ms * a[14] * FN;
+        for (int k = 0; k < 6; ++k) muu[k] += ms * a[8 + k];
+        mcc += ms * (a[8] + a[11] + a[13]);
+        for (int k = 0; k < 3; ++k) mccu[k] += ms * a[15 + k];
+        eInt += a[18] + a[22];
+        for (int k = 0; k < 3; ++k) eIntU[k] += a[19 + k] + a[23 + k];
+    }
+    m.perform = true;
+    m.N = N; m.rhoNX = rhoNX; m.rhoMX = rhoMX;
+    for (int k = 0; k < 3; ++k) { m.U[k] = 0; m.q[k] = 0; }
+    for (int k = 0; k < 6; ++k) { m.s[k] = 0; m.P[k] = 0; }
+    m.rhoN = m.p = m.T = m.Pr = m.nu = 0;
+    const double V = h.vol[c];
+    if (N > VSMALL) {
+        m.rhoN = rhoNX / V;
+        const double rhoMMean = rhoMX / V;
+        for (int k = 0; k < 3; ++k) m.U[k] = momX[k] / (rhoMMean * V);
+        const double linearKEMean = 0.5 * keX / V;
+        const double rhoNMean = rhoNX / V;
+        m.T = 2.0 / (3.0 * kB * rhoNMean) * (linearKEMean - 0.5 * rhoMMean * dot3(m.U, m.U));
+        m.p = m.rhoN * kB * m.T;
+        static const int ia[6] = {0, 0, 0, 1, 1, 2}, ib[6] = {0, 1, 2, 1, 2, 2};
+        for (int k = 0; k < 6; ++k) m.P[k] = m.rhoN * (muu[k] / N - (rhoM / N) * m.U[ia[k]] * m.U[ib[k]]);
+        const double sp = (m.P[0] + m.P[3] + m.P[5]) / 3.0;
+        for (int k = 0; k < 6; ++k) m.s[k] = m.P[k];
+        m.s[0] -= sp; m.s[3] -= sp; m.s[5] -= sp;
+        // heat flux vector (…USP.C:518-549)
+        const double Pfull[3][3] = {{m.P[0], m.P[1], m.P[2]}, {m.P[1], m.P[3], m.P[4]}, {m.P[2], m.P[4], m.P[5]}};
+        for (int k = 0; k < 3; ++k)
+            m.q[k] = m.rhoN * (0.5 * (mccu[k] / N) - 0.5 * (mcc / N) * m.U[k] + eIntU[k] / N - (eInt / N) * m.U[k])
+                     - Pfull[k][0] * m.U[0] - Pfull[k][1] * m.U[1] - Pfull[k][2] * m.U[2];
+        // small-sample debiasing (BGK :355, ESBGK :434, SBGK :530-534, USP :551-563)
+        const bool third = (model == UGF_BGK_SBGK || model == UGF_BGK_USP_SBGK);
+        if (third ? (N > 2.0) : (N > 1.0)) {
+            const double f1 = N / (N - 1.0);
+            m.p = f1 * m.p;
+            m.T = f1 * m.T;
+            if (model == UGF_BGK_ESBGK) for (int k = 0; k < 6; ++k) m.P[k] = f1 * m.P[k];
+            if (third) { const double f3 = (N * N) / (N - 1.0) / (N - 2.0); for (int k = 0; k < 3; ++k) m.q[k] = f3 * m.q[k]; }
+            if (model == UGF_BGK_USP_SBGK) for (int k = 0; k < 6; ++k) m.s[k] = f1 * m.s[k];
+        } else {
+            m.perform = false;
+        }
+    } else {
+        m.perform = false;
+    }
+    if (m.T > VSMALL) {
+        double visc = 0, Pr = 0;
+        for (int s = 0; s < nS; ++s) {
+            const ugf_species& S = h.sp[s];
+            const double a = S.alpha;
+            const double viscRef = 1.25 * (1.0 + a) * (2.0 + a) * std::sqrt(S.mass * kB * h.cfg.Tref)
+                                   / (a * (5.0 - 2.0 * S.omega) * (7.0 - 2.0 * S.omega) * std::sqrt(PI) * (S.d * S.d));
+            const double ns = M[(size_t)s * UGF_NMOM];
+            visc += ns * viscRef * std::pow(m.T / h.cfg.Tref, S.omega);
+            Pr += ns * (5.0 + S.rotationalDoF) / (7.5 + S.rotationalDoF);
+        }
+        visc /= N; Pr /= N;
+        m.Pr = Pr;
+        m.nu = (model == UGF_BGK_ESBGK ? Pr : 1.0) * m.p / visc;
+    } else {
+        m.perform = false;
+        m.Pr = 0; m.nu = 0;
+    }
+    // time blending, all cells (SBGK :749-755, USP :774-783)
+    const double th = h.cfg.theta, dt = h.cfg.deltaT;
+    if (model == UGF_BGK_SBGK || model == UGF_BGK_USP_SBGK) {
+        double* qp = &h.qPrev[3 * (size_t)c];
+        for (int k = 0; k < 3; ++k) { m.q[k] = th * m.q[k] / (1.0 + 0.5 * m.Pr * m.nu * dt) + (1.0 - th) * qp[k]; qp[k] = m.q[k]; }
+    }
+    if (model == UGF_BGK_USP_SBGK) {
+        double* spv = &h.sPrev[6 * (size_t)c];
+        for (int k = 0; k < 6; ++k) { m.s[k] = th * m.s[k] / (1.0 + 0.5 * m.nu * dt) + (1.0 - th) * spv[k]; spv[k] = m.s[k]; }
+    }
+}
+
+void relaxCell(ugfo_handle& h, int c, int64_t& nrel) {
+    const int model = h.cfg.bgkModel;
+    Macro m;
+    bgkMacro(h, c, m);
+    const bool envelope = (model == UGF_BGK_SBGK || model == UGF_BGK_USP_SBGK);
+    bool raised = false;
+    if (h.collModelId[c] == 0 && m.perform) {
+        const int beg = h.occOff[c];
+        const int N = h.occOff[c + 1] - beg;
+        const int32_t* ids = &h.occIds[beg];
+        const double dt = h.cfg.deltaT;
+        // number of relaxing parcels (…USP.C:917-923)
+        const double pc = m.N * (1.0 - std::exp(-m.nu * dt));
+        int nRel = (int)pc;
+        {
+            Stream rc(h.cfg.seed, KIND_BGK, 0, (uint32_t)h.step, (uint32_t)c, 0xFFFFFFFFu);
+            if (rc.u01() < (pc - nRel)) nRel++;
+        }
+        nRel = std::min(nRel, N);
+        // uniform nRel-subset: the reference shuffles the cell list 5 times and takes the first
+        // nRel (…USP.C:912-915,925); here each parcel draws one key from its own stream and the
+        // nRel smallest keys are taken (ties by index) - the same distribution over subsets.
+        std::vector<double> key(N);
+        for (int i = 0; i < N; ++i) {
+            Stream r(h.cfg.seed, KIND_BGK, 0, (uint32_t)h.step, (uint32_t)c, (uint32_t)i);
+            key[i] = r.u01();
+        }
+        std::vector<char> selected(N, 0);
+        for (int i = 0; i < N; ++i) {
+            int rank = 0;
+            for (int j = 0; j < N; ++j) rank += (key[j] < key[i]) || (key[j] == key[i] && j < i);
+            selected[i] = rank < nRel;
+        }
+        double& maxProb = h.maxProb[c];
+        for (int i = 0; i < N; ++i) {
+            if (!selected[i]) continue;
+            Parcel& p = h.P[ids[i]];
+            const double mass = h.sp[p.typeId].mass;
+            Stream r(h.cfg.seed, KIND_BGK, 0, (uint32_t)h.step, (uint32_t)c, (uint32_t)i);
+            (void)r.u01();  // the selection key
+            const double u0 = std::sqrt(2.0 * kB * m.T / mass);
+            double v[3];
+            if (model == UGF_BGK_BGK) {  // …BGK.C:782-796
+                double g[3]; r.gauss3(g);
+                for (int k = 0; k < 3; ++k) v[k] = g[k] / std::sqrt(2.0);
+            } else if (model == UGF_BGK_ESBGK) {  // …ESBGK.C:887-906
+                double g[3]; r.gauss3(g);
+                for (int k = 0; k < 3; ++k) g[k] = g[k] / std::sqrt(2.0);
+                const double f = 0.5 * (1 - m.Pr) / m.Pr;
+                const double S[3][3] = {{1 - f * (m.P[0] / m.p - 1), -f * (m.P[1] / m.p), -f * (m.P[2] / m.p)},
+                                        {-f * (m.P[1] / m.p), 1 - f * (m.P[3] / m.p - 1), -f * (m.P[4] / m.p)},
+                                        {-f * (m.P[2] / m.p), -f * (m.P[4] / m.p), 1 - f * (m.P[5] / m.p - 1)}};
+                for (int k = 0; k < 3; ++k) v[k] = S[k][0] * g[0] + S[k][1] * g[1] + S[k][2] * g[2];
+            } else {  // S-BGK (…SBGK.C:1009-1046) and USP (…USP.C:1047-1096)
+                double coeffQ, coeffS = 0;
+                if (model == UGF_BGK_SBGK) {
+                    coeffQ = 2.0 * (1.0 - m.Pr);
+                } else {
+                    const double tau = 0.5 * m.nu * dt;
+                    const double e = 1.0 + 2.0 / (std::exp(2.0 * tau) - 1.0);
+                    coeffQ = 2.0 * (1.0 - m.Pr * tau * e);
+                    coeffS = (1.0 - tau * e);
+                }
+                for (;;) {
+                    double g[3]; r.gauss3(g);
+                    for (int k = 0; k < 3; ++k) v[k] = g[k] / std::sqrt(2.0);
+                    const double vSq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+                    const double vTr = vSq / 3.0;
+                    double prob = 1.0 + coeffQ / (m.p * u0) * (m.q[0] * v[0] + m.q[1] * v[1] + m.q[2] * v[2]) * (vSq / 2.5 - 1.0);
+                    if (model == UGF_BGK_USP_SBGK)
+                        prob += coeffS / m.p * (m.s[0] * (v[0] * v[0] - vTr) + m.s[3] * (v[1] * v[1] - vTr) + m.s[5] * (v[2] * v[2] - vTr)
+                                                + 2.0 * m.s[1] * v[0] * v[1] + 2.0 * m.s[2] * v[0] * v[2] + 2.0 * m.s[4] * v[1] * v[2]);
+                    if (prob > maxProb && prob < 10.0) { maxProb = prob; raised = true; break; }
+                    if (r.u01() < prob / maxProb) break;
+                }
+            }
+            for (int k = 0; k < 3; ++k) p.U[k] = m.U[k] + u0 * v[k];
+            nrel++;
+        }
+        // conserveMomentumAndEnergy (…USP.C:996-1045)
+        const double FN = h.cfg.nParticle;
+        double keX = 0, momX[3] = {0, 0, 0};
+        for (int i = 0; i < N; ++i) {
+            const Parcel& p = h.P[ids[i]];
+            const double mass = h.sp[p.typeId].mass;
+            keX += mass * dot3(p.U, p.U) * FN;
+            for (int k = 0; k < 3; ++k) momX[k] += mass * p.U[k] * FN;
+        }
+        const double postU[3] = {momX[0] / m.rhoMX, momX[1] / m.rhoMX, momX[2] / m.rhoMX};
+        const double postT = m.N / (3.0 * (m.N - 1.0) * kB * m.rhoNX) * (keX - m.rhoMX * dot3(postU, postU));
+        if (postT > VSMALL) {
+            const double f = std::sqrt(m.T / postT);
+            for (int i = 0; i < N; ++i) {
+                Parcel& p = h.P[ids[i]];
+                for (int k = 0; k < 3; ++k) p.U[k] = m.U[k] + (p.U[k] - postU[k]) * f;
+            }
+        }
+    }
+    // resetProperties: envelope decay for every cell (…USP.C:859-863)
+    if (envelope && !raised) h.maxProb[c] *= (model == UGF_BGK_USP_SBGK ? 0.999 : 0.9999);
+}
+
+void relaxAll(ugfo_handle& h) {
+    if (h.cfg.bgkModel == UGF_BGK_NONE) return;
+    if (!(h.cfg.collisionModel == UGF_COLL_BGK || h.cfg.collisionModel == UGF_COLL_HYBRID)) return;
+    int64_t nrel = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nrel)
+    for (int c = 0; c < h.nCells; ++c) relaxCell(h, c, nrel);
+    h.cnt.bgkRelaxations += nrel;
+}
+
+// ---------------------------------------------------------------------------------
+// time-averaged fields  (uniGasVolFields.C:723-1352)
+// ---------------------------------------------------------------------------------
+void accumulateFields(ugfo_handle& h) {
+    h.sampleCounter++;
+    const double dt = h.cfg.deltaT;
+    const int interval = h.cfg.sampleInterval > 0 ? h.cfg.sampleInterval : 1;
+    if (interval <= h.sampleCounter) {
+        h.nAvTimeSteps++;
+        h.timeAvCounter += dt;
+        const int nS = h.nSpecies;
+        const double FN = h.cfg.nParticle;
+#pragma omp parallel for schedule(static)
+        for (int c = 0; c < h.nCells; ++c) {
+            double* A = &h.acc[(size_t)c * NACC];
+            for (int s = 0; s < nS; ++s) {
+                const double* a = &h.mom[((size_t)c * nS + s) * UGF_NMOM];
+                const ugf_species& S = h.sp[s];
+                const double ms = S.mass;
+                A[0] += dt * a[0];
+                A[1] += dt * (ms * a[0]);
+                A[2] += dt * (ms * (a[8] + a[11] + a[13]));
+                A[3] += dt * (ms * a[2]); A[4] += dt * (ms * a[3]); A[5] += dt * (ms * a[4]);
+                A[6] += dt * a[18];
+                A[7] += dt * (S.rotationalDoF * a[0]);
+                A[8] += dt * (a[1] * FN);
+                A[9] += dt * (ms * a[1] * FN);
+                A[10] += dt * (ms * a[5] * FN); A[11] += dt * (ms * a[6] * FN); A[12] += dt * (ms * a[7] * FN);
+                A[13] += dt * (ms * a[14] * FN);
+                A[14] += dt * (S.rotationalDoF > 0 ? a[0] : 0.0);
+                A[15] += dt * ((5.0 + S.rotationalDoF) * a[0]);
+            }
+        }
+        for (size_t i = 0; i < h.bm.size(); ++i) h.bacc[i] += dt * h.bm[i];
+        h.sampleCounter = 0;
+    }
+    // boundaryMeas_.clean(); cellMeas_.clean()  (uniGasCloud.C:864-866)
+    std::fill(h.bm.begin(), h.bm.end(), 0.0);
+}
+
+void deriveFields(ugfo_handle& h, double* cellF, double* wallF) {
+    const double t = h.timeAvCounter;
+    if (cellF) {
+        for (int c = 0; c < h.nCells; ++c) {
+            const double* A = &h.acc[(size_t)c * NACC];
+            double* F = &cellF[(size_t)c * UGF_NFIELD];
+            for (int k = 0; k < UGF_NFIELD; ++k) F[k] = 0;
+            const double V = h.vol[c];
+            if (A[0] > VSMALL) {
+                F[0] = A[0] / t;
+                F[1] = A[8] / (t * V);
+                F[2] = A[9] / (t * V);
+                const double rhoMMean = A[9] / (V * t);
+                for (int k = 0; k < 3; ++k) F[3 + k] = A[10 + k] / (rhoMMean * V * t);
+                const double linearKEMean = 0.5 * A[13] / (V * t);
+                const double rhoNMean = A[8] / (V * t);
+                F[6] = 2.0 / (3.0 * kB * rhoNMean) * (linearKEMean - 0.5 * rhoMMean * dot3(&F[3], &F[3]));
+                F[9] = F[1] * kB * F[6];
+            } else {
+                F[0] = 0.001;  // uniGasVolFields.C:907-908
+            }
+            if (A[7] > VSMALL && t > VSMALL) F[7] = (2.0 / kB) * ((A[6] / t) / (A[7] / t));
+            double nRotDof = 0;
+            if (A[0] > VSMALL) nRotDof = A[7] / A[0];
+            F[8] = (3.0 * F[6] + nRotDof * F[7]) / (3.0 + nRotDof);
+            // Mach number (:1078-1121)
+            double gamma = 0, Cv_p = 0;
+            if (A[0] > VSMALL) {
+                const double molecularMass = A[1] / A[0];
+                const double Cp = A[15] / A[0], Cv = Cp - 2.0;
+                Cv_p = Cv / NA;
+                gamma = Cp / Cv;
+                if (F[6] > VSMALL && molecularMass > VSMALL) {
+                    const double a = std::sqrt(gamma * (kB / molecularMass) * F[6]);
+                    F[10] = std::sqrt(dot3(&F[3], &F[3])) / a;
+                }
+            }
+            if (F[0] > VSMALL && F[10] > VSMALL && gamma > VSMALL && Cv_p > VSMALL)
+                F[11] = 1.0 / std::sqrt(F[0] * (double)h.nAvTimeSteps);  // densityError (:1248)
+        }
+    }
+    if (wallF) {
+        for (int b = 0; b < h.nBFaces; ++b) {
+            double* F = &wallF[(size_t)b * UGF_NWALLFIELD];
+            for (int k = 0; k < UGF_NWALLFIELD; ++k) F[k] = 0;
+            const int patch = h.facePatch[b];
+            if (h.pKind[patch] != UGF_PATCH_WALL) continue;
+            const double* B = &h.bacc[(size_t)b * UGF_NBM];
+            const double nPart = h.cfg.nParticle;
+            if (B[0] > VSMALL) {  // :1274-1301
+                F[0] = B[0] * nPart / t;
+                F[1] = B[1] * nPart / t;
+                for (int k = 0; k < 3; ++k) F[2 + k] = B[3 + k] * nPart / (F[1] * t);
+                const double rhoMMean = B[1] * nPart / t, linearKEMean = B[2] * nPart / t, rhoNMean = B[0] * nPart / t;
+                F[5] = 2.0 / (3.0 * kB * rhoNMean) * (linearKEMean - 0.5 * rhoMMean * dot3(&F[2], &F[2]));
+            }
+            F[6] = B[8] / t;
+            for (int k = 0; k < 3; ++k) F[7 + k] = B[9 + k] / t;
+            const double* S = &h.Sf[3 * (size_t)(b + h.nInternal)];
+            double nw[3], fA;
+            unitNormal(S, nw, fA);
+            F[10] = dot3(&F[7], nw);  // p = fD & n
+            const double ft[3] = {F[7] - F[10] * nw[0], F[8] - F[10] * nw[1], F[9] - F[10] * nw[2]};
+            F[11] = std::sqrt(dot3(ft, ft));  // tau = sqrt((fD&t1)^2 + (fD&t2)^2)
+        }
+    }
+}
+
+void energyTotals(ugfo_handle& h) {
+    double ke = 0, er = 0, mx = 0, my = 0, mz = 0;
+    int64_t n = 0;
+    for (const Parcel& p : h.P) {
+        if (p.cell < 0) continue;
+        const double m = h.sp[p.typeId].mass;
+        ke += 0.5 * m * dot3(p.U, p.U);
+        er += p.ERot;
+        mx += m * p.U[0]; my += m * p.U[1]; mz += m * p.U[2];
+        ++n;
+    }
+    h.cnt.linearKineticEnergy = ke; h.cnt.rotationalEnergy = er;
+    h.cnt.momentum[0] = mx; h.cnt.momentum[1] = my; h.cnt.momentum[2] = mz;
+    h.cnt.nParcels = n;
+}
+
+void resetStepCounters(ugfo_handle& h) {
+    h.cnt.collisionCandidates = h.cnt.collisions = h.cnt.bgkRelaxations = 0;
+    h.cnt.inserted = h.cnt.deleted = h.cnt.migrated = h.cnt.wallHits = 0;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C API — mirrors include/ugf.h with the prefix ugfo_ so that the same test driver can
+// talk to either library.
+// =====================================================================================
+extern "C" {
+
+int ugfo_abi_version(void) { return UGF_ABI_VERSION; }
+
+static std::string g_createErr;
+
+const char* ugfo_last_error(const ugfo_handle* h) { return h ? h->err.c_str() : g_createErr.c_str(); }
+
+int ugfo_create(const ugf_config* cfg, ugfo_handle** out) {
+    if (!cfg || !out) { g_createErr = "null argument"; return 1; }
+    if (cfg->abiVersion != UGF_ABI_VERSION) { g_createErr = "ABI version mismatch"; return 1; }
+    if (cfg->macroInterpolation) { g_createErr = "macroInterpolation true is not supported"; return 1; }
+    ugfo_handle* h = new ugfo_handle();
+    h->cfg = *cfg;
+    std::memset(&h->cnt, 0, sizeof(h->cnt));
+    *out = h;
+    return 0;
+}
+
+int ugfo_destroy(ugfo_handle* h) { delete h; return 0; }
+
+int ugfo_set_species(ugfo_handle* h, int32_t n, const ugf_species* sp) {
+    if (n < 1 || n > UGF_MAX_SPECIES) return fail(h, "species count out of range");
+    for (int i = 0; i < n; ++i) {
+        if (sp[i].vibrationalDoF > 0) return fail(h, "vibrational modes are not supported yet");
+        if (sp[i].nElectronicLevels < 1 || sp[i].nElectronicLevels > UGF_MAX_ELEC_LEVELS) return fail(h, "bad nElectronicLevels");
+        h->sp[i] = sp[i];
+    }
+    h->nSpecies = n;
+    return 0;
+}
+
+int ugfo_set_mesh(ugfo_handle* h, const ugf_mesh* m) {
+    h->nCells = m->nCells; h->nFaces = m->nFaces; h->nInternal = m->nInternalFaces; h->nPatches = m->nPatches;
+    h->nBFaces = m->nFaces - m->nInternalFaces;
+    h->owner.assign(m->owner, m->owner + m->nFaces);
+    h->neighbour.assign(m->neighbour, m->neighbour + m->nInternalFaces);
+    h->Sf.assign(m->faceAreas, m->faceAreas + 3 * (size_t)m->nFaces);
+    h->Cf.assign(m->faceCentres, m->faceCentres + 3 * (size_t)m->nFaces);
+    h->cfOff.assign(m->cellFaceOffsets, m->cellFaceOffsets + m->nCells + 1);
+    h->cf.assign(m->cellFaces, m->cellFaces + h->cfOff[m->nCells]);
+    h->vol.assign(m->cellVolumes, m->cellVolumes + m->nCells);
+    h->cc.assign(m->cellCentres, m->cellCentres + 3 * (size_t)m->nCells);
+    h->bbMin.assign(m->cellBbMin, m->cellBbMin + 3 * (size_t)m->nCells);
+    h->bbMax.assign(m->cellBbMax, m->cellBbMax + 3 * (size_t)m->nCells);
+    h->pStart.assign(m->patchStart, m->patchStart + m->nPatches);
+    h->pSize.assign(m->patchSize, m->patchSize + m->nPatches);
+    h->pKind.assign(m->patchKind, m->patchKind + m->nPatches);
+    h->pPartner.assign(m->patchPartner, m->patchPartner + m->nPatches);
+    h->pSep.assign(m->patchSeparation, m->patchSeparation + 3 * (size_t)m->nPatches);
+    if (m->points && m->facePointOffsets && m->facePoints) {
+        h->points.assign(m->points, m->points + 3 * (size_t)m->nPoints);
+        h->fpOff.assign(m->facePointOffsets, m->facePointOffsets + m->nFaces + 1);
+        h->fp.assign(m->facePoints, m->facePoints + h->fpOff[m->nFaces]);
+    }
+    h->facePatch.assign(h->nBFaces, -1);
+    for (int p = 0; p < h->nPatches; ++p)
+        for (int k = 0; k < h->pSize[p]; ++k) h->facePatch[h->pStart[p] + k - h->nInternal] = p;
+    for (int b = 0; b < h->nBFaces; ++b) if (h->facePatch[b] < 0) return fail(h, "boundary face not covered by a patch");
+    h->wall.assign(h->nPatches, WallModel());
+    h->sigmaTcRMax.assign(h->nCells, 0.0);
+    h->collModelId.assign(h->nCells, h->cfg.collisionModel == UGF_COLL_DSMC ? 1 : 0);  // uniGasCloud.C:713,723,731
+    h->subLevels.assign(3 * (size_t)h->nCells, 1);
+    h->maxProb.assign(h->nCells, 1.0);
+    h->qPrev.assign(3 * (size_t)h->nCells, 0.0);
+    h->sPrev.assign(6 * (size_t)h->nCells, 0.0);
+    h->bm.assign((size_t)h->nBFaces * UGF_NBM, 0.0);
+    h->bacc.assign((size_t)h->nBFaces * UGF_NBM, 0.0);
+    h->acc.assign((size_t)h->nCells * NACC, 0.0);
+    h->packBuf.resize(h->nPatches);
+    return 0;
+}
+
+int ugfo_set_patch_model(ugfo_handle* h, int32_t patch, int32_t model, const double* prm, int32_t n) {
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->pKind[patch] != UGF_PATCH_WALL) return fail(h, "patch models apply to wall patches only");
+    WallModel w;
+    w.model = model;
+    if (model == UGF_WALL_DIFFUSE || model == UGF_WALL_MIXED) {
+        if (n < 4) return fail(h, "diffuse wall needs T, Ux, Uy, Uz");
+        w.T = prm[0]; w.Uw[0] = prm[1]; w.Uw[1] = prm[2]; w.Uw[2] = prm[3];
+        if (model == UGF_WALL_MIXED) { if (n < 5) return fail(h, "mixed wall needs diffuseFraction"); w.diffuseFraction = prm[4]; }
+    } else if (model != UGF_WALL_SPECULAR && model != UGF_WALL_DELETION) {
+        return fail(h, "unknown wall model");
+    }
+    h->wall[patch] = w;
+    return 0;
+}
+
+int ugfo_set_inflow(ugfo_handle* h, int32_t patch, const ugf_inflow* in) {
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->points.empty()) return fail(h, "inflow needs mesh points/facePoints");
+    InflowPatch ip; ip.patch = patch; ip.in = *in;
+    h->inflows.push_back(ip);
+    return 0;
+}
+
+int ugfo_upload_parcels(ugfo_handle* h, const ugf_parcels* p) {
+    if (p->n > h->cfg.parcelCapacity) return fail(h, "parcel count exceeds parcelCapacity");
+    h->P.resize(p->n);
+    for (int64_t i = 0; i < p->n; ++i) {
+        Parcel& q = h->P[i];
+        q.x[0] = p->x[i]; q.x[1] = p->y[i]; q.x[2] = p->z[i];
+        q.U[0] = p->Ux[i]; q.U[1] = p->Uy[i]; q.U[2] = p->Uz[i];
+        q.cell = p->cell[i];
+        q.typeId = p->typeId ? p->typeId[i] : 0;
+        q.ERot = p->ERot ? p->ERot[i] : 0.0;
+        q.newParcel = p->newParcel ? p->newParcel[i] : 0;
+        q.sf = 0;
+        if (q.cell < 0 || q.cell >= h->nCells) return fail(h, "parcel cell out of range");
+        if (q.typeId < 0 || q.typeId >= h->nSpecies) return fail(h, "parcel typeId out of range");
+    }
+    h->occValid = false; h->momValid = false;
+    h->nBeforeInsert = p->n;
+    h->cnt.nParcels = p->n;
+    return 0;
+}
+
+int ugfo_upload_cell_state(ugfo_handle* h, const double* s, const int32_t* id, const int32_t* lv, const double* cwf) {
+    if (s) h->sigmaTcRMax.assign(s, s + h->nCells);
+    if (id) h->collModelId.assign(id, id + h->nCells);
+    if (lv) {
+        h->subLevels.assign(lv, lv + 3 * (size_t)h->nCells);
+        for (int32_t v : h->subLevels) if (v < 1) return fail(h, "subCellLevels must be >= 1");
+    }
+    if (cwf) for (int c = 0; c < h->nCells; ++c) if (cwf[c] != 1.0) return fail(h, "cell weighting is not supported yet (cellWeightFactor must be 1)");
+    return 0;
+}
+
+int ugfo_set_deltaT(ugfo_handle* h, double dt) { h->cfg.deltaT = dt; return 0; }
+
+static void openStep(ugfo_handle* h) {
+    if (!h->stepOpen) { resetStepCounters(*h); h->stepOpen = true; }
+}
+
+int ugfo_control_before_move(ugfo_handle* h) { openStep(h); doInflow(*h); return 0; }
+
+int ugfo_move(ugfo_handle* h) {
+    for (int p = 0; p < h->nPatches; ++p)
+        if (h->pKind[p] == UGF_PATCH_WALL && h->wall[p].model == UGF_WALL_UNSET)
+            return fail(h, "wall patch without a boundary model");  // uniGasBoundaries.C:448-488
+    openStep(h);
+    // parcels that were not inserted this step start the step at stepFraction 0
+    for (int64_t i = 0; i < (int64_t)h->P.size(); ++i) if (!h->P[i].newParcel) h->P[i].sf = 0;
+    moveRange(*h, 0, (int64_t)h->P.size(), true);
+    h->receivedStart = (int64_t)h->P.size();
+    return 0;
+}
+
+int ugfo_sort(ugfo_handle* h) { buildOccupancy(*h); return 0; }
+int ugfo_reorder(ugfo_handle* h) { reorder(*h); return 0; }
+int ugfo_sample(ugfo_handle* h) { sampleAll(*h); return 0; }
+
+int ugfo_collide(ugfo_handle* h) {
+    reorder(*h);
+    if (!h->momValid) sampleAll(*h);  // sampling precedes collisions (uniGasCloud.C:846-850)
+    collideAll(*h);
+    return 0;
+}
+
+int ugfo_relax(ugfo_handle* h) {
+    reorder(*h);
+    if (!h->momValid) sampleAll(*h);
+    relaxAll(*h);
+    return 0;
+}
+
+int ugfo_accumulate_fields(ugfo_handle* h) {
+    if (!h->momValid) sampleAll(*h);
+    accumulateFields(*h);
+    return 0;
+}
+
+int ugfo_end_step(ugfo_handle* h) { h->step++; h->cnt.step = h->step; h->stepOpen = false; return 0; }
+
+int ugfo_step(ugfo_handle* h, int32_t nSteps) {
+    for (int s = 0; s < nSteps; ++s) {
+        resetStepCounters(*h);
+        h->stepOpen = true;
+        int rc;
+        if (!h->inflows.empty()) doInflow(*h); else h->nBeforeInsert = (int64_t)h->P.size();
+        if ((rc = ugfo_move(h))) return rc;
+        if (h->cnt.migrated) return fail(h, "ugf_step is single-rank: a parcel reached a processor patch");
+        buildOccupancy(*h);
+        reorder(*h);
+        sampleAll(*h);
+        collideAll(*h);
+        relaxAll(*h);
+        accumulateFields(*h);
+        ugfo_end_step(h);
+    }
+    return 0;
+}
+
+int ugfo_migrate_counts(ugfo_handle* h, int64_t* counts) {
+    for (int p = 0; p < h->nPatches; ++p) counts[p] = 0;
+    for (const Parcel& q : h->P) if (q.cell <= -2) counts[h->facePatch[-2 - q.cell]]++;
+    return 0;
+}
+
+int ugfo_migrate_pack(ugfo_handle* h, int32_t patch, double** buf, int64_t* n) {
+    std::vector<double>& b = h->packBuf[patch];
+    b.clear();
+    for (Parcel& q : h->P) {
+        if (q.cell > -2 || h->facePatch[-2 - q.cell] != patch) continue;
+        const int lface = (-2 - q.cell) + h->nInternal - h->pStart[patch];
+        const double rec[UGF_MIGRATE_STRIDE] = {q.x[0], q.x[1], q.x[2], q.U[0], q.U[1], q.U[2], q.ERot, q.sf, (double)lface, (double)q.typeId};
+        b.insert(b.end(), rec, rec + UGF_MIGRATE_STRIDE);
+        q.cell = -1;
+    }
+    *buf = b.data();
+    *n = (int64_t)(b.size() / UGF_MIGRATE_STRIDE);
+    return 0;
+}
+
+int ugfo_migrate_unpack(ugfo_handle* h, int32_t patch, const double* buf, int64_t n) {
+    if (h->pKind[patch] != UGF_PATCH_PROCESSOR) return fail(h, "unpack on a non-processor patch");
+    for (int64_t i = 0; i < n; ++i) {
+        const double* r = buf + i * UGF_MIGRATE_STRIDE;
+        Parcel q;
+        for (int k = 0; k < 3; ++k) { q.x[k] = r[k]; q.U[k] = r[3 + k]; }
+        q.ERot = r[6]; q.sf = r[7];
+        const int lf = (int)r[8];
+        if (lf < 0 || lf >= h->pSize[patch]) return fail(h, "received face index out of range");
+        q.cell = h->owner[h->pStart[patch] + lf];
+        q.typeId = (int)r[9];
+        q.newParcel = 0;
+        h->P.push_back(q);
+    }
+    h->occValid = false; h->momValid = false;
+    return 0;
+}
+
+int ugfo_move_received(ugfo_handle* h) {
+    if (h->receivedStart < 0) return fail(h, "ugf_move_received before ugf_move");
+    moveRange(*h, h->receivedStart, (int64_t)h->P.size(), false);
+    h->receivedStart = (int64_t)h->P.size();
+    return 0;
+}
+
+int ugfo_stream(ugfo_handle*, void** s) { *s = nullptr; return 0; }
+
+int ugfo_counters_get(ugfo_handle* h, ugf_counters* out) { energyTotals(*h); *out = h->cnt; return 0; }
+
+int ugfo_num_parcels(ugfo_handle* h, int64_t* n) {
+    int64_t k = 0;
+    for (const Parcel& q : h->P) k += (q.cell >= 0);
+    *n = k;
+    return 0;
+}
+
+int ugfo_download_parcels(ugfo_handle* h, ugf_parcels* p) {
+    const int64_t n = (int64_t)h->P.size();
+    if (p->n < n) return fail(h, "download buffer too small");
+    for (int64_t i = 0; i < n; ++i) {
+        const Parcel& q = h->P[i];
+        if (p->x) p->x[i] = q.x[0];
+        if (p->y) p->y[i] = q.x[1];
+        if (p->z) p->z[i] = q.x[2];
+        if (p->Ux) p->Ux[i] = q.U[0];
+        if (p->Uy) p->Uy[i] = q.U[1];
+        if (p->Uz) p->Uz[i] = q.U[2];
+        if (p->cell) p->cell[i] = q.cell;
+        if (p->typeId) p->typeId[i] = q.typeId;
+        if (p->ERot) p->ERot[i] = q.ERot;
+        if (p->newParcel) p->newParcel[i] = q.newParcel;
+    }
+    p->n = n;
+    return 0;
+}
+
+int ugfo_download_cell_occupancy(ugfo_handle* h, int32_t* off, int32_t* ids) {
+    if (!h->occValid) return fail(h, "cell occupancy not built (call ugf_sort)");
+    std::copy(h->occOff.begin(), h->occOff.end(), off);
+    if (ids) std::copy(h->occIds.begin(), h->occIds.end(), ids);
+    return 0;
+}
+
+int ugfo_download_cell_moments(ugfo_handle* h, double* m) {
+    if (!h->momValid) return fail(h, "cell moments not sampled");
+    std::copy(h->mom.begin(), h->mom.end(), m);
+    return 0;
+}
+
+int ugfo_download_cell_state(ugfo_handle* h, double* s, double* mp, double* q, double* sp) {
+    if (s) std::copy(h->sigmaTcRMax.begin(), h->sigmaTcRMax.end(), s);
+    if (mp) std::copy(h->maxProb.begin(), h->maxProb.end(), mp);
+    if (q) std::copy(h->qPrev.begin(), h->qPrev.end(), q);
+    if (sp) std::copy(h->sPrev.begin(), h->sPrev.end(), sp);
+    return 0;
+}
+
+int ugfo_download_fields(ugfo_handle* h, double* cellF, double* wallF, int32_t reset) {
+    deriveFields(*h, cellF, wallF);
+    if (reset) {
+        std::fill(h->acc.begin(), h->acc.end(), 0.0);
+        std::fill(h->bacc.begin(), h->bacc.end(), 0.0);
+        h->timeAvCounter = 0; h->nAvTimeSteps = 0;
+    }
+    return 0;
+}
+
+int ugfo_download_boundary_meas(ugfo_handle* h, double* bm) { std::copy(h->bm.begin(), h->bm.end(), bm); return 0; }
+
+int ugfo_phase_times(ugfo_handle*, double* ms) { for (int i = 0; i < 6; ++i) ms[i] = 0; return 0; }
+int ugfo_launch_count(ugfo_handle*, int64_t* n) { *n = 0; return 0; }
+
+// Known-answer hook for the RNG: one Philox4x32-10 block.
+void ugfo_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+// First n uniforms of a stream, for cross-checking the CUDA generator.
+void ugfo_stream_u01(uint64_t seed, uint32_t kind, uint32_t aux, uint32_t a, uint32_t b, uint32_t c, int32_t n, double* out) {
+    Stream s(seed, kind, aux, a, b, c);
+    for (int i = 0; i < n; ++i) out[i] = s.u01();
+}
+int ugfo_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"

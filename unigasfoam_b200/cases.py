@@ -1,0 +1,188 @@
+"""BASELINE.json's configurations as concrete synthetic cases.
+
+Each builder returns a `Case`: the mesh, the uniGasProperties / boundariesDict
+dictionaries (reference key names), deltaT, the initial parcels (uniGasMeshFill
+semantics, U/uniGasInitialisation/derived/uniGasMeshFill/uniGasMeshFill.C:174-296) and
+the initial cell state.  Host-side numpy only: initialisation runs once and is outside
+the per-step hot path.
+"""
+from dataclasses import dataclass, field
+import math
+
+import numpy as np
+
+from . import mesh as _mesh
+
+kB = 1.38065e-23  # OpenFOAM physicoChemical::k default
+
+# moleculeProperties presets
+ARGON_GUIDE = dict(mass=66.3e-27, diameter=4.17e-10, omega=0.81, alpha=1.0, rotationalDegreesOfFreedom=0,
+                   vibrationalModes=0, charge=0, numberOfElectronicLevels=1, electronicEnergyList=[0.0], degeneracyList=[1])
+# tutorials/uniGasFoam/hypersonicCylinder/constant/uniGasProperties:88-106
+ARGON_TUTORIAL = dict(ARGON_GUIDE, diameter=3.595e-10, omega=0.734)
+# Bird (1994) Appendix A; not in the reference repo
+NITROGEN = dict(mass=46.5e-27, diameter=4.17e-10, omega=0.74, alpha=1.0, rotationalDegreesOfFreedom=2,
+                vibrationalModes=0, charge=0, numberOfElectronicLevels=1, electronicEnergyList=[0.0], degeneracyList=[1])
+
+
+def vhs_mean_free_path(n, T, sp, Tref):
+    """Bird eq 4.65."""
+    return 1.0 / (math.sqrt(2.0) * math.pi * sp["diameter"] ** 2 * n * (Tref / T) ** (sp["omega"] - 0.5))
+
+
+def vhs_collision_rate(n, T, sp, Tref):
+    """Equilibrium collision rate per molecule, Bird eq 4.64 (coded at uniGasVolFields.C:1150-1151)."""
+    return 4.0 * sp["diameter"] ** 2 * n * math.sqrt(math.pi * kB * Tref / sp["mass"]) * (T / Tref) ** (1.0 - sp["omega"])
+
+
+def most_probable_speed(T, m):
+    return math.sqrt(2.0 * kB * T / m)
+
+
+@dataclass
+class Case:
+    name: str
+    mesh: object
+    uniGasProperties: dict
+    boundariesDict: dict
+    deltaT: float
+    position: np.ndarray
+    U: np.ndarray
+    cell: np.ndarray
+    typeId: np.ndarray = None
+    ERot: np.ndarray = None
+    sigmaTcRMax: float = 0.0
+    cellCollModelId: np.ndarray = None
+    subCellLevels: np.ndarray = None
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_parcels(self):
+        return len(self.cell)
+
+    def make_cloud(self, cloud_cls=None, **kw):
+        if cloud_cls is None:
+            from .cloud import UniGasCloud as cloud_cls
+        cl = cloud_cls(self.mesh, self.uniGasProperties, self.boundariesDict, self.deltaT, **kw)
+        cl.setParcels(self.position, self.U, self.cell, self.typeId, self.ERot)
+        cl.setCellState(sigmaTcRMax=self.sigmaTcRMax, cellCollModelId=self.cellCollModelId, subCellLevels=self.subCellLevels)
+        return cl
+
+
+def _uniform_in_cells(mesh, cells, rng):
+    """Uniform points in hex cells.  Axis-aligned boxes: uniform in the bounding box.  Extruded
+    2-D cells: triangle split of the zMin quad, uniform height (tet.randomPoint analogue)."""
+    lo, hi = mesh.cell_bb_min[cells], mesh.cell_bb_max[cells]
+    if mesh.meta_axis_aligned:
+        return lo + rng.random((len(cells), 3)) * (hi - lo)
+    # general extruded quads: use the cell's zMin face (patch order guarantees it exists for nz = 1)
+    quad = mesh.cell_quads[cells]  # [n,4,2] xy of the 4 corners, counter-clockwise
+    a, b, c, d = quad[:, 0], quad[:, 1], quad[:, 2], quad[:, 3]
+    A1 = 0.5 * np.abs(np.cross(b - a, c - a))
+    A2 = 0.5 * np.abs(np.cross(c - a, d - a))
+    pick = rng.random(len(cells)) * (A1 + A2) < A1
+    s, t = rng.random(len(cells)), rng.random(len(cells))
+    fl = s + t > 1
+    s = np.where(fl, 1 - s, s); t = np.where(fl, 1 - t, t)
+    p1 = a + s[:, None] * (b - a) + t[:, None] * (c - a)
+    p2 = a + s[:, None] * (c - a) + t[:, None] * (d - a)
+    xy = np.where(pick[:, None], p1, p2)
+    z = lo[:, 2] + rng.random(len(cells)) * (hi[:, 2] - lo[:, 2])
+    return np.column_stack([xy, z])
+
+
+def mesh_fill(mesh, species, names, number_densities, T, velocity, nParticle, rng, Trot=None, cells=None):
+    """uniGasMeshFill::setInitialConfiguration (…/uniGasMeshFill.C:174-278), per cell instead of per tet:
+    N = n V / F_N with stochastic rounding, uniform position, Maxwellian + drift, equipartition ERot."""
+    pos, vel, cel, tid, erot = [], [], [], [], []
+    all_cells = np.arange(mesh.n_cells) if cells is None else np.asarray(cells)
+    for ti, name in enumerate(names):
+        sp = species[name]
+        req = number_densities[name] / nParticle * mesh.cell_volumes[all_cells]
+        cnt = np.floor(req).astype(np.int64)
+        cnt += (req - cnt) > rng.random(len(all_cells))
+        cl = np.repeat(all_cells, cnt)
+        n = len(cl)
+        pos.append(_uniform_in_cells(mesh, cl, rng))
+        vel.append(math.sqrt(kB * T / sp["mass"]) * rng.standard_normal((n, 3)) + np.asarray(velocity)[None, :])
+        cel.append(cl); tid.append(np.full(n, ti, np.int32))
+        rd = sp.get("rotationalDegreesOfFreedom", 0)
+        tr = T if Trot is None else Trot
+        if rd == 0:
+            erot.append(np.zeros(n))
+        elif rd == 2:
+            erot.append(-np.log(1.0 - rng.random(n)) * kB * tr)
+        else:
+            erot.append(rng.gamma(0.5 * rd, kB * tr, n))
+    pos = np.concatenate(pos); vel = np.concatenate(vel); cel = np.concatenate(cel)
+    tid = np.concatenate(tid); erot = np.concatenate(erot)
+    # the cloud is a linked list in insertion order: cell-major here
+    order = np.argsort(cel, kind="stable")
+    pos, vel, cel, tid, erot = pos[order], vel[order], cel[order], tid[order], erot[order]
+    for d in range(3):  # empty directions: particles sit on the mesh mid-plane (deviationFromMeshCentre)
+        if not mesh.solution_d[d]:
+            pos[:, d] = 0.5 * (mesh.points[:, d].min() + mesh.points[:, d].max())
+    return pos, vel, cel.astype(np.int32), tid, erot
+
+
+def _props(species_name, sp, nParticle, mode="dsmc", binary="variableHardSphere", bgk="noBGKCollision", Tref=273.0, **cp):
+    return {
+        "nEquivalentParticles": nParticle,
+        "chemicalReactions": False, "cellWeightedSimulation": False, "axisymmetricSimulation": False,
+        "adaptiveSimulation": False,
+        "collisionModel": mode, "bgkCollisionModel": bgk,
+        "dsmcCollisionPartnerModel": "noTimeCounter", "dsmcCollisionModel": binary,
+        "collisionProperties": dict(Tref=Tref, **cp),
+        "typeIdList": [species_name], "moleculeProperties": {species_name: sp},
+    }
+
+
+def closed_box(n=32, parcels=1_000_000, wall="specular", T0=300.0, number_density=1e20, species=("Ar", ARGON_GUIDE),
+               Tref=273.0, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", seed=1, dt_mct=0.2,
+               lambda_per_dx=2.0, velocity=(0.0, 0.0, 0.0), Trot=None, **cp):
+    """Config 1: 3-D closed box of gas at equilibrium, n^3 cells, dx = lambda/2, dt = 0.2 MCT."""
+    name, sp = species
+    lam = vhs_mean_free_path(number_density, T0, sp, Tref)
+    dx = lam / lambda_per_dx
+    L = n * dx
+    m = _mesh.box_mesh(n, n, n, L, L, L)
+    m.meta_axis_aligned = True
+    nParticle = number_density * L ** 3 / parcels
+    rng = np.random.default_rng(seed)
+    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: number_density}, T0, velocity, nParticle, rng, Trot=Trot)
+    dt = dt_mct / vhs_collision_rate(number_density, T0, sp, Tref)
+    if wall == "specular":
+        model = lambda p: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasSpecularWallPatch"}
+    else:
+        model = lambda p: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasDiffuseWallPatch",
+                           "uniGasDiffuseWallPatchProperties": {"temperature": T0, "velocity": [0, 0, 0]}}
+    bd = {"uniGasPatchBoundaries": [model(p.name) for p in m.patches]}
+    sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(T0, sp["mass"])  # uniGasMeshFill.C:284-296
+    return Case("closed_box", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
+                erot if sp.get("rotationalDegreesOfFreedom", 0) else None, sig0,
+                meta=dict(n=number_density, T0=T0, lam=lam, L=L, Tref=Tref, species=sp))
+
+
+def couette(nx=1000, ny=500, ppc=20, Kn=0.1, Tw=273.0, Uw=150.0, number_density=1e20, species=("Ar", ARGON_GUIDE),
+            Tref=273.0, courant=0.5, seed=2, n_ranks=1, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", **cp):
+    """Config 2: 2-D Couette flow, x cyclic, y walls diffuse at Tw moving at -+Uw, z empty; H = lambda/Kn."""
+    name, sp = species
+    lam = vhs_mean_free_path(number_density, Tw, sp, Tref)
+    H = lam / Kn
+    dy = H / ny
+    dx = dy
+    Lx = nx * dx
+    kinds = {"xMin": ("left", "cyclic"), "xMax": ("right", "cyclic"), "yMin": ("bottom", "wall"), "yMax": ("top", "wall"),
+             "zMin": ("back", "empty"), "zMax": ("front", "empty")}
+    m = _mesh.box_mesh(nx, ny, 1, Lx, H, dx, kinds, cyclic_pairs=[("xMin", "xMax")], solution_d=(1, 1, 0))
+    m.meta_axis_aligned = True
+    nParticle = number_density * dx * dy * dx / ppc
+    rng = np.random.default_rng(seed)
+    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: number_density}, Tw, (0, 0, 0), nParticle, rng)
+    dt = courant * dx / most_probable_speed(Tw, sp["mass"])
+    wallp = lambda p, u: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasDiffuseWallPatch",
+                          "uniGasDiffuseWallPatchProperties": {"temperature": Tw, "velocity": [u, 0, 0]}}
+    bd = {"uniGasPatchBoundaries": [wallp("bottom", -Uw), wallp("top", Uw)]}
+    sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(Tw, sp["mass"])
+    return Case("couette", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
+                None, sig0, meta=dict(n=number_density, Tw=Tw, Uw=Uw, lam=lam, H=H, Lx=Lx, Tref=Tref, species=sp))

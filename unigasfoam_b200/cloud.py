@@ -1,0 +1,365 @@
+"""Host-side mirror of uniGasCloud (U/clouds/uniGasCloud.{H,C}) over the libugf C ABI.
+
+The constructor takes the same dictionaries a uniGasFoam case holds
+(constant/uniGasProperties, system/boundariesDict, controlDict's deltaT) as Python
+dicts with the reference's key names, resolves the run-time-selected model names
+through the same words the reference's selection tables use, and forwards every
+per-step call to the CUDA library.  Method names follow the reference
+(evolve, info, cellOccupancy, buildCellOccupancy, ...).
+
+There is no CPU path here: `api` defaults to libugf.so and construction fails if it is
+missing.  Tests pass the oracle's Api object to drive the CPU restatement through the
+same code (oracle/oracle_cloud.py).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import UgfError
+
+
+def _species_struct(d):
+    """moleculeProperties.<name> -> ugf_species (U/parcels/uniGasParcelI.H:40-141)."""
+    s = _capi.Species()
+    s.mass = float(d["mass"])
+    s.d = float(d["diameter"])
+    s.omega = float(d["omega"])
+    s.alpha = float(d.get("alpha", 1.0))
+    s.rotationalDoF = int(d.get("rotationalDegreesOfFreedom", 0))
+    s.vibrationalDoF = int(d.get("vibrationalModes", 0))
+    for i, v in enumerate(d.get("characteristicVibrationalTemperature", [])):
+        s.thetaV[i] = float(v)
+    for i, v in enumerate(d.get("dissociationTemperature", [])):
+        s.thetaD[i] = float(v)
+    for i, v in enumerate(d.get("Zref", [])):
+        s.Zref[i] = float(v)
+    for i, v in enumerate(d.get("referenceTempForZref", [])):
+        s.TrefZv[i] = float(v)
+    s.charge = int(d.get("charge", 0))
+    elist = list(d.get("electronicEnergyList", [0.0]))
+    glist = list(d.get("degeneracyList", [1]))
+    s.nElectronicLevels = int(d.get("numberOfElectronicLevels", len(elist)))
+    for i, v in enumerate(elist):
+        s.electronicEnergy[i] = float(v)
+    for i, v in enumerate(glist):
+        s.degeneracy[i] = int(v)
+    return s
+
+
+def _lookup(table, word, key):
+    if word not in table:
+        # FatalIOErrorInLookup (e.g. U/dsmcCollisions/basic/dsmcCollisionModel/dsmcCollisionModel.C:71-80)
+        raise UgfError(f"Unknown {key} type {word!r}. Valid types: {sorted(table)}")
+    return table[word]
+
+
+class UniGasCloud:
+    def __init__(self, mesh, uniGasProperties, boundariesDict=None, deltaT=None, *, api=None, device=0,
+                 seed=20261017, parcelCapacity=None, sampleInterval=1, measureWalls=True, rank=0, nRanks=1):
+        self.api = api if api is not None else _capi.libugf()
+        self.mesh = mesh
+        props = uniGasProperties
+        self.typeIdList = list(props["typeIdList"])
+        cp = props.get("collisionProperties", {})
+        cfg = _capi.Config()
+        cfg.abiVersion = _capi.UGF_ABI_VERSION
+        cfg.device = device
+        cfg.seed = seed + rank
+        cfg.nParticle = float(props["nEquivalentParticles"])
+        cfg.deltaT = float(deltaT)
+        for k in range(3):
+            cfg.solutionD[k] = int(mesh.solution_d[k])
+        mode = props.get("collisionModel", "dsmc")
+        cfg.collisionModel = _lookup(_capi.COLLISION_MODEL, mode, "collisionModel")
+        cfg.partnerModel = _lookup(_capi.PARTNER_MODEL, props.get("dsmcCollisionPartnerModel", "noTimeCounter"), "dsmcCollisionPartnerModel")
+        cfg.binaryModel = _lookup(_capi.BINARY_MODEL, props.get("dsmcCollisionModel", "noDSMCCollision"), "dsmcCollisionModel")
+        cfg.bgkModel = _lookup(_capi.BGK_MODEL, props.get("bgkCollisionModel", "noBGKCollision"), "bgkCollisionModel")
+        cfg.nSubCycles = int(cp.get("nSubCycles", 1))
+        cfg.macroInterpolation = int(bool(cp.get("macroInterpolation", False)))
+        cfg.Tref = float(cp.get("Tref", 273.0))
+        cfg.theta = float(cp.get("theta", 1.0))
+        cfg.rotationalRelaxationCollisionNumber = float(cp.get("rotationalRelaxationCollisionNumber", 5.0))
+        cfg.electronicRelaxationCollisionNumber = float(cp.get("electronicRelaxationCollisionNumber", 500.0))
+        cfg.parcelCapacity = int(parcelCapacity) if parcelCapacity else 0
+        cfg.sampleInterval = int(sampleInterval)
+        cfg.measureWalls = int(bool(measureWalls))
+        cfg.rank, cfg.nRanks = rank, nRanks
+        for key in ("cellWeightedSimulation", "axisymmetricSimulation", "adaptiveSimulation", "chemicalReactions"):
+            if props.get(key, False):
+                raise UgfError(f"{key} true is not supported by the B200 path yet (SURVEY §8f)")
+        self.cfg = cfg
+        self._h = _capi.H()
+        self._pending_capacity = cfg.parcelCapacity == 0
+        self._created = False
+        self._species = (_capi.Species * len(self.typeIdList))(
+            *[_species_struct(props["moleculeProperties"][name]) for name in self.typeIdList])
+        self._boundariesDict = boundariesDict or {}
+        if not self._pending_capacity:
+            self._create()
+
+    # -- construction -----------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.api.last_error(self._h if self._created else None)
+            raise UgfError(msg.decode() if msg else f"libugf status {rc}")
+
+    def _create(self):
+        rc = self.api.create(C.byref(self.cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self.api.last_error(None)
+            raise UgfError(msg.decode() if msg else "ugf_create failed")
+        self._created = True
+        self._check(self.api.set_species(self._h, len(self.typeIdList), self._species))
+        cm = self.mesh.as_c()
+        self._check(self.api.set_mesh(self._h, C.byref(cm)))
+        bd = self._boundariesDict
+        for entry in bd.get("uniGasPatchBoundaries", []):
+            patch = self.mesh.patch_index(entry["patchBoundaryProperties"]["patch"])
+            word = entry["boundaryModel"]
+            model = _lookup(_capi.WALL_MODEL, word, "boundaryModel")
+            pr = entry.get(word + "Properties", {})
+            params = []
+            if model in (1, 3):
+                params = [float(pr["temperature"])] + [float(v) for v in pr["velocity"]]
+                if model == 3:
+                    params.append(float(pr["diffuseFraction"]))
+            if self.mesh.patches[patch].kind != "wall":
+                # uniGasBoundaries.C:448-488 wants a model on every non-constraint patch, but only wall
+                # patches ever reach controlParticle: accept and ignore.
+                continue
+            arr = (C.c_double * max(len(params), 1))(*params)
+            self._check(self.api.set_patch_model(self._h, patch, model, arr, len(params)))
+        for entry in bd.get("uniGasGeneralBoundaries", []):
+            word = entry["boundaryModel"]
+            if word != "uniGasFreeStreamInflowPatch":
+                raise UgfError(f"general boundary model {word!r} is not supported (only uniGasFreeStreamInflowPatch)")
+            patch = self.mesh.patch_index(entry["generalBoundaryProperties"]["patch"])
+            pr = entry[word + "Properties"]
+            inf = _capi.Inflow()
+            ids = [self.typeIdList.index(n) for n in pr["typeIds"]]
+            inf.nTypeIds = len(ids)
+            for i, t in enumerate(ids):
+                inf.typeIds[i] = t
+                inf.numberDensities[i] = float(pr["numberDensities"][self.typeIdList[t]])
+            inf.translationalTemperature = float(pr["translationalTemperature"])
+            inf.rotationalTemperature = float(pr.get("rotationalTemperature", 0.0))
+            inf.vibrationalTemperature = float(pr.get("vibrationalTemperature", 0.0))
+            inf.electronicTemperature = float(pr.get("electronicTemperature", 0.0))
+            for k in range(3):
+                inf.velocity[k] = float(pr["velocity"][k])
+            self._check(self.api.set_inflow(self._h, patch, C.byref(inf)))
+
+    def close(self):
+        if self._created:
+            self.api.destroy(self._h)
+            self._created = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state upload -------------------------------------------------------------
+    @staticmethod
+    def _f64(a):
+        return np.ascontiguousarray(a, dtype=np.float64)
+
+    @staticmethod
+    def _i32(a):
+        return np.ascontiguousarray(a, dtype=np.int32)
+
+    def setParcels(self, position, U, cell, typeId=None, ERot=None, newParcel=None):
+        """addNewParcel for a whole configuration (U/clouds/uniGasCloud.C:260-290)."""
+        n = len(cell)
+        if self._pending_capacity:
+            self.cfg.parcelCapacity = max(int(n * 1.25) + 1024, 4096)
+            self._pending_capacity = False
+            self._create()
+        position = np.asarray(position, dtype=np.float64)
+        U = np.asarray(U, dtype=np.float64)
+        cols = [self._f64(position[:, k]) for k in range(3)] + [self._f64(U[:, k]) for k in range(3)]
+        cl = self._i32(cell)
+        p = _capi.Parcels()
+        p.n = n
+        PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz = [c.ctypes.data_as(PD) for c in cols]
+        p.cell = cl.ctypes.data_as(PI)
+        keep = [cols, cl]
+        if typeId is not None:
+            t = self._i32(typeId); keep.append(t); p.typeId = t.ctypes.data_as(PI)
+        if ERot is not None:
+            e = self._f64(ERot); keep.append(e); p.ERot = e.ctypes.data_as(PD)
+        if newParcel is not None:
+            q = self._i32(newParcel); keep.append(q); p.newParcel = q.ctypes.data_as(PI)
+        self._check(self.api.upload_parcels(self._h, C.byref(p)))
+
+    def setCellState(self, sigmaTcRMax=None, cellCollModelId=None, subCellLevels=None, cellWeightFactor=None):
+        PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        nC = self.mesh.n_cells
+        a = self._f64(np.broadcast_to(sigmaTcRMax, (nC,))) if sigmaTcRMax is not None else None
+        b = self._i32(np.broadcast_to(cellCollModelId, (nC,))) if cellCollModelId is not None else None
+        c = self._i32(np.broadcast_to(subCellLevels, (nC, 3))) if subCellLevels is not None else None
+        d = self._f64(np.broadcast_to(cellWeightFactor, (nC,))) if cellWeightFactor is not None else None
+        self._check(self.api.upload_cell_state(
+            self._h,
+            a.ctypes.data_as(PD) if a is not None else None,
+            b.ctypes.data_as(PI) if b is not None else None,
+            c.ctypes.data_as(PI) if c is not None else None,
+            d.ctypes.data_as(PD) if d is not None else None))
+
+    def setDeltaT(self, dt):
+        self._check(self.api.set_deltaT(self._h, float(dt)))
+        self.cfg.deltaT = float(dt)
+
+    # -- the loop -------------------------------------------------------------------
+    def evolve(self, nSteps=1):
+        """uniGasCloud::evolve (U/clouds/uniGasCloud.C:821-869)."""
+        self._check(self.api.step(self._h, int(nSteps)))
+
+    def controlBeforeMove(self):
+        self._check(self.api.control_before_move(self._h))
+
+    def move(self):
+        self._check(self.api.move(self._h))
+
+    def buildCellOccupancy(self):
+        self._check(self.api.sort(self._h))
+
+    def reorder(self):
+        self._check(self.api.reorder(self._h))
+
+    def calculateFields(self):
+        """cellMeas_.calculateFields() (U/cellMeasurements/cellMeasurements.C:408-513)."""
+        self._check(self.api.sample(self._h))
+
+    def collide(self):
+        self._check(self.api.collide(self._h))
+
+    def relax(self):
+        self._check(self.api.relax(self._h))
+
+    def accumulateFields(self):
+        self._check(self.api.accumulate_fields(self._h))
+
+    def endStep(self):
+        self._check(self.api.end_step(self._h))
+
+    # -- migration --------------------------------------------------------------------
+    def migrateCounts(self):
+        out = (C.c_int64 * len(self.mesh.patches))()
+        self._check(self.api.migrate_counts(self._h, out))
+        return np.array(out[:], dtype=np.int64)
+
+    def migratePack(self, patch):
+        buf = C.POINTER(C.c_double)()
+        n = C.c_int64()
+        self._check(self.api.migrate_pack(self._h, patch, C.byref(buf), C.byref(n)))
+        return buf, n.value
+
+    def migrateUnpack(self, patch, buf_ptr, n):
+        self._check(self.api.migrate_unpack(self._h, patch, buf_ptr, int(n)))
+
+    def moveReceived(self):
+        self._check(self.api.move_received(self._h))
+
+    def stream(self):
+        s = C.c_void_p()
+        self._check(self.api.stream(self._h, C.byref(s)))
+        return s.value
+
+    # -- results ------------------------------------------------------------------------
+    def counters(self):
+        c = _capi.Counters()
+        self._check(self.api.counters_get(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def info(self):
+        """uniGasCloud::info (U/clouds/uniGasCloud.C:878-920) as a dict."""
+        c = self.counters()
+        n = c["nParcels"]
+        nMol = n * self.cfg.nParticle
+        out = {"nParticles": n, "deltaT": self.cfg.deltaT}
+        if n:
+            out["avgLinearKE"] = c["linearKineticEnergy"] * self.cfg.nParticle / nMol
+            out["avgRotationalE"] = c["rotationalEnergy"] * self.cfg.nParticle / nMol
+            out["totalEnergy"] = (c["linearKineticEnergy"] + c["rotationalEnergy"]) * self.cfg.nParticle
+        return out
+
+    def size(self):
+        n = C.c_int64()
+        self._check(self.api.num_parcels(self._h, C.byref(n)))
+        return n.value
+
+    def parcels(self):
+        cap = int(self.cfg.parcelCapacity)
+        PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        f = [np.empty(cap, np.float64) for _ in range(7)]
+        ii = [np.empty(cap, np.int32) for _ in range(2)]
+        p = _capi.Parcels()
+        p.n = cap
+        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz, p.ERot = [a.ctypes.data_as(PD) for a in f]
+        p.cell, p.typeId = [a.ctypes.data_as(PI) for a in ii]
+        self._check(self.api.download_parcels(self._h, C.byref(p)))
+        n = p.n
+        return {
+            "position": np.stack([f[0][:n], f[1][:n], f[2][:n]], axis=1),
+            "U": np.stack([f[3][:n], f[4][:n], f[5][:n]], axis=1),
+            "ERot": f[6][:n].copy(), "cell": ii[0][:n].copy(), "typeId": ii[1][:n].copy(),
+        }
+
+    def cellOccupancy(self):
+        """(offsets [nCells+1], ids [n]) - CloudWithModels::cellOccupancy as CSR."""
+        nC = self.mesh.n_cells
+        off = np.empty(nC + 1, np.int32)
+        PI = C.POINTER(C.c_int32)
+        self._check(self.api.download_cell_occupancy(self._h, off.ctypes.data_as(PI), None))
+        ids = np.empty(int(off[-1]), np.int32)
+        self._check(self.api.download_cell_occupancy(self._h, off.ctypes.data_as(PI), ids.ctypes.data_as(PI)))
+        return off, ids
+
+    def cellMoments(self):
+        a = np.empty((self.mesh.n_cells, len(self.typeIdList), _capi.UGF_NMOM), np.float64)
+        self._check(self.api.download_cell_moments(self._h, a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a
+
+    def cellState(self):
+        nC = self.mesh.n_cells
+        PD = C.POINTER(C.c_double)
+        s, mp, q, sp = np.empty(nC), np.empty(nC), np.empty((nC, 3)), np.empty((nC, 6))
+        self._check(self.api.download_cell_state(self._h, s.ctypes.data_as(PD), mp.ctypes.data_as(PD),
+                                                 q.ctypes.data_as(PD), sp.ctypes.data_as(PD)))
+        return {"sigmaTcRMax": s, "maxProb": mp, "qPrev": q, "sPrev": sp}
+
+    def fields(self, resetAtOutput=False):
+        """uniGasVolFields at write time: dict of per-cell and per-boundary-face arrays."""
+        nC, nB = self.mesh.n_cells, self.mesh.n_boundary_faces
+        PD = C.POINTER(C.c_double)
+        cf = np.empty((nC, _capi.UGF_NFIELD))
+        wf = np.empty((max(nB, 1), _capi.UGF_NWALLFIELD))
+        self._check(self.api.download_fields(self._h, cf.ctypes.data_as(PD), wf.ctypes.data_as(PD), int(resetAtOutput)))
+        wf = wf[:nB]
+        return {
+            "uniGasRhoNMean": cf[:, 0], "rhoN": cf[:, 1], "rhoM": cf[:, 2], "UMean": cf[:, 3:6],
+            "translationalT": cf[:, 6], "rotationalT": cf[:, 7], "overallT": cf[:, 8], "p": cf[:, 9],
+            "Ma": cf[:, 10], "densityError": cf[:, 11],
+            "wall_rhoN": wf[:, 0], "wall_rhoM": wf[:, 1], "wall_UMean": wf[:, 2:5], "wall_translationalT": wf[:, 5],
+            "surfaceHeatTransfer": wf[:, 6], "fD": wf[:, 7:10], "wall_p": wf[:, 10], "surfaceShearStress": wf[:, 11],
+        }
+
+    def boundaryMeasurements(self):
+        nB = self.mesh.n_boundary_faces
+        a = np.empty((max(nB, 1), _capi.UGF_NBM))
+        self._check(self.api.download_boundary_meas(self._h, a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a[:nB]
+
+    def phaseTimes(self):
+        a = (C.c_double * 6)()
+        self._check(self.api.phase_times(self._h, a))
+        return dict(zip(("inflow", "move", "sort", "cell", "relax", "fields"), a[:]))
+
+    def launchCount(self):
+        n = C.c_int64()
+        self._check(self.api.launch_count(self._h, C.byref(n)))
+        return n.value

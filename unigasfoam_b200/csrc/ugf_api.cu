@@ -1,0 +1,1177 @@
+// ugf_api.cu — libugf: handle, device memory and the extern "C" entry points of include/ugf.h.
+//
+// Host side of the B200 particle loop.  One handle owns one GPU's resident state (two SoA parcel buffers,
+// the flattened mesh, per-cell arrays) and one CUDA stream; every call enqueues kernels on that stream and
+// only the entry points that return host data synchronise.  There is no CPU fallback: any CUDA failure is
+// reported through the status code / ugf_last_error.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -ffp-contract=off (see
+// __graft_entry__.build).  -fmad=false keeps the tracking arithmetic bit-identical to the CPU oracle.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/ugf.h"
+#include "ugf_bgk.cuh"
+#include "ugf_cell.cuh"
+#include "ugf_common.cuh"
+#include "ugf_fields.cuh"
+#include "ugf_inflow.cuh"
+#include "ugf_move.cuh"
+#include "ugf_sort.cuh"
+
+using namespace ugf;
+
+namespace {
+
+struct InflowHost {
+    int patch;
+    ugf_inflow in;
+    InflowDev dev;
+    int nSlots;
+    long long maxInsert;
+    std::vector<void*> owned;
+};
+
+__global__ void set_n_kernel(const int* total, long long* dN) { *dN = *total; }
+
+__global__ void __launch_bounds__(256) hist_kernel(const int* __restrict__ cell, const long long* dN, int* __restrict__ cellCount) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = -1;
+    if (i < *dN) c = cell[i];
+    const bool live = c >= 0;
+    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        const unsigned peers = __match_any_sync(liveMask, c);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cellCount[c], __popc(peers));
+    }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(int* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+}  // namespace
+
+struct ugf_handle {
+    ugf_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    int numSMs = NUM_SMS;
+    long long launches = 0;
+
+    int nSpecies = 0;
+    ugf_species spHost[UGF_MAX_SPECIES];
+    DevParams prm;
+    bool hasRot = false, multi = false;
+
+    // mesh
+    bool meshSet = false;
+    int nCells = 0, nFaces = 0, nInternal = 0, nBFaces = 0, nPatches = 0, nSlots = 0;
+    MeshDev mesh{};
+    std::vector<DevPatch> patchesHost;
+    std::vector<int> patchKind, patchStart, patchSize;
+    std::vector<int32_t> ownerHost;
+    std::vector<double> SfHost, CfHost, pointsHost;
+    std::vector<int32_t> fpOffHost, fpHost;
+    int* dCfOff = nullptr; double4* dPlane = nullptr; int* dNbr = nullptr; int* dBfPatch = nullptr; int* dBfOwner = nullptr;
+    DevPatch* dPatches = nullptr; double* dVol = nullptr; double* dBbMin = nullptr; double* dBbMax = nullptr; double* dBfS = nullptr;
+    bool hasProcessor = false;
+
+    // parcels
+    long long capacity = 0;
+    ParcelBuf buf[2]{};
+    int cur = 0;
+    double* dSf = nullptr;
+    long long* dN = nullptr;
+    long long nUpper = 0;           // host upper bound of *dN
+    long long* pinN = nullptr;      // pinned readback of *dN
+    cudaEvent_t evN = nullptr;
+    bool nPending = false;
+    long long newFrom = 0;          // parcels >= newFrom were inserted this step
+    bool inflowDone = false;        // control_before_move ran since the last move
+    bool stepOpen = false;          // phase-wise driving: counters were reset for the current step
+    long long recvStart = -1;
+
+    // cells
+    int* dCellCount = nullptr; int* dOff = nullptr; int* dPerm = nullptr; int* dBlockSums = nullptr; int* dTotal = nullptr;
+    int* dMigCount = nullptr; int* dMigBlock = nullptr;
+    double* dMom = nullptr; double* dAcc = nullptr; double* dBm = nullptr; double* dBacc = nullptr;
+    double* dSigma = nullptr; int* dCollId = nullptr; double* dMaxProb = nullptr; double* dQPrev = nullptr; double* dSPrev = nullptr;
+    double* dKeyScratch = nullptr;
+    DevCounters* dCnt = nullptr;
+    int* dErr = nullptr;
+    double* dTot = nullptr;
+    bool histValid = false, occValid = false, occIdentity = false, momValid = false;
+    bool subLevelsAllOne = true;
+
+    std::vector<InflowHost> inflows;
+    std::vector<double*> packBuf;
+    std::vector<long long> packCap;
+
+    // fields
+    double timeAvCounter = 0;
+    long long nAvTimeSteps = 0;
+    int sampleCounter = 0;
+
+    long long step = 0;
+    int cellCap = 128;
+    int cellBlocks = 0, bgkBlocks = 0, segBlocks = 0;
+    size_t cellSmem = 0, bgkSmem = 0;
+    cudaEvent_t ev[7]{};
+    double phaseMs[6] = {0, 0, 0, 0, 0, 0};
+    bool timingValid = false;
+};
+
+namespace {
+
+std::string g_createErr;
+
+int fail(ugf_handle* h, const std::string& m) {
+    if (h) h->err = m; else g_createErr = m;
+    return 1;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+#define LAUNCHED()                                                                                 \
+    do {                                                                                           \
+        h->launches++;                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, std::string("kernel launch: ") + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+template <class F>
+void dispatch(const ugf_handle* h, F&& f) {
+    if (h->hasRot) {
+        if (h->multi) f(std::true_type{}, std::true_type{}); else f(std::true_type{}, std::false_type{});
+    } else {
+        if (h->multi) f(std::false_type{}, std::true_type{}); else f(std::false_type{}, std::false_type{});
+    }
+}
+
+template <class T>
+int dalloc(ugf_handle* h, T** p, size_t n) {
+    CU(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+
+template <class T>
+int upload(ugf_handle* h, T* dst, const T* src, size_t n) {
+    if (n) CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+inline unsigned grid_for(long long n, int block) { return (unsigned)std::max<long long>(1, (n + block - 1) / block); }
+
+int check_device_error(ugf_handle* h) {
+    int e = 0;
+    CU(cudaMemcpyAsync(&e, h->dErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (e == 1) return fail(h, "parcel capacity exceeded while inserting parcels (raise parcelCapacity)");
+    if (e == 2) return fail(h, "received parcel with a face index outside the processor patch");
+    if (e) return fail(h, "device error flag " + std::to_string(e));
+    return 0;
+}
+
+// Wait for the pending read-back of the array length, if any.
+int refresh_n(ugf_handle* h) {
+    if (h->nPending) {
+        CU(cudaEventSynchronize(h->evN));
+        h->nUpper = *h->pinN;
+        h->nPending = false;
+    }
+    return 0;
+}
+
+int request_n(ugf_handle* h) {
+    CU(cudaMemcpyAsync(h->pinN, h->dN, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->evN, h->stream));
+    h->nPending = true;
+    return 0;
+}
+
+void build_params(ugf_handle* h) {
+    DevParams& p = h->prm;
+    std::memset(&p, 0, sizeof(p));
+    p.seed = h->cfg.seed;
+    p.nParticle = h->cfg.nParticle;
+    p.deltaT = h->cfg.deltaT;
+    p.Tref = h->cfg.Tref;
+    p.theta = h->cfg.theta;
+    p.invZrot = 1.0 / h->cfg.rotationalRelaxationCollisionNumber;
+    p.invZel = 1.0 / h->cfg.electronicRelaxationCollisionNumber;
+    for (int k = 0; k < 3; ++k) p.solD[k] = h->cfg.solutionD[k];
+    p.collisionModel = h->cfg.collisionModel;
+    p.binaryModel = h->cfg.binaryModel;
+    p.bgkModel = h->cfg.bgkModel;
+    p.nSpecies = h->nSpecies;
+    p.measureWalls = h->cfg.measureWalls;
+    for (int i = 0; i < h->nSpecies; ++i) {
+        const ugf_species& s = h->spHost[i];
+        DevSpecies& d = p.sp[i];
+        d.mass = s.mass; d.d = s.d; d.omega = s.omega; d.alpha = s.alpha; d.E0 = s.electronicEnergy[0];
+        d.rotDoF = s.rotationalDoF; d.charge = s.charge; d.nElec = s.nElectronicLevels; d.g0 = s.degeneracy[0];
+    }
+    for (int i = 0; i < h->nSpecies; ++i)
+        for (int j = 0; j < h->nSpecies; ++j) {
+            const double om = 0.5 * (h->spHost[i].omega + h->spHost[j].omega);
+            p.pairInvGamma[i * UGF_MAX_SPECIES + j] = 1.0 / std::exp(std::lgamma(2.5 - om));
+        }
+}
+
+int alloc_parcels(ugf_handle* h) {
+    if (h->buf[0].x) return 0;
+    const size_t cap = (size_t)h->capacity;
+    for (int b = 0; b < 2; ++b) {
+        ParcelBuf& P = h->buf[b];
+        if (dalloc(h, &P.x, cap) || dalloc(h, &P.y, cap) || dalloc(h, &P.z, cap) || dalloc(h, &P.ux, cap) ||
+            dalloc(h, &P.uy, cap) || dalloc(h, &P.uz, cap) || dalloc(h, &P.cell, cap))
+            return 1;
+        if (h->hasRot && dalloc(h, &P.erot, cap)) return 1;
+        if (h->multi && dalloc(h, &P.type, cap)) return 1;
+    }
+    if (dalloc(h, &h->dPerm, cap)) return 1;
+    if (dalloc(h, &h->dMigBlock, cap / 1024 + 2)) return 1;
+    return 0;
+}
+
+// cell occupancy: (histogram if needed) -> scan -> index scatter -> per-cell segment sort
+int do_sort(ugf_handle* h) {
+    if (refresh_n(h)) return 1;
+    const int nC = h->nCells;
+    if (!h->histValid) {
+        CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * nC, h->stream));
+        hist_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dCellCount);
+        LAUNCHED();
+    }
+    const int nb = (nC + SCAN_TILE - 1) / SCAN_TILE;
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums);
+    LAUNCHED();
+    scan_top_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->dBlockSums, nb, h->dTotal, nullptr);
+    LAUNCHED();
+    scan_final_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums, h->dTotal, h->dOff);
+    LAUNCHED();
+    scatter_index_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dOff, h->dCellCount, h->dPerm);
+    LAUNCHED();
+    segment_sort_kernel<<<h->segBlocks, SEG_THREADS, 0, h->stream>>>(h->dOff, nC, h->dPerm);
+    LAUNCHED();
+    h->histValid = false;
+    h->occValid = true;
+    h->occIdentity = false;
+    return 0;
+}
+
+// after a gather the array is cell-major and its length is the live count
+int after_gather(ugf_handle* h) {
+    h->cur ^= 1;
+    set_n_kernel<<<1, 1, 0, h->stream>>>(h->dTotal, h->dN);
+    LAUNCHED();
+    h->occIdentity = true;
+    return request_n(h);
+}
+
+int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool doCollide) {
+    CellArgs a{};
+    a.nCells = h->nCells;
+    a.off = h->dOff;
+    a.perm = h->occIdentity ? nullptr : h->dPerm;
+    a.in = h->buf[h->cur];
+    a.out = gather ? h->buf[h->cur ^ 1] : h->buf[h->cur];
+    a.gather = gather ? 1 : 0;
+    a.doSample = doSample ? 1 : 0;
+    a.doCollide = doCollide ? 1 : 0;
+    a.mom = h->dMom;
+    a.vol = h->dVol;
+    a.sigmaTcRMax = h->dSigma;
+    a.collModelId = h->dCollId;
+    a.step = (uint32_t)h->step;
+    a.cnt = h->dCnt;
+    a.cap = h->cellCap;
+    const DevParams prm = h->prm;
+    dispatch(h, [&](auto R, auto M) {
+        cell_kernel<decltype(R)::value, decltype(M)::value><<<h->cellBlocks, CELL_THREADS, h->cellSmem, h->stream>>>(prm, a);
+    });
+    LAUNCHED();
+    if (doSample) h->momValid = true;
+    if (gather) return after_gather(h);
+    return 0;
+}
+
+bool dsmc_active(const ugf_handle* h) {
+    return (h->cfg.collisionModel == UGF_COLL_DSMC || h->cfg.collisionModel == UGF_COLL_HYBRID) && h->cfg.binaryModel != UGF_BINARY_NONE;
+}
+bool bgk_active(const ugf_handle* h) {
+    return (h->cfg.collisionModel == UGF_COLL_BGK || h->cfg.collisionModel == UGF_COLL_HYBRID) && h->cfg.bgkModel != UGF_BGK_NONE;
+}
+
+int run_bgk_kernel(ugf_handle* h) {
+    BgkArgs a{};
+    a.nCells = h->nCells;
+    a.off = h->dOff;
+    a.P = h->buf[h->cur];
+    a.mom = h->dMom;
+    a.vol = h->dVol;
+    a.collModelId = h->dCollId;
+    a.maxProb = h->dMaxProb;
+    a.qPrev = h->dQPrev;
+    a.sPrev = h->dSPrev;
+    a.keyScratch = h->dKeyScratch;
+    a.step = (uint32_t)h->step;
+    a.cnt = h->dCnt;
+    a.cap = h->cellCap;
+    const DevParams prm = h->prm;
+    if (h->multi) bgk_kernel<true><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
+    else bgk_kernel<false><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
+    LAUNCHED();
+    return 0;
+}
+
+int do_inflow(ugf_handle* h) {
+    if (refresh_n(h)) return 1;
+    h->newFrom = h->nUpper;  // exact: refresh_n just ran or no gather happened since
+    const DevParams prm = h->prm;
+    for (InflowHost& f : h->inflows) {
+        if (h->nUpper + f.maxInsert > h->capacity) return fail(h, "parcelCapacity too small for the inflow patches");
+        inflow_count_kernel<<<grid_for(f.nSlots, 256), 256, 0, h->stream>>>(prm, f.dev, (uint32_t)h->step);
+        LAUNCHED();
+        inflow_scan_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(f.dev.nIns, f.nSlots, f.dev.insOff, h->dN, h->capacity, h->dCnt, h->dErr);
+        LAUNCHED();
+        const InflowDev dev = f.dev;
+        ParcelBuf P = h->buf[h->cur];
+        const uint32_t step = (uint32_t)h->step;
+        dispatch(h, [&](auto R, auto M) {
+            inflow_insert_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(f.nSlots, 128), 128, 0, h->stream>>>(prm, dev, P, step);
+        });
+        LAUNCHED();
+        h->nUpper += f.maxInsert;
+    }
+    h->inflowDone = true;
+    h->histValid = false; h->occValid = false; h->momValid = false;
+    return 0;
+}
+
+int do_move(ugf_handle* h, long long begin, bool received) {
+    for (int p = 0; p < h->nPatches; ++p)
+        if (h->patchKind[p] == UGF_PATCH_WALL && h->patchesHost[p].wallModel == UGF_WALL_UNSET)
+            return fail(h, "wall patch without a boundary model");  // uniGasBoundaries.C:448-488
+    if (!received) {
+        CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * h->nCells, h->stream));
+        CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
+    }
+    MoveArgs a{};
+    a.mesh = h->mesh;
+    a.P = h->buf[h->cur];
+    a.dN = h->dN;
+    a.begin = begin;
+    a.newFrom = received ? (1LL << 62) : h->newFrom;
+    a.sf = h->dSf;
+    a.useSfIn = received ? 1 : 0;
+    a.step = (uint32_t)h->step;
+    a.aux = received ? 1u : 0u;
+    a.cellCount = h->dCellCount;
+    a.migCount = h->dMigCount;
+    a.bm = h->dBm;
+    a.cnt = h->dCnt;
+    const long long count = h->nUpper - begin;
+    if (count > 0) {
+        const DevParams prm = h->prm;
+        dispatch(h, [&](auto R, auto M) {
+            move_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
+        });
+        LAUNCHED();
+    }
+    h->histValid = true;
+    h->occValid = false;
+    h->momValid = false;
+    return 0;
+}
+
+int do_accumulate(ugf_handle* h) {
+    h->sampleCounter++;
+    const int interval = h->cfg.sampleInterval > 0 ? h->cfg.sampleInterval : 1;
+    int accumulate = 0;
+    if (interval <= h->sampleCounter) {
+        h->nAvTimeSteps++;
+        h->timeAvCounter += h->cfg.deltaT;
+        accumulate = 1;
+        accumulate_cells_kernel<<<grid_for(h->nCells, 256), 256, 0, h->stream>>>(h->prm, h->nCells, h->dMom, h->dAcc);
+        LAUNCHED();
+        h->sampleCounter = 0;
+    }
+    const long long nb = (long long)h->nBFaces * UGF_NBM;
+    if (nb > 0 && h->cfg.measureWalls) {
+        accumulate_walls_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(h->cfg.deltaT, accumulate, nb, h->dBm, h->dBacc);
+        LAUNCHED();
+    }
+    return 0;
+}
+
+int zero_step_counters(ugf_handle* h) {
+    CU(cudaMemsetAsync(h->dCnt, 0, sizeof(DevCounters), h->stream));
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int ugf_abi_version(void) { return UGF_ABI_VERSION; }
+
+const char* ugf_last_error(const ugf_handle* h) { return h ? h->err.c_str() : g_createErr.c_str(); }
+
+int ugf_create(const ugf_config* cfg, ugf_handle** out) {
+    ugf_handle* h = nullptr;
+    if (!cfg || !out) return fail(nullptr, "null argument");
+    if (cfg->abiVersion != UGF_ABI_VERSION) return fail(nullptr, "ABI version mismatch");
+    if (cfg->macroInterpolation) return fail(nullptr, "macroInterpolation true is not supported");
+    if (cfg->partnerModel != UGF_PARTNER_NTC) return fail(nullptr, "only dsmcCollisionPartnerModel noTimeCounter is supported");
+    if (cfg->parcelCapacity <= 0 || cfg->parcelCapacity > 2000000000LL) return fail(nullptr, "parcelCapacity out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libugf has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "device ordinal out of range");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    h = new ugf_handle();
+    h->cfg = *cfg;
+    h->capacity = cfg->parcelCapacity;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->numSMs = prop.multiProcessorCount;
+    if (const char* s = std::getenv("UGF_CELL_CAP")) h->cellCap = std::max(32, std::atoi(s));
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_createErr = std::string(what) + ": " + cudaGetErrorString(err);
+        delete h;
+        return 1;
+    };
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->evN, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < 7; ++i)
+        if ((e = cudaEventCreate(&h->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMallocHost((void**)&h->pinN, sizeof(long long))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMalloc((void**)&h->dN, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dCnt, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dErr, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dTot, 6 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dTotal, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemsetAsync(h->dN, 0, sizeof(long long), h->stream);
+    cudaMemsetAsync(h->dCnt, 0, sizeof(DevCounters), h->stream);
+    cudaMemsetAsync(h->dErr, 0, sizeof(int), h->stream);
+    cudaMemsetAsync(h->dTotal, 0, sizeof(int), h->stream);
+    *out = h;
+    return 0;
+}
+
+int ugf_destroy(ugf_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    for (int b = 0; b < 2; ++b) {
+        ParcelBuf& P = h->buf[b];
+        cudaFree(P.x); cudaFree(P.y); cudaFree(P.z); cudaFree(P.ux); cudaFree(P.uy); cudaFree(P.uz);
+        cudaFree(P.erot); cudaFree(P.cell); cudaFree(P.type);
+    }
+    void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
+                    h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock,
+                    h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch,
+                    h->dCnt, h->dErr, h->dTot};
+    for (void* p : ptrs) cudaFree(p);
+    for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
+    for (double* p : h->packBuf) cudaFree(p);
+    if (h->pinN) cudaFreeHost(h->pinN);
+    if (h->evN) cudaEventDestroy(h->evN);
+    for (int i = 0; i < 7; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int ugf_set_species(ugf_handle* h, int32_t n, const ugf_species* sp) {
+    if (!h) return 1;
+    if (n < 1 || n > UGF_MAX_SPECIES) return fail(h, "species count out of range");
+    if (h->buf[0].x) return fail(h, "ugf_set_species must precede ugf_upload_parcels");
+    h->hasRot = false;
+    for (int i = 0; i < n; ++i) {
+        if (sp[i].vibrationalDoF > 0) return fail(h, "vibrational modes are not supported yet");
+        if (sp[i].nElectronicLevels != 1) return fail(h, "species with more than one electronic level are not supported by the CUDA path yet");
+        if (!(sp[i].mass > 0) || !(sp[i].d > 0)) return fail(h, "species mass and diameter must be positive");
+        h->spHost[i] = sp[i];
+        if (sp[i].rotationalDoF > 0) h->hasRot = true;
+    }
+    h->nSpecies = n;
+    h->multi = n > 1;
+    build_params(h);
+    return 0;
+}
+
+int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
+    if (!h || !m) return 1;
+    if (h->nSpecies == 0) return fail(h, "ugf_set_species must precede ugf_set_mesh");
+    if (h->meshSet) return fail(h, "mesh already set");
+    CU(cudaSetDevice(h->cfg.device));
+    h->nCells = m->nCells; h->nFaces = m->nFaces; h->nInternal = m->nInternalFaces; h->nPatches = m->nPatches;
+    h->nBFaces = m->nFaces - m->nInternalFaces;
+    const int nC = h->nCells, nB = h->nBFaces, nI = h->nInternal;
+    if (nC <= 0 || nB < 0) return fail(h, "bad mesh sizes");
+    h->nSlots = m->cellFaceOffsets[nC];
+    // flatten: per (cell, local face) an outward plane and the cell behind it
+    std::vector<double4> plane(h->nSlots);
+    std::vector<int> nbr(h->nSlots);
+    for (int c = 0; c < nC; ++c) {
+        for (int j = m->cellFaceOffsets[c]; j < m->cellFaceOffsets[c + 1]; ++j) {
+            const int f = m->cellFaces[j];
+            if (f < 0 || f >= m->nFaces) return fail(h, "cellFaces entry out of range");
+            const bool own = m->owner[f] == c;
+            if (!own && !(f < nI && m->neighbour[f] == c)) return fail(h, "cellFaces lists a face that does not touch the cell");
+            const double* S = m->faceAreas + 3 * (size_t)f;
+            const double* C = m->faceCentres + 3 * (size_t)f;
+            const double d = S[0] * C[0] + S[1] * C[1] + S[2] * C[2];
+            double4 pl;
+            if (own) { pl.x = S[0]; pl.y = S[1]; pl.z = S[2]; pl.w = d; }
+            else { pl.x = -S[0]; pl.y = -S[1]; pl.z = -S[2]; pl.w = -d; }
+            plane[j] = pl;
+            nbr[j] = f < nI ? (own ? m->neighbour[f] : m->owner[f]) : -(f - nI + 1);
+        }
+    }
+    std::vector<int> bfPatch(std::max(nB, 1), -1), bfOwner(std::max(nB, 1), 0);
+    std::vector<double> bfS(3 * (size_t)std::max(nB, 1), 0.0);
+    h->patchesHost.assign(h->nPatches, DevPatch{});
+    h->patchKind.assign(m->patchKind, m->patchKind + h->nPatches);
+    h->patchStart.assign(m->patchStart, m->patchStart + h->nPatches);
+    h->patchSize.assign(m->patchSize, m->patchSize + h->nPatches);
+    for (int p = 0; p < h->nPatches; ++p) {
+        DevPatch& d = h->patchesHost[p];
+        d.kind = m->patchKind[p];
+        d.startBfi = m->patchStart[p] - nI;
+        d.size = m->patchSize[p];
+        d.partnerStartBfi = -1;
+        d.wallModel = UGF_WALL_UNSET;
+        for (int k = 0; k < 3; ++k) d.sep[k] = m->patchSeparation[3 * p + k];
+        d.diffuseFraction = 1.0;
+        if (d.startBfi < 0 || d.startBfi + d.size > nB) return fail(h, "patch range outside the boundary faces");
+        if (d.kind == UGF_PATCH_CYCLIC) {
+            const int q = m->patchPartner[p];
+            if (q < 0 || q >= h->nPatches || m->patchKind[q] != UGF_PATCH_CYCLIC || m->patchSize[q] != d.size)
+                return fail(h, "cyclic patch without a matching partner");
+            d.partnerStartBfi = m->patchStart[q] - nI;
+        }
+        if (d.kind == UGF_PATCH_PROCESSOR) h->hasProcessor = true;
+        if (d.kind < UGF_PATCH_WALL || d.kind > UGF_PATCH_GENERIC) return fail(h, "unknown patch kind");
+        for (int k = 0; k < d.size; ++k) bfPatch[d.startBfi + k] = p;
+    }
+    for (int b = 0; b < nB; ++b) {
+        if (bfPatch[b] < 0) return fail(h, "boundary face not covered by a patch");
+        bfOwner[b] = m->owner[nI + b];
+        for (int k = 0; k < 3; ++k) bfS[3 * (size_t)b + k] = m->faceAreas[3 * (size_t)(nI + b) + k];
+    }
+    // host copies needed later (inflow geometry)
+    h->ownerHost.assign(m->owner, m->owner + m->nFaces);
+    h->SfHost.assign(m->faceAreas, m->faceAreas + 3 * (size_t)m->nFaces);
+    h->CfHost.assign(m->faceCentres, m->faceCentres + 3 * (size_t)m->nFaces);
+    if (m->points && m->facePointOffsets && m->facePoints) {
+        h->pointsHost.assign(m->points, m->points + 3 * (size_t)m->nPoints);
+        h->fpOffHost.assign(m->facePointOffsets, m->facePointOffsets + m->nFaces + 1);
+        h->fpHost.assign(m->facePoints, m->facePoints + h->fpOffHost[m->nFaces]);
+    }
+    if (dalloc(h, &h->dCfOff, (size_t)nC + 1) || dalloc(h, &h->dPlane, (size_t)h->nSlots) || dalloc(h, &h->dNbr, (size_t)h->nSlots) ||
+        dalloc(h, &h->dBfPatch, (size_t)nB) || dalloc(h, &h->dBfOwner, (size_t)nB) || dalloc(h, &h->dPatches, (size_t)h->nPatches) ||
+        dalloc(h, &h->dVol, (size_t)nC) || dalloc(h, &h->dBbMin, 3 * (size_t)nC) || dalloc(h, &h->dBbMax, 3 * (size_t)nC) ||
+        dalloc(h, &h->dBfS, 3 * (size_t)nB))
+        return 1;
+    if (upload(h, h->dCfOff, m->cellFaceOffsets, (size_t)nC + 1) || upload(h, h->dPlane, plane.data(), plane.size()) ||
+        upload(h, h->dNbr, nbr.data(), nbr.size()) || upload(h, h->dBfPatch, bfPatch.data(), (size_t)nB) ||
+        upload(h, h->dBfOwner, bfOwner.data(), (size_t)nB) || upload(h, h->dPatches, h->patchesHost.data(), (size_t)h->nPatches) ||
+        upload(h, h->dVol, m->cellVolumes, (size_t)nC) || upload(h, h->dBbMin, m->cellBbMin, 3 * (size_t)nC) ||
+        upload(h, h->dBbMax, m->cellBbMax, 3 * (size_t)nC) || upload(h, h->dBfS, bfS.data(), 3 * (size_t)nB))
+        return 1;
+    CU(cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
+    h->mesh.nCells = nC; h->mesh.nBFaces = nB; h->mesh.nPatches = h->nPatches;
+    h->mesh.cfOff = h->dCfOff; h->mesh.plane = h->dPlane; h->mesh.nbr = h->dNbr; h->mesh.bfPatch = h->dBfPatch;
+    h->mesh.bfOwner = h->dBfOwner; h->mesh.patches = h->dPatches; h->mesh.vol = h->dVol; h->mesh.bbMin = h->dBbMin; h->mesh.bbMax = h->dBbMax;
+
+    // per-cell arrays
+    const size_t nS = (size_t)h->nSpecies;
+    if (dalloc(h, &h->dCellCount, (size_t)nC) || dalloc(h, &h->dOff, (size_t)nC + 1) ||
+        dalloc(h, &h->dBlockSums, (size_t)std::max((nC + SCAN_TILE - 1) / SCAN_TILE, (int)(h->capacity / 1024 + 2)) + 2) ||
+        dalloc(h, &h->dMigCount, (size_t)h->nPatches) || dalloc(h, &h->dMom, (size_t)nC * nS * UGF_NMOM) ||
+        dalloc(h, &h->dAcc, (size_t)nC * NACC) || dalloc(h, &h->dBm, (size_t)nB * UGF_NBM) || dalloc(h, &h->dBacc, (size_t)nB * UGF_NBM) ||
+        dalloc(h, &h->dSigma, (size_t)nC) || dalloc(h, &h->dCollId, (size_t)nC) || dalloc(h, &h->dMaxProb, (size_t)nC) ||
+        dalloc(h, &h->dQPrev, 3 * (size_t)nC) || dalloc(h, &h->dSPrev, 6 * (size_t)nC))
+        return 1;
+    CU(cudaMemsetAsync(h->dOff, 0, sizeof(int) * ((size_t)nC + 1), h->stream));
+    CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * (size_t)nC, h->stream));
+    CU(cudaMemsetAsync(h->dMom, 0, sizeof(double) * (size_t)nC * nS * UGF_NMOM, h->stream));
+    CU(cudaMemsetAsync(h->dAcc, 0, sizeof(double) * (size_t)nC * NACC, h->stream));
+    CU(cudaMemsetAsync(h->dBm, 0, sizeof(double) * std::max<size_t>((size_t)nB * UGF_NBM, 1), h->stream));
+    CU(cudaMemsetAsync(h->dBacc, 0, sizeof(double) * std::max<size_t>((size_t)nB * UGF_NBM, 1), h->stream));
+    CU(cudaMemsetAsync(h->dSigma, 0, sizeof(double) * (size_t)nC, h->stream));
+    CU(cudaMemsetAsync(h->dQPrev, 0, sizeof(double) * 3 * (size_t)nC, h->stream));
+    CU(cudaMemsetAsync(h->dSPrev, 0, sizeof(double) * 6 * (size_t)nC, h->stream));
+    {
+        std::vector<int> ids((size_t)nC, h->cfg.collisionModel == UGF_COLL_DSMC ? 1 : 0);  // uniGasCloud.C:713,723,731
+        std::vector<double> ones((size_t)nC, 1.0);
+        if (upload(h, h->dCollId, ids.data(), ids.size()) || upload(h, h->dMaxProb, ones.data(), ones.size())) return 1;
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    if (h->hasProcessor && dalloc(h, &h->dSf, (size_t)h->capacity)) return 1;
+    if (bgk_active(h) && dalloc(h, &h->dKeyScratch, (size_t)h->capacity)) return 1;
+    h->packBuf.assign(h->nPatches, nullptr);
+    h->packCap.assign(h->nPatches, 0);
+
+    // launch geometry: persistent grids sized to the SM count
+    h->cellSmem = (size_t)CELL_WARPS * h->cellCap * (h->hasRot ? 4 : 3) * sizeof(double) + (size_t)CELL_WARPS * h->cellCap;
+    h->bgkSmem = (size_t)BGK_WARPS * h->cellCap * 4 * sizeof(double) + (size_t)BGK_WARPS * h->cellCap;
+    int occCell = 1, occBgk = 1, occSeg = 1;
+    cudaError_t e1 = cudaSuccess;
+    dispatch(h, [&](auto R, auto M) {
+        auto k = cell_kernel<decltype(R)::value, decltype(M)::value>;
+        e1 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cellSmem);
+        if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occCell, k, CELL_THREADS, h->cellSmem);
+    });
+    CU(e1);
+    if (h->multi) {
+        CU(cudaFuncSetAttribute(bgk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->bgkSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occBgk, bgk_kernel<true>, BGK_THREADS, h->bgkSmem));
+    } else {
+        CU(cudaFuncSetAttribute(bgk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->bgkSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occBgk, bgk_kernel<false>, BGK_THREADS, h->bgkSmem));
+    }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occSeg, segment_sort_kernel, SEG_THREADS, 0));
+    auto persistent = [&](int occ, int warpsPerBlock) {
+        const int need = (nC + warpsPerBlock - 1) / warpsPerBlock;
+        return std::max(1, std::min(need, h->numSMs * std::max(occ, 1)));
+    };
+    h->cellBlocks = persistent(occCell, CELL_WARPS);
+    h->bgkBlocks = persistent(occBgk, BGK_WARPS);
+    h->segBlocks = persistent(occSeg, SEG_THREADS / 32);
+    h->meshSet = true;
+    return 0;
+}
+
+int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t model, const double* prm, int32_t n) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->patchKind[patch] != UGF_PATCH_WALL) return fail(h, "patch models apply to wall patches only");
+    DevPatch& d = h->patchesHost[patch];
+    if (model == UGF_WALL_DIFFUSE || model == UGF_WALL_MIXED) {
+        if (n < 4 || !prm) return fail(h, "diffuse wall needs T, Ux, Uy, Uz");
+        d.T = prm[0]; d.Uw[0] = prm[1]; d.Uw[1] = prm[2]; d.Uw[2] = prm[3];
+        if (model == UGF_WALL_MIXED) { if (n < 5) return fail(h, "mixed wall needs diffuseFraction"); d.diffuseFraction = prm[4]; }
+    } else if (model != UGF_WALL_SPECULAR && model != UGF_WALL_DELETION) {
+        return fail(h, "unknown wall model");
+    }
+    d.wallModel = model;
+    CU(cudaMemcpyAsync(h->dPatches + patch, &d, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->pointsHost.empty()) return fail(h, "inflow needs mesh points/facePoints");
+    if (in->nTypeIds < 1 || in->nTypeIds > h->nSpecies) return fail(h, "inflow typeIds out of range");
+    InflowHost f;
+    f.patch = patch;
+    f.in = *in;
+    const int nF = h->patchSize[patch];
+    f.nSlots = nF * in->nTypeIds;
+    std::vector<int> faceBfi(nF), faceCell(nF), triOff(nF + 1, 0);
+    std::vector<double> geom((size_t)nF * INFLOW_GEOM), tri;
+    const double sqrtPi = std::sqrt(PI);
+    f.maxInsert = 0;
+    for (int lf = 0; lf < nF; ++lf) {
+        const int face = h->patchStart[patch] + lf;
+        faceBfi[lf] = face - h->nInternal;
+        faceCell[lf] = h->ownerHost[face];
+        const double* S = &h->SfHost[3 * (size_t)face];
+        const double* fC = &h->CfHost[3 * (size_t)face];
+        const double fA = std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+        const int np = h->fpOffHost[face + 1] - h->fpOffHost[face];
+        if (np < 3) return fail(h, "inflow face with fewer than 3 points");
+        const int32_t* fp = &h->fpHost[h->fpOffHost[face]];
+        const double* p0 = &h->pointsHost[3 * (size_t)fp[0]];
+        double cum = 0;
+        for (int t = 0; t < np - 2; ++t) {
+            const double* a = &h->pointsHost[3 * (size_t)fp[t + 1]];
+            const double* b = &h->pointsHost[3 * (size_t)fp[t + 2]];
+            const double e1[3] = {a[0] - p0[0], a[1] - p0[1], a[2] - p0[2]};
+            const double e2[3] = {b[0] - p0[0], b[1] - p0[1], b[2] - p0[2]};
+            const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            cum += 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz) / fA;
+            const double rec[INFLOW_TRI] = {a[0], a[1], a[2], b[0], b[1], b[2], (t == np - 3) ? 1.0 : cum};
+            tri.insert(tri.end(), rec, rec + INFLOW_TRI);
+        }
+        triOff[lf + 1] = triOff[lf] + (np - 2);
+        const double n[3] = {S[0] / -fA, S[1] / -fA, S[2] / -fA};
+        double t1[3] = {fC[0] - p0[0], fC[1] - p0[1], fC[2] - p0[2]};
+        const double m1 = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+        for (int k = 0; k < 3; ++k) t1[k] /= m1;
+        double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+        const double m2 = std::sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+        for (int k = 0; k < 3; ++k) t2[k] /= m2;
+        double* g = &geom[(size_t)lf * INFLOW_GEOM];
+        g[0] = fA;
+        for (int k = 0; k < 3; ++k) { g[1 + k] = n[k]; g[4 + k] = t1[k]; g[7 + k] = t2[k]; g[10 + k] = p0[k]; }
+        for (int iD = 0; iD < in->nTypeIds; ++iD) {
+            const int t = in->typeIds[iD];
+            if (t < 0 || t >= h->nSpecies) return fail(h, "inflow typeId out of range");
+            const double cmp = std::sqrt(2.0 * kB * in->translationalTemperature / h->spHost[t].mass);
+            const double sCos = (in->velocity[0] * n[0] + in->velocity[1] * n[1] + in->velocity[2] * n[2]) / cmp;
+            const double accum = (fA * in->numberDensities[iD] * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
+                                 / (2.0 * sqrtPi * h->cfg.nParticle);
+            f.maxInsert += (long long)std::max(accum, 0.0) + 2;
+        }
+    }
+    InflowDev& d = f.dev;
+    std::memset(&d, 0, sizeof(d));
+    d.nFaces = nF; d.nTypeIds = in->nTypeIds;
+    for (int i = 0; i < in->nTypeIds; ++i) { d.typeIds[i] = in->typeIds[i]; d.numDen[i] = in->numberDensities[i]; }
+    d.Ttr = in->translationalTemperature; d.Trot = in->rotationalTemperature;
+    for (int k = 0; k < 3; ++k) d.vel[k] = in->velocity[k];
+    int *dBfi, *dCell, *dTriOff, *dNIns, *dInsOff;
+    double *dGeom, *dTri;
+    if (dalloc(h, &dBfi, (size_t)nF) || dalloc(h, &dCell, (size_t)nF) || dalloc(h, &dTriOff, (size_t)nF + 1) || dalloc(h, &dGeom, geom.size()) ||
+        dalloc(h, &dTri, tri.size()) || dalloc(h, &dNIns, (size_t)f.nSlots) || dalloc(h, &dInsOff, (size_t)f.nSlots + 1))
+        return 1;
+    f.owned = {dBfi, dCell, dTriOff, dGeom, dTri, dNIns, dInsOff};
+    if (upload(h, dBfi, faceBfi.data(), faceBfi.size()) || upload(h, dCell, faceCell.data(), faceCell.size()) ||
+        upload(h, dTriOff, triOff.data(), triOff.size()) || upload(h, dGeom, geom.data(), geom.size()) || upload(h, dTri, tri.data(), tri.size()))
+        return 1;
+    CU(cudaStreamSynchronize(h->stream));
+    d.faceBfi = dBfi; d.faceCell = dCell; d.triOff = dTriOff; d.geom = dGeom; d.tri = dTri; d.nIns = dNIns; d.insOff = dInsOff;
+    h->inflows.push_back(f);
+    return 0;
+}
+
+int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (p->n > h->capacity) return fail(h, "parcel count exceeds parcelCapacity");
+    if (p->n >= 2147483647LL) return fail(h, "parcel count exceeds int32 indexing");
+    CU(cudaSetDevice(h->cfg.device));
+    if (alloc_parcels(h)) return 1;
+    const size_t n = (size_t)p->n;
+    for (size_t i = 0; i < n; ++i) {
+        if (p->cell[i] < 0 || p->cell[i] >= h->nCells) return fail(h, "parcel cell out of range");
+        if (p->typeId && (p->typeId[i] < 0 || p->typeId[i] >= h->nSpecies)) return fail(h, "parcel typeId out of range");
+        if (p->newParcel && p->newParcel[i]) return fail(h, "uploaded parcels must have newParcel == 0");
+    }
+    ParcelBuf& P = h->buf[h->cur];
+    if (upload(h, P.x, p->x, n) || upload(h, P.y, p->y, n) || upload(h, P.z, p->z, n) || upload(h, P.ux, p->Ux, n) ||
+        upload(h, P.uy, p->Uy, n) || upload(h, P.uz, p->Uz, n) || upload(h, P.cell, p->cell, n))
+        return 1;
+    std::vector<uint8_t> types;
+    if (h->hasRot) {
+        if (p->ERot) { if (upload(h, P.erot, p->ERot, n)) return 1; }
+        else CU(cudaMemsetAsync(P.erot, 0, n * sizeof(double), h->stream));
+    }
+    if (h->multi) {
+        types.assign(n, 0);
+        if (p->typeId) for (size_t i = 0; i < n; ++i) types[i] = (uint8_t)p->typeId[i];
+        if (upload(h, P.type, types.data(), n)) return 1;
+    }
+    const long long nn = p->n;
+    CU(cudaMemcpyAsync(h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->nUpper = nn; h->nPending = false; h->newFrom = nn; h->recvStart = -1;
+    h->histValid = h->occValid = h->occIdentity = h->momValid = false;
+    return 0;
+}
+
+int ugf_upload_cell_state(ugf_handle* h, const double* s, const int32_t* id, const int32_t* lv, const double* cwf) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    const size_t nC = (size_t)h->nCells;
+    if (lv) for (size_t i = 0; i < 3 * nC; ++i) {
+        if (lv[i] < 1) return fail(h, "subCellLevels must be >= 1");
+        if (lv[i] != 1) return fail(h, "subCellLevels > 1 are not supported by the CUDA path yet");
+    }
+    if (cwf) for (size_t c = 0; c < nC; ++c) if (cwf[c] != 1.0) return fail(h, "cell weighting is not supported yet (cellWeightFactor must be 1)");
+    if (s && upload(h, h->dSigma, s, nC)) return 1;
+    if (id && upload(h, h->dCollId, id, nC)) return 1;
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int ugf_set_deltaT(ugf_handle* h, double dt) {
+    if (!h) return 1;
+    h->cfg.deltaT = dt;
+    h->prm.deltaT = dt;
+    return 0;
+}
+
+// ---- phases ---------------------------------------------------------------------------------------------
+
+static int open_step(ugf_handle* h) {
+    if (!h->stepOpen) {
+        if (zero_step_counters(h)) return 1;
+        h->stepOpen = true;
+    }
+    return 0;
+}
+
+int ugf_control_before_move(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (open_step(h)) return 1;
+    return do_inflow(h);
+}
+
+int ugf_move(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (refresh_n(h)) return 1;
+    if (open_step(h)) return 1;
+    if (!h->inflowDone) h->newFrom = h->nUpper;
+    if (do_move(h, 0, false)) return 1;
+    if (h->inflowDone) {  // the insert count is only known on the device: make the host mirror exact again
+        if (request_n(h) || refresh_n(h)) return 1;
+    }
+    h->inflowDone = false;
+    h->recvStart = h->nUpper;
+    return 0;
+}
+
+int ugf_sort(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    return do_sort(h);
+}
+
+int ugf_reorder(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (!h->occValid && do_sort(h)) return 1;
+    if (h->occIdentity) return 0;
+    ParcelBuf in = h->buf[h->cur], out = h->buf[h->cur ^ 1];
+    dispatch(h, [&](auto R, auto M) {
+        reorder_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(in, out, h->dPerm, h->dTotal);
+    });
+    LAUNCHED();
+    return after_gather(h);
+}
+
+int ugf_sample(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (!h->occValid && do_sort(h)) return 1;
+    return run_cell_kernel(h, false, true, false);
+}
+
+int ugf_collide(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (!h->occValid && do_sort(h)) return 1;
+    return run_cell_kernel(h, !h->occIdentity, !h->momValid, dsmc_active(h));
+}
+
+int ugf_relax(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (!h->occValid && do_sort(h)) return 1;
+    if (!h->occIdentity || !h->momValid) {
+        if (run_cell_kernel(h, !h->occIdentity, !h->momValid, false)) return 1;
+    }
+    if (!bgk_active(h)) return 0;
+    return run_bgk_kernel(h);
+}
+
+int ugf_accumulate_fields(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (!h->momValid) {
+        if (!h->occValid && do_sort(h)) return 1;
+        if (run_cell_kernel(h, false, true, false)) return 1;
+    }
+    return do_accumulate(h);
+}
+
+int ugf_end_step(ugf_handle* h) {
+    if (!h) return 1;
+    h->step++;
+    h->stepOpen = false;
+    return 0;
+}
+
+int ugf_step(ugf_handle* h, int32_t nSteps) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (h->hasProcessor) return fail(h, "ugf_step is single-rank: the mesh has processor patches (drive the phases and ugf_migrate_* instead)");
+    CU(cudaSetDevice(h->cfg.device));
+    for (int s = 0; s < nSteps; ++s) {
+        if (refresh_n(h)) return 1;
+        if (zero_step_counters(h)) return 1;
+        const bool last = (s == nSteps - 1);
+        if (last) CU(cudaEventRecord(h->ev[0], h->stream));
+        if (!h->inflows.empty()) { if (do_inflow(h)) return 1; } else h->newFrom = h->nUpper;
+        if (last) CU(cudaEventRecord(h->ev[1], h->stream));
+        if (do_move(h, 0, false)) return 1;
+        h->inflowDone = false;
+        if (last) CU(cudaEventRecord(h->ev[2], h->stream));
+        if (do_sort(h)) return 1;
+        if (last) CU(cudaEventRecord(h->ev[3], h->stream));
+        if (run_cell_kernel(h, true, true, dsmc_active(h))) return 1;
+        if (last) CU(cudaEventRecord(h->ev[4], h->stream));
+        if (bgk_active(h) && run_bgk_kernel(h)) return 1;
+        if (last) CU(cudaEventRecord(h->ev[5], h->stream));
+        if (do_accumulate(h)) return 1;
+        if (last) CU(cudaEventRecord(h->ev[6], h->stream));
+        h->step++;
+    }
+    h->timingValid = true;
+    return 0;
+}
+
+// ---- migration --------------------------------------------------------------------------------------------
+
+int ugf_migrate_counts(ugf_handle* h, int64_t* counts) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    std::vector<int> c(std::max(h->nPatches, 1), 0);
+    CU(cudaMemcpyAsync(c.data(), h->dMigCount, sizeof(int) * h->nPatches, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int p = 0; p < h->nPatches; ++p) counts[p] = c[p];
+    return 0;
+}
+
+int ugf_migrate_pack(ugf_handle* h, int32_t patch, double** devBuf, int64_t* nPacked) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (patch < 0 || patch >= h->nPatches || h->patchKind[patch] != UGF_PATCH_PROCESSOR) return fail(h, "pack on a non-processor patch");
+    int count = 0;
+    CU(cudaMemcpyAsync(&count, h->dMigCount + patch, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (count > h->packCap[patch]) {
+        if (h->packBuf[patch]) CU(cudaFree(h->packBuf[patch]));
+        h->packCap[patch] = std::max<long long>(2LL * count, 1024);
+        if (dalloc(h, &h->packBuf[patch], (size_t)h->packCap[patch] * UGF_MIGRATE_STRIDE)) return 1;
+    }
+    *devBuf = h->packBuf[patch];
+    *nPacked = count;
+    if (count == 0) return 0;
+    const unsigned nb = grid_for(h->nUpper, 1024);
+    ParcelBuf P = h->buf[h->cur];
+    mig_count_kernel<<<nb, 1024, 0, h->stream>>>(h->mesh, P.cell, h->dN, patch, h->dMigBlock);
+    LAUNCHED();
+    scan_top_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->dMigBlock, (int)nb, h->dBlockSums, nullptr);
+    LAUNCHED();
+    double* buf = h->packBuf[patch];
+    dispatch(h, [&](auto R, auto M) {
+        mig_pack_kernel<decltype(R)::value, decltype(M)::value><<<nb, 1024, 0, h->stream>>>(h->mesh, P, h->dSf, h->dN, patch, h->dMigBlock, buf);
+    });
+    LAUNCHED();
+    CU(cudaMemsetAsync(h->dMigCount + patch, 0, sizeof(int), h->stream));
+    return 0;
+}
+
+int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64_t n) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (patch < 0 || patch >= h->nPatches || h->patchKind[patch] != UGF_PATCH_PROCESSOR) return fail(h, "unpack on a non-processor patch");
+    if (n <= 0) return 0;
+    if (h->nPending) return fail(h, "ugf_migrate_unpack must follow ugf_move");
+    if (h->nUpper + n > h->capacity) return fail(h, "parcelCapacity too small for the received parcels");
+    ParcelBuf P = h->buf[h->cur];
+    const long long base = h->nUpper;
+    dispatch(h, [&](auto R, auto M) {
+        mig_unpack_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(n, 256), 256, 0, h->stream>>>(h->mesh, P, h->dSf, base, n, patch, devBuf, h->dErr);
+    });
+    LAUNCHED();
+    h->nUpper += n;
+    const long long nn = h->nUpper;
+    // the host mirror is exact here (no insertion since the last refresh), so the device length follows it
+    CU(cudaMemcpyAsync(h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->occValid = false; h->momValid = false;
+    return 0;
+}
+
+int ugf_move_received(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (h->recvStart < 0) return fail(h, "ugf_move_received before ugf_move");
+    if (do_move(h, h->recvStart, true)) return 1;
+    h->recvStart = h->nUpper;
+    return 0;
+}
+
+int ugf_stream(ugf_handle* h, void** s) {
+    if (!h) return 1;
+    *s = (void*)h->stream;
+    return 0;
+}
+
+// ---- results ------------------------------------------------------------------------------------------------
+
+int ugf_num_parcels(ugf_handle* h, int64_t* n) {
+    if (!h) return 1;
+    ugf_counters c;
+    if (ugf_counters_get(h, &c)) return 1;
+    *n = c.nParcels;
+    return 0;
+}
+
+int ugf_counters_get(ugf_handle* h, ugf_counters* out) {
+    if (!h) return 1;
+    std::memset(out, 0, sizeof(*out));
+    CU(cudaSetDevice(h->cfg.device));
+    if (refresh_n(h)) return 1;
+    DevCounters c;
+    double tot[6] = {0, 0, 0, 0, 0, 0};
+    if (h->buf[0].x) {
+        CU(cudaMemsetAsync(h->dTot, 0, 6 * sizeof(double), h->stream));
+        ParcelBuf P = h->buf[h->cur];
+        const DevParams prm = h->prm;
+        dispatch(h, [&](auto R, auto M) {
+            totals_kernel<decltype(R)::value, decltype(M)::value><<<h->numSMs * 4, 256, 0, h->stream>>>(prm, P, h->dN, h->dTot);
+        });
+        LAUNCHED();
+        CU(cudaMemcpyAsync(tot, h->dTot, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaMemcpyAsync(&c, h->dCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (check_device_error(h)) return 1;
+    out->step = h->step;
+    out->nParcels = (int64_t)tot[5];
+    out->collisionCandidates = (int64_t)c.cand;
+    out->collisions = (int64_t)c.coll;
+    out->bgkRelaxations = (int64_t)c.bgk;
+    out->inserted = (int64_t)c.inserted;
+    out->deleted = (int64_t)c.deleted;
+    out->migrated = (int64_t)c.migrated;
+    out->wallHits = (int64_t)c.wallHits;
+    out->stuck = (int64_t)c.stuck;
+    out->linearKineticEnergy = tot[0];
+    out->rotationalEnergy = tot[1];
+    out->momentum[0] = tot[2]; out->momentum[1] = tot[3]; out->momentum[2] = tot[4];
+    return 0;
+}
+
+int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    CU(cudaSetDevice(h->cfg.device));
+    long long n = 0;
+    CU(cudaMemcpyAsync(&n, h->dN, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (p->n < n) return fail(h, "download buffer too small");
+    const ParcelBuf& P = h->buf[h->cur];
+    const size_t nb = (size_t)n;
+    auto dl = [&](double* dst, const double* src) -> int {
+        if (dst && nb) CU(cudaMemcpyAsync(dst, src, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    };
+    if (dl(p->x, P.x) || dl(p->y, P.y) || dl(p->z, P.z) || dl(p->Ux, P.ux) || dl(p->Uy, P.uy) || dl(p->Uz, P.uz)) return 1;
+    if (p->cell && nb) CU(cudaMemcpyAsync(p->cell, P.cell, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (p->ERot) {
+        if (h->hasRot) { if (dl(p->ERot, P.erot)) return 1; }
+        else std::fill(p->ERot, p->ERot + nb, 0.0);
+    }
+    std::vector<uint8_t> types;
+    if (p->typeId) {
+        if (h->multi && nb) {
+            types.resize(nb);
+            CU(cudaMemcpyAsync(types.data(), P.type, nb, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (p->typeId) for (size_t i = 0; i < nb; ++i) p->typeId[i] = h->multi ? types[i] : 0;
+    if (p->newParcel) std::fill(p->newParcel, p->newParcel + nb, 0);
+    p->n = n;
+    return 0;
+}
+
+int ugf_download_cell_occupancy(ugf_handle* h, int32_t* off, int32_t* ids) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (!h->occValid) return fail(h, "cell occupancy not built (call ugf_sort)");
+    CU(cudaMemcpyAsync(off, h->dOff, sizeof(int) * ((size_t)h->nCells + 1), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (ids) {
+        const int n = off[h->nCells];
+        if (h->occIdentity) { for (int i = 0; i < n; ++i) ids[i] = i; }
+        else if (n) {
+            CU(cudaMemcpyAsync(ids, h->dPerm, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+    }
+    return 0;
+}
+
+int ugf_download_cell_moments(ugf_handle* h, double* m) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (!h->momValid) return fail(h, "cell moments not sampled");
+    CU(cudaMemcpyAsync(m, h->dMom, sizeof(double) * (size_t)h->nCells * h->nSpecies * UGF_NMOM, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int ugf_download_cell_state(ugf_handle* h, double* s, double* mp, double* q, double* sp) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    const size_t nC = (size_t)h->nCells;
+    if (s) CU(cudaMemcpyAsync(s, h->dSigma, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->stream));
+    if (mp) CU(cudaMemcpyAsync(mp, h->dMaxProb, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->stream));
+    if (q) CU(cudaMemcpyAsync(q, h->dQPrev, sizeof(double) * 3 * nC, cudaMemcpyDeviceToHost, h->stream));
+    if (sp) CU(cudaMemcpyAsync(sp, h->dSPrev, sizeof(double) * 6 * nC, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int ugf_download_fields(ugf_handle* h, double* cellF, double* wallF, int32_t reset) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    CU(cudaSetDevice(h->cfg.device));
+    const int nC = h->nCells, nB = h->nBFaces;
+    double* tmp = nullptr;
+    const size_t need = std::max((size_t)nC * UGF_NFIELD, (size_t)std::max(nB, 1) * UGF_NWALLFIELD);
+    if (dalloc(h, &tmp, need)) return 1;
+    const double t = h->timeAvCounter;
+    if (cellF) {
+        derive_cells_kernel<<<grid_for(nC, 256), 256, 0, h->stream>>>(nC, h->dAcc, h->dVol, t, (double)h->nAvTimeSteps, tmp);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(cellF, tmp, sizeof(double) * (size_t)nC * UGF_NFIELD, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    if (wallF && nB > 0) {
+        derive_walls_kernel<<<grid_for(nB, 256), 256, 0, h->stream>>>(h->prm, h->mesh, h->dBacc, h->dBfS, t, tmp);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(wallF, tmp, sizeof(double) * (size_t)nB * UGF_NWALLFIELD, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(cudaFree(tmp));
+    if (reset) {
+        CU(cudaMemsetAsync(h->dAcc, 0, sizeof(double) * (size_t)nC * NACC, h->stream));
+        CU(cudaMemsetAsync(h->dBacc, 0, sizeof(double) * std::max<size_t>((size_t)nB * UGF_NBM, 1), h->stream));
+        h->timeAvCounter = 0; h->nAvTimeSteps = 0;
+    }
+    return 0;
+}
+
+int ugf_download_boundary_meas(ugf_handle* h, double* bm) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (h->nBFaces > 0) {
+        CU(cudaMemcpyAsync(bm, h->dBm, sizeof(double) * (size_t)h->nBFaces * UGF_NBM, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int ugf_phase_times(ugf_handle* h, double* ms) {
+    if (!h) return 1;
+    for (int i = 0; i < 6; ++i) ms[i] = 0;
+    if (!h->timingValid) return 0;
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 6; ++i) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+        ms[i] = t;
+    }
+    return 0;
+}
+
+int ugf_launch_count(ugf_handle* h, int64_t* n) {
+    if (!h) return 1;
+    *n = h->launches;
+    return 0;
+}
+
+}  // extern "C"

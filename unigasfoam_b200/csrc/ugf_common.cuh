@@ -1,0 +1,99 @@
+// ugf_common.cuh — device-side types shared by the sm_100a kernels of libugf.
+//
+// Data layout in HBM:
+//   parcels   SoA, fp64 x,y,z,Ux,Uy,Uz (+ERot), int32 cell (+uint8 typeId); two buffers (ping-pong) so that the
+//             cell kernel can gather through the occupancy permutation and write cell-major order.
+//   mesh      CSR cell->face slots; per slot an outward-oriented face plane {Sx,Sy,Sz,S.Cf} (32 B) and the id of
+//             the cell behind it (>=0) or -(boundaryFace+1).
+//   cells     offsets[nCells+1], perm[n], moments [cell][species][UGF_NMOM], accumulators [cell][NACC].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ugf.h"
+
+namespace ugf {
+
+// OpenFOAM DimensionedConstants defaults.
+constexpr double kB = 1.38065e-23;
+constexpr double NAvo = 6.02214e+23;
+constexpr double PI = 3.14159265358979323846;
+constexpr double TWO_PI = 6.28318530717958647692;
+constexpr double VSMALL = 1e-300;
+constexpr double SMALL = 1e-15;
+
+constexpr int NACC = 16;             // time-averaged accumulators per cell
+constexpr int MAX_TRACK_ITERS = 4096;
+constexpr int NUM_SMS = 148;
+
+enum { KIND_MOVE = 1, KIND_NTC = 2, KIND_BGK = 3, KIND_INFLOW = 4 };
+
+struct DevSpecies {
+    double mass, d, omega, alpha, E0;  // E0 = electronicEnergy[0]
+    int rotDoF, charge, nElec, g0;
+};
+
+struct DevPatch {
+    int kind;             // UGF_PATCH_*
+    int startBfi;         // first boundary-face index of the patch
+    int size;
+    int partnerStartBfi;  // cyclic: startBfi of the partner patch
+    int wallModel;        // UGF_WALL_*
+    int pad;
+    double sep[3];
+    double T;
+    double Uw[3];
+    double diffuseFraction;
+};
+
+struct DevParams {
+    uint64_t seed;
+    double nParticle, deltaT, Tref, theta, invZrot, invZel;
+    int solD[3];
+    int collisionModel, binaryModel, bgkModel, nSpecies, measureWalls;
+    DevSpecies sp[UGF_MAX_SPECIES];
+    double pairInvGamma[UGF_MAX_SPECIES * UGF_MAX_SPECIES];  // 1/Gamma(5/2 - omega_pq)
+};
+
+struct DevCounters {
+    unsigned long long cand, coll, bgk, inserted, deleted, migrated, wallHits, stuck;
+};
+
+struct ParcelBuf {
+    double *x, *y, *z, *ux, *uy, *uz, *erot;
+    int* cell;
+    uint8_t* type;
+};
+
+struct MeshDev {
+    int nCells, nBFaces, nPatches;
+    const int* cfOff;         // [nCells+1]
+    const double4* plane;     // [slots] outward {Sx,Sy,Sz,S.Cf}
+    const int* nbr;           // [slots] cell behind the face, or -(bfi+1)
+    const int* bfPatch;       // [nBFaces]
+    const int* bfOwner;       // [nBFaces]
+    const DevPatch* patches;  // [nPatches]
+    const double* vol;        // [nCells]
+    const double* bbMin;      // [nCells*3]
+    const double* bbMax;      // [nCells*3]
+};
+
+__device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+    return ax * bx + ay * by + az * bz;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+}  // namespace ugf

@@ -1,0 +1,197 @@
+// ugf_inflow.cuh — free-stream insertion and multi-rank parcel migration (pack / unpack).
+//
+// Inflow replaces uniGasFreeStreamInflowPatch::controlParcelsBeforeMove
+// (U/boundaries/derived/generalBoundaries/uniGasFreeStreamInflowPatch/uniGasFreeStreamInflowPatch.C:111-128) =
+// uniGasGeneralBoundary::computeParcelsToInsert (…/uniGasGeneralBoundary.C:115-169, Bird eq 4.22) +
+// insertParcels (:537-761, Bird eq 12.5).  Per-face triangle fans are flattened once on the host; the per-step
+// work is count -> single-block scan -> insert, so new parcels land at deterministic indices (face-major,
+// species, k), the same order the oracle appends them in.
+//
+// Migration replaces the transfer loop of OpenFOAM's Cloud::move: parcels stopped on a processor
+// face (cell = -2 - boundaryFace) are compacted, in index order, into a send buffer of UGF_MIGRATE_STRIDE
+// doubles per parcel; received records are appended and resume tracking from their stepFraction.
+#pragma once
+#include "ugf_common.cuh"
+#include "ugf_move.cuh"
+#include "ugf_sort.cuh"
+
+namespace ugf {
+
+constexpr int INFLOW_GEOM = 13;  // fA, n[3] (into the domain), t1[3], t2[3], p0[3]
+constexpr int INFLOW_TRI = 7;    // a[3], b[3], cumulative area fraction
+
+struct InflowDev {
+    int nFaces, nTypeIds;
+    int typeIds[UGF_MAX_SPECIES];
+    double numDen[UGF_MAX_SPECIES];
+    double Ttr, Trot;
+    double vel[3];
+    const int* faceBfi;
+    const int* faceCell;
+    const double* geom;
+    const int* triOff;
+    const double* tri;
+    int* nIns;
+    int* insOff;
+};
+
+__global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ InflowDev f, uint32_t step) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= f.nFaces * f.nTypeIds) return;
+    const int face = slot / f.nTypeIds, iD = slot % f.nTypeIds;
+    const double* g = f.geom + (size_t)face * INFLOW_GEOM;
+    const DevSpecies& s = prm.sp[f.typeIds[iD]];
+    const double fA = g[0];
+    const double cmp = sqrt(2.0 * kB * f.Ttr / s.mass);
+    const double sCos = (f.vel[0] * g[1] + f.vel[1] * g[2] + f.vel[2] * g[3]) / cmp;
+    const double sqrtPi = sqrt(PI);
+    const double accum = (fA * f.numDen[iD] * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
+                         / (2.0 * sqrtPi * prm.nParticle);
+    Stream rc(prm.seed, KIND_INFLOW, (uint32_t)iD, step, (uint32_t)f.faceBfi[face], 0);
+    int nIns = max((int)accum, 0);
+    if ((accum - nIns) > rc.u01()) ++nIns;
+    f.nIns[slot] = nIns;
+}
+
+// single block: insOff = exclusive scan of nIns; insOff[nSlots] = old array length (base); *dN += total
+__global__ void __launch_bounds__(SCAN_THREADS) inflow_scan_kernel(const int* __restrict__ nIns, int nSlots, int* __restrict__ insOff,
+                                                                  long long* dN, long long capacity, DevCounters* cnt, int* errFlag) {
+    __shared__ int sm[33];
+    int carry = 0;
+    for (int base = 0; base < nSlots; base += SCAN_THREADS) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < nSlots ? nIns[idx] : 0;
+        int t;
+        const int ex = block_exclusive_scan(v, &t, sm);
+        if (idx < nSlots) insOff[idx] = carry + ex;
+        carry += t;
+    }
+    if (threadIdx.x == 0) {
+        const long long base = *dN;
+        insOff[nSlots] = (int)base;
+        if (base + carry > capacity) { *errFlag = 1; insOff[nSlots] = -1; }
+        else { *dN = base + carry; atomicAdd(&cnt->inserted, (unsigned long long)carry); }
+    }
+}
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ InflowDev f,
+                                                            ParcelBuf P, uint32_t step) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nSlots = f.nFaces * f.nTypeIds;
+    if (slot >= nSlots) return;
+    const int base = f.insOff[nSlots];
+    if (base < 0) return;
+    const int nIns = f.nIns[slot];
+    if (nIns == 0) return;
+    const int face = slot / f.nTypeIds, iD = slot % f.nTypeIds;
+    const double* g = f.geom + (size_t)face * INFLOW_GEOM;
+    const double n[3] = {g[1], g[2], g[3]}, t1[3] = {g[4], g[5], g[6]}, t2[3] = {g[7], g[8], g[9]}, p0[3] = {g[10], g[11], g[12]};
+    const int typeId = f.typeIds[iD];
+    const DevSpecies& s = prm.sp[typeId];
+    const double cmp = sqrt(2.0 * kB * f.Ttr / s.mass);
+    const double vn = f.vel[0] * n[0] + f.vel[1] * n[1] + f.vel[2] * n[2];
+    const double sCos = vn / cmp;
+    const int tb = f.triOff[face], te = f.triOff[face + 1];
+    const int cellI = f.faceCell[face];
+    const uint32_t bfi = (uint32_t)f.faceBfi[face];
+    for (int i = 0; i < nIns; ++i) {
+        Stream r(prm.seed, KIND_INFLOW, (uint32_t)iD, step, bfi, (uint32_t)(i + 1));
+        const double triSel = r.u01();
+        int sel = tb;
+        for (int t = tb; t < te; ++t) { sel = t; if (f.tri[(size_t)t * INFLOW_TRI + 6] >= triSel) break; }
+        const double* tr = f.tri + (size_t)sel * INFLOW_TRI;
+        double bs = r.u01(), bt = r.u01();
+        if (bs + bt > 1) { bs = 1 - bs; bt = 1 - bt; }
+        double x[3];
+        for (int k = 0; k < 3; ++k) x[k] = (1 - bs - bt) * p0[k] + bs * tr[k] + bt * tr[3 + k];
+        const double A = sCos + sqrt(sCos * sCos + 2.0);
+        const double B = 0.5 * (1.0 + sCos * (sCos - sqrt(sCos * sCos + 2.0)));
+        double scaling = 3.0;
+        if (sCos < -3) scaling = fabs(sCos) + 1;
+        double Pp = -1, uNormal, uNormalThermal;
+        if (fabs(vn) > VSMALL) {
+            do {  // Bird eq 12.5
+                uNormalThermal = scaling * (2.0 * r.u01() - 1);
+                uNormal = uNormalThermal + sCos;
+                if (uNormal < 0.0) Pp = -1;
+                else Pp = 2.0 * uNormal / A * exp(B - uNormalThermal * uNormalThermal);
+            } while (Pp < r.u01());
+        } else {
+            uNormal = sqrt(-log(1.0 - r.u01()));
+        }
+        double g1, g2;
+        r.gauss2(g1, g2);
+        const double cth = sqrt(kB * f.Ttr / s.mass);
+        const double vt1 = t1[0] * f.vel[0] + t1[1] * f.vel[1] + t1[2] * f.vel[2];
+        const double vt2 = t2[0] * f.vel[0] + t2[1] * f.vel[1] + t2[2] * f.vel[2];
+        double U[3];
+        for (int k = 0; k < 3; ++k) U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
+        const double erot = equipartition_rotational_energy(r, f.Trot, s.rotDoF);
+        const long long dst = (long long)base + f.insOff[slot] + i;
+        P.x[dst] = x[0]; P.y[dst] = x[1]; P.z[dst] = x[2];
+        P.ux[dst] = U[0]; P.uy[dst] = U[1]; P.uz[dst] = U[2];
+        P.cell[dst] = cellI;
+        if (HAS_ROT) P.erot[dst] = erot;
+        if (MULTI) P.type[dst] = (uint8_t)typeId;
+    }
+}
+
+// ---- migration ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool on_patch(const MeshDev& mesh, int cell, int patch) {
+    return cell <= -2 && mesh.bfPatch[-2 - cell] == patch;
+}
+
+__global__ void __launch_bounds__(1024) mig_count_kernel(MeshDev mesh, const int* __restrict__ cell, const long long* dN, int patch,
+                                                         int* __restrict__ blockCounts) {
+    __shared__ int sm[33];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int flag = (i < *dN) && on_patch(mesh, cell[i], patch);
+    int total;
+    block_exclusive_scan(flag, &total, sm);
+    if (threadIdx.x == 0) blockCounts[blockIdx.x] = total;
+}
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(1024) mig_pack_kernel(MeshDev mesh, ParcelBuf P, const double* __restrict__ sf, const long long* dN, int patch,
+                                                        const int* __restrict__ blockOffsets, double* __restrict__ buf) {
+    __shared__ int sm[33];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = -1;
+    if (i < *dN) c = P.cell[i];
+    const int flag = (i < *dN) && on_patch(mesh, c, patch);
+    int total;
+    const int ex = block_exclusive_scan(flag, &total, sm);
+    if (flag) {
+        double* r = buf + (size_t)(blockOffsets[blockIdx.x] + ex) * UGF_MIGRATE_STRIDE;
+        const int bfi = -2 - c;
+        r[0] = P.x[i]; r[1] = P.y[i]; r[2] = P.z[i];
+        r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
+        r[6] = HAS_ROT ? P.erot[i] : 0.0;
+        r[7] = sf[i];
+        r[8] = (double)(bfi - mesh.patches[patch].startBfi);
+        r[9] = MULTI ? (double)P.type[i] : 0.0;
+        P.cell[i] = -1;
+    }
+}
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(256) mig_unpack_kernel(MeshDev mesh, ParcelBuf P, double* __restrict__ sf, long long base, long long n, int patch,
+                                                         const double* __restrict__ buf, int* errFlag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* r = buf + (size_t)i * UGF_MIGRATE_STRIDE;
+    const long long dst = base + i;
+    const int lf = (int)r[8];
+    const DevPatch& pt = mesh.patches[patch];
+    if (lf < 0 || lf >= pt.size) { *errFlag = 2; P.cell[dst] = -1; return; }
+    P.x[dst] = r[0]; P.y[dst] = r[1]; P.z[dst] = r[2];
+    P.ux[dst] = r[3]; P.uy[dst] = r[4]; P.uz[dst] = r[5];
+    if (HAS_ROT) P.erot[dst] = r[6];
+    sf[dst] = r[7];
+    P.cell[dst] = mesh.bfOwner[pt.startBfi + lf];
+    if (MULTI) P.type[dst] = (uint8_t)r[9];
+}
+
+}  // namespace ugf

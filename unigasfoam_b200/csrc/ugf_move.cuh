@@ -1,0 +1,262 @@
+// ugf_move.cuh — parcel move: ballistic advance with face-crossing tracking, patch interactions and the
+// per-cell histogram of destination cells fused in.
+//
+// Replaces Cloud<uniGasParcel>::move + uniGasParcel::move (U/parcels/uniGasParcel.C:35-108), hitWallPatch and
+// the wall models of U/boundaries/basic/uniGasPatchBoundary/uniGasPatchBoundary.C:130-403.
+// One thread per parcel; parcels are cell-major from the previous step so neighbouring lanes read the same
+// face planes (L1 broadcast) and the histogram atomics are aggregated per warp with match.any.
+//
+// HBM-bound: algorithmic traffic 80 B/parcel (read x,U,cell = 52; write x,cell = 28); U is only rewritten on
+// wall/symmetry hits.  All tracking arithmetic is plain IEEE mul/add/div in the same order as the oracle
+// (library is compiled with -fmad=false), so final positions and cells match it bit for bit.
+#pragma once
+#include "ugf_common.cuh"
+#include "ugf_rng.cuh"
+
+namespace ugf {
+
+// 32-byte plane record through the read-only path (two 16-byte loads)
+__device__ __forceinline__ double4 load_plane(const double4* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    double4 r;
+    r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    return r;
+}
+
+__device__ __forceinline__ void unit_normal(const double4& pl, double nw[3], double& fA) {
+    fA = sqrt(pl.x * pl.x + pl.y * pl.y + pl.z * pl.z);
+    nw[0] = pl.x / fA; nw[1] = pl.y / fA; nw[2] = pl.z / fA;
+}
+
+// equipartitionRotationalEnergy (U/clouds/uniGasCloud.C:975-1017)
+__device__ inline double equipartition_rotational_energy(Stream& r, double T, int rotDoF) {
+    if (rotDoF < 1) return 0.0;
+    if (rotDoF == 2) return -log(1.0 - r.u01()) * kB * T;
+    const double a = 0.5 * rotDoF - 1;
+    double energyRatio, Pp;
+    const double eps = r.u01();
+    do {
+        energyRatio = 10 * r.u01();
+        Pp = pow(energyRatio / a, a) * exp(a - energyRatio);
+    } while (Pp < eps);
+    return energyRatio * kB * T;
+}
+
+struct WallPre { double IE; double mom[3]; };
+
+// measurePropertiesBeforeControl / AfterControl (uniGasPatchBoundary.C:130-302): slots in DESIGN.md §walls
+__device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, const DevSpecies& s, const double U[3],
+                                    double erot, const double nw[3], double fA, WallPre& pre, bool after) {
+    const double m = s.mass;
+    const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
+    const double inv = 1.0 / fmax(fabs(Un) * fA, VSMALL);
+    const double UU = dot3(U[0], U[1], U[2], U[0], U[1], U[2]);
+    double* b = bm + (size_t)bfi * UGF_NBM;
+    atomicAdd(&b[0], inv);
+    atomicAdd(&b[1], m * inv);
+    atomicAdd(&b[2], 0.5 * m * UU * inv);
+    atomicAdd(&b[3], m * U[0] * inv);
+    atomicAdd(&b[4], m * U[1] * inv);
+    atomicAdd(&b[5], m * U[2] * inv);
+    if (s.rotDoF > 0) {
+        atomicAdd(&b[6], erot * inv);
+        atomicAdd(&b[7], s.rotDoF * inv);
+        atomicAdd(&b[12], inv);
+    }
+    if (s.E0 != 0.0) atomicAdd(&b[14], s.E0 * inv);
+    const double IE = 0.5 * m * UU + erot + s.E0;
+    if (!after) {
+        pre.IE = IE;
+        pre.mom[0] = m * U[0]; pre.mom[1] = m * U[1]; pre.mom[2] = m * U[2];
+        atomicAdd(&b[15], 1.0);
+    } else {
+        const double nPart = prm.nParticle;
+        const double dq = nPart * (pre.IE - IE) / (prm.deltaT * fA);
+        if (dq != 0.0) atomicAdd(&b[8], dq);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double d = nPart * (pre.mom[k] - m * U[k]) / (prm.deltaT * fA);
+            if (d != 0.0) atomicAdd(&b[9 + k], d);
+        }
+    }
+}
+
+// diffuseReflection (uniGasPatchBoundary.C:305-388)
+__device__ inline void diffuse_reflection(Stream& r, const DevSpecies& s, double U[3], double& erot, const double nw[3],
+                                          double T, const double Uw[3]) {
+    double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
+    double Ut[3] = {U[0] - Un * nw[0], U[1] - Un * nw[1], U[2] - Un * nw[2]};
+    double magUt = sqrt(dot3(Ut[0], Ut[1], Ut[2], Ut[0], Ut[1], Ut[2]));
+    while (magUt < SMALL) {
+        U[0] = U[0] * (0.8 + 0.2 * r.u01());
+        U[1] = U[1] * (0.8 + 0.2 * r.u01());
+        U[2] = U[2] * (0.8 + 0.2 * r.u01());
+        Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
+        for (int k = 0; k < 3; ++k) Ut[k] = U[k] - Un * nw[k];
+        magUt = sqrt(dot3(Ut[0], Ut[1], Ut[2], Ut[0], Ut[1], Ut[2]));
+        if (dot3(U[0], U[1], U[2], U[0], U[1], U[2]) == 0.0) {  // reference would spin forever on U == 0
+            const double a0 = fabs(nw[0]), a1 = fabs(nw[1]), a2 = fabs(nw[2]);
+            const int kmin = a0 <= a1 ? (a0 <= a2 ? 0 : 2) : (a1 <= a2 ? 1 : 2);
+            double e[3] = {0, 0, 0};
+            e[kmin] = 1.0;
+            const double en = dot3(e[0], e[1], e[2], nw[0], nw[1], nw[2]);
+            for (int k = 0; k < 3; ++k) Ut[k] = e[k] - en * nw[k];
+            magUt = sqrt(dot3(Ut[0], Ut[1], Ut[2], Ut[0], Ut[1], Ut[2]));
+        }
+    }
+    const double tw1[3] = {Ut[0] / magUt, Ut[1] / magUt, Ut[2] / magUt};
+    const double tw2[3] = {nw[1] * tw1[2] - nw[2] * tw1[1], nw[2] * tw1[0] - nw[0] * tw1[2], nw[0] * tw1[1] - nw[1] * tw1[0]};
+    double g1, g2;
+    r.gauss2(g1, g2);
+    const double gn = sqrt(-2.0 * log(fmax(1 - r.u01(), VSMALL)));
+    const double c = sqrt(kB * T / s.mass);
+    for (int k = 0; k < 3; ++k) U[k] = c * (g1 * tw1[k] + g2 * tw2[k] - gn * nw[k]);
+    erot = equipartition_rotational_energy(r, T, s.rotDoF);
+    for (int k = 0; k < 3; ++k) U[k] += Uw[k];
+}
+
+struct MoveArgs {
+    MeshDev mesh;
+    ParcelBuf P;
+    const long long* dN;   // device: current array length
+    long long begin;       // first parcel index of this launch
+    long long newFrom;     // parcels with index >= newFrom were inserted this step (newParcel == 1)
+    double* sf;            // per-parcel step fraction: in for received parcels, out for migrants (may be null)
+    int useSfIn;           // 1: start from sf[i] (received parcels)
+    uint32_t step;
+    uint32_t aux;          // stream aux: 0 for the step's first move, 1 for received parcels
+    int* cellCount;        // [nCells] histogram of destination cells
+    int* migCount;         // [nPatches]
+    double* bm;            // [nBFaces][UGF_NBM]
+    DevCounters* cnt;
+};
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(256) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
+    const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = *a.dN;
+    const bool valid = i < n;
+    int cell = -1;
+    int nDeleted = 0, nWall = 0, nStuck = 0, nMig = 0;
+    if (valid) cell = a.P.cell[i];
+    if (valid && cell >= 0) {
+        double x[3] = {a.P.x[i], a.P.y[i], a.P.z[i]};
+        double U[3] = {a.P.ux[i], a.P.uy[i], a.P.uz[i]};
+        double erot = 0.0;
+        if (HAS_ROT) erot = a.P.erot[i];
+        int type = 0;
+        if (MULTI) type = a.P.type[i];
+        const DevSpecies& sp = prm.sp[type];
+        Stream r(prm.seed, KIND_MOVE, a.aux, a.step, (uint32_t)i, 0);
+        double sf = 0.0;
+        if (a.useSfIn) sf = a.sf[i];
+        else if (i >= a.newFrom) sf = r.u01();  // U/parcels/uniGasParcel.C:47-53
+        bool changedU = false;
+        const double dt = prm.deltaT;
+        int iters = 0;
+        while (cell >= 0 && sf < 1) {
+            const double rem = 1 - sf;
+            const double s = rem * dt;
+            double disp[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) disp[k] = prm.solD[k] ? s * U[k] : 0.0;  // constrainDirection
+            double lamMin = 1.0;
+            int hit = -1;
+            const int jb = a.mesh.cfOff[cell], je = a.mesh.cfOff[cell + 1];
+            for (int j = jb; j < je; ++j) {
+                const double4 pl = load_plane(&a.mesh.plane[j]);
+                const double nd = pl.x * disp[0] + pl.y * disp[1] + pl.z * disp[2];
+                const double num = pl.w - (pl.x * x[0] + pl.y * x[1] + pl.z * x[2]);
+                if (nd > 0) {
+                    double lam = num / nd;
+                    if (lam < 0) lam = 0;
+                    if (lam < lamMin) { lamMin = lam; hit = j; }
+                }
+            }
+            if (hit < 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x[k] = x[k] + disp[k];
+                sf = 1;
+                break;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] = x[k] + lamMin * disp[k];
+            sf = sf + rem * lamMin;
+            const int nb = __ldg(&a.mesh.nbr[hit]);
+            if (nb >= 0) {
+                cell = nb;
+            } else {
+                const int bfi = -nb - 1;
+                const int patch = __ldg(&a.mesh.bfPatch[bfi]);
+                const DevPatch& pt = a.mesh.patches[patch];
+                const double4 pl = load_plane(&a.mesh.plane[hit]);
+                if (pt.kind == UGF_PATCH_WALL) {
+                    nWall++;
+                    if (pt.wallModel == UGF_WALL_DELETION) {
+                        cell = -1; nDeleted++;
+                    } else {
+                        double nw[3], fA;
+                        unit_normal(pl, nw, fA);
+                        WallPre pre;
+                        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, U, erot, nw, fA, pre, false);
+                        bool diffuse = (pt.wallModel == UGF_WALL_DIFFUSE);
+                        if (pt.wallModel == UGF_WALL_MIXED) diffuse = (pt.diffuseFraction > r.u01());
+                        if (diffuse) {
+                            diffuse_reflection(r, sp, U, erot, nw, pt.T, pt.Uw);
+                        } else {
+                            const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
+                            if (Un > 0.0) for (int k = 0; k < 3; ++k) U[k] = U[k] - 2.0 * Un * nw[k];
+                        }
+                        changedU = true;
+                        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, U, erot, nw, fA, pre, true);
+                    }
+                } else if (pt.kind == UGF_PATCH_SYMMETRY) {
+                    double nw[3], fA;
+                    unit_normal(pl, nw, fA);
+                    const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
+                    for (int k = 0; k < 3; ++k) U[k] = U[k] - 2.0 * Un * nw[k];
+                    changedU = true;
+                } else if (pt.kind == UGF_PATCH_CYCLIC) {
+                    cell = __ldg(&a.mesh.bfOwner[pt.partnerStartBfi + (bfi - pt.startBfi)]);
+                    for (int k = 0; k < 3; ++k) x[k] = x[k] + pt.sep[k];
+                } else if (pt.kind == UGF_PATCH_PROCESSOR) {
+                    for (int k = 0; k < 3; ++k) x[k] = x[k] + pt.sep[k];
+                    cell = -2 - bfi;
+                    nMig++;
+                    if (a.sf) a.sf[i] = sf;
+                    atomicAdd(&a.migCount[patch], 1);
+                } else if (pt.kind == UGF_PATCH_GENERIC) {
+                    cell = -1; nDeleted++;
+                } else {
+                    cell = -1; nStuck++;
+                }
+            }
+            if (++iters > MAX_TRACK_ITERS) { cell = -1; nStuck++; break; }
+        }
+        a.P.x[i] = x[0]; a.P.y[i] = x[1]; a.P.z[i] = x[2];
+        a.P.cell[i] = cell;
+        if (changedU) {
+            a.P.ux[i] = U[0]; a.P.uy[i] = U[1]; a.P.uz[i] = U[2];
+            if (HAS_ROT) a.P.erot[i] = erot;
+        }
+    }
+    // histogram of destination cells, aggregated over lanes that landed in the same cell
+    const bool live = valid && cell >= 0;
+    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        const unsigned peers = __match_any_sync(liveMask, cell);
+        const int lane = threadIdx.x & 31;
+        if (lane == __ffs(peers) - 1) atomicAdd(&a.cellCount[cell], __popc(peers));
+    }
+    const int lane = threadIdx.x & 31;
+    const int sd = warp_sum_int(nDeleted), sw = warp_sum_int(nWall), ss = warp_sum_int(nStuck), sm = warp_sum_int(nMig);
+    if (lane == 0) {
+        if (sd) atomicAdd(&a.cnt->deleted, (unsigned long long)sd);
+        if (sw) atomicAdd(&a.cnt->wallHits, (unsigned long long)sw);
+        if (ss) atomicAdd(&a.cnt->stuck, (unsigned long long)ss);
+        if (sm) atomicAdd(&a.cnt->migrated, (unsigned long long)sm);
+    }
+}
+
+}  // namespace ugf

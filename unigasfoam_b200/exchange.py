@@ -1,0 +1,131 @@
+"""Multi-rank parcel migration: the transfer loop of OpenFOAM's Cloud::move.
+
+One process per GPU / subdomain.  After `cloud.move()` every rank packs the parcels that stopped on its
+processor patches (device-side, in index order), the packed records travel with ONE variable-split
+all_to_all per round over the data group (NCCL over NVLink on GPUs, gloo in CPU tests), are appended on
+the receiving side and resume tracking from their stepFraction; rounds repeat until no rank has anything
+in flight - the same termination rule as the reference's transfer loop.
+
+Only plumbing lives here (torch.distributed); packing, unpacking and tracking are libugf kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._capi import UGF_MIGRATE_STRIDE as STRIDE
+
+
+class _DevArray:
+    """Raw device pointer exposed through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def _sender_tag(tag):
+    return tag
+
+
+def _receiver_view(tag):
+    """The tag the *sender* used for the patch that matches a local patch with `tag`."""
+    return ("i",) if tag[0] == "i" else ("c", tag[2], tag[1])
+
+
+class Exchanger:
+    def __init__(self, cloud, mesh, rank, world, data_group=None, meta_group=None, cuda=False):
+        self.cloud, self.mesh, self.rank, self.world = cloud, mesh, rank, world
+        self.data_group, self.meta_group, self.cuda = data_group, meta_group, cuda
+        self.proc = [(i, p.partner, tuple(p.tag)) for i, p in enumerate(mesh.patches) if p.kind == "processor"]
+        # message order between a pair of ranks: by the sender's patch tag
+        self.send_order = {b: sorted([q for q in self.proc if q[1] == b], key=lambda q: _sender_tag(q[2])) for b in range(world)}
+        self.recv_order = {b: sorted([q for q in self.proc if q[1] == b], key=lambda q: _receiver_view(q[2])) for b in range(world)}
+        k = torch.tensor([max(len(v) for v in self.send_order.values()) if self.send_order else 0], dtype=torch.int64)
+        dist.all_reduce(k, op=dist.ReduceOp.MAX, group=meta_group)
+        self.K = max(int(k.item()), 1)
+        self.rounds = 0
+        self.sent = 0
+        self._stream = None
+        if cuda:
+            self._stream = torch.cuda.ExternalStream(cloud.stream())
+
+    def _wrap(self, ptr, n):
+        """float64 tensor over n doubles at a raw pointer (host for the oracle, device for libugf)."""
+        if n == 0:
+            return torch.empty(0, dtype=torch.float64, device="cuda" if self.cuda else "cpu")
+        addr = C.cast(ptr, C.c_void_p).value
+        if self.cuda:
+            return torch.as_tensor(_DevArray(addr, n), device="cuda")
+        return torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)))
+
+    def exchange(self):
+        """One transfer round.  Returns the number of parcels in flight over all ranks (0 = done)."""
+        counts = self.cloud.migrateCounts()
+        # counts[b*K + slot]: what this rank sends to rank b through its slot-th patch facing b
+        vec = torch.zeros(self.world * self.K, dtype=torch.int64)
+        for b in range(self.world):
+            for slot, (patch, _, _) in enumerate(self.send_order[b]):
+                vec[b * self.K + slot] = int(counts[patch])
+        allv = [torch.zeros_like(vec) for _ in range(self.world)]
+        dist.all_gather(allv, vec, group=self.meta_group)
+        allv = torch.stack(allv).view(self.world, self.world, self.K)  # [sender, receiver, slot]
+        total = int(allv.sum().item())
+        if total == 0:
+            return 0
+        self.rounds += 1
+        ctx = torch.cuda.stream(self._stream) if self.cuda else _Null()
+        with ctx:
+            chunks, in_splits = [], []
+            for b in range(self.world):
+                nb = 0
+                for patch, _, _ in self.send_order[b]:
+                    buf, n = self.cloud.migratePack(patch)
+                    if n:
+                        chunks.append(self._wrap(buf, n * STRIDE))
+                    nb += n
+                in_splits.append(nb * STRIDE)
+            self.sent += sum(in_splits) // STRIDE
+            dev = "cuda" if self.cuda else "cpu"
+            send = torch.cat(chunks) if chunks else torch.empty(0, dtype=torch.float64, device=dev)
+            out_splits = [int(allv[b, self.rank].sum().item()) * STRIDE for b in range(self.world)]
+            recv = torch.empty(sum(out_splits), dtype=torch.float64, device=dev)
+            dist.all_to_all_single(recv, send, out_splits, in_splits, group=self.data_group)
+            off = 0
+            for b in range(self.world):
+                for slot, (patch, _, _) in enumerate(self.recv_order[b]):
+                    n = int(allv[b, self.rank, slot].item())
+                    if n:
+                        ptr = C.cast(recv.data_ptr() + off * 8, C.POINTER(C.c_double))
+                        self.cloud.migrateUnpack(patch, ptr, n)
+                        off += n * STRIDE
+            self.cloud.moveReceived()
+            if self.cuda:
+                self._stream.synchronize()  # recv must outlive the kernels reading it
+        return total
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64):
+    """uniGasCloud::evolve across ranks: the phases of ugf_step with the transfer loop after the move."""
+    for _ in range(n_steps):
+        if inflow:
+            cloud.controlBeforeMove()
+        cloud.move()
+        for _r in range(max_rounds):
+            if exchanger.exchange() == 0:
+                break
+        else:
+            raise RuntimeError("parcel migration did not settle")
+        cloud.buildCellOccupancy()
+        cloud.collide()
+        cloud.relax()
+        cloud.accumulateFields()
+        cloud.endStep()

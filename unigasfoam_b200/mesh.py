@@ -1,0 +1,403 @@
+"""polyMesh stand-ins for blockMesh and decomposePar (host side, numpy).
+
+`PolyMesh` holds exactly what OpenFOAM's polyMesh exposes to uniGasFoam's particle loop
+(points, faces, owner, neighbour, patches) plus the derived geometry primitiveMesh
+computes (faceAreas, faceCentres, cellVolumes, cellCentres), laid out as include/ugf.h's
+`ugf_mesh` wants it.  `structured_block` is the blockMesh stand-in (one hex block with an
+arbitrary point map); `decompose` is the decomposePar stand-in (any cell->rank map,
+processor patches on the cuts, cyclic pairs split into processorCyclic patches).
+
+Reference: tutorials/uniGasFoam/*/system/blockMeshDict, decomposeParDict; face ordering
+follows OpenFOAM's (internal faces upper-triangular by owner/neighbour, then patches).
+"""
+from dataclasses import dataclass, field
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+@dataclass
+class Patch:
+    name: str
+    kind: str  # wall | symmetry | symmetryPlane | cyclic | empty | processor | patch
+    start: int
+    size: int
+    partner: int = -1  # cyclic: partner patch index; processor: peer rank
+    separation: tuple = (0.0, 0.0, 0.0)
+    peer_patch: int = -1  # processor: index of the matching patch on the peer rank
+    tag: tuple = ()
+
+
+@dataclass
+class PolyMesh:
+    points: np.ndarray  # [nPoints,3]
+    face_point_offsets: np.ndarray  # [nFaces+1]
+    face_points: np.ndarray
+    owner: np.ndarray  # [nFaces]
+    neighbour: np.ndarray  # [nInternal]
+    patches: list
+    solution_d: tuple = (1, 1, 1)
+    # derived
+    face_areas: np.ndarray = None
+    face_centres: np.ndarray = None
+    cell_volumes: np.ndarray = None
+    cell_centres: np.ndarray = None
+    cell_face_offsets: np.ndarray = None
+    cell_faces: np.ndarray = None
+    cell_bb_min: np.ndarray = None
+    cell_bb_max: np.ndarray = None
+    shape: tuple = None  # (nx, ny, nz) for structured blocks
+    cell_map: np.ndarray = None  # decompose: local cell -> global cell
+    meta_axis_aligned: bool = False  # every cell is an axis-aligned box
+    cell_quads: np.ndarray = None  # extruded 2-D meshes: [nCells,4,2] xy corners, counter-clockwise
+    _keep: list = field(default_factory=list, repr=False)
+
+    @property
+    def n_cells(self):
+        return int(self.owner.max()) + 1 if self.cell_volumes is None else len(self.cell_volumes)
+
+    @property
+    def n_faces(self):
+        return len(self.owner)
+
+    @property
+    def n_internal(self):
+        return len(self.neighbour)
+
+    @property
+    def n_boundary_faces(self):
+        return self.n_faces - self.n_internal
+
+    def patch_index(self, name):
+        for i, p in enumerate(self.patches):
+            if p.name == name:
+                return i
+        raise KeyError(name)
+
+    def boundary_face_patch(self):
+        out = np.full(self.n_boundary_faces, -1, np.int32)
+        for i, p in enumerate(self.patches):
+            out[p.start - self.n_internal : p.start - self.n_internal + p.size] = i
+        return out
+
+    # -- primitiveMesh geometry ------------------------------------------------
+    def compute_geometry(self, n_cells=None):
+        pts = self.points
+        off = self.face_point_offsets
+        nF = len(self.owner)
+        nv = np.diff(off)
+        Sf = np.zeros((nF, 3))
+        Cf = np.zeros((nF, 3))
+        for k in np.unique(nv):  # faces grouped by vertex count (all quads for hex blocks)
+            sel = np.nonzero(nv == k)[0]
+            idx = off[sel][:, None] + np.arange(k)[None, :]
+            P = pts[self.face_points[idx]]  # [n,k,3]
+            if k == 3:
+                n2 = np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
+                Sf[sel] = 0.5 * n2
+                Cf[sel] = P.mean(axis=1)
+                continue
+            fc = P.mean(axis=1)
+            sumN = np.zeros((len(sel), 3))
+            sumA = np.zeros(len(sel))
+            sumAc = np.zeros((len(sel), 3))
+            for t in range(k):
+                a, b = P[:, t], P[:, (t + 1) % k]
+                n = np.cross(b - a, fc - a)
+                c = a + b + fc
+                mag = np.linalg.norm(n, axis=1)
+                sumN += n
+                sumA += mag
+                sumAc += mag[:, None] * c
+            Sf[sel] = 0.5 * sumN
+            Cf[sel] = sumAc / (3.0 * sumA[:, None])
+        self.face_areas, self.face_centres = Sf, Cf
+        nI = len(self.neighbour)
+        nC = n_cells if n_cells is not None else int(self.owner.max()) + 1
+        # cell -> faces CSR, faces ascending within a cell
+        cells = np.concatenate([self.owner, self.neighbour])
+        faces = np.concatenate([np.arange(nF), np.arange(nI)])
+        order = np.lexsort((faces, cells))
+        self.cell_faces = faces[order].astype(np.int32)
+        counts = np.bincount(cells, minlength=nC)
+        self.cell_face_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        # cell centres / volumes by pyramid decomposition
+        cEst = np.zeros((nC, 3))
+        np.add.at(cEst, self.owner, Cf)
+        np.add.at(cEst, self.neighbour, Cf[:nI])
+        cEst /= counts[:, None]
+        vol3 = np.zeros(nC)
+        cc = np.zeros((nC, 3))
+        pyrO = np.einsum("ij,ij->i", Sf, Cf - cEst[self.owner])
+        pcO = 0.75 * Cf + 0.25 * cEst[self.owner]
+        np.add.at(vol3, self.owner, pyrO)
+        np.add.at(cc, self.owner, pyrO[:, None] * pcO)
+        pyrN = np.einsum("ij,ij->i", Sf[:nI], cEst[self.neighbour] - Cf[:nI])
+        pcN = 0.75 * Cf[:nI] + 0.25 * cEst[self.neighbour]
+        np.add.at(vol3, self.neighbour, pyrN)
+        np.add.at(cc, self.neighbour, pyrN[:, None] * pcN)
+        self.cell_centres = cc / vol3[:, None]
+        self.cell_volumes = vol3 / 3.0
+        # bounding box over cellPoints (noTimeCounter.C:112-127)
+        bbmin = np.full((nC, 3), np.inf)
+        bbmax = np.full((nC, 3), -np.inf)
+        fp_face = np.repeat(np.arange(nF), nv)
+        fp_pts = pts[self.face_points]
+        np.minimum.at(bbmin, self.owner[fp_face], fp_pts)
+        np.maximum.at(bbmax, self.owner[fp_face], fp_pts)
+        intm = fp_face < nI
+        np.minimum.at(bbmin, self.neighbour[fp_face[intm]], fp_pts[intm])
+        np.maximum.at(bbmax, self.neighbour[fp_face[intm]], fp_pts[intm])
+        self.cell_bb_min, self.cell_bb_max = bbmin, bbmax
+        return self
+
+    # -- C view -------------------------------------------------------------------
+    def as_c(self):
+        """ugf_mesh struct over contiguous copies (kept alive on self)."""
+        def f64(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self._keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_double))
+
+        def i32(a):
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            self._keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+        self._keep.clear()
+        m = _capi.Mesh()
+        m.nCells, m.nFaces, m.nInternalFaces = self.n_cells, self.n_faces, self.n_internal
+        m.nPatches, m.nPoints = len(self.patches), len(self.points)
+        m.owner, m.neighbour = i32(self.owner), i32(self.neighbour)
+        m.faceAreas, m.faceCentres = f64(self.face_areas), f64(self.face_centres)
+        m.cellFaceOffsets, m.cellFaces = i32(self.cell_face_offsets), i32(self.cell_faces)
+        m.cellVolumes, m.cellCentres = f64(self.cell_volumes), f64(self.cell_centres)
+        m.cellBbMin, m.cellBbMax = f64(self.cell_bb_min), f64(self.cell_bb_max)
+        m.patchStart = i32([p.start for p in self.patches])
+        m.patchSize = i32([p.size for p in self.patches])
+        m.patchKind = i32([_capi.PATCH_KIND[p.kind] for p in self.patches])
+        m.patchPartner = i32([p.partner for p in self.patches])
+        m.patchSeparation = f64(np.array([p.separation for p in self.patches], dtype=np.float64).reshape(-1, 3))
+        m.points = f64(self.points)
+        m.facePointOffsets, m.facePoints = i32(self.face_point_offsets), i32(self.face_points)
+        return m
+
+
+def structured_block(nx, ny, nz, point_map, patch_kinds, cyclic_pairs=(), solution_d=(1, 1, 1)):
+    """One hex block of nx*ny*nz cells.
+
+    point_map(I, J, K) -> (x, y, z) arrays for integer vertex indices.
+    patch_kinds: dict side -> (name, kind) for sides xMin,xMax,yMin,yMax,zMin,zMax.
+    cyclic_pairs: iterable of (sideA, sideB) made cyclic partners (translational).
+    """
+    K, J, I = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    X, Y, Z = point_map(I.astype(np.float64), J.astype(np.float64), K.astype(np.float64))
+    points = np.stack([np.broadcast_to(X, I.shape), np.broadcast_to(Y, I.shape), np.broadcast_to(Z, I.shape)], axis=-1).reshape(-1, 3)
+
+    def pid(i, j, k):
+        return i + (nx + 1) * (j + (ny + 1) * k)
+
+    def cid(i, j, k):
+        return i + nx * (j + ny * k)
+
+    def grid(ni, nj, nk):
+        k, j, i = np.meshgrid(np.arange(nk), np.arange(nj), np.arange(ni), indexing="ij")
+        return i.ravel(), j.ravel(), k.ravel()
+
+    def xface(i, j, k):  # normal +x
+        return np.stack([pid(i, j, k), pid(i, j + 1, k), pid(i, j + 1, k + 1), pid(i, j, k + 1)], axis=1)
+
+    def yface(i, j, k):  # normal +y
+        return np.stack([pid(i, j, k), pid(i, j, k + 1), pid(i + 1, j, k + 1), pid(i + 1, j, k)], axis=1)
+
+    def zface(i, j, k):  # normal +z
+        return np.stack([pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)], axis=1)
+
+    own, nei, fpts = [], [], []
+    i, j, k = grid(nx - 1, ny, nz)
+    own.append(cid(i, j, k)); nei.append(cid(i + 1, j, k)); fpts.append(xface(i + 1, j, k))
+    i, j, k = grid(nx, ny - 1, nz)
+    own.append(cid(i, j, k)); nei.append(cid(i, j + 1, k)); fpts.append(yface(i, j + 1, k))
+    i, j, k = grid(nx, ny, nz - 1)
+    own.append(cid(i, j, k)); nei.append(cid(i, j, k + 1)); fpts.append(zface(i, j, k + 1))
+    own = np.concatenate(own); nei = np.concatenate(nei); fpts = np.concatenate(fpts)
+    order = np.lexsort((nei, own))  # upper-triangular ordering
+    own, nei, fpts = own[order], nei[order], fpts[order]
+    n_internal = len(own)
+
+    sides = {}
+    j, k = grid(1, ny, nz)[1:]
+    z0 = np.zeros_like(j)
+    sides["xMin"] = (cid(z0, j, k), xface(z0, j, k)[:, ::-1])
+    sides["xMax"] = (cid(z0 + nx - 1, j, k), xface(z0 + nx, j, k))
+    i, _, k = grid(nx, 1, nz)
+    z0 = np.zeros_like(i)
+    sides["yMin"] = (cid(i, z0, k), yface(i, z0, k)[:, ::-1])
+    sides["yMax"] = (cid(i, z0 + ny - 1, k), yface(i, z0 + ny, k))
+    i, j, _ = grid(nx, ny, 1)
+    z0 = np.zeros_like(i)
+    sides["zMin"] = (cid(i, j, z0), zface(i, j, z0)[:, ::-1])
+    sides["zMax"] = (cid(i, j, z0 + nz - 1), zface(i, j, z0 + nz))
+
+    patches, b_own, b_fpts = [], [], []
+    start = n_internal
+    side_patch = {}
+    for side in ("xMin", "xMax", "yMin", "yMax", "zMin", "zMax"):
+        name, kind = patch_kinds[side]
+        o, f = sides[side]
+        side_patch[side] = len(patches)
+        patches.append(Patch(name=name, kind=kind, start=start, size=len(o)))
+        b_own.append(o); b_fpts.append(f)
+        start += len(o)
+    owner = np.concatenate([own] + b_own).astype(np.int32)
+    fpts = np.concatenate([fpts] + b_fpts).astype(np.int32)
+    mesh = PolyMesh(
+        points=points,
+        face_point_offsets=(4 * np.arange(len(owner) + 1)).astype(np.int32),
+        face_points=fpts.ravel(),
+        owner=owner,
+        neighbour=nei.astype(np.int32),
+        patches=patches,
+        solution_d=tuple(solution_d),
+        shape=(nx, ny, nz),
+    )
+    mesh.compute_geometry(n_cells=nx * ny * nz)
+    for a, b in cyclic_pairs:
+        pa, pb = side_patch[a], side_patch[b]
+        A, B = patches[pa], patches[pb]
+        assert A.kind == "cyclic" and B.kind == "cyclic" and A.size == B.size
+        sep = mesh.face_centres[B.start : B.start + B.size] - mesh.face_centres[A.start : A.start + A.size]
+        sepm = sep.mean(axis=0)
+        assert np.allclose(sep, sepm, rtol=0, atol=1e-9 * (np.abs(sepm).max() + 1e-300)), "cyclic pair is not translational"
+        A.partner, B.partner = pb, pa
+        A.separation, B.separation = tuple(sepm), tuple(-sepm)
+    return mesh
+
+
+def box_mesh(nx, ny, nz, lx, ly, lz, patch_kinds=None, cyclic_pairs=(), solution_d=(1, 1, 1), origin=(0.0, 0.0, 0.0)):
+    """Uniform Cartesian block (blockMesh with one hex and simpleGrading 1)."""
+    if patch_kinds is None:
+        patch_kinds = {s: (s, "wall") for s in ("xMin", "xMax", "yMin", "yMax", "zMin", "zMax")}
+
+    def pm(I, J, K):
+        return origin[0] + lx * I / nx, origin[1] + ly * J / ny, origin[2] + lz * K / nz
+
+    return structured_block(nx, ny, nz, pm, patch_kinds, cyclic_pairs, solution_d)
+
+
+def slab_partition(mesh, n_ranks, axis=0):
+    """Block partition of a structured mesh into n_ranks slabs along `axis` (decomposePar simple)."""
+    nx, ny, nz = mesh.shape
+    c = np.arange(nx * ny * nz)
+    ijk = (c % nx, (c // nx) % ny, c // (nx * ny))
+    n = mesh.shape[axis]
+    return np.minimum((ijk[axis] * n_ranks) // n, n_ranks - 1).astype(np.int32)
+
+
+def decompose(mesh, cell_rank, n_ranks):
+    """Split `mesh` into n_ranks sub-meshes with processor patches (decomposePar stand-in).
+
+    Returns a list of PolyMesh; each has `cell_map` (local -> global cell) and processor
+    patches whose `partner` is the peer rank and `peer_patch` the matching patch index there.
+    Faces of matching processor patches are in the same order on both sides.
+    """
+    nI = mesh.n_internal
+    own, nei = mesh.owner, mesh.neighbour
+    off = mesh.face_point_offsets
+    subs = []
+    for r in range(n_ranks):
+        local_cells = np.nonzero(cell_rank == r)[0]
+        g2l = np.full(mesh.n_cells, -1, np.int64)
+        g2l[local_cells] = np.arange(len(local_cells))
+        ro, rn = cell_rank[own[:nI]], cell_rank[nei]
+        # faces: (global face, flip) lists per local patch
+        f_int = np.nonzero((ro == r) & (rn == r))[0]
+        face_ids = [f_int]
+        flips = [np.zeros(len(f_int), bool)]
+        l_own = [g2l[own[f_int]]]
+        l_nei = g2l[nei[f_int]]
+        patches = []
+        start = len(f_int)
+        proc_groups = {}  # (peer, tag) -> (faces, flip, sep)
+        for pi, p in enumerate(mesh.patches):
+            f = np.arange(p.start, p.start + p.size)
+            mine = cell_rank[own[f]] == r
+            if p.kind == "cyclic":
+                q = mesh.patches[p.partner]
+                peer = cell_rank[own[q.start : q.start + q.size]]
+                stay = mine & (peer == r)
+                cross = mine & (peer != r)
+                for b in np.unique(peer[cross]):
+                    s = cross & (peer == b)
+                    proc_groups[(int(b), ("c", pi, p.partner))] = (f[s], np.zeros(s.sum(), bool), p.separation)
+                mine = stay
+            fl = f[mine]
+            patches.append(Patch(p.name, p.kind, start, len(fl), p.partner, p.separation))
+            face_ids.append(fl); flips.append(np.zeros(len(fl), bool)); l_own.append(g2l[own[fl]])
+            start += len(fl)
+        cutO = np.nonzero((ro == r) & (rn != r))[0]
+        cutN = np.nonzero((ro != r) & (rn == r))[0]
+        for b in np.unique(np.concatenate([rn[cutO], ro[cutN]])):
+            fo = cutO[rn[cutO] == b]
+            fn = cutN[ro[cutN] == b]
+            f = np.concatenate([fo, fn])
+            fl = np.concatenate([np.zeros(len(fo), bool), np.ones(len(fn), bool)])
+            o = np.argsort(f, kind="stable")
+            proc_groups[(int(b), ("i",))] = (f[o], fl[o], (0.0, 0.0, 0.0))
+        for (peer, tag) in sorted(proc_groups, key=lambda k: (k[0], k[1])):
+            f, fl, sep = proc_groups[(peer, tag)]
+            patches.append(Patch(f"procBoundary{r}to{peer}" + ("" if tag[0] == "i" else f"through{mesh.patches[tag[1]].name}"),
+                                 "processor", start, len(f), peer, tuple(sep), tag=tag))
+            face_ids.append(f); flips.append(fl)
+            l_own.append(np.where(fl, g2l[nei[np.minimum(f, nI - 1)]] if nI else -1, g2l[own[f]]))
+            start += len(f)
+        gf = np.concatenate(face_ids)
+        flip = np.concatenate(flips)
+        lo = np.concatenate(l_own).astype(np.int32)
+        # face vertex lists (reverse flipped faces so that the normal follows the new owner)
+        nv = np.diff(off)[gf]
+        assert (nv == nv[0]).all(), "decompose assumes a uniform vertex count per face"
+        k = int(nv[0])
+        verts = mesh.face_points[off[gf][:, None] + np.arange(k)[None, :]]
+        verts = np.where(flip[:, None], verts[:, ::-1], verts)
+        sub = PolyMesh(
+            points=mesh.points,
+            face_point_offsets=(k * np.arange(len(gf) + 1)).astype(np.int32),
+            face_points=verts.ravel().astype(np.int32),
+            owner=lo,
+            neighbour=l_nei.astype(np.int32),
+            patches=patches,
+            solution_d=mesh.solution_d,
+            cell_map=local_cells,
+        )
+        # geometry is inherited, not recomputed, so that every rank sees bit-identical planes
+        sgn = np.where(flip, -1.0, 1.0)[:, None]
+        sub.face_areas = mesh.face_areas[gf] * sgn
+        sub.face_centres = mesh.face_centres[gf]
+        nC = len(local_cells)
+        sub.cell_volumes = mesh.cell_volumes[local_cells]
+        sub.cell_centres = mesh.cell_centres[local_cells]
+        sub.cell_bb_min = mesh.cell_bb_min[local_cells]
+        sub.cell_bb_max = mesh.cell_bb_max[local_cells]
+        cells = np.concatenate([sub.owner, sub.neighbour])
+        faces = np.concatenate([np.arange(len(sub.owner)), np.arange(len(sub.neighbour))])
+        order = np.lexsort((faces, cells))
+        sub.cell_faces = faces[order].astype(np.int32)
+        sub.cell_face_offsets = np.concatenate([[0], np.cumsum(np.bincount(cells, minlength=nC))]).astype(np.int32)
+        subs.append(sub)
+    # match processor patches across ranks
+    for r, sub in enumerate(subs):
+        for p in sub.patches:
+            if p.kind != "processor":
+                continue
+            want = ("i",) if p.tag[0] == "i" else ("c", p.tag[2], p.tag[1])
+            peer = subs[p.partner]
+            for qi, q in enumerate(peer.patches):
+                if q.kind == "processor" and q.partner == r and q.tag == want:
+                    p.peer_patch = qi
+                    assert q.size == p.size
+                    break
+            assert p.peer_patch >= 0
+    return subs
