@@ -152,7 +152,7 @@ struct ugfo_handle {
     std::vector<InflowPatch> inflows;
 
     // cloud
-    std::vector<Parcel> P;
+    std::vector<Parcel> P, Pswap;
     int64_t nBeforeInsert = 0;
     int64_t receivedStart = -1;
     std::vector<int32_t> occOff, occIds;  // cell occupancy CSR
@@ -639,13 +639,43 @@ void doInflow(ugfo_handle& h) {
 // ---------------------------------------------------------------------------------
 void buildOccupancy(ugfo_handle& h) {
     const int nC = h.nCells;
-    h.occOff.assign(nC + 1, 0);
     const int64_t n = (int64_t)h.P.size();
-    for (int64_t i = 0; i < n; ++i) if (h.P[i].cell >= 0) h.occOff[h.P[i].cell + 1]++;
-    for (int c = 0; c < nC; ++c) h.occOff[c + 1] += h.occOff[c];
-    h.occIds.resize(h.occOff[nC]);
-    std::vector<int32_t> cur(h.occOff.begin(), h.occOff.end() - 1);
-    for (int64_t i = 0; i < n; ++i) if (h.P[i].cell >= 0) h.occIds[cur[h.P[i].cell]++] = (int32_t)i;
+    h.occOff.assign(nC + 1, 0);
+#ifdef _OPENMP
+    const int nT = std::max(1, std::min(omp_get_max_threads(), (int)(n / 65536) + 1));
+#else
+    const int nT = 1;
+#endif
+    // stable parallel counting sort: thread t owns the t-th contiguous chunk of the array
+    std::vector<std::vector<int32_t>> hist(nT);
+#pragma omp parallel num_threads(nT)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        std::vector<int32_t>& H = hist[t];
+        H.assign(nC, 0);
+        const int64_t b = n * t / nT, e = n * (t + 1) / nT;
+        for (int64_t i = b; i < e; ++i) if (h.P[i].cell >= 0) H[h.P[i].cell]++;
+#pragma omp barrier
+#pragma omp for schedule(static)
+        for (int c = 0; c < nC; ++c) {
+            int32_t run = 0;
+            for (int k = 0; k < nT; ++k) { const int32_t v = hist[k][c]; hist[k][c] = run; run += v; }
+            h.occOff[c + 1] = run;  // per-cell count, prefix-summed below
+        }
+#pragma omp single
+        {
+            for (int c = 0; c < nC; ++c) h.occOff[c + 1] += h.occOff[c];
+            h.occIds.resize(h.occOff[nC]);
+        }
+        for (int64_t i = b; i < e; ++i) {
+            const int c = h.P[i].cell;
+            if (c >= 0) h.occIds[h.occOff[c] + H[c]++] = (int32_t)i;
+        }
+    }
     h.occValid = true;
     h.occIdentity = false;
     h.cnt.nParcels = h.occOff[nC];
@@ -655,7 +685,8 @@ void reorder(ugfo_handle& h) {
     if (!h.occValid) buildOccupancy(h);
     if (h.occIdentity) return;
     const int64_t n = (int64_t)h.occIds.size();
-    std::vector<Parcel> Q(n);
+    std::vector<Parcel>& Q = h.Pswap;  // persistent second buffer (ping-pong), like the device path
+    Q.resize(n);
 #pragma omp parallel for schedule(static)
     for (int64_t j = 0; j < n; ++j) { Q[j] = h.P[h.occIds[j]]; h.occIds[j] = (int32_t)j; }
     h.P.swap(Q);

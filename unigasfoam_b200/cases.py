@@ -164,17 +164,36 @@ def closed_box(n=32, parcels=1_000_000, wall="specular", T0=300.0, number_densit
 
 
 def couette(nx=1000, ny=500, ppc=20, Kn=0.1, Tw=273.0, Uw=150.0, number_density=1e20, species=("Ar", ARGON_GUIDE),
-            Tref=273.0, courant=0.5, seed=2, n_ranks=1, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", **cp):
-    """Config 2: 2-D Couette flow, x cyclic, y walls diffuse at Tw moving at -+Uw, z empty; H = lambda/Kn."""
+            Tref=273.0, courant=0.5, seed=2, rank=0, n_ranks=1, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", **cp):
+    """Config 2: 2-D Couette flow, x cyclic, y walls diffuse at Tw moving at -+Uw, z empty; H = lambda/Kn.
+
+    n_ranks > 1 builds rank `rank`'s slab of a channel n_ranks*nx cells long (weak scaling: nx x ny cells per
+    rank): the x ends become processor patches to the neighbouring slabs, the periodic wrap a processorCyclic
+    pair with a +-n_ranks*Lx separation - what decomposePar makes of the cyclic channel."""
     name, sp = species
     lam = vhs_mean_free_path(number_density, Tw, sp, Tref)
     H = lam / Kn
     dy = H / ny
     dx = dy
     Lx = nx * dx
-    kinds = {"xMin": ("left", "cyclic"), "xMax": ("right", "cyclic"), "yMin": ("bottom", "wall"), "yMax": ("top", "wall"),
-             "zMin": ("back", "empty"), "zMax": ("front", "empty")}
-    m = _mesh.box_mesh(nx, ny, 1, Lx, H, dx, kinds, cyclic_pairs=[("xMin", "xMax")], solution_d=(1, 1, 0))
+    if n_ranks == 1:
+        kinds = {"xMin": ("left", "cyclic"), "xMax": ("right", "cyclic"), "yMin": ("bottom", "wall"), "yMax": ("top", "wall"),
+                 "zMin": ("back", "empty"), "zMax": ("front", "empty")}
+        m = _mesh.box_mesh(nx, ny, 1, Lx, H, dx, kinds, cyclic_pairs=[("xMin", "xMax")], solution_d=(1, 1, 0))
+    else:
+        lo, hi = (rank - 1) % n_ranks, (rank + 1) % n_ranks
+        kinds = {"xMin": (f"procBoundary{rank}to{lo}lo", "processor"), "xMax": (f"procBoundary{rank}to{hi}hi", "processor"),
+                 "yMin": ("bottom", "wall"), "yMax": ("top", "wall"), "zMin": ("back", "empty"), "zMax": ("front", "empty")}
+        m = _mesh.box_mesh(nx, ny, 1, Lx, H, dx, kinds, solution_d=(1, 1, 0), origin=(rank * Lx, 0.0, 0.0))
+        pl, ph = m.patches[0], m.patches[1]
+        pl.partner, ph.partner = lo, hi
+        pl.tag, ph.tag = ("c", 0, 1), ("c", 1, 0)  # my xMin matches the peer's xMax and vice versa
+        pl.peer_patch, ph.peer_patch = 1, 0
+        if rank == 0:
+            pl.separation = (n_ranks * Lx, 0.0, 0.0)
+        if rank == n_ranks - 1:
+            ph.separation = (-n_ranks * Lx, 0.0, 0.0)
+        seed = seed + 7919 * rank
     m.meta_axis_aligned = True
     nParticle = number_density * dx * dy * dx / ppc
     rng = np.random.default_rng(seed)
