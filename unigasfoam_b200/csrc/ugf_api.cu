@@ -413,10 +413,20 @@ int do_accumulate(ugf_handle* h) {
         LAUNCHED();
         h->sampleCounter = 0;
     }
-    const long long nb = (long long)h->nBFaces * UGF_NBM;
-    if (nb > 0 && h->cfg.measureWalls) {
-        accumulate_walls_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(h->cfg.deltaT, accumulate, nb, h->dBm, h->dBacc);
-        LAUNCHED();
+    if (h->cfg.measureWalls) {
+        // only wall patches carry boundary measurements; merge adjacent wall patches into one launch
+        int p = 0;
+        while (p < h->nPatches) {
+            if (h->patchKind[p] != UGF_PATCH_WALL || h->patchSize[p] == 0) { ++p; continue; }
+            const long long first = h->patchesHost[p].startBfi;
+            long long last = first + h->patchSize[p];
+            int q = p + 1;
+            while (q < h->nPatches && h->patchKind[q] == UGF_PATCH_WALL && h->patchesHost[q].startBfi == last) { last += h->patchSize[q]; ++q; }
+            const long long cnt = (last - first) * UGF_NBM;
+            accumulate_walls_kernel<<<grid_for(cnt, 256), 256, 0, h->stream>>>(h->cfg.deltaT, accumulate, cnt, h->dBm + first * UGF_NBM, h->dBacc + first * UGF_NBM);
+            LAUNCHED();
+            p = q;
+        }
     }
     return 0;
 }

@@ -163,8 +163,82 @@ __device__ inline void collide_pair(const DevParams& prm, Stream& r, const DevSp
     }
 }
 
+// NTC candidate selection and collisions for one cell (noTimeCounter.C:164-312); the whole warp calls this.
+// pu0..pt give random access to the cell's staged velocities / ERot / typeId (shared or global memory).
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(CELL_THREADS) cell_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ CellArgs a) {
+__device__ __noinline__ void ntc_collide(const DevParams& prm, const CellArgs& a, int cell, int n, double* pu0, double* pu1, double* pu2,
+                                         double* pe, const uint8_t* pt, int lane, unsigned long long& wCand, int& myColl) {
+    const double sMaxOld = a.sigmaTcRMax[cell];
+    const double selectedPairs = 0.5 * n * (n - 1) * prm.nParticle * sMaxOld * prm.deltaT / a.vol[cell];
+    int nCand = (int)selectedPairs;
+    {
+        Stream rc(prm.seed, KIND_NTC, 0, a.step, (uint32_t)cell, 0xFFFFFFFFu);
+        if (rc.u01() < (selectedPairs - nCand)) nCand++;
+    }
+    if (nCand == 0) return;
+    if (lane == 0) wCand += (unsigned long long)nCand;
+    double localMax = sMaxOld;
+    for (int base = 0; base < nCand; base += 32) {
+        const int k = base + lane;
+        bool act = k < nCand;
+        Stream r(prm.seed, KIND_NTC, 0, a.step, (uint32_t)cell, (uint32_t)k);
+        int cP = -1, cQ = -2;
+        int tP = 0, tQ = 0;
+        if (act) {
+            cP = r.position(n);
+            do { cQ = r.position(n); } while (cP == cQ);
+            if (MULTI) { tP = pt[cP]; tQ = pt[cQ]; }
+            // electron-electron pairs are skipped (noTimeCounter.C:245-247)
+            if (prm.sp[tP].charge == -1 && prm.sp[tQ].charge == -1) act = false;
+        }
+        unsigned pending = __ballot_sync(0xffffffffu, act);
+        while (pending) {
+            const bool mine = (pending >> lane) & 1u;
+            bool blocked = false;
+            for (unsigned mm = pending; mm; mm &= mm - 1) {
+                const int j = __ffs(mm) - 1;
+                const int pj = __shfl_sync(0xffffffffu, cP, j);
+                const int qj = __shfl_sync(0xffffffffu, cQ, j);
+                if (j < lane && (pj == cP || pj == cQ || qj == cP || qj == cQ)) blocked = true;
+            }
+            const bool ready = mine && !blocked;
+            if (ready) {
+                const DevSpecies& A = prm.sp[tP];
+                const DevSpecies& B = prm.sp[tQ];
+                double UP[3] = {pu0[cP], pu1[cP], pu2[cP]};
+                double UQ[3] = {pu0[cQ], pu1[cQ], pu2[cQ]};
+                const double d0 = UP[0] - UQ[0], d1 = UP[1] - UQ[1], d2 = UP[2] - UQ[2];
+                const double cR2 = d0 * d0 + d1 * d1 + d2 * d2;
+                double sig = 0.0;
+                if (!(cR2 < VSMALL)) {  // variableHardSphere.C:72-115
+                    const double dPQ = 0.5 * (A.d + B.d);
+                    const double omegaPQ = 0.5 * (A.omega + B.omega);
+                    const double mR = A.mass * B.mass / (A.mass + B.mass);
+                    const double sigmaTPQ = PI * dPQ * dPQ * pow(2.0 * kB * prm.Tref / (mR * cR2), omegaPQ - 0.5)
+                                            * prm.pairInvGamma[tP * UGF_MAX_SPECIES + tQ];
+                    sig = sigmaTPQ * sqrt(cR2);
+                }
+                if (sig > localMax) localMax = sig;
+                if ((sig / sMaxOld) > r.u01()) {
+                    double eP = 0.0, eQ = 0.0;
+                    if (HAS_ROT) { eP = pe[cP]; eQ = pe[cQ]; }
+                    collide_pair(prm, r, A, B, UP, UQ, eP, eQ);
+                    pu0[cP] = UP[0]; pu1[cP] = UP[1]; pu2[cP] = UP[2];
+                    pu0[cQ] = UQ[0]; pu1[cQ] = UQ[1]; pu2[cQ] = UQ[2];
+                    if (HAS_ROT) { pe[cP] = eP; pe[cQ] = eQ; }
+                    myColl++;
+                }
+            }
+            __syncwarp();
+            pending &= ~__ballot_sync(0xffffffffu, ready);
+        }
+    }
+    localMax = warp_max(localMax);
+    if (lane == 0 && localMax > sMaxOld) a.sigmaTcRMax[cell] = localMax;
+}
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ CellArgs a) {
     extern __shared__ double smemD[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -226,8 +300,11 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_kernel(const __grid_constan
         // ---- phase B: cell moments (pre-collision state) ----------------------------------------------
         if (a.doSample) {
             for (int s = 0; s < nS; ++s) {
-                double cnt = 0, su = 0, sv = 0, sw = 0, suu = 0, suv = 0, suw = 0, svv = 0, svw = 0, sww = 0, scc = 0;
-                double scu = 0, scv = 0, scw = 0, se = 0, seu = 0, sev = 0, sew = 0;
+                // value index: 0-2 U, 3-8 uu uv uw vv vw ww, 9 cc, 10-12 cc*U, 13 count, 14-17 ERot, ERot*U
+                constexpr int LOG = HAS_ROT ? 5 : 4;
+                double acc[1 << LOG];
+#pragma unroll
+                for (int k = 0; k < (1 << LOG); ++k) acc[k] = 0.0;
                 for (int j = lane; j < n; j += 32) {
                     double u, v, w, e = 0.0;
                     int t = 0;
@@ -243,114 +320,32 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_kernel(const __grid_constan
                     }
                     if (MULTI && t != s) continue;
                     const double cc = u * u + v * v + w * w;
-                    cnt += 1.0;
-                    su += u; sv += v; sw += w;
-                    suu += u * u; suv += u * v; suw += u * w; svv += v * v; svw += v * w; sww += w * w;
-                    scc += cc;
-                    scu += cc * u; scv += cc * v; scw += cc * w;
-                    if (HAS_ROT) { se += e; seu += e * u; sev += e * v; sew += e * w; }
+                    acc[0] += u; acc[1] += v; acc[2] += w;
+                    acc[3] += u * u; acc[4] += u * v; acc[5] += u * w; acc[6] += v * v; acc[7] += v * w; acc[8] += w * w;
+                    acc[9] += cc;
+                    acc[10] += cc * u; acc[11] += cc * v; acc[12] += cc * w;
+                    acc[13] += 1.0;
+                    if (HAS_ROT) { acc[14] += e; acc[15] += e * u; acc[16] += e * v; acc[17] += e * w; }
                 }
-                cnt = MULTI ? warp_sum(cnt) : (double)n;
-                su = warp_sum(su); sv = warp_sum(sv); sw = warp_sum(sw);
-                suu = warp_sum(suu); suv = warp_sum(suv); suw = warp_sum(suw);
-                svv = warp_sum(svv); svw = warp_sum(svw); sww = warp_sum(sww);
-                scc = warp_sum(scc);
-                scu = warp_sum(scu); scv = warp_sum(scv); scw = warp_sum(scw);
-                if (HAS_ROT) { se = warp_sum(se); seu = warp_sum(seu); sev = warp_sum(sev); sew = warp_sum(sew); }
-                double o = 0.0;  // lane k holds moment slot k
-                o = (lane == 0 || lane == 1) ? cnt : o;
-                o = (lane == 2 || lane == 5) ? su : o;
-                o = (lane == 3 || lane == 6) ? sv : o;
-                o = (lane == 4 || lane == 7) ? sw : o;
-                o = (lane == 8) ? suu : o;
-                o = (lane == 9) ? suv : o;
-                o = (lane == 10) ? suw : o;
-                o = (lane == 11) ? svv : o;
-                o = (lane == 12) ? svw : o;
-                o = (lane == 13) ? sww : o;
-                o = (lane == 14) ? scc : o;
-                o = (lane == 15) ? scu : o;
-                o = (lane == 16) ? scv : o;
-                o = (lane == 17) ? scw : o;
-                if (HAS_ROT) {
-                    o = (lane == 18) ? se : o;
-                    o = (lane == 19) ? seu : o;
-                    o = (lane == 20) ? sev : o;
-                    o = (lane == 21) ? sew : o;
-                }
-                o = (lane == 26) ? cnt * prm.sp[s].E0 : o;
+                const double tot = warp_reduce_transpose<LOG>(acc, lane);  // lane l: total of value l
+                // lane k writes moment slot k (DESIGN.md section moments): pull the value that slot needs
+                int src = -1;
+                if (lane < 2) src = 13;
+                else if (lane < 5) src = lane - 2;
+                else if (lane < 8) src = lane - 5;
+                else if (lane < 18) src = lane - 5;
+                else if (lane < 22) src = HAS_ROT ? lane - 4 : -1;
+                else if (lane == 26) src = 13;
+                double o = __shfl_sync(0xffffffffu, tot, src & 31);
+                if (src < 0) o = 0.0;
+                if (lane == 26) o = o * prm.sp[s].E0;
                 a.mom[((size_t)cell * nS + s) * UGF_NMOM + lane] = o;
             }
         }
 
-        // ---- phase C: NTC collisions (noTimeCounter.C:164-312) ------------------------------------------
+        // ---- phase C: NTC collisions (noTimeCounter.C:164-312), out of line to keep the streaming part lean ----
         if (collideHere) {
-            const double sMaxOld = a.sigmaTcRMax[cell];
-            const double selectedPairs = 0.5 * n * (n - 1) * prm.nParticle * sMaxOld * prm.deltaT / a.vol[cell];
-            int nCand = (int)selectedPairs;
-            {
-                Stream rc(prm.seed, KIND_NTC, 0, a.step, (uint32_t)cell, 0xFFFFFFFFu);
-                if (rc.u01() < (selectedPairs - nCand)) nCand++;
-            }
-            if (lane == 0) wCand += (unsigned long long)nCand;
-            double localMax = sMaxOld;
-            for (int base = 0; base < nCand; base += 32) {
-                const int k = base + lane;
-                bool act = k < nCand;
-                Stream r(prm.seed, KIND_NTC, 0, a.step, (uint32_t)cell, (uint32_t)k);
-                int cP = -1, cQ = -2;
-                int tP = 0, tQ = 0;
-                if (act) {
-                    cP = r.position(n);
-                    do { cQ = r.position(n); } while (cP == cQ);
-                    if (MULTI) { tP = pt[cP]; tQ = pt[cQ]; }
-                    // electron-electron pairs are skipped (noTimeCounter.C:245-247)
-                    if (prm.sp[tP].charge == -1 && prm.sp[tQ].charge == -1) act = false;
-                }
-                unsigned pending = __ballot_sync(0xffffffffu, act);
-                while (pending) {
-                    const bool mine = (pending >> lane) & 1u;
-                    bool blocked = false;
-                    for (unsigned mm = pending; mm; mm &= mm - 1) {
-                        const int j = __ffs(mm) - 1;
-                        const int pj = __shfl_sync(0xffffffffu, cP, j);
-                        const int qj = __shfl_sync(0xffffffffu, cQ, j);
-                        if (j < lane && (pj == cP || pj == cQ || qj == cP || qj == cQ)) blocked = true;
-                    }
-                    const bool ready = mine && !blocked;
-                    if (ready) {
-                        const DevSpecies& A = prm.sp[tP];
-                        const DevSpecies& B = prm.sp[tQ];
-                        double UP[3] = {pu0[cP], pu1[cP], pu2[cP]};
-                        double UQ[3] = {pu0[cQ], pu1[cQ], pu2[cQ]};
-                        const double d0 = UP[0] - UQ[0], d1 = UP[1] - UQ[1], d2 = UP[2] - UQ[2];
-                        const double cR2 = d0 * d0 + d1 * d1 + d2 * d2;
-                        double sig = 0.0;
-                        if (!(cR2 < VSMALL)) {  // variableHardSphere.C:72-115
-                            const double dPQ = 0.5 * (A.d + B.d);
-                            const double omegaPQ = 0.5 * (A.omega + B.omega);
-                            const double mR = A.mass * B.mass / (A.mass + B.mass);
-                            const double sigmaTPQ = PI * dPQ * dPQ * pow(2.0 * kB * prm.Tref / (mR * cR2), omegaPQ - 0.5)
-                                                    * prm.pairInvGamma[tP * UGF_MAX_SPECIES + tQ];
-                            sig = sigmaTPQ * sqrt(cR2);
-                        }
-                        if (sig > localMax) localMax = sig;
-                        if ((sig / sMaxOld) > r.u01()) {
-                            double eP = 0.0, eQ = 0.0;
-                            if (HAS_ROT) { eP = pe[cP]; eQ = pe[cQ]; }
-                            collide_pair(prm, r, A, B, UP, UQ, eP, eQ);
-                            pu0[cP] = UP[0]; pu1[cP] = UP[1]; pu2[cP] = UP[2];
-                            pu0[cQ] = UQ[0]; pu1[cQ] = UQ[1]; pu2[cQ] = UQ[2];
-                            if (HAS_ROT) { pe[cP] = eP; pe[cQ] = eQ; }
-                            myColl++;
-                        }
-                    }
-                    __syncwarp();
-                    pending &= ~__ballot_sync(0xffffffffu, ready);
-                }
-            }
-            localMax = warp_max(localMax);
-            if (lane == 0) a.sigmaTcRMax[cell] = localMax;
+            ntc_collide<HAS_ROT, MULTI>(prm, a, cell, n, pu0, pu1, pu2, pe, pt, lane, wCand, myColl);
 
             // ---- phase D: write the collided velocities to their final place -------------------------------
             if (useSmem) {

@@ -96,4 +96,27 @@ __device__ __forceinline__ double warp_max(double v) {
 
 __device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
+// Transposing warp reduction: every lane brings 2^LOG partial sums; on return lane l holds the warp total of
+// value (l mod 2^LOG).  Costs 2^LOG - 1 (+1 if LOG < 5) 64-bit shuffles instead of 5 * 2^LOG for one butterfly
+// per value: at each step a lane keeps half of its values and trades the other half with its partner.
+template <int LOG>
+__device__ __forceinline__ double warp_reduce_transpose(double (&v)[1 << LOG], int lane) {
+#pragma unroll
+    for (int s = 0; s < LOG; ++s) {
+        const int m = 1 << s;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int k = 0; k < ((1 << LOG) >> (s + 1)); ++k) {
+            const double a = v[2 * k], b = v[2 * k + 1];
+            const double send = up ? a : b;
+            const double keep = up ? b : a;
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    double r = v[0];
+#pragma unroll
+    for (int m = 1 << LOG; m < 32; m <<= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+    return r;
+}
+
 }  // namespace ugf

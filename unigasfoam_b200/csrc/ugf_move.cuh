@@ -132,42 +132,105 @@ struct MoveArgs {
     DevCounters* cnt;
 };
 
+enum { HIT_CHANGED_U = 1, HIT_DELETED = 2, HIT_STUCK = 8, HIT_MIGRATED = 16 };
+
+struct HitState {
+    double x[3], U[3], erot, sf;
+    int cell, nDraws, flags, nWall;
+};
+
+// Boundary-face interaction: the rare path of the tracking loop, kept out of line so that the hot loop
+// (internal-face hops) stays small in registers.  The parcel's Philox stream is rebuilt here at draw
+// position nDraws (counter-based: no state has to live across the hot loop).
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(256) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
+__device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& a, int bfi, int hitSlot, long long i, int type, HitState& st) {
+    const int patch = __ldg(&a.mesh.bfPatch[bfi]);
+    const DevPatch& pt = a.mesh.patches[patch];
+    const DevSpecies& sp = prm.sp[type];
+    if (pt.kind == UGF_PATCH_WALL) {
+        st.nWall++;
+        if (pt.wallModel == UGF_WALL_DELETION) {
+            st.cell = -1; st.flags |= HIT_DELETED;
+            return;
+        }
+        const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
+        double nw[3], fA;
+        unit_normal(pl, nw, fA);
+        WallPre pre;
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, st.U, st.erot, nw, fA, pre, false);
+        bool diffuse = (pt.wallModel == UGF_WALL_DIFFUSE);
+        if (pt.wallModel != UGF_WALL_SPECULAR) {
+            Stream r(prm.seed, KIND_MOVE, a.aux, a.step, (uint32_t)i, 0);
+            r.c3 = (uint32_t)(st.nDraws >> 1);
+            if (st.nDraws & 1) { r.block(); r.have = 1; }
+            if (pt.wallModel == UGF_WALL_MIXED) diffuse = (pt.diffuseFraction > r.u01());
+            if (diffuse) diffuse_reflection(r, sp, st.U, st.erot, nw, pt.T, pt.Uw);
+            st.nDraws = 2 * (int)r.c3 - r.have;
+        }
+        if (!diffuse) {
+            const double Un = dot3(st.U[0], st.U[1], st.U[2], nw[0], nw[1], nw[2]);
+            if (Un > 0.0) for (int k = 0; k < 3; ++k) st.U[k] = st.U[k] - 2.0 * Un * nw[k];
+        }
+        st.flags |= HIT_CHANGED_U;
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, st.U, st.erot, nw, fA, pre, true);
+    } else if (pt.kind == UGF_PATCH_SYMMETRY) {
+        const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
+        double nw[3], fA;
+        unit_normal(pl, nw, fA);
+        const double Un = dot3(st.U[0], st.U[1], st.U[2], nw[0], nw[1], nw[2]);
+        for (int k = 0; k < 3; ++k) st.U[k] = st.U[k] - 2.0 * Un * nw[k];
+        st.flags |= HIT_CHANGED_U;
+    } else if (pt.kind == UGF_PATCH_CYCLIC) {
+        st.cell = __ldg(&a.mesh.bfOwner[pt.partnerStartBfi + (bfi - pt.startBfi)]);
+        for (int k = 0; k < 3; ++k) st.x[k] = st.x[k] + pt.sep[k];
+    } else if (pt.kind == UGF_PATCH_PROCESSOR) {
+        for (int k = 0; k < 3; ++k) st.x[k] = st.x[k] + pt.sep[k];
+        st.cell = -2 - bfi;
+        st.flags |= HIT_MIGRATED;
+        if (a.sf) a.sf[i] = st.sf;
+        atomicAdd(&a.migCount[patch], 1);
+    } else if (pt.kind == UGF_PATCH_GENERIC) {
+        st.cell = -1; st.flags |= HIT_DELETED;
+    } else {
+        st.cell = -1; st.flags |= HIT_STUCK;
+    }
+}
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
     const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = *a.dN;
     const bool valid = i < n;
     int cell = -1;
-    int nDeleted = 0, nWall = 0, nStuck = 0, nMig = 0;
+    int flags = 0, nWall = 0;
     if (valid) cell = a.P.cell[i];
     if (valid && cell >= 0) {
-        double x[3] = {a.P.x[i], a.P.y[i], a.P.z[i]};
-        double U[3] = {a.P.ux[i], a.P.uy[i], a.P.uz[i]};
-        double erot = 0.0;
-        if (HAS_ROT) erot = a.P.erot[i];
-        int type = 0;
-        if (MULTI) type = a.P.type[i];
-        const DevSpecies& sp = prm.sp[type];
-        Stream r(prm.seed, KIND_MOVE, a.aux, a.step, (uint32_t)i, 0);
+        double x0 = a.P.x[i], x1 = a.P.y[i], x2 = a.P.z[i];
+        double U0 = a.P.ux[i], U1 = a.P.uy[i], U2 = a.P.uz[i];
+        int nDraws = 0;
         double sf = 0.0;
         if (a.useSfIn) sf = a.sf[i];
-        else if (i >= a.newFrom) sf = r.u01();  // U/parcels/uniGasParcel.C:47-53
-        bool changedU = false;
+        else if (i >= a.newFrom) {  // U/parcels/uniGasParcel.C:47-53
+            Stream r(prm.seed, KIND_MOVE, a.aux, a.step, (uint32_t)i, 0);
+            sf = r.u01();
+            nDraws = 1;
+        }
         const double dt = prm.deltaT;
+        const bool s0 = prm.solD[0] != 0, s1 = prm.solD[1] != 0, s2 = prm.solD[2] != 0;
         int iters = 0;
+        double erot = 0.0;
+        bool erotLoaded = false;
         while (cell >= 0 && sf < 1) {
             const double rem = 1 - sf;
             const double s = rem * dt;
-            double disp[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) disp[k] = prm.solD[k] ? s * U[k] : 0.0;  // constrainDirection
+            const double d0 = s0 ? s * U0 : 0.0, d1 = s1 ? s * U1 : 0.0, d2 = s2 ? s * U2 : 0.0;  // constrainDirection
             double lamMin = 1.0;
             int hit = -1;
-            const int jb = a.mesh.cfOff[cell], je = a.mesh.cfOff[cell + 1];
+            const int jb = __ldg(&a.mesh.cfOff[cell]), je = __ldg(&a.mesh.cfOff[cell + 1]);
             for (int j = jb; j < je; ++j) {
                 const double4 pl = load_plane(&a.mesh.plane[j]);
-                const double nd = pl.x * disp[0] + pl.y * disp[1] + pl.z * disp[2];
-                const double num = pl.w - (pl.x * x[0] + pl.y * x[1] + pl.z * x[2]);
+                const double nd = pl.x * d0 + pl.y * d1 + pl.z * d2;
+                const double num = pl.w - (pl.x * x0 + pl.y * x1 + pl.z * x2);
                 if (nd > 0) {
                     double lam = num / nd;
                     if (lam < 0) lam = 0;
@@ -175,87 +238,56 @@ __global__ void __launch_bounds__(256) move_kernel(const __grid_constant__ DevPa
                 }
             }
             if (hit < 0) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) x[k] = x[k] + disp[k];
+                x0 = x0 + d0; x1 = x1 + d1; x2 = x2 + d2;
                 sf = 1;
                 break;
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) x[k] = x[k] + lamMin * disp[k];
+            x0 = x0 + lamMin * d0; x1 = x1 + lamMin * d1; x2 = x2 + lamMin * d2;
             sf = sf + rem * lamMin;
             const int nb = __ldg(&a.mesh.nbr[hit]);
             if (nb >= 0) {
                 cell = nb;
             } else {
-                const int bfi = -nb - 1;
-                const int patch = __ldg(&a.mesh.bfPatch[bfi]);
-                const DevPatch& pt = a.mesh.patches[patch];
-                const double4 pl = load_plane(&a.mesh.plane[hit]);
-                if (pt.kind == UGF_PATCH_WALL) {
-                    nWall++;
-                    if (pt.wallModel == UGF_WALL_DELETION) {
-                        cell = -1; nDeleted++;
-                    } else {
-                        double nw[3], fA;
-                        unit_normal(pl, nw, fA);
-                        WallPre pre;
-                        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, U, erot, nw, fA, pre, false);
-                        bool diffuse = (pt.wallModel == UGF_WALL_DIFFUSE);
-                        if (pt.wallModel == UGF_WALL_MIXED) diffuse = (pt.diffuseFraction > r.u01());
-                        if (diffuse) {
-                            diffuse_reflection(r, sp, U, erot, nw, pt.T, pt.Uw);
-                        } else {
-                            const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
-                            if (Un > 0.0) for (int k = 0; k < 3; ++k) U[k] = U[k] - 2.0 * Un * nw[k];
-                        }
-                        changedU = true;
-                        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, U, erot, nw, fA, pre, true);
-                    }
-                } else if (pt.kind == UGF_PATCH_SYMMETRY) {
-                    double nw[3], fA;
-                    unit_normal(pl, nw, fA);
-                    const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
-                    for (int k = 0; k < 3; ++k) U[k] = U[k] - 2.0 * Un * nw[k];
-                    changedU = true;
-                } else if (pt.kind == UGF_PATCH_CYCLIC) {
-                    cell = __ldg(&a.mesh.bfOwner[pt.partnerStartBfi + (bfi - pt.startBfi)]);
-                    for (int k = 0; k < 3; ++k) x[k] = x[k] + pt.sep[k];
-                } else if (pt.kind == UGF_PATCH_PROCESSOR) {
-                    for (int k = 0; k < 3; ++k) x[k] = x[k] + pt.sep[k];
-                    cell = -2 - bfi;
-                    nMig++;
-                    if (a.sf) a.sf[i] = sf;
-                    atomicAdd(&a.migCount[patch], 1);
-                } else if (pt.kind == UGF_PATCH_GENERIC) {
-                    cell = -1; nDeleted++;
-                } else {
-                    cell = -1; nStuck++;
-                }
+                HitState st;
+                st.x[0] = x0; st.x[1] = x1; st.x[2] = x2;
+                st.U[0] = U0; st.U[1] = U1; st.U[2] = U2;
+                if (HAS_ROT && !erotLoaded) { erot = a.P.erot[i]; erotLoaded = true; }
+                st.erot = erot; st.sf = sf; st.cell = cell; st.nDraws = nDraws; st.flags = flags; st.nWall = nWall;
+                int type = 0;
+                if (MULTI) type = a.P.type[i];
+                boundary_hit<HAS_ROT, MULTI>(prm, a, -nb - 1, hit, i, type, st);
+                x0 = st.x[0]; x1 = st.x[1]; x2 = st.x[2];
+                U0 = st.U[0]; U1 = st.U[1]; U2 = st.U[2];
+                erot = st.erot; cell = st.cell; nDraws = st.nDraws; flags = st.flags; nWall = st.nWall;
             }
-            if (++iters > MAX_TRACK_ITERS) { cell = -1; nStuck++; break; }
+            if (++iters > MAX_TRACK_ITERS) { cell = -1; flags |= HIT_STUCK; break; }
         }
-        a.P.x[i] = x[0]; a.P.y[i] = x[1]; a.P.z[i] = x[2];
+        a.P.x[i] = x0; a.P.y[i] = x1; a.P.z[i] = x2;
         a.P.cell[i] = cell;
-        if (changedU) {
-            a.P.ux[i] = U[0]; a.P.uy[i] = U[1]; a.P.uz[i] = U[2];
+        if (flags & HIT_CHANGED_U) {
+            a.P.ux[i] = U0; a.P.uy[i] = U1; a.P.uz[i] = U2;
             if (HAS_ROT) a.P.erot[i] = erot;
         }
     }
     // histogram of destination cells, aggregated over lanes that landed in the same cell
+    const int lane = threadIdx.x & 31;
     const bool live = valid && cell >= 0;
     const unsigned liveMask = __ballot_sync(0xffffffffu, live);
     if (live) {
         const unsigned peers = __match_any_sync(liveMask, cell);
-        const int lane = threadIdx.x & 31;
         if (lane == __ffs(peers) - 1) atomicAdd(&a.cellCount[cell], __popc(peers));
     }
-    const int lane = threadIdx.x & 31;
-    const int sd = warp_sum_int(nDeleted), sw = warp_sum_int(nWall), ss = warp_sum_int(nStuck), sm = warp_sum_int(nMig);
-    if (lane == 0) {
-        if (sd) atomicAdd(&a.cnt->deleted, (unsigned long long)sd);
-        if (sw) atomicAdd(&a.cnt->wallHits, (unsigned long long)sw);
-        if (ss) atomicAdd(&a.cnt->stuck, (unsigned long long)ss);
-        if (sm) atomicAdd(&a.cnt->migrated, (unsigned long long)sm);
+    if (__any_sync(0xffffffffu, (flags | nWall) != 0)) {
+        const int sd = __popc(__ballot_sync(0xffffffffu, (flags & HIT_DELETED) != 0));
+        const int ss = __popc(__ballot_sync(0xffffffffu, (flags & HIT_STUCK) != 0));
+        const int sm = __popc(__ballot_sync(0xffffffffu, (flags & HIT_MIGRATED) != 0));
+        const int sw = warp_sum_int(nWall);
+        if (lane == 0) {
+            if (sd) atomicAdd(&a.cnt->deleted, (unsigned long long)sd);
+            if (ss) atomicAdd(&a.cnt->stuck, (unsigned long long)ss);
+            if (sm) atomicAdd(&a.cnt->migrated, (unsigned long long)sm);
+            if (sw) atomicAdd(&a.cnt->wallHits, (unsigned long long)sw);
+        }
     }
 }
 
