@@ -445,7 +445,9 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
         const double s = rem * dt;
         double disp[3];
         for (int k = 0; k < 3; ++k) disp[k] = h.cfg.solutionD[k] ? s * p.U[k] : 0.0;  // constrainDirection
-        double lamMin = 1.0;
+        // First face crossed: minimise lambda = num/nd over faces with nd > 0 (lambda clamped at 0).  Fractions are
+        // compared by cross-multiplication, so there is one division per hop; (bnum, bnd) = (1, 1) encodes "end of step".
+        double bnum = 1.0, bnd = 1.0;
         int hit = -1;
         bool hitFlip = false;
         const int c = p.cell;
@@ -454,22 +456,20 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
             const bool own = (h.owner[f] == c);
             const double* S = &h.Sf[3 * (size_t)f];
             const double* C = &h.Cf[3 * (size_t)f];
-            double nd = S[0] * disp[0] + S[1] * disp[1] + S[2] * disp[2];
-            double num = (S[0] * C[0] + S[1] * C[1] + S[2] * C[2]) - (S[0] * p.x[0] + S[1] * p.x[1] + S[2] * p.x[2]);
+            double nd = std::fma(S[2], disp[2], std::fma(S[1], disp[1], S[0] * disp[0]));
+            double num = (S[0] * C[0] + S[1] * C[1] + S[2] * C[2]) - std::fma(S[2], p.x[2], std::fma(S[1], p.x[1], S[0] * p.x[0]));
             if (!own) { nd = -nd; num = -num; }
-            if (nd > 0) {
-                double lam = num / nd;
-                if (lam < 0) lam = 0;
-                if (lam < lamMin) { lamMin = lam; hit = f; hitFlip = !own; }
-            }
+            if (num < 0) num = 0;
+            if (nd > 0 && num * bnd < bnum * nd) { bnum = num; bnd = nd; hit = f; hitFlip = !own; }
         }
         if (hit < 0) {
             for (int k = 0; k < 3; ++k) p.x[k] = p.x[k] + disp[k];
             p.sf = 1;
             break;
         }
-        for (int k = 0; k < 3; ++k) p.x[k] = p.x[k] + lamMin * disp[k];
-        p.sf = p.sf + rem * lamMin;
+        const double lamMin = bnum / bnd;
+        for (int k = 0; k < 3; ++k) p.x[k] = std::fma(lamMin, disp[k], p.x[k]);
+        p.sf = std::fma(rem, lamMin, p.sf);
         if (hit < h.nInternal) {
             p.cell = hitFlip ? h.owner[hit] : h.neighbour[hit];
         } else {

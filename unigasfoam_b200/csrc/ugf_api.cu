@@ -123,7 +123,7 @@ struct ugf_handle {
     int sampleCounter = 0;
 
     long long step = 0;
-    int cellCap = 128;
+    int cellCap = CELL_CAP;
     int cellBlocks = 0, bgkBlocks = 0, segBlocks = 0;
     size_t cellSmem = 0, bgkSmem = 0;
     cudaEvent_t ev[7]{};
@@ -464,7 +464,6 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     h->capacity = cfg->parcelCapacity;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->numSMs = prop.multiProcessorCount;
-    if (const char* s = std::getenv("UGF_CELL_CAP")) h->cellCap = std::max(32, std::atoi(s));
     auto bail = [&](const char* what, cudaError_t err) {
         g_createErr = std::string(what) + ": " + cudaGetErrorString(err);
         delete h;
@@ -645,7 +644,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     h->packCap.assign(h->nPatches, 0);
 
     // launch geometry: persistent grids sized to the SM count
-    h->cellSmem = (size_t)CELL_WARPS * h->cellCap * (h->hasRot ? 4 : 3) * sizeof(double) + (size_t)CELL_WARPS * h->cellCap;
+    h->cellSmem = cell_smem_bytes(h->hasRot);
     h->bgkSmem = (size_t)BGK_WARPS * h->cellCap * 4 * sizeof(double) + (size_t)BGK_WARPS * h->cellCap;
     int occCell = 1, occBgk = 1, occSeg = 1;
     cudaError_t e1 = cudaSuccess;
@@ -667,7 +666,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         const int need = (nC + warpsPerBlock - 1) / warpsPerBlock;
         return std::max(1, std::min(need, h->numSMs * std::max(occ, 1)));
     };
-    h->cellBlocks = persistent(occCell, CELL_WARPS);
+    h->cellBlocks = persistent(occCell, CELL_WARPS * CELL_CHUNK);
     h->bgkBlocks = persistent(occBgk, BGK_WARPS);
     h->segBlocks = persistent(occSeg, SEG_THREADS / 32);
     h->meshSet = true;

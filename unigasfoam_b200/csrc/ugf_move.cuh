@@ -7,8 +7,9 @@
 // face planes (L1 broadcast) and the histogram atomics are aggregated per warp with match.any.
 //
 // HBM-bound: algorithmic traffic 80 B/parcel (read x,U,cell = 52; write x,cell = 28); U is only rewritten on
-// wall/symmetry hits.  All tracking arithmetic is plain IEEE mul/add/div in the same order as the oracle
-// (library is compiled with -fmad=false), so final positions and cells match it bit for bit.
+// wall/symmetry hits.  All tracking arithmetic is IEEE mul/add/div plus explicit fma() in the same order as the
+// oracle (the library is compiled with -fmad=false, so nothing else is contracted), hence final positions and
+// cells match it bit for bit.
 #pragma once
 #include "ugf_common.cuh"
 #include "ugf_rng.cuh"
@@ -224,26 +225,29 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
             const double rem = 1 - sf;
             const double s = rem * dt;
             const double d0 = s0 ? s * U0 : 0.0, d1 = s1 ? s * U1 : 0.0, d2 = s2 ? s * U2 : 0.0;  // constrainDirection
-            double lamMin = 1.0;
+            // first face crossed: min of num/nd over faces with nd > 0, compared by cross-multiplication
+            // (one division per hop, branch-free loop body); (bnum, bnd) = (1, 1) encodes "end of step"
+            double bnum = 1.0, bnd = 1.0;
             int hit = -1;
             const int jb = __ldg(&a.mesh.cfOff[cell]), je = __ldg(&a.mesh.cfOff[cell + 1]);
             for (int j = jb; j < je; ++j) {
                 const double4 pl = load_plane(&a.mesh.plane[j]);
-                const double nd = pl.x * d0 + pl.y * d1 + pl.z * d2;
-                const double num = pl.w - (pl.x * x0 + pl.y * x1 + pl.z * x2);
-                if (nd > 0) {
-                    double lam = num / nd;
-                    if (lam < 0) lam = 0;
-                    if (lam < lamMin) { lamMin = lam; hit = j; }
-                }
+                const double nd = fma(pl.z, d2, fma(pl.y, d1, pl.x * d0));
+                double num = pl.w - fma(pl.z, x2, fma(pl.y, x1, pl.x * x0));
+                num = num < 0 ? 0.0 : num;
+                const bool better = (nd > 0) && (num * bnd < bnum * nd);
+                bnum = better ? num : bnum;
+                bnd = better ? nd : bnd;
+                hit = better ? j : hit;
             }
             if (hit < 0) {
                 x0 = x0 + d0; x1 = x1 + d1; x2 = x2 + d2;
                 sf = 1;
                 break;
             }
-            x0 = x0 + lamMin * d0; x1 = x1 + lamMin * d1; x2 = x2 + lamMin * d2;
-            sf = sf + rem * lamMin;
+            const double lamMin = bnum / bnd;
+            x0 = fma(lamMin, d0, x0); x1 = fma(lamMin, d1, x1); x2 = fma(lamMin, d2, x2);
+            sf = fma(rem, lamMin, sf);
             const int nb = __ldg(&a.mesh.nbr[hit]);
             if (nb >= 0) {
                 cell = nb;
