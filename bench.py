@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--nx", type=int, default=1000)
     ap.add_argument("--ny", type=int, default=500)
     ap.add_argument("--ppc", type=int, default=20)
+    ap.add_argument("--case", default="couette", choices=["couette", "box"], help="box = config 1 style dense-collision case (tuning only)")
+    ap.add_argument("--box-n", type=int, default=64)
+    ap.add_argument("--box-parcels", type=int, default=8_000_000)
     ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-state", action="store_true")
@@ -92,10 +95,14 @@ class ClockSampler:
 
 def build_case(args, rank, world):
     from unigasfoam_b200 import cases
+    if args.case == "box":
+        return cases.closed_box(n=args.box_n, parcels=args.box_parcels, wall="diffuse")
     return cases.couette(nx=args.nx, ny=args.ny, ppc=args.ppc, rank=rank, n_ranks=world)
 
 
 def workload_name(args):
+    if args.case == "box":
+        return f"closedbox3d_argon_{args.box_n}^3cells_{args.box_parcels}parcels_dsmc_ntc_vhs_dt0.2mct"
     return f"couette2d_argon_kn0.1_{args.nx}x{args.ny}cells_{args.ppc}ppc_dsmc_ntc_vhs"
 
 

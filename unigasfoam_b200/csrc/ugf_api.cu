@@ -107,6 +107,7 @@ struct ugf_handle {
     double* dMom = nullptr; double* dAcc = nullptr; double* dBm = nullptr; double* dBacc = nullptr;
     double* dSigma = nullptr; int* dCollId = nullptr; double* dMaxProb = nullptr; double* dQPrev = nullptr; double* dSPrev = nullptr;
     double* dKeyScratch = nullptr;
+    int* dOwner = nullptr;           // NTC conflict marks, one per parcel slot
     DevCounters* dCnt = nullptr;
     int* dErr = nullptr;
     double* dTot = nullptr;
@@ -124,8 +125,8 @@ struct ugf_handle {
 
     long long step = 0;
     int cellCap = CELL_CAP;
-    int cellBlocks = 0, bgkBlocks = 0, segBlocks = 0;
-    size_t cellSmem = 0, bgkSmem = 0;
+    int cellBlocks = 0, ntcBlocks = 0, bgkBlocks = 0, segBlocks = 0;
+    size_t cellSmem = 0, ntcSmem = 0, bgkSmem = 0;
     cudaEvent_t ev[7]{};
     double phaseMs[6] = {0, 0, 0, 0, 0, 0};
     bool timingValid = false;
@@ -246,6 +247,8 @@ int alloc_parcels(ugf_handle* h) {
         if (h->multi && dalloc(h, &P.type, cap)) return 1;
     }
     if (dalloc(h, &h->dPerm, cap)) return 1;
+    if (dalloc(h, &h->dOwner, cap)) return 1;
+    CU(cudaMemsetAsync(h->dOwner, 0x7f, cap * sizeof(int), h->stream));
     if (dalloc(h, &h->dMigBlock, cap / 1024 + 2)) return 1;
     return 0;
 }
@@ -285,7 +288,9 @@ int after_gather(ugf_handle* h) {
     return request_n(h);
 }
 
-int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool doCollide) {
+// streaming kernel: gather through the occupancy permutation (optional) + cell moments (optional)
+int run_cell_kernel(ugf_handle* h, bool gather, bool doSample) {
+    if (!gather && !doSample) return 0;
     CellArgs a{};
     a.nCells = h->nCells;
     a.off = h->dOff;
@@ -294,14 +299,7 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool doCollide) {
     a.out = gather ? h->buf[h->cur ^ 1] : h->buf[h->cur];
     a.gather = gather ? 1 : 0;
     a.doSample = doSample ? 1 : 0;
-    a.doCollide = doCollide ? 1 : 0;
     a.mom = h->dMom;
-    a.vol = h->dVol;
-    a.sigmaTcRMax = h->dSigma;
-    a.collModelId = h->dCollId;
-    a.step = (uint32_t)h->step;
-    a.cnt = h->dCnt;
-    a.cap = h->cellCap;
     const DevParams prm = h->prm;
     dispatch(h, [&](auto R, auto M) {
         cell_kernel<decltype(R)::value, decltype(M)::value><<<h->cellBlocks, CELL_THREADS, h->cellSmem, h->stream>>>(prm, a);
@@ -309,6 +307,26 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool doCollide) {
     LAUNCHED();
     if (doSample) h->momValid = true;
     if (gather) return after_gather(h);
+    return 0;
+}
+
+// NTC collisions in place on the cell-major buffer
+int run_ntc_kernel(ugf_handle* h) {
+    NtcArgs a{};
+    a.nCells = h->nCells;
+    a.off = h->dOff;
+    a.P = h->buf[h->cur];
+    a.vol = h->dVol;
+    a.sigmaTcRMax = h->dSigma;
+    a.collModelId = h->dCollId;
+    a.owner = h->dOwner;
+    a.step = (uint32_t)h->step;
+    a.cnt = h->dCnt;
+    const DevParams prm = h->prm;
+    dispatch(h, [&](auto R, auto M) {
+        ntc_kernel<decltype(R)::value, decltype(M)::value><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+    });
+    LAUNCHED();
     return 0;
 }
 
@@ -498,7 +516,7 @@ int ugf_destroy(ugf_handle* h) {
     }
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock,
-                    h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch,
+                    h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner,
                     h->dCnt, h->dErr, h->dTot};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
@@ -646,12 +664,14 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     // launch geometry: persistent grids sized to the SM count
     h->cellSmem = cell_smem_bytes(h->hasRot);
     h->bgkSmem = (size_t)BGK_WARPS * h->cellCap * 4 * sizeof(double) + (size_t)BGK_WARPS * h->cellCap;
-    int occCell = 1, occBgk = 1, occSeg = 1;
+    int occCell = 1, occNtc = 1, occBgk = 1, occSeg = 1;
     cudaError_t e1 = cudaSuccess;
     dispatch(h, [&](auto R, auto M) {
         auto k = cell_kernel<decltype(R)::value, decltype(M)::value>;
         e1 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cellSmem);
         if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occCell, k, CELL_THREADS, h->cellSmem);
+        auto kn = ntc_kernel<decltype(R)::value, decltype(M)::value>;
+        if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occNtc, kn, NTC_THREADS, 0);
     });
     CU(e1);
     if (h->multi) {
@@ -666,7 +686,19 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         const int need = (nC + warpsPerBlock - 1) / warpsPerBlock;
         return std::max(1, std::min(need, h->numSMs * std::max(occ, 1)));
     };
+    // The streaming kernel's cp.async fills need L1 lines while in flight: fewer resident blocks leave a larger
+    // L1 next to the shared-memory carve-out and raise the achievable memory-level parallelism (profiles/).
+    int cellBps = 4, cellCarve = -1;
+    if (const char* e = std::getenv("UGF_CELL_BPS")) cellBps = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("UGF_CELL_CARVEOUT")) cellCarve = std::atoi(e);
+    occCell = std::min(occCell, cellBps);
+    if (cellCarve < 0) cellCarve = (int)std::min<size_t>(100, (occCell * (h->cellSmem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    dispatch(h, [&](auto R, auto M) {
+        e1 = cudaFuncSetAttribute(cell_kernel<decltype(R)::value, decltype(M)::value>, cudaFuncAttributePreferredSharedMemoryCarveout, cellCarve);
+    });
+    CU(e1);
     h->cellBlocks = persistent(occCell, CELL_WARPS * CELL_CHUNK);
+    h->ntcBlocks = persistent(occNtc, NTC_WARPS * 32);
     h->bgkBlocks = persistent(occBgk, BGK_WARPS);
     h->segBlocks = persistent(occSeg, SEG_THREADS / 32);
     h->meshSet = true;
@@ -874,21 +906,21 @@ int ugf_reorder(ugf_handle* h) {
 int ugf_sample(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (!h->occValid && do_sort(h)) return 1;
-    return run_cell_kernel(h, false, true, false);
+    return run_cell_kernel(h, false, true);
 }
 
 int ugf_collide(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (!h->occValid && do_sort(h)) return 1;
-    return run_cell_kernel(h, !h->occIdentity, !h->momValid, dsmc_active(h));
+    if (run_cell_kernel(h, !h->occIdentity, !h->momValid)) return 1;  // sampling precedes collisions
+    if (!dsmc_active(h)) return 0;
+    return run_ntc_kernel(h);
 }
 
 int ugf_relax(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (!h->occValid && do_sort(h)) return 1;
-    if (!h->occIdentity || !h->momValid) {
-        if (run_cell_kernel(h, !h->occIdentity, !h->momValid, false)) return 1;
-    }
+    if (run_cell_kernel(h, !h->occIdentity, !h->momValid)) return 1;
     if (!bgk_active(h)) return 0;
     return run_bgk_kernel(h);
 }
@@ -897,7 +929,7 @@ int ugf_accumulate_fields(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (!h->momValid) {
         if (!h->occValid && do_sort(h)) return 1;
-        if (run_cell_kernel(h, false, true, false)) return 1;
+        if (run_cell_kernel(h, false, true)) return 1;
     }
     return do_accumulate(h);
 }
@@ -925,7 +957,8 @@ int ugf_step(ugf_handle* h, int32_t nSteps) {
         if (last) CU(cudaEventRecord(h->ev[2], h->stream));
         if (do_sort(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[3], h->stream));
-        if (run_cell_kernel(h, true, true, dsmc_active(h))) return 1;
+        if (run_cell_kernel(h, true, true)) return 1;
+        if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[4], h->stream));
         if (bgk_active(h) && run_bgk_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[5], h->stream));

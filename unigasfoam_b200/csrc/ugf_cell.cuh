@@ -7,18 +7,23 @@
 //                   (U/dsmcCollisions/derived/*), and the kinetic samplers they call
 //                   (U/clouds/uniGasCloud.C:1129-1189, 1267-1326).
 //
-// One warp per cell (grid-stride over cells, persistent CTAs).  The cell's velocities (and ERot, typeId) are
-// staged in shared memory, moments are reduced with warp shuffles and written as one coalesced 256-byte block
-// per (cell, species), and the collided velocities are written straight into the cell-major output buffer.
-// Sampling uses the pre-collision state, as the reference does (uniGasCloud.C:846-850).
+// Two kernels, both one warp per run of consecutive cells (persistent CTAs, grid-stride over chunks of
+// CELL_CHUNK cells):
+//   cell_kernel  streaming: the run's parcels are pulled through the permutation into shared memory with cp.async
+//                (every load of the run in flight at once), moments are reduced by 4 lanes per cell and written
+//                as one 256-byte block per (cell, species), and the run is written cell-major, fully coalesced.
+//                Sampling sees the pre-collision state, as in the reference (uniGasCloud.C:846-850).
+//   ntc_kernel   collisions, in place on the cell-major buffer: candidate counts for 8 cells at a time (one cell
+//                per lane); only runs that drew candidates are staged.  The candidates of all cells of a run are
+//                spread over the 32 lanes, each with its own Philox stream (step, cell, candidate#); a candidate
+//                commits as soon as no earlier uncommitted candidate shares a parcel with it, which reproduces
+//                the reference's sequential candidate loop exactly (same results as the oracle's serial loop).
+// The split keeps the transcendental-heavy collision code (pow, sincos, Philox) out of the streaming kernel, whose
+// register budget and shared-memory footprint decide how much HBM traffic can be kept in flight.
 //
-// NTC candidates of a cell are processed 32 at a time, one per lane, each from its own Philox stream
-// (step, cell, candidate#).  A candidate commits as soon as no earlier uncommitted candidate shares a parcel
-// with it, which reproduces the reference's sequential candidate loop exactly (same results as the oracle's
-// serial loop) while independent pairs collide in parallel.
-//
-// HBM-bound: per parcel 4 (perm) + 52/60 (gather) read, 52/60 written; per cell 8 (offsets) + 16 (sigmaTcRMax)
-// + 256 x species (moments).
+// HBM traffic: cell_kernel per parcel 4 (perm) + 56/64 (gather incl. cell id) read, 52/60 written, per cell
+// 4 (offsets) + 256 x species (moments); ntc_kernel per cell 4 + 8 + 8 + 4, plus 24-32 B/parcel read and
+// written for the runs that collide.
 #pragma once
 #include "ugf_common.cuh"
 #include "ugf_rng.cuh"
@@ -33,15 +38,9 @@ struct CellArgs {
     const int* off;
     const int* perm;  // null: identity (array already cell-major)
     ParcelBuf in, out;
-    int gather;       // 1: write the cell-major copy into `out`; 0: operate in place on `in`
-    int doSample, doCollide;
+    int gather;       // 1: write the cell-major copy into `out`; 0: sample only
+    int doSample;
     double* mom;
-    const double* vol;
-    double* sigmaTcRMax;
-    const int* collModelId;
-    uint32_t step;
-    DevCounters* cnt;
-    int cap;  // staging capacity per warp, parcels
 };
 
 // postCollisionRotationalEnergy (U/clouds/uniGasCloud.C:1129-1189)
@@ -173,79 +172,53 @@ __device__ __forceinline__ int ntc_candidates(const DevParams& prm, uint32_t ste
     return nCand;
 }
 
-// NTC candidate loop for one cell (noTimeCounter.C:195-312); the whole warp calls this, out of line so that
-// the streaming part of the kernel stays lean.  pu0..pt give random access to the cell's staged velocities /
-// ERot / typeId (shared or global memory).
-template <bool HAS_ROT, bool MULTI>
-__device__ __noinline__ int ntc_collide(const DevParams& prm, const CellArgs& a, int cell, int n, int nCand, double sMaxOld,
-                                        double* pu0, double* pu1, double* pu2, double* pe, const uint8_t* pt, int lane) {
-    int myColl = 0;
-    double localMax = sMaxOld;
-    for (int base = 0; base < nCand; base += 32) {
-        const int k = base + lane;
-        bool act = k < nCand;
-        Stream r(prm.seed, KIND_NTC, 0, a.step, (uint32_t)cell, (uint32_t)k);
-        int cP = -1, cQ = -2;
-        int tP = 0, tQ = 0;
-        if (act) {
-            cP = r.position(n);
-            do { cQ = r.position(n); } while (cP == cQ);
-            if (MULTI) { tP = pt[cP]; tQ = pt[cQ]; }
-            // electron-electron pairs are skipped (noTimeCounter.C:245-247)
-            if (prm.sp[tP].charge == -1 && prm.sp[tQ].charge == -1) act = false;
-        }
-        unsigned pending = __ballot_sync(0xffffffffu, act);
-        while (pending) {
-            const bool mine = (pending >> lane) & 1u;
-            bool blocked = false;
-            for (unsigned mm = pending; mm; mm &= mm - 1) {
-                const int j = __ffs(mm) - 1;
-                const int pj = __shfl_sync(0xffffffffu, cP, j);
-                const int qj = __shfl_sync(0xffffffffu, cQ, j);
-                if (j < lane && (pj == cP || pj == cQ || qj == cP || qj == cQ)) blocked = true;
-            }
-            const bool ready = mine && !blocked;
-            if (ready) {
-                const DevSpecies& A = prm.sp[tP];
-                const DevSpecies& B = prm.sp[tQ];
-                double UP[3] = {pu0[cP], pu1[cP], pu2[cP]};
-                double UQ[3] = {pu0[cQ], pu1[cQ], pu2[cQ]};
-                const double d0 = UP[0] - UQ[0], d1 = UP[1] - UQ[1], d2 = UP[2] - UQ[2];
-                const double cR2 = d0 * d0 + d1 * d1 + d2 * d2;
-                double sig = 0.0;
-                if (!(cR2 < VSMALL)) {  // variableHardSphere.C:72-115
-                    const double dPQ = 0.5 * (A.d + B.d);
-                    const double omegaPQ = 0.5 * (A.omega + B.omega);
-                    const double mR = A.mass * B.mass / (A.mass + B.mass);
-                    const double sigmaTPQ = PI * dPQ * dPQ * pow(2.0 * kB * prm.Tref / (mR * cR2), omegaPQ - 0.5)
-                                            * prm.pairInvGamma[tP * UGF_MAX_SPECIES + tQ];
-                    sig = sigmaTPQ * sqrt(cR2);
-                }
-                if (sig > localMax) localMax = sig;
-                if ((sig / sMaxOld) > r.u01()) {
-                    double eP = 0.0, eQ = 0.0;
-                    if (HAS_ROT) { eP = pe[cP]; eQ = pe[cQ]; }
-                    collide_pair(prm, r, A, B, UP, UQ, eP, eQ);
-                    pu0[cP] = UP[0]; pu1[cP] = UP[1]; pu2[cP] = UP[2];
-                    pu0[cQ] = UQ[0]; pu1[cQ] = UQ[1]; pu2[cQ] = UQ[2];
-                    if (HAS_ROT) { pe[cP] = eP; pe[cQ] = eQ; }
-                    myColl++;
-                }
-            }
-            __syncwarp();
-            pending &= ~__ballot_sync(0xffffffffu, ready);
-        }
-    }
-    localMax = warp_max(localMax);
-    if (lane == 0 && localMax > sMaxOld) a.sigmaTcRMax[cell] = localMax;
-    return myColl;
+// sigma_T c_r of a pair (variableHardSphere.C:72-115; the VSS and LB models code the same expression)
+__device__ __forceinline__ double sigma_tcr(const DevParams& prm, const DevSpecies& A, const DevSpecies& B, int tP, int tQ, double cR2) {
+    if (cR2 < VSMALL) return 0.0;
+    const double dPQ = 0.5 * (A.d + B.d);
+    const double omegaPQ = 0.5 * (A.omega + B.omega);
+    const double mR = A.mass * B.mass / (A.mass + B.mass);
+    const double sigmaTPQ = PI * dPQ * dPQ * pow(2.0 * kB * prm.Tref / (mR * cR2), omegaPQ - 0.5) * prm.pairInvGamma[tP * UGF_MAX_SPECIES + tQ];
+    return sigmaTPQ * sqrt(cR2);
+}
+
+constexpr int CELL_CHUNK = 8;    // consecutive cells examined by one warp per iteration
+constexpr int CELL_CAP = 128;    // parcels staged per warp; larger cells take the single-cell paths
+constexpr int CELL_ITERS = CELL_CAP / 32;
+constexpr int CELL_LPC = 32 / CELL_CHUNK;  // lanes cooperating on one cell in the moment phase (4)
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ double select4(int q, double v0, double v1, double v2, double v3) {
+    const double lo = (q & 1) ? v1 : v0;
+    const double hi = (q & 1) ? v3 : v2;
+    return (q & 2) ? hi : lo;
+}
+
+// ---- streaming kernel -----------------------------------------------------------------------------------------
+// shared memory per warp: three double arrays (+ERot) that hold the run's velocities for the moment phase and
+// are then reused for its positions, int cell ids, typeId bytes.  Keeping the carve-out this small matters: the
+// cp.async.ca fills in flight need L1 lines, so a large shared-memory carve-out (small L1) caps the memory-level
+// parallelism (measured: profiles/README.md).
+__host__ __device__ constexpr int cell_doubles_per_parcel(bool hasRot) { return hasRot ? 4 : 3; }
+__host__ __device__ constexpr size_t cell_smem_bytes(bool hasRot) {
+    return (size_t)CELL_WARPS * CELL_CAP * (cell_doubles_per_parcel(hasRot) * sizeof(double) + sizeof(int) + 1);
 }
 
 // Moments of one cell for every species from a randomly accessible view (pu0.. indexed 0..n-1), written as
-// one coalesced 256-byte block per (cell, species): lane k stores slot k (DESIGN.md section moments).
+// one coalesced 256-byte block per (cell, species): lane k stores slot k (DESIGN.md section moments).  Used for
+// cells that do not fit a staged run; `accumulate` adds to the block instead of overwriting it.
 template <bool HAS_ROT, bool MULTI>
 __device__ __forceinline__ void cell_moments(const DevParams& prm, double* __restrict__ mom, int cell, int n, const double* pu0,
-                                             const double* pu1, const double* pu2, const double* pe, const uint8_t* pt, int lane) {
+                                             const double* pu1, const double* pu2, const double* pe, const uint8_t* pt, int lane, bool accumulate) {
     const int nS = prm.nSpecies;
     for (int s = 0; s < nS; ++s) {
         // value index: 0-2 U, 3-8 uu uv uw vv vw ww, 9 cc, 10-12 cc*U, 13 count, 14-17 ERot, ERot*U
@@ -275,146 +248,55 @@ __device__ __forceinline__ void cell_moments(const DevParams& prm, double* __res
         double o = __shfl_sync(0xffffffffu, tot, src & 31);
         if (src < 0) o = 0.0;
         if (lane == 26) o = o * prm.sp[s].E0;
-        mom[((size_t)cell * nS + s) * UGF_NMOM + lane] = o;
+        double* at = mom + ((size_t)cell * nS + s) * UGF_NMOM + lane;
+        *at = accumulate ? *at + o : o;
     }
 }
 
-// One cell whose parcels do not fit the staging buffer together with its neighbours (or not at all): the
-// general path.  Stages in shared memory when n <= cap, otherwise works on the output arrays in global memory.
+// A cell larger than the staging buffer: slices of CELL_CAP parcels go through shared memory one after another.
 template <bool HAS_ROT, bool MULTI>
-__device__ __noinline__ void cell_single(const DevParams& prm, const CellArgs& a, int cell, int beg, int n, double* sU0, double* sU1,
-                                         double* sU2, double* sE, uint8_t* sT, int lane) {
-    const int cap = a.cap;  // == CELL_CAP
-    const bool collideHere = a.doCollide && n > 1 && a.collModelId[cell] == 1;
-    const bool useSmem = n <= cap;
-    const ParcelBuf& fin = a.gather ? a.out : a.in;
-    if (a.gather || useSmem) {
-        for (int j = lane; j < n; j += 32) {
-            const int src = a.perm ? a.perm[beg + j] : beg + j;
+__device__ __noinline__ void stream_giant_cell(const DevParams& prm, const CellArgs& a, int cell, int beg, int n, double* sU0, double* sU1,
+                                               double* sU2, double* sE, uint8_t* sT, int lane) {
+    for (int b = 0; b < n; b += CELL_CAP) {
+        const int m = min(CELL_CAP, n - b);
+        __syncwarp();
+        for (int j = lane; j < m; j += 32) {
+            const int dst = beg + b + j;
+            const int src = a.perm ? a.perm[dst] : dst;
             const double ux = a.in.ux[src], uy = a.in.uy[src], uz = a.in.uz[src];
-            double e = 0.0;
-            if (HAS_ROT) e = a.in.erot[src];
-            uint8_t t = 0;
-            if (MULTI) t = a.in.type[src];
+            sU0[j] = ux; sU1[j] = uy; sU2[j] = uz;
+            if (HAS_ROT) sE[j] = a.in.erot[src];
+            if (MULTI) sT[j] = a.in.type[src];
             if (a.gather) {
-                a.out.x[beg + j] = a.in.x[src];
-                a.out.y[beg + j] = a.in.y[src];
-                a.out.z[beg + j] = a.in.z[src];
-                a.out.cell[beg + j] = cell;
-                if (MULTI) a.out.type[beg + j] = t;
-            }
-            if (useSmem) {
-                sU0[j] = ux; sU1[j] = uy; sU2[j] = uz;
-                if (HAS_ROT) sE[j] = e;
-                if (MULTI) sT[j] = t;
-            } else {
-                a.out.ux[beg + j] = ux; a.out.uy[beg + j] = uy; a.out.uz[beg + j] = uz;
-                if (HAS_ROT) a.out.erot[beg + j] = e;
+                a.out.x[dst] = a.in.x[src]; a.out.y[dst] = a.in.y[src]; a.out.z[dst] = a.in.z[src];
+                a.out.ux[dst] = ux; a.out.uy[dst] = uy; a.out.uz[dst] = uz;
+                a.out.cell[dst] = cell;
+                if (HAS_ROT) a.out.erot[dst] = sE[j];
+                if (MULTI) a.out.type[dst] = sT[j];
             }
         }
         __syncwarp();
-    }
-    // randomly accessible view: shared memory, or the final arrays (gathered copy / in place).  A cell larger than
-    // the staging buffer that is sampled through a permutation without gathering has no such view: the host never
-    // asks for that combination with collisions, and sampling falls back to a strided pass below.
-    double *pu0, *pu1, *pu2, *pe;
-    uint8_t* pt;
-    const bool direct = useSmem || a.gather || a.perm == nullptr;
-    if (useSmem) { pu0 = sU0; pu1 = sU1; pu2 = sU2; pe = sE; pt = sT; }
-    else { pu0 = fin.ux + beg; pu1 = fin.uy + beg; pu2 = fin.uz + beg; pe = HAS_ROT ? fin.erot + beg : nullptr; pt = MULTI ? fin.type + beg : nullptr; }
-    if (a.doSample) {
-        if (direct) {
-            cell_moments<HAS_ROT, MULTI>(prm, a.mom, cell, n, pu0, pu1, pu2, pe, pt, lane);
-        } else {
-            // giant cell, sample-only through the permutation: stage slices of `cap` parcels and add up
-            const int nS = prm.nSpecies;
-            for (int s = 0; s < nS; ++s) a.mom[((size_t)cell * nS + s) * UGF_NMOM + lane] = 0.0;
-            for (int b = 0; b < n; b += cap) {
-                const int m = min(cap, n - b);
-                __syncwarp();
-                for (int j = lane; j < m; j += 32) {
-                    const int src = a.perm[beg + b + j];
-                    sU0[j] = a.in.ux[src]; sU1[j] = a.in.uy[src]; sU2[j] = a.in.uz[src];
-                    if (HAS_ROT) sE[j] = a.in.erot[src];
-                    if (MULTI) sT[j] = a.in.type[src];
-                }
-                __syncwarp();
-                for (int s = 0; s < nS; ++s) {
-                    const size_t at = ((size_t)cell * nS + s) * UGF_NMOM + lane;
-                    const double prev = a.mom[at];
-                    cell_moments<HAS_ROT, MULTI>(prm, a.mom, cell, m, sU0, sU1, sU2, sE, sT, lane);
-                    a.mom[at] += prev;
-                }
-            }
-        }
-    }
-    if (collideHere) {
-        const double sMaxOld = a.sigmaTcRMax[cell];
-        const int nCand = ntc_candidates(prm, a.step, cell, n, sMaxOld, a.vol[cell]);
-        if (lane == 0 && nCand > 0) atomicAdd(&a.cnt->cand, (unsigned long long)nCand);
-        if (nCand > 0) {
-            const int nc = warp_sum_int(ntc_collide<HAS_ROT, MULTI>(prm, a, cell, n, nCand, sMaxOld, pu0, pu1, pu2, pe, pt, lane));
-            if (lane == 0 && nc > 0) atomicAdd(&a.cnt->coll, (unsigned long long)nc);
-        }
-    }
-    if (useSmem && (a.gather || collideHere)) {
-        for (int j = lane; j < n; j += 32) {
-            fin.ux[beg + j] = sU0[j]; fin.uy[beg + j] = sU1[j]; fin.uz[beg + j] = sU2[j];
-            if (HAS_ROT) fin.erot[beg + j] = sE[j];
-        }
+        if (a.doSample) cell_moments<HAS_ROT, MULTI>(prm, a.mom, cell, m, sU0, sU1, sU2, sE, sT, lane, b > 0);
     }
     __syncwarp();
 }
 
-constexpr int CELL_CHUNK = 8;    // consecutive cells examined by one warp per iteration
-constexpr int CELL_CAP = 128;    // parcels staged per warp (fast path); larger cells take cell_single
-constexpr int CELL_ITERS = CELL_CAP / 32;
-constexpr int CELL_LPC = 32 / CELL_CHUNK;  // lanes cooperating on one cell in the moment phase (4)
-
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// shared-memory doubles per staged parcel: U, x (gather only) (+ERot); then int cell ids and typeId bytes
-__host__ __device__ constexpr int cell_doubles_per_parcel(bool hasRot) { return hasRot ? 7 : 6; }
-__host__ __device__ constexpr size_t cell_smem_bytes(bool hasRot) {
-    return (size_t)CELL_WARPS * CELL_CAP * (cell_doubles_per_parcel(hasRot) * sizeof(double) + sizeof(int) + 1);
-}
-
-__device__ __forceinline__ double select4(int q, double v0, double v1, double v2, double v3) {
-    const double lo = (q & 1) ? v1 : v0;
-    const double hi = (q & 1) ? v3 : v2;
-    return (q & 2) ? hi : lo;
-}
-
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(CELL_THREADS, 3) cell_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ CellArgs a) {
+__global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ CellArgs a) {
     extern __shared__ double smemD[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     constexpr int cap = CELL_CAP;
     constexpr int perWarp = cap * cell_doubles_per_parcel(HAS_ROT);
-    double* sU0 = smemD + (size_t)wib * perWarp;
-    double* sU1 = sU0 + cap;
-    double* sU2 = sU1 + cap;
-    double* sX0 = sU2 + cap;
-    double* sX1 = sX0 + cap;
-    double* sX2 = sX1 + cap;
-    double* sE = sX2 + cap;  // valid only if HAS_ROT
-    int* sC = reinterpret_cast<int*>(smemD + (size_t)CELL_WARPS * perWarp) + (size_t)wib * cap;
-    uint8_t* sT = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(smemD + (size_t)CELL_WARPS * perWarp) + (size_t)CELL_WARPS * cap) + (size_t)wib * cap;
+    double* const sU0 = smemD + (size_t)wib * perWarp;
+    double* const sU1 = sU0 + cap;
+    double* const sU2 = sU1 + cap;
+    double* const sE = sU2 + cap;  // valid only if HAS_ROT
+    int* const sC = reinterpret_cast<int*>(smemD + (size_t)CELL_WARPS * perWarp) + (size_t)wib * cap;
+    uint8_t* const sT = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(smemD + (size_t)CELL_WARPS * perWarp) + (size_t)CELL_WARPS * cap) + (size_t)wib * cap;
     const int warpsTotal = gridDim.x * CELL_WARPS;
     const int nChunks = (a.nCells + CELL_CHUNK - 1) / CELL_CHUNK;
-    const ParcelBuf& fin = a.gather ? a.out : a.in;
     const int nS = prm.nSpecies;
-    unsigned long long wCand = 0;
-    int myColl = 0;
 
     for (int chunk = blockIdx.x * CELL_WARPS + wib; chunk < nChunks; chunk += warpsTotal) {
         const int c0 = chunk * CELL_CHUNK;
@@ -428,12 +310,12 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) cell_kernel(const __grid_cons
             const int k = __popc(fit);
             if (k == 0) {  // a single cell larger than the buffer
                 const int e0 = __shfl_sync(0xffffffffu, offv, done + 1);
-                cell_single<HAS_ROT, MULTI>(prm, a, c0 + done, b0, e0 - b0, sU0, sU1, sU2, sE, sT, lane);
+                stream_giant_cell<HAS_ROT, MULTI>(prm, a, c0 + done, b0, e0 - b0, sU0, sU1, sU2, sE, sT, lane);
                 done += 1;
                 continue;
             }
             const int ntot = __shfl_sync(0xffffffffu, offv, done + k) - b0;
-            // ---- gather the run into shared memory with cp.async: every load of the run is in flight at once ----
+            // ---- phase 1: velocities (+ERot, cell id) of the run into shared memory, all copies in flight at once ----
             int srcs[CELL_ITERS];
 #pragma unroll
             for (int it = 0; it < CELL_ITERS; ++it) {
@@ -448,31 +330,10 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) cell_kernel(const __grid_cons
                     cp_async8(&sU0[j], &a.in.ux[src]);
                     cp_async8(&sU1[j], &a.in.uy[src]);
                     cp_async8(&sU2[j], &a.in.uz[src]);
-                    if (a.gather) {
-                        cp_async8(&sX0[j], &a.in.x[src]);
-                        cp_async8(&sX1[j], &a.in.y[src]);
-                        cp_async8(&sX2[j], &a.in.z[src]);
-                        cp_async4(&sC[j], &a.in.cell[src]);
-                    }
+                    if (a.gather) cp_async4(&sC[j], &a.in.cell[src]);
                     if (HAS_ROT) cp_async8(&sE[j], &a.in.erot[src]);
                     if (MULTI) sT[j] = a.in.type[src];
                 }
-            }
-            // ---- per-cell scalars while the copies fly, one cell per lane: size, NTC candidate count ----------------
-            const int myEnd = __shfl_down_sync(0xffffffffu, offv, 1);
-            const int myCell = c0 + lane;
-            const bool mineInRun = lane >= done && lane < done + k;
-            const int myN = mineInRun ? myEnd - offv : 0;
-            int myCand = 0;
-            double mySMax = 0.0;
-            if (a.doCollide && myN > 1 && a.collModelId[myCell] == 1) {
-                mySMax = a.sigmaTcRMax[myCell];
-                myCand = ntc_candidates(prm, a.step, myCell, myN, mySMax, a.vol[myCell]);
-            }
-            const unsigned candMask = __ballot_sync(0xffffffffu, myCand > 0);
-            if (candMask) {
-                const int candSum = warp_sum_int(myCand);
-                if (lane == 0) wCand += (unsigned long long)candSum;
             }
             cp_async_wait_all();
             __syncwarp();
@@ -526,35 +387,159 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) cell_kernel(const __grid_cons
                     }
                 }
             }
-            // ---- NTC collisions for the cells of the run that drew candidates --------------------------------------
-            for (unsigned cm = candMask; cm; cm &= cm - 1) {
-                const int c = __ffs(cm) - 1;
-                const int s0 = __shfl_sync(0xffffffffu, offv, c) - b0;
-                const int n = __shfl_sync(0xffffffffu, offv, c + 1) - b0 - s0;
-                const int nCand = __shfl_sync(0xffffffffu, myCand, c);
-                const double sMaxOld = __shfl_sync(0xffffffffu, mySMax, c);
-                myColl += ntc_collide<HAS_ROT, MULTI>(prm, a, c0 + c, n, nCand, sMaxOld, sU0 + s0, sU1 + s0, sU2 + s0, sE + s0, sT + s0, lane);
-            }
-            __syncwarp();
-            // ---- write the run to its final place, coalesced ----------------------------------------------------------
-            if (a.gather || candMask) {
+            if (a.gather) {
+                // ---- write velocities cell-major (coalesced), then reuse the buffers for the positions (phase 2) ----
+                __syncwarp();
 #pragma unroll
                 for (int it = 0; it < CELL_ITERS; ++it) {
                     const int j = it * 32 + lane;
                     if (j < ntot) {
-                        fin.ux[b0 + j] = sU0[j]; fin.uy[b0 + j] = sU1[j]; fin.uz[b0 + j] = sU2[j];
-                        if (a.gather) {
-                            fin.x[b0 + j] = sX0[j]; fin.y[b0 + j] = sX1[j]; fin.z[b0 + j] = sX2[j];
-                            fin.cell[b0 + j] = sC[j];
-                            if (MULTI) fin.type[b0 + j] = sT[j];
-                        }
-                        if (HAS_ROT) fin.erot[b0 + j] = sE[j];
+                        const double u = sU0[j], v = sU1[j], w = sU2[j];
+                        a.out.ux[b0 + j] = u; a.out.uy[b0 + j] = v; a.out.uz[b0 + j] = w;
+                        a.out.cell[b0 + j] = sC[j];
+                        if (HAS_ROT) a.out.erot[b0 + j] = sE[j];
+                        if (MULTI) a.out.type[b0 + j] = sT[j];
+                        cp_async8(&sU0[j], &a.in.x[srcs[it]]);  // same lane, same slot: no cross-lane hazard
+                        cp_async8(&sU1[j], &a.in.y[srcs[it]]);
+                        cp_async8(&sU2[j], &a.in.z[srcs[it]]);
                     }
+                }
+                cp_async_wait_all();
+#pragma unroll
+                for (int it = 0; it < CELL_ITERS; ++it) {
+                    const int j = it * 32 + lane;
+                    if (j < ntot) { a.out.x[b0 + j] = sU0[j]; a.out.y[b0 + j] = sU1[j]; a.out.z[b0 + j] = sU2[j]; }
                 }
             }
             __syncwarp();
             done += k;
         }
+    }
+}
+
+// ---- NTC kernel -----------------------------------------------------------------------------------------------------
+// In place on the cell-major buffer.  One warp takes 32 consecutive cells: lane l computes cell l's candidate
+// count (noTimeCounter.C:184-191), then the candidates of all 32 cells are laid out over the lanes (candidate g of
+// the warp = candidate kk of cell slot cs), so sparse per-cell counts still fill the warp.  Each candidate draws
+// from its own Philox stream (step, cell, kk) and touches only its two parcels, directly in global memory - no
+// staging, no limit on the cell size.  A candidate commits when no earlier uncommitted candidate shares a parcel
+// with it (owner marks = lowest lane touching a parcel), which reproduces the reference's sequential per-cell
+// candidate loop (noTimeCounter.C:195-312) exactly.
+struct NtcArgs {
+    int nCells;
+    const int* off;
+    ParcelBuf P;  // cell-major, collided in place
+    const double* vol;
+    double* sigmaTcRMax;
+    const int* collModelId;
+    int* owner;   // [capacity] conflict marks, 0x7f7f7f7f when idle
+    uint32_t step;
+    DevCounters* cnt;
+};
+
+constexpr int NTC_THREADS = 256;
+constexpr int NTC_WARPS = NTC_THREADS / 32;
+constexpr int NTC_IDLE = 0x7f7f7f7f;
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ NtcArgs a) {
+    __shared__ double sMaxW[NTC_WARPS][32];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    double* const sM = sMaxW[wib];
+    const int warpsTotal = gridDim.x * NTC_WARPS;
+    const int nChunks = (a.nCells + 31) / 32;
+    unsigned long long wCand = 0;
+    int myColl = 0;
+
+    for (int chunk = blockIdx.x * NTC_WARPS + wib; chunk < nChunks; chunk += warpsTotal) {
+        const int c0 = chunk * 32;
+        const int myCell = c0 + lane;
+        const bool valid = myCell < a.nCells;
+        const int myBeg = valid ? a.off[myCell] : 0;
+        const int myEnd = valid ? a.off[myCell + 1] : 0;
+        const int myN = myEnd - myBeg;
+        int myCand = 0;
+        double mySMax = 0.0;
+        if (myN > 1 && a.collModelId[myCell] == 1) {
+            mySMax = a.sigmaTcRMax[myCell];
+            myCand = ntc_candidates(prm, a.step, myCell, myN, mySMax, a.vol[myCell]);
+        }
+        if (!__any_sync(0xffffffffu, myCand > 0)) continue;
+        int incl = myCand;  // inclusive prefix of the candidate counts over the 32 cells
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - myCand;
+        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) wCand += (unsigned long long)T;
+        sM[lane] = mySMax;
+        __syncwarp();
+        for (int base = 0; base < T; base += 32) {
+            const int g = base + lane;
+            bool act = g < T;
+            // cell slot of candidate g: number of cells whose inclusive prefix is <= g
+            int cs = 0;
+#pragma unroll
+            for (int stp = 16; stp > 0; stp >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, cs + stp - 1);
+                if (v <= g) cs += stp;
+            }
+            cs &= 31;
+            const int kk = g - __shfl_sync(0xffffffffu, excl, cs);
+            const int beg = __shfl_sync(0xffffffffu, myBeg, cs);
+            const int n = __shfl_sync(0xffffffffu, myN, cs);
+            const double sMaxOld = __shfl_sync(0xffffffffu, mySMax, cs);
+            Stream r(prm.seed, KIND_NTC, 0, a.step, (uint32_t)(c0 + cs), (uint32_t)kk);
+            int gP = 0, gQ = 0;
+            int tP = 0, tQ = 0;
+            if (act) {
+                const int cP = r.position(n);
+                int cQ;
+                do { cQ = r.position(n); } while (cP == cQ);
+                gP = beg + cP; gQ = beg + cQ;
+                if (MULTI) { tP = a.P.type[gP]; tQ = a.P.type[gQ]; }
+                if (prm.sp[tP].charge == -1 && prm.sp[tQ].charge == -1) act = false;  // noTimeCounter.C:245-247
+            }
+            double lmax = 0.0;
+            unsigned pending = __ballot_sync(0xffffffffu, act);
+            while (pending) {
+                const bool mine = (pending >> lane) & 1u;
+                if (mine) { atomicMin(&a.owner[gP], lane); atomicMin(&a.owner[gQ], lane); }
+                __syncwarp();
+                const bool ready = mine && __ldcg(&a.owner[gP]) == lane && __ldcg(&a.owner[gQ]) == lane;
+                __syncwarp();
+                if (mine) { __stcg(&a.owner[gP], NTC_IDLE); __stcg(&a.owner[gQ], NTC_IDLE); }
+                if (ready) {
+                    const DevSpecies& A = prm.sp[tP];
+                    const DevSpecies& B = prm.sp[tQ];
+                    double UP[3] = {__ldcg(&a.P.ux[gP]), __ldcg(&a.P.uy[gP]), __ldcg(&a.P.uz[gP])};
+                    double UQ[3] = {__ldcg(&a.P.ux[gQ]), __ldcg(&a.P.uy[gQ]), __ldcg(&a.P.uz[gQ])};
+                    const double d0 = UP[0] - UQ[0], d1 = UP[1] - UQ[1], d2 = UP[2] - UQ[2];
+                    const double sig = sigma_tcr(prm, A, B, tP, tQ, d0 * d0 + d1 * d1 + d2 * d2);
+                    if (sig > lmax) lmax = sig;
+                    if ((sig / sMaxOld) > r.u01()) {
+                        double eP = 0.0, eQ = 0.0;
+                        if (HAS_ROT) { eP = __ldcg(&a.P.erot[gP]); eQ = __ldcg(&a.P.erot[gQ]); }
+                        collide_pair(prm, r, A, B, UP, UQ, eP, eQ);
+                        __stcg(&a.P.ux[gP], UP[0]); __stcg(&a.P.uy[gP], UP[1]); __stcg(&a.P.uz[gP], UP[2]);
+                        __stcg(&a.P.ux[gQ], UQ[0]); __stcg(&a.P.uy[gQ], UQ[1]); __stcg(&a.P.uz[gQ], UQ[2]);
+                        if (HAS_ROT) { __stcg(&a.P.erot[gP], eP); __stcg(&a.P.erot[gQ], eQ); }
+                        myColl++;
+                    }
+                }
+                __syncwarp();
+                pending &= ~__ballot_sync(0xffffffffu, ready);
+            }
+            // running per-cell maximum of sigma_T c_r (positive doubles order like their bit patterns)
+            if (lmax > sMaxOld) atomicMax(reinterpret_cast<unsigned long long*>(&sM[cs]), (unsigned long long)__double_as_longlong(lmax));
+        }
+        __syncwarp();
+        const double m = sM[lane];
+        if (m > mySMax) a.sigmaTcRMax[myCell] = m;
+        __syncwarp();
     }
     const int wc = warp_sum_int(myColl);
     if (lane == 0) {
