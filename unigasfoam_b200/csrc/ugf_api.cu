@@ -85,6 +85,7 @@ struct ugf_handle {
     int* dCfOff = nullptr; double4* dPlane = nullptr; int* dNbr = nullptr; int* dBfPatch = nullptr; int* dBfOwner = nullptr;
     DevPatch* dPatches = nullptr; double* dVol = nullptr; double* dBbMin = nullptr; double* dBbMax = nullptr; double* dBfS = nullptr;
     bool hasProcessor = false;
+    int moveNF = 0;  // uniform face-slot count per cell (4 or 6), 0 = general CSR
 
     // parcels
     long long capacity = 0;
@@ -409,7 +410,10 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     if (count > 0) {
         const DevParams prm = h->prm;
         dispatch(h, [&](auto R, auto M) {
-            move_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
+            constexpr bool r = decltype(R)::value, mm = decltype(M)::value;
+            if (h->moveNF == 6) move_kernel<r, mm, 6><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
+            else if (h->moveNF == 4) move_kernel<r, mm, 4><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
+            else move_kernel<r, mm, 0><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
         });
         LAUNCHED();
     }
@@ -556,10 +560,14 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     h->nBFaces = m->nFaces - m->nInternalFaces;
     const int nC = h->nCells, nB = h->nBFaces, nI = h->nInternal;
     if (nC <= 0 || nB < 0) return fail(h, "bad mesh sizes");
-    h->nSlots = m->cellFaceOffsets[nC];
-    // flatten: per (cell, local face) an outward plane and the cell behind it
-    std::vector<double4> plane(h->nSlots);
-    std::vector<int> nbr(h->nSlots);
+    // flatten: per (cell, local face) an outward plane and the cell behind it.  Faces whose area vector has no
+    // component in any solved direction (the front/back faces of a 2-D case) can never be crossed - the tracking
+    // displacement is zero along empty directions (U/parcels/uniGasParcel.C:64-71) - and are left out.
+    std::vector<double4> plane;
+    std::vector<int> nbr, cfOffDev((size_t)nC + 1, 0);
+    plane.reserve(m->cellFaceOffsets[nC]);
+    nbr.reserve(m->cellFaceOffsets[nC]);
+    int uniformNF = -1;
     for (int c = 0; c < nC; ++c) {
         for (int j = m->cellFaceOffsets[c]; j < m->cellFaceOffsets[c + 1]; ++j) {
             const int f = m->cellFaces[j];
@@ -568,14 +576,22 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
             if (!own && !(f < nI && m->neighbour[f] == c)) return fail(h, "cellFaces lists a face that does not touch the cell");
             const double* S = m->faceAreas + 3 * (size_t)f;
             const double* C = m->faceCentres + 3 * (size_t)f;
+            bool reachable = false;
+            for (int k = 0; k < 3; ++k) if (h->cfg.solutionD[k] && S[k] != 0.0) reachable = true;
+            if (!reachable) continue;
             const double d = S[0] * C[0] + S[1] * C[1] + S[2] * C[2];
             double4 pl;
             if (own) { pl.x = S[0]; pl.y = S[1]; pl.z = S[2]; pl.w = d; }
             else { pl.x = -S[0]; pl.y = -S[1]; pl.z = -S[2]; pl.w = -d; }
-            plane[j] = pl;
-            nbr[j] = f < nI ? (own ? m->neighbour[f] : m->owner[f]) : -(f - nI + 1);
+            plane.push_back(pl);
+            nbr.push_back(f < nI ? (own ? m->neighbour[f] : m->owner[f]) : -(f - nI + 1));
         }
+        cfOffDev[c + 1] = (int)plane.size();
+        const int cnt = cfOffDev[c + 1] - cfOffDev[c];
+        if (c == 0) uniformNF = cnt; else if (cnt != uniformNF) uniformNF = 0;
     }
+    h->nSlots = (int)plane.size();
+    h->moveNF = (uniformNF == 4 || uniformNF == 6) ? uniformNF : 0;
     std::vector<int> bfPatch(std::max(nB, 1), -1), bfOwner(std::max(nB, 1), 0);
     std::vector<double> bfS(3 * (size_t)std::max(nB, 1), 0.0);
     h->patchesHost.assign(h->nPatches, DevPatch{});
@@ -621,7 +637,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         dalloc(h, &h->dVol, (size_t)nC) || dalloc(h, &h->dBbMin, 3 * (size_t)nC) || dalloc(h, &h->dBbMax, 3 * (size_t)nC) ||
         dalloc(h, &h->dBfS, 3 * (size_t)nB))
         return 1;
-    if (upload(h, h->dCfOff, m->cellFaceOffsets, (size_t)nC + 1) || upload(h, h->dPlane, plane.data(), plane.size()) ||
+    if (upload(h, h->dCfOff, cfOffDev.data(), (size_t)nC + 1) || upload(h, h->dPlane, plane.data(), plane.size()) ||
         upload(h, h->dNbr, nbr.data(), nbr.size()) || upload(h, h->dBfPatch, bfPatch.data(), (size_t)nB) ||
         upload(h, h->dBfOwner, bfOwner.data(), (size_t)nB) || upload(h, h->dPatches, h->patchesHost.data(), (size_t)h->nPatches) ||
         upload(h, h->dVol, m->cellVolumes, (size_t)nC) || upload(h, h->dBbMin, m->cellBbMin, 3 * (size_t)nC) ||

@@ -197,7 +197,10 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
     }
 }
 
-template <bool HAS_ROT, bool MULTI>
+// NF > 0: every cell has exactly NF face slots (hex meshes: 6, or 4 after the never-hit faces of an empty
+// direction were pruned at set-up): no offset loads and a fully unrolled face loop, so all plane loads of a hop are
+// issued together.  NF == 0: general polyhedra through the CSR offsets.
+template <bool HAS_ROT, bool MULTI, int NF>
 __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
     const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = *a.dN;
@@ -229,16 +232,33 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
             // (one division per hop, branch-free loop body); (bnum, bnd) = (1, 1) encodes "end of step"
             double bnum = 1.0, bnd = 1.0;
             int hit = -1;
-            const int jb = __ldg(&a.mesh.cfOff[cell]), je = __ldg(&a.mesh.cfOff[cell + 1]);
-            for (int j = jb; j < je; ++j) {
-                const double4 pl = load_plane(&a.mesh.plane[j]);
-                const double nd = fma(pl.z, d2, fma(pl.y, d1, pl.x * d0));
-                double num = pl.w - fma(pl.z, x2, fma(pl.y, x1, pl.x * x0));
-                num = num < 0 ? 0.0 : num;
-                const bool better = (nd > 0) && (num * bnd < bnum * nd);
-                bnum = better ? num : bnum;
-                bnd = better ? nd : bnd;
-                hit = better ? j : hit;
+            if (NF > 0) {
+                const int jb = cell * NF;
+                double4 pl[NF > 0 ? NF : 1];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) pl[f] = load_plane(&a.mesh.plane[jb + f]);
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const double nd = fma(pl[f].z, d2, fma(pl[f].y, d1, pl[f].x * d0));
+                    double num = pl[f].w - fma(pl[f].z, x2, fma(pl[f].y, x1, pl[f].x * x0));
+                    num = num < 0 ? 0.0 : num;
+                    const bool better = (nd > 0) && (num * bnd < bnum * nd);
+                    bnum = better ? num : bnum;
+                    bnd = better ? nd : bnd;
+                    hit = better ? jb + f : hit;
+                }
+            } else {
+                const int jb = __ldg(&a.mesh.cfOff[cell]), je = __ldg(&a.mesh.cfOff[cell + 1]);
+                for (int j = jb; j < je; ++j) {
+                    const double4 pl = load_plane(&a.mesh.plane[j]);
+                    const double nd = fma(pl.z, d2, fma(pl.y, d1, pl.x * d0));
+                    double num = pl.w - fma(pl.z, x2, fma(pl.y, x1, pl.x * x0));
+                    num = num < 0 ? 0.0 : num;
+                    const bool better = (nd > 0) && (num * bnd < bnum * nd);
+                    bnum = better ? num : bnum;
+                    bnd = better ? nd : bnd;
+                    hit = better ? j : hit;
+                }
             }
             if (hit < 0) {
                 x0 = x0 + d0; x1 = x1 + d1; x2 = x2 + d2;
