@@ -1,0 +1,73 @@
+"""Two GPUs, one process each: slab decomposition, device-side pack/unpack, all_to_all over NCCL.  Each rank also
+runs the CPU oracle through the same Exchanger (gloo) and the two must agree bit for bit on collision-free
+tracking.  Skipped on single-GPU boxes (the CPU twin of this test is tests/test_multirank_gloo.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from unigasfoam_b200 import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    meta = dist.new_group(backend="gloo")
+    from oracle.oracle_cloud import OracleCloud
+    from unigasfoam_b200.cloud import UniGasCloud
+    from unigasfoam_b200.exchange import Exchanger, evolve_distributed
+    ok = True
+    msgs = []
+    for binary, steps in (("noDSMCCollision", 6), ("variableHardSphere", 4)):
+        case = cases.couette(nx=32, ny=16, ppc=20, rank=rank, n_ranks=world, binary=binary, Kn=0.5)
+        if binary == "noDSMCCollision":
+            for e in case.boundariesDict["uniGasPatchBoundaries"]:
+                e["boundaryModel"] = "uniGasSpecularWallPatch"
+            case.deltaT *= 5.0
+        kw = dict(parcelCapacity=4 * case.n_parcels, rank=rank, nRanks=world)
+        g = case.make_cloud(UniGasCloud, device=rank, **kw)
+        r = case.make_cloud(OracleCloud, **kw)
+        exg = Exchanger(g, case.mesh, rank, world, data_group=None, meta_group=meta, cuda=True)
+        exr = Exchanger(r, case.mesh, rank, world, data_group=meta, meta_group=meta, cuda=False)
+        evolve_distributed(g, exg, steps)
+        evolve_distributed(r, exr, steps)
+        pg, pr = g.parcels(), r.parcels()
+        same_cells = np.array_equal(pg["cell"], pr["cell"])
+        if binary == "noDSMCCollision":
+            good = same_cells and np.array_equal(pg["position"], pr["position"]) and np.array_equal(pg["U"], pr["U"])
+        else:
+            close = (np.abs(pg["U"] - pr["U"]) <= 1e-9 * np.abs(pr["U"]).max()).all(1).mean() if same_cells else 0.0
+            good = same_cells and close > 0.999 and g.counters()["collisions"] == r.counters()["collisions"]
+        msgs.append((binary, good, exg.sent, exr.sent, g.size(), r.size()))
+        ok = ok and good and exg.sent == exr.sent and exg.sent > 0
+    res = [None] * world
+    dist.all_gather_object(res, (ok, msgs), group=meta)
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier(group=meta)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_migration_matches_oracle(tmp_path, GpuCloud):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert all(ok for ok, _ in res), res

@@ -1,0 +1,70 @@
+"""Statistical parity of sampled fields, GPU vs CPU oracle with INDEPENDENT seeds (BASELINE.json north_star):
+n, U, T, p and wall shear / heat flux agree within 3 sigma of the statistical error and the domain means within 1 %
+over equal sample counts.  sigma is measured from the scatter along the homogeneous (x) direction of each run."""
+import numpy as np
+import pytest
+
+from unigasfoam_b200 import cases
+
+pytestmark = pytest.mark.gpu
+
+NX, NY = 48, 32
+
+
+def run(cloud_cls, seed, warm=150, steps=400):
+    case = cases.couette(nx=NX, ny=NY, ppc=50, Kn=0.2, Uw=300.0, courant=0.4)
+    cl = case.make_cloud(cloud_cls, seed=seed)
+    cl.evolve(warm)
+    cl.fields(resetAtOutput=True)
+    cl.evolve(steps)
+    return case, cl.fields(), cl.counters()
+
+
+def profile(a):
+    a = a.reshape(NY, NX)
+    return a.mean(1), a.std(1, ddof=1) / np.sqrt(NX)
+
+
+def test_couette_fields_within_3_sigma_and_1_percent(GpuCloud, OracleCloud):
+    case, fg, cg = run(GpuCloud, seed=101)
+    _, fr, cr = run(OracleCloud, seed=202)
+    assert cg["nParcels"] == cr["nParcels"] == case.n_parcels and cg["stuck"] == 0
+    for name, get in [("rhoN", lambda f: f["rhoN"]), ("Ux", lambda f: f["UMean"][:, 0]), ("translationalT", lambda f: f["translationalT"]),
+                      ("p", lambda f: f["p"])]:
+        mg, sg = profile(get(fg))
+        mr, sr = profile(get(fr))
+        sigma = np.sqrt(sg ** 2 + sr ** 2)
+        z = np.abs(mg - mr) / sigma
+        assert z.max() < 4.5 and (z > 3).mean() < 0.1, (name, z.max())  # 32 rows: allow the expected 3-sigma tail
+        if name != "Ux":
+            assert abs(mg.mean() - mr.mean()) < 0.01 * abs(mr.mean()), name
+    # antisymmetric Couette profile with velocity slip at Kn = 0.2
+    ux, _ = profile(fg["UMean"][:, 0])
+    assert ux[0] < -150 and ux[-1] > 150 and abs(ux[0] + ux[-1]) < 15
+    assert abs(ux[0]) < 300  # slip
+    nI = case.mesh.n_internal
+    for wall in ("bottom", "top"):
+        p = case.mesh.patches[case.mesh.patch_index(wall)]
+        sl = slice(p.start - nI, p.start - nI + p.size)
+        for key, tol in (("surfaceShearStress", 0.03), ("wall_p", 0.01), ("surfaceHeatTransfer", None)):
+            a, b = fg[key][sl], fr[key][sl]
+            sigma = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+            assert abs(a.mean() - b.mean()) < 3.5 * sigma, (wall, key, a.mean(), b.mean(), sigma)
+            if tol:
+                assert abs(a.mean() - b.mean()) < tol * abs(b.mean()), (wall, key)
+        assert fg["surfaceHeatTransfer"][sl].mean() < 0  # viscous heating flows into the wall (sign: q = E_in - E_out < 0 ... into gas)
+
+
+def test_equilibrium_collision_rate_on_gpu(GpuCloud):
+    import math
+    case = cases.closed_box(n=16, parcels=200000, seed=41)
+    cl = case.make_cloud(GpuCloud)
+    cl.evolve(15)
+    coll = []
+    for _ in range(30):
+        cl.evolve(1)
+        coll.append(cl.counters()["collisions"])
+    cnt = np.bincount(case.cell, minlength=case.mesh.n_cells).astype(float)
+    nu = cases.vhs_collision_rate(case.meta["n"], case.meta["T0"], case.meta["species"], case.meta["Tref"])
+    expect = 0.5 * case.n_parcels * nu * case.deltaT * (cnt * (cnt - 1)).sum() / (cnt ** 2).sum()
+    assert abs(np.mean(coll) - expect) < 4 * math.sqrt(expect / len(coll)) + 0.01 * expect

@@ -1,0 +1,83 @@
+"""World-size-2 run of the multi-rank path on CPU (gloo): slab decomposition with processor / processorCyclic
+patches, pack -> all_to_all -> unpack -> resume tracking, iterate until nothing is in flight.  The CPU oracle stands
+in for the device library behind the same Exchanger; the result must equal the single-domain run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from unigasfoam_b200 import cases
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, steps, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle_cloud import OracleCloud
+    from unigasfoam_b200.exchange import Exchanger, evolve_distributed
+    case = cases.couette(nx=12, ny=8, ppc=12, rank=rank, n_ranks=world, binary="noDSMCCollision")
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        e["boundaryModel"] = "uniGasSpecularWallPatch"
+    case.deltaT *= 6.0  # several cells per step: parcels cross slabs, some wrap around the periodic end
+    cl = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels, rank=rank, nRanks=world)
+    ex = Exchanger(cl, case.mesh, rank, world, cuda=False)
+    n0 = torch.tensor([cl.size()])
+    dist.all_reduce(n0)
+    evolve_distributed(cl, ex, steps)
+    p = cl.parcels()
+    n1 = torch.tensor([cl.size()])
+    dist.all_reduce(n1)
+    res = dict(rank=rank, n0=int(n0), n1=int(n1), pos=p["position"], U=p["U"], cell=p["cell"], rounds=ex.rounds, sent=ex.sent,
+               stuck=cl.counters()["stuck"], x0=rank * case.meta["Lx"], Lx=case.meta["Lx"],
+               init=(case.position.copy(), case.U.copy()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_migration_matches_single_domain(tmp_path, OracleCloud):
+    world, steps = 2, 5
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(world, _free_port(), steps, out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    assert res[0]["n0"] == res[0]["n1"] == sum(len(r["cell"]) for r in res)  # parcels conserved across ranks
+    assert all(r["stuck"] == 0 for r in res)
+    assert sum(r["sent"] for r in res) > 50 and all(r["rounds"] >= steps for r in res)
+    for r in res:  # every parcel ended inside its rank's slab
+        assert (r["pos"][:, 0] >= r["x0"] - 1e-12).all() and (r["pos"][:, 0] <= r["x0"] + r["Lx"] * (1 + 1e-12)).all()
+    # single-domain reference: the same parcels in one periodic channel of twice the length
+    one = cases.couette(nx=24, ny=8, ppc=12, binary="noDSMCCollision")
+    for e in one.boundariesDict["uniGasPatchBoundaries"]:
+        e["boundaryModel"] = "uniGasSpecularWallPatch"
+    one.deltaT *= 6.0
+    pos = np.concatenate([r["init"][0] for r in res])
+    U = np.concatenate([r["init"][1] for r in res])
+    dx = one.meta["Lx"] / 24
+    dy = one.meta["H"] / 8
+    ci = np.minimum((pos[:, 0] / dx).astype(int), 23) + 24 * np.minimum((pos[:, 1] / dy).astype(int), 7)
+    one.position, one.U, one.cell, one.typeId = pos, U, ci.astype(np.int32), np.zeros(len(ci), np.int32)
+    ref = one.make_cloud(OracleCloud, parcelCapacity=4 * len(ci))
+    ref.evolve(steps)
+    pr = ref.parcels()
+    got = np.concatenate([np.column_stack([r["pos"], r["U"]]) for r in res])
+    want = np.column_stack([pr["position"], pr["U"]])
+    key = lambda a: a[np.lexsort(np.round(a / (np.abs(a).max(0) + 1e-300), 9).T[::-1])]
+    g, w = key(got), key(want)
+    assert g.shape == w.shape
+    err = np.abs(g - w) / (np.abs(w).max(0) + 1e-300)
+    assert err.max() < 1e-11, (err.max(), np.unravel_index(err.argmax(), err.shape))
