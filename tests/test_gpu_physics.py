@@ -66,5 +66,7 @@ def test_equilibrium_collision_rate_on_gpu(GpuCloud):
         coll.append(cl.counters()["collisions"])
     cnt = np.bincount(case.cell, minlength=case.mesh.n_cells).astype(float)
     nu = cases.vhs_collision_rate(case.meta["n"], case.meta["T0"], case.meta["species"], case.meta["Tref"])
-    expect = 0.5 * case.n_parcels * nu * case.deltaT * (cnt * (cnt - 1)).sum() / (cnt ** 2).sum()
+    # per cell the rate goes as N(N-1) and the uniform-gas formula as <N>^2: equal once the cell counts are Poisson,
+    # which they are after the warm-up steps
+    expect = 0.5 * case.n_parcels * nu * case.deltaT
     assert abs(np.mean(coll) - expect) < 4 * math.sqrt(expect / len(coll)) + 0.01 * expect

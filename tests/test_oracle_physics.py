@@ -65,8 +65,7 @@ def test_equilibrium_collision_rate_and_candidates(OracleCloud):
     sp = case.meta["species"]
     nu = cases.vhs_collision_rate(case.meta["n"], case.meta["T0"], sp, case.meta["Tref"])
     expect = 0.5 * N * nu * case.deltaT
-    # finite-N: pairs are drawn from N(N-1) not N^2 per cell
-    expect *= (cnt * (cnt - 1)).sum() / (cnt.astype(float) ** 2).sum()
+    # (per cell the rate goes as N(N-1), the formula as <N>^2: equal once the cell counts are Poisson, after warm-up)
     mean = np.mean(coll[10:])
     sigma = math.sqrt(expect / len(coll[10:]))
     assert abs(mean - expect) < 4 * sigma + 0.01 * expect, (mean, expect)
