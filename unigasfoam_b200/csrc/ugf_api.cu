@@ -290,7 +290,7 @@ int after_gather(ugf_handle* h) {
 }
 
 // streaming kernel: gather through the occupancy permutation (optional) + cell moments (optional)
-int run_cell_kernel(ugf_handle* h, bool gather, bool doSample) {
+int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate = false) {
     if (!gather && !doSample) return 0;
     CellArgs a{};
     a.nCells = h->nCells;
@@ -301,6 +301,8 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample) {
     a.gather = gather ? 1 : 0;
     a.doSample = doSample ? 1 : 0;
     a.mom = h->dMom;
+    a.acc = h->dAcc;
+    a.accDt = (accumulate && doSample) ? h->cfg.deltaT : 0.0;
     const DevParams prm = h->prm;
     dispatch(h, [&](auto R, auto M) {
         cell_kernel<decltype(R)::value, decltype(M)::value><<<h->cellBlocks, CELL_THREADS, h->cellSmem, h->stream>>>(prm, a);
@@ -423,7 +425,14 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     return 0;
 }
 
-int do_accumulate(ugf_handle* h) {
+// true if the next do_accumulate() call falls on a sampling step (fieldPropertiesDict sampleInterval)
+bool next_step_samples(const ugf_handle* h) {
+    const int interval = h->cfg.sampleInterval > 0 ? h->cfg.sampleInterval : 1;
+    return interval <= h->sampleCounter + 1;
+}
+
+// cellsDone: the streaming kernel already added this step's cell sums to the accumulators
+int do_accumulate(ugf_handle* h, bool cellsDone = false) {
     h->sampleCounter++;
     const int interval = h->cfg.sampleInterval > 0 ? h->cfg.sampleInterval : 1;
     int accumulate = 0;
@@ -431,8 +440,10 @@ int do_accumulate(ugf_handle* h) {
         h->nAvTimeSteps++;
         h->timeAvCounter += h->cfg.deltaT;
         accumulate = 1;
-        accumulate_cells_kernel<<<grid_for(h->nCells, 256), 256, 0, h->stream>>>(h->prm, h->nCells, h->dMom, h->dAcc);
-        LAUNCHED();
+        if (!cellsDone) {
+            accumulate_cells_kernel<<<grid_for(h->nCells, 256), 256, 0, h->stream>>>(h->prm, h->nCells, h->dMom, h->dAcc);
+            LAUNCHED();
+        }
         h->sampleCounter = 0;
     }
     if (h->cfg.measureWalls) {
@@ -973,12 +984,13 @@ int ugf_step(ugf_handle* h, int32_t nSteps) {
         if (last) CU(cudaEventRecord(h->ev[2], h->stream));
         if (do_sort(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[3], h->stream));
-        if (run_cell_kernel(h, true, true)) return 1;
+        const bool fuseAcc = next_step_samples(h);
+        if (run_cell_kernel(h, true, true, fuseAcc)) return 1;
         if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[4], h->stream));
         if (bgk_active(h) && run_bgk_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[5], h->stream));
-        if (do_accumulate(h)) return 1;
+        if (do_accumulate(h, fuseAcc)) return 1;
         if (last) CU(cudaEventRecord(h->ev[6], h->stream));
         h->step++;
     }

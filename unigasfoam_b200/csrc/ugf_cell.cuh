@@ -41,6 +41,8 @@ struct CellArgs {
     int gather;       // 1: write the cell-major copy into `out`; 0: sample only
     int doSample;
     double* mom;
+    double* acc;      // time-averaged accumulators [nCells][NACC]; updated in the same pass when accDt != 0
+    double accDt;
 };
 
 // postCollisionRotationalEnergy (U/clouds/uniGasCloud.C:1129-1189)
@@ -213,6 +215,31 @@ __host__ __device__ constexpr size_t cell_smem_bytes(bool hasRot) {
     return (size_t)CELL_WARPS * CELL_CAP * (cell_doubles_per_parcel(hasRot) * sizeof(double) + sizeof(int) + 1);
 }
 
+// Contribution of one species' cell sums to accumulator slot k of uniGasVolFields::calculateField
+// (uniGasVolFields.C:761-797; slot list in DESIGN.md section fields).  CWF = RWF = 1.
+__device__ __forceinline__ double acc_term(const DevParams& prm, int s, int k, double cnt, double su, double sv, double sw, double scc, double se) {
+    const DevSpecies& S = prm.sp[s];
+    const double m = S.mass, FN = prm.nParticle;
+    switch (k) {
+        case 0: return cnt;
+        case 1: return m * cnt;
+        case 2: return m * scc;
+        case 3: return m * su;
+        case 4: return m * sv;
+        case 5: return m * sw;
+        case 6: return se;
+        case 7: return S.rotDoF * cnt;
+        case 8: return cnt * FN;
+        case 9: return m * cnt * FN;
+        case 10: return m * su * FN;
+        case 11: return m * sv * FN;
+        case 12: return m * sw * FN;
+        case 13: return m * scc * FN;
+        case 14: return S.rotDoF > 0 ? cnt : 0.0;
+        default: return (5.0 + S.rotDoF) * cnt;
+    }
+}
+
 // Moments of one cell for every species from a randomly accessible view (pu0.. indexed 0..n-1), written as
 // one coalesced 256-byte block per (cell, species): lane k stores slot k (DESIGN.md section moments).  Used for
 // cells that do not fit a staged run; `accumulate` adds to the block instead of overwriting it.
@@ -277,6 +304,15 @@ __device__ __noinline__ void stream_giant_cell(const DevParams& prm, const CellA
         }
         __syncwarp();
         if (a.doSample) cell_moments<HAS_ROT, MULTI>(prm, a.mom, cell, m, sU0, sU1, sU2, sE, sT, lane, b > 0);
+    }
+    __syncwarp();
+    if (a.doSample && a.accDt != 0.0 && lane < NACC) {  // uniGasVolFields accumulation from the finished block
+        double add = 0.0;
+        for (int s = 0; s < prm.nSpecies; ++s) {
+            const double* mm = a.mom + ((size_t)cell * prm.nSpecies + s) * UGF_NMOM;
+            add += acc_term(prm, s, lane, mm[0], mm[2], mm[3], mm[4], mm[14], mm[18]);
+        }
+        a.acc[(size_t)cell * NACC + lane] += a.accDt * add;
     }
     __syncwarp();
 }
@@ -346,6 +382,10 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                 const int ce = __shfl_sync(0xffffffffu, offv, (ci + 1) & 31);
                 const int s0 = cb - b0;
                 const int n = cellValid ? ce - cb : 0;
+                const bool doAcc = a.accDt != 0.0;
+                double* arow = a.acc + (size_t)(c0 + ci) * NACC + q;  // this lane's 4 accumulator slots: q, q+4, q+8, q+12
+                double ac0 = 0, ac1 = 0, ac2 = 0, ac3 = 0;
+                if (doAcc && cellValid) { ac0 = arow[0]; ac1 = arow[4]; ac2 = arow[8]; ac3 = arow[12]; }
                 for (int s = 0; s < nS; ++s) {
                     double su = 0, sv = 0, sw = 0, suu = 0, suv = 0, suw = 0, svv = 0, svw = 0, sww = 0, scc = 0, scu = 0, scv = 0, scw = 0, cnt = 0;
                     double se = 0, seu = 0, sev = 0, sew = 0;
@@ -385,7 +425,14 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                         mrow[24] = select4(q, 0.0, 0.0, cnt * prm.sp[s].E0, 0.0);
                         mrow[28] = 0.0;
                     }
+                    if (doAcc) {  // uniGasVolFields accumulation fused in: slot 4t + q
+                        ac0 += a.accDt * acc_term(prm, s, q, cnt, su, sv, sw, scc, se);
+                        ac1 += a.accDt * acc_term(prm, s, q + 4, cnt, su, sv, sw, scc, se);
+                        ac2 += a.accDt * acc_term(prm, s, q + 8, cnt, su, sv, sw, scc, se);
+                        ac3 += a.accDt * acc_term(prm, s, q + 12, cnt, su, sv, sw, scc, se);
+                    }
                 }
+                if (doAcc && cellValid) { arow[0] = ac0; arow[4] = ac1; arow[8] = ac2; arow[12] = ac3; }
             }
             if (a.gather) {
                 // ---- write velocities cell-major (coalesced), then reuse the buffers for the positions (phase 2) ----
