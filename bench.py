@@ -147,7 +147,7 @@ def main():
     if not os.path.exists(g.LIB):
         g.build()
     from unigasfoam_b200.cloud import UniGasCloud
-    from unigasfoam_b200.exchange import Exchanger, evolve_distributed
+    from unigasfoam_b200.exchange import Exchanger, SlotExchanger, evolve_distributed
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libugf has no CPU fallback")
@@ -163,7 +163,17 @@ def main():
     nC = case.mesh.n_cells
     t_case = time.perf_counter() - t_case
     stream = torch.cuda.ExternalStream(cloud.stream())
-    ex = Exchanger(cloud, case.mesh, rank, world, data_group=None, meta_group=meta, cuda=True) if world > 1 else None
+    ex = None
+    if world > 1:
+        # slot capacity from one exact-count round: 4x the busiest processor patch of a warm-up step
+        probe = Exchanger(cloud, case.mesh, rank, world, data_group=None, meta_group=meta, cuda=True)
+        cloud.move()
+        worst = torch.tensor([int(cloud.migrateCounts().max())], device="cuda")
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        while probe.exchange() > 0:
+            pass
+        cloud.buildCellOccupancy(); cloud.collide(); cloud.relax(); cloud.accumulateFields(); cloud.endStep()
+        ex = SlotExchanger(cloud, case.mesh, rank, world, slot_capacity=max(4096, 4 * int(worst.item())), group=None, cuda=True)
 
     def step(n):
         if world == 1:
@@ -296,7 +306,7 @@ def main():
             "e2e_host_state": host_state, "case_build_s": t_case,
         }
         if world > 1:
-            out["migration"] = {"rounds": ex.rounds, "parcels_sent_rank0": ex.sent}
+            out["migration"] = {"rounds": ex.rounds, "slot_capacity": ex.cap, "protocol": "fixed-slot send/recv + in-flight all-reduce"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -274,6 +274,10 @@ int ugf_relax(ugf_handle* h);
 int ugf_accumulate_fields(ugf_handle* h);
 /* End-of-step bookkeeping when phases are driven one by one: step counter ++. */
 int ugf_end_step(ugf_handle* h);
+/* Everything of evolve() that follows the move and the parcel transfers, in one call and with the same kernel
+ * fusion as ugf_step: occupancy -> reorder + sample (+ field accumulation) -> collide -> relax -> wall fields ->
+ * end of step (U/clouds/uniGasCloud.C:839-866).  Multi-rank drivers call it once the transfer loop has settled. */
+int ugf_finish_step(ugf_handle* h);
 
 /* ---- multi-rank parcel migration (Cloud::move transfer loop, OpenFOAM; §2.1 of SURVEY) ---- */
 
@@ -289,6 +293,18 @@ int ugf_migrate_pack(ugf_handle* h, int32_t patch, double** devBuf, int64_t* nPa
 int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64_t n);
 /* Continue tracking the parcels appended since the last ugf_move / ugf_move_received. */
 int ugf_move_received(ugf_handle* h);
+/* Fixed-slot variant of pack/unpack for drivers that must not synchronise with the host: every processor patch
+ * (in ascending patch order, k = 0,1,...) owns slot k of a caller-provided device buffer.  A slot is
+ * (slotCapacity + 1) records of UGF_MIGRATE_STRIDE doubles: record 0 is a header whose first double is the
+ * number of parcels that follow.  ugf_migrate_pack_slots fills the slots from the parcels waiting on the
+ * processor patches (index order, stable) and removes them from the cloud; ugf_migrate_unpack_slots appends
+ * the parcels found in received slots (slot k = what the peer packed for the patch matching patch k).  Neither
+ * call blocks; a slot overflow raises the handle's device error flag (reported by ugf_counters_get). */
+int ugf_migrate_pack_slots(ugf_handle* h, double* devSend, int64_t slotCapacity);
+int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotCapacity);
+/* Device address of an int64 holding the number of parcels currently waiting on processor patches (valid after
+ * ugf_move / ugf_move_received): all-reduce it to decide whether another transfer round is needed. */
+int ugf_migrate_inflight(ugf_handle* h, int64_t** devCounter);
 /* Raw stream (cudaStream_t) the handle launches on, for interop with NCCL / torch. */
 int ugf_stream(ugf_handle* h, void** stream);
 

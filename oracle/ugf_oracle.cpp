@@ -178,6 +178,7 @@ struct ugfo_handle {
     bool stepOpen = false;
     ugf_counters cnt;
     std::vector<std::vector<double>> packBuf;
+    int64_t inflight = 0;
 };
 
 namespace {
@@ -1150,6 +1151,10 @@ void resetStepCounters(ugfo_handle& h) {
 // =====================================================================================
 extern "C" {
 
+static void countInflight(ugfo_handle* h);
+int ugfo_migrate_pack(ugfo_handle* h, int32_t patch, double** buf, int64_t* n);
+int ugfo_migrate_unpack(ugfo_handle* h, int32_t patch, const double* buf, int64_t n);
+
 int ugfo_abi_version(void) { return UGF_ABI_VERSION; }
 
 static std::string g_createErr;
@@ -1294,6 +1299,7 @@ int ugfo_move(ugfo_handle* h) {
     for (int64_t i = 0; i < (int64_t)h->P.size(); ++i) if (!h->P[i].newParcel) h->P[i].sf = 0;
     moveRange(*h, 0, (int64_t)h->P.size(), true);
     h->receivedStart = (int64_t)h->P.size();
+    countInflight(h);
     return 0;
 }
 
@@ -1322,6 +1328,16 @@ int ugfo_accumulate_fields(ugfo_handle* h) {
 }
 
 int ugfo_end_step(ugfo_handle* h) { h->step++; h->cnt.step = h->step; h->stepOpen = false; return 0; }
+
+int ugfo_finish_step(ugfo_handle* h) {
+    buildOccupancy(*h);
+    reorder(*h);
+    sampleAll(*h);
+    collideAll(*h);
+    relaxAll(*h);
+    accumulateFields(*h);
+    return ugfo_end_step(h);
+}
 
 int ugfo_step(ugfo_handle* h, int32_t nSteps) {
     for (int s = 0; s < nSteps; ++s) {
@@ -1385,8 +1401,46 @@ int ugfo_move_received(ugfo_handle* h) {
     if (h->receivedStart < 0) return fail(h, "ugf_move_received before ugf_move");
     moveRange(*h, h->receivedStart, (int64_t)h->P.size(), false);
     h->receivedStart = (int64_t)h->P.size();
+    countInflight(h);
     return 0;
 }
+
+static void countInflight(ugfo_handle* h) {
+    int64_t n = 0;
+    for (const Parcel& q : h->P) n += (q.cell <= -2);
+    h->inflight = n;
+}
+
+int ugfo_migrate_pack_slots(ugfo_handle* h, double* send, int64_t slotCapacity) {
+    int k = 0;
+    for (int p = 0; p < h->nPatches; ++p) {
+        if (h->pKind[p] != UGF_PATCH_PROCESSOR) continue;
+        double* slot = send + (size_t)k * (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+        double* buf; int64_t n;
+        ugfo_migrate_pack(h, p, &buf, &n);
+        if (n > slotCapacity) return fail(h, "migration slot overflow (raise the slot capacity)");
+        for (int j = 0; j < UGF_MIGRATE_STRIDE; ++j) slot[j] = 0.0;
+        slot[0] = (double)n;
+        std::copy(buf, buf + n * UGF_MIGRATE_STRIDE, slot + UGF_MIGRATE_STRIDE);
+        ++k;
+    }
+    return 0;
+}
+
+int ugfo_migrate_unpack_slots(ugfo_handle* h, const double* recv, int64_t slotCapacity) {
+    int k = 0;
+    for (int p = 0; p < h->nPatches; ++p) {
+        if (h->pKind[p] != UGF_PATCH_PROCESSOR) continue;
+        const double* slot = recv + (size_t)k * (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+        const int64_t n = (int64_t)slot[0];
+        if (n < 0 || n > slotCapacity) return fail(h, "corrupt migration slot header");
+        if (int rc = ugfo_migrate_unpack(h, p, slot + UGF_MIGRATE_STRIDE, n)) return rc;
+        ++k;
+    }
+    return 0;
+}
+
+int ugfo_migrate_inflight(ugfo_handle* h, int64_t** p) { *p = &h->inflight; return 0; }
 
 int ugfo_stream(ugfo_handle*, void** s) { *s = nullptr; return 0; }
 

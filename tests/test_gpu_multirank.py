@@ -30,10 +30,10 @@ def _worker(rank, world, port, out):
     meta = dist.new_group(backend="gloo")
     from oracle.oracle_cloud import OracleCloud
     from unigasfoam_b200.cloud import UniGasCloud
-    from unigasfoam_b200.exchange import Exchanger, evolve_distributed
+    from unigasfoam_b200.exchange import Exchanger, SlotExchanger, evolve_distributed
     ok = True
     msgs = []
-    for binary, steps in (("noDSMCCollision", 6), ("variableHardSphere", 4)):
+    for binary, steps, slots in (("noDSMCCollision", 6, False), ("variableHardSphere", 4, False), ("noDSMCCollision", 6, True), ("variableHardSphere", 4, True)):
         case = cases.couette(nx=32, ny=16, ppc=20, rank=rank, n_ranks=world, binary=binary, Kn=0.5)
         if binary == "noDSMCCollision":
             for e in case.boundariesDict["uniGasPatchBoundaries"]:
@@ -42,8 +42,12 @@ def _worker(rank, world, port, out):
         kw = dict(parcelCapacity=4 * case.n_parcels, rank=rank, nRanks=world)
         g = case.make_cloud(UniGasCloud, device=rank, **kw)
         r = case.make_cloud(OracleCloud, **kw)
-        exg = Exchanger(g, case.mesh, rank, world, data_group=None, meta_group=meta, cuda=True)
-        exr = Exchanger(r, case.mesh, rank, world, data_group=meta, meta_group=meta, cuda=False)
+        if slots:
+            exg = SlotExchanger(g, case.mesh, rank, world, slot_capacity=2000, group=None, cuda=True)
+            exr = SlotExchanger(r, case.mesh, rank, world, slot_capacity=2000, group=meta, cuda=False)
+        else:
+            exg = Exchanger(g, case.mesh, rank, world, data_group=None, meta_group=meta, cuda=True)
+            exr = Exchanger(r, case.mesh, rank, world, data_group=meta, meta_group=meta, cuda=False)
         evolve_distributed(g, exg, steps)
         evolve_distributed(r, exr, steps)
         pg, pr = g.parcels(), r.parcels()
@@ -53,8 +57,8 @@ def _worker(rank, world, port, out):
         else:
             close = (np.abs(pg["U"] - pr["U"]) <= 1e-9 * np.abs(pr["U"]).max()).all(1).mean() if same_cells else 0.0
             good = same_cells and close > 0.999 and g.counters()["collisions"] == r.counters()["collisions"]
-        msgs.append((binary, good, exg.sent, exr.sent, g.size(), r.size()))
-        ok = ok and good and exg.sent == exr.sent and exg.sent > 0
+        msgs.append((binary, slots, good, exg.rounds, exr.rounds, g.size(), r.size()))
+        ok = ok and good and exg.rounds == exr.rounds and g.counters()["migrated"] > 0
     res = [None] * world
     dist.all_gather_object(res, (ok, msgs), group=meta)
     if rank == 0:

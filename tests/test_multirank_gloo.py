@@ -21,24 +21,24 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, steps, out):
+def _worker(rank, world, port, steps, out, slots):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle.oracle_cloud import OracleCloud
-    from unigasfoam_b200.exchange import Exchanger, evolve_distributed
+    from unigasfoam_b200.exchange import Exchanger, SlotExchanger, evolve_distributed
     case = cases.couette(nx=12, ny=8, ppc=12, rank=rank, n_ranks=world, binary="noDSMCCollision")
     for e in case.boundariesDict["uniGasPatchBoundaries"]:
         e["boundaryModel"] = "uniGasSpecularWallPatch"
     case.deltaT *= 6.0  # several cells per step: parcels cross slabs, some wrap around the periodic end
     cl = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels, rank=rank, nRanks=world)
-    ex = Exchanger(cl, case.mesh, rank, world, cuda=False)
+    ex = SlotExchanger(cl, case.mesh, rank, world, slot_capacity=600, cuda=False) if slots else Exchanger(cl, case.mesh, rank, world, cuda=False)
     n0 = torch.tensor([cl.size()])
     dist.all_reduce(n0)
     evolve_distributed(cl, ex, steps)
     p = cl.parcels()
     n1 = torch.tensor([cl.size()])
     dist.all_reduce(n1)
-    res = dict(rank=rank, n0=int(n0), n1=int(n1), pos=p["position"], U=p["U"], cell=p["cell"], rounds=ex.rounds, sent=ex.sent,
+    res = dict(rank=rank, n0=int(n0), n1=int(n1), pos=p["position"], U=p["U"], cell=p["cell"], rounds=ex.rounds, sent=getattr(ex, 'sent', 10 ** 6),
                stuck=cl.counters()["stuck"], x0=rank * case.meta["Lx"], Lx=case.meta["Lx"],
                init=(case.position.copy(), case.U.copy()))
     gathered = [None] * world
@@ -50,10 +50,11 @@ def _worker(rank, world, port, steps, out):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_migration_matches_single_domain(tmp_path, OracleCloud):
+@pytest.mark.parametrize("slots", [False, True], ids=["exact-count", "fixed-slot"])
+def test_two_rank_migration_matches_single_domain(tmp_path, OracleCloud, slots):
     world, steps = 2, 5
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(world, _free_port(), steps, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), steps, out, slots), nprocs=world, join=True)
     res = torch.load(out, weights_only=False)
     assert res[0]["n0"] == res[0]["n1"] == sum(len(r["cell"]) for r in res)  # parcels conserved across ranks
     assert all(r["stuck"] == 0 for r in res)

@@ -130,10 +130,14 @@ SIGNATURES = {
     "relax": (C.c_int, [H]),
     "accumulate_fields": (C.c_int, [H]),
     "end_step": (C.c_int, [H]),
+    "finish_step": (C.c_int, [H]),
     "migrate_counts": (C.c_int, [H, PI64]),
     "migrate_pack": (C.c_int, [H, i32, P(PF), PI64]),
     "migrate_unpack": (C.c_int, [H, i32, PF, i64]),
     "move_received": (C.c_int, [H]),
+    "migrate_pack_slots": (C.c_int, [H, PF, i64]),
+    "migrate_unpack_slots": (C.c_int, [H, PF, i64]),
+    "migrate_inflight": (C.c_int, [H, P(PI64)]),
     "stream": (C.c_int, [H, P(C.c_void_p)]),
     "counters_get": (C.c_int, [H, P(Counters)]),
     "num_parcels": (C.c_int, [H, PI64]),

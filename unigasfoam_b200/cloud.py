@@ -246,6 +246,10 @@ class UniGasCloud:
     def endStep(self):
         self._check(self.api.end_step(self._h))
 
+    def finishStep(self):
+        """buildCellOccupancy ... cellMeas_.clean() of evolve() in one call (U/clouds/uniGasCloud.C:839-866)."""
+        self._check(self.api.finish_step(self._h))
+
     # -- migration --------------------------------------------------------------------
     def migrateCounts(self):
         out = (C.c_int64 * len(self.mesh.patches))()
@@ -260,6 +264,17 @@ class UniGasCloud:
 
     def migrateUnpack(self, patch, buf_ptr, n):
         self._check(self.api.migrate_unpack(self._h, patch, buf_ptr, int(n)))
+
+    def migratePackSlots(self, send_ptr, slot_capacity):
+        self._check(self.api.migrate_pack_slots(self._h, send_ptr, int(slot_capacity)))
+
+    def migrateUnpackSlots(self, recv_ptr, slot_capacity):
+        self._check(self.api.migrate_unpack_slots(self._h, recv_ptr, int(slot_capacity)))
+
+    def migrateInflightPtr(self):
+        p = C.POINTER(C.c_int64)()
+        self._check(self.api.migrate_inflight(self._h, C.byref(p)))
+        return C.cast(p, C.c_void_p).value
 
     def moveReceived(self):
         self._check(self.api.move_received(self._h))

@@ -104,7 +104,11 @@ struct ugf_handle {
 
     // cells
     int* dCellCount = nullptr; int* dOff = nullptr; int* dPerm = nullptr; int* dBlockSums = nullptr; int* dTotal = nullptr;
-    int* dMigCount = nullptr; int* dMigBlock = nullptr;
+    int* dMigCount = nullptr; int* dMigBlock = nullptr; int* dMigTotals = nullptr;
+    unsigned long long* dInflight = nullptr; long long* dRecvStart = nullptr;
+    long long nAtMove = 0;          // exact array length when the step's move was launched
+    bool slotRound = false;         // received parcels of this round came through the slot path
+    MigSlots migSlots{};
     double* dMom = nullptr; double* dAcc = nullptr; double* dBm = nullptr; double* dBacc = nullptr;
     double* dSigma = nullptr; int* dCollId = nullptr; double* dMaxProb = nullptr; double* dQPrev = nullptr; double* dSPrev = nullptr;
     double* dKeyScratch = nullptr;
@@ -186,6 +190,8 @@ int check_device_error(ugf_handle* h) {
     CU(cudaStreamSynchronize(h->stream));
     if (e == 1) return fail(h, "parcel capacity exceeded while inserting parcels (raise parcelCapacity)");
     if (e == 2) return fail(h, "received parcel with a face index outside the processor patch");
+    if (e == 3) return fail(h, "migration slot overflow: more parcels crossed a processor patch than slotCapacity");
+    if (e == 4) return fail(h, "corrupt migration slot header");
     if (e) return fail(h, "device error flag " + std::to_string(e));
     return 0;
 }
@@ -250,7 +256,7 @@ int alloc_parcels(ugf_handle* h) {
     if (dalloc(h, &h->dPerm, cap)) return 1;
     if (dalloc(h, &h->dOwner, cap)) return 1;
     CU(cudaMemsetAsync(h->dOwner, 0x7f, cap * sizeof(int), h->stream));
-    if (dalloc(h, &h->dMigBlock, cap / 1024 + 2)) return 1;
+    if (dalloc(h, &h->dMigBlock, (size_t)MIG_MAXP * (cap / 1024 + 2))) return 1;
     return 0;
 }
 
@@ -394,6 +400,7 @@ int do_move(ugf_handle* h, long long begin, bool received) {
         CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * h->nCells, h->stream));
         CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
     }
+    CU(cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream));
     MoveArgs a{};
     a.mesh = h->mesh;
     a.P = h->buf[h->cur];
@@ -406,6 +413,8 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.aux = received ? 1u : 0u;
     a.cellCount = h->dCellCount;
     a.migCount = h->dMigCount;
+    a.inflight = h->dInflight;
+    a.dBegin = (received && h->slotRound) ? h->dRecvStart : nullptr;
     a.bm = h->dBm;
     a.cnt = h->dCnt;
     const long long count = h->nUpper - begin;
@@ -512,6 +521,11 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     if ((e = cudaMalloc((void**)&h->dErr, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dTot, 6 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dTotal, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dMigTotals, MIG_MAXP * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dInflight, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dRecvStart, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->dRecvStart, 0, sizeof(long long), h->stream);
     cudaMemsetAsync(h->dN, 0, sizeof(long long), h->stream);
     cudaMemsetAsync(h->dCnt, 0, sizeof(DevCounters), h->stream);
     cudaMemsetAsync(h->dErr, 0, sizeof(int), h->stream);
@@ -530,7 +544,7 @@ int ugf_destroy(ugf_handle* h) {
         cudaFree(P.erot); cudaFree(P.cell); cudaFree(P.type);
     }
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
-                    h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock,
+                    h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner,
                     h->dCnt, h->dErr, h->dTot};
     for (void* p : ptrs) cudaFree(p);
@@ -625,7 +639,11 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
                 return fail(h, "cyclic patch without a matching partner");
             d.partnerStartBfi = m->patchStart[q] - nI;
         }
-        if (d.kind == UGF_PATCH_PROCESSOR) h->hasProcessor = true;
+        if (d.kind == UGF_PATCH_PROCESSOR) {
+            h->hasProcessor = true;
+            if (h->migSlots.nProc < MIG_MAXP) h->migSlots.patch[h->migSlots.nProc] = p;
+            h->migSlots.nProc++;
+        }
         if (d.kind < UGF_PATCH_WALL || d.kind > UGF_PATCH_GENERIC) return fail(h, "unknown patch kind");
         for (int k = 0; k < d.size; ++k) bfPatch[d.startBfi + k] = p;
     }
@@ -910,6 +928,8 @@ int ugf_move(ugf_handle* h) {
     }
     h->inflowDone = false;
     h->recvStart = h->nUpper;
+    h->nAtMove = h->nUpper;
+    h->slotRound = false;
     return 0;
 }
 
@@ -966,6 +986,17 @@ int ugf_end_step(ugf_handle* h) {
     h->step++;
     h->stepOpen = false;
     return 0;
+}
+
+int ugf_finish_step(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (do_sort(h)) return 1;
+    const bool fuseAcc = next_step_samples(h);
+    if (run_cell_kernel(h, true, true, fuseAcc)) return 1;
+    if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
+    if (bgk_active(h) && run_bgk_kernel(h)) return 1;
+    if (do_accumulate(h, fuseAcc)) return 1;
+    return ugf_end_step(h);
 }
 
 int ugf_step(ugf_handle* h, int32_t nSteps) {
@@ -1062,8 +1093,68 @@ int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64
 int ugf_move_received(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (h->recvStart < 0) return fail(h, "ugf_move_received before ugf_move");
+    if (h->slotRound) {
+        // received through slots: the exact start lives on the device (dRecvStart); launch over everything appended
+        // since the step's move and let the kernel skip what precedes it
+        if (do_move(h, h->nAtMove, true)) return 1;
+        return 0;
+    }
     if (do_move(h, h->recvStart, true)) return 1;
     h->recvStart = h->nUpper;
+    return 0;
+}
+
+int ugf_migrate_pack_slots(ugf_handle* h, double* devSend, int64_t slotCapacity) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (h->migSlots.nProc > MIG_MAXP) return fail(h, "too many processor patches for the slot path");
+    if (h->migSlots.nProc == 0) return 0;
+    if (slotCapacity < 1) return fail(h, "slotCapacity must be positive");
+    const int nb = (int)grid_for(h->nUpper, 1024);
+    ParcelBuf P = h->buf[h->cur];
+    const MigSlots ms = h->migSlots;
+    mig_count_all_kernel<<<nb, 1024, 0, h->stream>>>(h->mesh, ms, P.cell, h->dN, h->dMigBlock, nb);
+    LAUNCHED();
+    mig_scan_kernel<<<ms.nProc, SCAN_THREADS, 0, h->stream>>>(h->dMigBlock, nb, h->dMigTotals);
+    LAUNCHED();
+    dispatch(h, [&](auto R, auto M) {
+        mig_pack_all_kernel<decltype(R)::value, decltype(M)::value><<<nb, 1024, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dN, h->dMigBlock, h->dMigTotals, nb,
+                                                                                                 devSend, (long long)slotCapacity, h->dErr);
+    });
+    LAUNCHED();
+    CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
+    return 0;
+}
+
+int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotCapacity) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (h->migSlots.nProc > MIG_MAXP) return fail(h, "too many processor patches for the slot path");
+    if (h->migSlots.nProc == 0) return 0;
+    if (h->nUpper + (long long)h->migSlots.nProc * slotCapacity > h->capacity)
+        return fail(h, "parcelCapacity too small for the migration slots (needs room for nProcPatches x slotCapacity parcels)");
+    ParcelBuf P = h->buf[h->cur];
+    mig_mark_start_kernel<<<1, 1, 0, h->stream>>>(h->dRecvStart, h->dN);
+    LAUNCHED();
+    const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+    for (int k = 0; k < h->migSlots.nProc; ++k) {
+        const double* slot = devRecv + k * slotStride;
+        const int patch = h->migSlots.patch[k];
+        dispatch(h, [&](auto R, auto M) {
+            mig_unpack_slot_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(slotCapacity, 256), 256, 0, h->stream>>>(
+                h->mesh, P, h->dSf, h->dN, h->capacity, patch, slot, (long long)slotCapacity, h->dErr);
+        });
+        LAUNCHED();
+        mig_bump_kernel<<<1, 1, 0, h->stream>>>(h->dN, slot, h->capacity);
+        LAUNCHED();
+        h->nUpper += slotCapacity;
+    }
+    h->slotRound = true;
+    h->occValid = false; h->momValid = false;
+    return 0;
+}
+
+int ugf_migrate_inflight(ugf_handle* h, int64_t** dev) {
+    if (!h) return 1;
+    *dev = reinterpret_cast<int64_t*>(h->dInflight);
     return 0;
 }
 

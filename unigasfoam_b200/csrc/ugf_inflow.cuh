@@ -194,4 +194,120 @@ __global__ void __launch_bounds__(256) mig_unpack_kernel(MeshDev mesh, ParcelBuf
     if (MULTI) P.type[dst] = (uint8_t)r[9];
 }
 
+// ---- fixed-slot migration: all processor patches in two passes over the parcels, no host round trip ------------
+constexpr int MIG_MAXP = 8;  // processor patches per rank the slot path handles
+
+struct MigSlots {
+    int nProc;
+    int patch[MIG_MAXP];
+};
+
+__device__ __forceinline__ int mig_slot_of(const MeshDev& mesh, const MigSlots& ms, int cell) {
+    if (cell > -2) return -1;
+    const int p = mesh.bfPatch[-2 - cell];
+    int slot = -1;
+#pragma unroll
+    for (int k = 0; k < MIG_MAXP; ++k) if (k < ms.nProc && ms.patch[k] == p) slot = k;
+    return slot;
+}
+
+__global__ void __launch_bounds__(1024) mig_count_all_kernel(MeshDev mesh, MigSlots ms, const int* __restrict__ cell, const long long* dN,
+                                                             int* __restrict__ blockCounts, int nBlocks) {
+    __shared__ int cnt[MIG_MAXP];
+    if (threadIdx.x < MIG_MAXP) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = (i < *dN) ? mig_slot_of(mesh, ms, cell[i]) : -1;
+    if (__any_sync(0xffffffffu, slot >= 0)) {
+        for (int k = 0; k < ms.nProc; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, slot == k);
+            if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[k], __popc(m));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ms.nProc) blockCounts[threadIdx.x * nBlocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// one block per slot: exclusive scan of that slot's per-block counts in place, total to totals[slot]
+__global__ void __launch_bounds__(SCAN_THREADS) mig_scan_kernel(int* blockCounts, int nBlocks, int* totals) {
+    __shared__ int sm[33];
+    int* b = blockCounts + (size_t)blockIdx.x * nBlocks;
+    int carry = 0;
+    for (int base = 0; base < nBlocks; base += SCAN_THREADS) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < nBlocks ? b[idx] : 0;
+        int t;
+        const int ex = block_exclusive_scan(v, &t, sm);
+        if (idx < nBlocks) b[idx] = carry + ex;
+        carry += t;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(1024) mig_pack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const long long* dN,
+                                                            const int* __restrict__ blockOffsets, const int* __restrict__ totals, int nBlocks,
+                                                            double* __restrict__ send, long long slotCapacity, int* errFlag) {
+    __shared__ int sm[33];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = -1;
+    if (i < *dN) c = P.cell[i];
+    const int slot = mig_slot_of(mesh, ms, c);
+    const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+    if (blockIdx.x == 0 && threadIdx.x < ms.nProc) {  // headers
+        double* hdr = send + threadIdx.x * slotStride;
+        const int tot = totals[threadIdx.x];
+        hdr[0] = (double)(tot <= slotCapacity ? tot : slotCapacity);
+        for (int j = 1; j < UGF_MIGRATE_STRIDE; ++j) hdr[j] = 0.0;
+        if (tot > slotCapacity) *errFlag = 3;
+    }
+    if (!__syncthreads_or(slot >= 0)) return;
+    for (int k = 0; k < ms.nProc; ++k) {
+        int total;
+        const int ex = block_exclusive_scan(slot == k ? 1 : 0, &total, sm);
+        if (slot == k) {
+            const long long pos = (long long)blockOffsets[k * nBlocks + blockIdx.x] + ex;
+            if (pos < slotCapacity) {
+                double* r = send + k * slotStride + (1 + pos) * UGF_MIGRATE_STRIDE;
+                const int bfi = -2 - c;
+                r[0] = P.x[i]; r[1] = P.y[i]; r[2] = P.z[i];
+                r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
+                r[6] = HAS_ROT ? P.erot[i] : 0.0;
+                r[7] = sf[i];
+                r[8] = (double)(bfi - mesh.patches[ms.patch[k]].startBfi);
+                r[9] = MULTI ? (double)P.type[i] : 0.0;
+            }
+            P.cell[i] = -1;
+        }
+    }
+}
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(256) mig_unpack_slot_kernel(MeshDev mesh, ParcelBuf P, double* __restrict__ sf, const long long* dN, long long capacity,
+                                                              int patch, const double* __restrict__ slot, long long slotCapacity, int* errFlag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)slot[0];
+    if (n < 0 || n > slotCapacity) { if (i == 0) *errFlag = 4; return; }
+    if (i >= n) return;
+    const long long dst = *dN + i;
+    if (dst >= capacity) { *errFlag = 1; return; }
+    const double* r = slot + (1 + i) * UGF_MIGRATE_STRIDE;
+    const int lf = (int)r[8];
+    const DevPatch& pt = mesh.patches[patch];
+    if (lf < 0 || lf >= pt.size) { *errFlag = 2; P.cell[dst] = -1; return; }
+    P.x[dst] = r[0]; P.y[dst] = r[1]; P.z[dst] = r[2];
+    P.ux[dst] = r[3]; P.uy[dst] = r[4]; P.uz[dst] = r[5];
+    if (HAS_ROT) P.erot[dst] = r[6];
+    sf[dst] = r[7];
+    P.cell[dst] = mesh.bfOwner[pt.startBfi + lf];
+    if (MULTI) P.type[dst] = (uint8_t)r[9];
+}
+
+__global__ void mig_bump_kernel(long long* dN, const double* slot, long long capacity) {
+    const long long n = (long long)slot[0];
+    if (n > 0 && *dN + n <= capacity) *dN += n;
+}
+
+__global__ void mig_mark_start_kernel(long long* dRecvStart, const long long* dN) { *dRecvStart = *dN; }
+
 }  // namespace ugf

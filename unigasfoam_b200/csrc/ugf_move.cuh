@@ -129,6 +129,8 @@ struct MoveArgs {
     uint32_t aux;          // stream aux: 0 for the step's first move, 1 for received parcels
     int* cellCount;        // [nCells] histogram of destination cells
     int* migCount;         // [nPatches]
+    unsigned long long* inflight;  // parcels waiting on processor patches, all patches
+    const long long* dBegin;       // if set: only parcels with index >= *dBegin are tracked (received parcels)
     double* bm;            // [nBFaces][UGF_NBM]
     DevCounters* cnt;
 };
@@ -190,6 +192,7 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
         st.flags |= HIT_MIGRATED;
         if (a.sf) a.sf[i] = st.sf;
         atomicAdd(&a.migCount[patch], 1);
+        atomicAdd(a.inflight, 1ull);
     } else if (pt.kind == UGF_PATCH_GENERIC) {
         st.cell = -1; st.flags |= HIT_DELETED;
     } else {
@@ -204,7 +207,8 @@ template <bool HAS_ROT, bool MULTI, int NF>
 __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
     const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = *a.dN;
-    const bool valid = i < n;
+    bool valid = i < n;
+    if (a.dBegin && i < *a.dBegin) valid = false;
     int cell = -1;
     int flags = 0, nWall = 0;
     if (valid) cell = a.P.cell[i];

@@ -105,6 +105,61 @@ class Exchanger:
         return total
 
 
+class SlotExchanger:
+    """Fixed-slot transfer rounds without per-round host bookkeeping.
+
+    Every processor patch owns one slot (header + slot_capacity records) of a persistent send and a persistent
+    receive buffer.  A round is: device-side pack of all patches (two passes over the cell ids) -> one grouped
+    NCCL send/recv with the neighbours only -> device-side unpack (counts come from the slot headers) -> resume
+    tracking -> all-reduce of the device-resident in-flight counter, the only value the host reads back.
+    """
+
+    def __init__(self, cloud, mesh, rank, world, slot_capacity, group=None, cuda=False):
+        self.cloud, self.mesh, self.rank, self.world, self.group, self.cuda = cloud, mesh, rank, world, group, cuda
+        self.cap = int(slot_capacity)
+        proc = [(i, p.partner, tuple(p.tag)) for i, p in enumerate(mesh.patches) if p.kind == "processor"]
+        self.slot_of = {patch: k for k, (patch, _, _) in enumerate(proc)}
+        stride = (self.cap + 1) * STRIDE
+        dev = "cuda" if cuda else "cpu"
+        self.send = torch.zeros(max(len(proc), 1), stride, dtype=torch.float64, device=dev)
+        self.recv = torch.zeros(max(len(proc), 1), stride, dtype=torch.float64, device=dev)
+        peers = sorted({b for _, b, _ in proc})
+        # order of messages between a pair of ranks: by the sender's patch tag (see Exchanger)
+        self.sends = [(self.slot_of[q[0]], b) for b in peers for q in sorted([q for q in proc if q[1] == b], key=lambda q: _sender_tag(q[2]))]
+        self.recvs = [(self.slot_of[q[0]], b) for b in peers for q in sorted([q for q in proc if q[1] == b], key=lambda q: _receiver_view(q[2]))]
+        self.rounds = 0
+        self._stream = torch.cuda.ExternalStream(cloud.stream()) if cuda else None
+        ptr = cloud.migrateInflightPtr()
+        if cuda:
+            self._inflight = torch.as_tensor(_DevI64(ptr), device="cuda")
+        else:
+            self._inflight = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(1,)))
+        self._sp = C.cast(self.send.data_ptr(), C.POINTER(C.c_double))
+        self._rp = C.cast(self.recv.data_ptr(), C.POINTER(C.c_double))
+
+    def exchange(self):
+        """One transfer round; returns the number of parcels still in flight over all ranks afterwards."""
+        self.rounds += 1
+        ctx = torch.cuda.stream(self._stream) if self.cuda else _Null()
+        with ctx:
+            self.cloud.migratePackSlots(self._sp, self.cap)
+            ops = [dist.P2POp(dist.isend, self.send[k], b, self.group) for k, b in self.sends]
+            ops += [dist.P2POp(dist.irecv, self.recv[k], b, self.group) for k, b in self.recvs]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            self.cloud.migrateUnpackSlots(self._rp, self.cap)
+            self.cloud.moveReceived()
+            total = self._inflight.clone()
+            dist.all_reduce(total, group=self.group)
+            return int(total.item())
+
+
+class _DevI64:
+    def __init__(self, ptr):
+        self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+
+
 class _Null:
     def __enter__(self):
         return self
@@ -114,7 +169,8 @@ class _Null:
 
 
 def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64):
-    """uniGasCloud::evolve across ranks: the phases of ugf_step with the transfer loop after the move."""
+    """uniGasCloud::evolve across ranks: the phases of ugf_step with the transfer loop after the move.  Both
+    exchangers return 0 from exchange() once no rank has parcels in flight (the reference's termination rule)."""
     for _ in range(n_steps):
         if inflow:
             cloud.controlBeforeMove()
@@ -124,8 +180,4 @@ def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64)
                 break
         else:
             raise RuntimeError("parcel migration did not settle")
-        cloud.buildCellOccupancy()
-        cloud.collide()
-        cloud.relax()
-        cloud.accumulateFields()
-        cloud.endStep()
+        cloud.finishStep()
