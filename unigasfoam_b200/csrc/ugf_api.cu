@@ -97,6 +97,7 @@ struct ugf_handle {
     long long* pinN = nullptr;      // pinned readback of *dN
     cudaEvent_t evN = nullptr;
     bool nPending = false;
+    long long appendBound = 0;      // upper bound of the parcels appended since the pending read-back was requested
     long long newFrom = 0;          // parcels >= newFrom were inserted this step
     bool inflowDone = false;        // control_before_move ran since the last move
     bool stepOpen = false;          // phase-wise driving: counters were reset for the current step
@@ -108,6 +109,7 @@ struct ugf_handle {
     unsigned long long* dInflight = nullptr; long long* dRecvStart = nullptr;
     long long nAtMove = 0;          // exact array length when the step's move was launched
     bool slotRound = false;         // received parcels of this round came through the slot path
+    bool nExact = true;             // nUpper is the exact array length (needed by the exact-count unpack)
     MigSlots migSlots{};
     double* dMom = nullptr; double* dAcc = nullptr; double* dBm = nullptr; double* dBacc = nullptr;
     double* dSigma = nullptr; int* dCollId = nullptr; double* dMaxProb = nullptr; double* dQPrev = nullptr; double* dSPrev = nullptr;
@@ -200,8 +202,28 @@ int check_device_error(ugf_handle* h) {
 int refresh_n(ugf_handle* h) {
     if (h->nPending) {
         CU(cudaEventSynchronize(h->evN));
-        h->nUpper = *h->pinN;
+        h->nUpper = std::min<long long>(h->capacity, *h->pinN + h->appendBound);
         h->nPending = false;
+    }
+    return 0;
+}
+
+// Non-blocking variant for drivers that keep the GPU queue full: take the exact length if its read-back has landed,
+// otherwise fall back to the capacity as launch bound (kernels compare against the device-resident length anyway).
+int refresh_n_lazy(ugf_handle* h, bool* exact) {
+    *exact = true;
+    if (h->nPending) {
+        const cudaError_t q = cudaEventQuery(h->evN);
+        if (q == cudaSuccess) {
+            h->nUpper = std::min<long long>(h->capacity, *h->pinN + h->appendBound);
+            h->nPending = false;
+            *exact = (h->appendBound == 0);
+        } else if (q == cudaErrorNotReady) {
+            h->nUpper = h->capacity;
+            *exact = false;
+        } else {
+            return fail(h, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+        }
     }
     return 0;
 }
@@ -210,6 +232,7 @@ int request_n(ugf_handle* h) {
     CU(cudaMemcpyAsync(h->pinN, h->dN, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->evN, h->stream));
     h->nPending = true;
+    h->appendBound = 0;  // the copy is ordered after everything appended so far
     return 0;
 }
 
@@ -256,7 +279,7 @@ int alloc_parcels(ugf_handle* h) {
     if (dalloc(h, &h->dPerm, cap)) return 1;
     if (dalloc(h, &h->dOwner, cap)) return 1;
     CU(cudaMemsetAsync(h->dOwner, 0x7f, cap * sizeof(int), h->stream));
-    if (dalloc(h, &h->dMigBlock, (size_t)MIG_MAXP * (cap / 1024 + 2))) return 1;
+    if (dalloc(h, &h->dMigBlock, (size_t)2 * MIG_MAXP * (cap / 1024 + 2))) return 1;  // per-(slot, block) counts and offsets
     return 0;
 }
 
@@ -386,6 +409,7 @@ int do_inflow(ugf_handle* h) {
         });
         LAUNCHED();
         h->nUpper += f.maxInsert;
+        h->appendBound += f.maxInsert;
     }
     h->inflowDone = true;
     h->histValid = false; h->occValid = false; h->momValid = false;
@@ -919,16 +943,21 @@ int ugf_control_before_move(ugf_handle* h) {
 
 int ugf_move(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
-    if (refresh_n(h)) return 1;
+    h->nExact = true;
+    if (h->hasProcessor && h->inflows.empty() && !h->inflowDone) {
+        if (refresh_n_lazy(h, &h->nExact)) return 1;  // multi-rank, no insertion: do not stall the host on the previous step
+    } else if (refresh_n(h)) {
+        return 1;
+    }
     if (open_step(h)) return 1;
-    if (!h->inflowDone) h->newFrom = h->nUpper;
+    if (!h->inflowDone) h->newFrom = h->nExact ? h->nUpper : (1LL << 62);
     if (do_move(h, 0, false)) return 1;
     if (h->inflowDone) {  // the insert count is only known on the device: make the host mirror exact again
         if (request_n(h) || refresh_n(h)) return 1;
     }
     h->inflowDone = false;
     h->recvStart = h->nUpper;
-    h->nAtMove = h->nUpper;
+    h->nAtMove = h->nExact ? h->nUpper : 0;
     h->slotRound = false;
     return 0;
 }
@@ -1073,7 +1102,12 @@ int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (patch < 0 || patch >= h->nPatches || h->patchKind[patch] != UGF_PATCH_PROCESSOR) return fail(h, "unpack on a non-processor patch");
     if (n <= 0) return 0;
-    if (h->nPending) return fail(h, "ugf_migrate_unpack must follow ugf_move");
+    if (h->nPending && h->nExact) return fail(h, "ugf_migrate_unpack must follow ugf_move");
+    if (!h->nExact) {  // the exact-count path appends at a host-known index: wait for the length now
+        if (refresh_n(h)) return 1;
+        h->nExact = true;
+        h->recvStart = h->nUpper;
+    }
     if (h->nUpper + n > h->capacity) return fail(h, "parcelCapacity too small for the received parcels");
     ParcelBuf P = h->buf[h->cur];
     const long long base = h->nUpper;
@@ -1082,6 +1116,7 @@ int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64
     });
     LAUNCHED();
     h->nUpper += n;
+    h->appendBound += n;
     const long long nn = h->nUpper;
     // the host mirror is exact here (no insertion since the last refresh), so the device length follows it
     CU(cudaMemcpyAsync(h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
@@ -1109,16 +1144,18 @@ int ugf_migrate_pack_slots(ugf_handle* h, double* devSend, int64_t slotCapacity)
     if (h->migSlots.nProc > MIG_MAXP) return fail(h, "too many processor patches for the slot path");
     if (h->migSlots.nProc == 0) return 0;
     if (slotCapacity < 1) return fail(h, "slotCapacity must be positive");
-    const int nb = (int)grid_for(h->nUpper, 1024);
+    const int nb = (int)grid_for(h->nUpper, MIG_TILE);
     ParcelBuf P = h->buf[h->cur];
     const MigSlots ms = h->migSlots;
-    mig_count_all_kernel<<<nb, 1024, 0, h->stream>>>(h->mesh, ms, P.cell, h->dN, h->dMigBlock, nb);
+    int* counts = h->dMigBlock;
+    int* offsets = h->dMigBlock + (size_t)MIG_MAXP * (h->capacity / 1024 + 2);
+    mig_count_all_kernel<<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P.cell, h->dN, counts, nb);
     LAUNCHED();
-    mig_scan_kernel<<<ms.nProc, SCAN_THREADS, 0, h->stream>>>(h->dMigBlock, nb, h->dMigTotals);
+    mig_scan_kernel<<<ms.nProc, SCAN_THREADS, 0, h->stream>>>(counts, offsets, nb, h->dMigTotals);
     LAUNCHED();
     dispatch(h, [&](auto R, auto M) {
-        mig_pack_all_kernel<decltype(R)::value, decltype(M)::value><<<nb, 1024, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dN, h->dMigBlock, h->dMigTotals, nb,
-                                                                                                 devSend, (long long)slotCapacity, h->dErr);
+        mig_pack_all_kernel<decltype(R)::value, decltype(M)::value><<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dN, counts, offsets, h->dMigTotals, nb,
+                                                                                                        devSend, (long long)slotCapacity, h->dErr);
     });
     LAUNCHED();
     CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
@@ -1129,7 +1166,7 @@ int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotC
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (h->migSlots.nProc > MIG_MAXP) return fail(h, "too many processor patches for the slot path");
     if (h->migSlots.nProc == 0) return 0;
-    if (h->nUpper + (long long)h->migSlots.nProc * slotCapacity > h->capacity)
+    if (h->nExact && h->nUpper + (long long)h->migSlots.nProc * slotCapacity > h->capacity)
         return fail(h, "parcelCapacity too small for the migration slots (needs room for nProcPatches x slotCapacity parcels)");
     ParcelBuf P = h->buf[h->cur];
     mig_mark_start_kernel<<<1, 1, 0, h->stream>>>(h->dRecvStart, h->dN);
@@ -1143,9 +1180,10 @@ int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotC
                 h->mesh, P, h->dSf, h->dN, h->capacity, patch, slot, (long long)slotCapacity, h->dErr);
         });
         LAUNCHED();
-        mig_bump_kernel<<<1, 1, 0, h->stream>>>(h->dN, slot, h->capacity);
+        mig_bump_kernel<<<1, 1, 0, h->stream>>>(h->dN, slot, h->capacity, h->dErr);
         LAUNCHED();
-        h->nUpper += slotCapacity;
+        h->nUpper = std::min<long long>(h->capacity, h->nUpper + slotCapacity);  // upper bound; overflow raises the device flag
+        h->appendBound += slotCapacity;
     }
     h->slotRound = true;
     h->occValid = false; h->momValid = false;

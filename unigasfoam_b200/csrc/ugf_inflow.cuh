@@ -211,48 +211,66 @@ __device__ __forceinline__ int mig_slot_of(const MeshDev& mesh, const MigSlots& 
     return slot;
 }
 
-__global__ void __launch_bounds__(1024) mig_count_all_kernel(MeshDev mesh, MigSlots ms, const int* __restrict__ cell, const long long* dN,
-                                                             int* __restrict__ blockCounts, int nBlocks) {
+constexpr int MIG_THREADS = 256;
+constexpr int MIG_PER_THREAD = 8;
+constexpr int MIG_TILE = MIG_THREADS * MIG_PER_THREAD;  // parcels per block in the slot pack passes
+
+// pass 1: per (slot, block) number of waiting parcels; 8 consecutive cell ids per thread
+__global__ void __launch_bounds__(MIG_THREADS) mig_count_all_kernel(MeshDev mesh, MigSlots ms, const int* __restrict__ cell, const long long* dN,
+                                                                    int* __restrict__ blockCounts, int nBlocks) {
     __shared__ int cnt[MIG_MAXP];
     if (threadIdx.x < MIG_MAXP) cnt[threadIdx.x] = 0;
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = (i < *dN) ? mig_slot_of(mesh, ms, cell[i]) : -1;
-    if (__any_sync(0xffffffffu, slot >= 0)) {
-        for (int k = 0; k < ms.nProc; ++k) {
-            const unsigned m = __ballot_sync(0xffffffffu, slot == k);
-            if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[k], __popc(m));
+    const long long n = *dN;
+    const long long base = (long long)blockIdx.x * MIG_TILE + (long long)threadIdx.x * MIG_PER_THREAD;
+    int c[MIG_PER_THREAD];
+    if (base + MIG_PER_THREAD <= n) {
+        const int4 v0 = __ldg(reinterpret_cast<const int4*>(cell + base));
+        const int4 v1 = __ldg(reinterpret_cast<const int4*>(cell + base) + 1);
+        c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y; c[6] = v1.z; c[7] = v1.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < MIG_PER_THREAD; ++e) c[e] = (base + e < n) ? cell[base + e] : -1;
+    }
+    int mn = c[0];
+#pragma unroll
+    for (int e = 1; e < MIG_PER_THREAD; ++e) mn = min(mn, c[e]);
+    if (mn <= -2) {  // rare: some of this thread's parcels wait on a processor patch
+#pragma unroll
+        for (int e = 0; e < MIG_PER_THREAD; ++e) {
+            const int slot = mig_slot_of(mesh, ms, c[e]);
+            if (slot >= 0) atomicAdd(&cnt[slot], 1);
         }
     }
     __syncthreads();
     if (threadIdx.x < ms.nProc) blockCounts[threadIdx.x * nBlocks + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// one block per slot: exclusive scan of that slot's per-block counts in place, total to totals[slot]
-__global__ void __launch_bounds__(SCAN_THREADS) mig_scan_kernel(int* blockCounts, int nBlocks, int* totals) {
+// one block per slot: exclusive scan of that slot's per-block counts -> blockOffsets, total to totals[slot]
+__global__ void __launch_bounds__(SCAN_THREADS) mig_scan_kernel(const int* __restrict__ blockCounts, int* __restrict__ blockOffsets, int nBlocks, int* totals) {
     __shared__ int sm[33];
-    int* b = blockCounts + (size_t)blockIdx.x * nBlocks;
+    const int* b = blockCounts + (size_t)blockIdx.x * nBlocks;
+    int* o = blockOffsets + (size_t)blockIdx.x * nBlocks;
     int carry = 0;
     for (int base = 0; base < nBlocks; base += SCAN_THREADS) {
         const int idx = base + threadIdx.x;
         const int v = idx < nBlocks ? b[idx] : 0;
         int t;
         const int ex = block_exclusive_scan(v, &t, sm);
-        if (idx < nBlocks) b[idx] = carry + ex;
+        if (idx < nBlocks) o[idx] = carry + ex;
         carry += t;
     }
     if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
+// pass 2: blocks whose tile holds no waiting parcel return after reading their counts; the others rank their
+// waiting parcels in index order per slot and write the records
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(1024) mig_pack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const long long* dN,
-                                                            const int* __restrict__ blockOffsets, const int* __restrict__ totals, int nBlocks,
-                                                            double* __restrict__ send, long long slotCapacity, int* errFlag) {
+__global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const long long* dN,
+                                                                   const int* __restrict__ blockCounts, const int* __restrict__ blockOffsets,
+                                                                   const int* __restrict__ totals, int nBlocks, double* __restrict__ send,
+                                                                   long long slotCapacity, int* errFlag) {
     __shared__ int sm[33];
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int c = -1;
-    if (i < *dN) c = P.cell[i];
-    const int slot = mig_slot_of(mesh, ms, c);
     const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
     if (blockIdx.x == 0 && threadIdx.x < ms.nProc) {  // headers
         double* hdr = send + threadIdx.x * slotStride;
@@ -261,15 +279,31 @@ __global__ void __launch_bounds__(1024) mig_pack_all_kernel(MeshDev mesh, MigSlo
         for (int j = 1; j < UGF_MIGRATE_STRIDE; ++j) hdr[j] = 0.0;
         if (tot > slotCapacity) *errFlag = 3;
     }
-    if (!__syncthreads_or(slot >= 0)) return;
+    int any = 0;
+    for (int k = 0; k < ms.nProc; ++k) any |= blockCounts[k * nBlocks + blockIdx.x];
+    if (any == 0) return;
+    const long long n = *dN;
+    const long long base = (long long)blockIdx.x * MIG_TILE + (long long)threadIdx.x * MIG_PER_THREAD;
+    int slot[MIG_PER_THREAD], c[MIG_PER_THREAD];
+#pragma unroll
+    for (int e = 0; e < MIG_PER_THREAD; ++e) {
+        c[e] = (base + e < n) ? P.cell[base + e] : -1;
+        slot[e] = mig_slot_of(mesh, ms, c[e]);
+    }
     for (int k = 0; k < ms.nProc; ++k) {
+        if (blockCounts[k * nBlocks + blockIdx.x] == 0) continue;  // uniform over the block
+        int mine = 0;
+#pragma unroll
+        for (int e = 0; e < MIG_PER_THREAD; ++e) mine += (slot[e] == k);
         int total;
-        const int ex = block_exclusive_scan(slot == k ? 1 : 0, &total, sm);
-        if (slot == k) {
-            const long long pos = (long long)blockOffsets[k * nBlocks + blockIdx.x] + ex;
+        int pos = block_exclusive_scan(mine, &total, sm) + blockOffsets[k * nBlocks + blockIdx.x];
+#pragma unroll
+        for (int e = 0; e < MIG_PER_THREAD; ++e) {
+            if (slot[e] != k) continue;
+            const long long i = base + e;
             if (pos < slotCapacity) {
-                double* r = send + k * slotStride + (1 + pos) * UGF_MIGRATE_STRIDE;
-                const int bfi = -2 - c;
+                double* r = send + k * slotStride + (1 + (long long)pos) * UGF_MIGRATE_STRIDE;
+                const int bfi = -2 - c[e];
                 r[0] = P.x[i]; r[1] = P.y[i]; r[2] = P.z[i];
                 r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
                 r[6] = HAS_ROT ? P.erot[i] : 0.0;
@@ -278,6 +312,7 @@ __global__ void __launch_bounds__(1024) mig_pack_all_kernel(MeshDev mesh, MigSlo
                 r[9] = MULTI ? (double)P.type[i] : 0.0;
             }
             P.cell[i] = -1;
+            ++pos;
         }
     }
 }
@@ -303,9 +338,11 @@ __global__ void __launch_bounds__(256) mig_unpack_slot_kernel(MeshDev mesh, Parc
     if (MULTI) P.type[dst] = (uint8_t)r[9];
 }
 
-__global__ void mig_bump_kernel(long long* dN, const double* slot, long long capacity) {
+__global__ void mig_bump_kernel(long long* dN, const double* slot, long long capacity, int* errFlag) {
     const long long n = (long long)slot[0];
-    if (n > 0 && *dN + n <= capacity) *dN += n;
+    if (n <= 0) return;
+    if (*dN + n <= capacity) *dN += n;
+    else *errFlag = 1;
 }
 
 __global__ void mig_mark_start_kernel(long long* dRecvStart, const long long* dN) { *dRecvStart = *dN; }
