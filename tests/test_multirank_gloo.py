@@ -34,7 +34,9 @@ def _worker(rank, world, port, steps, out, slots):
     ex = SlotExchanger(cl, case.mesh, rank, world, slot_capacity=600, cuda=False) if slots else Exchanger(cl, case.mesh, rank, world, cuda=False)
     n0 = torch.tensor([cl.size()])
     dist.all_reduce(n0)
-    evolve_distributed(cl, ex, steps)
+    evolve_distributed(cl, ex, steps, fixed_rounds=2 if slots else None)
+    if slots:
+        ex.check_settled()
     p = cl.parcels()
     n1 = torch.tensor([cl.size()])
     dist.all_reduce(n1)

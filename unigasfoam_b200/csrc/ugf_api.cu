@@ -424,7 +424,7 @@ int do_move(ugf_handle* h, long long begin, bool received) {
         CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * h->nCells, h->stream));
         CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
     }
-    CU(cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream));
+    if (!(received && h->slotRound)) CU(cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream));
     MoveArgs a{};
     a.mesh = h->mesh;
     a.P = h->buf[h->cur];
@@ -1149,7 +1149,7 @@ int ugf_migrate_pack_slots(ugf_handle* h, double* devSend, int64_t slotCapacity)
     const MigSlots ms = h->migSlots;
     int* counts = h->dMigBlock;
     int* offsets = h->dMigBlock + (size_t)MIG_MAXP * (h->capacity / 1024 + 2);
-    mig_count_all_kernel<<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P.cell, h->dN, counts, nb);
+    mig_count_all_kernel<<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P.cell, h->dN, h->slotRound ? h->dRecvStart : nullptr, counts, nb);
     LAUNCHED();
     mig_scan_kernel<<<ms.nProc, SCAN_THREADS, 0, h->stream>>>(counts, offsets, nb, h->dMigTotals);
     LAUNCHED();
@@ -1169,22 +1169,16 @@ int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotC
     if (h->nExact && h->nUpper + (long long)h->migSlots.nProc * slotCapacity > h->capacity)
         return fail(h, "parcelCapacity too small for the migration slots (needs room for nProcPatches x slotCapacity parcels)");
     ParcelBuf P = h->buf[h->cur];
-    mig_mark_start_kernel<<<1, 1, 0, h->stream>>>(h->dRecvStart, h->dN);
+    const MigSlots ms = h->migSlots;
+    dispatch(h, [&](auto R, auto M) {
+        mig_unpack_all_kernel<decltype(R)::value, decltype(M)::value><<<dim3(grid_for(slotCapacity, 256), ms.nProc), 256, 0, h->stream>>>(
+            h->mesh, ms, P, h->dSf, h->dN, h->capacity, devRecv, (long long)slotCapacity, h->dErr);
+    });
     LAUNCHED();
-    const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
-    for (int k = 0; k < h->migSlots.nProc; ++k) {
-        const double* slot = devRecv + k * slotStride;
-        const int patch = h->migSlots.patch[k];
-        dispatch(h, [&](auto R, auto M) {
-            mig_unpack_slot_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(slotCapacity, 256), 256, 0, h->stream>>>(
-                h->mesh, P, h->dSf, h->dN, h->capacity, patch, slot, (long long)slotCapacity, h->dErr);
-        });
-        LAUNCHED();
-        mig_bump_kernel<<<1, 1, 0, h->stream>>>(h->dN, slot, h->capacity, h->dErr);
-        LAUNCHED();
-        h->nUpper = std::min<long long>(h->capacity, h->nUpper + slotCapacity);  // upper bound; overflow raises the device flag
-        h->appendBound += slotCapacity;
-    }
+    mig_commit_kernel<<<1, 1, 0, h->stream>>>(h->dN, h->dRecvStart, h->dInflight, devRecv, ms.nProc, (long long)slotCapacity, h->capacity, h->dErr);
+    LAUNCHED();
+    h->nUpper = std::min<long long>(h->capacity, h->nUpper + (long long)ms.nProc * slotCapacity);  // upper bound; overflow raises the device flag
+    h->appendBound += (long long)ms.nProc * slotCapacity;
     h->slotRound = true;
     h->occValid = false; h->momValid = false;
     return 0;

@@ -216,9 +216,15 @@ constexpr int MIG_PER_THREAD = 8;
 constexpr int MIG_TILE = MIG_THREADS * MIG_PER_THREAD;  // parcels per block in the slot pack passes
 
 // pass 1: per (slot, block) number of waiting parcels; 8 consecutive cell ids per thread
+// dStart (optional): only parcels with index >= *dStart can be waiting (second and later transfer rounds of a step:
+// only what was received in this step); tiles entirely below it are skipped.
 __global__ void __launch_bounds__(MIG_THREADS) mig_count_all_kernel(MeshDev mesh, MigSlots ms, const int* __restrict__ cell, const long long* dN,
-                                                                    int* __restrict__ blockCounts, int nBlocks) {
+                                                                    const long long* dStart, int* __restrict__ blockCounts, int nBlocks) {
     __shared__ int cnt[MIG_MAXP];
+    if (dStart && (long long)(blockIdx.x + 1) * MIG_TILE <= *dStart) {
+        if (threadIdx.x < ms.nProc) blockCounts[threadIdx.x * nBlocks + blockIdx.x] = 0;
+        return;
+    }
     if (threadIdx.x < MIG_MAXP) cnt[threadIdx.x] = 0;
     __syncthreads();
     const long long n = *dN;
@@ -317,18 +323,24 @@ __global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh,
     }
 }
 
+// Unpack every slot in one launch (blockIdx.y = slot): slot k appends after the parcels of slots < k.
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(256) mig_unpack_slot_kernel(MeshDev mesh, ParcelBuf P, double* __restrict__ sf, const long long* dN, long long capacity,
-                                                              int patch, const double* __restrict__ slot, long long slotCapacity, int* errFlag) {
+__global__ void __launch_bounds__(256) mig_unpack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, double* __restrict__ sf, const long long* dN,
+                                                             long long capacity, const double* __restrict__ recv, long long slotCapacity, int* errFlag) {
+    const int k = blockIdx.y;
+    const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+    const double* slot = recv + k * slotStride;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = (long long)slot[0];
     if (n < 0 || n > slotCapacity) { if (i == 0) *errFlag = 4; return; }
     if (i >= n) return;
-    const long long dst = *dN + i;
+    long long base = *dN;
+    for (int j = 0; j < k; ++j) base += (long long)recv[j * slotStride];
+    const long long dst = base + i;
     if (dst >= capacity) { *errFlag = 1; return; }
     const double* r = slot + (1 + i) * UGF_MIGRATE_STRIDE;
     const int lf = (int)r[8];
-    const DevPatch& pt = mesh.patches[patch];
+    const DevPatch& pt = mesh.patches[ms.patch[k]];
     if (lf < 0 || lf >= pt.size) { *errFlag = 2; P.cell[dst] = -1; return; }
     P.x[dst] = r[0]; P.y[dst] = r[1]; P.z[dst] = r[2];
     P.ux[dst] = r[3]; P.uy[dst] = r[4]; P.uz[dst] = r[5];
@@ -338,13 +350,18 @@ __global__ void __launch_bounds__(256) mig_unpack_slot_kernel(MeshDev mesh, Parc
     if (MULTI) P.type[dst] = (uint8_t)r[9];
 }
 
-__global__ void mig_bump_kernel(long long* dN, const double* slot, long long capacity, int* errFlag) {
-    const long long n = (long long)slot[0];
-    if (n <= 0) return;
-    if (*dN + n <= capacity) *dN += n;
-    else *errFlag = 1;
+// after the unpack: remember where the received parcels start, extend the array, reset the in-flight tally
+__global__ void mig_commit_kernel(long long* dN, long long* dRecvStart, unsigned long long* inflight, const double* recv, int nProc,
+                                  long long slotCapacity, long long capacity, int* errFlag) {
+    const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+    long long add = 0;
+    for (int k = 0; k < nProc; ++k) {
+        const long long n = (long long)recv[k * slotStride];
+        if (n > 0 && n <= slotCapacity) add += n;
+    }
+    *dRecvStart = *dN;
+    if (*dN + add <= capacity) *dN += add; else *errFlag = 1;
+    *inflight = 0ull;
 }
-
-__global__ void mig_mark_start_kernel(long long* dRecvStart, const long long* dN) { *dRecvStart = *dN; }
 
 }  // namespace ugf

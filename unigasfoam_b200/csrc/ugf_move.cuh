@@ -206,6 +206,7 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
 template <bool HAS_ROT, bool MULTI, int NF>
 __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
     const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.dBegin && a.begin + (long long)(blockIdx.x + 1) * blockDim.x <= *a.dBegin) return;  // whole block precedes the received range
     const long long n = *a.dN;
     bool valid = i < n;
     if (a.dBegin && i < *a.dBegin) valid = false;

@@ -123,6 +123,10 @@ class SlotExchanger:
         dev = "cuda" if cuda else "cpu"
         self.send = torch.zeros(max(len(proc), 1), stride, dtype=torch.float64, device=dev)
         self.recv = torch.zeros(max(len(proc), 1), stride, dtype=torch.float64, device=dev)
+        # second and later rounds of a step only carry parcels that were received in this step: small slots
+        self.cap2 = max(256, self.cap // 16)
+        self.send2 = torch.zeros(max(len(proc), 1), (self.cap2 + 1) * STRIDE, dtype=torch.float64, device=dev)
+        self.recv2 = torch.zeros(max(len(proc), 1), (self.cap2 + 1) * STRIDE, dtype=torch.float64, device=dev)
         peers = sorted({b for _, b, _ in proc})
         # order of messages between a pair of ranks: by the sender's patch tag (see Exchanger)
         self.sends = [(self.slot_of[q[0]], b) for b in peers for q in sorted([q for q in proc if q[1] == b], key=lambda q: _sender_tag(q[2]))]
@@ -136,23 +140,65 @@ class SlotExchanger:
             self._inflight = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(1,)))
         self._sp = C.cast(self.send.data_ptr(), C.POINTER(C.c_double))
         self._rp = C.cast(self.recv.data_ptr(), C.POINTER(C.c_double))
+        self._sp2 = C.cast(self.send2.data_ptr(), C.POINTER(C.c_double))
+        self._rp2 = C.cast(self.recv2.data_ptr(), C.POINTER(C.c_double))
+        self._round_in_step = 0
+
+    def begin_step(self):
+        """Call after cloud.move(): the next round is the first of the step (full-size slots)."""
+        self._round_in_step = 0
+
+    def _round(self):
+        self.rounds += 1
+        first = self._round_in_step == 0
+        self._round_in_step += 1
+        send, recv, sp, rp, cap = (self.send, self.recv, self._sp, self._rp, self.cap) if first else \
+                                  (self.send2, self.recv2, self._sp2, self._rp2, self.cap2)
+        self.cloud.migratePackSlots(sp, cap)
+        ops = [dist.P2POp(dist.isend, send[k], b, self.group) for k, b in self.sends]
+        ops += [dist.P2POp(dist.irecv, recv[k], b, self.group) for k, b in self.recvs]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.cloud.migrateUnpackSlots(rp, cap)
+        self.cloud.moveReceived()
 
     def exchange(self):
         """One transfer round; returns the number of parcels still in flight over all ranks afterwards."""
-        self.rounds += 1
         ctx = torch.cuda.stream(self._stream) if self.cuda else _Null()
         with ctx:
-            self.cloud.migratePackSlots(self._sp, self.cap)
-            ops = [dist.P2POp(dist.isend, self.send[k], b, self.group) for k, b in self.sends]
-            ops += [dist.P2POp(dist.irecv, self.recv[k], b, self.group) for k, b in self.recvs]
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-            self.cloud.migrateUnpackSlots(self._rp, self.cap)
-            self.cloud.moveReceived()
+            self._round()
             total = self._inflight.clone()
             dist.all_reduce(total, group=self.group)
             return int(total.item())
+
+    # -- fixed-round mode: no host synchronisation inside the step ---------------------------------------------
+    def exchange_fixed(self, n_rounds):
+        """n_rounds transfer rounds back to back with no host synchronisation and no global collective; whatever
+        is still in flight afterwards is added to a device-resident tally that check_settled() reduces over all
+        ranks.  A parcel left in flight (n_rounds too small for this decomposition) is therefore reported loudly
+        at the next check, never dropped silently."""
+        ctx = torch.cuda.stream(self._stream) if self.cuda else _Null()
+        with ctx:
+            for _ in range(n_rounds):
+                self._round()
+            if not hasattr(self, "_left"):
+                self._left = torch.zeros_like(self._inflight)
+            self._left += self._inflight
+
+    def check_settled(self):
+        """Collective: raises if any rank had parcels waiting on a processor patch after a fixed-round step."""
+        if not hasattr(self, "_left"):
+            return
+        ctx = torch.cuda.stream(self._stream) if self.cuda else _Null()
+        with ctx:
+            total = self._left.clone()
+            dist.all_reduce(total, group=self.group)
+            n = int(total.item())
+            self._left.zero_()
+        if n != 0:
+            raise RuntimeError(f"{n} parcels were still waiting on processor patches after the fixed number of transfer "
+                               "rounds: raise the round count for this decomposition")
 
 
 class _DevI64:
@@ -168,16 +214,26 @@ class _Null:
         return False
 
 
-def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64):
+def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64, fixed_rounds=None):
     """uniGasCloud::evolve across ranks: the phases of ugf_step with the transfer loop after the move.  Both
-    exchangers return 0 from exchange() once no rank has parcels in flight (the reference's termination rule)."""
+    exchangers return 0 from exchange() once no rank has parcels in flight (the reference's termination rule).
+    fixed_rounds (SlotExchanger only): run exactly that many rounds without host synchronisation and verify
+    quiescence one step later."""
     for _ in range(n_steps):
         if inflow:
             cloud.controlBeforeMove()
         cloud.move()
+        if hasattr(exchanger, "begin_step"):
+            exchanger.begin_step()
+        if fixed_rounds:
+            exchanger.exchange_fixed(fixed_rounds)
+            cloud.finishStep()
+            continue
         for _r in range(max_rounds):
             if exchanger.exchange() == 0:
                 break
         else:
             raise RuntimeError("parcel migration did not settle")
         cloud.finishStep()
+    if fixed_rounds:
+        exchanger.check_settled()
