@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--nx", type=int, default=1000)
     ap.add_argument("--ny", type=int, default=500)
     ap.add_argument("--ppc", type=int, default=20)
-    ap.add_argument("--case", default="couette", choices=["couette", "box"], help="box = config 1 style dense-collision case (tuning only)")
+    ap.add_argument("--case", default="couette", choices=["couette", "box", "cylinder"], help="box = config 1 style dense-collision case (tuning only)")
+    ap.add_argument("--collision", default="dsmc", choices=["dsmc", "bgk", "hybrid"], help="box case only (tuning)")
     ap.add_argument("--box-n", type=int, default=64)
     ap.add_argument("--box-parcels", type=int, default=8_000_000)
     ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the bounded cpu_baseline sample")
@@ -96,13 +97,24 @@ class ClockSampler:
 def build_case(args, rank, world):
     from unigasfoam_b200 import cases
     if args.case == "box":
-        return cases.closed_box(n=args.box_n, parcels=args.box_parcels, wall="diffuse")
+        kw = {}
+        if args.collision != "dsmc":
+            kw = dict(mode=args.collision, bgk="unifiedStochasticParticleSBGK", theta=0.1)
+        c = cases.closed_box(n=args.box_n, parcels=args.box_parcels, wall="diffuse", **kw)
+        if args.collision == "hybrid":
+            import numpy as np
+            c.cellCollModelId = (np.arange(c.mesh.n_cells) % 2).astype(np.int32)
+        return c
+    if args.case == "cylinder":
+        return cases.cylinder(nr=500, ntheta=1000, ppc=20)
     return cases.couette(nx=args.nx, ny=args.ny, ppc=args.ppc, rank=rank, n_ranks=world)
 
 
 def workload_name(args):
+    if args.case == "cylinder":
+        return "cylinder2d_mach10_argon_500x1000cells_20ppc_inflow_outflow_dsmc_ntc_vhs"
     if args.case == "box":
-        return f"closedbox3d_argon_{args.box_n}^3cells_{args.box_parcels}parcels_dsmc_ntc_vhs_dt0.2mct"
+        return f"closedbox3d_argon_{args.box_n}^3cells_{args.box_parcels}parcels_{args.collision}_dt0.2mct"
     return f"couette2d_argon_kn0.1_{args.nx}x{args.ny}cells_{args.ppc}ppc_dsmc_ntc_vhs"
 
 
@@ -159,7 +171,7 @@ def main():
 
     t_case = time.perf_counter()
     case = build_case(args, rank, world)
-    cloud = case.make_cloud(UniGasCloud, device=local, measureWalls=True, seed=20261017)
+    cloud = case.make_cloud(UniGasCloud, device=local, measureWalls=True, seed=20261017, parcelCapacity=int(1.5 * case.n_parcels) + 4096)
     nC = case.mesh.n_cells
     t_case = time.perf_counter() - t_case
     stream = torch.cuda.ExternalStream(cloud.stream())

@@ -78,8 +78,9 @@ def _uniform_in_cells(mesh, cells, rng):
     # general extruded quads: use the cell's zMin face (patch order guarantees it exists for nz = 1)
     quad = mesh.cell_quads[cells]  # [n,4,2] xy of the 4 corners, counter-clockwise
     a, b, c, d = quad[:, 0], quad[:, 1], quad[:, 2], quad[:, 3]
-    A1 = 0.5 * np.abs(np.cross(b - a, c - a))
-    A2 = 0.5 * np.abs(np.cross(c - a, d - a))
+    cross2 = lambda p, q: p[:, 0] * q[:, 1] - p[:, 1] * q[:, 0]
+    A1 = 0.5 * np.abs(cross2(b - a, c - a))
+    A2 = 0.5 * np.abs(cross2(c - a, d - a))
     pick = rng.random(len(cells)) * (A1 + A2) < A1
     s, t = rng.random(len(cells)), rng.random(len(cells))
     fl = s + t > 1
@@ -205,3 +206,38 @@ def couette(nx=1000, ny=500, ppc=20, Kn=0.1, Tw=273.0, Uw=150.0, number_density=
     sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(Tw, sp["mass"])
     return Case("couette", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
                 None, sig0, meta=dict(n=number_density, Tw=Tw, Uw=Uw, lam=lam, H=H, Lx=Lx, Tref=Tref, species=sp))
+
+
+def cylinder(nr=100, ntheta=200, ppc=20, n_inf=4.247e20, T_inf=200.0, U_inf=2634.7, T_wall=500.0, r0=0.5 * 0.3048, r1=2.0 * 0.3048,
+             lz=0.1 * 0.3048, grading=5.0, species=("Ar", ARGON_TUTORIAL), Tref=1000.0, courant=0.3, seed=3,
+             binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", **cp):
+    """Config 3: 2-D hypersonic (Mach 10) argon flow over a cylinder - the geometry, free stream and wall of
+    tutorials/uniGasFoam/hypersonicCylinder (system/blockMeshDict, system/boundariesDict) without its cell
+    weighting / adaptation: free-stream inflow on the upstream half of the outer arc, deleting outflow on the
+    downstream half, diffuse isothermal cylinder, symmetry axis."""
+    name, sp = species
+    m = _mesh.half_annulus_mesh(nr, ntheta, r0, r1, lz, grading)
+    m.meta_axis_aligned = False
+    n_parcels = ppc * m.n_cells
+    nParticle = n_inf * m.cell_volumes.sum() / n_parcels
+    rng = np.random.default_rng(seed)
+    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: n_inf}, T_inf, (U_inf, 0.0, 0.0), nParticle, rng)
+    dr_min = (m.cell_bb_max - m.cell_bb_min)[:, :2].min()
+    dt = courant * dr_min / (U_inf + most_probable_speed(T_inf, sp["mass"]))
+    inflow = {"generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasFreeStreamInflowPatch",
+              "uniGasFreeStreamInflowPatchProperties": {"typeIds": [name], "numberDensities": {name: n_inf}, "translationalTemperature": T_inf,
+                                                        "rotationalTemperature": T_inf, "vibrationalTemperature": T_inf,
+                                                        "electronicTemperature": T_inf, "velocity": [U_inf, 0.0, 0.0]}}
+    bd = {
+        "uniGasPatchBoundaries": [
+            {"patchBoundaryProperties": {"patch": "cylinder"}, "boundaryModel": "uniGasDiffuseWallPatch",
+             "uniGasDiffuseWallPatchProperties": {"velocity": [0, 0, 0], "temperature": T_wall}},
+            {"patchBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasDeletionPatch"},
+            {"patchBoundaryProperties": {"patch": "outlet"}, "boundaryModel": "uniGasDeletionPatch"},
+        ],
+        "uniGasGeneralBoundaries": [inflow],
+    }
+    sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(T_inf, sp["mass"])
+    return Case("cylinder", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
+                erot if sp.get("rotationalDegreesOfFreedom", 0) else None, sig0,
+                meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, r0=r0, r1=r1, Tref=Tref, species=sp))

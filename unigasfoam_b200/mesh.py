@@ -276,6 +276,48 @@ def structured_block(nx, ny, nz, point_map, patch_kinds, cyclic_pairs=(), soluti
     return mesh
 
 
+def split_patch(mesh, name, n_first, name_a, name_b, kind_a=None, kind_b=None):
+    """Split patch `name` into its first n_first faces and the rest (blockMesh lists several face sets per side)."""
+    pi = mesh.patch_index(name)
+    p = mesh.patches[pi]
+    assert 0 < n_first < p.size and p.kind != "cyclic"
+    a = Patch(name_a, kind_a or p.kind, p.start, n_first)
+    b = Patch(name_b, kind_b or p.kind, p.start + n_first, p.size - n_first)
+    mesh.patches[pi : pi + 1] = [a, b]
+    for q in mesh.patches:  # cyclic partners are stored as patch indices
+        if q.kind == "cyclic" and q.partner > pi:
+            q.partner += 1
+    return mesh
+
+
+def half_annulus_mesh(nr, ntheta, r0, r1, lz, grading=5.0):
+    """Half O-grid around a cylinder on the symmetry axis: the topology of tutorials/uniGasFoam/hypersonicCylinder
+    (system/blockMeshDict), as one block.  i runs radially outwards (last/first cell size = grading), j in theta
+    from 0 (downstream axis) to pi (upstream axis), one cell in z.  Patches: cylinder (wall), outlet / inlet (outer
+    arc, type patch), axisDown / axisUp (symmetryPlane), back / front (empty)."""
+    g = float(grading)
+
+    def pm(I, J, K):
+        t = I / nr
+        frac = t if abs(g - 1.0) < 1e-12 else (g ** t - 1.0) / (g - 1.0)
+        r = r0 + (r1 - r0) * frac
+        th = np.pi * J / ntheta
+        return r * np.cos(th), r * np.sin(th), lz * (K - 0.5)
+
+    kinds = {"xMin": ("cylinder", "wall"), "xMax": ("outer", "patch"), "yMin": ("axisDown", "symmetryPlane"), "yMax": ("axisUp", "symmetryPlane"),
+             "zMin": ("back", "empty"), "zMax": ("front", "empty")}
+    m = structured_block(nr, ntheta, 1, pm, kinds, solution_d=(1, 1, 0))
+    split_patch(m, "outer", ntheta // 2, "outlet", "inlet")
+    # exact axis: the theta = 0 and theta = pi point rows must sit on y = 0 (sin(pi) is 1.2e-16, not 0)
+    c = np.arange(nr * ntheta)
+    ci, cj = c % nr, c // nr
+    def corner(i, j):
+        p = m.points[i + (nr + 1) * j]  # k = 0 layer
+        return p[:, :2]
+    m.cell_quads = np.stack([corner(ci, cj), corner(ci + 1, cj), corner(ci + 1, cj + 1), corner(ci, cj + 1)], axis=1)
+    return m
+
+
 def box_mesh(nx, ny, nz, lx, ly, lz, patch_kinds=None, cyclic_pairs=(), solution_d=(1, 1, 1), origin=(0.0, 0.0, 0.0)):
     """Uniform Cartesian block (blockMesh with one hex and simpleGrading 1)."""
     if patch_kinds is None:
