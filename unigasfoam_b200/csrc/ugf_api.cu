@@ -86,6 +86,9 @@ struct ugf_handle {
     DevPatch* dPatches = nullptr; double* dVol = nullptr; double* dBbMin = nullptr; double* dBbMax = nullptr; double* dBfS = nullptr;
     bool hasProcessor = false;
     int moveNF = 0;  // uniform face-slot count per cell (4 or 6), 0 = general CSR
+    int moveBps = 4;          // resident CTAs per SM of the streamed move kernel
+    int cellTask = 8, cellFlags = 0;
+    bool moveDirect = false;  // tuning: UGF_MOVE_DIRECT=1 runs the step's move with the one-thread-per-parcel kernel
 
     // parcels
     long long capacity = 0;
@@ -117,6 +120,7 @@ struct ugf_handle {
     int* dOwner = nullptr;           // NTC conflict marks, one per parcel slot
     DevCounters* dCnt = nullptr;
     int* dErr = nullptr;
+    int* dTask = nullptr;            // cell_kernel task counter
     double* dTot = nullptr;
     bool histValid = false, occValid = false, occIdentity = false, momValid = false;
     bool subLevelsAllOne = true;
@@ -132,7 +136,7 @@ struct ugf_handle {
 
     long long step = 0;
     int cellCap = CELL_CAP;
-    int cellBlocks = 0, ntcBlocks = 0, bgkBlocks = 0, segBlocks = 0;
+    int cellBlocks = 0, ntcBlocks = 0, bgkBlocks = 0;
     size_t cellSmem = 0, ntcSmem = 0, bgkSmem = 0;
     cudaEvent_t ev[7]{};
     double phaseMs[6] = {0, 0, 0, 0, 0, 0};
@@ -268,13 +272,14 @@ void build_params(ugf_handle* h) {
 int alloc_parcels(ugf_handle* h) {
     if (h->buf[0].x) return 0;
     const size_t cap = (size_t)h->capacity;
+    const size_t capPad = (cap + MOVE_TILE - 1) / MOVE_TILE * MOVE_TILE;  // move_stream_kernel copies whole tiles
     for (int b = 0; b < 2; ++b) {
         ParcelBuf& P = h->buf[b];
-        if (dalloc(h, &P.x, cap) || dalloc(h, &P.y, cap) || dalloc(h, &P.z, cap) || dalloc(h, &P.ux, cap) ||
-            dalloc(h, &P.uy, cap) || dalloc(h, &P.uz, cap) || dalloc(h, &P.cell, cap))
+        if (dalloc(h, &P.x, capPad) || dalloc(h, &P.y, capPad) || dalloc(h, &P.z, capPad) || dalloc(h, &P.ux, capPad) ||
+            dalloc(h, &P.uy, capPad) || dalloc(h, &P.uz, capPad) || dalloc(h, &P.cell, capPad))
             return 1;
-        if (h->hasRot && dalloc(h, &P.erot, cap)) return 1;
-        if (h->multi && dalloc(h, &P.type, cap)) return 1;
+        if (h->hasRot && dalloc(h, &P.erot, capPad)) return 1;
+        if (h->multi && dalloc(h, &P.type, capPad)) return 1;
     }
     if (dalloc(h, &h->dPerm, cap)) return 1;
     if (dalloc(h, &h->dOwner, cap)) return 1;
@@ -299,13 +304,14 @@ int do_sort(ugf_handle* h) {
     LAUNCHED();
     scan_final_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums, h->dTotal, h->dOff);
     LAUNCHED();
-    scatter_index_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dOff, h->dCellCount, h->dPerm);
+    scatter_index_kernel<<<grid_for(h->nUpper, 256 * SCAT_ROWS), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dOff, h->dCellCount, h->dPerm);
     LAUNCHED();
-    segment_sort_kernel<<<h->segBlocks, SEG_THREADS, 0, h->stream>>>(h->dOff, nC, h->dPerm);
+    segment_sort_kernel<<<grid_for(((long long)nC + SEG_CHUNK - 1) / SEG_CHUNK, SEG_THREADS / 32), SEG_THREADS, 0, h->stream>>>(h->dOff, nC, h->dPerm);
     LAUNCHED();
     h->histValid = false;
     h->occValid = true;
     h->occIdentity = false;
+
     return 0;
 }
 
@@ -332,6 +338,10 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
     a.mom = h->dMom;
     a.acc = h->dAcc;
     a.accDt = (accumulate && doSample) ? h->cfg.deltaT : 0.0;
+    a.taskCounter = h->dTask;
+    a.taskCells = h->cellTask;
+    a.flags = h->cellFlags;
+    CU(cudaMemsetAsync(h->dTask, 0, sizeof(int), h->stream));
     const DevParams prm = h->prm;
     dispatch(h, [&](auto R, auto M) {
         cell_kernel<decltype(R)::value, decltype(M)::value><<<h->cellBlocks, CELL_THREADS, h->cellSmem, h->stream>>>(prm, a);
@@ -444,11 +454,26 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     const long long count = h->nUpper - begin;
     if (count > 0) {
         const DevParams prm = h->prm;
+        const bool streamed = !received && begin == 0 && !h->moveDirect;
+        const unsigned grid = streamed ? (unsigned)std::min<long long>(grid_for(count, MOVE_WARPS * 32), (long long)h->numSMs * h->moveBps)
+                                       : grid_for(count, 256);
         dispatch(h, [&](auto R, auto M) {
             constexpr bool r = decltype(R)::value, mm = decltype(M)::value;
-            if (h->moveNF == 6) move_kernel<r, mm, 6><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
-            else if (h->moveNF == 4) move_kernel<r, mm, 4><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
-            else move_kernel<r, mm, 0><<<grid_for(count, 256), 256, 0, h->stream>>>(prm, a);
+            if (streamed) {
+#define UGF_MOVE_STREAM(NF_)                                                                                      \
+    do {                                                                                                          \
+        if (h->moveBps == 3) move_stream_kernel<r, mm, NF_, 3><<<grid, MOVE_WARPS * 32, 0, h->stream>>>(prm, a);    \
+        else move_stream_kernel<r, mm, NF_, 4><<<grid, MOVE_WARPS * 32, 0, h->stream>>>(prm, a);                   \
+    } while (0)
+                if (h->moveNF == 6) UGF_MOVE_STREAM(6);
+                else if (h->moveNF == 4) UGF_MOVE_STREAM(4);
+                else UGF_MOVE_STREAM(0);
+#undef UGF_MOVE_STREAM
+            } else {
+                if (h->moveNF == 6) move_kernel<r, mm, 6><<<grid, 256, 0, h->stream>>>(prm, a);
+                else if (h->moveNF == 4) move_kernel<r, mm, 4><<<grid, 256, 0, h->stream>>>(prm, a);
+                else move_kernel<r, mm, 0><<<grid, 256, 0, h->stream>>>(prm, a);
+            }
         });
         LAUNCHED();
     }
@@ -543,6 +568,7 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     if ((e = cudaMalloc((void**)&h->dN, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dCnt, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dErr, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dTask, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dTot, 6 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dTotal, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dMigTotals, MIG_MAXP * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -570,7 +596,7 @@ int ugf_destroy(ugf_handle* h) {
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner,
-                    h->dCnt, h->dErr, h->dTot};
+                    h->dCnt, h->dErr, h->dTot, h->dTask};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -616,7 +642,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     std::vector<int> nbr, cfOffDev((size_t)nC + 1, 0);
     plane.reserve(m->cellFaceOffsets[nC]);
     nbr.reserve(m->cellFaceOffsets[nC]);
-    int uniformNF = -1;
+    int uniformNF = -1, planeNoZ = 1;
     for (int c = 0; c < nC; ++c) {
         for (int j = m->cellFaceOffsets[c]; j < m->cellFaceOffsets[c + 1]; ++j) {
             const int f = m->cellFaces[j];
@@ -630,8 +656,10 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
             if (!reachable) continue;
             const double d = S[0] * C[0] + S[1] * C[1] + S[2] * C[2];
             double4 pl;
-            if (own) { pl.x = S[0]; pl.y = S[1]; pl.z = S[2]; pl.w = d; }
-            else { pl.x = -S[0]; pl.y = -S[1]; pl.z = -S[2]; pl.w = -d; }
+            // storage order {Sx, Sy, S.Cf, Sz}: see load_plane / load_plane_noz
+            if (own) { pl.x = S[0]; pl.y = S[1]; pl.z = d; pl.w = S[2]; }
+            else { pl.x = -S[0]; pl.y = -S[1]; pl.z = -d; pl.w = -S[2]; }
+            if (S[2] != 0.0) planeNoZ = 0;
             plane.push_back(pl);
             nbr.push_back(f < nI ? (own ? m->neighbour[f] : m->owner[f]) : -(f - nI + 1));
         }
@@ -697,7 +725,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         upload(h, h->dBbMax, m->cellBbMax, 3 * (size_t)nC) || upload(h, h->dBfS, bfS.data(), 3 * (size_t)nB))
         return 1;
     CU(cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
-    h->mesh.nCells = nC; h->mesh.nBFaces = nB; h->mesh.nPatches = h->nPatches;
+    h->mesh.nCells = nC; h->mesh.nBFaces = nB; h->mesh.nPatches = h->nPatches; h->mesh.planeNoZ = planeNoZ;
     h->mesh.cfOff = h->dCfOff; h->mesh.plane = h->dPlane; h->mesh.nbr = h->dNbr; h->mesh.bfPatch = h->dBfPatch;
     h->mesh.bfOwner = h->dBfOwner; h->mesh.patches = h->dPatches; h->mesh.vol = h->dVol; h->mesh.bbMin = h->dBbMin; h->mesh.bbMax = h->dBbMax;
 
@@ -733,7 +761,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     // launch geometry: persistent grids sized to the SM count
     h->cellSmem = cell_smem_bytes(h->hasRot);
     h->bgkSmem = (size_t)BGK_WARPS * h->cellCap * 4 * sizeof(double) + (size_t)BGK_WARPS * h->cellCap;
-    int occCell = 1, occNtc = 1, occBgk = 1, occSeg = 1;
+    int occCell = 1, occNtc = 1, occBgk = 1;
     cudaError_t e1 = cudaSuccess;
     dispatch(h, [&](auto R, auto M) {
         auto k = cell_kernel<decltype(R)::value, decltype(M)::value>;
@@ -750,7 +778,6 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         CU(cudaFuncSetAttribute(bgk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->bgkSmem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occBgk, bgk_kernel<false>, BGK_THREADS, h->bgkSmem));
     }
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occSeg, segment_sort_kernel, SEG_THREADS, 0));
     auto persistent = [&](int occ, int warpsPerBlock) {
         const int need = (nC + warpsPerBlock - 1) / warpsPerBlock;
         return std::max(1, std::min(need, h->numSMs * std::max(occ, 1)));
@@ -758,6 +785,10 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     // The streaming kernel's cp.async fills need L1 lines while in flight: fewer resident blocks leave a larger
     // L1 next to the shared-memory carve-out and raise the achievable memory-level parallelism (profiles/).
     int cellBps = 4, cellCarve = -1;
+    if (const char* e = std::getenv("UGF_MOVE_DIRECT")) h->moveDirect = std::atoi(e) != 0;
+    if (const char* e = std::getenv("UGF_MOVE_BPS")) h->moveBps = std::max(3, std::min(4, std::atoi(e)));
+    if (const char* e = std::getenv("UGF_CELL_TASK")) h->cellTask = std::max(1, std::min(CELL_TASK_MAX, std::atoi(e)));
+    if (const char* e = std::getenv("UGF_CELL_FLAGS")) h->cellFlags = std::atoi(e);
     if (const char* e = std::getenv("UGF_CELL_BPS")) cellBps = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("UGF_CELL_CARVEOUT")) cellCarve = std::atoi(e);
     occCell = std::min(occCell, cellBps);
@@ -766,10 +797,9 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         e1 = cudaFuncSetAttribute(cell_kernel<decltype(R)::value, decltype(M)::value>, cudaFuncAttributePreferredSharedMemoryCarveout, cellCarve);
     });
     CU(e1);
-    h->cellBlocks = persistent(occCell, CELL_WARPS * CELL_CHUNK);
+    h->cellBlocks = persistent(occCell, CELL_WARPS * h->cellTask);
     h->ntcBlocks = persistent(occNtc, NTC_WARPS * 32);
     h->bgkBlocks = persistent(occBgk, BGK_WARPS);
-    h->segBlocks = persistent(occSeg, SEG_THREADS / 32);
     h->meshSet = true;
     return 0;
 }

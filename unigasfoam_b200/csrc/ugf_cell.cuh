@@ -7,8 +7,8 @@
 //                   (U/dsmcCollisions/derived/*), and the kinetic samplers they call
 //                   (U/clouds/uniGasCloud.C:1129-1189, 1267-1326).
 //
-// Two kernels, both one warp per run of consecutive cells (persistent CTAs, grid-stride over chunks of
-// CELL_CHUNK cells):
+// Two kernels, both one warp per run of consecutive cells (persistent CTAs; cell_kernel claims tasks of CELL_TASK
+// cells from a global counter, ntc_kernel strides over chunks of 32 cells):
 //   cell_kernel  streaming: the run's parcels are pulled through the permutation into shared memory with cp.async
 //                (every load of the run in flight at once), moments are reduced by 4 lanes per cell and written
 //                as one 256-byte block per (cell, species), and the run is written cell-major, fully coalesced.
@@ -43,6 +43,9 @@ struct CellArgs {
     double* mom;
     double* acc;      // time-averaged accumulators [nCells][NACC]; updated in the same pass when accDt != 0
     double accDt;
+    int* taskCounter; // zero at launch: next unclaimed task of taskCells cells
+    int taskCells;    // <= CELL_TASK_MAX
+    int flags;        // tuning: 1 = positions pass through registers (L2 loads, no staging); 2 = velocities loaded with L2 loads
 };
 
 // postCollisionRotationalEnergy (U/clouds/uniGasCloud.C:1129-1189)
@@ -184,7 +187,8 @@ __device__ __forceinline__ double sigma_tcr(const DevParams& prm, const DevSpeci
     return sigmaTPQ * sqrt(cR2);
 }
 
-constexpr int CELL_CHUNK = 8;    // consecutive cells examined by one warp per iteration
+constexpr int CELL_CHUNK = 8;    // most cells staged together as one run (moment phase: 32 / CELL_CHUNK lanes per cell)
+constexpr int CELL_TASK_MAX = 24; // most consecutive cells a warp claims at a time (their CSR offsets sit in lanes 0..taskCells)
 constexpr int CELL_CAP = 128;    // parcels staged per warp; larger cells take the single-cell paths
 constexpr int CELL_ITERS = CELL_CAP / 32;
 constexpr int CELL_LPC = 32 / CELL_CHUNK;  // lanes cooperating on one cell in the moment phase (4)
@@ -330,19 +334,29 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
     double* const sE = sU2 + cap;  // valid only if HAS_ROT
     int* const sC = reinterpret_cast<int*>(smemD + (size_t)CELL_WARPS * perWarp) + (size_t)wib * cap;
     uint8_t* const sT = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(smemD + (size_t)CELL_WARPS * perWarp) + (size_t)CELL_WARPS * cap) + (size_t)wib * cap;
-    const int warpsTotal = gridDim.x * CELL_WARPS;
-    const int nChunks = (a.nCells + CELL_CHUNK - 1) / CELL_CHUNK;
+    const int CELL_TASK = a.taskCells;
+    const int nTasks = (a.nCells + CELL_TASK - 1) / CELL_TASK;
     const int nS = prm.nSpecies;
 
-    for (int chunk = blockIdx.x * CELL_WARPS + wib; chunk < nChunks; chunk += warpsTotal) {
-        const int c0 = chunk * CELL_CHUNK;
-        const int nc = min(CELL_CHUNK, a.nCells - c0);
-        const int offv = (lane <= nc) ? a.off[c0 + lane] : 0x7fffffff;  // lanes 0..nc hold the chunk's CSR offsets
+    // Tasks of CELL_TASK consecutive cells are claimed from a global counter (zeroed by the host before the launch):
+    // warps that draw sparse cells simply claim more tasks.  The id of the following task and its CSR offsets are
+    // requested while the current one is processed, so neither round trip is exposed.
+    int task = 0, offNext = 0x7fffffff;
+    if (lane == 0) task = atomicAdd(a.taskCounter, 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task < nTasks && lane <= min(CELL_TASK, a.nCells - task * CELL_TASK)) offNext = a.off[task * CELL_TASK + lane];
+    while (task < nTasks) {
+        const int c0 = task * CELL_TASK;
+        const int nc = min(CELL_TASK, a.nCells - c0);
+        const int offv = offNext;  // lanes 0..nc hold the task's CSR offsets
+        int taskNext = 0;
+        if (lane == 0) taskNext = atomicAdd(a.taskCounter, 1);
+        bool nextRequested = false;
         int done = 0;
         while (done < nc) {
-            // largest run of cells [done, done+k) whose parcels fit the staging buffer together
+            // largest run of cells [done, done+k), k <= CELL_CHUNK, whose parcels fit the staging buffer together
             const int b0 = __shfl_sync(0xffffffffu, offv, done);
-            const unsigned fit = __ballot_sync(0xffffffffu, lane > done && lane <= nc && (offv - b0) <= cap);
+            const unsigned fit = __ballot_sync(0xffffffffu, lane > done && lane <= nc && lane <= done + CELL_CHUNK && (offv - b0) <= cap);
             const int k = __popc(fit);
             if (k == 0) {  // a single cell larger than the buffer
                 const int e0 = __shfl_sync(0xffffffffu, offv, done + 1);
@@ -362,7 +376,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
             for (int it = 0; it < CELL_ITERS; ++it) {
                 const int j = it * 32 + lane;
                 const int src = srcs[it];
-                if (src >= 0) {
+                if (src >= 0 && !(a.flags & 2)) {
                     cp_async8(&sU0[j], &a.in.ux[src]);
                     cp_async8(&sU1[j], &a.in.uy[src]);
                     cp_async8(&sU2[j], &a.in.uz[src]);
@@ -370,6 +384,31 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                     if (HAS_ROT) cp_async8(&sE[j], &a.in.erot[src]);
                     if (MULTI) sT[j] = a.in.type[src];
                 }
+            }
+            if (a.flags & 2) {
+                double u[CELL_ITERS], v[CELL_ITERS], w[CELL_ITERS];
+#pragma unroll
+                for (int it = 0; it < CELL_ITERS; ++it) {
+                    const int src = srcs[it];
+                    if (src >= 0) { u[it] = __ldcg(&a.in.ux[src]); v[it] = __ldcg(&a.in.uy[src]); w[it] = __ldcg(&a.in.uz[src]); }
+                }
+#pragma unroll
+                for (int it = 0; it < CELL_ITERS; ++it) {
+                    const int j = it * 32 + lane;
+                    const int src = srcs[it];
+                    if (src >= 0) {
+                        sU0[j] = u[it]; sU1[j] = v[it]; sU2[j] = w[it];
+                        if (a.gather) sC[j] = __ldcg(&a.in.cell[src]);
+                        if (HAS_ROT) sE[j] = __ldcg(&a.in.erot[src]);
+                        if (MULTI) sT[j] = a.in.type[src];
+                    }
+                }
+            }
+            if (!nextRequested) {  // the first copies of this task are in flight: fetch the next task's offsets behind them
+                nextRequested = true;
+                taskNext = __shfl_sync(0xffffffffu, taskNext, 0);
+                offNext = 0x7fffffff;
+                if (taskNext < nTasks && lane <= min(CELL_TASK, a.nCells - taskNext * CELL_TASK)) offNext = a.off[taskNext * CELL_TASK + lane];
             }
             cp_async_wait_all();
             __syncwarp();
@@ -446,21 +485,41 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                         a.out.cell[b0 + j] = sC[j];
                         if (HAS_ROT) a.out.erot[b0 + j] = sE[j];
                         if (MULTI) a.out.type[b0 + j] = sT[j];
-                        cp_async8(&sU0[j], &a.in.x[srcs[it]]);  // same lane, same slot: no cross-lane hazard
-                        cp_async8(&sU1[j], &a.in.y[srcs[it]]);
-                        cp_async8(&sU2[j], &a.in.z[srcs[it]]);
+                        if (!(a.flags & 1)) {
+                            cp_async8(&sU0[j], &a.in.x[srcs[it]]);  // same lane, same slot: no cross-lane hazard
+                            cp_async8(&sU1[j], &a.in.y[srcs[it]]);
+                            cp_async8(&sU2[j], &a.in.z[srcs[it]]);
+                        }
                     }
                 }
-                cp_async_wait_all();
+                if (a.flags & 1) {
+                    double px[CELL_ITERS], py[CELL_ITERS], pz[CELL_ITERS];
 #pragma unroll
-                for (int it = 0; it < CELL_ITERS; ++it) {
-                    const int j = it * 32 + lane;
-                    if (j < ntot) { a.out.x[b0 + j] = sU0[j]; a.out.y[b0 + j] = sU1[j]; a.out.z[b0 + j] = sU2[j]; }
+                    for (int it = 0; it < CELL_ITERS; ++it)
+                        if (srcs[it] >= 0) { px[it] = __ldcg(&a.in.x[srcs[it]]); py[it] = __ldcg(&a.in.y[srcs[it]]); pz[it] = __ldcg(&a.in.z[srcs[it]]); }
+#pragma unroll
+                    for (int it = 0; it < CELL_ITERS; ++it) {
+                        const int j = it * 32 + lane;
+                        if (srcs[it] >= 0) { a.out.x[b0 + j] = px[it]; a.out.y[b0 + j] = py[it]; a.out.z[b0 + j] = pz[it]; }
+                    }
+                } else {
+                    cp_async_wait_all();
+#pragma unroll
+                    for (int it = 0; it < CELL_ITERS; ++it) {
+                        const int j = it * 32 + lane;
+                        if (j < ntot) { a.out.x[b0 + j] = sU0[j]; a.out.y[b0 + j] = sU1[j]; a.out.z[b0 + j] = sU2[j]; }
+                    }
                 }
             }
             __syncwarp();
             done += k;
         }
+        if (!nextRequested) {  // a task of giant cells only
+            taskNext = __shfl_sync(0xffffffffu, taskNext, 0);
+            offNext = 0x7fffffff;
+            if (taskNext < nTasks && lane <= min(CELL_TASK, a.nCells - taskNext * CELL_TASK)) offNext = a.off[taskNext * CELL_TASK + lane];
+        }
+        task = taskNext;
     }
 }
 

@@ -3,7 +3,7 @@
 // Data layout in HBM:
 //   parcels   SoA, fp64 x,y,z,Ux,Uy,Uz (+ERot), int32 cell (+uint8 typeId); two buffers (ping-pong) so that the
 //             cell kernel can gather through the occupancy permutation and write cell-major order.
-//   mesh      CSR cell->face slots; per slot an outward-oriented face plane {Sx,Sy,Sz,S.Cf} (32 B) and the id of
+//   mesh      CSR cell->face slots; per slot an outward-oriented face plane {Sx,Sy,S.Cf,Sz} (32 B) and the id of
 //             the cell behind it (>=0) or -(boundaryFace+1).
 //   cells     offsets[nCells+1], perm[n], moments [cell][species][UGF_NMOM], accumulators [cell][NACC].
 #pragma once
@@ -68,7 +68,8 @@ struct ParcelBuf {
 struct MeshDev {
     int nCells, nBFaces, nPatches;
     const int* cfOff;         // [nCells+1]
-    const double4* plane;     // [slots] outward {Sx,Sy,Sz,S.Cf}
+    int planeNoZ;             // 1: every stored plane has Sz == 0 exactly (straight-extruded 2-D mesh)
+    const double4* plane;     // [slots] outward plane stored as {Sx,Sy,S.Cf,Sz}
     const int* nbr;           // [slots] cell behind the face, or -(bfi+1)
     const int* bfPatch;       // [nBFaces]
     const int* bfOwner;       // [nBFaces]

@@ -13,15 +13,24 @@
 #pragma once
 #include "ugf_common.cuh"
 #include "ugf_rng.cuh"
+#include "ugf_sort.cuh"
 
 namespace ugf {
 
-// 32-byte plane record through the read-only path (two 16-byte loads)
+// 32-byte plane record, stored as {Sx, Sy, S.Cf, Sz}, through the read-only path (two 16-byte loads); returned as
+// {x, y, z, w} = {Sx, Sy, Sz, S.Cf}
 __device__ __forceinline__ double4 load_plane(const double4* p) {
     const double2 a = __ldg(reinterpret_cast<const double2*>(p));
     const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
     double4 r;
-    r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    r.x = a.x; r.y = a.y; r.w = b.x; r.z = b.y;
+    return r;
+}
+// meshes whose reachable faces all have Sz == 0 (straight-extruded 2-D cases): 24 of the 32 bytes
+__device__ __forceinline__ double4 load_plane_noz(const double4* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    double4 r;
+    r.x = a.x; r.y = a.y; r.w = __ldg(reinterpret_cast<const double*>(p) + 2); r.z = 0.0;
     return r;
 }
 
@@ -200,22 +209,40 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
     }
 }
 
+// ---- bulk-copy (TMA) staging helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// One parcel's track (thread i), its stores and the warp-aggregated histogram / counter updates.  Every lane of
+// the warp must call it (valid = false for lanes without a parcel).
 // NF > 0: every cell has exactly NF face slots (hex meshes: 6, or 4 after the never-hit faces of an empty
-// direction were pruned at set-up): no offset loads and a fully unrolled face loop, so all plane loads of a hop are
-// issued together.  NF == 0: general polyhedra through the CSR offsets.
+// direction were pruned at set-up): no offset loads and a fully unrolled face loop, so all plane loads of a hop
+// and the ids of the cells behind them are issued together (one dependent memory level per hop).
+// NF == 0: general polyhedra through the CSR offsets.
 template <bool HAS_ROT, bool MULTI, int NF>
-__global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
-    const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a.dBegin && a.begin + (long long)(blockIdx.x + 1) * blockDim.x <= *a.dBegin) return;  // whole block precedes the received range
-    const long long n = *a.dN;
-    bool valid = i < n;
-    if (a.dBegin && i < *a.dBegin) valid = false;
-    int cell = -1;
+__device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArgs& a, const long long i, const bool valid, int cell, double x0,
+                                             double x1, double x2, double U0, double U1, double U2) {
     int flags = 0, nWall = 0;
-    if (valid) cell = a.P.cell[i];
     if (valid && cell >= 0) {
-        double x0 = a.P.x[i], x1 = a.P.y[i], x2 = a.P.z[i];
-        double U0 = a.P.ux[i], U1 = a.P.uy[i], U2 = a.P.uz[i];
         int nDraws = 0;
         double sf = 0.0;
         if (a.useSfIn) sf = a.sf[i];
@@ -236,12 +263,28 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
             // first face crossed: min of num/nd over faces with nd > 0, compared by cross-multiplication
             // (one division per hop, branch-free loop body); (bnum, bnd) = (1, 1) encodes "end of step"
             double bnum = 1.0, bnd = 1.0;
-            int hit = -1;
+            int hit = -1, nb = 0;
             if (NF > 0) {
                 const int jb = cell * NF;
                 double4 pl[NF > 0 ? NF : 1];
+                int nbs[NF > 0 ? NF : 1];
+                if (a.mesh.planeNoZ) {
 #pragma unroll
-                for (int f = 0; f < NF; ++f) pl[f] = load_plane(&a.mesh.plane[jb + f]);
+                    for (int f = 0; f < NF; ++f) pl[f] = load_plane_noz(&a.mesh.plane[jb + f]);
+                } else {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) pl[f] = load_plane(&a.mesh.plane[jb + f]);
+                }
+                if (NF == 4) {
+                    const int4 v = __ldg(reinterpret_cast<const int4*>(a.mesh.nbr + jb));
+                    nbs[0] = v.x; nbs[1] = v.y; nbs[2] = v.z; nbs[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int f = 0; f < NF; f += 2) {
+                        const int2 v = __ldg(reinterpret_cast<const int2*>(a.mesh.nbr + jb + f));
+                        nbs[f] = v.x; nbs[f + 1] = v.y;
+                    }
+                }
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
                     const double nd = fma(pl[f].z, d2, fma(pl[f].y, d1, pl[f].x * d0));
@@ -251,11 +294,13 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
                     bnum = better ? num : bnum;
                     bnd = better ? nd : bnd;
                     hit = better ? jb + f : hit;
+                    nb = better ? nbs[f] : nb;
                 }
             } else {
                 const int jb = __ldg(&a.mesh.cfOff[cell]), je = __ldg(&a.mesh.cfOff[cell + 1]);
                 for (int j = jb; j < je; ++j) {
                     const double4 pl = load_plane(&a.mesh.plane[j]);
+                    const int nbj = __ldg(&a.mesh.nbr[j]);
                     const double nd = fma(pl.z, d2, fma(pl.y, d1, pl.x * d0));
                     double num = pl.w - fma(pl.z, x2, fma(pl.y, x1, pl.x * x0));
                     num = num < 0 ? 0.0 : num;
@@ -263,6 +308,7 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
                     bnum = better ? num : bnum;
                     bnd = better ? nd : bnd;
                     hit = better ? j : hit;
+                    nb = better ? nbj : nb;
                 }
             }
             if (hit < 0) {
@@ -273,7 +319,6 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
             const double lamMin = bnum / bnd;
             x0 = fma(lamMin, d0, x0); x1 = fma(lamMin, d1, x1); x2 = fma(lamMin, d2, x2);
             sf = fma(rem, lamMin, sf);
-            const int nb = __ldg(&a.mesh.nbr[hit]);
             if (nb >= 0) {
                 cell = nb;
             } else {
@@ -301,10 +346,10 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
     // histogram of destination cells, aggregated over lanes that landed in the same cell
     const int lane = threadIdx.x & 31;
     const bool live = valid && cell >= 0;
-    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
-    if (live) {
-        const unsigned peers = __match_any_sync(liveMask, cell);
-        if (lane == __ffs(peers) - 1) atomicAdd(&a.cellCount[cell], __popc(peers));
+    {
+        int head, cnt, rank;
+        warp_runs(live ? cell : -1, lane, head, cnt, rank);
+        if (live && rank == 0) atomicAdd(&a.cellCount[cell], cnt);
     }
     if (__any_sync(0xffffffffu, (flags | nWall) != 0)) {
         const int sd = __popc(__ballot_sync(0xffffffffu, (flags & HIT_DELETED) != 0));
@@ -317,6 +362,91 @@ __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ De
             if (sm) atomicAdd(&a.cnt->migrated, (unsigned long long)sm);
             if (sw) atomicAdd(&a.cnt->wallHits, (unsigned long long)sw);
         }
+    }
+}
+
+// Direct kernel, one thread per parcel of [begin, n): used for the resumed tracks of received parcels (small,
+// unaligned ranges).
+template <bool HAS_ROT, bool MULTI, int NF>
+__global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
+    const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.dBegin && a.begin + (long long)(blockIdx.x + 1) * blockDim.x <= *a.dBegin) return;  // whole block precedes the received range
+    const long long n = *a.dN;
+    bool valid = i < n;
+    if (a.dBegin && i < *a.dBegin) valid = false;
+    int cell = -1;
+    double x0 = 0, x1 = 0, x2 = 0, U0 = 0, U1 = 0, U2 = 0;
+    if (valid) cell = a.P.cell[i];
+    if (valid && cell >= 0) {
+        x0 = a.P.x[i]; x1 = a.P.y[i]; x2 = a.P.z[i];
+        U0 = a.P.ux[i]; U1 = a.P.uy[i]; U2 = a.P.uz[i];
+    }
+    track_parcel<HAS_ROT, MULTI, NF>(prm, a, i, valid, cell, x0, x1, x2, U0, U1, U2);
+}
+
+// The step's main move: persistent CTAs (a multiple of the SM count) whose warps each stream tiles of 32 parcels
+// through a private MOVE_STAGES-deep ring in shared memory.  The seven per-parcel arrays of a tile (x, y, z, Ux, Uy,
+// Uz, cell: 1664 B) are brought in by cp.async.bulk (1-D TMA) copies that complete on the ring slot's mbarrier,
+// MOVE_STAGES tiles ahead of the one being tracked, so the HBM stream stays in flight while the lanes sit in the
+// dependent cell -> planes -> next-cell load chain of the tracking loop.  Warps never wait for each other (no
+// block barrier in the loop).  Tiles are always copied whole (the SoA arrays are allocated in multiples of
+// MOVE_TILE), begin must be 0.
+constexpr int MOVE_TILE = 256;   // allocation granule of the SoA arrays (parcels)
+constexpr int MOVE_WARPS = 8;
+constexpr int MOVE_STAGES = 2;
+
+template <bool HAS_ROT, bool MULTI, int NF, int BPS>
+__global__ void __launch_bounds__(MOVE_WARPS * 32, BPS) move_stream_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
+    __shared__ __align__(128) double sD[MOVE_WARPS][MOVE_STAGES][6][32];
+    __shared__ __align__(16) int sC[MOVE_WARPS][MOVE_STAGES][32];
+    __shared__ __align__(8) uint64_t bar[MOVE_WARPS][MOVE_STAGES];
+    const long long n = *a.dN;
+    const long long nTiles = (n + 31) / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long stride = (long long)gridDim.x * MOVE_WARPS;
+    auto issue = [&](long long tile, int s) {
+        const long long b = tile * 32;
+        constexpr unsigned bytesD = 32 * sizeof(double), bytesC = 32 * sizeof(int);
+        uint64_t* br = &bar[w][s];
+        mbar_expect_tx(br, 6 * bytesD + bytesC);
+        bulk_g2s(sD[w][s][0], a.P.x + b, bytesD, br);
+        bulk_g2s(sD[w][s][1], a.P.y + b, bytesD, br);
+        bulk_g2s(sD[w][s][2], a.P.z + b, bytesD, br);
+        bulk_g2s(sD[w][s][3], a.P.ux + b, bytesD, br);
+        bulk_g2s(sD[w][s][4], a.P.uy + b, bytesD, br);
+        bulk_g2s(sD[w][s][5], a.P.uz + b, bytesD, br);
+        bulk_g2s(sC[w][s], a.P.cell + b, bytesC, br);
+    };
+    const long long first = (long long)blockIdx.x * MOVE_WARPS + w;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < MOVE_STAGES; ++s) mbar_init(&bar[w][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < MOVE_STAGES; ++s) {
+            const long long t = first + (long long)s * stride;
+            if (t < nTiles) issue(t, s);
+        }
+    }
+    __syncwarp();
+    int k = 0;
+    for (long long tile = first; tile < nTiles; tile += stride, ++k) {
+        const int s = k % MOVE_STAGES;
+        mbar_wait(&bar[w][s], (unsigned)(k / MOVE_STAGES) & 1u);
+        const long long i = tile * 32 + lane;
+        const bool valid = i < n;
+        const int cell = valid ? sC[w][s][lane] : -1;
+        const double x0 = sD[w][s][0][lane], x1 = sD[w][s][1][lane], x2 = sD[w][s][2][lane];
+        const double U0 = sD[w][s][3][lane], U1 = sD[w][s][4][lane], U2 = sD[w][s][5][lane];
+        __syncwarp();  // the slot is in registers: refill it with the tile MOVE_STAGES ahead
+        if (lane == 0) {
+            const long long t = tile + (long long)MOVE_STAGES * stride;
+            if (t < nTiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(t, s);
+            }
+        }
+        track_parcel<HAS_ROT, MULTI, NF>(prm, a, i, valid, cell, x0, x1, x2, U0, U1, U2);
     }
 }
 

@@ -8,7 +8,8 @@
 // Pipeline: histogram (fused into move_kernel) -> exclusive scan (3 small kernels over nCells ints)
 //           -> index scatter (4 B read + 4 B write per parcel) -> per-cell segment sort (in place, skipped
 //           when the segment is already ascending, which is the common case because the array is cell-major
-//           from the previous step).  The payload is moved once, by the cell kernel's gather.
+//           from the previous step; in the fused step this happens inside the cell kernel, on the ids it has
+//           just loaded).  The payload is moved once, by the cell kernel's gather.
 #pragma once
 #include "ugf_common.cuh"
 
@@ -98,26 +99,51 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(int* __restric
     if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = *total;
 }
 
+// Lanes of a warp that hold the same key in a run of consecutive lanes (the common case: parcels are nearly
+// cell-major) are aggregated without match.any: head = first lane of the run, cnt = its length, rank = position
+// in it.  Equal keys in separate runs simply issue separate atomics.
+__device__ __forceinline__ void warp_runs(int key, int lane, int& head, int& cnt, int& rank) {
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+    const int end = above ? __ffs(above) - 1 : 32;
+    cnt = end - head;
+    rank = lane - head;
+}
+
 // perm[offsets[cell] + slot] = i, slot claimed through the per-cell cursor (lanes of a warp that share a
-// cell claim a contiguous run with one atomic and keep their relative order).
+// cell claim a contiguous run with one atomic and keep their relative order).  A warp takes SCAT_ROWS rows of 32
+// consecutive parcels and keeps all their load -> atomic -> store chains in flight together (the kernel is
+// bound by the latency of that chain, not by its 8 B/parcel).
+constexpr int SCAT_ROWS = 4;
 __global__ void __launch_bounds__(256) scatter_index_kernel(const int* __restrict__ cell, const long long* __restrict__ dN,
                                                             const int* __restrict__ offsets, int* __restrict__ cursor,
                                                             int* __restrict__ perm) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long wbase = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * SCAT_ROWS) + lane;
     const long long n = *dN;
-    int c = -1;
-    if (i < n) c = cell[i];
-    const bool live = c >= 0;
-    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
-    if (live) {
-        const unsigned peers = __match_any_sync(liveMask, c);
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&cursor[c], __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        perm[offsets[c] + base + rank] = (int)i;
+    int c[SCAT_ROWS], base[SCAT_ROWS], off[SCAT_ROWS], head[SCAT_ROWS], rank[SCAT_ROWS];
+#pragma unroll
+    for (int r = 0; r < SCAT_ROWS; ++r) {
+        const long long i = wbase + r * 32;
+        c[r] = (i < n) ? cell[i] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < SCAT_ROWS; ++r) {
+        int cnt;
+        warp_runs(c[r], lane, head[r], cnt, rank[r]);
+        base[r] = 0;
+        off[r] = 0;
+        if (c[r] >= 0) {
+            if (rank[r] == 0) base[r] = atomicAdd(&cursor[c[r]], cnt);
+            off[r] = offsets[c[r]];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < SCAT_ROWS; ++r) {
+        const int b = __shfl_sync(0xffffffffu, base[r], head[r]);
+        if (c[r] >= 0) perm[off[r] + b + rank[r]] = (int)(wbase + r * 32);
     }
 }
 
@@ -125,7 +151,7 @@ __global__ void __launch_bounds__(256) scatter_index_kernel(const int* __restric
 // Ascending-only bitonic network (partner = i ^ (k-1) for the first sub-step of a merge, then i ^ j): the
 // lower index always takes the minimum, so virtual +inf padding beyond n never moves.
 constexpr int SEG_THREADS = 256;
-constexpr int SEG_SMEM_INTS = 1024;  // per-warp staging for segments of 33..1024 ids
+constexpr int SEG_SMEM_INTS = 512;  // per-warp staging: a chunk of cells, or one segment of 33..512 ids
 
 __device__ __forceinline__ int warp_sort32(int v, int lane) {
 #pragma unroll
@@ -164,39 +190,102 @@ __device__ inline void warp_sort_mem(int* a, int n, int lane) {
     }
 }
 
+// One warp per chunk of SEG_CHUNK consecutive cells, SEG_LPC lanes per cell.  The scatter claims slots in atomic
+// order, and a cell's parcels come from several warps (its own previous range plus arrivals from neighbour cells
+// whose ranges lie far away in the array), so most segments are NOT ascending.  The chunk's ids are staged in
+// shared memory and every cell is rank-sorted by its own lanes, all cells of the chunk in parallel (ids are
+// unique: rank = number of smaller ids in the segment; for cells of <= 32 parcels only the first id of every
+// run of consecutive ids is ranked); only displaced ids are written back.  Chunks that do not fit the staging
+// buffer fall back to one whole-warp bitonic sort per cell.
+constexpr int SEG_CHUNK = 8;
+constexpr int SEG_LPC = 32 / SEG_CHUNK;
+
+__device__ inline void warp_sort_segment(int* seg, int n, int* sm, int lane) {
+    bool bad = false;
+    for (int i = lane + 1; i < n; i += 32) bad |= seg[i - 1] > seg[i];
+    if (!__any_sync(0xffffffffu, bad)) return;
+    if (n <= 32) {
+        int v = lane < n ? seg[lane] : 0x7fffffff;
+        v = warp_sort32(v, lane);
+        if (lane < n) seg[lane] = v;
+    } else if (n <= SEG_SMEM_INTS) {
+        for (int i = lane; i < n; i += 32) sm[i] = seg[i];
+        __syncwarp();
+        warp_sort_mem(sm, n, lane);
+        for (int i = lane; i < n; i += 32) seg[i] = sm[i];
+    } else {
+        warp_sort_mem(seg, n, lane);  // giant cells: in global memory (correct, slow)
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(SEG_THREADS) segment_sort_kernel(const int* __restrict__ offsets, int nCells, int* __restrict__ perm) {
     __shared__ int stage[(SEG_THREADS / 32) * SEG_SMEM_INTS];
+    __shared__ int runRank[SEG_THREADS / 32][SEG_CHUNK][32];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int warpsTotal = gridDim.x * (SEG_THREADS / 32);
     int* sm = stage + wib * SEG_SMEM_INTS;
-    for (int c = blockIdx.x * (SEG_THREADS / 32) + wib; c < nCells; c += warpsTotal) {
-        const int beg = offsets[c];
-        const int n = offsets[c + 1] - beg;
-        if (n <= 1) continue;
-        int* seg = perm + beg;
-        if (n <= 32) {
-            int v = lane < n ? seg[lane] : 0x7fffffff;
-            const int prev = __shfl_up_sync(0xffffffffu, v, 1);
-            const bool bad = lane > 0 && lane < n && prev > v;
-            if (!__any_sync(0xffffffffu, bad)) continue;
-            v = warp_sort32(v, lane);
-            if (lane < n) seg[lane] = v;
-            continue;
+    const int chunk = blockIdx.x * (SEG_THREADS / 32) + wib;
+    const int c0 = chunk * SEG_CHUNK;
+    if (c0 >= nCells) return;
+    const int nc = min(SEG_CHUNK, nCells - c0);
+    const int offv = (lane <= nc) ? offsets[c0 + lane] : 0;
+    const int b0 = __shfl_sync(0xffffffffu, offv, 0);
+    const int ntot = __shfl_sync(0xffffffffu, offv, nc) - b0;
+    if (ntot <= SEG_SMEM_INTS) {
+        for (int j = lane; j < ntot; j += 32) sm[j] = perm[b0 + j];
+        __syncwarp();
+        const int g = lane / SEG_LPC, q = lane % SEG_LPC;
+        const int cb = __shfl_sync(0xffffffffu, offv, g);
+        const int ce = __shfl_sync(0xffffffffu, offv, (g + 1) & 31);
+        const int n = (g < nc) ? ce - cb : 0;
+        const int* seg = sm + (cb - b0);
+        const bool small = n <= 32;
+        // A segment is a concatenation of runs of consecutive ids (each claimed by one group of adjacent source
+        // lanes), laid down in atomic order: only the runs have to be ranked, by their first id.
+        unsigned heads = 0;
+        if (small)
+            for (int i = q; i < n; i += SEG_LPC)
+                if (i == 0 || seg[i - 1] + 1 != seg[i]) heads |= 1u << i;
+#pragma unroll
+        for (int m = 1; m < SEG_LPC; m <<= 1) heads |= __shfl_xor_sync(0xffffffffu, heads, m);
+        const bool sorted1 = (heads == 1u) || n == 0;  // a single run: already ascending
+        unsigned todo = (small && !sorted1) ? heads : 0u;
+        while (__any_sync(0xffffffffu, todo != 0)) {
+            int part = 0, h = 0;
+            const bool act = todo != 0;  // uniform over the cell's lanes
+            if (act) {
+                h = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int v = seg[h];
+                for (int m = q; m < n; m += SEG_LPC) part += seg[m] < v;
+            }
+#pragma unroll
+            for (int m = 1; m < SEG_LPC; m <<= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+            if (act && q == 0) runRank[wib][g][h] = part;
         }
-        bool bad = false;
-        for (int i = lane + 1; i < n; i += 32) bad |= seg[i - 1] > seg[i];
-        if (!__any_sync(0xffffffffu, bad)) continue;
-        if (n <= SEG_SMEM_INTS) {
-            for (int i = lane; i < n; i += 32) sm[i] = seg[i];
-            __syncwarp();
-            warp_sort_mem(sm, n, lane);
-            for (int i = lane; i < n; i += 32) seg[i] = sm[i];
-            __syncwarp();
-        } else {
-            __syncwarp();
-            warp_sort_mem(seg, n, lane);  // giant cells: in global memory (correct, slow)
+        __syncwarp();
+        if (small) {
+            if (!sorted1)
+                for (int i = q; i < n; i += SEG_LPC) {
+                    const int h = 31 - __clz(heads & (0xffffffffu >> (31 - i)));
+                    const int rank = runRank[wib][g][h] + (i - h);
+                    if (rank != i) perm[cb + rank] = seg[i];
+                }
+        } else {  // larger cells of a staged chunk: plain rank sort by the cell's lanes
+            for (int i = q; i < n; i += SEG_LPC) {
+                const int v = seg[i];
+                int rank = 0;
+                for (int m = 0; m < n; ++m) rank += seg[m] < v;
+                if (rank != i) perm[cb + rank] = v;
+            }
         }
+        return;
+    }
+    for (int g = 0; g < nc; ++g) {
+        const int b = __shfl_sync(0xffffffffu, offv, g);
+        const int e = __shfl_sync(0xffffffffu, offv, g + 1);
+        if (e - b > 1) warp_sort_segment(perm + b, e - b, sm, lane);
     }
 }
 
