@@ -2,7 +2,7 @@
 # A/B of tuning switches on the bench workload; prints value, ms/step and the per-phase device times.
 run() {
   echo "== $*"
-  env "$@" python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-host-state 2>&1 | python -c "
+  env "$@" python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-host-state $BENCH_ARGS 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     l=l.strip()

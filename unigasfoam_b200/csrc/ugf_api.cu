@@ -393,7 +393,6 @@ int run_bgk_kernel(ugf_handle* h) {
     a.keyScratch = h->dKeyScratch;
     a.step = (uint32_t)h->step;
     a.cnt = h->dCnt;
-    a.cap = h->cellCap;
     const DevParams prm = h->prm;
     if (h->multi) bgk_kernel<true><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
     else bgk_kernel<false><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
@@ -760,7 +759,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
 
     // launch geometry: persistent grids sized to the SM count
     h->cellSmem = cell_smem_bytes(h->hasRot);
-    h->bgkSmem = (size_t)BGK_WARPS * h->cellCap * 4 * sizeof(double) + (size_t)BGK_WARPS * h->cellCap;
+    h->bgkSmem = (size_t)BGK_WARPS * sizeof(BgkWarpSmem);
     int occCell = 1, occNtc = 1, occBgk = 1;
     cudaError_t e1 = cudaSuccess;
     dispatch(h, [&](auto R, auto M) {
@@ -799,7 +798,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     CU(e1);
     h->cellBlocks = persistent(occCell, CELL_WARPS * h->cellTask);
     h->ntcBlocks = persistent(occNtc, NTC_WARPS * 32);
-    h->bgkBlocks = persistent(occBgk, BGK_WARPS);
+    h->bgkBlocks = persistent(occBgk, BGK_WARPS * BGK_CHUNK);
     h->meshSet = true;
     return 0;
 }

@@ -1,4 +1,4 @@
-// ugf_bgk.cuh — stochastic-particle BGK-family relaxation, one warp per cell.
+// ugf_bgk.cuh — stochastic-particle BGK-family relaxation.
 //
 // Replaces bgkCollisionModel::collide for
 //   stochasticParticleBGK          (U/bgkCollisions/derived/stochasticParticleBGK/stochasticParticleBGK.C:628-796)
@@ -8,10 +8,20 @@
 // i.e. calculateProperties (cell macroscopic state from the pre-collision moments), selection of the relaxing
 // parcels, sampling of the target distribution, conserveMomentumAndEnergy and resetProperties.
 //
-// The cell's velocities are staged in shared memory; the macroscopic state is computed redundantly by all lanes
-// from the 256-byte moment block; the acceptance-rejection envelope (maxProb) follows the reference's
-// sequential semantics: lanes sample speculatively, and everything after the first lane that raised the
-// envelope is re-sampled against the raised value.
+// One warp per chunk of BGK_CHUNK consecutive cells, in place on the cell-major buffer:
+//   A  lane c computes cell c's macroscopic state (no redundant work) and its number of relaxing parcels;
+//   B  the chunk's velocities are staged in shared memory (one coalesced pass) and every parcel draws its
+//      selection key from its own Philox stream (step, cell, slot);
+//   C  the nRel smallest keys of each cell are selected (rank among the cell's keys) and compacted into one list
+//      for the whole chunk, so that
+//   D  the expensive part - Philox + Box-Muller + acceptance-rejection per relaxing parcel - runs with all 32 lanes
+//      busy whatever the per-cell counts are.  The acceptance-rejection envelope (maxProb) follows the reference's
+//      sequential semantics: lanes sample speculatively; within a cell, everything after the first lane that raised
+//      the envelope is re-sampled against the raised value;
+//   E  momentum / energy sums by 4 lanes per cell, F the conservation rescale and one coalesced write-back.
+// Cells larger than the staging capacity take a whole-warp path working in global memory.
+//
+// HBM traffic: 24 B read + 24 B written per parcel of a BGK cell, 256 B x species + 100 B per cell.
 //
 // Deviation from the reference, statistically equivalent: the relaxing subset is the nRel smallest of one
 // uniform key per parcel instead of "shuffle the cell list five times and take the first nRel" — both are a
@@ -19,11 +29,15 @@
 #pragma once
 #include "ugf_common.cuh"
 #include "ugf_rng.cuh"
+#include "ugf_sort.cuh"
 
 namespace ugf {
 
-constexpr int BGK_THREADS = 256;
+constexpr int BGK_THREADS = 128;
 constexpr int BGK_WARPS = BGK_THREADS / 32;
+constexpr int BGK_CHUNK = 8;             // cells per warp chunk
+constexpr int BGK_LPC = 32 / BGK_CHUNK;  // lanes per cell in the conservation sums
+constexpr int BGK_CAP = 256;             // parcels staged per run of cells
 
 struct BgkArgs {
     int nCells;
@@ -38,7 +52,6 @@ struct BgkArgs {
     double* keyScratch;  // [capacity] selection keys for cells larger than the staging capacity
     uint32_t step;
     DevCounters* cnt;
-    int cap;
 };
 
 struct Macro {
@@ -46,37 +59,34 @@ struct Macro {
     double N, rhoN, p, T, U[3], q[3], s[6], P[6], Pr, nu, rhoNX, rhoMX;
 };
 
-// calculateProperties for one cell (…USP.C:379-800), all lanes redundantly; lane 0 stores the blended
-// heat flux / shear stress for the next step (…USP.C:777-783).
-__device__ inline void bgk_macro(const DevParams& prm, const double* __restrict__ momCell, double V, int lane,
-                                 double* qPrevCell, double* sPrevCell, Macro& m) {
+// calculateProperties for one cell (…USP.C:379-800), by one thread; it also stores the blended heat flux /
+// shear stress for the next step (…USP.C:777-783).
+__device__ inline void bgk_macro(const DevParams& prm, const double* __restrict__ momCell, double V, double* qPrevCell, double* sPrevCell,
+                                 Macro& m) {
     const int nS = prm.nSpecies;
     const int model = prm.bgkModel;
     const double FN = prm.nParticle;
     double N = 0, rhoM = 0, rhoNX = 0, rhoMX = 0, momX[3] = {0, 0, 0}, keX = 0;
     double muu[6] = {0, 0, 0, 0, 0, 0}, mcc = 0, mccu[3] = {0, 0, 0}, eInt = 0, eIntU[3] = {0, 0, 0};
-    double nSp[UGF_MAX_SPECIES];
-#pragma unroll
-    for (int s = 0; s < UGF_MAX_SPECIES; ++s) nSp[s] = 0;
+    double visc = 0, Pr = 0;
     for (int s = 0; s < nS; ++s) {
-        const double mv = momCell[(size_t)s * UGF_NMOM + lane];
+        const double* mv = momCell + (size_t)s * UGF_NMOM;
         const double ms = prm.sp[s].mass;
-        const double a0 = __shfl_sync(0xffffffffu, mv, 0), a1 = __shfl_sync(0xffffffffu, mv, 1);
+        const double a0 = mv[0], a1 = mv[1];
         N += a0; rhoM += ms * a0;
-        nSp[s] = a0;
         rhoNX += a1 * FN; rhoMX += ms * a1 * FN;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) momX[k] += ms * __shfl_sync(0xffffffffu, mv, 5 + k) * FN;
-        keX += ms * __shfl_sync(0xffffffffu, mv, 14) * FN;
+        for (int k = 0; k < 3; ++k) momX[k] += ms * mv[5 + k] * FN;
+        keX += ms * mv[14] * FN;
         double uu[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { uu[k] = __shfl_sync(0xffffffffu, mv, 8 + k); muu[k] += ms * uu[k]; }
+        for (int k = 0; k < 6; ++k) { uu[k] = mv[8 + k]; muu[k] += ms * uu[k]; }
         mcc += ms * (uu[0] + uu[3] + uu[5]);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) mccu[k] += ms * __shfl_sync(0xffffffffu, mv, 15 + k);
-        eInt += __shfl_sync(0xffffffffu, mv, 18) + __shfl_sync(0xffffffffu, mv, 22);
+        for (int k = 0; k < 3; ++k) mccu[k] += ms * mv[15 + k];
+        eInt += mv[18] + mv[22];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) eIntU[k] += __shfl_sync(0xffffffffu, mv, 19 + k) + __shfl_sync(0xffffffffu, mv, 23 + k);
+        for (int k = 0; k < 3; ++k) eIntU[k] += mv[19 + k] + mv[23 + k];
     }
     m.perform = true;
     m.N = N; m.rhoNX = rhoNX; m.rhoMX = rhoMX;
@@ -122,14 +132,14 @@ __device__ inline void bgk_macro(const DevParams& prm, const double* __restrict_
         m.perform = false;
     }
     if (m.T > VSMALL) {
-        double visc = 0, Pr = 0;
         for (int s = 0; s < nS; ++s) {
             const DevSpecies& S = prm.sp[s];
+            const double nSp = momCell[(size_t)s * UGF_NMOM];
             const double al = S.alpha;
             const double viscRef = 1.25 * (1.0 + al) * (2.0 + al) * sqrt(S.mass * kB * prm.Tref)
                                    / (al * (5.0 - 2.0 * S.omega) * (7.0 - 2.0 * S.omega) * sqrt(PI) * (S.d * S.d));
-            visc += nSp[s] * viscRef * pow(m.T / prm.Tref, S.omega);
-            Pr += nSp[s] * (5.0 + S.rotDoF) / (7.5 + S.rotDoF);
+            visc += nSp * viscRef * pow(m.T / prm.Tref, S.omega);
+            Pr += nSp * (5.0 + S.rotDoF) / (7.5 + S.rotDoF);
         }
         visc /= N; Pr /= N;
         m.Pr = Pr;
@@ -143,17 +153,15 @@ __device__ inline void bgk_macro(const DevParams& prm, const double* __restrict_
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             m.q[k] = th * m.q[k] / (1.0 + 0.5 * m.Pr * m.nu * dt) + (1.0 - th) * qPrevCell[k];
+            qPrevCell[k] = m.q[k];
         }
-        __syncwarp();
-        if (lane == 0) for (int k = 0; k < 3; ++k) qPrevCell[k] = m.q[k];
     }
     if (model == UGF_BGK_USP_SBGK) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             m.s[k] = th * m.s[k] / (1.0 + 0.5 * m.nu * dt) + (1.0 - th) * sPrevCell[k];
+            sPrevCell[k] = m.s[k];
         }
-        __syncwarp();
-        if (lane == 0) for (int k = 0; k < 6; ++k) sPrevCell[k] = m.s[k];
     }
 }
 
@@ -203,136 +211,303 @@ __device__ inline bool bgk_sample(const DevParams& prm, Stream& r, const Macro& 
     }
 }
 
+// number of relaxing parcels of a cell (…USP.C:917-923): stochastic rounding of N (1 - exp(-nu dt))
+__device__ __forceinline__ int bgk_count(const DevParams& prm, uint32_t step, int cell, const Macro& m, int n) {
+    const double pc = m.N * (1.0 - exp(-m.nu * prm.deltaT));
+    int nRel = (int)pc;
+    Stream rc(prm.seed, KIND_BGK, 0, step, (uint32_t)cell, 0xFFFFFFFFu);
+    if (rc.u01() < (pc - nRel)) nRel++;
+    return min(nRel, n);
+}
+
+struct BgkWarpSmem {
+    Macro mac[BGK_CHUNK];
+    double u[3][BGK_CAP];
+    double key[BGK_CAP];
+    double E[BGK_CHUNK];
+    double pU[BGK_CHUNK][3];
+    double fscale[BGK_CHUNK];  // < 0: no rescale
+    int nRel[BGK_CHUNK];
+    int raised[BGK_CHUNK];
+    int active[BGK_CHUNK];
+    int cb[BGK_CHUNK + 1];     // cell begins of the current run, relative to its first parcel
+    unsigned short sel[BGK_CAP];
+    unsigned char cellOf[BGK_CAP];
+    unsigned char type[BGK_CAP];
+};
+
+// A cell larger than the staging capacity: the whole warp works on it in global memory (keys in keyScratch).
+template <bool MULTI>
+__device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs& a, int cell, int beg, int n, const Macro& m, int nRel, double& E,
+                                            int& raisedOut, int& myRel, int lane) {
+    double* pu0 = a.P.ux + beg; double* pu1 = a.P.uy + beg; double* pu2 = a.P.uz + beg; double* pk = a.keyScratch + beg;
+    const uint8_t* pt = MULTI ? a.P.type + beg : nullptr;
+    for (int j = lane; j < n; j += 32) {
+        Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)cell, (uint32_t)j);
+        pk[j] = r.u01();
+    }
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        bool sel = false;
+        double mass = prm.sp[0].mass;
+        if (j < n) {
+            const double kj = pk[j];
+            int rank = 0;
+            for (int i = 0; i < n; ++i) {
+                const double ki = pk[i];
+                rank += (ki < kj) || (ki == kj && i < j);
+            }
+            sel = rank < nRel;
+            if (MULTI) mass = prm.sp[pt[j]].mass;
+        }
+        const double u0 = sqrt(2.0 * kB * m.T / mass);
+        unsigned pending = __ballot_sync(0xffffffffu, sel);
+        double v[3] = {0, 0, 0};
+        while (pending) {
+            const bool mine = (pending >> lane) & 1u;
+            bool rz = false;
+            double newE = E;
+            if (mine) {
+                Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)cell, (uint32_t)j);
+                (void)r.u01();  // the selection key
+                rz = bgk_sample(prm, r, m, u0, newE, v);
+            }
+            const unsigned raisedMask = __ballot_sync(0xffffffffu, mine && rz);
+            unsigned commitMask;
+            if (!raisedMask) {
+                commitMask = pending;
+                pending = 0;
+            } else {
+                const int first = __ffs(raisedMask) - 1;
+                const unsigned upto = (first == 31) ? 0xffffffffu : ((2u << first) - 1u);
+                commitMask = pending & upto;
+                pending &= ~upto;
+                E = __shfl_sync(0xffffffffu, newE, first);
+                raisedOut = 1;
+            }
+            if ((commitMask >> lane) & 1u) {
+                pu0[j] = m.U[0] + u0 * v[0];
+                pu1[j] = m.U[1] + u0 * v[1];
+                pu2[j] = m.U[2] + u0 * v[2];
+                myRel++;
+            }
+        }
+    }
+    __syncwarp();
+    // conserveMomentumAndEnergy (…USP.C:996-1045)
+    const double FN = prm.nParticle;
+    double keX = 0, mx = 0, my = 0, mz = 0;
+    for (int j = lane; j < n; j += 32) {
+        const double mass = MULTI ? prm.sp[pt[j]].mass : prm.sp[0].mass;
+        const double u = pu0[j], vv = pu1[j], w = pu2[j];
+        keX += mass * (u * u + vv * vv + w * w) * FN;
+        mx += mass * u * FN; my += mass * vv * FN; mz += mass * w * FN;
+    }
+    keX = warp_sum(keX); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
+    const double pU[3] = {mx / m.rhoMX, my / m.rhoMX, mz / m.rhoMX};
+    const double postT = m.N / (3.0 * (m.N - 1.0) * kB * m.rhoNX) * (keX - m.rhoMX * (pU[0] * pU[0] + pU[1] * pU[1] + pU[2] * pU[2]));
+    if (postT > VSMALL) {
+        const double f = sqrt(m.T / postT);
+        for (int j = lane; j < n; j += 32) {
+            pu0[j] = m.U[0] + (pu0[j] - pU[0]) * f;
+            pu1[j] = m.U[1] + (pu1[j] - pU[1]) * f;
+            pu2[j] = m.U[2] + (pu2[j] - pU[2]) * f;
+        }
+    }
+    __syncwarp();
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ BgkArgs a) {
-    extern __shared__ double smemD[];
+    extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int cap = a.cap;
-    const int perWarp = cap * 4;
-    double* sU0 = smemD + (size_t)wib * perWarp;
-    double* sU1 = sU0 + cap;
-    double* sU2 = sU1 + cap;
-    double* sK = sU2 + cap;
-    uint8_t* sT = reinterpret_cast<uint8_t*>(smemD + (size_t)BGK_WARPS * perWarp) + (size_t)wib * cap;
+    BgkWarpSmem& S = reinterpret_cast<BgkWarpSmem*>(smemRaw)[wib];
     const int warpsTotal = gridDim.x * BGK_WARPS;
     const int nS = prm.nSpecies;
     const int model = prm.bgkModel;
     const bool envelope = (model == UGF_BGK_SBGK || model == UGF_BGK_USP_SBGK);
+    const int nChunks = (a.nCells + BGK_CHUNK - 1) / BGK_CHUNK;
+    const double FN = prm.nParticle;
     int myRel = 0;
 
-    for (int cell = blockIdx.x * BGK_WARPS + wib; cell < a.nCells; cell += warpsTotal) {
-        const int beg = a.off[cell];
-        const int n = a.off[cell + 1] - beg;
-        Macro m;
-        bgk_macro(prm, a.mom + (size_t)cell * nS * UGF_NMOM, a.vol[cell], lane, a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
-        bool raised = false;
-        double E = envelope ? a.maxProb[cell] : 1.0;
-        if (a.collModelId[cell] == 0 && m.perform) {
-            const bool useSmem = n <= cap;
-            double *pu0, *pu1, *pu2, *pk;
-            uint8_t* pt;
-            if (useSmem) {
-                pu0 = sU0; pu1 = sU1; pu2 = sU2; pk = sK; pt = sT;
-                for (int j = lane; j < n; j += 32) {
-                    sU0[j] = a.P.ux[beg + j]; sU1[j] = a.P.uy[beg + j]; sU2[j] = a.P.uz[beg + j];
-                    if (MULTI) sT[j] = a.P.type[beg + j];
+    for (int chunk = blockIdx.x * BGK_WARPS + wib; chunk < nChunks; chunk += warpsTotal) {
+        const int c0 = chunk * BGK_CHUNK;
+        const int nc = min(BGK_CHUNK, a.nCells - c0);
+        const int offv = (lane <= nc) ? a.off[c0 + lane] : 0x7fffffff;
+        const int offNext = __shfl_down_sync(0xffffffffu, offv, 1);
+        // ---- A: macroscopic state and relaxing count, one cell per lane ------------------------------------------------
+        double Eold = 1.0;
+        if (lane < nc) {
+            const int cell = c0 + lane;
+            Macro m;
+            bgk_macro(prm, a.mom + (size_t)cell * nS * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
+            if (envelope) Eold = a.maxProb[cell];
+            const bool act = a.collModelId[cell] == 0 && m.perform;
+            S.mac[lane] = m;
+            S.E[lane] = Eold;
+            S.raised[lane] = 0;
+            S.active[lane] = act ? 1 : 0;
+            S.nRel[lane] = act ? bgk_count(prm, a.step, cell, m, offNext - offv) : 0;
+        }
+        __syncwarp();
+        const unsigned activeMask = __ballot_sync(0xffffffffu, lane < nc && S.active[lane & (BGK_CHUNK - 1)] != 0);
+        int done = 0;
+        while (done < nc) {
+            const int b0 = __shfl_sync(0xffffffffu, offv, done);
+            const unsigned fit = __ballot_sync(0xffffffffu, lane > done && lane <= nc && (offv - b0) <= BGK_CAP);
+            const int k = __popc(fit);
+            if (k == 0) {  // a single cell larger than the staging buffer
+                const int n = __shfl_sync(0xffffffffu, offv, done + 1) - b0;
+                if ((activeMask >> done) & 1u) {
+                    double E = S.E[done];
+                    int rs = 0;
+                    bgk_giant_cell<MULTI>(prm, a, c0 + done, b0, n, S.mac[done], S.nRel[done], E, rs, myRel, lane);
+                    __syncwarp();
+                    if (lane == 0) { S.E[done] = E; if (rs) S.raised[done] = 1; }
+                    __syncwarp();
                 }
-            } else {
-                pu0 = a.P.ux + beg; pu1 = a.P.uy + beg; pu2 = a.P.uz + beg; pk = a.keyScratch + beg;
-                pt = MULTI ? a.P.type + beg : nullptr;
+                done += 1;
+                continue;
             }
-            // number of relaxing parcels (…USP.C:917-923)
-            const double dt = prm.deltaT;
-            const double pc = m.N * (1.0 - exp(-m.nu * dt));
-            int nRel = (int)pc;
-            {
-                Stream rc(prm.seed, KIND_BGK, 0, a.step, (uint32_t)cell, 0xFFFFFFFFu);
-                if (rc.u01() < (pc - nRel)) nRel++;
-            }
-            nRel = min(nRel, n);
-            for (int j = lane; j < n; j += 32) {
-                Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)cell, (uint32_t)j);
-                pk[j] = r.u01();
+            const unsigned runMask = ((k >= 32 ? 0u : (1u << k)) - 1u) << done;
+            if (!(activeMask & runMask)) { done += k; continue; }
+            const int ntot = __shfl_sync(0xffffffffu, offv, done + k) - b0;
+            const int cbv = __shfl_sync(0xffffffffu, offv, (done + lane) & 31) - b0;
+            if (lane <= k) S.cb[lane] = cbv;
+            __syncwarp();
+            // ---- B: stage velocities, cell slot of every parcel, selection keys ----------------------------------------
+            for (int f = lane; f < ntot; f += 32) {
+                int g = 0;
+#pragma unroll
+                for (int t = 1; t < BGK_CHUNK; ++t) g += (t < k && S.cb[t] <= f) ? 1 : 0;
+                S.cellOf[f] = (unsigned char)g;
+                S.u[0][f] = a.P.ux[b0 + f]; S.u[1][f] = a.P.uy[b0 + f]; S.u[2][f] = a.P.uz[b0 + f];
+                if (MULTI) S.type[f] = a.P.type[b0 + f];
+                if (S.nRel[done + g] > 0) {
+                    Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)(c0 + done + g), (uint32_t)(f - S.cb[g]));
+                    S.key[f] = r.u01();
+                }
             }
             __syncwarp();
-            for (int base = 0; base < n; base += 32) {
-                const int j = base + lane;
+            // ---- C: the nRel smallest keys of every cell, compacted over the run ---------------------------------------
+            int nSel = 0;
+            for (int base = 0; base < ntot; base += 32) {
+                const int f = base + lane;
                 bool sel = false;
-                double mass = prm.sp[0].mass;
-                if (j < n) {
-                    const double kj = pk[j];
-                    int rank = 0;
-                    for (int i = 0; i < n; ++i) {
-                        const double ki = pk[i];
-                        rank += (ki < kj) || (ki == kj && i < j);
+                if (f < ntot) {
+                    const int g = S.cellOf[f];
+                    const int nRel = S.nRel[done + g];
+                    if (nRel > 0) {
+                        const int cb = S.cb[g], ce = S.cb[g + 1];
+                        const double kj = S.key[f];
+                        int rank = 0;
+                        for (int i = cb; i < ce; ++i) {
+                            const double ki = S.key[i];
+                            rank += (ki < kj) || (ki == kj && i < f);
+                        }
+                        sel = rank < nRel;
                     }
-                    sel = rank < nRel;
-                    if (MULTI) mass = prm.sp[pt[j]].mass;
                 }
+                const unsigned sm = __ballot_sync(0xffffffffu, sel);
+                if (sel) S.sel[nSel + __popc(sm & ((1u << lane) - 1u))] = (unsigned short)f;
+                nSel += __popc(sm);
+            }
+            __syncwarp();
+            // ---- D: sample the target distribution for the selected parcels, all cells of the run together -----------
+            for (int base = 0; base < nSel; base += 32) {
+                const int t = base + lane;
+                const bool mine0 = t < nSel;
+                const int f = mine0 ? S.sel[t] : 0;
+                const int g = S.cellOf[f];
+                const int cl = done + g;
+                const Macro& m = S.mac[cl];
+                const double mass = MULTI ? prm.sp[S.type[f]].mass : prm.sp[0].mass;
                 const double u0 = sqrt(2.0 * kB * m.T / mass);
-                unsigned pending = __ballot_sync(0xffffffffu, sel);
+                int head, cnt, rnk;
+                warp_runs(mine0 ? g : -1, lane, head, cnt, rnk);  // the list is cell-major: a cell's lanes are adjacent
+                const unsigned cellMask = (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u)) << head;
+                unsigned pending = __ballot_sync(0xffffffffu, mine0);
                 double v[3] = {0, 0, 0};
                 while (pending) {
                     const bool mine = (pending >> lane) & 1u;
                     bool rz = false;
-                    double newE = E;
+                    double E = 1.0;
                     if (mine) {
-                        Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)cell, (uint32_t)j);
+                        Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)(c0 + cl), (uint32_t)(f - S.cb[g]));
                         (void)r.u01();  // the selection key
-                        rz = bgk_sample(prm, r, m, u0, newE, v);
+                        E = S.E[cl];
+                        rz = bgk_sample(prm, r, m, u0, E, v);
                     }
-                    const unsigned raisedMask = __ballot_sync(0xffffffffu, mine && rz);
-                    unsigned commitMask;
-                    if (!raisedMask) {
-                        commitMask = pending;
-                        pending = 0;
-                    } else {
-                        const int first = __ffs(raisedMask) - 1;
-                        const unsigned upto = (first == 31) ? 0xffffffffu : ((2u << first) - 1u);
-                        commitMask = pending & upto;
-                        pending &= ~upto;
-                        E = __shfl_sync(0xffffffffu, newE, first);
-                        raised = true;
-                    }
-                    if ((commitMask >> lane) & 1u) {
-                        pu0[j] = m.U[0] + u0 * v[0];
-                        pu1[j] = m.U[1] + u0 * v[1];
-                        pu2[j] = m.U[2] + u0 * v[2];
+                    const unsigned raisedMask = __ballot_sync(0xffffffffu, mine && rz) & cellMask;
+                    const int firstR = raisedMask ? __ffs(raisedMask) - 1 : 32;
+                    const bool ok = mine && lane <= firstR;  // nothing earlier in this cell raised the envelope
+                    __syncwarp();
+                    if (ok) {
+                        if (rz) { S.E[cl] = E; S.raised[cl] = 1; }
+                        S.u[0][f] = m.U[0] + u0 * v[0];
+                        S.u[1][f] = m.U[1] + u0 * v[1];
+                        S.u[2][f] = m.U[2] + u0 * v[2];
                         myRel++;
                     }
+                    pending &= ~__ballot_sync(0xffffffffu, ok);
+                    __syncwarp();
                 }
             }
             __syncwarp();
-            // conserveMomentumAndEnergy (…USP.C:996-1045)
-            const double FN = prm.nParticle;
-            double keX = 0, mx = 0, my = 0, mz = 0;
-            for (int j = lane; j < n; j += 32) {
-                const double mass = MULTI ? prm.sp[pt[j]].mass : prm.sp[0].mass;
-                const double u = pu0[j], vv = pu1[j], w = pu2[j];
-                keX += mass * (u * u + vv * vv + w * w) * FN;
-                mx += mass * u * FN; my += mass * vv * FN; mz += mass * w * FN;
-            }
-            keX = warp_sum(keX); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
-            const double pU[3] = {mx / m.rhoMX, my / m.rhoMX, mz / m.rhoMX};
-            const double postT = m.N / (3.0 * (m.N - 1.0) * kB * m.rhoNX) * (keX - m.rhoMX * (pU[0] * pU[0] + pU[1] * pU[1] + pU[2] * pU[2]));
-            const bool rescale = postT > VSMALL;
-            const double f = rescale ? sqrt(m.T / postT) : 1.0;
-            if (rescale || useSmem) {
-                for (int j = lane; j < n; j += 32) {
-                    double u = pu0[j], vv = pu1[j], w = pu2[j];
-                    if (rescale) {
-                        u = m.U[0] + (u - pU[0]) * f;
-                        vv = m.U[1] + (vv - pU[1]) * f;
-                        w = m.U[2] + (w - pU[2]) * f;
+            // ---- E: conserveMomentumAndEnergy (…USP.C:996-1045), BGK_LPC lanes per cell --------------------------------
+            {
+                const int g = lane / BGK_LPC, q = lane % BGK_LPC;
+                const int cl = done + g;
+                const bool cellOn = g < k && S.active[cl & (BGK_CHUNK - 1)] != 0;
+                double keX = 0, mx = 0, my = 0, mz = 0;
+                if (cellOn) {
+                    const int cb = S.cb[g], ce = S.cb[g + 1];
+                    for (int i = cb + q; i < ce; i += BGK_LPC) {
+                        const double mass = MULTI ? prm.sp[S.type[i]].mass : prm.sp[0].mass;
+                        const double u = S.u[0][i], vv = S.u[1][i], w = S.u[2][i];
+                        keX += mass * (u * u + vv * vv + w * w) * FN;
+                        mx += mass * u * FN; my += mass * vv * FN; mz += mass * w * FN;
                     }
-                    a.P.ux[beg + j] = u; a.P.uy[beg + j] = vv; a.P.uz[beg + j] = w;
+                }
+#pragma unroll
+                for (int o = 1; o < BGK_LPC; o <<= 1) {
+                    keX += __shfl_xor_sync(0xffffffffu, keX, o);
+                    mx += __shfl_xor_sync(0xffffffffu, mx, o);
+                    my += __shfl_xor_sync(0xffffffffu, my, o);
+                    mz += __shfl_xor_sync(0xffffffffu, mz, o);
+                }
+                if (cellOn && q == 0) {
+                    const Macro& m = S.mac[cl];
+                    const double pU[3] = {mx / m.rhoMX, my / m.rhoMX, mz / m.rhoMX};
+                    const double postT = m.N / (3.0 * (m.N - 1.0) * kB * m.rhoNX) * (keX - m.rhoMX * (pU[0] * pU[0] + pU[1] * pU[1] + pU[2] * pU[2]));
+                    S.pU[g][0] = pU[0]; S.pU[g][1] = pU[1]; S.pU[g][2] = pU[2];
+                    S.fscale[g] = (postT > VSMALL) ? sqrt(m.T / postT) : -1.0;
                 }
             }
             __syncwarp();
+            // ---- F: rescale and write back (coalesced) -----------------------------------------------------------------
+            for (int f = lane; f < ntot; f += 32) {
+                const int g = S.cellOf[f];
+                const int cl = done + g;
+                if (!S.active[cl]) continue;
+                double u = S.u[0][f], vv = S.u[1][f], w = S.u[2][f];
+                const double fs = S.fscale[g];
+                if (fs >= 0.0) {
+                    const Macro& m = S.mac[cl];
+                    u = m.U[0] + (u - S.pU[g][0]) * fs;
+                    vv = m.U[1] + (vv - S.pU[g][1]) * fs;
+                    w = m.U[2] + (w - S.pU[g][2]) * fs;
+                }
+                a.P.ux[b0 + f] = u; a.P.uy[b0 + f] = vv; a.P.uz[b0 + f] = w;
+            }
+            __syncwarp();
+            done += k;
         }
         // resetProperties: envelope decay (…USP.C:859-863)
-        if (envelope && lane == 0) a.maxProb[cell] = raised ? E : E * (model == UGF_BGK_USP_SBGK ? 0.999 : 0.9999);
+        if (envelope && lane < nc) a.maxProb[c0 + lane] = S.raised[lane] ? S.E[lane] : Eold * (model == UGF_BGK_USP_SBGK ? 0.999 : 0.9999);
+        __syncwarp();
     }
     const int wr = warp_sum_int(myRel);
     if (lane == 0 && wr) atomicAdd(&a.cnt->bgk, (unsigned long long)wr);
