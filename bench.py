@@ -26,8 +26,8 @@ sys.path.insert(0, ROOT)
 B_ALG_PARCEL = 236.0  # algorithmic bytes per parcel-step, argon (SURVEY §8d / BASELINE.md §3)
 B_ALG_CELL = 380.0
 # per-kernel algorithmic bytes
-MOVE_B_PARCEL, MOVE_B_CELL = 80.0, 6 * 36.0 + 4.0 + 4.0
-CELL_B_PARCEL, CELL_B_CELL = 108.0, 8.0 + 16.0 + 4.0 + 256.0
+MOVE_B_PARCEL, MOVE_B_CELL = 80.0, 4 * 36.0 + 4.0 + 4.0   # 4 face slots per cell on the 2-D bench mesh
+CELL_B_PARCEL, CELL_B_CELL = 108.0, 4.0 + 256.0 + 2 * 128.0  # offsets, moment block, accumulator read + write
 SORT_B_PARCEL, SORT_B_CELL = 16.0, 16.0
 
 
@@ -238,7 +238,7 @@ def main():
     value = total_parcels * args.steps / (ms * 1e-3)
 
     # ---- per-kernel device times over a second pass of K steps (events inside the library, per phase) ----
-    phases = {k: 0.0 for k in ("inflow", "move", "sort", "cell", "relax", "fields")}
+    phases = {k: 0.0 for k in ("inflow", "move", "sort", "cell", "collide", "relax", "fields")}
     if world == 1:
         for _ in range(args.steps):
             cloud.evolve(1)
@@ -254,6 +254,17 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
     roofline = None
+    traffic = {}
+    try:  # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+    except Exception:
+        pass
+    default_workload = args.case == "couette" and (args.nx, args.ny, args.ppc) == (1000, 500, 20)
+    if world > 1:
+        step_bytes = B_ALG_PARCEL * n_parcels + B_ALG_CELL * nC  # per GPU
+        g = step_bytes / (ms / args.steps * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "whole step, per GPU (per-kernel split is reported at N=1)", "achieved": g, "peak": peak, "unit": "GB/s",
+                    "frac": g / peak, "traffic": None, "peak_source": peak_src}
     if world == 1 and phases["cell"] > 0:
         kb = {
             "move_kernel": (MOVE_B_PARCEL * n_parcels + MOVE_B_CELL * nC, phases["move"]),
@@ -263,8 +274,10 @@ def main():
         dom = max(kb, key=lambda k: kb[k][1])
         ach = kb[dom][0] / (kb[dom][1] * 1e-3) / 1e9
         step_bytes = B_ALG_PARCEL * n_parcels + B_ALG_CELL * nC
+        tkey = {"move_kernel": "move_stream_kernel", "cell_kernel": "cell_kernel"}.get(dom)
         roofline = {
-            "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": traffic.get(tkey) if default_workload else None, "traffic_source": traffic.get("source") if default_workload else None,
             "peak_source": peak_src,
             "per_kernel": {k: {"ms": v[1], "alg_bytes": v[0], "GBps": v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else None} for k, v in kb.items()},
             "phase_ms": phases,
@@ -277,6 +290,23 @@ def main():
     # step's control block (kernel parameter blocks incl. deltaT) and reads back the step's log quantities.
     e2e = None
     host_state = None
+    if world > 1:
+        barrier()
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(args.steps):
+            cloud.setDeltaT(case.deltaT)
+            evolve_distributed(cloud, ex, 1, fixed_rounds=fixed_rounds)
+            done += cloud.counters()["nParcels"]
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(done)], dtype=torch.float64, device="cuda")
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(tt[1].item()) / float(tmax[0].item()), "unit": "particle-steps/s",
+               "h2d_bytes_per_step": int(launches / args.steps * 1400), "d2h_bytes_per_step": 64 + 48 + 8 + 8,
+               "what": "per rank and step: move + transfer rounds + finishStep + counters() through the host API, state resident in HBM; max over ranks"}
     if world == 1:
         barrier()
         t0 = time.perf_counter()

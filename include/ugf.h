@@ -325,8 +325,10 @@ int ugf_download_cell_state(ugf_handle* h, double* sigmaTcRMax, double* maxProb,
 int ugf_download_fields(ugf_handle* h, double* cellFields, double* wallFields, int32_t resetAtOutput);
 /* Raw per-step boundary measurements of the last move: [nBoundaryFaces][UGF_NBM]. */
 int ugf_download_boundary_meas(ugf_handle* h, double* bm);
-/* Per-phase device time of the last ugf_step in ms: inflow, move, sort, cell(sample+collide), relax, fields. */
-int ugf_phase_times(ugf_handle* h, double* ms6);
+/* Per-phase device time of the last ugf_step in ms (UGF_NPHASE values): inflow, move, sort, cell (gather + sample +
+ * field accumulation), collide (NTC), relax (BGK family), fields (wall accumulation). */
+#define UGF_NPHASE 7
+int ugf_phase_times(ugf_handle* h, double* ms);
 /* Number of kernel launches issued by this handle so far. */
 int ugf_launch_count(ugf_handle* h, int64_t* n);
 

@@ -1506,7 +1506,7 @@ int ugfo_download_fields(ugfo_handle* h, double* cellF, double* wallF, int32_t r
 
 int ugfo_download_boundary_meas(ugfo_handle* h, double* bm) { std::copy(h->bm.begin(), h->bm.end(), bm); return 0; }
 
-int ugfo_phase_times(ugfo_handle*, double* ms) { for (int i = 0; i < 6; ++i) ms[i] = 0; return 0; }
+int ugfo_phase_times(ugfo_handle*, double* ms) { for (int i = 0; i < UGF_NPHASE; ++i) ms[i] = 0; return 0; }
 int ugfo_launch_count(ugfo_handle*, int64_t* n) { *n = 0; return 0; }
 
 // Known-answer hook for the RNG: one Philox4x32-10 block.

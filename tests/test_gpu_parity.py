@@ -156,6 +156,26 @@ def test_collide_conserves_and_tracks_oracle(GpuCloud, OracleCloud, binary):
     np.testing.assert_allclose(sg, sr, rtol=1e-12)
 
 
+@pytest.mark.parametrize("levels", [(2, 2, 2), (3, 1, 2)])
+def test_subcell_partner_selection_tracks_oracle(GpuCloud, OracleCloud, levels):
+    """subCellLevels > 1 (noTimeCounter.C:96-235): same candidates, same sub-cell partners, same collisions as the
+    oracle's sequential loop over three full steps (move + sort + collide), cells with mixed levels."""
+    case = cases.closed_box(n=6, parcels=13000, seed=12, dt_mct=0.8)
+    lv = np.ones((case.mesh.n_cells, 3), np.int32)
+    lv[::2] = levels  # every other cell keeps (1,1,1)
+    case.subCellLevels = lv
+    g, r = both(case, GpuCloud, OracleCloud)
+    for cl in (g, r):
+        cl.evolve(3)
+    cg, cr = g.counters(), r.counters()
+    assert cg["collisionCandidates"] == cr["collisionCandidates"] > 100
+    assert abs(cg["collisions"] - cr["collisions"]) <= 2
+    pg, pr = g.parcels(), r.parcels()
+    assert np.array_equal(pg["cell"], pr["cell"])
+    assert frac_close(pg["U"], pr["U"]) > 0.995
+    np.testing.assert_allclose(g.cellState()["sigmaTcRMax"], r.cellState()["sigmaTcRMax"], rtol=1e-12)
+
+
 def test_larsen_borgnakke_conserves_total_energy(GpuCloud, OracleCloud):
     case = cases.closed_box(n=6, parcels=20000, seed=9, binary="LarsenBorgnakkeVariableHardSphere", species=("N2", cases.NITROGEN),
                             dt_mct=1.0, Trot=150.0, rotationalRelaxationCollisionNumber=5.0, electronicRelaxationCollisionNumber=500.0)

@@ -71,6 +71,35 @@ def test_equilibrium_collision_rate_and_candidates(OracleCloud):
     assert abs(mean - expect) < 4 * sigma + 0.01 * expect, (mean, expect)
 
 
+def test_subcells_pair_neighbours_within_the_cell(OracleCloud):
+    """subCellLevels (2,2,2): a candidate's partner comes from its own virtual sub-cell whenever that holds another
+    parcel (noTimeCounter.C:205-235), so colliding pairs sit closer together than with whole-cell selection;
+    the candidate count (noTimeCounter.C:184) does not depend on the sub-cells."""
+    res = {}
+    for levels in (1, 2):
+        case = cases.closed_box(n=5, parcels=12000, seed=31, dt_mct=0.1)
+        case.subCellLevels = np.full((case.mesh.n_cells, 3), levels, np.int32)
+        cl = case.make_cloud(OracleCloud)
+        cl.buildCellOccupancy(); cl.reorder()
+        before = cl.parcels()
+        cl.collide()
+        after = cl.parcels()
+        c = cl.counters()
+        hit = np.flatnonzero((after["U"] != before["U"]).any(axis=1))
+        # partners share a cell: for every collided parcel, distance to the nearest other collided parcel of its cell
+        lo, hi = case.mesh.cell_bb_min, case.mesh.cell_bb_max
+        rel = (after["position"][hit] - lo[after["cell"][hit]]) / (hi - lo)[after["cell"][hit]]
+        octant = (rel >= 0.5).astype(int) @ np.array([1, 2, 4])
+        key = after["cell"][hit] * 8 + octant
+        _, counts = np.unique(key, return_counts=True)
+        res[levels] = (c["collisionCandidates"], c["collisions"], (counts % 2 == 0).mean())
+        cl.close()
+    assert res[1][0] == res[2][0]
+    assert abs(res[1][1] - res[2][1]) < 0.1 * res[1][1]
+    # with sub-cells nearly every (cell, octant) group holds an even number of collided parcels (whole pairs)
+    assert res[2][2] > 0.8 > res[1][2]
+
+
 def test_specular_box_conserves_energy_and_maxwellian(OracleCloud):
     case = cases.closed_box(n=6, parcels=30000, seed=23)
     cl = case.make_cloud(OracleCloud)

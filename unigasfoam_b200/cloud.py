@@ -370,9 +370,9 @@ class UniGasCloud:
         return a[:nB]
 
     def phaseTimes(self):
-        a = (C.c_double * 6)()
+        a = (C.c_double * _capi.UGF_NPHASE)()
         self._check(self.api.phase_times(self._h, a))
-        return dict(zip(("inflow", "move", "sort", "cell", "relax", "fields"), a[:]))
+        return dict(zip(("inflow", "move", "sort", "cell", "collide", "relax", "fields"), a[:]))
 
     def launchCount(self):
         n = C.c_int64()

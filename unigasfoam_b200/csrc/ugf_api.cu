@@ -118,6 +118,8 @@ struct ugf_handle {
     double* dSigma = nullptr; int* dCollId = nullptr; double* dMaxProb = nullptr; double* dQPrev = nullptr; double* dSPrev = nullptr;
     double* dKeyScratch = nullptr;
     int* dOwner = nullptr;           // NTC conflict marks, one per parcel slot
+    int* dSubLevels = nullptr;       // [nCells*3] sub-cell levels (allocated when some level > 1)
+    unsigned short* dSub = nullptr;  // [capacity] sub-cell index per parcel
     DevCounters* dCnt = nullptr;
     int* dErr = nullptr;
     int* dTask = nullptr;            // cell_kernel task counter
@@ -138,8 +140,8 @@ struct ugf_handle {
     int cellCap = CELL_CAP;
     int cellBlocks = 0, ntcBlocks = 0, bgkBlocks = 0;
     size_t cellSmem = 0, ntcSmem = 0, bgkSmem = 0;
-    cudaEvent_t ev[7]{};
-    double phaseMs[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[UGF_NPHASE + 1]{};
+    
     bool timingValid = false;
 };
 
@@ -362,12 +364,23 @@ int run_ntc_kernel(ugf_handle* h) {
     a.sigmaTcRMax = h->dSigma;
     a.collModelId = h->dCollId;
     a.owner = h->dOwner;
+    a.sub = h->dSub;
     a.step = (uint32_t)h->step;
     a.cnt = h->dCnt;
     const DevParams prm = h->prm;
-    dispatch(h, [&](auto R, auto M) {
-        ntc_kernel<decltype(R)::value, decltype(M)::value><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
-    });
+    if (!h->subLevelsAllOne) {
+        SubcellArgs sa{};
+        sa.P = h->buf[h->cur]; sa.dN = h->dN; sa.bbMin = h->dBbMin; sa.bbMax = h->dBbMax; sa.levels = h->dSubLevels; sa.sub = h->dSub;
+        subcell_index_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(prm, sa);
+        LAUNCHED();
+        dispatch(h, [&](auto R, auto M) {
+            ntc_kernel<decltype(R)::value, decltype(M)::value, true><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+        });
+    } else {
+        dispatch(h, [&](auto R, auto M) {
+            ntc_kernel<decltype(R)::value, decltype(M)::value, false><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+        });
+    }
     LAUNCHED();
     return 0;
 }
@@ -561,7 +574,7 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     };
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->evN, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    for (int i = 0; i < 7; ++i)
+    for (int i = 0; i < UGF_NPHASE + 1; ++i)
         if ((e = cudaEventCreate(&h->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMallocHost((void**)&h->pinN, sizeof(long long))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMalloc((void**)&h->dN, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -594,14 +607,14 @@ int ugf_destroy(ugf_handle* h) {
     }
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dInflight, h->dRecvStart,
-                    h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner,
+                    h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
                     h->dCnt, h->dErr, h->dTot, h->dTask};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
     if (h->pinN) cudaFreeHost(h->pinN);
     if (h->evN) cudaEventDestroy(h->evN);
-    for (int i = 0; i < 7; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < UGF_NPHASE + 1; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -766,7 +779,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         auto k = cell_kernel<decltype(R)::value, decltype(M)::value>;
         e1 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cellSmem);
         if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occCell, k, CELL_THREADS, h->cellSmem);
-        auto kn = ntc_kernel<decltype(R)::value, decltype(M)::value>;
+        auto kn = ntc_kernel<decltype(R)::value, decltype(M)::value, false>;
         if (e1 == cudaSuccess) e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occNtc, kn, NTC_THREADS, 0);
     });
     CU(e1);
@@ -936,9 +949,23 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p) {
 int ugf_upload_cell_state(ugf_handle* h, const double* s, const int32_t* id, const int32_t* lv, const double* cwf) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     const size_t nC = (size_t)h->nCells;
-    if (lv) for (size_t i = 0; i < 3 * nC; ++i) {
-        if (lv[i] < 1) return fail(h, "subCellLevels must be >= 1");
-        if (lv[i] != 1) return fail(h, "subCellLevels > 1 are not supported by the CUDA path yet");
+    if (lv) {
+        bool allOne = true;
+        for (size_t c = 0; c < nC; ++c) {
+            long long prod = 1;
+            for (int d = 0; d < 3; ++d) {
+                if (lv[3 * c + d] < 1) return fail(h, "subCellLevels must be >= 1");
+                prod *= lv[3 * c + d];
+                if (lv[3 * c + d] != 1) allOne = false;
+            }
+            if (prod > 65535) return fail(h, "more than 65535 sub-cells in a cell");
+        }
+        if (!allOne) {
+            if (!h->dSubLevels && dalloc(h, &h->dSubLevels, 3 * nC)) return 1;
+            if (!h->dSub && dalloc(h, &h->dSub, (size_t)h->capacity)) return 1;
+            if (upload(h, h->dSubLevels, lv, 3 * nC)) return 1;
+        }
+        h->subLevelsAllOne = allOne;
     }
     if (cwf) for (size_t c = 0; c < nC; ++c) if (cwf[c] != 1.0) return fail(h, "cell weighting is not supported yet (cellWeightFactor must be 1)");
     if (s && upload(h, h->dSigma, s, nC)) return 1;
@@ -1075,12 +1102,13 @@ int ugf_step(ugf_handle* h, int32_t nSteps) {
         if (last) CU(cudaEventRecord(h->ev[3], h->stream));
         const bool fuseAcc = next_step_samples(h);
         if (run_cell_kernel(h, true, true, fuseAcc)) return 1;
-        if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[4], h->stream));
-        if (bgk_active(h) && run_bgk_kernel(h)) return 1;
+        if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[5], h->stream));
-        if (do_accumulate(h, fuseAcc)) return 1;
+        if (bgk_active(h) && run_bgk_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[6], h->stream));
+        if (do_accumulate(h, fuseAcc)) return 1;
+        if (last) CU(cudaEventRecord(h->ev[7], h->stream));
         h->step++;
     }
     h->timingValid = true;
@@ -1379,10 +1407,10 @@ int ugf_download_boundary_meas(ugf_handle* h, double* bm) {
 
 int ugf_phase_times(ugf_handle* h, double* ms) {
     if (!h) return 1;
-    for (int i = 0; i < 6; ++i) ms[i] = 0;
+    for (int i = 0; i < UGF_NPHASE; ++i) ms[i] = 0;
     if (!h->timingValid) return 0;
     CU(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < UGF_NPHASE; ++i) {
         float t = 0;
         CU(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
         ms[i] = t;

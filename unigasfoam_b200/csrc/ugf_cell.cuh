@@ -539,15 +539,48 @@ struct NtcArgs {
     double* sigmaTcRMax;
     const int* collModelId;
     int* owner;   // [capacity] conflict marks, 0x7f7f7f7f when idle
+    const unsigned short* sub;  // [capacity] virtual sub-cell of every parcel (SUBCELLS only)
     uint32_t step;
     DevCounters* cnt;
 };
+
+// Virtual Cartesian sub-cell of every parcel (noTimeCounter.C:96-161): index = sum over solved directions of
+// int(L_d (x_d - min_d) / (max_d - min_d)) * weight_d, with the cell's point bounding box; the index is clamped to
+// L_d - 1 (the reference overflows its list for a parcel exactly on the max face).
+struct SubcellArgs {
+    ParcelBuf P;
+    const long long* dN;
+    const double* bbMin;
+    const double* bbMax;
+    const int* levels;  // [nCells*3]
+    unsigned short* sub;
+};
+
+__global__ void __launch_bounds__(256) subcell_index_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ SubcellArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *a.dN) return;
+    const int c = a.P.cell[i];
+    if (c < 0) return;
+    const double x[3] = {a.P.x[i], a.P.y[i], a.P.z[i]};
+    int sc = 0, w = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (!prm.solD[d]) continue;
+        const int L = __ldg(&a.levels[3 * (size_t)c + d]);
+        const double mn = __ldg(&a.bbMin[3 * (size_t)c + d]), mx = __ldg(&a.bbMax[3 * (size_t)c + d]);
+        int k = (int)(L * (x[d] - mn) / (mx - mn));
+        k = k < 0 ? 0 : (k > L - 1 ? L - 1 : k);
+        sc += k * w;
+        w *= L;
+    }
+    a.sub[i] = (unsigned short)sc;
+}
 
 constexpr int NTC_THREADS = 256;
 constexpr int NTC_WARPS = NTC_THREADS / 32;
 constexpr int NTC_IDLE = 0x7f7f7f7f;
 
-template <bool HAS_ROT, bool MULTI>
+template <bool HAS_ROT, bool MULTI, bool SUBCELLS>
 __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ NtcArgs a) {
     __shared__ double sMaxW[NTC_WARPS][32];
     const int lane = threadIdx.x & 31;
@@ -604,7 +637,26 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
             if (act) {
                 const int cP = r.position(n);
                 int cQ;
-                do { cQ = r.position(n); } while (cP == cQ);
+                int nSC = 0;
+                unsigned short scP = 0;
+                if (SUBCELLS) {  // partner from P's sub-cell if it holds another parcel (noTimeCounter.C:205-235)
+                    scP = a.sub[beg + cP];
+                    for (int i = 0; i < n; ++i) nSC += (a.sub[beg + i] == scP);
+                }
+                if (SUBCELLS && nSC > 1) {
+                    do {
+                        int t = r.position(nSC);
+                        cQ = 0;
+                        for (int i = 0; i < n; ++i) {
+                            if (a.sub[beg + i] == scP) {
+                                if (t == 0) { cQ = i; break; }
+                                --t;
+                            }
+                        }
+                    } while (cP == cQ);
+                } else {
+                    do { cQ = r.position(n); } while (cP == cQ);
+                }
                 gP = beg + cP; gQ = beg + cQ;
                 if (MULTI) { tP = a.P.type[gP]; tQ = a.P.type[gQ]; }
                 if (prm.sp[tP].charge == -1 && prm.sp[tQ].charge == -1) act = false;  // noTimeCounter.C:245-247
