@@ -159,7 +159,7 @@ def main():
     if not os.path.exists(g.LIB):
         g.build()
     from unigasfoam_b200.cloud import UniGasCloud
-    from unigasfoam_b200.exchange import Exchanger, SlotExchanger, evolve_distributed
+    from unigasfoam_b200.exchange import Exchanger, PeerExchanger, SlotExchanger, evolve_distributed
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libugf has no CPU fallback")
@@ -185,7 +185,11 @@ def main():
         while probe.exchange() > 0:
             pass
         cloud.buildCellOccupancy(); cloud.collide(); cloud.relax(); cloud.accumulateFields(); cloud.endStep()
-        ex = SlotExchanger(cloud, case.mesh, rank, world, slot_capacity=max(4096, 4 * int(worst.item())), group=None, cuda=True)
+        slot_cap = max(4096, 4 * int(worst.item()))
+        if os.environ.get("UGF_EXCHANGE", "peer") == "nccl":
+            ex = SlotExchanger(cloud, case.mesh, rank, world, slot_capacity=slot_cap, group=None, cuda=True)
+        else:
+            ex = PeerExchanger(cloud, case.mesh, rank, world, slot_capacity=slot_cap, group=None, meta_group=meta)
         # rounds this decomposition needs per step, measured with the exact termination rule over a few steps
         need = 1
         for _ in range(3):
@@ -362,7 +366,9 @@ def main():
         }
         if world > 1:
             out["migration"] = {"rounds": ex.rounds, "slot_capacity": ex.cap, "rounds_per_step": fixed_rounds,
-                                "protocol": "fixed-slot neighbour send/recv, rounds per step measured with the exact termination rule during warm-up, quiescence verified by a lagged all-reduce"}
+                                "transport": "NVLink peer memory (pack kernel writes the neighbour's receive slot, device-side flag wait)" if isinstance(ex, PeerExchanger)
+                                else "NCCL grouped send/recv between neighbours",
+                                "protocol": "fixed slots per processor patch, rounds per step measured with the exact termination rule during warm-up, quiescence verified by a lagged all-reduce"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -302,6 +302,21 @@ int ugf_move_received(ugf_handle* h);
  * call blocks; a slot overflow raises the handle's device error flag (reported by ugf_counters_get). */
 int ugf_migrate_pack_slots(ugf_handle* h, double* devSend, int64_t slotCapacity);
 int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotCapacity);
+/* NVLink peer-memory variant of the slot transfer: no send buffer and no NCCL call on the data path.  Every rank
+ * allocates its receive region with ugf_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; the 64-byte handle is passed
+ * to the neighbours by the caller), maps the neighbours' regions with ugf_peer_open, and then per transfer round
+ *   ugf_migrate_pack_peer   packs every processor patch k straight into dstSlots[k] - the matching receive slot in
+ *                           the neighbour's memory - and then stores `epoch` to dstFlags[k] (system-scope release);
+ *   ugf_migrate_unpack_peer waits on the device until its own flags [nProcPatches] have reached `epoch`, then unpacks
+ *                           devRecv like ugf_migrate_unpack_slots.
+ * Neither call blocks the host.  Slot layout as above; epochs must increase from round to round and callers must
+ * alternate between two receive buffers from one round to the next (a slot is rewritten only after the round in
+ * between has been acknowledged by both sides).  A wait that sees no signal for several seconds raises the handle's
+ * device error flag instead of hanging. */
+int ugf_peer_alloc(ugf_handle* h, int64_t bytes, void** devPtr, unsigned char* ipcHandle64);
+int ugf_peer_open(ugf_handle* h, const unsigned char* ipcHandle64, void** devPtr);
+int ugf_migrate_pack_peer(ugf_handle* h, double* const* dstSlots, uint64_t* const* dstFlags, int64_t slotCapacity, uint64_t epoch);
+int ugf_migrate_unpack_peer(ugf_handle* h, const double* devRecv, const uint64_t* devFlags, int64_t slotCapacity, uint64_t epoch);
 /* Device address of an int64 holding the number of parcels currently waiting on processor patches (valid after
  * ugf_move / ugf_move_received): all-reduce it to decide whether another transfer round is needed. */
 int ugf_migrate_inflight(ugf_handle* h, int64_t** devCounter);

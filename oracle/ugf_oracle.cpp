@@ -1440,6 +1440,13 @@ int ugfo_migrate_unpack_slots(ugfo_handle* h, const double* recv, int64_t slotCa
     return 0;
 }
 
+// NVLink peer-memory transfer is a device-library feature; the oracle exports the symbols so that both libraries
+// bind the same table, and reports that it has no such path.
+int ugfo_peer_alloc(ugfo_handle* h, int64_t, void**, unsigned char*) { return fail(h, "peer-memory transfer is not available in the CPU oracle"); }
+int ugfo_peer_open(ugfo_handle* h, const unsigned char*, void**) { return fail(h, "peer-memory transfer is not available in the CPU oracle"); }
+int ugfo_migrate_pack_peer(ugfo_handle* h, double* const*, uint64_t* const*, int64_t, uint64_t) { return fail(h, "peer-memory transfer is not available in the CPU oracle"); }
+int ugfo_migrate_unpack_peer(ugfo_handle* h, const double*, const uint64_t*, int64_t, uint64_t) { return fail(h, "peer-memory transfer is not available in the CPU oracle"); }
+
 int ugfo_migrate_inflight(ugfo_handle* h, int64_t** p) { *p = &h->inflight; return 0; }
 
 int ugfo_stream(ugfo_handle*, void** s) { *s = nullptr; return 0; }

@@ -30,10 +30,11 @@ def _worker(rank, world, port, out):
     meta = dist.new_group(backend="gloo")
     from oracle.oracle_cloud import OracleCloud
     from unigasfoam_b200.cloud import UniGasCloud
-    from unigasfoam_b200.exchange import Exchanger, SlotExchanger, evolve_distributed
+    from unigasfoam_b200.exchange import Exchanger, PeerExchanger, SlotExchanger, evolve_distributed
     ok = True
     msgs = []
-    for binary, steps, slots in (("noDSMCCollision", 6, False), ("variableHardSphere", 4, False), ("noDSMCCollision", 6, True), ("variableHardSphere", 4, True)):
+    for binary, steps, slots in (("noDSMCCollision", 6, False), ("variableHardSphere", 4, False), ("noDSMCCollision", 6, True), ("variableHardSphere", 4, True),
+                                 ("noDSMCCollision", 6, "peer"), ("variableHardSphere", 4, "peer")):
         case = cases.couette(nx=32, ny=16, ppc=20, rank=rank, n_ranks=world, binary=binary, Kn=0.5)
         if binary == "noDSMCCollision":
             for e in case.boundariesDict["uniGasPatchBoundaries"]:
@@ -42,7 +43,10 @@ def _worker(rank, world, port, out):
         kw = dict(parcelCapacity=4 * case.n_parcels, rank=rank, nRanks=world)
         g = case.make_cloud(UniGasCloud, device=rank, **kw)
         r = case.make_cloud(OracleCloud, **kw)
-        if slots:
+        if slots == "peer":  # NVLink peer-memory transfer on the device path
+            exg = PeerExchanger(g, case.mesh, rank, world, slot_capacity=2000, group=None, meta_group=meta)
+            exr = SlotExchanger(r, case.mesh, rank, world, slot_capacity=2000, group=meta, cuda=False)
+        elif slots:
             exg = SlotExchanger(g, case.mesh, rank, world, slot_capacity=2000, group=None, cuda=True)
             exr = SlotExchanger(r, case.mesh, rank, world, slot_capacity=2000, group=meta, cuda=False)
         else:

@@ -138,6 +138,10 @@ SIGNATURES = {
     "move_received": (C.c_int, [H]),
     "migrate_pack_slots": (C.c_int, [H, PF, i64]),
     "migrate_unpack_slots": (C.c_int, [H, PF, i64]),
+    "peer_alloc": (C.c_int, [H, i64, P(C.c_void_p), C.c_char_p]),
+    "peer_open": (C.c_int, [H, C.c_char_p, P(C.c_void_p)]),
+    "migrate_pack_peer": (C.c_int, [H, P(C.c_void_p), P(C.c_void_p), i64, C.c_uint64]),
+    "migrate_unpack_peer": (C.c_int, [H, C.c_void_p, C.c_void_p, i64, C.c_uint64]),
     "migrate_inflight": (C.c_int, [H, P(PI64)]),
     "stream": (C.c_int, [H, P(C.c_void_p)]),
     "counters_get": (C.c_int, [H, P(Counters)]),

@@ -271,6 +271,28 @@ class UniGasCloud:
     def migrateUnpackSlots(self, recv_ptr, slot_capacity):
         self._check(self.api.migrate_unpack_slots(self._h, recv_ptr, int(slot_capacity)))
 
+    # NVLink peer-memory transfer (ugf_peer_* / ugf_migrate_*_peer): raw device addresses in, nothing copied by the host
+    def peerAlloc(self, nbytes):
+        """Receive region in this GPU's memory; returns (device address, 64-byte cudaIpc handle)."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self.api.peer_alloc(self._h, int(nbytes), C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def peerOpen(self, handle):
+        ptr = C.c_void_p()
+        self._check(self.api.peer_open(self._h, C.create_string_buffer(bytes(handle), 64), C.byref(ptr)))
+        return ptr.value
+
+    def migratePackPeer(self, dst_slots, dst_flags, slot_capacity, epoch):
+        n = len(dst_slots)
+        a = (C.c_void_p * max(n, 1))(*dst_slots)
+        b = (C.c_void_p * max(n, 1))(*dst_flags)
+        self._check(self.api.migrate_pack_peer(self._h, a, b, int(slot_capacity), int(epoch)))
+
+    def migrateUnpackPeer(self, recv_addr, flags_addr, slot_capacity, epoch):
+        self._check(self.api.migrate_unpack_peer(self._h, C.c_void_p(recv_addr), C.c_void_p(flags_addr), int(slot_capacity), int(epoch)))
+
     def migrateInflightPtr(self):
         p = C.POINTER(C.c_int64)()
         self._check(self.api.migrate_inflight(self._h, C.byref(p)))

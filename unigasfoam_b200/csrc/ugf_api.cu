@@ -108,7 +108,9 @@ struct ugf_handle {
 
     // cells
     int* dCellCount = nullptr; int* dOff = nullptr; int* dPerm = nullptr; int* dBlockSums = nullptr; int* dTotal = nullptr;
-    int* dMigCount = nullptr; int* dMigBlock = nullptr; int* dMigTotals = nullptr;
+    int* dMigCount = nullptr; int* dMigBlock = nullptr; int* dMigTotals = nullptr; int* dMigList = nullptr;
+    long long lastSlotCapacity = 0;  // slot capacity of the latest ugf_migrate_unpack_slots
+    bool migSearchPack = false;      // tuning: UGF_MIG_SEARCH_PACK=1 packs by searching the cell ids instead of the migrant lists
     unsigned long long* dInflight = nullptr; long long* dRecvStart = nullptr;
     long long nAtMove = 0;          // exact array length when the step's move was launched
     bool slotRound = false;         // received parcels of this round came through the slot path
@@ -128,6 +130,7 @@ struct ugf_handle {
     bool subLevelsAllOne = true;
 
     std::vector<InflowHost> inflows;
+    std::vector<void*> peerOwned, peerOpened;  // NVLink peer-memory transfer buffers (cudaIpc)
     std::vector<double*> packBuf;
     std::vector<long long> packCap;
 
@@ -200,6 +203,7 @@ int check_device_error(ugf_handle* h) {
     if (e == 2) return fail(h, "received parcel with a face index outside the processor patch");
     if (e == 3) return fail(h, "migration slot overflow: more parcels crossed a processor patch than slotCapacity");
     if (e == 4) return fail(h, "corrupt migration slot header");
+    if (e == 5) return fail(h, "timed out waiting for a neighbour's migration slot (peer-memory transfer)");
     if (e) return fail(h, "device error flag " + std::to_string(e));
     return 0;
 }
@@ -461,9 +465,13 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.migCount = h->dMigCount;
     a.inflight = h->dInflight;
     a.dBegin = (received && h->slotRound) ? h->dRecvStart : nullptr;
+    a.ms = h->migSlots;
+    a.migList = (h->migSlots.nProc <= MIG_MAXP) ? h->dMigList : nullptr;
+    a.migListCap = MIG_LIST_CAP;
     a.bm = h->dBm;
     a.cnt = h->dCnt;
-    const long long count = h->nUpper - begin;
+    long long count = h->nUpper - begin;
+    if (a.dBegin) count = std::min<long long>(count, (long long)h->migSlots.nProc * h->lastSlotCapacity);  // what one unpack can append
     if (count > 0) {
         const DevParams prm = h->prm;
         const bool streamed = !received && begin == 0 && !h->moveDirect;
@@ -531,6 +539,37 @@ int do_accumulate(ugf_handle* h, bool cellsDone = false) {
             p = q;
         }
     }
+    return 0;
+}
+
+// device-side pack of every processor patch into the given slot addresses: from the migrant lists of the move
+// kernel when they can hold a full slot, else by two passes over the cell ids
+int pack_slots_to(ugf_handle* h, const MigDst& dst, long long slotCapacity) {
+    if (h->dMigList && slotCapacity <= MIG_LIST_CAP && !h->migSearchPack) {
+        ParcelBuf P = h->buf[h->cur];
+        const MigSlots ms = h->migSlots;
+        dispatch(h, [&](auto R, auto M) {
+            mig_pack_list_kernel<decltype(R)::value, decltype(M)::value><<<ms.nProc, 1024, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dMigCount, h->dMigList, MIG_LIST_CAP,
+                                                                                                          dst, slotCapacity, h->dErr);
+        });
+        LAUNCHED();
+        return 0;
+    }
+    const int nb = (int)grid_for(h->nUpper, MIG_TILE);
+    ParcelBuf P = h->buf[h->cur];
+    const MigSlots ms = h->migSlots;
+    int* counts = h->dMigBlock;
+    int* offsets = h->dMigBlock + (size_t)MIG_MAXP * (h->capacity / 1024 + 2);
+    mig_count_all_kernel<<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P.cell, h->dN, h->slotRound ? h->dRecvStart : nullptr, counts, nb);
+    LAUNCHED();
+    mig_scan_kernel<<<ms.nProc, SCAN_THREADS, 0, h->stream>>>(counts, offsets, nb, h->dMigTotals);
+    LAUNCHED();
+    dispatch(h, [&](auto R, auto M) {
+        mig_pack_all_kernel<decltype(R)::value, decltype(M)::value><<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dN, counts, offsets, h->dMigTotals, nb,
+                                                                                                        dst, slotCapacity, h->dErr);
+    });
+    LAUNCHED();
+    CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
     return 0;
 }
 
@@ -606,12 +645,14 @@ int ugf_destroy(ugf_handle* h) {
         cudaFree(P.erot); cudaFree(P.cell); cudaFree(P.type);
     }
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
-                    h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dInflight, h->dRecvStart,
+                    h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
                     h->dCnt, h->dErr, h->dTot, h->dTask};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
+    for (void* p : h->peerOpened) cudaIpcCloseMemHandle(p);
+    for (void* p : h->peerOwned) cudaFree(p);
     if (h->pinN) cudaFreeHost(h->pinN);
     if (h->evN) cudaEventDestroy(h->evN);
     for (int i = 0; i < UGF_NPHASE + 1; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -766,6 +807,8 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         CU(cudaStreamSynchronize(h->stream));
     }
     if (h->hasProcessor && dalloc(h, &h->dSf, (size_t)h->capacity)) return 1;
+    if (h->hasProcessor && dalloc(h, &h->dMigList, (size_t)MIG_MAXP * MIG_LIST_CAP)) return 1;
+    if (const char* e = std::getenv("UGF_MIG_SEARCH_PACK")) h->migSearchPack = std::atoi(e) != 0;
     if (bgk_active(h) && dalloc(h, &h->dKeyScratch, (size_t)h->capacity)) return 1;
     h->packBuf.assign(h->nPatches, nullptr);
     h->packCap.assign(h->nPatches, 0);
@@ -1201,22 +1244,62 @@ int ugf_migrate_pack_slots(ugf_handle* h, double* devSend, int64_t slotCapacity)
     if (h->migSlots.nProc > MIG_MAXP) return fail(h, "too many processor patches for the slot path");
     if (h->migSlots.nProc == 0) return 0;
     if (slotCapacity < 1) return fail(h, "slotCapacity must be positive");
-    const int nb = (int)grid_for(h->nUpper, MIG_TILE);
-    ParcelBuf P = h->buf[h->cur];
-    const MigSlots ms = h->migSlots;
-    int* counts = h->dMigBlock;
-    int* offsets = h->dMigBlock + (size_t)MIG_MAXP * (h->capacity / 1024 + 2);
-    mig_count_all_kernel<<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P.cell, h->dN, h->slotRound ? h->dRecvStart : nullptr, counts, nb);
-    LAUNCHED();
-    mig_scan_kernel<<<ms.nProc, SCAN_THREADS, 0, h->stream>>>(counts, offsets, nb, h->dMigTotals);
-    LAUNCHED();
-    dispatch(h, [&](auto R, auto M) {
-        mig_pack_all_kernel<decltype(R)::value, decltype(M)::value><<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dN, counts, offsets, h->dMigTotals, nb,
-                                                                                                        devSend, (long long)slotCapacity, h->dErr);
-    });
-    LAUNCHED();
-    CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
+    MigDst dst{};
+    const MigSlots& ms = h->migSlots;
+    for (int k = 0; k < ms.nProc; ++k) dst.slot[k] = devSend + (size_t)k * (size_t)(slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+    return pack_slots_to(h, dst, slotCapacity);
+}
+
+int ugf_peer_alloc(ugf_handle* h, int64_t bytes, void** devPtr, unsigned char* ipcHandle64) {
+    if (!h || !devPtr || !ipcHandle64 || bytes <= 0) return fail(h, "ugf_peer_alloc: bad argument");
+    CU(cudaSetDevice(h->cfg.device));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, (size_t)bytes));
+    CU(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t hd;
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU(cudaIpcGetMemHandle(&hd, p));
+    std::memcpy(ipcHandle64, &hd, 64);
+    h->peerOwned.push_back(p);
+    *devPtr = p;
     return 0;
+}
+
+int ugf_peer_open(ugf_handle* h, const unsigned char* ipcHandle64, void** devPtr) {
+    if (!h || !devPtr || !ipcHandle64) return fail(h, "ugf_peer_open: bad argument");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, ipcHandle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peerOpened.push_back(p);
+    *devPtr = p;
+    return 0;
+}
+
+int ugf_migrate_pack_peer(ugf_handle* h, double* const* dstSlots, uint64_t* const* dstFlags, int64_t slotCapacity, uint64_t epoch) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (h->migSlots.nProc > MIG_MAXP) return fail(h, "too many processor patches for the slot path");
+    if (h->migSlots.nProc == 0) return 0;
+    if (slotCapacity < 1) return fail(h, "slotCapacity must be positive");
+    MigDst dst{};
+    MigFlags fl{};
+    for (int k = 0; k < h->migSlots.nProc; ++k) {
+        dst.slot[k] = dstSlots[k];
+        fl.flag[k] = reinterpret_cast<unsigned long long*>(dstFlags[k]);
+    }
+    if (pack_slots_to(h, dst, slotCapacity)) return 1;
+    mig_signal_kernel<<<1, 32, 0, h->stream>>>(fl, h->migSlots.nProc, (unsigned long long)epoch);
+    LAUNCHED();
+    return 0;
+}
+
+int ugf_migrate_unpack_peer(ugf_handle* h, const double* devRecv, const uint64_t* devFlags, int64_t slotCapacity, uint64_t epoch) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (h->migSlots.nProc == 0) return 0;
+    mig_wait_kernel<<<1, 32, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(devFlags), h->migSlots.nProc, (unsigned long long)epoch, h->dErr);
+    LAUNCHED();
+    return ugf_migrate_unpack_slots(h, devRecv, slotCapacity);
 }
 
 int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotCapacity) {
@@ -1237,6 +1320,7 @@ int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotC
     h->nUpper = std::min<long long>(h->capacity, h->nUpper + (long long)ms.nProc * slotCapacity);  // upper bound; overflow raises the device flag
     h->appendBound += (long long)ms.nProc * slotCapacity;
     h->slotRound = true;
+    h->lastSlotCapacity = slotCapacity;
     h->occValid = false; h->momValid = false;
     return 0;
 }

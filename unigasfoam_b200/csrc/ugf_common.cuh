@@ -65,6 +65,13 @@ struct ParcelBuf {
     uint8_t* type;
 };
 
+constexpr int MIG_MAXP = 8;  // processor patches per rank the slot path handles
+
+struct MigSlots {
+    int nProc;
+    int patch[MIG_MAXP];
+};
+
 struct MeshDev {
     int nCells, nBFaces, nPatches;
     const int* cfOff;         // [nCells+1]

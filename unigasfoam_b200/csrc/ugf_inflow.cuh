@@ -195,11 +195,10 @@ __global__ void __launch_bounds__(256) mig_unpack_kernel(MeshDev mesh, ParcelBuf
 }
 
 // ---- fixed-slot migration: all processor patches in two passes over the parcels, no host round trip ------------
-constexpr int MIG_MAXP = 8;  // processor patches per rank the slot path handles
-
-struct MigSlots {
-    int nProc;
-    int patch[MIG_MAXP];
+// where slot k of a pack goes: the local send buffer (NCCL path) or, over NVLink peer memory, directly the matching
+// receive slot of the neighbouring rank
+struct MigDst {
+    double* slot[MIG_MAXP];
 };
 
 __device__ __forceinline__ int mig_slot_of(const MeshDev& mesh, const MigSlots& ms, int cell) {
@@ -274,12 +273,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) mig_scan_kernel(const int* __res
 template <bool HAS_ROT, bool MULTI>
 __global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const long long* dN,
                                                                    const int* __restrict__ blockCounts, const int* __restrict__ blockOffsets,
-                                                                   const int* __restrict__ totals, int nBlocks, double* __restrict__ send,
+                                                                   const int* __restrict__ totals, int nBlocks, const MigDst dst,
                                                                    long long slotCapacity, int* errFlag) {
     __shared__ int sm[33];
-    const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
     if (blockIdx.x == 0 && threadIdx.x < ms.nProc) {  // headers
-        double* hdr = send + threadIdx.x * slotStride;
+        double* hdr = dst.slot[threadIdx.x];
         const int tot = totals[threadIdx.x];
         hdr[0] = (double)(tot <= slotCapacity ? tot : slotCapacity);
         for (int j = 1; j < UGF_MIGRATE_STRIDE; ++j) hdr[j] = 0.0;
@@ -308,7 +306,7 @@ __global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh,
             if (slot[e] != k) continue;
             const long long i = base + e;
             if (pos < slotCapacity) {
-                double* r = send + k * slotStride + (1 + (long long)pos) * UGF_MIGRATE_STRIDE;
+                double* r = dst.slot[k] + (1 + (long long)pos) * UGF_MIGRATE_STRIDE;
                 const int bfi = -2 - c[e];
                 r[0] = P.x[i]; r[1] = P.y[i]; r[2] = P.z[i];
                 r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
@@ -362,6 +360,91 @@ __global__ void mig_commit_kernel(long long* dN, long long* dRecvStart, unsigned
     *dRecvStart = *dN;
     if (*dN + add <= capacity) *dN += add; else *errFlag = 1;
     *inflight = 0ull;
+}
+
+// Pack from the migrant lists the move kernel filled (one block per processor patch): the indices are sorted
+// ascending in shared memory (bitonic; the records must leave in index order, like the search-based pack above)
+// and the records written straight to the slot.  No pass over the cloud at all.
+constexpr int MIG_LIST_CAP = 8192;  // migrants per patch and round the list path handles (32 KB of shared memory)
+
+template <bool HAS_ROT, bool MULTI>
+__global__ void __launch_bounds__(1024) mig_pack_list_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, int* __restrict__ migCount,
+                                                             const int* __restrict__ migList, int listCap, const MigDst dst, long long slotCapacity,
+                                                             int* errFlag) {
+    __shared__ int s[MIG_LIST_CAP];
+    const int k = blockIdx.x;
+    const int patch = ms.patch[k];
+    int n = migCount[patch];
+    if (n > listCap || n > slotCapacity) {
+        if (threadIdx.x == 0) *errFlag = 3;
+        n = (int)min((long long)min(n, listCap), slotCapacity);
+    }
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) s[j] = j < n ? migList[(size_t)k * listCap + j] : 0x7fffffff;
+    __syncthreads();
+    for (int kk = 2; kk <= m; kk <<= 1)
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            for (int t = threadIdx.x; t < m; t += blockDim.x) {
+                const int p = t ^ jj;
+                if (p > t) {
+                    const int x = s[t], y = s[p];
+                    const bool up = (t & kk) == 0;
+                    if ((x > y) == up) { s[t] = y; s[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    double* slot = dst.slot[k];
+    if (threadIdx.x == 0) {
+        slot[0] = (double)n;
+        for (int j = 1; j < UGF_MIGRATE_STRIDE; ++j) slot[j] = 0.0;
+    }
+    const int startBfi = mesh.patches[patch].startBfi;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int i = s[j];
+        double* r = slot + (1 + (long long)j) * UGF_MIGRATE_STRIDE;
+        const int bfi = -2 - P.cell[i];
+        r[0] = P.x[i]; r[1] = P.y[i]; r[2] = P.z[i];
+        r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
+        r[6] = HAS_ROT ? P.erot[i] : 0.0;
+        r[7] = sf[i];
+        r[8] = (double)(bfi - startBfi);
+        r[9] = MULTI ? (double)P.type[i] : 0.0;
+        P.cell[i] = -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) migCount[patch] = 0;
+}
+
+// ---- NVLink peer-memory transfer: the pack kernel above has written straight into the neighbours' receive slots ----
+// signal: one thread per processor patch publishes the round's epoch in the receiver's flag word, after a system-scope
+// fence that orders it behind the records written by the (completed) pack kernel.
+struct MigFlags {
+    unsigned long long* flag[MIG_MAXP];
+};
+
+__global__ void mig_signal_kernel(const MigFlags f, int nProc, unsigned long long epoch) {
+    __threadfence_system();
+    if ((int)threadIdx.x < nProc) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.flag[threadIdx.x]), "l"(epoch) : "memory");
+    }
+}
+
+// wait: spin until every local flag has reached the epoch (the neighbours' records for this round are complete);
+// gives up after ~4 s of GPU clock with the handle's error flag raised rather than hanging the device.
+__global__ void mig_wait_kernel(const unsigned long long* flags, int nProc, unsigned long long epoch, int* errFlag) {
+    if ((int)threadIdx.x < nProc) {
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > 8000000000LL) { *errFlag = 5; break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
 }
 
 }  // namespace ugf

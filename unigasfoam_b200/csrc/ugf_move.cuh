@@ -139,7 +139,10 @@ struct MoveArgs {
     int* cellCount;        // [nCells] histogram of destination cells
     int* migCount;         // [nPatches]
     unsigned long long* inflight;  // parcels waiting on processor patches, all patches
-    const long long* dBegin;       // if set: only parcels with index >= *dBegin are tracked (received parcels)
+    const long long* dBegin;       // if set: the launch covers the parcels from index *dBegin on (received parcels)
+    MigSlots ms;                   // processor patches in slot order
+    int* migList;                  // [MIG_MAXP][migListCap] indices of the parcels waiting on each processor patch (or null)
+    int migListCap;
     double* bm;            // [nBFaces][UGF_NBM]
     DevCounters* cnt;
 };
@@ -200,7 +203,13 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
         st.cell = -2 - bfi;
         st.flags |= HIT_MIGRATED;
         if (a.sf) a.sf[i] = st.sf;
-        atomicAdd(&a.migCount[patch], 1);
+        const int pos = atomicAdd(&a.migCount[patch], 1);
+        if (a.migList) {  // remember who waits here: the pack kernel then never has to search the whole cloud
+            int slot = -1;
+#pragma unroll
+            for (int k = 0; k < MIG_MAXP; ++k) if (k < a.ms.nProc && a.ms.patch[k] == patch) slot = k;
+            if (slot >= 0 && pos < a.migListCap) a.migList[(size_t)slot * a.migListCap + pos] = (int)i;
+        }
         atomicAdd(a.inflight, 1ull);
     } else if (pt.kind == UGF_PATCH_GENERIC) {
         st.cell = -1; st.flags |= HIT_DELETED;
@@ -369,11 +378,10 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
 // unaligned ranges).
 template <bool HAS_ROT, bool MULTI, int NF>
 __global__ void __launch_bounds__(256, 4) move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
-    const long long i = a.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a.dBegin && a.begin + (long long)(blockIdx.x + 1) * blockDim.x <= *a.dBegin) return;  // whole block precedes the received range
+    const long long i = (a.dBegin ? *a.dBegin : a.begin) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = *a.dN;
-    bool valid = i < n;
-    if (a.dBegin && i < *a.dBegin) valid = false;
+    if (i - threadIdx.x >= n) return;  // whole block beyond the array
+    const bool valid = i < n;
     int cell = -1;
     double x0 = 0, x1 = 0, x2 = 0, U0 = 0, U1 = 0, U2 = 0;
     if (valid) cell = a.P.cell[i];

@@ -201,6 +201,63 @@ class SlotExchanger:
                                "rounds: raise the round count for this decomposition")
 
 
+class PeerExchanger(SlotExchanger):
+    """Fixed-slot transfer rounds over NVLink peer memory: the pack kernel writes each processor patch's records
+    straight into the matching receive slot in the neighbour's HBM and raises a flag there; the neighbour's
+    unpack waits for the flag on the device.  No send buffer, no NCCL call and no host synchronisation on the data
+    path (torch.distributed is only used once, to pass the cudaIpc handles and the slot maps around).
+
+    Receive region per rank: 2 buffers x nProc slots x (cap + 1) records, then 2 x nProc flag words.  Round R (counted
+    over the whole run) uses buffer R % 2 and epoch R + 1: a slot is rewritten two rounds later, after the round in
+    between has been acknowledged by both sides (ugf.h)."""
+
+    def __init__(self, cloud, mesh, rank, world, slot_capacity, group=None, meta_group=None):
+        super().__init__(cloud, mesh, rank, world, slot_capacity, group=group, cuda=True)
+        self.send = self.recv = self.send2 = self.recv2 = None  # the NCCL path's staging buffers are not needed
+        nproc = len(self.slot_of)
+        self.nproc = nproc
+        self.slot_bytes = (self.cap + 1) * STRIDE * 8
+        self.region_bytes = 2 * nproc * self.slot_bytes + 2 * nproc * 8
+        self.base, handle = cloud.peerAlloc(max(self.region_bytes, 64))
+        # what every rank publishes: its handle, its slot count and, per sending peer, the local slots in the order
+        # the peer's messages arrive (same pairing rule as the NCCL path: i-th send to b <-> i-th receive from a)
+        recv_from = {}
+        for k, b in self.recvs:
+            recv_from.setdefault(b, []).append(k)
+        pub = [None] * world
+        dist.all_gather_object(pub, dict(handle=handle, nproc=nproc, slot_bytes=self.slot_bytes, recv_from=recv_from), group=meta_group)
+        self.peer_base = {}
+        for b in sorted({b for _, b in self.sends}):
+            if pub[b]["slot_bytes"] != self.slot_bytes:
+                raise RuntimeError("neighbouring ranks disagree on the migration slot capacity")
+            self.peer_base[b] = self.base if b == rank else cloud.peerOpen(pub[b]["handle"])
+        # destination (slot address for buffer 0, flag address for buffer 0, strides to buffer 1) of my slot k
+        self.dst = [None] * nproc
+        ordinal = {}
+        for k, b in self.sends:
+            i = ordinal.get(b, 0)
+            ordinal[b] = i + 1
+            kb = pub[b]["recv_from"][rank][i]
+            nb = pub[b]["nproc"]
+            base = self.peer_base[b]
+            self.dst[k] = (base + kb * self.slot_bytes, nb * self.slot_bytes, base + 2 * nb * self.slot_bytes + kb * 8, nb * 8)
+        self.round_no = 0
+        dist.barrier(group=meta_group)  # every region is mapped before the first round writes into it
+
+    def _round(self):
+        self.rounds += 1
+        self._round_in_step += 1
+        buf = self.round_no % 2
+        epoch = self.round_no + 1
+        self.round_no += 1
+        slots = [d[0] + buf * d[1] for d in self.dst]
+        flags = [d[2] + buf * d[3] for d in self.dst]
+        self.cloud.migratePackPeer(slots, flags, self.cap, epoch)
+        self.cloud.migrateUnpackPeer(self.base + buf * self.nproc * self.slot_bytes,
+                                     self.base + 2 * self.nproc * self.slot_bytes + buf * self.nproc * 8, self.cap, epoch)
+        self.cloud.moveReceived()
+
+
 class _DevI64:
     def __init__(self, ptr):
         self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
