@@ -331,7 +331,9 @@ int ugf_num_parcels(ugf_handle* h, int64_t* n);
 int ugf_download_parcels(ugf_handle* h, ugf_parcels* p);
 /* cellOccupancy() (CWM/CloudWithModels/CloudWithModelsI.H:65-75) as CSR: offsets [nCells+1], ids [n]. */
 int ugf_download_cell_occupancy(ugf_handle* h, int32_t* offsets, int32_t* ids);
-/* Moments of the last ugf_sample/ugf_collide: [nCells][nSpecies][UGF_NMOM]. */
+/* Moments of the last ugf_sample / ugf_collide / ugf_relax: [nCells][nSpecies][UGF_NMOM].  ugf_step and
+ * ugf_finish_step keep them only when a BGK model is active (it reads them); a pure-DSMC step folds them into the
+ * field accumulators without storing them - call ugf_sample to get them. */
 int ugf_download_cell_moments(ugf_handle* h, double* moments);
 /* sigmaTcRMax [nCells]; BGK persistent state maxProb [nCells], qPrev [nCells*3], sPrev [nCells*6] (NULL skips). */
 int ugf_download_cell_state(ugf_handle* h, double* sigmaTcRMax, double* maxProb, double* qPrev, double* sPrev);

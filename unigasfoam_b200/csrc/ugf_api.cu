@@ -87,7 +87,7 @@ struct ugf_handle {
     bool hasProcessor = false;
     int moveNF = 0;  // uniform face-slot count per cell (4 or 6), 0 = general CSR
     int moveBps = 4;          // resident CTAs per SM of the streamed move kernel
-    int cellTask = 8, cellFlags = 0;
+    int cellTask = 0, cellFlags = 0;  // cellTask 0: chosen per launch from the mean cell occupancy
     bool moveDirect = false;  // tuning: UGF_MOVE_DIRECT=1 runs the step's move with the one-thread-per-parcel kernel
 
     // parcels
@@ -331,7 +331,9 @@ int after_gather(ugf_handle* h) {
 }
 
 // streaming kernel: gather through the occupancy permutation (optional) + cell moments (optional)
-int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate = false) {
+// keepMoments = false (fused step without a BGK model): the 256-byte moment block per (cell, species) is consumed in
+// registers by the field accumulation and not written to HBM
+int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate = false, bool keepMoments = true) {
     if (!gather && !doSample) return 0;
     CellArgs a{};
     a.nCells = h->nCells;
@@ -341,11 +343,14 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
     a.out = gather ? h->buf[h->cur ^ 1] : h->buf[h->cur];
     a.gather = gather ? 1 : 0;
     a.doSample = doSample ? 1 : 0;
+    a.writeMom = keepMoments ? 1 : 0;
     a.mom = h->dMom;
     a.acc = h->dAcc;
     a.accDt = (accumulate && doSample) ? h->cfg.deltaT : 0.0;
     a.taskCounter = h->dTask;
-    a.taskCells = h->cellTask;
+    // a task should fill the staging buffer once: cells per task from the mean occupancy (UGF_CELL_TASK overrides)
+    a.taskCells = h->cellTask > 0 ? h->cellTask
+                                  : std::max(2, std::min(CELL_CHUNK, (int)((double)CELL_CAP * h->nCells / (double)std::max<long long>(h->nUpper, 1))));
     a.flags = h->cellFlags;
     CU(cudaMemsetAsync(h->dTask, 0, sizeof(int), h->stream));
     const DevParams prm = h->prm;
@@ -353,7 +358,7 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
         cell_kernel<decltype(R)::value, decltype(M)::value><<<h->cellBlocks, CELL_THREADS, h->cellSmem, h->stream>>>(prm, a);
     });
     LAUNCHED();
-    if (doSample) h->momValid = true;
+    if (doSample) h->momValid = keepMoments;
     if (gather) return after_gather(h);
     return 0;
 }
@@ -852,7 +857,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         e1 = cudaFuncSetAttribute(cell_kernel<decltype(R)::value, decltype(M)::value>, cudaFuncAttributePreferredSharedMemoryCarveout, cellCarve);
     });
     CU(e1);
-    h->cellBlocks = persistent(occCell, CELL_WARPS * h->cellTask);
+    h->cellBlocks = persistent(occCell, CELL_WARPS * 2);
     h->ntcBlocks = persistent(occNtc, NTC_WARPS * 32);
     h->bgkBlocks = persistent(occBgk, BGK_WARPS * BGK_CHUNK);
     h->meshSet = true;
@@ -1120,7 +1125,7 @@ int ugf_finish_step(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (do_sort(h)) return 1;
     const bool fuseAcc = next_step_samples(h);
-    if (run_cell_kernel(h, true, true, fuseAcc)) return 1;
+    if (run_cell_kernel(h, true, true, fuseAcc, bgk_active(h))) return 1;
     if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
     if (bgk_active(h) && run_bgk_kernel(h)) return 1;
     if (do_accumulate(h, fuseAcc)) return 1;
@@ -1144,7 +1149,7 @@ int ugf_step(ugf_handle* h, int32_t nSteps) {
         if (do_sort(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[3], h->stream));
         const bool fuseAcc = next_step_samples(h);
-        if (run_cell_kernel(h, true, true, fuseAcc)) return 1;
+        if (run_cell_kernel(h, true, true, fuseAcc, bgk_active(h))) return 1;
         if (last) CU(cudaEventRecord(h->ev[4], h->stream));
         if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[5], h->stream));

@@ -40,6 +40,7 @@ struct CellArgs {
     ParcelBuf in, out;
     int gather;       // 1: write the cell-major copy into `out`; 0: sample only
     int doSample;
+    int writeMom;     // 0: the moment blocks of staged cells are not stored (nothing downstream reads them: pure DSMC step)
     double* mom;
     double* acc;      // time-averaged accumulators [nCells][NACC]; updated in the same pass when accDt != 0
     double accDt;
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                             sev += __shfl_xor_sync(0xffffffffu, sev, m); sew += __shfl_xor_sync(0xffffffffu, sew, m);
                         }
                     }
-                    if (cellValid) {
+                    if (cellValid && a.writeMom) {
                         // the cell's 4 lanes write its 32 slots, 4 consecutive slots (one 32-byte sector) per store
                         double* mrow = a.mom + ((size_t)(c0 + ci) * nS + s) * UGF_NMOM + q;
                         mrow[0] = select4(q, cnt, cnt, su, sv);
