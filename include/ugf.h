@@ -75,7 +75,10 @@ enum {
     UGF_WALL_DIFFUSE = 1,  /* uniGasDiffuseWallPatch   params: T, Ux, Uy, Uz */
     UGF_WALL_SPECULAR = 2, /* uniGasSpecularWallPatch  params: none */
     UGF_WALL_MIXED = 3,    /* uniGasMixedDiffuseSpecularWallPatch params: T, Ux, Uy, Uz, diffuseFraction */
-    UGF_WALL_DELETION = 4  /* uniGasDeletionPatch      params: none */
+    UGF_WALL_DELETION = 4, /* uniGasDeletionPatch      params: none */
+    UGF_WALL_CLL = 5       /* uniGasCLLWallPatch (Cercignani-Lampis-Lord) params: T, Ux, Uy, Uz, normalAccommCoeff,
+                              tangentialAccommCoeff, rotEnergyAccommCoeff
+                              (U/boundaries/derived/patchBoundaries/uniGasCLLWallPatch/uniGasCLLWallPatch.C:80-254) */
 };
 
 /* ---- plain-old-data inputs ------------------------------------------------ */

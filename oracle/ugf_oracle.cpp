@@ -128,7 +128,7 @@ struct Parcel {  // uniGasParcel (U/parcels/uniGasParcel.H:217-239) + particle p
     int32_t newParcel;
 };
 
-struct WallModel { int model = UGF_WALL_UNSET; double T = 0, Uw[3] = {0, 0, 0}, diffuseFraction = 1; };
+struct WallModel { int model = UGF_WALL_UNSET; double T = 0, Uw[3] = {0, 0, 0}, diffuseFraction = 1, alphaN = 1, sigmaT = 1, alphaR = 1; };
 
 struct InflowPatch { int patch; ugf_inflow in; };
 
@@ -426,6 +426,73 @@ void diffuseReflection(const ugfo_handle& h, Stream& r, Parcel& p, const double 
     for (int k = 0; k < 3; ++k) p.U[k] += Uw[k];
 }
 
+// uniGasCLLWallPatch::controlParticle (uniGasCLLWallPatch.C:80-254): Cercignani-Lampis-Lord kernel with normal /
+// tangential / rotational accommodation.  Draw order as in the reference; -log(1-u) for its -log(u);
+// rotDoF 3 uses sqrt(alphaR) where the reference writes sqrt(-alphaR) (NaN for any positive coefficient).
+void cllReflection(const ugfo_handle& h, Stream& r, Parcel& p, const double nw[3], const WallModel& w) {
+    bool degenerate = false;  // U == 0: no incident tangential speed, tangent chosen arbitrarily
+    double Un = dot3(p.U, nw);
+    double Ut[3] = {p.U[0] - Un * nw[0], p.U[1] - Un * nw[1], p.U[2] - Un * nw[2]};
+    double magUt = std::sqrt(dot3(Ut, Ut));
+    while (magUt < SMALL) {
+        p.U[0] = p.U[0] * (0.8 + 0.2 * r.u01());
+        p.U[1] = p.U[1] * (0.8 + 0.2 * r.u01());
+        p.U[2] = p.U[2] * (0.8 + 0.2 * r.u01());
+        Un = dot3(p.U, nw);
+        for (int k = 0; k < 3; ++k) Ut[k] = p.U[k] - Un * nw[k];
+        magUt = std::sqrt(dot3(Ut, Ut));
+        if (dot3(p.U, p.U) == 0.0) {  // reference would spin forever on U == 0; pick a tangent
+            const int kmin = std::fabs(nw[0]) <= std::fabs(nw[1]) ? (std::fabs(nw[0]) <= std::fabs(nw[2]) ? 0 : 2)
+                                                                 : (std::fabs(nw[1]) <= std::fabs(nw[2]) ? 1 : 2);
+            double e[3] = {0, 0, 0};
+            e[kmin] = 1.0;
+            const double en = dot3(e, nw);
+            for (int k = 0; k < 3; ++k) Ut[k] = e[k] - en * nw[k];
+            magUt = std::sqrt(dot3(Ut, Ut));
+            degenerate = true;
+            break;
+        }
+    }
+    const double tw1[3] = {Ut[0] / magUt, Ut[1] / magUt, Ut[2] / magUt};
+    const double tw2[3] = {nw[1] * tw1[2] - nw[2] * tw1[1], nw[2] * tw1[0] - nw[0] * tw1[2], nw[0] * tw1[1] - nw[1] * tw1[0]};
+    const ugf_species& s = h.sp[p.typeId];
+    const double T = w.T;
+    const double alphaT = w.sigmaT * (2.0 - w.sigmaT), alphaN = w.alphaN, alphaR = w.alphaR;
+    const double cmp = std::sqrt(2.0 * kB * T / s.mass);
+    const double utN = degenerate ? 0.0 : magUt / cmp;
+    const double unN = Un / cmp;
+    const double thetaNormal = TWO_PI * r.u01();
+    const double rNormal = std::sqrt(-alphaN * std::log(std::max(1 - r.u01(), VSMALL)));
+    const double thetaTangential = TWO_PI * r.u01();
+    const double rTangential = std::sqrt(-alphaT * std::log(std::max(1 - r.u01(), VSMALL)));
+    const double um = std::sqrt(1.0 - alphaN) * unN;
+    const double vN = std::sqrt(rNormal * rNormal + um * um + 2.0 * rNormal * um * std::cos(thetaNormal));
+    const double vT1 = std::sqrt(1.0 - alphaT) * utN + rTangential * std::cos(thetaTangential);
+    const double vT2 = rTangential * std::sin(thetaTangential);
+    double U[3];
+    for (int k = 0; k < 3; ++k) U[k] = cmp * (vT1 * tw1[k] + vT2 * tw2[k] - vN * nw[k]);
+    const double wN = dot3(w.Uw, nw), w1 = dot3(w.Uw, tw1), w2 = dot3(w.Uw, tw2);
+    const double uN = dot3(U, nw), u1 = dot3(U, tw1), u2 = dot3(U, tw2);
+    for (int k = 0; k < 3; ++k)
+        p.U[k] = (uN * nw[k] + wN * nw[k] * alphaN) + (u1 * tw1[k] + w1 * tw1[k] * alphaT) + (u2 * tw2[k] + w2 * tw2[k] * alphaT);
+    if (s.rotationalDoF == 2) {
+        const double om = std::sqrt(p.ERot * (1.0 - alphaR) / (kB * T));
+        const double rRot = std::sqrt(-alphaR * std::log(std::max(1.0 - r.u01(), VSMALL)));
+        const double thetaRot = TWO_PI * r.u01();
+        p.ERot = kB * T * (rRot * rRot + om * om + 2.0 * rRot * om * std::cos(thetaRot));
+    } else if (s.rotationalDoF == 3) {
+        double X, A;
+        do {
+            X = 4.0 * r.u01();
+            A = 2.7182818 * X * X * std::exp(-(X * X));
+        } while (A < r.u01());
+        const double om = std::sqrt(p.ERot * (1.0 - alphaR) / (kB * T));
+        const double rRot = std::sqrt(alphaR) * X;
+        const double thetaRot = 2.0 * r.u01() - 1.0;
+        p.ERot = kB * T * (rRot * rRot + om * om + 2.0 * rRot * om * std::cos(thetaRot));
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // move: face-plane walker standing in for particle::trackToAndHitFace
 // ---------------------------------------------------------------------------------
@@ -489,7 +556,9 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
                     if (h.cfg.measureWalls) measureWall(h, p, bfi, nw, fA, &preIE, preIMom, false);
                     bool diffuse = (w.model == UGF_WALL_DIFFUSE);
                     if (w.model == UGF_WALL_MIXED) diffuse = (w.diffuseFraction > r.u01());
-                    if (diffuse) {
+                    if (w.model == UGF_WALL_CLL) {
+                        cllReflection(h, r, p, nw, w);
+                    } else if (diffuse) {
                         diffuseReflection(h, r, p, nw, w.T, w.Uw);
                     } else {
                         const double Un = dot3(p.U, nw);
@@ -729,7 +798,8 @@ void sampleAll(ugfo_handle& h) {
 // ---------------------------------------------------------------------------------
 // NTC  (noTimeCounter.C:66-343)
 // ---------------------------------------------------------------------------------
-void collideCell(ugfo_handle& h, int c, int64_t& cand, int64_t& coll) {
+// subCycle: sub-cycle index, dtSub = deltaT / nSubCycles (noTimeCounterSubCycled.C:86,190; 0 and deltaT for noTimeCounter)
+void collideCell(ugfo_handle& h, int c, int subCycle, double dtSub, int64_t& cand, int64_t& coll) {
     if (h.collModelId[c] != 1) return;
     const int beg = h.occOff[c];
     const int nC = h.occOff[c + 1] - beg;
@@ -762,16 +832,16 @@ void collideCell(ugfo_handle& h, int c, int64_t& cand, int64_t& coll) {
     }
     const double sMaxOld = h.sigmaTcRMax[c];
     // :184  CWF = RWF = 1
-    const double selectedPairs = 0.5 * nC * (nC - 1) * h.cfg.nParticle * sMaxOld * h.cfg.deltaT / h.vol[c];
+    const double selectedPairs = 0.5 * nC * (nC - 1) * h.cfg.nParticle * sMaxOld * dtSub / h.vol[c];
     int nCand = (int)selectedPairs;
     {
-        Stream rc(h.cfg.seed, KIND_NTC, 0, (uint32_t)h.step, (uint32_t)c, 0xFFFFFFFFu);
+        Stream rc(h.cfg.seed, KIND_NTC, (uint32_t)subCycle, (uint32_t)h.step, (uint32_t)c, 0xFFFFFFFFu);
         if (rc.u01() < (selectedPairs - nCand)) nCand++;
     }
     cand += nCand;
     double sMax = sMaxOld;
     for (int k = 0; k < nCand; ++k) {
-        Stream r(h.cfg.seed, KIND_NTC, 0, (uint32_t)h.step, (uint32_t)c, (uint32_t)k);
+        Stream r(h.cfg.seed, KIND_NTC, (uint32_t)subCycle, (uint32_t)h.step, (uint32_t)c, (uint32_t)k);
         const int cP = r.position(nC);
         int cQ = -1;
         if (nSub > 1 && (int)sub[which[cP]].size() > 1) {
@@ -797,8 +867,13 @@ void collideAll(ugfo_handle& h) {
     if (h.cfg.binaryModel == UGF_BINARY_NONE) return;
     if (!(h.cfg.collisionModel == UGF_COLL_DSMC || h.cfg.collisionModel == UGF_COLL_HYBRID)) return;
     int64_t cand = 0, coll = 0;
+    // noTimeCounterSubCycled repeats the whole pass nSubCycles times with deltaT / nSubCycles (…SubCycled.C:86-190);
+    // cells are independent, so the sub-cycles of a cell can run back to back
+    const int nSub = h.cfg.partnerModel == UGF_PARTNER_NTC_SUBCYCLED ? std::max(1, h.cfg.nSubCycles) : 1;
+    const double dtSub = nSub > 1 ? h.cfg.deltaT / nSub : h.cfg.deltaT;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : cand, coll)
-    for (int c = 0; c < h.nCells; ++c) collideCell(h, c, cand, coll);
+    for (int c = 0; c < h.nCells; ++c)
+        for (int sub = 0; sub < nSub; ++sub) collideCell(h, c, sub, dtSub, cand, coll);
     h.cnt.collisionCandidates += cand;
     h.cnt.collisions += coll;
 }
@@ -1231,10 +1306,14 @@ int ugfo_set_patch_model(ugfo_handle* h, int32_t patch, int32_t model, const dou
     if (h->pKind[patch] != UGF_PATCH_WALL) return fail(h, "patch models apply to wall patches only");
     WallModel w;
     w.model = model;
-    if (model == UGF_WALL_DIFFUSE || model == UGF_WALL_MIXED) {
+    if (model == UGF_WALL_DIFFUSE || model == UGF_WALL_MIXED || model == UGF_WALL_CLL) {
         if (n < 4) return fail(h, "diffuse wall needs T, Ux, Uy, Uz");
         w.T = prm[0]; w.Uw[0] = prm[1]; w.Uw[1] = prm[2]; w.Uw[2] = prm[3];
         if (model == UGF_WALL_MIXED) { if (n < 5) return fail(h, "mixed wall needs diffuseFraction"); w.diffuseFraction = prm[4]; }
+        if (model == UGF_WALL_CLL) {
+            if (n < 7) return fail(h, "CLL wall needs normalAccommCoeff, tangentialAccommCoeff, rotEnergyAccommCoeff");
+            w.alphaN = prm[4]; w.sigmaT = prm[5]; w.alphaR = prm[6];
+        }
     } else if (model != UGF_WALL_SPECULAR && model != UGF_WALL_DELETION) {
         return fail(h, "unknown wall model");
     }

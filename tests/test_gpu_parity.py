@@ -176,6 +176,25 @@ def test_subcell_partner_selection_tracks_oracle(GpuCloud, OracleCloud, levels):
     np.testing.assert_allclose(g.cellState()["sigmaTcRMax"], r.cellState()["sigmaTcRMax"], rtol=1e-12)
 
 
+def test_ntc_subcycled_tracks_oracle(GpuCloud, OracleCloud):
+    """dsmcCollisionPartnerModel noTimeCounterSubCycled (nSubCycles 3): three NTC passes with deltaT/3 each
+    (noTimeCounterSubCycled.C:86-190) - same candidates and collisions as the oracle, and about as many candidates in
+    total as one noTimeCounter pass."""
+    counts = {}
+    for partner in ("noTimeCounter", "noTimeCounterSubCycled"):
+        case = cases.closed_box(n=6, parcels=20000, seed=14, dt_mct=0.9, nSubCycles=3)
+        case.uniGasProperties["dsmcCollisionPartnerModel"] = partner
+        g, r = both(case, GpuCloud, OracleCloud)
+        for cl in (g, r):
+            cl.evolve(2)
+        cg, cr = g.counters(), r.counters()
+        assert cg["collisionCandidates"] == cr["collisionCandidates"] > 500
+        assert abs(cg["collisions"] - cr["collisions"]) <= 2
+        assert frac_close(g.parcels()["U"], r.parcels()["U"]) > 0.995
+        counts[partner] = cg["collisionCandidates"]
+    assert abs(counts["noTimeCounter"] - counts["noTimeCounterSubCycled"]) < 0.15 * counts["noTimeCounter"]
+
+
 def test_larsen_borgnakke_conserves_total_energy(GpuCloud, OracleCloud):
     case = cases.closed_box(n=6, parcels=20000, seed=9, binary="LarsenBorgnakkeVariableHardSphere", species=("N2", cases.NITROGEN),
                             dt_mct=1.0, Trot=150.0, rotationalRelaxationCollisionNumber=5.0, electronicRelaxationCollisionNumber=500.0)
@@ -241,6 +260,28 @@ def test_diffuse_walls_couette_matches_oracle(GpuCloud, OracleCloud):
     assert np.abs(fr["surfaceHeatTransfer"][wall]).max() > 0
     np.testing.assert_allclose(fg["fD"][wall], fr["fD"][wall], rtol=1e-6, atol=1e-9 * np.abs(fr["fD"]).max())
     np.testing.assert_allclose(fg["rhoN"], fr["rhoN"], rtol=1e-12)
+
+
+def test_cll_walls_match_oracle(GpuCloud, OracleCloud):
+    """uniGasCLLWallPatch on the Couette walls (partial accommodation, moving walls) and, with nitrogen, Lord's
+    rotational-energy extension: same hits on the same faces, same reflected state to round-off, same measurements."""
+    for species in (("Ar", cases.ARGON_GUIDE), ("N2", cases.NITROGEN)):
+        case = cases.couette(nx=24, ny=16, ppc=30, Kn=0.5, species=species)
+        for e in case.boundariesDict["uniGasPatchBoundaries"]:
+            old = e["uniGasDiffuseWallPatchProperties"]
+            e["boundaryModel"] = "uniGasCLLWallPatch"
+            e["uniGasCLLWallPatchProperties"] = dict(old, normalAccommCoeff=0.8, tangentialAccommCoeff=0.9, rotEnergyAccommCoeff=0.7)
+        g, r = both(case, GpuCloud, OracleCloud)
+        for cl in (g, r):
+            cl.evolve(3)
+        bg, br = g.fields(), r.fields()
+        pg, pr = g.parcels(), r.parcels()
+        assert g.counters()["wallHits"] == r.counters()["wallHits"] > 50
+        assert np.array_equal(pg["cell"], pr["cell"])
+        assert frac_close(pg["U"], pr["U"]) > 0.999
+        if species[0] == "N2":
+            assert frac_close(pg["ERot"][:, None], pr["ERot"][:, None]) > 0.999
+        np.testing.assert_allclose(bg["fD"], br["fD"], rtol=1e-6, atol=1e-8 * np.abs(br["fD"]).max())
 
 
 @pytest.mark.parametrize("bgk", ["stochasticParticleBGK", "stochasticParticleESBGK", "stochasticParticleSBGK", "unifiedStochasticParticleSBGK"])

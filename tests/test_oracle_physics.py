@@ -100,6 +100,24 @@ def test_subcells_pair_neighbours_within_the_cell(OracleCloud):
     assert res[2][2] > 0.8 > res[1][2]
 
 
+def test_ntc_subcycled_keeps_the_equilibrium_collision_rate(OracleCloud):
+    """noTimeCounterSubCycled with nSubCycles = 4: four passes at deltaT/4 give the same expected number of accepted
+    collisions per step as one noTimeCounter pass (Bird 4.64: 1/2 N nu deltaT per cell)."""
+    rates = {}
+    for partner in ("noTimeCounter", "noTimeCounterSubCycled"):
+        case = cases.closed_box(n=6, parcels=30000, seed=17, dt_mct=0.5, nSubCycles=4)
+        case.uniGasProperties["dsmcCollisionPartnerModel"] = partner
+        cl = case.make_cloud(OracleCloud)
+        cl.evolve(10)  # let sigmaTcRMax settle
+        n = 0
+        for _ in range(10):
+            cl.evolve(1)
+            n += cl.counters()["collisions"]
+        rates[partner] = n / 10
+        cl.close()
+    assert abs(rates["noTimeCounter"] - rates["noTimeCounterSubCycled"]) < 0.04 * rates["noTimeCounter"]
+
+
 def test_specular_box_conserves_energy_and_maxwellian(OracleCloud):
     case = cases.closed_box(n=6, parcels=30000, seed=23)
     cl = case.make_cloud(OracleCloud)
@@ -132,6 +150,41 @@ def test_diffuse_wall_pressure_and_zero_net_heat_flux(OracleCloud):
     qscale = p_expect * cases.most_probable_speed(case.meta["T0"], case.meta["species"]["mass"])
     assert abs(f["surfaceHeatTransfer"][walls].mean()) < 0.02 * qscale
     assert f["surfaceShearStress"][walls].mean() < 0.1 * p_expect
+
+
+def _with_cll_walls(case, alphaN, sigmaT, alphaR=1.0, T=None, U=(0.0, 0.0, 0.0)):
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        old = e.get(e["boundaryModel"] + "Properties", {})
+        e["boundaryModel"] = "uniGasCLLWallPatch"
+        e["uniGasCLLWallPatchProperties"] = {"temperature": old.get("temperature", T), "velocity": list(old.get("velocity", U)),
+                                            "normalAccommCoeff": alphaN, "tangentialAccommCoeff": sigmaT, "rotEnergyAccommCoeff": alphaR}
+    return case
+
+
+def test_cll_wall_limits(OracleCloud):
+    """uniGasCLLWallPatch (uniGasCLLWallPatch.C:80-254).  Zero accommodation is a specular wall: kinetic energy is
+    conserved and |U.n| is mirrored.  Full accommodation keeps a gas at the wall temperature in equilibrium: wall
+    pressure n k T, no net heat flux (the CLL kernel satisfies detailed balance)."""
+    case = _with_cll_walls(cases.closed_box(n=4, parcels=20000, seed=26, wall="diffuse", binary="noDSMCCollision", dt_mct=0.5), 0.0, 0.0)
+    cl = case.make_cloud(OracleCloud)
+    e0 = cl.counters()["linearKineticEnergy"]
+    cl.evolve(20)
+    c = cl.counters()
+    assert c["wallHits"] > 1000
+    assert abs(c["linearKineticEnergy"] - e0) < 1e-9 * e0
+    cl.close()
+    case = _with_cll_walls(cases.closed_box(n=4, parcels=40000, seed=27, wall="diffuse", binary="noDSMCCollision", dt_mct=0.5), 1.0, 1.0)
+    cl = case.make_cloud(OracleCloud)
+    cl.evolve(60)
+    f = cl.fields()
+    walls = f["wall_p"] != 0
+    p_expect = case.meta["n"] * kB * case.meta["T0"]
+    assert abs(f["wall_p"][walls].mean() - p_expect) < 0.03 * p_expect
+    qscale = p_expect * cases.most_probable_speed(case.meta["T0"], case.meta["species"]["mass"])
+    assert abs(f["surfaceHeatTransfer"][walls].mean()) < 0.02 * qscale
+    T = (2.0 / 3.0) * cl.counters()["linearKineticEnergy"] / (cl.size() * kB)
+    assert abs(T - case.meta["T0"]) < 0.02 * case.meta["T0"]
+    cl.close()
 
 
 @pytest.mark.parametrize("bgk", ["stochasticParticleBGK", "stochasticParticleESBGK", "stochasticParticleSBGK", "unifiedStochasticParticleSBGK"])

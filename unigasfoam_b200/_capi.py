@@ -41,6 +41,7 @@ WALL_MODEL = {
     "uniGasSpecularWallPatch": 2,
     "uniGasMixedDiffuseSpecularWallPatch": 3,
     "uniGasDeletionPatch": 4,
+    "uniGasCLLWallPatch": 5,
 }
 
 i32, i64, u64, f64 = C.c_int32, C.c_int64, C.c_uint64, C.c_double

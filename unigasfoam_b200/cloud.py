@@ -120,10 +120,12 @@ class UniGasCloud:
             model = _lookup(_capi.WALL_MODEL, word, "boundaryModel")
             pr = entry.get(word + "Properties", {})
             params = []
-            if model in (1, 3):
+            if model in (1, 3, 5):
                 params = [float(pr["temperature"])] + [float(v) for v in pr["velocity"]]
                 if model == 3:
                     params.append(float(pr["diffuseFraction"]))
+                if model == 5:  # uniGasCLLWallPatch.C:49-55
+                    params += [float(pr["normalAccommCoeff"]), float(pr["tangentialAccommCoeff"]), float(pr["rotEnergyAccommCoeff"])]
             if self.mesh.patches[patch].kind != "wall":
                 # uniGasBoundaries.C:448-488 wants a model on every non-constraint patch, but only wall
                 # patches ever reach controlParticle: accept and ignore.

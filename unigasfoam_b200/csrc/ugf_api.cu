@@ -377,20 +377,28 @@ int run_ntc_kernel(ugf_handle* h) {
     a.step = (uint32_t)h->step;
     a.cnt = h->dCnt;
     const DevParams prm = h->prm;
+    // noTimeCounterSubCycled: the whole pass nSubCycles times with deltaT / nSubCycles (…SubCycled.C:86-190)
+    const int nSub = h->cfg.partnerModel == UGF_PARTNER_NTC_SUBCYCLED ? std::max(1, h->cfg.nSubCycles) : 1;
+    a.dtSub = nSub > 1 ? h->cfg.deltaT / nSub : h->cfg.deltaT;
     if (!h->subLevelsAllOne) {
         SubcellArgs sa{};
         sa.P = h->buf[h->cur]; sa.dN = h->dN; sa.bbMin = h->dBbMin; sa.bbMax = h->dBbMax; sa.levels = h->dSubLevels; sa.sub = h->dSub;
         subcell_index_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(prm, sa);
         LAUNCHED();
-        dispatch(h, [&](auto R, auto M) {
-            ntc_kernel<decltype(R)::value, decltype(M)::value, true><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
-        });
-    } else {
-        dispatch(h, [&](auto R, auto M) {
-            ntc_kernel<decltype(R)::value, decltype(M)::value, false><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
-        });
     }
-    LAUNCHED();
+    for (int sub = 0; sub < nSub; ++sub) {
+        a.sub_cycle = (uint32_t)sub;
+        if (!h->subLevelsAllOne) {
+            dispatch(h, [&](auto R, auto M) {
+                ntc_kernel<decltype(R)::value, decltype(M)::value, true><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+            });
+        } else {
+            dispatch(h, [&](auto R, auto M) {
+                ntc_kernel<decltype(R)::value, decltype(M)::value, false><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+            });
+        }
+        LAUNCHED();
+    }
     return 0;
 }
 
@@ -597,7 +605,8 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     if (!cfg || !out) return fail(nullptr, "null argument");
     if (cfg->abiVersion != UGF_ABI_VERSION) return fail(nullptr, "ABI version mismatch");
     if (cfg->macroInterpolation) return fail(nullptr, "macroInterpolation true is not supported");
-    if (cfg->partnerModel != UGF_PARTNER_NTC) return fail(nullptr, "only dsmcCollisionPartnerModel noTimeCounter is supported");
+    if (cfg->partnerModel != UGF_PARTNER_NTC && cfg->partnerModel != UGF_PARTNER_NTC_SUBCYCLED) return fail(nullptr, "unknown dsmcCollisionPartnerModel");
+    if (cfg->partnerModel == UGF_PARTNER_NTC_SUBCYCLED && cfg->nSubCycles < 1) return fail(nullptr, "noTimeCounterSubCycled needs nSubCycles >= 1");
     if (cfg->parcelCapacity <= 0 || cfg->parcelCapacity > 2000000000LL) return fail(nullptr, "parcelCapacity out of range");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -869,10 +878,14 @@ int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t model, const doubl
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
     if (h->patchKind[patch] != UGF_PATCH_WALL) return fail(h, "patch models apply to wall patches only");
     DevPatch& d = h->patchesHost[patch];
-    if (model == UGF_WALL_DIFFUSE || model == UGF_WALL_MIXED) {
+    if (model == UGF_WALL_DIFFUSE || model == UGF_WALL_MIXED || model == UGF_WALL_CLL) {
         if (n < 4 || !prm) return fail(h, "diffuse wall needs T, Ux, Uy, Uz");
         d.T = prm[0]; d.Uw[0] = prm[1]; d.Uw[1] = prm[2]; d.Uw[2] = prm[3];
         if (model == UGF_WALL_MIXED) { if (n < 5) return fail(h, "mixed wall needs diffuseFraction"); d.diffuseFraction = prm[4]; }
+        if (model == UGF_WALL_CLL) {
+            if (n < 7) return fail(h, "CLL wall needs normalAccommCoeff, tangentialAccommCoeff, rotEnergyAccommCoeff");
+            d.alphaN = prm[4]; d.sigmaT = prm[5]; d.alphaR = prm[6];
+        }
     } else if (model != UGF_WALL_SPECULAR && model != UGF_WALL_DELETION) {
         return fail(h, "unknown wall model");
     }

@@ -170,10 +170,11 @@ __device__ inline void collide_pair(const DevParams& prm, Stream& r, const DevSp
 
 // NTC candidates for one cell: n_sel = 1/2 N (N-1) F_N (sigma_T c_r)max dt / V with stochastic rounding
 // (noTimeCounter.C:184-191); the rounding draw comes from the cell's own stream.
-__device__ __forceinline__ int ntc_candidates(const DevParams& prm, uint32_t step, int cell, int n, double sMaxOld, double vol) {
-    const double selectedPairs = 0.5 * n * (n - 1) * prm.nParticle * sMaxOld * prm.deltaT / vol;
+__device__ __forceinline__ int ntc_candidates(const DevParams& prm, uint32_t step, uint32_t sub, double dtSub, int cell, int n, double sMaxOld,
+                                              double vol) {
+    const double selectedPairs = 0.5 * n * (n - 1) * prm.nParticle * sMaxOld * dtSub / vol;
     int nCand = (int)selectedPairs;
-    Stream rc(prm.seed, KIND_NTC, 0, step, (uint32_t)cell, 0xFFFFFFFFu);
+    Stream rc(prm.seed, KIND_NTC, sub, step, (uint32_t)cell, 0xFFFFFFFFu);
     if (rc.u01() < (selectedPairs - nCand)) nCand++;
     return nCand;
 }
@@ -542,6 +543,8 @@ struct NtcArgs {
     int* owner;   // [capacity] conflict marks, 0x7f7f7f7f when idle
     const unsigned short* sub;  // [capacity] virtual sub-cell of every parcel (SUBCELLS only)
     uint32_t step;
+    uint32_t sub_cycle;  // noTimeCounterSubCycled: pass index (stream aux), 0 for noTimeCounter
+    double dtSub;        // deltaT / nSubCycles (noTimeCounterSubCycled.C:190), deltaT for noTimeCounter
     DevCounters* cnt;
 };
 
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
         double mySMax = 0.0;
         if (myN > 1 && a.collModelId[myCell] == 1) {
             mySMax = a.sigmaTcRMax[myCell];
-            myCand = ntc_candidates(prm, a.step, myCell, myN, mySMax, a.vol[myCell]);
+            myCand = ntc_candidates(prm, a.step, a.sub_cycle, a.dtSub, myCell, myN, mySMax, a.vol[myCell]);
         }
         if (!__any_sync(0xffffffffu, myCand > 0)) continue;
         int incl = myCand;  // inclusive prefix of the candidate counts over the 32 cells
@@ -632,7 +635,7 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
             const int beg = __shfl_sync(0xffffffffu, myBeg, cs);
             const int n = __shfl_sync(0xffffffffu, myN, cs);
             const double sMaxOld = __shfl_sync(0xffffffffu, mySMax, cs);
-            Stream r(prm.seed, KIND_NTC, 0, a.step, (uint32_t)(c0 + cs), (uint32_t)kk);
+            Stream r(prm.seed, KIND_NTC, a.sub_cycle, a.step, (uint32_t)(c0 + cs), (uint32_t)kk);
             int gP = 0, gQ = 0;
             int tP = 0, tQ = 0;
             if (act) {

@@ -44,6 +44,7 @@ struct DevPatch {
     double T;
     double Uw[3];
     double diffuseFraction;
+    double alphaN, sigmaT, alphaR;  // CLL: normalAccommCoeff, tangentialAccommCoeff, rotEnergyAccommCoeff
 };
 
 struct DevParams {

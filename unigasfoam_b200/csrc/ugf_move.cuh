@@ -126,6 +126,74 @@ __device__ inline void diffuse_reflection(Stream& r, const DevSpecies& s, double
     for (int k = 0; k < 3; ++k) U[k] += Uw[k];
 }
 
+// uniGasCLLWallPatch::controlParticle (uniGasCLLWallPatch.C:80-254), same restatement as the oracle's cllReflection
+__device__ inline void cll_reflection(Stream& r, const DevSpecies& s, double U[3], double& erot, const double nw[3], const DevPatch& pt) {
+    bool degenerate = false;
+    double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
+    double Ut[3] = {U[0] - Un * nw[0], U[1] - Un * nw[1], U[2] - Un * nw[2]};
+    double magUt = sqrt(dot3(Ut[0], Ut[1], Ut[2], Ut[0], Ut[1], Ut[2]));
+    while (magUt < SMALL) {
+        U[0] = U[0] * (0.8 + 0.2 * r.u01());
+        U[1] = U[1] * (0.8 + 0.2 * r.u01());
+        U[2] = U[2] * (0.8 + 0.2 * r.u01());
+        Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
+        for (int k = 0; k < 3; ++k) Ut[k] = U[k] - Un * nw[k];
+        magUt = sqrt(dot3(Ut[0], Ut[1], Ut[2], Ut[0], Ut[1], Ut[2]));
+        if (dot3(U[0], U[1], U[2], U[0], U[1], U[2]) == 0.0) {
+            const double a0 = fabs(nw[0]), a1 = fabs(nw[1]), a2 = fabs(nw[2]);
+            const int kmin = a0 <= a1 ? (a0 <= a2 ? 0 : 2) : (a1 <= a2 ? 1 : 2);
+            double e[3] = {0, 0, 0};
+            e[kmin] = 1.0;
+            const double en = dot3(e[0], e[1], e[2], nw[0], nw[1], nw[2]);
+            for (int k = 0; k < 3; ++k) Ut[k] = e[k] - en * nw[k];
+            magUt = sqrt(dot3(Ut[0], Ut[1], Ut[2], Ut[0], Ut[1], Ut[2]));
+            degenerate = true;
+            break;
+        }
+    }
+    const double tw1[3] = {Ut[0] / magUt, Ut[1] / magUt, Ut[2] / magUt};
+    const double tw2[3] = {nw[1] * tw1[2] - nw[2] * tw1[1], nw[2] * tw1[0] - nw[0] * tw1[2], nw[0] * tw1[1] - nw[1] * tw1[0]};
+    const double T = pt.T;
+    const double alphaT = pt.sigmaT * (2.0 - pt.sigmaT), alphaN = pt.alphaN, alphaR = pt.alphaR;
+    const double cmp = sqrt(2.0 * kB * T / s.mass);
+    const double utN = degenerate ? 0.0 : magUt / cmp;
+    const double unN = Un / cmp;
+    const double thetaNormal = TWO_PI * r.u01();
+    const double rNormal = sqrt(-alphaN * log(fmax(1 - r.u01(), VSMALL)));
+    const double thetaTangential = TWO_PI * r.u01();
+    const double rTangential = sqrt(-alphaT * log(fmax(1 - r.u01(), VSMALL)));
+    const double um = sqrt(1.0 - alphaN) * unN;
+    const double vN = sqrt(rNormal * rNormal + um * um + 2.0 * rNormal * um * cos(thetaNormal));
+    const double vT1 = sqrt(1.0 - alphaT) * utN + rTangential * cos(thetaTangential);
+    const double vT2 = rTangential * sin(thetaTangential);
+    double V[3];
+    for (int k = 0; k < 3; ++k) V[k] = cmp * (vT1 * tw1[k] + vT2 * tw2[k] - vN * nw[k]);
+    const double wN = dot3(pt.Uw[0], pt.Uw[1], pt.Uw[2], nw[0], nw[1], nw[2]);
+    const double w1 = dot3(pt.Uw[0], pt.Uw[1], pt.Uw[2], tw1[0], tw1[1], tw1[2]);
+    const double w2 = dot3(pt.Uw[0], pt.Uw[1], pt.Uw[2], tw2[0], tw2[1], tw2[2]);
+    const double uN = dot3(V[0], V[1], V[2], nw[0], nw[1], nw[2]);
+    const double u1 = dot3(V[0], V[1], V[2], tw1[0], tw1[1], tw1[2]);
+    const double u2 = dot3(V[0], V[1], V[2], tw2[0], tw2[1], tw2[2]);
+    for (int k = 0; k < 3; ++k)
+        U[k] = (uN * nw[k] + wN * nw[k] * alphaN) + (u1 * tw1[k] + w1 * tw1[k] * alphaT) + (u2 * tw2[k] + w2 * tw2[k] * alphaT);
+    if (s.rotDoF == 2) {
+        const double om = sqrt(erot * (1.0 - alphaR) / (kB * T));
+        const double rRot = sqrt(-alphaR * log(fmax(1.0 - r.u01(), VSMALL)));
+        const double thetaRot = TWO_PI * r.u01();
+        erot = kB * T * (rRot * rRot + om * om + 2.0 * rRot * om * cos(thetaRot));
+    } else if (s.rotDoF == 3) {
+        double X, A;
+        do {
+            X = 4.0 * r.u01();
+            A = 2.7182818 * X * X * exp(-(X * X));
+        } while (A < r.u01());
+        const double om = sqrt(erot * (1.0 - alphaR) / (kB * T));
+        const double rRot = sqrt(alphaR) * X;
+        const double thetaRot = 2.0 * r.u01() - 1.0;
+        erot = kB * T * (rRot * rRot + om * om + 2.0 * rRot * om * cos(thetaRot));
+    }
+}
+
 struct MoveArgs {
     MeshDev mesh;
     ParcelBuf P;
@@ -174,15 +242,17 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
         WallPre pre;
         if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, st.U, st.erot, nw, fA, pre, false);
         bool diffuse = (pt.wallModel == UGF_WALL_DIFFUSE);
+        const bool cll = (pt.wallModel == UGF_WALL_CLL);
         if (pt.wallModel != UGF_WALL_SPECULAR) {
             Stream r(prm.seed, KIND_MOVE, a.aux, a.step, (uint32_t)i, 0);
             r.c3 = (uint32_t)(st.nDraws >> 1);
             if (st.nDraws & 1) { r.block(); r.have = 1; }
             if (pt.wallModel == UGF_WALL_MIXED) diffuse = (pt.diffuseFraction > r.u01());
-            if (diffuse) diffuse_reflection(r, sp, st.U, st.erot, nw, pt.T, pt.Uw);
+            if (cll) cll_reflection(r, sp, st.U, st.erot, nw, pt);
+            else if (diffuse) diffuse_reflection(r, sp, st.U, st.erot, nw, pt.T, pt.Uw);
             st.nDraws = 2 * (int)r.c3 - r.have;
         }
-        if (!diffuse) {
+        if (!diffuse && !cll) {
             const double Un = dot3(st.U[0], st.U[1], st.U[2], nw[0], nw[1], nw[2]);
             if (Un > 0.0) for (int k = 0; k < 3; ++k) st.U[k] = st.U[k] - 2.0 * Un * nw[k];
         }
