@@ -238,6 +238,11 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* mesh);
 /* uniGasBoundaries: patchToModelId_ (U/boundaries/basic/uniGasBoundaries/uniGasBoundaries.C:420-490).
  * params: see UGF_WALL_*.  Only wall-kind patches take a model. */
 int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t wallModel, const double* params, int32_t nParams);
+/* The *FieldPatch variants (uniGasDiffuseWallFieldPatch, uniGasMixedDiffuseSpecularWallFieldPatch,
+ * uniGasCLLWallFieldPatch: …/uniGasDiffuseWallFieldPatch/uniGasDiffuseWallFieldPatch.C:104-121): wall temperature and
+ * velocity per boundary face instead of per patch, i.e. the boundaryT / boundaryU fields on this patch.
+ * T [patchSize], U [patchSize*3] (host); call after ugf_set_patch_model on the same patch. */
+int ugf_set_patch_wall_fields(ugf_handle* h, int32_t patch, const double* T, const double* U);
 /* uniGasFreeStreamInflowPatch on a patch (any kind). */
 int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* inflow);
 /* addNewParcel over a whole initial configuration (U/clouds/uniGasCloud.C:260-290). Replaces the cloud. */

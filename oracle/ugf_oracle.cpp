@@ -128,7 +128,11 @@ struct Parcel {  // uniGasParcel (U/parcels/uniGasParcel.H:217-239) + particle p
     int32_t newParcel;
 };
 
-struct WallModel { int model = UGF_WALL_UNSET; double T = 0, Uw[3] = {0, 0, 0}, diffuseFraction = 1, alphaN = 1, sigmaT = 1, alphaR = 1; };
+struct WallModel {
+    int model = UGF_WALL_UNSET;
+    double T = 0, Uw[3] = {0, 0, 0}, diffuseFraction = 1, alphaN = 1, sigmaT = 1, alphaR = 1;
+    std::vector<double> faceT, faceU;  // *FieldPatch variants: boundaryT / boundaryU per face of the patch
+};
 
 struct InflowPatch { int patch; ugf_inflow in; };
 
@@ -546,7 +550,14 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
             const int kind = h.pKind[patch];
             const double* S = &h.Sf[3 * (size_t)hit];
             if (kind == UGF_PATCH_WALL) {
-                const WallModel& w = h.wall[patch];
+                WallModel wl = h.wall[patch];
+                if (!h.wall[patch].faceT.empty()) {  // …WallFieldPatch.C:108-114: this face's boundaryT / boundaryU
+                    const int lf = hit - h.pStart[patch];
+                    wl.T = h.wall[patch].faceT[lf];
+                    for (int k = 0; k < 3; ++k) wl.Uw[k] = h.wall[patch].faceU[3 * (size_t)lf + k];
+                    wl.faceT.clear(); wl.faceU.clear();
+                }
+                const WallModel& w = wl;
                 t.wallHits++;
                 if (w.model == UGF_WALL_DELETION) {
                     p.cell = -1; t.deleted++;
@@ -1318,6 +1329,15 @@ int ugfo_set_patch_model(ugfo_handle* h, int32_t patch, int32_t model, const dou
         return fail(h, "unknown wall model");
     }
     h->wall[patch] = w;
+    return 0;
+}
+
+int ugfo_set_patch_wall_fields(ugfo_handle* h, int32_t patch, const double* T, const double* U) {
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->pKind[patch] != UGF_PATCH_WALL || h->wall[patch].model == UGF_WALL_UNSET) return fail(h, "wall fields need a wall patch with a model");
+    const size_t n = (size_t)h->pSize[patch];
+    h->wall[patch].faceT.assign(T, T + n);
+    h->wall[patch].faceU.assign(U, U + 3 * n);
     return 0;
 }
 

@@ -284,6 +284,35 @@ def test_cll_walls_match_oracle(GpuCloud, OracleCloud):
         np.testing.assert_allclose(bg["fD"], br["fD"], rtol=1e-6, atol=1e-8 * np.abs(br["fD"]).max())
 
 
+def test_wall_field_patch_matches_oracle_and_follows_the_field(GpuCloud, OracleCloud):
+    """uniGasDiffuseWallFieldPatch: wall temperature / velocity per face (boundaryT, boundaryU).  A bottom wall that
+    is hot on its right half: GPU == oracle, and the parcels leaving the hot faces carry the hot temperature."""
+    case = cases.couette(nx=24, ny=16, ppc=40, Kn=0.5, binary="noDSMCCollision")
+    nx = 24
+    T = np.where(np.arange(nx) < nx // 2, 273.0, 1200.0)
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        old = e.pop("uniGasDiffuseWallPatchProperties")
+        e["boundaryModel"] = "uniGasDiffuseWallFieldPatch"
+        e["uniGasDiffuseWallFieldPatchProperties"] = {}
+        e["boundaryT"] = T if e["patchBoundaryProperties"]["patch"] == "bottom" else old["temperature"]
+        e["boundaryU"] = np.tile(np.asarray(old["velocity"], float), (nx, 1))
+    g, r = both(case, GpuCloud, OracleCloud)
+    for cl in (g, r):
+        cl.move()
+    bg, br = g.boundaryMeasurements(), r.boundaryMeasurements()
+    assert (bg[:, 15] == br[:, 15]).all() and br[:, 15].sum() > 100
+    np.testing.assert_allclose(bg, br, rtol=1e-9, atol=1e-12 * np.abs(br).max())
+    assert frac_close(g.parcels()["U"], r.parcels()["U"]) > 0.9999
+    for cl in (g, r):
+        cl.buildCellOccupancy(); cl.collide(); cl.accumulateFields(); cl.endStep()
+    g.evolve(30)
+    f = g.fields()
+    p = case.mesh.patches[case.mesh.patch_index("bottom")]
+    b0 = p.start - case.mesh.n_internal
+    q = f["surfaceHeatTransfer"][b0:b0 + p.size]
+    assert q[nx // 2:].mean() < 5 * q[:nx // 2].mean() - 1e-12 and q[nx // 2:].mean() < 0  # the hot half heats the gas
+
+
 @pytest.mark.parametrize("bgk", ["stochasticParticleBGK", "stochasticParticleESBGK", "stochasticParticleSBGK", "unifiedStochasticParticleSBGK"])
 def test_bgk_family_conserves_and_tracks_oracle(GpuCloud, OracleCloud, bgk):
     case = cases.closed_box(n=6, parcels=22000, seed=11, mode="bgk", bgk=bgk, binary="noDSMCCollision", dt_mct=2.0,

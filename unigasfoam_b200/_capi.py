@@ -42,6 +42,10 @@ WALL_MODEL = {
     "uniGasMixedDiffuseSpecularWallPatch": 3,
     "uniGasDeletionPatch": 4,
     "uniGasCLLWallPatch": 5,
+    # *FieldPatch variants: same kernels, wall T / U per face (boundaryT / boundaryU)
+    "uniGasDiffuseWallFieldPatch": 1,
+    "uniGasMixedDiffuseSpecularWallFieldPatch": 3,
+    "uniGasCLLWallFieldPatch": 5,
 }
 
 i32, i64, u64, f64 = C.c_int32, C.c_int64, C.c_uint64, C.c_double
@@ -118,6 +122,7 @@ SIGNATURES = {
     "set_species": (C.c_int, [H, i32, P(Species)]),
     "set_mesh": (C.c_int, [H, P(Mesh)]),
     "set_patch_model": (C.c_int, [H, i32, i32, PF, i32]),
+    "set_patch_wall_fields": (C.c_int, [H, i32, PF, PF]),
     "set_inflow": (C.c_int, [H, i32, P(Inflow)]),
     "upload_parcels": (C.c_int, [H, P(Parcels)]),
     "upload_cell_state": (C.c_int, [H, PF, PI32, PI32, PF]),

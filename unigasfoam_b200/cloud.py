@@ -120,6 +120,14 @@ class UniGasCloud:
             model = _lookup(_capi.WALL_MODEL, word, "boundaryModel")
             pr = entry.get(word + "Properties", {})
             params = []
+            field = word.endswith("FieldPatch")
+            if field:
+                # the reference reads the volFields boundaryT / boundaryU from the time directory
+                # (…WallFieldPatch.C:56-80); here their values on this patch come with the dictionary entry
+                nF = self.mesh.patches[patch].size
+                bT = self._f64(np.broadcast_to(np.asarray(entry["boundaryT"], float), (nF,)))
+                bU = self._f64(np.broadcast_to(np.asarray(entry["boundaryU"], float), (nF, 3)))
+                pr = dict(pr, temperature=float(bT.mean()), velocity=[float(v) for v in bU.mean(0)])
             if model in (1, 3, 5):
                 params = [float(pr["temperature"])] + [float(v) for v in pr["velocity"]]
                 if model == 3:
@@ -132,6 +140,9 @@ class UniGasCloud:
                 continue
             arr = (C.c_double * max(len(params), 1))(*params)
             self._check(self.api.set_patch_model(self._h, patch, model, arr, len(params)))
+            if field:
+                PD = C.POINTER(C.c_double)
+                self._check(self.api.set_patch_wall_fields(self._h, patch, bT.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
             if word != "uniGasFreeStreamInflowPatch":

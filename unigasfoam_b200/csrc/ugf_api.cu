@@ -130,6 +130,7 @@ struct ugf_handle {
     bool subLevelsAllOne = true;
 
     std::vector<InflowHost> inflows;
+    std::vector<double*> wallFieldOwned;      // boundaryT / boundaryU of *FieldPatch walls
     std::vector<void*> peerOwned, peerOpened;  // NVLink peer-memory transfer buffers (cudaIpc)
     std::vector<double*> packBuf;
     std::vector<long long> packCap;
@@ -665,6 +666,7 @@ int ugf_destroy(ugf_handle* h) {
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
+    for (double* p : h->wallFieldOwned) cudaFree(p);
     for (void* p : h->peerOpened) cudaIpcCloseMemHandle(p);
     for (void* p : h->peerOwned) cudaFree(p);
     if (h->pinN) cudaFreeHost(h->pinN);
@@ -890,6 +892,25 @@ int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t model, const doubl
         return fail(h, "unknown wall model");
     }
     d.wallModel = model;
+    CU(cudaMemcpyAsync(h->dPatches + patch, &d, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int ugf_set_patch_wall_fields(ugf_handle* h, int32_t patch, const double* T, const double* U) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->patchKind[patch] != UGF_PATCH_WALL || h->patchesHost[patch].wallModel == UGF_WALL_UNSET)
+        return fail(h, "wall fields need a wall patch with a model");
+    if (!T || !U) return fail(h, "null wall field");
+    DevPatch& d = h->patchesHost[patch];
+    const size_t n = (size_t)d.size;
+    double *dT = nullptr, *dU = nullptr;
+    if (dalloc(h, &dT, n) || dalloc(h, &dU, 3 * n)) return 1;
+    h->wallFieldOwned.push_back(dT);
+    h->wallFieldOwned.push_back(dU);
+    if (upload(h, dT, T, n) || upload(h, dU, U, 3 * n)) return 1;
+    d.faceT = dT; d.faceU = dU;
     CU(cudaMemcpyAsync(h->dPatches + patch, &d, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;

@@ -45,6 +45,8 @@ struct DevPatch {
     double Uw[3];
     double diffuseFraction;
     double alphaN, sigmaT, alphaR;  // CLL: normalAccommCoeff, tangentialAccommCoeff, rotEnergyAccommCoeff
+    const double* faceT;            // *FieldPatch variants: boundaryT [size] / boundaryU [size*3] on this patch, else null
+    const double* faceU;
 };
 
 struct DevParams {

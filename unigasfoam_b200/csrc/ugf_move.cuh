@@ -248,7 +248,14 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
             r.c3 = (uint32_t)(st.nDraws >> 1);
             if (st.nDraws & 1) { r.block(); r.have = 1; }
             if (pt.wallModel == UGF_WALL_MIXED) diffuse = (pt.diffuseFraction > r.u01());
-            if (cll) cll_reflection(r, sp, st.U, st.erot, nw, pt);
+            if (pt.faceT) {  // …WallFieldPatch.C:108-114: this face's boundaryT / boundaryU
+                DevPatch pf = pt;
+                const int lf = bfi - pt.startBfi;
+                pf.T = __ldg(&pt.faceT[lf]);
+                for (int k = 0; k < 3; ++k) pf.Uw[k] = __ldg(&pt.faceU[3 * (size_t)lf + k]);
+                if (cll) cll_reflection(r, sp, st.U, st.erot, nw, pf);
+                else if (diffuse) diffuse_reflection(r, sp, st.U, st.erot, nw, pf.T, pf.Uw);
+            } else if (cll) cll_reflection(r, sp, st.U, st.erot, nw, pt);
             else if (diffuse) diffuse_reflection(r, sp, st.U, st.erot, nw, pt.T, pt.Uw);
             st.nDraws = 2 * (int)r.c3 - r.have;
         }
