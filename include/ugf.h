@@ -200,6 +200,20 @@ typedef struct ugf_counters {
     double momentum[3];          /* sum m U */
 } ugf_counters;
 
+/* system/hybridDecompositionDict: uniGasHybridDecomposition (U/hybridDecomposition/basic/uniGasHybridDecomposition.C:48-76)
+ * + localKnudsen (U/hybridDecomposition/derived/localKnudsen/localKnudsen.C:52-55). */
+typedef struct ugf_decomposition {
+    int32_t decompositionInterval;         /* timeProperties.decompositionInterval (default 100) */
+    int32_t resetAtDecomposition;          /* timeProperties.resetAtDecomposition (default 1) */
+    double resetAtDecompositionUntilTime;  /* timeProperties.resetAtDecompositionUntilTime (default 1e300) */
+    double breakdownMax;                   /* localKnudsenProperties.breakdownMax (default 0.05) */
+    double theta;                          /* localKnudsenProperties.theta (default 1) */
+    int32_t smoothingPasses;               /* localKnudsenProperties.smoothingPasses (default 0) */
+    int32_t refinementPasses;              /* 3, hard-wired in the reference (uniGasHybridDecomposition.C:71) */
+    int32_t neighborLevels;                /* 3 (:72) */
+    double maxNeighborFraction;            /* 0.4 (:73) */
+} ugf_decomposition;
+
 /* Number of fp64 values per (cell, species) in the cell-moment block; see DESIGN.md
  * for the slot list.  (U/cellMeasurements/cellMeasurements.H:73-145) */
 #define UGF_NMOM 32
@@ -280,6 +294,17 @@ int ugf_relax(ugf_handle* h);
 /* uniGasVolFields::calculateField accumulation part (uniGasVolFields.C:723-837) +
  * cellMeas_/boundaryMeas_ clean (U/clouds/uniGasCloud.C:864-866). */
 int ugf_accumulate_fields(ugf_handle* h);
+/* decompositionModel localKnudsen (collisionModel hybrid only).  Once set, every step adds the step's cell sums to the
+ * decomposition's own time averages and every decompositionInterval-th step recomputes the DSMC / BGK mask
+ * (collModelId) from the gradient-length local Knudsen number: localKnudsen::decompose
+ * (U/hybridDecomposition/derived/localKnudsen/localKnudsen.C:216-582).  ugf_step / ugf_finish_step call it after the
+ * collisions like uniGasCloud::evolve does (U/clouds/uniGasCloud.C:862); phase-wise drivers call ugf_decompose after
+ * ugf_collide / ugf_relax.  Processor faces are treated as zero-gradient by the smoothing operator. */
+int ugf_set_decomposition(ugf_handle* h, const ugf_decomposition* d);
+int ugf_decompose(ugf_handle* h);
+/* collModelId [nCells] (0 = bgk, 1 = dsmc) and the time-blended Knudsen fields kn [nCells][4] = KnRho, KnT, KnU,
+ * KnGLL (either may be NULL). */
+int ugf_download_decomposition(ugf_handle* h, int32_t* collModelId, double* kn);
 /* End-of-step bookkeeping when phases are driven one by one: step counter ++. */
 int ugf_end_step(ugf_handle* h);
 /* Everything of evolve() that follows the move and the parcel transfers, in one call and with the same kernel

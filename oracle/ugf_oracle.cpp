@@ -178,6 +178,16 @@ struct ugfo_handle {
     int64_t nAvTimeSteps = 0;
     int sampleCounter = 0;
 
+    // localKnudsen hybrid decomposition (U/hybridDecomposition)
+    bool decompOn = false;
+    ugf_decomposition dec{};
+    int decTimeSteps = 0;
+    double decTimeAv = 0;
+    std::vector<double> knAcc;          // [nCells][KN_NACC + nSpecies]
+    std::vector<double> knFields;       // [nCells][4] KnRho, KnT, KnU, KnGLL
+    std::vector<double> faceW, faceMagSf;   // linear-interpolation weight of the owner side, |Sf|
+    std::vector<int32_t> ccOff, ccIds;  // mesh.cellCells(): neighbours across internal faces
+
     int64_t step = 0;
     bool stepOpen = false;
     ugf_counters cnt;
@@ -1101,6 +1111,233 @@ void relaxAll(ugfo_handle& h) {
 }
 
 // ---------------------------------------------------------------------------------
+// hybrid decomposition  (localKnudsen.C:216-582, uniGasHybridDecomposition.C:127-174)
+// ---------------------------------------------------------------------------------
+constexpr int KN_NACC = 7;  // 0 N, 1 rhoN X, 2 rhoM X, 3 linearKE X, 4-6 momentum X; then nParcels X per species
+
+void decompGeometry(ugfo_handle& h) {
+    h.faceW.assign(h.nFaces, 1.0);
+    h.faceMagSf.assign(h.nFaces, 0.0);
+    std::vector<std::vector<int32_t>> cc(h.nCells);
+    for (int f = 0; f < h.nFaces; ++f) {
+        const double* S = &h.Sf[3 * (size_t)f];
+        const double* C = &h.Cf[3 * (size_t)f];
+        h.faceMagSf[f] = std::sqrt(dot3(S, S));
+        if (f < h.nInternal) {  // surfaceInterpolation::makeWeights
+            const double* cP = &h.cc[3 * (size_t)h.owner[f]];
+            const double* cN = &h.cc[3 * (size_t)h.neighbour[f]];
+            const double dO[3] = {C[0] - cP[0], C[1] - cP[1], C[2] - cP[2]}, dN[3] = {cN[0] - C[0], cN[1] - C[1], cN[2] - C[2]};
+            const double sO = std::fabs(dot3(S, dO)), sN = std::fabs(dot3(S, dN));
+            h.faceW[f] = sN / (sO + sN);
+        }
+    }
+    for (int c = 0; c < h.nCells; ++c)  // cellCells in the order of the cell's faces
+        for (int j = h.cfOff[c]; j < h.cfOff[c + 1]; ++j) {
+            const int f = h.cf[j];
+            if (f < h.nInternal) cc[c].push_back(h.owner[f] == c ? h.neighbour[f] : h.owner[f]);
+        }
+    h.ccOff.assign(h.nCells + 1, 0);
+    h.ccIds.clear();
+    for (int c = 0; c < h.nCells; ++c) {
+        h.ccIds.insert(h.ccIds.end(), cc[c].begin(), cc[c].end());
+        h.ccOff[c + 1] = (int32_t)h.ccIds.size();
+    }
+}
+
+// fvc::average(fvc::interpolate(f)) followed by correctBoundaryConditions, for nComp scalars per cell (AoS).
+// vec3At >= 0: components vec3At..vec3At+2 form a vector (symmetry planes mirror it).  Boundary faces: zeroGradient
+// on wall / generic / processor patches, symmetry, cyclic (coupled, linear weights), empty faces take no part.
+void smoothFields(const ugfo_handle& h, std::vector<double>& f, int nComp, int vec3At) {
+    std::vector<double> out(f.size());
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < h.nCells; ++c) {
+        double num[16], den = 0;
+        for (int k = 0; k < nComp; ++k) num[k] = 0;
+        const double* fc = &f[(size_t)c * nComp];
+        for (int j = h.cfOff[c]; j < h.cfOff[c + 1]; ++j) {
+            const int face = h.cf[j];
+            const double A = h.faceMagSf[face];
+            double val[16];
+            if (face < h.nInternal) {
+                const double w = h.faceW[face];
+                const double* fo = &f[(size_t)h.owner[face] * nComp];
+                const double* fn = &f[(size_t)h.neighbour[face] * nComp];
+                for (int k = 0; k < nComp; ++k) val[k] = w * fo[k] + (1.0 - w) * fn[k];
+            } else {
+                const int patch = h.facePatch[face - h.nInternal];
+                const int kind = h.pKind[patch];
+                if (kind == UGF_PATCH_EMPTY) continue;
+                for (int k = 0; k < nComp; ++k) val[k] = fc[k];
+                if (kind == UGF_PATCH_SYMMETRY && vec3At >= 0) {
+                    const double* S = &h.Sf[3 * (size_t)face];
+                    const double n[3] = {S[0] / A, S[1] / A, S[2] / A};
+                    const double vn = fc[vec3At] * n[0] + fc[vec3At + 1] * n[1] + fc[vec3At + 2] * n[2];
+                    for (int k = 0; k < 3; ++k) val[vec3At + k] = fc[vec3At + k] - vn * n[k];
+                } else if (kind == UGF_PATCH_CYCLIC) {
+                    const int nf = h.pStart[h.pPartner[patch]] + (face - h.pStart[patch]);
+                    const int q = h.owner[nf];
+                    const double* S = &h.Sf[3 * (size_t)face];
+                    const double* Sn = &h.Sf[3 * (size_t)nf];
+                    const double An = h.faceMagSf[nf];
+                    const double* C = &h.Cf[3 * (size_t)face];
+                    const double* Cn = &h.Cf[3 * (size_t)nf];
+                    const double* cP = &h.cc[3 * (size_t)c];
+                    const double* cQ = &h.cc[3 * (size_t)q];
+                    const double di = ((C[0] - cP[0]) * S[0] + (C[1] - cP[1]) * S[1] + (C[2] - cP[2]) * S[2]) / A;
+                    const double dni = ((Cn[0] - cQ[0]) * Sn[0] + (Cn[1] - cQ[1]) * Sn[1] + (Cn[2] - cQ[2]) * Sn[2]) / An;
+                    const double w = dni / (di + dni);
+                    const double* fq = &f[(size_t)q * nComp];
+                    for (int k = 0; k < nComp; ++k) val[k] = w * fc[k] + (1.0 - w) * fq[k];
+                }
+            }
+            for (int k = 0; k < nComp; ++k) num[k] += A * val[k];
+            den += A;
+        }
+        for (int k = 0; k < nComp; ++k) out[(size_t)c * nComp + k] = num[k] / den;
+    }
+    f.swap(out);
+}
+
+void neighbourhood(const ugfo_handle& h, int cell, int nLevels, std::vector<int>& nb, std::vector<char>& mark) {
+    nb.clear();
+    nb.push_back(cell);
+    mark[cell] = 1;
+    size_t first = 0;
+    for (int level = 1; level <= nLevels; ++level) {
+        const size_t last = nb.size();
+        for (size_t i = first; i < last; ++i)
+            for (int j = h.ccOff[nb[i]]; j < h.ccOff[nb[i] + 1]; ++j) {
+                const int q = h.ccIds[j];
+                if (!mark[q]) { mark[q] = 1; nb.push_back(q); }
+            }
+        first = last;
+    }
+    for (int q : nb) mark[q] = 0;
+}
+
+// the sequential, in-place refinement sweeps (localKnudsen.C:428-541)
+void refineMask(const ugfo_handle& h, std::vector<int32_t>& id) {
+    std::vector<int> nb;
+    std::vector<char> mark(h.nCells, 0);
+    for (int pass = 1; pass <= h.dec.refinementPasses; ++pass) {
+        for (int which = 1; which >= 0; --which) {  // first the dsmc cells (1), then the bgk cells (0)
+            for (int c = 0; c < h.nCells; ++c) {
+                if (id[c] != which) continue;
+                int same = 0, other = 0;
+                for (int j = h.ccOff[c]; j < h.ccOff[c + 1]; ++j) (id[h.ccIds[j]] == which ? same : other)++;
+                if (same == 0 || (same == 1 && other > 1)) { id[c] = 1 - which; continue; }
+                neighbourhood(h, c, h.dec.neighborLevels, nb, mark);
+                int nSame = 0;
+                for (int q : nb) nSame += (id[q] == which);
+                if (nSame < h.dec.maxNeighborFraction * nb.size()) { id[c] = 1 - which; continue; }
+            }
+        }
+    }
+}
+
+void decompose(ugfo_handle& h) {
+    if (!h.decompOn || h.cfg.collisionModel != UGF_COLL_HYBRID) return;
+    if (!h.momValid) sampleAll(h);
+    const int nS = h.nSpecies, W = KN_NACC + nS;
+    const double dt = h.cfg.deltaT, FN = h.cfg.nParticle;
+    h.decTimeSteps++;
+    h.decTimeAv += dt;
+    for (int c = 0; c < h.nCells; ++c) {
+        double* a = &h.knAcc[(size_t)c * W];
+        for (int s = 0; s < nS; ++s) {
+            const double* m = &h.mom[((size_t)c * nS + s) * UGF_NMOM];
+            const double ms = h.sp[s].mass;
+            a[0] += dt * m[0];
+            a[1] += dt * (m[1] * FN);
+            a[2] += dt * (ms * m[1] * FN);
+            a[3] += dt * (ms * m[14] * FN);
+            for (int k = 0; k < 3; ++k) a[4 + k] += dt * (ms * m[5 + k] * FN);
+            a[KN_NACC + s] += dt * (m[1] * FN);
+        }
+    }
+    if (h.decTimeSteps != h.dec.decompositionInterval) return;
+    const double tAv = h.decTimeAv;
+    // 0 rhoN, 1 rhoM, 2 p, 3 T, 4-6 U; rhoN is not smoothed (localKnudsen.C:283-292)
+    std::vector<double> F((size_t)h.nCells * 7, 0.0);
+    for (int c = 0; c < h.nCells; ++c) {
+        const double* a = &h.knAcc[(size_t)c * W];
+        double* f = &F[(size_t)c * 7];
+        if (a[0] > VSMALL) {
+            const double V = h.vol[c];
+            f[0] = a[1] / (tAv * V);
+            f[1] = a[2] / (tAv * V);
+            const double rhoMMean = a[2] / (V * tAv);
+            for (int k = 0; k < 3; ++k) f[4 + k] = a[4 + k] / (rhoMMean * V * tAv);
+            const double linearKEMean = 0.5 * a[3] / (V * tAv);
+            const double rhoNMean = a[1] / (V * tAv);
+            f[3] = 2.0 / (3.0 * kB * rhoNMean) * (linearKEMean - 0.5 * rhoMMean * (f[4] * f[4] + f[5] * f[5] + f[6] * f[6]));
+            f[2] = f[0] * kB * f[3];
+        }
+    }
+    {
+        std::vector<double> G((size_t)h.nCells * 6);  // rhoM, p, T, U
+        for (int c = 0; c < h.nCells; ++c) for (int k = 0; k < 6; ++k) G[(size_t)c * 6 + k] = F[(size_t)c * 7 + 1 + k];
+        for (int pass = 1; pass <= h.dec.smoothingPasses; ++pass) smoothFields(h, G, 6, 3);
+        for (int c = 0; c < h.nCells; ++c) for (int k = 0; k < 6; ++k) F[(size_t)c * 7 + 1 + k] = G[(size_t)c * 6 + k];
+    }
+    for (int c = 0; c < h.nCells; ++c) {
+        const double* f = &F[(size_t)c * 7];
+        const double* a = &h.knAcc[(size_t)c * W];
+        double gRho = 0, gT = 0, gU = 0;
+        const double magU = std::sqrt(f[4] * f[4] + f[5] * f[5] + f[6] * f[6]);
+        for (int j = h.ccOff[c]; j < h.ccOff[c + 1]; ++j) {
+            const int q = h.ccIds[j];
+            const double* g = &F[(size_t)q * 7];
+            const double d[3] = {h.cc[3 * (size_t)q] - h.cc[3 * (size_t)c], h.cc[3 * (size_t)q + 1] - h.cc[3 * (size_t)c + 1],
+                                 h.cc[3 * (size_t)q + 2] - h.cc[3 * (size_t)c + 2]};
+            const double dist = std::sqrt(dot3(d, d));
+            gRho = std::max(gRho, std::fabs(g[1] - f[1]) / dist);
+            gT = std::max(gT, std::fabs(g[3] - f[3]) / dist);
+            gU = std::max(gU, std::fabs(std::sqrt(g[4] * g[4] + g[5] * g[5] + g[6] * g[6]) - magU) / dist);
+        }
+        double knRho, knT, knU, knG;
+        if (a[0] > VSMALL && f[3] > VSMALL) {
+            const double V = h.vol[c];
+            double mfp = 0;
+            for (int i = 0; i < nS; ++i) {
+                double inv = 0;
+                for (int q = 0; q < nS; ++q) {
+                    const double dPQ = 0.5 * (h.sp[i].d + h.sp[q].d), omegaPQ = 0.5 * (h.sp[i].omega + h.sp[q].omega);
+                    const double massRatio = h.sp[i].mass / h.sp[q].mass;
+                    if (a[KN_NACC + q] > VSMALL) {
+                        const double nDensQ = a[KN_NACC + q] / V;
+                        inv += PI * dPQ * dPQ * nDensQ * std::pow(h.cfg.Tref / f[3], omegaPQ - 0.5) * std::sqrt(1.0 + massRatio);  // Bird 4.76
+                    }
+                }
+                if (a[KN_NACC + i] > VSMALL) mfp += (1.0 / inv) * a[KN_NACC + i] / (f[0] * V);  // Bird 4.77
+            }
+            const double u0 = std::sqrt(2.0 * kB / (f[1] / f[0]) * f[3]);
+            knRho = mfp * gRho / f[1];
+            knT = mfp * gT / f[3];
+            knU = mfp * gU / std::max(magU, u0);
+            knG = std::max(std::max(knRho, knT), knU);
+        } else {
+            knRho = knT = knU = knG = 2.0 * h.dec.breakdownMax;
+        }
+        double* K = &h.knFields[(size_t)c * 4];
+        const double th = h.dec.theta;
+        K[0] = th * knRho + (1.0 - th) * K[0];
+        K[1] = th * knT + (1.0 - th) * K[1];
+        K[2] = th * knU + (1.0 - th) * K[2];
+        K[3] = th * knG + (1.0 - th) * K[3];
+    }
+    for (int pass = 1; pass <= h.dec.smoothingPasses; ++pass) smoothFields(h, h.knFields, 4, -1);
+    for (int c = 0; c < h.nCells; ++c) h.collModelId[c] = h.knFields[(size_t)c * 4 + 3] > h.dec.breakdownMax ? 1 : 0;
+    refineMask(h, h.collModelId);
+    h.decTimeSteps = 0;
+    const double timeNow = (double)(h.step + 1) * dt;
+    if (h.dec.resetAtDecomposition && timeNow < h.dec.resetAtDecompositionUntilTime + 0.5 * dt) {
+        h.decTimeAv = 0.0;
+        std::fill(h.knAcc.begin(), h.knAcc.end(), 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // time-averaged fields  (uniGasVolFields.C:723-1352)
 // ---------------------------------------------------------------------------------
 void accumulateFields(ugfo_handle& h) {
@@ -1426,6 +1663,29 @@ int ugfo_accumulate_fields(ugfo_handle* h) {
     return 0;
 }
 
+int ugfo_set_decomposition(ugfo_handle* h, const ugf_decomposition* d) {
+    if (h->cfg.collisionModel != UGF_COLL_HYBRID) return fail(h, "a decomposition model needs collisionModel hybrid");
+    if (h->nCells == 0) return fail(h, "mesh not set");
+    if (d->decompositionInterval < 1 || d->smoothingPasses < 0 || d->refinementPasses < 0 || d->neighborLevels < 0) return fail(h, "bad decomposition properties");
+    h->dec = *d;
+    h->decompOn = true;
+    h->decTimeSteps = 0;
+    h->decTimeAv = 0;
+    h->knAcc.assign((size_t)h->nCells * (KN_NACC + h->nSpecies), 0.0);
+    h->knFields.assign((size_t)h->nCells * 4, 0.0);
+    decompGeometry(*h);
+    return 0;
+}
+
+int ugfo_decompose(ugfo_handle* h) { decompose(*h); return 0; }
+
+int ugfo_download_decomposition(ugfo_handle* h, int32_t* id, double* kn) {
+    if (!h->decompOn) return fail(h, "no decomposition model set");
+    if (id) std::copy(h->collModelId.begin(), h->collModelId.end(), id);
+    if (kn) std::copy(h->knFields.begin(), h->knFields.end(), kn);
+    return 0;
+}
+
 int ugfo_end_step(ugfo_handle* h) { h->step++; h->cnt.step = h->step; h->stepOpen = false; return 0; }
 
 int ugfo_finish_step(ugfo_handle* h) {
@@ -1435,6 +1695,7 @@ int ugfo_finish_step(ugfo_handle* h) {
     collideAll(*h);
     relaxAll(*h);
     accumulateFields(*h);
+    decompose(*h);
     return ugfo_end_step(h);
 }
 
@@ -1452,6 +1713,7 @@ int ugfo_step(ugfo_handle* h, int32_t nSteps) {
         collideAll(*h);
         relaxAll(*h);
         accumulateFields(*h);
+        decompose(*h);
         ugfo_end_step(h);
     }
     return 0;

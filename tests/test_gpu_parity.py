@@ -409,3 +409,31 @@ def test_cylinder_inflow_outflow_matches_oracle(GpuCloud, OracleCloud):
     np.testing.assert_allclose(fg["rhoN"], fr["rhoN"], rtol=1e-9)
     wall = slice(0, 40)  # the cylinder patch comes first among the boundary faces
     np.testing.assert_allclose(fg["surfaceHeatTransfer"][wall], fr["surfaceHeatTransfer"][wall], rtol=1e-6, atol=1e-9 * np.abs(fr["surfaceHeatTransfer"]).max())
+
+
+def test_local_knudsen_decomposition_matches_oracle(GpuCloud, OracleCloud):
+    """decompositionModel localKnudsen in a hybrid run (hot top wall): the time averages, smoothed fields, Knudsen fields
+    and the refined DSMC / BGK mask follow the oracle through three decompositions; the parcels stay in lockstep, which
+    they only do while both sides relax / collide the same cells."""
+    case = cases.couette(nx=16, ny=12, ppc=60, Kn=0.2, mode="hybrid", bgk="unifiedStochasticParticleSBGK", theta=0.1)
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        if e["patchBoundaryProperties"]["patch"] == "top":
+            e["uniGasDiffuseWallPatchProperties"]["temperature"] = 900.0
+    g, r = both(case, GpuCloud, OracleCloud)
+    hd = {"decompositionModel": "localKnudsen", "timeProperties": {"decompositionInterval": 4, "resetAtDecomposition": True},
+          "localKnudsenProperties": {"breakdownMax": 0.14, "theta": 0.5, "smoothingPasses": 2}}
+    for cl in (g, r):
+        cl.setHybridDecomposition(hd)
+    split = False
+    for k in range(3):
+        for cl in (g, r):
+            cl.evolve(4)
+        dg, dr = g.hybridDecomposition(), r.hybridDecomposition()
+        for name in ("KnRho", "KnT", "KnU", "KnGLL"):
+            np.testing.assert_allclose(dg[name], dr[name], rtol=1e-7, err_msg=f"{name} after decomposition {k + 1}")
+        assert np.array_equal(dg["cellCollModelId"], dr["cellCollModelId"])
+        split = split or 0 < dr["cellCollModelId"].sum() < case.mesh.n_cells
+    assert split  # at least one of the masks mixes DSMC and BGK cells
+    cg, cr = g.counters(), r.counters()
+    assert cg["bgkRelaxations"] == cr["bgkRelaxations"] > 0 and abs(cg["collisions"] - cr["collisions"]) <= 2
+    assert frac_close(g.parcels()["U"], r.parcels()["U"], 1e-7) > 0.99

@@ -271,3 +271,71 @@ def test_inflow_flux_matches_bird_4_22(OracleCloud):
     U = cl.parcels()["U"]
     assert abs(U[:, 0].mean() - Uinf[0]) < 0.02 * Uinf[0]
     assert cl.counters()["stuck"] == 0
+
+
+def _hot_top_hybrid_couette(**kw):
+    case = cases.couette(nx=16, ny=12, ppc=60, Kn=0.2, mode="hybrid", bgk="unifiedStochasticParticleSBGK", theta=0.1, **kw)
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        if e["patchBoundaryProperties"]["patch"] == "top":
+            e["uniGasDiffuseWallPatchProperties"]["temperature"] = 900.0
+    return case
+
+
+def test_local_knudsen_matches_the_formulas(OracleCloud):
+    """localKnudsen::decompose with theta 1 and no smoothing against an independent numpy evaluation of
+    localKnudsen.C:294-383 from the time-averaged fields of the same window: KnX = lambda max_nb |X_nb - X| / (d X),
+    lambda from Bird 4.76/4.77, KnGLL = max of the three, mask = KnGLL > breakdownMax before the refinement."""
+    case = _hot_top_hybrid_couette()
+    cl = case.make_cloud(OracleCloud)
+    cl.setHybridDecomposition({"decompositionModel": "localKnudsen", "timeProperties": {"decompositionInterval": 8},
+                               "localKnudsenProperties": {"breakdownMax": 0.4, "theta": 1.0, "smoothingPasses": 0}})
+    cl.evolve(8)
+    d = cl.hybridDecomposition()
+    f = cl.fields()  # uniGasVolFields averaged over the same 8 steps
+    m, sp = case.mesh, case.meta["species"]
+    nI = m.n_internal
+    own, nei, cc = m.owner[:nI], m.neighbour, m.cell_centres
+    dist = np.linalg.norm(cc[nei] - cc[own], axis=1)
+    rho, T, magU = f["rhoM"], f["translationalT"], np.linalg.norm(f["UMean"], axis=1)
+    def maxgrad(x):
+        g = np.zeros(m.n_cells)
+        d_ = np.abs(x[nei] - x[own]) / dist
+        np.maximum.at(g, own, d_); np.maximum.at(g, nei, d_)
+        return g
+    lam = 1.0 / (math.pi * sp["diameter"] ** 2 * f["rhoN"] * (case.meta["Tref"] / T) ** (sp["omega"] - 0.5) * math.sqrt(2.0))
+    u0 = np.sqrt(2.0 * kB * T / sp["mass"])
+    knRho, knT, knU = lam * maxgrad(rho) / rho, lam * maxgrad(T) / T, lam * maxgrad(magU) / np.maximum(magU, u0)
+    np.testing.assert_allclose(d["KnRho"], knRho, rtol=1e-9)
+    np.testing.assert_allclose(d["KnT"], knT, rtol=1e-9)
+    np.testing.assert_allclose(d["KnU"], knU, rtol=1e-9)
+    np.testing.assert_allclose(d["KnGLL"], np.maximum(np.maximum(knRho, knT), knU), rtol=1e-9)
+    assert d["KnT"].reshape(12, 16)[-1].mean() > 2 * d["KnT"].reshape(12, 16)[5].mean()  # the temperature jump sits at the hot wall
+    raw = d["KnGLL"] > 0.4  # statistical scatter dominates at 60 parcels x 8 steps per cell: the raw mask is patchy
+    ids = d["cellCollModelId"].reshape(12, 16)
+    assert 0 < ids.sum() < m.n_cells
+    assert (d["cellCollModelId"] == raw).mean() > 0.5  # the refinement sweeps tidy the raw mask ...
+    iso = lambda a: ((a[1:-1, 1:-1] != a[:-2, 1:-1]) & (a[1:-1, 1:-1] != a[2:, 1:-1]) & (a[1:-1, 1:-1] != a[1:-1, :-2]) & (a[1:-1, 1:-1] != a[1:-1, 2:])).sum()
+    assert iso(ids) <= iso(raw.reshape(12, 16).astype(int))  # ... they do not create isolated cells
+    cl.close()
+
+
+def test_local_knudsen_smoothing_and_blending(OracleCloud):
+    """smoothingPasses reduce the cell-to-cell scatter of KnGLL; theta < 1 blends successive decompositions
+    (localKnudsen.C:392-395): K_2 = theta K_inst + (1 - theta) K_1 lies between the two."""
+    res = {}
+    for passes in (0, 4):
+        cl = _hot_top_hybrid_couette().make_cloud(OracleCloud)
+        cl.setHybridDecomposition({"timeProperties": {"decompositionInterval": 6}, "localKnudsenProperties": {"smoothingPasses": passes, "theta": 0.5}})
+        cl.evolve(6)
+        k1 = cl.hybridDecomposition()["KnGLL"].copy()
+        cl.evolve(6)
+        k2 = cl.hybridDecomposition()["KnGLL"].copy()
+        res[passes] = (k1, k2)
+        cl.close()
+    rough = lambda k: np.abs(np.diff(k.reshape(12, 16), axis=1)).mean() / k.mean()
+    assert rough(res[4][0]) < 0.6 * rough(res[0][0])
+    k1, k2 = res[0]
+    inst = (k2 - 0.5 * k1) / 0.5  # the second window's instantaneous value implied by the blend
+    assert (inst > 0).all() and np.isfinite(inst).all()
+    # the fields start from zero: K_1 = 0.5 K_inst,1 and K_2 = 0.5 K_inst,2 + 0.25 K_inst,1, i.e. K_2 / K_1 ~ 1.5
+    assert abs(np.median(k2 / k1) - 1.5) < 0.3

@@ -97,6 +97,14 @@ class Parcels(C.Structure):
     ]
 
 
+class Decomposition(C.Structure):
+    _fields_ = [
+        ("decompositionInterval", i32), ("resetAtDecomposition", i32), ("resetAtDecompositionUntilTime", f64),
+        ("breakdownMax", f64), ("theta", f64), ("smoothingPasses", i32), ("refinementPasses", i32), ("neighborLevels", i32),
+        ("maxNeighborFraction", f64),
+    ]
+
+
 class Counters(C.Structure):
     _fields_ = [
         ("step", i64), ("nParcels", i64), ("collisionCandidates", i64), ("collisions", i64), ("bgkRelaxations", i64),
@@ -136,6 +144,9 @@ SIGNATURES = {
     "collide": (C.c_int, [H]),
     "relax": (C.c_int, [H]),
     "accumulate_fields": (C.c_int, [H]),
+    "set_decomposition": (C.c_int, [H, P(Decomposition)]),
+    "decompose": (C.c_int, [H]),
+    "download_decomposition": (C.c_int, [H, PI32, PF]),
     "end_step": (C.c_int, [H]),
     "finish_step": (C.c_int, [H]),
     "migrate_counts": (C.c_int, [H, PI64]),

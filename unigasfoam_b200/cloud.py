@@ -222,6 +222,35 @@ class UniGasCloud:
             c.ctypes.data_as(PI) if c is not None else None,
             d.ctypes.data_as(PD) if d is not None else None))
 
+    def setHybridDecomposition(self, hybridDecompositionDict):
+        """system/hybridDecompositionDict: `decompositionModel localKnudsen` with its timeProperties and
+        localKnudsenProperties sub-dictionaries (same keys and defaults as the reference:
+        uniGasHybridDecomposition.C:66-73, localKnudsen.C:52-55)."""
+        d = hybridDecompositionDict
+        _lookup({"localKnudsen": 1}, d.get("decompositionModel", "localKnudsen"), "decompositionModel")
+        tp, kp = d.get("timeProperties", {}), d.get("localKnudsenProperties", {})
+        dec = _capi.Decomposition()
+        dec.decompositionInterval = int(tp.get("decompositionInterval", 100))
+        dec.resetAtDecomposition = int(bool(tp.get("resetAtDecomposition", True)))
+        dec.resetAtDecompositionUntilTime = float(tp.get("resetAtDecompositionUntilTime", 1e300))
+        dec.breakdownMax = float(kp.get("breakdownMax", 0.05))
+        dec.theta = float(kp.get("theta", 1.0))
+        dec.smoothingPasses = int(kp.get("smoothingPasses", 0))
+        dec.refinementPasses, dec.neighborLevels, dec.maxNeighborFraction = 3, 3, 0.4
+        self._check(self.api.set_decomposition(self._h, C.byref(dec)))
+
+    def decomposition(self):
+        """uniGasCloud::decomposition(), for phase-wise drivers (evolve() calls it itself)."""
+        self._check(self.api.decompose(self._h))
+
+    def hybridDecomposition(self):
+        """cellCollModelId (0 = bgk, 1 = dsmc) and the blended fields KnRho, KnT, KnU, KnGLL per cell."""
+        nC = self.mesh.n_cells
+        ids = np.empty(nC, np.int32)
+        kn = np.empty((nC, 4))
+        self._check(self.api.download_decomposition(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), kn.ctypes.data_as(C.POINTER(C.c_double))))
+        return dict(cellCollModelId=ids, KnRho=kn[:, 0], KnT=kn[:, 1], KnU=kn[:, 2], KnGLL=kn[:, 3])
+
     def setDeltaT(self, dt):
         self._check(self.api.set_deltaT(self._h, float(dt)))
         self.cfg.deltaT = float(dt)

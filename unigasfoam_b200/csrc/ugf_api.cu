@@ -22,6 +22,7 @@
 #include "ugf_bgk.cuh"
 #include "ugf_cell.cuh"
 #include "ugf_common.cuh"
+#include "ugf_decomp.cuh"
 #include "ugf_fields.cuh"
 #include "ugf_inflow.cuh"
 #include "ugf_move.cuh"
@@ -79,8 +80,8 @@ struct ugf_handle {
     MeshDev mesh{};
     std::vector<DevPatch> patchesHost;
     std::vector<int> patchKind, patchStart, patchSize;
-    std::vector<int32_t> ownerHost;
-    std::vector<double> SfHost, CfHost, pointsHost;
+    std::vector<int32_t> ownerHost, neighbourHost, cfOffHost, cfHost, patchPartnerHost;
+    std::vector<double> SfHost, CfHost, pointsHost, ccHost;
     std::vector<int32_t> fpOffHost, fpHost;
     int* dCfOff = nullptr; double4* dPlane = nullptr; int* dNbr = nullptr; int* dBfPatch = nullptr; int* dBfOwner = nullptr;
     DevPatch* dPatches = nullptr; double* dVol = nullptr; double* dBbMin = nullptr; double* dBbMax = nullptr; double* dBfS = nullptr;
@@ -128,6 +129,17 @@ struct ugf_handle {
     double* dTot = nullptr;
     bool histValid = false, occValid = false, occIdentity = false, momValid = false;
     bool subLevelsAllOne = true;
+
+    // localKnudsen hybrid decomposition
+    bool decompOn = false;
+    ugf_decomposition dec{};
+    int decTimeSteps = 0;
+    double decTimeAv = 0;
+    DecompGeom dgeom{};
+    double* dKnAcc = nullptr; double* dKnF[2] = {nullptr, nullptr}; double* dKnK[2] = {nullptr, nullptr};
+    int knCur = 0;                       // which dKnK buffer holds the Knudsen fields
+    std::vector<void*> decompOwned;
+    std::vector<int32_t> ccOffHost, ccIdsHost;  // mesh.cellCells() for the refinement sweeps
 
     std::vector<InflowHost> inflows;
     std::vector<double*> wallFieldOwned;      // boundaryT / boundaryU of *FieldPatch walls
@@ -587,6 +599,90 @@ int pack_slots_to(ugf_handle* h, const MigDst& dst, long long slotCapacity) {
     return 0;
 }
 
+// fetchCellNeighborhood (uniGasHybridDecomposition.C:127-174): the cell and everything within nLevels face hops
+void cell_neighbourhood(const ugf_handle* h, int cell, int nLevels, std::vector<int>& nb, std::vector<char>& mark) {
+    nb.clear();
+    nb.push_back(cell);
+    mark[cell] = 1;
+    size_t first = 0;
+    for (int level = 1; level <= nLevels; ++level) {
+        const size_t last = nb.size();
+        for (size_t i = first; i < last; ++i)
+            for (int j = h->ccOffHost[nb[i]]; j < h->ccOffHost[nb[i] + 1]; ++j) {
+                const int q = h->ccIdsHost[j];
+                if (!mark[q]) { mark[q] = 1; nb.push_back(q); }
+            }
+        first = last;
+    }
+    for (int q : nb) mark[q] = 0;
+}
+
+// The refinement sweeps of localKnudsen::decompose (localKnudsen.C:428-541) update the mask in place while walking
+// the cells in index order, so their result depends on that order: host code, on the downloaded mask.
+void refine_mask(const ugf_handle* h, std::vector<int32_t>& id) {
+    std::vector<int> nb;
+    std::vector<char> mark((size_t)h->nCells, 0);
+    for (int pass = 1; pass <= h->dec.refinementPasses; ++pass)
+        for (int which = 1; which >= 0; --which)  // dsmc cells first, then bgk cells
+            for (int c = 0; c < h->nCells; ++c) {
+                if (id[c] != which) continue;
+                int same = 0, other = 0;
+                for (int j = h->ccOffHost[c]; j < h->ccOffHost[c + 1]; ++j) (id[h->ccIdsHost[j]] == which ? same : other)++;
+                if (same == 0 || (same == 1 && other > 1)) { id[c] = 1 - which; continue; }
+                cell_neighbourhood(h, c, h->dec.neighborLevels, nb, mark);
+                int nSame = 0;
+                for (int q : nb) nSame += (id[q] == which);
+                if (nSame < h->dec.maxNeighborFraction * nb.size()) id[c] = 1 - which;
+            }
+}
+
+// uniGasCloud::decomposition (U/clouds/uniGasCloud.C:250-256): accumulate every step, re-decompose every interval
+int do_decompose(ugf_handle* h) {
+    if (!h->decompOn) return 0;
+    if (!h->momValid) return fail(h, "ugf_decompose needs the step's cell moments (ugf_sample / ugf_collide / ugf_relax first)");
+    const int nC = h->nCells, W = KN_NACC + h->nSpecies;
+    const unsigned grid = grid_for(nC, 256);
+    const DevParams prm = h->prm;
+    kn_accumulate_kernel<<<grid, 256, 0, h->stream>>>(prm, nC, h->dMom, h->dKnAcc);
+    LAUNCHED();
+    h->decTimeSteps++;
+    h->decTimeAv += h->cfg.deltaT;
+    if (h->decTimeSteps != h->dec.decompositionInterval) return 0;
+    const DecompGeom g = h->dgeom;
+    int cur = 0;
+    kn_derive_kernel<<<grid, 256, 0, h->stream>>>(nC, W, h->dKnAcc, h->dVol, h->decTimeAv, h->dKnF[cur]);
+    LAUNCHED();
+    for (int pass = 1; pass <= h->dec.smoothingPasses; ++pass) {  // rhoM, p, T, U; rhoN is not smoothed (:283-292)
+        kn_smooth_kernel<KN_NF, 4><<<grid, 256, 0, h->stream>>>(g, 1, h->dKnF[cur], h->dKnF[cur ^ 1]);
+        LAUNCHED();
+        cur ^= 1;
+    }
+    kn_kernel<<<grid, 256, 0, h->stream>>>(prm, g, W, h->dKnAcc, h->dKnF[cur], h->dec.breakdownMax, h->dec.theta, h->dKnK[h->knCur]);
+    LAUNCHED();
+    for (int pass = 1; pass <= h->dec.smoothingPasses; ++pass) {
+        kn_smooth_kernel<4, -1><<<grid, 256, 0, h->stream>>>(g, 0, h->dKnK[h->knCur], h->dKnK[h->knCur ^ 1]);
+        LAUNCHED();
+        h->knCur ^= 1;
+    }
+    kn_threshold_kernel<<<grid, 256, 0, h->stream>>>(nC, h->dKnK[h->knCur], h->dec.breakdownMax, h->dCollId);
+    LAUNCHED();
+    if (h->dec.refinementPasses > 0) {
+        std::vector<int32_t> id((size_t)nC);
+        CU(cudaMemcpyAsync(id.data(), h->dCollId, sizeof(int32_t) * (size_t)nC, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        refine_mask(h, id);
+        if (upload(h, h->dCollId, id.data(), (size_t)nC)) return 1;
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->decTimeSteps = 0;
+    const double timeNow = (double)(h->step + 1) * h->cfg.deltaT;
+    if (h->dec.resetAtDecomposition && timeNow < h->dec.resetAtDecompositionUntilTime + 0.5 * h->cfg.deltaT) {
+        h->decTimeAv = 0.0;
+        CU(cudaMemsetAsync(h->dKnAcc, 0, sizeof(double) * (size_t)nC * W, h->stream));
+    }
+    return 0;
+}
+
 int zero_step_counters(ugf_handle* h) {
     CU(cudaMemsetAsync(h->dCnt, 0, sizeof(DevCounters), h->stream));
     return 0;
@@ -667,6 +763,7 @@ int ugf_destroy(ugf_handle* h) {
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
     for (double* p : h->wallFieldOwned) cudaFree(p);
+    for (void* p : h->decompOwned) cudaFree(p);
     for (void* p : h->peerOpened) cudaIpcCloseMemHandle(p);
     for (void* p : h->peerOwned) cudaFree(p);
     if (h->pinN) cudaFreeHost(h->pinN);
@@ -775,6 +872,11 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     }
     // host copies needed later (inflow geometry)
     h->ownerHost.assign(m->owner, m->owner + m->nFaces);
+    h->neighbourHost.assign(m->neighbour, m->neighbour + nI);
+    h->cfOffHost.assign(m->cellFaceOffsets, m->cellFaceOffsets + nC + 1);
+    h->cfHost.assign(m->cellFaces, m->cellFaces + m->cellFaceOffsets[nC]);
+    h->patchPartnerHost.assign(m->patchPartner, m->patchPartner + h->nPatches);
+    h->ccHost.assign(m->cellCentres, m->cellCentres + 3 * (size_t)nC);
     h->SfHost.assign(m->faceAreas, m->faceAreas + 3 * (size_t)m->nFaces);
     h->CfHost.assign(m->faceCentres, m->faceCentres + 3 * (size_t)m->nFaces);
     if (m->points && m->facePointOffsets && m->facePoints) {
@@ -1148,6 +1250,109 @@ int ugf_accumulate_fields(ugf_handle* h) {
     return do_accumulate(h);
 }
 
+int ugf_set_decomposition(ugf_handle* h, const ugf_decomposition* d) {
+    if (!h || !h->meshSet || !d) return fail(h, "mesh not set");
+    if (h->cfg.collisionModel != UGF_COLL_HYBRID) return fail(h, "a decomposition model needs collisionModel hybrid");
+    if (d->decompositionInterval < 1 || d->smoothingPasses < 0 || d->refinementPasses < 0 || d->neighborLevels < 0)
+        return fail(h, "bad decomposition properties");
+    if (h->decompOn) return fail(h, "decomposition already set");
+    CU(cudaSetDevice(h->cfg.device));
+    const int nC = h->nCells, nI = h->nInternal;
+    // smoothing-operator slots per cell, in cell-face order, empty faces left out; mesh.cellCells() alongside
+    std::vector<int> off((size_t)nC + 1, 0), nb, info;
+    std::vector<double> w, A;
+    h->ccOffHost.assign((size_t)nC + 1, 0);
+    h->ccIdsHost.clear();
+    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    for (int c = 0; c < nC; ++c) {
+        for (int j = h->cfOffHost[c]; j < h->cfOffHost[c + 1]; ++j) {
+            const int f = h->cfHost[j];
+            const double* S = &h->SfHost[3 * (size_t)f];
+            const double* C = &h->CfHost[3 * (size_t)f];
+            const double magS = std::sqrt(dot(S, S));
+            if (f < nI) {  // surfaceInterpolation::makeWeights
+                const int o = h->ownerHost[f], n = h->neighbourHost[f];
+                const double* cP = &h->ccHost[3 * (size_t)o];
+                const double* cN = &h->ccHost[3 * (size_t)n];
+                const double dO[3] = {C[0] - cP[0], C[1] - cP[1], C[2] - cP[2]}, dN[3] = {cN[0] - C[0], cN[1] - C[1], cN[2] - C[2]};
+                const double sO = std::fabs(dot(S, dO)), sN = std::fabs(dot(S, dN));
+                nb.push_back(o == c ? n : o);
+                info.push_back(o == c ? DF_OWNER : DF_NEIGHBOUR);
+                w.push_back(sN / (sO + sN));
+                A.push_back(magS);
+                h->ccIdsHost.push_back(o == c ? n : o);
+                continue;
+            }
+            const int bfi = f - nI;
+            int patch = -1;
+            for (int p = 0; p < h->nPatches; ++p)
+                if (f >= h->patchStart[p] && f < h->patchStart[p] + h->patchSize[p]) patch = p;
+            const int kind = h->patchKind[patch];
+            if (kind == UGF_PATCH_EMPTY) continue;
+            if (kind == UGF_PATCH_CYCLIC) {  // coupled patch, linear weights from both sides' face-normal distances
+                const int nf = h->patchStart[h->patchPartnerHost[patch]] + (f - h->patchStart[patch]);
+                const int q = h->ownerHost[nf];
+                const double* Sn = &h->SfHost[3 * (size_t)nf];
+                const double* Cn = &h->CfHost[3 * (size_t)nf];
+                const double An = std::sqrt(dot(Sn, Sn));
+                const double* cP = &h->ccHost[3 * (size_t)c];
+                const double* cQ = &h->ccHost[3 * (size_t)q];
+                const double di = ((C[0] - cP[0]) * S[0] + (C[1] - cP[1]) * S[1] + (C[2] - cP[2]) * S[2]) / magS;
+                const double dni = ((Cn[0] - cQ[0]) * Sn[0] + (Cn[1] - cQ[1]) * Sn[1] + (Cn[2] - cQ[2]) * Sn[2]) / An;
+                nb.push_back(q);
+                info.push_back(DF_BOUNDARY | (bfi << 2));
+                w.push_back(dni / (di + dni));
+            } else {  // zero gradient (wall, patch, processor) or symmetry
+                nb.push_back(c);
+                info.push_back((kind == UGF_PATCH_SYMMETRY ? DF_SYMMETRY : DF_BOUNDARY) | (bfi << 2));
+                w.push_back(1.0);
+            }
+            A.push_back(magS);
+        }
+        off[c + 1] = (int)nb.size();
+        h->ccOffHost[c + 1] = (int32_t)h->ccIdsHost.size();
+    }
+    const int W = KN_NACC + h->nSpecies;
+    int *dOff, *dNb, *dInfo;
+    double *dW, *dA, *dCc;
+    if (dalloc(h, &dOff, off.size()) || dalloc(h, &dNb, nb.size()) || dalloc(h, &dInfo, info.size()) || dalloc(h, &dW, w.size()) ||
+        dalloc(h, &dA, A.size()) || dalloc(h, &dCc, 3 * (size_t)nC) || dalloc(h, &h->dKnAcc, (size_t)nC * W) ||
+        dalloc(h, &h->dKnF[0], (size_t)nC * KN_NF) || dalloc(h, &h->dKnF[1], (size_t)nC * KN_NF) || dalloc(h, &h->dKnK[0], (size_t)nC * 4) ||
+        dalloc(h, &h->dKnK[1], (size_t)nC * 4))
+        return 1;
+    h->decompOwned = {dOff, dNb, dInfo, dW, dA, dCc, h->dKnAcc, h->dKnF[0], h->dKnF[1], h->dKnK[0], h->dKnK[1]};
+    if (upload(h, dOff, off.data(), off.size()) || upload(h, dNb, nb.data(), nb.size()) || upload(h, dInfo, info.data(), info.size()) ||
+        upload(h, dW, w.data(), w.size()) || upload(h, dA, A.data(), A.size()) || upload(h, dCc, h->ccHost.data(), 3 * (size_t)nC))
+        return 1;
+    CU(cudaMemsetAsync(h->dKnAcc, 0, sizeof(double) * (size_t)nC * W, h->stream));
+    CU(cudaMemsetAsync(h->dKnK[0], 0, sizeof(double) * (size_t)nC * 4, h->stream));
+    CU(cudaMemsetAsync(h->dKnK[1], 0, sizeof(double) * (size_t)nC * 4, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->dgeom.nCells = nC; h->dgeom.off = dOff; h->dgeom.nb = dNb; h->dgeom.info = dInfo; h->dgeom.w = dW; h->dgeom.A = dA;
+    h->dgeom.bfS = h->dBfS; h->dgeom.cc = dCc; h->dgeom.vol = h->dVol;
+    h->dec = *d;
+    h->decompOn = true;
+    h->decTimeSteps = 0;
+    h->decTimeAv = 0;
+    h->knCur = 0;
+    return 0;
+}
+
+int ugf_decompose(ugf_handle* h) {
+    if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
+    if (!h->decompOn) return fail(h, "no decomposition model set");
+    return do_decompose(h);
+}
+
+int ugf_download_decomposition(ugf_handle* h, int32_t* id, double* kn) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (!h->decompOn) return fail(h, "no decomposition model set");
+    if (id) CU(cudaMemcpyAsync(id, h->dCollId, sizeof(int32_t) * (size_t)h->nCells, cudaMemcpyDeviceToHost, h->stream));
+    if (kn) CU(cudaMemcpyAsync(kn, h->dKnK[h->knCur], sizeof(double) * (size_t)h->nCells * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int ugf_end_step(ugf_handle* h) {
     if (!h) return 1;
     h->step++;
@@ -1163,6 +1368,7 @@ int ugf_finish_step(ugf_handle* h) {
     if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
     if (bgk_active(h) && run_bgk_kernel(h)) return 1;
     if (do_accumulate(h, fuseAcc)) return 1;
+    if (do_decompose(h)) return 1;
     return ugf_end_step(h);
 }
 
@@ -1190,6 +1396,7 @@ int ugf_step(ugf_handle* h, int32_t nSteps) {
         if (bgk_active(h) && run_bgk_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[6], h->stream));
         if (do_accumulate(h, fuseAcc)) return 1;
+        if (do_decompose(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[7], h->stream));
         h->step++;
     }
