@@ -508,8 +508,7 @@ int do_move(ugf_handle* h, long long begin, bool received) {
             if (streamed) {
 #define UGF_MOVE_STREAM(NF_)                                                                                      \
     do {                                                                                                          \
-        if (h->moveBps == 3) move_stream_kernel<r, mm, NF_, 3><<<grid, MOVE_WARPS * 32, 0, h->stream>>>(prm, a);    \
-        else move_stream_kernel<r, mm, NF_, 4><<<grid, MOVE_WARPS * 32, 0, h->stream>>>(prm, a);                   \
+        move_stream_kernel<r, mm, NF_, 4><<<grid, MOVE_WARPS * 32, 0, h->stream>>>(prm, a);                        \
     } while (0)
                 if (h->moveNF == 6) UGF_MOVE_STREAM(6);
                 else if (h->moveNF == 4) UGF_MOVE_STREAM(4);
@@ -959,7 +958,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     // L1 next to the shared-memory carve-out and raise the achievable memory-level parallelism (profiles/).
     int cellBps = 4, cellCarve = -1;
     if (const char* e = std::getenv("UGF_MOVE_DIRECT")) h->moveDirect = std::atoi(e) != 0;
-    if (const char* e = std::getenv("UGF_MOVE_BPS")) h->moveBps = std::max(3, std::min(4, std::atoi(e)));
+    if (const char* e = std::getenv("UGF_MOVE_BPS")) h->moveBps = std::max(1, std::min(4, std::atoi(e)));
     if (const char* e = std::getenv("UGF_CELL_TASK")) h->cellTask = std::max(1, std::min(CELL_TASK_MAX, std::atoi(e)));
     if (const char* e = std::getenv("UGF_CELL_FLAGS")) h->cellFlags = std::atoi(e);
     if (const char* e = std::getenv("UGF_CELL_BPS")) cellBps = std::max(1, std::atoi(e));

@@ -223,7 +223,7 @@ __device__ __forceinline__ int bgk_count(const DevParams& prm, uint32_t step, in
 struct BgkWarpSmem {
     Macro mac[BGK_CHUNK];
     double u[3][BGK_CAP];
-    double key[BGK_CAP];
+    unsigned long long key[BGK_CAP];  // selection key: the uniform's 53 random bits << 8 | slot in the run's cell-local order
     double E[BGK_CHUNK];
     double pU[BGK_CHUNK][3];
     double fscale[BGK_CHUNK];  // < 0: no rescale
@@ -386,8 +386,10 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                 S.u[0][f] = a.P.ux[b0 + f]; S.u[1][f] = a.P.uy[b0 + f]; S.u[2][f] = a.P.uz[b0 + f];
                 if (MULTI) S.type[f] = a.P.type[b0 + f];
                 if (S.nRel[done + g] > 0) {
+                    // ordering by (u01, index) == ordering by the uniform's 53-bit integer with the index appended
+                    // (u01 = integer * 2^-53 is monotone; f - cb < BGK_CAP = 2^8): one integer compare per pair
                     Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)(c0 + done + g), (uint32_t)(f - S.cb[g]));
-                    S.key[f] = r.u01();
+                    S.key[f] = (r.u53() << 8) | (unsigned long long)(f - S.cb[g]);
                 }
             }
             __syncwarp();
@@ -401,12 +403,9 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                     const int nRel = S.nRel[done + g];
                     if (nRel > 0) {
                         const int cb = S.cb[g], ce = S.cb[g + 1];
-                        const double kj = S.key[f];
+                        const unsigned long long kj = S.key[f];
                         int rank = 0;
-                        for (int i = cb; i < ce; ++i) {
-                            const double ki = S.key[i];
-                            rank += (ki < kj) || (ki == kj && i < f);
-                        }
+                        for (int i = cb; i < ce; ++i) rank += S.key[i] < kj;
                         sel = rank < nRel;
                     }
                 }
