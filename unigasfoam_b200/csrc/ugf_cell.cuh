@@ -599,14 +599,18 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
         const int c0 = chunk * 32;
         const int myCell = c0 + lane;
         const bool valid = myCell < a.nCells;
+        // all per-cell inputs are requested together: one memory round trip before the candidate counts
         const int myBeg = valid ? a.off[myCell] : 0;
         const int myEnd = valid ? a.off[myCell + 1] : 0;
+        const int myModel = valid ? a.collModelId[myCell] : 0;
+        const double sMaxIn = valid ? a.sigmaTcRMax[myCell] : 0.0;
+        const double myVol = valid ? a.vol[myCell] : 1.0;
         const int myN = myEnd - myBeg;
         int myCand = 0;
         double mySMax = 0.0;
-        if (myN > 1 && a.collModelId[myCell] == 1) {
-            mySMax = a.sigmaTcRMax[myCell];
-            myCand = ntc_candidates(prm, a.step, a.sub_cycle, a.dtSub, myCell, myN, mySMax, a.vol[myCell]);
+        if (myN > 1 && myModel == 1) {
+            mySMax = sMaxIn;
+            myCand = ntc_candidates(prm, a.step, a.sub_cycle, a.dtSub, myCell, myN, mySMax, myVol);
         }
         if (!__any_sync(0xffffffffu, myCand > 0)) continue;
         int incl = myCand;  // inclusive prefix of the candidate counts over the 32 cells
