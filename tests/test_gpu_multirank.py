@@ -73,6 +73,63 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_3d(rank, world, port, out):
+    """Config-5 shape: 3-D box of nitrogen with Larsen-Borgnakke collisions, cut in two by mesh.decompose
+    (decomposePar stand-in, processor patches with inherited geometry), NVLink peer-memory transfer on the GPUs,
+    gloo slots for the oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    meta = dist.new_group(backend="gloo")
+    from oracle.oracle_cloud import OracleCloud
+    from unigasfoam_b200 import mesh as ugmesh
+    from unigasfoam_b200.cloud import UniGasCloud
+    from unigasfoam_b200.exchange import PeerExchanger, SlotExchanger, evolve_distributed
+    case = cases.closed_box(n=8, parcels=40000, seed=41, wall="diffuse", binary="LarsenBorgnakkeVariableHardSphere",
+                            species=("N2", cases.NITROGEN), dt_mct=0.5, lambda_per_dx=0.6, Trot=250.0,
+                            rotationalRelaxationCollisionNumber=5.0, electronicRelaxationCollisionNumber=500.0)
+    part = ugmesh.slab_partition(case.mesh, world)
+    sub = ugmesh.decompose(case.mesh, part, world)[rank]
+    g2l = np.full(case.mesh.n_cells, -1)
+    g2l[sub.cell_map] = np.arange(sub.n_cells)
+    sel = part[case.cell] == rank
+    res = {}
+    for name, cls in (("gpu", UniGasCloud), ("oracle", OracleCloud)):
+        kw = dict(device=rank) if name == "gpu" else {}
+        cl = cls(sub, case.uniGasProperties, case.boundariesDict, case.deltaT, parcelCapacity=3 * int(sel.sum()) + 1024, rank=rank, nRanks=world, **kw)
+        cl.setParcels(case.position[sel], case.U[sel], g2l[case.cell[sel]], None, case.ERot[sel])
+        cl.setCellState(sigmaTcRMax=case.sigmaTcRMax)
+        if name == "gpu":
+            ex = PeerExchanger(cl, sub, rank, world, slot_capacity=4000, group=None, meta_group=meta)
+            evolve_distributed(cl, ex, 5, fixed_rounds=3)
+            ex.check_settled()
+        else:
+            ex = SlotExchanger(cl, sub, rank, world, slot_capacity=4000, group=meta, cuda=False)
+            evolve_distributed(cl, ex, 5)
+        res[name] = (cl.parcels(), cl.counters())
+    (pg, cg), (pr, cr) = res["gpu"], res["oracle"]
+    same = np.array_equal(pg["cell"], pr["cell"])
+    closeU = (np.abs(pg["U"] - pr["U"]) <= 1e-9 * np.abs(pr["U"]).max()).all(1).mean() if same else 0.0
+    closeE = (np.abs(pg["ERot"] - pr["ERot"]) <= 1e-9 * np.abs(pr["ERot"]).max()).mean() if same else 0.0
+    ok = bool(same and closeU > 0.995 and closeE > 0.995 and cg["migrated"] > 0 and abs(cg["collisions"] - cr["collisions"]) <= 2 and cg["stuck"] == 0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ok, dict(same=same, closeU=float(closeU), closeE=float(closeE), n=len(pg["cell"]), cg=cg["collisions"], cr=cr["collisions"])), group=meta)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier(group=meta)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_decomposed_3d_nitrogen_lb_matches_oracle(tmp_path, GpuCloud):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "res3d.pt")
+    mp.spawn(_worker_3d, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert all(ok for ok, _ in res), res
+
+
 @pytest.mark.timeout(600)
 def test_two_gpu_migration_matches_oracle(tmp_path, GpuCloud):
     if torch.cuda.device_count() < 2:
