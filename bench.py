@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--ppc", type=int, default=20)
     ap.add_argument("--case", default="couette", choices=["couette", "box", "cylinder"], help="box = config 1 style dense-collision case (tuning only)")
     ap.add_argument("--collision", default="dsmc", choices=["dsmc", "bgk", "hybrid"], help="box case only (tuning)")
+    ap.add_argument("--gas", default="argon", choices=["argon", "n2lb"], help="box case: n2lb = nitrogen with Larsen-Borgnakke (config 5 per-GPU shape)")
     ap.add_argument("--box-n", type=int, default=64)
     ap.add_argument("--box-parcels", type=int, default=8_000_000)
     ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the bounded cpu_baseline sample")
@@ -100,6 +101,9 @@ def build_case(args, rank, world):
         kw = {}
         if args.collision != "dsmc":
             kw = dict(mode=args.collision, bgk="unifiedStochasticParticleSBGK", theta=0.1)
+        if args.gas == "n2lb":
+            kw.update(binary="LarsenBorgnakkeVariableHardSphere", species=("N2", cases.NITROGEN), Trot=300.0,
+                      rotationalRelaxationCollisionNumber=5.0, electronicRelaxationCollisionNumber=500.0)
         c = cases.closed_box(n=args.box_n, parcels=args.box_parcels, wall="diffuse", **kw)
         if args.collision == "hybrid":
             import numpy as np
@@ -114,7 +118,7 @@ def workload_name(args):
     if args.case == "cylinder":
         return "cylinder2d_mach10_argon_500x1000cells_20ppc_inflow_outflow_dsmc_ntc_vhs"
     if args.case == "box":
-        return f"closedbox3d_argon_{args.box_n}^3cells_{args.box_parcels}parcels_{args.collision}_dt0.2mct"
+        return f"closedbox3d_{args.gas}_{args.box_n}^3cells_{args.box_parcels}parcels_{args.collision}_dt0.2mct"
     return f"couette2d_argon_kn0.1_{args.nx}x{args.ny}cells_{args.ppc}ppc_dsmc_ntc_vhs"
 
 

@@ -1610,8 +1610,10 @@ int ugf_counters_get(ugf_handle* h, ugf_counters* out) {
         CU(cudaMemcpyAsync(tot, h->dTot, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaMemcpyAsync(&c, h->dCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    int devErr = 0;
+    CU(cudaMemcpyAsync(&devErr, h->dErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));  // same round trip as the counters
     CU(cudaStreamSynchronize(h->stream));
-    if (check_device_error(h)) return 1;
+    if (devErr && check_device_error(h)) return 1;
     out->step = h->step;
     out->nParcels = (int64_t)tot[5];
     out->collisionCandidates = (int64_t)c.cand;

@@ -583,13 +583,18 @@ __global__ void __launch_bounds__(256) subcell_index_kernel(const __grid_constan
 constexpr int NTC_THREADS = 256;
 constexpr int NTC_WARPS = NTC_THREADS / 32;
 constexpr int NTC_IDLE = 0x7f7f7f7f;
+constexpr int NTC_MARKS = 1024;  // parcels per 32-cell chunk whose conflict marks live in shared memory (global marks beyond)
 
 template <bool HAS_ROT, bool MULTI, bool SUBCELLS>
 __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ NtcArgs a) {
     __shared__ double sMaxW[NTC_WARPS][32];
+    __shared__ int sMarkW[NTC_WARPS][NTC_MARKS];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     double* const sM = sMaxW[wib];
+    int* const sMark = sMarkW[wib];  // conflict marks of the chunk's parcels (slot = parcel - first parcel of the chunk)
+    for (int j = lane; j < NTC_MARKS; j += 32) sMark[j] = NTC_IDLE;
+    __syncwarp();
     const int warpsTotal = gridDim.x * NTC_WARPS;
     const int nChunks = (a.nCells + 31) / 32;
     unsigned long long wCand = 0;
@@ -621,6 +626,9 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
         }
         const int excl = incl - myCand;
         const int T = __shfl_sync(0xffffffffu, incl, 31);
+        const int chunkBeg = __shfl_sync(0xffffffffu, myBeg, 0);
+        const int chunkEnd = __shfl_sync(0xffffffffu, myEnd, min(31, a.nCells - 1 - c0));
+        const bool marksInSmem = (chunkEnd - chunkBeg) <= NTC_MARKS;
         if (lane == 0) wCand += (unsigned long long)T;
         sM[lane] = mySMax;
         __syncwarp();
@@ -673,11 +681,21 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
             unsigned pending = __ballot_sync(0xffffffffu, act);
             while (pending) {
                 const bool mine = (pending >> lane) & 1u;
-                if (mine) { atomicMin(&a.owner[gP], lane); atomicMin(&a.owner[gQ], lane); }
-                __syncwarp();
-                const bool ready = mine && __ldcg(&a.owner[gP]) == lane && __ldcg(&a.owner[gQ]) == lane;
-                __syncwarp();
-                if (mine) { __stcg(&a.owner[gP], NTC_IDLE); __stcg(&a.owner[gQ], NTC_IDLE); }
+                bool ready;
+                if (marksInSmem) {  // the usual case: the whole chunk fits, no global round trips for the marks
+                    volatile int* mk = sMark;
+                    if (mine) { atomicMin(&sMark[gP - chunkBeg], lane); atomicMin(&sMark[gQ - chunkBeg], lane); }
+                    __syncwarp();
+                    ready = mine && mk[gP - chunkBeg] == lane && mk[gQ - chunkBeg] == lane;
+                    __syncwarp();
+                    if (mine) { mk[gP - chunkBeg] = NTC_IDLE; mk[gQ - chunkBeg] = NTC_IDLE; }
+                } else {
+                    if (mine) { atomicMin(&a.owner[gP], lane); atomicMin(&a.owner[gQ], lane); }
+                    __syncwarp();
+                    ready = mine && __ldcg(&a.owner[gP]) == lane && __ldcg(&a.owner[gQ]) == lane;
+                    __syncwarp();
+                    if (mine) { __stcg(&a.owner[gP], NTC_IDLE); __stcg(&a.owner[gQ], NTC_IDLE); }
+                }
                 if (ready) {
                     const DevSpecies& A = prm.sp[tP];
                     const DevSpecies& B = prm.sp[tQ];
