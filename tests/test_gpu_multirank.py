@@ -120,6 +120,65 @@ def _worker_3d(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_cyl(rank, world, port, out):
+    """Config-3 shape: Mach-10 cylinder O-grid with free-stream inflow, deleting outflow, diffuse wall and symmetry
+    axis, cut along the wake axis by mesh.decompose: insertion on one rank, migration across the cut, outflow on the
+    other, every step."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    meta = dist.new_group(backend="gloo")
+    from oracle.oracle_cloud import OracleCloud
+    from unigasfoam_b200 import mesh as ugmesh
+    from unigasfoam_b200.cloud import UniGasCloud
+    from unigasfoam_b200.exchange import PeerExchanger, SlotExchanger, evolve_distributed
+    case = cases.cylinder(nr=16, ntheta=32, ppc=25)
+    part = ugmesh.slab_partition(case.mesh, world, axis=1)
+    sub = ugmesh.decompose(case.mesh, part, world)[rank]
+    g2l = np.full(case.mesh.n_cells, -1)
+    g2l[sub.cell_map] = np.arange(sub.n_cells)
+    sel = part[case.cell] == rank
+    res = {}
+    for name, cls in (("gpu", UniGasCloud), ("oracle", OracleCloud)):
+        kw = dict(device=rank) if name == "gpu" else {}
+        cl = cls(sub, case.uniGasProperties, case.boundariesDict, case.deltaT, parcelCapacity=4 * int(sel.sum()) + 4096, rank=rank, nRanks=world, **kw)
+        cl.setParcels(case.position[sel], case.U[sel], g2l[case.cell[sel]])
+        cl.setCellState(sigmaTcRMax=case.sigmaTcRMax)
+        if name == "gpu":
+            ex = PeerExchanger(cl, sub, rank, world, slot_capacity=4000, group=None, meta_group=meta)
+            evolve_distributed(cl, ex, 8, inflow=True, fixed_rounds=3)
+            ex.check_settled()
+        else:
+            ex = SlotExchanger(cl, sub, rank, world, slot_capacity=4000, group=meta, cuda=False)
+            evolve_distributed(cl, ex, 8, inflow=True)
+        res[name] = (cl.parcels(), cl.counters())
+    (pg, cg), (pr, cr) = res["gpu"], res["oracle"]
+    same = len(pg["cell"]) == len(pr["cell"]) and np.array_equal(pg["cell"], pr["cell"])
+    closeU = (np.abs(pg["U"] - pr["U"]) <= 1e-9 * np.abs(pr["U"]).max()).all(1).mean() if same else 0.0
+    closeX = (np.abs(pg["position"] - pr["position"]) <= 1e-12 * np.abs(pr["position"]).max()).all(1).mean() if same else 0.0
+    tot = torch.tensor([cg["inserted"], cg["deleted"], cg["migrated"]])
+    dist.all_reduce(tot, group=meta)
+    ok = bool(same and closeU > 0.99 and closeX > 0.99 and cg["stuck"] == 0 and cg["inserted"] == cr["inserted"] and cg["deleted"] == cr["deleted"]
+              and abs(cg["collisions"] - cr["collisions"]) <= 2 and (tot > 0).all())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ok, dict(same=bool(same), closeU=float(closeU), closeX=float(closeX), n=(len(pg["cell"]), len(pr["cell"])),
+                                               ins=(cg["inserted"], cr["inserted"]), dele=(cg["deleted"], cr["deleted"]), tot=tot.tolist())), group=meta)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier(group=meta)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_decomposed_cylinder_with_inflow_matches_oracle(tmp_path, GpuCloud):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "rescyl.pt")
+    mp.spawn(_worker_cyl, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert all(ok for ok, _ in res), res
+
+
 @pytest.mark.timeout(600)
 def test_two_gpu_decomposed_3d_nitrogen_lb_matches_oracle(tmp_path, GpuCloud):
     if torch.cuda.device_count() < 2:
