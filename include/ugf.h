@@ -225,8 +225,10 @@ typedef struct ugf_decomposition {
 /* Number of fp64 output fields per cell from ugf_download_fields
  * (U/macroscopicProperties/derived/volumetric/uniGasVolFields/uniGasVolFields.C:839-1254):
  * 0 uniGasRhoNMean, 1 rhoN, 2 rhoM, 3-5 UMean, 6 translationalT, 7 rotationalT,
- * 8 overallT, 9 p, 10 Ma, 11 densityError (0 if undefined). */
-#define UGF_NFIELD 12
+ * 8 overallT, 9 p, 10 Ma, 11 densityError (0 if undefined); measureMeanFreePath (:1124-1232, Bird eqs 4.76, 4.77,
+ * 4.74, 1.38; Tref = collisionProperties.Tref): 12 MFP, 13 dxMFP (largest sub-cell dimension / MFP), 14 MCR, 15 MCT,
+ * 16 dtMCT (deltaT / MCT); measureErrors (:1234-1254): 17 velocityError, 18 temperatureError. */
+#define UGF_NFIELD 19
 /* per wall face: 0 rhoN, 1 rhoM, 2-4 UMean, 5 translationalT, 6 q (surfaceHeatTransfer),
  * 7-9 fD, 10 p, 11 tau. */
 #define UGF_NWALLFIELD 12

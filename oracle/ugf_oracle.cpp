@@ -54,6 +54,7 @@ constexpr double kB = 1.38065e-23;         // physicoChemical::k
 constexpr double NA = 6.02214e+23;         // physicoChemical::NA
 constexpr double PI = 3.14159265358979323846;
 constexpr double TWO_PI = 6.28318530717958647692;
+constexpr double GREAT = 1e15;
 constexpr double VSMALL = 1e-300;
 constexpr double SMALL = 1e-15;
 
@@ -173,6 +174,7 @@ struct ugfo_handle {
     std::vector<double> bm;    // [nBFaces][UGF_NBM]
     // time-averaged accumulators (uniGasVolFields)
     std::vector<double> acc;   // [nCells][NACC]
+    std::vector<double> accS;  // [nCells][nSpecies] nParcelsXnParticle per species (mean free path fields)
     std::vector<double> bacc;  // [nBFaces][UGF_NBM]
     double timeAvCounter = 0;
     int64_t nAvTimeSteps = 0;
@@ -1368,6 +1370,7 @@ void accumulateFields(ugfo_handle& h) {
                 A[13] += dt * (ms * a[14] * FN);
                 A[14] += dt * (S.rotationalDoF > 0 ? a[0] : 0.0);
                 A[15] += dt * ((5.0 + S.rotationalDoF) * a[0]);
+                h.accS[(size_t)c * nS + s] += dt * (a[1] * FN);
             }
         }
         for (size_t i = 0; i < h.bm.size(); ++i) h.bacc[i] += dt * h.bm[i];
@@ -1414,8 +1417,46 @@ void deriveFields(ugfo_handle& h, double* cellF, double* wallF) {
                     F[10] = std::sqrt(dot3(&F[3], &F[3])) / a;
                 }
             }
-            if (F[0] > VSMALL && F[10] > VSMALL && gamma > VSMALL && Cv_p > VSMALL)
+            if (F[0] > VSMALL && F[10] > VSMALL && gamma > VSMALL && Cv_p > VSMALL) {
                 F[11] = 1.0 / std::sqrt(F[0] * (double)h.nAvTimeSteps);  // densityError (:1248)
+                F[17] = (1.0 / std::sqrt(F[0] * (double)h.nAvTimeSteps)) * (1.0 / (F[10] * std::sqrt(gamma)));  // velocityError (:1249)
+                F[18] = (1.0 / std::sqrt(F[0] * (double)h.nAvTimeSteps)) * std::sqrt(kB / Cv_p);               // temperatureError (:1250)
+            }
+            // mean free path / collision rate fields (:1124-1232)
+            {
+                const int nS = h.nSpecies;
+                const double* aS = &h.accS[(size_t)c * nS];
+                double MFP = 0, MCR = 0;
+                for (int i = 0; i < nS; ++i) {
+                    double mfpI = 0, mcrI = 0;
+                    for (int q = 0; q < nS; ++q) {
+                        const double dPQ = 0.5 * (h.sp[i].d + h.sp[q].d), omegaPQ = 0.5 * (h.sp[i].omega + h.sp[q].omega);
+                        const double massRatio = h.sp[i].mass / h.sp[q].mass;
+                        if (aS[q] > VSMALL && F[6] > VSMALL) {
+                            const double nDensQ = aS[q] / (V * t);
+                            const double reducedMass = h.sp[i].mass * h.sp[q].mass / (h.sp[i].mass + h.sp[q].mass);
+                            mfpI += PI * dPQ * dPQ * nDensQ * std::pow(h.cfg.Tref / F[6], omegaPQ - 0.5) * std::sqrt(1.0 + massRatio);
+                            mcrI += 2.0 * std::sqrt(PI) * dPQ * dPQ * nDensQ * std::pow(F[6] / h.cfg.Tref, 1.0 - omegaPQ) * std::sqrt(2.0 * kB * h.cfg.Tref / reducedMass);
+                        }
+                    }
+                    if (mfpI > VSMALL) mfpI = 1.0 / mfpI;
+                    if (F[1] > VSMALL) {
+                        const double nDensP = aS[i] / (V * t);
+                        MFP += mfpI * nDensP / F[1];
+                        MCR += mcrI * nDensP / F[1];
+                    }
+                }
+                if (MFP < VSMALL) MFP = GREAT;
+                F[12] = MFP;
+                F[14] = MCR;
+                if (MCR > VSMALL) { F[15] = 1.0 / MCR; F[16] = h.cfg.deltaT / F[15]; } else { F[15] = GREAT; F[16] = GREAT; }
+                double largest = 0.0;
+                for (int d = 0; d < 3; ++d) {
+                    const double dim = (h.bbMax[3 * (size_t)c + d] - h.bbMin[3 * (size_t)c + d]) / h.subLevels[3 * (size_t)c + d];
+                    if (h.cfg.solutionD[d] && largest < dim) largest = dim;
+                }
+                F[13] = largest / MFP;  // MFP > VSMALL always holds here (GREAT otherwise)
+            }
         }
     }
     if (wallF) {
@@ -1545,6 +1586,7 @@ int ugfo_set_mesh(ugfo_handle* h, const ugf_mesh* m) {
     h->bm.assign((size_t)h->nBFaces * UGF_NBM, 0.0);
     h->bacc.assign((size_t)h->nBFaces * UGF_NBM, 0.0);
     h->acc.assign((size_t)h->nCells * NACC, 0.0);
+    h->accS.assign((size_t)h->nCells * h->nSpecies, 0.0);
     h->packBuf.resize(h->nPatches);
     return 0;
 }
@@ -1866,6 +1908,7 @@ int ugfo_download_fields(ugfo_handle* h, double* cellF, double* wallF, int32_t r
     deriveFields(*h, cellF, wallF);
     if (reset) {
         std::fill(h->acc.begin(), h->acc.end(), 0.0);
+        std::fill(h->accS.begin(), h->accS.end(), 0.0);
         std::fill(h->bacc.begin(), h->bacc.end(), 0.0);
         h->timeAvCounter = 0; h->nAvTimeSteps = 0;
     }

@@ -437,3 +437,31 @@ def test_local_knudsen_decomposition_matches_oracle(GpuCloud, OracleCloud):
     cg, cr = g.counters(), r.counters()
     assert cg["bgkRelaxations"] == cr["bgkRelaxations"] > 0 and abs(cg["collisions"] - cr["collisions"]) <= 2
     assert frac_close(g.parcels()["U"], r.parcels()["U"], 1e-7) > 0.99
+
+
+def test_gas_mixture_lockstep_and_fields(GpuCloud, OracleCloud):
+    """typeIdList (Ar N2): the multi-species paths - typeId per parcel, per-species cell sums, cross-species NTC pairs
+    with Larsen-Borgnakke exchange for the nitrogen partner only, diffuse walls, per-species accumulators of the
+    mean-free-path fields - in lockstep with the oracle."""
+    case = cases.mixture_box(rotationalRelaxationCollisionNumber=5.0, electronicRelaxationCollisionNumber=500.0)
+    g, r = both(case, GpuCloud, OracleCloud)
+    for cl in (g, r):
+        cl.calculateFields()
+    mg, mr = g.cellMoments(), r.cellMoments()
+    assert mg.shape == mr.shape == (case.mesh.n_cells, 2, 32)
+    for k in range(32):
+        assert np.abs(mg[..., k] - mr[..., k]).max() <= 1e-11 * max(np.abs(mr[..., k]).max(), 1e-300), k
+    for cl in (g, r):
+        cl.evolve(6)
+    pg, pr = g.parcels(), r.parcels()
+    cg, cr = g.counters(), r.counters()
+    assert cg["collisionCandidates"] == cr["collisionCandidates"] > 1000 and abs(cg["collisions"] - cr["collisions"]) <= 2
+    assert cg["wallHits"] == cr["wallHits"] > 500
+    assert np.array_equal(pg["cell"], pr["cell"]) and np.array_equal(pg["typeId"], pr["typeId"])
+    assert set(np.unique(pg["typeId"])) == {0, 1}
+    assert frac_close(pg["U"], pr["U"]) > 0.995
+    assert frac_close(pg["ERot"][:, None], pr["ERot"][:, None]) > 0.995
+    assert (pg["ERot"][pg["typeId"] == 0] == 0).all()  # argon carries no rotational energy
+    fg, fr = g.fields(), r.fields()
+    for name in ("rhoN", "rhoM", "translationalT", "rotationalT", "overallT", "p", "MFP", "MCR", "dtMCT", "dxMFP", "densityError", "temperatureError"):
+        np.testing.assert_allclose(fg[name], fr[name], rtol=1e-6, err_msg=name)

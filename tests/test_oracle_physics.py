@@ -339,3 +339,24 @@ def test_local_knudsen_smoothing_and_blending(OracleCloud):
     assert (inst > 0).all() and np.isfinite(inst).all()
     # the fields start from zero: K_1 = 0.5 K_inst,1 and K_2 = 0.5 K_inst,2 + 0.25 K_inst,1, i.e. K_2 / K_1 ~ 1.5
     assert abs(np.median(k2 / k1) - 1.5) < 0.3
+
+
+def test_mean_free_path_fields_match_kinetic_theory(OracleCloud):
+    """measureMeanFreePath fields (uniGasVolFields.C:1124-1232) of a uniform gas at rest: MFP = VHS mean free path
+    (Bird 4.65), MCR = equilibrium collision rate (Bird 4.64), dtMCT = deltaT x MCR, dxMFP = cell size / MFP."""
+    case = cases.closed_box(n=5, parcels=60000, seed=33, dt_mct=0.3, lambda_per_dx=2.0, binary="noDSMCCollision")
+    cl = case.make_cloud(OracleCloud)
+    cl.evolve(10)
+    f = cl.fields()
+    lam = case.meta["lam"]
+    nu = cases.vhs_collision_rate(case.meta["n"], case.meta["T0"], case.meta["species"], case.meta["Tref"])
+    assert abs(f["MFP"].mean() - lam) < 0.02 * lam
+    assert abs(f["MCR"].mean() - nu) < 0.02 * nu
+    assert abs(f["dtMCT"].mean() - 0.3) < 0.02 * 0.3
+    assert abs(f["dxMFP"].mean() - 0.5) < 0.02 * 0.5
+    np.testing.assert_allclose(f["MCT"], 1.0 / f["MCR"], rtol=1e-12)
+    # statistical error estimates (:1234-1254): 1 / sqrt(N per cell x samples), velocity error scaled by 1 / (Ma sqrt(gamma))
+    nsamp = f["uniGasRhoNMean"] * 10
+    np.testing.assert_allclose(f["densityError"], 1.0 / np.sqrt(nsamp), rtol=1e-12)
+    np.testing.assert_allclose(f["velocityError"], f["densityError"] / (f["Ma"] * math.sqrt(5.0 / 3.0)), rtol=1e-9)
+    cl.close()

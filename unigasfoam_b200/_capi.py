@@ -14,7 +14,7 @@ UGF_MAX_ELEC_LEVELS = 16
 UGF_NMOM = 32
 UGF_NBM = 16
 UGF_NPHASE = 7
-UGF_NFIELD = 12
+UGF_NFIELD = 19
 UGF_NWALLFIELD = 12
 UGF_MIGRATE_STRIDE = 10
 

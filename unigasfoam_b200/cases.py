@@ -164,6 +164,38 @@ def closed_box(n=32, parcels=1_000_000, wall="specular", T0=300.0, number_densit
                 meta=dict(n=number_density, T0=T0, lam=lam, L=L, Tref=Tref, species=sp))
 
 
+def mixture_box(n=6, parcels=20000, fractions=(("Ar", None, 0.6), ("N2", None, 0.4)), T0=300.0, number_density=1e20, Tref=273.0,
+                binary="LarsenBorgnakkeVariableHardSphere", mode="dsmc", bgk="noBGKCollision", wall="diffuse", seed=5, dt_mct=0.5,
+                lambda_per_dx=1.0, Trot=None, **cp):
+    """Closed 3-D box holding a gas mixture (typeIdList with several species: the multi-species code paths -
+    typeId per parcel, per-species cell sums, cross-species collision pairs)."""
+    table = {"Ar": ARGON_GUIDE, "N2": NITROGEN}
+    names = [f[0] for f in fractions]
+    sps = {f[0]: (f[1] or table[f[0]]) for f in fractions}
+    dens = {f[0]: number_density * f[2] for f in fractions}
+    sp0 = sps[names[0]]
+    lam = vhs_mean_free_path(number_density, T0, sp0, Tref)
+    L = n * lam / lambda_per_dx
+    m = _mesh.box_mesh(n, n, n, L, L, L)
+    m.meta_axis_aligned = True
+    nParticle = number_density * L ** 3 / parcels
+    rng = np.random.default_rng(seed)
+    pos, vel, cel, tid, erot = mesh_fill(m, sps, names, dens, T0, (0.0, 0.0, 0.0), nParticle, rng, Trot=Trot)
+    dt = dt_mct / vhs_collision_rate(number_density, T0, sp0, Tref)
+    if wall == "specular":
+        model = lambda p: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasSpecularWallPatch"}
+    else:
+        model = lambda p: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasDiffuseWallPatch",
+                           "uniGasDiffuseWallPatchProperties": {"temperature": T0, "velocity": [0, 0, 0]}}
+    bd = {"uniGasPatchBoundaries": [model(p.name) for p in m.patches]}
+    props = _props(names[0], sp0, nParticle, mode, binary, bgk, Tref, **cp)
+    props["typeIdList"] = names
+    props["moleculeProperties"] = sps
+    sig0 = math.pi * sp0["diameter"] ** 2 * most_probable_speed(T0, sp0["mass"])
+    return Case("mixture_box", m, props, bd, dt, pos, vel, cel, tid, erot, sig0,
+                meta=dict(n=number_density, T0=T0, lam=lam, L=L, Tref=Tref, species=sps, fractions=dens))
+
+
 def couette(nx=1000, ny=500, ppc=20, Kn=0.1, Tw=273.0, Uw=150.0, number_density=1e20, species=("Ar", ARGON_GUIDE),
             Tref=273.0, courant=0.5, seed=2, rank=0, n_ranks=1, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", **cp):
     """Config 2: 2-D Couette flow, x cyclic, y walls diffuse at Tw moving at -+Uw, z empty; H = lambda/Kn.

@@ -423,6 +423,8 @@ class UniGasCloud:
             "uniGasRhoNMean": cf[:, 0], "rhoN": cf[:, 1], "rhoM": cf[:, 2], "UMean": cf[:, 3:6],
             "translationalT": cf[:, 6], "rotationalT": cf[:, 7], "overallT": cf[:, 8], "p": cf[:, 9],
             "Ma": cf[:, 10], "densityError": cf[:, 11],
+            "MFP": cf[:, 12], "dxMFP": cf[:, 13], "MCR": cf[:, 14], "MCT": cf[:, 15], "dtMCT": cf[:, 16],
+            "velocityError": cf[:, 17], "temperatureError": cf[:, 18],
             "wall_rhoN": wf[:, 0], "wall_rhoM": wf[:, 1], "wall_UMean": wf[:, 2:5], "wall_translationalT": wf[:, 5],
             "surfaceHeatTransfer": wf[:, 6], "fD": wf[:, 7:10], "wall_p": wf[:, 10], "surfaceShearStress": wf[:, 11],
         }

@@ -117,6 +117,7 @@ struct ugf_handle {
     bool slotRound = false;         // received parcels of this round came through the slot path
     bool nExact = true;             // nUpper is the exact array length (needed by the exact-count unpack)
     MigSlots migSlots{};
+    double* dAccS = nullptr;  // multi-species: per-species nParcelsXnParticle accumulators
     double* dMom = nullptr; double* dAcc = nullptr; double* dBm = nullptr; double* dBacc = nullptr;
     double* dSigma = nullptr; int* dCollId = nullptr; double* dMaxProb = nullptr; double* dQPrev = nullptr; double* dSPrev = nullptr;
     double* dKeyScratch = nullptr;
@@ -359,6 +360,7 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
     a.writeMom = keepMoments ? 1 : 0;
     a.mom = h->dMom;
     a.acc = h->dAcc;
+    a.accS = h->dAccS;
     a.accDt = (accumulate && doSample) ? h->cfg.deltaT : 0.0;
     a.taskCounter = h->dTask;
     // a task should fill the staging buffer once: cells per task from the mean occupancy (UGF_CELL_TASK overrides)
@@ -544,7 +546,7 @@ int do_accumulate(ugf_handle* h, bool cellsDone = false) {
         h->timeAvCounter += h->cfg.deltaT;
         accumulate = 1;
         if (!cellsDone) {
-            accumulate_cells_kernel<<<grid_for(h->nCells, 256), 256, 0, h->stream>>>(h->prm, h->nCells, h->dMom, h->dAcc);
+            accumulate_cells_kernel<<<grid_for(h->nCells, 256), 256, 0, h->stream>>>(h->prm, h->nCells, h->dMom, h->dAcc, h->dAccS);
             LAUNCHED();
         }
         h->sampleCounter = 0;
@@ -756,7 +758,7 @@ int ugf_destroy(ugf_handle* h) {
     }
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
-                    h->dMom, h->dAcc, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
+                    h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
                     h->dCnt, h->dErr, h->dTot, h->dTask};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
@@ -912,6 +914,10 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * (size_t)nC, h->stream));
     CU(cudaMemsetAsync(h->dMom, 0, sizeof(double) * (size_t)nC * nS * UGF_NMOM, h->stream));
     CU(cudaMemsetAsync(h->dAcc, 0, sizeof(double) * (size_t)nC * NACC, h->stream));
+    if (h->multi) {
+        if (dalloc(h, &h->dAccS, (size_t)nC * nS)) return 1;
+        CU(cudaMemsetAsync(h->dAccS, 0, sizeof(double) * (size_t)nC * nS, h->stream));
+    }
     CU(cudaMemsetAsync(h->dBm, 0, sizeof(double) * std::max<size_t>((size_t)nB * UGF_NBM, 1), h->stream));
     CU(cudaMemsetAsync(h->dBacc, 0, sizeof(double) * std::max<size_t>((size_t)nB * UGF_NBM, 1), h->stream));
     CU(cudaMemsetAsync(h->dSigma, 0, sizeof(double) * (size_t)nC, h->stream));
@@ -1707,7 +1713,8 @@ int ugf_download_fields(ugf_handle* h, double* cellF, double* wallF, int32_t res
     if (dalloc(h, &tmp, need)) return 1;
     const double t = h->timeAvCounter;
     if (cellF) {
-        derive_cells_kernel<<<grid_for(nC, 256), 256, 0, h->stream>>>(nC, h->dAcc, h->dVol, t, (double)h->nAvTimeSteps, tmp);
+        derive_cells_kernel<<<grid_for(nC, 256), 256, 0, h->stream>>>(h->prm, nC, h->dAcc, h->dAccS, h->dVol, h->dBbMin, h->dBbMax,
+                                                                      h->subLevelsAllOne ? nullptr : h->dSubLevels, t, (double)h->nAvTimeSteps, tmp);
         LAUNCHED();
         CU(cudaMemcpyAsync(cellF, tmp, sizeof(double) * (size_t)nC * UGF_NFIELD, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -1721,6 +1728,7 @@ int ugf_download_fields(ugf_handle* h, double* cellF, double* wallF, int32_t res
     CU(cudaFree(tmp));
     if (reset) {
         CU(cudaMemsetAsync(h->dAcc, 0, sizeof(double) * (size_t)nC * NACC, h->stream));
+        if (h->dAccS) CU(cudaMemsetAsync(h->dAccS, 0, sizeof(double) * (size_t)nC * h->nSpecies, h->stream));
         CU(cudaMemsetAsync(h->dBacc, 0, sizeof(double) * std::max<size_t>((size_t)nB * UGF_NBM, 1), h->stream));
         h->timeAvCounter = 0; h->nAvTimeSteps = 0;
     }

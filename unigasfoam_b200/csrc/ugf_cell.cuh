@@ -43,6 +43,7 @@ struct CellArgs {
     int writeMom;     // 0: the moment blocks of staged cells are not stored (nothing downstream reads them: pure DSMC step)
     double* mom;
     double* acc;      // time-averaged accumulators [nCells][NACC]; updated in the same pass when accDt != 0
+    double* accS;     // multi-species only: nParcelsXnParticle per species [nCells][nSpecies], else null
     double accDt;
     int* taskCounter; // zero at launch: next unclaimed task of taskCells cells
     int taskCells;    // <= CELL_TASK_MAX
@@ -317,6 +318,7 @@ __device__ __noinline__ void stream_giant_cell(const DevParams& prm, const CellA
         for (int s = 0; s < prm.nSpecies; ++s) {
             const double* mm = a.mom + ((size_t)cell * prm.nSpecies + s) * UGF_NMOM;
             add += acc_term(prm, s, lane, mm[0], mm[2], mm[3], mm[4], mm[14], mm[18]);
+            if (MULTI && a.accS && lane == 0) a.accS[(size_t)cell * prm.nSpecies + s] += a.accDt * (mm[1] * prm.nParticle);
         }
         a.acc[(size_t)cell * NACC + lane] += a.accDt * add;
     }
@@ -467,6 +469,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                         mrow[28] = 0.0;
                     }
                     if (doAcc) {  // uniGasVolFields accumulation fused in: slot 4t + q
+                        if (MULTI && a.accS && cellValid && q == 0) a.accS[(size_t)(c0 + ci) * nS + s] += a.accDt * (cnt * prm.nParticle);
                         ac0 += a.accDt * acc_term(prm, s, q, cnt, su, sv, sw, scc, se);
                         ac1 += a.accDt * acc_term(prm, s, q + 4, cnt, su, sv, sw, scc, se);
                         ac2 += a.accDt * acc_term(prm, s, q + 8, cnt, su, sv, sw, scc, se);

@@ -21,6 +21,7 @@ constexpr double PI = 3.14159265358979323846;
 constexpr double TWO_PI = 6.28318530717958647692;
 constexpr double VSMALL = 1e-300;
 constexpr double SMALL = 1e-15;
+constexpr double GREAT = 1e15;
 
 constexpr int NACC = 16;             // time-averaged accumulators per cell
 constexpr int MAX_TRACK_ITERS = 4096;

@@ -9,8 +9,10 @@
 
 namespace ugf {
 
+// accS (multi-species only, else null): nParcelsXnParticle per species for the mean-free-path fields; with one
+// species it equals accumulator slot 8.
 __global__ void __launch_bounds__(256) accumulate_cells_kernel(const __grid_constant__ DevParams prm, int nCells,
-                                                               const double* __restrict__ mom, double* __restrict__ acc) {
+                                                               const double* __restrict__ mom, double* __restrict__ acc, double* __restrict__ accS) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const double dt = prm.deltaT, FN = prm.nParticle;
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(256) accumulate_cells_kernel(const __grid_cons
         A[13] += dt * (ms * a[14] * FN);
         A[14] += dt * (S.rotDoF > 0 ? a0 : 0.0);
         A[15] += dt * ((5.0 + S.rotDoF) * a0);
+        if (accS) accS[(size_t)c * prm.nSpecies + s] += dt * (a1 * FN);
     }
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[(size_t)c * NACC + k] = A[k];
@@ -48,8 +51,10 @@ __global__ void __launch_bounds__(256) accumulate_walls_kernel(double dt, int ac
     if (v != 0.0) bm[i] = 0.0;
 }
 
-__global__ void __launch_bounds__(256) derive_cells_kernel(int nCells, const double* __restrict__ acc, const double* __restrict__ vol,
-                                                           double t, double nAvSteps, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) derive_cells_kernel(const __grid_constant__ DevParams prm, int nCells, const double* __restrict__ acc,
+                                                           const double* __restrict__ accS, const double* __restrict__ vol,
+                                                           const double* __restrict__ bbMin, const double* __restrict__ bbMax,
+                                                           const int* __restrict__ subLevels, double t, double nAvSteps, double* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const double* A = acc + (size_t)c * NACC;
@@ -85,7 +90,46 @@ __global__ void __launch_bounds__(256) derive_cells_kernel(int nCells, const dou
             F[10] = sqrt(F[3] * F[3] + F[4] * F[4] + F[5] * F[5]) / cs;
         }
     }
-    if (F[0] > VSMALL && F[10] > VSMALL && gamma > VSMALL && Cv_p > VSMALL) F[11] = 1.0 / sqrt(F[0] * nAvSteps);
+    if (F[0] > VSMALL && F[10] > VSMALL && gamma > VSMALL && Cv_p > VSMALL) {
+        F[11] = 1.0 / sqrt(F[0] * nAvSteps);                                         // densityError (:1248)
+        F[17] = (1.0 / sqrt(F[0] * nAvSteps)) * (1.0 / (F[10] * sqrt(gamma)));       // velocityError
+        F[18] = (1.0 / sqrt(F[0] * nAvSteps)) * sqrt(kB / Cv_p);                     // temperatureError
+    }
+    // mean free path / collision rate fields (uniGasVolFields.C:1124-1232)
+    {
+        const int nS = prm.nSpecies;
+        double MFP = 0, MCR = 0;
+        for (int i = 0; i < nS; ++i) {
+            double mfpI = 0, mcrI = 0;
+            for (int q = 0; q < nS; ++q) {
+                const double aq = accS ? accS[(size_t)c * nS + q] : A[8];
+                const double dPQ = 0.5 * (prm.sp[i].d + prm.sp[q].d), omegaPQ = 0.5 * (prm.sp[i].omega + prm.sp[q].omega);
+                const double massRatio = prm.sp[i].mass / prm.sp[q].mass;
+                if (aq > VSMALL && F[6] > VSMALL) {
+                    const double nDensQ = aq / (V * t);
+                    const double reducedMass = prm.sp[i].mass * prm.sp[q].mass / (prm.sp[i].mass + prm.sp[q].mass);
+                    mfpI += PI * dPQ * dPQ * nDensQ * pow(prm.Tref / F[6], omegaPQ - 0.5) * sqrt(1.0 + massRatio);
+                    mcrI += 2.0 * sqrt(PI) * dPQ * dPQ * nDensQ * pow(F[6] / prm.Tref, 1.0 - omegaPQ) * sqrt(2.0 * kB * prm.Tref / reducedMass);
+                }
+            }
+            if (mfpI > VSMALL) mfpI = 1.0 / mfpI;
+            if (F[1] > VSMALL) {
+                const double nDensP = (accS ? accS[(size_t)c * nS + i] : A[8]) / (V * t);
+                MFP += mfpI * nDensP / F[1];
+                MCR += mcrI * nDensP / F[1];
+            }
+        }
+        if (MFP < VSMALL) MFP = GREAT;
+        F[12] = MFP;
+        F[14] = MCR;
+        if (MCR > VSMALL) { F[15] = 1.0 / MCR; F[16] = prm.deltaT / F[15]; } else { F[15] = GREAT; F[16] = GREAT; }
+        double largest = 0.0;
+        for (int d = 0; d < 3; ++d) {
+            const double dim = (bbMax[3 * (size_t)c + d] - bbMin[3 * (size_t)c + d]) / (subLevels ? subLevels[3 * (size_t)c + d] : 1);
+            if (prm.solD[d] && largest < dim) largest = dim;
+        }
+        F[13] = largest / MFP;
+    }
 #pragma unroll
     for (int k = 0; k < UGF_NFIELD; ++k) out[(size_t)c * UGF_NFIELD + k] = F[k];
 }
