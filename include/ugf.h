@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UGF_ABI_VERSION 1
+#define UGF_ABI_VERSION 2
 #define UGF_MAX_SPECIES 8
 #define UGF_MAX_VIB_MODES 4
 #define UGF_MAX_ELEC_LEVELS 16
@@ -172,7 +172,11 @@ typedef struct ugf_inflow {
 } ugf_inflow;
 
 /* Parcels as host SoA.  Mandatory: x,y,z,Ux,Uy,Uz,cell.  Optional (NULL = default):
- * typeId (0), ERot (0), stepFraction/newParcel (0).  (U/parcels/uniGasParcel.H:217-239) */
+ * typeId (0), ERot (0), stepFraction/newParcel (0).  (U/parcels/uniGasParcel.H:217-239)
+ * cellWeight (the parcel's CWF, lagrangian/uniGas/cellWeight on disk) is implicit on the device: a parcel carries the
+ * cellWeightFactor of the cell it was in at the last weighting pass, which is what the reference guarantees after
+ * uniGasCloud::weighting() (U/clouds/uniGasCloud.C:203-220, 1353-1424).  On upload it is optional and must equal
+ * cellWeightFactor[cell] (checked); on download it is filled in when a pointer is given. */
 typedef struct ugf_parcels {
     int64_t n;
     double* x; double* y; double* z;
@@ -181,6 +185,7 @@ typedef struct ugf_parcels {
     int32_t* typeId;
     double* ERot;
     int32_t* newParcel;
+    double* cellWeight;
 } ugf_parcels;
 
 /* Per-step log quantities (noTimeCounter.C:318-342, …USP.C:976-992, uniGasCloud.C:878-920). */
@@ -198,6 +203,8 @@ typedef struct ugf_counters {
     double linearKineticEnergy;  /* sum 0.5 m |U|^2 over parcels (x F_N = info()) */
     double rotationalEnergy;     /* sum ERot */
     double momentum[3];          /* sum m U */
+    int64_t cloned;              /* parcels added by cellWeighting(), last step (U/clouds/uniGasCloud.C:1366-1407) */
+    int64_t weightDeleted;       /* parcels removed by cellWeighting(), last step (:1409-1420) */
 } ugf_counters;
 
 /* system/hybridDecompositionDict: uniGasHybridDecomposition (U/hybridDecomposition/basic/uniGasHybridDecomposition.C:48-76)
@@ -264,8 +271,16 @@ int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* inflow);
 /* addNewParcel over a whole initial configuration (U/clouds/uniGasCloud.C:260-290). Replaces the cloud. */
 int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p);
 /* Cell state carried between steps (U/clouds/uniGasCloud.H:189-201): sigmaTcRMax [nCells],
- * collModelId [nCells] (0 = bgk, 1 = dsmc), subCellLevels [nCells*3], cellWeightFactor [nCells] (must be 1).
- * NULL keeps the current value. */
+ * collModelId [nCells] (0 = bgk, 1 = dsmc), subCellLevels [nCells*3], cellWeightFactor [nCells] (> 0; all 1 until
+ * uploaded).  NULL keeps the current value.
+ * Uploading cellWeightFactor switches cell weighting on (cellWeightedSimulation, U/clouds/uniGasCloud.C:417): every
+ * step the move is followed by cellWeighting() (:1353-1424) - a parcel that arrives in a cell with a smaller factor
+ * is cloned, one that arrives in a cell with a larger factor survives with probability old/new - and the factor
+ * scales F_N in the NTC candidate count (noTimeCounter.C:168-184), the weighted cell sums (cellMeasurements.C:463-467),
+ * the BGK macroscopic state, the inflow count (uniGasGeneralBoundary.C:154-165), the wall heat flux / force
+ * (uniGasPatchBoundary.C:292-299) and the wall fields (uniGasVolFields.C:1276-1278).  Upload it before the parcels.
+ * A factor changed while parcels exist (uniGasDynamicAdapter.C:660-677) is applied by the next step's weighting pass
+ * (old factor of the parcel's previous cell / new factor of its current cell).  Single rank for now. */
 int ugf_upload_cell_state(ugf_handle* h, const double* sigmaTcRMax, const int32_t* collModelId,
                           const int32_t* subCellLevels, const double* cellWeightFactor);
 int ugf_set_deltaT(ugf_handle* h, double deltaT);

@@ -77,7 +77,7 @@ inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-enum { KIND_MOVE = 1, KIND_NTC = 2, KIND_BGK = 3, KIND_INFLOW = 4 };
+enum { KIND_MOVE = 1, KIND_NTC = 2, KIND_BGK = 3, KIND_INFLOW = 4, KIND_WEIGHT = 5 };
 
 // One stream = (seed, kind, aux) key + (a, b, c) counter prefix; the 4th counter word
 // counts Philox blocks.  Each block yields two uniforms in [0,1) with 53 random bits.
@@ -123,6 +123,7 @@ struct Parcel {  // uniGasParcel (U/parcels/uniGasParcel.H:217-239) + particle p
     double x[3];
     double U[3];
     double ERot;
+    double CWF;      // cell weight factor carried by the parcel (U/parcels/uniGasParcel.H:226)
     double sf;       // stepFraction
     int32_t cell;    // >=0 live; -1 deleted; <= -2 waiting on a processor face (-2 - boundaryFaceIndex)
     int32_t typeId;
@@ -162,10 +163,13 @@ struct ugfo_handle {
     int64_t receivedStart = -1;
     std::vector<int32_t> occOff, occIds;  // cell occupancy CSR
     bool occValid = false, occIdentity = false;
+    bool weightPending = false;   // a move happened since the last weighting() pass
 
     // cell state (U/clouds/uniGasCloud.H:189-201)
     std::vector<double> sigmaTcRMax;
     std::vector<int32_t> collModelId, subLevels;
+    std::vector<double> cellWF;   // cellWeightFactor_ (U/clouds/uniGasCloud.C:433); all 1 until uploaded
+    bool cellWeighted = false;    // cellWeightedSimulation: a cellWeightFactor field was uploaded
     // BGK persistent state
     std::vector<double> maxProb, qPrev, sPrev;
     // per-step measurements
@@ -200,6 +204,9 @@ struct ugfo_handle {
 namespace {
 
 inline int fail(ugfo_handle* h, const std::string& m) { if (h) h->err = m; return 1; }
+
+// nParticle * CWF of a cell (RWF = 1: no axisymmetric weighting)
+inline double FNc(const ugfo_handle& h, int c) { return h.cfg.nParticle * h.cellWF[c]; }
 
 inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
@@ -394,7 +401,7 @@ void measureWall(ugfo_handle& h, const Parcel& p, int bfi, const double nw[3], d
         *preIE = IE;
         for (int k = 0; k < 3; ++k) preIMom[k] = m * p.U[k];
     } else {
-        const double nPart = h.cfg.nParticle;
+        const double nPart = FNc(h, p.cell);  // nParticle*CWF of the wall cell (uniGasPatchBoundary.C:292-294)
         dq = nPart * (*preIE - IE) / (h.cfg.deltaT * fA);
         for (int k = 0; k < 3; ++k) dfd[k] = nPart * (preIMom[k] - m * p.U[k]) / (h.cfg.deltaT * fA);
     }
@@ -671,10 +678,10 @@ void doInflow(ugfo_handle& h) {
                 const ugf_species& s = h.sp[typeId];
                 const double cmp = std::sqrt(2.0 * kB * ip.in.translationalTemperature / s.mass);
                 const double sCos = dot3(ip.in.velocity, n) / cmp;
-                // Bird eq 4.22 (uniGasGeneralBoundary.C:157-165); CWF = RWF = 1
+                // Bird eq 4.22 (uniGasGeneralBoundary.C:154-165); CWF of the face's cell, RWF = 1
                 const double accum = (fA * ip.in.numberDensities[iD] * dt * cmp
                                       * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
-                                     / (2.0 * sqrtPi * h.cfg.nParticle);
+                                     / (2.0 * sqrtPi * FNc(h, cellI));
                 Stream rc(h.cfg.seed, KIND_INFLOW, (uint32_t)iD, (uint32_t)h.step, (uint32_t)bfi, 0);
                 int nIns = std::max((int)accum, 0);
                 if ((accum - nIns) > rc.u01()) ++nIns;
@@ -711,6 +718,7 @@ void doInflow(ugfo_handle& h) {
                     for (int k = 0; k < 3; ++k)
                         np_.U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
                     np_.ERot = equipartitionRotationalEnergy(r, ip.in.rotationalTemperature, s.rotationalDoF);
+                    np_.CWF = h.cellWF[cellI];  // uniGasGeneralBoundary.C:738
                     np_.sf = 0;
                     np_.cell = cellI;
                     np_.typeId = typeId;
@@ -730,7 +738,7 @@ void doInflow(ugfo_handle& h) {
 // cell occupancy: stable counting sort w.r.t. current array order; deleted parcels and
 // parcels waiting on a processor patch are dropped.  (CloudWithModels.C:110-138)
 // ---------------------------------------------------------------------------------
-void buildOccupancy(ugfo_handle& h) {
+void buildOccupancyRaw(ugfo_handle& h) {
     const int nC = h.nCells;
     const int64_t n = (int64_t)h.P.size();
     h.occOff.assign(nC + 1, 0);
@@ -772,6 +780,51 @@ void buildOccupancy(ugfo_handle& h) {
     h.occValid = true;
     h.occIdentity = false;
     h.cnt.nParcels = h.occOff[nC];
+}
+
+// uniGasCloud::cellWeighting (U/clouds/uniGasCloud.C:1353-1424), called by weighting() (:203-220) right after the
+// first buildCellOccupancy of evolve() (:839-842): every parcel takes the weight of the cell it now sits in; a parcel
+// that came from a heavier cell is cloned floor(old/new - 1) times plus once more with the remaining probability, a
+// parcel that came from a lighter cell survives with probability old/new.  Clones are appended to the cloud in
+// (cell, occupancy) order, so after the second buildCellOccupancy they follow the cell's own parcels in source order.
+// One uniform per parcel from its own stream (KIND_WEIGHT, step, array index) replaces the shared generator.
+void cellWeighting(ugfo_handle& h) {
+    int64_t cloned = 0, wdel = 0;
+    const int64_t nBefore = (int64_t)h.P.size();
+    for (int c = 0; c < h.nCells; ++c) {
+        for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
+            const int32_t idx = h.occIds[j];
+            const double oldW = h.P[idx].CWF;
+            const double newW = h.cellWF[c];
+            h.P[idx].CWF = newW;
+            if (oldW == newW) continue;
+            Stream r(h.cfg.seed, KIND_WEIGHT, 0, (uint32_t)h.step, (uint32_t)idx, 0);
+            if (oldW > newW) {
+                double prob = oldW / newW - 1.0;
+                while (prob > 1.0) { h.P.push_back(h.P[idx]); ++cloned; prob -= 1.0; }
+                if (prob > r.u01()) { h.P.push_back(h.P[idx]); ++cloned; }
+            } else if (oldW / newW < r.u01()) {
+                h.P[idx].cell = -1;
+                ++wdel;
+            }
+        }
+    }
+    (void)nBefore;
+    h.cnt.cloned += cloned;
+    h.cnt.weightDeleted += wdel;
+}
+
+// buildCellOccupancy; the first one after a move is followed by weighting() and a second buildCellOccupancy
+// (U/clouds/uniGasCloud.C:839-842, 203-220)
+void buildOccupancy(ugfo_handle& h) {
+    buildOccupancyRaw(h);
+    if (h.weightPending) {
+        h.weightPending = false;
+        if (h.cellWeighted) {
+            cellWeighting(h);
+            buildOccupancyRaw(h);
+        }
+    }
 }
 
 void reorder(ugfo_handle& h) {
@@ -854,8 +907,8 @@ void collideCell(ugfo_handle& h, int c, int subCycle, double dtSub, int64_t& can
         }
     }
     const double sMaxOld = h.sigmaTcRMax[c];
-    // :184  CWF = RWF = 1
-    const double selectedPairs = 0.5 * nC * (nC - 1) * h.cfg.nParticle * sMaxOld * dtSub / h.vol[c];
+    // :168,184  CWF of the cell, RWF = 1
+    const double selectedPairs = 0.5 * nC * (nC - 1) * FNc(h, c) * sMaxOld * dtSub / h.vol[c];
     int nCand = (int)selectedPairs;
     {
         Stream rc(h.cfg.seed, KIND_NTC, (uint32_t)subCycle, (uint32_t)h.step, (uint32_t)c, 0xFFFFFFFFu);
@@ -916,7 +969,7 @@ void bgkMacro(ugfo_handle& h, int c, Macro& m) {
     const int nS = h.nSpecies;
     const int model = h.cfg.bgkModel;
     const double* M = &h.mom[(size_t)c * nS * UGF_NMOM];
-    const double FN = h.cfg.nParticle;
+    const double FN = FNc(h, c);  // every parcel of the cell carries CWF = cellWF[c] after weighting()
     double N = 0, rhoM = 0, rhoNX = 0, rhoMX = 0, momX[3] = {0, 0, 0}, keX = 0;
     double muu[6] = {0, 0, 0, 0, 0, 0}, mcc = 0, mccu[3] = {0, 0, 0}, eInt = 0, eIntU[3] = {0, 0, 0};
     for (int s = 0; s < nS; ++s) {
@@ -1081,7 +1134,7 @@ void relaxCell(ugfo_handle& h, int c, int64_t& nrel) {
             nrel++;
         }
         // conserveMomentumAndEnergy (…USP.C:996-1045)
-        const double FN = h.cfg.nParticle;
+        const double FN = FNc(h, c);
         double keX = 0, momX[3] = {0, 0, 0};
         for (int i = 0; i < N; ++i) {
             const Parcel& p = h.P[ids[i]];
@@ -1241,10 +1294,11 @@ void decompose(ugfo_handle& h) {
     if (!h.decompOn || h.cfg.collisionModel != UGF_COLL_HYBRID) return;
     if (!h.momValid) sampleAll(h);
     const int nS = h.nSpecies, W = KN_NACC + nS;
-    const double dt = h.cfg.deltaT, FN = h.cfg.nParticle;
+    const double dt = h.cfg.deltaT;
     h.decTimeSteps++;
     h.decTimeAv += dt;
     for (int c = 0; c < h.nCells; ++c) {
+        const double FN = FNc(h, c);
         double* a = &h.knAcc[(size_t)c * W];
         for (int s = 0; s < nS; ++s) {
             const double* m = &h.mom[((size_t)c * nS + s) * UGF_NMOM];
@@ -1350,9 +1404,9 @@ void accumulateFields(ugfo_handle& h) {
         h.nAvTimeSteps++;
         h.timeAvCounter += dt;
         const int nS = h.nSpecies;
-        const double FN = h.cfg.nParticle;
 #pragma omp parallel for schedule(static)
         for (int c = 0; c < h.nCells; ++c) {
+            const double FN = FNc(h, c);
             double* A = &h.acc[(size_t)c * NACC];
             for (int s = 0; s < nS; ++s) {
                 const double* a = &h.mom[((size_t)c * nS + s) * UGF_NMOM];
@@ -1466,7 +1520,7 @@ void deriveFields(ugfo_handle& h, double* cellF, double* wallF) {
             const int patch = h.facePatch[b];
             if (h.pKind[patch] != UGF_PATCH_WALL) continue;
             const double* B = &h.bacc[(size_t)b * UGF_NBM];
-            const double nPart = h.cfg.nParticle;
+            const double nPart = FNc(h, h.owner[b + h.nInternal]);  // :1276-1278 CWF of the boundary cell
             if (B[0] > VSMALL) {  // :1274-1301
                 F[0] = B[0] * nPart / t;
                 F[1] = B[1] * nPart / t;
@@ -1505,6 +1559,7 @@ void energyTotals(ugfo_handle& h) {
 void resetStepCounters(ugfo_handle& h) {
     h.cnt.collisionCandidates = h.cnt.collisions = h.cnt.bgkRelaxations = 0;
     h.cnt.inserted = h.cnt.deleted = h.cnt.migrated = h.cnt.wallHits = 0;
+    h.cnt.cloned = h.cnt.weightDeleted = 0;
 }
 
 }  // namespace
@@ -1580,6 +1635,8 @@ int ugfo_set_mesh(ugfo_handle* h, const ugf_mesh* m) {
     h->sigmaTcRMax.assign(h->nCells, 0.0);
     h->collModelId.assign(h->nCells, h->cfg.collisionModel == UGF_COLL_DSMC ? 1 : 0);  // uniGasCloud.C:713,723,731
     h->subLevels.assign(3 * (size_t)h->nCells, 1);
+    h->cellWF.assign(h->nCells, 1.0);
+    h->cellWeighted = false;
     h->maxProb.assign(h->nCells, 1.0);
     h->qPrev.assign(3 * (size_t)h->nCells, 0.0);
     h->sPrev.assign(6 * (size_t)h->nCells, 0.0);
@@ -1641,6 +1698,8 @@ int ugfo_upload_parcels(ugfo_handle* h, const ugf_parcels* p) {
         q.newParcel = p->newParcel ? p->newParcel[i] : 0;
         q.sf = 0;
         if (q.cell < 0 || q.cell >= h->nCells) return fail(h, "parcel cell out of range");
+        q.CWF = h->cellWF[q.cell];  // implicit weights: a parcel carries its cell's factor (true after any weighting pass)
+        if (p->cellWeight && p->cellWeight[i] != q.CWF) return fail(h, "parcel cellWeight differs from the cellWeightFactor of its cell");
         if (q.typeId < 0 || q.typeId >= h->nSpecies) return fail(h, "parcel typeId out of range");
     }
     h->occValid = false; h->momValid = false;
@@ -1656,7 +1715,11 @@ int ugfo_upload_cell_state(ugfo_handle* h, const double* s, const int32_t* id, c
         h->subLevels.assign(lv, lv + 3 * (size_t)h->nCells);
         for (int32_t v : h->subLevels) if (v < 1) return fail(h, "subCellLevels must be >= 1");
     }
-    if (cwf) for (int c = 0; c < h->nCells; ++c) if (cwf[c] != 1.0) return fail(h, "cell weighting is not supported yet (cellWeightFactor must be 1)");
+    if (cwf) {
+        for (int c = 0; c < h->nCells; ++c) if (!(cwf[c] > 0.0)) return fail(h, "cellWeightFactor must be positive");
+        h->cellWF.assign(cwf, cwf + h->nCells);
+        h->cellWeighted = true;
+    }
     return 0;
 }
 
@@ -1675,7 +1738,9 @@ int ugfo_move(ugfo_handle* h) {
     openStep(h);
     // parcels that were not inserted this step start the step at stepFraction 0
     for (int64_t i = 0; i < (int64_t)h->P.size(); ++i) if (!h->P[i].newParcel) h->P[i].sf = 0;
+    if (h->cellWeighted && h->cfg.nRanks > 1) return fail(h, "cell weighting is single-rank for now (the migration record carries no weight)");
     moveRange(*h, 0, (int64_t)h->P.size(), true);
+    h->weightPending = true;
     h->receivedStart = (int64_t)h->P.size();
     countInflight(h);
     return 0;
@@ -1878,6 +1943,7 @@ int ugfo_download_parcels(ugfo_handle* h, ugf_parcels* p) {
         if (p->typeId) p->typeId[i] = q.typeId;
         if (p->ERot) p->ERot[i] = q.ERot;
         if (p->newParcel) p->newParcel[i] = q.newParcel;
+        if (p->cellWeight) p->cellWeight[i] = q.CWF;
     }
     p->n = n;
     return 0;

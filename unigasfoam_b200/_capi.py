@@ -7,7 +7,7 @@ declares and fails loudly if one is missing.
 import ctypes as C
 import os
 
-UGF_ABI_VERSION = 1
+UGF_ABI_VERSION = 2
 UGF_MAX_SPECIES = 8
 UGF_MAX_VIB_MODES = 4
 UGF_MAX_ELEC_LEVELS = 16
@@ -93,7 +93,7 @@ class Inflow(C.Structure):
 class Parcels(C.Structure):
     _fields_ = [
         ("n", i64), ("x", P(f64)), ("y", P(f64)), ("z", P(f64)), ("Ux", P(f64)), ("Uy", P(f64)), ("Uz", P(f64)),
-        ("cell", P(i32)), ("typeId", P(i32)), ("ERot", P(f64)), ("newParcel", P(i32)),
+        ("cell", P(i32)), ("typeId", P(i32)), ("ERot", P(f64)), ("newParcel", P(i32)), ("cellWeight", P(f64)),
     ]
 
 
@@ -109,7 +109,7 @@ class Counters(C.Structure):
     _fields_ = [
         ("step", i64), ("nParcels", i64), ("collisionCandidates", i64), ("collisions", i64), ("bgkRelaxations", i64),
         ("inserted", i64), ("deleted", i64), ("migrated", i64), ("wallHits", i64), ("stuck", i64),
-        ("linearKineticEnergy", f64), ("rotationalEnergy", f64), ("momentum", f64 * 3),
+        ("linearKineticEnergy", f64), ("rotationalEnergy", f64), ("momentum", f64 * 3), ("cloned", i64), ("weightDeleted", i64),
     ]
 
     def as_dict(self):

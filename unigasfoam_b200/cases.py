@@ -54,6 +54,7 @@ class Case:
     sigmaTcRMax: float = 0.0
     cellCollModelId: np.ndarray = None
     subCellLevels: np.ndarray = None
+    cellWeightFactor: np.ndarray = None   # uniGasCellWeightFactor (cellWeightedSimulation true)
     meta: dict = field(default_factory=dict)
 
     @property
@@ -63,7 +64,11 @@ class Case:
     def make_cloud(self, cloud_cls=None, **kw):
         if cloud_cls is None:
             from .cloud import UniGasCloud as cloud_cls
+        if self.cellWeightFactor is not None:  # handle must exist before the parcels: fix the capacity now (clones need room)
+            kw.setdefault("parcelCapacity", int(1.5 * self.n_parcels) + 4096)
         cl = cloud_cls(self.mesh, self.uniGasProperties, self.boundariesDict, self.deltaT, **kw)
+        if self.cellWeightFactor is not None:  # the parcels take the factor of their cell: the field goes in first
+            cl.setCellState(cellWeightFactor=self.cellWeightFactor)
         cl.setParcels(self.position, self.U, self.cell, self.typeId, self.ERot)
         cl.setCellState(sigmaTcRMax=self.sigmaTcRMax, cellCollModelId=self.cellCollModelId, subCellLevels=self.subCellLevels)
         return cl
@@ -92,14 +97,16 @@ def _uniform_in_cells(mesh, cells, rng):
     return np.column_stack([xy, z])
 
 
-def mesh_fill(mesh, species, names, number_densities, T, velocity, nParticle, rng, Trot=None, cells=None):
+def mesh_fill(mesh, species, names, number_densities, T, velocity, nParticle, rng, Trot=None, cells=None, cell_weight=None):
     """uniGasMeshFill::setInitialConfiguration (…/uniGasMeshFill.C:174-278), per cell instead of per tet:
-    N = n V / F_N with stochastic rounding, uniform position, Maxwellian + drift, equipartition ERot."""
+    N = n V / (F_N CWF) with stochastic rounding (:196-199), uniform position, Maxwellian + drift, equipartition ERot."""
     pos, vel, cel, tid, erot = [], [], [], [], []
     all_cells = np.arange(mesh.n_cells) if cells is None else np.asarray(cells)
     for ti, name in enumerate(names):
         sp = species[name]
         req = number_densities[name] / nParticle * mesh.cell_volumes[all_cells]
+        if cell_weight is not None:
+            req = req / np.asarray(cell_weight, float)[all_cells]
         cnt = np.floor(req).astype(np.int64)
         cnt += (req - cnt) > rng.random(len(all_cells))
         cl = np.repeat(all_cells, cnt)
@@ -126,6 +133,28 @@ def mesh_fill(mesh, species, names, number_densities, T, velocity, nParticle, rn
     return pos, vel, cel.astype(np.int32), tid, erot
 
 
+def cell_weight_factor(mesh, spec, number_density, nParticle):
+    """cellWeightFactor field of a case.  spec: None | array [nCells] | callable(mesh) -> array |
+    ("particlesPerSubCell", k): uniGasMeshFill's rule CWF = n V / (k nSubCells F_N) with one sub-cell per cell
+    and without its smoothing passes (U/uniGasInitialisation/derived/uniGasMeshFill/uniGasMeshFill.C:111-121)."""
+    if spec is None:
+        return None
+    if callable(spec):
+        w = spec(mesh)
+    elif isinstance(spec, tuple) and spec[0] == "particlesPerSubCell":
+        w = number_density * mesh.cell_volumes / (float(spec[1]) * nParticle)
+    else:
+        w = np.broadcast_to(np.asarray(spec, float), (mesh.n_cells,))
+    return np.ascontiguousarray(w, dtype=np.float64)
+
+
+def _weighted(case, w):
+    if w is not None:
+        case.cellWeightFactor = w
+        case.uniGasProperties["cellWeightedSimulation"] = True
+    return case
+
+
 def _props(species_name, sp, nParticle, mode="dsmc", binary="variableHardSphere", bgk="noBGKCollision", Tref=273.0, **cp):
     return {
         "nEquivalentParticles": nParticle,
@@ -140,7 +169,7 @@ def _props(species_name, sp, nParticle, mode="dsmc", binary="variableHardSphere"
 
 def closed_box(n=32, parcels=1_000_000, wall="specular", T0=300.0, number_density=1e20, species=("Ar", ARGON_GUIDE),
                Tref=273.0, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", seed=1, dt_mct=0.2,
-               lambda_per_dx=2.0, velocity=(0.0, 0.0, 0.0), Trot=None, **cp):
+               lambda_per_dx=2.0, velocity=(0.0, 0.0, 0.0), Trot=None, cellWeightFactor=None, **cp):
     """Config 1: 3-D closed box of gas at equilibrium, n^3 cells, dx = lambda/2, dt = 0.2 MCT."""
     name, sp = species
     lam = vhs_mean_free_path(number_density, T0, sp, Tref)
@@ -150,7 +179,8 @@ def closed_box(n=32, parcels=1_000_000, wall="specular", T0=300.0, number_densit
     m.meta_axis_aligned = True
     nParticle = number_density * L ** 3 / parcels
     rng = np.random.default_rng(seed)
-    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: number_density}, T0, velocity, nParticle, rng, Trot=Trot)
+    cwf = cell_weight_factor(m, cellWeightFactor, number_density, nParticle)
+    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: number_density}, T0, velocity, nParticle, rng, Trot=Trot, cell_weight=cwf)
     dt = dt_mct / vhs_collision_rate(number_density, T0, sp, Tref)
     if wall == "specular":
         model = lambda p: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasSpecularWallPatch"}
@@ -159,9 +189,9 @@ def closed_box(n=32, parcels=1_000_000, wall="specular", T0=300.0, number_densit
                            "uniGasDiffuseWallPatchProperties": {"temperature": T0, "velocity": [0, 0, 0]}}
     bd = {"uniGasPatchBoundaries": [model(p.name) for p in m.patches]}
     sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(T0, sp["mass"])  # uniGasMeshFill.C:284-296
-    return Case("closed_box", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
-                erot if sp.get("rotationalDegreesOfFreedom", 0) else None, sig0,
-                meta=dict(n=number_density, T0=T0, lam=lam, L=L, Tref=Tref, species=sp))
+    return _weighted(Case("closed_box", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
+                          erot if sp.get("rotationalDegreesOfFreedom", 0) else None, sig0,
+                          meta=dict(n=number_density, T0=T0, lam=lam, L=L, Tref=Tref, species=sp)), cwf)
 
 
 def mixture_box(n=6, parcels=20000, fractions=(("Ar", None, 0.6), ("N2", None, 0.4)), T0=300.0, number_density=1e20, Tref=273.0,
@@ -197,7 +227,7 @@ def mixture_box(n=6, parcels=20000, fractions=(("Ar", None, 0.6), ("N2", None, 0
 
 
 def couette(nx=1000, ny=500, ppc=20, Kn=0.1, Tw=273.0, Uw=150.0, number_density=1e20, species=("Ar", ARGON_GUIDE),
-            Tref=273.0, courant=0.5, seed=2, rank=0, n_ranks=1, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", **cp):
+            Tref=273.0, courant=0.5, seed=2, rank=0, n_ranks=1, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", cellWeightFactor=None, **cp):
     """Config 2: 2-D Couette flow, x cyclic, y walls diffuse at Tw moving at -+Uw, z empty; H = lambda/Kn.
 
     n_ranks > 1 builds rank `rank`'s slab of a channel n_ranks*nx cells long (weak scaling: nx x ny cells per
@@ -230,19 +260,20 @@ def couette(nx=1000, ny=500, ppc=20, Kn=0.1, Tw=273.0, Uw=150.0, number_density=
     m.meta_axis_aligned = True
     nParticle = number_density * dx * dy * dx / ppc
     rng = np.random.default_rng(seed)
-    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: number_density}, Tw, (0, 0, 0), nParticle, rng)
+    cwf = cell_weight_factor(m, cellWeightFactor, number_density, nParticle)
+    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: number_density}, Tw, (0, 0, 0), nParticle, rng, cell_weight=cwf)
     dt = courant * dx / most_probable_speed(Tw, sp["mass"])
     wallp = lambda p, u: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasDiffuseWallPatch",
                           "uniGasDiffuseWallPatchProperties": {"temperature": Tw, "velocity": [u, 0, 0]}}
     bd = {"uniGasPatchBoundaries": [wallp("bottom", -Uw), wallp("top", Uw)]}
     sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(Tw, sp["mass"])
-    return Case("couette", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
-                None, sig0, meta=dict(n=number_density, Tw=Tw, Uw=Uw, lam=lam, H=H, Lx=Lx, Tref=Tref, species=sp))
+    return _weighted(Case("couette", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
+                          None, sig0, meta=dict(n=number_density, Tw=Tw, Uw=Uw, lam=lam, H=H, Lx=Lx, Tref=Tref, species=sp)), cwf)
 
 
 def cylinder(nr=100, ntheta=200, ppc=20, n_inf=4.247e20, T_inf=200.0, U_inf=2634.7, T_wall=500.0, r0=0.5 * 0.3048, r1=2.0 * 0.3048,
              lz=0.1 * 0.3048, grading=5.0, species=("Ar", ARGON_TUTORIAL), Tref=1000.0, courant=0.3, seed=3,
-             binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", **cp):
+             binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision", cellWeightFactor=None, **cp):
     """Config 3: 2-D hypersonic (Mach 10) argon flow over a cylinder - the geometry, free stream and wall of
     tutorials/uniGasFoam/hypersonicCylinder (system/blockMeshDict, system/boundariesDict) without its cell
     weighting / adaptation: free-stream inflow on the upstream half of the outer arc, deleting outflow on the
@@ -253,7 +284,8 @@ def cylinder(nr=100, ntheta=200, ppc=20, n_inf=4.247e20, T_inf=200.0, U_inf=2634
     n_parcels = ppc * m.n_cells
     nParticle = n_inf * m.cell_volumes.sum() / n_parcels
     rng = np.random.default_rng(seed)
-    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: n_inf}, T_inf, (U_inf, 0.0, 0.0), nParticle, rng)
+    cwf = cell_weight_factor(m, cellWeightFactor, n_inf, nParticle)
+    pos, vel, cel, tid, erot = mesh_fill(m, {name: sp}, [name], {name: n_inf}, T_inf, (U_inf, 0.0, 0.0), nParticle, rng, cell_weight=cwf)
     dr_min = (m.cell_bb_max - m.cell_bb_min)[:, :2].min()
     dt = courant * dr_min / (U_inf + most_probable_speed(T_inf, sp["mass"]))
     inflow = {"generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasFreeStreamInflowPatch",
@@ -270,6 +302,6 @@ def cylinder(nr=100, ntheta=200, ppc=20, n_inf=4.247e20, T_inf=200.0, U_inf=2634
         "uniGasGeneralBoundaries": [inflow],
     }
     sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(T_inf, sp["mass"])
-    return Case("cylinder", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
-                erot if sp.get("rotationalDegreesOfFreedom", 0) else None, sig0,
-                meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, r0=r0, r1=r1, Tref=Tref, species=sp))
+    return _weighted(Case("cylinder", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
+                          erot if sp.get("rotationalDegreesOfFreedom", 0) else None, sig0,
+                          meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, r0=r0, r1=r1, Tref=Tref, species=sp)), cwf)

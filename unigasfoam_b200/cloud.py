@@ -85,7 +85,10 @@ class UniGasCloud:
         cfg.sampleInterval = int(sampleInterval)
         cfg.measureWalls = int(bool(measureWalls))
         cfg.rank, cfg.nRanks = rank, nRanks
-        for key in ("cellWeightedSimulation", "axisymmetricSimulation", "adaptiveSimulation", "chemicalReactions"):
+        # cellWeightedSimulation (U/clouds/uniGasCloud.C:417): the cellWeightFactor field itself comes through
+        # setCellState(cellWeightFactor=...) before the parcels, as the reference reads uniGasCellWeightFactor
+        self.cellWeighted = bool(props.get("cellWeightedSimulation", False))
+        for key in ("axisymmetricSimulation", "adaptiveSimulation", "chemicalReactions"):
             if props.get(key, False):
                 raise UgfError(f"{key} true is not supported by the B200 path yet (SURVEY §8f)")
         self.cfg = cfg
@@ -215,6 +218,8 @@ class UniGasCloud:
         b = self._i32(np.broadcast_to(cellCollModelId, (nC,))) if cellCollModelId is not None else None
         c = self._i32(np.broadcast_to(subCellLevels, (nC, 3))) if subCellLevels is not None else None
         d = self._f64(np.broadcast_to(cellWeightFactor, (nC,))) if cellWeightFactor is not None else None
+        if d is not None and not self.cellWeighted:
+            raise UgfError("cellWeightFactor given but cellWeightedSimulation is not true in uniGasProperties")
         self._check(self.api.upload_cell_state(
             self._h,
             a.ctypes.data_as(PD) if a is not None else None,
@@ -374,18 +379,18 @@ class UniGasCloud:
     def parcels(self):
         cap = int(self.cfg.parcelCapacity)
         PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
-        f = [np.empty(cap, np.float64) for _ in range(7)]
+        f = [np.empty(cap, np.float64) for _ in range(8)]
         ii = [np.empty(cap, np.int32) for _ in range(2)]
         p = _capi.Parcels()
         p.n = cap
-        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz, p.ERot = [a.ctypes.data_as(PD) for a in f]
+        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz, p.ERot, p.cellWeight = [a.ctypes.data_as(PD) for a in f]
         p.cell, p.typeId = [a.ctypes.data_as(PI) for a in ii]
         self._check(self.api.download_parcels(self._h, C.byref(p)))
         n = p.n
         return {
             "position": np.stack([f[0][:n], f[1][:n], f[2][:n]], axis=1),
             "U": np.stack([f[3][:n], f[4][:n], f[5][:n]], axis=1),
-            "ERot": f[6][:n].copy(), "cell": ii[0][:n].copy(), "typeId": ii[1][:n].copy(),
+            "ERot": f[6][:n].copy(), "cell": ii[0][:n].copy(), "typeId": ii[1][:n].copy(), "cellWeight": f[7][:n].copy(),
         }
 
     def cellOccupancy(self):

@@ -38,16 +38,20 @@ struct InflowHost {
     InflowDev dev;
     int nSlots;
     long long maxInsert;
+    std::vector<double> accum1;   // per (face, species) slot: expected insertions per second at F_N = 1, CWF = 1
+    std::vector<int> slotCell;    // owner cell of the slot's face
     std::vector<void*> owned;
 };
 
 __global__ void set_n_kernel(const int* total, long long* dN) { *dN = *total; }
 
-__global__ void __launch_bounds__(256) hist_kernel(const int* __restrict__ cell, const long long* dN, int* __restrict__ cellCount) {
+__global__ void __launch_bounds__(256) hist_kernel(const int* __restrict__ cell, const long long* dN, int* __restrict__ cellCount,
+                                                   const uint8_t* __restrict__ nclone) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int c = -1;
     if (i < *dN) c = cell[i];
     const bool live = c >= 0;
+    if (live && nclone && nclone[i]) atomicAdd(&cellCount[c], (int)nclone[i]);  // clones of cellWeighting()
     const unsigned liveMask = __ballot_sync(0xffffffffu, live);
     if (live) {
         const unsigned peers = __match_any_sync(liveMask, c);
@@ -129,6 +133,13 @@ struct ugf_handle {
     int* dTask = nullptr;            // cell_kernel task counter
     double* dTot = nullptr;
     bool histValid = false, occValid = false, occIdentity = false, momValid = false;
+    // cell weighting (cellWeightedSimulation)
+    double* dCwf[2] = {nullptr, nullptr};  // [cwfCur]: current cellWeightFactor; the other: the factors the parcels carry while cwfDirty
+    int cwfCur = 0;
+    bool cwfDirty = false;
+    std::vector<double> cwfHost, cwfHostPrev;
+    uint8_t* dNclone = nullptr;            // [capacity] clones per parcel decided by the move
+    bool cloneValid = false;               // dNclone belongs to the current (not yet gathered) array
     bool subLevelsAllOne = true;
 
     // localKnudsen hybrid decomposition
@@ -213,7 +224,7 @@ int check_device_error(ugf_handle* h) {
     int e = 0;
     CU(cudaMemcpyAsync(&e, h->dErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if (e == 1) return fail(h, "parcel capacity exceeded while inserting parcels (raise parcelCapacity)");
+    if (e == 1) return fail(h, "parcel capacity exceeded while inserting or cloning parcels (raise parcelCapacity)");
     if (e == 2) return fail(h, "received parcel with a face index outside the processor patch");
     if (e == 3) return fail(h, "migration slot overflow: more parcels crossed a processor patch than slotCapacity");
     if (e == 4) return fail(h, "corrupt migration slot header");
@@ -276,6 +287,9 @@ void build_params(ugf_handle* h) {
     p.bgkModel = h->cfg.bgkModel;
     p.nSpecies = h->nSpecies;
     p.measureWalls = h->cfg.measureWalls;
+    p.cwf = h->dCwf[0] ? h->dCwf[h->cwfCur] : nullptr;
+    p.cwfPrev = h->dCwf[0] ? h->dCwf[h->cwfCur ^ 1] : nullptr;
+    p.cwfDirty = h->cwfDirty ? 1 : 0;
     for (int i = 0; i < h->nSpecies; ++i) {
         const ugf_species& s = h->spHost[i];
         DevSpecies& d = p.sp[i];
@@ -314,17 +328,18 @@ int do_sort(ugf_handle* h) {
     const int nC = h->nCells;
     if (!h->histValid) {
         CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * nC, h->stream));
-        hist_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dCellCount);
+        hist_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dCellCount, h->cloneValid ? h->dNclone : nullptr);
         LAUNCHED();
     }
     const int nb = (nC + SCAN_TILE - 1) / SCAN_TILE;
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums);
     LAUNCHED();
-    scan_top_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->dBlockSums, nb, h->dTotal, nullptr);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->dBlockSums, nb, h->dTotal, nullptr, h->capacity, h->dErr);
     LAUNCHED();
     scan_final_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums, h->dTotal, h->dOff);
     LAUNCHED();
-    scatter_index_kernel<<<grid_for(h->nUpper, 256 * SCAT_ROWS), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dOff, h->dCellCount, h->dPerm);
+    scatter_index_kernel<<<grid_for(h->nUpper, 256 * SCAT_ROWS), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dOff, h->dCellCount, h->dPerm,
+                                                                                                    h->cloneValid ? h->dNclone : nullptr, h->capacity);
     LAUNCHED();
     segment_sort_kernel<<<grid_for(((long long)nC + SEG_CHUNK - 1) / SEG_CHUNK, SEG_THREADS / 32), SEG_THREADS, 0, h->stream>>>(h->dOff, nC, h->dPerm);
     LAUNCHED();
@@ -338,6 +353,7 @@ int do_sort(ugf_handle* h) {
 // after a gather the array is cell-major and its length is the live count
 int after_gather(ugf_handle* h) {
     h->cur ^= 1;
+    h->cloneValid = false;  // the clones are parcels of their own now
     set_n_kernel<<<1, 1, 0, h->stream>>>(h->dTotal, h->dN);
     LAUNCHED();
     h->occIdentity = true;
@@ -498,6 +514,9 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.migListCap = MIG_LIST_CAP;
     a.bm = h->dBm;
     a.cnt = h->dCnt;
+    a.nclone = h->prm.cwf ? h->dNclone : nullptr;
+    if (h->prm.cwf && (received || h->hasProcessor))
+        return fail(h, "cell weighting is single-rank for now (the migration record carries no weight)");
     long long count = h->nUpper - begin;
     if (a.dBegin) count = std::min<long long>(count, (long long)h->migSlots.nProc * h->lastSlotCapacity);  // what one unpack can append
     if (count > 0) {
@@ -527,6 +546,15 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     h->histValid = true;
     h->occValid = false;
     h->momValid = false;
+    if (h->prm.cwf) {
+        h->cloneValid = true;
+        if (h->cwfDirty) {  // every parcel now carries the new factors
+            CU(cudaMemcpyAsync(h->dCwf[h->cwfCur ^ 1], h->dCwf[h->cwfCur], sizeof(double) * h->nCells, cudaMemcpyDeviceToDevice, h->stream));
+            h->cwfHostPrev = h->cwfHost;
+            h->cwfDirty = false;
+            h->prm.cwfDirty = 0;
+        }
+    }
     return 0;
 }
 
@@ -759,7 +787,7 @@ int ugf_destroy(ugf_handle* h) {
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
-                    h->dCnt, h->dErr, h->dTot, h->dTask};
+                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -1023,6 +1051,19 @@ int ugf_set_patch_wall_fields(ugf_handle* h, int32_t patch, const double* T, con
     return 0;
 }
 
+// upper bound of the parcels one step can insert (sizes the launches and the capacity check of do_inflow); depends on
+// deltaT and, with cell weighting, on the factor of each inlet face's cell (uniGasGeneralBoundary.C:154-165)
+static void recompute_inflow_bounds(ugf_handle* h) {
+    for (InflowHost& f : h->inflows) {
+        f.maxInsert = 0;
+        for (size_t k = 0; k < f.accum1.size(); ++k) {
+            const double w = h->cwfHost.empty() ? 1.0 : h->cwfHost[f.slotCell[k]];
+            const double accum = f.accum1[k] * h->cfg.deltaT / (h->cfg.nParticle * w);
+            f.maxInsert += (long long)std::max(accum, 0.0) + 2;
+        }
+    }
+}
+
 int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
@@ -1078,6 +1119,8 @@ int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) {
             const double accum = (fA * in->numberDensities[iD] * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
                                  / (2.0 * sqrtPi * h->cfg.nParticle);
             f.maxInsert += (long long)std::max(accum, 0.0) + 2;
+            f.accum1.push_back(accum * h->cfg.nParticle / h->cfg.deltaT);
+            f.slotCell.push_back(faceCell[lf]);
         }
     }
     InflowDev& d = f.dev;
@@ -1112,6 +1155,8 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p) {
         if (p->cell[i] < 0 || p->cell[i] >= h->nCells) return fail(h, "parcel cell out of range");
         if (p->typeId && (p->typeId[i] < 0 || p->typeId[i] >= h->nSpecies)) return fail(h, "parcel typeId out of range");
         if (p->newParcel && p->newParcel[i]) return fail(h, "uploaded parcels must have newParcel == 0");
+        if (p->cellWeight && p->cellWeight[i] != (h->cwfHost.empty() ? 1.0 : h->cwfHost[p->cell[i]]))
+            return fail(h, "parcel cellWeight differs from the cellWeightFactor of its cell");
     }
     ParcelBuf& P = h->buf[h->cur];
     if (upload(h, P.x, p->x, n) || upload(h, P.y, p->y, n) || upload(h, P.z, p->z, n) || upload(h, P.ux, p->Ux, n) ||
@@ -1131,6 +1176,13 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p) {
     CU(cudaMemcpyAsync(h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->nUpper = nn; h->nPending = false; h->newFrom = nn; h->recvStart = -1;
+    h->cloneValid = false;
+    if (h->dCwf[0] && h->cwfDirty) {  // a fresh cloud carries the current factors
+        CU(cudaMemcpy(h->dCwf[h->cwfCur ^ 1], h->dCwf[h->cwfCur], sizeof(double) * h->nCells, cudaMemcpyDeviceToDevice));
+        h->cwfHostPrev = h->cwfHost;
+        h->cwfDirty = false;
+        h->prm.cwfDirty = 0;
+    }
     h->histValid = h->occValid = h->occIdentity = h->momValid = false;
     return 0;
 }
@@ -1156,7 +1208,33 @@ int ugf_upload_cell_state(ugf_handle* h, const double* s, const int32_t* id, con
         }
         h->subLevelsAllOne = allOne;
     }
-    if (cwf) for (size_t c = 0; c < nC; ++c) if (cwf[c] != 1.0) return fail(h, "cell weighting is not supported yet (cellWeightFactor must be 1)");
+    if (cwf) {  // cellWeightedSimulation: see include/ugf.h
+        for (size_t c = 0; c < nC; ++c) if (!(cwf[c] > 0.0)) return fail(h, "cellWeightFactor must be positive");
+        if (h->capacity >= (long long)CLONE_FLAG) return fail(h, "cell weighting needs parcelCapacity < 2^30");
+        if (h->cfg.nRanks > 1 || h->hasProcessor) return fail(h, "cell weighting is single-rank for now (the migration record carries no weight)");
+        const bool haveParcels = h->buf[0].x && h->nUpper > 0;
+        if (!h->dCwf[0]) {
+            if (dalloc(h, &h->dCwf[0], nC) || dalloc(h, &h->dCwf[1], nC)) return 1;
+            if (dalloc(h, &h->dNclone, (size_t)h->capacity + MOVE_TILE)) return 1;
+            h->cwfHostPrev.assign(nC, 1.0);  // parcels uploaded so far carry factor 1
+            if (upload(h, h->dCwf[1], h->cwfHostPrev.data(), nC)) return 1;
+            h->cwfCur = 0;
+        } else if (!h->cwfDirty) {
+            h->cwfCur ^= 1;  // the previous field stays behind as the factors the parcels carry
+            h->cwfHostPrev = h->cwfHost;
+        }
+        h->cwfHost.assign(cwf, cwf + nC);
+        if (upload(h, h->dCwf[h->cwfCur], cwf, nC)) return 1;
+        h->cwfDirty = haveParcels;
+        if (!haveParcels) {
+            h->cwfHostPrev = h->cwfHost;
+            if (upload(h, h->dCwf[h->cwfCur ^ 1], cwf, nC)) return 1;
+        }
+        h->prm.cwf = h->dCwf[h->cwfCur];
+        h->prm.cwfPrev = h->dCwf[h->cwfCur ^ 1];
+        h->prm.cwfDirty = h->cwfDirty ? 1 : 0;
+        recompute_inflow_bounds(h);
+    }
     if (s && upload(h, h->dSigma, s, nC)) return 1;
     if (id && upload(h, h->dCollId, id, nC)) return 1;
     CU(cudaStreamSynchronize(h->stream));
@@ -1167,6 +1245,7 @@ int ugf_set_deltaT(ugf_handle* h, double dt) {
     if (!h) return 1;
     h->cfg.deltaT = dt;
     h->prm.deltaT = dt;
+    recompute_inflow_bounds(h);
     return 0;
 }
 
@@ -1218,7 +1297,7 @@ int ugf_reorder(ugf_handle* h) {
     if (h->occIdentity) return 0;
     ParcelBuf in = h->buf[h->cur], out = h->buf[h->cur ^ 1];
     dispatch(h, [&](auto R, auto M) {
-        reorder_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(in, out, h->dPerm, h->dTotal);
+        reorder_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(h->cloneValid ? h->capacity : h->nUpper, 256), 256, 0, h->stream>>>(in, out, h->dPerm, h->dTotal);
     });
     LAUNCHED();
     return after_gather(h);
@@ -1438,7 +1517,7 @@ int ugf_migrate_pack(ugf_handle* h, int32_t patch, double** devBuf, int64_t* nPa
     ParcelBuf P = h->buf[h->cur];
     mig_count_kernel<<<nb, 1024, 0, h->stream>>>(h->mesh, P.cell, h->dN, patch, h->dMigBlock);
     LAUNCHED();
-    scan_top_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->dMigBlock, (int)nb, h->dBlockSums, nullptr);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->dMigBlock, (int)nb, h->dBlockSums, nullptr, 0x7fffffffLL, nullptr);
     LAUNCHED();
     double* buf = h->packBuf[patch];
     dispatch(h, [&](auto R, auto M) {
@@ -1630,6 +1709,8 @@ int ugf_counters_get(ugf_handle* h, ugf_counters* out) {
     out->migrated = (int64_t)c.migrated;
     out->wallHits = (int64_t)c.wallHits;
     out->stuck = (int64_t)c.stuck;
+    out->cloned = (int64_t)c.cloned;
+    out->weightDeleted = (int64_t)c.wdeleted;
     out->linearKineticEnergy = tot[0];
     out->rotationalEnergy = tot[1];
     out->momentum[0] = tot[2]; out->momentum[1] = tot[3]; out->momentum[2] = tot[4];
@@ -1665,6 +1746,17 @@ int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
     CU(cudaStreamSynchronize(h->stream));
     if (p->typeId) for (size_t i = 0; i < nb; ++i) p->typeId[i] = h->multi ? types[i] : 0;
     if (p->newParcel) std::fill(p->newParcel, p->newParcel + nb, 0);
+    if (p->cellWeight) {  // implicit on the device: the factor of the parcel's cell (the previous field while an update is pending)
+        std::vector<int> cells;
+        const int* cp = p->cell;
+        if (!cp && nb) {
+            cells.resize(nb);
+            CU(cudaMemcpy(cells.data(), P.cell, nb * sizeof(int), cudaMemcpyDeviceToHost));
+            cp = cells.data();
+        }
+        const std::vector<double>& w = h->cwfDirty ? h->cwfHostPrev : h->cwfHost;
+        for (size_t i = 0; i < nb; ++i) p->cellWeight[i] = (w.empty() || cp[i] < 0) ? 1.0 : w[cp[i]];
+    }
     p->n = n;
     return 0;
 }

@@ -61,11 +61,10 @@ struct Macro {
 
 // calculateProperties for one cell (…USP.C:379-800), by one thread; it also stores the blended heat flux /
 // shear stress for the next step (…USP.C:777-783).
-__device__ inline void bgk_macro(const DevParams& prm, const double* __restrict__ momCell, double V, double* qPrevCell, double* sPrevCell,
+__device__ inline void bgk_macro(const DevParams& prm, double FN, const double* __restrict__ momCell, double V, double* qPrevCell, double* sPrevCell,
                                  Macro& m) {
     const int nS = prm.nSpecies;
     const int model = prm.bgkModel;
-    const double FN = prm.nParticle;
     double N = 0, rhoM = 0, rhoNX = 0, rhoMX = 0, momX[3] = {0, 0, 0}, keX = 0;
     double muu[6] = {0, 0, 0, 0, 0, 0}, mcc = 0, mccu[3] = {0, 0, 0}, eInt = 0, eIntU[3] = {0, 0, 0};
     double visc = 0, Pr = 0;
@@ -296,7 +295,7 @@ __device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs&
     }
     __syncwarp();
     // conserveMomentumAndEnergy (…USP.C:996-1045)
-    const double FN = prm.nParticle;
+    const double FN = cell_fn(prm, cell);
     double keX = 0, mx = 0, my = 0, mz = 0;
     for (int j = lane; j < n; j += 32) {
         const double mass = MULTI ? prm.sp[pt[j]].mass : prm.sp[0].mass;
@@ -329,7 +328,6 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
     const int model = prm.bgkModel;
     const bool envelope = (model == UGF_BGK_SBGK || model == UGF_BGK_USP_SBGK);
     const int nChunks = (a.nCells + BGK_CHUNK - 1) / BGK_CHUNK;
-    const double FN = prm.nParticle;
     int myRel = 0;
 
     for (int chunk = blockIdx.x * BGK_WARPS + wib; chunk < nChunks; chunk += warpsTotal) {
@@ -342,7 +340,7 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
         if (lane < nc) {
             const int cell = c0 + lane;
             Macro m;
-            bgk_macro(prm, a.mom + (size_t)cell * nS * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
+            bgk_macro(prm, cell_fn(prm, cell), a.mom + (size_t)cell * nS * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
             if (envelope) Eold = a.maxProb[cell];
             const bool act = a.collModelId[cell] == 0 && m.perform;
             S.mac[lane] = m;
@@ -462,6 +460,7 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                 const bool cellOn = g < k && S.active[cl & (BGK_CHUNK - 1)] != 0;
                 double keX = 0, mx = 0, my = 0, mz = 0;
                 if (cellOn) {
+                    const double FN = cell_fn(prm, c0 + cl);
                     const int cb = S.cb[g], ce = S.cb[g + 1];
                     for (int i = cb + q; i < ce; i += BGK_LPC) {
                         const double mass = MULTI ? prm.sp[S.type[i]].mass : prm.sp[0].mass;

@@ -173,7 +173,7 @@ __device__ inline void collide_pair(const DevParams& prm, Stream& r, const DevSp
 // (noTimeCounter.C:184-191); the rounding draw comes from the cell's own stream.
 __device__ __forceinline__ int ntc_candidates(const DevParams& prm, uint32_t step, uint32_t sub, double dtSub, int cell, int n, double sMaxOld,
                                               double vol) {
-    const double selectedPairs = 0.5 * n * (n - 1) * prm.nParticle * sMaxOld * dtSub / vol;
+    const double selectedPairs = 0.5 * n * (n - 1) * cell_fn(prm, cell) * sMaxOld * dtSub / vol;  // noTimeCounter.C:168,184
     int nCand = (int)selectedPairs;
     Stream rc(prm.seed, KIND_NTC, sub, step, (uint32_t)cell, 0xFFFFFFFFu);
     if (rc.u01() < (selectedPairs - nCand)) nCand++;
@@ -223,10 +223,10 @@ __host__ __device__ constexpr size_t cell_smem_bytes(bool hasRot) {
 }
 
 // Contribution of one species' cell sums to accumulator slot k of uniGasVolFields::calculateField
-// (uniGasVolFields.C:761-797; slot list in DESIGN.md section fields).  CWF = RWF = 1.
-__device__ __forceinline__ double acc_term(const DevParams& prm, int s, int k, double cnt, double su, double sv, double sw, double scc, double se) {
+// (uniGasVolFields.C:761-797; slot list in DESIGN.md section fields).  FN = nParticle * CWF of the cell (cell_fn), RWF = 1.
+__device__ __forceinline__ double acc_term(const DevParams& prm, double FN, int s, int k, double cnt, double su, double sv, double sw, double scc, double se) {
     const DevSpecies& S = prm.sp[s];
-    const double m = S.mass, FN = prm.nParticle;
+    const double m = S.mass;
     switch (k) {
         case 0: return cnt;
         case 1: return m * cnt;
@@ -296,7 +296,7 @@ __device__ __noinline__ void stream_giant_cell(const DevParams& prm, const CellA
         __syncwarp();
         for (int j = lane; j < m; j += 32) {
             const int dst = beg + b + j;
-            const int src = a.perm ? a.perm[dst] : dst;
+            const int src = a.perm ? (a.perm[dst] & CLONE_MASK) : dst;
             const double ux = a.in.ux[src], uy = a.in.uy[src], uz = a.in.uz[src];
             sU0[j] = ux; sU1[j] = uy; sU2[j] = uz;
             if (HAS_ROT) sE[j] = a.in.erot[src];
@@ -315,10 +315,11 @@ __device__ __noinline__ void stream_giant_cell(const DevParams& prm, const CellA
     __syncwarp();
     if (a.doSample && a.accDt != 0.0 && lane < NACC) {  // uniGasVolFields accumulation from the finished block
         double add = 0.0;
+        const double FN = cell_fn(prm, cell);
         for (int s = 0; s < prm.nSpecies; ++s) {
             const double* mm = a.mom + ((size_t)cell * prm.nSpecies + s) * UGF_NMOM;
-            add += acc_term(prm, s, lane, mm[0], mm[2], mm[3], mm[4], mm[14], mm[18]);
-            if (MULTI && a.accS && lane == 0) a.accS[(size_t)cell * prm.nSpecies + s] += a.accDt * (mm[1] * prm.nParticle);
+            add += acc_term(prm, FN, s, lane, mm[0], mm[2], mm[3], mm[4], mm[14], mm[18]);
+            if (MULTI && a.accS && lane == 0) a.accS[(size_t)cell * prm.nSpecies + s] += a.accDt * (mm[1] * FN);
         }
         a.acc[(size_t)cell * NACC + lane] += a.accDt * add;
     }
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
 #pragma unroll
             for (int it = 0; it < CELL_ITERS; ++it) {
                 const int j = it * 32 + lane;
-                srcs[it] = (j < ntot) ? (a.perm ? a.perm[b0 + j] : b0 + j) : -1;
+                srcs[it] = (j < ntot) ? (a.perm ? (a.perm[b0 + j] & CLONE_MASK) : b0 + j) : -1;
             }
 #pragma unroll
             for (int it = 0; it < CELL_ITERS; ++it) {
@@ -428,7 +429,8 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                 const bool doAcc = a.accDt != 0.0;
                 double* arow = a.acc + (size_t)(c0 + ci) * NACC + q;  // this lane's 4 accumulator slots: q, q+4, q+8, q+12
                 double ac0 = 0, ac1 = 0, ac2 = 0, ac3 = 0;
-                if (doAcc && cellValid) { ac0 = arow[0]; ac1 = arow[4]; ac2 = arow[8]; ac3 = arow[12]; }
+                double FN = prm.nParticle;
+                if (doAcc && cellValid) { ac0 = arow[0]; ac1 = arow[4]; ac2 = arow[8]; ac3 = arow[12]; FN = cell_fn(prm, c0 + ci); }
                 for (int s = 0; s < nS; ++s) {
                     double su = 0, sv = 0, sw = 0, suu = 0, suv = 0, suw = 0, svv = 0, svw = 0, sww = 0, scc = 0, scu = 0, scv = 0, scw = 0, cnt = 0;
                     double se = 0, seu = 0, sev = 0, sew = 0;
@@ -469,11 +471,11 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                         mrow[28] = 0.0;
                     }
                     if (doAcc) {  // uniGasVolFields accumulation fused in: slot 4t + q
-                        if (MULTI && a.accS && cellValid && q == 0) a.accS[(size_t)(c0 + ci) * nS + s] += a.accDt * (cnt * prm.nParticle);
-                        ac0 += a.accDt * acc_term(prm, s, q, cnt, su, sv, sw, scc, se);
-                        ac1 += a.accDt * acc_term(prm, s, q + 4, cnt, su, sv, sw, scc, se);
-                        ac2 += a.accDt * acc_term(prm, s, q + 8, cnt, su, sv, sw, scc, se);
-                        ac3 += a.accDt * acc_term(prm, s, q + 12, cnt, su, sv, sw, scc, se);
+                        if (MULTI && a.accS && cellValid && q == 0) a.accS[(size_t)(c0 + ci) * nS + s] += a.accDt * (cnt * FN);
+                        ac0 += a.accDt * acc_term(prm, FN, s, q, cnt, su, sv, sw, scc, se);
+                        ac1 += a.accDt * acc_term(prm, FN, s, q + 4, cnt, su, sv, sw, scc, se);
+                        ac2 += a.accDt * acc_term(prm, FN, s, q + 8, cnt, su, sv, sw, scc, se);
+                        ac3 += a.accDt * acc_term(prm, FN, s, q + 12, cnt, su, sv, sw, scc, se);
                     }
                 }
                 if (doAcc && cellValid) { arow[0] = ac0; arow[4] = ac1; arow[8] = ac2; arow[12] = ac3; }

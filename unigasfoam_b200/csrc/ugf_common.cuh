@@ -27,7 +27,12 @@ constexpr int NACC = 16;             // time-averaged accumulators per cell
 constexpr int MAX_TRACK_ITERS = 4096;
 constexpr int NUM_SMS = 148;
 
-enum { KIND_MOVE = 1, KIND_NTC = 2, KIND_BGK = 3, KIND_INFLOW = 4 };
+enum { KIND_MOVE = 1, KIND_NTC = 2, KIND_BGK = 3, KIND_INFLOW = 4, KIND_WEIGHT = 5 };
+
+// Occupancy entries >= CLONE_FLAG stand for a clone of parcel (entry - CLONE_FLAG) made by cellWeighting(): they sort
+// behind the cell's own parcels, in source order, and the gather materialises them.  Parcel capacity < 2^30.
+constexpr int CLONE_FLAG = 0x40000000;
+constexpr int CLONE_MASK = CLONE_FLAG - 1;
 
 struct DevSpecies {
     double mass, d, omega, alpha, E0;  // E0 = electronicEnergy[0]
@@ -57,10 +62,15 @@ struct DevParams {
     int collisionModel, binaryModel, bgkModel, nSpecies, measureWalls;
     DevSpecies sp[UGF_MAX_SPECIES];
     double pairInvGamma[UGF_MAX_SPECIES * UGF_MAX_SPECIES];  // 1/Gamma(5/2 - omega_pq)
+    // cell weighting (cellWeightedSimulation): cellWeightFactor per cell, null = all 1.  cwfPrev = the factors the
+    // parcels still carry when the field was replaced since the last weighting pass (cwfDirty), else = cwf.
+    const double* cwf;
+    const double* cwfPrev;
+    int cwfDirty;
 };
 
 struct DevCounters {
-    unsigned long long cand, coll, bgk, inserted, deleted, migrated, wallHits, stuck;
+    unsigned long long cand, coll, bgk, inserted, deleted, migrated, wallHits, stuck, cloned, wdeleted;
 };
 
 struct ParcelBuf {
@@ -92,6 +102,11 @@ struct MeshDev {
 
 __device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) {
     return ax * bx + ay * by + az * bz;
+}
+
+// nParticle * CWF of a cell: every parcel of a cell carries the cell's factor after weighting() (RWF = 1)
+__device__ __forceinline__ double cell_fn(const DevParams& prm, int cell) {
+    return prm.cwf ? prm.nParticle * __ldg(&prm.cwf[cell]) : prm.nParticle;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

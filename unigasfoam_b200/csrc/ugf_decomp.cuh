@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) kn_accumulate_kernel(const __grid_constan
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const int nS = prm.nSpecies, W = KN_NACC + nS;
-    const double dt = prm.deltaT, FN = prm.nParticle;
+    const double dt = prm.deltaT, FN = cell_fn(prm, c);
     double* a = acc + (size_t)c * W;
     double v[KN_NACC];
 #pragma unroll

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) accumulate_cells_kernel(const __grid_cons
                                                                const double* __restrict__ mom, double* __restrict__ acc, double* __restrict__ accS) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
-    const double dt = prm.deltaT, FN = prm.nParticle;
+    const double dt = prm.deltaT, FN = cell_fn(prm, c);
     double A[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) A[k] = acc[(size_t)c * NACC + k];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) derive_walls_kernel(const __grid_constant
     const int patch = mesh.bfPatch[b];
     if (mesh.patches[patch].kind == UGF_PATCH_WALL) {
         const double* B = bacc + (size_t)b * UGF_NBM;
-        const double nPart = prm.nParticle;
+        const double nPart = cell_fn(prm, mesh.bfOwner[b]);  // uniGasVolFields.C:1276-1278: CWF of the boundary cell
         if (B[0] > VSMALL) {
             F[0] = B[0] * nPart / t;
             F[1] = B[1] * nPart / t;

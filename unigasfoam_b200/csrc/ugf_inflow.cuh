@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant
     const double sCos = (f.vel[0] * g[1] + f.vel[1] * g[2] + f.vel[2] * g[3]) / cmp;
     const double sqrtPi = sqrt(PI);
     const double accum = (fA * f.numDen[iD] * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
-                         / (2.0 * sqrtPi * prm.nParticle);
+                         / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));  // uniGasGeneralBoundary.C:154-165
     Stream rc(prm.seed, KIND_INFLOW, (uint32_t)iD, step, (uint32_t)f.faceBfi[face], 0);
     int nIns = max((int)accum, 0);
     if ((accum - nIns) > rc.u01()) ++nIns;

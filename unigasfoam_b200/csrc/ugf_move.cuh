@@ -56,7 +56,7 @@ __device__ inline double equipartition_rotational_energy(Stream& r, double T, in
 struct WallPre { double IE; double mom[3]; };
 
 // measurePropertiesBeforeControl / AfterControl (uniGasPatchBoundary.C:130-302): slots in DESIGN.md §walls
-__device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, const DevSpecies& s, const double U[3],
+__device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, int cell, const DevSpecies& s, const double U[3],
                                     double erot, const double nw[3], double fA, WallPre& pre, bool after) {
     const double m = s.mass;
     const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
@@ -81,7 +81,7 @@ __device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, c
         pre.mom[0] = m * U[0]; pre.mom[1] = m * U[1]; pre.mom[2] = m * U[2];
         atomicAdd(&b[15], 1.0);
     } else {
-        const double nPart = prm.nParticle;
+        const double nPart = cell_fn(prm, cell);  // nParticle * CWF of the wall cell (uniGasPatchBoundary.C:292-294)
         const double dq = nPart * (pre.IE - IE) / (prm.deltaT * fA);
         if (dq != 0.0) atomicAdd(&b[8], dq);
 #pragma unroll
@@ -213,9 +213,10 @@ struct MoveArgs {
     int migListCap;
     double* bm;            // [nBFaces][UGF_NBM]
     DevCounters* cnt;
+    uint8_t* nclone;       // cell weighting: clones each parcel gets from cellWeighting() (written for every parcel), else null
 };
 
-enum { HIT_CHANGED_U = 1, HIT_DELETED = 2, HIT_STUCK = 8, HIT_MIGRATED = 16 };
+enum { HIT_CHANGED_U = 1, HIT_DELETED = 2, HIT_STUCK = 8, HIT_MIGRATED = 16, HIT_WDELETED = 32 };
 
 struct HitState {
     double x[3], U[3], erot, sf;
@@ -240,7 +241,7 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
         double nw[3], fA;
         unit_normal(pl, nw, fA);
         WallPre pre;
-        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, st.U, st.erot, nw, fA, pre, false);
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, false);
         bool diffuse = (pt.wallModel == UGF_WALL_DIFFUSE);
         const bool cll = (pt.wallModel == UGF_WALL_CLL);
         if (pt.wallModel != UGF_WALL_SPECULAR) {
@@ -264,7 +265,7 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
             if (Un > 0.0) for (int k = 0; k < 3; ++k) st.U[k] = st.U[k] - 2.0 * Un * nw[k];
         }
         st.flags |= HIT_CHANGED_U;
-        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, sp, st.U, st.erot, nw, fA, pre, true);
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, true);
     } else if (pt.kind == UGF_PATCH_SYMMETRY) {
         const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
         double nw[3], fA;
@@ -293,6 +294,21 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
     } else {
         st.cell = -1; st.flags |= HIT_STUCK;
     }
+}
+
+// uniGasCloud::cellWeighting for one parcel (U/clouds/uniGasCloud.C:1360-1421): the parcel carried wOld and now sits
+// in a cell whose factor is wNew.  Returns the number of clones (>= 0) or -1 = delete.  The rare path of the move
+// (only parcels whose factor changes), out of line; one uniform from the parcel's own stream.
+__device__ __noinline__ int weighting_decision(uint64_t seed, uint32_t step, uint32_t i, double wOld, double wNew) {
+    Stream r(seed, KIND_WEIGHT, 0, step, i, 0);
+    if (wOld > wNew) {
+        double prob = wOld / wNew - 1.0;
+        int k = 0;
+        while (prob > 1.0 && k < 254) { ++k; prob -= 1.0; }
+        if (prob > r.u01()) ++k;
+        return k;
+    }
+    return (wOld / wNew < r.u01()) ? -1 : 0;
 }
 
 // ---- bulk-copy (TMA) staging helpers ---------------------------------------------------------------------------
@@ -327,7 +343,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 template <bool HAS_ROT, bool MULTI, int NF>
 __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArgs& a, const long long i, const bool valid, int cell, double x0,
                                              double x1, double x2, double U0, double U1, double U2) {
-    int flags = 0, nWall = 0;
+    int flags = 0, nWall = 0, nClone = 0;
     if (valid && cell >= 0) {
         int nDraws = 0;
         double sf = 0.0;
@@ -422,6 +438,19 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
             }
             if (++iters > MAX_TRACK_ITERS) { cell = -1; flags |= HIT_STUCK; break; }
         }
+        if (prm.cwf) {  // weighting() right after the move (U/clouds/uniGasCloud.C:839-842): old factor = the one of the
+                        // cell the parcel started the step in (re-read before it is overwritten), new = where it stopped
+            int k = 0;
+            if (cell >= 0) {
+                const int cell0 = a.P.cell[i];
+                const double wNew = __ldg(&prm.cwf[cell]);
+                const double wOld = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[cell0]) : __ldg(&prm.cwf[cell0]);
+                if (wOld != wNew) k = weighting_decision(prm.seed, a.step, (uint32_t)i, wOld, wNew);
+                if (k < 0) { cell = -1; flags |= HIT_WDELETED; k = 0; }
+            }
+            a.nclone[i] = (uint8_t)k;
+            nClone = k;
+        }
         a.P.x[i] = x0; a.P.y[i] = x1; a.P.z[i] = x2;
         a.P.cell[i] = cell;
         if (flags & HIT_CHANGED_U) {
@@ -436,6 +465,15 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
         int head, cnt, rank;
         warp_runs(live ? cell : -1, lane, head, cnt, rank);
         if (live && rank == 0) atomicAdd(&a.cellCount[cell], cnt);
+        if (nClone) atomicAdd(&a.cellCount[cell], nClone);  // clones take slots of the same cell
+    }
+    if (prm.cwf && __any_sync(0xffffffffu, (nClone | (flags & HIT_WDELETED)) != 0)) {
+        const int sc = warp_sum_int(nClone);
+        const int swd = __popc(__ballot_sync(0xffffffffu, (flags & HIT_WDELETED) != 0));
+        if (lane == 0) {
+            if (sc) atomicAdd(&a.cnt->cloned, (unsigned long long)sc);
+            if (swd) atomicAdd(&a.cnt->wdeleted, (unsigned long long)swd);
+        }
     }
     if (__any_sync(0xffffffffu, (flags | nWall) != 0)) {
         const int sd = __popc(__ballot_sync(0xffffffffu, (flags & HIT_DELETED) != 0));

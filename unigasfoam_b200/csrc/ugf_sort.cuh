@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int* __
 
 // single block: exclusive scan of blockSums in place; writes the grand total to *total and, if given, to
 // *dN (the live parcel count becomes the array length after the gather).
-__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(int* blockSums, int nb, int* total, long long* dN) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(int* blockSums, int nb, int* total, long long* dN, long long capacity, int* err) {
     __shared__ int sm[33];
     int carry = 0;
     for (int base = 0; base < nb; base += SCAN_THREADS) {
@@ -74,6 +74,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(int* blockSums, 
         carry += t;
     }
     if (threadIdx.x == 0) {
+        if (carry > capacity) {  // clones (cell weighting) outgrew the parcel arrays: report, and leave an empty occupancy
+            if (err) atomicCAS(err, 0, 1);  // behind so that no later kernel writes past the arrays
+            carry = 0;
+        }
         *total = carry;
         if (dN) *dN = carry;
     }
@@ -91,9 +95,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(int* __restric
     for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? counts[base + k] : 0; s += v[k]; }
     int t;
     int ex = block_exclusive_scan(s, &t, sm) + blockSums[blockIdx.x];
+    const bool dead = (*total == 0);  // empty cloud, or the capacity overflow flagged by scan_top_kernel
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < n) { offsets[base + k] = ex; counts[base + k] = 0; }
+        if (base + k < n) { offsets[base + k] = dead ? 0 : ex; counts[base + k] = 0; }
         ex += v[k];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = *total;
@@ -119,7 +124,8 @@ __device__ __forceinline__ void warp_runs(int key, int lane, int& head, int& cnt
 constexpr int SCAT_ROWS = 4;
 __global__ void __launch_bounds__(256) scatter_index_kernel(const int* __restrict__ cell, const long long* __restrict__ dN,
                                                             const int* __restrict__ offsets, int* __restrict__ cursor,
-                                                            int* __restrict__ perm) {
+                                                            int* __restrict__ perm, const uint8_t* __restrict__ nclone,
+                                                            long long capacity) {
     const int lane = threadIdx.x & 31;
     const long long wbase = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * SCAT_ROWS) + lane;
     const long long n = *dN;
@@ -143,7 +149,19 @@ __global__ void __launch_bounds__(256) scatter_index_kernel(const int* __restric
 #pragma unroll
     for (int r = 0; r < SCAT_ROWS; ++r) {
         const int b = __shfl_sync(0xffffffffu, base[r], head[r]);
-        if (c[r] >= 0) perm[off[r] + b + rank[r]] = (int)(wbase + r * 32);
+        if (c[r] >= 0 && (long long)off[r] + b + rank[r] < capacity) perm[off[r] + b + rank[r]] = (int)(wbase + r * 32);
+    }
+    if (nclone) {  // cell weighting: a parcel with k clones claims k more slots of its cell for entries CLONE_FLAG | id
+#pragma unroll
+        for (int r = 0; r < SCAT_ROWS; ++r) {
+            const long long i = wbase + r * 32;
+            const int k = (c[r] >= 0) ? nclone[i] : 0;
+            if (k) {
+                const int b = atomicAdd(&cursor[c[r]], k);
+                for (int j = 0; j < k; ++j)
+                    if ((long long)off[r] + b + j < capacity) perm[off[r] + b + j] = CLONE_FLAG | (int)i;
+            }
+        }
     }
 }
 
@@ -255,7 +273,7 @@ template <bool HAS_ROT, bool MULTI>
 __global__ void __launch_bounds__(256) reorder_kernel(ParcelBuf in, ParcelBuf out, const int* __restrict__ perm, const int* __restrict__ total) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= *total) return;
-    const int s = perm[j];
+    const int s = perm[j] & CLONE_MASK;
     out.x[j] = in.x[s]; out.y[j] = in.y[s]; out.z[j] = in.z[s];
     out.ux[j] = in.ux[s]; out.uy[j] = in.uy[s]; out.uz[j] = in.uz[s];
     out.cell[j] = in.cell[s];
