@@ -280,7 +280,8 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p);
  * the BGK macroscopic state, the inflow count (uniGasGeneralBoundary.C:154-165), the wall heat flux / force
  * (uniGasPatchBoundary.C:292-299) and the wall fields (uniGasVolFields.C:1276-1278).  Upload it before the parcels.
  * A factor changed while parcels exist (uniGasDynamicAdapter.C:660-677) is applied by the next step's weighting pass
- * (old factor of the parcel's previous cell / new factor of its current cell).  Single rank for now. */
+ * (old factor of the parcel's previous cell / new factor of its current cell).  Across processor patches the factor
+ * travels with the parcel (migration record slot 9). */
 int ugf_upload_cell_state(ugf_handle* h, const double* sigmaTcRMax, const int32_t* collModelId,
                           const int32_t* subCellLevels, const double* cellWeightFactor);
 int ugf_set_deltaT(ugf_handle* h, double deltaT);
@@ -334,7 +335,7 @@ int ugf_finish_step(ugf_handle* h);
 /* After ugf_move: number of parcels waiting on each processor patch [nPatches] (0 for other kinds). */
 int ugf_migrate_counts(ugf_handle* h, int64_t* sendCounts);
 /* Pack the parcels waiting on `patch` into a device buffer of UGF_MIGRATE_STRIDE doubles per parcel
- * (x,y,z,Ux,Uy,Uz,ERot,stepFraction,localFace,typeId as doubles) and remove them from the cloud.
+ * (x,y,z,Ux,Uy,Uz,ERot,stepFraction, localFace + 2^32 typeId, cellWeight; all doubles) and remove them from the cloud.
  * *devBuf is owned by the handle and valid until the next pack on the same patch. */
 #define UGF_MIGRATE_STRIDE 10
 int ugf_migrate_pack(ugf_handle* h, int32_t patch, double** devBuf, int64_t* nPacked);

@@ -1738,7 +1738,6 @@ int ugfo_move(ugfo_handle* h) {
     openStep(h);
     // parcels that were not inserted this step start the step at stepFraction 0
     for (int64_t i = 0; i < (int64_t)h->P.size(); ++i) if (!h->P[i].newParcel) h->P[i].sf = 0;
-    if (h->cellWeighted && h->cfg.nRanks > 1) return fail(h, "cell weighting is single-rank for now (the migration record carries no weight)");
     moveRange(*h, 0, (int64_t)h->P.size(), true);
     h->weightPending = true;
     h->receivedStart = (int64_t)h->P.size();
@@ -1838,7 +1837,7 @@ int ugfo_migrate_pack(ugfo_handle* h, int32_t patch, double** buf, int64_t* n) {
     for (Parcel& q : h->P) {
         if (q.cell > -2 || h->facePatch[-2 - q.cell] != patch) continue;
         const int lface = (-2 - q.cell) + h->nInternal - h->pStart[patch];
-        const double rec[UGF_MIGRATE_STRIDE] = {q.x[0], q.x[1], q.x[2], q.U[0], q.U[1], q.U[2], q.ERot, q.sf, (double)lface, (double)q.typeId};
+        const double rec[UGF_MIGRATE_STRIDE] = {q.x[0], q.x[1], q.x[2], q.U[0], q.U[1], q.U[2], q.ERot, q.sf, (double)lface + 4294967296.0 * (double)q.typeId, q.CWF};
         b.insert(b.end(), rec, rec + UGF_MIGRATE_STRIDE);
         q.cell = -1;
     }
@@ -1854,10 +1853,12 @@ int ugfo_migrate_unpack(ugfo_handle* h, int32_t patch, const double* buf, int64_
         Parcel q;
         for (int k = 0; k < 3; ++k) { q.x[k] = r[k]; q.U[k] = r[3 + k]; }
         q.ERot = r[6]; q.sf = r[7];
-        const int lf = (int)r[8];
+        const int type = (int)(r[8] * (1.0 / 4294967296.0));
+        const int lf = (int)(r[8] - 4294967296.0 * type);
         if (lf < 0 || lf >= h->pSize[patch]) return fail(h, "received face index out of range");
         q.cell = h->owner[h->pStart[patch] + lf];
-        q.typeId = (int)r[9];
+        q.typeId = type;
+        q.CWF = r[9];  // the weight factor travels with the parcel
         q.newParcel = 0;
         h->P.push_back(q);
     }

@@ -120,7 +120,7 @@ def _worker_3d(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def _worker_cyl(rank, world, port, out):
+def _worker_cyl(rank, world, port, out, weighted=False):
     """Config-3 shape: Mach-10 cylinder O-grid with free-stream inflow, deleting outflow, diffuse wall and symmetry
     axis, cut along the wake axis by mesh.decompose: insertion on one rank, migration across the cut, outflow on the
     other, every step."""
@@ -132,7 +132,9 @@ def _worker_cyl(rank, world, port, out):
     from unigasfoam_b200 import mesh as ugmesh
     from unigasfoam_b200.cloud import UniGasCloud
     from unigasfoam_b200.exchange import PeerExchanger, SlotExchanger, evolve_distributed
-    case = cases.cylinder(nr=16, ntheta=32, ppc=25)
+    # weighted: the reference tutorial's own setting (hypersonicCylinder: cellWeightedSimulation true) - the factor
+    # follows the cell volume, parcels are cloned / deleted as they cross cells and carry their factor across the cut
+    case = cases.cylinder(nr=16, ntheta=32, ppc=25, cellWeightFactor=("particlesPerSubCell", 25) if weighted else None)
     part = ugmesh.slab_partition(case.mesh, world, axis=1)
     sub = ugmesh.decompose(case.mesh, part, world)[rank]
     g2l = np.full(case.mesh.n_cells, -1)
@@ -142,6 +144,8 @@ def _worker_cyl(rank, world, port, out):
     for name, cls in (("gpu", UniGasCloud), ("oracle", OracleCloud)):
         kw = dict(device=rank) if name == "gpu" else {}
         cl = cls(sub, case.uniGasProperties, case.boundariesDict, case.deltaT, parcelCapacity=4 * int(sel.sum()) + 4096, rank=rank, nRanks=world, **kw)
+        if weighted:
+            cl.setCellState(cellWeightFactor=case.cellWeightFactor[sub.cell_map])
         cl.setParcels(case.position[sel], case.U[sel], g2l[case.cell[sel]])
         cl.setCellState(sigmaTcRMax=case.sigmaTcRMax)
         if name == "gpu":
@@ -156,7 +160,10 @@ def _worker_cyl(rank, world, port, out):
     same = len(pg["cell"]) == len(pr["cell"]) and np.array_equal(pg["cell"], pr["cell"])
     closeU = (np.abs(pg["U"] - pr["U"]) <= 1e-9 * np.abs(pr["U"]).max()).all(1).mean() if same else 0.0
     closeX = (np.abs(pg["position"] - pr["position"]) <= 1e-12 * np.abs(pr["position"]).max()).all(1).mean() if same else 0.0
-    tot = torch.tensor([cg["inserted"], cg["deleted"], cg["migrated"]])
+    tot = torch.tensor([cg["inserted"], cg["deleted"], cg["migrated"]] + ([cg["cloned"], cg["weightDeleted"]] if weighted else []))
+    if weighted:
+        same = same and cg["cloned"] == cr["cloned"] and cg["weightDeleted"] == cr["weightDeleted"] and np.array_equal(pg["cellWeight"], pr["cellWeight"]) \
+            and np.array_equal(pg["cellWeight"], case.cellWeightFactor[sub.cell_map][pg["cell"]])
     dist.all_reduce(tot, group=meta)
     ok = bool(same and closeU > 0.99 and closeX > 0.99 and cg["stuck"] == 0 and cg["inserted"] == cr["inserted"] and cg["deleted"] == cr["deleted"]
               and abs(cg["collisions"] - cr["collisions"]) <= 2 and (tot > 0).all())
@@ -175,6 +182,16 @@ def test_two_gpu_decomposed_cylinder_with_inflow_matches_oracle(tmp_path, GpuClo
         pytest.skip("needs 2 GPUs")
     out = str(tmp_path / "rescyl.pt")
     mp.spawn(_worker_cyl, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert all(ok for ok, _ in res), res
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_decomposed_weighted_cylinder_matches_oracle(tmp_path, GpuCloud):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "rescylw.pt")
+    mp.spawn(_worker_cyl, args=(2, _free_port(), out, True), nprocs=2, join=True)
     res = torch.load(out, weights_only=False)
     assert all(ok for ok, _ in res), res
 

@@ -84,3 +84,53 @@ def test_two_rank_migration_matches_single_domain(tmp_path, OracleCloud, slots):
     assert g.shape == w.shape
     err = np.abs(g - w) / (np.abs(w).max(0) + 1e-300)
     assert err.max() < 1e-11, (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+def _worker_weighted(rank, world, port, steps, out):
+    """Decomposed, cell-weighted cylinder (the reference tutorial's setting) on the oracle: a parcel that crosses the
+    cut carries its weight factor in the migration record and is cloned / deleted against the factor of the cell it
+    lands in on the other rank."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle_cloud import OracleCloud
+    from unigasfoam_b200 import mesh as ugmesh
+    from unigasfoam_b200.exchange import SlotExchanger, evolve_distributed
+    case = cases.cylinder(nr=12, ntheta=24, ppc=20, cellWeightFactor=("particlesPerSubCell", 20))
+    part = ugmesh.slab_partition(case.mesh, world, axis=1)
+    sub = ugmesh.decompose(case.mesh, part, world)[rank]
+    g2l = np.full(case.mesh.n_cells, -1)
+    g2l[sub.cell_map] = np.arange(sub.n_cells)
+    sel = part[case.cell] == rank
+    W = case.cellWeightFactor[sub.cell_map]
+    cl = OracleCloud(sub, case.uniGasProperties, case.boundariesDict, case.deltaT, parcelCapacity=4 * int(sel.sum()) + 4096, rank=rank, nRanks=world)
+    cl.setCellState(cellWeightFactor=W)
+    cl.setParcels(case.position[sel], case.U[sel], g2l[case.cell[sel]])
+    cl.setCellState(sigmaTcRMax=case.sigmaTcRMax)
+    ex = SlotExchanger(cl, sub, rank, world, slot_capacity=4000, cuda=False)
+    tally = np.zeros(3)
+    for _ in range(steps):
+        evolve_distributed(cl, ex, 1, inflow=True)
+        c = cl.counters()
+        tally += [c["cloned"], c["weightDeleted"], c["migrated"]]
+    p = cl.parcels()
+    res = dict(ok=bool(np.array_equal(p["cellWeight"], W[p["cell"]])), tally=tally, n=len(p["cell"]), stuck=cl.counters()["stuck"],
+               real=float(W[p["cell"]].sum()), real0=float(case.cellWeightFactor[case.cell[sel]].sum()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_cell_weighted_cylinder(tmp_path, OracleCloud):
+    world, steps = 2, 12
+    out = str(tmp_path / "resw.pt")
+    mp.spawn(_worker_weighted, args=(world, _free_port(), steps, out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    assert all(r["ok"] and r["stuck"] == 0 for r in res), res
+    tot = sum(r["tally"] for r in res)
+    assert (tot > 0).all(), tot  # clones, deletions and migrations all happened
+    real, real0 = sum(r["real"] for r in res), sum(r["real0"] for r in res)
+    assert abs(real / real0 - 1) < 0.05  # real molecules (sum of weights) stay put over a few steps of a uniform free stream

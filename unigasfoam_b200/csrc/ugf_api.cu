@@ -100,6 +100,7 @@ struct ugf_handle {
     ParcelBuf buf[2]{};
     int cur = 0;
     double* dSf = nullptr;
+    double* dWq = nullptr;          // cell weighting on a decomposed case: factor carried by each parcel in flight
     long long* dN = nullptr;
     long long nUpper = 0;           // host upper bound of *dN
     long long* pinN = nullptr;      // pinned readback of *dN
@@ -502,6 +503,7 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.begin = begin;
     a.newFrom = received ? (1LL << 62) : h->newFrom;
     a.sf = h->dSf;
+    a.wq = h->dWq;
     a.useSfIn = received ? 1 : 0;
     a.step = (uint32_t)h->step;
     a.aux = received ? 1u : 0u;
@@ -515,8 +517,6 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.bm = h->dBm;
     a.cnt = h->dCnt;
     a.nclone = h->prm.cwf ? h->dNclone : nullptr;
-    if (h->prm.cwf && (received || h->hasProcessor))
-        return fail(h, "cell weighting is single-rank for now (the migration record carries no weight)");
     long long count = h->nUpper - begin;
     if (a.dBegin) count = std::min<long long>(count, (long long)h->migSlots.nProc * h->lastSlotCapacity);  // what one unpack can append
     if (count > 0) {
@@ -604,7 +604,7 @@ int pack_slots_to(ugf_handle* h, const MigDst& dst, long long slotCapacity) {
         ParcelBuf P = h->buf[h->cur];
         const MigSlots ms = h->migSlots;
         dispatch(h, [&](auto R, auto M) {
-            mig_pack_list_kernel<decltype(R)::value, decltype(M)::value><<<ms.nProc, 1024, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dMigCount, h->dMigList, MIG_LIST_CAP,
+            mig_pack_list_kernel<decltype(R)::value, decltype(M)::value><<<ms.nProc, 1024, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dWq, h->dMigCount, h->dMigList, MIG_LIST_CAP,
                                                                                                           dst, slotCapacity, h->dErr);
         });
         LAUNCHED();
@@ -620,7 +620,7 @@ int pack_slots_to(ugf_handle* h, const MigDst& dst, long long slotCapacity) {
     mig_scan_kernel<<<ms.nProc, SCAN_THREADS, 0, h->stream>>>(counts, offsets, nb, h->dMigTotals);
     LAUNCHED();
     dispatch(h, [&](auto R, auto M) {
-        mig_pack_all_kernel<decltype(R)::value, decltype(M)::value><<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dN, counts, offsets, h->dMigTotals, nb,
+        mig_pack_all_kernel<decltype(R)::value, decltype(M)::value><<<nb, MIG_THREADS, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dWq, h->dN, counts, offsets, h->dMigTotals, nb,
                                                                                                         dst, slotCapacity, h->dErr);
     });
     LAUNCHED();
@@ -787,7 +787,7 @@ int ugf_destroy(ugf_handle* h) {
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
-                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone};
+                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -1211,11 +1211,11 @@ int ugf_upload_cell_state(ugf_handle* h, const double* s, const int32_t* id, con
     if (cwf) {  // cellWeightedSimulation: see include/ugf.h
         for (size_t c = 0; c < nC; ++c) if (!(cwf[c] > 0.0)) return fail(h, "cellWeightFactor must be positive");
         if (h->capacity >= (long long)CLONE_FLAG) return fail(h, "cell weighting needs parcelCapacity < 2^30");
-        if (h->cfg.nRanks > 1 || h->hasProcessor) return fail(h, "cell weighting is single-rank for now (the migration record carries no weight)");
         const bool haveParcels = h->buf[0].x && h->nUpper > 0;
         if (!h->dCwf[0]) {
             if (dalloc(h, &h->dCwf[0], nC) || dalloc(h, &h->dCwf[1], nC)) return 1;
             if (dalloc(h, &h->dNclone, (size_t)h->capacity + MOVE_TILE)) return 1;
+            if (h->hasProcessor && dalloc(h, &h->dWq, (size_t)h->capacity)) return 1;
             h->cwfHostPrev.assign(nC, 1.0);  // parcels uploaded so far carry factor 1
             if (upload(h, h->dCwf[1], h->cwfHostPrev.data(), nC)) return 1;
             h->cwfCur = 0;
@@ -1521,7 +1521,7 @@ int ugf_migrate_pack(ugf_handle* h, int32_t patch, double** devBuf, int64_t* nPa
     LAUNCHED();
     double* buf = h->packBuf[patch];
     dispatch(h, [&](auto R, auto M) {
-        mig_pack_kernel<decltype(R)::value, decltype(M)::value><<<nb, 1024, 0, h->stream>>>(h->mesh, P, h->dSf, h->dN, patch, h->dMigBlock, buf);
+        mig_pack_kernel<decltype(R)::value, decltype(M)::value><<<nb, 1024, 0, h->stream>>>(h->mesh, P, h->dSf, h->dWq, h->dN, patch, h->dMigBlock, buf);
     });
     LAUNCHED();
     CU(cudaMemsetAsync(h->dMigCount + patch, 0, sizeof(int), h->stream));
@@ -1542,7 +1542,7 @@ int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64
     ParcelBuf P = h->buf[h->cur];
     const long long base = h->nUpper;
     dispatch(h, [&](auto R, auto M) {
-        mig_unpack_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(n, 256), 256, 0, h->stream>>>(h->mesh, P, h->dSf, base, n, patch, devBuf, h->dErr);
+        mig_unpack_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(n, 256), 256, 0, h->stream>>>(h->mesh, P, h->dSf, h->dWq, base, n, patch, devBuf, h->dErr);
     });
     LAUNCHED();
     h->nUpper += n;
@@ -1642,7 +1642,7 @@ int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotC
     const MigSlots ms = h->migSlots;
     dispatch(h, [&](auto R, auto M) {
         mig_unpack_all_kernel<decltype(R)::value, decltype(M)::value><<<dim3(grid_for(slotCapacity, 256), ms.nProc), 256, 0, h->stream>>>(
-            h->mesh, ms, P, h->dSf, h->dN, h->capacity, devRecv, (long long)slotCapacity, h->dErr);
+            h->mesh, ms, P, h->dSf, h->dWq, h->dN, h->capacity, devRecv, (long long)slotCapacity, h->dErr);
     });
     LAUNCHED();
     mig_commit_kernel<<<1, 1, 0, h->stream>>>(h->dN, h->dRecvStart, h->dInflight, devRecv, ms.nProc, (long long)slotCapacity, h->capacity, h->dErr);

@@ -143,6 +143,10 @@ __device__ __forceinline__ bool on_patch(const MeshDev& mesh, int cell, int patc
     return cell <= -2 && mesh.bfPatch[-2 - cell] == patch;
 }
 
+// record slot 8 = local face index + MIG_TYPE_SHIFT * typeId (both exact in a double); slot 9 = the cell weight factor the
+// parcel carries (cell weighting; 1 otherwise)
+constexpr double MIG_TYPE_SHIFT = 4294967296.0;
+
 __global__ void __launch_bounds__(1024) mig_count_kernel(MeshDev mesh, const int* __restrict__ cell, const long long* dN, int patch,
                                                          int* __restrict__ blockCounts) {
     __shared__ int sm[33];
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(1024) mig_count_kernel(MeshDev mesh, const int
 }
 
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(1024) mig_pack_kernel(MeshDev mesh, ParcelBuf P, const double* __restrict__ sf, const long long* dN, int patch,
+__global__ void __launch_bounds__(1024) mig_pack_kernel(MeshDev mesh, ParcelBuf P, const double* __restrict__ sf, const double* __restrict__ wq, const long long* dN, int patch,
                                                         const int* __restrict__ blockOffsets, double* __restrict__ buf) {
     __shared__ int sm[33];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,20 +174,21 @@ __global__ void __launch_bounds__(1024) mig_pack_kernel(MeshDev mesh, ParcelBuf 
         r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
         r[6] = HAS_ROT ? P.erot[i] : 0.0;
         r[7] = sf[i];
-        r[8] = (double)(bfi - mesh.patches[patch].startBfi);
-        r[9] = MULTI ? (double)P.type[i] : 0.0;
+        r[8] = (double)(bfi - mesh.patches[patch].startBfi) + (MULTI ? MIG_TYPE_SHIFT * (double)P.type[i] : 0.0);
+        r[9] = wq ? wq[i] : 1.0;
         P.cell[i] = -1;
     }
 }
 
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(256) mig_unpack_kernel(MeshDev mesh, ParcelBuf P, double* __restrict__ sf, long long base, long long n, int patch,
+__global__ void __launch_bounds__(256) mig_unpack_kernel(MeshDev mesh, ParcelBuf P, double* __restrict__ sf, double* __restrict__ wq, long long base, long long n, int patch,
                                                          const double* __restrict__ buf, int* errFlag) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double* r = buf + (size_t)i * UGF_MIGRATE_STRIDE;
     const long long dst = base + i;
-    const int lf = (int)r[8];
+    const int type = (int)(r[8] * (1.0 / MIG_TYPE_SHIFT));
+    const int lf = (int)(r[8] - MIG_TYPE_SHIFT * type);
     const DevPatch& pt = mesh.patches[patch];
     if (lf < 0 || lf >= pt.size) { *errFlag = 2; P.cell[dst] = -1; return; }
     P.x[dst] = r[0]; P.y[dst] = r[1]; P.z[dst] = r[2];
@@ -191,7 +196,8 @@ __global__ void __launch_bounds__(256) mig_unpack_kernel(MeshDev mesh, ParcelBuf
     if (HAS_ROT) P.erot[dst] = r[6];
     sf[dst] = r[7];
     P.cell[dst] = mesh.bfOwner[pt.startBfi + lf];
-    if (MULTI) P.type[dst] = (uint8_t)r[9];
+    if (MULTI) P.type[dst] = (uint8_t)type;
+    if (wq) wq[dst] = r[9];
 }
 
 // ---- fixed-slot migration: all processor patches in two passes over the parcels, no host round trip ------------
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) mig_scan_kernel(const int* __res
 // pass 2: blocks whose tile holds no waiting parcel return after reading their counts; the others rank their
 // waiting parcels in index order per slot and write the records
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const long long* dN,
+__global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const double* __restrict__ wq, const long long* dN,
                                                                    const int* __restrict__ blockCounts, const int* __restrict__ blockOffsets,
                                                                    const int* __restrict__ totals, int nBlocks, const MigDst dst,
                                                                    long long slotCapacity, int* errFlag) {
@@ -312,8 +318,8 @@ __global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh,
                 r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
                 r[6] = HAS_ROT ? P.erot[i] : 0.0;
                 r[7] = sf[i];
-                r[8] = (double)(bfi - mesh.patches[ms.patch[k]].startBfi);
-                r[9] = MULTI ? (double)P.type[i] : 0.0;
+                r[8] = (double)(bfi - mesh.patches[ms.patch[k]].startBfi) + (MULTI ? MIG_TYPE_SHIFT * (double)P.type[i] : 0.0);
+                r[9] = wq ? wq[i] : 1.0;
             }
             P.cell[i] = -1;
             ++pos;
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(MIG_THREADS) mig_pack_all_kernel(MeshDev mesh,
 
 // Unpack every slot in one launch (blockIdx.y = slot): slot k appends after the parcels of slots < k.
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(256) mig_unpack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, double* __restrict__ sf, const long long* dN,
+__global__ void __launch_bounds__(256) mig_unpack_all_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, double* __restrict__ sf, double* __restrict__ wq, const long long* dN,
                                                              long long capacity, const double* __restrict__ recv, long long slotCapacity, int* errFlag) {
     const int k = blockIdx.y;
     const long long slotStride = (slotCapacity + 1) * UGF_MIGRATE_STRIDE;
@@ -337,7 +343,8 @@ __global__ void __launch_bounds__(256) mig_unpack_all_kernel(MeshDev mesh, MigSl
     const long long dst = base + i;
     if (dst >= capacity) { *errFlag = 1; return; }
     const double* r = slot + (1 + i) * UGF_MIGRATE_STRIDE;
-    const int lf = (int)r[8];
+    const int type = (int)(r[8] * (1.0 / MIG_TYPE_SHIFT));
+    const int lf = (int)(r[8] - MIG_TYPE_SHIFT * type);
     const DevPatch& pt = mesh.patches[ms.patch[k]];
     if (lf < 0 || lf >= pt.size) { *errFlag = 2; P.cell[dst] = -1; return; }
     P.x[dst] = r[0]; P.y[dst] = r[1]; P.z[dst] = r[2];
@@ -345,7 +352,8 @@ __global__ void __launch_bounds__(256) mig_unpack_all_kernel(MeshDev mesh, MigSl
     if (HAS_ROT) P.erot[dst] = r[6];
     sf[dst] = r[7];
     P.cell[dst] = mesh.bfOwner[pt.startBfi + lf];
-    if (MULTI) P.type[dst] = (uint8_t)r[9];
+    if (MULTI) P.type[dst] = (uint8_t)type;
+    if (wq) wq[dst] = r[9];
 }
 
 // after the unpack: remember where the received parcels start, extend the array, reset the in-flight tally
@@ -368,7 +376,7 @@ __global__ void mig_commit_kernel(long long* dN, long long* dRecvStart, unsigned
 constexpr int MIG_LIST_CAP = 8192;  // migrants per patch and round the list path handles (32 KB of shared memory)
 
 template <bool HAS_ROT, bool MULTI>
-__global__ void __launch_bounds__(1024) mig_pack_list_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, int* __restrict__ migCount,
+__global__ void __launch_bounds__(1024) mig_pack_list_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const double* __restrict__ wq, int* __restrict__ migCount,
                                                              const int* __restrict__ migList, int listCap, const MigDst dst, long long slotCapacity,
                                                              int* errFlag) {
     __shared__ int s[MIG_LIST_CAP];
@@ -409,8 +417,8 @@ __global__ void __launch_bounds__(1024) mig_pack_list_kernel(MeshDev mesh, MigSl
         r[3] = P.ux[i]; r[4] = P.uy[i]; r[5] = P.uz[i];
         r[6] = HAS_ROT ? P.erot[i] : 0.0;
         r[7] = sf[i];
-        r[8] = (double)(bfi - startBfi);
-        r[9] = MULTI ? (double)P.type[i] : 0.0;
+        r[8] = (double)(bfi - startBfi) + (MULTI ? MIG_TYPE_SHIFT * (double)P.type[i] : 0.0);
+        r[9] = wq ? wq[i] : 1.0;
         P.cell[i] = -1;
     }
     __syncthreads();

@@ -213,6 +213,7 @@ struct MoveArgs {
     int migListCap;
     double* bm;            // [nBFaces][UGF_NBM]
     DevCounters* cnt;
+    double* wq;            // cell weighting + processor patches: the factor a parcel in flight carries (out for migrants, in for received)
     uint8_t* nclone;       // cell weighting: clones each parcel gets from cellWeighting() (written for every parcel), else null
 };
 
@@ -281,6 +282,10 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
         st.cell = -2 - bfi;
         st.flags |= HIT_MIGRATED;
         if (a.sf) a.sf[i] = st.sf;
+        if (prm.cwf && a.wq && !a.useSfIn) {  // first hop: the factor of the cell the step started in (still in P.cell)
+            const int c0 = a.P.cell[i];
+            a.wq[i] = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[c0]) : __ldg(&prm.cwf[c0]);
+        }
         const int pos = atomicAdd(&a.migCount[patch], 1);
         if (a.migList) {  // remember who waits here: the pack kernel then never has to search the whole cloud
             int slot = -1;
@@ -442,9 +447,14 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
                         // cell the parcel started the step in (re-read before it is overwritten), new = where it stopped
             int k = 0;
             if (cell >= 0) {
-                const int cell0 = a.P.cell[i];
                 const double wNew = __ldg(&prm.cwf[cell]);
-                const double wOld = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[cell0]) : __ldg(&prm.cwf[cell0]);
+                double wOld;
+                if (a.useSfIn) {
+                    wOld = a.wq[i];  // received parcel: the factor travelled with it
+                } else {
+                    const int cell0 = a.P.cell[i];
+                    wOld = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[cell0]) : __ldg(&prm.cwf[cell0]);
+                }
                 if (wOld != wNew) k = weighting_decision(prm.seed, a.step, (uint32_t)i, wOld, wNew);
                 if (k < 0) { cell = -1; flags |= HIT_WDELETED; k = 0; }
             }
