@@ -87,6 +87,7 @@ struct ugf_handle {
     std::vector<int32_t> ownerHost, neighbourHost, cfOffHost, cfHost, patchPartnerHost;
     std::vector<double> SfHost, CfHost, pointsHost, ccHost;
     std::vector<int32_t> fpOffHost, fpHost;
+    double* dRec2d = nullptr;
     int* dCfOff = nullptr; double4* dPlane = nullptr; int* dNbr = nullptr; int* dBfPatch = nullptr; int* dBfOwner = nullptr;
     DevPatch* dPatches = nullptr; double* dVol = nullptr; double* dBbMin = nullptr; double* dBbMax = nullptr; double* dBfS = nullptr;
     bool hasProcessor = false;
@@ -131,7 +132,9 @@ struct ugf_handle {
     unsigned short* dSub = nullptr;  // [capacity] sub-cell index per parcel
     DevCounters* dCnt = nullptr;
     int* dErr = nullptr;
-    int* dTask = nullptr;            // cell_kernel task counter
+    int* dTask = nullptr;            // cell_kernel task counters (two, used alternately: each launch zeroes the other one)
+    int taskSel = 0;
+    bool cellCountZero = false;      // dCellCount is all zero (left so by the segment sort)
     double* dTot = nullptr;
     bool histValid = false, occValid = false, occIdentity = false, momValid = false;
     // cell weighting (cellWeightedSimulation)
@@ -328,22 +331,22 @@ int do_sort(ugf_handle* h) {
     if (refresh_n(h)) return 1;
     const int nC = h->nCells;
     if (!h->histValid) {
-        CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * nC, h->stream));
+        if (!h->cellCountZero) CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * nC, h->stream));
+        h->cellCountZero = false;
         hist_kernel<<<grid_for(h->nUpper, 256), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dCellCount, h->cloneValid ? h->dNclone : nullptr);
         LAUNCHED();
     }
     const int nb = (nC + SCAN_TILE - 1) / SCAN_TILE;
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums);
     LAUNCHED();
-    scan_top_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->dBlockSums, nb, h->dTotal, nullptr, h->capacity, h->dErr);
-    LAUNCHED();
-    scan_final_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums, h->dTotal, h->dOff);
+    scan_final_self_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums, nb, h->dTotal, h->dOff, h->capacity, h->dErr);
     LAUNCHED();
     scatter_index_kernel<<<grid_for(h->nUpper, 256 * SCAT_ROWS), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dOff, h->dCellCount, h->dPerm,
                                                                                                     h->cloneValid ? h->dNclone : nullptr, h->capacity);
     LAUNCHED();
-    segment_sort_kernel<<<grid_for(((long long)nC + SEG_CHUNK - 1) / SEG_CHUNK, SEG_THREADS / 32), SEG_THREADS, 0, h->stream>>>(h->dOff, nC, h->dPerm);
+    segment_sort_kernel<<<grid_for(((long long)nC + SEG_CHUNK - 1) / SEG_CHUNK, SEG_THREADS / 32), SEG_THREADS, 0, h->stream>>>(h->dOff, nC, h->dPerm, h->dCellCount);
     LAUNCHED();
+    h->cellCountZero = true;
     h->histValid = false;
     h->occValid = true;
     h->occIdentity = false;
@@ -352,11 +355,13 @@ int do_sort(ugf_handle* h) {
 }
 
 // after a gather the array is cell-major and its length is the live count
-int after_gather(ugf_handle* h) {
+int after_gather(ugf_handle* h, bool setN = true) {
     h->cur ^= 1;
     h->cloneValid = false;  // the clones are parcels of their own now
-    set_n_kernel<<<1, 1, 0, h->stream>>>(h->dTotal, h->dN);
-    LAUNCHED();
+    if (setN) {  // the cell kernel writes the new length itself
+        set_n_kernel<<<1, 1, 0, h->stream>>>(h->dTotal, h->dN);
+        LAUNCHED();
+    }
     h->occIdentity = true;
     return request_n(h);
 }
@@ -379,19 +384,22 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
     a.acc = h->dAcc;
     a.accS = h->dAccS;
     a.accDt = (accumulate && doSample) ? h->cfg.deltaT : 0.0;
-    a.taskCounter = h->dTask;
+    a.taskCounter = h->dTask + h->taskSel;
+    a.taskReset = h->dTask + (h->taskSel ^ 1);
+    h->taskSel ^= 1;
+    a.dN = gather ? h->dN : nullptr;
+    a.total = h->dTotal;
     // a task should fill the staging buffer once: cells per task from the mean occupancy (UGF_CELL_TASK overrides)
     a.taskCells = h->cellTask > 0 ? h->cellTask
                                   : std::max(2, std::min(CELL_CHUNK, (int)((double)CELL_CAP * h->nCells / (double)std::max<long long>(h->nUpper, 1))));
     a.flags = h->cellFlags;
-    CU(cudaMemsetAsync(h->dTask, 0, sizeof(int), h->stream));
     const DevParams prm = h->prm;
     dispatch(h, [&](auto R, auto M) {
         cell_kernel<decltype(R)::value, decltype(M)::value><<<h->cellBlocks, CELL_THREADS, h->cellSmem, h->stream>>>(prm, a);
     });
     LAUNCHED();
     if (doSample) h->momValid = keepMoments;
-    if (gather) return after_gather(h);
+    if (gather) return after_gather(h, false);
     return 0;
 }
 
@@ -492,10 +500,11 @@ int do_move(ugf_handle* h, long long begin, bool received) {
         if (h->patchKind[p] == UGF_PATCH_WALL && h->patchesHost[p].wallModel == UGF_WALL_UNSET)
             return fail(h, "wall patch without a boundary model");  // uniGasBoundaries.C:448-488
     if (!received) {
-        CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * h->nCells, h->stream));
-        CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
+        if (!h->cellCountZero) CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * h->nCells, h->stream));
+        if (h->hasProcessor) CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
     }
-    if (!(received && h->slotRound)) CU(cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream));
+    h->cellCountZero = false;
+    if (h->hasProcessor && !(received && h->slotRound)) CU(cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream));
     MoveArgs a{};
     a.mesh = h->mesh;
     a.P = h->buf[h->cur];
@@ -532,11 +541,13 @@ int do_move(ugf_handle* h, long long begin, bool received) {
         move_stream_kernel<r, mm, NF_, 4><<<grid, MOVE_WARPS * 32, 0, h->stream>>>(prm, a);                        \
     } while (0)
                 if (h->moveNF == 6) UGF_MOVE_STREAM(6);
+                else if (h->moveNF == 4 && h->mesh.rec2d) UGF_MOVE_STREAM(NF_REC2D);
                 else if (h->moveNF == 4) UGF_MOVE_STREAM(4);
                 else UGF_MOVE_STREAM(0);
 #undef UGF_MOVE_STREAM
             } else {
                 if (h->moveNF == 6) move_kernel<r, mm, 6><<<grid, 256, 0, h->stream>>>(prm, a);
+                else if (h->moveNF == 4 && h->mesh.rec2d) move_kernel<r, mm, NF_REC2D><<<grid, 256, 0, h->stream>>>(prm, a);
                 else if (h->moveNF == 4) move_kernel<r, mm, 4><<<grid, 256, 0, h->stream>>>(prm, a);
                 else move_kernel<r, mm, 0><<<grid, 256, 0, h->stream>>>(prm, a);
             }
@@ -759,7 +770,8 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     if ((e = cudaMalloc((void**)&h->dN, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dCnt, sizeof(DevCounters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dErr, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaMalloc((void**)&h->dTask, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dTask, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemsetAsync(h->dTask, 0, 2 * sizeof(int), h->stream);
     if ((e = cudaMalloc((void**)&h->dTot, 6 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dTotal, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dMigTotals, MIG_MAXP * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -787,7 +799,7 @@ int ugf_destroy(ugf_handle* h) {
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
-                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq};
+                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -927,6 +939,22 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     CU(cudaStreamSynchronize(h->stream));  // host staging vectors go out of scope
     h->mesh.nCells = nC; h->mesh.nBFaces = nB; h->mesh.nPatches = h->nPatches; h->mesh.planeNoZ = planeNoZ;
     h->mesh.cfOff = h->dCfOff; h->mesh.plane = h->dPlane; h->mesh.nbr = h->dNbr; h->mesh.bfPatch = h->dBfPatch;
+    if (h->moveNF == 4 && planeNoZ && !(std::getenv("UGF_MOVE_REC") && std::atoi(std::getenv("UGF_MOVE_REC")) == 0)) {
+        // packed per-cell record of the move kernel (one 128-byte line per cell), see track_parcel
+        std::vector<double> rec((size_t)nC * 16, 0.0);
+        for (int c = 0; c < nC; ++c) {
+            double* r = &rec[(size_t)c * 16];
+            int* ri = reinterpret_cast<int*>(r + 12);
+            for (int f = 0; f < 4; ++f) {
+                const double4& pl = plane[(size_t)c * 4 + f];
+                r[2 * f] = pl.x; r[2 * f + 1] = pl.y; r[8 + f] = pl.z;
+                ri[f] = nbr[(size_t)c * 4 + f];
+            }
+        }
+        if (dalloc(h, &h->dRec2d, rec.size()) || upload(h, h->dRec2d, rec.data(), rec.size())) return 1;
+        CU(cudaStreamSynchronize(h->stream));
+        h->mesh.rec2d = h->dRec2d;
+    }
     h->mesh.bfOwner = h->dBfOwner; h->mesh.patches = h->dPatches; h->mesh.vol = h->dVol; h->mesh.bbMin = h->dBbMin; h->mesh.bbMax = h->dBbMax;
 
     // per-cell arrays
@@ -938,6 +966,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         dalloc(h, &h->dSigma, (size_t)nC) || dalloc(h, &h->dCollId, (size_t)nC) || dalloc(h, &h->dMaxProb, (size_t)nC) ||
         dalloc(h, &h->dQPrev, 3 * (size_t)nC) || dalloc(h, &h->dSPrev, 6 * (size_t)nC))
         return 1;
+    CU(cudaMemsetAsync(h->dMigCount, 0, sizeof(int) * std::max(h->nPatches, 1), h->stream));
     CU(cudaMemsetAsync(h->dOff, 0, sizeof(int) * ((size_t)nC + 1), h->stream));
     CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * (size_t)nC, h->stream));
     CU(cudaMemsetAsync(h->dMom, 0, sizeof(double) * (size_t)nC * nS * UGF_NMOM, h->stream));

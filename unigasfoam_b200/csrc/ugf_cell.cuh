@@ -46,6 +46,9 @@ struct CellArgs {
     double* accS;     // multi-species only: nParcelsXnParticle per species [nCells][nSpecies], else null
     double accDt;
     int* taskCounter; // zero at launch: next unclaimed task of taskCells cells
+    int* taskReset;   // the counter of the next launch: zeroed here, so no memset sits between the kernels of a step
+    long long* dN;    // gather: the array length becomes the live count *total (else null)
+    const int* total;
     int taskCells;    // <= CELL_TASK_MAX
     int flags;        // tuning: 1 = positions pass through registers (L2 loads, no staging); 2 = velocities loaded with L2 loads
 };
@@ -346,6 +349,10 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
     // Tasks of CELL_TASK consecutive cells are claimed from a global counter (zeroed by the host before the launch):
     // warps that draw sparse cells simply claim more tasks.  The id of the following task and its CSR offsets are
     // requested while the current one is processed, so neither round trip is exposed.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *a.taskReset = 0;
+        if (a.dN) *a.dN = *a.total;
+    }
     int task = 0, offNext = 0x7fffffff;
     if (lane == 0) task = atomicAdd(a.taskCounter, 1);
     task = __shfl_sync(0xffffffffu, task, 0);
@@ -429,8 +436,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                 const bool doAcc = a.accDt != 0.0;
                 double* arow = a.acc + (size_t)(c0 + ci) * NACC + q;  // this lane's 4 accumulator slots: q, q+4, q+8, q+12
                 double ac0 = 0, ac1 = 0, ac2 = 0, ac3 = 0;
-                double FN = prm.nParticle;
-                if (doAcc && cellValid) { ac0 = arow[0]; ac1 = arow[4]; ac2 = arow[8]; ac3 = arow[12]; FN = cell_fn(prm, c0 + ci); }
+                if (doAcc && cellValid) { ac0 = arow[0]; ac1 = arow[4]; ac2 = arow[8]; ac3 = arow[12]; }
                 for (int s = 0; s < nS; ++s) {
                     double su = 0, sv = 0, sw = 0, suu = 0, suv = 0, suw = 0, svv = 0, svw = 0, sww = 0, scc = 0, scu = 0, scv = 0, scw = 0, cnt = 0;
                     double se = 0, seu = 0, sev = 0, sew = 0;
@@ -471,6 +477,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                         mrow[28] = 0.0;
                     }
                     if (doAcc) {  // uniGasVolFields accumulation fused in: slot 4t + q
+                        const double FN = (prm.cwf && cellValid) ? prm.nParticle * __ldg(&prm.cwf[c0 + ci]) : prm.nParticle;
                         if (MULTI && a.accS && cellValid && q == 0) a.accS[(size_t)(c0 + ci) * nS + s] += a.accDt * (cnt * FN);
                         ac0 += a.accDt * acc_term(prm, FN, s, q, cnt, su, sv, sw, scc, se);
                         ac1 += a.accDt * acc_term(prm, FN, s, q + 4, cnt, su, sv, sw, scc, se);

@@ -92,6 +92,7 @@ struct MeshDev {
     int planeNoZ;             // 1: every stored plane has Sz == 0 exactly (straight-extruded 2-D mesh)
     const double4* plane;     // [slots] outward plane stored as {Sx,Sy,S.Cf,Sz}
     const int* nbr;           // [slots] cell behind the face, or -(bfi+1)
+    const double* rec2d;      // straight 2-D meshes with 4 slots per cell: [nCells][16] = {Sx,Sy}x4, {S.Cf}x4, nbr x4 (as ints), pad; else null
     const int* bfPatch;       // [nBFaces]
     const int* bfOwner;       // [nBFaces]
     const DevPatch* patches;  // [nPatches]

@@ -17,20 +17,16 @@
 
 namespace ugf {
 
-// 32-byte plane record, stored as {Sx, Sy, S.Cf, Sz}, through the read-only path (two 16-byte loads); returned as
-// {x, y, z, w} = {Sx, Sy, Sz, S.Cf}
-__device__ __forceinline__ double4 load_plane(const double4* p) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    double4 r;
-    r.x = a.x; r.y = a.y; r.w = b.x; r.z = b.y;
-    return r;
+// One 256-bit load through the read-only path (LDG.E.256.CONSTANT, sm_100+): a lane that sits alone in its cell pays
+// one L1 wavefront per load instruction whatever its width, so the plane records are fetched in as few as possible.
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
-// meshes whose reachable faces all have Sz == 0 (straight-extruded 2-D cases): 24 of the 32 bytes
-__device__ __forceinline__ double4 load_plane_noz(const double4* p) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+
+// 32-byte plane record, stored as {Sx, Sy, S.Cf, Sz}; returned as {x, y, z, w} = {Sx, Sy, Sz, S.Cf}
+__device__ __forceinline__ double4 load_plane(const double4* p) {
     double4 r;
-    r.x = a.x; r.y = a.y; r.w = __ldg(reinterpret_cast<const double*>(p) + 2); r.z = 0.0;
+    ldg256(reinterpret_cast<const double*>(p), r.x, r.y, r.w, r.z);
     return r;
 }
 
@@ -345,9 +341,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 // direction were pruned at set-up): no offset loads and a fully unrolled face loop, so all plane loads of a hop
 // and the ids of the cells behind them are issued together (one dependent memory level per hop).
 // NF == 0: general polyhedra through the CSR offsets.
-template <bool HAS_ROT, bool MULTI, int NF>
+// NFT == NF_REC2D: 4 slots per cell read from the packed 2-D record (mesh.rec2d).
+constexpr int NF_REC2D = 14;
+template <bool HAS_ROT, bool MULTI, int NFT>
 __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArgs& a, const long long i, const bool valid, int cell, double x0,
                                              double x1, double x2, double U0, double U1, double U2) {
+    constexpr bool REC2D = (NFT == NF_REC2D);
+    constexpr int NF = REC2D ? 4 : NFT;
     int flags = 0, nWall = 0, nClone = 0;
     if (valid && cell >= 0) {
         int nDraws = 0;
@@ -375,14 +375,21 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
                 const int jb = cell * NF;
                 double4 pl[NF > 0 ? NF : 1];
                 int nbs[NF > 0 ? NF : 1];
-                if (a.mesh.planeNoZ) {
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) pl[f] = load_plane_noz(&a.mesh.plane[jb + f]);
+                if (REC2D) {
+                    // straight 2-D mesh: the cell's whole record {Sx,Sy}x4, {S.Cf}x4, nbr x4 is one 128-byte line,
+                    // fetched with three 256-bit loads and one 128-bit load
+                    const double* rp = a.mesh.rec2d + (size_t)cell * 16;
+                    ldg256(rp, pl[0].x, pl[0].y, pl[1].x, pl[1].y);
+                    ldg256(rp + 4, pl[2].x, pl[2].y, pl[3].x, pl[3].y);
+                    ldg256(rp + 8, pl[0].w, pl[1].w, pl[2].w, pl[3].w);
+                    const int4 v = __ldg(reinterpret_cast<const int4*>(rp + 12));
+                    nbs[0] = v.x; nbs[1] = v.y; nbs[2] = v.z; nbs[3] = v.w;
                 } else {
 #pragma unroll
                     for (int f = 0; f < NF; ++f) pl[f] = load_plane(&a.mesh.plane[jb + f]);
                 }
-                if (NF == 4) {
+                if (REC2D) {
+                } else if (NF == 4) {
                     const int4 v = __ldg(reinterpret_cast<const int4*>(a.mesh.nbr + jb));
                     nbs[0] = v.x; nbs[1] = v.y; nbs[2] = v.z; nbs[3] = v.w;
                 } else {
@@ -394,8 +401,9 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
                 }
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
-                    const double nd = fma(pl[f].z, d2, fma(pl[f].y, d1, pl[f].x * d0));
-                    double num = pl[f].w - fma(pl[f].z, x2, fma(pl[f].y, x1, pl[f].x * x0));
+                    // REC2D: Sz == 0 exactly, and fma(0, finite, t) == t, so the z terms are dropped (same bits)
+                    const double nd = REC2D ? fma(pl[f].y, d1, pl[f].x * d0) : fma(pl[f].z, d2, fma(pl[f].y, d1, pl[f].x * d0));
+                    double num = pl[f].w - (REC2D ? fma(pl[f].y, x1, pl[f].x * x0) : fma(pl[f].z, x2, fma(pl[f].y, x1, pl[f].x * x0)));
                     num = num < 0 ? 0.0 : num;
                     const bool better = (nd > 0) && (num * bnd < bnum * nd);
                     bnum = better ? num : bnum;

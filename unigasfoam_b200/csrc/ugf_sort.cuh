@@ -104,6 +104,44 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(int* __restric
     if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = *total;
 }
 
+// The occupancy build's variant without the single-block pass in between: every block sums the raw block totals
+// written by scan_reduce_kernel itself (a few thousand ints at most), so the scan is two launches instead of three.
+// The last block publishes the grand total and raises the capacity flag (cell-weighting clones can outgrow the arrays:
+// an empty occupancy is left behind so that no later kernel writes past them).
+__global__ void __launch_bounds__(SCAN_THREADS) scan_final_self_kernel(int* __restrict__ counts, int n, const int* __restrict__ blockSums, int nb,
+                                                                      int* __restrict__ total, int* __restrict__ offsets, long long capacity,
+                                                                      int* err) {
+    __shared__ int sm[33];
+    int pre = 0, tot = 0;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const int b = blockSums[j];
+        tot += b;
+        if (j < blockIdx.x) pre += b;
+    }
+    int sPre, sTot;
+    block_exclusive_scan(pre, &sPre, sm);
+    block_exclusive_scan(tot, &sTot, sm);
+    const int grand = sTot;
+    const bool dead = grand > capacity;
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? counts[base + k] : 0; s += v[k]; }
+    int t;
+    int ex = block_exclusive_scan(s, &t, sm) + sPre;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) { offsets[base + k] = dead ? 0 : ex; counts[base + k] = 0; }
+        ex += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        offsets[n] = dead ? 0 : grand;
+        *total = dead ? 0 : grand;
+        if (dead && err) atomicCAS(err, 0, 1);
+    }
+}
+
 // Lanes of a warp that hold the same key in a run of consecutive lanes (the common case: parcels are nearly
 // cell-major) are aggregated without match.any: head = first lane of the run, cnt = its length, rank = position
 // in it.  Equal keys in separate runs simply issue separate atomics.
@@ -235,7 +273,8 @@ __device__ inline void warp_sort_segment(int* seg, int n, int* sm, int lane) {
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(SEG_THREADS) segment_sort_kernel(const int* __restrict__ offsets, int nCells, int* __restrict__ perm) {
+__global__ void __launch_bounds__(SEG_THREADS) segment_sort_kernel(const int* __restrict__ offsets, int nCells, int* __restrict__ perm,
+                                                                  int* __restrict__ cursor) {
     __shared__ int stage[(SEG_THREADS / 32) * SEG_SMEM_INTS];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -245,6 +284,7 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_sort_kernel(const int* __
     if (c0 >= nCells) return;
     const int nc = min(SEG_CHUNK, nCells - c0);
     const int offv = (lane <= nc) ? offsets[c0 + lane] : 0;
+    if (lane < nc) cursor[c0 + lane] = 0;  // the scatter is done with the cursors: leave the histogram array zeroed for the next move
     const int g = lane / SEG_LPC, q = lane % SEG_LPC;
     const int cb = __shfl_sync(0xffffffffu, offv, g);
     const int ce = __shfl_sync(0xffffffffu, offv, (g + 1) & 31);
