@@ -285,6 +285,9 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p);
 int ugf_upload_cell_state(ugf_handle* h, const double* sigmaTcRMax, const int32_t* collModelId,
                           const int32_t* subCellLevels, const double* cellWeightFactor);
 int ugf_set_deltaT(ugf_handle* h, double deltaT);
+/* Restart: continue the step count (and with it the counter-based random streams) from Time::timeIndex as stored in
+ * <time>/uniform/time (U/clouds/uniGasCloud.C:581-593 reads deltaT from the same dictionary). */
+int ugf_set_time_index(ugf_handle* h, int64_t index);
 
 /* ---- the hot path ----------------------------------------------------------- */
 

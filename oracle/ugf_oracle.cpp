@@ -1724,6 +1724,7 @@ int ugfo_upload_cell_state(ugfo_handle* h, const double* s, const int32_t* id, c
 }
 
 int ugfo_set_deltaT(ugfo_handle* h, double dt) { h->cfg.deltaT = dt; return 0; }
+int ugfo_set_time_index(ugfo_handle* h, int64_t index) { h->step = index; h->cnt.step = index; return 0; }
 
 static void openStep(ugfo_handle* h) {
     if (!h->stepOpen) { resetStepCounters(*h); h->stepOpen = true; }

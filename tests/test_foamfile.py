@@ -1,0 +1,136 @@
+"""On-disk formats: the reader against field files shipped with the reference, write -> read round
+trips that return the same bits, and checkpoint / restart of a run (the restarted cloud continues exactly like the
+uninterrupted one because the step index - and with it every counter-based stream - is restored)."""
+import os
+
+import numpy as np
+import pytest
+
+from unigasfoam_b200 import cases, foamfile
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "openfoam")
+
+
+def test_reads_reference_tutorial_fields():
+    f = foamfile.read_vol_field(os.path.join(GOLD, "uspRhoNMean_Ar"))
+    assert f["class"] == "volScalarField" and f["object"] == "uspRhoNMean_Ar"
+    assert f["dimensions"] == [0, 0, 0, 0, 0, 0, 0] and f["uniform"] and f["internal"] == 1.0
+    assert list(f["boundary"]) == ["inlet", "outlet", "nozzle", "surface", "axis", "frontWedge", "backWedge"]
+    assert f["boundary"]["inlet"] == {"type": "calculated", "value": "uniform 1"}
+    assert f["boundary"]["axis"]["type"] == "symmetry" and f["boundary"]["backWedge"]["type"] == "symmetryPlane"
+    u = foamfile.read_vol_field(os.path.join(GOLD, "U"))
+    assert u["class"] == "volVectorField" and u["dimensions"] == [0, 1, -1, 0, 0, 0, 0]
+    assert u["uniform"] and np.array_equal(u["internal"], [0.0, 0.0, 0.0])
+    assert np.array_equal(foamfile.expand_internal(u, 5), np.zeros((5, 3)))
+    t = foamfile.read_vol_field(os.path.join(GOLD, "transT"))
+    assert t["dimensions"] == [0, 0, 0, 1, 0, 0, 0] and t["uniform"]
+    assert foamfile.expand_internal(t, 4).shape == (4,)
+
+
+def test_vol_field_round_trip_bit_exact(tmp_path):
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal(1000) * 1e-17 + rng.random(1000)
+    v = rng.standard_normal((1000, 3)) * 1e3
+    foamfile.write_vol_field(str(tmp_path / "uniGasSigmaTcRMax"), "0.001", [0, 3, -1, 0, 0, 0, 0], s, ["walls", "inlet"])
+    foamfile.write_vol_field(str(tmp_path / "uniGasSubCellLevels"), "0.001", [0] * 7, v, {"walls": "zeroGradient", "sym": "symmetry"}, vector=True)
+    a = foamfile.read_vol_field(str(tmp_path / "uniGasSigmaTcRMax"))
+    b = foamfile.read_vol_field(str(tmp_path / "uniGasSubCellLevels"))
+    assert not a["uniform"] and np.array_equal(a["internal"], s) and a["dimensions"] == [0, 3, -1, 0, 0, 0, 0]
+    assert a["boundary"] == {"walls": {"type": "zeroGradient"}, "inlet": {"type": "zeroGradient"}}
+    assert np.array_equal(b["internal"], v) and b["class"] == "volVectorField" and b["boundary"]["sym"]["type"] == "symmetry"
+    foamfile.write_vol_field(str(tmp_path / "w"), "0", [0] * 7, np.full(7, 2.5), ["p"])
+    w = foamfile.read_vol_field(str(tmp_path / "w"))
+    assert w["uniform"] and w["internal"] == 2.5 and np.array_equal(foamfile.expand_internal(w, 7), np.full(7, 2.5))
+
+
+def test_lagrangian_round_trip_and_layout(tmp_path):
+    rng = np.random.default_rng(1)
+    n = 257
+    p = dict(position=rng.standard_normal((n, 3)), U=rng.standard_normal((n, 3)) * 300, cell=rng.integers(0, 99, n).astype(np.int32),
+             typeId=rng.integers(0, 2, n).astype(np.int32), ERot=rng.random(n) * 1e-21, cellWeight=rng.random(n) + 0.5)
+    d = foamfile.write_lagrangian(str(tmp_path), "0.002", p)
+    assert sorted(os.listdir(d)) == sorted(["positions", "U", "cellWeight", "radialWeight", "ERot", "ELevel", "typeId", "newParcel", "vibLevel"])
+    head = open(os.path.join(d, "positions")).read(1200)
+    assert "class       Cloud<uniGasParcel>;" in head and 'location    "0.002/lagrangian/uniGas";' in head
+    assert "class       vectorField;" in open(os.path.join(d, "U")).read(1200)
+    q = foamfile.read_lagrangian(str(tmp_path), "0.002")
+    for k in ("position", "U", "cell", "typeId", "ERot", "cellWeight"):
+        assert np.array_equal(q[k], p[k]), k
+    assert (q["radialWeight"] == 1).all() and (q["ELevel"] == 0).all() and q["vibLevel"] == [[]] * n
+    # empty cloud
+    foamfile.write_lagrangian(str(tmp_path), "0", dict(position=np.empty((0, 3)), U=np.empty((0, 3)), cell=np.empty(0, np.int32)))
+    assert len(foamfile.read_lagrangian(str(tmp_path), "0")["cell"]) == 0
+    # vibrational levels as the reference writes them: one label list per parcel
+    p3 = dict(position=np.zeros((3, 3)), U=np.zeros((3, 3)), cell=np.zeros(3, np.int32), vibLevel=[[0], [2], [1]])
+    foamfile.write_lagrangian(str(tmp_path), "1", p3)
+    assert foamfile.read_lagrangian(str(tmp_path), "1")["vibLevel"] == [[0], [2], [1]]
+
+
+def test_field_count_mismatch_is_an_error(tmp_path):
+    p = dict(position=np.zeros((4, 3)), U=np.zeros((4, 3)), cell=np.zeros(4, np.int32))
+    d = foamfile.write_lagrangian(str(tmp_path), "0", p)
+    foamfile.write_io_field(os.path.join(d, "ERot"), "scalarField", "0/lagrangian/uniGas", np.zeros(3), "scalar")
+    with pytest.raises(foamfile.FoamFormatError, match="ERot"):
+        foamfile.read_lagrangian(str(tmp_path), "0")
+    with open(os.path.join(d, "U"), "w") as f:
+        f.write("FoamFile { version 2.0; format binary; class vectorField; object U; }\n4\n(")
+    with pytest.raises(foamfile.FoamFormatError, match="ascii"):
+        foamfile.read_io_field(os.path.join(d, "U"), "vector")
+
+
+def _restart_equals_uninterrupted(Cloud, tmp_path, case, **kw):
+    a = case.make_cloud(Cloud, **kw)
+    a.evolve(3)
+    t = a.writeTime(str(tmp_path), "3e-06")
+    assert os.path.exists(os.path.join(t, "uniGasSigmaTcRMax")) and os.path.exists(os.path.join(t, "uniform", "time"))
+    a.evolve(3)
+    b = Cloud(case.mesh, case.uniGasProperties, case.boundariesDict, case.deltaT, **kw)
+    d = b.readTime(str(tmp_path), "3e-06")
+    assert d["index"] == 3
+    b.evolve(3)
+    pa, pb = a.parcels(), b.parcels()
+    for k in ("cell", "position", "U", "ERot", "cellWeight"):
+        assert np.array_equal(pa[k], pb[k]), k
+    ca, cb = a.counters(), b.counters()
+    assert ca["step"] == cb["step"] == 6 and ca["collisions"] == cb["collisions"]
+    assert np.array_equal(a.cellState()["sigmaTcRMax"], b.cellState()["sigmaTcRMax"])
+
+
+def test_oracle_restart_continues_bit_exact(tmp_path, OracleCloud):
+    case = cases.closed_box(n=6, parcels=15000, seed=21, wall="diffuse", species=("N2", cases.NITROGEN),
+                            binary="LarsenBorgnakkeVariableHardSphere", Trot=280.0)
+    _restart_equals_uninterrupted(OracleCloud, tmp_path, case)
+
+
+def test_oracle_restart_cell_weighted(tmp_path, OracleCloud):
+    def ramp(mesh):
+        x = mesh.cell_centres[:, 0]
+        return 0.6 + 1.2 * (x - x.min()) / (x.max() - x.min())
+    case = cases.closed_box(n=6, parcels=15000, seed=22, cellWeightFactor=ramp)
+    _restart_equals_uninterrupted(OracleCloud, tmp_path, case, parcelCapacity=40000)
+
+
+@pytest.mark.gpu
+def test_gpu_restart_continues_bit_exact(tmp_path, GpuCloud):
+    def ramp(mesh):
+        x = mesh.cell_centres[:, 0]
+        return 0.6 + 1.2 * (x - x.min()) / (x.max() - x.min())
+    case = cases.closed_box(n=6, parcels=15000, seed=23, wall="diffuse", cellWeightFactor=ramp)
+    _restart_equals_uninterrupted(GpuCloud, tmp_path, case, parcelCapacity=40000)
+
+
+@pytest.mark.gpu
+def test_gpu_reads_what_the_oracle_wrote(tmp_path, GpuCloud, OracleCloud):
+    """A time directory is the exchange format between implementations: the oracle writes, libugf restarts from it and
+    both continue in lockstep."""
+    case = cases.couette(nx=24, ny=12, ppc=20, binary="noDSMCCollision")
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:  # specular walls: no libm calls, so the continuation is bit-exact
+        e["boundaryModel"] = "uniGasSpecularWallPatch"
+    r = case.make_cloud(OracleCloud)
+    r.evolve(2)
+    r.writeTime(str(tmp_path), "2")
+    g = GpuCloud(case.mesh, case.uniGasProperties, case.boundariesDict, case.deltaT)
+    g.readTime(str(tmp_path), "2")
+    r.evolve(3); g.evolve(3)
+    pg, pr = g.parcels(), r.parcels()
+    assert np.array_equal(pg["cell"], pr["cell"]) and np.array_equal(pg["position"], pr["position"]) and np.array_equal(pg["U"], pr["U"])

@@ -135,6 +135,7 @@ SIGNATURES = {
     "upload_parcels": (C.c_int, [H, P(Parcels)]),
     "upload_cell_state": (C.c_int, [H, PF, PI32, PI32, PF]),
     "set_deltaT": (C.c_int, [H, f64]),
+    "set_time_index": (C.c_int, [H, i64]),
     "step": (C.c_int, [H, i32]),
     "control_before_move": (C.c_int, [H]),
     "move": (C.c_int, [H]),

@@ -93,6 +93,7 @@ class UniGasCloud:
                 raise UgfError(f"{key} true is not supported by the B200 path yet (SURVEY §8f)")
         self.cfg = cfg
         self._h = _capi.H()
+        self._cellCollModelId = self._subCellLevels = self._cellWeightFactor = None  # host copies for writeTime
         self._pending_capacity = cfg.parcelCapacity == 0
         self._created = False
         self._species = (_capi.Species * len(self.typeIdList))(
@@ -186,7 +187,7 @@ class UniGasCloud:
     def _i32(a):
         return np.ascontiguousarray(a, dtype=np.int32)
 
-    def setParcels(self, position, U, cell, typeId=None, ERot=None, newParcel=None):
+    def setParcels(self, position, U, cell, typeId=None, ERot=None, newParcel=None, cellWeight=None):
         """addNewParcel for a whole configuration (U/clouds/uniGasCloud.C:260-290)."""
         n = len(cell)
         if self._pending_capacity:
@@ -209,6 +210,8 @@ class UniGasCloud:
             e = self._f64(ERot); keep.append(e); p.ERot = e.ctypes.data_as(PD)
         if newParcel is not None:
             q = self._i32(newParcel); keep.append(q); p.newParcel = q.ctypes.data_as(PI)
+        if cellWeight is not None:
+            w = self._f64(cellWeight); keep.append(w); p.cellWeight = w.ctypes.data_as(PD)
         self._check(self.api.upload_parcels(self._h, C.byref(p)))
 
     def setCellState(self, sigmaTcRMax=None, cellCollModelId=None, subCellLevels=None, cellWeightFactor=None):
@@ -218,6 +221,12 @@ class UniGasCloud:
         b = self._i32(np.broadcast_to(cellCollModelId, (nC,))) if cellCollModelId is not None else None
         c = self._i32(np.broadcast_to(subCellLevels, (nC, 3))) if subCellLevels is not None else None
         d = self._f64(np.broadcast_to(cellWeightFactor, (nC,))) if cellWeightFactor is not None else None
+        if b is not None:
+            self._cellCollModelId = b.astype(float)
+        if c is not None:
+            self._subCellLevels = c.astype(float)
+        if d is not None:
+            self._cellWeightFactor = d.copy()
         if d is not None and not self.cellWeighted:
             raise UgfError("cellWeightFactor given but cellWeightedSimulation is not true in uniGasProperties")
         self._check(self.api.upload_cell_state(
@@ -255,6 +264,52 @@ class UniGasCloud:
         kn = np.empty((nC, 4))
         self._check(self.api.download_decomposition(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), kn.ctypes.data_as(C.POINTER(C.c_double))))
         return dict(cellCollModelId=ids, KnRho=kn[:, 0], KnT=kn[:, 1], KnU=kn[:, 2], KnGLL=kn[:, 3])
+
+    # -- write / restart (OpenFOAM time directories, unigasfoam_b200/foamfile.py) ----------------------
+    def writeTime(self, case_dir, time_name):
+        """What uniGasFoam leaves in <time>/ for the cloud: lagrangian/uniGas/*, uniGas{SigmaTcRMax, CellWeightFactor,
+        SubCellLevels, CollisionModelId} and uniform/time (U/parcels/uniGasParcelIO.C:141-181, U/clouds/uniGasCloud.C:433-488)."""
+        from . import foamfile
+        p = self.parcels()
+        st = self.cellState()
+        mode = self.cfg.collisionModel
+        ids = self._cellCollModelId
+        if ids is None:
+            ids = np.full(self.mesh.n_cells, 1.0 if mode == _capi.COLLISION_MODEL["dsmc"] else 0.0)
+        c = self.counters()
+        return foamfile.write_cloud_time(case_dir, time_name, self.mesh, p, st["sigmaTcRMax"], self._cellWeightFactor, self._subCellLevels,
+                                         ids, deltaT=self.cfg.deltaT, index=c["step"])
+
+    def readTime(self, case_dir, time_name):
+        """Restart from a time directory written by writeTime or by the reference solver (ASCII): cell state first, then
+        the parcels, then the step count."""
+        from . import foamfile
+        d = foamfile.read_cloud_time(case_dir, time_name, self.mesh.n_cells)
+        p = d["parcels"]
+        if (p["radialWeight"] != 1.0).any():
+            raise UgfError("radialWeight != 1: axisymmetric weighting is not supported")
+        if any(len(v) for v in p["vibLevel"]) or (p["ELevel"] != 0).any():
+            raise UgfError("vibrational / excited electronic levels are not supported")
+        kw = {}
+        if d["sigmaTcRMax"] is not None:
+            kw["sigmaTcRMax"] = d["sigmaTcRMax"]
+        if d["collisionModelId"] is not None and self.cfg.collisionModel == _capi.COLLISION_MODEL["hybrid"]:
+            kw["cellCollModelId"] = np.rint(d["collisionModelId"]).astype(np.int32)
+        if d["subCellLevels"] is not None and (d["subCellLevels"] != 1).any():
+            kw["subCellLevels"] = np.rint(d["subCellLevels"]).astype(np.int32)
+        if self.cellWeighted and d["cellWeightFactor"] is not None:
+            kw["cellWeightFactor"] = d["cellWeightFactor"]
+        if self._pending_capacity:
+            self.cfg.parcelCapacity = max(int(len(p["cell"]) * 1.25) + 1024, 4096)
+            self._pending_capacity = False
+            self._create()
+        if kw:
+            self.setCellState(**kw)
+        self.setParcels(p["position"], p["U"], p["cell"], p["typeId"], p["ERot"], cellWeight=p["cellWeight"] if self.cellWeighted else None)
+        if d.get("deltaT") is not None:
+            self.setDeltaT(d["deltaT"])
+        self._check(self.api.set_time_index(self._h, int(d.get("index", 0))))
+        return d
 
     def setDeltaT(self, dt):
         self._check(self.api.set_deltaT(self._h, float(dt)))

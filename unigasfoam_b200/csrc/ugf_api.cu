@@ -1466,6 +1466,13 @@ int ugf_download_decomposition(ugf_handle* h, int32_t* id, double* kn) {
     return 0;
 }
 
+int ugf_set_time_index(ugf_handle* h, int64_t index) {
+    if (!h) return 1;
+    if (index < 0) return fail(h, "time index must be >= 0");
+    h->step = index;
+    return 0;
+}
+
 int ugf_end_step(ugf_handle* h) {
     if (!h) return 1;
     h->step++;
