@@ -396,6 +396,12 @@ int ugf_download_cell_state(ugf_handle* h, double* sigmaTcRMax, double* maxProb,
 int ugf_download_fields(ugf_handle* h, double* cellFields, double* wallFields, int32_t resetAtOutput);
 /* Raw per-step boundary measurements of the last move: [nBoundaryFaces][UGF_NBM]. */
 int ugf_download_boundary_meas(ugf_handle* h, double* bm);
+/* The raw time-weighted sums behind ugf_download_fields: acc [nCells][16] (slot list in DESIGN.md: 0 sum dt N, 8 .. 13
+ * the XnParticle sums of number, mass, momentum, kinetic energy), accSpecies [nCells][nSpecies] (nParcelsXnParticle per
+ * species) and the averaging time / step count.  uniGasDynamicAdapter::adapt accumulates exactly these sums over its
+ * own interval (U/dynamicAdaptation/uniGasDynamicAdapter.C:510-527); the host-side adapter differences two downloads
+ * instead of keeping a second set of accumulators on the device.  Any pointer may be NULL. */
+int ugf_download_accumulators(ugf_handle* h, double* acc, double* accSpecies, double* timeAvCounter, int64_t* nAvTimeSteps);
 /* Per-phase device time of the last ugf_step in ms (UGF_NPHASE values): inflow, move, sort, cell (gather + sample +
  * field accumulation), collide (NTC), relax (BGK family), fields (wall accumulation). */
 #define UGF_NPHASE 7

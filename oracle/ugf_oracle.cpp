@@ -1983,6 +1983,14 @@ int ugfo_download_fields(ugfo_handle* h, double* cellF, double* wallF, int32_t r
     return 0;
 }
 
+int ugfo_download_accumulators(ugfo_handle* h, double* acc, double* accS, double* timeAv, int64_t* nAv) {
+    if (acc) std::copy(h->acc.begin(), h->acc.end(), acc);
+    if (accS) std::copy(h->accS.begin(), h->accS.end(), accS);
+    if (timeAv) *timeAv = h->timeAvCounter;
+    if (nAv) *nAv = h->nAvTimeSteps;
+    return 0;
+}
+
 int ugfo_download_boundary_meas(ugfo_handle* h, double* bm) { std::copy(h->bm.begin(), h->bm.end(), bm); return 0; }
 
 int ugfo_phase_times(ugfo_handle*, double* ms) { for (int i = 0; i < UGF_NPHASE; ++i) ms[i] = 0; return 0; }

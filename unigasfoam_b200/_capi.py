@@ -136,6 +136,7 @@ SIGNATURES = {
     "upload_cell_state": (C.c_int, [H, PF, PI32, PI32, PF]),
     "set_deltaT": (C.c_int, [H, f64]),
     "set_time_index": (C.c_int, [H, i64]),
+    "download_accumulators": (C.c_int, [H, PF, PF, PF, PI64]),
     "step": (C.c_int, [H, i32]),
     "control_before_move": (C.c_int, [H]),
     "move": (C.c_int, [H]),

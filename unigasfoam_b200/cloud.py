@@ -88,12 +88,15 @@ class UniGasCloud:
         # cellWeightedSimulation (U/clouds/uniGasCloud.C:417): the cellWeightFactor field itself comes through
         # setCellState(cellWeightFactor=...) before the parcels, as the reference reads uniGasCellWeightFactor
         self.cellWeighted = bool(props.get("cellWeightedSimulation", False))
-        for key in ("axisymmetricSimulation", "adaptiveSimulation", "chemicalReactions"):
+        # adaptiveSimulation: unigasfoam_b200.adapter.UniGasDynamicAdapter drives the cloud (host side, every adaptationInterval steps)
+        self.adaptive = bool(props.get("adaptiveSimulation", False))
+        for key in ("axisymmetricSimulation", "chemicalReactions"):
             if props.get(key, False):
                 raise UgfError(f"{key} true is not supported by the B200 path yet (SURVEY §8f)")
         self.cfg = cfg
         self._h = _capi.H()
         self._cellCollModelId = self._subCellLevels = self._cellWeightFactor = None  # host copies for writeTime
+        self._adapter = None
         self._pending_capacity = cfg.parcelCapacity == 0
         self._created = False
         self._species = (_capi.Species * len(self.typeIdList))(
@@ -475,6 +478,8 @@ class UniGasCloud:
         """uniGasVolFields at write time: dict of per-cell and per-boundary-face arrays."""
         nC, nB = self.mesh.n_cells, self.mesh.n_boundary_faces
         PD = C.POINTER(C.c_double)
+        if resetAtOutput and self._adapter is not None:
+            self._adapter.before_reset()  # its interval sums are differences of the accumulators about to be zeroed
         cf = np.empty((nC, _capi.UGF_NFIELD))
         wf = np.empty((max(nB, 1), _capi.UGF_NWALLFIELD))
         self._check(self.api.download_fields(self._h, cf.ctypes.data_as(PD), wf.ctypes.data_as(PD), int(resetAtOutput)))
@@ -488,6 +493,16 @@ class UniGasCloud:
             "wall_rhoN": wf[:, 0], "wall_rhoM": wf[:, 1], "wall_UMean": wf[:, 2:5], "wall_translationalT": wf[:, 5],
             "surfaceHeatTransfer": wf[:, 6], "fD": wf[:, 7:10], "wall_p": wf[:, 10], "surfaceShearStress": wf[:, 11],
         }
+
+    def accumulators(self):
+        """Raw time-weighted sums of uniGasVolFields (see ugf_download_accumulators): dict acc [nCells,16],
+        species [nCells,nSpecies], timeAvCounter, nAvTimeSteps."""
+        nC, nS = self.mesh.n_cells, len(self.typeIdList)
+        PD = C.POINTER(C.c_double)
+        acc, sp = np.empty((nC, 16)), np.empty((nC, nS))
+        t, n = C.c_double(), C.c_int64()
+        self._check(self.api.download_accumulators(self._h, acc.ctypes.data_as(PD), sp.ctypes.data_as(PD), C.byref(t), C.byref(n)))
+        return {"acc": acc, "species": sp, "timeAvCounter": t.value, "nAvTimeSteps": n.value}
 
     def boundaryMeasurements(self):
         nB = self.mesh.n_boundary_faces

@@ -1863,6 +1863,22 @@ int ugf_download_fields(ugf_handle* h, double* cellF, double* wallF, int32_t res
     return 0;
 }
 
+int ugf_download_accumulators(ugf_handle* h, double* acc, double* accS, double* timeAv, int64_t* nAv) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t nC = (size_t)h->nCells, nS = (size_t)h->nSpecies;
+    std::vector<double> tmp;
+    if (accS && !h->dAccS && !acc) tmp.resize(nC * NACC);
+    double* a = acc ? acc : (tmp.empty() ? nullptr : tmp.data());
+    if (a) CU(cudaMemcpyAsync(a, h->dAcc, sizeof(double) * nC * NACC, cudaMemcpyDeviceToHost, h->stream));
+    if (accS && h->dAccS) CU(cudaMemcpyAsync(accS, h->dAccS, sizeof(double) * nC * nS, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (accS && !h->dAccS) for (size_t c = 0; c < nC; ++c) accS[c] = a[c * NACC + 8];  // one species: slot 8
+    if (timeAv) *timeAv = h->timeAvCounter;
+    if (nAv) *nAv = h->nAvTimeSteps;
+    return 0;
+}
+
 int ugf_download_boundary_meas(ugf_handle* h, double* bm) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (h->nBFaces > 0) {
