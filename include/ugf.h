@@ -229,6 +229,10 @@ typedef struct ugf_decomposition {
  * (U/boundaryMeasurements/boundaryMeasurements.C:70-121). */
 #define UGF_NBM 16
 
+/* Number of fp64 values per (tracked face, species) of the face tracker: 0 parcels, 1 mass, 2-4 momentum, 5 energy, each
+ * weighted with the parcel's cell weight factor (U/faceTracker/uniGasFaceTracker.C:90-152). */
+#define UGF_NFT 6
+
 /* Number of fp64 output fields per cell from ugf_download_fields
  * (U/macroscopicProperties/derived/volumetric/uniGasVolFields/uniGasVolFields.C:839-1254):
  * 0 uniGasRhoNMean, 1 rhoN, 2 rhoM, 3-5 UMean, 6 translationalT, 7 rotationalT,
@@ -396,6 +400,16 @@ int ugf_download_cell_state(ugf_handle* h, double* sigmaTcRMax, double* maxProb,
 int ugf_download_fields(ugf_handle* h, double* cellFields, double* wallFields, int32_t resetAtOutput);
 /* Raw per-step boundary measurements of the last move: [nBoundaryFaces][UGF_NBM]. */
 int ugf_download_boundary_meas(ugf_handle* h, double* bm);
+/* uniGasFaceTracker (U/faceTracker/uniGasFaceTracker.C:90-152; called from uniGasParcel::move at every face hit,
+ * U/parcels/uniGasParcel.C:85): number, mass, momentum and energy carried through faces, per species.  The reference
+ * tallies every face of the mesh every step and its consumers (uniGasMassFluxSurface) read the faces of their face zone;
+ * here only the registered faces are tallied (global face labels, internal or boundary; NULL / 0 switches it off) and
+ * the tallies run on until downloaded with reset != 0 - the consumer's sums over sampling steps.  Internal faces: signed
+ * with the direction of travel relative to the face area vector (owner -> neighbour); boundary faces: booked after the
+ * patch interaction with the sign of the velocity the parcel then has; cyclic faces: booked on the partner face. */
+int ugf_set_face_tracker(ugf_handle* h, int32_t nFaces, const int32_t* faces);
+/* out [nFaces][nSpecies][UGF_NFT] in the order of the registered list. */
+int ugf_download_face_tracker(ugf_handle* h, double* out, int32_t reset);
 /* The raw time-weighted sums behind ugf_download_fields: acc [nCells][16] (slot list in DESIGN.md: 0 sum dt N, 8 .. 13
  * the XnParticle sums of number, mass, momentum, kinetic energy), accSpecies [nCells][nSpecies] (nParcelsXnParticle per
  * species) and the averaging time / step count.  uniGasDynamicAdapter::adapt accumulates exactly these sums over its

@@ -164,6 +164,9 @@ struct ugfo_handle {
     std::vector<int32_t> occOff, occIds;  // cell occupancy CSR
     bool occValid = false, occIdentity = false;
     bool weightPending = false;   // a move happened since the last weighting() pass
+    std::vector<int32_t> faceTrack;   // [nFaces] k + 1 of a tracked face, 0 otherwise (uniGasFaceTracker)
+    std::vector<double> ft;           // [nTracked][nSpecies][UGF_NFT]
+    int nTracked = 0;
 
     // cell state (U/clouds/uniGasCloud.H:189-201)
     std::vector<double> sigmaTcRMax;
@@ -614,6 +617,27 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
                 p.cell = -1; t.deleted++;
             } else {  // empty patch hit: mesh/solutionD mismatch
                 p.cell = -1; t.stuck++;
+            }
+        }
+        if (h.nTracked) {  // uniGasFaceTracker::updateFields (U/faceTracker/uniGasFaceTracker.C:90-152), after the patch interaction
+            int face = hit;
+            if (hit >= h.nInternal) {
+                const int patch = h.facePatch[hit - h.nInternal];
+                if (h.pKind[patch] == UGF_PATCH_CYCLIC) face = h.pStart[h.pPartner[patch]] + (hit - h.pStart[patch]);
+            }
+            const int k = h.faceTrack[face] - 1;
+            if (k >= 0) {
+                const double* S = &h.Sf[3 * (size_t)hit];
+                const double sgn = (hit < h.nInternal) ? (hitFlip ? -1.0 : 1.0) : (dot3(p.U, S) >= 0.0 ? 1.0 : -1.0);
+                const ugf_species& s = h.sp[p.typeId];
+                const double w = p.CWF;
+                const double e = 0.5 * s.mass * dot3(p.U, p.U) + p.ERot + s.electronicEnergy[0];
+                double* tt = &h.ft[((size_t)k * h.nSpecies + p.typeId) * UGF_NFT];
+                const double add[UGF_NFT] = {sgn * w, sgn * s.mass * w, s.mass * p.U[0] * w, s.mass * p.U[1] * w, s.mass * p.U[2] * w, sgn * e * w};
+                for (int q = 0; q < UGF_NFT; ++q) {
+#pragma omp atomic
+                    tt[q] += add[q];
+                }
             }
         }
         if (++iters > MAX_TRACK_ITERS) { p.cell = -1; t.stuck++; break; }
@@ -1988,6 +2012,28 @@ int ugfo_download_accumulators(ugfo_handle* h, double* acc, double* accS, double
     if (accS) std::copy(h->accS.begin(), h->accS.end(), accS);
     if (timeAv) *timeAv = h->timeAvCounter;
     if (nAv) *nAv = h->nAvTimeSteps;
+    return 0;
+}
+
+int ugfo_set_face_tracker(ugfo_handle* h, int32_t n, const int32_t* faces) {
+    h->faceTrack.assign(h->nFaces, 0);
+    h->nTracked = 0;
+    h->ft.clear();
+    if (n <= 0 || !faces) return 0;
+    for (int k = 0; k < n; ++k) {
+        if (faces[k] < 0 || faces[k] >= h->nFaces) return fail(h, "tracked face out of range");
+        if (h->faceTrack[faces[k]]) return fail(h, "face listed twice in the face tracker");
+        h->faceTrack[faces[k]] = k + 1;
+    }
+    h->nTracked = n;
+    h->ft.assign((size_t)n * h->nSpecies * UGF_NFT, 0.0);
+    return 0;
+}
+
+int ugfo_download_face_tracker(ugfo_handle* h, double* out, int32_t reset) {
+    if (!h->nTracked) return fail(h, "no face tracker set");
+    if (out) std::copy(h->ft.begin(), h->ft.end(), out);
+    if (reset) std::fill(h->ft.begin(), h->ft.end(), 0.0);
     return 0;
 }
 

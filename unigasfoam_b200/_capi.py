@@ -16,6 +16,7 @@ UGF_NBM = 16
 UGF_NPHASE = 7
 UGF_NFIELD = 19
 UGF_NWALLFIELD = 12
+UGF_NFT = 6
 UGF_MIGRATE_STRIDE = 10
 
 # run-time selection tables: dictionary word -> enum  (include/ugf.h cites the reference tables)
@@ -137,6 +138,8 @@ SIGNATURES = {
     "set_deltaT": (C.c_int, [H, f64]),
     "set_time_index": (C.c_int, [H, i64]),
     "download_accumulators": (C.c_int, [H, PF, PF, PF, PI64]),
+    "set_face_tracker": (C.c_int, [H, i32, PI32]),
+    "download_face_tracker": (C.c_int, [H, PF, i32]),
     "step": (C.c_int, [H, i32]),
     "control_before_move": (C.c_int, [H]),
     "move": (C.c_int, [H]),

@@ -504,6 +504,19 @@ class UniGasCloud:
         self._check(self.api.download_accumulators(self._h, acc.ctypes.data_as(PD), sp.ctypes.data_as(PD), C.byref(t), C.byref(n)))
         return {"acc": acc, "species": sp, "timeAvCounter": t.value, "nAvTimeSteps": n.value}
 
+    def setFaceTracker(self, faces):
+        """Faces whose crossings uniGasFaceTracker tallies (the union of the face zones the surface models read)."""
+        f = self._i32(faces)
+        self._trackedFaces = f.copy()
+        self._check(self.api.set_face_tracker(self._h, len(f), f.ctypes.data_as(C.POINTER(C.c_int32)) if len(f) else None))
+
+    def faceTracker(self, reset=False):
+        """[nTracked, nSpecies, 6]: parcels, mass, momentum (3), energy carried through each tracked face since the last reset."""
+        n, nS = len(self._trackedFaces), len(self.typeIdList)
+        out = np.empty((n, nS, _capi.UGF_NFT))
+        self._check(self.api.download_face_tracker(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), int(reset)))
+        return out
+
     def boundaryMeasurements(self):
         nB = self.mesh.n_boundary_faces
         a = np.empty((max(nB, 1), _capi.UGF_NBM))

@@ -143,6 +143,10 @@ struct ugf_handle {
     bool cwfDirty = false;
     std::vector<double> cwfHost, cwfHostPrev;
     uint8_t* dNclone = nullptr;            // [capacity] clones per parcel decided by the move
+    // face tracker
+    int nTracked = 0;
+    int* dSlotTrack = nullptr; int* dBfTrack = nullptr; double* dFt = nullptr;
+    std::vector<int> slotFaceHost;         // face label of every stored face slot (set_mesh)
     bool cloneValid = false;               // dNclone belongs to the current (not yet gathered) array
     bool subLevelsAllOne = true;
 
@@ -526,6 +530,9 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.bm = h->dBm;
     a.cnt = h->dCnt;
     a.nclone = h->prm.cwf ? h->dNclone : nullptr;
+    a.slotTrack = h->nTracked ? h->dSlotTrack : nullptr;
+    a.bfTrack = h->dBfTrack;
+    a.ft = h->dFt;
     long long count = h->nUpper - begin;
     if (a.dBegin) count = std::min<long long>(count, (long long)h->migSlots.nProc * h->lastSlotCapacity);  // what one unpack can append
     if (count > 0) {
@@ -799,7 +806,7 @@ int ugf_destroy(ugf_handle* h) {
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
-                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d};
+                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dSlotTrack, h->dBfTrack, h->dFt};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -846,6 +853,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     // component in any solved direction (the front/back faces of a 2-D case) can never be crossed - the tracking
     // displacement is zero along empty directions (U/parcels/uniGasParcel.C:64-71) - and are left out.
     std::vector<double4> plane;
+    h->slotFaceHost.clear();
     std::vector<int> nbr, cfOffDev((size_t)nC + 1, 0);
     plane.reserve(m->cellFaceOffsets[nC]);
     nbr.reserve(m->cellFaceOffsets[nC]);
@@ -868,6 +876,7 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
             else { pl.x = -S[0]; pl.y = -S[1]; pl.z = -d; pl.w = -S[2]; }
             if (S[2] != 0.0) planeNoZ = 0;
             plane.push_back(pl);
+            h->slotFaceHost.push_back(f);
             nbr.push_back(f < nI ? (own ? m->neighbour[f] : m->owner[f]) : -(f - nI + 1));
         }
         cfOffDev[c + 1] = (int)plane.size();
@@ -1876,6 +1885,57 @@ int ugf_download_accumulators(ugf_handle* h, double* acc, double* accS, double* 
     if (accS && !h->dAccS) for (size_t c = 0; c < nC; ++c) accS[c] = a[c * NACC + 8];  // one species: slot 8
     if (timeAv) *timeAv = h->timeAvCounter;
     if (nAv) *nAv = h->nAvTimeSteps;
+    return 0;
+}
+
+int ugf_set_face_tracker(ugf_handle* h, int32_t n, const int32_t* faces) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->dSlotTrack); cudaFree(h->dBfTrack); cudaFree(h->dFt);
+    h->dSlotTrack = nullptr; h->dBfTrack = nullptr; h->dFt = nullptr;
+    h->nTracked = 0;
+    if (n <= 0 || !faces) return 0;
+    std::vector<int> faceIdx((size_t)h->nFaces, 0);  // k + 1 of a tracked face
+    for (int k = 0; k < n; ++k) {
+        if (faces[k] < 0 || faces[k] >= h->nFaces) return fail(h, "tracked face out of range");
+        if (faceIdx[faces[k]]) return fail(h, "face listed twice in the face tracker");
+        faceIdx[faces[k]] = k + 1;
+    }
+    std::vector<int> slotTrack(h->slotFaceHost.size(), 0), bfTrack((size_t)std::max(h->nBFaces, 1), 0);
+    size_t slot = 0;
+    // slots were stored cell by cell in cellFaces order, skipping the never-hit faces: walk them the same way
+    for (int c = 0; c < h->nCells; ++c)
+        for (int j = h->cfOffHost[c]; j < h->cfOffHost[c + 1]; ++j) {
+            const int f = h->cfHost[j];
+            if (slot < h->slotFaceHost.size() && h->slotFaceHost[slot] == f) {
+                if (f < h->nInternal && faceIdx[f]) slotTrack[slot] = (h->ownerHost[f] == c) ? faceIdx[f] : -faceIdx[f];
+                ++slot;
+            }
+        }
+    for (int p = 0; p < h->nPatches; ++p)
+        for (int k = 0; k < h->patchSize[p]; ++k) {
+            int f = h->patchStart[p] + k;
+            const int b = f - h->nInternal;
+            if (h->patchKind[p] == UGF_PATCH_CYCLIC) f = h->patchStart[h->patchPartnerHost[p]] + k;  // booked on the partner face
+            bfTrack[b] = faceIdx[f];
+        }
+    const size_t nv = (size_t)n * h->nSpecies * UGF_NFT;
+    if (dalloc(h, &h->dSlotTrack, slotTrack.size()) || dalloc(h, &h->dBfTrack, bfTrack.size()) || dalloc(h, &h->dFt, nv)) return 1;
+    if (upload(h, h->dSlotTrack, slotTrack.data(), slotTrack.size()) || upload(h, h->dBfTrack, bfTrack.data(), bfTrack.size())) return 1;
+    CU(cudaMemsetAsync(h->dFt, 0, sizeof(double) * nv, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->nTracked = n;
+    return 0;
+}
+
+int ugf_download_face_tracker(ugf_handle* h, double* out, int32_t reset) {
+    if (!h || !h->nTracked) return fail(h, "no face tracker set");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t nv = (size_t)h->nTracked * h->nSpecies * UGF_NFT;
+    if (out) CU(cudaMemcpyAsync(out, h->dFt, sizeof(double) * nv, cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CU(cudaMemsetAsync(h->dFt, 0, sizeof(double) * nv, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

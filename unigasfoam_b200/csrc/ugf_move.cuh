@@ -210,8 +210,40 @@ struct MoveArgs {
     double* bm;            // [nBFaces][UGF_NBM]
     DevCounters* cnt;
     double* wq;            // cell weighting + processor patches: the factor a parcel in flight carries (out for migrants, in for received)
+    const int* slotTrack;  // face tracker: per face slot, +-(k+1) if the face is entry k of the tracked list (+: the slot's cell owns the
+                           // face), 0 otherwise; null = no tracker
+    const int* bfTrack;    // per boundary face: k+1 of the face the crossing is booked on (cyclic: the partner face), 0 = not tracked
+    double* ft;            // [nTracked][nSpecies][UGF_NFT] running tallies
     uint8_t* nclone;       // cell weighting: clones each parcel gets from cellWeighting() (written for every parcel), else null
 };
+
+// uniGasFaceTracker::updateFields (U/faceTracker/uniGasFaceTracker.C:90-152) for one crossing of a tracked face: number,
+// mass, momentum and energy carried through it, weighted with the parcel's cell weight factor and signed with the
+// direction of travel relative to the face area vector (momentum unsigned, as in the reference).  Rare path (only the
+// faces of the registered face zones), out of line.
+__device__ __noinline__ void face_tally(const DevParams& prm, const MoveArgs& a, long long i, int trk, double U0, double U1, double U2, int type,
+                                        double erot, bool haveErot, bool hasRot) {
+    const int k = (trk > 0 ? trk : -trk) - 1;
+    const double sgn = trk > 0 ? 1.0 : -1.0;
+    double w = 1.0;
+    if (prm.cwf) {
+        if (a.useSfIn) w = a.wq[i];
+        else {
+            const int c0 = a.P.cell[i];
+            w = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[c0]) : __ldg(&prm.cwf[c0]);
+        }
+    }
+    const DevSpecies& s = prm.sp[type];
+    if (hasRot && !haveErot) erot = a.P.erot[i];
+    const double e = 0.5 * s.mass * (U0 * U0 + U1 * U1 + U2 * U2) + (hasRot ? erot : 0.0) + s.E0;
+    double* t = a.ft + ((size_t)k * prm.nSpecies + type) * UGF_NFT;
+    atomicAdd(&t[0], sgn * w);
+    atomicAdd(&t[1], sgn * s.mass * w);
+    atomicAdd(&t[2], s.mass * U0 * w);
+    atomicAdd(&t[3], s.mass * U1 * w);
+    atomicAdd(&t[4], s.mass * U2 * w);
+    atomicAdd(&t[5], sgn * e * w);
+}
 
 enum { HIT_CHANGED_U = 1, HIT_DELETED = 2, HIT_STUCK = 8, HIT_MIGRATED = 16, HIT_WDELETED = 32 };
 
@@ -224,7 +256,7 @@ struct HitState {
 // (internal-face hops) stays small in registers.  The parcel's Philox stream is rebuilt here at draw
 // position nDraws (counter-based: no state has to live across the hot loop).
 template <bool HAS_ROT, bool MULTI>
-__device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& a, int bfi, int hitSlot, long long i, int type, HitState& st) {
+__device__ __forceinline__ void boundary_interaction(const DevParams& prm, const MoveArgs& a, int bfi, int hitSlot, long long i, int type, HitState& st) {
     const int patch = __ldg(&a.mesh.bfPatch[bfi]);
     const DevPatch& pt = a.mesh.patches[patch];
     const DevSpecies& sp = prm.sp[type];
@@ -294,6 +326,19 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
         st.cell = -1; st.flags |= HIT_DELETED;
     } else {
         st.cell = -1; st.flags |= HIT_STUCK;
+    }
+}
+
+template <bool HAS_ROT, bool MULTI>
+__device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& a, int bfi, int hitSlot, long long i, int type, HitState& st) {
+    boundary_interaction<HAS_ROT, MULTI>(prm, a, bfi, hitSlot, i, type, st);
+    if (a.slotTrack) {  // face tracker: boundary faces are booked after the patch interaction, with the sign of the velocity
+        const int trk = __ldg(&a.bfTrack[bfi]);  // the parcel has now (uniGasFaceTracker.C:107-135); cyclic: on the partner face
+        if (trk) {
+            const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
+            const double un = st.U[0] * pl.x + st.U[1] * pl.y + st.U[2] * pl.z;
+            face_tally(prm, a, i, un >= 0.0 ? trk : -trk, st.U[0], st.U[1], st.U[2], type, st.erot, true, HAS_ROT);
+        }
     }
 }
 
@@ -435,6 +480,14 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
             x0 = fma(lamMin, d0, x0); x1 = fma(lamMin, d1, x1); x2 = fma(lamMin, d2, x2);
             sf = fma(rem, lamMin, sf);
             if (nb >= 0) {
+                if (a.slotTrack) {  // face tracker on: is this one of the registered faces?
+                    const int trk = __ldg(&a.slotTrack[hit]);
+                    if (trk) {
+                        int type = 0;
+                        if (MULTI) type = a.P.type[i];
+                        face_tally(prm, a, i, trk, U0, U1, U2, type, erot, erotLoaded, HAS_ROT);
+                    }
+                }
                 cell = nb;
             } else {
                 HitState st;
