@@ -171,6 +171,19 @@ typedef struct ugf_inflow {
     double velocity[3];
 } ugf_inflow;
 
+/* boundariesDict: uniGasLiouFangPressureInletPatchProperties
+ * (U/boundaries/derived/generalBoundaries/uniGasLiouFangPressureInletPatch/uniGasLiouFangPressureInletPatch.C:54-103):
+ * subsonic pressure inlet - number density p / (k T), inflow velocity per face relaxed towards the mean velocity of the
+ * parcels in the face's cell after the collisions of every step (:126-174). */
+typedef struct ugf_pressure_inlet {
+    int32_t nTypeIds;
+    int32_t typeIds[UGF_MAX_SPECIES];
+    double moleFractions[UGF_MAX_SPECIES];
+    double inletPressure;
+    double inletTemperature;
+    double theta;              /* default 1 */
+} ugf_pressure_inlet;
+
 /* Parcels as host SoA.  Mandatory: x,y,z,Ux,Uy,Uz,cell.  Optional (NULL = default):
  * typeId (0), ERot (0), stepFraction/newParcel (0).  (U/parcels/uniGasParcel.H:217-239)
  * cellWeight (the parcel's CWF, lagrangian/uniGas/cellWeight on disk) is implicit on the device: a parcel carries the
@@ -272,6 +285,11 @@ int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t wallModel, const d
 int ugf_set_patch_wall_fields(ugf_handle* h, int32_t patch, const double* T, const double* U);
 /* uniGasFreeStreamInflowPatch on a patch (any kind). */
 int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* inflow);
+/* uniGasLiouFangPressureInletPatch on a patch.  The insertion itself is the free-stream one with a velocity per face
+ * (uniGasGeneralBoundary.C:369-425, 1003-1230); the count formula is evaluated with speed ratios up to 5. */
+int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* inlet);
+/* Inlet velocity per face of a pressure inlet [patchSize*3] (diagnostic / restart). */
+int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U);
 /* addNewParcel over a whole initial configuration (U/clouds/uniGasCloud.C:260-290). Replaces the cloud. */
 int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p);
 /* Cell state carried between steps (U/clouds/uniGasCloud.H:189-201): sigmaTcRMax [nCells],

@@ -136,7 +136,14 @@ struct WallModel {
     std::vector<double> faceT, faceU;  // *FieldPatch variants: boundaryT / boundaryU per face of the patch
 };
 
-struct InflowPatch { int patch; ugf_inflow in; };
+struct InflowPatch {
+    int patch; ugf_inflow in;
+    // uniGasLiouFangPressureInletPatch: mole fractions, relaxation factor, inflow velocity per face
+    bool pressure = false;
+    double molFrac[UGF_MAX_SPECIES] = {1, 1, 1, 1, 1, 1, 1, 1};
+    double theta = 1.0;
+    std::vector<double> faceVel;
+};
 
 constexpr int NACC = 16;
 
@@ -697,13 +704,15 @@ void doInflow(ugfo_handle& h) {
             double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
             const double m2 = std::sqrt(dot3(t2, t2));
             for (int k = 0; k < 3; ++k) t2[k] /= m2;
+            const double* vel = ip.pressure ? &ip.faceVel[3 * (size_t)lf] : ip.in.velocity;
             for (int iD = 0; iD < ip.in.nTypeIds; ++iD) {
                 const int typeId = ip.in.typeIds[iD];
                 const ugf_species& s = h.sp[typeId];
                 const double cmp = std::sqrt(2.0 * kB * ip.in.translationalTemperature / s.mass);
-                const double sCos = dot3(ip.in.velocity, n) / cmp;
+                const double sCosFull = dot3(vel, n) / cmp;
+                const double sCos = (ip.pressure && sCosFull > 5.0) ? 5.0 : sCosFull;  // count only: the device library's insertion bound
                 // Bird eq 4.22 (uniGasGeneralBoundary.C:154-165); CWF of the face's cell, RWF = 1
-                const double accum = (fA * ip.in.numberDensities[iD] * dt * cmp
+                const double accum = ip.molFrac[iD] * (fA * ip.in.numberDensities[iD] * dt * cmp
                                       * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
                                      / (2.0 * sqrtPi * FNc(h, cellI));
                 Stream rc(h.cfg.seed, KIND_INFLOW, (uint32_t)iD, (uint32_t)h.step, (uint32_t)bfi, 0);
@@ -720,15 +729,15 @@ void doInflow(ugfo_handle& h) {
                     if (bs + bt > 1) { bs = 1 - bs; bt = 1 - bt; }
                     Parcel np_;
                     for (int k = 0; k < 3; ++k) np_.x[k] = (1 - bs - bt) * p0[k] + bs * a[k] + bt * b[k];
-                    const double A = sCos + std::sqrt(sCos * sCos + 2.0);
-                    const double B = 0.5 * (1.0 + sCos * (sCos - std::sqrt(sCos * sCos + 2.0)));
+                    const double A = sCosFull + std::sqrt(sCosFull * sCosFull + 2.0);
+                    const double B = 0.5 * (1.0 + sCosFull * (sCosFull - std::sqrt(sCosFull * sCosFull + 2.0)));
                     double scaling = 3.0;
-                    if (sCos < -3) scaling = std::fabs(sCos) + 1;
+                    if (sCosFull < -3) scaling = std::fabs(sCosFull) + 1;
                     double Pp = -1, uNormal, uNormalThermal;
-                    if (std::fabs(dot3(ip.in.velocity, n)) > VSMALL) {
+                    if (std::fabs(dot3(vel, n)) > VSMALL) {
                         do {  // Bird eq 12.5
                             uNormalThermal = scaling * (2.0 * r.u01() - 1);
-                            uNormal = uNormalThermal + sCos;
+                            uNormal = uNormalThermal + sCosFull;
                             if (uNormal < 0.0) Pp = -1;
                             else Pp = 2.0 * uNormal / A * std::exp(B - uNormalThermal * uNormalThermal);
                         } while (Pp < r.u01());
@@ -738,7 +747,7 @@ void doInflow(ugfo_handle& h) {
                     double g1, g2;
                     r.gauss2(g1, g2);
                     const double cth = std::sqrt(kB * ip.in.translationalTemperature / s.mass);
-                    const double vt1 = dot3(t1, ip.in.velocity), vt2 = dot3(t2, ip.in.velocity);
+                    const double vt1 = dot3(t1, vel), vt2 = dot3(t2, vel);
                     for (int k = 0; k < 3; ++k)
                         np_.U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
                     np_.ERot = equipartitionRotationalEnergy(r, ip.in.rotationalTemperature, s.rotationalDoF);
@@ -1420,6 +1429,32 @@ void decompose(ugfo_handle& h) {
 // ---------------------------------------------------------------------------------
 // time-averaged fields  (uniGasVolFields.C:723-1352)
 // ---------------------------------------------------------------------------------
+// uniGasLiouFangPressureInletPatch::controlParcelsAfterCollisions (…/uniGasLiouFangPressureInletPatch.C:126-174)
+void updateInletVelocities(ugfo_handle& h) {
+    bool any = false;
+    for (const InflowPatch& ip : h.inflows) any = any || ip.pressure;
+    if (!any) return;
+    if (!h.occValid) buildOccupancy(h);
+    for (InflowPatch& ip : h.inflows) {
+        if (!ip.pressure) continue;
+        for (int lf = 0; lf < h.pSize[ip.patch]; ++lf) {
+            const int c = h.owner[h.pStart[ip.patch] + lf];
+            const double w = FNc(h, c);
+            double mom[3] = {0, 0, 0}, mass = 0;
+            for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
+                const Parcel& p = h.P[h.occIds[j]];
+                const double m = w * h.sp[p.typeId].mass;
+                for (int k = 0; k < 3; ++k) mom[k] += m * p.U[k];
+                mass += m;
+            }
+            for (int k = 0; k < 3; ++k) {
+                const double nv = mass > 0 ? mom[k] / mass : 0.0;
+                ip.faceVel[3 * (size_t)lf + k] = ip.theta * nv + (1.0 - ip.theta) * ip.faceVel[3 * (size_t)lf + k];
+            }
+        }
+    }
+}
+
 void accumulateFields(ugfo_handle& h) {
     h.sampleCounter++;
     const double dt = h.cfg.deltaT;
@@ -1709,6 +1744,29 @@ int ugfo_set_inflow(ugfo_handle* h, int32_t patch, const ugf_inflow* in) {
     return 0;
 }
 
+int ugfo_set_pressure_inlet(ugfo_handle* h, int32_t patch, const ugf_pressure_inlet* pin) {
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->points.empty()) return fail(h, "inflow needs mesh points/facePoints");
+    if (!(pin->theta >= 0.0 && pin->theta <= 1.0)) return fail(h, "Theta must be a value between 0 and 1");
+    InflowPatch ip; ip.patch = patch;
+    std::memset(&ip.in, 0, sizeof(ip.in));
+    ip.in.nTypeIds = pin->nTypeIds;
+    const double n = pin->inletPressure / (kB * pin->inletTemperature);  // …LiouFangPressureInletPatch.C:102
+    for (int i = 0; i < pin->nTypeIds; ++i) { ip.in.typeIds[i] = pin->typeIds[i]; ip.in.numberDensities[i] = n; ip.molFrac[i] = pin->moleFractions[i]; }
+    ip.in.translationalTemperature = ip.in.rotationalTemperature = ip.in.vibrationalTemperature = ip.in.electronicTemperature = pin->inletTemperature;
+    ip.pressure = true;
+    ip.theta = pin->theta;
+    ip.faceVel.assign(3 * (size_t)h->pSize[patch], 0.0);
+    h->inflows.push_back(ip);
+    return 0;
+}
+
+int ugfo_download_inlet_velocity(ugfo_handle* h, int32_t patch, double* U) {
+    for (const InflowPatch& ip : h->inflows)
+        if (ip.patch == patch && ip.pressure) { std::copy(ip.faceVel.begin(), ip.faceVel.end(), U); return 0; }
+    return fail(h, "no pressure inlet on this patch");
+}
+
 int ugfo_upload_parcels(ugfo_handle* h, const ugf_parcels* p) {
     if (p->n > h->cfg.parcelCapacity) return fail(h, "parcel count exceeds parcelCapacity");
     h->P.resize(p->n);
@@ -1790,6 +1848,7 @@ int ugfo_relax(ugfo_handle* h) {
 
 int ugfo_accumulate_fields(ugfo_handle* h) {
     if (!h->momValid) sampleAll(*h);
+    updateInletVelocities(*h);
     accumulateFields(*h);
     return 0;
 }
@@ -1825,6 +1884,7 @@ int ugfo_finish_step(ugfo_handle* h) {
     sampleAll(*h);
     collideAll(*h);
     relaxAll(*h);
+    updateInletVelocities(*h);
     accumulateFields(*h);
     decompose(*h);
     return ugfo_end_step(h);
@@ -1843,7 +1903,8 @@ int ugfo_step(ugfo_handle* h, int32_t nSteps) {
         sampleAll(*h);
         collideAll(*h);
         relaxAll(*h);
-        accumulateFields(*h);
+        updateInletVelocities(*h);
+    accumulateFields(*h);
         decompose(*h);
         ugfo_end_step(h);
     }

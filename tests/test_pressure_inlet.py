@@ -1,0 +1,86 @@
+"""uniGasLiouFangPressureInletPatch (U/boundaries/derived/generalBoundaries/uniGasLiouFangPressureInletPatch/
+uniGasLiouFangPressureInletPatch.C:54-174): a reservoir at (p, T) feeding a channel.  Number density p / (k T); the
+inflow velocity of each inlet face follows the gas in its cell."""
+import numpy as np
+import pytest
+
+from unigasfoam_b200 import cases
+from unigasfoam_b200.cloud import UgfError
+
+
+def reservoir_case(theta=0.2, p_in=None, seed=51, **kw):
+    """The cylinder O-grid with its outer upstream arc as pressure inlet at the conditions of the gas inside, the
+    downstream arc deleting: gas at rest starts to drain towards the outlet and the inlet replaces it."""
+    case = cases.cylinder(nr=12, ntheta=24, ppc=25, U_inf=0.0, T_wall=200.0, seed=seed, **kw)
+    n, T = case.meta["n"], case.meta["T_inf"]
+    inlet = {"generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasLiouFangPressureInletPatch",
+             "uniGasLiouFangPressureInletPatchProperties": {"typeIds": ["Ar"], "moleFractions": {"Ar": 1.0}, "theta": theta,
+                                                            "inletPressure": (p_in if p_in is not None else n * cases.kB * T), "inletTemperature": T}}
+    case.boundariesDict["uniGasGeneralBoundaries"] = [inlet]
+    return case
+
+
+def test_oracle_pressure_inlet_feeds_at_reservoir_density(OracleCloud):
+    """Reservoir at four times the pressure of the gas inside: the first step inserts the effusion flux of the
+    reservoir gas, n c_mp / (2 sqrt(pi)) per area and time with n = p / (k T); then the inlet cells fill with inward
+    moving gas, the face velocities turn inward and the insertion rate grows with the speed ratio (Bird 4.22)."""
+    case0 = reservoir_case(binary="noDSMCCollision")
+    p0 = case0.meta["n"] * cases.kB * case0.meta["T_inf"]
+    case = reservoir_case(binary="noDSMCCollision", p_in=4 * p0, theta=0.5)
+    cl = case.make_cloud(OracleCloud, parcelCapacity=6 * case.n_parcels)
+    m = case.mesh
+    p = m.patches[m.patch_index("inlet")]
+    S = m.face_areas[p.start:p.start + p.size]
+    area = np.sqrt((S * S).sum(1)).sum()
+    cmp_ = cases.most_probable_speed(case.meta["T_inf"], case.meta["species"]["mass"])
+    expect = 4 * case.meta["n"] * cmp_ / (2 * np.sqrt(np.pi)) * area * case.deltaT / cl.cfg.nParticle
+    ins = []
+    for _ in range(80):
+        cl.evolve(1); ins.append(cl.counters()["inserted"])
+    assert expect > 50 and abs(ins[0] / expect - 1) < 4 / np.sqrt(expect)   # step 1: inlet velocity still zero
+    U = cl.inletVelocity("inlet")
+    nin = -S / np.sqrt((S * S).sum(1))[:, None]
+    un = (U * nin).sum(1)
+    assert un.mean() > 0.1 * cmp_ and (un > 0).mean() > 0.8
+    assert np.mean(ins[-20:]) > 1.15 * expect
+    assert cl.counters()["stuck"] == 0
+
+
+def test_pressure_inlet_theta_is_checked(OracleCloud):
+    case = reservoir_case(theta=1.5)
+    with pytest.raises(UgfError, match="Theta"):
+        case.make_cloud(OracleCloud)
+
+
+@pytest.mark.gpu
+def test_gpu_pressure_inlet_in_lockstep_with_oracle(GpuCloud, OracleCloud):
+    """Collision-free, specular cylinder: identical parcel states, hence identical cell mean velocities, inlet
+    velocities and insertion counts, step after step."""
+    case = reservoir_case(binary="noDSMCCollision", theta=0.3, p_in=None)
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        if e["boundaryModel"] == "uniGasDiffuseWallPatch":
+            e["boundaryModel"] = "uniGasSpecularWallPatch"
+    g = case.make_cloud(GpuCloud, parcelCapacity=4 * case.n_parcels)
+    r = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels)
+    for _ in range(12):
+        g.evolve(1); r.evolve(1)
+        cg, cr = g.counters(), r.counters()
+        assert cg["inserted"] == cr["inserted"] and cg["deleted"] == cr["deleted"] and cg["nParcels"] == cr["nParcels"]
+        assert np.allclose(g.inletVelocity("inlet"), r.inletVelocity("inlet"), rtol=1e-12, atol=1e-9)
+    pg, pr = g.parcels(), r.parcels()
+    assert np.array_equal(pg["cell"], pr["cell"])
+    assert (np.abs(pg["U"] - pr["U"]) <= 1e-9 * np.abs(pr["U"]).max()).all(1).mean() > 0.999
+    assert np.abs(r.inletVelocity("inlet")).max() > 1.0
+
+
+@pytest.mark.gpu
+def test_gpu_pressure_inlet_with_collisions_and_weights(GpuCloud, OracleCloud):
+    case = reservoir_case(theta=0.2, cellWeightFactor=("particlesPerSubCell", 25))
+    g = case.make_cloud(GpuCloud, parcelCapacity=4 * case.n_parcels)
+    r = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels)
+    ig = ir = 0
+    for _ in range(20):
+        g.evolve(1); r.evolve(1)
+        ig += g.counters()["inserted"]; ir += r.counters()["inserted"]
+    assert abs(ig - ir) <= 0.02 * ir + 5
+    assert np.allclose(g.inletVelocity("inlet"), r.inletVelocity("inlet"), rtol=0.2, atol=0.05 * np.abs(r.inletVelocity("inlet")).max())

@@ -91,6 +91,13 @@ class Inflow(C.Structure):
     ]
 
 
+class PressureInlet(C.Structure):
+    _fields_ = [
+        ("nTypeIds", i32), ("typeIds", i32 * UGF_MAX_SPECIES), ("moleFractions", f64 * UGF_MAX_SPECIES),
+        ("inletPressure", f64), ("inletTemperature", f64), ("theta", f64),
+    ]
+
+
 class Parcels(C.Structure):
     _fields_ = [
         ("n", i64), ("x", P(f64)), ("y", P(f64)), ("z", P(f64)), ("Ux", P(f64)), ("Uy", P(f64)), ("Uz", P(f64)),
@@ -133,6 +140,8 @@ SIGNATURES = {
     "set_patch_model": (C.c_int, [H, i32, i32, PF, i32]),
     "set_patch_wall_fields": (C.c_int, [H, i32, PF, PF]),
     "set_inflow": (C.c_int, [H, i32, P(Inflow)]),
+    "set_pressure_inlet": (C.c_int, [H, i32, P(PressureInlet)]),
+    "download_inlet_velocity": (C.c_int, [H, i32, PF]),
     "upload_parcels": (C.c_int, [H, P(Parcels)]),
     "upload_cell_state": (C.c_int, [H, PF, PI32, PI32, PF]),
     "set_deltaT": (C.c_int, [H, f64]),

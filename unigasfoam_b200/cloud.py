@@ -152,10 +152,22 @@ class UniGasCloud:
                 self._check(self.api.set_patch_wall_fields(self._h, patch, bT.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
-            if word != "uniGasFreeStreamInflowPatch":
-                raise UgfError(f"general boundary model {word!r} is not supported (only uniGasFreeStreamInflowPatch)")
+            if word not in ("uniGasFreeStreamInflowPatch", "uniGasLiouFangPressureInletPatch"):
+                raise UgfError(f"general boundary model {word!r} is not supported (uniGasFreeStreamInflowPatch, uniGasLiouFangPressureInletPatch)")
             patch = self.mesh.patch_index(entry["generalBoundaryProperties"]["patch"])
             pr = entry[word + "Properties"]
+            if word == "uniGasLiouFangPressureInletPatch":  # …/uniGasLiouFangPressureInletPatch.C:54-103
+                pin = _capi.PressureInlet()
+                ids = [self.typeIdList.index(n) for n in pr["typeIds"]]
+                pin.nTypeIds = len(ids)
+                for i, t in enumerate(ids):
+                    pin.typeIds[i] = t
+                    pin.moleFractions[i] = float(pr["moleFractions"][self.typeIdList[t]])
+                pin.inletPressure = float(pr["inletPressure"])
+                pin.inletTemperature = float(pr["inletTemperature"])
+                pin.theta = float(pr.get("theta", 1.0))
+                self._check(self.api.set_pressure_inlet(self._h, patch, C.byref(pin)))
+                continue
             inf = _capi.Inflow()
             ids = [self.typeIdList.index(n) for n in pr["typeIds"]]
             inf.nTypeIds = len(ids)
@@ -516,6 +528,13 @@ class UniGasCloud:
         out = np.empty((n, nS, _capi.UGF_NFT))
         self._check(self.api.download_face_tracker(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), int(reset)))
         return out
+
+    def inletVelocity(self, patch_name):
+        """Inflow velocity per face of a uniGasLiouFangPressureInletPatch."""
+        p = self.mesh.patch_index(patch_name)
+        U = np.empty((self.mesh.patches[p].size, 3))
+        self._check(self.api.download_inlet_velocity(self._h, p, U.ctypes.data_as(C.POINTER(C.c_double))))
+        return U
 
     def boundaryMeasurements(self):
         nB = self.mesh.n_boundary_faces

@@ -38,6 +38,7 @@ struct InflowHost {
     InflowDev dev;
     int nSlots;
     long long maxInsert;
+    bool pressureInlet = false;
     std::vector<double> accum1;   // per (face, species) slot: expected insertions per second at F_N = 1, CWF = 1
     std::vector<int> slotCell;    // owner cell of the slot's face
     std::vector<void*> owned;
@@ -1102,7 +1103,9 @@ static void recompute_inflow_bounds(ugf_handle* h) {
     }
 }
 
-int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) {
+// common part of the free-stream and the pressure inlet: geometry of the patch faces, insertion bound, device tables.
+// pin != null: pressure inlet (mole fractions, velocity per face, relaxation factor)
+static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in, const ugf_pressure_inlet* pin) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
     if (h->pointsHost.empty()) return fail(h, "inflow needs mesh points/facePoints");
@@ -1153,8 +1156,9 @@ int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) {
             const int t = in->typeIds[iD];
             if (t < 0 || t >= h->nSpecies) return fail(h, "inflow typeId out of range");
             const double cmp = std::sqrt(2.0 * kB * in->translationalTemperature / h->spHost[t].mass);
-            const double sCos = (in->velocity[0] * n[0] + in->velocity[1] * n[1] + in->velocity[2] * n[2]) / cmp;
-            const double accum = (fA * in->numberDensities[iD] * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
+            double sCos = (in->velocity[0] * n[0] + in->velocity[1] * n[1] + in->velocity[2] * n[2]) / cmp;
+            if (pin) sCos = 5.0;  // the face velocities follow the flow: bound the insertions with a speed ratio of 5
+            const double accum = (pin ? pin->moleFractions[iD] : 1.0) * (fA * in->numberDensities[iD] * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
                                  / (2.0 * sqrtPi * h->cfg.nParticle);
             f.maxInsert += (long long)std::max(accum, 0.0) + 2;
             f.accum1.push_back(accum * h->cfg.nParticle / h->cfg.deltaT);
@@ -1167,6 +1171,8 @@ int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) {
     for (int i = 0; i < in->nTypeIds; ++i) { d.typeIds[i] = in->typeIds[i]; d.numDen[i] = in->numberDensities[i]; }
     d.Ttr = in->translationalTemperature; d.Trot = in->rotationalTemperature;
     for (int k = 0; k < 3; ++k) d.vel[k] = in->velocity[k];
+    for (int i = 0; i < UGF_MAX_SPECIES; ++i) d.molFrac[i] = (pin && i < in->nTypeIds) ? pin->moleFractions[i] : 1.0;
+    d.theta = pin ? pin->theta : 1.0;
     int *dBfi, *dCell, *dTriOff, *dNIns, *dInsOff;
     double *dGeom, *dTri;
     if (dalloc(h, &dBfi, (size_t)nF) || dalloc(h, &dCell, (size_t)nF) || dalloc(h, &dTriOff, (size_t)nF + 1) || dalloc(h, &dGeom, geom.size()) ||
@@ -1178,7 +1184,54 @@ int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) {
         return 1;
     CU(cudaStreamSynchronize(h->stream));
     d.faceBfi = dBfi; d.faceCell = dCell; d.triOff = dTriOff; d.geom = dGeom; d.tri = dTri; d.nIns = dNIns; d.insOff = dInsOff;
+    if (pin) {  // inletVelocity_ starts at zero (…LiouFangPressureInletPatch.C:63)
+        double* dVel;
+        if (dalloc(h, &dVel, 3 * (size_t)nF)) return 1;
+        CU(cudaMemsetAsync(dVel, 0, sizeof(double) * 3 * (size_t)nF, h->stream));
+        f.owned.push_back(dVel);
+        d.faceVel = dVel;
+        f.pressureInlet = true;
+    }
     h->inflows.push_back(f);
+    return 0;
+}
+
+int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) { return set_inflow_common(h, patch, in, nullptr); }
+
+int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* pin) {
+    if (!h || !pin) return 1;
+    if (!(pin->theta >= 0.0 && pin->theta <= 1.0)) return fail(h, "Theta must be a value between 0 and 1");  // :69-75
+    if (pin->nTypeIds < 1 || pin->nTypeIds > UGF_MAX_SPECIES) return fail(h, "inflow typeIds out of range");
+    ugf_inflow in{};
+    in.nTypeIds = pin->nTypeIds;
+    const double n = pin->inletPressure / (kB * pin->inletTemperature);  // :102
+    for (int i = 0; i < pin->nTypeIds; ++i) { in.typeIds[i] = pin->typeIds[i]; in.numberDensities[i] = n; }
+    in.translationalTemperature = in.rotationalTemperature = in.vibrationalTemperature = in.electronicTemperature = pin->inletTemperature;
+    return set_inflow_common(h, patch, &in, pin);
+}
+
+int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U) {
+    if (!h) return 1;
+    for (InflowHost& f : h->inflows)
+        if (f.patch == patch && f.pressureInlet) {
+            CU(cudaMemcpyAsync(U, f.dev.faceVel, sizeof(double) * 3 * (size_t)f.dev.nFaces, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            return 0;
+        }
+    return fail(h, "no pressure inlet on this patch");
+}
+
+// controlParcelsAfterCollisions of the pressure inlets: needs the cell-major array and its offsets (after the gather)
+static int update_inlet_velocities(ugf_handle* h) {
+    for (InflowHost& f : h->inflows) {
+        if (!f.pressureInlet) continue;
+        const DevParams prm = h->prm;
+        const InflowDev dev = f.dev;
+        ParcelBuf P = h->buf[h->cur];
+        if (h->multi) inlet_velocity_kernel<true><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff);
+        else inlet_velocity_kernel<false><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff);
+        LAUNCHED();
+    }
     return 0;
 }
 
@@ -1369,6 +1422,7 @@ int ugf_accumulate_fields(ugf_handle* h) {
         if (!h->occValid && do_sort(h)) return 1;
         if (run_cell_kernel(h, false, true)) return 1;
     }
+    if (h->occValid && h->occIdentity && update_inlet_velocities(h)) return 1;  // boundaries_.controlAfterCollisions()
     return do_accumulate(h);
 }
 
@@ -1496,6 +1550,7 @@ int ugf_finish_step(ugf_handle* h) {
     if (run_cell_kernel(h, true, true, fuseAcc, bgk_active(h))) return 1;
     if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
     if (bgk_active(h) && run_bgk_kernel(h)) return 1;
+    if (update_inlet_velocities(h)) return 1;
     if (do_accumulate(h, fuseAcc)) return 1;
     if (do_decompose(h)) return 1;
     return ugf_end_step(h);
@@ -1523,6 +1578,7 @@ int ugf_step(ugf_handle* h, int32_t nSteps) {
         if (dsmc_active(h) && run_ntc_kernel(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[5], h->stream));
         if (bgk_active(h) && run_bgk_kernel(h)) return 1;
+        if (update_inlet_velocities(h)) return 1;
         if (last) CU(cudaEventRecord(h->ev[6], h->stream));
         if (do_accumulate(h, fuseAcc)) return 1;
         if (do_decompose(h)) return 1;

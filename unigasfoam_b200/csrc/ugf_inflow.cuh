@@ -26,6 +26,9 @@ struct InflowDev {
     double numDen[UGF_MAX_SPECIES];
     double Ttr, Trot;
     double vel[3];
+    double molFrac[UGF_MAX_SPECIES];  // 1 for free-stream patches (numDen is per species there)
+    double* faceVel;                  // pressure inlets: inflow velocity per face [nFaces*3], else null (vel everywhere)
+    double theta;                     // pressure inlets: relaxation of faceVel towards the cell mean velocity
     const int* faceBfi;
     const int* faceCell;
     const double* geom;
@@ -43,9 +46,11 @@ __global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant
     const DevSpecies& s = prm.sp[f.typeIds[iD]];
     const double fA = g[0];
     const double cmp = sqrt(2.0 * kB * f.Ttr / s.mass);
-    const double sCos = (f.vel[0] * g[1] + f.vel[1] * g[2] + f.vel[2] * g[3]) / cmp;
+    const double* vel = f.faceVel ? f.faceVel + 3 * (size_t)face : f.vel;
+    double sCos = (vel[0] * g[1] + vel[1] * g[2] + vel[2] * g[3]) / cmp;
+    if (f.faceVel && sCos > 5.0) sCos = 5.0;  // the host's insertion bound assumes speed ratios <= 5 on pressure inlets
     const double sqrtPi = sqrt(PI);
-    const double accum = (fA * f.numDen[iD] * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
+    const double accum = f.molFrac[iD] * (fA * f.numDen[iD] * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
                          / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));  // uniGasGeneralBoundary.C:154-165
     Stream rc(prm.seed, KIND_INFLOW, (uint32_t)iD, step, (uint32_t)f.faceBfi[face], 0);
     int nIns = max((int)accum, 0);
@@ -90,7 +95,8 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
     const int typeId = f.typeIds[iD];
     const DevSpecies& s = prm.sp[typeId];
     const double cmp = sqrt(2.0 * kB * f.Ttr / s.mass);
-    const double vn = f.vel[0] * n[0] + f.vel[1] * n[1] + f.vel[2] * n[2];
+    const double* vel = f.faceVel ? f.faceVel + 3 * (size_t)face : f.vel;
+    const double vn = vel[0] * n[0] + vel[1] * n[1] + vel[2] * n[2];
     const double sCos = vn / cmp;
     const int tb = f.triOff[face], te = f.triOff[face + 1];
     const int cellI = f.faceCell[face];
@@ -123,8 +129,8 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
         double g1, g2;
         r.gauss2(g1, g2);
         const double cth = sqrt(kB * f.Ttr / s.mass);
-        const double vt1 = t1[0] * f.vel[0] + t1[1] * f.vel[1] + t1[2] * f.vel[2];
-        const double vt2 = t2[0] * f.vel[0] + t2[1] * f.vel[1] + t2[2] * f.vel[2];
+        const double vt1 = t1[0] * vel[0] + t1[1] * vel[1] + t1[2] * vel[2];
+        const double vt2 = t2[0] * vel[0] + t2[1] * vel[1] + t2[2] * vel[2];
         double U[3];
         for (int k = 0; k < 3; ++k) U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
         const double erot = equipartition_rotational_energy(r, f.Trot, s.rotDoF);
@@ -134,6 +140,29 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
         P.cell[dst] = cellI;
         if (HAS_ROT) P.erot[dst] = erot;
         if (MULTI) P.type[dst] = (uint8_t)typeId;
+    }
+}
+
+// uniGasLiouFangPressureInletPatch::controlParcelsAfterCollisions (…/uniGasLiouFangPressureInletPatch.C:126-174): the
+// inflow velocity of every inlet face moves towards the mass-weighted mean velocity of the parcels now in its cell.  One
+// thread per face, summing in cell-list order (the oracle's order: identical bits); the array is cell-major here.
+template <bool MULTI>
+__global__ void __launch_bounds__(128) inlet_velocity_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ InflowDev f, ParcelBuf P,
+                                                             const int* __restrict__ off) {
+    const int face = blockIdx.x * blockDim.x + threadIdx.x;
+    if (face >= f.nFaces) return;
+    const int c = f.faceCell[face];
+    const double w = cell_fn(prm, c);  // nParticle * CWF: the same for every parcel of the cell
+    double mom[3] = {0, 0, 0}, mass = 0;
+    for (int j = off[c]; j < off[c + 1]; ++j) {
+        const double m = w * (MULTI ? prm.sp[P.type[j]].mass : prm.sp[0].mass);
+        mom[0] += m * P.ux[j]; mom[1] += m * P.uy[j]; mom[2] += m * P.uz[j];
+        mass += m;
+    }
+    double* v = f.faceVel + 3 * (size_t)face;
+    for (int k = 0; k < 3; ++k) {
+        const double nv = mass > 0 ? mom[k] / mass : 0.0;
+        v[k] = f.theta * nv + (1.0 - f.theta) * v[k];
     }
 }
 
