@@ -1,0 +1,115 @@
+"""The reference's own case dictionaries (tutorials/uniGasFoam/hypersonicCylinder, copied as fixtures under
+tests/golden/openfoam/hypersonicCylinder) parsed and run: SURVEY §8c lists them as the fixtures that pin schemas and
+constants.  The mesh is this repo's O-grid with the tutorial's patch names (the tutorial's blockMeshDict is not
+read); `macroInterpolation true` of the tutorial is switched off (cell values), everything else is taken as written:
+hybrid USP-SBGK / NTC-VHS, cell weighting, dynamic adaptation, local-Knudsen decomposition, free-stream inflow."""
+import os
+
+import numpy as np
+import pytest
+
+from unigasfoam_b200 import cases, foamdict, mesh as ugmesh
+from unigasfoam_b200.adapter import UniGasDynamicAdapter
+
+CASE = os.path.join(os.path.dirname(__file__), "golden", "openfoam", "hypersonicCylinder")
+
+
+def test_parses_the_tutorial_dictionaries():
+    ld = foamdict.load_case(CASE)
+    p = ld["uniGasProperties"]
+    assert p["nEquivalentParticles"] == 5.85e11 and p["cellWeightedSimulation"] is True and p["axisymmetricSimulation"] is False
+    assert p["cellWeightedProperties"] == {"minParticlesPerSubCell": 20, "particlesPerSubCell": 20}
+    assert p["adaptiveProperties"]["adaptationInterval"] == 100 and p["adaptiveProperties"]["subCellAdaptation"] is True
+    assert p["collisionModel"] == "hybrid" and p["bgkCollisionModel"] == "unifiedStochasticParticleSBGK"
+    assert p["dsmcCollisionModel"] == "variableHardSphere" and p["dsmcCollisionPartnerModel"] == "noTimeCounter"
+    assert p["collisionProperties"] == {"Tref": 1000, "macroInterpolation": True, "theta": 0.1}
+    assert p["typeIdList"] == ["Ar"]
+    ar = p["moleculeProperties"]["Ar"]
+    assert ar["mass"] == 66.3e-27 and ar["diameter"] == 3.595e-10 and ar["omega"] == 0.734 and ar["alpha"] == 1.0
+    assert ar["characteristicVibrationalTemperature"] == [] and ar["electronicEnergyList"] == [0] and ar["degeneracyList"] == [1]
+    assert ld["deltaT"] == 5e-8
+    bd = ld["boundariesDict"]
+    assert [e["boundaryModel"] for e in bd["uniGasPatchBoundaries"]] == ["uniGasDiffuseWallPatch", "uniGasDeletionPatch", "uniGasDeletionPatch"]
+    assert bd["uniGasPatchBoundaries"][0]["patchBoundaryProperties"]["patch"] == "cylinder"
+    assert bd["uniGasPatchBoundaries"][0]["uniGasDiffuseWallPatchProperties"] == {"velocity": [0, 0, 0], "temperature": 500}
+    fs = bd["uniGasGeneralBoundaries"][0]["uniGasFreeStreamInflowPatchProperties"]
+    assert fs["velocity"] == [2634.7, 0, 0] and fs["numberDensities"] == {"Ar": 4.247e20} and fs["typeIds"] == ["Ar"]
+    assert bd["uniGasCyclicBoundaries"] == []
+    hd = ld["hybridDecompositionDict"]
+    assert hd["decompositionModel"] == "localKnudsen" and hd["localKnudsenProperties"] == {"breakdownMax": 0.05, "theta": 0.2, "smoothingPasses": 5}
+    assert hd["timeProperties"]["resetAtDecomposition"] is True
+    fp = ld["fieldPropertiesDict"]["uniGasFields"][0]
+    assert fp["fieldModel"] == "uniGasVolFields" and fp["uniGasVolFieldsProperties"]["measureMeanFreePath"] is True
+    assert foamdict.sample_interval(ld["fieldPropertiesDict"]) == 1
+    ini = ld["uniGasInitialisationDict"]["configurations"][0]
+    assert ini["type"] == "uniGasMeshFill" and ini["numberDensities"] == {"Ar": 4.247e20}
+
+
+def test_parser_errors_and_syntax_corners():
+    d = foamdict.parse('a 1; b (1 2 3); c { d on; e "x y"; } f{g 2.5e3;} h ((1 2) (3 4)); k; // tail\n/* block */ l word;')
+    assert d == {"a": 1, "b": [1, 2, 3], "c": {"d": True, "e": "x y"}, "f": {"g": 2500.0}, "h": [[1, 2], [3, 4]], "k": None, "l": "word"}
+    assert foamdict.parse("m ( n { o 1; } n { o 2; } );") == {"m": [{"o": 1}, {"o": 2}]}
+    for bad in ("a 1", "a { b 1;", "a ( 1 2;", "} a 1;"):
+        with pytest.raises(foamdict.FoamDictError):
+            foamdict.parse(bad)
+
+
+def tutorial_case(seed=61):
+    m = ugmesh.half_annulus_mesh(20, 32, 0.5 * 0.3048, 2.0 * 0.3048, 0.1 * 0.3048, 5.0)
+    m.meta_axis_aligned = False
+    case, ld = cases.from_case_dir(CASE, m, seed=seed, overrides={"collisionProperties": {"macroInterpolation": False}})
+    ld["uniGasProperties"]["adaptiveProperties"]["adaptationInterval"] = 20  # the run below is short
+    ld["hybridDecompositionDict"]["timeProperties"]["decompositionInterval"] = 20
+    return case, ld
+
+
+def run_tutorial(Cloud, steps, seed=61):
+    case, ld = tutorial_case(seed)
+    cl = case.make_cloud(Cloud, parcelCapacity=8 * case.n_parcels, sampleInterval=foamdict.sample_interval(ld["fieldPropertiesDict"]))
+    cl.setHybridDecomposition(ld["hybridDecompositionDict"])
+    ad = UniGasDynamicAdapter(cl, case.uniGasProperties)
+    tally = dict(inserted=0, deleted=0, wallHits=0, collisions=0, bgkRelaxations=0, cloned=0, weightDeleted=0)
+    done = 0
+    while done < steps:
+        ad.run(20)
+        done += 20
+        ad.cellCollModelId = cl.hybridDecomposition()["cellCollModelId"]
+        c = cl.counters()
+        for k in tally:
+            tally[k] += c[k]
+    return case, cl, ad, tally
+
+
+def test_oracle_runs_the_tutorial_case(OracleCloud):
+    case, cl, ad, tally = run_tutorial(OracleCloud, 100)
+    assert case.uniGasProperties["cellWeightedSimulation"] and case.deltaT == 5e-8
+    cnt0 = np.bincount(case.cell, minlength=case.mesh.n_cells)
+    assert abs(cnt0.mean() - 20) < 1  # uniGasMeshFill's weight rule: particlesPerSubCell parcels in every cell
+    c = cl.counters()
+    assert c["stuck"] == 0 and c["step"] == 100
+    assert all(tally[k] > 0 for k in ("inserted", "deleted", "wallHits", "cloned", "weightDeleted"))
+    assert tally["collisions"] + tally["bgkRelaxations"] > 0
+    assert cl.cfg.deltaT != 5e-8  # timeStepAdaptation has acted
+    f = cl.fields()
+    assert np.isfinite(f["rhoN"]).all() and np.isfinite(f["translationalT"]).all()
+    # free stream is still free stream upstream; gas piles up and heats in front of the cylinder
+    x, y = case.mesh.cell_centres[:, 0], case.mesh.cell_centres[:, 1]
+    r = np.hypot(x, y)
+    up = (x < 0) & (r > 0.5)
+    nose = (x < 0) & (np.abs(y) < 0.06) & (r < 0.19)
+    assert abs(np.median(f["rhoN"][up]) / 4.247e20 - 1) < 0.15
+    assert f["rhoN"][nose].mean() > 1.5 * 4.247e20 and f["translationalT"][nose].mean() > 2 * 200
+
+
+@pytest.mark.gpu
+def test_gpu_runs_the_tutorial_case_like_the_oracle(GpuCloud, OracleCloud):
+    _, g, ag, tg = run_tutorial(GpuCloud, 60)
+    case, r, ar, tr = run_tutorial(OracleCloud, 60)
+    for k in ("inserted", "deleted", "wallHits"):
+        assert abs(tg[k] - tr[k]) <= 0.1 * tr[k] + 10, (k, tg[k], tr[k])
+    assert abs(g.counters()["nParcels"] / r.counters()["nParcels"] - 1) < 0.05
+    assert g.cfg.deltaT == pytest.approx(r.cfg.deltaT, rel=0.05)
+    fg, fr = g.fields(), r.fields()
+    dens = lambda f: np.average(f["rhoN"], weights=case.mesh.cell_volumes)
+    assert dens(fg) == pytest.approx(dens(fr), rel=0.03)
+    assert g.counters()["stuck"] == 0

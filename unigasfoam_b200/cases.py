@@ -8,6 +8,7 @@ the per-step hot path.
 """
 from dataclasses import dataclass, field
 import math
+import os
 
 import numpy as np
 
@@ -305,3 +306,42 @@ def cylinder(nr=100, ntheta=200, ppc=20, n_inf=4.247e20, T_inf=200.0, U_inf=2634
     return _weighted(Case("cylinder", m, _props(name, sp, nParticle, mode, binary, bgk, Tref, **cp), bd, dt, pos, vel, cel, tid,
                           erot if sp.get("rotationalDegreesOfFreedom", 0) else None, sig0,
                           meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, r0=r0, r1=r1, Tref=Tref, species=sp)), cwf)
+
+
+def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=None):
+    """A uniGasFoam case directory (constant/uniGasProperties, system/{controlDict, boundariesDict,
+    uniGasInitialisationDict, ...}) on a given mesh -> Case: the dictionaries are used as they are
+    (unigasfoam_b200.foamdict.load_case), the initial parcels come from the `uniGasMeshFill` configuration
+    (U/uniGasInitialisation/derived/uniGasMeshFill/uniGasMeshFill.C:60-296) including its cell-weight rule when
+    cellWeightedSimulation is on.  particles_per_cell overrides cellWeightedProperties.particlesPerSubCell (coarse test
+    meshes).  Returns (case, loaded) where loaded holds the remaining dictionaries (field properties, hybrid
+    decomposition, controlDict)."""
+    from . import foamdict
+    ld = foamdict.load_case(case_dir, overrides)
+    props = ld["uniGasProperties"]
+    init = (ld["uniGasInitialisationDict"] or {}).get("configurations", [])
+    if len(init) != 1 or init[0].get("type") != "uniGasMeshFill":
+        raise ValueError("from_case_dir handles a single uniGasMeshFill configuration")
+    cfgi = init[0]
+    names = props["typeIdList"]
+    dens = {n: float(cfgi["numberDensities"][n]) for n in names}
+    ntot = sum(dens.values())
+    FN = float(props["nEquivalentParticles"])
+    T = float(cfgi["translationalTemperature"])
+    Trot = float(cfgi.get("rotationalTemperature", T))
+    vel = [float(v) for v in cfgi["velocity"]]
+    cwf = None
+    if props.get("cellWeightedSimulation", False):
+        pps = particles_per_cell or int(props["cellWeightedProperties"]["particlesPerSubCell"])
+        cwf = cell_weight_factor(mesh, ("particlesPerSubCell", pps), ntot, FN)
+    rng = np.random.default_rng(seed)
+    sps = props["moleculeProperties"]
+    pos, velp, cel, tid, erot = mesh_fill(mesh, sps, names, dens, T, vel, FN, rng, Trot=Trot, cell_weight=cwf)
+    sp0 = sps[names[int(np.argmax([dens[n] for n in names]))]]
+    sig0 = math.pi * sp0["diameter"] ** 2 * most_probable_speed(T, sp0["mass"])  # uniGasMeshFill.C:284-296
+    any_rot = any(sps[n].get("rotationalDegreesOfFreedom", 0) for n in names)
+    case = Case(os.path.basename(os.path.normpath(case_dir)), mesh, props, ld["boundariesDict"], ld["deltaT"], pos, velp, cel, tid,
+                erot if any_rot else None, sig0, meta=dict(n=ntot, T_inf=T, U_inf=vel, species=sp0, Tref=float(props.get("collisionProperties", {}).get("Tref", 273.0))))
+    if cwf is not None:
+        case.cellWeightFactor = cwf
+    return case, ld
