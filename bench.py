@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--box-n", type=int, default=64)
     ap.add_argument("--box-parcels", type=int, default=8_000_000)
     ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the bounded cpu_baseline sample")
+    ap.add_argument("--weighted", action="store_true", help="cylinder case: cell-weighted simulation (tuning / overhead measurement)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-state", action="store_true")
     return ap.parse_args()
@@ -110,13 +111,14 @@ def build_case(args, rank, world):
             c.cellCollModelId = (np.arange(c.mesh.n_cells) % 2).astype(np.int32)
         return c
     if args.case == "cylinder":
-        return cases.cylinder(nr=500, ntheta=1000, ppc=20)
+        # --weighted: the reference tutorial's setting (cellWeightedSimulation, factor from uniGasMeshFill's rule)
+        return cases.cylinder(nr=500, ntheta=1000, ppc=20, cellWeightFactor=("particlesPerSubCell", 20) if args.weighted else None)
     return cases.couette(nx=args.nx, ny=args.ny, ppc=args.ppc, rank=rank, n_ranks=world)
 
 
 def workload_name(args):
     if args.case == "cylinder":
-        return "cylinder2d_mach10_argon_500x1000cells_20ppc_inflow_outflow_dsmc_ntc_vhs"
+        return "cylinder2d_mach10_argon_500x1000cells_20ppc_inflow_outflow_dsmc_ntc_vhs" + ("_cellweighted" if args.weighted else "")
     if args.case == "box":
         return f"closedbox3d_{args.gas}_{args.box_n}^3cells_{args.box_parcels}parcels_{args.collision}_dt0.2mct"
     return f"couette2d_argon_kn0.1_{args.nx}x{args.ny}cells_{args.ppc}ppc_dsmc_ntc_vhs"
