@@ -158,6 +158,19 @@ def test_gpu_weighting_large_ratio_multiple_clones(GpuCloud, OracleCloud):
 
 
 @pytest.mark.gpu
+def test_gpu_weighting_in_cells_larger_than_the_staging_buffer(GpuCloud, OracleCloud):
+    """~310 parcels per cell: the cell kernel's slice-by-slice path and the shared / global-memory segment sorts see
+    the clone entries too."""
+    case = cases.closed_box(n=4, parcels=20000, seed=18, binary="noDSMCCollision", cellWeightFactor=x_ramp(0.5, 2.0))
+    g, r = both(case, GpuCloud, OracleCloud)
+    for _ in range(4):
+        g.evolve(1); r.evolve(1)
+        pg, pr, cg, _ = assert_lockstep(g, r)
+        assert np.array_equal(pg["U"], pr["U"])
+    assert cg["cloned"] > 100 and np.bincount(pg["cell"]).max() > 2 * 128
+
+
+@pytest.mark.gpu
 def test_gpu_weighting_with_ntc_collisions(GpuCloud, OracleCloud):
     case = cases.closed_box(n=8, parcels=50000, seed=13, cellWeightFactor=x_ramp())
     g, r = both(case, GpuCloud, OracleCloud)

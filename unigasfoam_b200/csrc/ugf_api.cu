@@ -60,11 +60,6 @@ __global__ void __launch_bounds__(256) hist_kernel(const int* __restrict__ cell,
     }
 }
 
-__global__ void __launch_bounds__(256) iota_kernel(int* p, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = i;
-}
-
 }  // namespace
 
 struct ugf_handle {
