@@ -312,3 +312,109 @@ def read_cloud_time(case_dir, time_name, n_cells, cloud="uniGas"):
         out["index"] = int(kv.get("index", 0))
         out["deltaT"] = float(kv["deltaT"]) if "deltaT" in kv else None
     return out
+
+
+# ---- constant/polyMesh -----------------------------------------------------------------------------------------
+def write_polymesh(case_dir, mesh, region="constant/polyMesh"):
+    """points, faces, owner, neighbour, boundary of a PolyMesh in OpenFOAM's ASCII layout (what blockMesh writes)."""
+    d = os.path.join(case_dir, region)
+    os.makedirs(d, exist_ok=True)
+    nP, nF, nI, nC = len(mesh.points), mesh.n_faces, mesh.n_internal, mesh.n_cells
+    note = f'    note        "nPoints:{nP}  nCells:{nC}  nFaces:{nF}  nInternalFaces:{nI}";\n'
+
+    def hdr(cls, obj, with_note=False):
+        h = _header(cls, region, obj)
+        return h.replace(f"    class       {cls};\n", f"    class       {cls};\n" + (note if with_note else ""))
+
+    with open(os.path.join(d, "points"), "w") as f:
+        f.write(hdr("vectorField", "points"))
+        f.write(f"{nP}\n(\n" + _fmt_vectors(mesh.points) + "\n)\n")
+    off, fp = mesh.face_point_offsets, mesh.face_points
+    with open(os.path.join(d, "faces"), "w") as f:
+        f.write(hdr("faceList", "faces"))
+        f.write(f"{nF}\n(\n")
+        f.write("\n".join(f"{off[i + 1] - off[i]}(" + " ".join(str(int(v)) for v in fp[off[i]:off[i + 1]]) + ")" for i in range(nF)))
+        f.write("\n)\n")
+    for name, arr in (("owner", mesh.owner), ("neighbour", mesh.neighbour)):
+        with open(os.path.join(d, name), "w") as f:
+            f.write(hdr("labelList", name, with_note=True))
+            f.write(f"{len(arr)}\n(\n" + _fmt_labels(arr) + "\n)\n")
+    with open(os.path.join(d, "boundary"), "w") as f:
+        f.write(hdr("polyBoundaryMesh", "boundary"))
+        f.write(f"{len(mesh.patches)}\n(\n")
+        for p in mesh.patches:
+            f.write(f"    {p.name}\n    {{\n        type            {p.kind};\n")
+            if p.kind == "cyclic":
+                f.write(f"        neighbourPatch  {mesh.patches[p.partner].name};\n")
+            if p.kind == "processor":
+                f.write(f"        myProcNo        0;\n        neighbProcNo    {p.partner};\n")
+            f.write(f"        nFaces          {p.size};\n        startFace       {p.start};\n    }}\n")
+        f.write(")\n")
+    return d
+
+
+def read_polymesh(case_dir, region="constant/polyMesh"):
+    """constant/polyMesh -> PolyMesh with its derived geometry (primitiveMesh: face areas / centres, cell centres /
+    volumes, cell -> faces).  Patch types as in the boundary file; cyclic partners from neighbourPatch; directions whose
+    faces are all on `empty` patches are not solved (polyMesh::solutionD)."""
+    from . import foamdict, mesh as _mesh
+    d = os.path.join(case_dir, region)
+
+    def body(name):
+        hdr, rest = _split_header(_strip(open(os.path.join(d, name)).read()))
+        return _list_body(rest)
+
+    nP, inner, _, _ = body("points")
+    pts = _numbers(inner).reshape(nP, 3)
+    nF, inner, _, _ = body("faces")
+    sizes, flat = [], []
+    for m in re.finditer(r"(\d+)\s*\(([^()]*)\)", inner):
+        ids = m.group(2).split()
+        if len(ids) != int(m.group(1)):
+            raise FoamFormatError("faces: entry size mismatch")
+        sizes.append(len(ids)); flat.extend(ids)
+    if len(sizes) != nF:
+        raise FoamFormatError(f"faces: {len(sizes)} entries, header says {nF}")
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    fpt = np.array(flat, dtype=np.int32)
+    nO, inner, uni, _ = body("owner")
+    owner = _numbers(inner, int).astype(np.int32) if inner is not None else np.full(nO, int(uni), np.int32)
+    nN, inner, uni, _ = body("neighbour")
+    neigh = _numbers(inner or "", int).astype(np.int32)
+    if len(owner) != nF or len(neigh) != nN:
+        raise FoamFormatError("owner / neighbour size mismatch")
+    text = _strip(open(os.path.join(d, "boundary")).read())
+    _, rest = _split_header(text)
+    m = re.match(r"\s*(\d+)\s*\(", rest)
+    if not m:
+        raise FoamFormatError("boundary: list expected")
+    ent = foamdict.parse(rest[m.end():rest.rindex(")")])  # the entries of the list are `name { ... }`: a dictionary body
+    if len(ent) != int(m.group(1)):
+        raise FoamFormatError("boundary: patch count mismatch")
+    names = list(ent)
+    patches = []
+    for name in names:
+        e = ent[name]
+        kind = e["type"]
+        if kind in ("symmetryPlane", "symmetry", "wedge"):
+            kind = "symmetryPlane" if kind != "symmetry" else "symmetry"
+        partner = -1
+        if kind == "cyclic":
+            partner = names.index(e["neighbourPatch"])
+        if kind == "processor":
+            partner = int(e["neighbProcNo"])
+        patches.append(_mesh.Patch(name, kind, int(e["startFace"]), int(e["nFaces"]), partner))
+    pm = _mesh.PolyMesh(pts, off, fpt, owner, neigh, patches)
+    pm.compute_geometry()
+    sol = [1, 1, 1]
+    for p in patches:  # polyMesh::calcDirections: the normals of the empty patches mark the unsolved direction
+        if p.kind == "empty" and p.size:
+            S = np.abs(pm.face_areas[p.start:p.start + p.size]).sum(0)
+            sol[int(np.argmax(S))] = 0
+    pm.solution_d = tuple(sol)
+    for p in patches:  # cyclic separation: offset between the two patches' face centres
+        if p.kind == "cyclic":
+            q = patches[p.partner]
+            sep = pm.face_centres[q.start:q.start + q.size].mean(0) - pm.face_centres[p.start:p.start + p.size].mean(0)
+            p.separation = tuple(float(v) for v in sep)
+    return pm
