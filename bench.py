@@ -361,7 +361,7 @@ def main():
 
     # ---- cpu baseline: the oracle on this host's cores, bounded sample --------------------------------------
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # N = 1 only: under torchrun the ranks share the host cores
         from oracle.oracle_cloud import OracleCloud, num_threads
         ocase = case if world == 1 else build_case(args, 0, 1)
         oc = ocase.make_cloud(OracleCloud)

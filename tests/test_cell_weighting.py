@@ -89,6 +89,38 @@ def test_oracle_weighted_inflow_count(OracleCloud):
     assert abs(nw / nb - 0.25) < 0.03, (nb, nw)
 
 
+def test_oracle_clone_and_delete_probabilities(OracleCloud):
+    """cellWeighting() parcel by parcel (U/clouds/uniGasCloud.C:1366-1420): crossing into a cell whose factor is r times
+    smaller yields floor(1/r - 1) clones plus one more with the remaining probability; crossing the other way the
+    parcel survives with probability r.  One step across a sharp factor step, counted per crossing."""
+    lo, hi = 0.4, 1.0   # hi -> lo: 1.5 clones on average; lo -> hi: survives with probability 0.4
+    def step(mesh):
+        mid = 0.5 * (mesh.points[:, 0].min() + mesh.points[:, 0].max())
+        return np.where(mesh.cell_centres[:, 0] < mid, lo, hi)
+    case = cases.closed_box(n=8, parcels=120000, seed=19, binary="noDSMCCollision", cellWeightFactor=step)
+    W = case.cellWeightFactor
+    cl = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels)
+    w0 = W[case.cell]
+    cl.move(); cl.buildCellOccupancy()
+    c = cl.counters()
+    # replay the move without weighting to know who crossed: same seed, factor field all equal
+    ref = cases.closed_box(n=8, parcels=120000, seed=19, binary="noDSMCCollision", cellWeightFactor=1.0)
+    rc = ref.make_cloud(OracleCloud, parcelCapacity=4 * ref.n_parcels)
+    # same initial parcels? the fill divides by the factor, so rebuild the weighted cloud's parcels in the reference cloud
+    rc.setParcels(case.position, case.U, case.cell)
+    rc.move()
+    w1 = W[rc.parcels()["cell"]]
+    down = (w0 == hi) & (w1 == lo)
+    up = (w0 == lo) & (w1 == hi)
+    nd, nu = int(down.sum()), int(up.sum())
+    assert nd > 1000 and nu > 1000
+    exp_clones, var_clones = nd * (hi / lo - 1.0), nd * 0.25   # 1 + Bernoulli(0.5) per crossing
+    assert abs(c["cloned"] - exp_clones) < 4 * np.sqrt(var_clones), (c["cloned"], exp_clones)
+    p_del = 1.0 - lo / hi
+    assert abs(c["weightDeleted"] - nu * p_del) < 4 * np.sqrt(nu * p_del * (1 - p_del)), (c["weightDeleted"], nu * p_del)
+    assert c["nParcels"] == case.n_parcels + c["cloned"] - c["weightDeleted"]
+
+
 def test_cell_weight_needs_the_switch(OracleCloud):
     case = cases.closed_box(n=4, parcels=2000, seed=1)
     cl = case.make_cloud(OracleCloud)

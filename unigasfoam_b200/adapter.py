@@ -116,7 +116,12 @@ class FaceOperators:
 
 
 class UniGasDynamicAdapter:
-    def __init__(self, cloud, uniGasProperties):
+    def __init__(self, cloud, uniGasProperties, reduce_min=None, reduce_max=None):
+        """reduce_min / reduce_max: callables float -> float that reduce over the ranks of a decomposed run (the reference's
+        reduce(deltaT, minOp) at :382-385 and reduce(maxCellWeightRatio, maxOp) at :493-496); identity on one rank.
+        Smoothing across processor patches is zero-gradient here."""
+        self.reduce_min = reduce_min or (lambda v: v)
+        self.reduce_max = reduce_max or (lambda v: v)
         self.cloud, self.mesh = cloud, cloud.mesh
         props = uniGasProperties
         ap = props.get("adaptiveProperties", {})
@@ -223,7 +228,7 @@ class UniGasDynamicAdapter:
             deltaT *= self.maxCourantNumber / co
         elif mct > VSMALL and co > VSMALL:
             deltaT *= min(self.maxTimeStepMCTRatio / mct, self.maxCourantNumber / co)
-        return deltaT, mct, co
+        return float(self.reduce_min(deltaT)), mct, co
 
     def calculate_sub_cell_levels(self, csr, collId):
         """calculateSubCellLevels (:390-431)."""
@@ -250,7 +255,7 @@ class UniGasDynamicAdapter:
             passes += 1
             cwf = self.ops.average_interpolate(cwf)
             cwf = np.maximum(np.minimum(cap, cwf), SMALL)
-            if not (self.ops.max_neighbour_ratio(cwf) > 1.0 + self.maxCellWeightRatio and passes < self.maxSmoothingPasses):
+            if not (self.reduce_max(self.ops.max_neighbour_ratio(cwf)) > 1.0 + self.maxCellWeightRatio and passes < self.maxSmoothingPasses):
                 break
         return cwf, passes
 
