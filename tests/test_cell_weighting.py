@@ -227,6 +227,24 @@ def test_gpu_weighting_bgk_relaxation(GpuCloud, OracleCloud):
 
 
 @pytest.mark.gpu
+def test_gpu_weighting_hybrid_mask_and_sub_cells(GpuCloud, OracleCloud):
+    """Everything the reference tutorials switch on at once: hybrid run (every other cell USP-SBGK, the rest NTC + VHS with
+    2 x 2 x 1 sub-cells) under a factor ramp."""
+    case = cases.closed_box(n=6, parcels=40000, seed=24, mode="hybrid", bgk="unifiedStochasticParticleSBGK", number_density=4e20,
+                            cellWeightFactor=x_ramp(0.6, 1.7), theta=0.5)
+    nC = case.mesh.n_cells
+    case.cellCollModelId = (np.arange(nC) % 2).astype(np.int32)
+    case.subCellLevels = np.tile(np.array([2, 2, 1], np.int32), (nC, 1))
+    g, r = both(case, GpuCloud, OracleCloud)
+    for _ in range(6):
+        g.evolve(1); r.evolve(1)
+    pg, pr, cg, cr = assert_lockstep(g, r, keys=("cloned", "weightDeleted", "nParcels", "collisionCandidates"), exact=False)
+    assert cg["collisions"] > 0 and cg["bgkRelaxations"] > 0
+    assert abs(cg["collisions"] - cr["collisions"]) <= 2 and abs(cg["bgkRelaxations"] - cr["bgkRelaxations"]) <= 2
+    assert frac_close(pg["U"], pr["U"], rtol=1e-8) > 0.99
+
+
+@pytest.mark.gpu
 def test_gpu_weighted_cylinder_inflow_walls_fields(GpuCloud, OracleCloud):
     """Graded O-grid with uniGasMeshFill's rule (CWF proportional to the cell volume: the same number of parcels in
     every cell), free-stream inflow, deleting outflow, diffuse wall: insertion counts, parcels, wall and volume fields."""

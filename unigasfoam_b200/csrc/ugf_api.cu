@@ -357,6 +357,8 @@ int do_sort(ugf_handle* h) {
 // after a gather the array is cell-major and its length is the live count
 int after_gather(ugf_handle* h, bool setN = true) {
     h->cur ^= 1;
+    if (h->cloneValid) h->nUpper = h->capacity;  // the gather may have materialised clones: the array can be longer than the
+                                                 // old bound until the length read-back below has landed
     h->cloneValid = false;  // the clones are parcels of their own now
     if (setN) {  // the cell kernel writes the new length itself
         set_n_kernel<<<1, 1, 0, h->stream>>>(h->dTotal, h->dN);
