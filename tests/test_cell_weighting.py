@@ -245,6 +245,31 @@ def test_gpu_weighting_hybrid_mask_and_sub_cells(GpuCloud, OracleCloud):
 
 
 @pytest.mark.gpu
+def test_gpu_weighting_mixture_with_rotation_and_tracker(GpuCloud, OracleCloud):
+    """Argon / nitrogen mixture (typeId and ERot travel with the clones through the gather), Larsen-Borgnakke collisions,
+    diffuse walls, per-species face tallies - the multi-species and rotational template paths under a factor ramp."""
+    case = cases.mixture_box(n=6, parcels=30000, seed=25, cellWeightFactor=x_ramp(0.6, 1.8))
+    m = case.mesh
+    nI = m.n_internal
+    mid = 0.5 * (m.points[:, 0].min() + m.points[:, 0].max())
+    zone = np.nonzero((np.abs(m.face_areas[:nI, 0]) > 0) & (np.abs(m.face_centres[:nI, 0] - mid) < 1e-9 * mid))[0].astype(np.int32)
+    assert len(zone) == 36
+    g, r = both(case, GpuCloud, OracleCloud)
+    g.setFaceTracker(zone); r.setFaceTracker(zone)
+    for _ in range(6):
+        g.evolve(1); r.evolve(1)
+    pg, pr, cg, cr = assert_lockstep(g, r, exact=False)
+    assert np.array_equal(pg["typeId"], pr["typeId"]) and set(np.unique(pg["typeId"])) == {0, 1}
+    assert frac_close(pg["U"], pr["U"], rtol=1e-8) > 0.99
+    assert (np.abs(pg["ERot"] - pr["ERot"]) <= 1e-8 * np.abs(pr["ERot"]).max()).mean() > 0.99
+    assert (pg["ERot"][pg["typeId"] == 0] == 0).all() and (pg["ERot"][pg["typeId"] == 1] > 0).mean() > 0.99
+    assert abs(cg["collisions"] - cr["collisions"]) <= 2 and cg["cloned"] > 100
+    tg, tr = g.faceTracker(), r.faceTracker()
+    assert tr.shape == (36, 2, 6) and np.abs(tr[:, 1, 0]).sum() > 0
+    assert np.allclose(tg, tr, rtol=1e-6, atol=1e-6 * np.abs(tr).max(axis=(0, 1), keepdims=True))
+
+
+@pytest.mark.gpu
 def test_gpu_weighted_cylinder_inflow_walls_fields(GpuCloud, OracleCloud):
     """Graded O-grid with uniGasMeshFill's rule (CWF proportional to the cell volume: the same number of parcels in
     every cell), free-stream inflow, deleting outflow, diffuse wall: insertion counts, parcels, wall and volume fields."""

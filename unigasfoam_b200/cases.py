@@ -197,7 +197,7 @@ def closed_box(n=32, parcels=1_000_000, wall="specular", T0=300.0, number_densit
 
 def mixture_box(n=6, parcels=20000, fractions=(("Ar", None, 0.6), ("N2", None, 0.4)), T0=300.0, number_density=1e20, Tref=273.0,
                 binary="LarsenBorgnakkeVariableHardSphere", mode="dsmc", bgk="noBGKCollision", wall="diffuse", seed=5, dt_mct=0.5,
-                lambda_per_dx=1.0, Trot=None, **cp):
+                lambda_per_dx=1.0, Trot=None, cellWeightFactor=None, **cp):
     """Closed 3-D box holding a gas mixture (typeIdList with several species: the multi-species code paths -
     typeId per parcel, per-species cell sums, cross-species collision pairs)."""
     table = {"Ar": ARGON_GUIDE, "N2": NITROGEN}
@@ -211,7 +211,8 @@ def mixture_box(n=6, parcels=20000, fractions=(("Ar", None, 0.6), ("N2", None, 0
     m.meta_axis_aligned = True
     nParticle = number_density * L ** 3 / parcels
     rng = np.random.default_rng(seed)
-    pos, vel, cel, tid, erot = mesh_fill(m, sps, names, dens, T0, (0.0, 0.0, 0.0), nParticle, rng, Trot=Trot)
+    cwf = cell_weight_factor(m, cellWeightFactor, number_density, nParticle)
+    pos, vel, cel, tid, erot = mesh_fill(m, sps, names, dens, T0, (0.0, 0.0, 0.0), nParticle, rng, Trot=Trot, cell_weight=cwf)
     dt = dt_mct / vhs_collision_rate(number_density, T0, sp0, Tref)
     if wall == "specular":
         model = lambda p: {"patchBoundaryProperties": {"patch": p}, "boundaryModel": "uniGasSpecularWallPatch"}
@@ -223,8 +224,8 @@ def mixture_box(n=6, parcels=20000, fractions=(("Ar", None, 0.6), ("N2", None, 0
     props["typeIdList"] = names
     props["moleculeProperties"] = sps
     sig0 = math.pi * sp0["diameter"] ** 2 * most_probable_speed(T0, sp0["mass"])
-    return Case("mixture_box", m, props, bd, dt, pos, vel, cel, tid, erot, sig0,
-                meta=dict(n=number_density, T0=T0, lam=lam, L=L, Tref=Tref, species=sps, fractions=dens))
+    return _weighted(Case("mixture_box", m, props, bd, dt, pos, vel, cel, tid, erot, sig0,
+                          meta=dict(n=number_density, T0=T0, lam=lam, L=L, Tref=Tref, species=sps, fractions=dens)), cwf)
 
 
 def couette(nx=1000, ny=500, ppc=20, Kn=0.1, Tw=273.0, Uw=150.0, number_density=1e20, species=("Ar", ARGON_GUIDE),
