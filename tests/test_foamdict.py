@@ -156,3 +156,67 @@ def test_unsupported_switches_fail_loudly(OracleCloud):
     ld = foamdict.load_case(CASE)
     with pytest.raises(UgfError, match="macroInterpolation"):
         OracleCloud(m, ld["uniGasProperties"], {}, ld["deltaT"], parcelCapacity=1000)
+
+
+# ---- the supersonicPlate tutorial on its own mesh layout; macroInterpolation (cell values) is the one override ------
+PLATE = os.path.join(GOLD, "supersonicPlate")
+
+
+def run_plate(Cloud, steps, seed=71):
+    """tutorials/uniGasFoam/supersonicPlate (hybrid USP-SBGK / NTC-VHS, cell weighting, time-step / sub-cell /
+    cell-weight adaptation every 10 steps, local-Knudsen decomposition, free-stream inflow at Mach 1.5, diffuse plate) on
+    the tutorial's three-block mesh at a fifth of its resolution."""
+    m = ugmesh.plate_mesh(nx=(10, 20, 15), ny=40)
+    case, ld = cases.from_case_dir(PLATE, m, seed=seed, overrides={"collisionProperties": {"macroInterpolation": False}})
+    cl = case.make_cloud(Cloud, parcelCapacity=3 * case.n_parcels, sampleInterval=foamdict.sample_interval(ld["fieldPropertiesDict"]))
+    cl.setHybridDecomposition(ld["hybridDecompositionDict"])
+    ad = UniGasDynamicAdapter(cl, case.uniGasProperties)
+    if case.subCellLevels is not None:
+        ad.subCellLevels = case.subCellLevels.copy()
+    tally = dict(inserted=0, deleted=0, wallHits=0, collisions=0, bgkRelaxations=0, cloned=0, weightDeleted=0)
+    for _ in range(steps // 10):
+        ad.run(10)
+        c = cl.counters()
+        for k in tally:
+            tally[k] += c[k]
+    return case, ld, cl, ad, tally
+
+
+def test_oracle_runs_supersonic_plate(OracleCloud):
+    case, ld, cl, ad, tally = run_plate(OracleCloud, 30)
+    p = case.uniGasProperties
+    assert p["collisionModel"] == "hybrid" and p["adaptiveProperties"]["adaptationInterval"] == 10
+    assert p["collisionProperties"]["theta"] == 0.1 and p["collisionProperties"]["Tref"] == 273
+    assert ld["deltaT"] == 5e-9 and case.deltaT > 5 * ld["deltaT"]         # setInitialConfiguration raised the time step
+    assert case.subCellLevels is not None and case.subCellLevels.max() > 1 and (case.subCellLevels[:, 2] == 1).all()
+    cnt0 = np.bincount(case.cell, minlength=case.mesh.n_cells)
+    nSub = case.subCellLevels.prod(1)
+    assert abs((cnt0 / nSub).mean() - 20) < 1                              # particlesPerSubCell parcels in every sub-cell
+    c = cl.counters()
+    assert c["stuck"] == 0 and c["step"] == 30
+    assert tally["inserted"] > 0 and tally["deleted"] > 0 and tally["wallHits"] > 0
+    f = cl.fields()
+    assert np.isfinite(f["rhoN"]).all()
+    x, y = case.mesh.cell_centres[:, 0], case.mesh.cell_centres[:, 1]
+    free = (y > 3e-3) & (x < 2e-3)
+    assert abs(np.median(f["rhoN"][free]) / 3.416e22 - 1) < 0.05
+    assert abs(np.median(f["UMean"][free, 0]) / 484.0 - 1) < 0.05
+    near = (y < 1.5e-4) & (x > 0.7e-3) & (x < 1.4e-3)                      # the gas right above the plate has been slowed down
+    assert f["UMean"][near, 0].mean() < 0.8 * 484.0
+    assert np.abs(f["surfaceShearStress"]).max() > 0
+
+
+@pytest.mark.gpu
+def test_gpu_runs_supersonic_plate_like_the_oracle(GpuCloud, OracleCloud):
+    case, _, g, ag, tg = run_plate(GpuCloud, 20)
+    _, _, r, ar, tr = run_plate(OracleCloud, 20)
+    for k in ("inserted", "deleted", "wallHits"):
+        assert abs(tg[k] - tr[k]) <= 0.05 * tr[k] + 10, (k, tg[k], tr[k])
+    assert abs(g.counters()["nParcels"] / r.counters()["nParcels"] - 1) < 0.02
+    assert g.cfg.deltaT == pytest.approx(r.cfg.deltaT, rel=0.05)
+    assert np.array_equal(ag.subCellLevels, ar.subCellLevels) or (np.abs(ag.subCellLevels - ar.subCellLevels) <= 1).all()
+    fg, fr = g.fields(), r.fields()
+    V = case.mesh.cell_volumes
+    assert np.average(fg["rhoN"], weights=V) == pytest.approx(np.average(fr["rhoN"], weights=V), rel=0.01)
+    assert np.average(fg["UMean"][:, 0], weights=V) == pytest.approx(np.average(fr["UMean"][:, 0], weights=V), rel=0.02)
+    assert g.counters()["stuck"] == 0

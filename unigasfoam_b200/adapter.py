@@ -312,6 +312,30 @@ class UniGasDynamicAdapter:
         self._begin_interval()
         return True
 
+    def set_initial_configuration(self, speciesRhoN, transT, U):
+        """setInitialConfiguration (:708-775), called by uniGasMeshFill before the parcels are created: the adaptation
+        quantities of the uniform initial state, smoothed, give the first time step and sub-cell levels.  Returns
+        (deltaT, subCellLevels); the cloud's time step is set when a cloud is attached."""
+        nC, nS = self.mesh.n_cells, len(self.species)
+        sp = np.tile(np.asarray(speciesRhoN, float), (nC, 1))
+        rhoN = np.full(nC, float(np.sum(speciesRhoN)))
+        deltaT = self.cloud.cfg.deltaT
+        tsr, cou, csr = self.adaptation_quantities(rhoN, np.full(nC, float(transT)), np.tile(np.asarray(U, float), (nC, 1)), sp, deltaT)
+        for _ in range(self.smoothingPasses):
+            tsr = self.ops.average_interpolate(tsr)
+            cou = self.ops.average_interpolate(cou)
+            csr = self.ops.average_interpolate(csr)
+        self.prevCellSizeMFPRatio = csr
+        if self.timeStepAdaptation:
+            deltaT, _, _ = self.calculate_time_step(tsr, cou, deltaT, self.cellCollModelId)
+            if hasattr(self.cloud, "setDeltaT"):
+                self.cloud.setDeltaT(deltaT)
+            else:
+                self.cloud.cfg.deltaT = deltaT
+        if self.subCellAdaptation:
+            self.subCellLevels = self.calculate_sub_cell_levels(csr, self.cellCollModelId)
+        return deltaT, self.subCellLevels
+
     def begin(self):
         self._begin_interval()
 

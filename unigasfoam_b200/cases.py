@@ -331,18 +331,31 @@ def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=Non
     T = float(cfgi["translationalTemperature"])
     Trot = float(cfgi.get("rotationalTemperature", T))
     vel = [float(v) for v in cfgi["velocity"]]
+    deltaT, levels = ld["deltaT"], None
+    if props.get("adaptiveSimulation", False):  # uniGasMeshFill.C:101-109: first time step and sub-cell levels from the initial state
+        from types import SimpleNamespace
+        from .adapter import UniGasDynamicAdapter
+        stand_in = SimpleNamespace(mesh=mesh, cellWeighted=bool(props.get("cellWeightedSimulation", False)), _subCellLevels=None,
+                                   _cellWeightFactor=None, cfg=SimpleNamespace(deltaT=deltaT, nParticle=FN))
+        ad0 = UniGasDynamicAdapter(stand_in, props)
+        deltaT, levels = ad0.set_initial_configuration([dens[n] for n in names], T, vel)
+        if not ad0.subCellAdaptation:
+            levels = None
     cwf = None
     if props.get("cellWeightedSimulation", False):
         pps = particles_per_cell or int(props["cellWeightedProperties"]["particlesPerSubCell"])
-        cwf = cell_weight_factor(mesh, ("particlesPerSubCell", pps), ntot, FN)
+        nSub = 1.0 if levels is None else levels.prod(1).astype(float)
+        cwf = cell_weight_factor(mesh, ("particlesPerSubCell", pps), ntot, FN) / nSub   # uniGasMeshFill.C:111-121
     rng = np.random.default_rng(seed)
     sps = props["moleculeProperties"]
     pos, velp, cel, tid, erot = mesh_fill(mesh, sps, names, dens, T, vel, FN, rng, Trot=Trot, cell_weight=cwf)
     sp0 = sps[names[int(np.argmax([dens[n] for n in names]))]]
     sig0 = math.pi * sp0["diameter"] ** 2 * most_probable_speed(T, sp0["mass"])  # uniGasMeshFill.C:284-296
     any_rot = any(sps[n].get("rotationalDegreesOfFreedom", 0) for n in names)
-    case = Case(os.path.basename(os.path.normpath(case_dir)), mesh, props, ld["boundariesDict"], ld["deltaT"], pos, velp, cel, tid,
+    case = Case(os.path.basename(os.path.normpath(case_dir)), mesh, props, ld["boundariesDict"], deltaT, pos, velp, cel, tid,
                 erot if any_rot else None, sig0, meta=dict(n=ntot, T_inf=T, U_inf=vel, species=sp0, Tref=float(props.get("collisionProperties", {}).get("Tref", 273.0))))
     if cwf is not None:
         case.cellWeightFactor = cwf
+    if levels is not None and (levels != 1).any():
+        case.subCellLevels = levels
     return case, ld

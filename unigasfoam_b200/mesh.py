@@ -290,6 +290,84 @@ def split_patch(mesh, name, n_first, name_a, name_b, kind_a=None, kind_b=None):
     return mesh
 
 
+def merge_patches(mesh, name_a, name_b, new_name=None):
+    """Make the faces of patch `name_b` part of patch `name_a` (blockMesh lists several face sets under one patch, e.g. the
+    left and the top side of a block as `inlet`): the boundary faces are reordered so that b's follow a's, before the
+    geometry is computed.  Neither patch may be cyclic."""
+    ia, ib = mesh.patch_index(name_a), mesh.patch_index(name_b)
+    pa, pb = mesh.patches[ia], mesh.patches[ib]
+    assert pa.kind != "cyclic" and pb.kind != "cyclic" and pa.kind == pb.kind and ia != ib
+    nF = mesh.n_faces
+    order = list(range(mesh.n_internal))
+    new_patches = []
+    for k, p in enumerate(mesh.patches):
+        if k == ib:
+            continue
+        start = len(order)
+        order.extend(range(p.start, p.start + p.size))
+        size = p.size
+        if k == ia:
+            order.extend(range(pb.start, pb.start + pb.size))
+            size += pb.size
+        new_patches.append(Patch(new_name if (k == ia and new_name) else p.name, p.kind, start, size, p.partner, p.separation))
+    order = np.asarray(order)
+    assert len(order) == nF
+    off = mesh.face_point_offsets
+    sizes = np.diff(off)[order]
+    new_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    new_fp = np.concatenate([mesh.face_points[off[f]:off[f + 1]] for f in order]).astype(np.int32)
+    mesh.face_point_offsets, mesh.face_points = new_off, new_fp
+    mesh.owner = mesh.owner[order]
+    # cyclic partners are patch indices: shift those above the removed patch
+    for q in new_patches:
+        if q.kind == "cyclic" and q.partner > ib:
+            q.partner -= 1
+    mesh.patches = new_patches
+    if mesh.face_areas is not None:
+        n_cells = mesh.n_cells
+        mesh.compute_geometry(n_cells)
+    return mesh
+
+
+def _graded(t, g):
+    """blockMesh simpleGrading: position fraction of vertex fraction t when last / first cell size = g."""
+    g = float(g)
+    return t if abs(g - 1.0) < 1e-12 else (g ** t - 1.0) / (g - 1.0)
+
+
+def plate_mesh(nx=(50, 100, 75), ny=200, x_breaks=(0.0, 0.5e-3, 1.5e-3, 3.0e-3), height=5.0e-3, lz=0.02e-3, gx=(1.0, 1.0, 4.0), gy=5.0):
+    """The mesh of tutorials/uniGasFoam/supersonicPlate (system/blockMeshDict): three hex blocks side by side along x
+    (cell counts nx, gradings gx), ny cells in y with grading gy, one cell in z.  Patches as in the tutorial: inlet
+    (left side and top, type patch), outlet (right, patch), symmetryFront / plate (wall) / symmetryBack along the
+    bottom, emptyBoundaries."""
+    nxt = int(sum(nx))
+    edges = np.concatenate([[0], np.cumsum(nx)])
+
+    def xmap(I):
+        x = np.zeros_like(I)
+        for b in range(len(nx)):
+            sel = (I >= edges[b]) & (I <= edges[b + 1])
+            t = (I - edges[b]) / nx[b]
+            frac = t if abs(gx[b] - 1.0) < 1e-12 else (gx[b] ** t - 1.0) / (gx[b] - 1.0)
+            x = np.where(sel, x_breaks[b] + (x_breaks[b + 1] - x_breaks[b]) * frac, x)
+        return x
+
+    def pm(I, J, K):
+        t = J / ny
+        fy = t if abs(gy - 1.0) < 1e-12 else (gy ** t - 1.0) / (gy - 1.0)
+        return xmap(I), height * fy, lz * (K - 0.5)
+
+    kinds = {"xMin": ("inlet", "patch"), "xMax": ("outlet", "patch"), "yMin": ("bottom", "symmetry"), "yMax": ("inletTop", "patch"),
+             "zMin": ("emptyBack", "empty"), "zMax": ("emptyBoundaries", "empty")}
+    m = structured_block(nxt, ny, 1, pm, kinds, solution_d=(1, 1, 0))
+    split_patch(m, "bottom", int(nx[0]), "symmetryFront", "rest")
+    split_patch(m, "rest", int(nx[1]), "plate", "symmetryBack", kind_a="wall")
+    merge_patches(m, "inlet", "inletTop")
+    merge_patches(m, "emptyBoundaries", "emptyBack")
+    m.meta_axis_aligned = True
+    return m
+
+
 def half_annulus_mesh(nr, ntheta, r0, r1, lz, grading=5.0):
     """Half O-grid around a cylinder on the symmetry axis: the topology of tutorials/uniGasFoam/hypersonicCylinder
     (system/blockMeshDict), as one block.  i runs radially outwards (last/first cell size = grading), j in theta
