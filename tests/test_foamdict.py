@@ -225,3 +225,40 @@ def test_gpu_runs_supersonic_plate_like_the_oracle(GpuCloud, OracleCloud):
     assert np.average(fg["rhoN"], weights=V) == pytest.approx(np.average(fr["rhoN"], weights=V), rel=0.01)
     assert np.average(fg["UMean"][:, 0], weights=V) == pytest.approx(np.average(fr["UMean"][:, 0], weights=V), rel=0.02)
     assert g.counters()["stuck"] == 0
+
+
+def test_mesh_field_fill_from_a_time_directory(tmp_path, OracleCloud):
+    """`type uniGasMeshFieldFill` (the initialisation of the plume / expansion tutorials): every cell is filled at the
+    state the fields of the start time directory give it (numberDensity_<species>, transT, rotT, U)."""
+    import shutil
+    from unigasfoam_b200 import foamfile
+    case_dir = tmp_path / "fieldFill"
+    shutil.copytree(CASE, case_dir)
+    (case_dir / "system" / "uniGasInitialisationDict").write_text(
+        "FoamFile { version 2.0; format ascii; class dictionary; object uniGasInitialisationDict; }\n"
+        "configurations ( configuration { type uniGasMeshFieldFill; typeIdList (Ar); } );\n")
+    m = ugmesh.half_annulus_mesh(10, 16, 0.5 * 0.3048, 2.0 * 0.3048, 0.1 * 0.3048, 3.0)
+    m.meta_axis_aligned = False
+    x = m.cell_centres[:, 0]
+    n = 4.247e20 * (1.0 + 0.8 * (x - x.min()) / (x.max() - x.min()))
+    T = 200.0 + 300.0 * (x > 0)
+    U = np.column_stack([1000.0 * (x < 0), np.zeros(m.n_cells), np.zeros(m.n_cells)])
+    os.makedirs(case_dir / "0")
+    patches = {p.name: ("empty" if p.kind == "empty" else "calculated") for p in m.patches}
+    foamfile.write_vol_field(str(case_dir / "0" / "numberDensity_Ar"), "0", [0, -3, 0, 0, 0, 0, 0], n, patches)
+    foamfile.write_vol_field(str(case_dir / "0" / "transT"), "0", [0, 0, 0, 1, 0, 0, 0], T, patches)
+    foamfile.write_vol_field(str(case_dir / "0" / "rotT"), "0", [0, 0, 0, 1, 0, 0, 0], np.zeros(m.n_cells), patches)
+    foamfile.write_vol_field(str(case_dir / "0" / "U"), "0", [0, 1, -1, 0, 0, 0, 0], U, patches, vector=True)
+    FN = 4.247e20 * m.cell_volumes.sum() / 40000
+    case, _ = cases.from_case_dir(str(case_dir), m, seed=5, overrides={
+        "nEquivalentParticles": FN, "cellWeightedSimulation": False, "adaptiveSimulation": False, "collisionModel": "dsmc",
+        "collisionProperties": {"macroInterpolation": False}})
+    cnt = np.bincount(case.cell, minlength=m.n_cells)
+    expect = n * m.cell_volumes / FN
+    assert abs(cnt.sum() / expect.sum() - 1) < 0.01 and np.corrcoef(cnt, expect)[0, 1] > 0.97
+    Tp = case.meta["species"]["mass"] * ((case.U - U[case.cell]) ** 2).sum(1) / (3 * cases.kB)
+    assert abs(Tp[x[case.cell] > 0].mean() / 500.0 - 1) < 0.03 and abs(Tp[x[case.cell] < 0].mean() / 200.0 - 1) < 0.03
+    assert abs(case.U[x[case.cell] < 0, 0].mean() / 1000.0 - 1) < 0.02 and abs(case.U[x[case.cell] > 0, 0].mean()) < 10.0
+    cl = case.make_cloud(OracleCloud, parcelCapacity=3 * case.n_parcels)
+    cl.evolve(3)
+    assert cl.counters()["stuck"] == 0

@@ -317,10 +317,11 @@ class UniGasDynamicAdapter:
         quantities of the uniform initial state, smoothed, give the first time step and sub-cell levels.  Returns
         (deltaT, subCellLevels); the cloud's time step is set when a cloud is attached."""
         nC, nS = self.mesh.n_cells, len(self.species)
-        sp = np.tile(np.asarray(speciesRhoN, float), (nC, 1))
-        rhoN = np.full(nC, float(np.sum(speciesRhoN)))
+        sp = np.stack([np.broadcast_to(np.asarray(v, float), (nC,)) for v in speciesRhoN], axis=1)  # scalars or per-cell fields
+        rhoN = sp.sum(1)
         deltaT = self.cloud.cfg.deltaT
-        tsr, cou, csr = self.adaptation_quantities(rhoN, np.full(nC, float(transT)), np.tile(np.asarray(U, float), (nC, 1)), sp, deltaT)
+        tsr, cou, csr = self.adaptation_quantities(rhoN, np.broadcast_to(np.asarray(transT, float), (nC,)).copy(),
+                                                   np.broadcast_to(np.asarray(U, float), (nC, 3)).copy(), sp, deltaT)
         for _ in range(self.smoothingPasses):
             tsr = self.ops.average_interpolate(tsr)
             cou = self.ops.average_interpolate(cou)

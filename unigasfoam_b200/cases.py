@@ -100,12 +100,15 @@ def _uniform_in_cells(mesh, cells, rng):
 
 def mesh_fill(mesh, species, names, number_densities, T, velocity, nParticle, rng, Trot=None, cells=None, cell_weight=None):
     """uniGasMeshFill::setInitialConfiguration (…/uniGasMeshFill.C:174-278), per cell instead of per tet:
-    N = n V / (F_N CWF) with stochastic rounding (:196-199), uniform position, Maxwellian + drift, equipartition ERot."""
+    N = n V / (F_N CWF) with stochastic rounding (:196-199), uniform position, Maxwellian + drift, equipartition ERot.
+    number_densities[name], T, Trot may be scalars or per-cell arrays and velocity a vector or [nCells,3] - the latter is
+    uniGasMeshFieldFill (…/uniGasMeshFieldFill/uniGasMeshFieldFill.C:60-330: every cell filled at its own state)."""
     pos, vel, cel, tid, erot = [], [], [], [], []
     all_cells = np.arange(mesh.n_cells) if cells is None else np.asarray(cells)
     for ti, name in enumerate(names):
         sp = species[name]
-        req = number_densities[name] / nParticle * mesh.cell_volumes[all_cells]
+        nd = np.broadcast_to(np.asarray(number_densities[name], float), (mesh.n_cells,))
+        req = nd[all_cells] / nParticle * mesh.cell_volumes[all_cells]
         if cell_weight is not None:
             req = req / np.asarray(cell_weight, float)[all_cells]
         cnt = np.floor(req).astype(np.int64)
@@ -113,16 +116,18 @@ def mesh_fill(mesh, species, names, number_densities, T, velocity, nParticle, rn
         cl = np.repeat(all_cells, cnt)
         n = len(cl)
         pos.append(_uniform_in_cells(mesh, cl, rng))
-        vel.append(math.sqrt(kB * T / sp["mass"]) * rng.standard_normal((n, 3)) + np.asarray(velocity)[None, :])
+        Tc = np.broadcast_to(np.asarray(T, float), (mesh.n_cells,))[cl]
+        Uc = np.broadcast_to(np.asarray(velocity, float), (mesh.n_cells, 3))[cl]
+        vel.append(np.sqrt(kB * Tc / sp["mass"])[:, None] * rng.standard_normal((n, 3)) + Uc)
         cel.append(cl); tid.append(np.full(n, ti, np.int32))
         rd = sp.get("rotationalDegreesOfFreedom", 0)
-        tr = T if Trot is None else Trot
+        tr = np.broadcast_to(np.asarray(T if Trot is None else Trot, float), (mesh.n_cells,))[cl]
         if rd == 0:
             erot.append(np.zeros(n))
         elif rd == 2:
             erot.append(-np.log(1.0 - rng.random(n)) * kB * tr)
         else:
-            erot.append(rng.gamma(0.5 * rd, kB * tr, n))
+            erot.append(rng.gamma(0.5 * rd, 1.0, n) * kB * tr)
     pos = np.concatenate(pos); vel = np.concatenate(vel); cel = np.concatenate(cel)
     tid = np.concatenate(tid); erot = np.concatenate(erot)
     # the cloud is a linked list in insertion order: cell-major here
@@ -309,7 +314,7 @@ def cylinder(nr=100, ntheta=200, ppc=20, n_inf=4.247e20, T_inf=200.0, U_inf=2634
                           meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, r0=r0, r1=r1, Tref=Tref, species=sp)), cwf)
 
 
-def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=None):
+def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=None, start_time="0"):
     """A uniGasFoam case directory (constant/uniGasProperties, system/{controlDict, boundariesDict,
     uniGasInitialisationDict, ...}) on a given mesh -> Case: the dictionaries are used as they are
     (unigasfoam_b200.foamdict.load_case), the initial parcels come from the `uniGasMeshFill` configuration
@@ -321,16 +326,24 @@ def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=Non
     ld = foamdict.load_case(case_dir, overrides)
     props = ld["uniGasProperties"]
     init = (ld["uniGasInitialisationDict"] or {}).get("configurations", [])
-    if len(init) != 1 or init[0].get("type") != "uniGasMeshFill":
-        raise ValueError("from_case_dir handles a single uniGasMeshFill configuration")
+    if len(init) != 1 or init[0].get("type") not in ("uniGasMeshFill", "uniGasMeshFieldFill"):
+        raise ValueError("from_case_dir handles a single uniGasMeshFill / uniGasMeshFieldFill configuration")
     cfgi = init[0]
     names = props["typeIdList"]
-    dens = {n: float(cfgi["numberDensities"][n]) for n in names}
-    ntot = sum(dens.values())
     FN = float(props["nEquivalentParticles"])
-    T = float(cfgi["translationalTemperature"])
-    Trot = float(cfgi.get("rotationalTemperature", T))
-    vel = [float(v) for v in cfgi["velocity"]]
+    if cfgi["type"] == "uniGasMeshFieldFill":  # per-cell state from the fields of the start time directory
+        from . import foamfile
+        t0 = os.path.join(case_dir, start_time)
+        fld = lambda f: foamfile.expand_internal(foamfile.read_vol_field(os.path.join(t0, f)), mesh.n_cells)
+        dens = {n: fld("numberDensity_" + n) for n in names}
+        T, Trot, vel = fld("transT"), fld("rotT"), fld("U")
+        ntot = sum(dens.values())
+    else:
+        dens = {n: float(cfgi["numberDensities"][n]) for n in names}
+        ntot = sum(dens.values())
+        T = float(cfgi["translationalTemperature"])
+        Trot = float(cfgi.get("rotationalTemperature", T))
+        vel = [float(v) for v in cfgi["velocity"]]
     deltaT, levels = ld["deltaT"], None
     if props.get("adaptiveSimulation", False):  # uniGasMeshFill.C:101-109: first time step and sub-cell levels from the initial state
         from types import SimpleNamespace
@@ -349,11 +362,11 @@ def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=Non
     rng = np.random.default_rng(seed)
     sps = props["moleculeProperties"]
     pos, velp, cel, tid, erot = mesh_fill(mesh, sps, names, dens, T, vel, FN, rng, Trot=Trot, cell_weight=cwf)
-    sp0 = sps[names[int(np.argmax([dens[n] for n in names]))]]
-    sig0 = math.pi * sp0["diameter"] ** 2 * most_probable_speed(T, sp0["mass"])  # uniGasMeshFill.C:284-296
+    sp0 = sps[names[int(np.argmax([np.mean(dens[n]) for n in names]))]]
+    sig0 = math.pi * sp0["diameter"] ** 2 * most_probable_speed(float(np.mean(T)), sp0["mass"])  # uniGasMeshFill.C:284-296
     any_rot = any(sps[n].get("rotationalDegreesOfFreedom", 0) for n in names)
     case = Case(os.path.basename(os.path.normpath(case_dir)), mesh, props, ld["boundariesDict"], deltaT, pos, velp, cel, tid,
-                erot if any_rot else None, sig0, meta=dict(n=ntot, T_inf=T, U_inf=vel, species=sp0, Tref=float(props.get("collisionProperties", {}).get("Tref", 273.0))))
+                erot if any_rot else None, sig0, meta=dict(n=float(np.mean(ntot)), T_inf=float(np.mean(T)), U_inf=np.asarray(vel, float).reshape(-1, 3).mean(0), species=sp0, Tref=float(props.get("collisionProperties", {}).get("Tref", 273.0))))
     if cwf is not None:
         case.cellWeightFactor = cwf
     if levels is not None and (levels != 1).any():
