@@ -310,6 +310,15 @@ int ugf_set_deltaT(ugf_handle* h, double deltaT);
 /* Restart: continue the step count (and with it the counter-based random streams) from Time::timeIndex as stored in
  * <time>/uniform/time (U/clouds/uniGasCloud.C:581-593 reads deltaT from the same dictionary). */
 int ugf_set_time_index(ugf_handle* h, int64_t index);
+/* Checkpoint of everything the loop carries between steps besides the parcels and the cell-state fields of
+ * ugf_upload_cell_state: step count, uniGasVolFields accumulators and counters (the reference stores them in
+ * <time>/uniform/volFieldsMethod_*, uniGasVolFields.C:550-669), BGK persistent state (maxProb, previous heat flux / shear
+ * stress), sigmaTcRMax, collision-model mask, local-Knudsen accumulators and blended Knudsen fields, pressure-inlet face
+ * velocities.  A flat array of doubles with a self-describing header; written by one implementation it can be read by
+ * another on the same mesh / species / model set-up (checked).  ugf_state_size gives the length in doubles. */
+int ugf_state_size(ugf_handle* h, int64_t* nDoubles);
+int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles);
+int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles);
 
 /* ---- the hot path ----------------------------------------------------------- */
 

@@ -1876,6 +1876,65 @@ int ugfo_download_decomposition(ugfo_handle* h, int32_t* id, double* kn) {
     return 0;
 }
 
+// ---- state checkpoint: the layout documented at ugf_state_* in unigasfoam_b200/csrc/ugf_api.cu ----------------------
+namespace {
+constexpr double STATE_MAGIC = 1431783237.0;
+long long inletVelocityDoubles(const ugfo_handle* h) {
+    long long n = 0;
+    for (const InflowPatch& ip : h->inflows) if (ip.pressure) n += (long long)ip.faceVel.size();
+    return n;
+}
+long long stateDoubles(const ugfo_handle* h) {
+    const long long nC = h->nCells, nS = h->nSpecies, nB = h->nBFaces;
+    long long n = 8 + 6 + nC * (1 + 1 + 1 + 3 + 6 + NACC + nS) + nB * UGF_NBM;
+    if (h->decompOn) n += nC * (KN_NACC + nS) + nC * 4;
+    return n + inletVelocityDoubles(h);
+}
+}  // namespace
+
+int ugfo_state_size(ugfo_handle* h, int64_t* n) { *n = stateDoubles(h); return 0; }
+
+int ugfo_state_save(ugfo_handle* h, double* buf, int64_t nDoubles) {
+    if (nDoubles != stateDoubles(h)) return fail(h, "state buffer has the wrong size");
+    double* p = buf;
+    const double hdr[8] = {STATE_MAGIC, 1.0, (double)h->nCells, (double)h->nSpecies, (double)h->nBFaces, h->decompOn ? 1.0 : 0.0,
+                           (double)inletVelocityDoubles(h), 0.0};
+    p = std::copy(hdr, hdr + 8, p);
+    const double sc[6] = {(double)h->step, h->timeAvCounter, (double)h->nAvTimeSteps, (double)h->sampleCounter, (double)h->decTimeSteps, h->decTimeAv};
+    p = std::copy(sc, sc + 6, p);
+    p = std::copy(h->sigmaTcRMax.begin(), h->sigmaTcRMax.end(), p);
+    for (int32_t v : h->collModelId) *p++ = v;
+    p = std::copy(h->maxProb.begin(), h->maxProb.end(), p);
+    p = std::copy(h->qPrev.begin(), h->qPrev.end(), p);
+    p = std::copy(h->sPrev.begin(), h->sPrev.end(), p);
+    p = std::copy(h->acc.begin(), h->acc.end(), p);
+    p = std::copy(h->accS.begin(), h->accS.end(), p);
+    p = std::copy(h->bacc.begin(), h->bacc.end(), p);
+    if (h->decompOn) { p = std::copy(h->knAcc.begin(), h->knAcc.end(), p); p = std::copy(h->knFields.begin(), h->knFields.end(), p); }
+    for (const InflowPatch& ip : h->inflows) if (ip.pressure) p = std::copy(ip.faceVel.begin(), ip.faceVel.end(), p);
+    return (p - buf) == nDoubles ? 0 : fail(h, "internal: state size mismatch");
+}
+
+int ugfo_state_load(ugfo_handle* h, const double* buf, int64_t nDoubles) {
+    if (nDoubles != stateDoubles(h) || nDoubles < 14) return fail(h, "state buffer has the wrong size for this set-up");
+    if (buf[0] != STATE_MAGIC || buf[1] != 1.0) return fail(h, "not a ugf state buffer (magic / version)");
+    if (buf[2] != (double)h->nCells || buf[3] != (double)h->nSpecies || buf[4] != (double)h->nBFaces || buf[5] != (h->decompOn ? 1.0 : 0.0) ||
+        buf[6] != (double)inletVelocityDoubles(h))
+        return fail(h, "state buffer was written for another mesh / species / model set-up");
+    const double* p = buf + 8;
+    h->step = (int64_t)p[0]; h->cnt.step = h->step; h->timeAvCounter = p[1]; h->nAvTimeSteps = (int64_t)p[2]; h->sampleCounter = (int)p[3];
+    h->decTimeSteps = (int)p[4]; h->decTimeAv = p[5];
+    p += 6;
+    auto take = [&](std::vector<double>& v) { std::copy(p, p + v.size(), v.begin()); p += v.size(); };
+    take(h->sigmaTcRMax);
+    for (int32_t& v : h->collModelId) v = (int32_t)*p++;
+    take(h->maxProb); take(h->qPrev); take(h->sPrev); take(h->acc); take(h->accS); take(h->bacc);
+    if (h->decompOn) { take(h->knAcc); take(h->knFields); }
+    for (InflowPatch& ip : h->inflows) if (ip.pressure) take(ip.faceVel);
+    h->momValid = false;
+    return 0;
+}
+
 int ugfo_end_step(ugfo_handle* h) { h->step++; h->cnt.step = h->step; h->stepOpen = false; return 0; }
 
 int ugfo_finish_step(ugfo_handle* h) {

@@ -161,3 +161,79 @@ def test_polymesh_round_trip_and_run(tmp_path, OracleCloud):
         a.evolve(4); b.evolve(4)
         pa, pb = a.parcels(), b.parcels()
         assert np.array_equal(pa["cell"], pb["cell"]) and np.allclose(pa["position"], pb["position"], rtol=1e-13, atol=1e-15)
+
+
+def _hybrid_adaptive_case():
+    """Everything that carries state between steps: hybrid run with the local-Knudsen mask, USP-SBGK persistent fields,
+    cell weighting with the adapter rewriting factors / levels / time step, time-averaged fields, a pressure inlet."""
+    from unigasfoam_b200.adapter import UniGasDynamicAdapter
+    case = cases.cylinder(nr=10, ntheta=16, ppc=25, seed=81, mode="hybrid", bgk="unifiedStochasticParticleSBGK", theta=0.3,
+                          cellWeightFactor=("particlesPerSubCell", 25), U_inf=600.0)
+    case.uniGasProperties["adaptiveSimulation"] = True
+    case.uniGasProperties["adaptiveProperties"] = dict(timeStepAdaptation=True, subCellAdaptation=True, cellWeightAdaptation=True,
+                                                       adaptationInterval=4, smoothingPasses=2, maxSubCellSizeMFPRatio=4.0)
+    case.uniGasProperties["cellWeightedProperties"] = {"particlesPerSubCell": 25}
+    n, T = case.meta["n"], case.meta["T_inf"]
+    case.boundariesDict["uniGasGeneralBoundaries"] = [{
+        "generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasLiouFangPressureInletPatch",
+        "uniGasLiouFangPressureInletPatchProperties": {"typeIds": ["Ar"], "moleFractions": {"Ar": 1.0}, "theta": 0.4,
+                                                       "inletPressure": 2 * n * cases.kB * T, "inletTemperature": T}}]
+    hd = {"decompositionModel": "localKnudsen", "timeProperties": {"decompositionInterval": 3, "resetAtDecomposition": True},
+          "localKnudsenProperties": {"breakdownMax": 0.05, "theta": 0.5, "smoothingPasses": 2}}
+    return case, hd, UniGasDynamicAdapter
+
+
+def _full_state_restart(Cloud, tmp_path):
+    case, hd, Adapter = _hybrid_adaptive_case()
+    kw = dict(parcelCapacity=6 * case.n_parcels)
+
+    def start(restore=None):
+        cl = case.make_cloud(Cloud, **kw) if restore is None else Cloud(case.mesh, case.uniGasProperties, case.boundariesDict, case.deltaT, **kw)
+        cl.setHybridDecomposition(hd)
+        if restore is not None:
+            cl.readTime(str(tmp_path), restore)
+        return cl
+    a = start()
+    ada = Adapter(a, case.uniGasProperties)
+    ada.run(8)                       # two adaptations; the second one has just uploaded factors the parcels do not carry yet
+    a.writeTime(str(tmp_path), "8")
+    assert os.path.exists(os.path.join(str(tmp_path), "8", "uniGasCellWeightFactorCarried"))
+    a.evolve(5)
+    b = start("8")
+    assert b.counters()["step"] == 8 and b.cfg.deltaT == pytest.approx(ada.last["deltaT"], rel=1e-15)
+    b.evolve(5)
+    pa, pb = a.parcels(), b.parcels()
+    for k in ("cell", "position", "U", "cellWeight"):
+        assert np.array_equal(pa[k], pb[k]), k
+    ca, cb = a.counters(), b.counters()
+    for k in ("step", "nParcels", "collisions", "bgkRelaxations", "inserted", "cloned", "weightDeleted"):
+        assert ca[k] == cb[k], k
+    fa, fb = a.fields(), b.fields()
+    for k in ("rhoN", "translationalT", "UMean"):
+        assert np.array_equal(fa[k], fb[k]), k
+    # wall tallies are floating-point atomics (device) / OpenMP atomics (oracle): two runs agree to summation order
+    same = lambda x, y: np.allclose(x, y, rtol=1e-10, atol=1e-10 * np.abs(y).max())
+    assert same(fa["surfaceHeatTransfer"], fb["surfaceHeatTransfer"]) and np.abs(fa["surfaceHeatTransfer"]).max() > 0
+    assert np.array_equal(a.hybridDecomposition()["cellCollModelId"], b.hybridDecomposition()["cellCollModelId"])
+    assert np.array_equal(a.inletVelocity("inlet"), b.inletVelocity("inlet"))
+    sa, sb = a.cellState(), b.cellState()
+    for k in ("sigmaTcRMax", "maxProb", "qPrev", "sPrev"):
+        assert np.array_equal(sa[k], sb[k]), k
+    assert same(a.state(), b.state())
+    return a
+
+
+def test_oracle_restart_restores_every_piece_of_state(tmp_path, OracleCloud):
+    a = _full_state_restart(OracleCloud, tmp_path)
+    bad = a.state()
+    bad[2] += 1
+    from unigasfoam_b200.cloud import UgfError
+    with pytest.raises(UgfError, match="another mesh"):
+        a.loadState(bad)
+    with pytest.raises(UgfError, match="wrong size"):
+        a.loadState(bad[:-1])
+
+
+@pytest.mark.gpu
+def test_gpu_restart_restores_every_piece_of_state(tmp_path, GpuCloud):
+    _full_state_restart(GpuCloud, tmp_path)

@@ -146,6 +146,9 @@ SIGNATURES = {
     "upload_cell_state": (C.c_int, [H, PF, PI32, PI32, PF]),
     "set_deltaT": (C.c_int, [H, f64]),
     "set_time_index": (C.c_int, [H, i64]),
+    "state_size": (C.c_int, [H, PI64]),
+    "state_save": (C.c_int, [H, PF, i64]),
+    "state_load": (C.c_int, [H, PF, i64]),
     "download_accumulators": (C.c_int, [H, PF, PF, PF, PI64]),
     "set_face_tracker": (C.c_int, [H, i32, PI32]),
     "download_face_tracker": (C.c_int, [H, PF, i32]),

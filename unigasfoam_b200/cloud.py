@@ -12,6 +12,7 @@ missing.  Tests pass the oracle's Api object to drive the CPU restatement throug
 same code (oracle/oracle_cloud.py).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -97,6 +98,8 @@ class UniGasCloud:
         self._h = _capi.H()
         self._cellCollModelId = self._subCellLevels = self._cellWeightFactor = None  # host copies for writeTime
         self._adapter = None
+        self._cwfCarried = None    # the factor field the parcels still carry while a newer one waits for the next weighting pass
+        self._nParcelsSet = False
         self._pending_capacity = cfg.parcelCapacity == 0
         self._created = False
         self._species = (_capi.Species * len(self.typeIdList))(
@@ -228,6 +231,8 @@ class UniGasCloud:
         if cellWeight is not None:
             w = self._f64(cellWeight); keep.append(w); p.cellWeight = w.ctypes.data_as(PD)
         self._check(self.api.upload_parcels(self._h, C.byref(p)))
+        self._nParcelsSet = True
+        self._cwfCarried = None
 
     def setCellState(self, sigmaTcRMax=None, cellCollModelId=None, subCellLevels=None, cellWeightFactor=None):
         PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
@@ -241,6 +246,8 @@ class UniGasCloud:
         if c is not None:
             self._subCellLevels = c.astype(float)
         if d is not None:
+            if self._created and self._nParcelsSet and self._cwfCarried is None:
+                self._cwfCarried = self._cellWeightFactor.copy() if self._cellWeightFactor is not None else np.ones(nC)
             self._cellWeightFactor = d.copy()
         if d is not None and not self.cellWeighted:
             raise UgfError("cellWeightFactor given but cellWeightedSimulation is not true in uniGasProperties")
@@ -281,6 +288,18 @@ class UniGasCloud:
         return dict(cellCollModelId=ids, KnRho=kn[:, 0], KnT=kn[:, 1], KnU=kn[:, 2], KnGLL=kn[:, 3])
 
     # -- write / restart (OpenFOAM time directories, unigasfoam_b200/foamfile.py) ----------------------
+    def state(self):
+        """ugf_state_save: everything carried between steps besides parcels and cell-state fields, as a float64 array."""
+        n = C.c_int64()
+        self._check(self.api.state_size(self._h, C.byref(n)))
+        buf = np.empty(n.value)
+        self._check(self.api.state_save(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), n.value))
+        return buf
+
+    def loadState(self, buf):
+        buf = self._f64(buf)
+        self._check(self.api.state_load(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), len(buf)))
+
     def writeTime(self, case_dir, time_name):
         """What uniGasFoam leaves in <time>/ for the cloud: lagrangian/uniGas/*, uniGas{SigmaTcRMax, CellWeightFactor,
         SubCellLevels, CollisionModelId} and uniform/time (U/parcels/uniGasParcelIO.C:141-181, U/clouds/uniGasCloud.C:433-488)."""
@@ -292,8 +311,13 @@ class UniGasCloud:
         if ids is None:
             ids = np.full(self.mesh.n_cells, 1.0 if mode == _capi.COLLISION_MODEL["dsmc"] else 0.0)
         c = self.counters()
-        return foamfile.write_cloud_time(case_dir, time_name, self.mesh, p, st["sigmaTcRMax"], self._cellWeightFactor, self._subCellLevels,
-                                         ids, deltaT=self.cfg.deltaT, index=c["step"])
+        t = foamfile.write_cloud_time(case_dir, time_name, self.mesh, p, st["sigmaTcRMax"], self._cellWeightFactor, self._subCellLevels,
+                                      ids, deltaT=self.cfg.deltaT, index=c["step"])
+        if self._cwfCarried is not None:  # a factor field uploaded since the last step: the parcels still carry the previous one
+            foamfile.write_vol_field(os.path.join(t, "uniGasCellWeightFactorCarried"), time_name, [0] * 7, self._cwfCarried,
+                                     [q.name for q in self.mesh.patches])
+        np.save(os.path.join(t, "uniform", "ugfState.npy"), self.state())  # accumulators, BGK / decomposition / inlet state
+        return t
 
     def readTime(self, case_dir, time_name):
         """Restart from a time directory written by writeTime or by the reference solver (ASCII): cell state first, then
@@ -318,12 +342,22 @@ class UniGasCloud:
             self.cfg.parcelCapacity = max(int(len(p["cell"]) * 1.25) + 1024, 4096)
             self._pending_capacity = False
             self._create()
+        carried = os.path.join(case_dir, time_name, "uniGasCellWeightFactorCarried")
+        new_cwf = None
+        if self.cellWeighted and os.path.exists(carried):  # restore "parcels carry the previous field, the new one is pending"
+            new_cwf = kw.get("cellWeightFactor")
+            kw["cellWeightFactor"] = foamfile.expand_internal(foamfile.read_vol_field(carried), self.mesh.n_cells)
         if kw:
             self.setCellState(**kw)
         self.setParcels(p["position"], p["U"], p["cell"], p["typeId"], p["ERot"], cellWeight=p["cellWeight"] if self.cellWeighted else None)
+        if new_cwf is not None:
+            self.setCellState(cellWeightFactor=new_cwf)
         if d.get("deltaT") is not None:
             self.setDeltaT(d["deltaT"])
         self._check(self.api.set_time_index(self._h, int(d.get("index", 0))))
+        sp = os.path.join(case_dir, time_name, "uniform", "ugfState.npy")
+        if os.path.exists(sp):  # written by writeTime: makes the restart exact for BGK / hybrid runs and the field averages
+            self.loadState(np.load(sp))
         return d
 
     def setDeltaT(self, dt):
@@ -334,12 +368,15 @@ class UniGasCloud:
     def evolve(self, nSteps=1):
         """uniGasCloud::evolve (U/clouds/uniGasCloud.C:821-869)."""
         self._check(self.api.step(self._h, int(nSteps)))
+        if nSteps > 0:
+            self._cwfCarried = None
 
     def controlBeforeMove(self):
         self._check(self.api.control_before_move(self._h))
 
     def move(self):
         self._check(self.api.move(self._h))
+        self._cwfCarried = None  # the weighting pass rides on the move
 
     def buildCellOccupancy(self):
         self._check(self.api.sort(self._h))

@@ -1533,6 +1533,99 @@ int ugf_set_time_index(ugf_handle* h, int64_t index) {
     return 0;
 }
 
+// ---- state checkpoint (ugf_state_*): flat array of doubles, same layout as the oracle's ---------------------------------
+// header [8]: magic, version, nCells, nSpecies, nBFaces, decomposition on, inlet velocity doubles, reserved
+// scalars [6]: step, timeAvCounter, nAvTimeSteps, sampleCounter, decTimeSteps, decTimeAv
+// sigmaTcRMax [nC], collModelId [nC], maxProb [nC], qPrev [3 nC], sPrev [6 nC], acc [16 nC], accSpecies [nS nC],
+// bacc [16 nB], then if decomposition: knAcc [(7 + nS) nC], knFields [4 nC]; then the pressure inlets' face velocities
+namespace {
+constexpr double STATE_MAGIC = 1431783237.0;  // "UGFS"
+long long inlet_velocity_doubles(const ugf_handle* h) {
+    long long n = 0;
+    for (const InflowHost& f : h->inflows) if (f.pressureInlet) n += 3LL * f.dev.nFaces;
+    return n;
+}
+long long state_doubles(const ugf_handle* h) {
+    const long long nC = h->nCells, nS = h->nSpecies, nB = h->nBFaces;
+    long long n = 8 + 6 + nC * (1 + 1 + 1 + 3 + 6 + NACC + nS) + nB * UGF_NBM;
+    if (h->decompOn) n += nC * (KN_NACC + nS) + nC * 4;
+    return n + inlet_velocity_doubles(h);
+}
+}  // namespace
+
+int ugf_state_size(ugf_handle* h, int64_t* n) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    *n = state_doubles(h);
+    return 0;
+}
+
+int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (nDoubles != state_doubles(h)) return fail(h, "state buffer has the wrong size");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t nC = (size_t)h->nCells, nS = (size_t)h->nSpecies, nB = (size_t)h->nBFaces;
+    double* p = buf;
+    const double hdr[8] = {STATE_MAGIC, 1.0, (double)nC, (double)nS, (double)nB, h->decompOn ? 1.0 : 0.0, (double)inlet_velocity_doubles(h), 0.0};
+    std::copy(hdr, hdr + 8, p); p += 8;
+    const double sc[6] = {(double)h->step, h->timeAvCounter, (double)h->nAvTimeSteps, (double)h->sampleCounter, (double)h->decTimeSteps, h->decTimeAv};
+    std::copy(sc, sc + 6, p); p += 6;
+    auto d2h = [&](const double* src, size_t n) -> int {
+        if (n) CU(cudaMemcpyAsync(p, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+        p += n;
+        return 0;
+    };
+    if (d2h(h->dSigma, nC)) return 1;
+    std::vector<int> ids(nC);
+    CU(cudaMemcpyAsync(ids.data(), h->dCollId, sizeof(int) * nC, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (size_t c = 0; c < nC; ++c) p[c] = ids[c];
+    p += nC;
+    if (d2h(h->dMaxProb, nC) || d2h(h->dQPrev, 3 * nC) || d2h(h->dSPrev, 6 * nC)) return 1;
+    double* accAt = p;
+    if (d2h(h->dAcc, NACC * nC)) return 1;
+    double* accSAt = p;
+    if (h->dAccS) { if (d2h(h->dAccS, nS * nC)) return 1; } else p += nS * nC;
+    if (d2h(h->dBacc, UGF_NBM * nB)) return 1;
+    if (h->decompOn) { if (d2h(h->dKnAcc, (KN_NACC + nS) * nC) || d2h(h->dKnK[h->knCur], 4 * nC)) return 1; }
+    for (const InflowHost& f : h->inflows) if (f.pressureInlet && d2h(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+    CU(cudaStreamSynchronize(h->stream));
+    if (!h->dAccS) for (size_t c = 0; c < nC; ++c) accSAt[c] = accAt[c * NACC + 8];  // one species: nParcelsXnParticle = slot 8
+    return 0;
+}
+
+int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
+    if (!h || !h->meshSet) return fail(h, "mesh not set");
+    if (nDoubles != state_doubles(h) || nDoubles < 14) return fail(h, "state buffer has the wrong size for this set-up");
+    const size_t nC = (size_t)h->nCells, nS = (size_t)h->nSpecies, nB = (size_t)h->nBFaces;
+    if (buf[0] != STATE_MAGIC || buf[1] != 1.0) return fail(h, "not a ugf state buffer (magic / version)");
+    if (buf[2] != (double)nC || buf[3] != (double)nS || buf[4] != (double)nB || buf[5] != (h->decompOn ? 1.0 : 0.0) ||
+        buf[6] != (double)inlet_velocity_doubles(h))
+        return fail(h, "state buffer was written for another mesh / species / model set-up");
+    CU(cudaSetDevice(h->cfg.device));
+    const double* p = buf + 8;
+    h->step = (long long)p[0]; h->timeAvCounter = p[1]; h->nAvTimeSteps = (long long)p[2]; h->sampleCounter = (int)p[3];
+    h->decTimeSteps = (int)p[4]; h->decTimeAv = p[5];
+    p += 6;
+    auto h2d = [&](double* dst, size_t n) -> int {
+        if (n && dst) CU(cudaMemcpyAsync(dst, p, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+        p += n;
+        return 0;
+    };
+    if (h2d(h->dSigma, nC)) return 1;
+    std::vector<int> ids(nC);
+    for (size_t c = 0; c < nC; ++c) ids[c] = (int)p[c];
+    p += nC;
+    CU(cudaMemcpyAsync(h->dCollId, ids.data(), sizeof(int) * nC, cudaMemcpyHostToDevice, h->stream));
+    if (h2d(h->dMaxProb, nC) || h2d(h->dQPrev, 3 * nC) || h2d(h->dSPrev, 6 * nC) || h2d(h->dAcc, NACC * nC) || h2d(h->dAccS, nS * nC) ||
+        h2d(h->dBacc, UGF_NBM * nB))
+        return 1;
+    if (h->decompOn) { if (h2d(h->dKnAcc, (KN_NACC + nS) * nC) || h2d(h->dKnK[h->knCur], 4 * nC)) return 1; }
+    for (InflowHost& f : h->inflows) if (f.pressureInlet && h2d(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+    CU(cudaStreamSynchronize(h->stream));  // ids and the caller's buffer may go away
+    h->momValid = false;
+    return 0;
+}
+
 int ugf_end_step(ugf_handle* h) {
     if (!h) return 1;
     h->step++;
