@@ -237,3 +237,31 @@ def test_oracle_restart_restores_every_piece_of_state(tmp_path, OracleCloud):
 @pytest.mark.gpu
 def test_gpu_restart_restores_every_piece_of_state(tmp_path, GpuCloud):
     _full_state_restart(GpuCloud, tmp_path)
+
+
+@pytest.mark.gpu
+def test_gpu_continues_a_hybrid_run_the_oracle_wrote(tmp_path, GpuCloud, OracleCloud):
+    """The time directory plus the state array are implementation-neutral: the oracle runs and writes a hybrid, weighted
+    case, libugf restarts from it, and the two continue in lockstep (same counters, velocities to round-off)."""
+    def ramp(mesh):
+        x = mesh.cell_centres[:, 0]
+        return 0.7 + 0.9 * (x - x.min()) / (x.max() - x.min())
+    case = cases.closed_box(n=6, parcels=30000, seed=83, mode="hybrid", bgk="unifiedStochasticParticleSBGK", number_density=4e20, theta=0.5,
+                            cellWeightFactor=ramp)
+    case.cellCollModelId = (np.arange(case.mesh.n_cells) % 2).astype(np.int32)
+    r = case.make_cloud(OracleCloud)
+    r.evolve(4)
+    r.writeTime(str(tmp_path), "4")
+    g = GpuCloud(case.mesh, case.uniGasProperties, case.boundariesDict, case.deltaT, parcelCapacity=int(1.5 * case.n_parcels) + 4096)
+    g.readTime(str(tmp_path), "4")
+    assert np.allclose(g.state(), r.state(), rtol=1e-12, atol=0)
+    r.evolve(4); g.evolve(4)
+    cg, cr = g.counters(), r.counters()
+    for k in ("step", "nParcels", "cloned", "weightDeleted", "collisionCandidates"):
+        assert cg[k] == cr[k], k
+    assert abs(cg["collisions"] - cr["collisions"]) <= 2 and abs(cg["bgkRelaxations"] - cr["bgkRelaxations"]) <= 2
+    pg, pr = g.parcels(), r.parcels()
+    assert np.array_equal(pg["cell"], pr["cell"])
+    assert (np.abs(pg["U"] - pr["U"]) <= 1e-8 * np.abs(pr["U"]).max()).all(1).mean() > 0.99
+    fg, fr = g.fields(), r.fields()
+    assert np.allclose(fg["rhoN"], fr["rhoN"], rtol=1e-9) and np.allclose(fg["translationalT"], fr["translationalT"], rtol=1e-6)
