@@ -1,0 +1,169 @@
+"""<time>/uniform/volFieldsMethod_<fieldName>: uniGasVolFields' accumulator dictionary under the
+reference's entry names (writeOut / readIn, uniGasVolFields.C:549-669).  Checked: the entry list and list shapes are the
+reference's, write -> read returns the same bits, the counted-list grammar OpenFOAM itself emits (N{v} uniform lists,
+0(), white space) is read, and a run whose averages were carried over through the dictionary alone reports the same
+fields as the uninterrupted one."""
+import os
+
+import numpy as np
+import pytest
+
+from unigasfoam_b200 import cases, volfields_io as vio
+
+# the entries of uniGasVolFields::writeOut in its order (uniGasVolFields.C:625-662)
+REFERENCE_ENTRIES = [
+    "nTimeSteps", "timeCounter", "rhoNMean", "rhoNMeanXnParticle", "rhoNMeanInt", "molsElec", "rhoMMean", "rhoMMeanXnParticle",
+    "linearKEMean", "linearKEMeanXnParticle", "rotationalEMean", "rotationalDofMean", "momentumMean", "momentumMeanXnParticle",
+    "vibrationalETotal", "electronicETotal", "nParcels", "nParcelsXnParticle", "mccSpecies", "nGroundElectronicLevel",
+    "nFirstElectronicLevel", "mfp", "mcr", "rhoNBF", "rhoMBF", "linearKEBF", "rotationalEBF", "rotationalDofBF", "qBF",
+    "totalvDofBF", "speciesRhoNIntBF", "speciesRhoNElecBF", "momentumBF", "fDBF", "vibrationalEBF", "electronicEBF",
+    "speciesRhoNBF", "mccSpeciesBF"]
+
+
+def test_counted_list_grammar():
+    d = vio.parse_volfields_method("""
+        FoamFile { version 2.0; format ascii; class dictionary; location "1/uniform"; object volFieldsMethod_Ar; }
+        nTimeSteps 12; timeCounter 1.5e-05; // comment
+        a 4(1 2.5 -3e-2 4);
+        u 5{0.25};
+        v 2((1 2 3) (4 5 6));
+        w 3{(1 0 -1)};
+        bf 3(2(1 2) 0() 4{7});
+        vbf 2(2((1 2 3)
+                 (4 5 6)) 1((7 8 9)));
+        deep 2(1(2(5 6)) 1(0()));
+        empty 0();
+    """)
+    assert d["nTimeSteps"] == 12 and d["timeCounter"] == 1.5e-05
+    assert np.array_equal(d["a"], [1, 2.5, -0.03, 4]) and np.array_equal(d["u"], np.full(5, 0.25))
+    assert np.array_equal(d["v"], [[1, 2, 3], [4, 5, 6]]) and np.array_equal(d["w"], [[1, 0, -1]] * 3)
+    assert [list(x) for x in d["bf"]] == [[1, 2], [], [7, 7, 7, 7]]
+    assert np.array_equal(d["vbf"][0], [[1, 2, 3], [4, 5, 6]]) and np.array_equal(d["vbf"][1], [[7, 8, 9]])
+    assert list(d["deep"][0][0]) == [5, 6] and len(d["deep"][1][0]) == 0 and len(d["empty"]) == 0
+    with pytest.raises(vio.VolFieldsFormatError, match="announces 3"):
+        vio.parse_volfields_method("FoamFile { format ascii; }\na 3(1 2);")
+    with pytest.raises(vio.VolFieldsFormatError, match="missing ;"):
+        vio.parse_volfields_method("FoamFile { format ascii; }\na 2(1 2)\nb 1;")
+    with pytest.raises(Exception, match="ascii"):
+        vio.parse_volfields_method("FoamFile { format binary; }\na 2(1 2);")
+
+
+def test_field_names_from_the_tutorial_dictionary(tmp_path, OracleCloud):
+    from unigasfoam_b200 import foamdict
+    fp = foamdict.read(os.path.join(os.path.dirname(__file__), "golden", "openfoam", "hypersonicCylinder", "system", "fieldPropertiesDict"))
+    assert foamdict.vol_field_names(fp) == ["Ar"] and foamdict.vol_field_names(fp, averaging_only=True) == ["Ar"]
+    case = _couette()
+    a = case.make_cloud(OracleCloud)
+    a.evolve(2)
+    t = a.writeTime(str(tmp_path), "2", fieldNames=foamdict.vol_field_names(fp))
+    assert sorted(os.listdir(os.path.join(t, "uniform"))) == ["time", "ugfState.npy", "volFieldsMethod_Ar"]
+
+
+def _couette(**kw):
+    return cases.couette(nx=12, ny=8, ppc=30, seed=5, **kw)
+
+
+def test_entries_shapes_and_bit_exact_round_trip(tmp_path, OracleCloud):
+    case = _couette()
+    a = case.make_cloud(OracleCloud)
+    a.evolve(6)
+    path = a.writeVolFieldsMethod(str(tmp_path), "6e-06", "Ar")
+    assert path.endswith(os.path.join("6e-06", "uniform", "volFieldsMethod_Ar"))
+    head = open(path).read(900)
+    assert "class       dictionary;" in head and 'location    "6e-06/uniform";' in head and "object      volFieldsMethod_Ar;" in head
+    d = vio.read_volfields_method(path)
+    assert list(d) == REFERENCE_ENTRIES
+    m = case.mesh
+    nC, nP = m.n_cells, len(m.patches)
+    assert d["nTimeSteps"] == 6 and d["timeCounter"] == pytest.approx(6 * case.deltaT, rel=1e-14)
+    assert d["rhoNMean"].shape == (nC,) and d["momentumMean"].shape == (nC, 3)
+    assert len(d["nParcels"]) == 1 and d["nParcels"][0].shape == (nC,) and len(d["vibrationalETotal"][0]) == 0
+    assert len(d["rhoNBF"]) == nP and [len(x) for x in d["rhoNBF"]] == [p.size for p in m.patches]
+    assert [np.shape(x) for x in d["fDBF"]] == [(p.size, 3) if p.size else (0,) for p in m.patches]
+    assert len(d["speciesRhoNBF"]) == 1 and len(d["speciesRhoNBF"][0]) == nP
+    # the numbers are the accumulators, bit for bit
+    acc = a.accumulators()
+    assert np.array_equal(d["rhoNMean"], acc["acc"][:, 0]) and np.array_equal(d["linearKEMeanXnParticle"], acc["acc"][:, 13])
+    assert np.array_equal(d["momentumMeanXnParticle"], acc["acc"][:, 10:13]) and np.array_equal(d["nParcelsXnParticle"][0], acc["species"][:, 0])
+    assert np.array_equal(d["nParcels"][0], d["rhoNMean"]) and np.array_equal(d["mccSpecies"][0], d["linearKEMean"])
+    # every parcel of one species: mass x number, and the diffuse walls did tally something
+    mAr = case.uniGasProperties["moleculeProperties"]["Ar"]["mass"]
+    assert np.allclose(d["rhoMMean"], mAr * d["rhoNMean"], rtol=1e-14)
+    walls = [i for i, p in enumerate(m.patches) if p.kind == "wall"]
+    assert walls and all(d["rhoNBF"][i].sum() > 0 and np.abs(d["qBF"][i]).sum() > 0 for i in walls)
+    assert all(np.array_equal(d["mccSpeciesBF"][0][i], 2.0 * d["linearKEBF"][i]) for i in walls)
+    # back into a state array: the same bits, slot 15 rebuilt to round-off
+    s0 = a.state()
+    blank = s0.copy()
+    v = vio.state_views(blank)
+    v["acc"][:] = 0; v["accSpecies"][:] = 0; v["bacc"][:, :13] = 0; v["scalars"][1:3] = 0
+    s1 = vio.apply_volfields_method(d, m, blank)
+    v0, v1 = vio.state_views(s0), vio.state_views(s1)
+    assert np.array_equal(v0["acc"][:, :15], v1["acc"][:, :15]) and np.allclose(v0["acc"][:, 15], v1["acc"][:, 15], rtol=1e-14)
+    assert np.array_equal(v0["accSpecies"], v1["accSpecies"]) and np.array_equal(v0["bacc"][:, :13], v1["bacc"][:, :13])
+    assert np.array_equal(v0["scalars"], v1["scalars"])
+    with pytest.raises(vio.VolFieldsFormatError, match="patches"):
+        vio.apply_volfields_method(dict(d, rhoNBF=d["rhoNBF"][:-1]), m, s0)
+    with pytest.raises(vio.VolFieldsFormatError, match="cells"):
+        vio.apply_volfields_method(dict(d, rhoNMean=d["rhoNMean"][:-1]), m, s0)
+
+
+def _averages_continue_through_the_dictionary(Cloud, tmp_path, case):
+    """averagingAcrossManyRuns: a restarted run (parcels + cell state from the time directory, averages from the
+    dictionary only - ugfState.npy removed) reports the fields of the uninterrupted run."""
+    a = case.make_cloud(Cloud)
+    a.evolve(5)
+    t = a.writeTime(str(tmp_path), "5")
+    a.writeVolFieldsMethod(str(tmp_path), "5", "Ar")
+    os.remove(os.path.join(t, "uniform", "ugfState.npy"))
+    a.evolve(4)
+    b = Cloud(case.mesh, case.uniGasProperties, case.boundariesDict, case.deltaT)
+    b.readTime(str(tmp_path), "5")
+    assert b.accumulators()["nAvTimeSteps"] == 0  # nothing carried over yet
+    assert b.readVolFieldsMethod(str(tmp_path), "5", "missing") is None
+    d = b.readVolFieldsMethod(str(tmp_path), "5", "Ar")
+    assert d["nTimeSteps"] == 5 and b.accumulators()["nAvTimeSteps"] == 5
+    b.evolve(4)
+    fa, fb = a.fields(), b.fields()
+    for k in fa:
+        assert np.allclose(fa[k], fb[k], rtol=1e-12, atol=0), k
+    assert b.accumulators()["nAvTimeSteps"] == 9
+    return fa
+
+
+def test_oracle_averages_continue_through_the_dictionary(tmp_path, OracleCloud):
+    f = _averages_continue_through_the_dictionary(OracleCloud, tmp_path, _couette(binary="noDSMCCollision"))
+    assert (f["rhoN"] > 0).all() and (f["wall_rhoN"] > 0).any()
+
+
+def test_mixture_lists_per_species(tmp_path, OracleCloud):
+    case = cases.mixture_box(n=4, parcels=6000, seed=3)
+    a = case.make_cloud(OracleCloud)
+    a.evolve(3)
+    d = vio.read_volfields_method(a.writeVolFieldsMethod(str(tmp_path), "3", "mixture"))
+    acc = a.accumulators()
+    assert len(d["nParcelsXnParticle"]) == 2 and len(d["electronicETotal"]) == 2 and len(d["mccSpeciesBF"]) == 2
+    for s in range(2):
+        assert np.array_equal(d["nParcelsXnParticle"][s], acc["species"][:, s])
+    assert np.allclose(d["nParcelsXnParticle"][0] + d["nParcelsXnParticle"][1], d["rhoNMeanXnParticle"], rtol=1e-13)
+    s1 = vio.apply_volfields_method(d, case.mesh, a.state())
+    assert np.array_equal(vio.state_views(s1)["bacc"], vio.state_views(a.state())["bacc"])  # slot 14 left alone for mixtures
+
+
+@pytest.mark.gpu
+def test_gpu_averages_continue_through_the_dictionary(tmp_path, GpuCloud):
+    _averages_continue_through_the_dictionary(GpuCloud, tmp_path, _couette(binary="noDSMCCollision"))
+
+
+@pytest.mark.gpu
+def test_gpu_reads_the_dictionary_the_oracle_wrote(tmp_path, GpuCloud, OracleCloud):
+    """The dictionary as exchange format: oracle accumulators -> file -> libugf state -> the same fields."""
+    case = _couette()
+    r = case.make_cloud(OracleCloud)
+    r.evolve(4)
+    r.writeVolFieldsMethod(str(tmp_path), "4", "Ar")
+    g = case.make_cloud(GpuCloud)
+    g.readVolFieldsMethod(str(tmp_path), "4", "Ar")
+    fr, fg = r.fields(), g.fields()
+    for k in fr:
+        assert np.allclose(fr[k], fg[k], rtol=1e-12, atol=0), k

@@ -300,9 +300,11 @@ class UniGasCloud:
         buf = self._f64(buf)
         self._check(self.api.state_load(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), len(buf)))
 
-    def writeTime(self, case_dir, time_name):
+    def writeTime(self, case_dir, time_name, fieldNames=()):
         """What uniGasFoam leaves in <time>/ for the cloud: lagrangian/uniGas/*, uniGas{SigmaTcRMax, CellWeightFactor,
-        SubCellLevels, CollisionModelId} and uniform/time (U/parcels/uniGasParcelIO.C:141-181, U/clouds/uniGasCloud.C:433-488)."""
+        SubCellLevels, CollisionModelId} and uniform/time (U/parcels/uniGasParcelIO.C:141-181, U/clouds/uniGasCloud.C:433-488);
+        for every name in fieldNames (the `field` words of the uniGasVolFields entries of fieldPropertiesDict) also
+        uniform/volFieldsMethod_<name> (uniGasVolFields.C:609-669)."""
         from . import foamfile
         p = self.parcels()
         st = self.cellState()
@@ -316,7 +318,12 @@ class UniGasCloud:
         if self._cwfCarried is not None:  # a factor field uploaded since the last step: the parcels still carry the previous one
             foamfile.write_vol_field(os.path.join(t, "uniGasCellWeightFactorCarried"), time_name, [0] * 7, self._cwfCarried,
                                      [q.name for q in self.mesh.patches])
-        np.save(os.path.join(t, "uniform", "ugfState.npy"), self.state())  # accumulators, BGK / decomposition / inlet state
+        st = self.state()
+        np.save(os.path.join(t, "uniform", "ugfState.npy"), st)  # accumulators, BGK / decomposition / inlet state
+        if fieldNames:
+            from . import volfields_io
+            for name in fieldNames:
+                volfields_io.write_volfields_method(case_dir, time_name, name, self.mesh, st)
         return t
 
     def readTime(self, case_dir, time_name):
@@ -358,6 +365,23 @@ class UniGasCloud:
         sp = os.path.join(case_dir, time_name, "uniform", "ugfState.npy")
         if os.path.exists(sp):  # written by writeTime: makes the restart exact for BGK / hybrid runs and the field averages
             self.loadState(np.load(sp))
+        return d
+
+    def writeVolFieldsMethod(self, case_dir, time_name, fieldName):
+        """uniGasVolFields::writeOut (uniGasVolFields.C:609-669): the accumulators of the field object `fieldName` as
+        <time>/uniform/volFieldsMethod_<fieldName>, under the reference's entry names (unigasfoam_b200/volfields_io.py)."""
+        from . import volfields_io
+        return volfields_io.write_volfields_method(case_dir, time_name, fieldName, self.mesh, self.state())
+
+    def readVolFieldsMethod(self, case_dir, time_name, fieldName):
+        """uniGasVolFields::readIn (uniGasVolFields.C:549-605, `averagingAcrossManyRuns`): continue the time averages of a
+        dictionary written by writeVolFieldsMethod or by the reference solver on the same mesh.  -> the entries read."""
+        from . import volfields_io
+        path = os.path.join(case_dir, time_name, "uniform", "volFieldsMethod_" + fieldName)
+        if not os.path.exists(path):  # READ_IF_PRESENT
+            return None
+        d = volfields_io.read_volfields_method(path)
+        self.loadState(volfields_io.apply_volfields_method(d, self.mesh, self.state()))
         return d
 
     def setDeltaT(self, dt):

@@ -175,3 +175,16 @@ def sample_interval(fieldPropertiesDict):
         if f.get("fieldModel") == "uniGasVolFields":
             return int(f.get("timeProperties", {}).get("sampleInterval", 1))
     return 1
+
+
+def vol_field_names(fieldPropertiesDict, averaging_only=False):
+    """The `field` words of the uniGasVolFields entries (uniGasVolFields.C:54): the names behind
+    uniform/volFieldsMethod_<field>; with averaging_only, just the entries that set `averagingAcrossManyRuns`."""
+    out = []
+    for f in (fieldPropertiesDict or {}).get("uniGasFields", []):
+        if f.get("fieldModel") != "uniGasVolFields":
+            continue
+        pr = f.get("uniGasVolFieldsProperties", {})
+        if "field" in pr and (not averaging_only or pr.get("averagingAcrossManyRuns", False)):
+            out.append(str(pr["field"]))
+    return out
