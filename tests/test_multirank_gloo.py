@@ -134,3 +134,74 @@ def test_two_rank_cell_weighted_cylinder(tmp_path, OracleCloud):
     assert (tot > 0).all(), tot  # clones, deletions and migrations all happened
     real, real0 = sum(r["real"] for r in res), sum(r["real0"] for r in res)
     assert abs(real / real0 - 1) < 0.05  # real molecules (sum of weights) stay put over a few steps of a uniform free stream
+
+
+def _worker_halo(rank, world, port, out):
+    """fvc::average(fvc::interpolate) and fvc::smooth on a decomposed mesh with the processor-face halo (SURVEY 8e:
+    'hybrid-mask and adaptation smoothing need a 1-cell halo of cell fields')."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unigasfoam_b200 import mesh as ugmesh
+    from unigasfoam_b200.adapter import FaceOperators
+    from unigasfoam_b200.exchange import ProcessorHalo, group_reducers
+    res = {}
+    for name, (full, part) in _halo_meshes(world).items():
+        sub = ugmesh.decompose(full, part, world)[rank]
+        halo = ProcessorHalo(sub, rank, world)
+        _, rmax = group_reducers()
+        ops = FaceOperators(sub, halo, rmax)
+        f, v = _halo_fields(full.n_cells)
+        fs, vs = f[sub.cell_map], v[sub.cell_map]
+        a1 = ops.average_interpolate(fs)
+        a2 = ops.average_interpolate(ops.average_interpolate(fs))  # the halo carries the updated values of the second pass
+        av = ops.average_interpolate(vs, vector=True)
+        sm = ops.smooth(fs, 1.3)
+        zg = FaceOperators(sub).average_interpolate(fs)  # no halo: zero-gradient processor faces
+        res[name] = dict(cells=sub.cell_map, a1=a1, a2=a2, av=av, sm=sm, zg=zg, calls=halo.calls, nproc=halo.n)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _halo_meshes(world):
+    from unigasfoam_b200 import mesh as ugmesh
+    c = cases.couette(nx=12, ny=8, ppc=1, binary="noDSMCCollision").mesh  # x cyclic: the cut gives processor + processorCyclic patches
+    a = ugmesh.half_annulus_mesh(8, 16, 0.1, 0.5, 0.01, grading=4.0)  # graded: interpolation weights != 1/2, symmetry planes
+    return {"couette": (c, ugmesh.slab_partition(c, world, axis=0)), "annulus": (a, ugmesh.slab_partition(a, world, axis=1))}
+
+
+def _halo_fields(n):
+    rng = np.random.default_rng(11)
+    return np.exp(3.0 * rng.standard_normal(n)), rng.standard_normal((n, 3))
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_smoothing_operators_match_single_domain(tmp_path):
+    from unigasfoam_b200.adapter import FaceOperators
+    world = 2
+    out = str(tmp_path / "halo.pt")
+    mp.spawn(_worker_halo, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    for name, (full, _) in _halo_meshes(world).items():
+        ops = FaceOperators(full)
+        f, v = _halo_fields(full.n_cells)
+        want = dict(a1=ops.average_interpolate(f), a2=ops.average_interpolate(ops.average_interpolate(f)),
+                    av=ops.average_interpolate(v, vector=True), sm=ops.smooth(f, 1.3))
+        assert all(r[name]["nproc"] > 0 for r in res)
+        assert len({r[name]["calls"] for r in res}) == 1  # the smoothing wave stopped on both ranks in the same sweep
+        for k, w in want.items():
+            got = np.empty_like(w)
+            for r in res:
+                got[r[name]["cells"]] = r[name][k]
+            if k == "sm":
+                assert np.array_equal(got, w), (name, k)  # maxima of the same quotients: bit-identical
+                assert (got >= f).all() and (got > f).any()
+            else:
+                assert np.allclose(got, w, rtol=1e-13, atol=1e-13 * np.abs(w).max()), (name, k)
+        zg = np.empty(full.n_cells)
+        for r in res:
+            zg[r[name]["cells"]] = r[name]["zg"]
+        assert not np.allclose(zg, want["a1"], rtol=1e-6)  # without the halo the cut is visible in the result

@@ -125,8 +125,8 @@ def _averages_continue_through_the_dictionary(Cloud, tmp_path, case):
     assert d["nTimeSteps"] == 5 and b.accumulators()["nAvTimeSteps"] == 5
     b.evolve(4)
     fa, fb = a.fields(), b.fields()
-    for k in fa:
-        assert np.allclose(fa[k], fb[k], rtol=1e-12, atol=0), k
+    for k in fa:  # atol: the device tallies wall hits with atomics, sums that cancel (wall momentum) differ in the last bits per run
+        assert np.allclose(fa[k], fb[k], rtol=1e-9, atol=1e-9 * np.abs(fa[k]).max()), k
     assert b.accumulators()["nAvTimeSteps"] == 9
     return fa
 
@@ -166,4 +166,4 @@ def test_gpu_reads_the_dictionary_the_oracle_wrote(tmp_path, GpuCloud, OracleClo
     g.readVolFieldsMethod(str(tmp_path), "4", "Ar")
     fr, fg = r.fields(), g.fields()
     for k in fr:
-        assert np.allclose(fr[k], fg[k], rtol=1e-12, atol=0), k
+        assert np.allclose(fr[k], fg[k], rtol=1e-12, atol=1e-12 * np.abs(fr[k]).max()), k

@@ -33,10 +33,15 @@ VSMALL, SMALL, GREAT, VGREAT = 1e-300, 1e-15, 1e15, 1e300
 
 class FaceOperators:
     """fvc::average(fvc::interpolate(.)) and fvc::smooth on a PolyMesh (zero-gradient / symmetry / cyclic boundary faces,
-    empty faces take no part, processor faces zero-gradient)."""
+    empty faces take no part).  Processor faces are coupled like in OpenFOAM when a `halo` is given - a callable that takes
+    this rank's values on its processor faces ([nProcFaces, k], patch order) and returns the neighbour ranks' values on the
+    same faces (`exchange.ProcessorHalo`); `reduce_max` then makes the smoothing wave stop on all ranks together.  Without
+    a halo processor faces are zero-gradient."""
 
-    def __init__(self, mesh):
+    def __init__(self, mesh, halo=None, reduce_max=None):
         m = mesh
+        self.halo = halo
+        self.reduce_max = reduce_max or (lambda v: v)
         nI = m.n_internal
         self.nC, self.nI = m.n_cells, nI
         self.own, self.nei = np.asarray(m.owner[:nI]), np.asarray(m.neighbour[:nI])
@@ -47,7 +52,7 @@ class FaceOperators:
         sO, sN = np.abs((S[:nI] * dO).sum(1)), np.abs((S[:nI] * dN).sum(1))
         self.w = sN / (sO + sN)  # surfaceInterpolation::makeWeights
         # boundary faces that take part: (face, owner, partner owner or -1, weight of the owner side, unit normal, symmetry?)
-        bf, bo, bq, bw, sym = [], [], [], [], []
+        bf, bo, bq, bw, sym, proc = [], [], [], [], [], []
         for p in m.patches:
             if p.kind == "empty" or p.size == 0:
                 continue
@@ -64,8 +69,17 @@ class FaceOperators:
                 w = dni / (di + dni)
             bf.append(f); bo.append(o); bq.append(q); bw.append(w)
             sym.append(np.full(p.size, p.kind in ("symmetry", "symmetryPlane")))
+            proc.append(np.full(p.size, p.kind == "processor"))
         cat = lambda L, dt: np.concatenate(L).astype(dt) if L else np.empty(0, dt)
         self.bf, self.bo, self.bq, self.bw, self.bsym = cat(bf, int), cat(bo, int), cat(bq, int), cat(bw, float), cat(sym, bool)
+        self.bproc = cat(proc, bool) if halo is not None else np.zeros(len(self.bf), bool)
+        self.po = self.bo[self.bproc]  # owner cells of the processor faces, in the order the halo exchanges them
+        if halo is not None:
+            # weights of a coupled face (processorFvPatch::makeWeights): the neighbour's own normal distance is my dni
+            f = self.bf[self.bproc]
+            di = ((Cf[f] - m.cell_centres[self.po]) * S[f]).sum(1) / self.A[f]
+            dni = halo(di[:, None])[:, 0]
+            self.bw[self.bproc] = dni / (di + dni)
         self.bn = S[self.bf] / self.A[self.bf][:, None] if len(self.bf) else np.empty((0, 3))
         den = np.zeros(self.nC)
         np.add.at(den, self.own, self.A[:nI]); np.add.at(den, self.nei, self.A[:nI]); np.add.at(den, self.bo, self.A[self.bf])
@@ -86,6 +100,9 @@ class FaceOperators:
             cyc = self.bq >= 0
             if cyc.any():
                 val[cyc] = self.bw[cyc, None] * F[self.bo[cyc]] + (1.0 - self.bw[cyc, None]) * F[self.bq[cyc]]
+            if self.halo is not None:  # also with no processor faces of its own a rank takes part in the exchange
+                pr = self.bproc
+                val[pr] = self.bw[pr, None] * F[self.po] + (1.0 - self.bw[pr, None]) * self.halo(F[self.po])
             if vector and self.bsym.any():  # symmetry planes mirror a vector: the face value has no normal component
                 s = self.bsym
                 vn = (F[self.bo[s]] * self.bn[s]).sum(1)
@@ -96,15 +113,21 @@ class FaceOperators:
 
     def smooth(self, f, ratio):
         """fvc::smooth(f, ratio): raise values until every cell is within a factor `ratio` of each neighbour across an
-        internal face - the least such field above f (what the smoothData wave converges to)."""
+        internal, cyclic or (with a halo) processor face - the least such field above f (what the smoothData wave
+        converges to; FaceCellWave carries it through cyclic and processor patches)."""
         v = np.array(f, float)
-        for _ in range(10 * (self.nC + 1)):
+        cyc = self.bq >= 0
+        for _ in range(10 * (self.nC + 1) if self.halo is None else 10 ** 9):
             lo_o = v[self.nei] / ratio
             lo_n = v[self.own] / ratio
             new = v.copy()
             np.maximum.at(new, self.own, lo_o)
             np.maximum.at(new, self.nei, lo_n)
-            if np.array_equal(new, v):
+            if cyc.any():
+                np.maximum.at(new, self.bo[cyc], v[self.bq[cyc]] / ratio)
+            if self.halo is not None:  # the wave crosses processor faces
+                np.maximum.at(new, self.po, self.halo(v[self.po][:, None])[:, 0] / ratio)
+            if not self.reduce_max(0.0 if np.array_equal(new, v) else 1.0):
                 break
             v = new
         return v
@@ -116,10 +139,12 @@ class FaceOperators:
 
 
 class UniGasDynamicAdapter:
-    def __init__(self, cloud, uniGasProperties, reduce_min=None, reduce_max=None):
+    def __init__(self, cloud, uniGasProperties, reduce_min=None, reduce_max=None, halo=None):
         """reduce_min / reduce_max: callables float -> float that reduce over the ranks of a decomposed run (the reference's
         reduce(deltaT, minOp) at :382-385 and reduce(maxCellWeightRatio, maxOp) at :493-496); identity on one rank.
-        Smoothing across processor patches is zero-gradient here."""
+        halo: exchange of cell values across processor faces (FaceOperators; `exchange.ProcessorHalo`) - with it the
+        smoothing of the ratios and of the cell weight factors sees the neighbour subdomains, as the reference's does;
+        without it processor faces are zero-gradient."""
         self.reduce_min = reduce_min or (lambda v: v)
         self.reduce_max = reduce_max or (lambda v: v)
         self.cloud, self.mesh = cloud, cloud.mesh
@@ -143,7 +168,7 @@ class UniGasDynamicAdapter:
         self.species = [props["moleculeProperties"][n] for n in props["typeIdList"]]
         self.Tref = float(props.get("collisionProperties", {}).get("Tref", 273.0))
         self.bgkName = props.get("bgkCollisionModel", "noBGKCollision")
-        self.ops = FaceOperators(self.mesh)
+        self.ops = FaceOperators(self.mesh, halo, reduce_max if halo is not None else None)
         nC = self.mesh.n_cells
         self.prevCellSizeMFPRatio = np.zeros((nC, 3))
         self.timeSteps = 0

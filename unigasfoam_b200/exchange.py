@@ -258,6 +258,62 @@ class PeerExchanger(SlotExchanger):
         self.cloud.moveReceived()
 
 
+class ProcessorHalo:
+    """Cell values across processor faces: `halo(a)` takes this rank's values on its processor faces ([nProcFaces, k] in
+    patch order - the owner-cell values for fvc::interpolate / FaceCellWave) and returns what the neighbour ranks hold on
+    the same faces.  One message per neighbour rank and call (the patches facing that rank concatenated in tag order, as
+    the migration does), every 10-100 steps (hybrid-mask and adaptation smoothing), so this is plumbing, not a
+    kernel: host arrays over the process group (staged through the GPU when the group is NCCL).  Every rank of the group
+    must make the same sequence of calls."""
+
+    def __init__(self, mesh, rank, world, group=None, cuda=False):
+        self.rank, self.group, self.cuda = rank, group, cuda
+        off, self.proc = 0, []
+        for p in mesh.patches:  # the order FaceOperators lists processor faces in (empty patches are skipped there too)
+            if p.kind == "processor" and p.size:
+                self.proc.append((off, p.size, p.partner, tuple(p.tag)))
+                off += p.size
+        self.n = off
+        peers = sorted({q[2] for q in self.proc})
+        self.send_order = {b: sorted([q for q in self.proc if q[2] == b], key=lambda q: _sender_tag(q[3])) for b in peers}
+        self.recv_order = {b: sorted([q for q in self.proc if q[2] == b], key=lambda q: _receiver_view(q[3])) for b in peers}
+        self.calls = 0
+
+    def __call__(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] != self.n:
+            raise ValueError(f"halo: expected [{self.n}, k] values on the processor faces, got {a.shape}")
+        self.calls += 1
+        out = np.empty_like(a)
+        dev = "cuda" if self.cuda else "cpu"
+        ops, recv = [], {}
+        for b in self.send_order:
+            snd = torch.from_numpy(np.concatenate([a[o:o + n] for o, n, _, _ in self.send_order[b]])).to(dev)
+            recv[b] = torch.empty_like(snd)
+            ops.append(dist.P2POp(dist.isend, snd, b, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[b], b, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for b, buf in recv.items():
+            buf, at = buf.cpu().numpy(), 0
+            for o, n, _, _ in self.recv_order[b]:
+                out[o:o + n] = buf[at:at + n]
+                at += n
+        return out
+
+
+def group_reducers(group=None, cuda=False):
+    """(reduce_min, reduce_max) over the ranks of a process group for UniGasDynamicAdapter / FaceOperators."""
+    def make(op):
+        def red(v):
+            t = torch.tensor([float(v)], dtype=torch.float64, device="cuda" if cuda else "cpu")
+            dist.all_reduce(t, op=op, group=group)
+            return float(t.item())
+        return red
+    return make(dist.ReduceOp.MIN), make(dist.ReduceOp.MAX)
+
+
 class _DevI64:
     def __init__(self, ptr):
         self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
