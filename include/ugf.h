@@ -285,6 +285,14 @@ int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t wallModel, const d
 int ugf_set_patch_wall_fields(ugf_handle* h, int32_t patch, const double* T, const double* U);
 /* uniGasFreeStreamInflowPatch on a patch (any kind). */
 int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* inflow);
+/* uniGasFreeStreamInflowFieldPatch on a patch (U/boundaries/derived/generalBoundaries/uniGasFreeStreamInflowFieldPatch/
+ * uniGasFreeStreamInflowFieldPatch.C:50-228): the free-stream insertion with number density, temperatures and velocity
+ * per face of the patch, i.e. the values of the volFields boundaryNumberDensity_<species>, boundaryTransT, boundaryRotT
+ * and boundaryU on this patch (computeParcelsToInsert / insertParcels with per-face lists, uniGasGeneralBoundary.C:
+ * 115-169, 537-761).  numberDensity [nTypeIds][patchSize], transT / rotT [patchSize] (rotT may be NULL), U [patchSize*3]
+ * (host). */
+int ugf_set_inflow_fields(ugf_handle* h, int32_t patch, int32_t nTypeIds, const int32_t* typeIds, const double* numberDensity,
+                          const double* transT, const double* rotT, const double* U);
 /* uniGasLiouFangPressureInletPatch on a patch.  The insertion itself is the free-stream one with a velocity per face
  * (uniGasGeneralBoundary.C:369-425, 1003-1230); the count formula is evaluated with speed ratios up to 5. */
 int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* inlet);

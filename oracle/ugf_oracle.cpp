@@ -143,6 +143,10 @@ struct InflowPatch {
     double molFrac[UGF_MAX_SPECIES] = {1, 1, 1, 1, 1, 1, 1, 1};
     double theta = 1.0;
     std::vector<double> faceVel;
+    // uniGasFreeStreamInflowFieldPatch (…/uniGasFreeStreamInflowFieldPatch.C:50-228): values per face of the patch;
+    // faceVel holds boundaryU then.  faceN [nTypeIds][nFaces], faceTtr / faceTrot [nFaces]
+    bool fields = false;
+    std::vector<double> faceN, faceTtr, faceTrot;
 };
 
 constexpr int NACC = 16;
@@ -704,15 +708,18 @@ void doInflow(ugfo_handle& h) {
             double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
             const double m2 = std::sqrt(dot3(t2, t2));
             for (int k = 0; k < 3; ++k) t2[k] /= m2;
-            const double* vel = ip.pressure ? &ip.faceVel[3 * (size_t)lf] : ip.in.velocity;
+            const double* vel = (ip.pressure || ip.fields) ? &ip.faceVel[3 * (size_t)lf] : ip.in.velocity;
+            const double Ttr = ip.fields ? ip.faceTtr[lf] : ip.in.translationalTemperature;
+            const double Trot = ip.fields ? ip.faceTrot[lf] : ip.in.rotationalTemperature;
             for (int iD = 0; iD < ip.in.nTypeIds; ++iD) {
                 const int typeId = ip.in.typeIds[iD];
                 const ugf_species& s = h.sp[typeId];
-                const double cmp = std::sqrt(2.0 * kB * ip.in.translationalTemperature / s.mass);
+                const double numDen = ip.fields ? ip.faceN[(size_t)iD * h.pSize[patch] + lf] : ip.in.numberDensities[iD];
+                const double cmp = std::sqrt(2.0 * kB * Ttr / s.mass);
                 const double sCosFull = dot3(vel, n) / cmp;
                 const double sCos = (ip.pressure && sCosFull > 5.0) ? 5.0 : sCosFull;  // count only: the device library's insertion bound
                 // Bird eq 4.22 (uniGasGeneralBoundary.C:154-165); CWF of the face's cell, RWF = 1
-                const double accum = ip.molFrac[iD] * (fA * ip.in.numberDensities[iD] * dt * cmp
+                const double accum = ip.molFrac[iD] * (fA * numDen * dt * cmp
                                       * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
                                      / (2.0 * sqrtPi * FNc(h, cellI));
                 Stream rc(h.cfg.seed, KIND_INFLOW, (uint32_t)iD, (uint32_t)h.step, (uint32_t)bfi, 0);
@@ -746,11 +753,11 @@ void doInflow(ugfo_handle& h) {
                     }
                     double g1, g2;
                     r.gauss2(g1, g2);
-                    const double cth = std::sqrt(kB * ip.in.translationalTemperature / s.mass);
+                    const double cth = std::sqrt(kB * Ttr / s.mass);
                     const double vt1 = dot3(t1, vel), vt2 = dot3(t2, vel);
                     for (int k = 0; k < 3; ++k)
                         np_.U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
-                    np_.ERot = equipartitionRotationalEnergy(r, ip.in.rotationalTemperature, s.rotationalDoF);
+                    np_.ERot = equipartitionRotationalEnergy(r, Trot, s.rotationalDoF);
                     np_.CWF = h.cellWF[cellI];  // uniGasGeneralBoundary.C:738
                     np_.sf = 0;
                     np_.cell = cellI;
@@ -1740,6 +1747,31 @@ int ugfo_set_inflow(ugfo_handle* h, int32_t patch, const ugf_inflow* in) {
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
     if (h->points.empty()) return fail(h, "inflow needs mesh points/facePoints");
     InflowPatch ip; ip.patch = patch; ip.in = *in;
+    h->inflows.push_back(ip);
+    return 0;
+}
+
+int ugfo_set_inflow_fields(ugfo_handle* h, int32_t patch, int32_t nTypeIds, const int32_t* typeIds, const double* numberDensity,
+                           const double* transT, const double* rotT, const double* U) {
+    if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
+    if (h->points.empty()) return fail(h, "inflow needs mesh points/facePoints");
+    if (!typeIds || !numberDensity || !transT || !U) return fail(h, "null inflow field");
+    if (nTypeIds < 1 || nTypeIds > UGF_MAX_SPECIES) return fail(h, "inflow typeIds out of range");
+    InflowPatch ip; ip.patch = patch;
+    std::memset(&ip.in, 0, sizeof(ip.in));
+    ip.in.nTypeIds = nTypeIds;
+    for (int i = 0; i < nTypeIds; ++i) ip.in.typeIds[i] = typeIds[i];
+    const size_t nF = (size_t)h->pSize[patch];
+    for (size_t f = 0; f < nF; ++f) {
+        if (!(transT[f] > 0.0)) return fail(h, "inflow needs a positive temperature and a non-negative number density on every face");
+        for (int i = 0; i < nTypeIds; ++i)
+            if (!(numberDensity[(size_t)i * nF + f] >= 0.0)) return fail(h, "inflow needs a positive temperature and a non-negative number density on every face");
+    }
+    ip.fields = true;
+    ip.faceN.assign(numberDensity, numberDensity + (size_t)nTypeIds * nF);
+    ip.faceTtr.assign(transT, transT + nF);
+    if (rotT) ip.faceTrot.assign(rotT, rotT + nF); else ip.faceTrot.assign(nF, 0.0);
+    ip.faceVel.assign(U, U + 3 * nF);
     h->inflows.push_back(ip);
     return 0;
 }

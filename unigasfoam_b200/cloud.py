@@ -155,10 +155,26 @@ class UniGasCloud:
                 self._check(self.api.set_patch_wall_fields(self._h, patch, bT.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
-            if word not in ("uniGasFreeStreamInflowPatch", "uniGasLiouFangPressureInletPatch"):
-                raise UgfError(f"general boundary model {word!r} is not supported (uniGasFreeStreamInflowPatch, uniGasLiouFangPressureInletPatch)")
+            if word not in ("uniGasFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch"):
+                raise UgfError(f"general boundary model {word!r} is not supported (uniGasFreeStreamInflowPatch, "
+                               "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch)")
             patch = self.mesh.patch_index(entry["generalBoundaryProperties"]["patch"])
             pr = entry[word + "Properties"]
+            if word == "uniGasFreeStreamInflowFieldPatch":
+                # the reference reads the volFields boundaryNumberDensity_<species>, boundaryTransT, boundaryRotT, boundaryU from
+                # the time directory (…/uniGasFreeStreamInflowFieldPatch.C:65-183); here their values on this patch come with
+                # the dictionary entry (scalars / one vector are broadcast over the faces), as for the wall field patches
+                nF = self.mesh.patches[patch].size
+                ids = np.array([self.typeIdList.index(n) for n in pr["typeIds"]], np.int32)
+                bn = self._f64(np.stack([np.broadcast_to(np.asarray(entry["boundaryNumberDensity"][self.typeIdList[t]], float), (nF,))
+                                         for t in ids]))
+                bT = self._f64(np.broadcast_to(np.asarray(entry["boundaryTransT"], float), (nF,)))
+                bR = self._f64(np.broadcast_to(np.asarray(entry.get("boundaryRotT", 0.0), float), (nF,)))
+                bU = self._f64(np.broadcast_to(np.asarray(entry["boundaryU"], float), (nF, 3)))
+                PD = C.POINTER(C.c_double)
+                self._check(self.api.set_inflow_fields(self._h, patch, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), bn.ctypes.data_as(PD),
+                                                       bT.ctypes.data_as(PD), bR.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
+                continue
             if word == "uniGasLiouFangPressureInletPatch":  # …/uniGasLiouFangPressureInletPatch.C:54-103
                 pin = _capi.PressureInlet()
                 ids = [self.typeIdList.index(n) for n in pr["typeIds"]]

@@ -1101,8 +1101,10 @@ static void recompute_inflow_bounds(ugf_handle* h) {
 }
 
 // common part of the free-stream and the pressure inlet: geometry of the patch faces, insertion bound, device tables.
-// pin != null: pressure inlet (mole fractions, velocity per face, relaxation factor)
-static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in, const ugf_pressure_inlet* pin) {
+// pin != null: pressure inlet (mole fractions, velocity per face, relaxation factor); fld != null: number density,
+// temperatures and velocity per face (uniGasFreeStreamInflowFieldPatch)
+struct InflowFields { const double *numDen, *transT, *rotT, *U; };  // numDen [nTypeIds][nFaces]
+static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in, const ugf_pressure_inlet* pin, const InflowFields* fld = nullptr) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
     if (h->pointsHost.empty()) return fail(h, "inflow needs mesh points/facePoints");
@@ -1152,10 +1154,14 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
         for (int iD = 0; iD < in->nTypeIds; ++iD) {
             const int t = in->typeIds[iD];
             if (t < 0 || t >= h->nSpecies) return fail(h, "inflow typeId out of range");
-            const double cmp = std::sqrt(2.0 * kB * in->translationalTemperature / h->spHost[t].mass);
-            double sCos = (in->velocity[0] * n[0] + in->velocity[1] * n[1] + in->velocity[2] * n[2]) / cmp;
+            const double Ttr = fld ? fld->transT[lf] : in->translationalTemperature;
+            const double* vel = fld ? fld->U + 3 * (size_t)lf : in->velocity;
+            const double numDen = fld ? fld->numDen[(size_t)iD * nF + lf] : in->numberDensities[iD];
+            if (!(Ttr > 0.0) || !(numDen >= 0.0)) return fail(h, "inflow needs a positive temperature and a non-negative number density on every face");
+            const double cmp = std::sqrt(2.0 * kB * Ttr / h->spHost[t].mass);
+            double sCos = (vel[0] * n[0] + vel[1] * n[1] + vel[2] * n[2]) / cmp;
             if (pin) sCos = 5.0;  // the face velocities follow the flow: bound the insertions with a speed ratio of 5
-            const double accum = (pin ? pin->moleFractions[iD] : 1.0) * (fA * in->numberDensities[iD] * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
+            const double accum = (pin ? pin->moleFractions[iD] : 1.0) * (fA * numDen * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
                                  / (2.0 * sqrtPi * h->cfg.nParticle);
             f.maxInsert += (long long)std::max(accum, 0.0) + 2;
             f.accum1.push_back(accum * h->cfg.nParticle / h->cfg.deltaT);
@@ -1170,6 +1176,7 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
     for (int k = 0; k < 3; ++k) d.vel[k] = in->velocity[k];
     for (int i = 0; i < UGF_MAX_SPECIES; ++i) d.molFrac[i] = (pin && i < in->nTypeIds) ? pin->moleFractions[i] : 1.0;
     d.theta = pin ? pin->theta : 1.0;
+    d.pressure = pin ? 1 : 0;
     int *dBfi, *dCell, *dTriOff, *dNIns, *dInsOff;
     double *dGeom, *dTri;
     if (dalloc(h, &dBfi, (size_t)nF) || dalloc(h, &dCell, (size_t)nF) || dalloc(h, &dTriOff, (size_t)nF + 1) || dalloc(h, &dGeom, geom.size()) ||
@@ -1189,11 +1196,37 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
         d.faceVel = dVel;
         f.pressureInlet = true;
     }
+    if (fld) {  // per-face tables: velocity [nF*3], number density per slot [nF*nTypeIds], (Ttr, Trot) [nF*2]
+        std::vector<double> fN((size_t)f.nSlots), fT(2 * (size_t)nF);
+        for (int lf = 0; lf < nF; ++lf) {
+            for (int iD = 0; iD < in->nTypeIds; ++iD) fN[(size_t)lf * in->nTypeIds + iD] = fld->numDen[(size_t)iD * nF + lf];
+            fT[2 * (size_t)lf] = fld->transT[lf];
+            fT[2 * (size_t)lf + 1] = fld->rotT ? fld->rotT[lf] : 0.0;
+        }
+        double *dVel, *dN, *dT;
+        if (dalloc(h, &dVel, 3 * (size_t)nF) || dalloc(h, &dN, fN.size()) || dalloc(h, &dT, fT.size())) return 1;
+        f.owned.push_back(dVel); f.owned.push_back(dN); f.owned.push_back(dT);
+        if (upload(h, dVel, fld->U, 3 * (size_t)nF) || upload(h, dN, fN.data(), fN.size()) || upload(h, dT, fT.data(), fT.size())) return 1;
+        CU(cudaStreamSynchronize(h->stream));
+        d.faceVel = dVel; d.faceN = dN; d.faceT = dT;
+    }
     h->inflows.push_back(f);
     return 0;
 }
 
 int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) { return set_inflow_common(h, patch, in, nullptr); }
+
+int ugf_set_inflow_fields(ugf_handle* h, int32_t patch, int32_t nTypeIds, const int32_t* typeIds, const double* numberDensity,
+                          const double* transT, const double* rotT, const double* U) {
+    if (!h) return 1;
+    if (!typeIds || !numberDensity || !transT || !U) return fail(h, "null inflow field");
+    if (nTypeIds < 1 || nTypeIds > UGF_MAX_SPECIES) return fail(h, "inflow typeIds out of range");
+    ugf_inflow in{};
+    in.nTypeIds = nTypeIds;
+    for (int i = 0; i < nTypeIds; ++i) in.typeIds[i] = typeIds[i];
+    const InflowFields fld{numberDensity, transT, rotT, U};
+    return set_inflow_common(h, patch, &in, nullptr, &fld);
+}
 
 int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* pin) {
     if (!h || !pin) return 1;

@@ -27,8 +27,11 @@ struct InflowDev {
     double Ttr, Trot;
     double vel[3];
     double molFrac[UGF_MAX_SPECIES];  // 1 for free-stream patches (numDen is per species there)
-    double* faceVel;                  // pressure inlets: inflow velocity per face [nFaces*3], else null (vel everywhere)
+    double* faceVel;                  // pressure inlets and field patches: inflow velocity per face [nFaces*3], else null (vel everywhere)
     double theta;                     // pressure inlets: relaxation of faceVel towards the cell mean velocity
+    int pressure;                     // pressure inlet (speed ratio of the count formula capped at 5)
+    const double* faceN;              // uniGasFreeStreamInflowFieldPatch: number density per slot [nFaces*nTypeIds], else null
+    const double* faceT;              // uniGasFreeStreamInflowFieldPatch: translational, rotational temperature per face [nFaces*2], else null
     const int* faceBfi;
     const int* faceCell;
     const double* geom;
@@ -45,12 +48,14 @@ __global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant
     const double* g = f.geom + (size_t)face * INFLOW_GEOM;
     const DevSpecies& s = prm.sp[f.typeIds[iD]];
     const double fA = g[0];
-    const double cmp = sqrt(2.0 * kB * f.Ttr / s.mass);
+    const double Ttr = f.faceT ? f.faceT[2 * (size_t)face] : f.Ttr;
+    const double numDen = f.faceN ? f.faceN[slot] : f.numDen[iD];
+    const double cmp = sqrt(2.0 * kB * Ttr / s.mass);
     const double* vel = f.faceVel ? f.faceVel + 3 * (size_t)face : f.vel;
     double sCos = (vel[0] * g[1] + vel[1] * g[2] + vel[2] * g[3]) / cmp;
-    if (f.faceVel && sCos > 5.0) sCos = 5.0;  // the host's insertion bound assumes speed ratios <= 5 on pressure inlets
+    if (f.pressure && sCos > 5.0) sCos = 5.0;  // the host's insertion bound assumes speed ratios <= 5 on pressure inlets
     const double sqrtPi = sqrt(PI);
-    const double accum = f.molFrac[iD] * (fA * f.numDen[iD] * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
+    const double accum = f.molFrac[iD] * (fA * numDen * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
                          / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));  // uniGasGeneralBoundary.C:154-165
     Stream rc(prm.seed, KIND_INFLOW, (uint32_t)iD, step, (uint32_t)f.faceBfi[face], 0);
     int nIns = max((int)accum, 0);
@@ -94,7 +99,9 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
     const double n[3] = {g[1], g[2], g[3]}, t1[3] = {g[4], g[5], g[6]}, t2[3] = {g[7], g[8], g[9]}, p0[3] = {g[10], g[11], g[12]};
     const int typeId = f.typeIds[iD];
     const DevSpecies& s = prm.sp[typeId];
-    const double cmp = sqrt(2.0 * kB * f.Ttr / s.mass);
+    const double Ttr = f.faceT ? f.faceT[2 * (size_t)face] : f.Ttr;
+    const double Trot = f.faceT ? f.faceT[2 * (size_t)face + 1] : f.Trot;
+    const double cmp = sqrt(2.0 * kB * Ttr / s.mass);
     const double* vel = f.faceVel ? f.faceVel + 3 * (size_t)face : f.vel;
     const double vn = vel[0] * n[0] + vel[1] * n[1] + vel[2] * n[2];
     const double sCos = vn / cmp;
@@ -128,12 +135,12 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
         }
         double g1, g2;
         r.gauss2(g1, g2);
-        const double cth = sqrt(kB * f.Ttr / s.mass);
+        const double cth = sqrt(kB * Ttr / s.mass);
         const double vt1 = t1[0] * vel[0] + t1[1] * vel[1] + t1[2] * vel[2];
         const double vt2 = t2[0] * vel[0] + t2[1] * vel[1] + t2[2] * vel[2];
         double U[3];
         for (int k = 0; k < 3; ++k) U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
-        const double erot = equipartition_rotational_energy(r, f.Trot, s.rotDoF);
+        const double erot = equipartition_rotational_energy(r, Trot, s.rotDoF);
         const long long dst = (long long)base + f.insOff[slot] + i;
         P.x[dst] = x[0]; P.y[dst] = x[1]; P.z[dst] = x[2];
         P.ux[dst] = U[0]; P.uy[dst] = U[1]; P.uz[dst] = U[2];
