@@ -167,3 +167,45 @@ def test_gpu_reads_the_dictionary_the_oracle_wrote(tmp_path, GpuCloud, OracleClo
     fr, fg = r.fields(), g.fields()
     for k in fr:
         assert np.allclose(fr[k], fg[k], rtol=1e-12, atol=1e-12 * np.abs(fr[k]).max()), k
+
+
+def test_output_fields_under_the_reference_names(tmp_path, OracleCloud):
+    """uniGasVolFields at write time (uniGasVolFields.C:67-357, 1256-1428): rhoN_<f>, p_<f>, UMean_<f>, ... as volFields with
+    the reference's dimensions; wall measurements on the wall patches, constraint patches by their type."""
+    from unigasfoam_b200 import foamfile
+    case = _couette()
+    a = case.make_cloud(OracleCloud)
+    a.evolve(6)
+    files = a.writeFields(str(tmp_path), "6e-06", "Ar")
+    names = sorted(os.path.basename(p) for p in files)
+    want = ["uniGasRhoNMean", "rhoN", "rhoM", "p", "translationalT", "rotationalT", "vibrationalT", "electronicT", "overallT",
+            "surfaceHeatTransfer", "surfaceShearStress", "Ma", "UMean", "fD", "variableHardSphereMeanFreePath", "subCellSizeMFPRatio",
+            "meanCollisionRate", "meanCollisionTime", "timeStepMCTRatio", "densityError", "velocityError", "temperatureError"]
+    assert names == sorted(n + "_Ar" for n in want)
+    assert len(a.writeFields(str(tmp_path), "6e-06", "x", measureMeanFreePath=False, measureErrors=False)) == 14
+    f, m = a.fields(), case.mesh
+    nI = m.n_internal
+    rd = lambda n: foamfile.read_vol_field(str(tmp_path / "6e-06" / (n + "_Ar")))
+    p = rd("p")
+    assert p["class"] == "volScalarField" and p["dimensions"] == [1, -1, -2, 0, 0, 0, 0] and np.array_equal(p["internal"], f["p"])
+    u = rd("UMean")
+    assert u["class"] == "volVectorField" and u["dimensions"] == [0, 1, -1, 0, 0, 0, 0] and np.array_equal(u["internal"], f["UMean"])
+    assert rd("rhoM")["dimensions"] == [1, -3, 0, 0, 0, 0, 0] and rd("surfaceHeatTransfer")["dimensions"] == [1, 0, -3, 0, 0, 0, 0]
+    assert rd("variableHardSphereMeanFreePath")["dimensions"] == [0, 1, 0, 0, 0, 0, 0] and rd("meanCollisionRate")["dimensions"] == [0, 0, -1, 0, 0, 0, 0]
+    q, fd, rn = rd("surfaceHeatTransfer"), rd("fD"), rd("rhoN")
+    assert q["uniform"] and q["internal"] == 0.0
+    seen_wall = 0
+    for pt in m.patches:
+        sl = slice(pt.start - nI, pt.start - nI + pt.size)
+        if pt.kind == "wall":
+            seen_wall += 1
+            assert p["boundary"][pt.name]["type"] == "calculated"
+            assert np.array_equal(foamfile.boundary_values(p, pt.name, pt.size), f["wall_p"][sl])
+            assert np.array_equal(foamfile.boundary_values(q, pt.name, pt.size), f["surfaceHeatTransfer"][sl])
+            assert np.array_equal(foamfile.boundary_values(fd, pt.name, pt.size), f["fD"][sl])
+            assert np.array_equal(foamfile.boundary_values(u, pt.name, pt.size), f["wall_UMean"][sl])
+            own = np.asarray(m.owner[pt.start:pt.start + pt.size])
+            assert np.array_equal(foamfile.boundary_values(rn, pt.name, pt.size), f["rhoN"][own])  # :1370-1372: the cell value
+        else:
+            assert p["boundary"][pt.name] == {"type": pt.kind}
+    assert seen_wall == 2 and np.abs(f["wall_p"]).max() > 0

@@ -383,6 +383,69 @@ class UniGasCloud:
             self.loadState(np.load(sp))
         return d
 
+    # name, key of fields() (None: zero field), dimensions [kg m s K mol A cd], boundary rule, wall key, vector
+    # (uniGasVolFields.C:67-357).  Boundary rules follow :1256-1394: "cell" - every wall / generic patch face takes the value
+    # of its cell; "wall" - wall faces take the wall measurement, generic patch faces the cell value; "surface" - wall faces
+    # take the wall measurement, everything else is zero; "zero".  Constraint patches (empty, cyclic, symmetry, processor) are
+    # written by their type.  rotationalT / overallT on walls carry the cell value (the wall value is not derived here).
+    _OUTPUT_FIELDS = (
+        ("uniGasRhoNMean", "uniGasRhoNMean", [0, -3, 0, 0, 0, 0, 0], "cell", None, False),
+        ("rhoN", "rhoN", [0, -3, 0, 0, 0, 0, 0], "cell", None, False),
+        ("rhoM", "rhoM", [1, -3, 0, 0, 0, 0, 0], "cell", None, False),
+        ("p", "p", [1, -1, -2, 0, 0, 0, 0], "wall", "wall_p", False),
+        ("translationalT", "translationalT", [0, 0, 0, 1, 0, 0, 0], "wall", "wall_translationalT", False),
+        ("rotationalT", "rotationalT", [0, 0, 0, 1, 0, 0, 0], "cell", None, False),
+        ("vibrationalT", None, [0, 0, 0, 1, 0, 0, 0], "zero", None, False),
+        ("electronicT", None, [0, 0, 0, 1, 0, 0, 0], "zero", None, False),
+        ("overallT", "overallT", [0, 0, 0, 1, 0, 0, 0], "cell", None, False),
+        ("surfaceHeatTransfer", None, [1, 0, -3, 0, 0, 0, 0], "surface", "surfaceHeatTransfer", False),
+        ("surfaceShearStress", None, [1, -1, -2, 0, 0, 0, 0], "surface", "surfaceShearStress", False),
+        ("Ma", "Ma", [0] * 7, "cell", None, False),
+        ("UMean", "UMean", [0, 1, -1, 0, 0, 0, 0], "wall", "wall_UMean", True),
+        ("fD", None, [1, -1, -2, 0, 0, 0, 0], "surface", "fD", True),
+    )
+    _MFP_FIELDS = (("variableHardSphereMeanFreePath", "MFP", [0, 1, 0, 0, 0, 0, 0]), ("subCellSizeMFPRatio", "dxMFP", [0] * 7),
+                   ("meanCollisionRate", "MCR", [0, 0, -1, 0, 0, 0, 0]), ("meanCollisionTime", "MCT", [0, 0, 1, 0, 0, 0, 0]),
+                   ("timeStepMCTRatio", "dtMCT", [0] * 7))
+    _ERROR_FIELDS = (("densityError", "densityError", [0] * 7), ("velocityError", "velocityError", [0] * 7),
+                     ("temperatureError", "temperatureError", [0] * 7))
+
+    def writeFields(self, case_dir, time_name, fieldName, resetAtOutput=False, measureMeanFreePath=True, measureErrors=True):
+        """The output volFields of a uniGasVolFields entry at write time, under the reference's names and dimensions
+        (`rhoN_<field>`, `p_<field>`, `UMean_<field>`, `surfaceHeatTransfer_<field>` ..., uniGasVolFields.C:67-357,
+        1397-1428): cell values as internalField, boundary values by the rules above.  -> the list of files written."""
+        from . import foamfile
+        f = self.fields(resetAtOutput=resetAtOutput)
+        m = self.mesh
+        nI = m.n_internal
+        t = os.path.join(case_dir, time_name)
+        os.makedirs(t, exist_ok=True)
+        todo = list(self._OUTPUT_FIELDS)
+        if measureMeanFreePath:
+            todo += [(n, k, d, "cell", None, False) for n, k, d in self._MFP_FIELDS]
+        if measureErrors:
+            todo += [(n, k, d, "zero", None, False) for n, k, d in self._ERROR_FIELDS]
+        out = []
+        for name, key, dims, rule, wkey, vector in todo:
+            internal = f[key] if key is not None else (np.zeros((m.n_cells, 3)) if vector else np.zeros(m.n_cells))
+            patches = {}
+            for p in m.patches:
+                if p.kind not in ("wall", "patch"):
+                    patches[p.name] = p.kind
+                    continue
+                own = np.asarray(m.owner[p.start:p.start + p.size])
+                if p.kind == "wall" and rule in ("wall", "surface"):
+                    val = f[wkey][p.start - nI:p.start - nI + p.size]
+                elif rule in ("cell", "wall"):
+                    val = internal[own]
+                else:
+                    val = np.zeros(3) if vector else 0.0
+                patches[p.name] = {"type": "calculated", "value": val}
+            path = os.path.join(t, f"{name}_{fieldName}")
+            foamfile.write_vol_field(path, time_name, dims, internal, patches, vector=vector)
+            out.append(path)
+        return out
+
     def writeVolFieldsMethod(self, case_dir, time_name, fieldName):
         """uniGasVolFields::writeOut (uniGasVolFields.C:609-669): the accumulators of the field object `fieldName` as
         <time>/uniform/volFieldsMethod_<fieldName>, under the reference's entry names (unigasfoam_b200/volfields_io.py)."""

@@ -106,7 +106,8 @@ def write_lagrangian(case_dir, time_name, parcels, cloud="uniGas"):
 
 def write_vol_field(path, location, dimensions, internal, patches, vector=False):
     """volScalarField / volVectorField with zeroGradient (or given) patch types; patches: list of names or
-    dict name -> type word."""
+    dict name -> type word, or name -> {"type": word, "value": scalar / vector / array per face} (what a `calculated`
+    patch of an output field carries)."""
     internal = np.asarray(internal, float)
     cls = "volVectorField" if vector else "volScalarField"
     typ = "vector" if vector else "scalar"
@@ -128,8 +129,46 @@ def write_vol_field(path, location, dimensions, internal, patches, vector=False)
             f.write("\n)\n;\n\n")
         f.write("boundaryField\n{\n")
         for name, t in ptypes.items():
+            if isinstance(t, dict):
+                f.write(f"    {name}\n    {{\n        type            {t['type']};\n")
+                if "value" in t:
+                    f.write("        value           " + _patch_value(t["value"], vector) + ";\n")
+                f.write("    }\n")
+                continue
             f.write(f"    {name}\n    {{\n        type            {t};\n    }}\n")
         f.write("}\n\n\n// ************************************************************************* //\n")
+
+
+def _patch_value(v, vector):
+    v = np.asarray(v, float)
+    one = "(" + " ".join(repr(float(c)) for c in v) + ")" if vector and v.ndim == 1 else (repr(float(v)) if v.ndim == 0 else None)
+    if one is not None:
+        return "uniform " + one
+    if len(v) == 0:
+        return f"nonuniform List<{'vector' if vector else 'scalar'}> 0()"
+    body = " ".join("(" + " ".join(repr(float(c)) for c in r) + ")" for r in v) if vector else " ".join(repr(float(x)) for x in v)
+    return f"nonuniform List<{'vector' if vector else 'scalar'}> {len(v)}({body})"
+
+
+def boundary_values(field, patch, n_faces):
+    """The `value` entry of one patch of a field read by read_vol_field -> array [n_faces] / [n_faces,3] (None if the
+    patch has no value entry)."""
+    e = field["boundary"][patch]
+    if "value" not in e:
+        return None
+    vector = field["class"] == "volVectorField"
+    txt = e["value"]
+    if txt.startswith("uniform"):
+        v = _numbers(txt[len("uniform"):])
+        return np.tile(v, (n_faces, 1)) if vector else np.full(n_faces, float(v[0]))
+    m = re.match(r"nonuniform\s+List<\w+>\s*(\d+)\s*\((.*)\)\s*$", txt, re.S)
+    if not m:
+        raise FoamFormatError(f"{patch}: uniform or nonuniform List<T> value expected")
+    a = _numbers(m.group(2))
+    a = a.reshape(-1, 3) if vector else a
+    if len(a) != int(m.group(1)) or len(a) != n_faces:
+        raise FoamFormatError(f"{patch}: {len(a)} values for {n_faces} faces")
+    return a
 
 
 # ---- reading ---------------------------------------------------------------------------------------------
