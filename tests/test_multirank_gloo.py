@@ -205,3 +205,79 @@ def test_two_rank_smoothing_operators_match_single_domain(tmp_path):
         for r in res:
             zg[r[name]["cells"]] = r[name]["zg"]
         assert not np.allclose(zg, want["a1"], rtol=1e-6)  # without the halo the cut is visible in the result
+
+
+def _adaptive_props(full):
+    case = cases.cylinder(nr=8, ntheta=16, ppc=5, binary="noDSMCCollision")
+    props = dict(case.uniGasProperties)
+    props["adaptiveSimulation"] = True
+    props["adaptiveProperties"] = dict(timeStepAdaptation=True, subCellAdaptation=True, adaptationInterval=10, smoothingPasses=6)
+    return props, case.uniGasProperties["nEquivalentParticles"] if "nEquivalentParticles" in case.uniGasProperties else 1.0
+
+
+def _initial_state(mesh_cells_xyz):
+    """A non-uniform initial state (density over two decades, temperature ramp) so that the smoothing passes matter."""
+    x, y = mesh_cells_xyz[:, 0], mesh_cells_xyz[:, 1]
+    r = np.hypot(x, y)
+    n = 1e21 * np.exp(-6.0 * (r - r.min()) / (r.max() - r.min())) * (1.0 + 0.5 * np.sin(2.3 * np.arctan2(y, x) + 0.4))  # not symmetric about the cut
+    T = 200.0 + 300.0 * (r - r.min()) / (r.max() - r.min())
+    U = np.column_stack([300.0 * np.cos(np.arctan2(y, x)), 100.0 * np.ones_like(x), np.zeros_like(x)])
+    return n, T, U
+
+
+def _stand_in(mesh, dt):
+    from types import SimpleNamespace
+    return SimpleNamespace(mesh=mesh, cellWeighted=False, _subCellLevels=None, _cellWeightFactor=None, _adapter=None,
+                           cfg=SimpleNamespace(deltaT=dt, nParticle=1e10))
+
+
+def _worker_adapter(rank, world, port, out):
+    """uniGasDynamicAdapter::setInitialConfiguration (:708-775) on a decomposed mesh: ratios smoothed through the halo,
+    time step reduced over the ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unigasfoam_b200 import mesh as ugmesh
+    from unigasfoam_b200.adapter import UniGasDynamicAdapter
+    from unigasfoam_b200.exchange import ProcessorHalo, group_reducers
+    full = _halo_meshes(world)["annulus"][0]
+    sub = ugmesh.decompose(full, ugmesh.slab_partition(full, world, axis=1), world)[rank]
+    props, _ = _adaptive_props(full)
+    rmin, rmax = group_reducers()
+    n, T, U = _initial_state(full.cell_centres)
+    res = {}
+    for label, halo in (("halo", ProcessorHalo(sub, rank, world)), ("cut", None)):
+        ad = UniGasDynamicAdapter(_stand_in(sub, 1e-6), props, reduce_min=rmin, reduce_max=rmax, halo=halo)
+        dt, levels = ad.set_initial_configuration([n[sub.cell_map]], T[sub.cell_map], U[sub.cell_map])
+        res[label] = dict(dt=dt, levels=levels, csr=ad.prevCellSizeMFPRatio)
+    res["cells"] = sub.cell_map
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_adapter_initial_configuration_matches_single_domain(tmp_path):
+    from unigasfoam_b200.adapter import UniGasDynamicAdapter
+    world = 2
+    out = str(tmp_path / "adapt.pt")
+    mp.spawn(_worker_adapter, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    full = _halo_meshes(world)["annulus"][0]
+    props, _ = _adaptive_props(full)
+    n, T, U = _initial_state(full.cell_centres)
+    ad = UniGasDynamicAdapter(_stand_in(full, 1e-6), props)
+    dt, levels = ad.set_initial_configuration([n], T, U)
+    assert dt != 1e-6 and levels.max() > levels.min()          # the state does drive both decisions
+    assert all(r["halo"]["dt"] == res[0]["halo"]["dt"] for r in res)
+    assert res[0]["halo"]["dt"] == pytest.approx(dt, rel=1e-12)
+    got_l, got_c, cut_c = np.empty_like(levels), np.empty_like(ad.prevCellSizeMFPRatio), np.empty_like(ad.prevCellSizeMFPRatio)
+    for r in res:
+        got_l[r["cells"]] = r["halo"]["levels"]
+        got_c[r["cells"]] = r["halo"]["csr"]
+        cut_c[r["cells"]] = r["cut"]["csr"]
+    assert np.allclose(got_c, ad.prevCellSizeMFPRatio, rtol=1e-12)
+    assert np.array_equal(got_l, levels)
+    assert not np.allclose(cut_c, ad.prevCellSizeMFPRatio, rtol=1e-3)   # zero-gradient processor faces leave a seam
