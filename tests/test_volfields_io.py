@@ -180,7 +180,7 @@ def test_output_fields_under_the_reference_names(tmp_path, OracleCloud):
     names = sorted(os.path.basename(p) for p in files)
     want = ["uniGasRhoNMean", "rhoN", "rhoM", "p", "translationalT", "rotationalT", "vibrationalT", "electronicT", "overallT",
             "surfaceHeatTransfer", "surfaceShearStress", "Ma", "UMean", "fD", "variableHardSphereMeanFreePath", "subCellSizeMFPRatio",
-            "meanCollisionRate", "meanCollisionTime", "timeStepMCTRatio", "densityError", "velocityError", "temperatureError"]
+            "meanCollisionRate", "meanCollisionTime", "timeStepMCTRatio", "densityError", "velocityError", "temperatureError", "pressureError"]
     assert names == sorted(n + "_Ar" for n in want)
     assert len(a.writeFields(str(tmp_path), "6e-06", "x", measureMeanFreePath=False, measureErrors=False)) == 14
     f, m = a.fields(), case.mesh
@@ -209,3 +209,7 @@ def test_output_fields_under_the_reference_names(tmp_path, OracleCloud):
         else:
             assert p["boundary"][pt.name] == {"type": pt.kind}
     assert seen_wall == 2 and np.abs(f["wall_p"]).max() > 0
+    # measureErrors (:1246-1250): pressureError = sqrt(gamma) densityError, argon gamma = 5/3
+    ok = f["densityError"] > 0
+    assert ok.any() and np.allclose(f["pressureError"][ok], np.sqrt(5.0 / 3.0) * f["densityError"][ok], rtol=1e-12)
+    assert np.array_equal(rd("pressureError")["internal"], f["pressureError"])

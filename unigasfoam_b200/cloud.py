@@ -408,7 +408,7 @@ class UniGasCloud:
                    ("meanCollisionRate", "MCR", [0, 0, -1, 0, 0, 0, 0]), ("meanCollisionTime", "MCT", [0, 0, 1, 0, 0, 0, 0]),
                    ("timeStepMCTRatio", "dtMCT", [0] * 7))
     _ERROR_FIELDS = (("densityError", "densityError", [0] * 7), ("velocityError", "velocityError", [0] * 7),
-                     ("temperatureError", "temperatureError", [0] * 7))
+                     ("temperatureError", "temperatureError", [0] * 7), ("pressureError", "pressureError", [0] * 7))
 
     def writeFields(self, case_dir, time_name, fieldName, resetAtOutput=False, measureMeanFreePath=True, measureErrors=True):
         """The output volFields of a uniGasVolFields entry at write time, under the reference's names and dimensions
@@ -636,7 +636,12 @@ class UniGasCloud:
         wf = np.empty((max(nB, 1), _capi.UGF_NWALLFIELD))
         self._check(self.api.download_fields(self._h, cf.ctypes.data_as(PD), wf.ctypes.data_as(PD), int(resetAtOutput)))
         wf = wf[:nB]
+        # pressureError = sqrt(gamma) densityError (uniGasVolFields.C:1250) with gamma recovered from velocityError =
+        # densityError / (Ma sqrt(gamma)) (:1248): no extra device field
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pErr = np.where((cf[:, 17] > 0) & (cf[:, 10] > 0), cf[:, 11] * cf[:, 11] / (cf[:, 17] * cf[:, 10]), 0.0)
         return {
+            "pressureError": pErr,
             "uniGasRhoNMean": cf[:, 0], "rhoN": cf[:, 1], "rhoM": cf[:, 2], "UMean": cf[:, 3:6],
             "translationalT": cf[:, 6], "rotationalT": cf[:, 7], "overallT": cf[:, 8], "p": cf[:, 9],
             "Ma": cf[:, 10], "densityError": cf[:, 11],
