@@ -296,6 +296,12 @@ int ugf_set_inflow_fields(ugf_handle* h, int32_t patch, int32_t nTypeIds, const 
 /* uniGasLiouFangPressureInletPatch on a patch.  The insertion itself is the free-stream one with a velocity per face
  * (uniGasGeneralBoundary.C:369-425, 1003-1230); the count formula is evaluated with speed ratios up to 5. */
 int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* inlet);
+/* uniGasWangPressureInletPatch on a patch (U/boundaries/derived/generalBoundaries/uniGasWangPressureInletPatch/
+ * uniGasWangPressureInletPatch.C:54-281): number density p / (k T) as above; the inflow velocity of a face is the mean
+ * momentum over the mean mass of all parcels seen in its cell since the start and, after 100 steps, is corrected by
+ * (p_cell - p_in) / (rho a) along the outward normal (:258-266).  `theta` of the struct is not used.  The running sums
+ * and the step count travel in ugf_state_save. */
+int ugf_set_wang_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* inlet);
 /* Inlet velocity per face of a pressure inlet [patchSize*3] (diagnostic / restart). */
 int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U);
 /* addNewParcel over a whole initial configuration (U/clouds/uniGasCloud.C:260-290). Replaces the cloud. */

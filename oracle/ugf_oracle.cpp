@@ -147,7 +147,13 @@ struct InflowPatch {
     // faceVel holds boundaryU then.  faceN [nTypeIds][nFaces], faceTtr / faceTrot [nFaces]
     bool fields = false;
     std::vector<double> faceN, faceTtr, faceTrot;
+    // uniGasWangPressureInletPatch (…/uniGasWangPressureInletPatch.C:54-281): running sums per face (0 parcels, 1 mass, 2-4
+    // momentum, 5-7 sum U^2, 8-10 sum U), step count, inlet pressure, mixture molecular mass, gamma * R
+    bool wang = false;
+    std::vector<double> wangSums;
+    double wangSteps = 0.0, wangP = 0.0, wangM = 0.0, wangGammaR = 0.0;
 };
+constexpr int WANG_NSUM = 11;
 
 constexpr int NACC = 16;
 
@@ -1444,6 +1450,48 @@ void updateInletVelocities(ugfo_handle& h) {
     if (!h.occValid) buildOccupancy(h);
     for (InflowPatch& ip : h.inflows) {
         if (!ip.pressure) continue;
+        if (ip.wang) {  // …/uniGasWangPressureInletPatch.C:131-281
+            ip.wangSteps += 1.0;
+            for (int lf = 0; lf < h.pSize[ip.patch]; ++lf) {
+                const int f = h.pStart[ip.patch] + lf;
+                const int c = h.owner[f];
+                const double w = FNc(h, c);
+                double mom[3] = {0, 0, 0}, mass = 0, nP = 0, sq[3] = {0, 0, 0}, su[3] = {0, 0, 0};
+                for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
+                    const Parcel& p = h.P[h.occIds[j]];
+                    bool mine = false;
+                    for (int i = 0; i < ip.in.nTypeIds; ++i) mine = mine || ip.in.typeIds[i] == p.typeId;
+                    if (!mine) continue;
+                    const double m = w * h.sp[p.typeId].mass;
+                    for (int k = 0; k < 3; ++k) { mom[k] += m * p.U[k]; sq[k] += p.U[k] * p.U[k]; su[k] += p.U[k]; }
+                    mass += m;
+                    nP += 1.0;
+                }
+                double* S = &ip.wangSums[(size_t)lf * WANG_NSUM];
+                S[0] += nP; S[1] += mass;
+                for (int k = 0; k < 3; ++k) S[2 + k] += mom[k];
+                if (S[0] > 1) {
+                    for (int k = 0; k < 3; ++k) { S[5 + k] += sq[k]; S[8 + k] += su[k]; }
+                    const double massDensity = S[1] / (h.vol[c] * ip.wangSteps);
+                    const double numberDensity = massDensity / ip.wangM;
+                    double m2 = 0, mm = 0;
+                    for (int k = 0; k < 3; ++k) { m2 += S[5 + k] / S[0]; const double a = S[8 + k] / S[0]; mm += a * a; }
+                    double T = (0.5 * ip.wangM) * (2.0 / (3.0 * kB)) * (m2 - mm);
+                    if (T < VSMALL) T = 300.0;
+                    const double pressure = numberDensity * kB * T;
+                    const double sound = std::sqrt(ip.wangGammaR * T);
+                    const double* Sf = &h.Sf[3 * (size_t)f];
+                    const double fA = std::sqrt(dot3(Sf, Sf));
+                    double* v = &ip.faceVel[3 * (size_t)lf];
+                    for (int k = 0; k < 3; ++k) v[k] = S[2 + k] / S[1];
+                    if (ip.wangSteps > 100) {
+                        const double corr = (pressure - ip.wangP) / (massDensity * sound);
+                        for (int k = 0; k < 3; ++k) v[k] += corr * -(Sf[k] / -fA);  // the same unit normal the device table holds
+                    }
+                }
+            }
+            continue;
+        }
         for (int lf = 0; lf < h.pSize[ip.patch]; ++lf) {
             const int c = h.owner[h.pStart[ip.patch] + lf];
             const double w = FNc(h, c);
@@ -1793,6 +1841,24 @@ int ugfo_set_pressure_inlet(ugfo_handle* h, int32_t patch, const ugf_pressure_in
     return 0;
 }
 
+int ugfo_set_wang_pressure_inlet(ugfo_handle* h, int32_t patch, const ugf_pressure_inlet* pin) {
+    const int rc = ugfo_set_pressure_inlet(h, patch, pin);
+    if (rc) return rc;
+    InflowPatch& ip = h->inflows.back();
+    double M = 0, cp = 0, cv = 0;
+    for (int i = 0; i < pin->nTypeIds; ++i) {
+        const ugf_species& sp = h->sp[pin->typeIds[i]];
+        M += sp.mass * pin->moleFractions[i];
+        cp += (5.0 + sp.rotationalDoF) * pin->moleFractions[i];
+        cv += (3.0 + sp.rotationalDoF) * pin->moleFractions[i];
+    }
+    if (!(M > 0.0)) { h->inflows.pop_back(); return fail(h, "mole fractions of the pressure inlet sum to zero"); }
+    ip.wang = true;
+    ip.wangSums.assign((size_t)WANG_NSUM * h->pSize[patch], 0.0);
+    ip.wangP = pin->inletPressure; ip.wangM = M; ip.wangGammaR = (cp / cv) * (kB / M);
+    return 0;
+}
+
 int ugfo_download_inlet_velocity(ugfo_handle* h, int32_t patch, double* U) {
     for (const InflowPatch& ip : h->inflows)
         if (ip.patch == patch && ip.pressure) { std::copy(ip.faceVel.begin(), ip.faceVel.end(), U); return 0; }
@@ -1913,7 +1979,7 @@ namespace {
 constexpr double STATE_MAGIC = 1431783237.0;
 long long inletVelocityDoubles(const ugfo_handle* h) {
     long long n = 0;
-    for (const InflowPatch& ip : h->inflows) if (ip.pressure) n += (long long)ip.faceVel.size();
+    for (const InflowPatch& ip : h->inflows) if (ip.pressure) n += (long long)ip.faceVel.size() + (ip.wang ? (long long)ip.wangSums.size() + 1 : 0);
     return n;
 }
 long long stateDoubles(const ugfo_handle* h) {
@@ -1943,7 +2009,11 @@ int ugfo_state_save(ugfo_handle* h, double* buf, int64_t nDoubles) {
     p = std::copy(h->accS.begin(), h->accS.end(), p);
     p = std::copy(h->bacc.begin(), h->bacc.end(), p);
     if (h->decompOn) { p = std::copy(h->knAcc.begin(), h->knAcc.end(), p); p = std::copy(h->knFields.begin(), h->knFields.end(), p); }
-    for (const InflowPatch& ip : h->inflows) if (ip.pressure) p = std::copy(ip.faceVel.begin(), ip.faceVel.end(), p);
+    for (const InflowPatch& ip : h->inflows) {
+        if (!ip.pressure) continue;
+        p = std::copy(ip.faceVel.begin(), ip.faceVel.end(), p);
+        if (ip.wang) { p = std::copy(ip.wangSums.begin(), ip.wangSums.end(), p); *p++ = ip.wangSteps; }
+    }
     return (p - buf) == nDoubles ? 0 : fail(h, "internal: state size mismatch");
 }
 
@@ -1962,7 +2032,11 @@ int ugfo_state_load(ugfo_handle* h, const double* buf, int64_t nDoubles) {
     for (int32_t& v : h->collModelId) v = (int32_t)*p++;
     take(h->maxProb); take(h->qPrev); take(h->sPrev); take(h->acc); take(h->accS); take(h->bacc);
     if (h->decompOn) { take(h->knAcc); take(h->knFields); }
-    for (InflowPatch& ip : h->inflows) if (ip.pressure) take(ip.faceVel);
+    for (InflowPatch& ip : h->inflows) {
+        if (!ip.pressure) continue;
+        take(ip.faceVel);
+        if (ip.wang) { take(ip.wangSums); ip.wangSteps = *p++; }
+    }
     h->momValid = false;
     return 0;
 }

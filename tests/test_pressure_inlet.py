@@ -84,3 +84,88 @@ def test_gpu_pressure_inlet_with_collisions_and_weights(GpuCloud, OracleCloud):
         ig += g.counters()["inserted"]; ir += r.counters()["inserted"]
     assert abs(ig - ir) <= 0.02 * ir + 5
     assert np.allclose(g.inletVelocity("inlet"), r.inletVelocity("inlet"), rtol=0.2, atol=0.05 * np.abs(r.inletVelocity("inlet")).max())
+
+
+# ---- uniGasWangPressureInletPatch (…/uniGasWangPressureInletPatch/uniGasWangPressureInletPatch.C:54-281) ------------------
+def wang_case(p_in=None, **kw):
+    case = reservoir_case(p_in=p_in, **kw)
+    e = case.boundariesDict["uniGasGeneralBoundaries"][0]
+    pr = e.pop("uniGasLiouFangPressureInletPatchProperties")
+    pr.pop("theta")
+    e["boundaryModel"] = "uniGasWangPressureInletPatch"
+    e["uniGasWangPressureInletPatchProperties"] = pr
+    return case
+
+
+def test_oracle_wang_inlet_velocity_is_the_running_mean_then_pressure_corrected(OracleCloud):
+    """Collision-free gas at rest behind an inlet at the same pressure: up to step 100 the face velocity is the running
+    mass-weighted mean velocity of the parcels seen in the face's cell (checked against sums kept by the test); from step
+    101 the characteristic correction (p_cell - p_in) / (rho a) along the outward normal is added (:258-266)."""
+    case = wang_case(binary="noDSMCCollision")
+    cl = case.make_cloud(OracleCloud, parcelCapacity=6 * case.n_parcels)
+    m = case.mesh
+    pt = m.patches[m.patch_index("inlet")]
+    own = np.asarray(m.owner[pt.start:pt.start + pt.size])
+    S = m.face_areas[pt.start:pt.start + pt.size]
+    nout = S / np.sqrt((S * S).sum(1))[:, None]
+    mAr = case.meta["species"]["mass"]
+    n0, T0 = case.meta["n"], case.meta["T_inf"]
+    p_in = n0 * cases.kB * T0
+    expect0 = n0 * cases.most_probable_speed(T0, mAr) / (2 * np.sqrt(np.pi)) * np.sqrt((S * S).sum(1)).sum() * case.deltaT / cl.cfg.nParticle
+    N, SU, SQ = np.zeros(pt.size), np.zeros((pt.size, 3)), np.zeros((pt.size, 3))
+    for step in range(1, 106):
+        cl.evolve(1)
+        if step == 1:
+            ins = cl.counters()["inserted"]
+            assert abs(ins / expect0 - 1) < 4 / np.sqrt(expect0)        # n = p / (k T), velocity still zero (:107)
+        q = cl.parcels()
+        for i, c in enumerate(own):
+            sel = q["cell"] == c
+            N[i] += sel.sum(); SU[i] += q["U"][sel].sum(0); SQ[i] += (q["U"][sel] ** 2).sum(0)
+        v = cl.inletVelocity("inlet")
+        mean = SU / N[:, None]                                          # one species, one weight: momentum / mass = mean velocity
+        if step <= 100:
+            assert np.allclose(v, mean, rtol=1e-9, atol=1e-9 * np.abs(mean).max()), step
+        else:
+            V = m.cell_volumes[own]
+            rho = N * cl.cfg.nParticle * mAr / (V * step)
+            T = mAr / (3 * cases.kB) * ((SQ / N[:, None]).sum(1) - ((SU / N[:, None]) ** 2).sum(1))
+            a = np.sqrt(5.0 / 3.0 * cases.kB / mAr * T)
+            corr = (rho / mAr * cases.kB * T - p_in) / (rho * a)
+            assert np.allclose(v, mean + corr[:, None] * nout, rtol=1e-8, atol=1e-8 * np.abs(mean).max()), step
+            assert np.abs(corr).max() > 0
+    assert cl.counters()["stuck"] == 0
+
+
+def test_oracle_wang_inlet_state_survives_a_restart(tmp_path, OracleCloud):
+    case = wang_case(binary="noDSMCCollision")
+    a = case.make_cloud(OracleCloud, parcelCapacity=6 * case.n_parcels)
+    a.evolve(4)
+    a.writeTime(str(tmp_path), "4")
+    a.evolve(4)
+    b = OracleCloud(case.mesh, case.uniGasProperties, case.boundariesDict, case.deltaT, parcelCapacity=6 * case.n_parcels)
+    b.readTime(str(tmp_path), "4")
+    b.evolve(4)
+    assert np.array_equal(a.inletVelocity("inlet"), b.inletVelocity("inlet")) and np.abs(a.inletVelocity("inlet")).max() > 0
+    assert np.array_equal(a.parcels()["U"], b.parcels()["U"])
+
+
+@pytest.mark.gpu
+def test_gpu_wang_inlet_in_lockstep_with_oracle(GpuCloud, OracleCloud):
+    case = wang_case(binary="noDSMCCollision", p_in=None)
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        if e["boundaryModel"] == "uniGasDiffuseWallPatch":
+            e["boundaryModel"] = "uniGasSpecularWallPatch"
+    g = case.make_cloud(GpuCloud, parcelCapacity=4 * case.n_parcels)
+    r = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels)
+    for step in range(104):                                             # through the switch-on of the pressure correction
+        g.evolve(1); r.evolve(1)
+        if step % 8 == 0 or step > 98:
+            cg, cr = g.counters(), r.counters()
+            assert cg["inserted"] == cr["inserted"] and cg["deleted"] == cr["deleted"] and cg["nParcels"] == cr["nParcels"], step
+            assert np.allclose(g.inletVelocity("inlet"), r.inletVelocity("inlet"), rtol=1e-10, atol=1e-8), step
+    pg, pr = g.parcels(), r.parcels()
+    assert np.array_equal(pg["cell"], pr["cell"])
+    assert (np.abs(pg["U"] - pr["U"]) <= 1e-9 * np.abs(pr["U"]).max()).all(1).mean() > 0.999
+    sg, sr = g.state(), r.state()                                       # running sums and step count in the shared state layout
+    assert len(sg) == len(sr) and np.allclose(sg, sr, rtol=1e-9, atol=1e-9 * np.abs(sr).max())

@@ -155,9 +155,10 @@ class UniGasCloud:
                 self._check(self.api.set_patch_wall_fields(self._h, patch, bT.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
-            if word not in ("uniGasFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch"):
+            if word not in ("uniGasFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch",
+                            "uniGasWangPressureInletPatch"):
                 raise UgfError(f"general boundary model {word!r} is not supported (uniGasFreeStreamInflowPatch, "
-                               "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch)")
+                               "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch, uniGasWangPressureInletPatch)")
             patch = self.mesh.patch_index(entry["generalBoundaryProperties"]["patch"])
             pr = entry[word + "Properties"]
             if word == "uniGasFreeStreamInflowFieldPatch":
@@ -175,7 +176,7 @@ class UniGasCloud:
                 self._check(self.api.set_inflow_fields(self._h, patch, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), bn.ctypes.data_as(PD),
                                                        bT.ctypes.data_as(PD), bR.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
                 continue
-            if word == "uniGasLiouFangPressureInletPatch":  # …/uniGasLiouFangPressureInletPatch.C:54-103
+            if word in ("uniGasLiouFangPressureInletPatch", "uniGasWangPressureInletPatch"):  # …/uniGasLiouFangPressureInletPatch.C:54-103
                 pin = _capi.PressureInlet()
                 ids = [self.typeIdList.index(n) for n in pr["typeIds"]]
                 pin.nTypeIds = len(ids)
@@ -185,7 +186,11 @@ class UniGasCloud:
                 pin.inletPressure = float(pr["inletPressure"])
                 pin.inletTemperature = float(pr["inletTemperature"])
                 pin.theta = float(pr.get("theta", 1.0))
-                self._check(self.api.set_pressure_inlet(self._h, patch, C.byref(pin)))
+                if word == "uniGasWangPressureInletPatch":  # …/uniGasWangPressureInletPatch.C:54-116 (no theta)
+                    pin.theta = 1.0
+                    self._check(self.api.set_wang_pressure_inlet(self._h, patch, C.byref(pin)))
+                else:
+                    self._check(self.api.set_pressure_inlet(self._h, patch, C.byref(pin)))
                 continue
             inf = _capi.Inflow()
             ids = [self.typeIdList.index(n) for n in pr["typeIds"]]

@@ -39,6 +39,8 @@ struct InflowHost {
     int nSlots;
     long long maxInsert;
     bool pressureInlet = false;
+    bool wang = false;            // uniGasWangPressureInletPatch: running sums per face, step count
+    double wangSteps = 0.0;
     std::vector<double> accum1;   // per (face, species) slot: expected insertions per second at F_N = 1, CWF = 1
     std::vector<int> slotCell;    // owner cell of the slot's face
     std::vector<void*> owned;
@@ -1104,7 +1106,8 @@ static void recompute_inflow_bounds(ugf_handle* h) {
 // pin != null: pressure inlet (mole fractions, velocity per face, relaxation factor); fld != null: number density,
 // temperatures and velocity per face (uniGasFreeStreamInflowFieldPatch)
 struct InflowFields { const double *numDen, *transT, *rotT, *U; };  // numDen [nTypeIds][nFaces]
-static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in, const ugf_pressure_inlet* pin, const InflowFields* fld = nullptr) {
+static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in, const ugf_pressure_inlet* pin, const InflowFields* fld = nullptr,
+                             bool wang = false) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
     if (h->pointsHost.empty()) return fail(h, "inflow needs mesh points/facePoints");
@@ -1195,6 +1198,22 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
         f.owned.push_back(dVel);
         d.faceVel = dVel;
         f.pressureInlet = true;
+        if (wang) {  // …/uniGasWangPressureInletPatch.C:133-157: mixture molecular mass, gamma, R = k / m
+            double M = 0, cp = 0, cv = 0;
+            for (int i = 0; i < in->nTypeIds; ++i) {
+                const ugf_species& sp = h->spHost[in->typeIds[i]];
+                M += sp.mass * pin->moleFractions[i];
+                cp += (5.0 + sp.rotationalDoF) * pin->moleFractions[i];
+                cv += (3.0 + sp.rotationalDoF) * pin->moleFractions[i];
+            }
+            if (!(M > 0.0)) return fail(h, "mole fractions of the pressure inlet sum to zero");
+            double* dS;
+            if (dalloc(h, &dS, (size_t)WANG_NSUM * nF)) return 1;
+            CU(cudaMemsetAsync(dS, 0, sizeof(double) * WANG_NSUM * (size_t)nF, h->stream));
+            f.owned.push_back(dS);
+            d.wangSums = dS; d.wangP = pin->inletPressure; d.wangM = M; d.wangGammaR = (cp / cv) * (kB / M);
+            f.wang = true;
+        }
     }
     if (fld) {  // per-face tables: velocity [nF*3], number density per slot [nF*nTypeIds], (Ttr, Trot) [nF*2]
         std::vector<double> fN((size_t)f.nSlots), fT(2 * (size_t)nF);
@@ -1240,6 +1259,17 @@ int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inle
     return set_inflow_common(h, patch, &in, pin);
 }
 
+int ugf_set_wang_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* pin) {
+    if (!h || !pin) return 1;
+    if (pin->nTypeIds < 1 || pin->nTypeIds > UGF_MAX_SPECIES) return fail(h, "inflow typeIds out of range");
+    ugf_inflow in{};
+    in.nTypeIds = pin->nTypeIds;
+    const double n = pin->inletPressure / (kB * pin->inletTemperature);  // …/uniGasWangPressureInletPatch.C:107
+    for (int i = 0; i < pin->nTypeIds; ++i) { in.typeIds[i] = pin->typeIds[i]; in.numberDensities[i] = n; }
+    in.translationalTemperature = in.rotationalTemperature = in.vibrationalTemperature = in.electronicTemperature = pin->inletTemperature;
+    return set_inflow_common(h, patch, &in, pin, nullptr, true);
+}
+
 int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U) {
     if (!h) return 1;
     for (InflowHost& f : h->inflows)
@@ -1258,6 +1288,13 @@ static int update_inlet_velocities(ugf_handle* h) {
         const DevParams prm = h->prm;
         const InflowDev dev = f.dev;
         ParcelBuf P = h->buf[h->cur];
+        if (f.wang) {
+            f.wangSteps += 1.0;  // nTimeSteps_ (:133)
+            if (h->multi) wang_inlet_velocity_kernel<true><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff, h->dVol, f.wangSteps);
+            else wang_inlet_velocity_kernel<false><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff, h->dVol, f.wangSteps);
+            LAUNCHED();
+            continue;
+        }
         if (h->multi) inlet_velocity_kernel<true><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff);
         else inlet_velocity_kernel<false><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff);
         LAUNCHED();
@@ -1575,7 +1612,7 @@ namespace {
 constexpr double STATE_MAGIC = 1431783237.0;  // "UGFS"
 long long inlet_velocity_doubles(const ugf_handle* h) {
     long long n = 0;
-    for (const InflowHost& f : h->inflows) if (f.pressureInlet) n += 3LL * f.dev.nFaces;
+    for (const InflowHost& f : h->inflows) if (f.pressureInlet) n += 3LL * f.dev.nFaces + (f.wang ? (long long)WANG_NSUM * f.dev.nFaces + 1 : 0);
     return n;
 }
 long long state_doubles(const ugf_handle* h) {
@@ -1620,7 +1657,11 @@ int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles) {
     if (h->dAccS) { if (d2h(h->dAccS, nS * nC)) return 1; } else p += nS * nC;
     if (d2h(h->dBacc, UGF_NBM * nB)) return 1;
     if (h->decompOn) { if (d2h(h->dKnAcc, (KN_NACC + nS) * nC) || d2h(h->dKnK[h->knCur], 4 * nC)) return 1; }
-    for (const InflowHost& f : h->inflows) if (f.pressureInlet && d2h(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+    for (const InflowHost& f : h->inflows) {
+        if (!f.pressureInlet) continue;
+        if (d2h(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+        if (f.wang) { if (d2h(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; *p++ = f.wangSteps; }
+    }
     CU(cudaStreamSynchronize(h->stream));
     if (!h->dAccS) for (size_t c = 0; c < nC; ++c) accSAt[c] = accAt[c * NACC + 8];  // one species: nParcelsXnParticle = slot 8
     return 0;
@@ -1653,7 +1694,11 @@ int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
         h2d(h->dBacc, UGF_NBM * nB))
         return 1;
     if (h->decompOn) { if (h2d(h->dKnAcc, (KN_NACC + nS) * nC) || h2d(h->dKnK[h->knCur], 4 * nC)) return 1; }
-    for (InflowHost& f : h->inflows) if (f.pressureInlet && h2d(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+    for (InflowHost& f : h->inflows) {
+        if (!f.pressureInlet) continue;
+        if (h2d(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+        if (f.wang) { if (h2d(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; f.wangSteps = *p++; }
+    }
     CU(cudaStreamSynchronize(h->stream));  // ids and the caller's buffer may go away
     h->momValid = false;
     return 0;

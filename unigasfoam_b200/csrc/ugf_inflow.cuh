@@ -30,6 +30,10 @@ struct InflowDev {
     double* faceVel;                  // pressure inlets and field patches: inflow velocity per face [nFaces*3], else null (vel everywhere)
     double theta;                     // pressure inlets: relaxation of faceVel towards the cell mean velocity
     int pressure;                     // pressure inlet (speed ratio of the count formula capped at 5)
+    // uniGasWangPressureInletPatch: running sums per face [nFaces*WANG_NSUM] (else null), inlet pressure, mixture molecular
+    // mass, gamma * R of the mixture
+    double* wangSums;
+    double wangP, wangM, wangGammaR;
     const double* faceN;              // uniGasFreeStreamInflowFieldPatch: number density per slot [nFaces*nTypeIds], else null
     const double* faceT;              // uniGasFreeStreamInflowFieldPatch: translational, rotational temperature per face [nFaces*2], else null
     const int* faceBfi;
@@ -170,6 +174,54 @@ __global__ void __launch_bounds__(128) inlet_velocity_kernel(const __grid_consta
     for (int k = 0; k < 3; ++k) {
         const double nv = mass > 0 ? mom[k] / mass : 0.0;
         v[k] = f.theta * nv + (1.0 - f.theta) * v[k];
+    }
+}
+
+// uniGasWangPressureInletPatch::controlParcelsAfterCollisions (…/uniGasWangPressureInletPatch.C:131-281): running sums of the
+// parcels seen in each inlet face's cell since the start -> inlet velocity = mean momentum / mean mass, after 100 steps
+// corrected with the characteristic relation (p_cell - p_in) / (rho a) along the outward normal.  Sums per face: 0 parcels,
+// 1 mass, 2-4 momentum, 5-7 sum U^2 per component, 8-10 sum U per component (the last two only advance once more than one
+// parcel has been seen, :206-209).  One thread per face, cell-list order (= the oracle's: identical bits).
+constexpr int WANG_NSUM = 11;
+template <bool MULTI>
+__global__ void __launch_bounds__(128) wang_inlet_velocity_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ InflowDev f, ParcelBuf P,
+                                                                  const int* __restrict__ off, const double* __restrict__ vol, double nTimeSteps) {
+    const int face = blockIdx.x * blockDim.x + threadIdx.x;
+    if (face >= f.nFaces) return;
+    const int c = f.faceCell[face];
+    const double w = cell_fn(prm, c);
+    double mom[3] = {0, 0, 0}, mass = 0, nP = 0, sq[3] = {0, 0, 0}, su[3] = {0, 0, 0};
+    for (int j = off[c]; j < off[c + 1]; ++j) {
+        const int t = MULTI ? P.type[j] : 0;
+        bool mine = false;
+        for (int i = 0; i < f.nTypeIds; ++i) mine = mine || f.typeIds[i] == t;
+        if (!mine) continue;
+        const double m = w * prm.sp[t].mass;
+        const double U[3] = {P.ux[j], P.uy[j], P.uz[j]};
+        for (int k = 0; k < 3; ++k) { mom[k] += m * U[k]; sq[k] += U[k] * U[k]; su[k] += U[k]; }
+        mass += m;
+        nP += 1.0;
+    }
+    double* S = f.wangSums + (size_t)face * WANG_NSUM;
+    S[0] += nP; S[1] += mass;
+    for (int k = 0; k < 3; ++k) S[2 + k] += mom[k];
+    if (S[0] > 1) {
+        for (int k = 0; k < 3; ++k) { S[5 + k] += sq[k]; S[8 + k] += su[k]; }
+        const double massDensity = S[1] / (vol[c] * nTimeSteps);
+        const double numberDensity = massDensity / f.wangM;
+        double m2 = 0, mm = 0;
+        for (int k = 0; k < 3; ++k) { m2 += S[5 + k] / S[0]; const double a = S[8 + k] / S[0]; mm += a * a; }
+        double T = (0.5 * f.wangM) * (2.0 / (3.0 * kB)) * (m2 - mm);
+        if (T < VSMALL) T = 300.0;
+        const double pressure = numberDensity * kB * T;
+        const double sound = sqrt(f.wangGammaR * T);
+        const double* g = f.geom + (size_t)face * INFLOW_GEOM;  // g[1..3]: unit normal into the domain
+        double* v = f.faceVel + 3 * (size_t)face;
+        for (int k = 0; k < 3; ++k) v[k] = S[2 + k] / S[1];
+        if (nTimeSteps > 100) {
+            const double corr = (pressure - f.wangP) / (massDensity * sound);
+            for (int k = 0; k < 3; ++k) v[k] += corr * -g[1 + k];
+        }
     }
 }
 
