@@ -176,3 +176,30 @@ def test_oracle_sort_is_stable_counting_sort(OracleCloud):
     off, ids = cl.cellOccupancy()
     assert np.array_equal(ids, np.argsort(case.cell, kind="stable"))
     assert np.array_equal(np.diff(off), np.bincount(case.cell, minlength=case.mesh.n_cells))
+
+
+def test_weighted_partition_balances_parcels_not_cells():
+    """decomposeParDict `weightField uniGasRhoNMean_Ar` (hypersonicCylinder tutorial): on a cell-weighted-free cylinder case
+    the parcels pile up in the small cells near the body, equal-cell slabs are unbalanced, weighted slabs are not."""
+    from unigasfoam_b200 import cases, mesh as ugmesh
+    case = cases.cylinder(nr=96, ntheta=8, ppc=2)
+    m = case.mesh
+    x = m.cell_centres
+    w = np.exp(-5.0 * (np.hypot(x[:, 0], x[:, 1]) - case.meta["r0"]) / (case.meta["r1"] - case.meta["r0"]))  # a shock-layer-like pile-up
+    for ranks in (2, 4, 8):
+        plain = ugmesh.slab_partition(m, ranks, axis=0)
+        wtd = ugmesh.weighted_slab_partition(m, ranks, w, axis=0)
+        per = lambda part: np.bincount(part, weights=w, minlength=ranks)
+        assert set(wtd) == set(range(ranks)) and (np.diff(wtd.reshape(m.shape[::-1])[0, 0]) >= 0).all()   # contiguous slabs, none empty
+        assert ugmesh.load_imbalance(per(wtd)) < 0.5 * ugmesh.load_imbalance(per(plain))
+        assert ugmesh.load_imbalance(per(wtd)) < 25.0
+        subs = ugmesh.decompose(m, wtd, ranks)
+        assert sum(s.n_cells for s in subs) == m.n_cells
+    assert np.array_equal(ugmesh.weighted_slab_partition(m, 4, np.ones(m.n_cells), axis=0), ugmesh.slab_partition(m, 4, axis=0))
+    assert np.array_equal(ugmesh.weighted_slab_partition(m, 4, np.zeros(m.n_cells), axis=0), ugmesh.slab_partition(m, 4, axis=0))
+    assert ugmesh.load_imbalance([100, 100, 100, 100]) == 0.0 and ugmesh.load_imbalance([150, 50]) == 50.0
+    with pytest.raises(ValueError):
+        ugmesh.weighted_slab_partition(m, 4, np.ones(3))
+    # all the weight in one layer: every rank still gets cells
+    spike = np.zeros(m.n_cells); spike[:m.shape[0]:m.shape[0]] = 1.0
+    assert set(ugmesh.weighted_slab_partition(m, 8, spike, axis=0)) == set(range(8))

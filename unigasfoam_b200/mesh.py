@@ -416,6 +416,43 @@ def slab_partition(mesh, n_ranks, axis=0):
     return np.minimum((ijk[axis] * n_ranks) // n, n_ranks - 1).astype(np.int32)
 
 
+def weighted_slab_partition(mesh, n_ranks, weights, axis=0):
+    """Slabs along `axis` of a structured mesh cut at equal cumulative *weight* instead of equal cell count - the
+    decomposeParDict `weightField uniGasRhoNMean_<species>` the tutorials hint at (hypersonicCylinder/system/
+    decomposeParDict): with the time-averaged parcel count per cell as weight every rank gets the same number of parcels
+    (the 1 -> 8 target needs the partitioner to balance parcels, not cells).  Every rank keeps at least one
+    layer of cells."""
+    nx, ny, nz = mesh.shape
+    c = np.arange(nx * ny * nz)
+    ijk = (c % nx, (c // nx) % ny, c // (nx * ny))
+    n = mesh.shape[axis]
+    if n < n_ranks:
+        raise ValueError(f"{n} layers along axis {axis} cannot feed {n_ranks} ranks")
+    w = np.asarray(weights, float)
+    if w.shape != (mesh.n_cells,) or (w < 0).any():
+        raise ValueError("weights: one non-negative value per cell")
+    layer = np.bincount(ijk[axis], weights=w, minlength=n)
+    if layer.sum() <= 0:
+        return slab_partition(mesh, n_ranks, axis)
+    cum = np.cumsum(layer)
+    # layer i goes to the rank whose share of the total its mid-point falls into, then every rank is made non-empty
+    r = np.minimum(((cum - 0.5 * layer) / cum[-1] * n_ranks).astype(int), n_ranks - 1)
+    r = np.maximum.accumulate(r)
+    for k in range(n):                      # no rank skipped from the left ...
+        r[k] = min(r[k], (r[k - 1] + 1) if k else 0)
+    for k in range(n - 1, -1, -1):          # ... and none left empty at the right end
+        r[k] = max(r[k], n_ranks - (n - k))
+    return r[ijk[axis]].astype(np.int32)
+
+
+def load_imbalance(parcels_per_rank):
+    """uniGasDynamicLoadBalancing::calculate (U/dynamicLoadBalancing/uniGasDynamicLoadBalancing.C:48-68): the number the
+    reference prints as `Maximum imbalance` - max |N_rank - N/nRanks| / (N/nRanks) in per cent."""
+    n = np.asarray(parcels_per_rank, float)
+    ideal = n.sum() / len(n)
+    return 100.0 * np.abs(n - ideal).max() / ideal if ideal > 0 else 0.0
+
+
 def decompose(mesh, cell_rank, n_ranks):
     """Split `mesh` into n_ranks sub-meshes with processor patches (decomposePar stand-in).
 
