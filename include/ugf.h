@@ -302,6 +302,14 @@ int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inle
  * (p_cell - p_in) / (rho a) along the outward normal (:258-266).  `theta` of the struct is not used.  The running sums
  * and the step count travel in ugf_state_save. */
 int ugf_set_wang_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* inlet);
+/* uniGasLiouFangPressureOutletPatch on a patch (U/boundaries/derived/generalBoundaries/uniGasLiouFangPressureOutletPatch/
+ * uniGasLiouFangPressureOutletPatch.C:50-322).  The struct is read as: inletPressure = outletPressure, inletTemperature =
+ * the outlet temperature before the first evaluation (300 K in the reference, :74), theta unused.  After the collisions of
+ * every step the running sums of each outlet face's cell give density, temperature and pressure there and, with the
+ * characteristic relations of Liou & Fang (2000, eq 26), the number density, temperature and velocity the face inserts
+ * with at the next step.  The device caps a slot's insertions at the count of a gas at twice p_e / (k T_0), T_0 and a speed
+ * ratio of 5 (the bound the array capacity is checked against); reaching it is an error, not a silent clamp. */
+int ugf_set_pressure_outlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* outlet);
 /* Inlet velocity per face of a pressure inlet [patchSize*3] (diagnostic / restart). */
 int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U);
 /* addNewParcel over a whole initial configuration (U/clouds/uniGasCloud.C:260-290). Replaces the cloud. */

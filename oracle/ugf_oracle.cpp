@@ -150,6 +150,10 @@ struct InflowPatch {
     // uniGasWangPressureInletPatch (…/uniGasWangPressureInletPatch.C:54-281): running sums per face (0 parcels, 1 mass, 2-4
     // momentum, 5-7 sum U^2, 8-10 sum U), step count, inlet pressure, mixture molecular mass, gamma * R
     bool wang = false;
+    // uniGasLiouFangPressureOutletPatch (…/uniGasLiouFangPressureOutletPatch.C:50-322): the same sums; faceN [nFaces*nTypeIds]
+    // (face-major here), faceTtr = faceTrot and faceVel follow the flow; capN / capT: the device library's insertion bound
+    bool outlet = false;
+    double capN = 0.0, capT = 0.0;
     std::vector<double> wangSums;
     double wangSteps = 0.0, wangP = 0.0, wangM = 0.0, wangGammaR = 0.0;
 };
@@ -180,6 +184,7 @@ struct ugfo_handle {
     int64_t receivedStart = -1;
     std::vector<int32_t> occOff, occIds;  // cell occupancy CSR
     bool occValid = false, occIdentity = false;
+    bool outletBoundHit = false;  // a pressure-outlet face asked for more parcels than the device library's bound
     bool weightPending = false;   // a move happened since the last weighting() pass
     std::vector<int32_t> faceTrack;   // [nFaces] k + 1 of a tracked face, 0 otherwise (uniGasFaceTracker)
     std::vector<double> ft;           // [nTracked][nSpecies][UGF_NFT]
@@ -715,19 +720,27 @@ void doInflow(ugfo_handle& h) {
             const double m2 = std::sqrt(dot3(t2, t2));
             for (int k = 0; k < 3; ++k) t2[k] /= m2;
             const double* vel = (ip.pressure || ip.fields) ? &ip.faceVel[3 * (size_t)lf] : ip.in.velocity;
-            const double Ttr = ip.fields ? ip.faceTtr[lf] : ip.in.translationalTemperature;
-            const double Trot = ip.fields ? ip.faceTrot[lf] : ip.in.rotationalTemperature;
+            const bool perFace = ip.fields || ip.outlet;
+            const double Ttr = perFace ? ip.faceTtr[lf] : ip.in.translationalTemperature;
+            const double Trot = perFace ? ip.faceTrot[lf] : ip.in.rotationalTemperature;
             for (int iD = 0; iD < ip.in.nTypeIds; ++iD) {
                 const int typeId = ip.in.typeIds[iD];
                 const ugf_species& s = h.sp[typeId];
-                const double numDen = ip.fields ? ip.faceN[(size_t)iD * h.pSize[patch] + lf] : ip.in.numberDensities[iD];
+                const double numDen = ip.outlet ? ip.faceN[(size_t)lf * ip.in.nTypeIds + iD]
+                                      : ip.fields ? ip.faceN[(size_t)iD * h.pSize[patch] + lf] : ip.in.numberDensities[iD];
                 const double cmp = std::sqrt(2.0 * kB * Ttr / s.mass);
                 const double sCosFull = dot3(vel, n) / cmp;
                 const double sCos = (ip.pressure && sCosFull > 5.0) ? 5.0 : sCosFull;  // count only: the device library's insertion bound
                 // Bird eq 4.22 (uniGasGeneralBoundary.C:154-165); CWF of the face's cell, RWF = 1
-                const double accum = ip.molFrac[iD] * (fA * numDen * dt * cmp
-                                      * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
-                                     / (2.0 * sqrtPi * FNc(h, cellI));
+                double accum = ip.molFrac[iD] * (fA * numDen * dt * cmp
+                                * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
+                               / (2.0 * sqrtPi * FNc(h, cellI));
+                if (ip.outlet) {  // the device library's insertion bound; reaching it is an error there
+                    const double cmpCap = std::sqrt(2.0 * kB * ip.capT / s.mass);
+                    const double cap = ip.molFrac[iD] * (fA * ip.capN * dt * cmpCap * (std::exp(-25.0) + sqrtPi * 5.0 * (1 + std::erf(5.0))))
+                                       / (2.0 * sqrtPi * FNc(h, cellI));
+                    if (!(accum <= cap)) { accum = accum > cap ? cap : 0.0; h.outletBoundHit = true; }
+                }
                 Stream rc(h.cfg.seed, KIND_INFLOW, (uint32_t)iD, (uint32_t)h.step, (uint32_t)bfi, 0);
                 int nIns = std::max((int)accum, 0);
                 if ((accum - nIns) > rc.u01()) ++nIns;
@@ -1450,6 +1463,54 @@ void updateInletVelocities(ugfo_handle& h) {
     if (!h.occValid) buildOccupancy(h);
     for (InflowPatch& ip : h.inflows) {
         if (!ip.pressure) continue;
+        if (ip.outlet) {  // …/uniGasLiouFangPressureOutletPatch.C:144-322
+            ip.wangSteps += 1.0;
+            for (int lf = 0; lf < h.pSize[ip.patch]; ++lf) {
+                const int f = h.pStart[ip.patch] + lf;
+                const int c = h.owner[f];
+                const double w = FNc(h, c);
+                double mom[3] = {0, 0, 0}, mass = 0, nP = 0, sq[3] = {0, 0, 0}, su[3] = {0, 0, 0};
+                for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
+                    const Parcel& p = h.P[h.occIds[j]];
+                    bool mine = false;
+                    for (int i = 0; i < ip.in.nTypeIds; ++i) mine = mine || ip.in.typeIds[i] == p.typeId;
+                    if (mine) {
+                        const double m = w * h.sp[p.typeId].mass;
+                        for (int k = 0; k < 3; ++k) mom[k] += m * p.U[k];
+                        mass += m;
+                    }
+                    for (int k = 0; k < 3; ++k) { sq[k] += p.U[k] * p.U[k]; su[k] += p.U[k]; }
+                    nP += 1.0;
+                }
+                double* S = &ip.wangSums[(size_t)lf * WANG_NSUM];
+                S[0] += nP; S[1] += mass;
+                for (int k = 0; k < 3; ++k) S[2 + k] += mom[k];
+                if (S[0] > 1) {
+                    for (int k = 0; k < 3; ++k) { S[5 + k] += sq[k]; S[8 + k] += su[k]; }
+                    const double massDensity = S[1] / (h.vol[c] * ip.wangSteps);
+                    const double numberDensity = massDensity / ip.wangM;
+                    double m2 = 0, mm = 0;
+                    for (int k = 0; k < 3; ++k) { m2 += S[5 + k] / S[0]; const double a = S[8 + k] / S[0]; mm += a * a; }
+                    double T = (0.5 * ip.wangM) * (2.0 / (3.0 * kB)) * (m2 - mm);
+                    if (T < VSMALL) T = 300.0;
+                    const double pressure = numberDensity * kB * T;
+                    const double sound = std::sqrt(ip.wangGammaR * T);
+                    const double rhoE = massDensity + (ip.wangP - pressure) / (sound * sound);   // Liou & Fang 2000, eq 26
+                    const double* Sf = &h.Sf[3 * (size_t)f];
+                    const double fA = std::sqrt(dot3(Sf, Sf));
+                    double* v = &ip.faceVel[3 * (size_t)lf];
+                    for (int k = 0; k < 3; ++k) v[k] = S[1] > 0 ? S[2 + k] / S[1] : 0.0;
+                    if (massDensity > 0) {
+                        const double corr = (pressure - ip.wangP) / (massDensity * sound);
+                        for (int k = 0; k < 3; ++k) v[k] += corr * -(Sf[k] / -fA);
+                    }
+                    const double nE = rhoE > 0 ? rhoE / ip.wangM : 0.0;
+                    for (int i = 0; i < ip.in.nTypeIds; ++i) ip.faceN[(size_t)lf * ip.in.nTypeIds + i] = nE;
+                    if (rhoE > 0) { const double TE = ip.wangP / ((kB / ip.wangM) * rhoE); ip.faceTtr[lf] = TE; ip.faceTrot[lf] = TE; }
+                }
+            }
+            continue;
+        }
         if (ip.wang) {  // …/uniGasWangPressureInletPatch.C:131-281
             ip.wangSteps += 1.0;
             for (int lf = 0; lf < h.pSize[ip.patch]; ++lf) {
@@ -1859,6 +1920,23 @@ int ugfo_set_wang_pressure_inlet(ugfo_handle* h, int32_t patch, const ugf_pressu
     return 0;
 }
 
+int ugfo_set_pressure_outlet(ugfo_handle* h, int32_t patch, const ugf_pressure_inlet* pout) {
+    if (!(pout->inletPressure > 0.0) || !(pout->inletTemperature > 0.0)) return fail(h, "pressure outlet needs a positive pressure and initial temperature");
+    ugf_pressure_inlet q = *pout;
+    q.theta = 1.0;
+    const int rc = ugfo_set_wang_pressure_inlet(h, patch, &q);
+    if (rc) return rc;
+    InflowPatch& ip = h->inflows.back();
+    const size_t nF = (size_t)h->pSize[patch];
+    ip.outlet = true;
+    ip.capN = 2.0 * pout->inletPressure / (kB * pout->inletTemperature);
+    ip.capT = pout->inletTemperature;
+    ip.faceN.assign(nF * pout->nTypeIds, 0.0);
+    ip.faceTtr.assign(nF, pout->inletTemperature);
+    ip.faceTrot.assign(nF, pout->inletTemperature);
+    return 0;
+}
+
 int ugfo_download_inlet_velocity(ugfo_handle* h, int32_t patch, double* U) {
     for (const InflowPatch& ip : h->inflows)
         if (ip.patch == patch && ip.pressure) { std::copy(ip.faceVel.begin(), ip.faceVel.end(), U); return 0; }
@@ -1979,7 +2057,7 @@ namespace {
 constexpr double STATE_MAGIC = 1431783237.0;
 long long inletVelocityDoubles(const ugfo_handle* h) {
     long long n = 0;
-    for (const InflowPatch& ip : h->inflows) if (ip.pressure) n += (long long)ip.faceVel.size() + (ip.wang ? (long long)ip.wangSums.size() + 1 : 0);
+    for (const InflowPatch& ip : h->inflows) if (ip.pressure) n += (long long)ip.faceVel.size() + (ip.wang ? (long long)ip.wangSums.size() + 1 : 0) + (ip.outlet ? (long long)ip.faceN.size() + 2LL * (long long)ip.faceTtr.size() : 0);
     return n;
 }
 long long stateDoubles(const ugfo_handle* h) {
@@ -2013,6 +2091,10 @@ int ugfo_state_save(ugfo_handle* h, double* buf, int64_t nDoubles) {
         if (!ip.pressure) continue;
         p = std::copy(ip.faceVel.begin(), ip.faceVel.end(), p);
         if (ip.wang) { p = std::copy(ip.wangSums.begin(), ip.wangSums.end(), p); *p++ = ip.wangSteps; }
+        if (ip.outlet) {
+            p = std::copy(ip.faceN.begin(), ip.faceN.end(), p);
+            for (size_t f = 0; f < ip.faceTtr.size(); ++f) { *p++ = ip.faceTtr[f]; *p++ = ip.faceTrot[f]; }
+        }
     }
     return (p - buf) == nDoubles ? 0 : fail(h, "internal: state size mismatch");
 }
@@ -2036,6 +2118,10 @@ int ugfo_state_load(ugfo_handle* h, const double* buf, int64_t nDoubles) {
         if (!ip.pressure) continue;
         take(ip.faceVel);
         if (ip.wang) { take(ip.wangSums); ip.wangSteps = *p++; }
+        if (ip.outlet) {
+            take(ip.faceN);
+            for (size_t f = 0; f < ip.faceTtr.size(); ++f) { ip.faceTtr[f] = *p++; ip.faceTrot[f] = *p++; }
+        }
     }
     h->momValid = false;
     return 0;
@@ -2171,7 +2257,11 @@ int ugfo_migrate_inflight(ugfo_handle* h, int64_t** p) { *p = &h->inflight; retu
 
 int ugfo_stream(ugfo_handle*, void** s) { *s = nullptr; return 0; }
 
-int ugfo_counters_get(ugfo_handle* h, ugf_counters* out) { energyTotals(*h); *out = h->cnt; return 0; }
+int ugfo_counters_get(ugfo_handle* h, ugf_counters* out) {
+    if (h->outletBoundHit)
+        return fail(h, "pressure outlet: a face asked for more parcels than the insertion bound (outlet pressure at the initial outlet temperature, speed ratio 5) allows");
+    energyTotals(*h); *out = h->cnt; return 0;
+}
 
 int ugfo_num_parcels(ugfo_handle* h, int64_t* n) {
     int64_t k = 0;

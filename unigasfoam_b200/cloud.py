@@ -156,9 +156,10 @@ class UniGasCloud:
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
             if word not in ("uniGasFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch",
-                            "uniGasWangPressureInletPatch"):
+                            "uniGasWangPressureInletPatch", "uniGasLiouFangPressureOutletPatch"):
                 raise UgfError(f"general boundary model {word!r} is not supported (uniGasFreeStreamInflowPatch, "
-                               "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch, uniGasWangPressureInletPatch)")
+                               "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch, uniGasWangPressureInletPatch, "
+                               "uniGasLiouFangPressureOutletPatch)")
             patch = self.mesh.patch_index(entry["generalBoundaryProperties"]["patch"])
             pr = entry[word + "Properties"]
             if word == "uniGasFreeStreamInflowFieldPatch":
@@ -175,6 +176,18 @@ class UniGasCloud:
                 PD = C.POINTER(C.c_double)
                 self._check(self.api.set_inflow_fields(self._h, patch, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), bn.ctypes.data_as(PD),
                                                        bT.ctypes.data_as(PD), bR.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
+                continue
+            if word == "uniGasLiouFangPressureOutletPatch":  # …/uniGasLiouFangPressureOutletPatch.C:50-118
+                pout = _capi.PressureInlet()
+                ids = [self.typeIdList.index(n) for n in pr["typeIds"]]
+                pout.nTypeIds = len(ids)
+                for i, t in enumerate(ids):
+                    pout.typeIds[i] = t
+                    pout.moleFractions[i] = float(pr["moleFractions"][self.typeIdList[t]])
+                pout.inletPressure = float(pr["outletPressure"])
+                pout.inletTemperature = float(pr.get("initialOutletTemperature", 300.0))  # outletTemperature_ starts at 300 K (:74)
+                pout.theta = 1.0
+                self._check(self.api.set_pressure_outlet(self._h, patch, C.byref(pout)))
                 continue
             if word in ("uniGasLiouFangPressureInletPatch", "uniGasWangPressureInletPatch"):  # …/uniGasLiouFangPressureInletPatch.C:54-103
                 pin = _capi.PressureInlet()

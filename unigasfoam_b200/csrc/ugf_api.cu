@@ -39,7 +39,8 @@ struct InflowHost {
     int nSlots;
     long long maxInsert;
     bool pressureInlet = false;
-    bool wang = false;            // uniGasWangPressureInletPatch: running sums per face, step count
+    bool wang = false;            // uniGasWangPressureInletPatch / pressure outlet: running sums per face, step count
+    bool outlet = false;          // uniGasLiouFangPressureOutletPatch: number density and temperature per face follow the flow
     double wangSteps = 0.0;
     std::vector<double> accum1;   // per (face, species) slot: expected insertions per second at F_N = 1, CWF = 1
     std::vector<int> slotCell;    // owner cell of the slot's face
@@ -235,6 +236,7 @@ int check_device_error(ugf_handle* h) {
     if (e == 3) return fail(h, "migration slot overflow: more parcels crossed a processor patch than slotCapacity");
     if (e == 4) return fail(h, "corrupt migration slot header");
     if (e == 5) return fail(h, "timed out waiting for a neighbour's migration slot (peer-memory transfer)");
+    if (e == 6) return fail(h, "pressure outlet: a face asked for more parcels than the insertion bound (outlet pressure at the initial outlet temperature, speed ratio 5) allows");
     if (e) return fail(h, "device error flag " + std::to_string(e));
     return 0;
 }
@@ -1107,7 +1109,7 @@ static void recompute_inflow_bounds(ugf_handle* h) {
 // temperatures and velocity per face (uniGasFreeStreamInflowFieldPatch)
 struct InflowFields { const double *numDen, *transT, *rotT, *U; };  // numDen [nTypeIds][nFaces]
 static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in, const ugf_pressure_inlet* pin, const InflowFields* fld = nullptr,
-                             bool wang = false) {
+                             bool wang = false, bool outlet = false) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
     if (h->pointsHost.empty()) return fail(h, "inflow needs mesh points/facePoints");
@@ -1214,6 +1216,17 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
             d.wangSums = dS; d.wangP = pin->inletPressure; d.wangM = M; d.wangGammaR = (cp / cv) * (kB / M);
             f.wang = true;
         }
+        if (outlet) {  // outletNumberDensity_ 0, outletTemperature_ 300 K, outletVelocity_ 0 at the start (…PressureOutletPatch.C:61-74)
+            std::vector<double> fT(2 * (size_t)nF, pin->inletTemperature);
+            double *dN, *dT;
+            if (dalloc(h, &dN, (size_t)f.nSlots) || dalloc(h, &dT, fT.size())) return 1;
+            CU(cudaMemsetAsync(dN, 0, sizeof(double) * (size_t)f.nSlots, h->stream));
+            f.owned.push_back(dN); f.owned.push_back(dT);
+            if (upload(h, dT, fT.data(), fT.size())) return 1;
+            CU(cudaStreamSynchronize(h->stream));
+            d.faceN = dN; d.faceT = dT; d.outlet = 1; d.capN = in->numberDensities[0]; d.capT = pin->inletTemperature; d.err = h->dErr;
+            f.outlet = true;
+        }
     }
     if (fld) {  // per-face tables: velocity [nF*3], number density per slot [nF*nTypeIds], (Ttr, Trot) [nF*2]
         std::vector<double> fN((size_t)f.nSlots), fT(2 * (size_t)nF);
@@ -1270,6 +1283,18 @@ int ugf_set_wang_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure
     return set_inflow_common(h, patch, &in, pin, nullptr, true);
 }
 
+int ugf_set_pressure_outlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* pout) {
+    if (!h || !pout) return 1;
+    if (pout->nTypeIds < 1 || pout->nTypeIds > UGF_MAX_SPECIES) return fail(h, "inflow typeIds out of range");
+    if (!(pout->inletPressure > 0.0) || !(pout->inletTemperature > 0.0)) return fail(h, "pressure outlet needs a positive pressure and initial temperature");
+    ugf_inflow in{};
+    in.nTypeIds = pout->nTypeIds;
+    const double n = 2.0 * pout->inletPressure / (kB * pout->inletTemperature);  // the bound's number density: twice p_e / (k T_0)
+    for (int i = 0; i < pout->nTypeIds; ++i) { in.typeIds[i] = pout->typeIds[i]; in.numberDensities[i] = n; }
+    in.translationalTemperature = in.rotationalTemperature = in.vibrationalTemperature = in.electronicTemperature = pout->inletTemperature;
+    return set_inflow_common(h, patch, &in, pout, nullptr, true, true);
+}
+
 int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U) {
     if (!h) return 1;
     for (InflowHost& f : h->inflows)
@@ -1288,6 +1313,13 @@ static int update_inlet_velocities(ugf_handle* h) {
         const DevParams prm = h->prm;
         const InflowDev dev = f.dev;
         ParcelBuf P = h->buf[h->cur];
+        if (f.outlet) {
+            f.wangSteps += 1.0;  // nTimeSteps_ (…PressureOutletPatch.C:146)
+            if (h->multi) outlet_state_kernel<true><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff, h->dVol, f.wangSteps);
+            else outlet_state_kernel<false><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff, h->dVol, f.wangSteps);
+            LAUNCHED();
+            continue;
+        }
         if (f.wang) {
             f.wangSteps += 1.0;  // nTimeSteps_ (:133)
             if (h->multi) wang_inlet_velocity_kernel<true><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff, h->dVol, f.wangSteps);
@@ -1612,7 +1644,7 @@ namespace {
 constexpr double STATE_MAGIC = 1431783237.0;  // "UGFS"
 long long inlet_velocity_doubles(const ugf_handle* h) {
     long long n = 0;
-    for (const InflowHost& f : h->inflows) if (f.pressureInlet) n += 3LL * f.dev.nFaces + (f.wang ? (long long)WANG_NSUM * f.dev.nFaces + 1 : 0);
+    for (const InflowHost& f : h->inflows) if (f.pressureInlet) n += 3LL * f.dev.nFaces + (f.wang ? (long long)WANG_NSUM * f.dev.nFaces + 1 : 0) + (f.outlet ? (long long)f.nSlots + 2LL * f.dev.nFaces : 0);
     return n;
 }
 long long state_doubles(const ugf_handle* h) {
@@ -1661,6 +1693,7 @@ int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles) {
         if (!f.pressureInlet) continue;
         if (d2h(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
         if (f.wang) { if (d2h(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; *p++ = f.wangSteps; }
+        if (f.outlet && (d2h(f.dev.faceN, (size_t)f.nSlots) || d2h(f.dev.faceT, 2 * (size_t)f.dev.nFaces))) return 1;
     }
     CU(cudaStreamSynchronize(h->stream));
     if (!h->dAccS) for (size_t c = 0; c < nC; ++c) accSAt[c] = accAt[c * NACC + 8];  // one species: nParcelsXnParticle = slot 8
@@ -1698,6 +1731,7 @@ int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
         if (!f.pressureInlet) continue;
         if (h2d(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
         if (f.wang) { if (h2d(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; f.wangSteps = *p++; }
+        if (f.outlet && (h2d(f.dev.faceN, (size_t)f.nSlots) || h2d(f.dev.faceT, 2 * (size_t)f.dev.nFaces))) return 1;
     }
     CU(cudaStreamSynchronize(h->stream));  // ids and the caller's buffer may go away
     h->momValid = false;

@@ -34,8 +34,14 @@ struct InflowDev {
     // mass, gamma * R of the mixture
     double* wangSums;
     double wangP, wangM, wangGammaR;
-    const double* faceN;              // uniGasFreeStreamInflowFieldPatch: number density per slot [nFaces*nTypeIds], else null
-    const double* faceT;              // uniGasFreeStreamInflowFieldPatch: translational, rotational temperature per face [nFaces*2], else null
+    double* faceN;                    // field patch / pressure outlet: number density per slot [nFaces*nTypeIds], else null
+    double* faceT;                    // field patch / pressure outlet: translational, rotational temperature per face [nFaces*2], else null
+    // uniGasLiouFangPressureOutletPatch: faceN / faceT / faceVel follow the flow (outlet_state_kernel); the count of a slot is
+    // capped at the count a gas at (capN, capT) with a speed ratio of 5 would give - the host's insertion bound - and a hit
+    // raises device error 6
+    int outlet;
+    double capN, capT;
+    int* err;
     const int* faceBfi;
     const int* faceCell;
     const double* geom;
@@ -59,8 +65,14 @@ __global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant
     double sCos = (vel[0] * g[1] + vel[1] * g[2] + vel[2] * g[3]) / cmp;
     if (f.pressure && sCos > 5.0) sCos = 5.0;  // the host's insertion bound assumes speed ratios <= 5 on pressure inlets
     const double sqrtPi = sqrt(PI);
-    const double accum = f.molFrac[iD] * (fA * numDen * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
-                         / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));  // uniGasGeneralBoundary.C:154-165
+    double accum = f.molFrac[iD] * (fA * numDen * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
+                   / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));  // uniGasGeneralBoundary.C:154-165
+    if (f.outlet) {
+        const double cmpCap = sqrt(2.0 * kB * f.capT / s.mass);
+        const double cap = f.molFrac[iD] * (fA * f.capN * prm.deltaT * cmpCap * (exp(-25.0) + sqrtPi * 5.0 * (1 + erf(5.0))))
+                           / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));
+        if (!(accum <= cap)) { accum = accum > cap ? cap : 0.0; atomicExch(f.err, 6); }
+    }
     Stream rc(prm.seed, KIND_INFLOW, (uint32_t)iD, step, (uint32_t)f.faceBfi[face], 0);
     int nIns = max((int)accum, 0);
     if ((accum - nIns) > rc.u01()) ++nIns;
@@ -221,6 +233,62 @@ __global__ void __launch_bounds__(128) wang_inlet_velocity_kernel(const __grid_c
         if (nTimeSteps > 100) {
             const double corr = (pressure - f.wangP) / (massDensity * sound);
             for (int k = 0; k < 3; ++k) v[k] += corr * -g[1 + k];
+        }
+    }
+}
+
+// uniGasLiouFangPressureOutletPatch::controlParcelsAfterCollisions (…/uniGasLiouFangPressureOutletPatch.C:144-322): the same
+// running sums as the Wang inlet, except that the parcel count and the velocity moments run over all species (:196-207);
+// from them the cell's density, temperature and pressure, then (Liou & Fang 2000, eq 26) the outlet state
+//   rho_e = rho + (p_e - p) / a^2,  n_e = rho_e / m,  T_e = p_e / (R rho_e),  u_e = <m u> / <m> + (p - p_e) / (rho a) n_out.
+// A non-positive rho_e (the reference would divide by it) switches the face's insertion off for the step.
+template <bool MULTI>
+__global__ void __launch_bounds__(128) outlet_state_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ InflowDev f, ParcelBuf P,
+                                                           const int* __restrict__ off, const double* __restrict__ vol, double nTimeSteps) {
+    const int face = blockIdx.x * blockDim.x + threadIdx.x;
+    if (face >= f.nFaces) return;
+    const int c = f.faceCell[face];
+    const double w = cell_fn(prm, c);
+    double mom[3] = {0, 0, 0}, mass = 0, nP = 0, sq[3] = {0, 0, 0}, su[3] = {0, 0, 0};
+    for (int j = off[c]; j < off[c + 1]; ++j) {
+        const int t = MULTI ? P.type[j] : 0;
+        bool mine = false;
+        for (int i = 0; i < f.nTypeIds; ++i) mine = mine || f.typeIds[i] == t;
+        const double U[3] = {P.ux[j], P.uy[j], P.uz[j]};
+        if (mine) {
+            const double m = w * prm.sp[t].mass;
+            for (int k = 0; k < 3; ++k) mom[k] += m * U[k];
+            mass += m;
+        }
+        for (int k = 0; k < 3; ++k) { sq[k] += U[k] * U[k]; su[k] += U[k]; }
+        nP += 1.0;
+    }
+    double* S = f.wangSums + (size_t)face * WANG_NSUM;
+    S[0] += nP; S[1] += mass;
+    for (int k = 0; k < 3; ++k) S[2 + k] += mom[k];
+    if (S[0] > 1) {
+        for (int k = 0; k < 3; ++k) { S[5 + k] += sq[k]; S[8 + k] += su[k]; }
+        const double massDensity = S[1] / (vol[c] * nTimeSteps);
+        const double numberDensity = massDensity / f.wangM;
+        double m2 = 0, mm = 0;
+        for (int k = 0; k < 3; ++k) { m2 += S[5 + k] / S[0]; const double a = S[8 + k] / S[0]; mm += a * a; }
+        double T = (0.5 * f.wangM) * (2.0 / (3.0 * kB)) * (m2 - mm);
+        if (T < VSMALL) T = 300.0;
+        const double pressure = numberDensity * kB * T;
+        const double sound = sqrt(f.wangGammaR * T);
+        const double rhoE = massDensity + (f.wangP - pressure) / (sound * sound);
+        const double* g = f.geom + (size_t)face * INFLOW_GEOM;  // g[1..3]: unit normal into the domain
+        double* v = f.faceVel + 3 * (size_t)face;
+        for (int k = 0; k < 3; ++k) v[k] = S[1] > 0 ? S[2 + k] / S[1] : 0.0;
+        if (massDensity > 0) {
+            const double corr = (pressure - f.wangP) / (massDensity * sound);
+            for (int k = 0; k < 3; ++k) v[k] += corr * -g[1 + k];
+        }
+        const double nE = rhoE > 0 ? rhoE / f.wangM : 0.0;
+        for (int i = 0; i < f.nTypeIds; ++i) f.faceN[(size_t)face * f.nTypeIds + i] = nE;
+        if (rhoE > 0) {
+            const double TE = f.wangP / ((kB / f.wangM) * rhoE);
+            f.faceT[2 * (size_t)face] = TE; f.faceT[2 * (size_t)face + 1] = TE;
         }
     }
 }
