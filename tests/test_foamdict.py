@@ -262,3 +262,27 @@ def test_mesh_field_fill_from_a_time_directory(tmp_path, OracleCloud):
     cl = case.make_cloud(OracleCloud, parcelCapacity=3 * case.n_parcels)
     cl.evolve(3)
     assert cl.counters()["stuck"] == 0
+
+
+def test_decompose_par_dict_to_partition():
+    """system/decomposeParDict of the hypersonicCylinder tutorial (10 subdomains, scotch, weightField commented out) ->
+    a cell-to-rank map; with the weightField switched on the slabs are cut at equal weight."""
+    import numpy as np
+    from unigasfoam_b200 import mesh as ugmesh
+    d = foamdict.read(os.path.join(GOLD, "hypersonicCylinder", "system", "decomposeParDict"))
+    assert d["numberOfSubdomains"] == 10 and d["method"] == "scotch" and "weightField" not in d
+    m = ugmesh.half_annulus_mesh(40, 20, 0.1, 0.5, 0.01, grading=4.0)
+    part, n = foamdict.partition_from_dict(m, d)
+    assert n == 10 and set(part) == set(range(10)) and np.array_equal(part, ugmesh.slab_partition(m, 10, 0))
+    w = np.exp(-8.0 * (np.hypot(m.cell_centres[:, 0], m.cell_centres[:, 1]) - 0.1))
+    with pytest.raises(foamdict.FoamDictError, match="weightField"):
+        foamdict.partition_from_dict(m, dict(d, weightField="uniGasRhoNMean_Ar"))
+    wp, _ = foamdict.partition_from_dict(m, dict(d, weightField="uniGasRhoNMean_Ar"), weights=w)
+    per = lambda p: np.bincount(p, weights=w, minlength=10)
+    assert ugmesh.load_imbalance(per(wp)) < ugmesh.load_imbalance(per(part))
+    simple = {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [1, 4, 1]}}
+    sp, _ = foamdict.partition_from_dict(m, simple)
+    assert np.array_equal(sp, ugmesh.slab_partition(m, 4, 1))
+    with pytest.raises(foamdict.FoamDictError, match="one direction"):
+        foamdict.partition_from_dict(m, {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [2, 2, 1]}})
+    assert sum(s.n_cells for s in ugmesh.decompose(m, wp, 10)) == m.n_cells

@@ -188,3 +188,25 @@ def vol_field_names(fieldPropertiesDict, averaging_only=False):
         if "field" in pr and (not averaging_only or pr.get("averagingAcrossManyRuns", False)):
             out.append(str(pr["field"]))
     return out
+
+
+def partition_from_dict(mesh, decomposeParDict, weights=None, axis=0):
+    """system/decomposeParDict -> cell-to-rank map for `mesh.decompose`.  `numberOfSubdomains` ranks; `method simple` with
+    `simpleCoeffs { n (nx ny nz); }` cuts along the direction with more than one part (one direction only here);
+    `scotch` / `hierarchical` / anything else falls back to slabs along `axis`.  With `weightField <name>` the caller
+    passes that field's cell values as `weights` and the slabs are cut at equal weight (the commented
+    `weightField uniGasRhoNMean_Ar` of the hypersonicCylinder tutorial).  -> (cell_rank, n_ranks)"""
+    from . import mesh as ugmesh
+    n = int(decomposeParDict["numberOfSubdomains"])
+    if decomposeParDict.get("method") == "simple":
+        parts = [int(v) for v in (decomposeParDict.get("simpleCoeffs") or decomposeParDict.get("coeffs") or {}).get("n", [n, 1, 1])]
+        split = [i for i, k in enumerate(parts) if k > 1]
+        if len(split) > 1 or (split and parts[split[0]] != n):
+            raise FoamDictError(f"simpleCoeffs n {parts}: only a split along one direction into numberOfSubdomains parts is supported")
+        if split:
+            axis = split[0]
+    if "weightField" in decomposeParDict:
+        if weights is None:
+            raise FoamDictError(f"decomposeParDict names weightField {decomposeParDict['weightField']}: pass its cell values as `weights`")
+        return ugmesh.weighted_slab_partition(mesh, n, weights, axis), n
+    return ugmesh.slab_partition(mesh, n, axis), n
