@@ -286,3 +286,40 @@ def test_decompose_par_dict_to_partition():
     with pytest.raises(foamdict.FoamDictError, match="one direction"):
         foamdict.partition_from_dict(m, {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [2, 2, 1]}})
     assert sum(s.n_cells for s in ugmesh.decompose(m, wp, 10)) == m.n_cells
+
+
+def test_oracle_solver_loop_writes_what_the_reference_leaves(tmp_path, OracleCloud):
+    """unigasfoam_b200.solver.run_case: the uniGasFoam time loop on the tutorial's own dictionaries - write times from
+    controlDict, fields / accumulator dictionaries per fieldPropertiesDict entry, restart from latestTime."""
+    from unigasfoam_b200 import foamfile, solver
+    m = ugmesh.half_annulus_mesh(12, 16, 0.5 * 0.3048, 2.0 * 0.3048, 0.1 * 0.3048, 5.0)
+    m.meta_axis_aligned = False
+    ov = {"collisionProperties": {"macroInterpolation": False}, "adaptiveProperties": {"maxSubCellSizeMFPRatio": 8.0, "adaptationInterval": 4}}
+    out = str(tmp_path)
+    # endTime in seconds: ten steps of the (adapted) time step are not known beforehand, so drive by writeControl timeStep and stop by time
+    case0, _ = cases.from_case_dir(CASE, m, overrides=ov, particles_per_cell=8)
+    end = 10.5 * case0.deltaT
+    lines = []
+    r = solver.run_case(CASE, m, OracleCloud, out_dir=out, overrides=ov, particles_per_cell=8,
+                        control={"writeControl": "timeStep", "writeInterval": 5, "endTime": end, "startFrom": "startTime"}, log=lines.append)
+    assert r["steps"] >= 10 and len(r["written"]) >= 2 and len(lines) == len(r["written"]) and "Number of particles" in lines[0]
+    first = os.path.join(out, r["written"][0])
+    have = set(os.listdir(first))
+    assert {"lagrangian", "uniform", "uniGasSigmaTcRMax", "uniGasCellWeightFactor", "uniGasSubCellLevels", "uniGasCollisionModelId",
+            "rhoN_Ar", "p_Ar", "UMean_Ar", "translationalT_Ar", "surfaceHeatTransfer_Ar", "fD_Ar", "variableHardSphereMeanFreePath_Ar",
+            "densityError_Ar"} <= have
+    assert {"time", "volFieldsMethod_Ar"} <= set(os.listdir(os.path.join(first, "uniform")))
+    rho = foamfile.read_vol_field(os.path.join(first, "rhoN_Ar"))
+    assert rho["dimensions"] == [0, -3, 0, 0, 0, 0, 0] and np.median(foamfile.expand_internal(rho, m.n_cells)) > 1e20
+    # resetAtOutput on (until 2e-3 s): the fields of a write average over the steps since the previous one, and the
+    # accumulator dictionary, written after the reset (uniGasVolFields.C:1433-1507), starts again from zero
+    from unigasfoam_b200 import volfields_io
+    d2 = volfields_io.read_volfields_method(os.path.join(out, r["written"][1], "uniform", "volFieldsMethod_Ar"))
+    assert d2["nTimeSteps"] == 0 and not d2["rhoNMean"].any()
+    # startFrom latestTime: the run picks up the last time directory and goes on from its step index
+    n_before = r["cloud"].counters()["step"]
+    r2 = solver.run_case(CASE, m, OracleCloud, out_dir=out, overrides=ov, particles_per_cell=8,
+                         control={"writeControl": "timeStep", "writeInterval": 5, "endTime": r["time"] + 3.5 * r["cloud"].cfg.deltaT,
+                                  "startFrom": "latestTime"})
+    assert r2["steps"] in (3, 4, 5) and r2["cloud"].counters()["step"] == n_before + r2["steps"]
+    assert solver.latest_time(out)[1] == r2["written"][-1] and solver.time_name(0.0) == "0" and solver.time_name(5e-4) == "0.0005"
