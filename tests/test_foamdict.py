@@ -323,3 +323,24 @@ def test_oracle_solver_loop_writes_what_the_reference_leaves(tmp_path, OracleClo
                                   "startFrom": "latestTime"})
     assert r2["steps"] in (3, 4, 5) and r2["cloud"].counters()["step"] == n_before + r2["steps"]
     assert solver.latest_time(out)[1] == r2["written"][-1] and solver.time_name(0.0) == "0" and solver.time_name(5e-4) == "0.0005"
+
+
+@pytest.mark.gpu
+def test_gpu_solver_loop_on_the_tutorial_case(tmp_path, GpuCloud):
+    """The same loop on libugf: the tutorial case runs from its dictionaries to a write time and restarts from it."""
+    from unigasfoam_b200 import foamfile, solver
+    m = ugmesh.half_annulus_mesh(12, 16, 0.5 * 0.3048, 2.0 * 0.3048, 0.1 * 0.3048, 5.0)
+    m.meta_axis_aligned = False
+    ov = {"collisionProperties": {"macroInterpolation": False}, "adaptiveProperties": {"maxSubCellSizeMFPRatio": 8.0, "adaptationInterval": 4}}
+    case0, _ = cases.from_case_dir(CASE, m, overrides=ov, particles_per_cell=8)
+    ctl = {"writeControl": "timeStep", "writeInterval": 5, "endTime": 10.5 * case0.deltaT, "startFrom": "startTime"}
+    r = solver.run_case(CASE, m, GpuCloud, out_dir=str(tmp_path), overrides=ov, particles_per_cell=8, control=ctl)
+    assert r["steps"] >= 10 and len(r["written"]) >= 2 and r["cloud"].counters()["stuck"] == 0
+    last = os.path.join(str(tmp_path), r["written"][-1])
+    rho = foamfile.expand_internal(foamfile.read_vol_field(os.path.join(last, "rhoN_Ar")), m.n_cells)
+    assert np.isfinite(rho).all() and np.median(rho) > 1e20
+    assert os.path.exists(os.path.join(last, "uniform", "volFieldsMethod_Ar")) and os.path.exists(os.path.join(last, "lagrangian", "uniGas", "positions"))
+    n_before = r["cloud"].counters()["step"]
+    r2 = solver.run_case(CASE, m, GpuCloud, out_dir=str(tmp_path), overrides=ov, particles_per_cell=8,
+                         control=dict(ctl, startFrom="latestTime", endTime=r["time"] + 3.5 * r["cloud"].cfg.deltaT))
+    assert r2["cloud"].counters()["step"] == n_before + r2["steps"] and r2["steps"] >= 3
