@@ -135,3 +135,57 @@ def test_gpu_uniform_fields_equal_the_free_stream_patch(GpuCloud):
     pa, pb = a.parcels(), b.parcels()
     for k in ("cell", "position", "U", "ERot"):
         assert np.array_equal(pa[k], pb[k]), k
+
+
+def test_field_patch_values_come_from_the_time_directory(tmp_path, OracleCloud):
+    """The reference's *FieldPatch models read boundaryT / boundaryU / boundaryNumberDensity_<species> / boundaryTransT /
+    boundaryRotT from the start time directory: written there as volFields, picked up by cases.field_patch_values, the
+    run equals the one with the values given in the dictionary entry."""
+    from unigasfoam_b200 import foamfile
+    base = cases.cylinder(nr=8, ntheta=16, ppc=20, binary="noDSMCCollision", seed=12)
+    n, T, U = _varying(base)
+    direct = field_case(base, n=n, T=T, U=U)
+    for e in direct.boundariesDict["uniGasPatchBoundaries"]:
+        if e["boundaryModel"] == "uniGasDiffuseWallPatch":
+            nW = base.mesh.patches[base.mesh.patch_index(e["patchBoundaryProperties"]["patch"])].size
+            e["boundaryModel"] = "uniGasDiffuseWallFieldPatch"
+            e["uniGasDiffuseWallFieldPatchProperties"] = {}
+            e["boundaryT"] = np.linspace(300.0, 600.0, nW)
+            e["boundaryU"] = np.zeros((nW, 3))
+    m = base.mesh
+    # the same values as volFields in <case>/0
+    t0 = tmp_path / "0"
+    t0.mkdir()
+    g = direct.boundariesDict["uniGasGeneralBoundaries"][0]
+    w = [e for e in direct.boundariesDict["uniGasPatchBoundaries"] if e["boundaryModel"] == "uniGasDiffuseWallFieldPatch"][0]
+    inlet, wall = g["generalBoundaryProperties"]["patch"], w["patchBoundaryProperties"]["patch"]
+
+    def write(name, dims, per_patch, vector=False):
+        patches = {}
+        for p in m.patches:
+            if p.kind not in ("wall", "patch"):
+                patches[p.name] = p.kind
+            else:
+                patches[p.name] = {"type": "calculated", "value": per_patch.get(p.name, np.zeros(3) if vector else 0.0)}
+        zero = np.zeros((m.n_cells, 3)) if vector else np.zeros(m.n_cells)
+        foamfile.write_vol_field(str(t0 / name), "0", dims, zero, patches, vector=vector)
+
+    write("boundaryT", [0, 0, 0, 1, 0, 0, 0], {wall: w["boundaryT"]})
+    write("boundaryU", [0, 1, -1, 0, 0, 0, 0], {wall: w["boundaryU"], inlet: g["boundaryU"]}, vector=True)
+    write("boundaryNumberDensity_Ar", [0, -3, 0, 0, 0, 0, 0], {inlet: g["boundaryNumberDensity"]["Ar"]})
+    write("boundaryTransT", [0, 0, 0, 1, 0, 0, 0], {inlet: g["boundaryTransT"]})
+    write("boundaryRotT", [0, 0, 0, 1, 0, 0, 0], {inlet: np.broadcast_to(g["boundaryRotT"], T.shape)})
+    from_files = copy.deepcopy(direct)
+    for e in from_files.boundariesDict["uniGasPatchBoundaries"] + from_files.boundariesDict["uniGasGeneralBoundaries"]:
+        for k in ("boundaryT", "boundaryU", "boundaryNumberDensity", "boundaryTransT", "boundaryRotT"):
+            e.pop(k, None)
+    with pytest.raises(FileNotFoundError):
+        cases.field_patch_values(copy.deepcopy(from_files.boundariesDict), str(tmp_path), "1", m)
+    cases.field_patch_values(from_files.boundariesDict, str(tmp_path), "0", m)
+    g2 = from_files.boundariesDict["uniGasGeneralBoundaries"][0]
+    assert np.array_equal(g2["boundaryNumberDensity"]["Ar"], n) and np.array_equal(g2["boundaryTransT"], T) and np.array_equal(g2["boundaryU"], U)
+    a = direct.make_cloud(OracleCloud, parcelCapacity=4 * base.n_parcels)
+    b = from_files.make_cloud(OracleCloud, parcelCapacity=4 * base.n_parcels)
+    a.evolve(6); b.evolve(6)
+    pa, pb = a.parcels(), b.parcels()
+    assert a.counters()["wallHits"] > 0 and np.array_equal(pa["cell"], pb["cell"]) and np.array_equal(pa["U"], pb["U"])

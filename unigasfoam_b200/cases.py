@@ -314,6 +314,45 @@ def cylinder(nr=100, ntheta=200, ppc=20, n_inf=4.247e20, T_inf=200.0, U_inf=2634
                           meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, r0=r0, r1=r1, Tref=Tref, species=sp)), cwf)
 
 
+def field_patch_values(boundariesDict, case_dir, start_time, mesh):
+    """The *FieldPatch boundary models read volFields from the start time directory and use their values on the model's
+    patch: boundaryT / boundaryU for the wall field patches (e.g. …/uniGasDiffuseWallFieldPatch/uniGasDiffuseWallFieldPatch.C:
+    56-121), boundaryNumberDensity_<species> / boundaryTransT / boundaryRotT / boundaryU for uniGasFreeStreamInflowFieldPatch
+    (…/uniGasFreeStreamInflowFieldPatch.C:65-183).  UniGasCloud takes those values with the dictionary entry; this fills them
+    in from the files for every entry that does not carry them already."""
+    from . import foamfile
+    t0 = os.path.join(case_dir, start_time)
+    cache = {}
+
+    def on_patch(fname, patch_name):
+        if fname not in cache:
+            path = os.path.join(t0, fname)
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"{patch_name}: a field patch model needs {path}")
+            cache[fname] = foamfile.read_vol_field(path)
+        p = mesh.patches[mesh.patch_index(patch_name)]
+        v = foamfile.boundary_values(cache[fname], patch_name, p.size)
+        if v is None:
+            raise ValueError(f"{fname}: patch {patch_name} has no value entry")
+        return v
+
+    for e in boundariesDict.get("uniGasPatchBoundaries", []):
+        if e["boundaryModel"].endswith("FieldPatch"):
+            name = e["patchBoundaryProperties"]["patch"]
+            for k in ("boundaryT", "boundaryU"):
+                if k not in e:
+                    e[k] = on_patch(k, name)
+    for e in boundariesDict.get("uniGasGeneralBoundaries", []):
+        if e["boundaryModel"] == "uniGasFreeStreamInflowFieldPatch":
+            name = e["generalBoundaryProperties"]["patch"]
+            ids = e[e["boundaryModel"] + "Properties"]["typeIds"]
+            if "boundaryNumberDensity" not in e:
+                e["boundaryNumberDensity"] = {s: on_patch("boundaryNumberDensity_" + s, name) for s in ids}
+            for k in ("boundaryTransT", "boundaryRotT", "boundaryU"):
+                if k not in e:
+                    e[k] = on_patch(k, name)
+
+
 def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=None, start_time="0"):
     """A uniGasFoam case directory (constant/uniGasProperties, system/{controlDict, boundariesDict,
     uniGasInitialisationDict, ...}) on a given mesh -> Case: the dictionaries are used as they are
@@ -325,6 +364,7 @@ def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=Non
     from . import foamdict
     ld = foamdict.load_case(case_dir, overrides)
     props = ld["uniGasProperties"]
+    field_patch_values(ld["boundariesDict"], case_dir, start_time, mesh)
     init = (ld["uniGasInitialisationDict"] or {}).get("configurations", [])
     if len(init) != 1 or init[0].get("type") not in ("uniGasMeshFill", "uniGasMeshFieldFill"):
         raise ValueError("from_case_dir handles a single uniGasMeshFill / uniGasMeshFieldFill configuration")
