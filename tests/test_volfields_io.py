@@ -213,3 +213,33 @@ def test_output_fields_under_the_reference_names(tmp_path, OracleCloud):
     ok = f["densityError"] > 0
     assert ok.any() and np.allclose(f["pressureError"][ok], np.sqrt(5.0 / 3.0) * f["densityError"][ok], rtol=1e-12)
     assert np.array_equal(rd("pressureError")["internal"], f["pressureError"])
+
+
+def test_wall_rotational_and_overall_temperature(tmp_path, OracleCloud):
+    """rotationalT / overallT on wall patches (uniGasVolFields.C:1299-1330) from the wall accumulators: nitrogen between
+    diffuse 300 K walls - incident and re-emitted molecules both carry about k T per molecule of rotational energy."""
+    from unigasfoam_b200 import foamfile
+    case = cases.closed_box(n=5, parcels=40000, seed=13, wall="diffuse", species=("N2", cases.NITROGEN),
+                            binary="LarsenBorgnakkeVariableHardSphere", Trot=300.0)
+    a = case.make_cloud(OracleCloud)
+    a.evolve(30)
+    a.writeFields(str(tmp_path), "30", "N2")
+    m = case.mesh
+    rot, ov, tr = (foamfile.read_vol_field(str(tmp_path / "30" / (n + "_N2"))) for n in ("rotationalT", "overallT", "translationalT"))
+    walls = [p for p in m.patches if p.kind == "wall"]
+    assert walls
+    R = np.concatenate([foamfile.boundary_values(rot, p.name, p.size) for p in walls])
+    O = np.concatenate([foamfile.boundary_values(ov, p.name, p.size) for p in walls])
+    Tt = np.concatenate([foamfile.boundary_values(tr, p.name, p.size) for p in walls])
+    assert abs(R.mean() / 300.0 - 1) < 0.05 and (R > 150).all()
+    assert np.allclose(O, (3 * Tt + 2 * R) / 5, rtol=1e-12)      # rotDoF 2
+    # argon: no rotational energy at the wall, overallT = translationalT there
+    c2 = _couette()
+    b = c2.make_cloud(OracleCloud)
+    b.evolve(4)
+    b.writeFields(str(tmp_path), "4", "Ar")
+    rot, ov, tr = (foamfile.read_vol_field(str(tmp_path / "4" / (n + "_Ar"))) for n in ("rotationalT", "overallT", "translationalT"))
+    for p in c2.mesh.patches:
+        if p.kind == "wall":
+            assert not foamfile.boundary_values(rot, p.name, p.size).any()
+            assert np.allclose(foamfile.boundary_values(ov, p.name, p.size), foamfile.boundary_values(tr, p.name, p.size), rtol=1e-14)

@@ -405,17 +405,17 @@ class UniGasCloud:
     # (uniGasVolFields.C:67-357).  Boundary rules follow :1256-1394: "cell" - every wall / generic patch face takes the value
     # of its cell; "wall" - wall faces take the wall measurement, generic patch faces the cell value; "surface" - wall faces
     # take the wall measurement, everything else is zero; "zero".  Constraint patches (empty, cyclic, symmetry, processor) are
-    # written by their type.  rotationalT / overallT on walls carry the cell value (the wall value is not derived here).
+    # written by their type.  Wall rotationalT / overallT (:1299-1330) are derived in writeFields from the wall accumulators.
     _OUTPUT_FIELDS = (
         ("uniGasRhoNMean", "uniGasRhoNMean", [0, -3, 0, 0, 0, 0, 0], "cell", None, False),
         ("rhoN", "rhoN", [0, -3, 0, 0, 0, 0, 0], "cell", None, False),
         ("rhoM", "rhoM", [1, -3, 0, 0, 0, 0, 0], "cell", None, False),
         ("p", "p", [1, -1, -2, 0, 0, 0, 0], "wall", "wall_p", False),
         ("translationalT", "translationalT", [0, 0, 0, 1, 0, 0, 0], "wall", "wall_translationalT", False),
-        ("rotationalT", "rotationalT", [0, 0, 0, 1, 0, 0, 0], "cell", None, False),
+        ("rotationalT", "rotationalT", [0, 0, 0, 1, 0, 0, 0], "wall", "wall_rotationalT", False),
         ("vibrationalT", None, [0, 0, 0, 1, 0, 0, 0], "zero", None, False),
         ("electronicT", None, [0, 0, 0, 1, 0, 0, 0], "zero", None, False),
-        ("overallT", "overallT", [0, 0, 0, 1, 0, 0, 0], "cell", None, False),
+        ("overallT", "overallT", [0, 0, 0, 1, 0, 0, 0], "wall", "wall_overallT", False),
         ("surfaceHeatTransfer", None, [1, 0, -3, 0, 0, 0, 0], "surface", "surfaceHeatTransfer", False),
         ("surfaceShearStress", None, [1, -1, -2, 0, 0, 0, 0], "surface", "surfaceShearStress", False),
         ("Ma", "Ma", [0] * 7, "cell", None, False),
@@ -432,8 +432,13 @@ class UniGasCloud:
         """The output volFields of a uniGasVolFields entry at write time, under the reference's names and dimensions
         (`rhoN_<field>`, `p_<field>`, `UMean_<field>`, `surfaceHeatTransfer_<field>` ..., uniGasVolFields.C:67-357,
         1397-1428): cell values as internalField, boundary values by the rules above.  -> the list of files written."""
-        from . import foamfile
+        from . import foamfile, volfields_io
+        bacc = volfields_io.state_views(self.state())["bacc"].copy()  # before a reset: rotationalEBF 6, rotationalDofBF 7, rhoNBF 0
         f = self.fields(resetAtOutput=resetAtOutput)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f["wall_rotationalT"] = np.where(bacc[:, 7] > 1e-300, (2.0 / 1.38065e-23) * bacc[:, 6] / bacc[:, 7], 0.0)       # :1299-1308
+            nRot = np.where(bacc[:, 0] > 1e-300, bacc[:, 7] / bacc[:, 0], 0.0)
+            f["wall_overallT"] = (3.0 * f["wall_translationalT"] + nRot * f["wall_rotationalT"]) / (3.0 + nRot)             # :1318-1330
         m = self.mesh
         nI = m.n_internal
         t = os.path.join(case_dir, time_name)
