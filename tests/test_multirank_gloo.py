@@ -250,6 +250,8 @@ def _worker_adapter(rank, world, port, out):
         dt, levels = ad.set_initial_configuration([n[sub.cell_map]], T[sub.cell_map], U[sub.cell_map])
         res[label] = dict(dt=dt, levels=levels, csr=ad.prevCellSizeMFPRatio)
     res["cells"] = sub.cell_map
+    from unigasfoam_b200.exchange import max_imbalance
+    res["imbalance"] = max_imbalance(100 + 50 * rank)   # 100 and 150 parcels: 20 % off the mean of 125
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
     if rank == 0:
@@ -281,3 +283,5 @@ def test_two_rank_adapter_initial_configuration_matches_single_domain(tmp_path):
     assert np.allclose(got_c, ad.prevCellSizeMFPRatio, rtol=1e-12)
     assert np.array_equal(got_l, levels)
     assert not np.allclose(cut_c, ad.prevCellSizeMFPRatio, rtol=1e-3)   # zero-gradient processor faces leave a seam
+    from unigasfoam_b200 import mesh as ugmesh
+    assert all(r["imbalance"] == pytest.approx(20.0) for r in res) and ugmesh.load_imbalance([100, 150]) == pytest.approx(20.0)

@@ -314,6 +314,19 @@ def group_reducers(group=None, cuda=False):
     return make(dist.ReduceOp.MIN), make(dist.ReduceOp.MAX)
 
 
+def max_imbalance(n_local, group=None, cuda=False):
+    """uniGasDynamicLoadBalancing::calculate (U/dynamicLoadBalancing/uniGasDynamicLoadBalancing.C:48-68) over the ranks of a
+    decomposed run: max |N_rank - N / nRanks| / (N / nRanks) in per cent - the `Maximum imbalance` line of the reference's
+    log.  n_local = cloud.size() of this rank."""
+    dev = "cuda" if cuda else "cpu"
+    tot = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    ideal = float(tot.item()) / dist.get_world_size(group)
+    worst = torch.tensor([abs(float(n_local) - ideal)], dtype=torch.float64, device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+    return 100.0 * float(worst.item()) / ideal if ideal > 0 else 0.0
+
+
 class _DevI64:
     def __init__(self, ptr):
         self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
