@@ -9,11 +9,13 @@ for the reference can be run and leaves the files the reference would leave:
     <time>/uniform/time, <time>/uniform/volFieldsMethod_<field>, <time>/{rhoN,p,UMean,...}_<field>
 
 controlDict keys honoured: startFrom (latestTime / startTime), startTime, endTime, deltaT, writeControl (timeStep /
-runTime / adjustableRunTime), writeInterval, timePrecision.  fieldPropertiesDict: per uniGasVolFields entry `field`,
+runTime / adjustableRunTime), writeInterval, timePrecision, nTerminalOutputs (every that many steps the `Time =` line,
+uniGasCloud::info and the clock line go to `log`, uniGasFoam.C:76-104).  fieldPropertiesDict: per uniGasVolFields entry `field`,
 timeProperties.{sampleInterval, resetAtOutput, resetAtOutputUntilTime}, averagingAcrossManyRuns,
 measureMeanFreePath, measureErrors.
 """
 import os
+import time
 
 from . import _capi, cases, foamdict
 from .adapter import UniGasDynamicAdapter
@@ -84,7 +86,9 @@ def run_case(case_dir, mesh, Cloud, out_dir=None, overrides=None, control=None, 
     prec = int(ctl.get("timePrecision", 6))
     next_write = (int(t / interval + 1e-9) + 1) * interval if not by_step else None
     written, steps = [], 0
+    n_out, info_counter, t_wall = int(ctl.get("nTerminalOutputs", 1)), 0, time.perf_counter()
     while t < end * (1.0 - 1e-12):
+        info_counter += 1
         dt = cloud.cfg.deltaT  # the step runs with the time step set before it; the adapter may change it afterwards
         if adapter is not None:
             if hybrid and adapter.timeSteps == adapter.adaptationInterval - 1:
@@ -106,7 +110,16 @@ def run_case(case_dir, mesh, Cloud, out_dir=None, overrides=None, control=None, 
             if not by_step:
                 while next_write * (1.0 - 1e-9) <= t:
                     next_write += interval
-            if log:
-                c = cloud.counters()
-                log(f"Time = {name}  Number of particles = {c['nParcels']}  DSMC Collisions = {c['collisions']}")
+        if log and info_counter >= n_out:  # uniGasFoam.C:78-104, uniGasCloud::info (uniGasCloud.C:878-920)
+            i, c = cloud.info(), cloud.counters()
+            log(f"Time = {time_name(t, prec)}")
+            log(f"    Number of particles             = {i['nParticles']}")
+            if i["nParticles"]:
+                log(f"    Average linear kinetic energy   = {i['avgLinearKE']}")
+                log(f"    Average rotational energy       = {i['avgRotationalE']}")
+                log(f"    Total energy                    = {i['totalEnergy']}")
+            log(f"    DSMC Collisions                 = {c['collisions']}")
+            log(f"    BGK relaxations                 = {c['bgkRelaxations']}")
+            log(f"ClockTime = {time.perf_counter() - t_wall:.3f} s")
+            info_counter = 0
     return dict(cloud=cloud, adapter=adapter, written=written, time=t, steps=steps, case=case)
