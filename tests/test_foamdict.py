@@ -307,7 +307,9 @@ def test_oracle_solver_loop_writes_what_the_reference_leaves(tmp_path, OracleClo
     assert sum(l.startswith("Time = ") for l in lines) == r["steps"] // 10 and any("Number of particles" in l for l in lines)
     first = os.path.join(out, r["written"][0])
     have = set(os.listdir(first))
-    assert {"lagrangian", "uniform", "uniGasSigmaTcRMax", "uniGasCellWeightFactor", "uniGasSubCellLevels", "uniGasCollisionModelId",
+    # cleanLagrangian: only the latest write keeps its parcels
+    assert "lagrangian" not in have and os.path.isdir(os.path.join(out, r["written"][-1], "lagrangian"))
+    assert {"uniform", "uniGasSigmaTcRMax", "uniGasCellWeightFactor", "uniGasSubCellLevels", "uniGasCollisionModelId",
             "rhoN_Ar", "p_Ar", "UMean_Ar", "translationalT_Ar", "surfaceHeatTransfer_Ar", "fD_Ar", "variableHardSphereMeanFreePath_Ar",
             "densityError_Ar"} <= have
     assert {"time", "volFieldsMethod_Ar"} <= set(os.listdir(os.path.join(first, "uniform")))

@@ -15,6 +15,7 @@ timeProperties.{sampleInterval, resetAtOutput, resetAtOutputUntilTime}, averagin
 measureMeanFreePath, measureErrors.
 """
 import os
+import shutil
 import time
 
 from . import _capi, cases, foamdict
@@ -53,10 +54,12 @@ def _vol_fields(fp):
 
 
 def run_case(case_dir, mesh, Cloud, out_dir=None, overrides=None, control=None, seed=7, particles_per_cell=None,
-             capacity_factor=8, log=None):
+             capacity_factor=8, log=None, keep_lagrangian=False):
     """Runs the case of `case_dir` on `mesh` with the cloud class `Cloud` (UniGasCloud, or the oracle's in tests) from its
     start time to endTime and writes the time directories into `out_dir` (default: the case directory).  `control`
-    overrides controlDict entries (e.g. {"endTime": 1e-6}).  -> dict(cloud, adapter, written=[time names], time, steps)."""
+    overrides controlDict entries (e.g. {"endTime": 1e-6}).  Unless keep_lagrangian (the solver's -keep-lagrangian option),
+    the parcel files of the previous write time are removed after every write (uniGasCloud::cleanLagrangian,
+    U/clouds/uniGasCloud.C:1591-1618).  -> dict(cloud, adapter, written=[time names], time, steps)."""
     out_dir = out_dir or case_dir
     case, ld = cases.from_case_dir(case_dir, mesh, seed=seed, overrides=overrides, particles_per_cell=particles_per_cell)
     ctl = dict(ld["controlDict"], **(control or {}))
@@ -107,6 +110,8 @@ def run_case(case_dir, mesh, Cloud, out_dir=None, overrides=None, control=None, 
                                   measureMeanFreePath=f["mfp"], measureErrors=f["err"])
             cloud.writeTime(out_dir, name, fieldNames=[f["name"] for f in fields if f["carry"]])
             written.append(name)
+            if not keep_lagrangian and len(written) >= 2:
+                shutil.rmtree(os.path.join(out_dir, written[-2], "lagrangian"), ignore_errors=True)
             if not by_step:
                 while next_write * (1.0 - 1e-9) <= t:
                     next_write += interval
