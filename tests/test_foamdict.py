@@ -283,8 +283,14 @@ def test_decompose_par_dict_to_partition():
     simple = {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [1, 4, 1]}}
     sp, _ = foamdict.partition_from_dict(m, simple)
     assert np.array_equal(sp, ugmesh.slab_partition(m, 4, 1))
+    bp, nb = foamdict.partition_from_dict(m, {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [2, 2, 1]}})
+    assert nb == 4 and (np.bincount(bp) == m.n_cells // 4).all()
+    blocks = ugmesh.decompose(m, bp, 4)
+    assert sum(s.n_cells for s in blocks) == m.n_cells and all(sum(p.kind == "processor" for p in s.patches) >= 2 for s in blocks)
     with pytest.raises(foamdict.FoamDictError, match="one direction"):
-        foamdict.partition_from_dict(m, {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [2, 2, 1]}})
+        foamdict.partition_from_dict(m, {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [2, 2, 1]}, "weightField": "w"}, weights=w)
+    with pytest.raises(foamdict.FoamDictError, match="multiply"):
+        foamdict.partition_from_dict(m, {"numberOfSubdomains": 4, "method": "simple", "simpleCoeffs": {"n": [2, 3, 1]}})
     assert sum(s.n_cells for s in ugmesh.decompose(m, wp, 10)) == m.n_cells
 
 

@@ -200,9 +200,13 @@ def partition_from_dict(mesh, decomposeParDict, weights=None, axis=0):
     n = int(decomposeParDict["numberOfSubdomains"])
     if decomposeParDict.get("method") == "simple":
         parts = [int(v) for v in (decomposeParDict.get("simpleCoeffs") or decomposeParDict.get("coeffs") or {}).get("n", [n, 1, 1])]
+        if parts[0] * parts[1] * parts[2] != n:
+            raise FoamDictError(f"simpleCoeffs n {parts} does not multiply to numberOfSubdomains {n}")
         split = [i for i, k in enumerate(parts) if k > 1]
-        if len(split) > 1 or (split and parts[split[0]] != n):
-            raise FoamDictError(f"simpleCoeffs n {parts}: only a split along one direction into numberOfSubdomains parts is supported")
+        if len(split) > 1:
+            if "weightField" in decomposeParDict:
+                raise FoamDictError(f"simpleCoeffs n {parts} with a weightField: only a split along one direction is supported")
+            return ugmesh.block_partition(mesh, parts), n
         if split:
             axis = split[0]
     if "weightField" in decomposeParDict:

@@ -416,6 +416,18 @@ def slab_partition(mesh, n_ranks, axis=0):
     return np.minimum((ijk[axis] * n_ranks) // n, n_ranks - 1).astype(np.int32)
 
 
+def block_partition(mesh, parts):
+    """decomposePar `method simple` with `n (px py pz)`: px x py x pz blocks of a structured mesh, rank = bx + px (by + py bz)."""
+    nx, ny, nz = mesh.shape
+    px, py, pz = (int(v) for v in parts)
+    if px < 1 or py < 1 or pz < 1 or px > nx or py > ny or pz > nz:
+        raise ValueError(f"cannot cut a {mesh.shape} mesh into {parts} blocks")
+    c = np.arange(nx * ny * nz)
+    i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+    b = lambda idx, n, p: np.minimum((idx * p) // n, p - 1)
+    return (b(i, nx, px) + px * (b(j, ny, py) + py * b(k, nz, pz))).astype(np.int32)
+
+
 def weighted_slab_partition(mesh, n_ranks, weights, axis=0):
     """Slabs along `axis` of a structured mesh cut at equal cumulative *weight* instead of equal cell count - the
     decomposeParDict `weightField uniGasRhoNMean_<species>` the tutorials hint at (hypersonicCylinder/system/
