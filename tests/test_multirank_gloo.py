@@ -285,3 +285,62 @@ def test_two_rank_adapter_initial_configuration_matches_single_domain(tmp_path):
     assert not np.allclose(cut_c, ad.prevCellSizeMFPRatio, rtol=1e-3)   # zero-gradient processor faces leave a seam
     from unigasfoam_b200 import mesh as ugmesh
     assert all(r["imbalance"] == pytest.approx(20.0) for r in res) and ugmesh.load_imbalance([100, 150]) == pytest.approx(20.0)
+
+
+def _worker_blocks(rank, world, port, steps, out):
+    """2 x 2 block decomposition (decomposePar simple n (2 2 1)) of the periodic channel: every rank has a processor
+    neighbour in x (also through the cyclic pair) and one in y; parcels that leave through a corner need two transfers."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle_cloud import OracleCloud
+    from unigasfoam_b200 import mesh as ugmesh
+    from unigasfoam_b200.exchange import Exchanger, evolve_distributed, max_imbalance
+    case = _block_case()
+    part = ugmesh.block_partition(case.mesh, (2, 2, 1))
+    sub = ugmesh.decompose(case.mesh, part, world)[rank]
+    g2l = np.full(case.mesh.n_cells, -1)
+    g2l[sub.cell_map] = np.arange(sub.n_cells)
+    sel = part[case.cell] == rank
+    cl = OracleCloud(sub, case.uniGasProperties, case.boundariesDict, case.deltaT, parcelCapacity=4 * int(sel.sum()) + 4096, rank=rank, nRanks=world)
+    cl.setParcels(case.position[sel], case.U[sel], g2l[case.cell[sel]])
+    ex = Exchanger(cl, sub, rank, world, cuda=False)
+    evolve_distributed(cl, ex, steps)
+    p = cl.parcels()
+    res = dict(pos=p["position"], U=p["U"], cells=sub.cell_map[p["cell"]], rounds=ex.rounds, stuck=cl.counters()["stuck"],
+               nproc=sum(q.kind == "processor" for q in sub.patches), imbalance=max_imbalance(cl.size()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _block_case():
+    case = cases.couette(nx=12, ny=8, ppc=10, binary="noDSMCCollision", seed=17)
+    for e in case.boundariesDict["uniGasPatchBoundaries"]:
+        e["boundaryModel"] = "uniGasSpecularWallPatch"
+    case.deltaT *= 5.0
+    return case
+
+
+@pytest.mark.timeout(300)
+def test_four_rank_block_decomposition_matches_single_domain(tmp_path, OracleCloud):
+    world, steps = 4, 4
+    out = str(tmp_path / "blocks.pt")
+    mp.spawn(_worker_blocks, args=(world, _free_port(), steps, out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    case = _block_case()
+    ref = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels)
+    ref.evolve(steps)
+    pr = ref.parcels()
+    assert all(r["stuck"] == 0 for r in res) and all(r["nproc"] >= 2 for r in res) and max(r["rounds"] for r in res) >= steps
+    assert sum(len(r["cells"]) for r in res) == len(pr["cell"])
+    got = np.concatenate([np.column_stack([r["pos"], r["U"], r["cells"]]) for r in res])
+    want = np.column_stack([pr["position"], pr["U"], pr["cell"]])
+    key = lambda a: a[np.lexsort(np.round(a[:, :6] / (np.abs(a[:, :6]).max(0) + 1e-300), 9).T[::-1])]
+    g, w = key(got), key(want)
+    assert np.array_equal(g[:, 6], w[:, 6])                                  # every parcel in the same (global) cell
+    err = np.abs(g[:, :6] - w[:, :6]) / (np.abs(w[:, :6]).max(0) + 1e-300)
+    assert err.max() < 1e-11
+    assert res[0]["imbalance"] < 15.0
