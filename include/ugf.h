@@ -471,6 +471,16 @@ int ugf_download_accumulators(ugf_handle* h, double* acc, double* accSpecies, do
 int ugf_phase_times(ugf_handle* h, double* ms);
 /* Number of kernel launches issued by this handle so far. */
 int ugf_launch_count(ugf_handle* h, int64_t* n);
+/* Bytes this handle has moved between host and device since ugf_create: every explicit host -> device and device -> host
+ * copy, and the argument blocks of the per-step kernels (what a launch sends besides its grid).  Measurement only: bench.py
+ * differences two calls around its end-to-end loop.  Any pointer may be NULL.  (No reference analogue.) */
+int ugf_transfer_bytes(ugf_handle* h, int64_t* h2d, int64_t* d2h, int64_t* kernelArgs);
+/* Page-locked host memory for callers that hand the parcels over every step (the solver owns the parcel list, as
+ * uniGasCloud does: U/clouds/uniGasCloudI.H:375-378): ugf_upload_parcels / ugf_download_parcels from / into such
+ * buffers run as asynchronous DMA at PCIe rate instead of through the driver's pageable staging.  Freed by ugf_host_free
+ * or with the handle. */
+int ugf_host_alloc(ugf_handle* h, int64_t bytes, void** ptr);
+int ugf_host_free(ugf_handle* h, void* ptr);
 
 #ifdef __cplusplus
 }

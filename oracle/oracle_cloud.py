@@ -43,3 +43,13 @@ def num_threads():
     f = api().lib.ugfo_num_threads
     f.restype = ctypes.c_int
     return f()
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle's parallel loops (bench.py: all host cores, whatever OMP_NUM_THREADS the launcher left)."""
+    import ctypes
+    f = api().lib.ugfo_set_num_threads
+    f.argtypes = [ctypes.c_int]
+    f.restype = None
+    f(int(n))
+    return num_threads()

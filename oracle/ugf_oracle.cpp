@@ -224,6 +224,7 @@ struct ugfo_handle {
     ugf_counters cnt;
     std::vector<std::vector<double>> packBuf;
     int64_t inflight = 0;
+    std::vector<int64_t> migIdx;  // indices of the parcels waiting on processor patches (ascending), filled by moveRange
 };
 
 namespace {
@@ -668,12 +669,30 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
 
 void moveRange(ugfo_handle& h, int64_t begin, int64_t end, bool fresh) {
     int64_t deleted = 0, wallHits = 0, stuck = 0, migrated = 0;
-#pragma omp parallel for schedule(static) reduction(+ : deleted, wallHits, stuck, migrated)
-    for (int64_t i = begin; i < end; ++i) {
-        MoveTally t;
-        moveParcel(h, h.P[i], i, t, fresh);
-        deleted += t.deleted; wallHits += t.wallHits; stuck += t.stuck; migrated += t.migrated;
+    // parcels that stop on a processor patch are remembered (index order) so that the transfer loop costs what it moves,
+    // not a pass over the cloud per call - as a rank's transfer lists do in Cloud::move
+    if (fresh) h.migIdx.clear();
+    int nT = 1;
+#ifdef _OPENMP
+    nT = omp_get_max_threads();
+#endif
+    std::vector<std::vector<int64_t>> local((size_t)nT);
+#pragma omp parallel reduction(+ : deleted, wallHits, stuck, migrated)
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        std::vector<int64_t>& mine = local[(size_t)tid];
+#pragma omp for schedule(static)
+        for (int64_t i = begin; i < end; ++i) {
+            MoveTally t;
+            moveParcel(h, h.P[i], i, t, fresh);
+            deleted += t.deleted; wallHits += t.wallHits; stuck += t.stuck; migrated += t.migrated;
+            if (h.P[i].cell <= -2) mine.push_back(i);
+        }
     }
+    for (const auto& v : local) h.migIdx.insert(h.migIdx.end(), v.begin(), v.end());  // static schedule: already ascending
     h.cnt.deleted += deleted; h.cnt.wallHits += wallHits; h.cnt.stuck += stuck; h.cnt.migrated += migrated;
     h.occValid = false;
     h.momValid = false;
@@ -895,6 +914,7 @@ void reorder(ugfo_handle& h) {
 #pragma omp parallel for schedule(static)
     for (int64_t j = 0; j < n; ++j) { Q[j] = h.P[h.occIds[j]]; h.occIds[j] = (int32_t)j; }
     h.P.swap(Q);
+    h.migIdx.clear();
     h.occIdentity = true;
 }
 
@@ -1946,6 +1966,7 @@ int ugfo_download_inlet_velocity(ugfo_handle* h, int32_t patch, double* U) {
 int ugfo_upload_parcels(ugfo_handle* h, const ugf_parcels* p) {
     if (p->n > h->cfg.parcelCapacity) return fail(h, "parcel count exceeds parcelCapacity");
     h->P.resize(p->n);
+    h->migIdx.clear();
     for (int64_t i = 0; i < p->n; ++i) {
         Parcel& q = h->P[i];
         q.x[0] = p->x[i]; q.x[1] = p->y[i]; q.x[2] = p->z[i];
@@ -2164,14 +2185,15 @@ int ugfo_step(ugfo_handle* h, int32_t nSteps) {
 
 int ugfo_migrate_counts(ugfo_handle* h, int64_t* counts) {
     for (int p = 0; p < h->nPatches; ++p) counts[p] = 0;
-    for (const Parcel& q : h->P) if (q.cell <= -2) counts[h->facePatch[-2 - q.cell]]++;
+    for (const int64_t i : h->migIdx) { const Parcel& q = h->P[(size_t)i]; if (q.cell <= -2) counts[h->facePatch[-2 - q.cell]]++; }
     return 0;
 }
 
 int ugfo_migrate_pack(ugfo_handle* h, int32_t patch, double** buf, int64_t* n) {
     std::vector<double>& b = h->packBuf[patch];
     b.clear();
-    for (Parcel& q : h->P) {
+    for (const int64_t i : h->migIdx) {
+        Parcel& q = h->P[(size_t)i];
         if (q.cell > -2 || h->facePatch[-2 - q.cell] != patch) continue;
         const int lface = (-2 - q.cell) + h->nInternal - h->pStart[patch];
         const double rec[UGF_MIGRATE_STRIDE] = {q.x[0], q.x[1], q.x[2], q.U[0], q.U[1], q.U[2], q.ERot, q.sf, (double)lface + 4294967296.0 * (double)q.typeId, q.CWF};
@@ -2185,6 +2207,7 @@ int ugfo_migrate_pack(ugfo_handle* h, int32_t patch, double** buf, int64_t* n) {
 
 int ugfo_migrate_unpack(ugfo_handle* h, int32_t patch, const double* buf, int64_t n) {
     if (h->pKind[patch] != UGF_PATCH_PROCESSOR) return fail(h, "unpack on a non-processor patch");
+    if (h->P.capacity() < h->P.size() + (size_t)n) h->P.reserve(h->P.size() + (size_t)n + h->P.size() / 8 + 1024);
     for (int64_t i = 0; i < n; ++i) {
         const double* r = buf + i * UGF_MIGRATE_STRIDE;
         Parcel q;
@@ -2213,7 +2236,7 @@ int ugfo_move_received(ugfo_handle* h) {
 
 static void countInflight(ugfo_handle* h) {
     int64_t n = 0;
-    for (const Parcel& q : h->P) n += (q.cell <= -2);
+    for (const int64_t i : h->migIdx) n += (h->P[(size_t)i].cell <= -2);
     h->inflight = n;
 }
 
@@ -2357,6 +2380,9 @@ int ugfo_download_boundary_meas(ugfo_handle* h, double* bm) { std::copy(h->bm.be
 
 int ugfo_phase_times(ugfo_handle*, double* ms) { for (int i = 0; i < UGF_NPHASE; ++i) ms[i] = 0; return 0; }
 int ugfo_launch_count(ugfo_handle*, int64_t* n) { *n = 0; return 0; }
+int ugfo_transfer_bytes(ugfo_handle*, int64_t* a, int64_t* b, int64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return 0; }
+int ugfo_host_alloc(ugfo_handle*, int64_t bytes, void** ptr) { *ptr = std::malloc((size_t)std::max<int64_t>(bytes, 1)); return *ptr ? 0 : 1; }
+int ugfo_host_free(ugfo_handle*, void* ptr) { std::free(ptr); return 0; }
 
 // Known-answer hook for the RNG: one Philox4x32-10 block.
 void ugfo_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
@@ -2370,6 +2396,15 @@ int ugfo_num_threads(void) {
     return omp_get_max_threads();
 #else
     return 1;
+#endif
+}
+// Thread count of the timed CPU baseline: bench.py sets it to the host's core count explicitly (a launcher such as torchrun
+// exports OMP_NUM_THREADS=1 to its ranks).
+void ugfo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
 #endif
 }
 

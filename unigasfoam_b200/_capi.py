@@ -191,6 +191,9 @@ SIGNATURES = {
     "download_boundary_meas": (C.c_int, [H, PF]),
     "phase_times": (C.c_int, [H, PF]),
     "launch_count": (C.c_int, [H, PI64]),
+    "transfer_bytes": (C.c_int, [H, PI64, PI64, PI64]),
+    "host_alloc": (C.c_int, [H, i64, P(C.c_void_p)]),
+    "host_free": (C.c_int, [H, C.c_void_p]),
 }
 
 

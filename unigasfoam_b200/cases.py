@@ -412,3 +412,233 @@ def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=Non
     if levels is not None and (levels != 1).any():
         case.subCellLevels = levels
     return case, ld
+
+
+# ---- BASELINE configs 3 / 4 / 5 at their stated size: per-rank blocks, parcels generated with torch ---------------------
+
+_HEX_TETS = ((0, 1, 3, 7), (0, 3, 2, 7), (0, 2, 6, 7), (0, 6, 4, 7), (0, 4, 5, 7), (0, 5, 1, 7))  # six tets around the 0-7 diagonal
+
+
+def fill_parcels_torch(mesh, sp, number_density, T, velocity, nParticle, cell_weight=None, Trot=None, seed=1, device=None, chunk=8_000_000):
+    """uniGasMeshFill for the large bench / full-size test cases (…/uniGasMeshFill.C:174-278): same rule as mesh_fill -
+    N = n V / (F_N CWF) per cell with stochastic rounding, uniform position in the cell, Maxwellian + drift, equipartition
+    ERot - but vectorised with torch on `device` (the GPU when there is one: synthetic input generation, not the product
+    path) and without mesh_fill's fixed draw order.  Hex cells of structured blocks are split into six tets, a tet is
+    chosen by volume and the point is uniform in it (tetPointRef::randomPoint).  One species.
+    -> position [n,3], U [n,3], cell [n] (cell-major), ERot [n] or None; numpy, host."""
+    import torch
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    f64 = dict(dtype=torch.float64, device=device)
+    nC = mesh.n_cells
+    vol = torch.as_tensor(mesh.cell_volumes, **f64)
+    req = float(number_density) / float(nParticle) * vol
+    if cell_weight is not None:
+        req = req / torch.as_tensor(np.asarray(cell_weight, float), **f64)
+    cnt = torch.floor(req)
+    cnt = (cnt + ((req - cnt) > torch.rand(nC, generator=gen, **f64)).to(torch.float64)).to(torch.int64)
+    off = torch.zeros(nC + 1, dtype=torch.int64, device=device)
+    off[1:] = torch.cumsum(cnt, 0)
+    n = int(off[-1].item())
+    pos = np.empty((n, 3)); vel = np.empty((n, 3)); cel = np.empty(n, np.int32)
+    rd = int(sp.get("rotationalDegreesOfFreedom", 0))
+    erot = np.empty(n) if rd else None
+    axis_aligned = bool(mesh.meta_axis_aligned)
+    if axis_aligned:
+        lo_all, hi_all = torch.as_tensor(mesh.cell_bb_min, **f64), torch.as_tensor(mesh.cell_bb_max, **f64)
+    else:
+        corners = torch.as_tensor(mesh.points, **f64)[torch.as_tensor(_mesh.hex_corners(mesh).astype(np.int64), device=device)]  # [nC,8,3]
+        tets = torch.as_tensor(_HEX_TETS, dtype=torch.int64, device=device)
+        a = corners[:, tets[:, 0]]
+        tv = torch.linalg.det(torch.stack([corners[:, tets[:, 1]] - a, corners[:, tets[:, 2]] - a, corners[:, tets[:, 3]] - a], dim=-2)).abs()  # [nC,6]
+        cum = torch.cumsum(tv, 1)
+    Uinf = torch.as_tensor(np.asarray(velocity, float), **f64)
+    sig = math.sqrt(kB * float(T) / sp["mass"])
+    mids = [0.5 * (mesh.points[:, d].min() + mesh.points[:, d].max()) for d in range(3)]
+    c0 = 0
+    offh = off.cpu().numpy()
+    while c0 < nC:  # chunks of whole cells holding <= `chunk` parcels
+        c1 = int(np.searchsorted(offh, offh[c0] + chunk, side="right")) - 1
+        c1 = min(max(c1, c0 + 1), nC)
+        b, e = int(offh[c0]), int(offh[c1])
+        m = e - b
+        if m:
+            cl = torch.repeat_interleave(torch.arange(c0, c1, device=device), cnt[c0:c1])
+            if axis_aligned:
+                p = lo_all[cl] + torch.rand(m, 3, generator=gen, **f64) * (hi_all[cl] - lo_all[cl])
+            else:
+                u = torch.rand(m, generator=gen, **f64) * cum[cl, 5]
+                ti = (u[:, None] >= cum[cl, :5]).sum(1)                      # tet by volume
+                v = corners[cl[:, None], tets[ti]]                           # [m,4,3]
+                w = -torch.log(1.0 - torch.rand(m, 4, generator=gen, **f64))  # uniform barycentric coordinates
+                w = w / w.sum(1, keepdim=True)
+                p = (w[:, :, None] * v).sum(1)
+            for d in range(3):
+                if not mesh.solution_d[d]:
+                    p[:, d] = mids[d]
+            pos[b:e] = p.cpu().numpy()
+            vel[b:e] = (sig * torch.randn(m, 3, generator=gen, **f64) + Uinf).cpu().numpy()
+            cel[b:e] = cl.to(torch.int32).cpu().numpy()
+            if rd == 2:
+                tr = float(T if Trot is None else Trot)
+                erot[b:e] = (-torch.log(1.0 - torch.rand(m, generator=gen, **f64)) * (kB * tr)).cpu().numpy()
+            elif rd:
+                tr = float(T if Trot is None else Trot)
+                g = torch.distributions.Gamma(torch.tensor(0.5 * rd, **f64), torch.tensor(1.0, **f64))
+                erot[b:e] = (g.sample((m,)) * (kB * tr)).cpu().numpy()
+        c0 = c1
+    return pos, vel, cel, erot
+
+
+def _empty_patch_split(m, name, n_first, name_a, name_b, kind_a=None, kind_b=None):
+    """split_patch that also accepts n_first = 0 or = size: decomposePar keeps every patch on every rank, with zero faces where
+    the rank does not touch it."""
+    pi = m.patch_index(name)
+    p = m.patches[pi]
+    n_first = int(min(max(n_first, 0), p.size))
+    a = _mesh.Patch(name_a, kind_a or p.kind, p.start, n_first)
+    b = _mesh.Patch(name_b, kind_b or p.kind, p.start + n_first, p.size - n_first)
+    m.patches[pi:pi + 1] = [a, b]
+    return m
+
+
+def cylinder_block(rank=0, n_ranks=1, nr=1000, ntheta=2500, parcels=50_000_000, n_inf=4.247e20, T_inf=200.0, U_inf=2634.7, T_wall=500.0,
+                   r0=0.5 * 0.3048, r1=2.0 * 0.3048, lz=0.1 * 0.3048, grading=5.0, species=("Ar", ARGON_TUTORIAL), Tref=1000.0, courant=0.3,
+                   seed=3, hybrid=False, theta_blend=0.1, device=None):
+    """BASELINE configs[2] (hybrid=False: Mach-10 argon cylinder, DSMC NTC + VHS, 50 M parcels, 2.5 M cells) and configs[3]
+    (hybrid=True: the same topology at 10 n_inf, USP-SBGK in the upstream half - the compressed fore-body side - and NTC / VHS
+    in the wake half, 100 M parcels), SURVEY 8d rows 3 and 4, as rank `rank` of n_ranks blocks along theta (`method simple`,
+    n (1 n_ranks 1)): the geometry, free stream and wall of tutorials/uniGasFoam/hypersonicCylinder."""
+    name, sp = species
+    g = float(grading)
+
+    def pm(I, J, K):
+        t = I / nr
+        frac = t if abs(g - 1.0) < 1e-12 else (g ** t - 1.0) / (g - 1.0)
+        r = r0 + (r1 - r0) * frac
+        th = np.pi * J / ntheta
+        y = np.where((J == 0) | (J == ntheta), 0.0, r * np.sin(th))  # the axis rows sit on y = 0 exactly
+        return r * np.cos(th), y, lz * (K - 0.5)
+
+    kinds = {"xMin": ("cylinder", "wall"), "xMax": ("outer", "patch"), "yMin": ("axisDown", "symmetryPlane"), "yMax": ("axisUp", "symmetryPlane"),
+             "zMin": ("back", "empty"), "zMax": ("front", "empty")}
+    m, (i0, j0, k0) = _mesh.structured_subblock((nr, ntheta, 1), (1, n_ranks, 1), rank, pm, kinds, solution_d=(1, 1, 0))
+    nyl = m.shape[1]
+    _empty_patch_split(m, "outer", ntheta // 2 - j0, "outlet", "inlet")
+    m.meta_axis_aligned = False
+    if hybrid:
+        n_inf = 10.0 * n_inf
+    volume = 0.5 * math.pi * (r1 * r1 - r0 * r0) * lz  # the polygonal mesh differs from the annulus by O(1/ntheta^2): irrelevant for F_N
+    nParticle = n_inf * volume / parcels
+    pos, vel, cel, erot = fill_parcels_torch(m, sp, n_inf, T_inf, (U_inf, 0.0, 0.0), nParticle, seed=seed + 7919 * rank, device=device)
+    dr_min = (r1 - r0) * ((g ** (1.0 / nr) - 1.0) / (g - 1.0) if abs(g - 1.0) > 1e-12 else 1.0 / nr)
+    dt = courant * min(dr_min, math.pi * r0 / ntheta) / (U_inf + most_probable_speed(T_inf, sp["mass"]))
+    dens = n_inf
+    inflow = {"generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasFreeStreamInflowPatch",
+              "uniGasFreeStreamInflowPatchProperties": {"typeIds": [name], "numberDensities": {name: dens}, "translationalTemperature": T_inf,
+                                                        "rotationalTemperature": T_inf, "vibrationalTemperature": T_inf,
+                                                        "electronicTemperature": T_inf, "velocity": [U_inf, 0.0, 0.0]}}
+    bd = {
+        "uniGasPatchBoundaries": [
+            {"patchBoundaryProperties": {"patch": "cylinder"}, "boundaryModel": "uniGasDiffuseWallPatch",
+             "uniGasDiffuseWallPatchProperties": {"velocity": [0, 0, 0], "temperature": T_wall}},
+            {"patchBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasDeletionPatch"},
+            {"patchBoundaryProperties": {"patch": "outlet"}, "boundaryModel": "uniGasDeletionPatch"},
+        ],
+        "uniGasGeneralBoundaries": [inflow],
+    }
+    sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(T_inf, sp["mass"])
+    if hybrid:
+        props = _props(name, sp, nParticle, "hybrid", "variableHardSphere", "unifiedStochasticParticleSBGK", Tref, theta=theta_blend)
+    else:
+        props = _props(name, sp, nParticle, "dsmc", "variableHardSphere", "noBGKCollision", Tref)
+    case = Case("cylinder_hybrid" if hybrid else "cylinder", m, props, bd, dt, pos, vel, cel, None, None, sig0,
+                meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, r0=r0, r1=r1, Tref=Tref, species=sp, block=(i0, j0, k0)))
+    if hybrid:
+        c = np.arange(m.n_cells)
+        jg = (c // m.shape[0]) % nyl + j0
+        case.cellCollModelId = (jg < ntheta // 2).astype(np.int32)  # 1 = dsmc (wake half, theta < pi/2), 0 = bgk (upstream half)
+    return case
+
+
+def blunt_body_block(rank=0, n_ranks=8, n_eta=200, n_s=500, n_phi=250, ppc=20, n_inf=5e21, T_inf=200.0, mach=10.0, T_wall=500.0,
+                     species=("N2", NITROGEN), Tref=273.0, courant=0.3, seed=5, zrot=5.0, zelec=50.0, device=None, **geom):
+    """BASELINE configs[4]: 3-D nitrogen Mach-10 flow over a blunted cone (sphere-cone fore-body, body-fitted
+    grid revolved about the axis), Larsen-Borgnakke rotational relaxation, cell-weighted as every reference tutorial is
+    (ppc parcels in every cell at the free-stream state), 62.5 M parcels and 3.1 M cells per rank at the default size.
+    The full case is 8 blocks - 4 along the body x 2 in azimuth over a 90 degree sector between two symmetry planes; with
+    n_ranks < 8 the case is the part of it those ranks own: 4 ranks = the 45 degree sector (by symmetry the same flow), 2 / 1
+    ranks = its first two / first body blocks with the downstream cut as outflow.  `method simple`, n (1 4 2)."""
+    name, sp = species
+    if n_ranks not in (1, 2, 4, 8):
+        raise ValueError("blunt_body_block: 1, 2, 4 or 8 ranks")
+    ps, pp = (4, 2)
+    ns_blocks = min(n_ranks, 4)
+    np_blocks = 2 if n_ranks == 8 else 1
+    rs = _mesh.block_ranges(n_s, ps)
+    rp = _mesh.block_ranges(n_phi, pp)
+    gs = rs[ns_blocks - 1][1]                      # body cells of the part that is run
+    gp = rp[np_blocks - 1][1]
+    pm = _mesh.sphere_cone_map(n_eta, n_s, n_phi, **geom)
+    kinds = {"xMin": ("body", "wall"), "xMax": ("inlet", "patch"), "yMin": ("axis", "symmetry"), "yMax": ("outlet", "patch"),
+             "zMin": ("symmetryA", "symmetryPlane"), "zMax": ("symmetryB", "symmetryPlane")}
+    m, blk = _mesh.structured_subblock((n_eta, gs, gp), (1, ns_blocks, np_blocks), rank, pm, kinds)
+    m.meta_axis_aligned = False
+    a = math.sqrt(1.4 * kB * T_inf / sp["mass"])
+    U_inf = mach * a
+    target = ppc
+    # cellWeightedSimulation, uniGasMeshFill's rule (uniGasMeshFill.C:111-121): CWF = n V / (particlesPerSubCell F_N); F_N such
+    # that the median cell carries factor 1
+    # the same on every rank: tied to the cell in the middle of the global grid, which then carries factor 1
+    nParticle = n_inf * _blunt_reference_volume(n_eta, n_s, n_phi, geom) / target
+    cwf = n_inf * m.cell_volumes / (target * nParticle)
+    pos, vel, cel, erot = fill_parcels_torch(m, sp, n_inf, T_inf, (U_inf, 0.0, 0.0), nParticle, cell_weight=cwf, Trot=T_inf,
+                                             seed=seed + 7919 * rank, device=device)
+    dt = _blunt_reference_dt(n_eta, n_s, n_phi, geom, courant, U_inf + most_probable_speed(T_inf, sp["mass"]))
+    inflow = {"generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasFreeStreamInflowPatch",
+              "uniGasFreeStreamInflowPatchProperties": {"typeIds": [name], "numberDensities": {name: n_inf}, "translationalTemperature": T_inf,
+                                                        "rotationalTemperature": T_inf, "vibrationalTemperature": T_inf,
+                                                        "electronicTemperature": T_inf, "velocity": [U_inf, 0.0, 0.0]}}
+    bd = {
+        "uniGasPatchBoundaries": [
+            {"patchBoundaryProperties": {"patch": "body"}, "boundaryModel": "uniGasDiffuseWallPatch",
+             "uniGasDiffuseWallPatchProperties": {"velocity": [0, 0, 0], "temperature": T_wall}},
+            {"patchBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasDeletionPatch"},
+            {"patchBoundaryProperties": {"patch": "outlet"}, "boundaryModel": "uniGasDeletionPatch"},
+        ],
+        "uniGasGeneralBoundaries": [inflow],
+    }
+    props = _props(name, sp, nParticle, "dsmc", "LarsenBorgnakkeVariableHardSphere", "noBGKCollision", Tref,
+                   rotationalRelaxationCollisionNumber=zrot, electronicRelaxationCollisionNumber=zelec)
+    props["cellWeightedSimulation"] = True
+    props["cellWeightedProperties"] = {"particlesPerSubCell": target}
+    sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(T_inf, sp["mass"])
+    case = Case("blunt_body", m, props, bd, dt, pos, vel, cel, None, erot, sig0,
+                meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, Tref=Tref, species=sp, block=blk))
+    case.cellWeightFactor = np.ascontiguousarray(cwf)
+    return case
+
+
+def _blunt_reference_cell(n_eta, n_s, n_phi, geom):
+    """Extents (normal, along the body, azimuthal) and volume of the cell in the middle of the global blunt-body grid: the
+    rank-independent reference F_N and deltaT are tied to."""
+    pm = _mesh.sphere_cone_map(n_eta, n_s, n_phi, **geom)
+    i, j, k = n_eta // 2, n_s // 2, n_phi // 2
+    I, J, K = np.meshgrid(np.array([i, i + 1.0]), np.array([j, j + 1.0]), np.array([k, k + 1.0]), indexing="ij")
+    x, y, z = pm(I, J, K)
+    P = np.stack([np.broadcast_to(x, I.shape), np.broadcast_to(y, I.shape), np.broadcast_to(z, I.shape)], -1)
+    d_eta = np.linalg.norm(P[1, 0, 0] - P[0, 0, 0])
+    d_s = np.linalg.norm(P[0, 1, 0] - P[0, 0, 0])
+    d_phi = np.linalg.norm(P[0, 0, 1] - P[0, 0, 0])
+    return d_eta, d_s, d_phi
+
+
+def _blunt_reference_volume(n_eta, n_s, n_phi, geom):
+    a, b, c = _blunt_reference_cell(n_eta, n_s, n_phi, geom)
+    return a * b * c
+
+
+def _blunt_reference_dt(n_eta, n_s, n_phi, geom, courant, speed):
+    return courant * min(_blunt_reference_cell(n_eta, n_s, n_phi, geom)) / speed

@@ -161,6 +161,8 @@ class UniGasCloud:
                                "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch, uniGasWangPressureInletPatch, "
                                "uniGasLiouFangPressureOutletPatch)")
             patch = self.mesh.patch_index(entry["generalBoundaryProperties"]["patch"])
+            if self.mesh.patches[patch].size == 0:
+                continue  # a decomposed case: this rank holds no face of the patch
             pr = entry[word + "Properties"]
             if word == "uniGasFreeStreamInflowFieldPatch":
                 # the reference reads the volFields boundaryNumberDensity_<species>, boundaryTransT, boundaryRotT, boundaryU from
@@ -714,6 +716,51 @@ class UniGasCloud:
         a = (C.c_double * _capi.UGF_NPHASE)()
         self._check(self.api.phase_times(self._h, a))
         return dict(zip(("inflow", "move", "sort", "cell", "collide", "relax", "fields"), a[:]))
+
+    def transferBytes(self):
+        """(host -> device, device -> host, kernel-argument) bytes moved by this cloud since construction (ugf_transfer_bytes)."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.api.transfer_bytes(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def hostArray(self, n, dtype=np.float64):
+        """A page-locked numpy array of n items owned by the library (ugf_host_alloc): parcels handed over in such arrays
+        cross PCIe as asynchronous DMA.  Valid until the cloud is closed."""
+        dt = np.dtype(dtype)
+        ptr = C.c_void_p()
+        self._check(self.api.host_alloc(self._h, int(n) * dt.itemsize, C.byref(ptr)))
+        buf = (C.c_byte * (int(n) * dt.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dt, count=int(n))
+
+    def setParcelsSoA(self, n, x, y, z, Ux, Uy, Uz, cell, typeId=None, ERot=None):
+        """setParcels from structure-of-arrays columns that are already contiguous float64 / int32 (e.g. hostArray buffers):
+        no host-side copies."""
+        PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        p = _capi.Parcels()
+        p.n = int(n)
+        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz = [a.ctypes.data_as(PD) for a in (x, y, z, Ux, Uy, Uz)]
+        p.cell = cell.ctypes.data_as(PI)
+        if typeId is not None:
+            p.typeId = typeId.ctypes.data_as(PI)
+        if ERot is not None:
+            p.ERot = ERot.ctypes.data_as(PD)
+        self._check(self.api.upload_parcels(self._h, C.byref(p)))
+        self._nParcelsSet = True
+        self._cwfCarried = None
+
+    def parcelsInto(self, x, y, z, Ux, Uy, Uz, cell, ERot=None, typeId=None):
+        """Download the parcels into caller-owned columns (capacity = len(cell)); returns the count."""
+        PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        p = _capi.Parcels()
+        p.n = len(cell)
+        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz = [a.ctypes.data_as(PD) for a in (x, y, z, Ux, Uy, Uz)]
+        p.cell = cell.ctypes.data_as(PI)
+        if ERot is not None:
+            p.ERot = ERot.ctypes.data_as(PD)
+        if typeId is not None:
+            p.typeId = typeId.ctypes.data_as(PI)
+        self._check(self.api.download_parcels(self._h, C.byref(p)))
+        return int(p.n)
 
     def launchCount(self):
         n = C.c_int64()

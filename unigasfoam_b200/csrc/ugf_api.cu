@@ -71,6 +71,7 @@ struct ugf_handle {
     cudaStream_t stream = nullptr;
     int numSMs = NUM_SMS;
     long long launches = 0;
+    long long h2dBytes = 0, d2hBytes = 0, argBytes = 0;  // explicit copies and kernel-argument blocks since create
 
     int nSpecies = 0;
     ugf_species spHost[UGF_MAX_SPECIES];
@@ -145,7 +146,8 @@ struct ugf_handle {
     // face tracker
     int nTracked = 0;
     int* dSlotTrack = nullptr; int* dBfTrack = nullptr; double* dFt = nullptr;
-    std::vector<int> slotFaceHost;         // face label of every stored face slot (set_mesh)
+    std::vector<int> slotFaceHost;         // face label of every stored face slot (set_mesh), -1 for a padding slot
+    std::vector<int> slotOffHost;          // [nCells+1] first slot of every cell
     bool cloneValid = false;               // dNclone belongs to the current (not yet gathered) array
     bool subLevelsAllOne = true;
 
@@ -162,6 +164,7 @@ struct ugf_handle {
 
     std::vector<InflowHost> inflows;
     std::vector<double*> wallFieldOwned;      // boundaryT / boundaryU of *FieldPatch walls
+    std::vector<void*> hostOwned;              // pinned host buffers handed out by ugf_host_alloc
     std::vector<void*> peerOwned, peerOpened;  // NVLink peer-memory transfer buffers (cudaIpc)
     std::vector<double*> packBuf;
     std::vector<long long> packCap;
@@ -183,6 +186,20 @@ struct ugf_handle {
 namespace {
 
 std::string g_createErr;
+
+// every explicit host <-> device copy goes through these two so that ugf_transfer_bytes can report what a step really moved
+inline void count_copy(ugf_handle* h, size_t bytes, cudaMemcpyKind kind) {
+    if (kind == cudaMemcpyHostToDevice) h->h2dBytes += (long long)bytes;
+    else if (kind == cudaMemcpyDeviceToHost) h->d2hBytes += (long long)bytes;
+}
+inline cudaError_t countedMemcpyAsync(ugf_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    count_copy(h, bytes, kind);
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
+inline cudaError_t countedMemcpy(ugf_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    count_copy(h, bytes, kind);
+    return cudaMemcpy(dst, src, bytes, kind);
+}
 
 int fail(ugf_handle* h, const std::string& m) {
     if (h) h->err = m; else g_createErr = m;
@@ -221,15 +238,19 @@ int dalloc(ugf_handle* h, T** p, size_t n) {
 
 template <class T>
 int upload(ugf_handle* h, T* dst, const T* src, size_t n) {
-    if (n) CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    if (n) CU(countedMemcpyAsync(h, dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
+
+// bytes of a kernel's argument block (what the launch sends to the device besides the grid), summed over its arguments
+template <class... A>
+constexpr long long arg_bytes(const A&...) { return (long long)(0 + ... + sizeof(A)); }
 
 inline unsigned grid_for(long long n, int block) { return (unsigned)std::max<long long>(1, (n + block - 1) / block); }
 
 int check_device_error(ugf_handle* h) {
     int e = 0;
-    CU(cudaMemcpyAsync(&e, h->dErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, &e, h->dErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (e == 1) return fail(h, "parcel capacity exceeded while inserting or cloning parcels (raise parcelCapacity)");
     if (e == 2) return fail(h, "received parcel with a face index outside the processor patch");
@@ -272,7 +293,7 @@ int refresh_n_lazy(ugf_handle* h, bool* exact) {
 }
 
 int request_n(ugf_handle* h) {
-    CU(cudaMemcpyAsync(h->pinN, h->dN, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, h->pinN, h->dN, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->evN, h->stream));
     h->nPending = true;
     h->appendBound = 0;  // the copy is ordered after everything appended so far
@@ -343,6 +364,7 @@ int do_sort(ugf_handle* h) {
     const int nb = (nC + SCAN_TILE - 1) / SCAN_TILE;
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums);
     LAUNCHED();
+    h->argBytes += 20 + 56 + 56 + 32;  // the four occupancy kernels' argument blocks
     scan_final_self_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(h->dCellCount, nC, h->dBlockSums, nb, h->dTotal, h->dOff, h->capacity, h->dErr);
     LAUNCHED();
     scatter_index_kernel<<<grid_for(h->nUpper, 256 * SCAT_ROWS), 256, 0, h->stream>>>(h->buf[h->cur].cell, h->dN, h->dOff, h->dCellCount, h->dPerm,
@@ -404,6 +426,7 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
         cell_kernel<decltype(R)::value, decltype(M)::value><<<h->cellBlocks, CELL_THREADS, h->cellSmem, h->stream>>>(prm, a);
     });
     LAUNCHED();
+    h->argBytes += arg_bytes(prm, a);
     if (doSample) h->momValid = keepMoments;
     if (gather) return after_gather(h, false);
     return 0;
@@ -444,6 +467,7 @@ int run_ntc_kernel(ugf_handle* h) {
             });
         }
         LAUNCHED();
+        h->argBytes += arg_bytes(prm, a);
     }
     return 0;
 }
@@ -473,6 +497,7 @@ int run_bgk_kernel(ugf_handle* h) {
     if (h->multi) bgk_kernel<true><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
     else bgk_kernel<false><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
     LAUNCHED();
+    h->argBytes += arg_bytes(prm, a);
     return 0;
 }
 
@@ -493,6 +518,7 @@ int do_inflow(ugf_handle* h) {
             inflow_insert_kernel<decltype(R)::value, decltype(M)::value><<<grid_for(f.nSlots, 128), 128, 0, h->stream>>>(prm, dev, P, step);
         });
         LAUNCHED();
+        h->argBytes += 3 * arg_bytes(prm, dev) + 64;
         h->nUpper += f.maxInsert;
         h->appendBound += f.maxInsert;
     }
@@ -562,6 +588,7 @@ int do_move(ugf_handle* h, long long begin, bool received) {
             }
         });
         LAUNCHED();
+        h->argBytes += arg_bytes(prm, a);
     }
     h->histValid = true;
     h->occValid = false;
@@ -569,7 +596,7 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     if (h->prm.cwf) {
         h->cloneValid = true;
         if (h->cwfDirty) {  // every parcel now carries the new factors
-            CU(cudaMemcpyAsync(h->dCwf[h->cwfCur ^ 1], h->dCwf[h->cwfCur], sizeof(double) * h->nCells, cudaMemcpyDeviceToDevice, h->stream));
+            CU(countedMemcpyAsync(h, h->dCwf[h->cwfCur ^ 1], h->dCwf[h->cwfCur], sizeof(double) * h->nCells, cudaMemcpyDeviceToDevice, h->stream));
             h->cwfHostPrev = h->cwfHost;
             h->cwfDirty = false;
             h->prm.cwfDirty = 0;
@@ -611,6 +638,7 @@ int do_accumulate(ugf_handle* h, bool cellsDone = false) {
             const long long cnt = (last - first) * UGF_NBM;
             accumulate_walls_kernel<<<grid_for(cnt, 256), 256, 0, h->stream>>>(h->cfg.deltaT, accumulate, cnt, h->dBm + first * UGF_NBM, h->dBacc + first * UGF_NBM);
             LAUNCHED();
+            h->argBytes += 40;
             p = q;
         }
     }
@@ -717,7 +745,7 @@ int do_decompose(ugf_handle* h) {
     LAUNCHED();
     if (h->dec.refinementPasses > 0) {
         std::vector<int32_t> id((size_t)nC);
-        CU(cudaMemcpyAsync(id.data(), h->dCollId, sizeof(int32_t) * (size_t)nC, cudaMemcpyDeviceToHost, h->stream));
+        CU(countedMemcpyAsync(h, id.data(), h->dCollId, sizeof(int32_t) * (size_t)nC, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         refine_mask(h, id);
         if (upload(h, h->dCollId, id.data(), (size_t)nC)) return 1;
@@ -816,6 +844,7 @@ int ugf_destroy(ugf_handle* h) {
     for (void* p : h->decompOwned) cudaFree(p);
     for (void* p : h->peerOpened) cudaIpcCloseMemHandle(p);
     for (void* p : h->peerOwned) cudaFree(p);
+    for (void* p : h->hostOwned) cudaFreeHost(p);
     if (h->pinN) cudaFreeHost(h->pinN);
     if (h->evN) cudaEventDestroy(h->evN);
     for (int i = 0; i < UGF_NPHASE + 1; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -885,6 +914,30 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
         const int cnt = cfOffDev[c + 1] - cfOffDev[c];
         if (c == 0) uniformNF = cnt; else if (cnt != uniformNF) uniformNF = 0;
     }
+    // Cells with fewer reachable faces than their neighbours (wedges on the axis of a revolved block, prisms, cells that lost
+    // a collapsed face) are padded with null planes {0,0,0,0}: nd = 0 for every displacement, so such a slot is never
+    // selected, and the mesh keeps the unrolled 4- / 6-slot tracking loop.  UGF_MOVE_NF0=1 forces the general CSR walk.
+    const bool forceCsr = std::getenv("UGF_MOVE_NF0") && std::atoi(std::getenv("UGF_MOVE_NF0")) != 0;
+    int maxCnt = 0;
+    for (int c = 0; c < nC; ++c) maxCnt = std::max(maxCnt, cfOffDev[c + 1] - cfOffDev[c]);
+    if (!forceCsr && uniformNF != 4 && uniformNF != 6 && maxCnt <= 6 && maxCnt >= 1) {
+        const int target = maxCnt <= 4 ? 4 : 6;
+        std::vector<double4> plane2((size_t)nC * target, double4{0.0, 0.0, 0.0, 0.0});
+        std::vector<int> nbr2((size_t)nC * target), face2((size_t)nC * target, -1);
+        for (int c = 0; c < nC; ++c) {
+            const int b = cfOffDev[c], n = cfOffDev[c + 1] - b;
+            for (int k = 0; k < target; ++k) {
+                const size_t d = (size_t)c * target + k;
+                if (k < n) { plane2[d] = plane[b + k]; nbr2[d] = nbr[b + k]; face2[d] = h->slotFaceHost[b + k]; }
+                else nbr2[d] = c;
+            }
+        }
+        for (int c = 0; c <= nC; ++c) cfOffDev[c] = c * target;
+        plane.swap(plane2); nbr.swap(nbr2); h->slotFaceHost.swap(face2);
+        uniformNF = target;
+    }
+    if (forceCsr) uniformNF = 0;
+    h->slotOffHost = cfOffDev;
     h->nSlots = (int)plane.size();
     h->moveNF = (uniformNF == 4 || uniformNF == 6) ? uniformNF : 0;
     std::vector<int> bfPatch(std::max(nB, 1), -1), bfOwner(std::max(nB, 1), 0);
@@ -1067,7 +1120,7 @@ int ugf_set_patch_model(ugf_handle* h, int32_t patch, int32_t model, const doubl
         return fail(h, "unknown wall model");
     }
     d.wallModel = model;
-    CU(cudaMemcpyAsync(h->dPatches + patch, &d, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
+    CU(countedMemcpyAsync(h, h->dPatches + patch, &d, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1086,7 +1139,7 @@ int ugf_set_patch_wall_fields(ugf_handle* h, int32_t patch, const double* T, con
     h->wallFieldOwned.push_back(dU);
     if (upload(h, dT, T, n) || upload(h, dU, U, 3 * n)) return 1;
     d.faceT = dT; d.faceU = dU;
-    CU(cudaMemcpyAsync(h->dPatches + patch, &d, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
+    CU(countedMemcpyAsync(h, h->dPatches + patch, &d, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1299,7 +1352,7 @@ int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U) {
     if (!h) return 1;
     for (InflowHost& f : h->inflows)
         if (f.patch == patch && f.pressureInlet) {
-            CU(cudaMemcpyAsync(U, f.dev.faceVel, sizeof(double) * 3 * (size_t)f.dev.nFaces, cudaMemcpyDeviceToHost, h->stream));
+            CU(countedMemcpyAsync(h, U, f.dev.faceVel, sizeof(double) * 3 * (size_t)f.dev.nFaces, cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
             return 0;
         }
@@ -1363,12 +1416,12 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p) {
         if (upload(h, P.type, types.data(), n)) return 1;
     }
     const long long nn = p->n;
-    CU(cudaMemcpyAsync(h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CU(countedMemcpyAsync(h, h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->nUpper = nn; h->nPending = false; h->newFrom = nn; h->recvStart = -1;
     h->cloneValid = false;
     if (h->dCwf[0] && h->cwfDirty) {  // a fresh cloud carries the current factors
-        CU(cudaMemcpy(h->dCwf[h->cwfCur ^ 1], h->dCwf[h->cwfCur], sizeof(double) * h->nCells, cudaMemcpyDeviceToDevice));
+        CU(countedMemcpy(h, h->dCwf[h->cwfCur ^ 1], h->dCwf[h->cwfCur], sizeof(double) * h->nCells, cudaMemcpyDeviceToDevice));
         h->cwfHostPrev = h->cwfHost;
         h->cwfDirty = false;
         h->prm.cwfDirty = 0;
@@ -1622,8 +1675,8 @@ int ugf_decompose(ugf_handle* h) {
 int ugf_download_decomposition(ugf_handle* h, int32_t* id, double* kn) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (!h->decompOn) return fail(h, "no decomposition model set");
-    if (id) CU(cudaMemcpyAsync(id, h->dCollId, sizeof(int32_t) * (size_t)h->nCells, cudaMemcpyDeviceToHost, h->stream));
-    if (kn) CU(cudaMemcpyAsync(kn, h->dKnK[h->knCur], sizeof(double) * (size_t)h->nCells * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (id) CU(countedMemcpyAsync(h, id, h->dCollId, sizeof(int32_t) * (size_t)h->nCells, cudaMemcpyDeviceToHost, h->stream));
+    if (kn) CU(countedMemcpyAsync(h, kn, h->dKnK[h->knCur], sizeof(double) * (size_t)h->nCells * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1672,13 +1725,13 @@ int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles) {
     const double sc[6] = {(double)h->step, h->timeAvCounter, (double)h->nAvTimeSteps, (double)h->sampleCounter, (double)h->decTimeSteps, h->decTimeAv};
     std::copy(sc, sc + 6, p); p += 6;
     auto d2h = [&](const double* src, size_t n) -> int {
-        if (n) CU(cudaMemcpyAsync(p, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+        if (n) CU(countedMemcpyAsync(h, p, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
         p += n;
         return 0;
     };
     if (d2h(h->dSigma, nC)) return 1;
     std::vector<int> ids(nC);
-    CU(cudaMemcpyAsync(ids.data(), h->dCollId, sizeof(int) * nC, cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, ids.data(), h->dCollId, sizeof(int) * nC, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (size_t c = 0; c < nC; ++c) p[c] = ids[c];
     p += nC;
@@ -1714,7 +1767,7 @@ int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
     h->decTimeSteps = (int)p[4]; h->decTimeAv = p[5];
     p += 6;
     auto h2d = [&](double* dst, size_t n) -> int {
-        if (n && dst) CU(cudaMemcpyAsync(dst, p, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+        if (n && dst) CU(countedMemcpyAsync(h, dst, p, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
         p += n;
         return 0;
     };
@@ -1722,7 +1775,7 @@ int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
     std::vector<int> ids(nC);
     for (size_t c = 0; c < nC; ++c) ids[c] = (int)p[c];
     p += nC;
-    CU(cudaMemcpyAsync(h->dCollId, ids.data(), sizeof(int) * nC, cudaMemcpyHostToDevice, h->stream));
+    CU(countedMemcpyAsync(h, h->dCollId, ids.data(), sizeof(int) * nC, cudaMemcpyHostToDevice, h->stream));
     if (h2d(h->dMaxProb, nC) || h2d(h->dQPrev, 3 * nC) || h2d(h->dSPrev, 6 * nC) || h2d(h->dAcc, NACC * nC) || h2d(h->dAccS, nS * nC) ||
         h2d(h->dBacc, UGF_NBM * nB))
         return 1;
@@ -1796,7 +1849,7 @@ int ugf_step(ugf_handle* h, int32_t nSteps) {
 int ugf_migrate_counts(ugf_handle* h, int64_t* counts) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     std::vector<int> c(std::max(h->nPatches, 1), 0);
-    CU(cudaMemcpyAsync(c.data(), h->dMigCount, sizeof(int) * h->nPatches, cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, c.data(), h->dMigCount, sizeof(int) * h->nPatches, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (int p = 0; p < h->nPatches; ++p) counts[p] = c[p];
     return 0;
@@ -1806,7 +1859,7 @@ int ugf_migrate_pack(ugf_handle* h, int32_t patch, double** devBuf, int64_t* nPa
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (patch < 0 || patch >= h->nPatches || h->patchKind[patch] != UGF_PATCH_PROCESSOR) return fail(h, "pack on a non-processor patch");
     int count = 0;
-    CU(cudaMemcpyAsync(&count, h->dMigCount + patch, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, &count, h->dMigCount + patch, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (count > h->packCap[patch]) {
         if (h->packBuf[patch]) CU(cudaFree(h->packBuf[patch]));
@@ -1852,7 +1905,7 @@ int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64
     h->appendBound += n;
     const long long nn = h->nUpper;
     // the host mirror is exact here (no insertion since the last refresh), so the device length follows it
-    CU(cudaMemcpyAsync(h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CU(countedMemcpyAsync(h, h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->occValid = false; h->momValid = false;
     return 0;
@@ -1995,11 +2048,11 @@ int ugf_counters_get(ugf_handle* h, ugf_counters* out) {
             totals_kernel<decltype(R)::value, decltype(M)::value><<<h->numSMs * 4, 256, 0, h->stream>>>(prm, P, h->dN, h->dTot);
         });
         LAUNCHED();
-        CU(cudaMemcpyAsync(tot, h->dTot, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(countedMemcpyAsync(h, tot, h->dTot, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
-    CU(cudaMemcpyAsync(&c, h->dCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, &c, h->dCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     int devErr = 0;
-    CU(cudaMemcpyAsync(&devErr, h->dErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));  // same round trip as the counters
+    CU(countedMemcpyAsync(h, &devErr, h->dErr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));  // same round trip as the counters
     CU(cudaStreamSynchronize(h->stream));
     if (devErr && check_device_error(h)) return 1;
     out->step = h->step;
@@ -2024,17 +2077,17 @@ int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     CU(cudaSetDevice(h->cfg.device));
     long long n = 0;
-    CU(cudaMemcpyAsync(&n, h->dN, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, &n, h->dN, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (p->n < n) return fail(h, "download buffer too small");
     const ParcelBuf& P = h->buf[h->cur];
     const size_t nb = (size_t)n;
     auto dl = [&](double* dst, const double* src) -> int {
-        if (dst && nb) CU(cudaMemcpyAsync(dst, src, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (dst && nb) CU(countedMemcpyAsync(h, dst, src, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         return 0;
     };
     if (dl(p->x, P.x) || dl(p->y, P.y) || dl(p->z, P.z) || dl(p->Ux, P.ux) || dl(p->Uy, P.uy) || dl(p->Uz, P.uz)) return 1;
-    if (p->cell && nb) CU(cudaMemcpyAsync(p->cell, P.cell, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (p->cell && nb) CU(countedMemcpyAsync(h, p->cell, P.cell, nb * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (p->ERot) {
         if (h->hasRot) { if (dl(p->ERot, P.erot)) return 1; }
         else std::fill(p->ERot, p->ERot + nb, 0.0);
@@ -2043,7 +2096,7 @@ int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
     if (p->typeId) {
         if (h->multi && nb) {
             types.resize(nb);
-            CU(cudaMemcpyAsync(types.data(), P.type, nb, cudaMemcpyDeviceToHost, h->stream));
+            CU(countedMemcpyAsync(h, types.data(), P.type, nb, cudaMemcpyDeviceToHost, h->stream));
         }
     }
     CU(cudaStreamSynchronize(h->stream));
@@ -2054,7 +2107,7 @@ int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
         const int* cp = p->cell;
         if (!cp && nb) {
             cells.resize(nb);
-            CU(cudaMemcpy(cells.data(), P.cell, nb * sizeof(int), cudaMemcpyDeviceToHost));
+            CU(countedMemcpy(h, cells.data(), P.cell, nb * sizeof(int), cudaMemcpyDeviceToHost));
             cp = cells.data();
         }
         const std::vector<double>& w = h->cwfDirty ? h->cwfHostPrev : h->cwfHost;
@@ -2067,13 +2120,13 @@ int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
 int ugf_download_cell_occupancy(ugf_handle* h, int32_t* off, int32_t* ids) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (!h->occValid) return fail(h, "cell occupancy not built (call ugf_sort)");
-    CU(cudaMemcpyAsync(off, h->dOff, sizeof(int) * ((size_t)h->nCells + 1), cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, off, h->dOff, sizeof(int) * ((size_t)h->nCells + 1), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (ids) {
         const int n = off[h->nCells];
         if (h->occIdentity) { for (int i = 0; i < n; ++i) ids[i] = i; }
         else if (n) {
-            CU(cudaMemcpyAsync(ids, h->dPerm, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+            CU(countedMemcpyAsync(h, ids, h->dPerm, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
         }
     }
@@ -2083,7 +2136,7 @@ int ugf_download_cell_occupancy(ugf_handle* h, int32_t* off, int32_t* ids) {
 int ugf_download_cell_moments(ugf_handle* h, double* m) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (!h->momValid) return fail(h, "cell moments not sampled");
-    CU(cudaMemcpyAsync(m, h->dMom, sizeof(double) * (size_t)h->nCells * h->nSpecies * UGF_NMOM, cudaMemcpyDeviceToHost, h->stream));
+    CU(countedMemcpyAsync(h, m, h->dMom, sizeof(double) * (size_t)h->nCells * h->nSpecies * UGF_NMOM, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -2091,10 +2144,10 @@ int ugf_download_cell_moments(ugf_handle* h, double* m) {
 int ugf_download_cell_state(ugf_handle* h, double* s, double* mp, double* q, double* sp) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     const size_t nC = (size_t)h->nCells;
-    if (s) CU(cudaMemcpyAsync(s, h->dSigma, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->stream));
-    if (mp) CU(cudaMemcpyAsync(mp, h->dMaxProb, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->stream));
-    if (q) CU(cudaMemcpyAsync(q, h->dQPrev, sizeof(double) * 3 * nC, cudaMemcpyDeviceToHost, h->stream));
-    if (sp) CU(cudaMemcpyAsync(sp, h->dSPrev, sizeof(double) * 6 * nC, cudaMemcpyDeviceToHost, h->stream));
+    if (s) CU(countedMemcpyAsync(h, s, h->dSigma, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->stream));
+    if (mp) CU(countedMemcpyAsync(h, mp, h->dMaxProb, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->stream));
+    if (q) CU(countedMemcpyAsync(h, q, h->dQPrev, sizeof(double) * 3 * nC, cudaMemcpyDeviceToHost, h->stream));
+    if (sp) CU(countedMemcpyAsync(h, sp, h->dSPrev, sizeof(double) * 6 * nC, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -2111,13 +2164,13 @@ int ugf_download_fields(ugf_handle* h, double* cellF, double* wallF, int32_t res
         derive_cells_kernel<<<grid_for(nC, 256), 256, 0, h->stream>>>(h->prm, nC, h->dAcc, h->dAccS, h->dVol, h->dBbMin, h->dBbMax,
                                                                       h->subLevelsAllOne ? nullptr : h->dSubLevels, t, (double)h->nAvTimeSteps, tmp);
         LAUNCHED();
-        CU(cudaMemcpyAsync(cellF, tmp, sizeof(double) * (size_t)nC * UGF_NFIELD, cudaMemcpyDeviceToHost, h->stream));
+        CU(countedMemcpyAsync(h, cellF, tmp, sizeof(double) * (size_t)nC * UGF_NFIELD, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
     if (wallF && nB > 0) {
         derive_walls_kernel<<<grid_for(nB, 256), 256, 0, h->stream>>>(h->prm, h->mesh, h->dBacc, h->dBfS, t, tmp);
         LAUNCHED();
-        CU(cudaMemcpyAsync(wallF, tmp, sizeof(double) * (size_t)nB * UGF_NWALLFIELD, cudaMemcpyDeviceToHost, h->stream));
+        CU(countedMemcpyAsync(h, wallF, tmp, sizeof(double) * (size_t)nB * UGF_NWALLFIELD, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
     CU(cudaFree(tmp));
@@ -2137,8 +2190,8 @@ int ugf_download_accumulators(ugf_handle* h, double* acc, double* accS, double* 
     std::vector<double> tmp;
     if (accS && !h->dAccS && !acc) tmp.resize(nC * NACC);
     double* a = acc ? acc : (tmp.empty() ? nullptr : tmp.data());
-    if (a) CU(cudaMemcpyAsync(a, h->dAcc, sizeof(double) * nC * NACC, cudaMemcpyDeviceToHost, h->stream));
-    if (accS && h->dAccS) CU(cudaMemcpyAsync(accS, h->dAccS, sizeof(double) * nC * nS, cudaMemcpyDeviceToHost, h->stream));
+    if (a) CU(countedMemcpyAsync(h, a, h->dAcc, sizeof(double) * nC * NACC, cudaMemcpyDeviceToHost, h->stream));
+    if (accS && h->dAccS) CU(countedMemcpyAsync(h, accS, h->dAccS, sizeof(double) * nC * nS, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (accS && !h->dAccS) for (size_t c = 0; c < nC; ++c) accS[c] = a[c * NACC + 8];  // one species: slot 8
     if (timeAv) *timeAv = h->timeAvCounter;
@@ -2161,15 +2214,10 @@ int ugf_set_face_tracker(ugf_handle* h, int32_t n, const int32_t* faces) {
         faceIdx[faces[k]] = k + 1;
     }
     std::vector<int> slotTrack(h->slotFaceHost.size(), 0), bfTrack((size_t)std::max(h->nBFaces, 1), 0);
-    size_t slot = 0;
-    // slots were stored cell by cell in cellFaces order, skipping the never-hit faces: walk them the same way
     for (int c = 0; c < h->nCells; ++c)
-        for (int j = h->cfOffHost[c]; j < h->cfOffHost[c + 1]; ++j) {
-            const int f = h->cfHost[j];
-            if (slot < h->slotFaceHost.size() && h->slotFaceHost[slot] == f) {
-                if (f < h->nInternal && faceIdx[f]) slotTrack[slot] = (h->ownerHost[f] == c) ? faceIdx[f] : -faceIdx[f];
-                ++slot;
-            }
+        for (int slot = h->slotOffHost[c]; slot < h->slotOffHost[c + 1]; ++slot) {
+            const int f = h->slotFaceHost[slot];
+            if (f >= 0 && f < h->nInternal && faceIdx[f]) slotTrack[slot] = (h->ownerHost[f] == c) ? faceIdx[f] : -faceIdx[f];
         }
     for (int p = 0; p < h->nPatches; ++p)
         for (int k = 0; k < h->patchSize[p]; ++k) {
@@ -2191,7 +2239,7 @@ int ugf_download_face_tracker(ugf_handle* h, double* out, int32_t reset) {
     if (!h || !h->nTracked) return fail(h, "no face tracker set");
     CU(cudaSetDevice(h->cfg.device));
     const size_t nv = (size_t)h->nTracked * h->nSpecies * UGF_NFT;
-    if (out) CU(cudaMemcpyAsync(out, h->dFt, sizeof(double) * nv, cudaMemcpyDeviceToHost, h->stream));
+    if (out) CU(countedMemcpyAsync(h, out, h->dFt, sizeof(double) * nv, cudaMemcpyDeviceToHost, h->stream));
     if (reset) CU(cudaMemsetAsync(h->dFt, 0, sizeof(double) * nv, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
@@ -2200,9 +2248,34 @@ int ugf_download_face_tracker(ugf_handle* h, double* out, int32_t reset) {
 int ugf_download_boundary_meas(ugf_handle* h, double* bm) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (h->nBFaces > 0) {
-        CU(cudaMemcpyAsync(bm, h->dBm, sizeof(double) * (size_t)h->nBFaces * UGF_NBM, cudaMemcpyDeviceToHost, h->stream));
+        CU(countedMemcpyAsync(h, bm, h->dBm, sizeof(double) * (size_t)h->nBFaces * UGF_NBM, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
+    return 0;
+}
+
+int ugf_transfer_bytes(ugf_handle* h, int64_t* h2d, int64_t* d2h, int64_t* kernelArgs) {
+    if (!h) return 1;
+    if (h2d) *h2d = h->h2dBytes;
+    if (d2h) *d2h = h->d2hBytes;
+    if (kernelArgs) *kernelArgs = h->argBytes;
+    return 0;
+}
+
+int ugf_host_alloc(ugf_handle* h, int64_t bytes, void** ptr) {
+    if (!h || !ptr || bytes < 0) return fail(h, "ugf_host_alloc: bad argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+    h->hostOwned.push_back(*ptr);
+    return 0;
+}
+
+int ugf_host_free(ugf_handle* h, void* ptr) {
+    if (!h) return 1;
+    auto it = std::find(h->hostOwned.begin(), h->hostOwned.end(), ptr);
+    if (it == h->hostOwned.end()) return fail(h, "ugf_host_free: not a ugf_host_alloc pointer of this handle");
+    h->hostOwned.erase(it);
+    CU(cudaFreeHost(ptr));
     return 0;
 }
 

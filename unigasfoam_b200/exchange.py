@@ -363,3 +363,68 @@ def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64,
         cloud.finishStep()
     if fixed_rounds:
         exchanger.check_settled()
+
+
+class LocalSubdomains:
+    """All subdomains of a decomposed case inside ONE process: the transfer loop of Cloud::move between clouds that live in
+    the same address space (host pointers), with the exact termination rule.  Used by bench.py's reference arm - the CPU
+    restatement of an N-rank run on the host's cores, where a process per rank would only split the same cores - and by CPU
+    tests of the per-rank block builders.  clouds[r] / meshes[r] = rank r."""
+
+    def __init__(self, clouds, meshes):
+        self.clouds, self.meshes = clouds, meshes
+        self.links = []  # (rank, patch, peer rank, peer patch)
+        for r, m in enumerate(meshes):
+            for pi, p in enumerate(m.patches):
+                if p.kind != "processor":
+                    continue
+                peer = p.partner
+                want = _receiver_view(tuple(p.tag)) if p.tag else ("i",)
+                qi = p.peer_patch
+                if qi < 0:
+                    cands = [k for k, q in enumerate(meshes[peer].patches)
+                             if q.kind == "processor" and q.partner == r and (tuple(q.tag) if q.tag else ("i",)) == want]
+                    if len(cands) != 1:
+                        raise RuntimeError(f"rank {r} patch {p.name}: no unique matching processor patch on rank {peer}")
+                    qi = cands[0]
+                if meshes[peer].patches[qi].size != p.size:
+                    raise RuntimeError(f"processor patches {p.name} / {meshes[peer].patches[qi].name} differ in size")
+                self.links.append((r, pi, peer, qi))
+        self.rounds = 0
+
+    def exchange(self):
+        """One transfer round over all subdomains; returns the number of parcels that were in flight."""
+        total = 0
+        for cl in self.clouds:
+            total += int(cl.migrateCounts().sum())
+        if total == 0:
+            return 0
+        self.rounds += 1
+        packed = []
+        for r, pi, peer, qi in self.links:  # pack everything first: a parcel received in this round waits for the next one
+            buf, n = self.clouds[r].migratePack(pi)
+            if n:
+                rec = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(n * STRIDE,)).copy()
+                packed.append((peer, qi, rec, n))
+        for peer, qi, rec, n in packed:
+            self.clouds[peer].migrateUnpack(qi, rec.ctypes.data_as(C.POINTER(C.c_double)), n)
+        for cl in self.clouds:
+            cl.moveReceived()
+        return total
+
+    def evolve(self, n_steps=1, inflow=False, max_rounds=64):
+        for _ in range(n_steps):
+            for cl in self.clouds:
+                if inflow:
+                    cl.controlBeforeMove()
+                cl.move()
+            for _r in range(max_rounds):
+                if self.exchange() == 0:
+                    break
+            else:
+                raise RuntimeError("parcel migration did not settle")
+            for cl in self.clouds:
+                cl.finishStep()
+
+    def size(self):
+        return sum(cl.size() for cl in self.clouds)

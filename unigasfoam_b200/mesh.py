@@ -90,67 +90,88 @@ class PolyMesh:
         nv = np.diff(off)
         Sf = np.zeros((nF, 3))
         Cf = np.zeros((nF, 3))
-        for k in np.unique(nv):  # faces grouped by vertex count (all quads for hex blocks)
-            sel = np.nonzero(nv == k)[0]
-            idx = off[sel][:, None] + np.arange(k)[None, :]
-            P = pts[self.face_points[idx]]  # [n,k,3]
+        fmin = np.zeros((nF, 3))
+        fmax = np.zeros((nF, 3))
+        kinds = np.unique(nv) if nF == 0 or nv.min() != nv.max() else nv[:1]
+        for k in kinds:  # faces grouped by vertex count (all quads for hex blocks)
+            all_k = len(kinds) == 1
+            sel = slice(None) if all_k else np.nonzero(nv == k)[0]
+            if all_k:
+                P = pts[self.face_points.reshape(nF, k)]  # [n,k,3]
+            else:
+                idx = off[sel][:, None] + np.arange(k)[None, :]
+                P = pts[self.face_points[idx]]
+            fmin[sel] = P.min(axis=1)
+            fmax[sel] = P.max(axis=1)
             if k == 3:
                 n2 = np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
                 Sf[sel] = 0.5 * n2
                 Cf[sel] = P.mean(axis=1)
                 continue
             fc = P.mean(axis=1)
-            sumN = np.zeros((len(sel), 3))
-            sumA = np.zeros(len(sel))
-            sumAc = np.zeros((len(sel), 3))
+            sumN = np.zeros((len(fc), 3))
+            sumA = np.zeros(len(fc))
+            sumAc = np.zeros((len(fc), 3))
             for t in range(k):
                 a, b = P[:, t], P[:, (t + 1) % k]
                 n = np.cross(b - a, fc - a)
                 c = a + b + fc
-                mag = np.linalg.norm(n, axis=1)
+                mag = np.sqrt(n[:, 0] * n[:, 0] + n[:, 1] * n[:, 1] + n[:, 2] * n[:, 2])
                 sumN += n
                 sumA += mag
                 sumAc += mag[:, None] * c
             Sf[sel] = 0.5 * sumN
+            flat = sumA == 0.0  # collapsed faces (all vertices on one line, e.g. on the axis of a revolved block): never crossed
+            if flat.any():
+                sumA = np.where(flat, 1.0, sumA)
+                sumAc = np.where(flat[:, None], 3.0 * fc, sumAc)
             Cf[sel] = sumAc / (3.0 * sumA[:, None])
         self.face_areas, self.face_centres = Sf, Cf
         nI = len(self.neighbour)
         nC = n_cells if n_cells is not None else int(self.owner.max()) + 1
         # cell -> faces CSR, faces ascending within a cell
-        cells = np.concatenate([self.owner, self.neighbour])
-        faces = np.concatenate([np.arange(nF), np.arange(nI)])
-        order = np.lexsort((faces, cells))
-        self.cell_faces = faces[order].astype(np.int32)
+        if nI == 0 or (np.diff(self.owner[:nI]) >= 0).all():
+            # upper-triangular order: the faces a cell is neighbour of precede the faces it owns
+            cells = np.concatenate([self.neighbour, self.owner])
+            faces = np.concatenate([np.arange(nI), np.arange(nF)])
+            order = np.argsort(cells, kind="stable")
+            cf = faces[order]
+            # boundary faces of a cell follow its internal ones, but a cell's owned internal faces may interleave with
+            # nothing else: only the (neighbour-of, owner-of) split needs the upper-triangular property
+            chk = cells[order]
+            asc = (np.diff(cf) > 0) | (np.diff(chk) != 0)
+            if not asc.all():
+                order = np.lexsort((faces, cells))
+                cf = faces[order]
+            self.cell_faces = cf.astype(np.int32)
+        else:
+            cells = np.concatenate([self.owner, self.neighbour])
+            faces = np.concatenate([np.arange(nF), np.arange(nI)])
+            order = np.lexsort((faces, cells))
+            self.cell_faces = faces[order].astype(np.int32)
         counts = np.bincount(cells, minlength=nC)
         self.cell_face_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-        # cell centres / volumes by pyramid decomposition
-        cEst = np.zeros((nC, 3))
-        np.add.at(cEst, self.owner, Cf)
-        np.add.at(cEst, self.neighbour, Cf[:nI])
+        # cell centres / volumes by pyramid decomposition (scatter-adds in face order: owner part, then neighbour part)
+        on = np.concatenate([self.owner, self.neighbour])
+
+        def scatter3(a_own, a_nei):
+            w = np.concatenate([a_own, a_nei])
+            return np.stack([np.bincount(on, weights=w[:, d], minlength=nC) for d in range(3)], axis=1)
+
+        cEst = scatter3(Cf, Cf[:nI])
         cEst /= counts[:, None]
-        vol3 = np.zeros(nC)
-        cc = np.zeros((nC, 3))
         pyrO = np.einsum("ij,ij->i", Sf, Cf - cEst[self.owner])
         pcO = 0.75 * Cf + 0.25 * cEst[self.owner]
-        np.add.at(vol3, self.owner, pyrO)
-        np.add.at(cc, self.owner, pyrO[:, None] * pcO)
         pyrN = np.einsum("ij,ij->i", Sf[:nI], cEst[self.neighbour] - Cf[:nI])
         pcN = 0.75 * Cf[:nI] + 0.25 * cEst[self.neighbour]
-        np.add.at(vol3, self.neighbour, pyrN)
-        np.add.at(cc, self.neighbour, pyrN[:, None] * pcN)
+        vol3 = np.bincount(on, weights=np.concatenate([pyrO, pyrN]), minlength=nC)
+        cc = scatter3(pyrO[:, None] * pcO, pyrN[:, None] * pcN)
         self.cell_centres = cc / vol3[:, None]
         self.cell_volumes = vol3 / 3.0
-        # bounding box over cellPoints (noTimeCounter.C:112-127)
-        bbmin = np.full((nC, 3), np.inf)
-        bbmax = np.full((nC, 3), -np.inf)
-        fp_face = np.repeat(np.arange(nF), nv)
-        fp_pts = pts[self.face_points]
-        np.minimum.at(bbmin, self.owner[fp_face], fp_pts)
-        np.maximum.at(bbmax, self.owner[fp_face], fp_pts)
-        intm = fp_face < nI
-        np.minimum.at(bbmin, self.neighbour[fp_face[intm]], fp_pts[intm])
-        np.maximum.at(bbmax, self.neighbour[fp_face[intm]], fp_pts[intm])
-        self.cell_bb_min, self.cell_bb_max = bbmin, bbmax
+        # bounding box over cellPoints (noTimeCounter.C:112-127): min / max over the vertices of the cell's faces
+        starts = self.cell_face_offsets[:-1].astype(np.int64)
+        self.cell_bb_min = np.minimum.reduceat(fmin[self.cell_faces], starts, axis=0)
+        self.cell_bb_max = np.maximum.reduceat(fmax[self.cell_faces], starts, axis=0)
         return self
 
     # -- C view -------------------------------------------------------------------
@@ -570,3 +591,94 @@ def decompose(mesh, cell_rank, n_ranks):
                     break
             assert p.peer_patch >= 0
     return subs
+
+
+# ---- per-rank blocks of a structured mesh, built directly (no global mesh in memory) ---------------------------------
+
+def block_ranges(n, parts):
+    """The index ranges `method simple` gives `parts` blocks along an axis of n cells (same rule as block_partition)."""
+    idx = np.arange(n)
+    b = np.minimum((idx * parts) // n, parts - 1)
+    return [(int(np.nonzero(b == k)[0][0]), int(np.nonzero(b == k)[0][-1]) + 1) for k in range(parts)]
+
+
+def hex_corners(mesh):
+    """[nCells, 8] point labels of a structured block's cells: corner (di, dj, dk) at column di + 2 dj + 4 dk."""
+    nx, ny, nz = mesh.shape
+    c = np.arange(nx * ny * nz)
+    i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+    cols = []
+    for dk in (0, 1):
+        for dj in (0, 1):
+            for di in (0, 1):
+                cols.append((i + di) + (nx + 1) * ((j + dj) + (ny + 1) * (k + dk)))
+    return np.stack(cols, axis=1).astype(np.int32)
+
+
+def structured_subblock(global_shape, parts, rank, point_map, patch_kinds, solution_d=(1, 1, 1)):
+    """Block `rank` (= bx + px (by + py bz), the numbering of block_partition / decomposePar `simple`) of a structured mesh
+    of global_shape cells cut into parts = (px, py, pz) blocks, built on its own: what decomposePar would hand this rank,
+    without ever holding the global mesh.  point_map takes *global* vertex indices; patch_kinds names the sides of the
+    global block; sides that face another block become processor patches (`procBoundary<r>to<peer>`, same face order on
+    both sides).  -> (mesh, (i0, j0, k0)) with the block's first global cell index."""
+    px, py, pz = (int(v) for v in parts)
+    bx, by, bz = rank % px, (rank // px) % py, rank // (px * py)
+    rx, ry, rz = block_ranges(global_shape[0], px)[bx], block_ranges(global_shape[1], py)[by], block_ranges(global_shape[2], pz)[bz]
+    i0, j0, k0 = rx[0], ry[0], rz[0]
+
+    def pm(I, J, K):
+        return point_map(I + i0, J + j0, K + k0)
+
+    kinds, peers = {}, {}
+    for side, (b, p, step) in {"xMin": (bx, px, -1), "xMax": (bx, px, 1), "yMin": (by, py, -px), "yMax": (by, py, px),
+                               "zMin": (bz, pz, -px * py), "zMax": (bz, pz, px * py)}.items():
+        at_edge = (b == 0) if side.endswith("Min") else (b == p - 1)
+        if at_edge:
+            kinds[side] = patch_kinds[side]
+        else:
+            peer = rank + step
+            kinds[side] = (f"procBoundary{rank}to{peer}", "processor")
+            peers[side] = peer
+    m = structured_block(rx[1] - rx[0], ry[1] - ry[0], rz[1] - rz[0], pm, kinds, solution_d=solution_d)
+    for pi, side in enumerate(("xMin", "xMax", "yMin", "yMax", "zMin", "zMax")):
+        if side in peers:
+            q = m.patches[pi]
+            q.partner, q.tag = peers[side], ("i",)
+    have = {q.name for q in m.patches}
+    for side in ("xMin", "xMax", "yMin", "yMax", "zMin", "zMax"):  # decomposePar keeps every patch on every rank, empty where
+        name, kind = patch_kinds[side]                             # the rank does not touch it
+        if name not in have and kind != "cyclic":
+            m.patches.append(Patch(name, kind, m.n_faces, 0))
+            have.add(name)
+    return m, (i0, j0, k0)
+
+
+def sphere_cone_map(n_eta, n_s, n_phi, nose_radius=0.05, cone_half_angle_deg=30.0, cone_length=0.2, standoff=(0.02, 0.10),
+                    phi_max=0.5 * np.pi, grading=4.0):
+    """Point map of a blunted cone (sphere-cone fore-body) in a body-fitted grid: i runs along the body normal from the wall
+    (last / first cell size = grading) to the outer boundary, j along the body from the stagnation line, k in azimuth about the
+    x axis.  Every face is planar (isosceles trapezoids or meridian-plane quads) and the cells touching the axis (j = 0) are
+    wedges whose j = 0 side collapses onto the axis."""
+    a = np.deg2rad(cone_half_angle_deg)
+    th_t = 0.5 * np.pi - a                      # polar angle of the sphere / cone tangency point
+    s_sph = nose_radius * th_t
+    S = s_sph + cone_length
+    g = float(grading)
+
+    def pm(I, J, K):
+        s = S * J / n_s
+        on_sphere = s <= s_sph
+        th = np.where(on_sphere, s / nose_radius, th_t)
+        along = np.where(on_sphere, 0.0, s - s_sph)
+        bx = nose_radius * (1.0 - np.cos(th)) + along * np.cos(a)
+        br = nose_radius * np.sin(th) + along * np.sin(a)
+        nxm, nr = -np.cos(th), np.sin(th)       # outward normal in the meridian plane
+        t = I / n_eta
+        frac = t if abs(g - 1.0) < 1e-12 else (g ** t - 1.0) / (g - 1.0)
+        d = (standoff[0] + (standoff[1] - standoff[0]) * (s / S)) * frac
+        x = bx + d * nxm
+        r = np.where(J == 0, 0.0, br + d * nr)  # the stagnation line is the axis exactly
+        phi = -phi_max * K / n_phi              # (normal, along the body, azimuth) right-handed: revolve towards -z
+        return x, r * np.cos(phi), r * np.sin(phi)
+
+    return pm
