@@ -79,3 +79,100 @@ def test_config1_closed_box_1m_parcels_conserves_energy(GpuCloud):
     assert abs((sp ** 2).mean() - 3 * cases.kB * case.meta["T0"] / m) < 0.01 * 3 * cases.kB * case.meta["T0"] / m
     assert abs(sp.mean() - math.sqrt(8 * cases.kB * case.meta["T0"] / (math.pi * m))) < 0.01 * sp.mean()
     cl.close()
+
+
+def _inside_own_cell(mesh, p, sample=2_000_000, seed=0):
+    """Every parcel (of a random sample) lies inside all face planes of the cell it is filed under - general cells."""
+    n = len(p["cell"])
+    sel = np.random.default_rng(seed).choice(n, size=min(sample, n), replace=False)
+    cell, x = p["cell"][sel], p["position"][sel]
+    worst = np.zeros(len(sel))
+    nf = np.diff(mesh.cell_face_offsets)
+    A = np.linalg.norm(mesh.face_areas, axis=1)
+    for k in range(int(nf.max())):
+        has = nf[cell] > k
+        f = mesh.cell_faces[mesh.cell_face_offsets[cell[has]] + k]
+        sgn = np.where(mesh.owner[f] == cell[has], 1.0, -1.0)
+        ok = A[f] > 0
+        d = np.einsum("ij,ij->i", x[has] - mesh.face_centres[f], mesh.face_areas[f]) * sgn / np.where(ok, A[f], 1.0)
+        worst[has] = np.maximum(worst[has], np.where(ok, d, 0.0))
+    return worst.max()
+
+
+def _run_open_case(case, GpuCloud, steps):
+    """Steps an inflow / outflow case, returns (cloud, summed counters); checks the parcel balance of every step."""
+    cl = case.make_cloud(GpuCloud, parcelCapacity=int(1.6 * case.n_parcels) + 65536)
+    n = case.n_parcels
+    tot = dict(inserted=0, deleted=0, cloned=0, weightDeleted=0, collisions=0, bgkRelaxations=0, wallHits=0)
+    for _ in range(steps):
+        cl.evolve(1)
+        c = cl.counters()
+        assert c["stuck"] == 0
+        assert c["nParcels"] == n + c["inserted"] - c["deleted"] + c["cloned"] - c["weightDeleted"]  # nothing lost, nothing invented
+        n = c["nParcels"]
+        for k in tot:
+            tot[k] += c[k]
+    return cl, tot
+
+
+def _check_cell_major_and_occupancy(cl, mesh):
+    p = cl.parcels()
+    assert (np.diff(p["cell"]) >= 0).all()
+    cl.buildCellOccupancy()
+    off, ids = cl.cellOccupancy()
+    assert np.array_equal(np.diff(off), np.bincount(p["cell"], minlength=mesh.n_cells))
+    assert np.array_equal(ids, np.arange(len(ids)))
+    return p
+
+
+def test_config3_cylinder_50m_parcels(GpuCloud):
+    """configs[2]: 2-D Mach-10 argon cylinder, 1000 x 2500 cells, 50 M parcels, free-stream inflow / deleting outflow, diffuse
+    cylinder, NTC + VHS - on one GPU (the decomposed runs are bench.py's other_configs at N = 2 / 4)."""
+    case = cases.cylinder_block(0, 1)
+    assert case.mesh.n_cells == 2_500_000 and abs(case.n_parcels - 50_000_000) < 0.01 * 50_000_000
+    cl, tot = _run_open_case(case, GpuCloud, 6)
+    assert tot["inserted"] > 10_000 and tot["deleted"] > 10_000 and tot["wallHits"] > 1000 and tot["collisions"] > 10_000
+    p = _check_cell_major_and_occupancy(cl, case.mesh)
+    assert _inside_own_cell(case.mesh, p) < 1e-12
+    assert np.ptp(p["position"][:, 2]) == 0.0  # empty direction
+    # the free stream is still the free stream away from the body: mean velocity of the cloud within 2 % of U_inf
+    assert abs(p["U"][:, 0].mean() / case.meta["U_inf"] - 1.0) < 0.02
+    cl.close()
+
+
+def test_config4_hybrid_100m_parcels(GpuCloud):
+    """configs[3]: the cylinder topology at 10 n_inf, 100 M parcels, USP-SBGK relaxation in the upstream half and NTC + VHS in the
+    wake half (frozen mask, macroInterpolation false).  Both models act, and the relaxation conserves momentum and energy of
+    the BGK cells to round-off (checked through the global sums over a step without inflow / outflow contributions)."""
+    case = cases.cylinder_block(0, 1, parcels=100_000_000, hybrid=True)
+    assert case.mesh.n_cells == 2_500_000 and abs(case.n_parcels - 100_000_000) < 0.01 * 100_000_000
+    assert 0.45 < case.cellCollModelId.mean() < 0.55
+    cl, tot = _run_open_case(case, GpuCloud, 4)
+    assert tot["collisions"] > 10_000 and tot["bgkRelaxations"] > 100_000
+    # (no parcel download here: 100 M parcels are 7 GB of host arrays; configs[2] checks the filing on the same mesh)
+    # relax only: total momentum and kinetic energy of the cloud unchanged to round-off by the BGK step
+    c0 = cl.counters()
+    cl.calculateFields()
+    cl.relax()
+    c1 = cl.counters()
+    assert c1["bgkRelaxations"] > 10_000
+    assert abs(c1["linearKineticEnergy"] - c0["linearKineticEnergy"]) <= 1e-11 * c0["linearKineticEnergy"]
+    for k in range(3):
+        assert abs(c1["momentum"][k] - c0["momentum"][k]) <= 1e-10 * abs(c0["momentum"][0])
+    cl.close()
+
+
+def test_config5_blunt_body_shard_62m_parcels(GpuCloud):
+    """configs[4], one GPU's share: the first of the 8 blocks of the 3-D nitrogen blunted-cone case - 200 x 125 x 125 = 3.1 M
+    cells, 62.5 M parcels, Larsen-Borgnakke, cell-weighted, wedge cells on the axis, inflow, outflow, diffuse body."""
+    case = cases.blunt_body_block(0, 1)
+    assert case.mesh.n_cells == 200 * 125 * 125 and case.n_parcels == 20 * case.mesh.n_cells
+    assert case.ERot is not None and case.cellWeightFactor is not None
+    cl, tot = _run_open_case(case, GpuCloud, 5)
+    assert tot["inserted"] > 1000 and tot["deleted"] > 1000 and tot["cloned"] > 1000 and tot["wallHits"] > 1000 and tot["collisions"] > 1000
+    p = _check_cell_major_and_occupancy(cl, case.mesh)
+    assert _inside_own_cell(case.mesh, p) < 1e-12
+    assert (p["ERot"] >= 0).all()
+    kT = cases.kB * case.meta["T_inf"]
+    assert abs(p["ERot"].mean() / kT - 1.0) < 0.02  # rotDoF 2: <ERot> = k T in the (still mostly undisturbed) free stream
+    cl.close()

@@ -83,7 +83,7 @@ class PolyMesh:
         return out
 
     # -- primitiveMesh geometry ------------------------------------------------
-    def compute_geometry(self, n_cells=None):
+    def compute_geometry(self, n_cells=None, snap=False):
         pts = self.points
         off = self.face_point_offsets
         nF = len(self.owner)
@@ -126,6 +126,10 @@ class PolyMesh:
                 sumA = np.where(flat, 1.0, sumA)
                 sumAc = np.where(flat[:, None], 3.0 * fc, sumAc)
             Cf[sel] = sumAc / (3.0 * sumA[:, None])
+        if snap:  # round-off residue of a component that is zero by construction (the z component of the side faces of an
+            # extruded 2-D block, 1e-20 of the area): exactly zero, so that such meshes qualify for the packed 2-D cell record
+            A = np.sqrt((Sf * Sf).sum(1))
+            Sf[np.abs(Sf) < 1e-14 * A[:, None]] = 0.0
         self.face_areas, self.face_centres = Sf, Cf
         nI = len(self.neighbour)
         nC = n_cells if n_cells is not None else int(self.owner.max()) + 1
@@ -206,7 +210,7 @@ class PolyMesh:
         return m
 
 
-def structured_block(nx, ny, nz, point_map, patch_kinds, cyclic_pairs=(), solution_d=(1, 1, 1)):
+def structured_block(nx, ny, nz, point_map, patch_kinds, cyclic_pairs=(), solution_d=(1, 1, 1), snap=False):
     """One hex block of nx*ny*nz cells.
 
     point_map(I, J, K) -> (x, y, z) arrays for integer vertex indices.
@@ -284,7 +288,7 @@ def structured_block(nx, ny, nz, point_map, patch_kinds, cyclic_pairs=(), soluti
         solution_d=tuple(solution_d),
         shape=(nx, ny, nz),
     )
-    mesh.compute_geometry(n_cells=nx * ny * nz)
+    mesh.compute_geometry(n_cells=nx * ny * nz, snap=snap)
     for a, b in cyclic_pairs:
         pa, pb = side_patch[a], side_patch[b]
         A, B = patches[pa], patches[pb]
@@ -639,7 +643,7 @@ def structured_subblock(global_shape, parts, rank, point_map, patch_kinds, solut
             peer = rank + step
             kinds[side] = (f"procBoundary{rank}to{peer}", "processor")
             peers[side] = peer
-    m = structured_block(rx[1] - rx[0], ry[1] - ry[0], rz[1] - rz[0], pm, kinds, solution_d=solution_d)
+    m = structured_block(rx[1] - rx[0], ry[1] - ry[0], rz[1] - rz[0], pm, kinds, solution_d=solution_d, snap=True)
     for pi, side in enumerate(("xMin", "xMax", "yMin", "yMax", "zMin", "zMax")):
         if side in peers:
             q = m.patches[pi]
