@@ -134,7 +134,8 @@ def test_config3_cylinder_50m_parcels(GpuCloud):
     assert tot["inserted"] > 10_000 and tot["deleted"] > 10_000 and tot["wallHits"] > 1000 and tot["collisions"] > 10_000
     p = _check_cell_major_and_occupancy(cl, case.mesh)
     assert _inside_own_cell(case.mesh, p) < 1e-12
-    assert np.ptp(p["position"][:, 2]) == 0.0  # empty direction
+    lz = np.ptp(case.mesh.points[:, 2])
+    assert np.abs(p["position"][:, 2]).max() <= 0.5 * lz * (1 + 1e-12)  # empty direction: initial parcels on the mid-plane, inserted ones within the layer
     # the free stream is still the free stream away from the body: mean velocity of the cloud within 2 % of U_inf
     assert abs(p["U"][:, 0].mean() / case.meta["U_inf"] - 1.0) < 0.02
     cl.close()

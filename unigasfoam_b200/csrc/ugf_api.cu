@@ -88,13 +88,15 @@ struct ugf_handle {
     std::vector<double> SfHost, CfHost, pointsHost, ccHost;
     std::vector<int32_t> fpOffHost, fpHost;
     double* dRec2d = nullptr;
+    double* dMoveQD = nullptr; int* dMoveQI = nullptr;  // per-warp queues of the hop-compacting move
     int* dCfOff = nullptr; double4* dPlane = nullptr; int* dNbr = nullptr; int* dBfPatch = nullptr; int* dBfOwner = nullptr;
     DevPatch* dPatches = nullptr; double* dVol = nullptr; double* dBbMin = nullptr; double* dBbMax = nullptr; double* dBfS = nullptr;
     bool hasProcessor = false;
     int moveNF = 0;  // uniform face-slot count per cell (4 or 6), 0 = general CSR
-    int moveBps = 4;          // resident CTAs per SM of the streamed move kernel
+    int moveBps = 0;          // resident CTAs per SM of the streamed move kernel (0 = the variant's default; UGF_MOVE_BPS)
     int cellTask = 0, cellFlags = 0;  // cellTask 0: chosen per launch from the mean cell occupancy
     bool moveDirect = false;  // tuning: UGF_MOVE_DIRECT=1 runs the step's move with the one-thread-per-parcel kernel
+    bool moveV2 = true;       // hop-compacting streamed move (UGF_MOVE_V2=0: the lockstep kernel of round 1)
 
     // parcels
     long long capacity = 0;
@@ -345,6 +347,10 @@ int alloc_parcels(ugf_handle* h) {
         if (h->multi && dalloc(h, &P.type, capPad)) return 1;
     }
     if (dalloc(h, &h->dPerm, cap)) return 1;
+    {
+        const size_t warps = (size_t)h->numSMs * 4 * MOVE_WARPS;  // the largest grid the streamed move launches
+        if (dalloc(h, &h->dMoveQD, warps * MoveSmem<false>::queueDoubles) || dalloc(h, &h->dMoveQI, warps * MoveSmem<false>::queueInts)) return 1;
+    }
     if (dalloc(h, &h->dOwner, cap)) return 1;
     CU(cudaMemsetAsync(h->dOwner, 0x7f, cap * sizeof(int), h->stream));
     if (dalloc(h, &h->dMigBlock, (size_t)2 * MIG_MAXP * (cap / 1024 + 2))) return 1;  // per-(slot, block) counts and offsets
@@ -558,6 +564,8 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.bm = h->dBm;
     a.cnt = h->dCnt;
     a.nclone = h->prm.cwf ? h->dNclone : nullptr;
+    a.queueD = h->dMoveQD;
+    a.queueI = h->dMoveQI;
     a.slotTrack = h->nTracked ? h->dSlotTrack : nullptr;
     a.bfTrack = h->dBfTrack;
     a.ft = h->dFt;
@@ -566,11 +574,29 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     if (count > 0) {
         const DevParams prm = h->prm;
         const bool streamed = !received && begin == 0 && !h->moveDirect;
-        const unsigned grid = streamed ? (unsigned)std::min<long long>(grid_for(count, MOVE_WARPS * 32), (long long)h->numSMs * h->moveBps)
+        const unsigned grid = streamed ? (unsigned)std::min<long long>(grid_for(count, MOVE_WARPS * 32), (long long)h->numSMs * 4)
                                        : grid_for(count, 256);
         dispatch(h, [&](auto R, auto M) {
             constexpr bool r = decltype(R)::value, mm = decltype(M)::value;
-            if (streamed) {
+            if (streamed && h->moveV2) {
+                // hop-compacting kernel: the packed 2-D record only where z is an empty direction (z, Uz are then not staged)
+                const bool flat = h->moveNF == 4 && h->mesh.rec2d && !h->cfg.solutionD[2];
+#define UGF_MOVE_STREAM2(NF_, BPS_, FLAT_)                                                                                   \
+    do {                                                                                                                      \
+        auto kfn = move_stream2_kernel<r, mm, NF_, BPS_>;                                                                      \
+        static bool attrSet = false;                                                                                          \
+        if (!attrSet) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MoveSmem<FLAT_>::total); attrSet = true; } \
+        const unsigned g2 = (unsigned)std::min<long long>(grid_for(count, MOVE_WARPS * 32), (long long)h->numSMs * BPS_);        \
+        kfn<<<g2, MOVE_WARPS * 32, MoveSmem<FLAT_>::total, h->stream>>>(prm, a);                                               \
+    } while (0)
+                if (flat && h->moveBps == 3) UGF_MOVE_STREAM2(NF_REC2D, 3, true);
+                else if (flat) UGF_MOVE_STREAM2(NF_REC2D, 4, true);
+                else if (h->moveNF == 6 && h->moveBps != 3) UGF_MOVE_STREAM2(6, 2, false);  // 126 registers, no spills: measured 10 % faster than 3 CTAs / SM at 80
+                else if (h->moveNF == 6) UGF_MOVE_STREAM2(6, 3, false);
+                else if (h->moveNF == 4) UGF_MOVE_STREAM2(4, 3, false);
+                else UGF_MOVE_STREAM2(0, 3, false);
+#undef UGF_MOVE_STREAM2
+            } else if (streamed) {
 #define UGF_MOVE_STREAM(NF_)                                                                                      \
     do {                                                                                                          \
         move_stream_kernel<r, mm, NF_, 4><<<grid, MOVE_WARPS * 32, 0, h->stream>>>(prm, a);                        \
@@ -836,7 +862,7 @@ int ugf_destroy(ugf_handle* h) {
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
-                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dSlotTrack, h->dBfTrack, h->dFt};
+                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dMoveQD, h->dMoveQI, h->dSlotTrack, h->dBfTrack, h->dFt};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -1085,7 +1111,8 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     // L1 next to the shared-memory carve-out and raise the achievable memory-level parallelism (profiles/).
     int cellBps = 4, cellCarve = -1;
     if (const char* e = std::getenv("UGF_MOVE_DIRECT")) h->moveDirect = std::atoi(e) != 0;
-    if (const char* e = std::getenv("UGF_MOVE_BPS")) h->moveBps = std::max(1, std::min(4, std::atoi(e)));
+    if (const char* e = std::getenv("UGF_MOVE_V2")) h->moveV2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("UGF_MOVE_BPS")) h->moveBps = std::max(0, std::min(4, std::atoi(e)));
     if (const char* e = std::getenv("UGF_CELL_TASK")) h->cellTask = std::max(1, std::min(CELL_TASK_MAX, std::atoi(e)));
     if (const char* e = std::getenv("UGF_CELL_FLAGS")) h->cellFlags = std::atoi(e);
     if (const char* e = std::getenv("UGF_CELL_BPS")) cellBps = std::max(1, std::atoi(e));

@@ -215,6 +215,8 @@ struct MoveArgs {
     const int* bfTrack;    // per boundary face: k+1 of the face the crossing is booked on (cyclic: the partner face), 0 = not tracked
     double* ft;            // [nTracked][nSpecies][UGF_NFT] running tallies
     uint8_t* nclone;       // cell weighting: clones each parcel gets from cellWeighting() (written for every parcel), else null
+    double* queueD;        // move_stream2_kernel: per-warp queues of parcels in mid-track (7 * MQ_CAP doubles, 3 * MQ_CAP ints per warp)
+    int* queueI;
 };
 
 // uniGasFaceTracker::updateFields (U/faceTracker/uniGasFaceTracker.C:90-152) for one crossing of a tracked face: number,
@@ -369,6 +371,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// Warp-collective variants: every lane calls with the same arguments and one elected lane issues (elect.sync), so the call
+// site stays convergent and ptxas needs no per-lane loop around the uniform-datapath bulk copy.
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, unsigned bytes) {
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n @p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_elect(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile(
+        "{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n @p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     unsigned ok;
@@ -641,6 +656,309 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, BPS) move_stream_kernel(const
             }
         }
         track_parcel<HAS_ROT, MULTI, NF>(prm, a, i, valid, cell, x0, x1, x2, U0, U1, U2);
+    }
+}
+
+
+// ---- streamed move with hop compaction ---------------------------------------------------------------------------------
+// The tracking loop of track_parcel keeps a warp in lockstep over its 32 parcels: the second and third face crossing of a
+// tile run with half and a tenth of the lanes (16 of 32 active on average at Courant 0.5, profiles/ r1).  Here a pass of
+// the warp does at most MOVE_HOPS hops for 32 parcels.  A parcel whose track is over is finalised at once (its stores, the weighting
+// decision, the histogram); one that goes on is pushed - position, velocity, step fraction, cell, index, draw / iteration
+// counters - onto the warp's own queue (global memory, L2-resident).  Whenever the queue holds 32 parcels the next pass takes them instead
+// of a fresh tile, so second and later hops run on full warps, while the first hop of a tile stays tile-coherent (two or
+// three neighbouring cells per warp: broadcast plane loads, coalesced stores, run-aggregated histogram).  No block barrier,
+// the queue is private to the warp; results do not depend on the processing order (per-parcel Philox streams).
+// On straight 2-D meshes (packed record, z empty) z and Uz are neither staged nor queued nor written: the tracking does not
+// touch them (the rare boundary interaction reads them from global memory), which takes 24 of the 80 B per parcel off the bus.
+constexpr int MQ_CAP = 64;  // a pass pops 32 when the queue holds >= 32 and pushes <= 32
+constexpr int MOVE_HOPS = 2; // hops a pass runs in lockstep before the unfinished parcels are queued
+
+template <bool FLAT>
+struct MoveSmem {
+    static constexpr int ND = FLAT ? 4 : 6;  // staged double arrays per tile: x, y, (z), Ux, Uy, (Uz)
+    static constexpr int NQ = FLAT ? 5 : 7;  // queued doubles per parcel: the same + step fraction
+    static constexpr size_t ringBytes = (size_t)MOVE_STAGES * (ND * 32 * sizeof(double) + 32 * sizeof(int));
+    static constexpr size_t perWarp = ringBytes;
+    static constexpr size_t total = MOVE_WARPS * perWarp + MOVE_WARPS * MOVE_STAGES * sizeof(uint64_t);
+    // the queue of a warp lives in global memory (L2-resident: a few MB for the whole grid, touched by one parcel in ten):
+    // shared memory would take the L1 lines the plane loads live on (measured: L1 hit rate 68 % -> 38 % with a shared queue)
+    static constexpr size_t queueDoubles = (size_t)7 * MQ_CAP;  // per warp, sized for the 3-D layout
+    static constexpr size_t queueInts = (size_t)3 * MQ_CAP;
+};
+
+constexpr int MISC_DRAW_SHIFT = 13;  // misc = tracking iterations (13 bits) | Philox draws consumed so far << 13
+
+// One hop of one parcel.  Returns true when the track is over (end of step, deleted, waiting on a processor patch, stuck).
+template <bool HAS_ROT, bool MULTI, int NFT, bool FLAT>
+__device__ __forceinline__ bool hop_once(const DevParams& prm, const MoveArgs& a, const int i, int& cell, double& x0, double& x1, double& x2,
+                                         double& U0, double& U1, double& U2, double& sf, int& misc) {
+    constexpr bool REC2D = (NFT == NF_REC2D);
+    constexpr int NF = REC2D ? 4 : NFT;
+    const double rem = 1 - sf;
+    const double s = rem * prm.deltaT;
+    const double d0 = prm.solD[0] ? s * U0 : 0.0, d1 = prm.solD[1] ? s * U1 : 0.0;
+    const double d2 = FLAT ? 0.0 : (prm.solD[2] ? s * U2 : 0.0);  // constrainDirection
+    double bnum = 1.0, bnd = 1.0;
+    int hit = -1, nb = 0;
+    if (NF > 0) {
+        const int jb = cell * NF;
+        double4 pl[NF > 0 ? NF : 1];
+        int nbs[NF > 0 ? NF : 1];
+        if (REC2D) {
+            const double* rp = a.mesh.rec2d + (size_t)cell * 16;
+            ldg256(rp, pl[0].x, pl[0].y, pl[1].x, pl[1].y);
+            ldg256(rp + 4, pl[2].x, pl[2].y, pl[3].x, pl[3].y);
+            ldg256(rp + 8, pl[0].w, pl[1].w, pl[2].w, pl[3].w);
+            const int4 v = __ldg(reinterpret_cast<const int4*>(rp + 12));
+            nbs[0] = v.x; nbs[1] = v.y; nbs[2] = v.z; nbs[3] = v.w;
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) pl[f] = load_plane(&a.mesh.plane[jb + f]);
+            if (NF == 4) {
+                const int4 v = __ldg(reinterpret_cast<const int4*>(a.mesh.nbr + jb));
+                nbs[0] = v.x; nbs[1] = v.y; nbs[2] = v.z; nbs[3] = v.w;
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; f += 2) {
+                    const int2 v = __ldg(reinterpret_cast<const int2*>(a.mesh.nbr + jb + f));
+                    nbs[f] = v.x; nbs[f + 1] = v.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            // REC2D: Sz == 0 exactly, and fma(0, finite, t) == t, so the z terms are dropped (same bits)
+            const double nd = REC2D ? fma(pl[f].y, d1, pl[f].x * d0) : fma(pl[f].z, d2, fma(pl[f].y, d1, pl[f].x * d0));
+            double num = pl[f].w - (REC2D ? fma(pl[f].y, x1, pl[f].x * x0) : fma(pl[f].z, x2, fma(pl[f].y, x1, pl[f].x * x0)));
+            num = num < 0 ? 0.0 : num;
+            const bool better = (nd > 0) && (num * bnd < bnum * nd);
+            bnum = better ? num : bnum;
+            bnd = better ? nd : bnd;
+            hit = better ? jb + f : hit;
+            nb = better ? nbs[f] : nb;
+        }
+    } else {
+        const int jb = __ldg(&a.mesh.cfOff[cell]), je = __ldg(&a.mesh.cfOff[cell + 1]);
+        for (int j = jb; j < je; ++j) {
+            const double4 pl = load_plane(&a.mesh.plane[j]);
+            const int nbj = __ldg(&a.mesh.nbr[j]);
+            const double nd = fma(pl.z, d2, fma(pl.y, d1, pl.x * d0));
+            double num = pl.w - fma(pl.z, x2, fma(pl.y, x1, pl.x * x0));
+            num = num < 0 ? 0.0 : num;
+            const bool better = (nd > 0) && (num * bnd < bnum * nd);
+            bnum = better ? num : bnum;
+            bnd = better ? nd : bnd;
+            hit = better ? j : hit;
+            nb = better ? nbj : nb;
+        }
+    }
+    if (hit < 0) {
+        x0 = x0 + d0; x1 = x1 + d1;
+        if (!FLAT) x2 = x2 + d2;
+        sf = 1;
+        return true;
+    }
+    const double lamMin = bnum / bnd;
+    x0 = fma(lamMin, d0, x0); x1 = fma(lamMin, d1, x1);
+    if (!FLAT) x2 = fma(lamMin, d2, x2);
+    sf = fma(rem, lamMin, sf);
+    if (nb >= 0) {
+        if (a.slotTrack) {  // face tracker on: is this one of the registered faces?
+            const int trk = __ldg(&a.slotTrack[hit]);
+            if (trk) {
+                int type = 0;
+                if (MULTI) type = a.P.type[i];
+                face_tally(prm, a, i, trk, U0, U1, FLAT ? a.P.uz[i] : U2, type, 0.0, false, HAS_ROT);
+            }
+        }
+        cell = nb;
+    } else {
+        HitState st;
+        const double zin = FLAT ? a.P.z[i] : x2;
+        st.x[0] = x0; st.x[1] = x1; st.x[2] = zin;
+        st.U[0] = U0; st.U[1] = U1; st.U[2] = FLAT ? a.P.uz[i] : U2;
+        st.erot = 0.0;
+        if (HAS_ROT) st.erot = a.P.erot[i];  // an earlier wall hit of this track has stored its result already
+        st.sf = sf; st.cell = cell; st.nDraws = misc >> MISC_DRAW_SHIFT; st.flags = 0; st.nWall = 0;
+        int type = 0;
+        if (MULTI) type = a.P.type[i];
+        boundary_hit<HAS_ROT, MULTI>(prm, a, -nb - 1, hit, i, type, st);
+        x0 = st.x[0]; x1 = st.x[1];
+        if (!FLAT) x2 = st.x[2];
+        else if (st.x[2] != zin) a.P.z[i] = st.x[2];
+        U0 = st.U[0]; U1 = st.U[1];
+        if (!FLAT) U2 = st.U[2];
+        if (st.flags & HIT_CHANGED_U) {  // stored now: the queue does not carry what the tracking does not need
+            a.P.ux[i] = st.U[0]; a.P.uy[i] = st.U[1]; a.P.uz[i] = st.U[2];
+            if (HAS_ROT) a.P.erot[i] = st.erot;
+        }
+        cell = st.cell;
+        misc = (misc & ((1 << MISC_DRAW_SHIFT) - 1)) | (st.nDraws << MISC_DRAW_SHIFT);
+        // rare path (a boundary face): the step's counters are bumped right here instead of riding along in registers
+        if (st.nWall) atomicAdd(&a.cnt->wallHits, (unsigned long long)st.nWall);
+        if (st.flags & HIT_DELETED) atomicAdd(&a.cnt->deleted, 1ull);
+        if (st.flags & HIT_STUCK) atomicAdd(&a.cnt->stuck, 1ull);
+        if (st.flags & HIT_MIGRATED) atomicAdd(&a.cnt->migrated, 1ull);
+    }
+    misc += 1;
+    if ((misc & ((1 << MISC_DRAW_SHIFT) - 1)) > MAX_TRACK_ITERS) { cell = -1; atomicAdd(&a.cnt->stuck, 1ull); return true; }
+    return !(cell >= 0 && sf < 1);
+}
+
+template <bool HAS_ROT, bool MULTI, int NFT, int BPS>
+__global__ void __launch_bounds__(MOVE_WARPS * 32, BPS) move_stream2_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a) {
+    constexpr bool FLAT = (NFT == NF_REC2D);  // the host selects the packed 2-D record only when z is an empty direction
+    using L = MoveSmem<FLAT>;
+    constexpr int ND = L::ND;
+    extern __shared__ __align__(128) unsigned char moveSmem[];
+    // the warp index through a shuffle: the compiler then knows it (and the tile counters, queue length and ring addresses derived
+    // from it) to be warp-uniform and keeps them in uniform registers - the bulk copies need no per-lane loop, the loop control no
+    // vector registers
+    const int lane = threadIdx.x & 31, w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    unsigned char* const base = moveSmem + (size_t)w * L::perWarp;
+    double* const ringD = reinterpret_cast<double*>(base);                                                  // [STAGES][ND][32]
+    int* const ringC = reinterpret_cast<int*>(base + (size_t)MOVE_STAGES * ND * 32 * sizeof(double));        // [STAGES][32]
+    const size_t warpId = (size_t)blockIdx.x * MOVE_WARPS + w;
+    double* const qD = a.queueD + warpId * L::queueDoubles;  // [NQ][MQ_CAP]
+    int* const qI = a.queueI + warpId * L::queueInts;        // [3][MQ_CAP]
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(moveSmem + (size_t)MOVE_WARPS * L::perWarp) + w * MOVE_STAGES;
+    const int n = (int)*a.dN;  // parcel capacity < 2^31
+    const int nTiles = (n + 31) / 32;
+    const int stride = (int)gridDim.x * MOVE_WARPS;
+    auto issue = [&](int tile, int s) {
+        const size_t b = (size_t)tile * 32;
+        constexpr unsigned bytesD = 32 * sizeof(double), bytesC = 32 * sizeof(int);
+        uint64_t* br = &bar[s];
+        double* d = ringD + (size_t)s * ND * 32;
+        mbar_expect_tx_elect(br, ND * bytesD + bytesC);
+        bulk_g2s_elect(d, a.P.x + b, bytesD, br);
+        bulk_g2s_elect(d + 32, a.P.y + b, bytesD, br);
+        if (FLAT) {
+            bulk_g2s_elect(d + 64, a.P.ux + b, bytesD, br);
+            bulk_g2s_elect(d + 96, a.P.uy + b, bytesD, br);
+        } else {
+            bulk_g2s_elect(d + 64, a.P.z + b, bytesD, br);
+            bulk_g2s_elect(d + 96, a.P.ux + b, bytesD, br);
+            bulk_g2s_elect(d + 128, a.P.uy + b, bytesD, br);
+            bulk_g2s_elect(d + 160, a.P.uz + b, bytesD, br);
+        }
+        bulk_g2s_elect(ringC + s * 32, a.P.cell + b, bytesC, br);
+    };
+    const int first = (int)blockIdx.x * MOVE_WARPS + w;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < MOVE_STAGES; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < MOVE_STAGES; ++s) {
+        const int t = first + s * stride;
+        if (t < nTiles) issue(t, s);  // warp-collective: one elected lane issues
+    }
+    int qn = 0, k = 0;
+    int tile = first;
+    for (;;) {
+        bool active = false;
+        int i = 0;
+        int cell = -1, misc = 0;
+        double x0 = 0, x1 = 0, x2 = 0, U0 = 0, U1 = 0, U2 = 0, sf = 0;
+        if (qn >= 32 || (tile >= nTiles && qn > 0)) {  // a warp's worth of parcels in mid-track (or the last ones): continue those
+            const int take = qn < 32 ? qn : 32;
+            const int slot = qn - take + lane;
+            active = lane < take;
+            if (active) {
+                x0 = __ldcg(&qD[slot]); x1 = __ldcg(&qD[MQ_CAP + slot]);
+                if (FLAT) { U0 = __ldcg(&qD[2 * MQ_CAP + slot]); U1 = __ldcg(&qD[3 * MQ_CAP + slot]); sf = __ldcg(&qD[4 * MQ_CAP + slot]); }
+                else {
+                    x2 = __ldcg(&qD[2 * MQ_CAP + slot]); U0 = __ldcg(&qD[3 * MQ_CAP + slot]); U1 = __ldcg(&qD[4 * MQ_CAP + slot]);
+                    U2 = __ldcg(&qD[5 * MQ_CAP + slot]); sf = __ldcg(&qD[6 * MQ_CAP + slot]);
+                }
+                cell = __ldcg(&qI[slot]); i = __ldcg(&qI[MQ_CAP + slot]); misc = __ldcg(&qI[2 * MQ_CAP + slot]);
+            }
+            qn -= take;
+            __syncwarp();  // all reads done before this pass pushes into the same slots
+        } else if (tile < nTiles) {
+            const int s = k % MOVE_STAGES;
+            mbar_wait(&bar[s], (unsigned)(k / MOVE_STAGES) & 1u);
+            const double* d = ringD + (size_t)s * ND * 32;
+            i = tile * 32 + lane;
+            cell = (i < n) ? ringC[s * 32 + lane] : -1;
+            x0 = d[lane]; x1 = d[32 + lane];
+            if (FLAT) { U0 = d[64 + lane]; U1 = d[96 + lane]; }
+            else { x2 = d[64 + lane]; U0 = d[96 + lane]; U1 = d[128 + lane]; U2 = d[160 + lane]; }
+            __syncwarp();  // the slot is in registers: refill it with the tile MOVE_STAGES ahead
+            {
+                const int t = tile + MOVE_STAGES * stride;
+                if (t < nTiles) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(t, s);
+                }
+            }
+            active = cell >= 0;
+            if (active && i >= a.newFrom) {  // U/parcels/uniGasParcel.C:47-53
+                Stream r(prm.seed, KIND_MOVE, a.aux, a.step, (uint32_t)i, 0);
+                sf = r.u01();
+                misc = 1 << MISC_DRAW_SHIFT;
+                if (!(sf < 1)) active = true;
+            }
+            tile += stride;
+            ++k;
+        } else {
+            break;
+        }
+        // up to MOVE_HOPS hops in lockstep: the second hop still runs with close to half of the warp; whoever needs more
+        // (one parcel in ten at Courant 0.5) waits in the queue for a full warp
+        bool done = !active || !(sf < 1);
+#pragma unroll 1
+        for (int hop = 0; hop < MOVE_HOPS; ++hop) {
+            if (!done) done = hop_once<HAS_ROT, MULTI, NFT, FLAT>(prm, a, i, cell, x0, x1, x2, U0, U1, U2, sf, misc);
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+        // ---- finalise the parcels whose track is over ----
+        const bool fin = active && done;
+        int nClone = 0;
+        if (fin) {
+            if (prm.cwf) {  // weighting() right after the move (U/clouds/uniGasCloud.C:839-842), see track_parcel
+                int kc = 0;
+                if (cell >= 0) {
+                    const double wNew = __ldg(&prm.cwf[cell]);
+                    const int cell0 = a.P.cell[i];
+                    const double wOld = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[cell0]) : __ldg(&prm.cwf[cell0]);
+                    if (wOld != wNew) kc = weighting_decision(prm.seed, a.step, (uint32_t)i, wOld, wNew);
+                    if (kc < 0) { cell = -1; atomicAdd(&a.cnt->wdeleted, 1ull); kc = 0; }
+                }
+                a.nclone[i] = (uint8_t)kc;
+                nClone = kc;
+                if (kc) atomicAdd(&a.cnt->cloned, (unsigned long long)kc);
+            }
+            a.P.x[i] = x0; a.P.y[i] = x1;
+            if (!FLAT) a.P.z[i] = x2;
+            a.P.cell[i] = cell;
+        }
+        {
+            const bool live = fin && cell >= 0;
+            int head, cnt, rank;
+            warp_runs(live ? cell : -1, lane, head, cnt, rank);
+            if (live && rank == 0) atomicAdd(&a.cellCount[cell], cnt);
+            if (nClone) atomicAdd(&a.cellCount[cell], nClone);  // clones take slots of the same cell
+        }
+        // ---- the others wait in the queue for a full warp ----
+        const bool cont = active && !done;
+        const unsigned cm = __ballot_sync(0xffffffffu, cont);
+        if (cont) {
+            const int slot = qn + __popc(cm & ((1u << lane) - 1u));
+            __stcg(&qD[slot], x0); __stcg(&qD[MQ_CAP + slot], x1);
+            if (FLAT) { __stcg(&qD[2 * MQ_CAP + slot], U0); __stcg(&qD[3 * MQ_CAP + slot], U1); __stcg(&qD[4 * MQ_CAP + slot], sf); }
+            else {
+                __stcg(&qD[2 * MQ_CAP + slot], x2); __stcg(&qD[3 * MQ_CAP + slot], U0); __stcg(&qD[4 * MQ_CAP + slot], U1);
+                __stcg(&qD[5 * MQ_CAP + slot], U2); __stcg(&qD[6 * MQ_CAP + slot], sf);
+            }
+            __stcg(&qI[slot], cell); __stcg(&qI[MQ_CAP + slot], i); __stcg(&qI[2 * MQ_CAP + slot], misc);
+        }
+        qn += __popc(cm);
+        __syncwarp();
     }
 }
 
