@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UGF_ABI_VERSION 2
+#define UGF_ABI_VERSION 3
 #define UGF_MAX_SPECIES 8
 #define UGF_MAX_VIB_MODES 4
 #define UGF_MAX_ELEC_LEVELS 16
@@ -199,6 +199,8 @@ typedef struct ugf_parcels {
     double* ERot;
     int32_t* newParcel;
     double* cellWeight;
+    int32_t* vibLevel;   /* [n][UGF_MAX_VIB_MODES] vibrational quantum level per mode (uniGasParcel.H:238); NULL = 0 */
+    int32_t* ELevel;     /* [n] electronic level (uniGasParcel.H:232); NULL = 0 */
 } ugf_parcels;
 
 /* Per-step log quantities (noTimeCounter.C:318-342, …USP.C:976-992, uniGasCloud.C:878-920). */
@@ -218,6 +220,8 @@ typedef struct ugf_counters {
     double momentum[3];          /* sum m U */
     int64_t cloned;              /* parcels added by cellWeighting(), last step (U/clouds/uniGasCloud.C:1366-1407) */
     int64_t weightDeleted;       /* parcels removed by cellWeighting(), last step (:1409-1420) */
+    double vibrationalEnergy;    /* sum over parcels and modes of level * k * thetaV (info(): U/clouds/uniGasCloud.C:878-920) */
+    double electronicEnergy;     /* sum of electronicEnergyList[ELevel] */
 } ugf_counters;
 
 /* system/hybridDecompositionDict: uniGasHybridDecomposition (U/hybridDecomposition/basic/uniGasHybridDecomposition.C:48-76)
@@ -237,6 +241,10 @@ typedef struct ugf_decomposition {
 /* Number of fp64 values per (cell, species) in the cell-moment block; see DESIGN.md
  * for the slot list.  (U/cellMeasurements/cellMeasurements.H:73-145) */
 #define UGF_NMOM 32
+/* Internal-mode accumulators per (cell, species), kept only when a species has vibrational modes or more than one
+ * electronic level (uniGasVolFields.C:775-793): time-weighted sums of 0 nParcels, 1 electronicETotal, 2 nGroundElectronicLevel,
+ * 3 nFirstElectronicLevel, 4..7 vibrationalETotal per mode. */
+#define UGF_NINT 8
 
 /* Number of fp64 values per wall face in the boundary-measurement block
  * (U/boundaryMeasurements/boundaryMeasurements.C:70-121). */
@@ -251,8 +259,9 @@ typedef struct ugf_decomposition {
  * 0 uniGasRhoNMean, 1 rhoN, 2 rhoM, 3-5 UMean, 6 translationalT, 7 rotationalT,
  * 8 overallT, 9 p, 10 Ma, 11 densityError (0 if undefined); measureMeanFreePath (:1124-1232, Bird eqs 4.76, 4.77,
  * 4.74, 1.38; Tref = collisionProperties.Tref): 12 MFP, 13 dxMFP (largest sub-cell dimension / MFP), 14 MCR, 15 MCT,
- * 16 dtMCT (deltaT / MCT); measureErrors (:1234-1254): 17 velocityError, 18 temperatureError. */
-#define UGF_NFIELD 19
+ * 16 dtMCT (deltaT / MCT); measureErrors (:1234-1254): 17 velocityError, 18 temperatureError; 19 vibrationalT (:930-1010),
+ * 20 electronicT (:1012-1062).  overallT (8) weights all four modes (:1071-1079). */
+#define UGF_NFIELD 21
 /* per wall face: 0 rhoN, 1 rhoM, 2-4 UMean, 5 translationalT, 6 q (surfaceHeatTransfer),
  * 7-9 fD, 10 p, 11 tau. */
 #define UGF_NWALLFIELD 12
@@ -465,6 +474,9 @@ int ugf_download_face_tracker(ugf_handle* h, double* out, int32_t reset);
  * own interval (U/dynamicAdaptation/uniGasDynamicAdapter.C:510-527); the host-side adapter differences two downloads
  * instead of keeping a second set of accumulators on the device.  Any pointer may be NULL. */
 int ugf_download_accumulators(ugf_handle* h, double* acc, double* accSpecies, double* timeAvCounter, int64_t* nAvTimeSteps);
+/* The internal-mode accumulators [nCells][nSpecies][UGF_NINT] (zeros when no species carries vibrational modes or several
+ * electronic levels). */
+int ugf_download_internal_accumulators(ugf_handle* h, double* accInt);
 /* Per-phase device time of the last ugf_step in ms (UGF_NPHASE values): inflow, move, sort, cell (gather + sample +
  * field accumulation), collide (NTC), relax (BGK family), fields (wall accumulation). */
 #define UGF_NPHASE 7

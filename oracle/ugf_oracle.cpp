@@ -128,7 +128,16 @@ struct Parcel {  // uniGasParcel (U/parcels/uniGasParcel.H:217-239) + particle p
     int32_t cell;    // >=0 live; -1 deleted; <= -2 waiting on a processor face (-2 - boundaryFaceIndex)
     int32_t typeId;
     int32_t newParcel;
+    int32_t ELevel = 0;                                   // electronic level (U/parcels/uniGasParcel.H:232)
+    int32_t vib[UGF_MAX_VIB_MODES] = {0, 0, 0, 0};        // vibrational quantum level per mode (uniGasParcel.H:238)
 };
+
+inline double vibEnergy(const ugf_species& s, const Parcel& p) {  // sum over modes of level * k * thetaV
+    double e = 0;
+    for (int m = 0; m < s.vibrationalDoF; ++m) e += p.vib[m] * s.thetaV[m] * kB;
+    return e;
+}
+inline double elecEnergy(const ugf_species& s, const Parcel& p) { return s.electronicEnergy[p.ELevel]; }
 
 struct WallModel {
     int model = UGF_WALL_UNSET;
@@ -205,6 +214,9 @@ struct ugfo_handle {
     std::vector<double> acc;   // [nCells][NACC]
     std::vector<double> accS;  // [nCells][nSpecies] nParcelsXnParticle per species (mean free path fields)
     std::vector<double> bacc;  // [nBFaces][UGF_NBM]
+    std::vector<double> momE;  // [nCells][nSpecies][2] parcels in the ground / first electronic level at the last sample (species with > 1 level)
+    std::vector<double> accI;  // [nCells][nSpecies][UGF_NINT] internal-mode accumulators, only when a species has vibrational modes or > 1 electronic level
+    bool internalModes = false;
     double timeAvCounter = 0;
     int64_t nAvTimeSteps = 0;
     int sampleCounter = 0;
@@ -253,6 +265,63 @@ double equipartitionRotationalEnergy(Stream& r, double T, int rotDoF) {
         Pp = std::pow(energyRatio / a, a) * std::exp(a - energyRatio);
     } while (Pp < eps);
     return energyRatio * kB * T;
+}
+
+// equipartitionVibrationalEnergyLevel (U/clouds/uniGasCloud.C:1020-1050): level = int(-ln(R) T / thetaV) per mode; 1 - u is
+// used like for the rotational energy so that u = 0 cannot give inf (the reference redraws a zero instead)
+void equipartitionVibrationalEnergyLevel(Stream& r, double T, const ugf_species& s, int32_t* vib) {
+    for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) vib[m] = 0;
+    for (int m = 0; m < s.vibrationalDoF; ++m) vib[m] = (int32_t)(-std::log(1.0 - r.u01()) * T / s.thetaV[m]);
+}
+
+// equipartitionElectronicLevel (U/clouds/uniGasCloud.C:1053-1126): acceptance-rejection against the most populated level
+// (Liechty eqs 3.1.1 / 3.1.2); the threshold is drawn once per call, as the reference does
+int equipartitionElectronicLevel(Stream& r, double T, const ugf_species& s) {
+    const int jMax = s.nElectronicLevels;
+    if (jMax == 1) return 0;
+    if (T < VSMALL) return 0;
+    const double EMax = kB * T;
+    double expSum = 0.0;
+    for (int i = 0; i < jMax; ++i) expSum += s.degeneracy[i] * std::exp(-s.electronicEnergy[i] / EMax);
+    double boltzMax = 0.0;
+    int jSelect = 0;
+    for (int i = 0; i < jMax; ++i) {
+        const double boltz = s.degeneracy[i] * std::exp(-s.electronicEnergy[i] / EMax) / expSum;
+        if (boltzMax < boltz) { boltzMax = boltz; jSelect = i; }
+    }
+    const double expMax = s.degeneracy[jSelect] * std::exp(-s.electronicEnergy[jSelect] / EMax);
+    const double eps = r.u01();
+    int jDash;
+    double func;
+    do {
+        jDash = r.position(jMax);
+        func = s.degeneracy[jDash] * std::exp(-s.electronicEnergy[jDash] / EMax) / expMax;
+    } while (!(func > eps));
+    return jDash;
+}
+
+// postCollisionVibrationalEnergyLevel, postReaction = false (U/clouds/uniGasCloud.C:1192-1264): quantum-kinetic exchange with
+// the collision-temperature dependent vibrational collision number (Bird 2010 eqs 2, 3; Bird 5.42, 5.61)
+int postCollisionVibrationalEnergyLevel(Stream& r, int vibLevel, int iMax, double thetaV, double thetaD, double refTempZv, double omega,
+                                        double Zref, double Ec) {
+    int iDash = vibLevel;
+    const double TColl = (iMax * thetaV) / (3.5 - omega);
+    const double pow1 = std::pow(thetaD / TColl, 0.33333) - 1.0;
+    const double pow2 = std::pow(thetaD / refTempZv, 0.33333) - 1.0;
+    const double ZvP1 = std::pow(thetaD / TColl, omega);
+    const double ZvP2 = std::pow(Zref * std::pow(thetaD / refTempZv, -omega), pow1 / pow2);
+    const double Zv = ZvP1 * ZvP2;
+    const double inverseVibrationalCollisionNumber = 1.0 / (5.0 * Zv);
+    if (inverseVibrationalCollisionNumber > r.u01()) {
+        double func, EVib;
+        do {
+            const int i = (int)(r.u01() * (iMax + 1));  // Random::position<label>(0, iMax)
+            iDash = i < iMax ? i : iMax;
+            EVib = iDash * kB * thetaV;
+            func = std::pow(1.0 - EVib / Ec, 1.5 - omega);
+        } while (!(func > r.u01()));
+    }
+    return iDash;
 }
 
 double postCollisionRotationalEnergy(Stream& r, int rotDoF, double ChiB) {
@@ -357,7 +426,7 @@ void collidePair(const ugfo_handle& h, Stream& r, Parcel& p, Parcel& q) {
         scatterVSS(r, cRc, 0.5 * (a.alpha + b.alpha), 1.0, rel);
     } else {
         // Larsen-Borgnakke, serial application, P then Q
-        // (…/LarsenBorgnakkeVariableHardSphere.C:125-416; vibration not supported: modes must be 0)
+        // (…/LarsenBorgnakkeVariableHardSphere.C:125-416)
         const double omegaPQ = 0.5 * (a.omega + b.omega);
         const double mR = mP * mQ / mS;
         double Etr = 0.5 * mR * cRsqr;
@@ -365,11 +434,23 @@ void collidePair(const ugfo_handle& h, Stream& r, Parcel& p, Parcel& q) {
         const double invZrot = 1.0 / h.cfg.rotationalRelaxationCollisionNumber;
         const double invZel = 1.0 / h.cfg.electronicRelaxationCollisionNumber;
         const double preERotP = p.ERot, preERotQ = q.ERot;
-        // P: electronic, (vibrational), rotational
+        double preEVibP[UGF_MAX_VIB_MODES], preEVibQ[UGF_MAX_VIB_MODES];
+        for (int m = 0; m < a.vibrationalDoF; ++m) preEVibP[m] = p.vib[m] * a.thetaV[m] * kB;
+        for (int m = 0; m < b.vibrationalDoF; ++m) preEVibQ[m] = q.vib[m] * b.thetaV[m] * kB;
+        const double preEEleP = a.electronicEnergy[p.ELevel], preEEleQ = b.electronicEnergy[q.ELevel];
+        // P: electronic, vibrational (quantum-kinetic, mode by mode), rotational
         if (invZel > r.u01()) {
-            const double Ec = Etr + a.electronicEnergy[0];
-            const int lev = postCollisionElectronicEnergyLevel(r, Ec, a.nElectronicLevels, omegaPQ, a.electronicEnergy, a.degeneracy);
-            Etr = Ec - a.electronicEnergy[lev];
+            const double Ec = Etr + preEEleP;
+            p.ELevel = postCollisionElectronicEnergyLevel(r, Ec, a.nElectronicLevels, omegaPQ, a.electronicEnergy, a.degeneracy);
+            Etr = Ec - a.electronicEnergy[p.ELevel];
+        }
+        for (int m = 0; m < a.vibrationalDoF; ++m) {  // LarsenBorgnakkeVariableHardSphere.C:261-300
+            const double Ec = Etr + preEVibP[m];
+            const int iMax = (int)(Ec / (kB * a.thetaV[m]));
+            if (iMax > 0) {
+                p.vib[m] = postCollisionVibrationalEnergyLevel(r, p.vib[m], iMax, a.thetaV[m], a.thetaD[m], a.TrefZv[m], omegaPQ, a.Zref[m], Ec);
+                Etr = Ec - p.vib[m] * a.thetaV[m] * kB;
+            }
         }
         if (a.rotationalDoF > 0) {
             if (invZrot > r.u01()) {
@@ -380,9 +461,17 @@ void collidePair(const ugfo_handle& h, Stream& r, Parcel& p, Parcel& q) {
             }
         }
         if (invZel > r.u01()) {
-            const double Ec = Etr + b.electronicEnergy[0];
-            const int lev = postCollisionElectronicEnergyLevel(r, Ec, b.nElectronicLevels, omegaPQ, b.electronicEnergy, b.degeneracy);
-            Etr = Ec - b.electronicEnergy[lev];
+            const double Ec = Etr + preEEleQ;
+            q.ELevel = postCollisionElectronicEnergyLevel(r, Ec, b.nElectronicLevels, omegaPQ, b.electronicEnergy, b.degeneracy);
+            Etr = Ec - b.electronicEnergy[q.ELevel];
+        }
+        for (int m = 0; m < b.vibrationalDoF; ++m) {  // :337-376
+            const double Ec = Etr + preEVibQ[m];
+            const int iMax = (int)(Ec / (kB * b.thetaV[m]));
+            if (iMax > 0) {
+                q.vib[m] = postCollisionVibrationalEnergyLevel(r, q.vib[m], iMax, b.thetaV[m], b.thetaD[m], b.TrefZv[m], omegaPQ, b.Zref[m], Ec);
+                Etr = Ec - q.vib[m] * b.thetaV[m] * kB;
+            }
         }
         if (b.rotationalDoF > 0) {
             if (invZrot > r.u01()) {
@@ -419,9 +508,9 @@ void measureWall(ugfo_handle& h, const Parcel& p, int bfi, const double nw[3], d
     double* b = &h.bm[(size_t)bfi * UGF_NBM];
     const double add[UGF_NBM] = {
         inv, m * inv, 0.5 * m * UU * inv, m * p.U[0] * inv, m * p.U[1] * inv, m * p.U[2] * inv,
-        p.ERot * inv, s.rotationalDoF * inv, 0, 0, 0, 0, (s.rotationalDoF > 0 ? inv : 0.0), 0, s.electronicEnergy[0] * inv,
+        p.ERot * inv, s.rotationalDoF * inv, 0, 0, 0, 0, (s.rotationalDoF > 0 ? inv : 0.0), vibEnergy(s, p) * inv, elecEnergy(s, p) * inv,
         after ? 0.0 : 1.0};
-    const double IE = 0.5 * m * UU + p.ERot + s.electronicEnergy[0];
+    const double IE = 0.5 * m * UU + p.ERot + elecEnergy(s, p) + vibEnergy(s, p);
     double dq = 0, dfd[3] = {0, 0, 0};
     if (!after) {
         *preIE = IE;
@@ -472,6 +561,8 @@ void diffuseReflection(const ugfo_handle& h, Stream& r, Parcel& p, const double 
     const double c = std::sqrt(kB * T / s.mass);
     for (int k = 0; k < 3; ++k) p.U[k] = c * (g1 * tw1[k] + g2 * tw2[k] - gn * nw[k]);
     p.ERot = equipartitionRotationalEnergy(r, T, s.rotationalDoF);
+    if (s.vibrationalDoF > 0) equipartitionVibrationalEnergyLevel(r, T, s, p.vib);        // uniGasPatchBoundary.C:373-374
+    if (s.nElectronicLevels > 1) p.ELevel = equipartitionElectronicLevel(r, T, s);         // :376-383
     for (int k = 0; k < 3; ++k) p.U[k] += Uw[k];
 }
 
@@ -654,7 +745,7 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
                 const double sgn = (hit < h.nInternal) ? (hitFlip ? -1.0 : 1.0) : (dot3(p.U, S) >= 0.0 ? 1.0 : -1.0);
                 const ugf_species& s = h.sp[p.typeId];
                 const double w = p.CWF;
-                const double e = 0.5 * s.mass * dot3(p.U, p.U) + p.ERot + s.electronicEnergy[0];
+                const double e = 0.5 * s.mass * dot3(p.U, p.U) + p.ERot + elecEnergy(s, p) + vibEnergy(s, p);
                 double* tt = &h.ft[((size_t)k * h.nSpecies + p.typeId) * UGF_NFT];
                 const double add[UGF_NFT] = {sgn * w, sgn * s.mass * w, s.mass * p.U[0] * w, s.mass * p.U[1] * w, s.mass * p.U[2] * w, sgn * e * w};
                 for (int q = 0; q < UGF_NFT; ++q) {
@@ -796,6 +887,10 @@ void doInflow(ugfo_handle& h) {
                     for (int k = 0; k < 3; ++k)
                         np_.U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
                     np_.ERot = equipartitionRotationalEnergy(r, Trot, s.rotationalDoF);
+                    np_.ELevel = 0;
+                    for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) np_.vib[m] = 0;
+                    if (s.vibrationalDoF > 0) equipartitionVibrationalEnergyLevel(r, ip.in.vibrationalTemperature, s, np_.vib);  // uniGasGeneralBoundary.C:721-726
+                    if (s.nElectronicLevels > 1) np_.ELevel = equipartitionElectronicLevel(r, ip.in.electronicTemperature, s);   // :728-735
                     np_.CWF = h.cellWF[cellI];  // uniGasGeneralBoundary.C:738
                     np_.sf = 0;
                     np_.cell = cellI;
@@ -925,6 +1020,7 @@ void sampleCell(ugfo_handle& h, int c) {
     const int nS = h.nSpecies;
     double* M = &h.mom[(size_t)c * nS * UGF_NMOM];
     std::fill(M, M + (size_t)nS * UGF_NMOM, 0.0);
+    if (h.internalModes) std::fill(&h.momE[(size_t)c * nS * 2], &h.momE[(size_t)c * nS * 2] + (size_t)nS * 2, 0.0);
     for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
         const Parcel& p = h.P[h.occIds[j]];
         double* m = M + (size_t)p.typeId * UGF_NMOM;
@@ -938,7 +1034,15 @@ void sampleCell(ugfo_handle& h, int c) {
         m[15] += cc * u; m[16] += cc * v; m[17] += cc * w;
         m[18] += p.ERot;
         m[19] += p.ERot * u; m[20] += p.ERot * v; m[21] += p.ERot * w;
-        m[26] += h.sp[p.typeId].electronicEnergy[0];
+        const ugf_species& S = h.sp[p.typeId];
+        m[26] += elecEnergy(S, p);
+        if (S.nElectronicLevels > 1 && p.ELevel < 2) h.momE[((size_t)c * nS + p.typeId) * 2 + p.ELevel] += 1.0;  // cellMeasurements.C:499-510
+        if (S.vibrationalDoF > 0) {  // cellMeasurements.C:436-451, 489-492
+            const double ev = vibEnergy(S, p);
+            m[22] += ev;
+            m[23] += ev * u; m[24] += ev * v; m[25] += ev * w;
+            for (int k = 0; k < S.vibrationalDoF; ++k) m[27 + k] += p.vib[k] * kB * S.thetaV[k];
+        }
     }
 }
 
@@ -1620,6 +1724,14 @@ void accumulateFields(ugfo_handle& h) {
                 A[14] += dt * (S.rotationalDoF > 0 ? a[0] : 0.0);
                 A[15] += dt * ((5.0 + S.rotationalDoF) * a[0]);
                 h.accS[(size_t)c * nS + s] += dt * (a[1] * FN);
+                if (h.internalModes) {  // uniGasVolFields.C:775-793
+                    double* I = &h.accI[((size_t)c * nS + s) * UGF_NINT];
+                    I[0] += dt * a[0];
+                    I[1] += dt * a[26];
+                    I[2] += dt * h.momE[((size_t)c * nS + s) * 2];
+                    I[3] += dt * h.momE[((size_t)c * nS + s) * 2 + 1];
+                    for (int k = 0; k < UGF_MAX_VIB_MODES; ++k) I[4 + k] += dt * a[27 + k];
+                }
             }
         }
         for (size_t i = 0; i < h.bm.size(); ++i) h.bacc[i] += dt * h.bm[i];
@@ -1653,7 +1765,44 @@ void deriveFields(ugfo_handle& h, double* cellF, double* wallF) {
             if (A[7] > VSMALL && t > VSMALL) F[7] = (2.0 / kB) * ((A[6] / t) / (A[7] / t));
             double nRotDof = 0;
             if (A[0] > VSMALL) nRotDof = A[7] / A[0];
-            F[8] = (3.0 * F[6] + nRotDof * F[7]) / (3.0 + nRotDof);
+            double totalvDof = 0, totalEDof = 0;
+            if (h.internalModes) {
+                // vibrational temperature (uniGasVolFields.C:930-1010): per species and mode from the mean quantum level, modes
+                // weighted by their effective degrees of freedom, species by their share of the molecules with internal structure
+                double vibT = 0;
+                double molsElec = 0;
+                for (int s2 = 0; s2 < h.nSpecies; ++s2)
+                    if (h.sp[s2].nElectronicLevels > 1) molsElec += h.accI[((size_t)c * h.nSpecies + s2) * UGF_NINT];
+                double elecT = 0;
+                for (int s2 = 0; s2 < h.nSpecies; ++s2) {
+                    const ugf_species& S = h.sp[s2];
+                    const double* I = &h.accI[((size_t)c * h.nSpecies + s2) * UGF_NINT];
+                    double dofSpecies = 0, vibTID = 0, dofMode[UGF_MAX_VIB_MODES] = {0, 0, 0, 0}, vibTMode[UGF_MAX_VIB_MODES] = {0, 0, 0, 0};
+                    for (int v = 0; v < S.vibrationalDoF; ++v) {
+                        if (I[4 + v] > VSMALL && I[0] > VSMALL) {
+                            const double iMean = (I[4 + v] / I[0]) / (kB * S.thetaV[v]);
+                            vibTMode[v] = S.thetaV[v] / std::log(1.0 + 1.0 / iMean);
+                            dofMode[v] = (2.0 * S.thetaV[v] / vibTMode[v]) / (std::exp(S.thetaV[v] / vibTMode[v]) - 1.0);
+                        }
+                        dofSpecies += dofMode[v];
+                    }
+                    for (int v = 0; v < S.vibrationalDoF; ++v)
+                        if (dofSpecies > VSMALL) vibTID += vibTMode[v] * dofMode[v] / dofSpecies;
+                    totalvDof += dofSpecies;
+                    if (A[14] > VSMALL && A[0] > VSMALL && I[0] > VSMALL) vibT += vibTID * I[0] / A[14];
+                    // electronic temperature (:1012-1062): two-level Boltzmann ratio of the ground and first level populations
+                    if (S.nElectronicLevels > 1 && I[2] > VSMALL && I[3] > VSMALL && I[3] * S.degeneracy[0] != I[2] * S.degeneracy[1]) {
+                        const double elecTID = (S.electronicEnergy[1] - S.electronicEnergy[0]) /
+                                               (kB * std::log((I[2] * S.degeneracy[1]) / (I[3] * S.degeneracy[0])));
+                        const double fraction = I[0] / molsElec;
+                        if (elecTID > VSMALL) elecT += fraction * elecTID;
+                        totalEDof += fraction * ((2.0 * (I[1] / I[0])) / (kB * elecTID));
+                    }
+                }
+                F[19] = vibT;
+                F[20] = elecT;
+            }
+            F[8] = (3.0 * F[6] + nRotDof * F[7] + totalvDof * F[19] + totalEDof * F[20]) / (3.0 + nRotDof + totalvDof + totalEDof);
             // Mach number (:1078-1121)
             double gamma = 0, Cv_p = 0;
             if (A[0] > VSMALL) {
@@ -1736,17 +1885,20 @@ void deriveFields(ugfo_handle& h, double* cellF, double* wallF) {
 }
 
 void energyTotals(ugfo_handle& h) {
-    double ke = 0, er = 0, mx = 0, my = 0, mz = 0;
+    double ke = 0, er = 0, mx = 0, my = 0, mz = 0, ev = 0, ee = 0;
     int64_t n = 0;
     for (const Parcel& p : h.P) {
         if (p.cell < 0) continue;
         const double m = h.sp[p.typeId].mass;
         ke += 0.5 * m * dot3(p.U, p.U);
         er += p.ERot;
+        ev += vibEnergy(h.sp[p.typeId], p);
+        ee += elecEnergy(h.sp[p.typeId], p);
         mx += m * p.U[0]; my += m * p.U[1]; mz += m * p.U[2];
         ++n;
     }
     h.cnt.linearKineticEnergy = ke; h.cnt.rotationalEnergy = er;
+    h.cnt.vibrationalEnergy = ev; h.cnt.electronicEnergy = ee;
     h.cnt.momentum[0] = mx; h.cnt.momentum[1] = my; h.cnt.momentum[2] = mz;
     h.cnt.nParcels = n;
 }
@@ -1791,9 +1943,13 @@ int ugfo_destroy(ugfo_handle* h) { delete h; return 0; }
 int ugfo_set_species(ugfo_handle* h, int32_t n, const ugf_species* sp) {
     if (n < 1 || n > UGF_MAX_SPECIES) return fail(h, "species count out of range");
     for (int i = 0; i < n; ++i) {
-        if (sp[i].vibrationalDoF > 0) return fail(h, "vibrational modes are not supported yet");
+        if (sp[i].vibrationalDoF < 0 || sp[i].vibrationalDoF > UGF_MAX_VIB_MODES) return fail(h, "bad vibrationalDoF");
         if (sp[i].nElectronicLevels < 1 || sp[i].nElectronicLevels > UGF_MAX_ELEC_LEVELS) return fail(h, "bad nElectronicLevels");
+        for (int m = 0; m < sp[i].vibrationalDoF; ++m)
+            if (!(sp[i].thetaV[m] > 0) || !(sp[i].thetaD[m] > 0) || !(sp[i].Zref[m] > 0) || !(sp[i].TrefZv[m] > 0))
+                return fail(h, "vibrational mode needs positive characteristicVibrationalTemperature, dissociationTemperature, Zref and referenceTempForZref");
         h->sp[i] = sp[i];
+        if (sp[i].vibrationalDoF > 0 || sp[i].nElectronicLevels > 1) h->internalModes = true;
     }
     h->nSpecies = n;
     return 0;
@@ -1839,6 +1995,7 @@ int ugfo_set_mesh(ugfo_handle* h, const ugf_mesh* m) {
     h->bacc.assign((size_t)h->nBFaces * UGF_NBM, 0.0);
     h->acc.assign((size_t)h->nCells * NACC, 0.0);
     h->accS.assign((size_t)h->nCells * h->nSpecies, 0.0);
+    if (h->internalModes) { h->accI.assign((size_t)h->nCells * h->nSpecies * UGF_NINT, 0.0); h->momE.assign((size_t)h->nCells * h->nSpecies * 2, 0.0); }
     h->packBuf.resize(h->nPatches);
     return 0;
 }
@@ -1975,11 +2132,16 @@ int ugfo_upload_parcels(ugfo_handle* h, const ugf_parcels* p) {
         q.typeId = p->typeId ? p->typeId[i] : 0;
         q.ERot = p->ERot ? p->ERot[i] : 0.0;
         q.newParcel = p->newParcel ? p->newParcel[i] : 0;
+        q.ELevel = p->ELevel ? p->ELevel[i] : 0;
+        for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) q.vib[m] = p->vibLevel ? p->vibLevel[(size_t)i * UGF_MAX_VIB_MODES + m] : 0;
         q.sf = 0;
         if (q.cell < 0 || q.cell >= h->nCells) return fail(h, "parcel cell out of range");
         q.CWF = h->cellWF[q.cell];  // implicit weights: a parcel carries its cell's factor (true after any weighting pass)
         if (p->cellWeight && p->cellWeight[i] != q.CWF) return fail(h, "parcel cellWeight differs from the cellWeightFactor of its cell");
         if (q.typeId < 0 || q.typeId >= h->nSpecies) return fail(h, "parcel typeId out of range");
+        if (q.ELevel < 0 || q.ELevel >= h->sp[q.typeId].nElectronicLevels) return fail(h, "parcel ELevel out of range");
+        for (int m = 0; m < UGF_MAX_VIB_MODES; ++m)
+            if (q.vib[m] < 0 || q.vib[m] > 65535 || (m >= h->sp[q.typeId].vibrationalDoF && q.vib[m] != 0)) return fail(h, "parcel vibLevel out of range");
     }
     h->occValid = false; h->momValid = false;
     h->nBeforeInsert = p->n;
@@ -2085,7 +2247,7 @@ long long stateDoubles(const ugfo_handle* h) {
     const long long nC = h->nCells, nS = h->nSpecies, nB = h->nBFaces;
     long long n = 8 + 6 + nC * (1 + 1 + 1 + 3 + 6 + NACC + nS) + nB * UGF_NBM;
     if (h->decompOn) n += nC * (KN_NACC + nS) + nC * 4;
-    return n + inletVelocityDoubles(h);
+    return n + inletVelocityDoubles(h) + (h->internalModes ? nC * nS * UGF_NINT : 0);
 }
 }  // namespace
 
@@ -2095,7 +2257,7 @@ int ugfo_state_save(ugfo_handle* h, double* buf, int64_t nDoubles) {
     if (nDoubles != stateDoubles(h)) return fail(h, "state buffer has the wrong size");
     double* p = buf;
     const double hdr[8] = {STATE_MAGIC, 1.0, (double)h->nCells, (double)h->nSpecies, (double)h->nBFaces, h->decompOn ? 1.0 : 0.0,
-                           (double)inletVelocityDoubles(h), 0.0};
+                           (double)inletVelocityDoubles(h), h->internalModes ? 1.0 : 0.0};
     p = std::copy(hdr, hdr + 8, p);
     const double sc[6] = {(double)h->step, h->timeAvCounter, (double)h->nAvTimeSteps, (double)h->sampleCounter, (double)h->decTimeSteps, h->decTimeAv};
     p = std::copy(sc, sc + 6, p);
@@ -2117,6 +2279,7 @@ int ugfo_state_save(ugfo_handle* h, double* buf, int64_t nDoubles) {
             for (size_t f = 0; f < ip.faceTtr.size(); ++f) { *p++ = ip.faceTtr[f]; *p++ = ip.faceTrot[f]; }
         }
     }
+    if (h->internalModes) p = std::copy(h->accI.begin(), h->accI.end(), p);  // last block, announced by header word 7
     return (p - buf) == nDoubles ? 0 : fail(h, "internal: state size mismatch");
 }
 
@@ -2124,7 +2287,7 @@ int ugfo_state_load(ugfo_handle* h, const double* buf, int64_t nDoubles) {
     if (nDoubles != stateDoubles(h) || nDoubles < 14) return fail(h, "state buffer has the wrong size for this set-up");
     if (buf[0] != STATE_MAGIC || buf[1] != 1.0) return fail(h, "not a ugf state buffer (magic / version)");
     if (buf[2] != (double)h->nCells || buf[3] != (double)h->nSpecies || buf[4] != (double)h->nBFaces || buf[5] != (h->decompOn ? 1.0 : 0.0) ||
-        buf[6] != (double)inletVelocityDoubles(h))
+        buf[6] != (double)inletVelocityDoubles(h) || buf[7] != (h->internalModes ? 1.0 : 0.0))
         return fail(h, "state buffer was written for another mesh / species / model set-up");
     const double* p = buf + 8;
     h->step = (int64_t)p[0]; h->cnt.step = h->step; h->timeAvCounter = p[1]; h->nAvTimeSteps = (int64_t)p[2]; h->sampleCounter = (int)p[3];
@@ -2144,6 +2307,7 @@ int ugfo_state_load(ugfo_handle* h, const double* buf, int64_t nDoubles) {
             for (size_t f = 0; f < ip.faceTtr.size(); ++f) { ip.faceTtr[f] = *p++; ip.faceTrot[f] = *p++; }
         }
     }
+    if (h->internalModes) take(h->accI);
     h->momValid = false;
     return 0;
 }
@@ -2190,6 +2354,7 @@ int ugfo_migrate_counts(ugfo_handle* h, int64_t* counts) {
 }
 
 int ugfo_migrate_pack(ugfo_handle* h, int32_t patch, double** buf, int64_t* n) {
+    if (h->internalModes) return fail(h, "vibrational / electronic levels do not travel across processor patches yet");
     std::vector<double>& b = h->packBuf[patch];
     b.clear();
     for (const int64_t i : h->migIdx) {
@@ -2309,6 +2474,8 @@ int ugfo_download_parcels(ugfo_handle* h, ugf_parcels* p) {
         if (p->ERot) p->ERot[i] = q.ERot;
         if (p->newParcel) p->newParcel[i] = q.newParcel;
         if (p->cellWeight) p->cellWeight[i] = q.CWF;
+        if (p->ELevel) p->ELevel[i] = q.ELevel;
+        if (p->vibLevel) for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) p->vibLevel[(size_t)i * UGF_MAX_VIB_MODES + m] = q.vib[m];
     }
     p->n = n;
     return 0;
@@ -2341,11 +2508,17 @@ int ugfo_download_fields(ugfo_handle* h, double* cellF, double* wallF, int32_t r
         std::fill(h->acc.begin(), h->acc.end(), 0.0);
         std::fill(h->accS.begin(), h->accS.end(), 0.0);
         std::fill(h->bacc.begin(), h->bacc.end(), 0.0);
+        std::fill(h->accI.begin(), h->accI.end(), 0.0);
         h->timeAvCounter = 0; h->nAvTimeSteps = 0;
     }
     return 0;
 }
 
+int ugfo_download_internal_accumulators(ugfo_handle* h, double* accInt) {
+    if (h->internalModes) std::copy(h->accI.begin(), h->accI.end(), accInt);
+    else std::fill(accInt, accInt + (size_t)h->nCells * h->nSpecies * UGF_NINT, 0.0);
+    return 0;
+}
 int ugfo_download_accumulators(ugfo_handle* h, double* acc, double* accS, double* timeAv, int64_t* nAv) {
     if (acc) std::copy(h->acc.begin(), h->acc.end(), acc);
     if (accS) std::copy(h->accS.begin(), h->accS.end(), accS);

@@ -7,14 +7,15 @@ declares and fails loudly if one is missing.
 import ctypes as C
 import os
 
-UGF_ABI_VERSION = 2
+UGF_ABI_VERSION = 3
 UGF_MAX_SPECIES = 8
 UGF_MAX_VIB_MODES = 4
 UGF_MAX_ELEC_LEVELS = 16
 UGF_NMOM = 32
 UGF_NBM = 16
 UGF_NPHASE = 7
-UGF_NFIELD = 19
+UGF_NFIELD = 21
+UGF_NINT = 8
 UGF_NWALLFIELD = 12
 UGF_NFT = 6
 UGF_MIGRATE_STRIDE = 10
@@ -102,6 +103,7 @@ class Parcels(C.Structure):
     _fields_ = [
         ("n", i64), ("x", P(f64)), ("y", P(f64)), ("z", P(f64)), ("Ux", P(f64)), ("Uy", P(f64)), ("Uz", P(f64)),
         ("cell", P(i32)), ("typeId", P(i32)), ("ERot", P(f64)), ("newParcel", P(i32)), ("cellWeight", P(f64)),
+        ("vibLevel", P(i32)), ("ELevel", P(i32)),
     ]
 
 
@@ -118,6 +120,7 @@ class Counters(C.Structure):
         ("step", i64), ("nParcels", i64), ("collisionCandidates", i64), ("collisions", i64), ("bgkRelaxations", i64),
         ("inserted", i64), ("deleted", i64), ("migrated", i64), ("wallHits", i64), ("stuck", i64),
         ("linearKineticEnergy", f64), ("rotationalEnergy", f64), ("momentum", f64 * 3), ("cloned", i64), ("weightDeleted", i64),
+        ("vibrationalEnergy", f64), ("electronicEnergy", f64),
     ]
 
     def as_dict(self):
@@ -153,6 +156,7 @@ SIGNATURES = {
     "state_save": (C.c_int, [H, PF, i64]),
     "state_load": (C.c_int, [H, PF, i64]),
     "download_accumulators": (C.c_int, [H, PF, PF, PF, PI64]),
+    "download_internal_accumulators": (C.c_int, [H, PF]),
     "set_face_tracker": (C.c_int, [H, i32, PI32]),
     "download_face_tracker": (C.c_int, [H, PF, i32]),
     "step": (C.c_int, [H, i32]),

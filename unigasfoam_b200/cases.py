@@ -57,6 +57,8 @@ class Case:
     subCellLevels: np.ndarray = None
     cellWeightFactor: np.ndarray = None   # uniGasCellWeightFactor (cellWeightedSimulation true)
     meta: dict = field(default_factory=dict)
+    vibLevel: np.ndarray = None           # [n, nModes] vibrational quantum levels
+    ELevel: np.ndarray = None             # [n] electronic levels
 
     @property
     def n_parcels(self):
@@ -70,7 +72,7 @@ class Case:
         cl = cloud_cls(self.mesh, self.uniGasProperties, self.boundariesDict, self.deltaT, **kw)
         if self.cellWeightFactor is not None:  # the parcels take the factor of their cell: the field goes in first
             cl.setCellState(cellWeightFactor=self.cellWeightFactor)
-        cl.setParcels(self.position, self.U, self.cell, self.typeId, self.ERot)
+        cl.setParcels(self.position, self.U, self.cell, self.typeId, self.ERot, vibLevel=self.vibLevel, ELevel=self.ELevel)
         cl.setCellState(sigmaTcRMax=self.sigmaTcRMax, cellCollModelId=self.cellCollModelId, subCellLevels=self.subCellLevels)
         return cl
 
@@ -642,3 +644,40 @@ def _blunt_reference_volume(n_eta, n_s, n_phi, geom):
 
 def _blunt_reference_dt(n_eta, n_s, n_phi, geom, courant, speed):
     return courant * min(_blunt_reference_cell(n_eta, n_s, n_phi, geom)) / speed
+
+
+# ---- internal energy modes beyond rotation (a9: vibrational quantum levels, electronic levels) ---------------------------
+
+# a diatomic with one vibrational mode and three electronic levels, oxygen-like (Bird 1994 App. A for the VHS constants; level
+# energies / degeneracies of the O2 X, a, b states).  Zref is set low on purpose where a test wants fast vibrational relaxation.
+OXYGEN_VIB = dict(mass=53.12e-27, diameter=4.07e-10, omega=0.77, alpha=1.0, rotationalDegreesOfFreedom=2, vibrationalModes=1,
+                  characteristicVibrationalTemperature=[2256.0], dissociationTemperature=[59500.0], Zref=[17900.0], referenceTempForZref=[2256.0],
+                  charge=0, numberOfElectronicLevels=3, electronicEnergyList=[0.0, 1.5727e-19, 2.6203e-19], degeneracyList=[3, 2, 1])
+
+
+def equilibrium_levels(sp, T, n, rng):
+    """Boltzmann-distributed vibrational quantum levels [n, nModes] (harmonic oscillator: geometric in the level, which is what
+    equipartitionVibrationalEnergyLevel's int(-ln(R) T / thetaV) draws, U/clouds/uniGasCloud.C:1020-1050) and electronic levels
+    [n] (g_j exp(-E_j / k T), sampled exactly) of one species at temperature T."""
+    nm = int(sp.get("vibrationalModes", 0))
+    vib = np.zeros((n, max(nm, 1)), np.int32)
+    for m in range(nm):
+        vib[:, m] = np.floor(-np.log(1.0 - rng.random(n)) * T / sp["characteristicVibrationalTemperature"][m]).astype(np.int32)
+    E = np.asarray(sp.get("electronicEnergyList", [0.0]), float)
+    g = np.asarray(sp.get("degeneracyList", [1]), float)
+    w = g * np.exp(-E / (kB * T))
+    elev = rng.choice(len(E), size=n, p=w / w.sum()).astype(np.int32)
+    return vib[:, :nm] if nm else None, elev
+
+
+def with_internal_modes(case, Tvib=None, Tel=None, seed=11):
+    """Give the parcels of a single-species case vibrational / electronic levels at the given temperatures (default: the case's
+    temperature)."""
+    name = case.uniGasProperties["typeIdList"][0]
+    sp = case.uniGasProperties["moleculeProperties"][name]
+    T0 = case.meta.get("T0", case.meta.get("Tw", case.meta.get("T_inf")))
+    rng = np.random.default_rng(seed)
+    vib, _ = equilibrium_levels(sp, T0 if Tvib is None else Tvib, case.n_parcels, rng)
+    _, elev = equilibrium_levels(sp, T0 if Tel is None else Tel, case.n_parcels, rng)
+    case.vibLevel, case.ELevel = vib, elev
+    return case

@@ -241,7 +241,7 @@ class UniGasCloud:
     def _i32(a):
         return np.ascontiguousarray(a, dtype=np.int32)
 
-    def setParcels(self, position, U, cell, typeId=None, ERot=None, newParcel=None, cellWeight=None):
+    def setParcels(self, position, U, cell, typeId=None, ERot=None, newParcel=None, cellWeight=None, vibLevel=None, ELevel=None):
         """addNewParcel for a whole configuration (U/clouds/uniGasCloud.C:260-290)."""
         n = len(cell)
         if self._pending_capacity:
@@ -266,6 +266,13 @@ class UniGasCloud:
             q = self._i32(newParcel); keep.append(q); p.newParcel = q.ctypes.data_as(PI)
         if cellWeight is not None:
             w = self._f64(cellWeight); keep.append(w); p.cellWeight = w.ctypes.data_as(PD)
+        if vibLevel is not None:  # [n, nModes <= UGF_MAX_VIB_MODES] quantum levels; padded to the ABI's row length
+            v = np.zeros((n, _capi.UGF_MAX_VIB_MODES), np.int32)
+            vl = np.asarray(vibLevel, np.int32).reshape(n, -1)
+            v[:, :vl.shape[1]] = vl
+            keep.append(v); p.vibLevel = v.ctypes.data_as(PI)
+        if ELevel is not None:
+            e = self._i32(ELevel); keep.append(e); p.ELevel = e.ctypes.data_as(PI)
         self._check(self.api.upload_parcels(self._h, C.byref(p)))
         self._nParcelsSet = True
         self._cwfCarried = None
@@ -370,8 +377,12 @@ class UniGasCloud:
         p = d["parcels"]
         if (p["radialWeight"] != 1.0).any():
             raise UgfError("radialWeight != 1: axisymmetric weighting is not supported")
-        if any(len(v) for v in p["vibLevel"]) or (p["ELevel"] != 0).any():
-            raise UgfError("vibrational / excited electronic levels are not supported")
+        vib = None
+        if any(len(v) for v in p["vibLevel"]):
+            nm = max(len(v) for v in p["vibLevel"])
+            vib = np.zeros((len(p["cell"]), nm), np.int32)
+            for i, v in enumerate(p["vibLevel"]):
+                vib[i, :len(v)] = v
         kw = {}
         if d["sigmaTcRMax"] is not None:
             kw["sigmaTcRMax"] = d["sigmaTcRMax"]
@@ -392,7 +403,8 @@ class UniGasCloud:
             kw["cellWeightFactor"] = foamfile.expand_internal(foamfile.read_vol_field(carried), self.mesh.n_cells)
         if kw:
             self.setCellState(**kw)
-        self.setParcels(p["position"], p["U"], p["cell"], p["typeId"], p["ERot"], cellWeight=p["cellWeight"] if self.cellWeighted else None)
+        self.setParcels(p["position"], p["U"], p["cell"], p["typeId"], p["ERot"], cellWeight=p["cellWeight"] if self.cellWeighted else None,
+                        vibLevel=vib, ELevel=p["ELevel"] if (p["ELevel"] != 0).any() else None)
         if new_cwf is not None:
             self.setCellState(cellWeightFactor=new_cwf)
         if d.get("deltaT") is not None:
@@ -415,8 +427,8 @@ class UniGasCloud:
         ("p", "p", [1, -1, -2, 0, 0, 0, 0], "wall", "wall_p", False),
         ("translationalT", "translationalT", [0, 0, 0, 1, 0, 0, 0], "wall", "wall_translationalT", False),
         ("rotationalT", "rotationalT", [0, 0, 0, 1, 0, 0, 0], "wall", "wall_rotationalT", False),
-        ("vibrationalT", None, [0, 0, 0, 1, 0, 0, 0], "zero", None, False),
-        ("electronicT", None, [0, 0, 0, 1, 0, 0, 0], "zero", None, False),
+        ("vibrationalT", "vibrationalT", [0, 0, 0, 1, 0, 0, 0], "cell", None, False),
+        ("electronicT", "electronicT", [0, 0, 0, 1, 0, 0, 0], "cell", None, False),
         ("overallT", "overallT", [0, 0, 0, 1, 0, 0, 0], "wall", "wall_overallT", False),
         ("surfaceHeatTransfer", None, [1, 0, -3, 0, 0, 0, 0], "surface", "surfaceHeatTransfer", False),
         ("surfaceShearStress", None, [1, -1, -2, 0, 0, 0, 0], "surface", "surfaceShearStress", False),
@@ -603,7 +615,9 @@ class UniGasCloud:
         if n:
             out["avgLinearKE"] = c["linearKineticEnergy"] * self.cfg.nParticle / nMol
             out["avgRotationalE"] = c["rotationalEnergy"] * self.cfg.nParticle / nMol
-            out["totalEnergy"] = (c["linearKineticEnergy"] + c["rotationalEnergy"]) * self.cfg.nParticle
+            out["avgVibrationalE"] = c["vibrationalEnergy"] * self.cfg.nParticle / nMol
+            out["avgElectronicE"] = c["electronicEnergy"] * self.cfg.nParticle / nMol
+            out["totalEnergy"] = (c["linearKineticEnergy"] + c["rotationalEnergy"] + c["vibrationalEnergy"] + c["electronicEnergy"]) * self.cfg.nParticle
         return out
 
     def size(self):
@@ -615,14 +629,17 @@ class UniGasCloud:
         cap = int(self.cfg.parcelCapacity)
         PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         f = [np.empty(cap, np.float64) for _ in range(8)]
-        ii = [np.empty(cap, np.int32) for _ in range(2)]
+        ii = [np.empty(cap, np.int32) for _ in range(3)]
+        vib = np.empty((cap, _capi.UGF_MAX_VIB_MODES), np.int32)
         p = _capi.Parcels()
         p.n = cap
         p.x, p.y, p.z, p.Ux, p.Uy, p.Uz, p.ERot, p.cellWeight = [a.ctypes.data_as(PD) for a in f]
-        p.cell, p.typeId = [a.ctypes.data_as(PI) for a in ii]
+        p.cell, p.typeId, p.ELevel = [a.ctypes.data_as(PI) for a in ii]
+        p.vibLevel = vib.ctypes.data_as(PI)
         self._check(self.api.download_parcels(self._h, C.byref(p)))
         n = p.n
         return {
+            "ELevel": ii[2][:n].copy(), "vibLevel": vib[:n].copy(),
             "position": np.stack([f[0][:n], f[1][:n], f[2][:n]], axis=1),
             "U": np.stack([f[3][:n], f[4][:n], f[5][:n]], axis=1),
             "ERot": f[6][:n].copy(), "cell": ii[0][:n].copy(), "typeId": ii[1][:n].copy(), "cellWeight": f[7][:n].copy(),
@@ -671,7 +688,7 @@ class UniGasCloud:
             "translationalT": cf[:, 6], "rotationalT": cf[:, 7], "overallT": cf[:, 8], "p": cf[:, 9],
             "Ma": cf[:, 10], "densityError": cf[:, 11],
             "MFP": cf[:, 12], "dxMFP": cf[:, 13], "MCR": cf[:, 14], "MCT": cf[:, 15], "dtMCT": cf[:, 16],
-            "velocityError": cf[:, 17], "temperatureError": cf[:, 18],
+            "velocityError": cf[:, 17], "temperatureError": cf[:, 18], "vibrationalT": cf[:, 19], "electronicT": cf[:, 20],
             "wall_rhoN": wf[:, 0], "wall_rhoM": wf[:, 1], "wall_UMean": wf[:, 2:5], "wall_translationalT": wf[:, 5],
             "surfaceHeatTransfer": wf[:, 6], "fD": wf[:, 7:10], "wall_p": wf[:, 10], "surfaceShearStress": wf[:, 11],
         }
@@ -685,6 +702,12 @@ class UniGasCloud:
         t, n = C.c_double(), C.c_int64()
         self._check(self.api.download_accumulators(self._h, acc.ctypes.data_as(PD), sp.ctypes.data_as(PD), C.byref(t), C.byref(n)))
         return {"acc": acc, "species": sp, "timeAvCounter": t.value, "nAvTimeSteps": n.value}
+
+    def internalAccumulators(self):
+        """[nCells, nSpecies, UGF_NINT] time-weighted sums behind vibrationalT / electronicT (ugf_download_internal_accumulators)."""
+        a = np.empty((self.mesh.n_cells, len(self.typeIdList), _capi.UGF_NINT))
+        self._check(self.api.download_internal_accumulators(self._h, a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a
 
     def setFaceTracker(self, faces):
         """Faces whose crossings uniGasFaceTracker tallies (the union of the face zones the surface models read)."""

@@ -25,6 +25,7 @@
 #include "ugf_decomp.cuh"
 #include "ugf_fields.cuh"
 #include "ugf_inflow.cuh"
+#include "ugf_internal.cuh"
 #include "ugf_move.cuh"
 #include "ugf_sort.cuh"
 
@@ -77,6 +78,9 @@ struct ugf_handle {
     ugf_species spHost[UGF_MAX_SPECIES];
     DevParams prm;
     bool hasRot = false, multi = false;
+    bool hasVib = false, hasElec = false;   // some species has vibrational modes / more than one electronic level
+    DevSpeciesInt* dSpi = nullptr;          // per-species tables of those modes (DevParams::spi)
+    double* dMomI = nullptr; double* dAccI = nullptr;  // [nCells][nSpecies][UGF_NINT] per-step sums / time accumulators of the internal modes
 
     // mesh
     bool meshSet = false;
@@ -321,11 +325,13 @@ void build_params(ugf_handle* h) {
     p.cwf = h->dCwf[0] ? h->dCwf[h->cwfCur] : nullptr;
     p.cwfPrev = h->dCwf[0] ? h->dCwf[h->cwfCur ^ 1] : nullptr;
     p.cwfDirty = h->cwfDirty ? 1 : 0;
+    p.spi = h->dSpi;
     for (int i = 0; i < h->nSpecies; ++i) {
         const ugf_species& s = h->spHost[i];
         DevSpecies& d = p.sp[i];
         d.mass = s.mass; d.d = s.d; d.omega = s.omega; d.alpha = s.alpha; d.E0 = s.electronicEnergy[0];
         d.rotDoF = s.rotationalDoF; d.charge = s.charge; d.nElec = s.nElectronicLevels; d.g0 = s.degeneracy[0];
+        d.vibDoF = s.vibrationalDoF; d.pad = 0;
     }
     for (int i = 0; i < h->nSpecies; ++i)
         for (int j = 0; j < h->nSpecies; ++j) {
@@ -345,6 +351,8 @@ int alloc_parcels(ugf_handle* h) {
             return 1;
         if (h->hasRot && dalloc(h, &P.erot, capPad)) return 1;
         if (h->multi && dalloc(h, &P.type, capPad)) return 1;
+        if (h->hasVib && dalloc(h, &P.vib, capPad)) return 1;
+        if (h->hasElec && dalloc(h, &P.elev, capPad)) return 1;
     }
     if (dalloc(h, &h->dPerm, cap)) return 1;
     {
@@ -433,6 +441,13 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
     });
     LAUNCHED();
     h->argBytes += arg_bytes(prm, a);
+    if (doSample && h->dAccI) {  // vibrational / electronic sums of the same (pre-collision) state
+        InternalArgs ia{};
+        ia.nCells = h->nCells; ia.off = h->dOff; ia.perm = a.perm; ia.in = a.in;
+        ia.momI = h->dMomI; ia.accI = h->dAccI; ia.mom = keepMoments ? h->dMom : nullptr; ia.accDt = a.accDt;
+        internal_modes_kernel<<<grid_for(h->nCells, 8), 256, 0, h->stream>>>(prm, ia);
+        LAUNCHED();
+    }
     if (doSample) h->momValid = keepMoments;
     if (gather) return after_gather(h, false);
     return 0;
@@ -649,6 +664,11 @@ int do_accumulate(ugf_handle* h, bool cellsDone = false) {
         if (!cellsDone) {
             accumulate_cells_kernel<<<grid_for(h->nCells, 256), 256, 0, h->stream>>>(h->prm, h->nCells, h->dMom, h->dAcc, h->dAccS);
             LAUNCHED();
+            if (h->dAccI) {
+                const long long nI = (long long)h->nCells * h->nSpecies * UGF_NINT;
+                accumulate_internal_kernel<<<grid_for(nI, 256), 256, 0, h->stream>>>(nI, h->cfg.deltaT, h->dMomI, h->dAccI);
+                LAUNCHED();
+            }
         }
         h->sampleCounter = 0;
     }
@@ -835,7 +855,7 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     if ((e = cudaMalloc((void**)&h->dErr, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dTask, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemsetAsync(h->dTask, 0, 2 * sizeof(int), h->stream);
-    if ((e = cudaMalloc((void**)&h->dTot, 6 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dTot, 8 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dTotal, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dMigTotals, MIG_MAXP * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dInflight, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -857,12 +877,12 @@ int ugf_destroy(ugf_handle* h) {
     for (int b = 0; b < 2; ++b) {
         ParcelBuf& P = h->buf[b];
         cudaFree(P.x); cudaFree(P.y); cudaFree(P.z); cudaFree(P.ux); cudaFree(P.uy); cudaFree(P.uz);
-        cudaFree(P.erot); cudaFree(P.cell); cudaFree(P.type);
+        cudaFree(P.erot); cudaFree(P.cell); cudaFree(P.type); cudaFree(P.vib); cudaFree(P.elev);
     }
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
-                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dMoveQD, h->dMoveQI, h->dSlotTrack, h->dBfTrack, h->dFt};
+                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dMoveQD, h->dMoveQI, h->dSpi, h->dMomI, h->dAccI, h->dSlotTrack, h->dBfTrack, h->dFt};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -885,14 +905,33 @@ int ugf_set_species(ugf_handle* h, int32_t n, const ugf_species* sp) {
     if (h->buf[0].x) return fail(h, "ugf_set_species must precede ugf_upload_parcels");
     h->hasRot = false;
     for (int i = 0; i < n; ++i) {
-        if (sp[i].vibrationalDoF > 0) return fail(h, "vibrational modes are not supported yet");
-        if (sp[i].nElectronicLevels != 1) return fail(h, "species with more than one electronic level are not supported by the CUDA path yet");
+        if (sp[i].vibrationalDoF < 0 || sp[i].vibrationalDoF > UGF_MAX_VIB_MODES) return fail(h, "bad vibrationalDoF");
+        if (sp[i].nElectronicLevels < 1 || sp[i].nElectronicLevels > UGF_MAX_ELEC_LEVELS) return fail(h, "bad nElectronicLevels");
+        for (int m = 0; m < sp[i].vibrationalDoF; ++m)
+            if (!(sp[i].thetaV[m] > 0) || !(sp[i].thetaD[m] > 0) || !(sp[i].Zref[m] > 0) || !(sp[i].TrefZv[m] > 0))
+                return fail(h, "vibrational mode needs positive characteristicVibrationalTemperature, dissociationTemperature, Zref and referenceTempForZref");
         if (!(sp[i].mass > 0) || !(sp[i].d > 0)) return fail(h, "species mass and diameter must be positive");
         h->spHost[i] = sp[i];
         if (sp[i].rotationalDoF > 0) h->hasRot = true;
+        if (sp[i].vibrationalDoF > 0) h->hasVib = true;
+        if (sp[i].nElectronicLevels > 1) h->hasElec = true;
     }
     h->nSpecies = n;
     h->multi = n > 1;
+    if (h->hasVib || h->hasElec) {  // tables of the internal modes on the device (ugf_internal.cuh)
+        CU(cudaSetDevice(h->cfg.device));
+        std::vector<DevSpeciesInt> tab((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            std::memset(&tab[i], 0, sizeof(DevSpeciesInt));
+            for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) {
+                tab[i].thetaV[m] = sp[i].thetaV[m]; tab[i].thetaD[m] = sp[i].thetaD[m]; tab[i].Zref[m] = sp[i].Zref[m]; tab[i].TrefZv[m] = sp[i].TrefZv[m];
+            }
+            for (int k = 0; k < UGF_MAX_ELEC_LEVELS; ++k) { tab[i].elecE[k] = sp[i].electronicEnergy[k]; tab[i].g[k] = sp[i].degeneracy[k]; }
+        }
+        if (!h->dSpi && dalloc(h, &h->dSpi, (size_t)UGF_MAX_SPECIES)) return 1;
+        if (upload(h, h->dSpi, tab.data(), tab.size())) return 1;
+        CU(cudaStreamSynchronize(h->stream));
+    }
     build_params(h);
     return 0;
 }
@@ -1061,6 +1100,12 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     CU(cudaMemsetAsync(h->dCellCount, 0, sizeof(int) * (size_t)nC, h->stream));
     CU(cudaMemsetAsync(h->dMom, 0, sizeof(double) * (size_t)nC * nS * UGF_NMOM, h->stream));
     CU(cudaMemsetAsync(h->dAcc, 0, sizeof(double) * (size_t)nC * NACC, h->stream));
+    if (h->hasVib || h->hasElec) {
+        if (h->hasProcessor) return fail(h, "vibrational / electronic levels do not travel across processor patches yet");
+        if (dalloc(h, &h->dMomI, (size_t)nC * nS * UGF_NINT) || dalloc(h, &h->dAccI, (size_t)nC * nS * UGF_NINT)) return 1;
+        CU(cudaMemsetAsync(h->dMomI, 0, sizeof(double) * (size_t)nC * nS * UGF_NINT, h->stream));
+        CU(cudaMemsetAsync(h->dAccI, 0, sizeof(double) * (size_t)nC * nS * UGF_NINT, h->stream));
+    }
     if (h->multi) {
         if (dalloc(h, &h->dAccS, (size_t)nC * nS)) return 1;
         CU(cudaMemsetAsync(h->dAccS, 0, sizeof(double) * (size_t)nC * nS, h->stream));
@@ -1258,6 +1303,7 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
     d.nFaces = nF; d.nTypeIds = in->nTypeIds;
     for (int i = 0; i < in->nTypeIds; ++i) { d.typeIds[i] = in->typeIds[i]; d.numDen[i] = in->numberDensities[i]; }
     d.Ttr = in->translationalTemperature; d.Trot = in->rotationalTemperature;
+    d.Tvib = in->vibrationalTemperature; d.Tel = in->electronicTemperature;
     for (int k = 0; k < 3; ++k) d.vel[k] = in->velocity[k];
     for (int i = 0; i < UGF_MAX_SPECIES; ++i) d.molFrac[i] = (pin && i < in->nTypeIds) ? pin->moleFractions[i] : 1.0;
     d.theta = pin ? pin->theta : 1.0;
@@ -1432,10 +1478,42 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p) {
     if (upload(h, P.x, p->x, n) || upload(h, P.y, p->y, n) || upload(h, P.z, p->z, n) || upload(h, P.ux, p->Ux, n) ||
         upload(h, P.uy, p->Uy, n) || upload(h, P.uz, p->Uz, n) || upload(h, P.cell, p->cell, n))
         return 1;
-    std::vector<uint8_t> types;
+    std::vector<uint8_t> types, elevs;
+    std::vector<unsigned long long> vibs;
     if (h->hasRot) {
         if (p->ERot) { if (upload(h, P.erot, p->ERot, n)) return 1; }
         else CU(cudaMemsetAsync(P.erot, 0, n * sizeof(double), h->stream));
+    }
+    if (p->vibLevel && !h->hasVib) {
+        for (size_t i = 0; i < n * UGF_MAX_VIB_MODES; ++i) if (p->vibLevel[i] != 0) return fail(h, "vibLevel given but no species has vibrational modes");
+    }
+    if (p->ELevel && !h->hasElec) {
+        for (size_t i = 0; i < n; ++i) if (p->ELevel[i] != 0) return fail(h, "ELevel given but no species has more than one electronic level");
+    }
+    if (h->hasVib) {  // 16 bits per mode in one word per parcel
+        vibs.assign(n, 0ull);
+        if (p->vibLevel)
+            for (size_t i = 0; i < n; ++i) {
+                const int t = p->typeId ? p->typeId[i] : 0;
+                unsigned long long v = 0ull;
+                for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) {
+                    const int32_t l = p->vibLevel[i * UGF_MAX_VIB_MODES + m];
+                    if (l < 0 || l > 65535 || (m >= h->spHost[t].vibrationalDoF && l != 0)) return fail(h, "parcel vibLevel out of range");
+                    v |= (unsigned long long)l << (16 * m);
+                }
+                vibs[i] = v;
+            }
+        if (upload(h, P.vib, vibs.data(), n)) return 1;
+    }
+    if (h->hasElec) {
+        elevs.assign(n, 0);
+        if (p->ELevel)
+            for (size_t i = 0; i < n; ++i) {
+                const int t = p->typeId ? p->typeId[i] : 0;
+                if (p->ELevel[i] < 0 || p->ELevel[i] >= h->spHost[t].nElectronicLevels) return fail(h, "parcel ELevel out of range");
+                elevs[i] = (uint8_t)p->ELevel[i];
+            }
+        if (upload(h, P.elev, elevs.data(), n)) return 1;
     }
     if (h->multi) {
         types.assign(n, 0);
@@ -1731,7 +1809,7 @@ long long state_doubles(const ugf_handle* h) {
     const long long nC = h->nCells, nS = h->nSpecies, nB = h->nBFaces;
     long long n = 8 + 6 + nC * (1 + 1 + 1 + 3 + 6 + NACC + nS) + nB * UGF_NBM;
     if (h->decompOn) n += nC * (KN_NACC + nS) + nC * 4;
-    return n + inlet_velocity_doubles(h);
+    return n + inlet_velocity_doubles(h) + (h->dAccI ? nC * nS * UGF_NINT : 0);  // internal-mode accumulators: last block, header word 7
 }
 }  // namespace
 
@@ -1747,7 +1825,7 @@ int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles) {
     CU(cudaSetDevice(h->cfg.device));
     const size_t nC = (size_t)h->nCells, nS = (size_t)h->nSpecies, nB = (size_t)h->nBFaces;
     double* p = buf;
-    const double hdr[8] = {STATE_MAGIC, 1.0, (double)nC, (double)nS, (double)nB, h->decompOn ? 1.0 : 0.0, (double)inlet_velocity_doubles(h), 0.0};
+    const double hdr[8] = {STATE_MAGIC, 1.0, (double)nC, (double)nS, (double)nB, h->decompOn ? 1.0 : 0.0, (double)inlet_velocity_doubles(h), h->dAccI ? 1.0 : 0.0};
     std::copy(hdr, hdr + 8, p); p += 8;
     const double sc[6] = {(double)h->step, h->timeAvCounter, (double)h->nAvTimeSteps, (double)h->sampleCounter, (double)h->decTimeSteps, h->decTimeAv};
     std::copy(sc, sc + 6, p); p += 6;
@@ -1775,6 +1853,7 @@ int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles) {
         if (f.wang) { if (d2h(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; *p++ = f.wangSteps; }
         if (f.outlet && (d2h(f.dev.faceN, (size_t)f.nSlots) || d2h(f.dev.faceT, 2 * (size_t)f.dev.nFaces))) return 1;
     }
+    if (h->dAccI && d2h(h->dAccI, (size_t)UGF_NINT * nS * nC)) return 1;
     CU(cudaStreamSynchronize(h->stream));
     if (!h->dAccS) for (size_t c = 0; c < nC; ++c) accSAt[c] = accAt[c * NACC + 8];  // one species: nParcelsXnParticle = slot 8
     return 0;
@@ -1786,7 +1865,7 @@ int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
     const size_t nC = (size_t)h->nCells, nS = (size_t)h->nSpecies, nB = (size_t)h->nBFaces;
     if (buf[0] != STATE_MAGIC || buf[1] != 1.0) return fail(h, "not a ugf state buffer (magic / version)");
     if (buf[2] != (double)nC || buf[3] != (double)nS || buf[4] != (double)nB || buf[5] != (h->decompOn ? 1.0 : 0.0) ||
-        buf[6] != (double)inlet_velocity_doubles(h))
+        buf[6] != (double)inlet_velocity_doubles(h) || buf[7] != (h->dAccI ? 1.0 : 0.0))
         return fail(h, "state buffer was written for another mesh / species / model set-up");
     CU(cudaSetDevice(h->cfg.device));
     const double* p = buf + 8;
@@ -1813,6 +1892,7 @@ int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
         if (f.wang) { if (h2d(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; f.wangSteps = *p++; }
         if (f.outlet && (h2d(f.dev.faceN, (size_t)f.nSlots) || h2d(f.dev.faceT, 2 * (size_t)f.dev.nFaces))) return 1;
     }
+    if (h->dAccI && h2d(h->dAccI, (size_t)UGF_NINT * nS * nC)) return 1;
     CU(cudaStreamSynchronize(h->stream));  // ids and the caller's buffer may go away
     h->momValid = false;
     return 0;
@@ -2066,16 +2146,20 @@ int ugf_counters_get(ugf_handle* h, ugf_counters* out) {
     CU(cudaSetDevice(h->cfg.device));
     if (refresh_n(h)) return 1;
     DevCounters c;
-    double tot[6] = {0, 0, 0, 0, 0, 0};
+    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (h->buf[0].x) {
-        CU(cudaMemsetAsync(h->dTot, 0, 6 * sizeof(double), h->stream));
+        CU(cudaMemsetAsync(h->dTot, 0, 8 * sizeof(double), h->stream));
         ParcelBuf P = h->buf[h->cur];
         const DevParams prm = h->prm;
         dispatch(h, [&](auto R, auto M) {
             totals_kernel<decltype(R)::value, decltype(M)::value><<<h->numSMs * 4, 256, 0, h->stream>>>(prm, P, h->dN, h->dTot);
         });
         LAUNCHED();
-        CU(countedMemcpyAsync(h, tot, h->dTot, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (h->dSpi) {
+            internal_totals_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(prm, P, h->dN, h->dTot + 6);
+            LAUNCHED();
+        }
+        CU(countedMemcpyAsync(h, tot, h->dTot, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CU(countedMemcpyAsync(h, &c, h->dCnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     int devErr = 0;
@@ -2096,6 +2180,8 @@ int ugf_counters_get(ugf_handle* h, ugf_counters* out) {
     out->weightDeleted = (int64_t)c.wdeleted;
     out->linearKineticEnergy = tot[0];
     out->rotationalEnergy = tot[1];
+    out->vibrationalEnergy = tot[6];
+    out->electronicEnergy = tot[7];
     out->momentum[0] = tot[2]; out->momentum[1] = tot[3]; out->momentum[2] = tot[4];
     return 0;
 }
@@ -2129,6 +2215,21 @@ int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
     CU(cudaStreamSynchronize(h->stream));
     if (p->typeId) for (size_t i = 0; i < nb; ++i) p->typeId[i] = h->multi ? types[i] : 0;
     if (p->newParcel) std::fill(p->newParcel, p->newParcel + nb, 0);
+    if (p->vibLevel) {
+        if (h->hasVib && nb) {
+            std::vector<unsigned long long> v(nb);
+            CU(countedMemcpy(h, v.data(), P.vib, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nb; ++i)
+                for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) p->vibLevel[i * UGF_MAX_VIB_MODES + m] = (int32_t)((v[i] >> (16 * m)) & 0xFFFFull);
+        } else std::fill(p->vibLevel, p->vibLevel + nb * UGF_MAX_VIB_MODES, 0);
+    }
+    if (p->ELevel) {
+        if (h->hasElec && nb) {
+            std::vector<uint8_t> e(nb);
+            CU(countedMemcpy(h, e.data(), P.elev, nb, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nb; ++i) p->ELevel[i] = e[i];
+        } else std::fill(p->ELevel, p->ELevel + nb, 0);
+    }
     if (p->cellWeight) {  // implicit on the device: the factor of the parcel's cell (the previous field while an update is pending)
         std::vector<int> cells;
         const int* cp = p->cell;
@@ -2189,7 +2290,7 @@ int ugf_download_fields(ugf_handle* h, double* cellF, double* wallF, int32_t res
     const double t = h->timeAvCounter;
     if (cellF) {
         derive_cells_kernel<<<grid_for(nC, 256), 256, 0, h->stream>>>(h->prm, nC, h->dAcc, h->dAccS, h->dVol, h->dBbMin, h->dBbMax,
-                                                                      h->subLevelsAllOne ? nullptr : h->dSubLevels, t, (double)h->nAvTimeSteps, tmp);
+                                                                      h->subLevelsAllOne ? nullptr : h->dSubLevels, t, (double)h->nAvTimeSteps, tmp, h->dAccI);
         LAUNCHED();
         CU(countedMemcpyAsync(h, cellF, tmp, sizeof(double) * (size_t)nC * UGF_NFIELD, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -2205,7 +2306,21 @@ int ugf_download_fields(ugf_handle* h, double* cellF, double* wallF, int32_t res
         CU(cudaMemsetAsync(h->dAcc, 0, sizeof(double) * (size_t)nC * NACC, h->stream));
         if (h->dAccS) CU(cudaMemsetAsync(h->dAccS, 0, sizeof(double) * (size_t)nC * h->nSpecies, h->stream));
         CU(cudaMemsetAsync(h->dBacc, 0, sizeof(double) * std::max<size_t>((size_t)nB * UGF_NBM, 1), h->stream));
+        if (h->dAccI) CU(cudaMemsetAsync(h->dAccI, 0, sizeof(double) * (size_t)nC * h->nSpecies * UGF_NINT, h->stream));
         h->timeAvCounter = 0; h->nAvTimeSteps = 0;
+    }
+    return 0;
+}
+
+int ugf_download_internal_accumulators(ugf_handle* h, double* accInt) {
+    if (!h || !h->meshSet || !accInt) return fail(h, "mesh not set");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->nCells * h->nSpecies * UGF_NINT;
+    if (h->dAccI) {
+        CU(countedMemcpyAsync(h, accInt, h->dAccI, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else {
+        std::fill(accInt, accInt + n, 0.0);
     }
     return 0;
 }

@@ -27,6 +27,7 @@
 #pragma once
 #include "ugf_common.cuh"
 #include "ugf_rng.cuh"
+#include "ugf_internal.cuh"
 
 namespace ugf {
 
@@ -172,6 +173,68 @@ __device__ inline void collide_pair(const DevParams& prm, Stream& r, const DevSp
     }
 }
 
+// The energy-exchange part of LarsenBorgnakke*::collide for one partner with every internal mode (serial application: electronic,
+// vibrational mode by mode, rotational; …/LarsenBorgnakkeVariableHardSphere.C:232-323); Etr is the relative translational energy
+// carried from exchange to exchange.
+__device__ inline void lb_exchange_partner(const DevParams& prm, Stream& r, const DevSpecies& a, const DevSpeciesInt& A, double omegaPQ, double ChiB,
+                                           double& Etr, double& erot, unsigned long long& vib, int& elev) {
+    const double preERot = erot;
+    double preEVib[UGF_MAX_VIB_MODES];
+    for (int m = 0; m < a.vibDoF; ++m) preEVib[m] = vib_level(vib, m) * A.thetaV[m] * kB;
+    const double preEEle = A.elecE[elev];
+    if (prm.invZel > r.u01()) {
+        const double Ec = Etr + preEEle;
+        elev = post_collision_elec_level(r, Ec, a.nElec, omegaPQ, A);
+        Etr = Ec - A.elecE[elev];
+    }
+    for (int m = 0; m < a.vibDoF; ++m) {
+        const double Ec = Etr + preEVib[m];
+        const int iMax = (int)(Ec / (kB * A.thetaV[m]));
+        if (iMax > 0) {
+            const int lv = post_collision_vib_level(r, vib_level(vib, m), iMax, A.thetaV[m], A.thetaD[m], A.TrefZv[m], omegaPQ, A.Zref[m], Ec);
+            vib = vib_set(vib, m, lv);
+            Etr = Ec - lv * A.thetaV[m] * kB;
+        }
+    }
+    if (a.rotDoF > 0) {
+        if (prm.invZrot > r.u01()) {
+            const double Ec = Etr + preERot;
+            const double ratio = post_collision_rotational_energy(r, a.rotDoF, ChiB);
+            erot = ratio * Ec;
+            Etr = Ec - erot;
+        }
+    }
+}
+
+// Larsen-Borgnakke collision of a pair that carries vibrational / electronic levels (DevParams::spi set): out of line, the gases of
+// the BASELINE configurations never come here.
+__device__ __noinline__ void collide_pair_internal(const DevParams& prm, Stream& r, int tP, int tQ, double UP[3], double UQ[3], double& erotP,
+                                                   double& erotQ, unsigned long long& vibP, unsigned long long& vibQ, int& elevP, int& elevQ) {
+    const DevSpecies& a = prm.sp[tP];
+    const DevSpecies& b = prm.sp[tQ];
+    const double mP = a.mass, mQ = b.mass, mS = mP + mQ;
+    double Ucm[3], cRc[3];
+    for (int k = 0; k < 3; ++k) {
+        Ucm[k] = (mP * UP[k] + mQ * UQ[k]) / mS;
+        cRc[k] = UP[k] - UQ[k];
+    }
+    const double cRsqr = cRc[0] * cRc[0] + cRc[1] * cRc[1] + cRc[2] * cRc[2];
+    const double omegaPQ = 0.5 * (a.omega + b.omega);
+    const double mR = mP * mQ / mS;
+    double Etr = 0.5 * mR * cRsqr;
+    const double ChiB = 2.5 - omegaPQ;
+    lb_exchange_partner(prm, r, a, prm.spi[tP], omegaPQ, ChiB, Etr, erotP, vibP, elevP);
+    lb_exchange_partner(prm, r, b, prm.spi[tQ], omegaPQ, ChiB, Etr, erotQ, vibQ, elevQ);
+    const double cRnew = sqrt((2.0 * Etr) / mR);
+    double rel[3];
+    if (prm.binaryModel == UGF_BINARY_LB_VHS) scatter_vhs(r, cRnew, rel);
+    else scatter_vss(r, cRc, 0.5 * (a.alpha + b.alpha), cRnew / sqrt(cRsqr), rel);
+    for (int k = 0; k < 3; ++k) {
+        UP[k] = Ucm[k] + rel[k] * mQ / mS;
+        UQ[k] = Ucm[k] - rel[k] * mP / mS;
+    }
+}
+
 // NTC candidates for one cell: n_sel = 1/2 N (N-1) F_N (sigma_T c_r)max dt / V with stochastic rounding
 // (noTimeCounter.C:184-191); the rounding draw comes from the cell's own stream.
 __device__ __forceinline__ int ntc_candidates(const DevParams& prm, uint32_t step, uint32_t sub, double dtSub, int cell, int n, double sMaxOld,
@@ -310,6 +373,8 @@ __device__ __noinline__ void stream_giant_cell(const DevParams& prm, const CellA
                 a.out.cell[dst] = cell;
                 if (HAS_ROT) a.out.erot[dst] = sE[j];
                 if (MULTI) a.out.type[dst] = sT[j];
+                if (a.in.vib) a.out.vib[dst] = a.in.vib[src];
+                if (a.in.elev) a.out.elev[dst] = a.in.elev[src];
             }
         }
         __syncwarp();
@@ -499,6 +564,8 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                         a.out.cell[b0 + j] = sC[j];
                         if (HAS_ROT) a.out.erot[b0 + j] = sE[j];
                         if (MULTI) a.out.type[b0 + j] = sT[j];
+                        if (a.in.vib) a.out.vib[b0 + j] = a.in.vib[srcs[it]];
+                        if (a.in.elev) a.out.elev[b0 + j] = a.in.elev[srcs[it]];
                         if (!(a.flags & 1)) {
                             cp_async8(&sU0[j], &a.in.x[srcs[it]]);  // same lane, same slot: no cross-lane hazard
                             cp_async8(&sU1[j], &a.in.y[srcs[it]]);
@@ -719,6 +786,13 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
                     if ((sig / sMaxOld) > r.u01()) {
                         double eP = 0.0, eQ = 0.0;
                         if (HAS_ROT) { eP = __ldcg(&a.P.erot[gP]); eQ = __ldcg(&a.P.erot[gQ]); }
+                        if (prm.spi && prm.binaryModel >= UGF_BINARY_LB_VHS) {  // species with vibrational modes / several electronic levels
+                            unsigned long long vP = a.P.vib ? __ldcg(&a.P.vib[gP]) : 0ull, vQ = a.P.vib ? __ldcg(&a.P.vib[gQ]) : 0ull;
+                            int lP = a.P.elev ? (int)__ldcg(&a.P.elev[gP]) : 0, lQ = a.P.elev ? (int)__ldcg(&a.P.elev[gQ]) : 0;
+                            collide_pair_internal(prm, r, tP, tQ, UP, UQ, eP, eQ, vP, vQ, lP, lQ);
+                            if (a.P.vib) { __stcg(&a.P.vib[gP], vP); __stcg(&a.P.vib[gQ], vQ); }
+                            if (a.P.elev) { __stcg(&a.P.elev[gP], (uint8_t)lP); __stcg(&a.P.elev[gQ], (uint8_t)lQ); }
+                        } else
                         collide_pair(prm, r, A, B, UP, UQ, eP, eQ);
                         __stcg(&a.P.ux[gP], UP[0]); __stcg(&a.P.uy[gP], UP[1]); __stcg(&a.P.uz[gP], UP[2]);
                         __stcg(&a.P.ux[gQ], UQ[0]); __stcg(&a.P.uy[gQ], UQ[1]); __stcg(&a.P.uz[gQ], UQ[2]);

@@ -37,6 +37,16 @@ constexpr int CLONE_MASK = CLONE_FLAG - 1;
 struct DevSpecies {
     double mass, d, omega, alpha, E0;  // E0 = electronicEnergy[0]
     int rotDoF, charge, nElec, g0;
+    int vibDoF, pad;                   // number of vibrational modes
+};
+
+// Tables of a species' vibrational modes and electronic levels (moleculeProperties: characteristicVibrationalTemperature,
+// dissociationTemperature, Zref, referenceTempForZref, electronicEnergyList, degeneracyList); one device array for all species,
+// reached through DevParams::spi, which is null when no species has vibrational modes or more than one electronic level.
+struct DevSpeciesInt {
+    double thetaV[UGF_MAX_VIB_MODES], thetaD[UGF_MAX_VIB_MODES], Zref[UGF_MAX_VIB_MODES], TrefZv[UGF_MAX_VIB_MODES];
+    double elecE[UGF_MAX_ELEC_LEVELS];
+    int g[UGF_MAX_ELEC_LEVELS];
 };
 
 struct DevPatch {
@@ -67,6 +77,7 @@ struct DevParams {
     const double* cwf;
     const double* cwfPrev;
     int cwfDirty;
+    const DevSpeciesInt* spi;  // [nSpecies] or null (ugf_internal.cuh)
 };
 
 struct DevCounters {
@@ -77,6 +88,8 @@ struct ParcelBuf {
     double *x, *y, *z, *ux, *uy, *uz, *erot;
     int* cell;
     uint8_t* type;
+    unsigned long long* vib;  // vibrational quantum levels, 16 bits per mode, or null
+    uint8_t* elev;            // electronic level, or null
 };
 
 constexpr int MIG_MAXP = 8;  // processor patches per rank the slot path handles

@@ -6,6 +6,7 @@
 // reads its own 256-byte moment block, so every fetched sector is consumed.
 #pragma once
 #include "ugf_common.cuh"
+#include "ugf_internal.cuh"
 
 namespace ugf {
 
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(256) accumulate_walls_kernel(double dt, int ac
 __global__ void __launch_bounds__(256) derive_cells_kernel(const __grid_constant__ DevParams prm, int nCells, const double* __restrict__ acc,
                                                            const double* __restrict__ accS, const double* __restrict__ vol,
                                                            const double* __restrict__ bbMin, const double* __restrict__ bbMax,
-                                                           const int* __restrict__ subLevels, double t, double nAvSteps, double* __restrict__ out) {
+                                                           const int* __restrict__ subLevels, double t, double nAvSteps, double* __restrict__ out,
+                                                           const double* __restrict__ accI) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const double* A = acc + (size_t)c * NACC;
@@ -78,7 +80,9 @@ __global__ void __launch_bounds__(256) derive_cells_kernel(const __grid_constant
     if (A[7] > VSMALL && t > VSMALL) F[7] = (2.0 / kB) * ((A[6] / t) / (A[7] / t));
     double nRotDof = 0;
     if (A[0] > VSMALL) nRotDof = A[7] / A[0];
-    F[8] = (3.0 * F[6] + nRotDof * F[7]) / (3.0 + nRotDof);
+    double totalvDof = 0, totalEDof = 0;
+    if (accI) derive_internal(prm, accI + (size_t)c * prm.nSpecies * UGF_NINT, A[14], A[0], F[19], F[20], totalvDof, totalEDof);
+    F[8] = (3.0 * F[6] + nRotDof * F[7] + totalvDof * F[19] + totalEDof * F[20]) / (3.0 + nRotDof + totalvDof + totalEDof);
     double gamma = 0, Cv_p = 0;
     if (A[0] > VSMALL) {
         const double molecularMass = A[1] / A[0];

@@ -24,7 +24,7 @@ struct InflowDev {
     int nFaces, nTypeIds;
     int typeIds[UGF_MAX_SPECIES];
     double numDen[UGF_MAX_SPECIES];
-    double Ttr, Trot;
+    double Ttr, Trot, Tvib, Tel;
     double vel[3];
     double molFrac[UGF_MAX_SPECIES];  // 1 for free-stream patches (numDen is per species there)
     double* faceVel;                  // pressure inlets and field patches: inflow velocity per face [nFaces*3], else null (vel everywhere)
@@ -163,6 +163,11 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
         P.cell[dst] = cellI;
         if (HAS_ROT) P.erot[dst] = erot;
         if (MULTI) P.type[dst] = (uint8_t)typeId;
+        if (prm.spi) {  // uniGasGeneralBoundary.C:721-735: vibrational and electronic levels at the patch's temperatures
+            const DevSpeciesInt& S = prm.spi[typeId];
+            if (P.vib) P.vib[dst] = s.vibDoF > 0 ? equipartition_vib_levels(r, f.Tvib, S, s.vibDoF) : 0ull;
+            if (P.elev) P.elev[dst] = s.nElec > 1 ? (uint8_t)equipartition_elec_level(r, f.Tel, S, s.nElec) : (uint8_t)0;
+        }
     }
 }
 

@@ -14,6 +14,7 @@
 #include "ugf_common.cuh"
 #include "ugf_rng.cuh"
 #include "ugf_sort.cuh"
+#include "ugf_internal.cuh"
 
 namespace ugf {
 
@@ -53,7 +54,8 @@ struct WallPre { double IE; double mom[3]; };
 
 // measurePropertiesBeforeControl / AfterControl (uniGasPatchBoundary.C:130-302): slots in DESIGN.md §walls
 __device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, int cell, const DevSpecies& s, const double U[3],
-                                    double erot, const double nw[3], double fA, WallPre& pre, bool after) {
+                                    double erot, const double nw[3], double fA, WallPre& pre, bool after, double evib = 0.0, double eelIn = -1.0) {
+    const double eel = eelIn >= 0.0 ? eelIn : s.E0;  // electronic energy of the parcel's level (ground level when the species has one)
     const double m = s.mass;
     const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
     const double inv = 1.0 / fmax(fabs(Un) * fA, VSMALL);
@@ -70,8 +72,9 @@ __device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, i
         atomicAdd(&b[7], s.rotDoF * inv);
         atomicAdd(&b[12], inv);
     }
-    if (s.E0 != 0.0) atomicAdd(&b[14], s.E0 * inv);
-    const double IE = 0.5 * m * UU + erot + s.E0;
+    if (evib != 0.0) atomicAdd(&b[13], evib * inv);
+    if (eel != 0.0) atomicAdd(&b[14], eel * inv);
+    const double IE = 0.5 * m * UU + erot + eel + evib;
     if (!after) {
         pre.IE = IE;
         pre.mom[0] = m * U[0]; pre.mom[1] = m * U[1]; pre.mom[2] = m * U[2];
@@ -237,7 +240,12 @@ __device__ __noinline__ void face_tally(const DevParams& prm, const MoveArgs& a,
     }
     const DevSpecies& s = prm.sp[type];
     if (hasRot && !haveErot) erot = a.P.erot[i];
-    const double e = 0.5 * s.mass * (U0 * U0 + U1 * U1 + U2 * U2) + (hasRot ? erot : 0.0) + s.E0;
+    double eInt = s.E0;
+    if (prm.spi) {
+        eInt = prm.spi[type].elecE[a.P.elev ? a.P.elev[i] : 0];
+        if (a.P.vib) eInt += vib_energy(prm.spi[type], s.vibDoF, a.P.vib[i]);
+    }
+    const double e = 0.5 * s.mass * (U0 * U0 + U1 * U1 + U2 * U2) + (hasRot ? erot : 0.0) + eInt;
     double* t = a.ft + ((size_t)k * prm.nSpecies + type) * UGF_NFT;
     atomicAdd(&t[0], sgn * w);
     atomicAdd(&t[1], sgn * s.mass * w);
@@ -245,6 +253,24 @@ __device__ __noinline__ void face_tally(const DevParams& prm, const MoveArgs& a,
     atomicAdd(&t[3], s.mass * U1 * w);
     atomicAdd(&t[4], s.mass * U2 * w);
     atomicAdd(&t[5], sgn * e * w);
+}
+
+// diffuseReflection's tail (uniGasPatchBoundary.C:373-383): vibrational and electronic levels redrawn at the wall temperature, from
+// the same stream right after the rotational energy; the new levels go straight to the parcel arrays
+__device__ __noinline__ void wall_internal_levels(const DevParams& prm, const MoveArgs& a, Stream& r, int type, double T, long long i, double& evib,
+                                                  double& eel) {
+    const DevSpecies& sp = prm.sp[type];
+    const DevSpeciesInt& S = prm.spi[type];
+    if (sp.vibDoF > 0) {
+        const unsigned long long v = equipartition_vib_levels(r, T, S, sp.vibDoF);
+        a.P.vib[i] = v;
+        evib = vib_energy(S, sp.vibDoF, v);
+    }
+    if (sp.nElec > 1) {
+        const int lev = equipartition_elec_level(r, T, S, sp.nElec);
+        a.P.elev[i] = (uint8_t)lev;
+        eel = S.elecE[lev];
+    }
 }
 
 enum { HIT_CHANGED_U = 1, HIT_DELETED = 2, HIT_STUCK = 8, HIT_MIGRATED = 16, HIT_WDELETED = 32 };
@@ -272,7 +298,12 @@ __device__ __forceinline__ void boundary_interaction(const DevParams& prm, const
         double nw[3], fA;
         unit_normal(pl, nw, fA);
         WallPre pre;
-        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, false);
+        double evib = 0.0, eel = -1.0;  // internal modes beyond rotation (rare gases: DevParams::spi), read from / written to global memory here
+        if (prm.spi) {
+            if (a.P.vib) evib = vib_energy(prm.spi[type], sp.vibDoF, a.P.vib[i]);
+            eel = prm.spi[type].elecE[a.P.elev ? a.P.elev[i] : 0];
+        }
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, false, evib, eel);
         bool diffuse = (pt.wallModel == UGF_WALL_DIFFUSE);
         const bool cll = (pt.wallModel == UGF_WALL_CLL);
         if (pt.wallModel != UGF_WALL_SPECULAR) {
@@ -287,8 +318,12 @@ __device__ __forceinline__ void boundary_interaction(const DevParams& prm, const
                 for (int k = 0; k < 3; ++k) pf.Uw[k] = __ldg(&pt.faceU[3 * (size_t)lf + k]);
                 if (cll) cll_reflection(r, sp, st.U, st.erot, nw, pf);
                 else if (diffuse) diffuse_reflection(r, sp, st.U, st.erot, nw, pf.T, pf.Uw);
+                if (diffuse && !cll && prm.spi) wall_internal_levels(prm, a, r, type, pf.T, i, evib, eel);
             } else if (cll) cll_reflection(r, sp, st.U, st.erot, nw, pt);
-            else if (diffuse) diffuse_reflection(r, sp, st.U, st.erot, nw, pt.T, pt.Uw);
+            else if (diffuse) {
+                diffuse_reflection(r, sp, st.U, st.erot, nw, pt.T, pt.Uw);
+                if (prm.spi) wall_internal_levels(prm, a, r, type, pt.T, i, evib, eel);
+            }
             st.nDraws = 2 * (int)r.c3 - r.have;
         }
         if (!diffuse && !cll) {
@@ -296,7 +331,7 @@ __device__ __forceinline__ void boundary_interaction(const DevParams& prm, const
             if (Un > 0.0) for (int k = 0; k < 3; ++k) st.U[k] = st.U[k] - 2.0 * Un * nw[k];
         }
         st.flags |= HIT_CHANGED_U;
-        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, true);
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, true, evib, eel);
     } else if (pt.kind == UGF_PATCH_SYMMETRY) {
         const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
         double nw[3], fA;

@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(256) reorder_kernel(ParcelBuf in, ParcelBuf ou
     out.cell[j] = in.cell[s];
     if (HAS_ROT) out.erot[j] = in.erot[s];
     if (MULTI) out.type[j] = in.type[s];
+    if (in.vib) out.vib[j] = in.vib[s];
+    if (in.elev) out.elev[j] = in.elev[s];
 }
 
 }  // namespace ugf
