@@ -478,15 +478,17 @@ int run_ntc_kernel(ugf_handle* h) {
     }
     for (int sub = 0; sub < nSub; ++sub) {
         a.sub_cycle = (uint32_t)sub;
-        if (!h->subLevelsAllOne) {
-            dispatch(h, [&](auto R, auto M) {
-                ntc_kernel<decltype(R)::value, decltype(M)::value, true><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
-            });
-        } else {
-            dispatch(h, [&](auto R, auto M) {
-                ntc_kernel<decltype(R)::value, decltype(M)::value, false><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
-            });
-        }
+        const bool subc = !h->subLevelsAllOne, internal = h->dSpi != nullptr;
+        dispatch(h, [&](auto R, auto M) {
+            constexpr bool r = decltype(R)::value, mm = decltype(M)::value;
+            if (internal) {
+                if (subc) ntc_kernel<r, mm, true, true><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+                else ntc_kernel<r, mm, false, true><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+            } else {
+                if (subc) ntc_kernel<r, mm, true><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+                else ntc_kernel<r, mm, false><<<h->ntcBlocks, NTC_THREADS, 0, h->stream>>>(prm, a);
+            }
+        });
         LAUNCHED();
         h->argBytes += arg_bytes(prm, a);
     }

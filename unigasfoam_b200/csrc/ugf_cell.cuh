@@ -664,7 +664,9 @@ constexpr int NTC_WARPS = NTC_THREADS / 32;
 constexpr int NTC_IDLE = 0x7f7f7f7f;
 constexpr int NTC_MARKS = 1024;  // parcels per 32-cell chunk whose conflict marks live in shared memory (global marks beyond)
 
-template <bool HAS_ROT, bool MULTI, bool SUBCELLS>
+// INTERNAL: some species carries vibrational modes / several electronic levels (its own instantiation: the Larsen-Borgnakke exchange
+// with every mode is a large out-of-line function whose call site alone costs the common kernels registers)
+template <bool HAS_ROT, bool MULTI, bool SUBCELLS, bool INTERNAL = false>
 __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ NtcArgs a) {
     __shared__ double sMaxW[NTC_WARPS][32];
     __shared__ int sMarkW[NTC_WARPS][NTC_MARKS];
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
                     if ((sig / sMaxOld) > r.u01()) {
                         double eP = 0.0, eQ = 0.0;
                         if (HAS_ROT) { eP = __ldcg(&a.P.erot[gP]); eQ = __ldcg(&a.P.erot[gQ]); }
-                        if (prm.spi && prm.binaryModel >= UGF_BINARY_LB_VHS) {  // species with vibrational modes / several electronic levels
+                        if (INTERNAL && prm.binaryModel >= UGF_BINARY_LB_VHS) {  // species with vibrational modes / several electronic levels
                             unsigned long long vP = a.P.vib ? __ldcg(&a.P.vib[gP]) : 0ull, vQ = a.P.vib ? __ldcg(&a.P.vib[gQ]) : 0ull;
                             int lP = a.P.elev ? (int)__ldcg(&a.P.elev[gP]) : 0, lQ = a.P.elev ? (int)__ldcg(&a.P.elev[gQ]) : 0;
                             collide_pair_internal(prm, r, tP, tQ, UP, UQ, eP, eQ, vP, vQ, lP, lQ);
