@@ -127,6 +127,9 @@ struct ugf_handle {
     unsigned long long* dInflight = nullptr; long long* dRecvStart = nullptr;
     long long nAtMove = 0;          // exact array length when the step's move was launched
     bool slotRound = false;         // received parcels of this round came through the slot path
+    bool migFused = true;           // peer-memory rounds in two launches (pack + signal, wait + unpack + move); UGF_MIG_FUSED=0: six
+    bool recvMoved = false;         // the fused receive kernel has already continued the tracks of this round's parcels
+    unsigned int* dMigDone = nullptr;  // block counter of the fused receive kernel
     bool nExact = true;             // nUpper is the exact array length (needed by the exact-count unpack)
     MigSlots migSlots{};
     double* dAccS = nullptr;  // multi-species: per-species nParcelsXnParticle accumulators
@@ -550,6 +553,9 @@ int do_inflow(ugf_handle* h) {
     return 0;
 }
 
+MoveArgs make_move_args(ugf_handle* h, long long begin, bool received);
+int launch_move(ugf_handle* h, const MoveArgs& a, long long count, long long begin, bool received);
+
 int do_move(ugf_handle* h, long long begin, bool received) {
     for (int p = 0; p < h->nPatches; ++p)
         if (h->patchKind[p] == UGF_PATCH_WALL && h->patchesHost[p].wallModel == UGF_WALL_UNSET)
@@ -560,6 +566,13 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     }
     h->cellCountZero = false;
     if (h->hasProcessor && !(received && h->slotRound)) CU(cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream));
+    MoveArgs a = make_move_args(h, begin, received);
+    long long count = h->nUpper - begin;
+    if (a.dBegin) count = std::min<long long>(count, (long long)h->migSlots.nProc * h->lastSlotCapacity);  // what one unpack can append
+    return launch_move(h, a, count, begin, received);
+}
+
+MoveArgs make_move_args(ugf_handle* h, long long begin, bool received) {
     MoveArgs a{};
     a.mesh = h->mesh;
     a.P = h->buf[h->cur];
@@ -586,8 +599,10 @@ int do_move(ugf_handle* h, long long begin, bool received) {
     a.slotTrack = h->nTracked ? h->dSlotTrack : nullptr;
     a.bfTrack = h->dBfTrack;
     a.ft = h->dFt;
-    long long count = h->nUpper - begin;
-    if (a.dBegin) count = std::min<long long>(count, (long long)h->migSlots.nProc * h->lastSlotCapacity);  // what one unpack can append
+    return a;
+}
+
+int launch_move(ugf_handle* h, const MoveArgs& a, long long count, long long begin, bool received) {
     if (count > 0) {
         const DevParams prm = h->prm;
         const bool streamed = !received && begin == 0 && !h->moveDirect;
@@ -695,15 +710,18 @@ int do_accumulate(ugf_handle* h, bool cellsDone = false) {
 
 // device-side pack of every processor patch into the given slot addresses: from the migrant lists of the move
 // kernel when they can hold a full slot, else by two passes over the cell ids
-int pack_slots_to(ugf_handle* h, const MigDst& dst, long long slotCapacity) {
+int pack_slots_to(ugf_handle* h, const MigDst& dst, long long slotCapacity, const MigFlags* fl = nullptr, unsigned long long epoch = 0, bool* signalled = nullptr) {
+    if (signalled) *signalled = false;
     if (h->dMigList && slotCapacity <= MIG_LIST_CAP && !h->migSearchPack) {
         ParcelBuf P = h->buf[h->cur];
         const MigSlots ms = h->migSlots;
         dispatch(h, [&](auto R, auto M) {
             mig_pack_list_kernel<decltype(R)::value, decltype(M)::value><<<ms.nProc, 1024, 0, h->stream>>>(h->mesh, ms, P, h->dSf, h->dWq, h->dMigCount, h->dMigList, MIG_LIST_CAP,
-                                                                                                          dst, slotCapacity, h->dErr);
+                                                                                                          dst, slotCapacity, h->dErr, fl ? *fl : MigFlags{}, fl ? epoch : 0ull,
+                                                                                                          fl ? h->dInflight : nullptr);
         });
         LAUNCHED();
+        if (signalled && fl) *signalled = true;
         return 0;
     }
     const int nb = (int)grid_for(h->nUpper, MIG_TILE);
@@ -862,6 +880,9 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     if ((e = cudaMalloc((void**)&h->dMigTotals, MIG_MAXP * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dInflight, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->dRecvStart, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->dMigDone, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemsetAsync(h->dMigDone, 0, sizeof(unsigned int), h->stream);
+    if (const char* ev = std::getenv("UGF_MIG_FUSED")) h->migFused = std::atoi(ev) != 0;
     cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream);
     cudaMemsetAsync(h->dRecvStart, 0, sizeof(long long), h->stream);
     cudaMemsetAsync(h->dN, 0, sizeof(long long), h->stream);
@@ -882,7 +903,7 @@ int ugf_destroy(ugf_handle* h) {
         cudaFree(P.erot); cudaFree(P.cell); cudaFree(P.type); cudaFree(P.vib); cudaFree(P.elev);
     }
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
-                    h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart,
+                    h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart, h->dMigDone,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
                     h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dMoveQD, h->dMoveQI, h->dSpi, h->dMomI, h->dAccI, h->dSlotTrack, h->dBfTrack, h->dFt};
     for (void* p : ptrs) cudaFree(p);
@@ -2023,6 +2044,7 @@ int ugf_migrate_unpack(ugf_handle* h, int32_t patch, const double* devBuf, int64
 int ugf_move_received(ugf_handle* h) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (h->recvStart < 0) return fail(h, "ugf_move_received before ugf_move");
+    if (h->recvMoved) { h->recvMoved = false; return 0; }  // the fused receive kernel has tracked them already
     if (h->slotRound) {
         // received through slots: the exact start lives on the device (dRecvStart); launch over everything appended
         // since the step's move and let the kernel skip what precedes it
@@ -2083,18 +2105,50 @@ int ugf_migrate_pack_peer(ugf_handle* h, double* const* dstSlots, uint64_t* cons
         dst.slot[k] = dstSlots[k];
         fl.flag[k] = reinterpret_cast<unsigned long long*>(dstFlags[k]);
     }
-    if (pack_slots_to(h, dst, slotCapacity)) return 1;
-    mig_signal_kernel<<<1, 32, 0, h->stream>>>(fl, h->migSlots.nProc, (unsigned long long)epoch);
-    LAUNCHED();
+    bool signalled = false;
+    if (pack_slots_to(h, dst, slotCapacity, &fl, (unsigned long long)epoch, &signalled)) return 1;
+    if (!signalled) {  // the search-based pack (slots larger than the migrant lists): flags from their own launch
+        mig_signal_kernel<<<1, 32, 0, h->stream>>>(fl, h->migSlots.nProc, (unsigned long long)epoch);
+        LAUNCHED();
+        if (h->migFused) CU(cudaMemsetAsync(h->dInflight, 0, sizeof(unsigned long long), h->stream));  // the list pack does this itself
+    }
     return 0;
 }
 
 int ugf_migrate_unpack_peer(ugf_handle* h, const double* devRecv, const uint64_t* devFlags, int64_t slotCapacity, uint64_t epoch) {
     if (!h || !h->buf[0].x) return fail(h, "no parcels uploaded");
     if (h->migSlots.nProc == 0) return 0;
-    mig_wait_kernel<<<1, 32, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(devFlags), h->migSlots.nProc, (unsigned long long)epoch, h->dErr);
+    if (!h->migFused) {
+        mig_wait_kernel<<<1, 32, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(devFlags), h->migSlots.nProc, (unsigned long long)epoch, h->dErr);
+        LAUNCHED();
+        return ugf_migrate_unpack_slots(h, devRecv, slotCapacity);
+    }
+    // one launch: wait for the flags, append the records, continue their tracks, publish the new length
+    if (h->migSlots.nProc > MIG_MAXP) return fail(h, "too many processor patches for the slot path");
+    if (h->nExact && h->nUpper + (long long)h->migSlots.nProc * slotCapacity > h->capacity)
+        return fail(h, "parcelCapacity too small for the migration slots (needs room for nProcPatches x slotCapacity parcels)");
+    h->slotRound = true;
+    MoveArgs a = make_move_args(h, 0, true);
+    a.dBegin = nullptr;
+    RecvArgs ra{};
+    ra.ms = h->migSlots; ra.recv = devRecv; ra.flags = reinterpret_cast<const unsigned long long*>(devFlags); ra.epoch = (unsigned long long)epoch;
+    ra.slotCapacity = slotCapacity; ra.capacity = h->capacity; ra.dN = h->dN; ra.dRecvStart = h->dRecvStart; ra.done = h->dMigDone; ra.errFlag = h->dErr;
+    const DevParams prm = h->prm;
+    const dim3 grid(grid_for(slotCapacity, 256), h->migSlots.nProc);
+    dispatch(h, [&](auto R, auto M) {
+        constexpr bool r = decltype(R)::value, mm = decltype(M)::value;
+        if (h->moveNF == 6) mig_recv_move_kernel<r, mm, 6><<<grid, 256, 0, h->stream>>>(prm, a, ra);
+        else if (h->moveNF == 4 && h->mesh.rec2d) mig_recv_move_kernel<r, mm, NF_REC2D><<<grid, 256, 0, h->stream>>>(prm, a, ra);
+        else if (h->moveNF == 4) mig_recv_move_kernel<r, mm, 4><<<grid, 256, 0, h->stream>>>(prm, a, ra);
+        else mig_recv_move_kernel<r, mm, 0><<<grid, 256, 0, h->stream>>>(prm, a, ra);
+    });
     LAUNCHED();
-    return ugf_migrate_unpack_slots(h, devRecv, slotCapacity);
+    h->nUpper = std::min<long long>(h->capacity, h->nUpper + (long long)h->migSlots.nProc * slotCapacity);
+    h->appendBound += (long long)h->migSlots.nProc * slotCapacity;
+    h->lastSlotCapacity = slotCapacity;
+    h->recvMoved = true;  // ugf_move_received has nothing left to do for this round
+    h->occValid = false; h->momValid = false;
+    return 0;
 }
 
 int ugf_migrate_unpack_slots(ugf_handle* h, const double* devRecv, int64_t slotCapacity) {

@@ -536,10 +536,14 @@ __global__ void mig_commit_kernel(long long* dN, long long* dRecvStart, unsigned
 // and the records written straight to the slot.  No pass over the cloud at all.
 constexpr int MIG_LIST_CAP = 8192;  // migrants per patch and round the list path handles (32 KB of shared memory)
 
+struct MigFlags {
+    unsigned long long* flag[MIG_MAXP];
+};
+
 template <bool HAS_ROT, bool MULTI>
 __global__ void __launch_bounds__(1024) mig_pack_list_kernel(MeshDev mesh, MigSlots ms, ParcelBuf P, const double* __restrict__ sf, const double* __restrict__ wq, int* __restrict__ migCount,
                                                              const int* __restrict__ migList, int listCap, const MigDst dst, long long slotCapacity,
-                                                             int* errFlag) {
+                                                             int* errFlag, const MigFlags fl, unsigned long long epoch, unsigned long long* inflight) {
     __shared__ int s[MIG_LIST_CAP];
     const int k = blockIdx.x;
     const int patch = ms.patch[k];
@@ -582,17 +586,20 @@ __global__ void __launch_bounds__(1024) mig_pack_list_kernel(MeshDev mesh, MigSl
         r[9] = wq ? wq[i] : 1.0;
         P.cell[i] = -1;
     }
+    // peer-memory rounds (epoch != 0): the records went straight into the neighbour's receive slot - publish the round's epoch in its
+    // flag word behind them (system-scope release), one kernel instead of pack + signal
+    if (epoch) __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) migCount[patch] = 0;
+    if (threadIdx.x == 0) {
+        migCount[patch] = 0;
+        if (epoch) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl.flag[k]), "l"(epoch) : "memory");
+        if (k == 0 && inflight) *inflight = 0ull;  // everything that waited on a processor patch leaves with this round
+    }
 }
 
 // ---- NVLink peer-memory transfer: the pack kernel above has written straight into the neighbours' receive slots ----
 // signal: one thread per processor patch publishes the round's epoch in the receiver's flag word, after a system-scope
 // fence that orders it behind the records written by the (completed) pack kernel.
-struct MigFlags {
-    unsigned long long* flag[MIG_MAXP];
-};
-
 __global__ void mig_signal_kernel(const MigFlags f, int nProc, unsigned long long epoch) {
     __threadfence_system();
     if ((int)threadIdx.x < nProc) {
@@ -614,6 +621,85 @@ __global__ void mig_wait_kernel(const unsigned long long* flags, int nProc, unsi
         }
     }
     __threadfence_system();
+}
+
+// ---- fused receive: wait for the neighbours' flags, append their records and continue the tracks, all in one launch --------------
+// Replaces mig_wait_kernel + mig_unpack_all_kernel + mig_commit_kernel + move_kernel (four dependent launches per transfer round,
+// each a few microseconds of launch latency on an otherwise idle GPU).  Grid: x covers a slot, y = slot.  Every block first spins on
+// all local flags (the block needs every slot's count for its append position), then each thread places one record and tracks it to
+// the end of the step (or to the next processor patch).  The last block to finish publishes the new array length.
+struct RecvArgs {
+    MigSlots ms;
+    const double* recv;
+    const unsigned long long* flags;
+    unsigned long long epoch;  // 0: no flag wait (slots filled by a completed NCCL transfer)
+    long long slotCapacity, capacity;
+    long long* dN;
+    long long* dRecvStart;
+    unsigned int* done;        // zero on entry, zero again on exit
+    int* errFlag;
+};
+
+template <bool HAS_ROT, bool MULTI, int NF>
+__global__ void __launch_bounds__(256, 4) mig_recv_move_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ MoveArgs a,
+                                                              const __grid_constant__ RecvArgs ra) {
+    if (ra.epoch && (int)threadIdx.x < ra.ms.nProc) {
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ra.flags + threadIdx.x) : "memory");
+            if (v >= ra.epoch) break;
+            if (clock64() - t0 > 8000000000LL) { *ra.errFlag = 5; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int k = blockIdx.y;
+    const long long slotStride = (ra.slotCapacity + 1) * UGF_MIGRATE_STRIDE;
+    const double* slot = ra.recv + k * slotStride;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)slot[0];
+    if (n < 0 || n > ra.slotCapacity) { if (i == 0) *ra.errFlag = 4; n = 0; }
+    long long base = *ra.dN;
+    long long add = 0;
+    for (int j = 0; j < ra.ms.nProc; ++j) {
+        long long nj = (long long)ra.recv[j * slotStride];
+        if (nj < 0 || nj > ra.slotCapacity) nj = 0;
+        if (j < k) base += nj;
+        add += nj;
+    }
+    bool valid = i < n;
+    const long long dst = base + i;
+    if (valid && dst >= ra.capacity) { *ra.errFlag = 1; valid = false; }
+    int cell = -1;
+    double x0 = 0, x1 = 0, x2 = 0, U0 = 0, U1 = 0, U2 = 0;
+    if (valid) {
+        const double* r = slot + (1 + i) * UGF_MIGRATE_STRIDE;
+        const int type = (int)(r[8] * (1.0 / MIG_TYPE_SHIFT));
+        const int lf = (int)(r[8] - MIG_TYPE_SHIFT * type);
+        const DevPatch& pt = a.mesh.patches[ra.ms.patch[k]];
+        x0 = r[0]; x1 = r[1]; x2 = r[2]; U0 = r[3]; U1 = r[4]; U2 = r[5];
+        a.P.x[dst] = x0; a.P.y[dst] = x1; a.P.z[dst] = x2;
+        a.P.ux[dst] = U0; a.P.uy[dst] = U1; a.P.uz[dst] = U2;
+        if (HAS_ROT) a.P.erot[dst] = r[6];
+        a.sf[dst] = r[7];
+        if (MULTI) a.P.type[dst] = (uint8_t)type;
+        if (a.wq) a.wq[dst] = r[9];
+        if (lf < 0 || lf >= pt.size) { *ra.errFlag = 2; a.P.cell[dst] = -1; }
+        else { cell = a.mesh.bfOwner[pt.startBfi + lf]; a.P.cell[dst] = cell; }
+    }
+    track_parcel<HAS_ROT, MULTI, NF>(prm, a, dst, valid, cell, x0, x1, x2, U0, U1, U2);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(ra.done, 1u) == total - 1) {  // every block has read the old length and placed its records
+            *ra.dRecvStart = *ra.dN;
+            if (*ra.dN + add <= ra.capacity) *ra.dN += add; else *ra.errFlag = 1;
+            *ra.done = 0u;
+        }
+    }
 }
 
 }  // namespace ugf
