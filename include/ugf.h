@@ -97,7 +97,8 @@ typedef struct ugf_config {
     int32_t binaryModel;       /* UGF_BINARY_* */
     int32_t bgkModel;          /* UGF_BGK_* */
     int32_t nSubCycles;        /* noTimeCounterSubCycled only */
-    int32_t macroInterpolation;/* collisionProperties.macroInterpolation; must be 0 (cell values) */
+    int32_t macroInterpolation;/* collisionProperties.macroInterpolation: 1 = the BGK target fields are interpolated to the parcel's
+                                  position (interpolationCellPoint); needs ugf_set_macro_interpolation */
     double Tref;               /* collisionProperties.Tref */
     double theta;              /* collisionProperties.theta (default 1) */
     double rotationalRelaxationCollisionNumber; /* LB: Z_rot  (…LBVHS.C:60-63) */
@@ -237,6 +238,23 @@ typedef struct ugf_decomposition {
     int32_t neighborLevels;                /* 3 (:72) */
     double maxNeighborFraction;            /* 0.4 (:73) */
 } ugf_decomposition;
+
+/* interpolationCellPoint for collisionProperties.macroInterpolation true (U/bgkCollisions/derived/unifiedStochasticParticleSBGK/
+ * unifiedStochasticParticleSBGK.C:893-947 and the same block in the other three BGK models): the geometry OpenFOAM derives from the
+ * polyMesh, handed over once.  Point value = sum of pointWeights x cell value over pointCells (inverse-distance weights of
+ * volPointInterpolation, boundary points fed by their boundary faces' owner cells, cyclic partners merged; normalised per point);
+ * at points with a non-zero pointNormals entry (symmetry patches) vectors / tensors lose their normal components.  A cell is split
+ * into the tets (cell centre, tetPoints[t][0..2]); the value at a position is linear in the tet that contains it (cellPointWeight). */
+typedef struct ugf_cell_point {
+    int32_t nPoints;
+    const double* points;             /* [nPoints*3] */
+    const int32_t* tetOffsets;        /* [nCells+1] */
+    const int32_t* tetPoints;         /* [nTets*3] */
+    const int32_t* pointCellOffsets;  /* [nPoints+1] */
+    const int32_t* pointCells;
+    const double* pointWeights;
+    const double* pointNormals;       /* [nPoints*3] */
+} ugf_cell_point;
 
 /* Number of fp64 values per (cell, species) in the cell-moment block; see DESIGN.md
  * for the slot list.  (U/cellMeasurements/cellMeasurements.H:73-145) */
@@ -384,6 +402,8 @@ int ugf_accumulate_fields(ugf_handle* h);
  * collisions like uniGasCloud::evolve does (U/clouds/uniGasCloud.C:862); phase-wise drivers call ugf_decompose after
  * ugf_collide / ugf_relax.  Processor faces are treated as zero-gradient by the smoothing operator. */
 int ugf_set_decomposition(ugf_handle* h, const ugf_decomposition* d);
+/* Geometry for macroInterpolation (see ugf_cell_point); call after ugf_set_mesh when ugf_config.macroInterpolation is 1. */
+int ugf_set_macro_interpolation(ugf_handle* h, const ugf_cell_point* cp);
 int ugf_decompose(ugf_handle* h);
 /* collModelId [nCells] (0 = bgk, 1 = dsmc) and the time-blended Knudsen fields kn [nCells][4] = KnRho, KnT, KnU,
  * KnGLL (either may be NULL). */

@@ -236,6 +236,10 @@ struct ugfo_handle {
     ugf_counters cnt;
     std::vector<std::vector<double>> packBuf;
     int64_t inflight = 0;
+    // interpolationCellPoint geometry (collisionProperties.macroInterpolation), see ugf_cell_point
+    bool cpSet = false, relaxFailed = false;
+    std::vector<double> cpPoints, cpW, cpNormals;
+    std::vector<int32_t> cpTetOff, cpTetPts, cpPcOff, cpPc;
     std::vector<int64_t> migIdx;  // indices of the parcels waiting on processor patches (ascending), filled by moveRange
 };
 
@@ -1237,10 +1241,92 @@ void bgkMacro(ugfo_handle& h, int c, Macro& m) {
     }
 }
 
-void relaxCell(ugfo_handle& h, int c, int64_t& nrel) {
+// ---- macroInterpolation: interpolationCellPoint restated (…USP.C:893-947; OpenFOAM volPointInterpolation + cellPointWeight) ----
+constexpr int NIF = 22;  // interpolated values: 0 Pr, 1 nu, 2 p, 3 T, 4-6 U, 7-9 q, 10-15 shear stress, 16-21 pressure tensor
+
+inline void macroToFields(const Macro& m, double* f) {
+    f[0] = m.Pr; f[1] = m.nu; f[2] = m.p; f[3] = m.T;
+    for (int k = 0; k < 3; ++k) { f[4 + k] = m.U[k]; f[7 + k] = m.q[k]; }
+    for (int k = 0; k < 6; ++k) { f[10 + k] = m.s[k]; f[16 + k] = m.P[k]; }
+}
+inline void fieldsToMacro(const double* f, Macro& m) {
+    m.Pr = f[0]; m.nu = f[1]; m.p = f[2]; m.T = f[3];
+    for (int k = 0; k < 3; ++k) { m.U[k] = f[4 + k]; m.q[k] = f[7 + k]; }
+    for (int k = 0; k < 6; ++k) { m.s[k] = f[10 + k]; m.P[k] = f[16 + k]; }
+}
+// symmetric tensor (xx,xy,xz,yy,yz,zz) -> P T P with P = I - n n
+inline void projectSym(double* t, const double* n) {
+    const double T[3][3] = {{t[0], t[1], t[2]}, {t[1], t[3], t[4]}, {t[2], t[4], t[5]}};
+    double Pm[3][3], A[3][3], B[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Pm[i][j] = (i == j ? 1.0 : 0.0) - n[i] * n[j];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = 0; for (int k = 0; k < 3; ++k) A[i][j] += Pm[i][k] * T[k][j]; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { B[i][j] = 0; for (int k = 0; k < 3; ++k) B[i][j] += A[i][k] * Pm[k][j]; }
+    t[0] = B[0][0]; t[1] = B[0][1]; t[2] = B[0][2]; t[3] = B[1][1]; t[4] = B[1][2]; t[5] = B[2][2];
+}
+// cell values -> point values
+void pointFields(const ugfo_handle& h, const std::vector<double>& cellF, std::vector<double>& pointF) {
+    const int nP = (int)(h.cpPcOff.size() - 1);
+    pointF.assign((size_t)nP * NIF, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < nP; ++p) {
+        double* f = &pointF[(size_t)p * NIF];
+        for (int j = h.cpPcOff[p]; j < h.cpPcOff[p + 1]; ++j) {
+            const double w = h.cpW[j];
+            const double* cf = &cellF[(size_t)h.cpPc[j] * NIF];
+            for (int k = 0; k < NIF; ++k) f[k] += w * cf[k];
+        }
+        const double* n = &h.cpNormals[3 * (size_t)p];
+        if (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0) {  // symmetry patch: vectors / tensors keep their in-plane part
+            for (int v = 4; v <= 7; v += 3) {
+                const double vn = f[v] * n[0] + f[v + 1] * n[1] + f[v + 2] * n[2];
+                for (int k = 0; k < 3; ++k) f[v + k] -= vn * n[k];
+            }
+            projectSym(f + 10, n);
+            projectSym(f + 16, n);
+        }
+    }
+}
+// value at x in cell c: linear in the tet (cell centre, 3 face points) that contains x (cellPointWeight::findTetrahedron); if
+// round-off leaves x outside every tet, the tet it is least outside of
+void interpolateAt(const ugfo_handle& h, int c, const double* x, const std::vector<double>& cellF, const std::vector<double>& pointF, double* out) {
+    const double* cc = &h.cc[3 * (size_t)c];
+    const double tol = SMALL;
+    int best = -1;
+    double bestMin = -1e300, bw[4] = {1, 0, 0, 0};
+    for (int t = h.cpTetOff[c]; t < h.cpTetOff[c + 1]; ++t) {
+        const int32_t* tp = &h.cpTetPts[3 * (size_t)t];
+        double e[3][3], r[3];
+        for (int k = 0; k < 3; ++k) {
+            for (int q = 0; q < 3; ++q) e[q][k] = h.cpPoints[3 * (size_t)tp[q] + k] - cc[k];
+            r[k] = x[k] - cc[k];
+        }
+        const double c12[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2], e[1][0] * e[2][1] - e[1][1] * e[2][0]};
+        const double det = e[0][0] * c12[0] + e[0][1] * c12[1] + e[0][2] * c12[2];
+        if (!(std::fabs(det / h.vol[c]) > tol)) continue;
+        const double c20[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2], e[2][0] * e[0][1] - e[2][1] * e[0][0]};
+        const double c01[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2], e[0][0] * e[1][1] - e[0][1] * e[1][0]};
+        const double l1 = (r[0] * c12[0] + r[1] * c12[1] + r[2] * c12[2]) / det;
+        const double l2 = (r[0] * c20[0] + r[1] * c20[1] + r[2] * c20[2]) / det;
+        const double l3 = (r[0] * c01[0] + r[1] * c01[1] + r[2] * c01[2]) / det;
+        const double l0 = 1.0 - l1 - l2 - l3;
+        const double mn = std::min(std::min(l0, l1), std::min(l2, l3));
+        if (mn > bestMin) { bestMin = mn; best = t; bw[0] = l0; bw[1] = l1; bw[2] = l2; bw[3] = l3; }
+        if (mn + tol > 0) break;  // inside: the first such tet, as the reference's search
+    }
+    const double* cf = &cellF[(size_t)c * NIF];
+    if (best < 0) { for (int k = 0; k < NIF; ++k) out[k] = cf[k]; return; }
+    const int32_t* tp = &h.cpTetPts[3 * (size_t)best];
+    for (int k = 0; k < NIF; ++k)
+        out[k] = bw[0] * cf[k] + bw[1] * pointF[(size_t)tp[0] * NIF + k] + bw[2] * pointF[(size_t)tp[1] * NIF + k] + bw[3] * pointF[(size_t)tp[2] * NIF + k];
+}
+
+struct InterpCtx { const std::vector<Macro>* mac; const std::vector<double>* cellF; const std::vector<double>* pointF; };
+
+void relaxCell(ugfo_handle& h, int c, int64_t& nrel, const InterpCtx* ic = nullptr) {
     const int model = h.cfg.bgkModel;
-    Macro m;
-    bgkMacro(h, c, m);
+    Macro mCell;
+    if (ic) mCell = (*ic->mac)[c]; else bgkMacro(h, c, mCell);
+    const Macro& m = mCell;
     const bool envelope = (model == UGF_BGK_SBGK || model == UGF_BGK_USP_SBGK);
     bool raised = false;
     if (h.collModelId[c] == 0 && m.perform) {
@@ -1277,6 +1363,13 @@ void relaxCell(ugfo_handle& h, int c, int64_t& nrel) {
             const double mass = h.sp[p.typeId].mass;
             Stream r(h.cfg.seed, KIND_BGK, 0, (uint32_t)h.step, (uint32_t)c, (uint32_t)i);
             (void)r.u01();  // the selection key
+            Macro mi = mCell;  // target state: the cell's, or interpolated to the parcel's position (…USP.C:936-947)
+            if (ic) {
+                double f[NIF];
+                interpolateAt(h, c, p.x, *ic->cellF, *ic->pointF, f);
+                fieldsToMacro(f, mi);
+            }
+            const Macro& m = mi;
             const double u0 = std::sqrt(2.0 * kB * m.T / mass);
             double v[3];
             if (model == UGF_BGK_BGK) {  // …BGK.C:782-796
@@ -1341,8 +1434,22 @@ void relaxCell(ugfo_handle& h, int c, int64_t& nrel) {
 
 void relaxAll(ugfo_handle& h) {
     if (h.cfg.bgkModel == UGF_BGK_NONE) return;
+    if (h.cfg.macroInterpolation && !h.cpSet) { h.err = "macroInterpolation true needs ugf_set_macro_interpolation"; h.relaxFailed = true; return; }
     if (!(h.cfg.collisionModel == UGF_COLL_BGK || h.cfg.collisionModel == UGF_COLL_HYBRID)) return;
     int64_t nrel = 0;
+    if (h.cfg.macroInterpolation) {
+        // calculateProperties for every cell first, then the cell -> point interpolation of the target fields, then the cells
+        std::vector<Macro> mac((size_t)h.nCells);
+        std::vector<double> cellF((size_t)h.nCells * NIF), pointF;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int c = 0; c < h.nCells; ++c) { bgkMacro(h, c, mac[c]); macroToFields(mac[c], &cellF[(size_t)c * NIF]); }
+        pointFields(h, cellF, pointF);
+        const InterpCtx ic{&mac, &cellF, &pointF};
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nrel)
+        for (int c = 0; c < h.nCells; ++c) relaxCell(h, c, nrel, &ic);
+        h.cnt.bgkRelaxations += nrel;
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nrel)
     for (int c = 0; c < h.nCells; ++c) relaxCell(h, c, nrel);
     h.cnt.bgkRelaxations += nrel;
@@ -1930,7 +2037,6 @@ const char* ugfo_last_error(const ugfo_handle* h) { return h ? h->err.c_str() : 
 int ugfo_create(const ugf_config* cfg, ugfo_handle** out) {
     if (!cfg || !out) { g_createErr = "null argument"; return 1; }
     if (cfg->abiVersion != UGF_ABI_VERSION) { g_createErr = "ABI version mismatch"; return 1; }
-    if (cfg->macroInterpolation) { g_createErr = "macroInterpolation true is not supported"; return 1; }
     ugfo_handle* h = new ugfo_handle();
     h->cfg = *cfg;
     std::memset(&h->cnt, 0, sizeof(h->cnt));
@@ -2202,13 +2308,27 @@ int ugfo_relax(ugfo_handle* h) {
     reorder(*h);
     if (!h->momValid) sampleAll(*h);
     relaxAll(*h);
-    return 0;
+    return h->relaxFailed ? 1 : 0;
 }
 
 int ugfo_accumulate_fields(ugfo_handle* h) {
     if (!h->momValid) sampleAll(*h);
     updateInletVelocities(*h);
     accumulateFields(*h);
+    return 0;
+}
+
+int ugfo_set_macro_interpolation(ugfo_handle* h, const ugf_cell_point* cp) {
+    if (!h->nCells) return fail(h, "mesh not set");
+    const size_t nP = (size_t)cp->nPoints, nT = (size_t)cp->tetOffsets[h->nCells], nW = (size_t)cp->pointCellOffsets[nP];
+    h->cpPoints.assign(cp->points, cp->points + 3 * nP);
+    h->cpTetOff.assign(cp->tetOffsets, cp->tetOffsets + h->nCells + 1);
+    h->cpTetPts.assign(cp->tetPoints, cp->tetPoints + 3 * nT);
+    h->cpPcOff.assign(cp->pointCellOffsets, cp->pointCellOffsets + nP + 1);
+    h->cpPc.assign(cp->pointCells, cp->pointCells + nW);
+    h->cpW.assign(cp->pointWeights, cp->pointWeights + nW);
+    h->cpNormals.assign(cp->pointNormals, cp->pointNormals + 3 * nP);
+    h->cpSet = true;
     return 0;
 }
 
@@ -2320,6 +2440,7 @@ int ugfo_finish_step(ugfo_handle* h) {
     sampleAll(*h);
     collideAll(*h);
     relaxAll(*h);
+    if (h->relaxFailed) return 1;
     updateInletVelocities(*h);
     accumulateFields(*h);
     decompose(*h);
@@ -2339,8 +2460,9 @@ int ugfo_step(ugfo_handle* h, int32_t nSteps) {
         sampleAll(*h);
         collideAll(*h);
         relaxAll(*h);
+        if (h->relaxFailed) return 1;
         updateInletVelocities(*h);
-    accumulateFields(*h);
+        accumulateFields(*h);
         decompose(*h);
         ugfo_end_step(h);
     }

@@ -151,16 +151,18 @@ def test_all_tutorial_dictionaries_parse(name):
 
 
 def test_unsupported_switches_fail_loudly(OracleCloud):
-    """Radial weighting and macroInterpolation are not covered yet: constructing the cloud from such a case says so
-    instead of running something else."""
+    """Radial weighting is not covered yet: constructing the cloud from such a case says so instead of running something
+    else."""
     from unigasfoam_b200.cloud import UgfError
     m = cases.closed_box(n=3, parcels=100).mesh
     ld = foamdict.load_case(os.path.join(GOLD, "plumeImpingement"))
     with pytest.raises(UgfError, match="axisymmetricSimulation"):
         OracleCloud(m, ld["uniGasProperties"], {}, ld["deltaT"], parcelCapacity=1000)
+    # macroInterpolation true (set by every tutorial) is covered: tests/test_macro_interpolation.py runs the tutorial's
+    # collisionProperties as written
     ld = foamdict.load_case(CASE)
-    with pytest.raises(UgfError, match="macroInterpolation"):
-        OracleCloud(m, ld["uniGasProperties"], {}, ld["deltaT"], parcelCapacity=1000)
+    assert ld["uniGasProperties"]["collisionProperties"]["macroInterpolation"] is True
+    OracleCloud(m, ld["uniGasProperties"], {}, ld["deltaT"], parcelCapacity=1000).close()
 
 
 # ---- the supersonicPlate tutorial on its own mesh layout; macroInterpolation (cell values) is the one override ------

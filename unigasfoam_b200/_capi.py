@@ -84,6 +84,13 @@ class Mesh(C.Structure):
     ]
 
 
+class CellPoint(C.Structure):
+    _fields_ = [
+        ("nPoints", i32), ("points", P(f64)), ("tetOffsets", P(i32)), ("tetPoints", P(i32)), ("pointCellOffsets", P(i32)),
+        ("pointCells", P(i32)), ("pointWeights", P(f64)), ("pointNormals", P(f64)),
+    ]
+
+
 class Inflow(C.Structure):
     _fields_ = [
         ("nTypeIds", i32), ("typeIds", i32 * UGF_MAX_SPECIES), ("numberDensities", f64 * UGF_MAX_SPECIES),
@@ -169,6 +176,7 @@ SIGNATURES = {
     "relax": (C.c_int, [H]),
     "accumulate_fields": (C.c_int, [H]),
     "set_decomposition": (C.c_int, [H, P(Decomposition)]),
+    "set_macro_interpolation": (C.c_int, [H, P(CellPoint)]),
     "decompose": (C.c_int, [H]),
     "download_decomposition": (C.c_int, [H, PI32, PF]),
     "end_step": (C.c_int, [H]),

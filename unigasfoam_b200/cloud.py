@@ -153,6 +153,19 @@ class UniGasCloud:
             if field:
                 PD = C.POINTER(C.c_double)
                 self._check(self.api.set_patch_wall_fields(self._h, patch, bT.ctypes.data_as(PD), bU.ctypes.data_as(PD)))
+        if self.cfg.macroInterpolation:  # interpolationCellPoint geometry (mesh.cell_point_data restates what OpenFOAM derives)
+            from .mesh import cell_point_data
+            d = cell_point_data(self.mesh)
+            cp = _capi.CellPoint()
+            keep = [np.ascontiguousarray(self.mesh.points, np.float64), d["tetOffsets"], np.ascontiguousarray(d["tetPoints"]), d["pointCellOffsets"],
+                    d["pointCells"], d["pointWeights"], d["pointNormals"]]
+            PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+            cp.nPoints = len(self.mesh.points)
+            cp.points = keep[0].ctypes.data_as(PD)
+            cp.tetOffsets, cp.tetPoints = keep[1].ctypes.data_as(PI), keep[2].ctypes.data_as(PI)
+            cp.pointCellOffsets, cp.pointCells = keep[3].ctypes.data_as(PI), keep[4].ctypes.data_as(PI)
+            cp.pointWeights, cp.pointNormals = keep[5].ctypes.data_as(PD), keep[6].ctypes.data_as(PD)
+            self._check(self.api.set_macro_interpolation(self._h, C.byref(cp)))
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
             if word not in ("uniGasFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch",

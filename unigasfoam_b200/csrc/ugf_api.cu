@@ -80,6 +80,9 @@ struct ugf_handle {
     bool hasRot = false, multi = false;
     bool hasVib = false, hasElec = false;   // some species has vibrational modes / more than one electronic level
     DevSpeciesInt* dSpi = nullptr;          // per-species tables of those modes (DevParams::spi)
+    InterpDev interp{};                     // macroInterpolation geometry + work arrays (ugf_set_macro_interpolation)
+    Macro* dMacro = nullptr;
+    std::vector<void*> interpOwned;
     double* dMomI = nullptr; double* dAccI = nullptr;  // [nCells][nSpecies][UGF_NINT] per-step sums / time accumulators of the internal modes
 
     // mesh
@@ -520,6 +523,20 @@ int run_bgk_kernel(ugf_handle* h) {
     a.step = (uint32_t)h->step;
     a.cnt = h->dCnt;
     const DevParams prm = h->prm;
+    if (h->cfg.macroInterpolation) {
+        if (!h->dMacro) return fail(h, "macroInterpolation true needs ugf_set_macro_interpolation");
+        a.macroCell = h->dMacro;
+        a.ip = h->interp;
+        bgk_fields_kernel<<<grid_for(h->nCells, 128), 128, 0, h->stream>>>(prm, a);
+        LAUNCHED();
+        bgk_points_kernel<<<grid_for(h->interp.nPoints, 128), 128, 0, h->stream>>>(h->interp);
+        LAUNCHED();
+        if (h->multi) bgk_kernel<true, true><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
+        else bgk_kernel<false, true><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
+        LAUNCHED();
+        h->argBytes += 3 * arg_bytes(prm, a);
+        return 0;
+    }
     if (h->multi) bgk_kernel<true><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
     else bgk_kernel<false><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
     LAUNCHED();
@@ -844,7 +861,6 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     ugf_handle* h = nullptr;
     if (!cfg || !out) return fail(nullptr, "null argument");
     if (cfg->abiVersion != UGF_ABI_VERSION) return fail(nullptr, "ABI version mismatch");
-    if (cfg->macroInterpolation) return fail(nullptr, "macroInterpolation true is not supported");
     if (cfg->partnerModel != UGF_PARTNER_NTC && cfg->partnerModel != UGF_PARTNER_NTC_SUBCYCLED) return fail(nullptr, "unknown dsmcCollisionPartnerModel");
     if (cfg->partnerModel == UGF_PARTNER_NTC_SUBCYCLED && cfg->nSubCycles < 1) return fail(nullptr, "noTimeCounterSubCycled needs nSubCycles >= 1");
     if (cfg->parcelCapacity <= 0 || cfg->parcelCapacity > 2000000000LL) return fail(nullptr, "parcelCapacity out of range");
@@ -911,6 +927,7 @@ int ugf_destroy(ugf_handle* h) {
     for (double* p : h->packBuf) cudaFree(p);
     for (double* p : h->wallFieldOwned) cudaFree(p);
     for (void* p : h->decompOwned) cudaFree(p);
+    for (void* p : h->interpOwned) cudaFree(p);
     for (void* p : h->peerOpened) cudaIpcCloseMemHandle(p);
     for (void* p : h->peerOwned) cudaFree(p);
     for (void* p : h->hostOwned) cudaFreeHost(p);
@@ -1166,9 +1183,11 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     CU(e1);
     if (h->multi) {
         CU(cudaFuncSetAttribute(bgk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->bgkSmem));
+        CU(cudaFuncSetAttribute(bgk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->bgkSmem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occBgk, bgk_kernel<true>, BGK_THREADS, h->bgkSmem));
     } else {
         CU(cudaFuncSetAttribute(bgk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->bgkSmem));
+        CU(cudaFuncSetAttribute(bgk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->bgkSmem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occBgk, bgk_kernel<false>, BGK_THREADS, h->bgkSmem));
     }
     auto persistent = [&](int occ, int warpsPerBlock) {
@@ -1791,6 +1810,30 @@ int ugf_set_decomposition(ugf_handle* h, const ugf_decomposition* d) {
     h->decTimeSteps = 0;
     h->decTimeAv = 0;
     h->knCur = 0;
+    return 0;
+}
+
+int ugf_set_macro_interpolation(ugf_handle* h, const ugf_cell_point* cp) {
+    if (!h || !h->meshSet || !cp) return fail(h, "mesh not set");
+    if (h->dMacro) return fail(h, "macro interpolation already set");
+    if (h->hasProcessor) return fail(h, "macroInterpolation on a decomposed mesh is not supported (point values across processor patches need a halo)");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t nC = (size_t)h->nCells, nP = (size_t)cp->nPoints, nT = (size_t)cp->tetOffsets[nC], nW = (size_t)cp->pointCellOffsets[nP];
+    double *dPts = nullptr, *dW = nullptr, *dNrm = nullptr, *dCc = nullptr, *dCellF = nullptr, *dPointF = nullptr;
+    int *dTo = nullptr, *dTp = nullptr, *dPo = nullptr, *dPc = nullptr;
+    if (dalloc(h, &dPts, 3 * nP) || dalloc(h, &dW, nW) || dalloc(h, &dNrm, 3 * nP) || dalloc(h, &dCc, 3 * nC) || dalloc(h, &dCellF, nC * NIF) ||
+        dalloc(h, &dPointF, nP * NIF) || dalloc(h, &dTo, nC + 1) || dalloc(h, &dTp, 3 * nT) || dalloc(h, &dPo, nP + 1) || dalloc(h, &dPc, nW) ||
+        dalloc(h, &h->dMacro, nC))
+        return 1;
+    for (void* p : {(void*)dPts, (void*)dW, (void*)dNrm, (void*)dCc, (void*)dCellF, (void*)dPointF, (void*)dTo, (void*)dTp, (void*)dPo, (void*)dPc, (void*)h->dMacro})
+        h->interpOwned.push_back(p);
+    if (upload(h, dPts, cp->points, 3 * nP) || upload(h, dW, cp->pointWeights, nW) || upload(h, dNrm, cp->pointNormals, 3 * nP) ||
+        upload(h, dCc, h->ccHost.data(), 3 * nC) || upload(h, dTo, cp->tetOffsets, nC + 1) || upload(h, dTp, cp->tetPoints, 3 * nT) ||
+        upload(h, dPo, cp->pointCellOffsets, nP + 1) || upload(h, dPc, cp->pointCells, nW))
+        return 1;
+    CU(cudaStreamSynchronize(h->stream));
+    h->interp.points = dPts; h->interp.tetOff = dTo; h->interp.tetPts = dTp; h->interp.pcOff = dPo; h->interp.pc = dPc; h->interp.pw = dW;
+    h->interp.pnormal = dNrm; h->interp.cc = dCc; h->interp.cellF = dCellF; h->interp.pointF = dPointF; h->interp.nPoints = (int)nP;
     return 0;
 }
 

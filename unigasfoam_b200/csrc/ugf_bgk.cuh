@@ -39,6 +39,27 @@ constexpr int BGK_CHUNK = 8;             // cells per warp chunk
 constexpr int BGK_LPC = 32 / BGK_CHUNK;  // lanes per cell in the conservation sums
 constexpr int BGK_CAP = 256;             // parcels staged per run of cells
 
+// ---- macroInterpolation (collisionProperties.macroInterpolation true): interpolationCellPoint restated ----------------------------
+// calculateProperties runs for every cell in its own launch (bgk_fields_kernel: the complete Macro per cell, kept for the relaxation
+// kernel, and the NIF target values), bgk_points_kernel takes them to the mesh points (inverse-distance weights, ugf_cell_point), and
+// the relaxation kernel evaluates the target state of every relaxing parcel at its position: linear in the tet (cell centre + three
+// face points) that contains it (…USP.C:893-947; OpenFOAM volPointInterpolation / cellPointWeight).
+constexpr int NIF = 22;  // 0 Pr, 1 nu, 2 p, 3 T, 4-6 U, 7-9 q, 10-15 shear stress, 16-21 pressure tensor
+
+struct InterpDev {
+    const double* points;    // [nPoints*3]
+    const int* tetOff;       // [nCells+1]
+    const int* tetPts;       // [nTets*3]
+    const int* pcOff;        // [nPoints+1]
+    const int* pc;
+    const double* pw;
+    const double* pnormal;   // [nPoints*3]
+    const double* cc;        // [nCells*3] cell centres
+    double* cellF;           // [nCells*NIF]
+    double* pointF;          // [nPoints*NIF]
+    int nPoints;
+};
+
 struct BgkArgs {
     int nCells;
     const int* off;
@@ -52,6 +73,8 @@ struct BgkArgs {
     double* keyScratch;  // [capacity] selection keys for cells larger than the staging capacity
     uint32_t step;
     DevCounters* cnt;
+    struct Macro* macroCell;  // macroInterpolation: the cells' macroscopic state computed by bgk_fields_kernel, else null
+    InterpDev ip;
 };
 
 struct Macro {
@@ -219,6 +242,98 @@ __device__ __forceinline__ int bgk_count(const DevParams& prm, uint32_t step, in
     return min(nRel, n);
 }
 
+__device__ __forceinline__ void macro_to_fields(const Macro& m, double* f) {
+    f[0] = m.Pr; f[1] = m.nu; f[2] = m.p; f[3] = m.T;
+    for (int k = 0; k < 3; ++k) { f[4 + k] = m.U[k]; f[7 + k] = m.q[k]; }
+    for (int k = 0; k < 6; ++k) { f[10 + k] = m.s[k]; f[16 + k] = m.P[k]; }
+}
+
+__device__ inline void project_sym(double* t, const double* n) {  // symmetric tensor (xx,xy,xz,yy,yz,zz) -> P T P, P = I - n n
+    const double T[3][3] = {{t[0], t[1], t[2]}, {t[1], t[3], t[4]}, {t[2], t[4], t[5]}};
+    double Pm[3][3], A[3][3], B[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Pm[i][j] = (i == j ? 1.0 : 0.0) - n[i] * n[j];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = 0; for (int k = 0; k < 3; ++k) A[i][j] += Pm[i][k] * T[k][j]; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { B[i][j] = 0; for (int k = 0; k < 3; ++k) B[i][j] += A[i][k] * Pm[k][j]; }
+    t[0] = B[0][0]; t[1] = B[0][1]; t[2] = B[0][2]; t[3] = B[1][1]; t[4] = B[1][2]; t[5] = B[2][2];
+}
+
+// calculateProperties for every cell (one thread per cell): the Macro is kept for bgk_kernel, which must not evaluate it a second
+// time (the theta-blend of q / sigma advances the stored previous values)
+__global__ void __launch_bounds__(128) bgk_fields_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ BgkArgs a) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.nCells) return;
+    Macro m;
+    bgk_macro(prm, cell_fn(prm, cell), a.mom + (size_t)cell * prm.nSpecies * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
+    a.macroCell[cell] = m;
+    double f[NIF];
+    macro_to_fields(m, f);
+    for (int k = 0; k < NIF; ++k) a.ip.cellF[(size_t)cell * NIF + k] = f[k];
+}
+
+__global__ void __launch_bounds__(128) bgk_points_kernel(const __grid_constant__ InterpDev ip) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ip.nPoints) return;
+    double f[NIF];
+    for (int k = 0; k < NIF; ++k) f[k] = 0.0;
+    for (int j = ip.pcOff[p]; j < ip.pcOff[p + 1]; ++j) {
+        const double w = ip.pw[j];
+        const double* cf = ip.cellF + (size_t)ip.pc[j] * NIF;
+        for (int k = 0; k < NIF; ++k) f[k] += w * cf[k];
+    }
+    const double n[3] = {ip.pnormal[3 * (size_t)p], ip.pnormal[3 * (size_t)p + 1], ip.pnormal[3 * (size_t)p + 2]};
+    if (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0) {
+        for (int v = 4; v <= 7; v += 3) {
+            const double vn = f[v] * n[0] + f[v + 1] * n[1] + f[v + 2] * n[2];
+            for (int k = 0; k < 3; ++k) f[v + k] -= vn * n[k];
+        }
+        project_sym(f + 10, n);
+        project_sym(f + 16, n);
+    }
+    for (int k = 0; k < NIF; ++k) ip.pointF[(size_t)p * NIF + k] = f[k];
+}
+
+// target state at position x of cell `cell` (cellPointWeight::findTetrahedron + interpolationCellPoint::interpolate); out of line:
+// only the macroInterpolation instantiation of the relaxation kernel calls it
+__device__ __noinline__ void interpolate_macro(const InterpDev& ip, const double* __restrict__ vol, int cell, double x0, double x1, double x2, Macro& m) {
+    const double cc[3] = {ip.cc[3 * (size_t)cell], ip.cc[3 * (size_t)cell + 1], ip.cc[3 * (size_t)cell + 2]};
+    const double r[3] = {x0 - cc[0], x1 - cc[1], x2 - cc[2]};
+    const double V = vol[cell];
+    int best = -1;
+    double bestMin = -1e300, bw0 = 1, bw1 = 0, bw2 = 0, bw3 = 0;
+    for (int t = ip.tetOff[cell]; t < ip.tetOff[cell + 1]; ++t) {
+        const int* tp = ip.tetPts + 3 * (size_t)t;
+        double e[3][3];
+        for (int q = 0; q < 3; ++q)
+            for (int k = 0; k < 3; ++k) e[q][k] = ip.points[3 * (size_t)tp[q] + k] - cc[k];
+        const double c12[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2], e[1][0] * e[2][1] - e[1][1] * e[2][0]};
+        const double det = e[0][0] * c12[0] + e[0][1] * c12[1] + e[0][2] * c12[2];
+        if (!(fabs(det / V) > SMALL)) continue;
+        const double c20[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2], e[2][0] * e[0][1] - e[2][1] * e[0][0]};
+        const double c01[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2], e[0][0] * e[1][1] - e[0][1] * e[1][0]};
+        const double l1 = (r[0] * c12[0] + r[1] * c12[1] + r[2] * c12[2]) / det;
+        const double l2 = (r[0] * c20[0] + r[1] * c20[1] + r[2] * c20[2]) / det;
+        const double l3 = (r[0] * c01[0] + r[1] * c01[1] + r[2] * c01[2]) / det;
+        const double l0 = 1.0 - l1 - l2 - l3;
+        const double mn = fmin(fmin(l0, l1), fmin(l2, l3));
+        if (mn > bestMin) { bestMin = mn; best = t; bw0 = l0; bw1 = l1; bw2 = l2; bw3 = l3; }
+        if (mn + SMALL > 0) break;
+    }
+    const double* cf = ip.cellF + (size_t)cell * NIF;
+    double f[NIF];
+    if (best < 0) {
+        for (int k = 0; k < NIF; ++k) f[k] = cf[k];
+    } else {
+        const int* tp = ip.tetPts + 3 * (size_t)best;
+        const double* p0 = ip.pointF + (size_t)tp[0] * NIF;
+        const double* p1 = ip.pointF + (size_t)tp[1] * NIF;
+        const double* p2 = ip.pointF + (size_t)tp[2] * NIF;
+        for (int k = 0; k < NIF; ++k) f[k] = bw0 * cf[k] + bw1 * p0[k] + bw2 * p1[k] + bw3 * p2[k];
+    }
+    m.Pr = f[0]; m.nu = f[1]; m.p = f[2]; m.T = f[3];
+    for (int k = 0; k < 3; ++k) { m.U[k] = f[4 + k]; m.q[k] = f[7 + k]; }
+    for (int k = 0; k < 6; ++k) { m.s[k] = f[10 + k]; m.P[k] = f[16 + k]; }
+}
+
 struct BgkWarpSmem {
     Macro mac[BGK_CHUNK];
     double u[3][BGK_CAP];
@@ -236,7 +351,7 @@ struct BgkWarpSmem {
 };
 
 // A cell larger than the staging capacity: the whole warp works on it in global memory (keys in keyScratch).
-template <bool MULTI>
+template <bool MULTI, bool INTERP>
 __device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs& a, int cell, int beg, int n, const Macro& m, int nRel, double& E,
                                             int& raisedOut, int& myRel, int lane) {
     double* pu0 = a.P.ux + beg; double* pu1 = a.P.uy + beg; double* pu2 = a.P.uz + beg; double* pk = a.keyScratch + beg;
@@ -263,6 +378,8 @@ __device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs&
         const double u0 = sqrt(2.0 * kB * m.T / mass);
         unsigned pending = __ballot_sync(0xffffffffu, sel);
         double v[3] = {0, 0, 0};
+        Macro mi;
+        double u0i = u0;
         while (pending) {
             const bool mine = (pending >> lane) & 1u;
             bool rz = false;
@@ -270,6 +387,12 @@ __device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs&
             if (mine) {
                 Stream r(prm.seed, KIND_BGK, 0, a.step, (uint32_t)cell, (uint32_t)j);
                 (void)r.u01();  // the selection key
+                if (INTERP) {
+                    mi = m;
+                    interpolate_macro(a.ip, a.vol, cell, a.P.x[beg + j], a.P.y[beg + j], a.P.z[beg + j], mi);
+                    u0i = sqrt(2.0 * kB * mi.T / mass);
+                    rz = bgk_sample(prm, r, mi, u0i, newE, v);
+                } else
                 rz = bgk_sample(prm, r, m, u0, newE, v);
             }
             const unsigned raisedMask = __ballot_sync(0xffffffffu, mine && rz);
@@ -286,9 +409,9 @@ __device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs&
                 raisedOut = 1;
             }
             if ((commitMask >> lane) & 1u) {
-                pu0[j] = m.U[0] + u0 * v[0];
-                pu1[j] = m.U[1] + u0 * v[1];
-                pu2[j] = m.U[2] + u0 * v[2];
+                pu0[j] = (INTERP ? mi.U[0] : m.U[0]) + u0i * v[0];
+                pu1[j] = (INTERP ? mi.U[1] : m.U[1]) + u0i * v[1];
+                pu2[j] = (INTERP ? mi.U[2] : m.U[2]) + u0i * v[2];
                 myRel++;
             }
         }
@@ -317,7 +440,7 @@ __device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs&
     __syncwarp();
 }
 
-template <bool MULTI>
+template <bool MULTI, bool INTERP = false>
 __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ BgkArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
@@ -340,7 +463,8 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
         if (lane < nc) {
             const int cell = c0 + lane;
             Macro m;
-            bgk_macro(prm, cell_fn(prm, cell), a.mom + (size_t)cell * nS * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
+            if (INTERP) m = a.macroCell[cell];
+            else bgk_macro(prm, cell_fn(prm, cell), a.mom + (size_t)cell * nS * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
             if (envelope) Eold = a.maxProb[cell];
             const bool act = a.collModelId[cell] == 0 && m.perform;
             S.mac[lane] = m;
@@ -361,7 +485,7 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                 if ((activeMask >> done) & 1u) {
                     double E = S.E[done];
                     int rs = 0;
-                    bgk_giant_cell<MULTI>(prm, a, c0 + done, b0, n, S.mac[done], S.nRel[done], E, rs, myRel, lane);
+                    bgk_giant_cell<MULTI, INTERP>(prm, a, c0 + done, b0, n, S.mac[done], S.nRel[done], E, rs, myRel, lane);
                     __syncwarp();
                     if (lane == 0) { S.E[done] = E; if (rs) S.raised[done] = 1; }
                     __syncwarp();
@@ -419,8 +543,14 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                 const int f = mine0 ? S.sel[t] : 0;
                 const int g = S.cellOf[f];
                 const int cl = done + g;
-                const Macro& m = S.mac[cl];
+                const Macro& mc = S.mac[cl];
                 const double mass = MULTI ? prm.sp[S.type[f]].mass : prm.sp[0].mass;
+                Macro mi;
+                if (INTERP && mine0) {  // target state at the parcel's position instead of the cell's (…USP.C:936-947)
+                    mi = mc;
+                    interpolate_macro(a.ip, a.vol, c0 + cl, a.P.x[b0 + f], a.P.y[b0 + f], a.P.z[b0 + f], mi);
+                }
+                const Macro& m = (INTERP && mine0) ? mi : mc;
                 const double u0 = sqrt(2.0 * kB * m.T / mass);
                 int head, cnt, rnk;
                 warp_runs(mine0 ? g : -1, lane, head, cnt, rnk);  // the list is cell-major: a cell's lanes are adjacent

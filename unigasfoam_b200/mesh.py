@@ -686,3 +686,112 @@ def sphere_cone_map(n_eta, n_s, n_phi, nose_radius=0.05, cone_half_angle_deg=30.
         return x, r * np.cos(phi), r * np.sin(phi)
 
     return pm
+
+
+# ---- interpolationCellPoint support (collisionProperties.macroInterpolation) ------------------------------------------
+
+def cell_point_data(mesh):
+    """What OpenFOAM's interpolationCellPoint needs, restated from its definition (volPointInterpolation + cellPointWeight;
+    OpenFOAM is not in /root/reference, call sites: U/bgkCollisions/derived/*/…C `interpolationCellPoint<T>::New("cellPoint", psi)`):
+
+    * point values = inverse-distance weighted mean of the values of the cells around the point (weight 1 / |p - C_c|); on the
+      points of boundary faces of non-empty, non-coupled patches instead the inverse-distance weighted mean (1 / |p - C_f|) of the
+      values on those faces, which for the zeroGradient fields of the BGK models are the owner-cell values; points of a cyclic
+      pair see the cells on both sides; at points of symmetry patches vectors / tensors lose their normal components;
+    * a cell is split into tets (cell centre, face point 0, face point k, face point k + 1) over its faces in cell-face order;
+      the value at a position is linear in the tet that contains it.
+
+    -> dict(tetOffsets [nCells+1], tetPoints [nTets,3], pointCellOffsets [nPoints+1], pointCells, pointWeights (normalised),
+            pointNormals [nPoints,3]).  Processor patches are not handled (the point sums would need a halo)."""
+    if any(p.kind == "processor" and p.size for p in mesh.patches):
+        raise NotImplementedError("macroInterpolation on a decomposed mesh: point values across processor patches need a halo")
+    nP, nC, nF, nI = len(mesh.points), mesh.n_cells, mesh.n_faces, mesh.n_internal
+    off, fp = mesh.face_point_offsets, mesh.face_points
+    nv = np.diff(off)
+    # tets: per cell, over its faces in cell-face order, fan about the face's first point
+    cf_cell = np.repeat(np.arange(nC), np.diff(mesh.cell_face_offsets))
+    cf_face = mesh.cell_faces
+    ntri = nv[cf_face] - 2
+    tet_cell = np.repeat(cf_cell, ntri)
+    tet_face = np.repeat(cf_face, ntri)
+    k = np.arange(len(tet_face)) - np.repeat(np.concatenate([[0], np.cumsum(ntri)[:-1]]), ntri) + 1
+    base = fp[off[tet_face]]
+    pa = fp[off[tet_face] + k]
+    pb = fp[off[tet_face] + k + 1]
+    tet_points = np.stack([base, pa, pb], axis=1).astype(np.int32)
+    tet_offsets = np.concatenate([[0], np.cumsum(np.bincount(tet_cell, minlength=nC))]).astype(np.int32)
+    # point classes across cyclic pairs (translational): representative = smallest label
+    rep = np.arange(nP)
+    for pi, p in enumerate(mesh.patches):
+        if p.kind != "cyclic" or p.partner < pi:
+            continue
+        q = mesh.patches[p.partner]
+        sep = np.asarray(p.separation, float)
+        pa_pts = np.unique(np.concatenate([fp[off[f]:off[f + 1]] for f in range(p.start, p.start + p.size)]))
+        pb_pts = np.unique(np.concatenate([fp[off[f]:off[f + 1]] for f in range(q.start, q.start + q.size)]))
+        scale = np.abs(mesh.points).max() + 1e-300
+        key = lambda x: tuple(np.round(x / (1e-9 * scale)).astype(np.int64))
+        lut = {key(mesh.points[b]): b for b in pb_pts}
+        for a in pa_pts:
+            b = lut.get(key(mesh.points[a] + sep))
+            if b is not None:
+                ra, rb = rep[a], rep[b]
+                lo, hi = min(ra, rb), max(ra, rb)
+                rep[rep == hi] = lo
+    # boundary points: points of faces of non-empty, non-coupled patches
+    bface = []
+    sym_normals = np.zeros((nP, 3))
+    for p in mesh.patches:
+        if p.kind in ("empty", "cyclic", "processor") or p.size == 0:
+            continue
+        f = np.arange(p.start, p.start + p.size)
+        A = np.linalg.norm(mesh.face_areas[f], axis=1)
+        f = f[A > 0]  # collapsed faces carry nothing
+        bface.append(f)
+        if p.kind in ("symmetry", "symmetryPlane"):
+            for ff in f:
+                n = mesh.face_areas[ff] / np.linalg.norm(mesh.face_areas[ff])
+                sym_normals[fp[off[ff]:off[ff + 1]]] = n
+    bface = np.concatenate(bface) if bface else np.zeros(0, np.int64)
+    is_bpoint = np.zeros(nP, bool)
+    rows_p, rows_c, rows_w = [], [], []
+    if len(bface):
+        bf_pts = np.concatenate([fp[off[f]:off[f + 1]] for f in bface])
+        bf_face = np.repeat(bface, nv[bface])
+        is_bpoint[bf_pts] = True
+        d = np.linalg.norm(mesh.points[bf_pts] - mesh.face_centres[bf_face], axis=1)
+        rows_p.append(bf_pts); rows_c.append(mesh.owner[bf_face]); rows_w.append(1.0 / d)
+    # internal points: cells around the point (through the faces), each cell once
+    f_pts = fp
+    f_face = np.repeat(np.arange(nF), nv)
+    pc = np.concatenate([np.stack([f_pts, mesh.owner[f_face]], 1),
+                         np.stack([f_pts[f_face < nI], mesh.neighbour[f_face[f_face < nI]]], 1)])
+    pc = np.unique(pc, axis=0)
+    pc = pc[~is_bpoint[pc[:, 0]]]
+    d = np.linalg.norm(mesh.points[pc[:, 0]] - mesh.cell_centres[pc[:, 1]], axis=1)
+    rows_p.append(pc[:, 0]); rows_c.append(pc[:, 1]); rows_w.append(1.0 / d)
+    P_ = np.concatenate(rows_p); C_ = np.concatenate(rows_c); W_ = np.concatenate(rows_w)
+    # merge cyclic classes: every member gets the union of the members' contributions (coupled points are never boundary
+    # points in OpenFOAM; a class with a boundary member keeps that member's boundary rule for itself)
+    cls = rep[P_]
+    if (rep != np.arange(nP)).any():
+        members = {}
+        for pt in np.nonzero(rep != np.arange(nP))[0]:
+            members.setdefault(rep[pt], [rep[pt]]).append(pt)
+        extraP, extraC, extraW = [], [], []
+        for r, mem in members.items():
+            sel = np.isin(P_, mem) & ~is_bpoint[P_]
+            for pt in mem:
+                if is_bpoint[pt]:
+                    continue
+                other = sel & (P_ != pt)
+                extraP.append(np.full(other.sum(), pt)); extraC.append(C_[other]); extraW.append(W_[other])
+        if extraP:
+            P_ = np.concatenate([P_] + extraP); C_ = np.concatenate([C_] + extraC); W_ = np.concatenate([W_] + extraW)
+    order = np.lexsort((C_, P_))
+    P_, C_, W_ = P_[order], C_[order], W_[order]
+    wsum = np.bincount(P_, weights=W_, minlength=nP)
+    W_ = W_ / wsum[P_]
+    pc_off = np.concatenate([[0], np.cumsum(np.bincount(P_, minlength=nP))]).astype(np.int32)
+    return dict(tetOffsets=tet_offsets, tetPoints=tet_points, pointCellOffsets=pc_off, pointCells=C_.astype(np.int32),
+                pointWeights=np.ascontiguousarray(W_), pointNormals=np.ascontiguousarray(sym_normals))
