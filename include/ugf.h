@@ -320,6 +320,11 @@ int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* inflow);
  * (host). */
 int ugf_set_inflow_fields(ugf_handle* h, int32_t patch, int32_t nTypeIds, const int32_t* typeIds, const double* numberDensity,
                           const double* transT, const double* rotT, const double* U);
+/* uniGasChapmanEnskogFreeStreamInflowPatch on a patch (U/boundaries/derived/generalBoundaries/uniGasChapmanEnskogFreeStreamInflowPatch/
+ * uniGasChapmanEnskogFreeStreamInflowPatch.C:52-127): free-stream insertion from a Chapman-Enskog distribution with the given heat flux
+ * vector [3] and stress tensor [9, row-major] - the count of Bird 4.22 corrected by the normal stress and heat flux
+ * (uniGasGeneralBoundary.C:171-239), velocities by Garcia & Alder's acceptance-rejection (:763-1001). */
+int ugf_set_chapman_enskog_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* inflow, const double* heatFlux, const double* stress);
 /* uniGasLiouFangPressureInletPatch on a patch.  The insertion itself is the free-stream one with a velocity per face
  * (uniGasGeneralBoundary.C:369-425, 1003-1230); the count formula is evaluated with speed ratios up to 5. */
 int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* inlet);

@@ -165,6 +165,8 @@ struct InflowPatch {
     double capN = 0.0, capT = 0.0;
     std::vector<double> wangSums;
     double wangSteps = 0.0, wangP = 0.0, wangM = 0.0, wangGammaR = 0.0;
+    bool ce = false;               // uniGasChapmanEnskogFreeStreamInflowPatch
+    double ceQ[3] = {0, 0, 0}, ceS[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 constexpr int WANG_NSUM = 11;
 
@@ -849,6 +851,19 @@ void doInflow(ugfo_handle& h) {
                 double accum = ip.molFrac[iD] * (fA * numDen * dt * cmp
                                 * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
                                / (2.0 * sqrtPi * FNc(h, cellI));
+                double cePressure = 0.0;
+                if (ip.ce) {  // uniGasGeneralBoundary.C:171-239: normal stress and heat flux correct the Maxwellian flux
+                    for (int j = 0; j < ip.in.nTypeIds; ++j) cePressure += ip.in.numberDensities[j];
+                    cePressure *= kB * Ttr;
+                    const double qn = dot3(ip.ceQ, n);
+                    double sn[3];
+                    for (int k = 0; k < 3; ++k) sn[k] = ip.ceS[3 * k] * n[0] + ip.ceS[3 * k + 1] * n[1] + ip.ceS[3 * k + 2] * n[2];
+                    const double snn = dot3(sn, n);
+                    accum = (fA * numDen * dt * cmp
+                             * (std::exp(-(sCos * sCos)) * (1.0 - 0.5 * snn / cePressure - 0.4 * qn * sCos / cePressure / cmp)
+                                + sqrtPi * sCos * (1 + std::erf(sCos))))
+                            / (2.0 * sqrtPi * FNc(h, cellI));
+                }
                 if (ip.outlet) {  // the device library's insertion bound; reaching it is an error there
                     const double cmpCap = std::sqrt(2.0 * kB * ip.capT / s.mass);
                     const double cap = ip.molFrac[iD] * (fA * ip.capN * dt * cmpCap * (std::exp(-25.0) + sqrtPi * 5.0 * (1 + std::erf(5.0))))
@@ -869,6 +884,34 @@ void doInflow(ugfo_handle& h) {
                     if (bs + bt > 1) { bs = 1 - bs; bt = 1 - bt; }
                     Parcel np_;
                     for (int k = 0; k < 3; ++k) np_.x[k] = (1 - bs - bt) * p0[k] + bs * a[k] + bt * b[k];
+                    if (ip.ce) {  // Chapman-Enskog velocity (uniGasGeneralBoundary.C:880-940; Garcia & Alder 1998, Garcia 2006)
+                        double maxQ = -1.0, maxS = -1.0;
+                        for (int k = 0; k < 3; ++k) maxQ = std::max(maxQ, std::fabs(ip.ceQ[k]));
+                        for (int k = 0; k < 9; ++k) maxS = std::max(maxS, std::fabs(ip.ceS[k]));
+                        const double breakdown = std::max(2.0 * maxQ / (cePressure * cmp), maxS / cePressure);
+                        const double amplitude = 1.0 + 60.0 * breakdown;
+                        const double sC = sCosFull;
+                        const double lower = std::min(sC - 4.0, -5.0), upper = std::min(sC, 5.0);
+                        const double uMax = 0.5 * (sC - std::sqrt(sC * sC + 2.0));
+                        double Uc[3], gamma;
+                        do {
+                            double uN;
+                            if (std::fabs(dot3(vel, n)) > VSMALL) {
+                                do { uN = lower + r.u01() * (upper - lower); }
+                                while ((sC - uN) / (sC - uMax) * std::exp(uMax * uMax - uN * uN) < r.u01());
+                            } else {
+                                uN = -std::sqrt(-std::log(1.0 - r.u01()));
+                            }
+                            double g1c, g2c;
+                            r.gauss2(g1c, g2c);
+                            for (int k = 0; k < 3; ++k) Uc[k] = g1c / std::sqrt(2.0) * t1[k] + g2c / std::sqrt(2.0) * t2[k] - uN * n[k];
+                            const double* S9 = ip.ceS;
+                            gamma = 1.0 + (2.0 / cmp * dot3(ip.ceQ, Uc) * (0.4 * dot3(Uc, Uc) - 1.0)
+                                           - 2.0 * (S9[1] * Uc[0] * Uc[1] + S9[2] * Uc[0] * Uc[2] + S9[5] * Uc[1] * Uc[2])
+                                           - S9[0] * (Uc[0] * Uc[0] - Uc[2] * Uc[2]) - S9[4] * (Uc[1] * Uc[1] - Uc[2] * Uc[2])) / cePressure;
+                        } while (amplitude * r.u01() > gamma);
+                        for (int k = 0; k < 3; ++k) np_.U[k] = cmp * Uc[k] + vel[k];
+                    } else {
                     const double A = sCosFull + std::sqrt(sCosFull * sCosFull + 2.0);
                     const double B = 0.5 * (1.0 + sCosFull * (sCosFull - std::sqrt(sCosFull * sCosFull + 2.0)));
                     double scaling = 3.0;
@@ -890,6 +933,7 @@ void doInflow(ugfo_handle& h) {
                     const double vt1 = dot3(t1, vel), vt2 = dot3(t2, vel);
                     for (int k = 0; k < 3; ++k)
                         np_.U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
+                    }
                     np_.ERot = equipartitionRotationalEnergy(r, Trot, s.rotationalDoF);
                     np_.ELevel = 0;
                     for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) np_.vib[m] = 0;
@@ -2140,6 +2184,15 @@ int ugfo_set_inflow(ugfo_handle* h, int32_t patch, const ugf_inflow* in) {
     if (h->points.empty()) return fail(h, "inflow needs mesh points/facePoints");
     InflowPatch ip; ip.patch = patch; ip.in = *in;
     h->inflows.push_back(ip);
+    return 0;
+}
+
+int ugfo_set_chapman_enskog_inflow(ugfo_handle* h, int32_t patch, const ugf_inflow* in, const double* heatFlux, const double* stress) {
+    if (int rc = ugfo_set_inflow(h, patch, in)) return rc;
+    InflowPatch& ip = h->inflows.back();
+    ip.ce = true;
+    for (int k = 0; k < 3; ++k) ip.ceQ[k] = heatFlux[k];
+    for (int k = 0; k < 9; ++k) ip.ceS[k] = stress[k];
     return 0;
 }
 

@@ -150,6 +150,7 @@ SIGNATURES = {
     "set_patch_model": (C.c_int, [H, i32, i32, PF, i32]),
     "set_patch_wall_fields": (C.c_int, [H, i32, PF, PF]),
     "set_inflow": (C.c_int, [H, i32, P(Inflow)]),
+    "set_chapman_enskog_inflow": (C.c_int, [H, i32, P(Inflow), PF, PF]),
     "set_inflow_fields": (C.c_int, [H, i32, i32, PI32, PF, PF, PF, PF]),
     "set_pressure_inlet": (C.c_int, [H, i32, P(PressureInlet)]),
     "set_wang_pressure_inlet": (C.c_int, [H, i32, P(PressureInlet)]),

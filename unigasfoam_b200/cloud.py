@@ -168,7 +168,7 @@ class UniGasCloud:
             self._check(self.api.set_macro_interpolation(self._h, C.byref(cp)))
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
-            if word not in ("uniGasFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch",
+            if word not in ("uniGasFreeStreamInflowPatch", "uniGasChapmanEnskogFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch",
                             "uniGasWangPressureInletPatch", "uniGasLiouFangPressureOutletPatch"):
                 raise UgfError(f"general boundary model {word!r} is not supported (uniGasFreeStreamInflowPatch, "
                                "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch, uniGasWangPressureInletPatch, "
@@ -232,6 +232,12 @@ class UniGasCloud:
             inf.electronicTemperature = float(pr.get("electronicTemperature", 0.0))
             for k in range(3):
                 inf.velocity[k] = float(pr["velocity"][k])
+            if word == "uniGasChapmanEnskogFreeStreamInflowPatch":  # …/uniGasChapmanEnskogFreeStreamInflowPatch.C:66-67
+                q = self._f64(pr["heatFlux"]).reshape(3)
+                st = self._f64(pr["stress"]).reshape(9)
+                PD = C.POINTER(C.c_double)
+                self._check(self.api.set_chapman_enskog_inflow(self._h, patch, C.byref(inf), q.ctypes.data_as(PD), st.ctypes.data_as(PD)))
+                continue
             self._check(self.api.set_inflow(self._h, patch, C.byref(inf)))
 
     def close(self):

@@ -1276,7 +1276,7 @@ static void recompute_inflow_bounds(ugf_handle* h) {
 // temperatures and velocity per face (uniGasFreeStreamInflowFieldPatch)
 struct InflowFields { const double *numDen, *transT, *rotT, *U; };  // numDen [nTypeIds][nFaces]
 static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in, const ugf_pressure_inlet* pin, const InflowFields* fld = nullptr,
-                             bool wang = false, bool outlet = false) {
+                             bool wang = false, bool outlet = false, const double* ceQ = nullptr, const double* ceS = nullptr) {
     if (!h || !h->meshSet) return fail(h, "mesh not set");
     if (patch < 0 || patch >= h->nPatches) return fail(h, "patch out of range");
     if (h->pointsHost.empty()) return fail(h, "inflow needs mesh points/facePoints");
@@ -1333,8 +1333,18 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
             const double cmp = std::sqrt(2.0 * kB * Ttr / h->spHost[t].mass);
             double sCos = (vel[0] * n[0] + vel[1] * n[1] + vel[2] * n[2]) / cmp;
             if (pin) sCos = 5.0;  // the face velocities follow the flow: bound the insertions with a speed ratio of 5
-            const double accum = (pin ? pin->moleFractions[iD] : 1.0) * (fA * numDen * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
-                                 / (2.0 * sqrtPi * h->cfg.nParticle);
+            double accum = (pin ? pin->moleFractions[iD] : 1.0) * (fA * numDen * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
+                           / (2.0 * sqrtPi * h->cfg.nParticle);
+            if (ceQ) {  // Chapman-Enskog count (uniGasGeneralBoundary.C:171-239) for the capacity bound
+                double pr = 0.0;
+                for (int j = 0; j < in->nTypeIds; ++j) pr += in->numberDensities[j];
+                pr *= kB * Ttr;
+                const double qn = ceQ[0] * n[0] + ceQ[1] * n[1] + ceQ[2] * n[2];
+                double snn = 0.0;
+                for (int k = 0; k < 3; ++k) snn += (ceS[3 * k] * n[0] + ceS[3 * k + 1] * n[1] + ceS[3 * k + 2] * n[2]) * n[k];
+                accum = (fA * numDen * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) * (1.0 - 0.5 * snn / pr - 0.4 * qn * sCos / pr / cmp) + sqrtPi * sCos * (1 + std::erf(sCos))))
+                        / (2.0 * sqrtPi * h->cfg.nParticle);
+            }
             f.maxInsert += (long long)std::max(accum, 0.0) + 2;
             f.accum1.push_back(accum * h->cfg.nParticle / h->cfg.deltaT);
             f.slotCell.push_back(faceCell[lf]);
@@ -1346,6 +1356,14 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
     for (int i = 0; i < in->nTypeIds; ++i) { d.typeIds[i] = in->typeIds[i]; d.numDen[i] = in->numberDensities[i]; }
     d.Ttr = in->translationalTemperature; d.Trot = in->rotationalTemperature;
     d.Tvib = in->vibrationalTemperature; d.Tel = in->electronicTemperature;
+    if (ceQ) {
+        d.ce = 1;
+        for (int k = 0; k < 3; ++k) d.ceQ[k] = ceQ[k];
+        for (int k = 0; k < 9; ++k) d.ceS[k] = ceS[k];
+        d.cePressure = 0.0;
+        for (int j = 0; j < in->nTypeIds; ++j) d.cePressure += in->numberDensities[j];
+        d.cePressure *= kB * in->translationalTemperature;
+    }
     for (int k = 0; k < 3; ++k) d.vel[k] = in->velocity[k];
     for (int i = 0; i < UGF_MAX_SPECIES; ++i) d.molFrac[i] = (pin && i < in->nTypeIds) ? pin->moleFractions[i] : 1.0;
     d.theta = pin ? pin->theta : 1.0;
@@ -1415,6 +1433,11 @@ static int set_inflow_common(ugf_handle* h, int32_t patch, const ugf_inflow* in,
 }
 
 int ugf_set_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in) { return set_inflow_common(h, patch, in, nullptr); }
+
+int ugf_set_chapman_enskog_inflow(ugf_handle* h, int32_t patch, const ugf_inflow* in, const double* heatFlux, const double* stress) {
+    if (!heatFlux || !stress) return fail(h, "Chapman-Enskog inflow needs heatFlux [3] and stress [9]");
+    return set_inflow_common(h, patch, in, nullptr, nullptr, false, false, heatFlux, stress);
+}
 
 int ugf_set_inflow_fields(ugf_handle* h, int32_t patch, int32_t nTypeIds, const int32_t* typeIds, const double* numberDensity,
                           const double* transT, const double* rotT, const double* U) {

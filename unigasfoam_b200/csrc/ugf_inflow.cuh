@@ -26,6 +26,8 @@ struct InflowDev {
     double numDen[UGF_MAX_SPECIES];
     double Ttr, Trot, Tvib, Tel;
     double vel[3];
+    int ce;                           // uniGasChapmanEnskogFreeStreamInflowPatch: heat flux, stress (row-major), mixture pressure n k T
+    double ceQ[3], ceS[9], cePressure;
     double molFrac[UGF_MAX_SPECIES];  // 1 for free-stream patches (numDen is per species there)
     double* faceVel;                  // pressure inlets and field patches: inflow velocity per face [nFaces*3], else null (vel everywhere)
     double theta;                     // pressure inlets: relaxation of faceVel towards the cell mean velocity
@@ -67,6 +69,15 @@ __global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant
     const double sqrtPi = sqrt(PI);
     double accum = f.molFrac[iD] * (fA * numDen * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
                    / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));  // uniGasGeneralBoundary.C:154-165
+    if (f.ce) {  // :171-239: the normal stress and heat flux correct the Maxwellian flux
+        const double n[3] = {g[1], g[2], g[3]};
+        const double qn = f.ceQ[0] * n[0] + f.ceQ[1] * n[1] + f.ceQ[2] * n[2];
+        double snn = 0.0;
+        for (int k = 0; k < 3; ++k) snn += (f.ceS[3 * k] * n[0] + f.ceS[3 * k + 1] * n[1] + f.ceS[3 * k + 2] * n[2]) * n[k];
+        accum = (fA * numDen * prm.deltaT * cmp
+                 * (exp(-(sCos * sCos)) * (1.0 - 0.5 * snn / f.cePressure - 0.4 * qn * sCos / f.cePressure / cmp) + sqrtPi * sCos * (1 + erf(sCos))))
+                / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));
+    }
     if (f.outlet) {
         const double cmpCap = sqrt(2.0 * kB * f.capT / s.mass);
         const double cap = f.molFrac[iD] * (fA * f.capN * prm.deltaT * cmpCap * (exp(-25.0) + sqrtPi * 5.0 * (1 + erf(5.0))))
@@ -134,6 +145,35 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
         if (bs + bt > 1) { bs = 1 - bs; bt = 1 - bt; }
         double x[3];
         for (int k = 0; k < 3; ++k) x[k] = (1 - bs - bt) * p0[k] + bs * tr[k] + bt * tr[3 + k];
+        double U[3];
+        if (f.ce) {  // Chapman-Enskog velocity (uniGasGeneralBoundary.C:880-940), same draw order as the oracle
+            double maxQ = -1.0, maxS = -1.0;
+            for (int k = 0; k < 3; ++k) maxQ = fmax(maxQ, fabs(f.ceQ[k]));
+            for (int k = 0; k < 9; ++k) maxS = fmax(maxS, fabs(f.ceS[k]));
+            const double breakdown = fmax(2.0 * maxQ / (f.cePressure * cmp), maxS / f.cePressure);
+            const double amplitude = 1.0 + 60.0 * breakdown;
+            const double lower = fmin(sCos - 4.0, -5.0), upper = fmin(sCos, 5.0);
+            const double uMax = 0.5 * (sCos - sqrt(sCos * sCos + 2.0));
+            double Uc[3], gamma;
+            do {
+                double uN;
+                if (fabs(vn) > VSMALL) {
+                    do { uN = lower + r.u01() * (upper - lower); }
+                    while ((sCos - uN) / (sCos - uMax) * exp(uMax * uMax - uN * uN) < r.u01());
+                } else {
+                    uN = -sqrt(-log(1.0 - r.u01()));
+                }
+                double g1c, g2c;
+                r.gauss2(g1c, g2c);
+                for (int k = 0; k < 3; ++k) Uc[k] = g1c / sqrt(2.0) * t1[k] + g2c / sqrt(2.0) * t2[k] - uN * n[k];
+                const double* S9 = f.ceS;
+                const double qU = f.ceQ[0] * Uc[0] + f.ceQ[1] * Uc[1] + f.ceQ[2] * Uc[2];
+                const double UU = Uc[0] * Uc[0] + Uc[1] * Uc[1] + Uc[2] * Uc[2];
+                gamma = 1.0 + (2.0 / cmp * qU * (0.4 * UU - 1.0) - 2.0 * (S9[1] * Uc[0] * Uc[1] + S9[2] * Uc[0] * Uc[2] + S9[5] * Uc[1] * Uc[2])
+                               - S9[0] * (Uc[0] * Uc[0] - Uc[2] * Uc[2]) - S9[4] * (Uc[1] * Uc[1] - Uc[2] * Uc[2])) / f.cePressure;
+            } while (amplitude * r.u01() > gamma);
+            for (int k = 0; k < 3; ++k) U[k] = cmp * Uc[k] + vel[k];
+        } else {
         const double A = sCos + sqrt(sCos * sCos + 2.0);
         const double B = 0.5 * (1.0 + sCos * (sCos - sqrt(sCos * sCos + 2.0)));
         double scaling = 3.0;
@@ -154,8 +194,8 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
         const double cth = sqrt(kB * Ttr / s.mass);
         const double vt1 = t1[0] * vel[0] + t1[1] * vel[1] + t1[2] * vel[2];
         const double vt2 = t2[0] * vel[0] + t2[1] * vel[1] + t2[2] * vel[2];
-        double U[3];
         for (int k = 0; k < 3; ++k) U[k] = cth * (g1 * t1[k] + g2 * t2[k]) + vt1 * t1[k] + vt2 * t2[k] + cmp * uNormal * n[k];
+        }
         const double erot = equipartition_rotational_energy(r, Trot, s.rotDoF);
         const long long dst = (long long)base + f.insOff[slot] + i;
         P.x[dst] = x[0]; P.y[dst] = x[1]; P.z[dst] = x[2];
