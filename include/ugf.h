@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UGF_ABI_VERSION 3
+#define UGF_ABI_VERSION 4
 #define UGF_MAX_SPECIES 8
 #define UGF_MAX_VIB_MODES 4
 #define UGF_MAX_ELEC_LEVELS 16
@@ -108,6 +108,11 @@ typedef struct ugf_config {
     int32_t measureWalls;      /* 1 = accumulate boundaryMeasurements on wall faces */
     int32_t rank;              /* subdomain index (Pstream::myProcNo) */
     int32_t nRanks;
+    int32_t axisymmetric;      /* axisymmetricSimulation (U/clouds/uniGasCloud.C:420, 563-568): radial weighting factor
+                                  RWF(x) = 1 + (maxRWF - 1) sqrt(y^2 + z^2) / radialExtent (uniGasCloudI.H:116-120) on a wedge
+                                  mesh about the x axis whose side patches are symmetryPlane (uniGasBoundaries.C:438-445) */
+    double radialExtent;       /* axisymmetricProperties.radialExtentOfDomain */
+    double maxRWF;             /* axisymmetricProperties.maxRadialWeightingFactor */
 } ugf_config;
 
 /* moleculeProperties.<species>  (U/parcels/uniGasParcel.H:68-120, uniGasParcelI.H:40-141) */
@@ -190,7 +195,13 @@ typedef struct ugf_pressure_inlet {
  * cellWeight (the parcel's CWF, lagrangian/uniGas/cellWeight on disk) is implicit on the device: a parcel carries the
  * cellWeightFactor of the cell it was in at the last weighting pass, which is what the reference guarantees after
  * uniGasCloud::weighting() (U/clouds/uniGasCloud.C:203-220, 1353-1424).  On upload it is optional and must equal
- * cellWeightFactor[cell] (checked); on download it is filled in when a pointer is given. */
+ * cellWeightFactor[cell] (checked); on download it is filled in when a pointer is given.
+ * radialWeight (the parcel's RWF, lagrangian/uniGas/radialWeight) is implicit on the device in the same way: after
+ * axisymmetricWeighting() (U/clouds/uniGasCloud.C:1427-1570) every parcel carries RWF(its position); the initialisation
+ * models and the inflow patches hand out RWF(centre of the parcel's cell) instead (uniGasMeshFill.C:260,
+ * uniGasGeneralBoundary.C:739).  On upload it is optional: NULL = RWF(cell centre) as the initialisation models set it;
+ * given, all values must be RWF(position) or all RWF(cell centre) (checked to 1e-6, then recomputed); the
+ * first move weights against them.  On download it is filled in when a pointer is given. */
 typedef struct ugf_parcels {
     int64_t n;
     double* x; double* y; double* z;
@@ -202,6 +213,7 @@ typedef struct ugf_parcels {
     double* cellWeight;
     int32_t* vibLevel;   /* [n][UGF_MAX_VIB_MODES] vibrational quantum level per mode (uniGasParcel.H:238); NULL = 0 */
     int32_t* ELevel;     /* [n] electronic level (uniGasParcel.H:232); NULL = 0 */
+    double* radialWeight;/* [n] RWF (uniGasParcel.H:229); axisymmetric simulations only, see above */
 } ugf_parcels;
 
 /* Per-step log quantities (noTimeCounter.C:318-342, …USP.C:976-992, uniGasCloud.C:878-920). */

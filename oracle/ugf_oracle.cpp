@@ -124,6 +124,7 @@ struct Parcel {  // uniGasParcel (U/parcels/uniGasParcel.H:217-239) + particle p
     double U[3];
     double ERot;
     double CWF;      // cell weight factor carried by the parcel (U/parcels/uniGasParcel.H:226)
+    double RWF = 1.0;// radial weight factor carried by the parcel (uniGasParcel.H:229); 1 unless axisymmetricSimulation
     double sf;       // stepFraction
     int32_t cell;    // >=0 live; -1 deleted; <= -2 waiting on a processor face (-2 - boundaryFaceIndex)
     int32_t typeId;
@@ -249,8 +250,14 @@ namespace {
 
 inline int fail(ugfo_handle* h, const std::string& m) { if (h) h->err = m; return 1; }
 
-// nParticle * CWF of a cell (RWF = 1: no axisymmetric weighting)
+// nParticle * CWF of a cell; the radial factor comes on top where the reference applies it
 inline double FNc(const ugfo_handle& h, int c) { return h.cfg.nParticle * h.cellWF[c]; }
+// uniGasCloud::axiRWF (U/clouds/uniGasCloudI.H:116-120); 1 without axisymmetricSimulation
+inline double axiRWF(const ugfo_handle& h, const double* x) {
+    if (!h.cfg.axisymmetric) return 1.0;
+    const double radius = std::sqrt(x[1] * x[1] + x[2] * x[2]);
+    return 1.0 + (h.cfg.maxRWF - 1.0) * radius / h.cfg.radialExtent;
+}
 
 inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
@@ -522,7 +529,7 @@ void measureWall(ugfo_handle& h, const Parcel& p, int bfi, const double nw[3], d
         *preIE = IE;
         for (int k = 0; k < 3; ++k) preIMom[k] = m * p.U[k];
     } else {
-        const double nPart = FNc(h, p.cell);  // nParticle*CWF of the wall cell (uniGasPatchBoundary.C:292-294)
+        const double nPart = FNc(h, p.cell) * axiRWF(h, p.x);  // nParticle*CWF of the wall cell*RWF(hit position) (uniGasPatchBoundary.C:292-294)
         dq = nPart * (*preIE - IE) / (h.cfg.deltaT * fA);
         for (int k = 0; k < 3; ++k) dfd[k] = nPart * (preIMom[k] - m * p.U[k]) / (h.cfg.deltaT * fA);
     }
@@ -750,7 +757,7 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
                 const double* S = &h.Sf[3 * (size_t)hit];
                 const double sgn = (hit < h.nInternal) ? (hitFlip ? -1.0 : 1.0) : (dot3(p.U, S) >= 0.0 ? 1.0 : -1.0);
                 const ugf_species& s = h.sp[p.typeId];
-                const double w = p.CWF;
+                const double w = p.CWF * axiRWF(h, p.x);  // uniGasFaceTracker.C:98-99
                 const double e = 0.5 * s.mass * dot3(p.U, p.U) + p.ERot + elecEnergy(s, p) + vibEnergy(s, p);
                 double* tt = &h.ft[((size_t)k * h.nSpecies + p.typeId) * UGF_NFT];
                 const double add[UGF_NFT] = {sgn * w, sgn * s.mass * w, s.mass * p.U[0] * w, s.mass * p.U[1] * w, s.mass * p.U[2] * w, sgn * e * w};
@@ -837,6 +844,7 @@ void doInflow(ugfo_handle& h) {
             for (int k = 0; k < 3; ++k) t2[k] /= m2;
             const double* vel = (ip.pressure || ip.fields) ? &ip.faceVel[3 * (size_t)lf] : ip.in.velocity;
             const bool perFace = ip.fields || ip.outlet;
+            const double fnFace = FNc(h, cellI) * axiRWF(h, fC);  // nParticle * CWF(face cell) * RWF(face centre) (uniGasGeneralBoundary.C:154-155)
             const double Ttr = perFace ? ip.faceTtr[lf] : ip.in.translationalTemperature;
             const double Trot = perFace ? ip.faceTrot[lf] : ip.in.rotationalTemperature;
             for (int iD = 0; iD < ip.in.nTypeIds; ++iD) {
@@ -850,7 +858,7 @@ void doInflow(ugfo_handle& h) {
                 // Bird eq 4.22 (uniGasGeneralBoundary.C:154-165); CWF of the face's cell, RWF = 1
                 double accum = ip.molFrac[iD] * (fA * numDen * dt * cmp
                                 * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
-                               / (2.0 * sqrtPi * FNc(h, cellI));
+                               / (2.0 * sqrtPi * fnFace);
                 double cePressure = 0.0;
                 if (ip.ce) {  // uniGasGeneralBoundary.C:171-239: normal stress and heat flux correct the Maxwellian flux
                     for (int j = 0; j < ip.in.nTypeIds; ++j) cePressure += ip.in.numberDensities[j];
@@ -862,12 +870,12 @@ void doInflow(ugfo_handle& h) {
                     accum = (fA * numDen * dt * cmp
                              * (std::exp(-(sCos * sCos)) * (1.0 - 0.5 * snn / cePressure - 0.4 * qn * sCos / cePressure / cmp)
                                 + sqrtPi * sCos * (1 + std::erf(sCos))))
-                            / (2.0 * sqrtPi * FNc(h, cellI));
+                            / (2.0 * sqrtPi * fnFace);
                 }
                 if (ip.outlet) {  // the device library's insertion bound; reaching it is an error there
                     const double cmpCap = std::sqrt(2.0 * kB * ip.capT / s.mass);
                     const double cap = ip.molFrac[iD] * (fA * ip.capN * dt * cmpCap * (std::exp(-25.0) + sqrtPi * 5.0 * (1 + std::erf(5.0))))
-                                       / (2.0 * sqrtPi * FNc(h, cellI));
+                                       / (2.0 * sqrtPi * fnFace);
                     if (!(accum <= cap)) { accum = accum > cap ? cap : 0.0; h.outletBoundHit = true; }
                 }
                 Stream rc(h.cfg.seed, KIND_INFLOW, (uint32_t)iD, (uint32_t)h.step, (uint32_t)bfi, 0);
@@ -940,6 +948,7 @@ void doInflow(ugfo_handle& h) {
                     if (s.vibrationalDoF > 0) equipartitionVibrationalEnergyLevel(r, ip.in.vibrationalTemperature, s, np_.vib);  // uniGasGeneralBoundary.C:721-726
                     if (s.nElectronicLevels > 1) np_.ELevel = equipartitionElectronicLevel(r, ip.in.electronicTemperature, s);   // :728-735
                     np_.CWF = h.cellWF[cellI];  // uniGasGeneralBoundary.C:738
+                    np_.RWF = axiRWF(h, &h.cc[3 * (size_t)cellI]);  // :739 the factor of the cell centre
                     np_.sf = 0;
                     np_.cell = cellI;
                     np_.typeId = typeId;
@@ -1015,9 +1024,13 @@ void cellWeighting(ugfo_handle& h) {
     for (int c = 0; c < h.nCells; ++c) {
         for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
             const int32_t idx = h.occIds[j];
-            const double oldW = h.P[idx].CWF;
-            const double newW = h.cellWF[c];
-            h.P[idx].CWF = newW;
+            // axisymmetricWeighting / axisymmetricCellWeighting (:1427-1570): the same pass on RWF(position) or on the product
+            // of both factors; without axisymmetricSimulation RWF is 1 on both sides
+            const double newR = axiRWF(h, h.P[idx].x);
+            const double oldW = h.P[idx].CWF * h.P[idx].RWF;
+            const double newW = h.cellWF[c] * newR;
+            h.P[idx].CWF = h.cellWF[c];
+            h.P[idx].RWF = newR;
             if (oldW == newW) continue;
             Stream r(h.cfg.seed, KIND_WEIGHT, 0, (uint32_t)h.step, (uint32_t)idx, 0);
             if (oldW > newW) {
@@ -1041,7 +1054,7 @@ void buildOccupancy(ugfo_handle& h) {
     buildOccupancyRaw(h);
     if (h.weightPending) {
         h.weightPending = false;
-        if (h.cellWeighted) {
+        if (h.cellWeighted || h.cfg.axisymmetric) {
             cellWeighting(h);
             buildOccupancyRaw(h);
         }
@@ -1074,9 +1087,13 @@ void sampleCell(ugfo_handle& h, int c) {
         double* m = M + (size_t)p.typeId * UGF_NMOM;
         const double u = p.U[0], v = p.U[1], w = p.U[2];
         const double cc = u * u + v * v + w * w;
-        m[0] += 1.0; m[1] += 1.0;
+        // slots 1, 5-7 (and 31 with axisymmetricSimulation) are the sums the XnParticle fields take: weighted by the parcel's
+        // RWF (cellMeasurements.C:463-467); the cell's nParticle * CWF is applied by the consumers
+        const double rw = p.RWF;
+        m[0] += 1.0; m[1] += rw;
         m[2] += u; m[3] += v; m[4] += w;
-        m[5] += u; m[6] += v; m[7] += w;
+        m[5] += rw * u; m[6] += rw * v; m[7] += rw * w;
+        if (h.cfg.axisymmetric) m[31] += rw * cc;
         m[8] += u * u; m[9] += u * v; m[10] += u * w; m[11] += v * v; m[12] += v * w; m[13] += w * w;
         m[14] += cc;
         m[15] += cc * u; m[16] += cc * v; m[17] += cc * w;
@@ -1138,8 +1155,14 @@ void collideCell(ugfo_handle& h, int c, int subCycle, double dtSub, int64_t& can
         }
     }
     const double sMaxOld = h.sigmaTcRMax[c];
-    // :168,184  CWF of the cell, RWF = 1
-    const double selectedPairs = 0.5 * nC * (nC - 1) * FNc(h, c) * sMaxOld * dtSub / h.vol[c];
+    // :168-184  CWF of the cell; RWF = mean over the cell's parcels of axiRWF(position)
+    double rwfMean = 1.0;
+    if (h.cfg.axisymmetric) {
+        double sum = 0.0;
+        for (int i = 0; i < nC; ++i) sum += axiRWF(h, h.P[h.occIds[beg + i]].x);
+        rwfMean = sum / (double)nC;
+    }
+    const double selectedPairs = 0.5 * nC * (nC - 1) * (FNc(h, c) * rwfMean) * sMaxOld * dtSub / h.vol[c];
     int nCand = (int)selectedPairs;
     {
         Stream rc(h.cfg.seed, KIND_NTC, (uint32_t)subCycle, (uint32_t)h.step, (uint32_t)c, 0xFFFFFFFFu);
@@ -1209,7 +1232,7 @@ void bgkMacro(ugfo_handle& h, int c, Macro& m) {
         N += a[0]; rhoM += ms * a[0];
         rhoNX += a[1] * FN; rhoMX += ms * a[1] * FN;
         for (int k = 0; k < 3; ++k) momX[k] += ms * a[5 + k] * FN;
-        keX += ms * a[14] * FN;
+        keX += ms * a[h.cfg.axisymmetric ? 31 : 14] * FN;
         for (int k = 0; k < 6; ++k) muu[k] += ms * a[8 + k];
         mcc += ms * (a[8] + a[11] + a[13]);
         for (int k = 0; k < 3; ++k) mccu[k] += ms * a[15 + k];
@@ -1459,8 +1482,9 @@ void relaxCell(ugfo_handle& h, int c, int64_t& nrel, const InterpCtx* ic = nullp
         for (int i = 0; i < N; ++i) {
             const Parcel& p = h.P[ids[i]];
             const double mass = h.sp[p.typeId].mass;
-            keX += mass * dot3(p.U, p.U) * FN;
-            for (int k = 0; k < 3; ++k) momX[k] += mass * p.U[k] * FN;
+            const double wFN = FN * p.RWF;  // CWF*RWF*nParticle of the parcel (…USP.C:1017-1022)
+            keX += mass * dot3(p.U, p.U) * wFN;
+            for (int k = 0; k < 3; ++k) momX[k] += mass * p.U[k] * wFN;
         }
         const double postU[3] = {momX[0] / m.rhoMX, momX[1] / m.rhoMX, momX[2] / m.rhoMX};
         const double postT = m.N / (3.0 * (m.N - 1.0) * kB * m.rhoNX) * (keX - m.rhoMX * dot3(postU, postU));
@@ -1640,7 +1664,7 @@ void decompose(ugfo_handle& h) {
             a[0] += dt * m[0];
             a[1] += dt * (m[1] * FN);
             a[2] += dt * (ms * m[1] * FN);
-            a[3] += dt * (ms * m[14] * FN);
+            a[3] += dt * (ms * m[h.cfg.axisymmetric ? 31 : 14] * FN);
             for (int k = 0; k < 3; ++k) a[4 + k] += dt * (ms * m[5 + k] * FN);
             a[KN_NACC + s] += dt * (m[1] * FN);
         }
@@ -1750,7 +1774,7 @@ void updateInletVelocities(ugfo_handle& h) {
                     bool mine = false;
                     for (int i = 0; i < ip.in.nTypeIds; ++i) mine = mine || ip.in.typeIds[i] == p.typeId;
                     if (mine) {
-                        const double m = w * h.sp[p.typeId].mass;
+                        const double m = w * axiRWF(h, p.x) * h.sp[p.typeId].mass;  // nParticle*CWF*RWF(position)*mass
                         for (int k = 0; k < 3; ++k) mom[k] += m * p.U[k];
                         mass += m;
                     }
@@ -1798,7 +1822,7 @@ void updateInletVelocities(ugfo_handle& h) {
                     bool mine = false;
                     for (int i = 0; i < ip.in.nTypeIds; ++i) mine = mine || ip.in.typeIds[i] == p.typeId;
                     if (!mine) continue;
-                    const double m = w * h.sp[p.typeId].mass;
+                    const double m = w * axiRWF(h, p.x) * h.sp[p.typeId].mass;  // nParticle*CWF*RWF(position)*mass
                     for (int k = 0; k < 3; ++k) { mom[k] += m * p.U[k]; sq[k] += p.U[k] * p.U[k]; su[k] += p.U[k]; }
                     mass += m;
                     nP += 1.0;
@@ -1834,7 +1858,7 @@ void updateInletVelocities(ugfo_handle& h) {
             double mom[3] = {0, 0, 0}, mass = 0;
             for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
                 const Parcel& p = h.P[h.occIds[j]];
-                const double m = w * h.sp[p.typeId].mass;
+                const double m = w * axiRWF(h, p.x) * h.sp[p.typeId].mass;  // nParticle*CWF*RWF(position)*mass
                 for (int k = 0; k < 3; ++k) mom[k] += m * p.U[k];
                 mass += m;
             }
@@ -1871,7 +1895,7 @@ void accumulateFields(ugfo_handle& h) {
                 A[8] += dt * (a[1] * FN);
                 A[9] += dt * (ms * a[1] * FN);
                 A[10] += dt * (ms * a[5] * FN); A[11] += dt * (ms * a[6] * FN); A[12] += dt * (ms * a[7] * FN);
-                A[13] += dt * (ms * a[14] * FN);
+                A[13] += dt * (ms * a[h.cfg.axisymmetric ? 31 : 14] * FN);
                 A[14] += dt * (S.rotationalDoF > 0 ? a[0] : 0.0);
                 A[15] += dt * ((5.0 + S.rotationalDoF) * a[0]);
                 h.accS[(size_t)c * nS + s] += dt * (a[1] * FN);
@@ -2015,7 +2039,7 @@ void deriveFields(ugfo_handle& h, double* cellF, double* wallF) {
             const int patch = h.facePatch[b];
             if (h.pKind[patch] != UGF_PATCH_WALL) continue;
             const double* B = &h.bacc[(size_t)b * UGF_NBM];
-            const double nPart = FNc(h, h.owner[b + h.nInternal]);  // :1276-1278 CWF of the boundary cell
+            const double nPart = FNc(h, h.owner[b + h.nInternal]) * axiRWF(h, &h.Cf[3 * (size_t)(b + h.nInternal)]);  // :1276-1278 CWF of the boundary cell, RWF of the face centre
             if (B[0] > VSMALL) {  // :1274-1301
                 F[0] = B[0] * nPart / t;
                 F[1] = B[1] * nPart / t;
@@ -2081,6 +2105,10 @@ const char* ugfo_last_error(const ugfo_handle* h) { return h ? h->err.c_str() : 
 int ugfo_create(const ugf_config* cfg, ugfo_handle** out) {
     if (!cfg || !out) { g_createErr = "null argument"; return 1; }
     if (cfg->abiVersion != UGF_ABI_VERSION) { g_createErr = "ABI version mismatch"; return 1; }
+    if (cfg->axisymmetric && !(cfg->radialExtent > 0.0 && cfg->maxRWF >= 1.0)) {
+        g_createErr = "axisymmetricSimulation needs radialExtentOfDomain > 0 and maxRadialWeightingFactor >= 1";
+        return 1;
+    }
     ugfo_handle* h = new ugfo_handle();
     h->cfg = *cfg;
     std::memset(&h->cnt, 0, sizeof(h->cnt));
@@ -2301,6 +2329,23 @@ int ugfo_upload_parcels(ugfo_handle* h, const ugf_parcels* p) {
         if (q.ELevel < 0 || q.ELevel >= h->sp[q.typeId].nElectronicLevels) return fail(h, "parcel ELevel out of range");
         for (int m = 0; m < UGF_MAX_VIB_MODES; ++m)
             if (q.vib[m] < 0 || q.vib[m] > 65535 || (m >= h->sp[q.typeId].vibrationalDoF && q.vib[m] != 0)) return fail(h, "parcel vibLevel out of range");
+    }
+    if (h->cfg.axisymmetric) {
+        // radialWeight: RWF(cell centre) as the initialisation models hand it out (default), or RWF(position) as every parcel
+        // carries it after a weighting pass - the same rule as the device library (include/ugf.h, ugf_parcels)
+        bool asPos = p->radialWeight != nullptr, asCentre = true;
+        if (p->radialWeight)
+            for (int64_t i = 0; i < p->n; ++i) {
+                const Parcel& q = h->P[i];
+                const double rp = axiRWF(*h, q.x), rc = axiRWF(*h, &h->cc[3 * (size_t)q.cell]), r = p->radialWeight[i];
+                asPos = asPos && std::fabs(r - rp) <= 1e-6 * rp;
+                asCentre = asCentre && std::fabs(r - rc) <= 1e-6 * rc;
+            }
+        if (!asPos && !asCentre) return fail(h, "radialWeight must be RWF(position) for every parcel or RWF(cell centre) for every parcel");
+        for (int64_t i = 0; i < p->n; ++i) {
+            Parcel& q = h->P[i];
+            q.RWF = asPos ? axiRWF(*h, q.x) : axiRWF(*h, &h->cc[3 * (size_t)q.cell]);
+        }
     }
     h->occValid = false; h->momValid = false;
     h->nBeforeInsert = p->n;
@@ -2536,7 +2581,7 @@ int ugfo_migrate_pack(ugfo_handle* h, int32_t patch, double** buf, int64_t* n) {
         Parcel& q = h->P[(size_t)i];
         if (q.cell > -2 || h->facePatch[-2 - q.cell] != patch) continue;
         const int lface = (-2 - q.cell) + h->nInternal - h->pStart[patch];
-        const double rec[UGF_MIGRATE_STRIDE] = {q.x[0], q.x[1], q.x[2], q.U[0], q.U[1], q.U[2], q.ERot, q.sf, (double)lface + 4294967296.0 * (double)q.typeId, q.CWF};
+        const double rec[UGF_MIGRATE_STRIDE] = {q.x[0], q.x[1], q.x[2], q.U[0], q.U[1], q.U[2], q.ERot, q.sf, (double)lface + 4294967296.0 * (double)q.typeId, q.CWF * q.RWF};
         b.insert(b.end(), rec, rec + UGF_MIGRATE_STRIDE);
         q.cell = -1;
     }
@@ -2558,7 +2603,8 @@ int ugfo_migrate_unpack(ugfo_handle* h, int32_t patch, const double* buf, int64_
         if (lf < 0 || lf >= h->pSize[patch]) return fail(h, "received face index out of range");
         q.cell = h->owner[h->pStart[patch] + lf];
         q.typeId = type;
-        q.CWF = r[9];  // the weight factor travels with the parcel
+        q.CWF = r[9];  // the weight factor travels with the parcel (the product CWF * RWF: the next weighting pass only needs that)
+        q.RWF = 1.0;
         q.newParcel = 0;
         h->P.push_back(q);
     }
@@ -2649,6 +2695,7 @@ int ugfo_download_parcels(ugfo_handle* h, ugf_parcels* p) {
         if (p->ERot) p->ERot[i] = q.ERot;
         if (p->newParcel) p->newParcel[i] = q.newParcel;
         if (p->cellWeight) p->cellWeight[i] = q.CWF;
+        if (p->radialWeight) p->radialWeight[i] = q.RWF;
         if (p->ELevel) p->ELevel[i] = q.ELevel;
         if (p->vibLevel) for (int m = 0; m < UGF_MAX_VIB_MODES; ++m) p->vibLevel[(size_t)i * UGF_MAX_VIB_MODES + m] = q.vib[m];
     }

@@ -151,13 +151,16 @@ def test_all_tutorial_dictionaries_parse(name):
 
 
 def test_unsupported_switches_fail_loudly(OracleCloud):
-    """Radial weighting is not covered yet: constructing the cloud from such a case says so instead of running something
-    else."""
+    """chemicalReactions (out of scope) says so instead of running something else; the axisymmetric tutorials'
+    uniGasProperties construct a cloud as written (radial weighting: tests/test_axisymmetric.py)."""
     from unigasfoam_b200.cloud import UgfError
     m = cases.closed_box(n=3, parcels=100).mesh
     ld = foamdict.load_case(os.path.join(GOLD, "plumeImpingement"))
-    with pytest.raises(UgfError, match="axisymmetricSimulation"):
-        OracleCloud(m, ld["uniGasProperties"], {}, ld["deltaT"], parcelCapacity=1000)
+    cl = OracleCloud(m, ld["uniGasProperties"], {}, ld["deltaT"], parcelCapacity=1000)
+    assert cl.axisymmetric and cl.cfg.maxRWF == 1000.0 and cl.cfg.radialExtent == 7.5e-2
+    cl.close()
+    with pytest.raises(UgfError, match="chemicalReactions"):
+        OracleCloud(m, dict(ld["uniGasProperties"], chemicalReactions=True), {}, ld["deltaT"], parcelCapacity=1000)
     # macroInterpolation true (set by every tutorial) is covered: tests/test_macro_interpolation.py runs the tutorial's
     # collisionProperties as written
     ld = foamdict.load_case(CASE)

@@ -175,5 +175,8 @@ def test_config5_blunt_body_shard_62m_parcels(GpuCloud):
     assert _inside_own_cell(case.mesh, p) < 1e-12
     assert (p["ERot"] >= 0).all()
     kT = cases.kB * case.meta["T_inf"]
-    assert abs(p["ERot"].mean() / kT - 1.0) < 0.02  # rotDoF 2: <ERot> = k T in the (still mostly undisturbed) free stream
+    outer = (p["cell"] % 200) >= 100  # eta is the fastest cell index, 0 at the body: the outer half is still undisturbed free stream
+    assert abs(p["ERot"][outer].mean() / kT - 1.0) < 0.01  # rotDoF 2: <ERot> = k T
+    # near the body the diffuse wall (T_wall = 2.5 T_inf) and the first Mach-10 collisions have started to heat the rotational mode
+    assert 1.0 < p["ERot"][~outer].mean() / kT < 1.5
     cl.close()

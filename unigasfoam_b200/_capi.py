@@ -7,7 +7,7 @@ declares and fails loudly if one is missing.
 import ctypes as C
 import os
 
-UGF_ABI_VERSION = 3
+UGF_ABI_VERSION = 4
 UGF_MAX_SPECIES = 8
 UGF_MAX_VIB_MODES = 4
 UGF_MAX_ELEC_LEVELS = 16
@@ -61,6 +61,7 @@ class Config(C.Structure):
         ("bgkModel", i32), ("nSubCycles", i32), ("macroInterpolation", i32), ("Tref", f64), ("theta", f64),
         ("rotationalRelaxationCollisionNumber", f64), ("electronicRelaxationCollisionNumber", f64),
         ("parcelCapacity", i64), ("sampleInterval", i32), ("measureWalls", i32), ("rank", i32), ("nRanks", i32),
+        ("axisymmetric", i32), ("radialExtent", f64), ("maxRWF", f64),
     ]
 
 
@@ -110,7 +111,7 @@ class Parcels(C.Structure):
     _fields_ = [
         ("n", i64), ("x", P(f64)), ("y", P(f64)), ("z", P(f64)), ("Ux", P(f64)), ("Uy", P(f64)), ("Uz", P(f64)),
         ("cell", P(i32)), ("typeId", P(i32)), ("ERot", P(f64)), ("newParcel", P(i32)), ("cellWeight", P(f64)),
-        ("vibLevel", P(i32)), ("ELevel", P(i32)),
+        ("vibLevel", P(i32)), ("ELevel", P(i32)), ("radialWeight", P(f64)),
     ]
 
 

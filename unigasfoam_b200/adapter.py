@@ -265,15 +265,23 @@ class UniGasDynamicAdapter:
                 lv[:, d] = 1
         return lv
 
+    def _cell_rwf(self):
+        """uniGasCloud::axiRWF at the cell centres (uniGasCloudI.H:116-120); 1 without axisymmetricSimulation."""
+        cfg = self.cloud.cfg
+        if not cfg.axisymmetric:
+            return 1.0
+        cc = self.mesh.cell_centres
+        return 1.0 + (cfg.maxRWF - 1.0) * np.sqrt(cc[:, 1] * cc[:, 1] + cc[:, 2] * cc[:, 2]) / cfg.radialExtent
+
     def calculate_cell_weight_factor(self, rhoN, levels):
-        """calculateCellWeightFactor (:433-446); RWF = 1."""
+        """calculateCellWeightFactor (:433-446); RWF of the cell centre with axisymmetricSimulation (:442)."""
         nSub = levels.prod(1).astype(float)
-        return rhoN * self.mesh.cell_volumes / (self.particlesPerSubCell * nSub * self.cloud.cfg.nParticle)
+        return rhoN * self.mesh.cell_volumes / (self.particlesPerSubCell * nSub * self.cloud.cfg.nParticle * self._cell_rwf())
 
     def smooth_cell_weight_factor(self, rhoN, cwf, levels):
         """smoothCellWeightFactor (:448-500)."""
         nSub = levels.prod(1).astype(float)
-        cap = rhoN * self.mesh.cell_volumes / (self.minParticlesPerSubCell * nSub * self.cloud.cfg.nParticle)
+        cap = rhoN * self.mesh.cell_volumes / (self.minParticlesPerSubCell * nSub * self.cloud.cfg.nParticle * self._cell_rwf())  # :473
         cwf = self.ops.smooth(cwf, 1.3)
         passes = 0
         while True:

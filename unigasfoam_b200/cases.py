@@ -565,6 +565,76 @@ def cylinder_block(rank=0, n_ranks=1, nr=1000, ntheta=2500, parcels=50_000_000, 
     return case
 
 
+def radial_weight(props, points):
+    """uniGasCloud::axiRWF (U/clouds/uniGasCloudI.H:116-120) at points [n,3]; 1 without axisymmetricSimulation."""
+    pts = np.asarray(points, float)
+    if not props.get("axisymmetricSimulation", False):
+        return np.ones(len(pts))
+    ap = props["axisymmetricProperties"]
+    return 1.0 + (float(ap["maxRadialWeightingFactor"]) - 1.0) * np.sqrt(pts[:, 1] * pts[:, 1] + pts[:, 2] * pts[:, 2]) / float(ap["radialExtentOfDomain"])
+
+
+def axisymmetric_tube(nx=24, nr=16, length=None, radius=None, ppc=30, n_inf=1e20, T_inf=300.0, U_inf=200.0, T_wall=400.0, max_rwf=8.0,
+                      species=("Ar", ARGON_GUIDE), Tref=273.0, binary="variableHardSphere", mode="dsmc", bgk="noBGKCollision",
+                      cell_weighted=False, wall="uniGasDiffuseWallPatch", inlet="uniGasFreeStreamInflowPatch", half_angle_deg=0.5,
+                      courant=0.3, lambda_per_dx=2.0, seed=3, gr=1.0, device="cpu", **cp):
+    """Axisymmetric flow through a tube, the set-up of the reference's axisymmetric tutorials (plumeImpingement,
+    expansionInVacuum) in small: a wedge of +-half_angle about the x axis, one cell thick, side patches symmetryPlane, the
+    axis a collapsed symmetry patch; free-stream (or Liou-Fang pressure) inlet at x = 0, deletion outlet at x = length, wall at
+    r = radius; axisymmetricSimulation true with radialExtentOfDomain = radius.  Filled as uniGasMeshFill does it: N = n V /
+    (F_N CWF RWF(cell centre)) parcels per cell, which then carry RWF(cell centre) (uniGasMeshFill.C:196-260).  With
+    cell_weighted the factor field is uniGasMeshFill's n V / (ppc F_N RWF) (:111-121), so every cell starts with ppc parcels."""
+    name, sp = species
+    lam = vhs_mean_free_path(n_inf, T_inf, sp, Tref)
+    dx = lam / lambda_per_dx
+    length = nx * dx if length is None else length
+    radius = nr * dx if radius is None else radius
+    kinds = {"xMin": ("inlet", "patch"), "xMax": ("outlet", "patch"), "yMin": ("axis", "symmetry"), "yMax": ("wall", "wall"),
+             "zMin": ("backWedge", "symmetryPlane"), "zMax": ("frontWedge", "symmetryPlane")}
+    m = _mesh.structured_block(nx, nr, 1, _mesh.wedge_map(nx, nr, length, radius, half_angle_deg, gr=gr), kinds)
+    m.meta_axis_aligned = False
+    volume = m.cell_volumes.sum()
+    mode_bgk = mode != "dsmc"
+    props = _props(name, sp, 1.0, mode, binary if mode != "bgk" else "noDSMCCollision", bgk if mode_bgk else "noBGKCollision", Tref, **cp)
+    props["axisymmetricSimulation"] = True
+    props["axisymmetricProperties"] = {"radialExtentOfDomain": radius, "maxRadialWeightingFactor": max_rwf}
+    rwf_c = radial_weight(props, m.cell_centres)
+    if cell_weighted:
+        nParticle = n_inf * np.median(m.cell_volumes / rwf_c) / ppc   # the median cell carries factor 1
+        cwf = n_inf * m.cell_volumes / (ppc * nParticle * rwf_c)
+        props["cellWeightedSimulation"] = True
+        props["cellWeightedProperties"] = {"particlesPerSubCell": ppc, "minParticlesPerSubCell": ppc}
+    else:
+        nParticle = n_inf * (m.cell_volumes / rwf_c).sum() / (ppc * m.n_cells)
+        cwf = None
+    props["nEquivalentParticles"] = nParticle
+    pos, vel, cel, erot = fill_parcels_torch(m, sp, n_inf, T_inf, (U_inf, 0.0, 0.0), nParticle, cell_weight=rwf_c if cwf is None else cwf * rwf_c,
+                                             Trot=T_inf, seed=seed, device=device)
+    dt = courant * dx / (abs(U_inf) + most_probable_speed(T_inf, sp["mass"]))
+    if inlet == "uniGasFreeStreamInflowPatch":
+        general = {"generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": inlet,
+                   inlet + "Properties": {"typeIds": [name], "numberDensities": {name: n_inf}, "translationalTemperature": T_inf,
+                                          "rotationalTemperature": T_inf, "velocity": [U_inf, 0.0, 0.0]}}
+    else:  # the pressure inlets: uniGasLiouFangPressureInletPatch / uniGasWangPressureInletPatch
+        general = {"generalBoundaryProperties": {"patch": "inlet"}, "boundaryModel": inlet,
+                   inlet + "Properties": {"typeIds": [name], "moleFractions": {name: 1.0}, "inletPressure": n_inf * kB * T_inf,
+                                          "inletTemperature": T_inf, "theta": 0.2}}
+    wall_entry = {"patchBoundaryProperties": {"patch": "wall"}, "boundaryModel": wall}
+    if wall != "uniGasSpecularWallPatch":
+        wall_entry[wall + "Properties"] = {"velocity": [0, 0, 0], "temperature": T_wall}
+    bd = {"uniGasPatchBoundaries": [wall_entry,
+                                    {"patchBoundaryProperties": {"patch": "inlet"}, "boundaryModel": "uniGasDeletionPatch"},
+                                    {"patchBoundaryProperties": {"patch": "outlet"}, "boundaryModel": "uniGasDeletionPatch"}],
+          "uniGasGeneralBoundaries": [general]}
+    sig0 = math.pi * sp["diameter"] ** 2 * most_probable_speed(T_inf, sp["mass"])
+    case = Case("axisymmetric_tube", m, props, bd, dt, pos, vel, cel, None, erot, sig0,
+                meta=dict(n=n_inf, T_inf=T_inf, U_inf=U_inf, T_wall=T_wall, Tref=Tref, species=sp, radius=radius, length=length, lam=lam,
+                          rwf_centre=rwf_c, volume=volume))
+    if cwf is not None:
+        case.cellWeightFactor = np.ascontiguousarray(cwf)
+    return case
+
+
 def blunt_body_block(rank=0, n_ranks=8, n_eta=200, n_s=500, n_phi=250, ppc=20, n_inf=5e21, T_inf=200.0, mach=10.0, T_wall=500.0,
                      species=("N2", NITROGEN), Tref=273.0, courant=0.3, seed=5, zrot=5.0, zelec=50.0, device=None, **geom):
     """BASELINE configs[4]: 3-D nitrogen Mach-10 flow over a blunted cone (sphere-cone fore-body, body-fitted

@@ -91,9 +91,15 @@ class UniGasCloud:
         self.cellWeighted = bool(props.get("cellWeightedSimulation", False))
         # adaptiveSimulation: unigasfoam_b200.adapter.UniGasDynamicAdapter drives the cloud (host side, every adaptationInterval steps)
         self.adaptive = bool(props.get("adaptiveSimulation", False))
-        for key in ("axisymmetricSimulation", "chemicalReactions"):
-            if props.get(key, False):
-                raise UgfError(f"{key} true is not supported by the B200 path yet (SURVEY §8f)")
+        # axisymmetricSimulation (U/clouds/uniGasCloud.C:420, 563-568): radial weighting on a wedge mesh about the x axis
+        self.axisymmetric = bool(props.get("axisymmetricSimulation", False))
+        if self.axisymmetric:
+            ap = props["axisymmetricProperties"]
+            cfg.axisymmetric = 1
+            cfg.radialExtent = float(ap["radialExtentOfDomain"])
+            cfg.maxRWF = float(ap["maxRadialWeightingFactor"])
+        if props.get("chemicalReactions", False):
+            raise UgfError("chemicalReactions true is not supported by the B200 path (SURVEY §2: out of scope)")
         self.cfg = cfg
         self._h = _capi.H()
         self._cellCollModelId = self._subCellLevels = self._cellWeightFactor = None  # host copies for writeTime
@@ -260,7 +266,7 @@ class UniGasCloud:
     def _i32(a):
         return np.ascontiguousarray(a, dtype=np.int32)
 
-    def setParcels(self, position, U, cell, typeId=None, ERot=None, newParcel=None, cellWeight=None, vibLevel=None, ELevel=None):
+    def setParcels(self, position, U, cell, typeId=None, ERot=None, newParcel=None, cellWeight=None, vibLevel=None, ELevel=None, radialWeight=None):
         """addNewParcel for a whole configuration (U/clouds/uniGasCloud.C:260-290)."""
         n = len(cell)
         if self._pending_capacity:
@@ -292,6 +298,8 @@ class UniGasCloud:
             keep.append(v); p.vibLevel = v.ctypes.data_as(PI)
         if ELevel is not None:
             e = self._i32(ELevel); keep.append(e); p.ELevel = e.ctypes.data_as(PI)
+        if radialWeight is not None:
+            rw = self._f64(radialWeight); keep.append(rw); p.radialWeight = rw.ctypes.data_as(PD)
         self._check(self.api.upload_parcels(self._h, C.byref(p)))
         self._nParcelsSet = True
         self._cwfCarried = None
@@ -394,8 +402,8 @@ class UniGasCloud:
         from . import foamfile
         d = foamfile.read_cloud_time(case_dir, time_name, self.mesh.n_cells)
         p = d["parcels"]
-        if (p["radialWeight"] != 1.0).any():
-            raise UgfError("radialWeight != 1: axisymmetric weighting is not supported")
+        if not self.axisymmetric and (p["radialWeight"] != 1.0).any():
+            raise UgfError("radialWeight != 1 in the parcel files but axisymmetricSimulation is not true in uniGasProperties")
         vib = None
         if any(len(v) for v in p["vibLevel"]):
             nm = max(len(v) for v in p["vibLevel"])
@@ -423,7 +431,8 @@ class UniGasCloud:
         if kw:
             self.setCellState(**kw)
         self.setParcels(p["position"], p["U"], p["cell"], p["typeId"], p["ERot"], cellWeight=p["cellWeight"] if self.cellWeighted else None,
-                        vibLevel=vib, ELevel=p["ELevel"] if (p["ELevel"] != 0).any() else None)
+                        vibLevel=vib, ELevel=p["ELevel"] if (p["ELevel"] != 0).any() else None,
+                        radialWeight=p["radialWeight"] if self.axisymmetric else None)
         if new_cwf is not None:
             self.setCellState(cellWeightFactor=new_cwf)
         if d.get("deltaT") is not None:
@@ -647,12 +656,12 @@ class UniGasCloud:
     def parcels(self):
         cap = int(self.cfg.parcelCapacity)
         PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
-        f = [np.empty(cap, np.float64) for _ in range(8)]
+        f = [np.empty(cap, np.float64) for _ in range(9)]
         ii = [np.empty(cap, np.int32) for _ in range(3)]
         vib = np.empty((cap, _capi.UGF_MAX_VIB_MODES), np.int32)
         p = _capi.Parcels()
         p.n = cap
-        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz, p.ERot, p.cellWeight = [a.ctypes.data_as(PD) for a in f]
+        p.x, p.y, p.z, p.Ux, p.Uy, p.Uz, p.ERot, p.cellWeight, p.radialWeight = [a.ctypes.data_as(PD) for a in f]
         p.cell, p.typeId, p.ELevel = [a.ctypes.data_as(PI) for a in ii]
         p.vibLevel = vib.ctypes.data_as(PI)
         self._check(self.api.download_parcels(self._h, C.byref(p)))
@@ -662,6 +671,7 @@ class UniGasCloud:
             "position": np.stack([f[0][:n], f[1][:n], f[2][:n]], axis=1),
             "U": np.stack([f[3][:n], f[4][:n], f[5][:n]], axis=1),
             "ERot": f[6][:n].copy(), "cell": ii[0][:n].copy(), "typeId": ii[1][:n].copy(), "cellWeight": f[7][:n].copy(),
+            "radialWeight": f[8][:n].copy(),
         }
 
     def cellOccupancy(self):

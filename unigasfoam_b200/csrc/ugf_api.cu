@@ -150,6 +150,12 @@ struct ugf_handle {
     double* dTot = nullptr;
     bool histValid = false, occValid = false, occIdentity = false, momValid = false;
     // cell weighting (cellWeightedSimulation)
+    // axisymmetricSimulation: RWF of cell centres / boundary face centres; rwfCentre = the uploaded parcels carry RWF(cell centre)
+    // until their first move (DevParams)
+    double* dCellRwf = nullptr;
+    double* dBfRwf = nullptr;
+    std::vector<double> cellRwfHost, bfRwfHost;
+    bool rwfCentre = false;
     double* dCwf[2] = {nullptr, nullptr};  // [cwfCur]: current cellWeightFactor; the other: the factors the parcels carry while cwfDirty
     int cwfCur = 0;
     bool cwfDirty = false;
@@ -332,6 +338,12 @@ void build_params(ugf_handle* h) {
     p.cwfPrev = h->dCwf[0] ? h->dCwf[h->cwfCur ^ 1] : nullptr;
     p.cwfDirty = h->cwfDirty ? 1 : 0;
     p.spi = h->dSpi;
+    p.axi = h->cfg.axisymmetric ? 1 : 0;
+    p.rwfCentre = h->rwfCentre ? 1 : 0;
+    p.rwfMaxM1 = h->cfg.maxRWF - 1.0;
+    p.radialExtent = h->cfg.radialExtent;
+    p.cellRwf = h->dCellRwf;
+    p.bfRwf = h->dBfRwf;
     for (int i = 0; i < h->nSpecies; ++i) {
         const ugf_species& s = h->spHost[i];
         DevSpecies& d = p.sp[i];
@@ -447,6 +459,16 @@ int run_cell_kernel(ugf_handle* h, bool gather, bool doSample, bool accumulate =
     });
     LAUNCHED();
     h->argBytes += arg_bytes(prm, a);
+    if (doSample && prm.axi) {  // axisymmetricSimulation: the XnParticle sums weighted with every parcel's own RWF
+        AxiMomArgs xa{};
+        xa.nCells = h->nCells; xa.off = h->dOff;
+        xa.P = gather ? a.out : a.in;
+        xa.perm = gather ? nullptr : a.perm;
+        xa.mom = keepMoments ? h->dMom : nullptr; xa.acc = h->dAcc; xa.accS = h->dAccS; xa.accDt = a.accDt;
+        if (h->multi) axi_moments_kernel<true><<<grid_for(h->nCells, 8), 256, 0, h->stream>>>(prm, xa);
+        else axi_moments_kernel<false><<<grid_for(h->nCells, 8), 256, 0, h->stream>>>(prm, xa);
+        LAUNCHED();
+    }
     if (doSample && h->dAccI) {  // vibrational / electronic sums of the same (pre-collision) state
         InternalArgs ia{};
         ia.nCells = h->nCells; ia.off = h->dOff; ia.perm = a.perm; ia.in = a.in;
@@ -668,6 +690,7 @@ int launch_move(ugf_handle* h, const MoveArgs& a, long long count, long long beg
     h->histValid = true;
     h->occValid = false;
     h->momValid = false;
+    if (h->rwfCentre) { h->rwfCentre = false; h->prm.rwfCentre = 0; }  // the weighting pass that rode on this move left RWF(position) on every parcel
     if (h->prm.cwf) {
         h->cloneValid = true;
         if (h->cwfDirty) {  // every parcel now carries the new factors
@@ -864,6 +887,10 @@ int ugf_create(const ugf_config* cfg, ugf_handle** out) {
     if (cfg->partnerModel != UGF_PARTNER_NTC && cfg->partnerModel != UGF_PARTNER_NTC_SUBCYCLED) return fail(nullptr, "unknown dsmcCollisionPartnerModel");
     if (cfg->partnerModel == UGF_PARTNER_NTC_SUBCYCLED && cfg->nSubCycles < 1) return fail(nullptr, "noTimeCounterSubCycled needs nSubCycles >= 1");
     if (cfg->parcelCapacity <= 0 || cfg->parcelCapacity > 2000000000LL) return fail(nullptr, "parcelCapacity out of range");
+    if (cfg->axisymmetric && !(cfg->radialExtent > 0.0 && cfg->maxRWF >= 1.0))
+        return fail(nullptr, "axisymmetricSimulation needs radialExtentOfDomain > 0 and maxRadialWeightingFactor >= 1");
+    if (cfg->axisymmetric && !(cfg->solutionD[0] && cfg->solutionD[1] && cfg->solutionD[2]))
+        return fail(nullptr, "axisymmetricSimulation runs on a wedge mesh with symmetryPlane sides: all three directions are solved");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -1214,6 +1241,21 @@ int ugf_set_mesh(ugf_handle* h, const ugf_mesh* m) {
     h->ntcBlocks = persistent(occNtc, NTC_WARPS * 32);
     h->bgkBlocks = persistent(occBgk, BGK_WARPS * BGK_CHUNK);
     h->meshSet = true;
+    if (h->cfg.axisymmetric) {
+        // RWF of every cell centre and boundary face centre, evaluated on the host with the expression of uniGasCloudI.H:116-120
+        auto rwf = [&](const double* x) { return 1.0 + (h->cfg.maxRWF - 1.0) * std::sqrt(x[1] * x[1] + x[2] * x[2]) / h->cfg.radialExtent; };
+        h->cellRwfHost.resize(nC);
+        for (int c = 0; c < nC; ++c) h->cellRwfHost[c] = rwf(&h->ccHost[3 * (size_t)c]);
+        h->bfRwfHost.resize(std::max(nB, 1));
+        for (int b = 0; b < nB; ++b) h->bfRwfHost[b] = rwf(&h->CfHost[3 * (size_t)(nI + b)]);
+        if (dalloc(h, &h->dCellRwf, nC) || dalloc(h, &h->dBfRwf, (size_t)std::max(nB, 1))) return 1;
+        if (upload(h, h->dCellRwf, h->cellRwfHost.data(), nC) || upload(h, h->dBfRwf, h->bfRwfHost.data(), (size_t)std::max(nB, 1))) return 1;
+        h->prm.cellRwf = h->dCellRwf;
+        h->prm.bfRwf = h->dBfRwf;
+        // the weighting pass works on CWF * RWF: without cellWeightedSimulation the cell factors are a field of ones
+        std::vector<double> ones(nC, 1.0);
+        if (ugf_upload_cell_state(h, nullptr, nullptr, nullptr, ones.data())) return 1;
+    }
     return 0;
 }
 
@@ -1584,6 +1626,19 @@ int ugf_upload_parcels(ugf_handle* h, const ugf_parcels* p) {
         types.assign(n, 0);
         if (p->typeId) for (size_t i = 0; i < n; ++i) types[i] = (uint8_t)p->typeId[i];
         if (upload(h, P.type, types.data(), n)) return 1;
+    }
+    if (h->cfg.axisymmetric) {  // radialWeight: see include/ugf.h (ugf_parcels)
+        bool asPos = p->radialWeight != nullptr, asCentre = true;
+        if (p->radialWeight)
+            for (size_t i = 0; i < n; ++i) {
+                const double rp = 1.0 + (h->cfg.maxRWF - 1.0) * std::sqrt(p->y[i] * p->y[i] + p->z[i] * p->z[i]) / h->cfg.radialExtent;
+                const double rc = h->cellRwfHost[p->cell[i]], r = p->radialWeight[i];
+                asPos = asPos && std::fabs(r - rp) <= 1e-6 * rp;
+                asCentre = asCentre && std::fabs(r - rc) <= 1e-6 * rc;
+            }
+        if (!asPos && !asCentre) return fail(h, "radialWeight must be RWF(position) for every parcel or RWF(cell centre) for every parcel");
+        h->rwfCentre = !asPos;
+        h->prm.rwfCentre = h->rwfCentre ? 1 : 0;
     }
     const long long nn = p->n;
     CU(countedMemcpyAsync(h, h->dN, &nn, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
@@ -2362,6 +2417,21 @@ int ugf_download_parcels(ugf_handle* h, ugf_parcels* p) {
         }
         const std::vector<double>& w = h->cwfDirty ? h->cwfHostPrev : h->cwfHost;
         for (size_t i = 0; i < nb; ++i) p->cellWeight[i] = (w.empty() || cp[i] < 0) ? 1.0 : w[cp[i]];
+    }
+    if (p->radialWeight) {  // implicit on the device: RWF(position), or RWF(cell centre) before the first move of such an upload
+        if (!h->cfg.axisymmetric) std::fill(p->radialWeight, p->radialWeight + nb, 1.0);
+        else {
+            std::vector<double> y, z;
+            std::vector<int> cells;
+            const double *yp = p->y, *zp = p->z;
+            const int* cp = p->cell;
+            if (!yp && nb) { y.resize(nb); CU(countedMemcpy(h, y.data(), P.y, nb * sizeof(double), cudaMemcpyDeviceToHost)); yp = y.data(); }
+            if (!zp && nb) { z.resize(nb); CU(countedMemcpy(h, z.data(), P.z, nb * sizeof(double), cudaMemcpyDeviceToHost)); zp = z.data(); }
+            if (!cp && nb) { cells.resize(nb); CU(countedMemcpy(h, cells.data(), P.cell, nb * sizeof(int), cudaMemcpyDeviceToHost)); cp = cells.data(); }
+            for (size_t i = 0; i < nb; ++i)
+                p->radialWeight[i] = (h->rwfCentre && cp[i] >= 0) ? h->cellRwfHost[cp[i]]
+                                                                  : 1.0 + (h->cfg.maxRWF - 1.0) * std::sqrt(yp[i] * yp[i] + zp[i] * zp[i]) / h->cfg.radialExtent;
+        }
     }
     p->n = n;
     return 0;

@@ -99,7 +99,7 @@ __device__ inline void bgk_macro(const DevParams& prm, double FN, const double* 
         rhoNX += a1 * FN; rhoMX += ms * a1 * FN;
 #pragma unroll
         for (int k = 0; k < 3; ++k) momX[k] += ms * mv[5 + k] * FN;
-        keX += ms * mv[14] * FN;
+        keX += ms * mv[prm.axi ? 31 : 14] * FN;  // axisymmetric: the RWF-weighted sum (axi_moments_kernel)
         double uu[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { uu[k] = mv[8 + k]; muu[k] += ms * uu[k]; }
@@ -423,8 +423,9 @@ __device__ __noinline__ void bgk_giant_cell(const DevParams& prm, const BgkArgs&
     for (int j = lane; j < n; j += 32) {
         const double mass = MULTI ? prm.sp[pt[j]].mass : prm.sp[0].mass;
         const double u = pu0[j], vv = pu1[j], w = pu2[j];
-        keX += mass * (u * u + vv * vv + w * w) * FN;
-        mx += mass * u * FN; my += mass * vv * FN; mz += mass * w * FN;
+        const double wF = prm.axi ? FN * parcel_rwf(prm, cell, a.P.y[beg + j], a.P.z[beg + j]) : FN;  // CWF*RWF*nParticle (…USP.C:1017-1022)
+        keX += mass * (u * u + vv * vv + w * w) * wF;
+        mx += mass * u * wF; my += mass * vv * wF; mz += mass * w * wF;
     }
     keX = warp_sum(keX); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
     const double pU[3] = {mx / m.rhoMX, my / m.rhoMX, mz / m.rhoMX};
@@ -595,8 +596,9 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                     for (int i = cb + q; i < ce; i += BGK_LPC) {
                         const double mass = MULTI ? prm.sp[S.type[i]].mass : prm.sp[0].mass;
                         const double u = S.u[0][i], vv = S.u[1][i], w = S.u[2][i];
-                        keX += mass * (u * u + vv * vv + w * w) * FN;
-                        mx += mass * u * FN; my += mass * vv * FN; mz += mass * w * FN;
+                        const double wF = prm.axi ? FN * parcel_rwf(prm, c0 + cl, a.P.y[b0 + i], a.P.z[b0 + i]) : FN;
+                        keX += mass * (u * u + vv * vv + w * w) * wF;
+                        mx += mass * u * wF; my += mass * vv * wF; mz += mass * w * wF;
                     }
                 }
 #pragma unroll

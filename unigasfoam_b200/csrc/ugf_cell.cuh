@@ -235,11 +235,19 @@ __device__ __noinline__ void collide_pair_internal(const DevParams& prm, Stream&
     }
 }
 
+// axisymmetricSimulation: mean of RWF(position) over the cell's parcels in occupancy order (noTimeCounter.C:170-182); out of
+// line, one lane per cell
+__device__ __noinline__ double ntc_mean_rwf(const DevParams& prm, const ParcelBuf& P, int cell, int beg, int n) {
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += axi_rwf(prm, P.y[beg + i], P.z[beg + i]);
+    return sum / (double)n;
+}
+
 // NTC candidates for one cell: n_sel = 1/2 N (N-1) F_N (sigma_T c_r)max dt / V with stochastic rounding
 // (noTimeCounter.C:184-191); the rounding draw comes from the cell's own stream.
 __device__ __forceinline__ int ntc_candidates(const DevParams& prm, uint32_t step, uint32_t sub, double dtSub, int cell, int n, double sMaxOld,
-                                              double vol) {
-    const double selectedPairs = 0.5 * n * (n - 1) * cell_fn(prm, cell) * sMaxOld * dtSub / vol;  // noTimeCounter.C:168,184
+                                              double vol, double rwfMean = 1.0) {
+    const double selectedPairs = 0.5 * n * (n - 1) * (cell_fn(prm, cell) * rwfMean) * sMaxOld * dtSub / vol;  // noTimeCounter.C:168-184
     int nCand = (int)selectedPairs;
     Stream rc(prm.seed, KIND_NTC, sub, step, (uint32_t)cell, 0xFFFFFFFFu);
     if (rc.u01() < (selectedPairs - nCand)) nCand++;
@@ -302,12 +310,13 @@ __device__ __forceinline__ double acc_term(const DevParams& prm, double FN, int 
         case 5: return m * sw;
         case 6: return se;
         case 7: return S.rotDoF * cnt;
-        case 8: return cnt * FN;
-        case 9: return m * cnt * FN;
-        case 10: return m * su * FN;
-        case 11: return m * sv * FN;
-        case 12: return m * sw * FN;
-        case 13: return m * scc * FN;
+        // the XnParticle sums: with axisymmetricSimulation every parcel counts with its own RWF - axi_moments_kernel adds them
+        case 8: return prm.axi ? 0.0 : cnt * FN;
+        case 9: return prm.axi ? 0.0 : m * cnt * FN;
+        case 10: return prm.axi ? 0.0 : m * su * FN;
+        case 11: return prm.axi ? 0.0 : m * sv * FN;
+        case 12: return prm.axi ? 0.0 : m * sw * FN;
+        case 13: return prm.axi ? 0.0 : m * scc * FN;
         case 14: return S.rotDoF > 0 ? cnt : 0.0;
         default: return (5.0 + S.rotDoF) * cnt;
     }
@@ -387,7 +396,7 @@ __device__ __noinline__ void stream_giant_cell(const DevParams& prm, const CellA
         for (int s = 0; s < prm.nSpecies; ++s) {
             const double* mm = a.mom + ((size_t)cell * prm.nSpecies + s) * UGF_NMOM;
             add += acc_term(prm, FN, s, lane, mm[0], mm[2], mm[3], mm[4], mm[14], mm[18]);
-            if (MULTI && a.accS && lane == 0) a.accS[(size_t)cell * prm.nSpecies + s] += a.accDt * (mm[1] * FN);
+            if (MULTI && a.accS && lane == 0 && !prm.axi) a.accS[(size_t)cell * prm.nSpecies + s] += a.accDt * (mm[1] * FN);
         }
         a.acc[(size_t)cell * NACC + lane] += a.accDt * add;
     }
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
                     }
                     if (doAcc) {  // uniGasVolFields accumulation fused in: slot 4t + q
                         const double FN = (prm.cwf && cellValid) ? prm.nParticle * __ldg(&prm.cwf[c0 + ci]) : prm.nParticle;
-                        if (MULTI && a.accS && cellValid && q == 0) a.accS[(size_t)(c0 + ci) * nS + s] += a.accDt * (cnt * FN);
+                        if (MULTI && a.accS && cellValid && q == 0 && !prm.axi) a.accS[(size_t)(c0 + ci) * nS + s] += a.accDt * (cnt * FN);
                         ac0 += a.accDt * acc_term(prm, FN, s, q, cnt, su, sv, sw, scc, se);
                         ac1 += a.accDt * acc_term(prm, FN, s, q + 4, cnt, su, sv, sw, scc, se);
                         ac2 += a.accDt * acc_term(prm, FN, s, q + 8, cnt, su, sv, sw, scc, se);
@@ -602,6 +611,56 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) cell_kernel(const __grid_cons
         }
         task = taskNext;
     }
+}
+
+// ---- axisymmetricSimulation: the RWF-weighted cell sums -------------------------------------------------------------------
+// cellMeasurements.C:463-467 weights the XnParticle sums of every parcel with its own RWF.  One warp per cell over the
+// cell-major array, after cell_kernel: slots 1 (sum RWF), 5-7 (sum RWF U) and 31 (sum RWF |U|^2) of the cell's moment block
+// and the accumulators that take them (uniGasVolFields.C:789-797: slots 8-13, per-species nParcelsXnParticle).
+struct AxiMomArgs {
+    int nCells;
+    const int* off;
+    ParcelBuf P;  // cell-major, or reached through perm
+    const int* perm;
+    double* mom;  // or null
+    double* acc;
+    double* accS;
+    double accDt;
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256) axi_moments_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ AxiMomArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int cell = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (cell >= a.nCells) return;
+    const int b = a.off[cell], e = a.off[cell + 1];
+    const double FN = cell_fn(prm, cell);
+    double add[6] = {0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < prm.nSpecies; ++s) {
+        double sr = 0, su = 0, sv = 0, sw = 0, scc = 0;
+        for (int jj = b + lane; jj < e; jj += 32) {
+            const int j = a.perm ? (a.perm[jj] & CLONE_MASK) : jj;
+            if (MULTI && a.P.type[j] != s) continue;
+            const double rw = parcel_rwf(prm, cell, a.P.y[j], a.P.z[j]);
+            const double u = a.P.ux[j], v = a.P.uy[j], w = a.P.uz[j];
+            sr += rw; su += rw * u; sv += rw * v; sw += rw * w; scc += rw * (u * u + v * v + w * w);
+        }
+        sr = warp_sum(sr); su = warp_sum(su); sv = warp_sum(sv); sw = warp_sum(sw); scc = warp_sum(scc);
+        if (lane == 0) {
+            if (a.mom) {
+                double* m = a.mom + ((size_t)cell * prm.nSpecies + s) * UGF_NMOM;
+                m[1] = sr; m[5] = su; m[6] = sv; m[7] = sw; m[31] = scc;
+            }
+            if (a.accDt != 0.0) {
+                const double ms = prm.sp[s].mass;
+                add[0] += sr * FN; add[1] += ms * sr * FN; add[2] += ms * su * FN; add[3] += ms * sv * FN; add[4] += ms * sw * FN;
+                add[5] += ms * scc * FN;
+                if (a.accS) a.accS[(size_t)cell * prm.nSpecies + s] += a.accDt * (sr * FN);
+            }
+        }
+    }
+    if (lane == 0 && a.accDt != 0.0)
+        for (int k = 0; k < 6; ++k) a.acc[(size_t)cell * NACC + 8 + k] += a.accDt * add[k];
 }
 
 // ---- NTC kernel -----------------------------------------------------------------------------------------------------
@@ -696,7 +755,9 @@ __global__ void __launch_bounds__(NTC_THREADS, 2) ntc_kernel(const __grid_consta
         double mySMax = 0.0;
         if (myN > 1 && myModel == 1) {
             mySMax = sMaxIn;
-            myCand = ntc_candidates(prm, a.step, a.sub_cycle, a.dtSub, myCell, myN, mySMax, myVol);
+            double rwfMean = 1.0;
+            if (prm.axi) rwfMean = ntc_mean_rwf(prm, a.P, myCell, myBeg, myN);
+            myCand = ntc_candidates(prm, a.step, a.sub_cycle, a.dtSub, myCell, myN, mySMax, myVol, rwfMean);
         }
         if (!__any_sync(0xffffffffu, myCand > 0)) continue;
         int incl = myCand;  // inclusive prefix of the candidate counts over the 32 cells

@@ -78,6 +78,14 @@ struct DevParams {
     const double* cwfPrev;
     int cwfDirty;
     const DevSpeciesInt* spi;  // [nSpecies] or null (ugf_internal.cuh)
+    // axisymmetricSimulation: RWF(x) = 1 + rwfMaxM1 * sqrt(y^2 + z^2) / radialExtent (uniGasCloudI.H:116-120).  A parcel's RWF is
+    // implicit like its CWF: RWF(position) after any weighting pass; RWF(centre of its cell) - cellRwf - for parcels the inflow
+    // inserted this step and, while rwfCentre is set, for the uploaded parcels before their first move (include/ugf.h, ugf_parcels).
+    // cwf is never null in this mode (a field of ones without cellWeightedSimulation).
+    int axi, rwfCentre;
+    double rwfMaxM1, radialExtent;
+    const double* cellRwf;     // [nCells] RWF(cell centre)
+    const double* bfRwf;       // [nBFaces] RWF(boundary face centre)
 };
 
 struct DevCounters {
@@ -118,9 +126,20 @@ __device__ __forceinline__ double dot3(double ax, double ay, double az, double b
     return ax * bx + ay * by + az * bz;
 }
 
-// nParticle * CWF of a cell: every parcel of a cell carries the cell's factor after weighting() (RWF = 1)
+// nParticle * CWF of a cell: every parcel of a cell carries the cell's factor after weighting(); the radial factor comes on top
+// where the reference applies it
 __device__ __forceinline__ double cell_fn(const DevParams& prm, int cell) {
     return prm.cwf ? prm.nParticle * __ldg(&prm.cwf[cell]) : prm.nParticle;
+}
+// uniGasCloud::axiRWF (U/clouds/uniGasCloudI.H:116-120); callers test prm.axi first
+__device__ __forceinline__ double axi_rwf(const DevParams& prm, double y, double z) {
+    const double radius = sqrt(y * y + z * z);
+    return 1.0 + prm.rwfMaxM1 * radius / prm.radialExtent;
+}
+// the RWF a parcel of `cell` at (y, z) carries outside the move: RWF(position), or RWF(cell centre) before the first move of an
+// upload that said so
+__device__ __forceinline__ double parcel_rwf(const DevParams& prm, int cell, double y, double z) {
+    return prm.rwfCentre ? __ldg(&prm.cellRwf[cell]) : axi_rwf(prm, y, z);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

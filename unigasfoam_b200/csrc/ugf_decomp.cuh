@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) kn_accumulate_kernel(const __grid_constan
         v[0] += dt * m[0];
         v[1] += dt * (m1 * FN);
         v[2] += dt * (ms * m1 * FN);
-        v[3] += dt * (ms * m[14] * FN);
+        v[3] += dt * (ms * m[prm.axi ? 31 : 14] * FN);
 #pragma unroll
         for (int k = 0; k < 3; ++k) v[4 + k] += dt * (ms * m[5 + k] * FN);
         a[KN_NACC + s] += dt * (m1 * FN);

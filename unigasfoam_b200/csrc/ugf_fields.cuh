@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(256) derive_walls_kernel(const __grid_constant
     const int patch = mesh.bfPatch[b];
     if (mesh.patches[patch].kind == UGF_PATCH_WALL) {
         const double* B = bacc + (size_t)b * UGF_NBM;
-        const double nPart = cell_fn(prm, mesh.bfOwner[b]);  // uniGasVolFields.C:1276-1278: CWF of the boundary cell
+        double nPart = cell_fn(prm, mesh.bfOwner[b]);  // uniGasVolFields.C:1276-1278: CWF of the boundary cell, RWF of the face centre
+        if (prm.axi) nPart = nPart * __ldg(&prm.bfRwf[b]);
         if (B[0] > VSMALL) {
             F[0] = B[0] * nPart / t;
             F[1] = B[1] * nPart / t;

@@ -67,8 +67,10 @@ __global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant
     double sCos = (vel[0] * g[1] + vel[1] * g[2] + vel[2] * g[3]) / cmp;
     if (f.pressure && sCos > 5.0) sCos = 5.0;  // the host's insertion bound assumes speed ratios <= 5 on pressure inlets
     const double sqrtPi = sqrt(PI);
+    // nParticle * CWF(face cell) * RWF(face centre) (uniGasGeneralBoundary.C:154-155)
+    const double fnFace = prm.axi ? cell_fn(prm, f.faceCell[face]) * __ldg(&prm.bfRwf[f.faceBfi[face]]) : cell_fn(prm, f.faceCell[face]);
     double accum = f.molFrac[iD] * (fA * numDen * prm.deltaT * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos))))
-                   / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));  // uniGasGeneralBoundary.C:154-165
+                   / (2.0 * sqrtPi * fnFace);  // uniGasGeneralBoundary.C:154-165
     if (f.ce) {  // :171-239: the normal stress and heat flux correct the Maxwellian flux
         const double n[3] = {g[1], g[2], g[3]};
         const double qn = f.ceQ[0] * n[0] + f.ceQ[1] * n[1] + f.ceQ[2] * n[2];
@@ -76,12 +78,12 @@ __global__ void __launch_bounds__(256) inflow_count_kernel(const __grid_constant
         for (int k = 0; k < 3; ++k) snn += (f.ceS[3 * k] * n[0] + f.ceS[3 * k + 1] * n[1] + f.ceS[3 * k + 2] * n[2]) * n[k];
         accum = (fA * numDen * prm.deltaT * cmp
                  * (exp(-(sCos * sCos)) * (1.0 - 0.5 * snn / f.cePressure - 0.4 * qn * sCos / f.cePressure / cmp) + sqrtPi * sCos * (1 + erf(sCos))))
-                / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));
+                / (2.0 * sqrtPi * fnFace);
     }
     if (f.outlet) {
         const double cmpCap = sqrt(2.0 * kB * f.capT / s.mass);
         const double cap = f.molFrac[iD] * (fA * f.capN * prm.deltaT * cmpCap * (exp(-25.0) + sqrtPi * 5.0 * (1 + erf(5.0))))
-                           / (2.0 * sqrtPi * cell_fn(prm, f.faceCell[face]));
+                           / (2.0 * sqrtPi * fnFace);
         if (!(accum <= cap)) { accum = accum > cap ? cap : 0.0; atomicExch(f.err, 6); }
     }
     Stream rc(prm.seed, KIND_INFLOW, (uint32_t)iD, step, (uint32_t)f.faceBfi[face], 0);
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(128) inlet_velocity_kernel(const __grid_consta
     const double w = cell_fn(prm, c);  // nParticle * CWF: the same for every parcel of the cell
     double mom[3] = {0, 0, 0}, mass = 0;
     for (int j = off[c]; j < off[c + 1]; ++j) {
-        const double m = w * (MULTI ? prm.sp[P.type[j]].mass : prm.sp[0].mass);
+        const double m = (prm.axi ? w * axi_rwf(prm, P.y[j], P.z[j]) : w) * (MULTI ? prm.sp[P.type[j]].mass : prm.sp[0].mass);  // nParticle*CWF*RWF(position)*mass
         mom[0] += m * P.ux[j]; mom[1] += m * P.uy[j]; mom[2] += m * P.uz[j];
         mass += m;
     }
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(128) wang_inlet_velocity_kernel(const __grid_c
         bool mine = false;
         for (int i = 0; i < f.nTypeIds; ++i) mine = mine || f.typeIds[i] == t;
         if (!mine) continue;
-        const double m = w * prm.sp[t].mass;
+        const double m = (prm.axi ? w * axi_rwf(prm, P.y[j], P.z[j]) : w) * prm.sp[t].mass;  // nParticle*CWF*RWF(position)*mass
         const double U[3] = {P.ux[j], P.uy[j], P.uz[j]};
         for (int k = 0; k < 3; ++k) { mom[k] += m * U[k]; sq[k] += U[k] * U[k]; su[k] += U[k]; }
         mass += m;
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(128) outlet_state_kernel(const __grid_constant
         for (int i = 0; i < f.nTypeIds; ++i) mine = mine || f.typeIds[i] == t;
         const double U[3] = {P.ux[j], P.uy[j], P.uz[j]};
         if (mine) {
-            const double m = w * prm.sp[t].mass;
+            const double m = (prm.axi ? w * axi_rwf(prm, P.y[j], P.z[j]) : w) * prm.sp[t].mass;  // nParticle*CWF*RWF(position)*mass
             for (int k = 0; k < 3; ++k) mom[k] += m * U[k];
             mass += m;
         }

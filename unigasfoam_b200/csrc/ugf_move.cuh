@@ -54,7 +54,8 @@ struct WallPre { double IE; double mom[3]; };
 
 // measurePropertiesBeforeControl / AfterControl (uniGasPatchBoundary.C:130-302): slots in DESIGN.md §walls
 __device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, int cell, const DevSpecies& s, const double U[3],
-                                    double erot, const double nw[3], double fA, WallPre& pre, bool after, double evib = 0.0, double eelIn = -1.0) {
+                                    double erot, const double nw[3], double fA, WallPre& pre, bool after, double evib = 0.0, double eelIn = -1.0,
+                                    double hitY = 0.0, double hitZ = 0.0) {
     const double eel = eelIn >= 0.0 ? eelIn : s.E0;  // electronic energy of the parcel's level (ground level when the species has one)
     const double m = s.mass;
     const double Un = dot3(U[0], U[1], U[2], nw[0], nw[1], nw[2]);
@@ -80,7 +81,8 @@ __device__ inline void measure_wall(const DevParams& prm, double* bm, int bfi, i
         pre.mom[0] = m * U[0]; pre.mom[1] = m * U[1]; pre.mom[2] = m * U[2];
         atomicAdd(&b[15], 1.0);
     } else {
-        const double nPart = cell_fn(prm, cell);  // nParticle * CWF of the wall cell (uniGasPatchBoundary.C:292-294)
+        double nPart = cell_fn(prm, cell);  // nParticle * CWF of the wall cell * RWF(hit position) (uniGasPatchBoundary.C:292-294)
+        if (prm.axi) nPart = nPart * axi_rwf(prm, hitY, hitZ);
         const double dq = nPart * (pre.IE - IE) / (prm.deltaT * fA);
         if (dq != 0.0) atomicAdd(&b[8], dq);
 #pragma unroll
@@ -222,12 +224,23 @@ struct MoveArgs {
     int* queueI;
 };
 
+// The weight (CWF, times RWF with axisymmetricSimulation) a parcel carries into this step's weighting pass: the factor of the
+// cell it started the step in (still in P.cell; the previous field while a new one is pending) and RWF of the position it
+// started from (still in P.y / P.z) - or RWF of that cell's centre for parcels the inflow inserted this step and for uploaded
+// parcels that said so (DevParams::rwfCentre).  Must be called before the move writes the parcel back.
+__device__ __noinline__ double carried_weight(const DevParams& prm, const MoveArgs& a, long long i) {
+    const int c0 = a.P.cell[i];
+    double w = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[c0]) : __ldg(&prm.cwf[c0]);
+    if (prm.axi) w = w * ((i >= a.newFrom || prm.rwfCentre) ? __ldg(&prm.cellRwf[c0]) : axi_rwf(prm, a.P.y[i], a.P.z[i]));
+    return w;
+}
+
 // uniGasFaceTracker::updateFields (U/faceTracker/uniGasFaceTracker.C:90-152) for one crossing of a tracked face: number,
 // mass, momentum and energy carried through it, weighted with the parcel's cell weight factor and signed with the
 // direction of travel relative to the face area vector (momentum unsigned, as in the reference).  Rare path (only the
 // faces of the registered face zones), out of line.
 __device__ __noinline__ void face_tally(const DevParams& prm, const MoveArgs& a, long long i, int trk, double U0, double U1, double U2, int type,
-                                        double erot, bool haveErot, bool hasRot) {
+                                        double erot, bool haveErot, bool hasRot, double posY = 0.0, double posZ = 0.0) {
     const int k = (trk > 0 ? trk : -trk) - 1;
     const double sgn = trk > 0 ? 1.0 : -1.0;
     double w = 1.0;
@@ -237,6 +250,7 @@ __device__ __noinline__ void face_tally(const DevParams& prm, const MoveArgs& a,
             const int c0 = a.P.cell[i];
             w = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[c0]) : __ldg(&prm.cwf[c0]);
         }
+        if (prm.axi) w = w * axi_rwf(prm, posY, posZ);  // the carried CWF times RWF(position at the crossing) (uniGasFaceTracker.C:98-99)
     }
     const DevSpecies& s = prm.sp[type];
     if (hasRot && !haveErot) erot = a.P.erot[i];
@@ -303,7 +317,7 @@ __device__ __forceinline__ void boundary_interaction(const DevParams& prm, const
             if (a.P.vib) evib = vib_energy(prm.spi[type], sp.vibDoF, a.P.vib[i]);
             eel = prm.spi[type].elecE[a.P.elev ? a.P.elev[i] : 0];
         }
-        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, false, evib, eel);
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, false, evib, eel, st.x[1], st.x[2]);
         bool diffuse = (pt.wallModel == UGF_WALL_DIFFUSE);
         const bool cll = (pt.wallModel == UGF_WALL_CLL);
         if (pt.wallModel != UGF_WALL_SPECULAR) {
@@ -331,7 +345,7 @@ __device__ __forceinline__ void boundary_interaction(const DevParams& prm, const
             if (Un > 0.0) for (int k = 0; k < 3; ++k) st.U[k] = st.U[k] - 2.0 * Un * nw[k];
         }
         st.flags |= HIT_CHANGED_U;
-        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, true, evib, eel);
+        if (prm.measureWalls) measure_wall(prm, a.bm, bfi, st.cell, sp, st.U, st.erot, nw, fA, pre, true, evib, eel, st.x[1], st.x[2]);
     } else if (pt.kind == UGF_PATCH_SYMMETRY) {
         const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
         double nw[3], fA;
@@ -347,10 +361,7 @@ __device__ __forceinline__ void boundary_interaction(const DevParams& prm, const
         st.cell = -2 - bfi;
         st.flags |= HIT_MIGRATED;
         if (a.sf) a.sf[i] = st.sf;
-        if (prm.cwf && a.wq && !a.useSfIn) {  // first hop: the factor of the cell the step started in (still in P.cell)
-            const int c0 = a.P.cell[i];
-            a.wq[i] = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[c0]) : __ldg(&prm.cwf[c0]);
-        }
+        if (prm.cwf && a.wq && !a.useSfIn) a.wq[i] = carried_weight(prm, a, i);  // first hop: the weight the parcel started the step with
         const int pos = atomicAdd(&a.migCount[patch], 1);
         if (a.migList) {  // remember who waits here: the pack kernel then never has to search the whole cloud
             int slot = -1;
@@ -374,7 +385,7 @@ __device__ __noinline__ void boundary_hit(const DevParams& prm, const MoveArgs& 
         if (trk) {
             const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
             const double un = st.U[0] * pl.x + st.U[1] * pl.y + st.U[2] * pl.z;
-            face_tally(prm, a, i, un >= 0.0 ? trk : -trk, st.U[0], st.U[1], st.U[2], type, st.erot, true, HAS_ROT);
+            face_tally(prm, a, i, un >= 0.0 ? trk : -trk, st.U[0], st.U[1], st.U[2], type, st.erot, true, HAS_ROT, st.x[1], st.x[2]);
         }
     }
 }
@@ -535,7 +546,7 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
                     if (trk) {
                         int type = 0;
                         if (MULTI) type = a.P.type[i];
-                        face_tally(prm, a, i, trk, U0, U1, U2, type, erot, erotLoaded, HAS_ROT);
+                        face_tally(prm, a, i, trk, U0, U1, U2, type, erot, erotLoaded, HAS_ROT, x1, x2);
                     }
                 }
                 cell = nb;
@@ -558,14 +569,17 @@ __device__ __forceinline__ void track_parcel(const DevParams& prm, const MoveArg
                         // cell the parcel started the step in (re-read before it is overwritten), new = where it stopped
             int k = 0;
             if (cell >= 0) {
-                const double wNew = __ldg(&prm.cwf[cell]);
+                double wNew = __ldg(&prm.cwf[cell]);
                 double wOld;
                 if (a.useSfIn) {
                     wOld = a.wq[i];  // received parcel: the factor travelled with it
+                } else if (prm.axi) {
+                    wOld = carried_weight(prm, a, i);
                 } else {
                     const int cell0 = a.P.cell[i];
                     wOld = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[cell0]) : __ldg(&prm.cwf[cell0]);
                 }
+                if (prm.axi) wNew = wNew * axi_rwf(prm, x1, x2);  // axisymmetric(Cell)Weighting (uniGasCloud.C:1427-1570): RWF of where it stopped
                 if (wOld != wNew) k = weighting_decision(prm.seed, a.step, (uint32_t)i, wOld, wNew);
                 if (k < 0) { cell = -1; flags |= HIT_WDELETED; k = 0; }
             }
@@ -804,7 +818,7 @@ __device__ __forceinline__ bool hop_once(const DevParams& prm, const MoveArgs& a
             if (trk) {
                 int type = 0;
                 if (MULTI) type = a.P.type[i];
-                face_tally(prm, a, i, trk, U0, U1, FLAT ? a.P.uz[i] : U2, type, 0.0, false, HAS_ROT);
+                face_tally(prm, a, i, trk, U0, U1, FLAT ? a.P.uz[i] : U2, type, 0.0, false, HAS_ROT, x1, FLAT ? 0.0 : x2);
             }
         }
         cell = nb;
@@ -958,9 +972,15 @@ __global__ void __launch_bounds__(MOVE_WARPS * 32, BPS) move_stream2_kernel(cons
             if (prm.cwf) {  // weighting() right after the move (U/clouds/uniGasCloud.C:839-842), see track_parcel
                 int kc = 0;
                 if (cell >= 0) {
-                    const double wNew = __ldg(&prm.cwf[cell]);
-                    const int cell0 = a.P.cell[i];
-                    const double wOld = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[cell0]) : __ldg(&prm.cwf[cell0]);
+                    double wNew = __ldg(&prm.cwf[cell]);
+                    double wOld;
+                    if (prm.axi) {
+                        wOld = carried_weight(prm, a, i);
+                        wNew = wNew * axi_rwf(prm, x1, FLAT ? 0.0 : x2);
+                    } else {
+                        const int cell0 = a.P.cell[i];
+                        wOld = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[cell0]) : __ldg(&prm.cwf[cell0]);
+                    }
                     if (wOld != wNew) kc = weighting_decision(prm.seed, a.step, (uint32_t)i, wOld, wNew);
                     if (kc < 0) { cell = -1; atomicAdd(&a.cnt->wdeleted, 1ull); kc = 0; }
                 }

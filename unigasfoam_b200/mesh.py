@@ -688,6 +688,25 @@ def sphere_cone_map(n_eta, n_s, n_phi, nose_radius=0.05, cone_half_angle_deg=30.
     return pm
 
 
+def wedge_map(nx, nr, length, radius, half_angle_deg=0.5, r_inner=0.0, gx=1.0, gr=1.0):
+    """Point map of an axisymmetric wedge about the x axis, one cell thick in azimuth between the planes phi = -a and phi = +a
+    (the tutorials' blockMesh wedges, e.g. plumeImpingement/system/blockMeshDict: half angle 0.5 degrees, side patches typed
+    symmetryPlane as uniGasBoundaries.C:438-445 demands): i along x, j along r, k = 0 / 1 the two side planes.  With
+    r_inner = 0 the j = 0 faces collapse onto the axis (zero area; patch type symmetry as in the tutorials)."""
+    a = np.deg2rad(half_angle_deg)
+
+    def frac(t, g):
+        return t if abs(g - 1.0) < 1e-12 else (g ** t - 1.0) / (g - 1.0)
+
+    def pm(I, J, K):
+        x = length * frac(I / nx, gx)
+        r = np.where((J == 0) & (r_inner == 0.0), 0.0, r_inner + (radius - r_inner) * frac(J / nr, gr))
+        phi = -a + 2.0 * a * K
+        return x, r * np.cos(phi), r * np.sin(phi)
+
+    return pm
+
+
 # ---- interpolationCellPoint support (collisionProperties.macroInterpolation) ------------------------------------------
 
 def cell_point_data(mesh):
