@@ -354,6 +354,17 @@ int ugf_set_wang_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure
  * with at the next step.  The device caps a slot's insertions at the count of a gas at twice p_e / (k T_0), T_0 and a speed
  * ratio of 5 (the bound the array capacity is checked against); reaching it is an error, not a silent clamp. */
 int ugf_set_pressure_outlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* outlet);
+/* uniGasMassFlowRateInletPatch on a patch of type patch (U/boundaries/derived/generalBoundaries/uniGasMassFlowRateInletPatch/
+ * uniGasMassFlowRateInletPatch.C:53-302).  The struct is read as: moleFractions, inletTemperature, theta; inletPressure unused.
+ * After the collisions of every step the inlet velocity of each face relaxes (theta) towards the mean velocity of its cell (kept
+ * when it would point out of the domain), the number density of each species follows the parcels in the cell, and all are scaled
+ * by parcelsIn / parcelsToInsert so that the next step's count adds up to massFlowRate dt / (mean molecular mass F_N) plus the
+ * parcels that left through the patch this step (the face tracker's parcelIdFlux on the patch faces, kept by the move).  As in
+ * the reference the parcels themselves are inserted from a gas at rest at inletTemperature (:139-149) and the patch-wide
+ * parcelsToInsert sums over all species (scalarField += scalar, :262-271).  typeIds must be 0..nSpecies-1 (the reference indexes
+ * the tracker and the densities with the patch-local index); a patch whose cells are all empty is an error (0 / 0 there);
+ * decomposed meshes are refused (patch-wide sums).  initialVelocity [3] or NULL (zero). */
+int ugf_set_mass_flow_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* inlet, double massFlowRate, const double* initialVelocity);
 /* Inlet velocity per face of a pressure inlet [patchSize*3] (diagnostic / restart). */
 int ugf_download_inlet_velocity(ugf_handle* h, int32_t patch, double* U);
 /* addNewParcel over a whole initial configuration (U/clouds/uniGasCloud.C:260-290). Replaces the cloud. */

@@ -167,6 +167,11 @@ struct InflowPatch {
     std::vector<double> wangSums;
     double wangSteps = 0.0, wangP = 0.0, wangM = 0.0, wangGammaR = 0.0;
     bool ce = false;               // uniGasChapmanEnskogFreeStreamInflowPatch
+    // uniGasMassFlowRateInletPatch (…/uniGasMassFlowRateInletPatch.C:53-302): faceN [nFaces*nTypeIds] and faceVel follow the flow so
+    // that the patch lets in massFlowRate; outFlux [nFaces*nSpecies] = this step's parcelIdFlux of the face tracker on the patch faces
+    bool massFlow = false;
+    double massFlowRate = 0.0, patchArea = 0.0;
+    std::vector<double> outFlux, mfMolFrac;
     double ceQ[3] = {0, 0, 0}, ceS[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 constexpr int WANG_NSUM = 11;
@@ -199,6 +204,7 @@ struct ugfo_handle {
     bool outletBoundHit = false;  // a pressure-outlet face asked for more parcels than the device library's bound
     bool weightPending = false;   // a move happened since the last weighting() pass
     std::vector<int32_t> faceTrack;   // [nFaces] k + 1 of a tracked face, 0 otherwise (uniGasFaceTracker)
+    std::vector<int> patchFlux;       // [nPatches] index in inflows of the mass-flow inlet on that patch, or -1; empty without one
     std::vector<double> ft;           // [nTracked][nSpecies][UGF_NFT]
     int nTracked = 0;
 
@@ -741,6 +747,12 @@ void moveParcel(ugfo_handle& h, Parcel& p, int64_t idx, MoveTally& t, bool fresh
                 p.cell = -2 - bfi;
                 t.migrated++;
             } else if (kind == UGF_PATCH_GENERIC) {
+                if (!h.patchFlux.empty() && h.patchFlux[patch] >= 0) {  // uniGasFaceTracker::updateFields on the faces of a mass-flow inlet (:98-141)
+                    double* fl = h.inflows[h.patchFlux[patch]].outFlux.data() + (size_t)(hit - h.pStart[patch]) * h.nSpecies + p.typeId;
+                    const double add = (dot3(p.U, S) >= 0.0 ? 1.0 : -1.0) * (p.CWF * axiRWF(h, p.x));
+#pragma omp atomic
+                    *fl += add;
+                }
                 p.cell = -1; t.deleted++;
             } else {  // empty patch hit: mesh/solutionD mismatch
                 p.cell = -1; t.stuck++;
@@ -842,7 +854,11 @@ void doInflow(ugfo_handle& h) {
             double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
             const double m2 = std::sqrt(dot3(t2, t2));
             for (int k = 0; k < 3; ++k) t2[k] /= m2;
-            const double* vel = (ip.pressure || ip.fields) ? &ip.faceVel[3 * (size_t)lf] : ip.in.velocity;
+            const double* velCount = (ip.pressure || ip.fields) ? &ip.faceVel[3 * (size_t)lf] : ip.in.velocity;
+            // the mass-flow inlet counts with its inlet velocity but inserts from a gas at rest: controlParcelsBeforeMove zeroes
+            // inletVelocity_ before insertParcels (…MassFlowRateInletPatch.C:139-149)
+            static const double atRest[3] = {0.0, 0.0, 0.0};
+            const double* vel = ip.massFlow ? atRest : velCount;
             const bool perFace = ip.fields || ip.outlet;
             const double fnFace = FNc(h, cellI) * axiRWF(h, fC);  // nParticle * CWF(face cell) * RWF(face centre) (uniGasGeneralBoundary.C:154-155)
             const double Ttr = perFace ? ip.faceTtr[lf] : ip.in.translationalTemperature;
@@ -850,11 +866,12 @@ void doInflow(ugfo_handle& h) {
             for (int iD = 0; iD < ip.in.nTypeIds; ++iD) {
                 const int typeId = ip.in.typeIds[iD];
                 const ugf_species& s = h.sp[typeId];
-                const double numDen = ip.outlet ? ip.faceN[(size_t)lf * ip.in.nTypeIds + iD]
+                const double numDen = (ip.outlet || ip.massFlow) ? ip.faceN[(size_t)lf * ip.in.nTypeIds + iD]
                                       : ip.fields ? ip.faceN[(size_t)iD * h.pSize[patch] + lf] : ip.in.numberDensities[iD];
                 const double cmp = std::sqrt(2.0 * kB * Ttr / s.mass);
                 const double sCosFull = dot3(vel, n) / cmp;
-                const double sCos = (ip.pressure && sCosFull > 5.0) ? 5.0 : sCosFull;  // count only: the device library's insertion bound
+                const double sCosCount = dot3(velCount, n) / cmp;
+                const double sCos = (ip.pressure && sCosCount > 5.0) ? 5.0 : sCosCount;  // count only: the device library's insertion bound
                 // Bird eq 4.22 (uniGasGeneralBoundary.C:154-165); CWF of the face's cell, RWF = 1
                 double accum = ip.molFrac[iD] * (fA * numDen * dt * cmp
                                 * (std::exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + std::erf(sCos))))
@@ -1753,6 +1770,68 @@ void decompose(ugfo_handle& h) {
 
 // ---------------------------------------------------------------------------------
 // time-averaged fields  (uniGasVolFields.C:723-1352)
+// uniGasMassFlowRateInletPatch::controlParcelsAfterCollisions (…/uniGasMassFlowRateInletPatch.C:155-302): inflow velocity per
+// face relaxed towards the mean velocity of the cell (kept when it would point out of the domain), number density per face and
+// species from the parcels in the cell, scaled by parcelsIn / parcelsToInsert so that the next step's insertion count adds up to
+// the parcels the mass flow rate brings in plus the ones that left through the patch this step (the tracker's parcelIdFlux).
+// As written there: parcelsToInsert_ += adds every slot's count to EVERY species' total (a scalarField += scalar), and the
+// tracker's flux is read with the patch-local species index; the second is avoided by requiring typeIds = 0..n-1 (checked).
+void updateMassFlowInlet(ugfo_handle& h, InflowPatch& ip) {
+    const int nT = ip.in.nTypeIds, nF = h.pSize[ip.patch];
+    const double dt = h.cfg.deltaT, nParticle = h.cfg.nParticle;
+    double totalMass = 0.0;
+    for (int i = 0; i < nT; ++i) totalMass += h.sp[ip.in.typeIds[i]].mass * ip.mfMolFrac[i];
+    std::vector<double> parcelsIn(nT, 0.0);
+    double parcelsToInsert = 0.0;
+    const double T = ip.in.translationalTemperature;
+    for (int lf = 0; lf < nF; ++lf) {
+        const int f = h.pStart[ip.patch] + lf;
+        const int c = h.owner[f];
+        const double* Sf = &h.Sf[3 * (size_t)f];
+        const double fA = std::sqrt(dot3(Sf, Sf));
+        const double CWF = h.cellWF[c], RWFf = axiRWF(h, &h.Cf[3 * (size_t)f]);
+        for (int i = 0; i < nT; ++i) {
+            const double moleFlowRate = ip.mfMolFrac[i] * (ip.massFlowRate / totalMass);
+            parcelsIn[i] += moleFlowRate * dt * (fA / ip.patchArea) / (nParticle * CWF * RWFf) + ip.outFlux[(size_t)lf * h.nSpecies + i] / (CWF * RWFf);
+        }
+        double mom[3] = {0, 0, 0}, mass = 0.0;
+        double* nD = &ip.faceN[(size_t)lf * nT];
+        for (int i = 0; i < nT; ++i) nD[i] = 0.0;
+        for (int j = h.occOff[c]; j < h.occOff[c + 1]; ++j) {
+            const Parcel& p = h.P[h.occIds[j]];
+            const double pMass = nParticle * h.sp[p.typeId].mass;
+            const double RWF = axiRWF(h, p.x);
+            nD[p.typeId] += 1.0;
+            for (int k = 0; k < 3; ++k) mom[k] += pMass * CWF * RWF * p.U[k];
+            mass += pMass * CWF * RWF;
+        }
+        double* v = &ip.faceVel[3 * (size_t)lf];
+        const double prev[3] = {v[0], v[1], v[2]};
+        double nv[3] = {0, 0, 0};
+        if (mass > VSMALL) for (int k = 0; k < 3; ++k) nv[k] = mom[k] / mass;
+        for (int k = 0; k < 3; ++k) v[k] = ip.theta * nv[k] + (1.0 - ip.theta) * prev[k];
+        const double nIn[3] = {Sf[0] / -fA, Sf[1] / -fA, Sf[2] / -fA};
+        if (dot3(v, nIn) < 0.0) for (int k = 0; k < 3; ++k) v[k] = prev[k];
+        for (int i = 0; i < nT; ++i) nD[i] = nD[i] * nParticle * CWF * RWFf / h.vol[c];
+        double pti = 0.0;  // the face's slots first, then the faces: the order of the device kernels
+        for (int i = 0; i < nT; ++i) {
+            const double cmp = std::sqrt(2.0 * kB * T / h.sp[ip.in.typeIds[i]].mass);
+            const double sCos = dot3(v, nIn) / cmp;
+            pti += (fA * nD[i] * dt * cmp * (std::exp(-(sCos * sCos)) + std::sqrt(PI) * sCos * (1 + std::erf(sCos))))
+                   / (2.0 * std::sqrt(PI) * nParticle * CWF * RWFf);
+        }
+        parcelsToInsert += pti;
+    }
+    if (!(parcelsToInsert > 0.0)) {  // the reference divides by zero here (no parcel in any inlet cell): say so
+        h.err = "mass-flow-rate inlet: no parcels in the cells of the inlet patch (the reference's parcelsIn / parcelsToInsert is 0 / 0 here)";
+        h.relaxFailed = true;
+    } else {
+        for (int lf = 0; lf < nF; ++lf)
+            for (int i = 0; i < nT; ++i) ip.faceN[(size_t)lf * nT + i] = ip.faceN[(size_t)lf * nT + i] * (parcelsIn[i] / parcelsToInsert);
+    }
+    std::fill(ip.outFlux.begin(), ip.outFlux.end(), 0.0);  // uniGasFaceTracker::clean at the end of the step (uniGasCloud.C:864)
+}
+
 // ---------------------------------------------------------------------------------
 // uniGasLiouFangPressureInletPatch::controlParcelsAfterCollisions (…/uniGasLiouFangPressureInletPatch.C:126-174)
 void updateInletVelocities(ugfo_handle& h) {
@@ -1762,6 +1841,7 @@ void updateInletVelocities(ugfo_handle& h) {
     if (!h.occValid) buildOccupancy(h);
     for (InflowPatch& ip : h.inflows) {
         if (!ip.pressure) continue;
+        if (ip.massFlow) { updateMassFlowInlet(h, ip); continue; }
         if (ip.outlet) {  // …/uniGasLiouFangPressureOutletPatch.C:144-322
             ip.wangSteps += 1.0;
             for (int lf = 0; lf < h.pSize[ip.patch]; ++lf) {
@@ -2266,6 +2346,32 @@ int ugfo_set_pressure_inlet(ugfo_handle* h, int32_t patch, const ugf_pressure_in
     return 0;
 }
 
+int ugfo_set_mass_flow_inlet(ugfo_handle* h, int32_t patch, const ugf_pressure_inlet* pin, double massFlowRate, const double* initialVelocity) {
+    if (!(massFlowRate > 0.0) || !(pin->inletTemperature > 0.0)) return fail(h, "mass-flow-rate inlet needs a positive massFlowRate and inletTemperature");
+    if (pin->nTypeIds != h->nSpecies) return fail(h, "mass-flow-rate inlet: typeIds must list every species in typeIdList order");
+    for (int i = 0; i < pin->nTypeIds; ++i) if (pin->typeIds[i] != i) return fail(h, "mass-flow-rate inlet: typeIds must list every species in typeIdList order");
+    ugf_pressure_inlet q = *pin;
+    q.inletPressure = 0.0;  // no pressure in this model: the number densities come from the cells
+    if (int rc = ugfo_set_pressure_inlet(h, patch, &q)) return rc;
+    InflowPatch& ip = h->inflows.back();
+    const size_t nF = (size_t)h->pSize[patch];
+    ip.massFlow = true;
+    ip.massFlowRate = massFlowRate;
+    for (int i = 0; i < pin->nTypeIds; ++i) ip.molFrac[i] = 1.0;  // the count takes the per-species number densities as they are
+    double totalMass = 0.0;
+    for (int i = 0; i < pin->nTypeIds; ++i) totalMass += h->sp[i].mass * pin->moleFractions[i];
+    if (!(totalMass > 0.0)) { h->inflows.pop_back(); return fail(h, "mole fractions of the mass-flow-rate inlet sum to zero"); }
+    ip.patchArea = 0.0;
+    for (size_t lf = 0; lf < nF; ++lf) { const double* S = &h->Sf[3 * ((size_t)h->pStart[patch] + lf)]; ip.patchArea += std::sqrt(dot3(S, S)); }
+    ip.faceN.assign(nF * pin->nTypeIds, 0.0);
+    for (size_t lf = 0; lf < nF; ++lf) for (int k = 0; k < 3; ++k) ip.faceVel[3 * lf + k] = initialVelocity ? initialVelocity[k] : 0.0;
+    ip.outFlux.assign(nF * h->nSpecies, 0.0);
+    ip.mfMolFrac.assign(pin->moleFractions, pin->moleFractions + pin->nTypeIds);
+    h->patchFlux.assign(h->nPatches, -1);
+    for (size_t k = 0; k < h->inflows.size(); ++k) if (h->inflows[k].massFlow) h->patchFlux[h->inflows[k].patch] = (int)k;
+    return 0;
+}
+
 int ugfo_set_wang_pressure_inlet(ugfo_handle* h, int32_t patch, const ugf_pressure_inlet* pin) {
     const int rc = ugfo_set_pressure_inlet(h, patch, pin);
     if (rc) return rc;
@@ -2458,7 +2564,7 @@ namespace {
 constexpr double STATE_MAGIC = 1431783237.0;
 long long inletVelocityDoubles(const ugfo_handle* h) {
     long long n = 0;
-    for (const InflowPatch& ip : h->inflows) if (ip.pressure) n += (long long)ip.faceVel.size() + (ip.wang ? (long long)ip.wangSums.size() + 1 : 0) + (ip.outlet ? (long long)ip.faceN.size() + 2LL * (long long)ip.faceTtr.size() : 0);
+    for (const InflowPatch& ip : h->inflows) if (ip.pressure) n += (long long)ip.faceVel.size() + (ip.wang ? (long long)ip.wangSums.size() + 1 : 0) + (ip.outlet ? (long long)ip.faceN.size() + 2LL * (long long)ip.faceTtr.size() : 0) + (ip.massFlow ? (long long)ip.faceN.size() : 0);
     return n;
 }
 long long stateDoubles(const ugfo_handle* h) {
@@ -2491,6 +2597,7 @@ int ugfo_state_save(ugfo_handle* h, double* buf, int64_t nDoubles) {
     for (const InflowPatch& ip : h->inflows) {
         if (!ip.pressure) continue;
         p = std::copy(ip.faceVel.begin(), ip.faceVel.end(), p);
+        if (ip.massFlow) p = std::copy(ip.faceN.begin(), ip.faceN.end(), p);
         if (ip.wang) { p = std::copy(ip.wangSums.begin(), ip.wangSums.end(), p); *p++ = ip.wangSteps; }
         if (ip.outlet) {
             p = std::copy(ip.faceN.begin(), ip.faceN.end(), p);
@@ -2519,6 +2626,7 @@ int ugfo_state_load(ugfo_handle* h, const double* buf, int64_t nDoubles) {
     for (InflowPatch& ip : h->inflows) {
         if (!ip.pressure) continue;
         take(ip.faceVel);
+        if (ip.massFlow) take(ip.faceN);
         if (ip.wang) { take(ip.wangSums); ip.wangSteps = *p++; }
         if (ip.outlet) {
             take(ip.faceN);
@@ -2540,6 +2648,7 @@ int ugfo_finish_step(ugfo_handle* h) {
     relaxAll(*h);
     if (h->relaxFailed) return 1;
     updateInletVelocities(*h);
+    if (h->relaxFailed) return 1;
     accumulateFields(*h);
     decompose(*h);
     return ugfo_end_step(h);
@@ -2560,6 +2669,7 @@ int ugfo_step(ugfo_handle* h, int32_t nSteps) {
         relaxAll(*h);
         if (h->relaxFailed) return 1;
         updateInletVelocities(*h);
+        if (h->relaxFailed) return 1;
         accumulateFields(*h);
         decompose(*h);
         ugfo_end_step(h);

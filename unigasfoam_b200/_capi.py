@@ -156,6 +156,7 @@ SIGNATURES = {
     "set_pressure_inlet": (C.c_int, [H, i32, P(PressureInlet)]),
     "set_wang_pressure_inlet": (C.c_int, [H, i32, P(PressureInlet)]),
     "set_pressure_outlet": (C.c_int, [H, i32, P(PressureInlet)]),
+    "set_mass_flow_inlet": (C.c_int, [H, i32, P(PressureInlet), f64, P(f64)]),
     "download_inlet_velocity": (C.c_int, [H, i32, PF]),
     "upload_parcels": (C.c_int, [H, P(Parcels)]),
     "upload_cell_state": (C.c_int, [H, PF, PI32, PI32, PF]),

@@ -174,11 +174,11 @@ class UniGasCloud:
             self._check(self.api.set_macro_interpolation(self._h, C.byref(cp)))
         for entry in bd.get("uniGasGeneralBoundaries", []):
             word = entry["boundaryModel"]
-            if word not in ("uniGasFreeStreamInflowPatch", "uniGasChapmanEnskogFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch", "uniGasLiouFangPressureInletPatch",
-                            "uniGasWangPressureInletPatch", "uniGasLiouFangPressureOutletPatch"):
-                raise UgfError(f"general boundary model {word!r} is not supported (uniGasFreeStreamInflowPatch, "
-                               "uniGasFreeStreamInflowFieldPatch, uniGasLiouFangPressureInletPatch, uniGasWangPressureInletPatch, "
-                               "uniGasLiouFangPressureOutletPatch)")
+            known = ("uniGasFreeStreamInflowPatch", "uniGasChapmanEnskogFreeStreamInflowPatch", "uniGasFreeStreamInflowFieldPatch",
+                     "uniGasLiouFangPressureInletPatch", "uniGasWangPressureInletPatch", "uniGasLiouFangPressureOutletPatch",
+                     "uniGasMassFlowRateInletPatch")
+            if word not in known:
+                raise UgfError(f"general boundary model {word!r} is not supported ({', '.join(known)})")
             patch = self.mesh.patch_index(entry["generalBoundaryProperties"]["patch"])
             if self.mesh.patches[patch].size == 0:
                 continue  # a decomposed case: this rank holds no face of the patch
@@ -209,6 +209,18 @@ class UniGasCloud:
                 pout.inletTemperature = float(pr.get("initialOutletTemperature", 300.0))  # outletTemperature_ starts at 300 K (:74)
                 pout.theta = 1.0
                 self._check(self.api.set_pressure_outlet(self._h, patch, C.byref(pout)))
+                continue
+            if word == "uniGasMassFlowRateInletPatch":  # …/uniGasMassFlowRateInletPatch.C:53-125
+                pin = _capi.PressureInlet()
+                ids = [self.typeIdList.index(n) for n in pr["typeIds"]]
+                pin.nTypeIds = len(ids)
+                for i, t in enumerate(ids):
+                    pin.typeIds[i] = t
+                    pin.moleFractions[i] = float(pr["moleFractions"][self.typeIdList[t]])
+                pin.inletTemperature = float(pr["inletTemperature"])
+                pin.theta = float(pr.get("theta", 1.0))
+                v0 = self._f64(pr.get("initialVelocity", [0.0, 0.0, 0.0])).reshape(3)
+                self._check(self.api.set_mass_flow_inlet(self._h, patch, C.byref(pin), float(pr["massFlowRate"]), v0.ctypes.data_as(C.POINTER(C.c_double))))
                 continue
             if word in ("uniGasLiouFangPressureInletPatch", "uniGasWangPressureInletPatch"):  # …/uniGasLiouFangPressureInletPatch.C:54-103
                 pin = _capi.PressureInlet()

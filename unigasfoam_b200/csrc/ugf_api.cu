@@ -42,6 +42,8 @@ struct InflowHost {
     bool pressureInlet = false;
     bool wang = false;            // uniGasWangPressureInletPatch / pressure outlet: running sums per face, step count
     bool outlet = false;          // uniGasLiouFangPressureOutletPatch: number density and temperature per face follow the flow
+    bool massFlow = false;        // uniGasMassFlowRateInletPatch: number density and velocity per face follow the flow
+    double mfExpected = 0.0;      //   insertions the next step will make (device-computed, read back after every update)
     double wangSteps = 0.0;
     std::vector<double> accum1;   // per (face, species) slot: expected insertions per second at F_N = 1, CWF = 1
     std::vector<int> slotCell;    // owner cell of the slot's face
@@ -1304,6 +1306,7 @@ int ugf_set_patch_wall_fields(ugf_handle* h, int32_t patch, const double* T, con
 // deltaT and, with cell weighting, on the factor of each inlet face's cell (uniGasGeneralBoundary.C:154-165)
 static void recompute_inflow_bounds(ugf_handle* h) {
     for (InflowHost& f : h->inflows) {
+        if (f.massFlow) continue;  // bounded by the device-computed expectation instead (update_inlet_velocities)
         f.maxInsert = 0;
         for (size_t k = 0; k < f.accum1.size(); ++k) {
             const double w = h->cwfHost.empty() ? 1.0 : h->cwfHost[f.slotCell[k]];
@@ -1505,6 +1508,54 @@ int ugf_set_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inle
     return set_inflow_common(h, patch, &in, pin);
 }
 
+int ugf_set_mass_flow_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* pin, double massFlowRate, const double* initialVelocity) {
+    if (!h || !pin) return 1;
+    if (!(pin->theta >= 0.0 && pin->theta <= 1.0)) return fail(h, "Theta must be a value between 0 and 1");
+    if (!(massFlowRate > 0.0) || !(pin->inletTemperature > 0.0)) return fail(h, "mass-flow-rate inlet needs a positive massFlowRate and inletTemperature");
+    if (pin->nTypeIds != h->nSpecies) return fail(h, "mass-flow-rate inlet: typeIds must list every species in typeIdList order");
+    for (int i = 0; i < pin->nTypeIds; ++i) if (pin->typeIds[i] != i) return fail(h, "mass-flow-rate inlet: typeIds must list every species in typeIdList order");
+    if (h->hasProcessor) return fail(h, "mass-flow-rate inlet on a decomposed mesh is not supported (its patch-wide sums would need a reduction over the ranks)");
+    if (patch < 0 || patch >= h->nPatches || h->patchKind[patch] != UGF_PATCH_GENERIC) return fail(h, "mass-flow-rate inlet needs a patch of type patch");
+    double totalMass = 0.0;
+    for (int i = 0; i < pin->nTypeIds; ++i) totalMass += h->spHost[i].mass * pin->moleFractions[i];
+    if (!(totalMass > 0.0)) return fail(h, "mole fractions of the mass-flow-rate inlet sum to zero");
+    ugf_inflow in{};
+    in.nTypeIds = pin->nTypeIds;
+    for (int i = 0; i < pin->nTypeIds; ++i) { in.typeIds[i] = i; in.numberDensities[i] = 0.0; }  // inletNumberDensity_ starts at zero (:84-89)
+    in.translationalTemperature = in.rotationalTemperature = in.vibrationalTemperature = in.electronicTemperature = pin->inletTemperature;
+    ugf_pressure_inlet q = *pin;
+    for (int i = 0; i < pin->nTypeIds; ++i) q.moleFractions[i] = 1.0;  // the count takes the per-species number densities as they are
+    if (int rc = set_inflow_common(h, patch, &in, &q)) return rc;
+    InflowHost& f = h->inflows.back();
+    InflowDev& d = f.dev;
+    const size_t nF = (size_t)d.nFaces, nT = (size_t)d.nTypeIds;
+    double *dN, *dFlux, *dWork, *dTot;
+    if (dalloc(h, &dN, nF * nT) || dalloc(h, &dFlux, nF * (size_t)h->nSpecies) || dalloc(h, &dWork, nF * (nT + 1)) || dalloc(h, &dTot, 2)) return 1;
+    f.owned.push_back(dN); f.owned.push_back(dFlux); f.owned.push_back(dWork); f.owned.push_back(dTot);
+    CU(cudaMemsetAsync(dN, 0, sizeof(double) * nF * nT, h->stream));
+    CU(cudaMemsetAsync(dFlux, 0, sizeof(double) * nF * (size_t)h->nSpecies, h->stream));
+    CU(cudaMemsetAsync(dTot, 0, sizeof(double) * 2, h->stream));
+    std::vector<double> v0(3 * nF, 0.0);
+    if (initialVelocity) for (size_t lf = 0; lf < nF; ++lf) for (int k = 0; k < 3; ++k) v0[3 * lf + k] = initialVelocity[k];
+    if (upload(h, d.faceVel, v0.data(), v0.size())) return 1;
+    d.faceN = dN; d.outFlux = dFlux; d.mfWork = dWork; d.mfTotal = dTot;
+    d.massFlow = 1; d.massFlowRate = massFlowRate;
+    for (int i = 0; i < pin->nTypeIds; ++i) d.mfMolFrac[i] = pin->moleFractions[i];
+    d.patchArea = 0.0;
+    for (size_t lf = 0; lf < nF; ++lf) {
+        const double* S = &h->SfHost[3 * ((size_t)h->patchStart[patch] + lf)];
+        d.patchArea += std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+    }
+    f.massFlow = true;
+    f.mfExpected = 0.0;
+    f.maxInsert = (long long)f.nSlots + 2;
+    DevPatch& dp = h->patchesHost[patch];
+    dp.outFlux = dFlux;
+    CU(countedMemcpyAsync(h, h->dPatches + patch, &dp, sizeof(DevPatch), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int ugf_set_wang_pressure_inlet(ugf_handle* h, int32_t patch, const ugf_pressure_inlet* pin) {
     if (!h || !pin) return 1;
     if (pin->nTypeIds < 1 || pin->nTypeIds > UGF_MAX_SPECIES) return fail(h, "inflow typeIds out of range");
@@ -1546,6 +1597,21 @@ static int update_inlet_velocities(ugf_handle* h) {
         const DevParams prm = h->prm;
         const InflowDev dev = f.dev;
         ParcelBuf P = h->buf[h->cur];
+        if (f.massFlow) {
+            mass_flow_face_kernel<<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff, h->dVol, h->multi);
+            LAUNCHED();
+            mass_flow_scale_kernel<<<1, 256, 0, h->stream>>>(dev);
+            LAUNCHED();
+            // the next step's insertions are bounded by what the patch asks for: 16 bytes back to the host, once per step
+            double tot[2] = {0.0, 0.0};
+            CU(countedMemcpyAsync(h, tot, dev.mfTotal, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            if (tot[1] == 0.0)
+                return fail(h, "mass-flow-rate inlet: no parcels in the cells of the inlet patch (the reference's parcelsIn / parcelsToInsert is 0 / 0 here)");
+            f.mfExpected = tot[0];
+            f.maxInsert = (long long)std::ceil(std::max(tot[0], 0.0)) + f.nSlots + 2;
+            continue;
+        }
         if (f.outlet) {
             f.wangSteps += 1.0;  // nTimeSteps_ (…PressureOutletPatch.C:146)
             if (h->multi) outlet_state_kernel<true><<<grid_for(dev.nFaces, 128), 128, 0, h->stream>>>(prm, dev, P, h->dOff, h->dVol, f.wangSteps);
@@ -1946,7 +2012,7 @@ namespace {
 constexpr double STATE_MAGIC = 1431783237.0;  // "UGFS"
 long long inlet_velocity_doubles(const ugf_handle* h) {
     long long n = 0;
-    for (const InflowHost& f : h->inflows) if (f.pressureInlet) n += 3LL * f.dev.nFaces + (f.wang ? (long long)WANG_NSUM * f.dev.nFaces + 1 : 0) + (f.outlet ? (long long)f.nSlots + 2LL * f.dev.nFaces : 0);
+    for (const InflowHost& f : h->inflows) if (f.pressureInlet) n += 3LL * f.dev.nFaces + (f.wang ? (long long)WANG_NSUM * f.dev.nFaces + 1 : 0) + (f.outlet ? (long long)f.nSlots + 2LL * f.dev.nFaces : 0) + (f.massFlow ? (long long)f.nSlots : 0);
     return n;
 }
 long long state_doubles(const ugf_handle* h) {
@@ -1994,6 +2060,7 @@ int ugf_state_save(ugf_handle* h, double* buf, int64_t nDoubles) {
     for (const InflowHost& f : h->inflows) {
         if (!f.pressureInlet) continue;
         if (d2h(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+        if (f.massFlow && d2h(f.dev.faceN, (size_t)f.nSlots)) return 1;
         if (f.wang) { if (d2h(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; *p++ = f.wangSteps; }
         if (f.outlet && (d2h(f.dev.faceN, (size_t)f.nSlots) || d2h(f.dev.faceT, 2 * (size_t)f.dev.nFaces))) return 1;
     }
@@ -2032,7 +2099,24 @@ int ugf_state_load(ugf_handle* h, const double* buf, int64_t nDoubles) {
     if (h->decompOn) { if (h2d(h->dKnAcc, (KN_NACC + nS) * nC) || h2d(h->dKnK[h->knCur], 4 * nC)) return 1; }
     for (InflowHost& f : h->inflows) {
         if (!f.pressureInlet) continue;
+        const double* vL = p;
         if (h2d(f.dev.faceVel, 3 * (size_t)f.dev.nFaces)) return 1;
+        if (f.massFlow) {  // the insertion bound follows from the velocities and number densities just loaded: the slots' counts
+            const double* nD = p;
+            if (h2d(f.dev.faceN, (size_t)f.nSlots)) return 1;
+            double bound = 0.0;
+            for (int lf = 0; lf < f.dev.nFaces; ++lf)
+                for (int i = 0; i < f.dev.nTypeIds; ++i) {
+                    const double* S = &h->SfHost[3 * ((size_t)h->patchStart[f.patch] + lf)];
+                    const double fA = std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+                    const double cmp = std::sqrt(2.0 * kB * f.dev.Ttr / h->spHost[i].mass);
+                    const double w = h->cwfHost.empty() ? 1.0 : h->cwfHost[f.slotCell[(size_t)lf * f.dev.nTypeIds + i]];
+                    const double sCos = std::min(5.0, -(vL[3 * lf] * S[0] + vL[3 * lf + 1] * S[1] + vL[3 * lf + 2] * S[2]) / fA / cmp);
+                    bound += 1.000001 * fA * nD[(size_t)lf * f.dev.nTypeIds + i] * h->cfg.deltaT * cmp * (std::exp(-(sCos * sCos)) + std::sqrt(PI) * sCos * (1 + std::erf(sCos)))
+                             / (2.0 * std::sqrt(PI) * h->cfg.nParticle * w);
+                }
+            f.maxInsert = (long long)std::ceil(bound) + f.nSlots + 2;
+        }
         if (f.wang) { if (h2d(f.dev.wangSums, (size_t)WANG_NSUM * f.dev.nFaces)) return 1; f.wangSteps = *p++; }
         if (f.outlet && (h2d(f.dev.faceN, (size_t)f.nSlots) || h2d(f.dev.faceT, 2 * (size_t)f.dev.nFaces))) return 1;
     }

@@ -63,6 +63,7 @@ struct DevPatch {
     double alphaN, sigmaT, alphaR;  // CLL: normalAccommCoeff, tangentialAccommCoeff, rotEnergyAccommCoeff
     const double* faceT;            // *FieldPatch variants: boundaryT [size] / boundaryU [size*3] on this patch, else null
     const double* faceU;
+    double* outFlux;                // generic patch carrying a mass-flow-rate inlet: this step's parcelIdFlux [size*nSpecies], else null
 };
 
 struct DevParams {

@@ -44,6 +44,14 @@ struct InflowDev {
     int outlet;
     double capN, capT;
     int* err;
+    // uniGasMassFlowRateInletPatch: faceN / faceVel follow the flow (mass_flow_face_kernel, mass_flow_scale_kernel); parcels are
+    // inserted from a gas at rest (…MassFlowRateInletPatch.C:139-149).  mfWork [nFaces*(nTypeIds+1)]: per face the parcelsIn
+    // contribution of every species and the parcelsToInsert contribution; mfTotal [2]: expected insertions of the next step, ok flag
+    int massFlow;
+    double massFlowRate, patchArea, mfMolFrac[UGF_MAX_SPECIES];
+    double* outFlux;
+    double* mfWork;
+    double* mfTotal;
     const int* faceBfi;
     const int* faceCell;
     const double* geom;
@@ -131,7 +139,8 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
     const double Ttr = f.faceT ? f.faceT[2 * (size_t)face] : f.Ttr;
     const double Trot = f.faceT ? f.faceT[2 * (size_t)face + 1] : f.Trot;
     const double cmp = sqrt(2.0 * kB * Ttr / s.mass);
-    const double* vel = f.faceVel ? f.faceVel + 3 * (size_t)face : f.vel;
+    const double atRest[3] = {0.0, 0.0, 0.0};
+    const double* vel = f.massFlow ? atRest : (f.faceVel ? f.faceVel + 3 * (size_t)face : f.vel);
     const double vn = vel[0] * n[0] + vel[1] * n[1] + vel[2] * n[2];
     const double sCos = vn / cmp;
     const int tb = f.triOff[face], te = f.triOff[face + 1];
@@ -211,6 +220,88 @@ __global__ void __launch_bounds__(128) inflow_insert_kernel(const __grid_constan
             if (P.elev) P.elev[dst] = s.nElec > 1 ? (uint8_t)equipartition_elec_level(r, f.Tel, S, s.nElec) : (uint8_t)0;
         }
     }
+}
+
+// uniGasMassFlowRateInletPatch::controlParcelsAfterCollisions (…/uniGasMassFlowRateInletPatch.C:155-302), first half: per face
+// (one thread, cell-list order = the oracle's) the relaxed inlet velocity, the number density of every species from the parcels
+// in the cell, and the face's contributions to parcelsIn (per species) and parcelsToInsert.
+__global__ void __launch_bounds__(128) mass_flow_face_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ InflowDev f, ParcelBuf P,
+                                                             const int* __restrict__ off, const double* __restrict__ vol, bool multi) {
+    const int face = blockIdx.x * blockDim.x + threadIdx.x;
+    if (face >= f.nFaces) return;
+    const int nT = f.nTypeIds;
+    const int c = f.faceCell[face];
+    const double* g = f.geom + (size_t)face * INFLOW_GEOM;
+    const double fA = g[0];
+    const double nIn[3] = {g[1], g[2], g[3]};
+    const double nParticle = prm.nParticle, dt = prm.deltaT;
+    const double CWF = prm.cwf ? __ldg(&prm.cwf[c]) : 1.0;
+    const double RWFf = prm.axi ? __ldg(&prm.bfRwf[f.faceBfi[face]]) : 1.0;
+    double totalMass = 0.0;
+    for (int i = 0; i < nT; ++i) totalMass += prm.sp[f.typeIds[i]].mass * f.mfMolFrac[i];
+    double* work = f.mfWork + (size_t)face * (nT + 1);
+    for (int i = 0; i < nT; ++i) {
+        const double moleFlowRate = f.mfMolFrac[i] * (f.massFlowRate / totalMass);
+        double* fl = f.outFlux + (size_t)face * prm.nSpecies + i;
+        work[i] = moleFlowRate * dt * (fA / f.patchArea) / (nParticle * CWF * RWFf) + *fl / (CWF * RWFf);
+        *fl = 0.0;  // uniGasFaceTracker::clean at the end of the step (uniGasCloud.C:864)
+    }
+    double mom[3] = {0, 0, 0}, mass = 0.0;
+    double* nD = f.faceN + (size_t)face * nT;
+    for (int i = 0; i < nT; ++i) nD[i] = 0.0;
+    for (int j = off[c]; j < off[c + 1]; ++j) {
+        const int t = multi ? P.type[j] : 0;
+        const double pMass = nParticle * prm.sp[t].mass;
+        const double RWF = prm.axi ? axi_rwf(prm, P.y[j], P.z[j]) : 1.0;
+        nD[t] += 1.0;
+        mom[0] += pMass * CWF * RWF * P.ux[j]; mom[1] += pMass * CWF * RWF * P.uy[j]; mom[2] += pMass * CWF * RWF * P.uz[j];
+        mass += pMass * CWF * RWF;
+    }
+    double* v = f.faceVel + 3 * (size_t)face;
+    const double prev[3] = {v[0], v[1], v[2]};
+    double nv[3] = {0, 0, 0};
+    if (mass > VSMALL) for (int k = 0; k < 3; ++k) nv[k] = mom[k] / mass;
+    double nw[3];
+    for (int k = 0; k < 3; ++k) nw[k] = f.theta * nv[k] + (1.0 - f.theta) * prev[k];
+    if (nw[0] * nIn[0] + nw[1] * nIn[1] + nw[2] * nIn[2] < 0.0) for (int k = 0; k < 3; ++k) nw[k] = prev[k];
+    for (int k = 0; k < 3; ++k) v[k] = nw[k];
+    for (int i = 0; i < nT; ++i) nD[i] = nD[i] * nParticle * CWF * RWFf / vol[c];
+    double pti = 0.0;
+    const double sqrtPi = sqrt(PI);
+    for (int i = 0; i < nT; ++i) {
+        const double cmp = sqrt(2.0 * kB * f.Ttr / prm.sp[f.typeIds[i]].mass);
+        const double sCos = (nw[0] * nIn[0] + nw[1] * nIn[1] + nw[2] * nIn[2]) / cmp;
+        pti += (fA * nD[i] * dt * cmp * (exp(-(sCos * sCos)) + sqrtPi * sCos * (1 + erf(sCos)))) / (2.0 * sqrtPi * nParticle * CWF * RWFf);
+    }
+    work[nT] = pti;
+}
+
+// second half: the patch-wide sums in face order (one thread: the oracle's order, identical bits) and the scaling of the number
+// densities by parcelsIn / parcelsToInsert; mfTotal[0] = the insertions the next step will make, mfTotal[1] = 0 when the
+// reference's ratio is 0 / 0 (no parcel in any inlet cell)
+__global__ void mass_flow_scale_kernel(const __grid_constant__ InflowDev f) {
+    const int nT = f.nTypeIds;
+    if (blockIdx.x != 0) return;
+    __shared__ double sIn[UGF_MAX_SPECIES];
+    __shared__ double sTo;
+    if (threadIdx.x == 0) {
+        double pIn[UGF_MAX_SPECIES], pTo = 0.0;
+        for (int i = 0; i < nT; ++i) pIn[i] = 0.0;
+        for (int face = 0; face < f.nFaces; ++face) {
+            const double* work = f.mfWork + (size_t)face * (nT + 1);
+            for (int i = 0; i < nT; ++i) pIn[i] += work[i];
+        }
+        // parcelsToInsert_ += <slot count> adds to every species' total (scalarField += scalar): one total, species inside faces
+        for (int face = 0; face < f.nFaces; ++face) pTo += f.mfWork[(size_t)face * (nT + 1) + nT];
+        double tot = 0.0;
+        for (int i = 0; i < nT; ++i) { sIn[i] = pIn[i]; tot += pIn[i]; }
+        sTo = pTo;
+        f.mfTotal[0] = tot;
+        f.mfTotal[1] = pTo > 0.0 ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (!(sTo > 0.0)) return;
+    for (int s = threadIdx.x; s < f.nFaces * nT; s += blockDim.x) f.faceN[s] = f.faceN[s] * (sIn[s % nT] / sTo);
 }
 
 // uniGasLiouFangPressureInletPatch::controlParcelsAfterCollisions (…/uniGasLiouFangPressureInletPatch.C:126-174): the

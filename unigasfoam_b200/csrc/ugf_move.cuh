@@ -371,6 +371,20 @@ __device__ __forceinline__ void boundary_interaction(const DevParams& prm, const
         }
         atomicAdd(a.inflight, 1ull);
     } else if (pt.kind == UGF_PATCH_GENERIC) {
+        if (pt.outFlux) {  // uniGasFaceTracker::updateFields on the faces of a mass-flow-rate inlet (uniGasFaceTracker.C:98-141): sgn CWF RWF
+            double w = 1.0;
+            if (prm.cwf) {
+                if (a.useSfIn) w = a.wq[i];
+                else {
+                    const int c0 = a.P.cell[i];
+                    w = (prm.cwfDirty && i < a.newFrom) ? __ldg(&prm.cwfPrev[c0]) : __ldg(&prm.cwf[c0]);
+                }
+                if (prm.axi) w = w * axi_rwf(prm, st.x[1], st.x[2]);
+            }
+            const double4 pl = load_plane(&a.mesh.plane[hitSlot]);
+            const double un = st.U[0] * pl.x + st.U[1] * pl.y + st.U[2] * pl.z;
+            atomicAdd(&pt.outFlux[(size_t)(bfi - pt.startBfi) * prm.nSpecies + type], (un >= 0.0 ? 1.0 : -1.0) * w);
+        }
         st.cell = -1; st.flags |= HIT_DELETED;
     } else {
         st.cell = -1; st.flags |= HIT_STUCK;
