@@ -83,7 +83,8 @@ struct ugf_handle {
     bool hasVib = false, hasElec = false;   // some species has vibrational modes / more than one electronic level
     DevSpeciesInt* dSpi = nullptr;          // per-species tables of those modes (DevParams::spi)
     InterpDev interp{};                     // macroInterpolation geometry + work arrays (ugf_set_macro_interpolation)
-    Macro* dMacro = nullptr;
+    Macro* dMacro = nullptr;   // macroscopic state per cell (bgk_fields_kernel), allocated with the first relaxation
+    bool interpSet = false;    // ugf_set_macro_interpolation done
     std::vector<void*> interpOwned;
     double* dMomI = nullptr; double* dAccI = nullptr;  // [nCells][nSpecies][UGF_NINT] per-step sums / time accumulators of the internal modes
 
@@ -547,9 +548,10 @@ int run_bgk_kernel(ugf_handle* h) {
     a.step = (uint32_t)h->step;
     a.cnt = h->dCnt;
     const DevParams prm = h->prm;
+    if (h->cfg.macroInterpolation && !h->interpSet) return fail(h, "macroInterpolation true needs ugf_set_macro_interpolation");
+    if (!h->dMacro && dalloc(h, &h->dMacro, (size_t)h->nCells)) return 1;
+    a.macroCell = h->dMacro;
     if (h->cfg.macroInterpolation) {
-        if (!h->dMacro) return fail(h, "macroInterpolation true needs ugf_set_macro_interpolation");
-        a.macroCell = h->dMacro;
         a.ip = h->interp;
         bgk_fields_kernel<<<grid_for(h->nCells, 128), 128, 0, h->stream>>>(prm, a);
         LAUNCHED();
@@ -561,10 +563,12 @@ int run_bgk_kernel(ugf_handle* h) {
         h->argBytes += 3 * arg_bytes(prm, a);
         return 0;
     }
+    bgk_fields_kernel<<<grid_for(h->nCells, 128), 128, 0, h->stream>>>(prm, a);  // a.ip.cellF == null: the cells' state only
+    LAUNCHED();
     if (h->multi) bgk_kernel<true><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
     else bgk_kernel<false><<<h->bgkBlocks, BGK_THREADS, h->bgkSmem, h->stream>>>(prm, a);
     LAUNCHED();
-    h->argBytes += arg_bytes(prm, a);
+    h->argBytes += 2 * arg_bytes(prm, a);
     return 0;
 }
 
@@ -950,7 +954,7 @@ int ugf_destroy(ugf_handle* h) {
     void* ptrs[] = {h->dCfOff, h->dPlane, h->dNbr, h->dBfPatch, h->dBfOwner, h->dPatches, h->dVol, h->dBbMin, h->dBbMax, h->dBfS,
                     h->dSf, h->dN, h->dCellCount, h->dOff, h->dPerm, h->dBlockSums, h->dTotal, h->dMigCount, h->dMigBlock, h->dMigTotals, h->dMigList, h->dInflight, h->dRecvStart, h->dMigDone,
                     h->dMom, h->dAcc, h->dAccS, h->dBm, h->dBacc, h->dSigma, h->dCollId, h->dMaxProb, h->dQPrev, h->dSPrev, h->dKeyScratch, h->dOwner, h->dSubLevels, h->dSub,
-                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dMoveQD, h->dMoveQI, h->dSpi, h->dMomI, h->dAccI, h->dSlotTrack, h->dBfTrack, h->dFt};
+                    h->dCnt, h->dErr, h->dTot, h->dTask, h->dCwf[0], h->dCwf[1], h->dNclone, h->dWq, h->dRec2d, h->dMoveQD, h->dMoveQI, h->dSpi, h->dMomI, h->dAccI, h->dSlotTrack, h->dBfTrack, h->dFt, h->dMacro, h->dCellRwf, h->dBfRwf};
     for (void* p : ptrs) cudaFree(p);
     for (InflowHost& f : h->inflows) for (void* p : f.owned) cudaFree(p);
     for (double* p : h->packBuf) cudaFree(p);
@@ -1959,18 +1963,18 @@ int ugf_set_decomposition(ugf_handle* h, const ugf_decomposition* d) {
 
 int ugf_set_macro_interpolation(ugf_handle* h, const ugf_cell_point* cp) {
     if (!h || !h->meshSet || !cp) return fail(h, "mesh not set");
-    if (h->dMacro) return fail(h, "macro interpolation already set");
+    if (h->interpSet) return fail(h, "macro interpolation already set");
     if (h->hasProcessor) return fail(h, "macroInterpolation on a decomposed mesh is not supported (point values across processor patches need a halo)");
     CU(cudaSetDevice(h->cfg.device));
     const size_t nC = (size_t)h->nCells, nP = (size_t)cp->nPoints, nT = (size_t)cp->tetOffsets[nC], nW = (size_t)cp->pointCellOffsets[nP];
     double *dPts = nullptr, *dW = nullptr, *dNrm = nullptr, *dCc = nullptr, *dCellF = nullptr, *dPointF = nullptr;
     int *dTo = nullptr, *dTp = nullptr, *dPo = nullptr, *dPc = nullptr;
     if (dalloc(h, &dPts, 3 * nP) || dalloc(h, &dW, nW) || dalloc(h, &dNrm, 3 * nP) || dalloc(h, &dCc, 3 * nC) || dalloc(h, &dCellF, nC * NIF) ||
-        dalloc(h, &dPointF, nP * NIF) || dalloc(h, &dTo, nC + 1) || dalloc(h, &dTp, 3 * nT) || dalloc(h, &dPo, nP + 1) || dalloc(h, &dPc, nW) ||
-        dalloc(h, &h->dMacro, nC))
+        dalloc(h, &dPointF, nP * NIF) || dalloc(h, &dTo, nC + 1) || dalloc(h, &dTp, 3 * nT) || dalloc(h, &dPo, nP + 1) || dalloc(h, &dPc, nW))
         return 1;
-    for (void* p : {(void*)dPts, (void*)dW, (void*)dNrm, (void*)dCc, (void*)dCellF, (void*)dPointF, (void*)dTo, (void*)dTp, (void*)dPo, (void*)dPc, (void*)h->dMacro})
+    for (void* p : {(void*)dPts, (void*)dW, (void*)dNrm, (void*)dCc, (void*)dCellF, (void*)dPointF, (void*)dTo, (void*)dTp, (void*)dPo, (void*)dPc})
         h->interpOwned.push_back(p);
+    h->interpSet = true;
     if (upload(h, dPts, cp->points, 3 * nP) || upload(h, dW, cp->pointWeights, nW) || upload(h, dNrm, cp->pointNormals, 3 * nP) ||
         upload(h, dCc, h->ccHost.data(), 3 * nC) || upload(h, dTo, cp->tetOffsets, nC + 1) || upload(h, dTp, cp->tetPoints, 3 * nT) ||
         upload(h, dPo, cp->pointCellOffsets, nP + 1) || upload(h, dPc, cp->pointCells, nW))

@@ -265,9 +265,11 @@ __global__ void __launch_bounds__(128) bgk_fields_kernel(const __grid_constant__
     Macro m;
     bgk_macro(prm, cell_fn(prm, cell), a.mom + (size_t)cell * prm.nSpecies * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
     a.macroCell[cell] = m;
-    double f[NIF];
-    macro_to_fields(m, f);
-    for (int k = 0; k < NIF; ++k) a.ip.cellF[(size_t)cell * NIF + k] = f[k];
+    if (a.ip.cellF) {  // macroInterpolation: the fields the cell -> point interpolation takes
+        double f[NIF];
+        macro_to_fields(m, f);
+        for (int k = 0; k < NIF; ++k) a.ip.cellF[(size_t)cell * NIF + k] = f[k];
+    }
 }
 
 __global__ void __launch_bounds__(128) bgk_points_kernel(const __grid_constant__ InterpDev ip) {
@@ -341,6 +343,7 @@ struct BgkWarpSmem {
     double E[BGK_CHUNK];
     double pU[BGK_CHUNK][3];
     double fscale[BGK_CHUNK];  // < 0: no rescale
+    unsigned long long thr[BGK_CHUNK];  // parcels of the cell with key < thr relax
     int nRel[BGK_CHUNK];
     int raised[BGK_CHUNK];
     int active[BGK_CHUNK];
@@ -448,7 +451,6 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
     const int wib = threadIdx.x >> 5;
     BgkWarpSmem& S = reinterpret_cast<BgkWarpSmem*>(smemRaw)[wib];
     const int warpsTotal = gridDim.x * BGK_WARPS;
-    const int nS = prm.nSpecies;
     const int model = prm.bgkModel;
     const bool envelope = (model == UGF_BGK_SBGK || model == UGF_BGK_USP_SBGK);
     const int nChunks = (a.nCells + BGK_CHUNK - 1) / BGK_CHUNK;
@@ -463,9 +465,8 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
         double Eold = 1.0;
         if (lane < nc) {
             const int cell = c0 + lane;
-            Macro m;
-            if (INTERP) m = a.macroCell[cell];
-            else bgk_macro(prm, cell_fn(prm, cell), a.mom + (size_t)cell * nS * UGF_NMOM, a.vol[cell], a.qPrev + 3 * (size_t)cell, a.sPrev + 6 * (size_t)cell, m);
+            // calculateProperties ran in bgk_fields_kernel (one thread per cell, all lanes busy; here a chunk has BGK_CHUNK cells)
+            const Macro m = a.macroCell[cell];
             if (envelope) Eold = a.maxProb[cell];
             const bool act = a.collModelId[cell] == 0 && m.perform;
             S.mac[lane] = m;
@@ -501,12 +502,16 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
             if (lane <= k) S.cb[lane] = cbv;
             __syncwarp();
             // ---- B: stage velocities, cell slot of every parcel, selection keys ----------------------------------------
+            for (int f = lane; f < ntot; f += 32) {  // all copies of the run in flight while the keys below are drawn
+                cp_async8(&S.u[0][f], &a.P.ux[b0 + f]);
+                cp_async8(&S.u[1][f], &a.P.uy[b0 + f]);
+                cp_async8(&S.u[2][f], &a.P.uz[b0 + f]);
+            }
             for (int f = lane; f < ntot; f += 32) {
                 int g = 0;
 #pragma unroll
                 for (int t = 1; t < BGK_CHUNK; ++t) g += (t < k && S.cb[t] <= f) ? 1 : 0;
                 S.cellOf[f] = (unsigned char)g;
-                S.u[0][f] = a.P.ux[b0 + f]; S.u[1][f] = a.P.uy[b0 + f]; S.u[2][f] = a.P.uz[b0 + f];
                 if (MULTI) S.type[f] = a.P.type[b0 + f];
                 if (S.nRel[done + g] > 0) {
                     // ordering by (u01, index) == ordering by the uniform's 53-bit integer with the index appended
@@ -515,22 +520,55 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                     S.key[f] = (r.u53() << 8) | (unsigned long long)(f - S.cb[g]);
                 }
             }
+            cp_async_wait_all();
             __syncwarp();
             // ---- C: the nRel smallest keys of every cell, compacted over the run ---------------------------------------
+            // BGK_LPC lanes per cell find the cell's threshold key by extracting minima (nRel of them) or maxima (N - nRel of
+            // them), whichever is fewer: nRel N / BGK_LPC compares per cell instead of the N^2 of a rank count.  Keys are unique
+            // within a cell (the slot index is part of the key).
+            {
+                const int g = lane / BGK_LPC, q = lane % BGK_LPC;
+                const bool on = g < k;
+                const int nRel = on ? S.nRel[done + g] : 0;
+                const int cb = on ? S.cb[g] : 0, ce = on ? S.cb[g + 1] : 0;
+                const int N = ce - cb;
+                const bool fromBelow = nRel <= N - nRel;
+                int rounds = (nRel <= 0 || nRel >= N) ? 0 : (fromBelow ? nRel : N - nRel);
+                int maxRounds = rounds;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) maxRounds = max(maxRounds, __shfl_xor_sync(0xffffffffu, maxRounds, o));
+                unsigned long long prev = 0ull;
+                for (int rd = 0; rd < maxRounds; ++rd) {
+                    unsigned long long best = fromBelow ? ~0ull : 0ull;
+                    if (rd < rounds) {
+                        for (int i = cb + q; i < ce; i += BGK_LPC) {
+                            const unsigned long long kk = S.key[i];
+                            if (fromBelow) { if ((rd == 0 || kk > prev) && kk < best) best = kk; }
+                            else { if ((rd == 0 || kk < prev) && kk > best) best = kk; }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 1; o < BGK_LPC; o <<= 1) {
+                        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                        best = fromBelow ? (other < best ? other : best) : (other > best ? other : best);
+                    }
+                    if (rd < rounds) prev = best;
+                }
+                if (on && q == 0) {
+                    unsigned long long thr = 0ull;               // nRel == 0: nobody
+                    if (nRel >= N && nRel > 0) thr = ~0ull;      // everybody
+                    else if (rounds > 0) thr = fromBelow ? prev + 1ull : prev;  // key <= nRel-th smallest  /  key < (N - nRel)-th largest
+                    S.thr[g] = thr;
+                }
+            }
+            __syncwarp();
             int nSel = 0;
             for (int base = 0; base < ntot; base += 32) {
                 const int f = base + lane;
                 bool sel = false;
                 if (f < ntot) {
                     const int g = S.cellOf[f];
-                    const int nRel = S.nRel[done + g];
-                    if (nRel > 0) {
-                        const int cb = S.cb[g], ce = S.cb[g + 1];
-                        const unsigned long long kj = S.key[f];
-                        int rank = 0;
-                        for (int i = cb; i < ce; ++i) rank += S.key[i] < kj;
-                        sel = rank < nRel;
-                    }
+                    if (S.nRel[done + g] > 0) sel = S.key[f] < S.thr[g];
                 }
                 const unsigned sm = __ballot_sync(0xffffffffu, sel);
                 if (sel) S.sel[nSel + __popc(sm & ((1u << lane) - 1u))] = (unsigned short)f;

@@ -270,16 +270,6 @@ constexpr int CELL_CAP = 128;    // parcels staged per warp; larger cells take t
 constexpr int CELL_ITERS = CELL_CAP / 32;
 constexpr int CELL_LPC = 32 / CELL_CHUNK;  // lanes cooperating on one cell in the moment phase (4)
 
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 __device__ __forceinline__ double select4(int q, double v0, double v1, double v2, double v3) {
     const double lo = (q & 1) ? v1 : v0;
     const double hi = (q & 1) ? v3 : v2;
