@@ -77,7 +77,7 @@ struct BgkArgs {
     InterpDev ip;
 };
 
-struct Macro {
+struct alignas(16) Macro {
     bool perform;
     double N, rhoN, p, T, U[3], q[3], s[6], P[6], Pr, nu, rhoNX, rhoMX;
 };
@@ -336,8 +336,8 @@ __device__ __noinline__ void interpolate_macro(const InterpDev& ip, const double
     for (int k = 0; k < 6; ++k) { m.s[k] = f[10 + k]; m.P[k] = f[16 + k]; }
 }
 
-struct BgkWarpSmem {
-    Macro mac[BGK_CHUNK];
+struct alignas(16) BgkWarpSmem {
+    Macro macBuf[2][BGK_CHUNK];  // the chunk's macroscopic states; the next chunk's are copied in while this one is processed
     double u[3][BGK_CAP];
     unsigned long long key[BGK_CAP];  // selection key: the uniform's 53 random bits << 8 | slot in the run's cell-local order
     double E[BGK_CHUNK];
@@ -456,20 +456,44 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
     const int nChunks = (a.nCells + BGK_CHUNK - 1) / BGK_CHUNK;
     int myRel = 0;
 
-    for (int chunk = blockIdx.x * BGK_WARPS + wib; chunk < nChunks; chunk += warpsTotal) {
+    // The per-chunk inputs (CSR offsets, model id, envelope, macroscopic states) of the NEXT chunk are requested while the current
+    // one is processed: offsets / id / envelope into registers, the states by cp.async into the other half of macBuf.
+    auto request = [&](int chunkP, int buf, int& offR, int& idR, double& eR) {
+        offR = 0x7fffffff; idR = 1; eR = 1.0;
+        if (chunkP >= nChunks) return;
+        const int c0p = chunkP * BGK_CHUNK;
+        const int ncp = min(BGK_CHUNK, a.nCells - c0p);
+        if (lane <= ncp) offR = a.off[c0p + lane];
+        if (lane < ncp) {
+            idR = a.collModelId[c0p + lane];
+            if (envelope) eR = a.maxProb[c0p + lane];
+        }
+        constexpr int PER = (int)(sizeof(Macro) / 16);
+        const char* src = reinterpret_cast<const char*>(a.macroCell + c0p);
+        char* dst = reinterpret_cast<char*>(&S.macBuf[buf][0]);
+        for (int t = lane; t < ncp * PER; t += 32) cp_async16(dst + 16 * t, src + 16 * t);
+    };
+    int offR, idR;
+    double eR;
+    int cur = 0;
+    request(blockIdx.x * BGK_WARPS + wib, cur, offR, idR, eR);
+
+    for (int chunk = blockIdx.x * BGK_WARPS + wib; chunk < nChunks; chunk += warpsTotal, cur ^= 1) {
         const int c0 = chunk * BGK_CHUNK;
         const int nc = min(BGK_CHUNK, a.nCells - c0);
-        const int offv = (lane <= nc) ? a.off[c0 + lane] : 0x7fffffff;
+        const int offv = offR;
+        const int myId = idR;
+        double Eold = eR;
+        cp_async_wait_all();
+        __syncwarp();
+        Macro* const mac = S.macBuf[cur];
+        request(chunk + warpsTotal, cur ^ 1, offR, idR, eR);
         const int offNext = __shfl_down_sync(0xffffffffu, offv, 1);
-        // ---- A: macroscopic state and relaxing count, one cell per lane ------------------------------------------------
-        double Eold = 1.0;
+        // ---- A: relaxing count, one cell per lane (calculateProperties ran in bgk_fields_kernel, one thread per cell) -----------
         if (lane < nc) {
             const int cell = c0 + lane;
-            // calculateProperties ran in bgk_fields_kernel (one thread per cell, all lanes busy; here a chunk has BGK_CHUNK cells)
-            const Macro m = a.macroCell[cell];
-            if (envelope) Eold = a.maxProb[cell];
-            const bool act = a.collModelId[cell] == 0 && m.perform;
-            S.mac[lane] = m;
+            const Macro& m = mac[lane];
+            const bool act = myId == 0 && m.perform;
             S.E[lane] = Eold;
             S.raised[lane] = 0;
             S.active[lane] = act ? 1 : 0;
@@ -487,7 +511,7 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                 if ((activeMask >> done) & 1u) {
                     double E = S.E[done];
                     int rs = 0;
-                    bgk_giant_cell<MULTI, INTERP>(prm, a, c0 + done, b0, n, S.mac[done], S.nRel[done], E, rs, myRel, lane);
+                    bgk_giant_cell<MULTI, INTERP>(prm, a, c0 + done, b0, n, mac[done], S.nRel[done], E, rs, myRel, lane);
                     __syncwarp();
                     if (lane == 0) { S.E[done] = E; if (rs) S.raised[done] = 1; }
                     __syncwarp();
@@ -582,7 +606,7 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                 const int f = mine0 ? S.sel[t] : 0;
                 const int g = S.cellOf[f];
                 const int cl = done + g;
-                const Macro& mc = S.mac[cl];
+                const Macro& mc = mac[cl];
                 const double mass = MULTI ? prm.sp[S.type[f]].mass : prm.sp[0].mass;
                 Macro mi;
                 if (INTERP && mine0) {  // target state at the parcel's position instead of the cell's (…USP.C:936-947)
@@ -647,7 +671,7 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                     mz += __shfl_xor_sync(0xffffffffu, mz, o);
                 }
                 if (cellOn && q == 0) {
-                    const Macro& m = S.mac[cl];
+                    const Macro& m = mac[cl];
                     const double pU[3] = {mx / m.rhoMX, my / m.rhoMX, mz / m.rhoMX};
                     const double postT = m.N / (3.0 * (m.N - 1.0) * kB * m.rhoNX) * (keX - m.rhoMX * (pU[0] * pU[0] + pU[1] * pU[1] + pU[2] * pU[2]));
                     S.pU[g][0] = pU[0]; S.pU[g][1] = pU[1]; S.pU[g][2] = pU[2];
@@ -663,7 +687,7 @@ __global__ void __launch_bounds__(BGK_THREADS) bgk_kernel(const __grid_constant_
                 double u = S.u[0][f], vv = S.u[1][f], w = S.u[2][f];
                 const double fs = S.fscale[g];
                 if (fs >= 0.0) {
-                    const Macro& m = S.mac[cl];
+                    const Macro& m = mac[cl];
                     u = m.U[0] + (u - S.pU[g][0]) * fs;
                     vv = m.U[1] + (vv - S.pU[g][1]) * fs;
                     w = m.U[2] + (w - S.pU[g][2]) * fs;
