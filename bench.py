@@ -465,10 +465,11 @@ def main():
         dom = max(kb, key=lambda k: kb[k][1])
         ach = kb[dom][0] / (kb[dom][1] * 1e-3) / 1e9
         step_bytes = B_ALG_PARCEL * n_parcels + B_ALG_CELL * nC
-        tkey = {"move_kernel": "move_stream_kernel", "cell_kernel": "cell_kernel"}.get(dom)
+        tkeys = {"move_kernel": ("move_stream2_kernel", "move_stream_kernel"), "cell_kernel": ("cell_kernel",)}.get(dom, ())
+        tval = next((traffic[k] for k in tkeys if k in traffic), None)
         roofline = {
-            "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": traffic.get(tkey) if default_workload else None, "traffic_source": traffic.get("source") if default_workload else None,
+            "bound": "hbm", "kernel": {"move_kernel": "move_stream2_kernel (phase: move)"}.get(dom, dom), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": tval if default_workload else None, "traffic_source": traffic.get("source") if default_workload else None,
             "peak_source": peak_src,
             "per_kernel": {k: {"ms": v[1], "alg_bytes": v[0], "GBps": v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else None} for k, v in kb.items()},
             "phase_ms": phases,
