@@ -208,7 +208,7 @@ def run_reference(args, rank, world):
 class Runner:
     """One decomposed (or single) case on this rank's GPU: cloud, exchanger, stepping, device timing."""
 
-    def __init__(self, case, args, rank, world, local, meta, inflow, capacity_factor=1.5):
+    def __init__(self, case, args, rank, world, local, meta, inflow, capacity_factor=1.5, extra_rounds=0):
         import torch
         import torch.distributed as dist
         from unigasfoam_b200.cloud import UniGasCloud
@@ -239,7 +239,7 @@ class Runner:
                 self.ex = PeerExchanger(cloud, case.mesh, rank, world, slot_capacity=slot_cap, group=None, meta_group=meta)
             # rounds this decomposition needs per step, measured with the exact termination rule over a few steps
             need = 1
-            for _ in range(3):
+            for _ in range(5):
                 if inflow:
                     cloud.controlBeforeMove()
                 cloud.move()
@@ -252,7 +252,7 @@ class Runner:
             # a block decomposition with corners (more than two processor patches per rank) now and then needs one round more than
             # three probe steps show (a parcel crossing an edge of the block late in its track): one round of margin there
             n_proc = sum(1 for p in case.mesh.patches if p.kind == "processor")
-            self.fixed_rounds = need + (1 if n_proc > 2 else 0)
+            self.fixed_rounds = need + (1 if n_proc > 2 else 0) + extra_rounds
 
     def step(self, n):
         from unigasfoam_b200.exchange import evolve_distributed
@@ -332,7 +332,22 @@ def other_config(name, args, rank, world, local, meta, peak):
                  f"({world} of the 8 blocks of the 500 M-parcel case: 4 along the body x 2 in azimuth)")
         bpp = B_ALG_PARCEL_ROT
     t_case = time.perf_counter() - t0
-    run = Runner(case, args, rank, world, local, meta, inflow=True, capacity_factor=1.6)
+    # The fixed number of transfer rounds is measured over a few probe steps; a developing flow can need one more later (parcels
+    # crossing a block corner in three transfers).  The lagged quiescence check catches that on every rank at once: the
+    # configuration is then rerun from its initial state with a round more, never reported with parcels left behind.
+    last = None
+    for extra in range(3):
+        try:
+            return _other_config_run(case, label, bpp, t_case, extra, args, rank, world, local, meta, peak)
+        except RuntimeError as e:
+            if "transfer rounds" not in str(e):
+                raise
+            last = e
+    raise last
+
+
+def _other_config_run(case, label, bpp, t_case, extra_rounds, args, rank, world, local, meta, peak):
+    run = Runner(case, args, rank, world, local, meta, inflow=True, capacity_factor=1.6, extra_rounds=extra_rounds)
     try:
         nC = case.mesh.n_cells
         before = run.totals()

@@ -33,6 +33,8 @@ def api():
 
 
 class OracleCloud(UniGasCloud):
+    migrate_buffers = "host"
+
     def __init__(self, *a, **kw):
         kw["api"] = api()
         super().__init__(*a, **kw)

@@ -56,6 +56,8 @@ def _lookup(table, word, key):
 
 
 class UniGasCloud:
+    migrate_buffers = "device"   # ugf_migrate_pack hands out device pointers (the oracle's are host pointers)
+
     def __init__(self, mesh, uniGasProperties, boundariesDict=None, deltaT=None, *, api=None, device=0,
                  seed=20261017, parcelCapacity=None, sampleInterval=1, measureWalls=True, rank=0, nRanks=1):
         self.api = api if api is not None else _capi.libugf()

@@ -369,7 +369,9 @@ class LocalSubdomains:
     """All subdomains of a decomposed case inside ONE process: the transfer loop of Cloud::move between clouds that live in
     the same address space (host pointers), with the exact termination rule.  Used by bench.py's reference arm - the CPU
     restatement of an N-rank run on the host's cores, where a process per rank would only split the same cores - and by CPU
-    tests of the per-rank block builders.  clouds[r] / meshes[r] = rank r."""
+    tests of the per-rank block builders; with libugf clouds: all subdomains on ONE GPU (one handle each), which runs the
+    processor-patch path of the move, the pack / unpack kernels and the resumed tracks without a second device.
+    clouds[r] / meshes[r] = rank r."""
 
     def __init__(self, clouds, meshes):
         self.clouds, self.meshes = clouds, meshes
@@ -403,11 +405,16 @@ class LocalSubdomains:
         packed = []
         for r, pi, peer, qi in self.links:  # pack everything first: a parcel received in this round waits for the next one
             buf, n = self.clouds[r].migratePack(pi)
-            if n:
+            if n and getattr(self.clouds[r], "migrate_buffers", "host") == "device":
+                # libugf clouds on one GPU: the packed records stay in the sender's device buffer (valid until its next pack on
+                # that patch, i.e. the next round) and the receiver reads them from there
+                packed.append((peer, qi, buf, n))
+            elif n:
                 rec = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(n * STRIDE,)).copy()
                 packed.append((peer, qi, rec, n))
         for peer, qi, rec, n in packed:
-            self.clouds[peer].migrateUnpack(qi, rec.ctypes.data_as(C.POINTER(C.c_double)), n)
+            ptr = rec if not isinstance(rec, np.ndarray) else rec.ctypes.data_as(C.POINTER(C.c_double))
+            self.clouds[peer].migrateUnpack(qi, ptr, n)
         for cl in self.clouds:
             cl.moveReceived()
         return total
