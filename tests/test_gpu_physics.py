@@ -27,18 +27,19 @@ def run(cloud_cls, seed, warm=160, **kw):
     return case, windows, cl.counters()
 
 
-def rows(windows, key, comp=None):
-    """[K, NY]: per window the profile over y (mean along the homogeneous direction)."""
+def rows(windows, key, comp=None, shape=(NY, NX)):
+    """[K, rows]: per window the profile over the slow mesh index (mean along the fast one: the homogeneous direction of the
+    Couette cases, the circumference of the cylinder case)."""
     a = np.stack([w[key] if comp is None else w[key][:, comp] for w in windows])
-    return a.reshape(K, NY, NX).mean(2)
+    return a.reshape(K, shape[0], shape[1]).mean(2)
 
 
-def gate(name, wg, wr, key, comp=None, rel=0.01):
+def gate(name, wg, wr, key, comp=None, rel=0.01, shape=(NY, NX)):
     """The north-star gate for one sampled field: the domain means agree within 3 sigma of their standard error and within `rel`
     (antisymmetric fields, rel None: 3 sigma only); row by row the two profiles agree within the standard error of the rows - with
     2 (K - 1) = 18 degrees of freedom behind every sigma, 0.8 % of identical samplers' rows fall outside 3 sigma, so the bound on
     single rows among the 32 is 4.5 sigma, with at most one row in ten beyond 3."""
-    rg, rr = rows(wg, key, comp), rows(wr, key, comp)
+    rg, rr = rows(wg, key, comp, shape), rows(wr, key, comp, shape)
     mg, mr = rg.mean(0), rr.mean(0)
     sigma = np.sqrt(rg.var(0, ddof=1) / K + rr.var(0, ddof=1) / K)
     z = np.abs(mg - mr) / sigma
@@ -91,6 +92,54 @@ def test_bgk_couette_fields_within_3_sigma_and_1_percent(GpuCloud, OracleCloud):
     _, wr, cr = run(OracleCloud, seed=404, **kw)
     assert cg["bgkRelaxations"] > 1000 and cr["bgkRelaxations"] > 1000 and cg["stuck"] == 0
     all_gates(case, wg, wr, None)
+
+
+def test_nitrogen_larsen_borgnakke_couette_fields(GpuCloud, OracleCloud):
+    """The gate on the Larsen-Borgnakke path: nitrogen Couette flow, rotational temperature included."""
+    kw = dict(Kn=0.2, species=("N2", cases.NITROGEN), binary="LarsenBorgnakkeVariableHardSphere")
+    case, wg, cg = run(GpuCloud, seed=505, **kw)
+    _, wr, cr = run(OracleCloud, seed=606, **kw)
+    assert cg["collisions"] > 100 and cg["stuck"] == 0
+    all_gates(case, wg, wr, None)
+    gate("rotationalT", wg, wr, "rotationalT")
+    gate("overallT", wg, wr, "overallT")
+    # viscous heating reaches the rotational mode through the collisions: T_rot in the core well above the wall temperature
+    assert rows(wg, "rotationalT").mean(0)[NY // 2] > 1.05 * case.meta["Tw"]
+
+
+def test_cylinder_inflow_outflow_fields(GpuCloud, OracleCloud):
+    """The gate on an open flow: Mach-10 argon past the cylinder (free-stream inflow, deleting outflow, diffuse body) while the
+    bow shock forms, sector profiles (mean over the radius per azimuthal index) of n, U, T, p and the body's wall sums.  The flow
+    is not stationary over the windows: their scatter then contains the drift as well, which only widens sigma."""
+    nr, nth = 24, 48
+
+    def go(cloud_cls, seed):
+        case = cases.cylinder(nr=nr, ntheta=nth, ppc=40, seed=3)
+        cl = case.make_cloud(cloud_cls, seed=seed, parcelCapacity=4 * case.n_parcels)
+        cl.evolve(60)
+        cl.fields(resetAtOutput=True)
+        w = []
+        for _ in range(K):
+            cl.evolve(40)
+            w.append(cl.fields(resetAtOutput=True))
+        return case, w, cl.counters()
+
+    case, wg, cg = go(GpuCloud, 707)
+    _, wr, cr = go(OracleCloud, 808)
+    assert cg["stuck"] == 0 and cg["inserted"] > 0 and cg["deleted"] > 0
+    assert case.mesh.shape[:2] == (nr, nth)
+    shape = (nth, nr)  # cell index = i_r + nr * i_theta: rows = theta sectors
+    for name, key, comp, rel in (("rhoN", "rhoN", None, 0.01), ("Ux", "UMean", 0, 0.01), ("Uy", "UMean", 1, None), ("translationalT", "translationalT", None, 0.01),
+                                 ("p", "p", None, 0.01)):
+        gate(name, wg, wr, key, comp, rel=rel, shape=shape)
+    nI = case.mesh.n_internal
+    p = case.mesh.patches[case.mesh.patch_index("cylinder")]
+    sl = slice(p.start - nI, p.start - nI + p.size)
+    for key in ("wall_p", "surfaceHeatTransfer", "surfaceShearStress"):
+        a = np.array([w[key][sl].mean() for w in wg]); b = np.array([w[key][sl].mean() for w in wr])
+        sigma = np.sqrt(a.var(ddof=1) / K + b.var(ddof=1) / K)
+        assert abs(a.mean() - b.mean()) < 3.0 * sigma, (key, a.mean(), b.mean(), sigma)
+    assert np.mean([w["surfaceHeatTransfer"][sl].mean() for w in wg]) > 0  # the Mach-10 stream heats the body
 
 
 def test_equilibrium_collision_rate_on_gpu(GpuCloud):
