@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, steps, out, slots):
+def _worker(rank, world, port, steps, out, slots, tail=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle.oracle_cloud import OracleCloud
@@ -29,13 +29,17 @@ def _worker(rank, world, port, steps, out, slots):
     case = cases.couette(nx=12, ny=8, ppc=12, rank=rank, n_ranks=world, binary="noDSMCCollision")
     for e in case.boundariesDict["uniGasPatchBoundaries"]:
         e["boundaryModel"] = "uniGasSpecularWallPatch"
-    case.deltaT *= 6.0  # several cells per step: parcels cross slabs, some wrap around the periodic end
+    case.deltaT *= 40.0 if tail else 6.0  # several cells per step: parcels cross slabs, some wrap around the periodic end (tail: a whole slab and more)
     cl = case.make_cloud(OracleCloud, parcelCapacity=4 * case.n_parcels, rank=rank, nRanks=world)
     ex = SlotExchanger(cl, case.mesh, rank, world, slot_capacity=600, cuda=False) if slots else Exchanger(cl, case.mesh, rank, world, cuda=False)
     n0 = torch.tensor([cl.size()])
     dist.all_reduce(n0)
-    evolve_distributed(cl, ex, steps, fixed_rounds=2 if slots else None)
-    if slots:
+    if tail:  # one unsynchronised round (not enough here: some parcels wrap through two patches), then the exact tail
+        evolve_distributed(cl, ex, steps, fixed_rounds=1, exact_tail=True)
+        assert ex.tail_rounds > 0
+    else:
+        evolve_distributed(cl, ex, steps, fixed_rounds=2 if slots else None)
+    if slots and not tail:
         ex.check_settled()
     p = cl.parcels()
     n1 = torch.tensor([cl.size()])
@@ -52,11 +56,11 @@ def _worker(rank, world, port, steps, out, slots):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("slots", [False, True], ids=["exact-count", "fixed-slot"])
+@pytest.mark.parametrize("slots", [False, True, "tail"], ids=["exact-count", "fixed-slot", "fixed-slot-exact-tail"])
 def test_two_rank_migration_matches_single_domain(tmp_path, OracleCloud, slots):
     world, steps = 2, 5
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(world, _free_port(), steps, out, slots), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), steps, out, bool(slots), slots == "tail"), nprocs=world, join=True)
     res = torch.load(out, weights_only=False)
     assert res[0]["n0"] == res[0]["n1"] == sum(len(r["cell"]) for r in res)  # parcels conserved across ranks
     assert all(r["stuck"] == 0 for r in res)
@@ -67,7 +71,7 @@ def test_two_rank_migration_matches_single_domain(tmp_path, OracleCloud, slots):
     one = cases.couette(nx=24, ny=8, ppc=12, binary="noDSMCCollision")
     for e in one.boundariesDict["uniGasPatchBoundaries"]:
         e["boundaryModel"] = "uniGasSpecularWallPatch"
-    one.deltaT *= 6.0
+    one.deltaT *= 40.0 if slots == "tail" else 6.0
     pos = np.concatenate([r["init"][0] for r in res])
     U = np.concatenate([r["init"][1] for r in res])
     dx = one.meta["Lx"] / 24

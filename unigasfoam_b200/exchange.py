@@ -173,15 +173,34 @@ class SlotExchanger:
             return int(total.item())
 
     # -- fixed-round mode: no host synchronisation inside the step ---------------------------------------------
-    def exchange_fixed(self, n_rounds):
+    def exchange_fixed(self, n_rounds, exact_tail=False, max_rounds=512):
         """n_rounds transfer rounds back to back with no host synchronisation and no global collective; whatever
         is still in flight afterwards is added to a device-resident tally that check_settled() reduces over all
         ranks.  A parcel left in flight (n_rounds too small for this decomposition) is therefore reported loudly
-        at the next check, never dropped silently."""
+        at the next check, never dropped silently.
+
+        exact_tail: after the n_rounds unsynchronised rounds the in-flight count is reduced once and further rounds follow
+        until it is zero - the reference's termination rule with one collective per step instead of one per round, for
+        decompositions whose round count has a tail (block corners, an axis between symmetry planes)."""
         ctx = torch.cuda.stream(self._stream) if self.cuda else _Null()
         with ctx:
             for _ in range(n_rounds):
                 self._round()
+            if exact_tail:
+                total = self._inflight.clone()
+                dist.all_reduce(total, group=self.group)
+                left = int(total.item())
+                extra = 0
+                while left > 0:
+                    extra += 1
+                    if extra > max_rounds:
+                        raise RuntimeError("parcel migration did not settle")
+                    self._round()
+                    total = self._inflight.clone()
+                    dist.all_reduce(total, group=self.group)
+                    left = int(total.item())
+                self.tail_rounds = getattr(self, "tail_rounds", 0) + extra
+                return
             if not hasattr(self, "_left"):
                 self._left = torch.zeros_like(self._inflight)
             self._left += self._inflight
@@ -340,11 +359,12 @@ class _Null:
         return False
 
 
-def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64, fixed_rounds=None):
+def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64, fixed_rounds=None, exact_tail=False):
     """uniGasCloud::evolve across ranks: the phases of ugf_step with the transfer loop after the move.  Both
     exchangers return 0 from exchange() once no rank has parcels in flight (the reference's termination rule).
-    fixed_rounds (SlotExchanger only): run exactly that many rounds without host synchronisation and verify
-    quiescence one step later."""
+    fixed_rounds (SlotExchanger / PeerExchanger): run exactly that many rounds without host synchronisation and verify
+    quiescence one step later; with exact_tail the count is checked once per step after them and further rounds follow
+    until nothing is in flight (exact like the reference, one collective per step)."""
     for _ in range(n_steps):
         if inflow:
             cloud.controlBeforeMove()
@@ -352,7 +372,10 @@ def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64,
         if hasattr(exchanger, "begin_step"):
             exchanger.begin_step()
         if fixed_rounds:
-            exchanger.exchange_fixed(fixed_rounds)
+            if exact_tail:
+                exchanger.exchange_fixed(fixed_rounds, exact_tail=True, max_rounds=max_rounds)
+            else:
+                exchanger.exchange_fixed(fixed_rounds)
             cloud.finishStep()
             continue
         for _r in range(max_rounds):
@@ -361,7 +384,7 @@ def evolve_distributed(cloud, exchanger, n_steps=1, inflow=False, max_rounds=64,
         else:
             raise RuntimeError("parcel migration did not settle")
         cloud.finishStep()
-    if fixed_rounds:
+    if fixed_rounds and not exact_tail:
         exchanger.check_settled()
 
 
