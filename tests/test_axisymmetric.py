@@ -171,6 +171,56 @@ def test_bad_axisymmetric_properties_fail(OracleCloud):
         OracleCloud(case.mesh, props, case.boundariesDict, case.deltaT, parcelCapacity=1000)
 
 
+def test_restart_through_time_directories(tmp_path, OracleCloud):
+    """lagrangian/uniGas/radialWeight in the time directory: written after a step it holds RWF(position) and the restarted run
+    continues bit for bit; written before the first step it holds the initialisation's RWF(cell centre) and the restart's first
+    weighting pass clones / deletes exactly like the uninterrupted run's."""
+    import os
+    for steps_before in (3, 0):
+        case = cases.axisymmetric_tube(nx=8, nr=6, ppc=30, cell_weighted=True, seed=17)
+        kw = dict(parcelCapacity=4 * case.n_parcels)
+        a = case.make_cloud(OracleCloud, **kw)
+        if steps_before:
+            a.evolve(steps_before)
+        d = str(tmp_path / f"case{steps_before}")
+        t = a.writeTime(d, "1e-06")
+        assert os.path.exists(os.path.join(t, "lagrangian", "uniGas", "radialWeight"))
+        pw = a.parcels()
+        want = rwf_of(case, pw["position"]) if steps_before else rwf_of(case, case.mesh.cell_centres[pw["cell"]])
+        assert np.array_equal(pw["radialWeight"], want)
+        a.evolve(3)
+        b = OracleCloud(case.mesh, case.uniGasProperties, case.boundariesDict, case.deltaT, **kw)
+        b.readTime(d, "1e-06")
+        assert np.array_equal(b.parcels()["radialWeight"], want)
+        b.evolve(3)
+        pa, pb = a.parcels(), b.parcels()
+        for k in ("cell", "position", "U", "radialWeight", "cellWeight"):
+            assert np.array_equal(pa[k], pb[k]), (steps_before, k)
+        ca, cb = a.counters(), b.counters()
+        assert ca["cloned"] == cb["cloned"] and ca["weightDeleted"] == cb["weightDeleted"] and ca["collisions"] == cb["collisions"]
+
+
+def test_adapter_cell_weights_carry_the_radial_factor(OracleCloud):
+    """uniGasDynamicAdapter::calculateCellWeightFactor divides by RWF(cell centre) (uniGasDynamicAdapter.C:442): with the factor
+    field it computes every cell of a uniform gas ends up with the requested parcels per cell, on the axis and at the wall."""
+    from unigasfoam_b200.adapter import UniGasDynamicAdapter
+    case = cases.axisymmetric_tube(nx=6, nr=8, ppc=25, cell_weighted=True, U_inf=0.0, wall="uniGasSpecularWallPatch", seed=19)
+    props = dict(case.uniGasProperties, adaptiveSimulation=True,
+                 adaptiveProperties={"timeStepAdaptation": False, "subCellAdaptation": False, "cellWeightAdaptation": True, "adaptationInterval": 5,
+                                     "maxTimeStepMCTRatio": 0.2, "maxCourantNumber": 0.5, "maxSubCellSizeMFPRatio": 1.0})
+    cl = OracleCloud(case.mesh, props, case.boundariesDict, case.deltaT, parcelCapacity=4 * case.n_parcels)
+    cl.setCellState(cellWeightFactor=case.cellWeightFactor)
+    cl.setParcels(case.position, case.U, case.cell)
+    cl.setCellState(sigmaTcRMax=case.sigmaTcRMax)
+    ad = UniGasDynamicAdapter(cl, props)
+    rhoN = np.full(case.mesh.n_cells, case.meta["n"])
+    levels = np.ones((case.mesh.n_cells, 3), np.int32)
+    w = ad.calculate_cell_weight_factor(rhoN, levels)
+    expect = case.meta["n"] * case.mesh.cell_volumes / (25 * props["nEquivalentParticles"] * case.meta["rwf_centre"])
+    assert np.allclose(w, expect, rtol=1e-13)
+    assert np.allclose(w, case.cellWeightFactor, rtol=1e-12)  # the same rule uniGasMeshFill applies (uniGasMeshFill.C:111-121)
+
+
 # ---- GPU against the oracle ------------------------------------------------------------------------------------------------
 
 def _lockstep(g, r, steps, fields=True, rtol=1e-9):

@@ -80,7 +80,8 @@ class FaceOperators:
             di = ((Cf[f] - m.cell_centres[self.po]) * S[f]).sum(1) / self.A[f]
             dni = halo(di[:, None])[:, 0]
             self.bw[self.bproc] = dni / (di + dni)
-        self.bn = S[self.bf] / self.A[self.bf][:, None] if len(self.bf) else np.empty((0, 3))
+        # unit normals of the boundary faces; a face collapsed onto an axis has no area and no normal (its weight below is zero too)
+        self.bn = S[self.bf] / np.where(self.A[self.bf] > 0, self.A[self.bf], 1.0)[:, None] if len(self.bf) else np.empty((0, 3))
         den = np.zeros(self.nC)
         np.add.at(den, self.own, self.A[:nI]); np.add.at(den, self.nei, self.A[:nI]); np.add.at(den, self.bo, self.A[self.bf])
         self.den = den
