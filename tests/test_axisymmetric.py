@@ -221,6 +221,70 @@ def test_adapter_cell_weights_carry_the_radial_factor(OracleCloud):
     assert np.allclose(w, case.cellWeightFactor, rtol=1e-12)  # the same rule uniGasMeshFill applies (uniGasMeshFill.C:111-121)
 
 
+def test_plume_impingement_dictionaries_run_as_written(tmp_path, OracleCloud):
+    """The reference's axisymmetric tutorial plumeImpingement: its constant/uniGasProperties and system/*Dict copied unmodified
+    (tests/golden/openfoam/plumeImpingement; one adaptation threshold overridden, see below) - axisymmetric + cell-weighted + adaptive + hybrid USP-SBGK / NTC with
+    macroInterpolation true, Liou-Fang pressure inlet, two diffuse walls, deleting outlet, uniGasMeshFieldFill from the start time
+    directory - on a wedge with the tutorial's patch names and radial extent (its four graded blocks with the curved nozzle are not
+    rebuilt: one block, nozzle wall and outlet sharing the outer radius, impingement surface at the far end)."""
+    import os
+    import shutil
+    from unigasfoam_b200 import foamdict, foamfile, mesh as ugmesh
+    from unigasfoam_b200.adapter import UniGasDynamicAdapter
+    gold = os.path.join(os.path.dirname(__file__), "golden", "openfoam", "plumeImpingement")
+    case_dir = str(tmp_path / "plumeImpingement")
+    shutil.copytree(gold, case_dir)
+    nx, nr = 24, 10
+    kinds = {"xMin": ("inlet", "patch"), "xMax": ("surface", "wall"), "yMin": ("axis", "symmetry"), "yMax": ("outer", "patch"),
+             "zMin": ("backWedge", "symmetryPlane"), "zMax": ("frontWedge", "symmetryPlane")}
+    m = ugmesh.structured_block(nx, nr, 1, ugmesh.wedge_map(nx, nr, 0.139, 7.5e-2, 0.5), kinds)
+    ugmesh.split_patch(m, "outer", 8, "nozzle", "outlet", kind_a="wall", kind_b="patch")
+    m.meta_axis_aligned = False
+    assert [p.name for p in m.patches] == ["inlet", "surface", "axis", "nozzle", "outlet", "backWedge", "frontWedge"]
+    # the start time directory uniGasMeshFieldFill reads: gas at rest at the inlet state (1000 Pa, 300 K), thinning out towards the
+    # outlet half of the domain
+    t0 = os.path.join(case_dir, "0")
+    os.makedirs(t0)
+    names = [p.name for p in m.patches]
+    nC = m.n_cells
+    n_in = 1000.0 / (kB * 300.0)
+    n0 = n_in * np.where(m.cell_centres[:, 0] < 0.05, 1.0, 0.2)
+    foamfile.write_vol_field(os.path.join(t0, "numberDensity_Ar"), "0", [0, -3, 0, 0, 0, 0, 0], n0, names)
+    foamfile.write_vol_field(os.path.join(t0, "transT"), "0", [0, 0, 0, 1, 0, 0, 0], np.full(nC, 300.0), names)
+    foamfile.write_vol_field(os.path.join(t0, "rotT"), "0", [0, 0, 0, 1, 0, 0, 0], np.full(nC, 300.0), names)
+    foamfile.write_vol_field(os.path.join(t0, "U"), "0", [0, 1, -1, 0, 0, 0, 0], np.zeros((nC, 3)), names, vector=True)
+    # one test-scale accommodation, as for the other tutorials (tests/test_foamdict.py): the cells here are ~1000 mean free paths wide,
+    # so the sub-cell criterion (one sub-cell per mean free path, 20 parcels in each) is relaxed - else 4.7 M parcels in 240 cells
+    case, ld = cases.from_case_dir(case_dir, m, seed=5, overrides={"adaptiveProperties": {"maxSubCellSizeMFPRatio": 1.0e4}})
+    props = case.uniGasProperties
+    assert props["axisymmetricSimulation"] is True and props["collisionProperties"]["macroInterpolation"] is True
+    assert props["axisymmetricProperties"] == {"radialExtentOfDomain": 7.5e-2, "maxRadialWeightingFactor": 1000}
+    # uniGasMeshFill's rule with both weights: particlesPerSubCell parcels in every sub-cell, on the axis and at the outer radius
+    nSub = np.ones(nC) if case.subCellLevels is None else case.subCellLevels.prod(1)
+    cnt = np.bincount(case.cell, minlength=nC) / nSub
+    assert abs(cnt.mean() - 20) < 1.5 and cnt.reshape(nr, nx).mean(1).min() > 15
+    cl = case.make_cloud(OracleCloud, parcelCapacity=8 * case.n_parcels, sampleInterval=foamdict.sample_interval(ld["fieldPropertiesDict"]))
+    assert cl.axisymmetric and cl.cfg.macroInterpolation == 1
+    cl.setHybridDecomposition(ld["hybridDecompositionDict"])
+    ad = UniGasDynamicAdapter(cl, props)
+    if case.subCellLevels is not None:
+        ad.subCellLevels = case.subCellLevels.copy()
+    n = cl.size()
+    tally = dict(inserted=0, deleted=0, cloned=0, weightDeleted=0, collisions=0, bgkRelaxations=0, wallHits=0)
+    for _ in range(3):
+        ad.run(10)   # adaptationInterval 10 in the tutorial: three adaptations
+        ad.cellCollModelId = cl.hybridDecomposition()["cellCollModelId"]
+    c = cl.counters()
+    assert c["stuck"] == 0 and c["step"] == 30
+    p = cl.parcels()
+    assert np.array_equal(p["radialWeight"], rwf_of(case, p["position"]))
+    f = cl.fields()
+    assert np.isfinite(f["rhoN"]).all() and np.isfinite(f["translationalT"]).all() and (f["rhoN"] > 0).all()
+    assert abs(np.average(f["translationalT"], weights=m.cell_volumes) / 300.0 - 1.0) < 0.1
+    v = cl.inletVelocity("inlet")
+    assert np.isfinite(v).all()
+
+
 # ---- GPU against the oracle ------------------------------------------------------------------------------------------------
 
 def _lockstep(g, r, steps, fields=True, rtol=1e-9):

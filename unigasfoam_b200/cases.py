@@ -83,6 +83,27 @@ def _uniform_in_cells(mesh, cells, rng):
     lo, hi = mesh.cell_bb_min[cells], mesh.cell_bb_max[cells]
     if mesh.meta_axis_aligned:
         return lo + rng.random((len(cells), 3)) * (hi - lo)
+    if mesh.cell_quads is None:
+        # general hex cells of a structured block (wedges, bodies of revolution): six tets around the 0-7 diagonal, one chosen by
+        # volume, uniform point in it (tetPointRef::randomPoint, as uniGasMeshFill does per tet, uniGasMeshFill.C:174-278)
+        corners = mesh.points[_mesh.hex_corners(mesh)[cells]]            # [n,8,3]
+        tets = np.asarray(_HEX_TETS)
+        a = corners[:, tets[:, 0]]
+        e = np.stack([corners[:, tets[:, 1]] - a, corners[:, tets[:, 2]] - a, corners[:, tets[:, 3]] - a], axis=-2)  # [n,6,3,3]
+        cum = np.cumsum(np.abs(np.linalg.det(e)), axis=1)
+        pick = (rng.random(len(cells))[:, None] * cum[:, -1:] >= cum).sum(1).clip(0, 5)
+        idx = np.arange(len(cells))
+        a, e = a[idx, pick], e[idx, pick]
+        s, t, u = rng.random(len(cells)), rng.random(len(cells)), rng.random(len(cells))
+        # fold the unit cube into the unit tetrahedron (Rocchini & Cignoni)
+        f = s + t > 1.0
+        s, t = np.where(f, 1.0 - s, s), np.where(f, 1.0 - t, t)
+        g1 = t + u > 1.0
+        t2 = np.where(g1, 1.0 - u, t); u2 = np.where(g1, 1.0 - s - t, u)
+        g2 = ~g1 & (s + t + u > 1.0)
+        s2 = np.where(g2, 1.0 - t - u, s); u2 = np.where(g2, s + t + u - 1.0, u2)
+        s, t, u = s2, t2, u2
+        return a + s[:, None] * e[:, 0] + t[:, None] * e[:, 1] + u[:, None] * e[:, 2]
     # general extruded quads: use the cell's zMin face (patch order guarantees it exists for nz = 1)
     quad = mesh.cell_quads[cells]  # [n,4,2] xy of the 4 corners, counter-clockwise
     a, b, c, d = quad[:, 0], quad[:, 1], quad[:, 2], quad[:, 3]
@@ -397,13 +418,15 @@ def from_case_dir(case_dir, mesh, seed=7, overrides=None, particles_per_cell=Non
         if not ad0.subCellAdaptation:
             levels = None
     cwf = None
+    rwf_c = radial_weight(props, mesh.cell_centres)  # axisymmetricSimulation: RWF of the cell centres (uniGasMeshFill.C:117, 204, 260); else 1
     if props.get("cellWeightedSimulation", False):
         pps = particles_per_cell or int(props["cellWeightedProperties"]["particlesPerSubCell"])
         nSub = 1.0 if levels is None else levels.prod(1).astype(float)
-        cwf = cell_weight_factor(mesh, ("particlesPerSubCell", pps), ntot, FN) / nSub   # uniGasMeshFill.C:111-121
+        cwf = cell_weight_factor(mesh, ("particlesPerSubCell", pps), ntot, FN) / nSub / rwf_c   # uniGasMeshFill.C:111-121
     rng = np.random.default_rng(seed)
     sps = props["moleculeProperties"]
-    pos, velp, cel, tid, erot = mesh_fill(mesh, sps, names, dens, T, vel, FN, rng, Trot=Trot, cell_weight=cwf)
+    fill_w = cwf if not props.get("axisymmetricSimulation", False) else (rwf_c if cwf is None else cwf * rwf_c)
+    pos, velp, cel, tid, erot = mesh_fill(mesh, sps, names, dens, T, vel, FN, rng, Trot=Trot, cell_weight=fill_w)
     sp0 = sps[names[int(np.argmax([np.mean(dens[n]) for n in names]))]]
     sig0 = math.pi * sp0["diameter"] ** 2 * most_probable_speed(float(np.mean(T)), sp0["mass"])  # uniGasMeshFill.C:284-296
     any_rot = any(sps[n].get("rotationalDegreesOfFreedom", 0) for n in names)
