@@ -554,7 +554,7 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "particle-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.settle + warm, "ms_per_step": ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "settle_steps": args.settle, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, world, n_parcels, nC),
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
