@@ -2864,6 +2864,9 @@ int ugfo_set_face_tracker(ugfo_handle* h, int32_t n, const int32_t* faces) {
     h->nTracked = 0;
     h->ft.clear();
     if (n <= 0 || !faces) return 0;
+    if (h->cfg.axisymmetric)  // the same refusal as the device library: the weight a migrating parcel carries is CWF x RWF
+        for (int p = 0; p < h->nPatches; ++p)
+            if (h->pKind[p] == UGF_PATCH_PROCESSOR && h->pSize[p] > 0) return fail(h, "face tracker on a decomposed axisymmetric case is not supported");
     for (int k = 0; k < n; ++k) {
         if (faces[k] < 0 || faces[k] >= h->nFaces) return fail(h, "tracked face out of range");
         if (h->faceTrack[faces[k]]) return fail(h, "face listed twice in the face tracker");

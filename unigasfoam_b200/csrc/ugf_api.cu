@@ -2629,6 +2629,8 @@ int ugf_set_face_tracker(ugf_handle* h, int32_t n, const int32_t* faces) {
     h->dSlotTrack = nullptr; h->dBfTrack = nullptr; h->dFt = nullptr;
     h->nTracked = 0;
     if (n <= 0 || !faces) return 0;
+    if (h->cfg.axisymmetric && h->hasProcessor)  // the weight a migrating parcel carries is CWF x RWF; the tracker needs CWF alone
+        return fail(h, "face tracker on a decomposed axisymmetric case is not supported");
     std::vector<int> faceIdx((size_t)h->nFaces, 0);  // k + 1 of a tracked face
     for (int k = 0; k < n; ++k) {
         if (faces[k] < 0 || faces[k] >= h->nFaces) return fail(h, "tracked face out of range");
